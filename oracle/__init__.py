@@ -1,0 +1,205 @@
+"""CPU oracle for the ORBSLAMM hot path -- TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+legs may import this package; the product (orbslamm_b200) never does.
+
+Pieces:
+  * orb_oracle.c   restatement of ORBextractor.cc on restated OpenCV primitives
+  * slam_oracle.c  restatement of ORBmatcher / Optimizer(+g2o) arithmetic
+  * orb_cv2.py     the same extractor but calling the *real* OpenCV primitives
+                   through cv2 (what the reference itself calls) -- used to pin
+                   orb_oracle.c and as the reference-faithful CPU baseline.
+
+Parity status: the reference repository holds no golden vectors or tests for
+this path and cannot be compiled here (needs OpenCV C++/Eigen
+headers).  The extractor oracle is pinned against cv2 4.13.0 (same OpenCV
+primitives the reference calls); the optimizer oracle is pinned against an
+independent numpy/scipy twin.  Beyond that: "parity unpinned" by the reference.
+"""
+import ctypes
+import os
+import subprocess
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def build(force=False):
+    """Compile oracle/*.c into oracle/_build/liboracle.so (gcc, no FMA contraction)."""
+    out_dir = os.path.join(_HERE, "_build")
+    os.makedirs(out_dir, exist_ok=True)
+    so = os.path.join(out_dir, "liboracle.so")
+    srcs = [os.path.join(_HERE, f) for f in ("orb_oracle.c", "slam_oracle.c")]
+    srcs = [s for s in srcs if os.path.exists(s)]
+    deps = srcs + [os.path.join(_HERE, "..", "include", "orb_brief_pattern.inc")]
+    if (not force) and os.path.exists(so) and all(os.path.getmtime(so) >= os.path.getmtime(d) for d in deps):
+        return so
+    cmd = ["gcc", "-O2", "-ffp-contract=off", "-fno-fast-math", "-shared", "-fPIC", "-o", so] + srcs + ["-lm"]
+    subprocess.check_call(cmd)
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = ctypes.CDLL(build())
+        _declare(_LIB)
+    return _LIB
+
+
+class OrbParams(ctypes.Structure):
+    _fields_ = [("nfeatures", ctypes.c_int), ("nlevels", ctypes.c_int), ("ini_th", ctypes.c_int),
+                ("min_th", ctypes.c_int), ("scale_factor", ctypes.c_double),
+                ("scale", ctypes.c_float * 16), ("inv_scale", ctypes.c_float * 16),
+                ("sigma2", ctypes.c_float * 16), ("inv_sigma2", ctypes.c_float * 16),
+                ("features_per_level", ctypes.c_int * 16), ("umax", ctypes.c_int * 16)]
+
+
+class Cand(ctypes.Structure):
+    _fields_ = [("x", ctypes.c_float), ("y", ctypes.c_float), ("response", ctypes.c_float)]
+
+
+_u8p = ctypes.POINTER(ctypes.c_uint8)
+_i32p = ctypes.POINTER(ctypes.c_int)
+_f32p = ctypes.POINTER(ctypes.c_float)
+_f64p = ctypes.POINTER(ctypes.c_double)
+
+
+def _p(a, t):
+    return a.ctypes.data_as(t)
+
+
+def _declare(L):
+    L.oracle_fast_atan2.restype = ctypes.c_float
+    L.oracle_fast_atan2.argtypes = [ctypes.c_float, ctypes.c_float]
+    L.oracle_fast9_16.restype = ctypes.c_int
+    L.oracle_detect_cells.restype = ctypes.c_int
+    L.oracle_distribute_octree.restype = ctypes.c_int
+    L.oracle_orb_extract.restype = ctypes.c_int
+    L.oracle_orb_params_init.restype = ctypes.c_int
+    L.oracle_orb_params_init.argtypes = [ctypes.POINTER(OrbParams), ctypes.c_int, ctypes.c_float,
+                                         ctypes.c_int, ctypes.c_int, ctypes.c_int]
+
+
+def orb_params(nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7):
+    P = OrbParams()
+    rc = lib().oracle_orb_params_init(ctypes.byref(P), nfeatures, scale_factor, nlevels, ini_th, min_th)
+    if rc != 0:
+        raise ValueError("bad extractor parameters")
+    return P
+
+
+def resize_linear(src, dw, dh):
+    src = np.ascontiguousarray(src, np.uint8)
+    dst = np.empty((dh, dw), np.uint8)
+    lib().oracle_resize_linear_u8(_p(src, _u8p), src.shape[1], src.shape[0], src.strides[0],
+                                  _p(dst, _u8p), dw, dh, dw)
+    return dst
+
+
+def gaussian_blur7(src):
+    src = np.ascontiguousarray(src, np.uint8)
+    dst = np.empty_like(src)
+    lib().oracle_gaussian_blur7_u8(_p(src, _u8p), src.shape[1], src.shape[0], src.strides[0],
+                                   _p(dst, _u8p), dst.strides[0])
+    return dst
+
+
+def fast9_16(img, threshold, nms=True):
+    img = np.ascontiguousarray(img, np.uint8)
+    cap = img.size + 1
+    out = np.empty((cap, 3), np.int32)
+    n = lib().oracle_fast9_16(_p(img, _u8p), img.shape[1], img.shape[0], img.strides[0],
+                              int(threshold), int(bool(nms)), _p(out, _i32p), cap)
+    return out[:n].copy()
+
+
+def fast_atan2(y, x):
+    return float(lib().oracle_fast_atan2(float(y), float(x)))
+
+
+def level_size(P, w, h, level):
+    lw, lh = ctypes.c_int(), ctypes.c_int()
+    lib().oracle_level_size(ctypes.byref(P), w, h, level, ctypes.byref(lw), ctypes.byref(lh))
+    return lw.value, lh.value
+
+
+def pyramid(P, image):
+    """Un-bordered pyramid levels (ORBextractor.cc:1107-1132 minus the border)."""
+    image = np.ascontiguousarray(image, np.uint8)
+    h, w = image.shape
+    levels = [image]
+    for l in range(1, P.nlevels):
+        lw, lh = level_size(P, w, h, l)
+        levels.append(resize_linear(levels[-1], lw, lh))
+    return levels
+
+
+def detect_cells(level_img, ini_th, min_th):
+    img = np.ascontiguousarray(level_img, np.uint8)
+    cap = (img.shape[1] // 2 + 1) * (img.shape[0] // 2 + 1) + 16
+    out = np.empty((cap, 3), np.float32)
+    n = lib().oracle_detect_cells(_p(img, _u8p), img.shape[1], img.shape[0], img.strides[0],
+                                  int(ini_th), int(min_th), out.ctypes.data_as(ctypes.POINTER(Cand)), cap)
+    assert n <= cap
+    return out[:n].copy()
+
+
+def distribute_octree(cands, min_x, max_x, min_y, max_y, n_target):
+    cands = np.ascontiguousarray(cands, np.float32).reshape(-1, 3)
+    cap = len(cands) + 8
+    sel = np.empty(cap, np.int32)
+    n = lib().oracle_distribute_octree(cands.ctypes.data_as(ctypes.POINTER(Cand)), len(cands),
+                                       int(min_x), int(max_x), int(min_y), int(max_y), int(n_target),
+                                       _p(sel, _i32p), cap)
+    if n < 0:
+        raise ValueError("unsupported level shape for DistributeOctTree")
+    return sel[:n].copy()
+
+
+def ic_moments(P, level_img, x, y):
+    img = np.ascontiguousarray(level_img, np.uint8)
+    m01, m10 = ctypes.c_int(), ctypes.c_int()
+    lib().oracle_ic_moments(_p(img, _u8p), img.strides[0], int(x), int(y), P.umax,
+                            ctypes.byref(m01), ctypes.byref(m10))
+    return m01.value, m10.value
+
+
+def orb_descriptor(blur_img, x, y, angle_deg):
+    img = np.ascontiguousarray(blur_img, np.uint8)
+    d = np.empty(32, np.uint8)
+    lib().oracle_orb_descriptor(_p(img, _u8p), img.strides[0], int(x), int(y),
+                                ctypes.c_float(angle_deg), _p(d, _u8p))
+    return d
+
+
+def orb_extract(P, image):
+    """Full extractor on restated primitives.  Returns dict of SoA arrays."""
+    image = np.ascontiguousarray(image, np.uint8)
+    if image.size == 0:
+        return _empty_result(P.nlevels)
+    h, w = image.shape
+    cap = P.nfeatures * 2 + 64 * P.nlevels
+    while True:
+        kx = np.empty(cap, np.float32); ky = np.empty(cap, np.float32)
+        ka = np.empty(cap, np.float32); kr = np.empty(cap, np.float32)
+        ko = np.empty(cap, np.int32); ks = np.empty(cap, np.float32)
+        desc = np.empty((cap, 32), np.uint8)
+        lc = np.zeros(P.nlevels, np.int32)
+        n = lib().oracle_orb_extract(ctypes.byref(P), _p(image, _u8p), w, h, image.strides[0],
+                                     _p(kx, _f32p), _p(ky, _f32p), _p(ka, _f32p), _p(kr, _f32p),
+                                     _p(ko, _i32p), _p(ks, _f32p), _p(desc, _u8p), cap, _p(lc, _i32p))
+        if n < 0:
+            raise ValueError(f"oracle_orb_extract status {n}")
+        if n <= cap:
+            break
+        cap = n
+    return dict(x=kx[:n].copy(), y=ky[:n].copy(), angle=ka[:n].copy(), response=kr[:n].copy(),
+                octave=ko[:n].copy(), size=ks[:n].copy(), desc=desc[:n].copy(), level_counts=lc)
+
+
+def _empty_result(nlevels):
+    z = np.zeros(0, np.float32)
+    return dict(x=z, y=z, angle=z, response=z, octave=np.zeros(0, np.int32), size=z,
+                desc=np.zeros((0, 32), np.uint8), level_counts=np.zeros(nlevels, np.int32))
