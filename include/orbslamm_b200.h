@@ -1,0 +1,123 @@
+/*
+ * orbslamm_b200.h -- C-ABI of the B200-native ORBSLAMM hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types.
+ * The C++ classes in orbslamm_b200/host/ (ORBextractor / ORBmatcher / Optimizer,
+ * same signatures as the reference headers) are thin marshalling shims over these
+ * entry points.  Every function returns an int status: 0 = OK, <0 = error
+ * (see ORBS_E_*); no exception crosses this boundary.  There is NO CPU fallback:
+ * if no CUDA device is usable every entry point returns ORBS_E_CUDA.
+ *
+ * Reference interfaces replaced (paths relative to the reference checkout,
+ * S/ = SingleRobotScenario/):
+ *   orbx_*     S/include/ORBextractor.h:45-111   (ctor, operator(), getters, mvImagePyramid)
+ *   orbm_*     S/include/ORBmatcher.h:37-102     (DescriptorDistance, SearchByProjection)
+ *              S/src/Frame.cc:230-245,327-392    (AssignFeaturesToGrid / GetFeaturesInArea / PosInGrid)
+ *   orbo_*     S/include/Optimizer.h:37-68       (PoseOptimization, LocalBundleAdjustment, BundleAdjustment)
+ */
+#ifndef ORBSLAMM_B200_H
+#define ORBSLAMM_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ORBS_OK 0
+#define ORBS_E_INVALID (-1)   /* bad argument (null pointer, non-positive size, ...) */
+#define ORBS_E_CUDA (-2)      /* CUDA runtime error / no device (orbs_last_error() has the text) */
+#define ORBS_E_CAPACITY (-3)  /* caller-provided output capacity too small */
+#define ORBS_E_SHAPE (-4)     /* image shape the reference algorithm is undefined for */
+#define ORBS_E_STATE (-5)     /* call order violated (e.g. download before extract) */
+
+#define ORBS_MAX_LEVELS 16
+#define ORBS_FRAME_GRID_COLS 64   /* S/include/Frame.h:37-38 */
+#define ORBS_FRAME_GRID_ROWS 48
+
+/* thread-local text of the last error on this thread ("" if none) */
+const char *orbs_last_error(void);
+/* library/ABI version and the device the library would use; both cheap, no compute */
+int orbs_version(void);
+int orbs_device_count(void);
+
+/* ------------------------------------------------------------------ */
+/* ORB extractor  (replaces S/src/ORBextractor.cc)                       */
+typedef struct orbx_handle orbx_handle;
+
+/* ORBextractor::ORBextractor(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST),
+ * ORBextractor.cc:410-470.  `device` = CUDA ordinal.  Thresholds must be >= 1. */
+int orbx_create(orbx_handle **out, int nfeatures, float scale_factor, int nlevels,
+                int ini_th_fast, int min_th_fast, int device);
+int orbx_destroy(orbx_handle *h);
+
+/* GetLevels / GetScaleFactor(s) / GetInverseScaleFactors / GetScaleSigmaSquares /
+ * GetInverseScaleSigmaSquares (ORBextractor.h:63-85) + mnFeaturesPerLevel.  Any
+ * pointer may be NULL.  Arrays must hold nlevels entries. */
+int orbx_get_tables(const orbx_handle *h, int *nlevels, float *scale_factor, float *scale,
+                    float *inv_scale, float *sigma2, float *inv_sigma2, int *features_per_level);
+
+/* Upper bound of keypoints one frame of this shape can return (sum over levels of
+ * max(N_l + 3, 4 * nIni_l)); use it to size the output arrays. */
+int orbx_max_keypoints(orbx_handle *h, int width, int height, int *max_kp);
+
+/* ORBextractor::operator()(image, mask, keypoints, descriptors), ORBextractor.cc:1043-1105,
+ * for n_frames independent images of one shape.  HOST buffers in, HOST buffers out:
+ *   images      n_frames images, image f at images + f*frame_stride, rows `stride` bytes apart
+ *   kp_* / desc per-frame slabs of `cap` entries: frame f writes [f*cap, f*cap + counts[f])
+ *               kp_xy f32[.,2] (level-0 pixels), kp_angle f32 deg, kp_response f32,
+ *               kp_octave i32, kp_size f32, desc u8[.,32]   (cv::KeyPoint fields; class_id = -1)
+ *   counts      i32[n_frames]
+ * Empty image (width or height 0) -> counts = 0, status OK (ORBextractor.cc:1046-1047). */
+int orbx_extract(orbx_handle *h, const uint8_t *images, int n_frames, int width, int height,
+                 int stride, size_t frame_stride, float *kp_xy, float *kp_angle, float *kp_response,
+                 int32_t *kp_octave, float *kp_size, uint8_t *desc, int cap, int32_t *counts);
+
+/* Same, but the images are already in DEVICE memory and the results stay on the device
+ * inside the handle (see orbx_device_results).  Asynchronous on the handle's stream. */
+int orbx_extract_device(orbx_handle *h, const uint8_t *d_images, int n_frames, int width,
+                        int height, int stride, size_t frame_stride);
+
+/* Device-resident results of the last extract call.  slab = per-frame capacity (entries). */
+typedef struct {
+    int n_frames, slab;
+    const float *kp_xy;        /* [n_frames*slab, 2] */
+    const float *kp_angle;     /* [n_frames*slab] */
+    const float *kp_response;  /* [n_frames*slab] */
+    const int32_t *kp_octave;  /* [n_frames*slab] */
+    const float *kp_size;      /* [n_frames*slab] */
+    const uint8_t *desc;       /* [n_frames*slab, 32] */
+    const int32_t *counts;     /* [n_frames] */
+    const int32_t *level_counts; /* [n_frames, nlevels] */
+} orbx_device_view;
+int orbx_device_results(orbx_handle *h, orbx_device_view *view);
+
+/* Copy the device-resident results of the last orbx_extract_device to host slabs
+ * (same layout as orbx_extract) and synchronise. */
+int orbx_download(orbx_handle *h, float *kp_xy, float *kp_angle, float *kp_response,
+                  int32_t *kp_octave, float *kp_size, uint8_t *desc, int cap, int32_t *counts);
+
+/* mvImagePyramid[level] of frame `frame` of the last call (ORBextractor.h:87,
+ * ORBextractor.cc:1107-1132).  border = 0: the level itself (lw x lh);
+ * border = 1: with the 19-px BORDER_REFLECT_101 frame ((lw+38) x (lh+38)).
+ * Blocks until the data is on the host. */
+int orbx_level_size(orbx_handle *h, int width, int height, int level, int *lw, int *lh);
+int orbx_get_pyramid_level(orbx_handle *h, int frame, int level, int border, uint8_t *out,
+                           int out_stride);
+
+/* Stage inspection (tests): the FAST candidates of one level of one frame of the last call, i.e.
+ * vToDistributeKeys of ORBextractor.cc:775-829 as (x, y, response) int triplets relative to minBorder,
+ * in no particular order.  xys may be NULL to query the count. */
+int orbx_get_candidates(orbx_handle *h, int frame, int level, int32_t *xys, int cap, int *n_out);
+
+/* The CUDA stream (cudaStream_t) this handle launches on, for event timing. */
+void *orbx_stream(orbx_handle *h);
+int orbx_synchronize(orbx_handle *h);
+/* number of kernels this handle has launched since creation (bench bookkeeping) */
+long long orbx_kernel_launches(const orbx_handle *h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ORBSLAMM_B200_H */

@@ -1,0 +1,201 @@
+"""orbslamm_b200 -- B200-native (sm_100a) implementation of the ORBSLAMM hot path.
+
+Python here is only a thin ctypes binding over the C-ABI in include/orbslamm_b200.h
+(the product is liborbslamm_b200.so: hand-written CUDA + a C++ host driver).  There is
+no CPU fallback: if the shared library is missing or no CUDA device is usable, the calls
+raise.  The oracle/ package is never imported from here.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liborbslamm_b200.so")
+_lib = None
+
+ORBS_OK = 0
+
+
+class OrbsError(RuntimeError):
+    def __init__(self, code, text):
+        super().__init__(f"orbslamm_b200 error {code}: {text}")
+        self.code = code
+
+
+def load():
+    """Load the in-tree CUDA library.  Raises if it has not been built (python -m orbslamm_b200.build)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise OSError(f"{LIB_PATH} not built; run `python orbslamm_b200/build.py` (there is no CPU fallback)")
+        _lib = ctypes.CDLL(LIB_PATH)
+        _declare(_lib)
+    return _lib
+
+
+def _check(rc):
+    if rc != ORBS_OK:
+        raise OrbsError(rc, load().orbs_last_error().decode())
+
+
+class DeviceView(ctypes.Structure):
+    _fields_ = [("n_frames", ctypes.c_int), ("slab", ctypes.c_int),
+                ("kp_xy", ctypes.c_void_p), ("kp_angle", ctypes.c_void_p), ("kp_response", ctypes.c_void_p),
+                ("kp_octave", ctypes.c_void_p), ("kp_size", ctypes.c_void_p), ("desc", ctypes.c_void_p),
+                ("counts", ctypes.c_void_p), ("level_counts", ctypes.c_void_p)]
+
+
+def _declare(L):
+    c = ctypes
+    L.orbs_last_error.restype = c.c_char_p
+    L.orbs_version.restype = c.c_int
+    L.orbs_device_count.restype = c.c_int
+    vp, i, f, sz = c.c_void_p, c.c_int, c.c_float, c.c_size_t
+    L.orbx_create.argtypes = [c.POINTER(vp), i, f, i, i, i, i]
+    L.orbx_destroy.argtypes = [vp]
+    L.orbx_get_tables.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
+    L.orbx_max_keypoints.argtypes = [vp, i, i, c.POINTER(i)]
+    L.orbx_extract.argtypes = [vp, vp, i, i, i, i, sz, vp, vp, vp, vp, vp, vp, i, vp]
+    L.orbx_extract_device.argtypes = [vp, vp, i, i, i, i, sz]
+    L.orbx_device_results.argtypes = [vp, c.POINTER(DeviceView)]
+    L.orbx_download.argtypes = [vp, vp, vp, vp, vp, vp, vp, i, vp]
+    L.orbx_level_size.argtypes = [vp, i, i, i, c.POINTER(i), c.POINTER(i)]
+    L.orbx_get_pyramid_level.argtypes = [vp, i, i, i, vp, i]
+    L.orbx_get_candidates.argtypes = [vp, i, i, vp, i, c.POINTER(i)]
+    L.orbx_get_candidates.restype = c.c_int
+    L.orbx_stream.argtypes = [vp]
+    L.orbx_stream.restype = vp
+    L.orbx_synchronize.argtypes = [vp]
+    L.orbx_kernel_launches.argtypes = [vp]
+    L.orbx_kernel_launches.restype = c.c_longlong
+    for name in ("orbx_create", "orbx_destroy", "orbx_get_tables", "orbx_max_keypoints", "orbx_extract",
+                 "orbx_extract_device", "orbx_device_results", "orbx_download", "orbx_level_size",
+                 "orbx_get_pyramid_level", "orbx_synchronize"):
+        getattr(L, name).restype = c.c_int
+    from . import _bind_more
+    _bind_more.declare(L)
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data
+
+
+class ORBextractor:
+    """Mirror of iORB_SLAM::ORBextractor (reference S/include/ORBextractor.h:45-111).
+
+    __call__(image) plays operator()(image, mask, keypoints, descriptors): it returns a dict of
+    SoA keypoint arrays (cv::KeyPoint fields) and the N x 32 descriptor matrix.  `mask` is ignored
+    like in the reference.  extract_batch() is the batched form for many frames of one shape."""
+
+    HARRIS_SCORE = 0
+    FAST_SCORE = 1
+
+    def __init__(self, nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST, device=0):
+        self._L = load()
+        self._h = ctypes.c_void_p()
+        _check(self._L.orbx_create(ctypes.byref(self._h), int(nfeatures), float(scaleFactor), int(nlevels),
+                                   int(iniThFAST), int(minThFAST), int(device)))
+        self.nlevels = int(nlevels)
+        n = ctypes.c_int()
+        sf = ctypes.c_float()
+        self._scale = np.zeros(nlevels, np.float32); self._inv_scale = np.zeros(nlevels, np.float32)
+        self._sigma2 = np.zeros(nlevels, np.float32); self._inv_sigma2 = np.zeros(nlevels, np.float32)
+        self._nfeat = np.zeros(nlevels, np.int32)
+        _check(self._L.orbx_get_tables(self._h, ctypes.addressof(n), ctypes.addressof(sf), _ptr(self._scale),
+                                       _ptr(self._inv_scale), _ptr(self._sigma2), _ptr(self._inv_sigma2),
+                                       _ptr(self._nfeat)))
+        self._scale_factor = sf.value
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            self._L.orbx_destroy(h)
+
+    # getters of the reference class
+    def GetLevels(self): return self.nlevels
+    def GetScaleFactor(self): return self._scale_factor
+    def GetScaleFactors(self): return self._scale.copy()
+    def GetInverseScaleFactors(self): return self._inv_scale.copy()
+    def GetScaleSigmaSquares(self): return self._sigma2.copy()
+    def GetInverseScaleSigmaSquares(self): return self._inv_sigma2.copy()
+    def features_per_level(self): return self._nfeat.copy()
+
+    @property
+    def handle(self): return self._h
+
+    def max_keypoints(self, width, height):
+        n = ctypes.c_int()
+        _check(self._L.orbx_max_keypoints(self._h, int(width), int(height), ctypes.byref(n)))
+        return n.value
+
+    def extract_batch(self, images):
+        """images: u8 array [B, H, W] (host).  Returns list of per-frame dicts."""
+        images = np.ascontiguousarray(images, np.uint8)
+        assert images.ndim == 3
+        B, H, W = images.shape
+        if H == 0 or W == 0:
+            return [_empty() for _ in range(B)]
+        cap = self.max_keypoints(W, H)
+        xy = np.empty((B, cap, 2), np.float32); ang = np.empty((B, cap), np.float32)
+        resp = np.empty((B, cap), np.float32); octv = np.empty((B, cap), np.int32)
+        size = np.empty((B, cap), np.float32); desc = np.empty((B, cap, 32), np.uint8)
+        counts = np.zeros(B, np.int32)
+        _check(self._L.orbx_extract(self._h, _ptr(images), B, W, H, images.strides[1], images.strides[0], _ptr(xy), _ptr(ang),
+                                    _ptr(resp), _ptr(octv), _ptr(size), _ptr(desc), cap, _ptr(counts)))
+        out = []
+        for f in range(B):
+            n = int(counts[f])
+            out.append(dict(x=xy[f, :n, 0].copy(), y=xy[f, :n, 1].copy(), angle=ang[f, :n].copy(),
+                            response=resp[f, :n].copy(), octave=octv[f, :n].copy(), size=size[f, :n].copy(),
+                            desc=desc[f, :n].copy()))
+        return out
+
+    def __call__(self, image, mask=None):
+        image = np.asarray(image)
+        if image.size == 0:
+            return _empty()
+        assert image.dtype == np.uint8 and image.ndim == 2, "CV_8UC1 image expected (ORBextractor.cc:1050)"
+        return self.extract_batch(image[None])[0]
+
+    def extract_device(self, dev_ptr, n_frames, width, height, stride, frame_stride):
+        _check(self._L.orbx_extract_device(self._h, ctypes.c_void_p(dev_ptr), n_frames, width, height, stride, frame_stride))
+
+    def device_view(self):
+        v = DeviceView()
+        _check(self._L.orbx_device_results(self._h, ctypes.byref(v)))
+        return v
+
+    def download(self, n_frames, cap):
+        xy = np.empty((n_frames, cap, 2), np.float32); ang = np.empty((n_frames, cap), np.float32)
+        resp = np.empty((n_frames, cap), np.float32); octv = np.empty((n_frames, cap), np.int32)
+        size = np.empty((n_frames, cap), np.float32); desc = np.empty((n_frames, cap, 32), np.uint8)
+        counts = np.zeros(n_frames, np.int32)
+        _check(self._L.orbx_download(self._h, _ptr(xy), _ptr(ang), _ptr(resp), _ptr(octv), _ptr(size), _ptr(desc), cap, _ptr(counts)))
+        return dict(xy=xy, angle=ang, response=resp, octave=octv, size=size, desc=desc, counts=counts)
+
+    def pyramid_level(self, frame, level, width, height, border=False):
+        """mvImagePyramid[level] of a frame of the last call (optionally with the 19-px reflect-101 border)."""
+        lw, lh = ctypes.c_int(), ctypes.c_int()
+        _check(self._L.orbx_level_size(self._h, width, height, level, ctypes.byref(lw), ctypes.byref(lh)))
+        b = 19 if border else 0
+        out = np.empty((lh.value + 2 * b, lw.value + 2 * b), np.uint8)
+        _check(self._L.orbx_get_pyramid_level(self._h, frame, level, int(bool(border)), _ptr(out), out.strides[0]))
+        return out
+
+    def candidates(self, frame, level):
+        """FAST candidates (x, y, response) of one level, relative to minBorder, unordered (stage inspection)."""
+        n = ctypes.c_int()
+        _check(self._L.orbx_get_candidates(self._h, frame, level, None, 0, ctypes.byref(n)))
+        out = np.empty((max(n.value, 1), 3), np.int32)
+        _check(self._L.orbx_get_candidates(self._h, frame, level, _ptr(out), len(out), ctypes.byref(n)))
+        return out[:n.value]
+
+    def stream(self): return self._L.orbx_stream(self._h)
+    def synchronize(self): _check(self._L.orbx_synchronize(self._h))
+    def kernel_launches(self): return int(self._L.orbx_kernel_launches(self._h))
+
+
+def _empty():
+    z = np.zeros(0, np.float32)
+    return dict(x=z, y=z, angle=z, response=z, octave=np.zeros(0, np.int32), size=z, desc=np.zeros((0, 32), np.uint8))

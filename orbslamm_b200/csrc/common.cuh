@@ -1,0 +1,62 @@
+// common.cuh -- shared host/device helpers for the orbslamm_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include "../../include/orbslamm_b200.h"
+
+namespace orbs {
+
+void set_last_error(const std::string &s);
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
+
+#define ORBS_CUDA(call)                                                        \
+    do {                                                                       \
+        cudaError_t _e = (call);                                               \
+        if (_e != cudaSuccess) return orbs::cuda_fail(_e, #call, __FILE__, __LINE__); \
+    } while (0)
+
+#define ORBS_REQUIRE(cond, code, msg)                                          \
+    do {                                                                       \
+        if (!(cond)) { orbs::set_last_error(msg); return (code); }             \
+    } while (0)
+
+// growable device buffer
+struct DevBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+    int reserve(size_t n)
+    {
+        if (n <= bytes) return ORBS_OK;
+        if (p) { cudaFree(p); p = nullptr; bytes = 0; }
+        size_t want = n + n / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc", __FILE__, __LINE__);
+        bytes = want;
+        return ORBS_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+    template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+struct PinnedBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+    int reserve(size_t n)
+    {
+        if (n <= bytes) return ORBS_OK;
+        if (p) { cudaFreeHost(p); p = nullptr; bytes = 0; }
+        size_t want = n + n / 8 + 256;
+        cudaError_t e = cudaMallocHost(&p, want);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaMallocHost", __FILE__, __LINE__);
+        bytes = want;
+        return ORBS_OK;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; bytes = 0; }
+    template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace orbs

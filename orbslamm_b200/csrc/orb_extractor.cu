@@ -1,0 +1,521 @@
+// orb_extractor.cu -- host driver and C-ABI of the ORB extractor (orbx_*).
+//
+// Replaces ORBextractor (S/include/ORBextractor.h:45-111, S/src/ORBextractor.cc).  The handle owns
+// a CUDA stream and all device workspaces; a batch of frames is processed by a fixed sequence of
+// launches (see orb_kernels.cu).  No CPU fallback exists: every entry point fails with ORBS_E_CUDA
+// if the device is unusable.
+#include <math.h>
+#include <string.h>
+#include <vector>
+#include <mutex>
+#include "orb_extractor.cuh"
+#include "orb_kernels.cuh"   // kernels live in this translation unit
+
+namespace orbs {
+
+static thread_local std::string g_last_error;
+void set_last_error(const std::string &s) { g_last_error = s; }
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line)
+{
+    char buf[512];
+    snprintf(buf, sizeof buf, "CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e), file, line, what);
+    g_last_error = buf;
+    cudaGetLastError();
+    return ORBS_E_CUDA;
+}
+
+static inline int cv_round_f(float v) { return (int)lrintf(v); }
+static inline int cv_round_d(double v) { return (int)lrint(v); }
+
+}  // namespace orbs
+
+using namespace orbs;
+
+struct orbx_handle {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    // parameters and tables (ORBextractor.cc:410-470)
+    int nfeatures = 0, nlevels = 0, ini_th = 0, min_th = 0;
+    double scale_factor = 0;
+    float scale[ORBS_MAX_LEVELS], inv_scale[ORBS_MAX_LEVELS], sigma2[ORBS_MAX_LEVELS], inv_sigma2[ORBS_MAX_LEVELS];
+    int features_per_level[ORBS_MAX_LEVELS];
+    int umax[kHalfPatch + 1];
+    // plan for the current image shape
+    bool have_plan = false;
+    ExtractPlan plan;
+    int octree_smem = 0;
+    DevBuf d_cells, d_tiles, d_rs_tab;
+    // per-batch workspaces
+    int batch_cap = 0;
+    DevBuf d_stage;      // staged host images
+    size_t stage_pitch = 0, stage_frame = 0;
+    DevBuf d_pyr, d_blur, d_cand, d_knode, d_lvl_kp, d_counts /* cand_count | lvl_count | counts | err */;
+    DevBuf d_kp_xy, d_kp_angle, d_kp_resp, d_kp_oct, d_kp_size, d_desc;
+    PinnedBuf h_counts;
+    // state of the last call
+    int last_frames = 0;
+    const uint8_t *last_img0 = nullptr;
+    int last_pitch0 = 0;
+    size_t last_frame0 = 0;
+    long long launches = 0;
+    std::mutex mu;
+};
+
+static int build_plan(orbx_handle *h, int width, int height)
+{
+    ExtractPlan &P = h->plan;
+    memset(&P, 0, sizeof P);
+    P.nlevels = h->nlevels; P.width = width; P.height = height;
+    P.ini_th = h->ini_th; P.min_th = h->min_th;
+    memcpy(P.umax, h->umax, sizeof P.umax);
+    std::vector<CellDesc> cells;
+    std::vector<TileDesc> tiles;
+    std::vector<int2> rs;
+    size_t pyr_off = 0, cand_off = 0;
+    int kp_off = 0, kp_slab = 0;
+    int max_node_cap = 1;
+    for (int l = 0; l < h->nlevels; l++) {
+        LevelPlan &L = P.lv[l];
+        L.w = cv_round_f((float)width * h->inv_scale[l]);      // ORBextractor.cc:1111-1112
+        L.h = cv_round_f((float)height * h->inv_scale[l]);
+        ORBS_REQUIRE(L.w >= 1 && L.h >= 1 && L.w < 32768 && L.h < 32768, ORBS_E_SHAPE, "image shape unsupported (level collapses or >= 32768 px)");
+        L.pitch = (int)align_up(L.w, 64);
+        L.nfeat = h->features_per_level[l];
+        L.scale = h->scale[l];
+        L.patch = (int)(kPatch * h->scale[l]);
+        L.pyr_off = pyr_off;
+        pyr_off += align_up((size_t)L.pitch * L.h, 256);
+        // FAST cells (ORBextractor.cc:771-829)
+        const int maxBX = L.w - kEdge + 3, maxBY = L.h - kEdge + 3;
+        L.bw = maxBX - kMinBorder; L.bh = maxBY - kMinBorder;
+        L.cell_first = (int)cells.size();
+        L.cand_cap = 0;
+        const float fw = (float)L.bw, fh = (float)L.bh;
+        const int nCols = L.bw > 0 ? (int)(fw / 30.f) : 0, nRows = L.bh > 0 ? (int)(fh / 30.f) : 0;
+        if (nCols >= 1 && nRows >= 1) {
+            const int wCell = (int)ceilf(fw / nCols), hCell = (int)ceilf(fh / nRows);
+            ORBS_REQUIRE(nCols < 1024 && nRows < 1024, ORBS_E_SHAPE, "image too large (more than 1023 FAST cells per side)");
+            for (int i = 0; i < nRows; i++) {
+                const float iniY = (float)(kMinBorder + i * hCell);
+                float maxY = iniY + hCell + 6;
+                if (iniY >= maxBY - 3) continue;
+                if (maxY > maxBY) maxY = (float)maxBY;
+                for (int j = 0; j < nCols; j++) {
+                    const float iniX = (float)(kMinBorder + j * wCell);
+                    float maxX = iniX + wCell + 6;
+                    if (iniX >= maxBX - 6) continue;
+                    if (maxX > maxBX) maxX = (float)maxBX;
+                    CellDesc c;
+                    c.level = (short)l; c.x0 = (short)iniX; c.y0 = (short)iniY;
+                    c.cw = (short)((int)maxX - (int)iniX); c.ch = (short)((int)maxY - (int)iniY);
+                    c.ci = (short)i; c.cj = (short)j; c.addx = (short)(j * wCell); c.addy = (short)(i * hCell);
+                    if (c.cw > 66 || c.ch > 66) { set_last_error("internal: FAST cell larger than 66 px"); return ORBS_E_SHAPE; }
+                    if (c.cw > 6 && c.ch > 6) {
+                        cells.push_back(c);
+                        L.cand_cap += ((c.cw - 6 + 1) / 2) * ((c.ch - 6 + 1) / 2);
+                    }
+                }
+            }
+        }
+        L.cell_count = (int)cells.size() - L.cell_first;
+        // quad-tree roots (ORBextractor.cc:542-545)
+        if (L.cell_count > 0) {
+            L.n_ini = (int)roundf((float)L.bw / (float)L.bh);
+            ORBS_REQUIRE(L.n_ini >= 1, ORBS_E_SHAPE, "image more than twice as tall as wide: the reference's quad-tree has no root");
+            L.hx = (float)L.bw / (float)L.n_ini;
+        } else { L.n_ini = 1; L.hx = (float)(L.bw > 0 ? L.bw : 1); }
+        L.node_cap = L.nfeat + 3 > 4 * L.n_ini ? L.nfeat + 3 : 4 * L.n_ini;
+        if (L.cell_count == 0) L.node_cap = 1;
+        if (L.node_cap > max_node_cap) max_node_cap = L.node_cap;
+        L.kp_off = kp_off; kp_off += L.node_cap;
+        kp_slab += L.cell_count ? L.node_cap : 0;
+        L.cand_off = cand_off; cand_off += (size_t)L.cand_cap;
+        // blur tiles
+        L.tile_first = (int)tiles.size();
+        if (L.cell_count > 0)
+            for (int y = 0; y < L.h; y += kBlurTH)
+                for (int x = 0; x < L.w; x += kBlurTW) tiles.push_back(TileDesc{(short)l, (short)x, (short)y});
+        L.tile_count = (int)tiles.size() - L.tile_first;
+        // resize tables (cv::resize INTER_LINEAR, fixed point; level l from level l-1)
+        if (l > 0) {
+            const LevelPlan &S = P.lv[l - 1];
+            for (int axis = 0; axis < 2; axis++) {
+                const int ssize = axis ? S.h : S.w, dsize = axis ? L.h : L.w;
+                (axis ? L.rs_y_off : L.rs_x_off) = (int)rs.size();
+                const double inv = (double)dsize / ssize, sc = 1. / inv;
+                for (int d = 0; d < dsize; d++) {
+                    float fx = (float)((d + 0.5) * sc - 0.5);
+                    int sx = (int)floorf(fx);
+                    fx -= sx;
+                    if (sx < 0) { fx = 0; sx = 0; }
+                    if (sx >= ssize - 1) { fx = 0; sx = ssize - 1; }
+                    const int a0 = (short)cv_round_f((1.f - fx) * 2048.f), a1 = (short)cv_round_f(fx * 2048.f);
+                    rs.push_back(make_int2(sx, (a1 << 16) | (a0 & 0xffff)));
+                }
+            }
+        }
+    }
+    P.pyr_frame_bytes = pyr_off;
+    P.cand_frame_entries = cand_off ? cand_off : 1;
+    P.lvl_slab = kp_off;
+    P.kp_slab = kp_slab > 0 ? kp_slab : 1;
+    P.total_cells = (int)cells.size();
+    P.total_tiles = (int)tiles.size();
+    // octree shared memory: 64 B per node + scan scratch
+    h->octree_smem = max_node_cap * 64 + (512 + 1) * 4 + 64;
+    ORBS_REQUIRE(h->octree_smem <= 220 * 1024, ORBS_E_INVALID, "nfeatures too large for the on-chip quad-tree (per-level quota > ~3400)");
+    ORBS_CUDA(cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, h->octree_smem));
+    if (!cells.empty()) {
+        if (int rc = h->d_cells.reserve(cells.size() * sizeof(CellDesc))) return rc;
+        ORBS_CUDA(cudaMemcpyAsync(h->d_cells.p, cells.data(), cells.size() * sizeof(CellDesc), cudaMemcpyHostToDevice, h->stream));
+    }
+    if (!tiles.empty()) {
+        if (int rc = h->d_tiles.reserve(tiles.size() * sizeof(TileDesc))) return rc;
+        ORBS_CUDA(cudaMemcpyAsync(h->d_tiles.p, tiles.data(), tiles.size() * sizeof(TileDesc), cudaMemcpyHostToDevice, h->stream));
+    }
+    if (!rs.empty()) {
+        if (int rc = h->d_rs_tab.reserve(rs.size() * sizeof(int2))) return rc;
+        ORBS_CUDA(cudaMemcpyAsync(h->d_rs_tab.p, rs.data(), rs.size() * sizeof(int2), cudaMemcpyHostToDevice, h->stream));
+    }
+    ORBS_CUDA(cudaStreamSynchronize(h->stream));   // host vectors go out of scope
+    h->have_plan = true;
+    h->batch_cap = 0;
+    return ORBS_OK;
+}
+
+static int ensure_plan(orbx_handle *h, int width, int height)
+{
+    if (h->have_plan && h->plan.width == width && h->plan.height == height) return ORBS_OK;
+    h->have_plan = false;
+    return build_plan(h, width, height);
+}
+
+static int ensure_batch(orbx_handle *h, int n)
+{
+    if (n <= h->batch_cap) return ORBS_OK;
+    const ExtractPlan &P = h->plan;
+    int rc;
+    if ((rc = h->d_pyr.reserve(P.pyr_frame_bytes * n))) return rc;
+    if ((rc = h->d_blur.reserve(P.pyr_frame_bytes * n))) return rc;
+    if ((rc = h->d_cand.reserve(P.cand_frame_entries * n * sizeof(uint2)))) return rc;
+    if ((rc = h->d_knode.reserve(P.cand_frame_entries * n * sizeof(unsigned)))) return rc;
+    if ((rc = h->d_lvl_kp.reserve((size_t)P.lvl_slab * n * sizeof(uint2)))) return rc;
+    if ((rc = h->d_counts.reserve(((size_t)2 * P.nlevels * n + n + 16) * sizeof(int)))) return rc;
+    const size_t slab = (size_t)P.kp_slab * n;
+    if ((rc = h->d_kp_xy.reserve(slab * 8))) return rc;
+    if ((rc = h->d_kp_angle.reserve(slab * 4))) return rc;
+    if ((rc = h->d_kp_resp.reserve(slab * 4))) return rc;
+    if ((rc = h->d_kp_oct.reserve(slab * 4))) return rc;
+    if ((rc = h->d_kp_size.reserve(slab * 4))) return rc;
+    if ((rc = h->d_desc.reserve(slab * 32))) return rc;
+    if ((rc = h->h_counts.reserve(((size_t)n * (1 + P.nlevels) + 16) * sizeof(int)))) return rc;
+    h->batch_cap = n;
+    return ORBS_OK;
+}
+
+// device pointers into d_counts
+static inline int *cand_count_ptr(orbx_handle *h) { return h->d_counts.as<int>(); }
+static inline int *lvl_count_ptr(orbx_handle *h, int n) { return h->d_counts.as<int>() + (size_t)h->plan.nlevels * n; }
+static inline int *counts_ptr(orbx_handle *h, int n) { return h->d_counts.as<int>() + (size_t)2 * h->plan.nlevels * n; }
+static inline int *err_ptr(orbx_handle *h, int n) { return counts_ptr(h, n) + n; }
+
+static int launch_pipeline(orbx_handle *h, const uint8_t *d_img0, int n, int pitch0, size_t frame0)
+{
+    const ExtractPlan &P = h->plan;
+    cudaStream_t st = h->stream;
+    const int nb = h->batch_cap;     // layout of d_counts uses the allocated capacity
+    ORBS_CUDA(cudaMemsetAsync(h->d_counts.p, 0, ((size_t)2 * P.nlevels * nb + nb + 16) * sizeof(int), st));
+    uint8_t *pyr = h->d_pyr.as<uint8_t>();
+    // pyramid chain
+    for (int l = 1; l < P.nlevels; l++) {
+        const LevelPlan &S = P.lv[l - 1], &D = P.lv[l];
+        const uint8_t *src; int spitch; size_t sframe;
+        if (l == 1) { src = d_img0; spitch = pitch0; sframe = frame0; }
+        else { src = pyr + S.pyr_off; spitch = S.pitch; sframe = P.pyr_frame_bytes; }
+        dim3 grid((D.w + 63) / 64, (D.h + 3) / 4, n);
+        k_resize_level<<<grid, 256, 0, st>>>(src, S.w, S.h, spitch, sframe, pyr + D.pyr_off, D.w, D.h, D.pitch, P.pyr_frame_bytes,
+                                              h->d_rs_tab.as<int2>() + D.rs_x_off, h->d_rs_tab.as<int2>() + D.rs_y_off);
+        h->launches++;
+    }
+    if (P.total_cells > 0) {
+        k_fast_cells<<<dim3(P.total_cells, n), 128, 0, st>>>(P, h->d_cells.as<CellDesc>(), d_img0, pitch0, frame0, pyr,
+                                                             h->d_cand.as<uint2>(), cand_count_ptr(h), err_ptr(h, nb));
+        k_blur7<<<dim3(P.total_tiles, n), 256, 0, st>>>(P, h->d_tiles.as<TileDesc>(), d_img0, pitch0, frame0, pyr, h->d_blur.as<uint8_t>());
+        k_octree<<<dim3(P.nlevels, n), 512, h->octree_smem, st>>>(P, h->d_cand.as<uint2>(), cand_count_ptr(h), h->d_knode.as<unsigned>(),
+                                                                 h->d_lvl_kp.as<uint2>(), lvl_count_ptr(h, nb), err_ptr(h, nb));
+        const int warps_per_block = 8;
+        k_orient_describe<<<dim3((P.kp_slab + warps_per_block - 1) / warps_per_block, n), warps_per_block * 32, 0, st>>>(
+            P, d_img0, pitch0, frame0, pyr, h->d_blur.as<uint8_t>(), h->d_lvl_kp.as<uint2>(), lvl_count_ptr(h, nb),
+            h->d_kp_xy.as<float2>(), h->d_kp_angle.as<float>(), h->d_kp_resp.as<float>(), h->d_kp_oct.as<int>(),
+            h->d_kp_size.as<float>(), h->d_desc.as<uint8_t>(), counts_ptr(h, nb));
+        h->launches += 4;
+    }
+    ORBS_CUDA(cudaGetLastError());
+    h->last_frames = n; h->last_img0 = d_img0; h->last_pitch0 = pitch0; h->last_frame0 = frame0;
+    return ORBS_OK;
+}
+
+static int download_results(orbx_handle *h, float *kp_xy, float *kp_angle, float *kp_response, int32_t *kp_octave,
+                            float *kp_size, uint8_t *desc, int cap, int32_t *counts)
+{
+    const ExtractPlan &P = h->plan;
+    const int n = h->last_frames, nb = h->batch_cap;
+    ORBS_REQUIRE(n > 0, ORBS_E_STATE, "no extraction result to download");
+    cudaStream_t st = h->stream;
+    int *hc = h->h_counts.as<int>();
+    ORBS_CUDA(cudaMemcpyAsync(hc, counts_ptr(h, nb), (size_t)(n + 1) * sizeof(int), cudaMemcpyDeviceToHost, st));
+    // err flag sits right after counts[nb]; fetch separately when n != nb
+    int *herr = hc + n + 1;
+    ORBS_CUDA(cudaMemcpyAsync(herr, err_ptr(h, nb), sizeof(int), cudaMemcpyDeviceToHost, st));
+    ORBS_CUDA(cudaStreamSynchronize(st));
+    if (*herr != 0) { set_last_error(*herr == 1 ? "internal: FAST candidate buffer overflow" : "internal: quad-tree node capacity exceeded"); return ORBS_E_CAPACITY; }
+    for (int f = 0; f < n; f++) {
+        const int c = hc[f];
+        counts[f] = c;
+        if (c > cap) { set_last_error("output capacity too small; size with orbx_max_keypoints()"); return ORBS_E_CAPACITY; }
+    }
+    for (int f = 0; f < n; f++) {
+        const size_t c = (size_t)hc[f];
+        if (!c) continue;
+        const size_t so = (size_t)f * P.kp_slab, d = (size_t)f * cap;
+        if (kp_xy) ORBS_CUDA(cudaMemcpyAsync(kp_xy + 2 * d, h->d_kp_xy.as<float>() + 2 * so, c * 8, cudaMemcpyDeviceToHost, st));
+        if (kp_angle) ORBS_CUDA(cudaMemcpyAsync(kp_angle + d, h->d_kp_angle.as<float>() + so, c * 4, cudaMemcpyDeviceToHost, st));
+        if (kp_response) ORBS_CUDA(cudaMemcpyAsync(kp_response + d, h->d_kp_resp.as<float>() + so, c * 4, cudaMemcpyDeviceToHost, st));
+        if (kp_octave) ORBS_CUDA(cudaMemcpyAsync(kp_octave + d, h->d_kp_oct.as<int>() + so, c * 4, cudaMemcpyDeviceToHost, st));
+        if (kp_size) ORBS_CUDA(cudaMemcpyAsync(kp_size + d, h->d_kp_size.as<float>() + so, c * 4, cudaMemcpyDeviceToHost, st));
+        if (desc) ORBS_CUDA(cudaMemcpyAsync(desc + 32 * d, h->d_desc.as<uint8_t>() + 32 * so, c * 32, cudaMemcpyDeviceToHost, st));
+    }
+    ORBS_CUDA(cudaStreamSynchronize(st));
+    return ORBS_OK;
+}
+
+extern "C" {
+
+const char *orbs_last_error(void) { return g_last_error.c_str(); }
+int orbs_version(void) { return 100; }
+int orbs_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int orbx_create(orbx_handle **out, int nfeatures, float scale_factor, int nlevels, int ini_th, int min_th, int device)
+{
+    ORBS_REQUIRE(out, ORBS_E_INVALID, "orbx_create: null out pointer");
+    *out = nullptr;
+    ORBS_REQUIRE(nfeatures > 0 && nlevels >= 1 && nlevels <= ORBS_MAX_LEVELS && scale_factor > 1.0f, ORBS_E_INVALID,
+                 "orbx_create: need nfeatures > 0, 1 <= nlevels <= 16, scaleFactor > 1");
+    ORBS_REQUIRE(ini_th >= 1 && ini_th <= 254 && min_th >= 1 && min_th <= 254, ORBS_E_INVALID, "orbx_create: FAST thresholds must be in [1, 254]");
+    ORBS_CUDA(cudaSetDevice(device));
+    orbx_handle *h = new orbx_handle();
+    h->device = device;
+    cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete h; return cuda_fail(e, "cudaStreamCreate", __FILE__, __LINE__); }
+    h->nfeatures = nfeatures; h->nlevels = nlevels; h->ini_th = ini_th; h->min_th = min_th;
+    h->scale_factor = scale_factor;                       // member is double (ORBextractor.h:98)
+    h->scale[0] = 1.0f; h->sigma2[0] = 1.0f;
+    for (int i = 1; i < nlevels; i++) {
+        h->scale[i] = (float)(h->scale[i - 1] * h->scale_factor);
+        h->sigma2[i] = h->scale[i] * h->scale[i];
+    }
+    for (int i = 0; i < nlevels; i++) { h->inv_scale[i] = 1.0f / h->scale[i]; h->inv_sigma2[i] = 1.0f / h->sigma2[i]; }
+    const float factor = (float)(1.0f / h->scale_factor);
+    float desired = nfeatures * (1 - factor) / (1 - (float)pow((double)factor, (double)nlevels));
+    int sum = 0;
+    for (int l = 0; l < nlevels - 1; l++) {
+        h->features_per_level[l] = cv_round_f(desired);
+        sum += h->features_per_level[l];
+        desired *= factor;
+    }
+    h->features_per_level[nlevels - 1] = nfeatures - sum > 0 ? nfeatures - sum : 0;
+    int v, v0;
+    const int vmax = (int)floorf(kHalfPatch * sqrtf(2.f) / 2 + 1), vmin = (int)ceilf(kHalfPatch * sqrtf(2.f) / 2);
+    const double hp2 = kHalfPatch * kHalfPatch;
+    for (v = 0; v <= vmax; ++v) h->umax[v] = cv_round_d(sqrt(hp2 - v * v));
+    for (v = kHalfPatch, v0 = 0; v >= vmin; --v) {
+        while (h->umax[v0] == h->umax[v0 + 1]) ++v0;
+        h->umax[v] = v0;
+        ++v0;
+    }
+    *out = h;
+    return ORBS_OK;
+}
+
+int orbx_destroy(orbx_handle *h)
+{
+    if (!h) return ORBS_OK;
+    cudaSetDevice(h->device);
+    if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
+    DevBuf *bufs[] = {&h->d_cells, &h->d_tiles, &h->d_rs_tab, &h->d_stage, &h->d_pyr, &h->d_blur, &h->d_cand, &h->d_knode, &h->d_lvl_kp,
+                      &h->d_counts, &h->d_kp_xy, &h->d_kp_angle, &h->d_kp_resp, &h->d_kp_oct, &h->d_kp_size, &h->d_desc};
+    for (DevBuf *b : bufs) b->release();
+    h->h_counts.release();
+    delete h;
+    return ORBS_OK;
+}
+
+int orbx_get_tables(const orbx_handle *h, int *nlevels, float *scale_factor, float *scale, float *inv_scale, float *sigma2,
+                    float *inv_sigma2, int *features_per_level)
+{
+    ORBS_REQUIRE(h, ORBS_E_INVALID, "null handle");
+    if (nlevels) *nlevels = h->nlevels;
+    if (scale_factor) *scale_factor = (float)h->scale_factor;
+    for (int i = 0; i < h->nlevels; i++) {
+        if (scale) scale[i] = h->scale[i];
+        if (inv_scale) inv_scale[i] = h->inv_scale[i];
+        if (sigma2) sigma2[i] = h->sigma2[i];
+        if (inv_sigma2) inv_sigma2[i] = h->inv_sigma2[i];
+        if (features_per_level) features_per_level[i] = h->features_per_level[i];
+    }
+    return ORBS_OK;
+}
+
+int orbx_max_keypoints(orbx_handle *h, int width, int height, int *max_kp)
+{
+    ORBS_REQUIRE(h && max_kp, ORBS_E_INVALID, "null argument");
+    ORBS_REQUIRE(width > 0 && height > 0, ORBS_E_INVALID, "non-positive image size");
+    std::lock_guard<std::mutex> lk(h->mu);
+    ORBS_CUDA(cudaSetDevice(h->device));
+    if (int rc = ensure_plan(h, width, height)) return rc;
+    *max_kp = h->plan.kp_slab;
+    return ORBS_OK;
+}
+
+int orbx_level_size(orbx_handle *h, int width, int height, int level, int *lw, int *lh)
+{
+    ORBS_REQUIRE(h && lw && lh && level >= 0 && level < h->nlevels, ORBS_E_INVALID, "bad argument");
+    *lw = cv_round_f((float)width * h->inv_scale[level]);
+    *lh = cv_round_f((float)height * h->inv_scale[level]);
+    return ORBS_OK;
+}
+
+int orbx_extract_device(orbx_handle *h, const uint8_t *d_images, int n_frames, int width, int height, int stride, size_t frame_stride)
+{
+    ORBS_REQUIRE(h, ORBS_E_INVALID, "null handle");
+    ORBS_REQUIRE(n_frames > 0, ORBS_E_INVALID, "n_frames must be positive");
+    ORBS_REQUIRE(width > 0 && height > 0, ORBS_E_INVALID, "use orbx_extract for empty images");
+    ORBS_REQUIRE(d_images && stride >= width && (n_frames == 1 || frame_stride >= (size_t)stride * (height - 1) + width), ORBS_E_INVALID, "bad image pointer or strides");
+    std::lock_guard<std::mutex> lk(h->mu);
+    ORBS_CUDA(cudaSetDevice(h->device));
+    if (int rc = ensure_plan(h, width, height)) return rc;
+    if (int rc = ensure_batch(h, n_frames)) return rc;
+    return launch_pipeline(h, d_images, n_frames, stride, frame_stride);
+}
+
+int orbx_extract(orbx_handle *h, const uint8_t *images, int n_frames, int width, int height, int stride, size_t frame_stride,
+                 float *kp_xy, float *kp_angle, float *kp_response, int32_t *kp_octave, float *kp_size, uint8_t *desc, int cap,
+                 int32_t *counts)
+{
+    ORBS_REQUIRE(h && counts, ORBS_E_INVALID, "null handle or counts");
+    ORBS_REQUIRE(n_frames > 0, ORBS_E_INVALID, "n_frames must be positive");
+    if (width <= 0 || height <= 0) {               // empty image: silent return (ORBextractor.cc:1046-1047)
+        for (int f = 0; f < n_frames; f++) counts[f] = 0;
+        return ORBS_OK;
+    }
+    ORBS_REQUIRE(images && stride >= width, ORBS_E_INVALID, "bad image pointer or stride");
+    std::lock_guard<std::mutex> lk(h->mu);
+    ORBS_CUDA(cudaSetDevice(h->device));
+    if (int rc = ensure_plan(h, width, height)) return rc;
+    if (int rc = ensure_batch(h, n_frames)) return rc;
+    // stage the frames (pitch multiple of 64 for aligned rows)
+    const size_t pitch = align_up(width, 64), frame = pitch * height;
+    if (int rc = h->d_stage.reserve(frame * n_frames)) return rc;
+    if (n_frames == 1 || frame_stride == (size_t)stride * height) {
+        ORBS_CUDA(cudaMemcpy2DAsync(h->d_stage.p, pitch, images, stride, width, (size_t)height * n_frames, cudaMemcpyHostToDevice, h->stream));
+    } else {
+        for (int f = 0; f < n_frames; f++)
+            ORBS_CUDA(cudaMemcpy2DAsync(h->d_stage.as<uint8_t>() + f * frame, pitch, images + f * frame_stride, stride, width, height,
+                                        cudaMemcpyHostToDevice, h->stream));
+    }
+    if (int rc = launch_pipeline(h, h->d_stage.as<uint8_t>(), n_frames, (int)pitch, frame)) return rc;
+    return download_results(h, kp_xy, kp_angle, kp_response, kp_octave, kp_size, desc, cap, counts);
+}
+
+int orbx_device_results(orbx_handle *h, orbx_device_view *view)
+{
+    ORBS_REQUIRE(h && view, ORBS_E_INVALID, "null argument");
+    ORBS_REQUIRE(h->last_frames > 0, ORBS_E_STATE, "no extraction has run");
+    view->n_frames = h->last_frames; view->slab = h->plan.kp_slab;
+    view->kp_xy = h->d_kp_xy.as<float>(); view->kp_angle = h->d_kp_angle.as<float>();
+    view->kp_response = h->d_kp_resp.as<float>(); view->kp_octave = h->d_kp_oct.as<int>();
+    view->kp_size = h->d_kp_size.as<float>(); view->desc = h->d_desc.as<uint8_t>();
+    view->counts = counts_ptr(h, h->batch_cap); view->level_counts = lvl_count_ptr(h, h->batch_cap);
+    return ORBS_OK;
+}
+
+int orbx_download(orbx_handle *h, float *kp_xy, float *kp_angle, float *kp_response, int32_t *kp_octave, float *kp_size,
+                  uint8_t *desc, int cap, int32_t *counts)
+{
+    ORBS_REQUIRE(h && counts, ORBS_E_INVALID, "null handle or counts");
+    std::lock_guard<std::mutex> lk(h->mu);
+    ORBS_CUDA(cudaSetDevice(h->device));
+    return download_results(h, kp_xy, kp_angle, kp_response, kp_octave, kp_size, desc, cap, counts);
+}
+
+int orbx_get_pyramid_level(orbx_handle *h, int frame, int level, int border, uint8_t *out, int out_stride)
+{
+    ORBS_REQUIRE(h && out, ORBS_E_INVALID, "null argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    ORBS_REQUIRE(h->last_frames > 0 && frame >= 0 && frame < h->last_frames, ORBS_E_STATE, "no such frame in the last call");
+    ORBS_REQUIRE(level >= 0 && level < h->nlevels, ORBS_E_INVALID, "bad level");
+    ORBS_CUDA(cudaSetDevice(h->device));
+    const LevelPlan &L = h->plan.lv[level];
+    const uint8_t *src; int pitch;
+    if (level == 0) { src = h->last_img0 + (size_t)frame * h->last_frame0; pitch = h->last_pitch0; }
+    else { src = h->d_pyr.as<uint8_t>() + (size_t)frame * h->plan.pyr_frame_bytes + L.pyr_off; pitch = L.pitch; }
+    if (!border) {
+        ORBS_REQUIRE(out_stride >= L.w, ORBS_E_INVALID, "out_stride too small");
+        ORBS_CUDA(cudaMemcpy2DAsync(out, out_stride, src, pitch, L.w, L.h, cudaMemcpyDeviceToHost, h->stream));
+    } else {
+        const int W = L.w + 2 * kEdge, H = L.h + 2 * kEdge;
+        ORBS_REQUIRE(out_stride >= W, ORBS_E_INVALID, "out_stride too small");
+        DevBuf tmp;
+        if (int rc = tmp.reserve((size_t)W * H)) return rc;
+        k_border_copy<<<dim3((W + 255) / 256, H), 256, 0, h->stream>>>(src, L.w, L.h, pitch, tmp.as<uint8_t>(), kEdge);
+        h->launches++;
+        cudaError_t e = cudaMemcpy2DAsync(out, out_stride, tmp.p, W, W, H, cudaMemcpyDeviceToHost, h->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+        tmp.release();
+        if (e != cudaSuccess) return cuda_fail(e, "pyramid border copy", __FILE__, __LINE__);
+        return ORBS_OK;
+    }
+    ORBS_CUDA(cudaStreamSynchronize(h->stream));
+    return ORBS_OK;
+}
+
+int orbx_get_candidates(orbx_handle *h, int frame, int level, int32_t *xys, int cap, int *n_out)
+{
+    ORBS_REQUIRE(h && n_out, ORBS_E_INVALID, "null argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    ORBS_REQUIRE(h->last_frames > 0 && frame >= 0 && frame < h->last_frames, ORBS_E_STATE, "no such frame in the last call");
+    ORBS_REQUIRE(level >= 0 && level < h->nlevels, ORBS_E_INVALID, "bad level");
+    ORBS_CUDA(cudaSetDevice(h->device));
+    const LevelPlan &L = h->plan.lv[level];
+    int n = 0;
+    ORBS_CUDA(cudaMemcpyAsync(&n, cand_count_ptr(h) + frame * h->plan.nlevels + level, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    ORBS_CUDA(cudaStreamSynchronize(h->stream));
+    *n_out = n;
+    if (!xys || n == 0) return ORBS_OK;
+    ORBS_REQUIRE(n <= cap, ORBS_E_CAPACITY, "candidate output capacity too small");
+    std::vector<uint2> tmp(n);
+    ORBS_CUDA(cudaMemcpyAsync(tmp.data(), h->d_cand.as<uint2>() + (size_t)frame * h->plan.cand_frame_entries + L.cand_off,
+                              (size_t)n * sizeof(uint2), cudaMemcpyDeviceToHost, h->stream));
+    ORBS_CUDA(cudaStreamSynchronize(h->stream));
+    for (int i = 0; i < n; i++) {
+        xys[3 * i] = (int)(tmp[i].x & 0xffff); xys[3 * i + 1] = (int)(tmp[i].x >> 16); xys[3 * i + 2] = (int)(tmp[i].y & 0xff);
+    }
+    return ORBS_OK;
+}
+
+void *orbx_stream(orbx_handle *h) { return h ? (void *)h->stream : nullptr; }
+int orbx_synchronize(orbx_handle *h)
+{
+    ORBS_REQUIRE(h, ORBS_E_INVALID, "null handle");
+    ORBS_CUDA(cudaSetDevice(h->device));
+    ORBS_CUDA(cudaStreamSynchronize(h->stream));
+    return ORBS_OK;
+}
+long long orbx_kernel_launches(const orbx_handle *h) { return h ? h->launches : 0; }
+
+}  // extern "C"
