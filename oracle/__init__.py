@@ -203,3 +203,91 @@ def _empty_result(nlevels):
     z = np.zeros(0, np.float32)
     return dict(x=z, y=z, angle=z, response=z, octave=np.zeros(0, np.int32), size=z,
                 desc=np.zeros((0, 32), np.uint8), level_counts=np.zeros(nlevels, np.int32))
+
+
+# ------------------------------------------------------------------------------------------
+# matcher / optimizer (slam_oracle.c)
+class GridParams(ctypes.Structure):
+    _fields_ = [("min_x", ctypes.c_float), ("min_y", ctypes.c_float), ("max_x", ctypes.c_float),
+                ("max_y", ctypes.c_float), ("w_inv", ctypes.c_float), ("h_inv", ctypes.c_float)]
+
+
+def grid_params(min_x, min_y, max_x, max_y):
+    g = GridParams()
+    lib().oracle_grid_params_init(ctypes.byref(g), ctypes.c_float(min_x), ctypes.c_float(min_y),
+                                  ctypes.c_float(max_x), ctypes.c_float(max_y))
+    return g
+
+
+def descriptor_distance(a, b):
+    a = np.ascontiguousarray(a, np.uint8); b = np.ascontiguousarray(b, np.uint8)
+    return int(lib().oracle_descriptor_distance(_p(a, _u8p), _p(b, _u8p)))
+
+
+def project_last_frame(Tcw, K4, g, scale_factors, Xw, last_octave, th, valid):
+    """Projection block of SearchByProjection(Cur, Last).  Returns (valid, uv, radius, minl, maxl)."""
+    Tcw = np.ascontiguousarray(Tcw, np.float32).reshape(16); K4 = np.ascontiguousarray(K4, np.float32)
+    sf = np.ascontiguousarray(scale_factors, np.float32)
+    Xw = np.ascontiguousarray(Xw, np.float32).reshape(-1, 3); M = len(Xw)
+    lo = np.ascontiguousarray(last_octave, np.int32)
+    qv = np.ascontiguousarray(valid, np.uint8).copy()
+    uv = np.zeros((M, 2), np.float32); rad = np.zeros(M, np.float32)
+    mn = np.zeros(M, np.int32); mx = np.zeros(M, np.int32)
+    lib().oracle_project_last_frame(_p(Tcw, _f32p), _p(K4, _f32p), ctypes.byref(g), _p(sf, _f32p), M, _p(Xw, _f32p),
+                                    _p(lo, _i32p), ctypes.c_float(th), _p(qv, _u8p), _p(uv, _f32p), _p(rad, _f32p),
+                                    _p(mn, _i32p), _p(mx, _i32p))
+    return qv, uv, rad, mn, mx
+
+
+def search_by_projection(g, f_xy, f_octave, f_angle, f_desc, q_valid, q_uv, q_radius, q_minl, q_maxl, q_angle,
+                         q_desc, th_dist=100, ratio=0.0, check_ori=True, feat_match=None):
+    f_xy = np.ascontiguousarray(f_xy, np.float32).reshape(-1, 2); N = len(f_xy)
+    f_octave = np.ascontiguousarray(f_octave, np.int32); f_angle = np.ascontiguousarray(f_angle, np.float32)
+    f_desc = np.ascontiguousarray(f_desc, np.uint8)
+    q_valid = np.ascontiguousarray(q_valid, np.uint8); M = len(q_valid)
+    q_uv = np.ascontiguousarray(q_uv, np.float32); q_radius = np.ascontiguousarray(q_radius, np.float32)
+    q_minl = np.ascontiguousarray(q_minl, np.int32); q_maxl = np.ascontiguousarray(q_maxl, np.int32)
+    q_angle = np.ascontiguousarray(q_angle, np.float32); q_desc = np.ascontiguousarray(q_desc, np.uint8)
+    fm = np.full(N, -1, np.int32) if feat_match is None else np.ascontiguousarray(feat_match, np.int32).copy()
+    lib().oracle_search_by_projection.restype = ctypes.c_int
+    n = lib().oracle_search_by_projection(ctypes.byref(g), N, _p(f_xy, _f32p), _p(f_octave, _i32p), _p(f_angle, _f32p),
+                                          _p(f_desc, _u8p), M, _p(q_valid, _u8p), _p(q_uv, _f32p), _p(q_radius, _f32p),
+                                          _p(q_minl, _i32p), _p(q_maxl, _i32p), _p(q_angle, _f32p), _p(q_desc, _u8p),
+                                          int(th_dist), ctypes.c_float(ratio), int(bool(check_ori)), _p(fm, _i32p))
+    return n, fm
+
+
+def pose_optimization(Tcw, Xw, obs, inv_sigma2, K4):
+    """Optimizer::PoseOptimization.  Returns (Tcw_out f32[4,4], outlier u8[M], n_inliers)."""
+    T = np.ascontiguousarray(Tcw, np.float32).reshape(16).copy()
+    Xw = np.ascontiguousarray(Xw, np.float32).reshape(-1, 3); M = len(Xw)
+    obs = np.ascontiguousarray(obs, np.float32).reshape(-1, 2)
+    w = np.ascontiguousarray(inv_sigma2, np.float32); K4 = np.ascontiguousarray(K4, np.float32)
+    out = np.zeros(max(M, 1), np.uint8)
+    lib().oracle_pose_optimization.restype = ctypes.c_int
+    n = lib().oracle_pose_optimization(_p(T, _f32p), M, _p(Xw, _f32p), _p(obs, _f32p), _p(w, _f32p), _p(K4, _f32p),
+                                       _p(out, _u8p))
+    return T.reshape(4, 4), out[:M], n
+
+
+def bundle_adjust(poses, fixed, intr, points, e_kf, e_pt, e_uv, e_inv_sigma2, two_stage=True, its0=5, its1=10,
+                  robust=True):
+    """LocalBundleAdjustment (two_stage) / BundleAdjustment over flat arrays.  Returns dict."""
+    poses = np.ascontiguousarray(poses, np.float32).reshape(-1, 16).copy(); K = len(poses)
+    fixed = np.ascontiguousarray(fixed, np.uint8)
+    intr = np.ascontiguousarray(intr, np.float64)
+    if intr.ndim == 1:
+        intr = np.tile(intr, (K, 1))
+    intr = np.ascontiguousarray(intr)
+    points = np.ascontiguousarray(points, np.float32).reshape(-1, 3).copy(); P = len(points)
+    e_kf = np.ascontiguousarray(e_kf, np.int32); e_pt = np.ascontiguousarray(e_pt, np.int32); E = len(e_kf)
+    e_uv = np.ascontiguousarray(e_uv, np.float32); w = np.ascontiguousarray(e_inv_sigma2, np.float32)
+    chi2 = np.zeros(max(E, 1)); dok = np.zeros(max(E, 1), np.uint8); outl = np.zeros(max(E, 1), np.uint8)
+    stats = np.zeros(2, np.int32)
+    lib().oracle_bundle_adjust.restype = ctypes.c_int
+    rc = lib().oracle_bundle_adjust(K, _p(poses, _f32p), _p(fixed, _u8p), _p(intr, _f64p), P, _p(points, _f32p), E,
+                                    _p(e_kf, _i32p), _p(e_pt, _i32p), _p(e_uv, _f32p), _p(w, _f32p),
+                                    int(bool(two_stage)), int(its0), int(its1), int(bool(robust)), None,
+                                    _p(chi2, _f64p), _p(dok, _u8p), _p(outl, _u8p), _p(stats, _i32p))
+    return dict(poses=poses.reshape(K, 4, 4), points=points, chi2=chi2[:E], depth_ok=dok[:E], outlier=outl[:E],
+                lm_iterations=int(stats[0]), lm_trials=int(stats[1]), rc=rc)

@@ -1,0 +1,812 @@
+/*
+ * oracle/slam_oracle.c -- CPU restatement of the reference matcher and optimizer arithmetic.
+ *
+ * TEST INFRASTRUCTURE ONLY (see oracle/__init__.py): never linked into or called by the product.
+ *
+ * Matcher part follows (S/ = /root/reference/SingleRobotScenario/):
+ *   S/src/ORBmatcher.cc:45-137     SearchByProjection(Frame&, vector<MapPoint*>&, th)
+ *   S/src/ORBmatcher.cc:1330-1472  SearchByProjection(Frame& Cur, const Frame& Last, th, bMono)
+ *   S/src/ORBmatcher.cc:1603-1665  ComputeThreeMaxima, DescriptorDistance
+ *   S/src/Frame.cc:230-245,327-392 AssignFeaturesToGrid, GetFeaturesInArea, PosInGrid
+ * over flat arrays instead of Frame/MapPoint objects (monocular only: mvuRight < 0, every map point
+ * has Observations() > 0).  cv::Mat float algebra (Rcw*x3Dw+tcw) is restated as OpenCV 4.13's small
+ * gemm: fp32 products accumulated left to right in fp32, no FMA (pinned by tests against cv2.gemm).
+ *
+ * Optimizer part follows
+ *   S/src/Optimizer.cc:262-474 (PoseOptimization), :476-801 (LocalBundleAdjustment), :68-260 (BundleAdjustment)
+ * and the vendored g2o it drives (all fp64):
+ *   types/types_six_dof_expmap.{h,cpp}, types/se3quat.h, types/types_sba.h, core/robust_kernel_impl.cpp,
+ *   core/base_edge.h, core/base_{unary,binary}_edge.hpp, core/sparse_optimizer.cpp,
+ *   core/block_solver.hpp, core/optimization_algorithm_levenberg.cpp, solvers/linear_solver_{dense,eigen}.h
+ * Eigen (un-vendored, >=3.1, unpinned) supplies Quaterniond(R)/normalize/toRotationMatrix, Matrix3d::inverse
+ * and the LDLT factorisations; they are direct methods restated here (reduced system: profile LDLT without
+ * pivoting instead of SimplicialLDLT+AMD / pivoted dense LDLT -> equal up to fp64 rounding).  The reference
+ * holds no golden vectors for this path: parity unpinned by the reference; this file is pinned against an
+ * independent numpy twin (tests/test_oracle_ba.py).
+ */
+#include <math.h>
+#include <float.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* ======================================================================================== */
+/* Matcher                                                                                   */
+#define GRID_COLS 64
+#define GRID_ROWS 48
+#define TH_HIGH 100
+#define TH_LOW 50
+#define HISTO_LENGTH 30
+
+int oracle_descriptor_distance(const uint8_t *a, const uint8_t *b)     /* ORBmatcher.cc:1649-1665 */
+{
+    const int32_t *pa = (const int32_t *)a, *pb = (const int32_t *)b;
+    int dist = 0;
+    for (int i = 0; i < 8; i++, pa++, pb++) {
+        unsigned int v = *pa ^ *pb;
+        v = v - ((v >> 1) & 0x55555555);
+        v = (v & 0x33333333) + ((v >> 2) & 0x33333333);
+        dist += (((v + (v >> 4)) & 0xF0F0F0F) * 0x1010101) >> 24;
+    }
+    return dist;
+}
+
+typedef struct {
+    float min_x, min_y, max_x, max_y;      /* mnMinX.. (Frame.cc:436-463) */
+    float w_inv, h_inv;                    /* mfGridElementWidthInv / HeightInv (Frame.cc:101-102) */
+} oracle_grid_params;
+
+void oracle_grid_params_init(oracle_grid_params *g, float min_x, float min_y, float max_x, float max_y)
+{
+    g->min_x = min_x; g->min_y = min_y; g->max_x = max_x; g->max_y = max_y;
+    g->w_inv = (float)GRID_COLS / (max_x - min_x);
+    g->h_inv = (float)GRID_ROWS / (max_y - min_y);
+}
+
+/* AssignFeaturesToGrid + PosInGrid: CSR over cells indexed ix*GRID_ROWS+iy, items in ascending feature index */
+void oracle_grid_build(const oracle_grid_params *g, int N, const float *xy, int *cell_start /*[64*48+1]*/, int *cell_items /*[N]*/)
+{
+    const int nc = GRID_COLS * GRID_ROWS;
+    int *cell_of = (int *)malloc(sizeof(int) * (N > 0 ? N : 1));
+    memset(cell_start, 0, sizeof(int) * (nc + 1));
+    for (int i = 0; i < N; i++) {
+        int px = (int)roundf((xy[2 * i] - g->min_x) * g->w_inv);
+        int py = (int)roundf((xy[2 * i + 1] - g->min_y) * g->h_inv);
+        if (px < 0 || px >= GRID_COLS || py < 0 || py >= GRID_ROWS) { cell_of[i] = -1; continue; }
+        cell_of[i] = px * GRID_ROWS + py;
+        cell_start[cell_of[i] + 1]++;
+    }
+    for (int c = 0; c < nc; c++) cell_start[c + 1] += cell_start[c];
+    int *fill = (int *)calloc(nc, sizeof(int));
+    for (int i = 0; i < N; i++)
+        if (cell_of[i] >= 0) cell_items[cell_start[cell_of[i]] + fill[cell_of[i]]++] = i;
+    free(fill); free(cell_of);
+}
+
+/* GetFeaturesInArea (Frame.cc:327-380); returns count, indices in the reference's visiting order */
+int oracle_features_in_area(const oracle_grid_params *g, const int *cell_start, const int *cell_items,
+                            const float *xy, const int *octave, float x, float y, float r,
+                            int min_level, int max_level, int *out)
+{
+    int n = 0;
+    int c0 = (int)floorf((x - g->min_x - r) * g->w_inv); if (c0 < 0) c0 = 0;
+    if (c0 >= GRID_COLS) return 0;
+    int c1 = (int)ceilf((x - g->min_x + r) * g->w_inv); if (c1 > GRID_COLS - 1) c1 = GRID_COLS - 1;
+    if (c1 < 0) return 0;
+    int r0 = (int)floorf((y - g->min_y - r) * g->h_inv); if (r0 < 0) r0 = 0;
+    if (r0 >= GRID_ROWS) return 0;
+    int r1 = (int)ceilf((y - g->min_y + r) * g->h_inv); if (r1 > GRID_ROWS - 1) r1 = GRID_ROWS - 1;
+    if (r1 < 0) return 0;
+    const int check = (min_level > 0) || (max_level >= 0);
+    for (int ix = c0; ix <= c1; ix++)
+        for (int iy = r0; iy <= r1; iy++) {
+            const int c = ix * GRID_ROWS + iy;
+            for (int j = cell_start[c]; j < cell_start[c + 1]; j++) {
+                const int k = cell_items[j];
+                if (check) {
+                    if (octave[k] < min_level) continue;
+                    if (max_level >= 0 && octave[k] > max_level) continue;
+                }
+                const float dx = xy[2 * k] - x, dy = xy[2 * k + 1] - y;
+                if (fabsf(dx) < r && fabsf(dy) < r) out[n++] = k;
+            }
+        }
+    return n;
+}
+
+/* Projection block of SearchByProjection(Cur, Last), ORBmatcher.cc:1354-1391 (mono: bForward=bBackward=false).
+ * q_valid[i] in: last-frame slot holds a non-outlier map point; out: and it projects into the image with
+ * positive depth.  Tcw row-major 4x4 float. */
+void oracle_project_last_frame(const float *Tcw, const float *K4 /*fx,fy,cx,cy*/, const oracle_grid_params *g,
+                               const float *scale_factors, int M, const float *Xw, const int *last_octave,
+                               float th, uint8_t *q_valid, float *q_uv, float *q_radius, int *q_minl, int *q_maxl)
+{
+    for (int i = 0; i < M; i++) {
+        if (!q_valid[i]) continue;
+        q_valid[i] = 0;
+        float xc[3];
+        for (int r = 0; r < 3; r++) {       /* cv::gemm small-matrix path: fp32, sequential, no FMA */
+            float s = Tcw[4 * r] * Xw[3 * i];
+            s = s + Tcw[4 * r + 1] * Xw[3 * i + 1];
+            s = s + Tcw[4 * r + 2] * Xw[3 * i + 2];
+            xc[r] = s + Tcw[4 * r + 3];
+        }
+        const float invzc = (float)(1.0 / xc[2]);
+        if (invzc < 0) continue;
+        const float u = K4[0] * xc[0] * invzc + K4[2];
+        const float v = K4[1] * xc[1] * invzc + K4[3];
+        if (u < g->min_x || u > g->max_x) continue;
+        if (v < g->min_y || v > g->max_y) continue;
+        const int oct = last_octave[i];
+        q_uv[2 * i] = u; q_uv[2 * i + 1] = v;
+        q_radius[i] = th * scale_factors[oct];
+        q_minl[i] = oct - 1; q_maxl[i] = oct + 1;
+        q_valid[i] = 1;
+    }
+}
+
+static void three_maxima(const int *hist, int L, int *i1, int *i2, int *i3)   /* ORBmatcher.cc:1603-1644 */
+{
+    int max1 = 0, max2 = 0, max3 = 0;
+    *i1 = *i2 = *i3 = -1;
+    for (int i = 0; i < L; i++) {
+        const int s = hist[i];
+        if (s > max1) { max3 = max2; max2 = max1; max1 = s; *i3 = *i2; *i2 = *i1; *i1 = i; }
+        else if (s > max2) { max3 = max2; max2 = s; *i3 = *i2; *i2 = i; }
+        else if (s > max3) { max3 = s; *i3 = i; }
+    }
+    if (max2 < 0.1f * (float)max1) { *i2 = -1; *i3 = -1; }
+    else if (max3 < 0.1f * (float)max1) { *i3 = -1; }
+}
+
+/* Generic projection search over flat arrays; the sequential loop of ORBmatcher.cc:49-126 (ratio > 0: best and
+ * second best with the same-level ratio test, no orientation check) and :1353-1467 (ratio <= 0, check_ori).
+ * feat_match[N]: in = -1 or an id >= 0 for features that already hold a map point (they are skipped);
+ *                out = index of the query assigned to the feature.
+ * Returns nmatches. */
+int oracle_search_by_projection(const oracle_grid_params *g, int N, const float *f_xy, const int *f_octave,
+                                const float *f_angle, const uint8_t *f_desc,
+                                int M, const uint8_t *q_valid, const float *q_uv, const float *q_radius,
+                                const int *q_minl, const int *q_maxl, const float *q_angle, const uint8_t *q_desc,
+                                int th_dist, float ratio, int check_ori, int *feat_match)
+{
+    const int nc = GRID_COLS * GRID_ROWS;
+    int *cell_start = (int *)malloc(sizeof(int) * (nc + 1));
+    int *cell_items = (int *)malloc(sizeof(int) * (N > 0 ? N : 1));
+    int *cands = (int *)malloc(sizeof(int) * (N > 0 ? N : 1));
+    int *rot_bin = (int *)malloc(sizeof(int) * (N > 0 ? N : 1));     /* per feature: histogram bin of its match */
+    int hist[HISTO_LENGTH];
+    memset(hist, 0, sizeof hist);
+    oracle_grid_build(g, N, f_xy, cell_start, cell_items);
+    for (int i = 0; i < N; i++) rot_bin[i] = -1;
+    const float factor = 1.0f / HISTO_LENGTH;
+    int nmatches = 0;
+    for (int i = 0; i < M; i++) {
+        if (!q_valid[i]) continue;
+        const int nc_i = oracle_features_in_area(g, cell_start, cell_items, f_xy, f_octave, q_uv[2 * i], q_uv[2 * i + 1],
+                                                 q_radius[i], q_minl[i], q_maxl[i], cands);
+        if (nc_i == 0) continue;
+        int best = 256, best2 = 256, best_level = -1, best_level2 = -1, best_idx = -1;
+        for (int c = 0; c < nc_i; c++) {
+            const int k = cands[c];
+            if (feat_match[k] >= 0) continue;                 /* already holds a map point with observations */
+            const int d = oracle_descriptor_distance(q_desc + 32 * (size_t)i, f_desc + 32 * (size_t)k);
+            if (d < best) { best2 = best; best = d; best_level2 = best_level; best_level = f_octave[k]; best_idx = k; }
+            else if (d < best2) { best_level2 = f_octave[k]; best2 = d; }
+        }
+        if (best <= th_dist) {
+            if (ratio > 0 && best_level == best_level2 && best > ratio * best2) continue;
+            feat_match[best_idx] = i;
+            nmatches++;
+            if (check_ori) {
+                float rot = q_angle[i] - f_angle[best_idx];
+                if (rot < 0.0) rot += 360.0f;
+                int bin = (int)roundf(rot * factor);
+                if (bin == HISTO_LENGTH) bin = 0;
+                rot_bin[best_idx] = bin;
+                hist[bin]++;
+            }
+        }
+    }
+    if (check_ori) {
+        int i1, i2, i3;
+        three_maxima(hist, HISTO_LENGTH, &i1, &i2, &i3);
+        for (int k = 0; k < N; k++) {
+            const int b = rot_bin[k];
+            if (b >= 0 && b != i1 && b != i2 && b != i3) { feat_match[k] = -1; nmatches--; }
+        }
+    }
+    free(cell_start); free(cell_items); free(cands); free(rot_bin);
+    return nmatches;
+}
+
+/* ======================================================================================== */
+/* SE3 helpers (g2o::SE3Quat on Eigen::Quaterniond), fp64                                    */
+typedef struct { double q[4]; /* x y z w */ double t[3]; } se3;
+
+static void quat_from_R(const double R[9], double q[4])    /* Eigen::Quaterniond(Matrix3d) */
+{
+    double t = R[0] + R[4] + R[8];
+    if (t > 0) {
+        t = sqrt(t + 1.0);
+        q[3] = 0.5 * t;
+        t = 0.5 / t;
+        q[0] = (R[7] - R[5]) * t; q[1] = (R[2] - R[6]) * t; q[2] = (R[3] - R[1]) * t;
+    } else {
+        int i = 0;
+        if (R[4] > R[0]) i = 1;
+        if (R[8] > R[4 * i]) i = 2;
+        int j = (i + 1) % 3, k = (j + 1) % 3;
+        t = sqrt(R[4 * i] - R[4 * j] - R[4 * k] + 1.0);
+        q[i] = 0.5 * t;
+        t = 0.5 / t;
+        q[3] = (R[3 * k + j] - R[3 * j + k]) * t;
+        q[j] = (R[3 * j + i] + R[3 * i + j]) * t;
+        q[k] = (R[3 * k + i] + R[3 * i + k]) * t;
+    }
+}
+static void quat_normalize_pos(double q[4])                /* SE3Quat::normalizeRotation, se3quat.h:280-285 */
+{
+    if (q[3] < 0) { q[0] = -q[0]; q[1] = -q[1]; q[2] = -q[2]; q[3] = -q[3]; }
+    const double n = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+    q[0] /= n; q[1] /= n; q[2] /= n; q[3] /= n;
+}
+static void quat_rotate(const double q[4], const double v[3], double out[3])   /* Eigen _transformVector */
+{
+    double uv[3] = {q[1] * v[2] - q[2] * v[1], q[2] * v[0] - q[0] * v[2], q[0] * v[1] - q[1] * v[0]};
+    uv[0] += uv[0]; uv[1] += uv[1]; uv[2] += uv[2];
+    out[0] = v[0] + q[3] * uv[0] + (q[1] * uv[2] - q[2] * uv[1]);
+    out[1] = v[1] + q[3] * uv[1] + (q[2] * uv[0] - q[0] * uv[2]);
+    out[2] = v[2] + q[3] * uv[2] + (q[0] * uv[1] - q[1] * uv[0]);
+}
+static void quat_mul(const double a[4], const double b[4], double o[4])
+{
+    o[3] = a[3] * b[3] - a[0] * b[0] - a[1] * b[1] - a[2] * b[2];
+    o[0] = a[3] * b[0] + a[0] * b[3] + a[1] * b[2] - a[2] * b[1];
+    o[1] = a[3] * b[1] + a[1] * b[3] + a[2] * b[0] - a[0] * b[2];
+    o[2] = a[3] * b[2] + a[2] * b[3] + a[0] * b[1] - a[1] * b[0];
+}
+static void quat_to_R(const double q[4], double R[9])      /* Eigen toRotationMatrix */
+{
+    const double tx = 2 * q[0], ty = 2 * q[1], tz = 2 * q[2];
+    const double twx = tx * q[3], twy = ty * q[3], twz = tz * q[3];
+    const double txx = tx * q[0], txy = ty * q[0], txz = tz * q[0];
+    const double tyy = ty * q[1], tyz = tz * q[1], tzz = tz * q[2];
+    R[0] = 1 - (tyy + tzz); R[1] = txy - twz; R[2] = txz + twy;
+    R[3] = txy + twz; R[4] = 1 - (txx + tzz); R[5] = tyz - twx;
+    R[6] = txz - twy; R[7] = tyz + twx; R[8] = 1 - (txx + tyy);
+}
+static void se3_from_Tcw_f32(const float *T, se3 *s)       /* Converter::toSE3Quat, Converter.cc:37-47 */
+{
+    double R[9];
+    for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) R[3 * r + c] = T[4 * r + c];
+    quat_from_R(R, s->q);
+    quat_normalize_pos(s->q);
+    s->t[0] = T[3]; s->t[1] = T[7]; s->t[2] = T[11];
+}
+static void se3_to_Tcw_f32(const se3 *s, float *T)         /* Converter::toCvMat(SE3Quat), Converter.cc:49-72 */
+{
+    double R[9];
+    quat_to_R(s->q, R);
+    for (int r = 0; r < 3; r++) { for (int c = 0; c < 3; c++) T[4 * r + c] = (float)R[3 * r + c]; T[4 * r + 3] = (float)s->t[r]; }
+    T[12] = T[13] = T[14] = 0.f; T[15] = 1.f;
+}
+static void se3_map(const se3 *s, const double X[3], double out[3])
+{
+    quat_rotate(s->q, X, out);
+    out[0] += s->t[0]; out[1] += s->t[1]; out[2] += s->t[2];
+}
+static void mat3_mul(const double A[9], const double B[9], double C[9])
+{
+    for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) C[3 * r + c] = A[3 * r] * B[c] + A[3 * r + 1] * B[3 + c] + A[3 * r + 2] * B[6 + c];
+}
+/* SE3Quat::exp(update), update = (omega, upsilon); se3quat.h:223-257 */
+static void se3_exp(const double u[6], se3 *out)
+{
+    const double w[3] = {u[0], u[1], u[2]}, ups[3] = {u[3], u[4], u[5]};
+    const double theta = sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+    const double O[9] = {0, -w[2], w[1], w[2], 0, -w[0], -w[1], w[0], 0};
+    double O2[9], R[9], V[9];
+    mat3_mul(O, O, O2);
+    if (theta < 0.00001) {
+        for (int i = 0; i < 9; i++) { R[i] = (i % 4 == 0 ? 1.0 : 0.0) + O[i] + O2[i]; V[i] = R[i]; }
+    } else {
+        const double a = sin(theta) / theta, b = (1 - cos(theta)) / (theta * theta), c = (theta - sin(theta)) / pow(theta, 3);
+        for (int i = 0; i < 9; i++) {
+            R[i] = (i % 4 == 0 ? 1.0 : 0.0) + a * O[i] + b * O2[i];
+            V[i] = (i % 4 == 0 ? 1.0 : 0.0) + b * O[i] + c * O2[i];
+        }
+    }
+    quat_from_R(R, out->q);
+    for (int r = 0; r < 3; r++) out->t[r] = V[3 * r] * ups[0] + V[3 * r + 1] * ups[1] + V[3 * r + 2] * ups[2];
+    quat_normalize_pos(out->q);            /* SE3Quat(q, t) ctor normalises */
+}
+static void se3_mul(const se3 *a, const se3 *b, se3 *o)    /* SE3Quat::operator*, se3quat.h:104-110 */
+{
+    double rt[3];
+    quat_rotate(a->q, b->t, rt);
+    se3 r;
+    r.t[0] = a->t[0] + rt[0]; r.t[1] = a->t[1] + rt[1]; r.t[2] = a->t[2] + rt[2];
+    quat_mul(a->q, b->q, r.q);
+    quat_normalize_pos(r.q);
+    *o = r;
+}
+
+/* ======================================================================================== */
+/* Bundle adjustment problem over flat arrays                                                 */
+typedef struct {
+    int K, P, E;
+    se3 *pose; uint8_t *pose_fixed; const double *intr;     /* intr[K*4] fx fy cx cy */
+    double *pt;                                              /* [P*3]; pt_fixed => unary (pose-only) edges */
+    uint8_t pt_fixed_all;
+    const int *e_kf, *e_pt; const double *e_obs;            /* [E], [E], [E*2] */
+    const double *e_w;                                       /* information = w * I2 */
+    int *e_level; uint8_t *e_robust; double *e_err;          /* stored _error [E*2] */
+    double delta, dsqr;
+    /* active set / index mapping */
+    int *pose_idx, *pt_idx;                                  /* hessian index or -1 */
+    int nA, nL;                                              /* active free poses / landmarks */
+    int *act_edges; int nAE;
+    int *map_pose, *map_pt;                                  /* index -> vertex */
+    /* system */
+    double *Hpp /*[nA*36]*/, *Hll /*[nL*9]*/, *bp /*[nA*6]*/, *bl /*[nL*3]*/;
+    double *Hpl /*[E*18] per active edge slot*/;
+    double *x;                                               /* [6nA + 3nL] */
+    double *S, *bs;                                          /* reduced system (dense, 6nA) */
+    int *first;                                              /* profile */
+    double lambda, ni; int nbad;
+    const volatile int *stop;
+    int lm_iterations_done, lm_trials_done;
+} ba_t;
+
+static void ba_compute_error(ba_t *B, int e)
+{
+    /* EdgeSE3ProjectXYZ::computeError / OnlyPose, types_six_dof_expmap.h:90-95,153-157 */
+    double Xc[3];
+    se3_map(&B->pose[B->e_kf[e]], &B->pt[3 * B->e_pt[e]], Xc);
+    const double *in = &B->intr[4 * B->e_kf[e]];
+    const double px = Xc[0] / Xc[2], py = Xc[1] / Xc[2];       /* project2d */
+    B->e_err[2 * e] = B->e_obs[2 * e] - (px * in[0] + in[2]);
+    B->e_err[2 * e + 1] = B->e_obs[2 * e + 1] - (py * in[1] + in[3]);
+}
+static double ba_chi2(const ba_t *B, int e)                   /* BaseEdge::chi2, base_edge.h:58-61 */
+{
+    const double e0 = B->e_err[2 * e], e1 = B->e_err[2 * e + 1], w = B->e_w[e];
+    return e0 * (w * e0 + 0.0 * e1) + e1 * (0.0 * e0 + w * e1);
+}
+static void huber(const ba_t *B, double e, double rho[3])     /* robust_kernel_impl.cpp:78-91 */
+{
+    if (e <= B->dsqr) { rho[0] = e; rho[1] = 1.; rho[2] = 0.; }
+    else { const double s = sqrt(e); rho[0] = 2 * s * B->delta - B->dsqr; rho[1] = B->delta / s; rho[2] = -0.5 * rho[1] / e; }
+}
+static int ba_depth_positive(const ba_t *B, int e)
+{
+    double Xc[3];
+    se3_map(&B->pose[B->e_kf[e]], &B->pt[3 * B->e_pt[e]], Xc);
+    return Xc[2] > 0.0;
+}
+
+/* initializeOptimization(level 0) + buildIndexMapping, sparse_optimizer.cpp:166-267 */
+static void ba_init_active(ba_t *B)
+{
+    B->nAE = 0;
+    uint8_t *pose_act = (uint8_t *)calloc(B->K, 1), *pt_act = (uint8_t *)calloc(B->P > 0 ? B->P : 1, 1);
+    for (int e = 0; e < B->E; e++) {
+        if (B->e_level[e] != 0) continue;
+        if (B->pt_fixed_all && B->pose_fixed[B->e_kf[e]]) continue;      /* allVerticesFixed */
+        B->act_edges[B->nAE++] = e;
+        pose_act[B->e_kf[e]] = 1; pt_act[B->e_pt[e]] = 1;
+    }
+    B->nA = 0; B->nL = 0;
+    for (int k = 0; k < B->K; k++) {
+        B->pose_idx[k] = -1;
+        if (pose_act[k] && !B->pose_fixed[k]) { B->map_pose[B->nA] = k; B->pose_idx[k] = B->nA++; }
+    }
+    for (int p = 0; p < B->P; p++) {
+        B->pt_idx[p] = -1;
+        if (!B->pt_fixed_all && pt_act[p]) { B->map_pt[B->nL] = p; B->pt_idx[p] = B->nL++; }
+    }
+    free(pose_act); free(pt_act);
+}
+
+static void ba_compute_active_errors(ba_t *B) { for (int i = 0; i < B->nAE; i++) ba_compute_error(B, B->act_edges[i]); }
+static double ba_active_robust_chi2(const ba_t *B)            /* sparse_optimizer.cpp:100-114 */
+{
+    double chi = 0.0, rho[3];
+    for (int i = 0; i < B->nAE; i++) {
+        const int e = B->act_edges[i];
+        if (B->e_robust[e]) { huber(B, ba_chi2(B, e), rho); chi += rho[0]; }
+        else chi += ba_chi2(B, e);
+    }
+    return chi;
+}
+
+/* buildSystem: linearizeOplus + constructQuadraticForm per active edge, block_solver.hpp:506-564 */
+static void ba_build_system(ba_t *B)
+{
+    memset(B->Hpp, 0, sizeof(double) * 36 * (B->nA > 0 ? B->nA : 1));
+    memset(B->bp, 0, sizeof(double) * 6 * (B->nA > 0 ? B->nA : 1));
+    if (B->nL) { memset(B->Hll, 0, sizeof(double) * 9 * B->nL); memset(B->bl, 0, sizeof(double) * 3 * B->nL); }
+    for (int i = 0; i < B->nAE; i++) {
+        const int e = B->act_edges[i];
+        const int kf = B->e_kf[e], p = B->e_pt[e];
+        const int ip = B->pose_idx[kf], il = B->pt_fixed_all ? -1 : B->pt_idx[p];
+        const double *in = &B->intr[4 * kf];
+        const double fx = in[0], fy = in[1];
+        double Xc[3];
+        se3_map(&B->pose[kf], &B->pt[3 * p], Xc);
+        const double x = Xc[0], y = Xc[1], z = Xc[2];
+        double Jp[12], Jl[6];   /* 2x6 pose, 2x3 point */
+        if (B->pt_fixed_all) {                      /* EdgeSE3ProjectXYZOnlyPose::linearizeOplus, .cpp:266-288 */
+            const double invz = 1.0 / z, invz_2 = invz * invz;
+            Jp[0] = x * y * invz_2 * fx; Jp[1] = -(1 + (x * x * invz_2)) * fx; Jp[2] = y * invz * fx;
+            Jp[3] = -invz * fx; Jp[4] = 0; Jp[5] = x * invz_2 * fx;
+            Jp[6] = (1 + y * y * invz_2) * fy; Jp[7] = -x * y * invz_2 * fy; Jp[8] = -x * invz * fy;
+            Jp[9] = 0; Jp[10] = -invz * fy; Jp[11] = y * invz_2 * fy;
+        } else {                                    /* EdgeSE3ProjectXYZ::linearizeOplus, .cpp:103-139 */
+            const double z_2 = z * z;
+            double R[9];
+            quat_to_R(B->pose[kf].q, R);
+            const double tmp[6] = {fx, 0, -x / z * fx, 0, fy, -y / z * fy};
+            const double s = -1. / z;
+            for (int r = 0; r < 2; r++) for (int c = 0; c < 3; c++) {
+                const double st0 = s * tmp[3 * r], st1 = s * tmp[3 * r + 1], st2 = s * tmp[3 * r + 2];
+                Jl[3 * r + c] = st0 * R[c] + st1 * R[3 + c] + st2 * R[6 + c];
+            }
+            Jp[0] = x * y / z_2 * fx; Jp[1] = -(1 + (x * x / z_2)) * fx; Jp[2] = y / z * fx;
+            Jp[3] = -1. / z * fx; Jp[4] = 0; Jp[5] = x / z_2 * fx;
+            Jp[6] = (1 + y * y / z_2) * fy; Jp[7] = -x * y / z_2 * fy; Jp[8] = -x / z * fy;
+            Jp[9] = 0; Jp[10] = -1. / z * fy; Jp[11] = y / z_2 * fy;
+        }
+        /* constructQuadraticForm, base_binary_edge.hpp:55-120 / base_unary_edge.hpp:43-72 */
+        double w = B->e_w[e], rw = 1.0;
+        if (B->e_robust[e]) { double rho[3]; huber(B, ba_chi2(B, e), rho); rw = rho[1]; }
+        const double wo = rw * w;                              /* weightedOmega = rho' * omega */
+        const double r0 = -w * B->e_err[2 * e] * rw, r1 = -w * B->e_err[2 * e + 1] * rw;   /* omega_r */
+        if (ip >= 0) {
+            double *H = &B->Hpp[36 * ip], *b = &B->bp[6 * ip];
+            for (int a = 0; a < 6; a++) {
+                b[a] += Jp[a] * r0 + Jp[6 + a] * r1;
+                for (int c = 0; c < 6; c++) H[6 * a + c] += Jp[a] * wo * Jp[c] + Jp[6 + a] * wo * Jp[6 + c];
+            }
+        }
+        if (il >= 0) {
+            double *H = &B->Hll[9 * il], *b = &B->bl[3 * il];
+            for (int a = 0; a < 3; a++) {
+                b[a] += Jl[a] * r0 + Jl[3 + a] * r1;
+                for (int c = 0; c < 3; c++) H[3 * a + c] += Jl[a] * wo * Jl[c] + Jl[3 + a] * wo * Jl[3 + c];
+            }
+            double *W = &B->Hpl[18 * i];                       /* 6x3: Jp^T wo Jl */
+            if (ip >= 0)
+                for (int a = 0; a < 6; a++) for (int c = 0; c < 3; c++) W[3 * a + c] = Jp[a] * wo * Jl[c] + Jp[6 + a] * wo * Jl[3 + c];
+        }
+    }
+}
+
+static void inv3(const double *A, double *I)                  /* Matrix3d::inverse(): cofactors / determinant */
+{
+    const double c00 = A[4] * A[8] - A[5] * A[7], c01 = A[5] * A[6] - A[3] * A[8], c02 = A[3] * A[7] - A[4] * A[6];
+    const double det = A[0] * c00 + A[1] * c01 + A[2] * c02, id = 1.0 / det;
+    I[0] = c00 * id; I[1] = (A[2] * A[7] - A[1] * A[8]) * id; I[2] = (A[1] * A[5] - A[2] * A[4]) * id;
+    I[3] = c01 * id; I[4] = (A[0] * A[8] - A[2] * A[6]) * id; I[5] = (A[2] * A[3] - A[0] * A[5]) * id;
+    I[6] = c02 * id; I[7] = (A[1] * A[6] - A[0] * A[7]) * id; I[8] = (A[0] * A[4] - A[1] * A[3]) * id;
+}
+
+/* profile LDL^T of the dense symmetric n x n matrix S (row-major, lower part used), in place.
+ * returns 0 on a zero pivot (SimplicialLDLT's NumericalIssue). */
+static int ldlt_solve(double *S, int n, const int *first, const double *b, double *x)
+{
+    for (int i = 0; i < n; i++) {
+        for (int j = first[i]; j <= i; j++) {
+            double s = S[(size_t)i * n + j];
+            const int k0 = first[i] > first[j] ? first[i] : first[j];
+            for (int k = k0; k < j; k++) s -= S[(size_t)i * n + k] * S[(size_t)j * n + k] * S[(size_t)k * n + k];
+            if (j < i) S[(size_t)i * n + j] = s / S[(size_t)j * n + j];
+            else { if (s == 0.0 || !(s == s)) return 0; S[(size_t)i * n + i] = s; }
+        }
+    }
+    for (int i = 0; i < n; i++) { double s = b[i]; for (int k = first[i]; k < i; k++) s -= S[(size_t)i * n + k] * x[k]; x[i] = s; }
+    for (int i = 0; i < n; i++) x[i] /= S[(size_t)i * n + i];
+    for (int i = n - 1; i >= 0; i--) { const double xi = x[i]; for (int k = first[i]; k < i; k++) x[k] -= S[(size_t)i * n + k] * xi; }
+    return 1;
+}
+
+/* setLambda + solve (Schur) + restoreDiagonal are folded: lambda is added on the fly. block_solver.hpp:358-490,568-608 */
+static int ba_solve(ba_t *B)
+{
+    const int nA = B->nA, nL = B->nL, n = 6 * nA;
+    const double lam = B->lambda;
+    double *S = B->S, *bs = B->bs;
+    memset(S, 0, sizeof(double) * (size_t)n * n);
+    for (int i = 0; i < nA; i++)
+        for (int a = 0; a < 6; a++) {
+            for (int c = 0; c < 6; c++) S[(size_t)(6 * i + a) * n + 6 * i + c] = B->Hpp[36 * i + 6 * a + c];
+            S[(size_t)(6 * i + a) * n + 6 * i + a] += lam;
+            bs[6 * i + a] = B->bp[6 * i + a];
+        }
+    for (int i = 0; i < n; i++) B->first[i] = (i / 6) * 6;
+    double *Dinv = NULL, *dbl = NULL;
+    int *lm_edges_start = NULL, *lm_edges = NULL;
+    if (nL) {
+        Dinv = (double *)malloc(sizeof(double) * 9 * nL);
+        /* per-landmark list of active-edge slots (sorted by pose index like the CCS column) */
+        lm_edges_start = (int *)calloc(nL + 1, sizeof(int));
+        for (int i = 0; i < B->nAE; i++) { const int e = B->act_edges[i]; if (B->pose_idx[B->e_kf[e]] >= 0) lm_edges_start[B->pt_idx[B->e_pt[e]] + 1]++; }
+        for (int l = 0; l < nL; l++) lm_edges_start[l + 1] += lm_edges_start[l];
+        lm_edges = (int *)malloc(sizeof(int) * (lm_edges_start[nL] > 0 ? lm_edges_start[nL] : 1));
+        int *fill = (int *)calloc(nL, sizeof(int));
+        for (int i = 0; i < B->nAE; i++) {
+            const int e = B->act_edges[i];
+            if (B->pose_idx[B->e_kf[e]] < 0) continue;
+            const int l = B->pt_idx[B->e_pt[e]];
+            lm_edges[lm_edges_start[l] + fill[l]++] = i;
+        }
+        free(fill);
+        for (int l = 0; l < nL; l++) {             /* sort slots of a landmark by pose index (insertion) */
+            int *a = lm_edges + lm_edges_start[l]; const int m = lm_edges_start[l + 1] - lm_edges_start[l];
+            for (int u = 1; u < m; u++) { int v = a[u], w = u; while (w > 0 && B->pose_idx[B->e_kf[B->act_edges[a[w - 1]]]] > B->pose_idx[B->e_kf[B->act_edges[v]]]) { a[w] = a[w - 1]; w--; } a[w] = v; }
+        }
+        for (int l = 0; l < nL; l++) {
+            double D[9];
+            memcpy(D, &B->Hll[9 * l], sizeof D);
+            D[0] += lam; D[4] += lam; D[8] += lam;
+            double *Di = &Dinv[9 * l];
+            inv3(D, Di);
+            const double *bl = &B->bl[3 * l];
+            const double db[3] = {Di[0] * bl[0] + Di[1] * bl[1] + Di[2] * bl[2], Di[3] * bl[0] + Di[4] * bl[1] + Di[5] * bl[2],
+                                  Di[6] * bl[0] + Di[7] * bl[1] + Di[8] * bl[2]};
+            for (int u = lm_edges_start[l]; u < lm_edges_start[l + 1]; u++) {
+                const int s1 = lm_edges[u], i1 = B->pose_idx[B->e_kf[B->act_edges[s1]]];
+                const double *W1 = &B->Hpl[18 * s1];
+                double BD[18];
+                for (int a = 0; a < 6; a++) for (int c = 0; c < 3; c++) BD[3 * a + c] = W1[3 * a] * Di[c] + W1[3 * a + 1] * Di[3 + c] + W1[3 * a + 2] * Di[6 + c];
+                for (int a = 0; a < 6; a++) bs[6 * i1 + a] -= W1[3 * a] * db[0] + W1[3 * a + 1] * db[1] + W1[3 * a + 2] * db[2];
+                for (int v = u; v < lm_edges_start[l + 1]; v++) {
+                    const int s2 = lm_edges[v], i2 = B->pose_idx[B->e_kf[B->act_edges[s2]]];
+                    const double *W2 = &B->Hpl[18 * s2];
+                    /* upper block (i1, i2) -= BD * W2^T ; stored into lower part (i2 rows, i1 cols) transposed */
+                    for (int a = 0; a < 6; a++) for (int c = 0; c < 6; c++) {
+                        const double val = BD[3 * a] * W2[3 * c] + BD[3 * a + 1] * W2[3 * c + 1] + BD[3 * a + 2] * W2[3 * c + 2];
+                        if (i1 == i2) { S[(size_t)(6 * i1 + a) * n + 6 * i1 + c] -= val; }
+                        else S[(size_t)(6 * i2 + c) * n + 6 * i1 + a] -= val;
+                    }
+                    if (i2 != i1) for (int c = 0; c < 6; c++) if (B->first[6 * i2 + c] > 6 * i1) B->first[6 * i2 + c] = 6 * i1;
+                }
+            }
+        }
+    }
+    double *xp = B->x;
+    const int ok = n > 0 ? ldlt_solve(S, n, B->first, bs, xp) : 1;
+    if (ok && nL) {
+        /* x_l = Dinv (b_l - Hpl^T x_p), block_solver.hpp:463-487 */
+        dbl = (double *)malloc(sizeof(double) * 3 * nL);
+        memcpy(dbl, B->bl, sizeof(double) * 3 * nL);
+        for (int l = 0; l < nL; l++)
+            for (int u = lm_edges_start[l]; u < lm_edges_start[l + 1]; u++) {
+                const int s1 = lm_edges[u], i1 = B->pose_idx[B->e_kf[B->act_edges[s1]]];
+                const double *W1 = &B->Hpl[18 * s1];
+                for (int c = 0; c < 3; c++) for (int a = 0; a < 6; a++) dbl[3 * l + c] -= W1[3 * a + c] * xp[6 * i1 + a];
+            }
+        for (int l = 0; l < nL; l++) {
+            const double *Di = &Dinv[9 * l], *c = &dbl[3 * l];
+            double *xl = &B->x[n + 3 * l];
+            for (int a = 0; a < 3; a++) xl[a] = Di[3 * a] * c[0] + Di[3 * a + 1] * c[1] + Di[3 * a + 2] * c[2];
+        }
+    }
+    free(Dinv); free(dbl); free(lm_edges_start); free(lm_edges);
+    return ok;
+}
+
+static void ba_update(ba_t *B)                                /* SparseOptimizer::update + oplusImpl */
+{
+    for (int i = 0; i < B->nA; i++) {
+        se3 d, r;
+        se3_exp(&B->x[6 * i], &d);
+        se3_mul(&d, &B->pose[B->map_pose[i]], &r);
+        B->pose[B->map_pose[i]] = r;
+    }
+    for (int l = 0; l < B->nL; l++) { double *p = &B->pt[3 * B->map_pt[l]]; const double *x = &B->x[6 * B->nA + 3 * l]; p[0] += x[0]; p[1] += x[1]; p[2] += x[2]; }
+}
+
+static int ba_terminate(const ba_t *B) { return B->stop && *B->stop; }
+
+enum { LM_OK = 0, LM_TERMINATE = 1 };
+/* OptimizationAlgorithmLevenberg::solve, optimization_algorithm_levenberg.cpp:61-164 */
+static int ba_lm_iteration(ba_t *B, int iteration)
+{
+    ba_compute_active_errors(B);
+    double currentChi = ba_active_robust_chi2(B), tempChi = currentChi;
+    const double iniChi = currentChi;
+    ba_build_system(B);
+    if (iteration == 0) {                                     /* computeLambdaInit, :166-180 */
+        double maxDiag = 0.;
+        for (int i = 0; i < B->nA; i++) for (int j = 0; j < 6; j++) maxDiag = fmax(fabs(B->Hpp[36 * i + 7 * j]), maxDiag);
+        for (int l = 0; l < B->nL; l++) for (int j = 0; j < 3; j++) maxDiag = fmax(fabs(B->Hll[9 * l + 4 * j]), maxDiag);
+        B->lambda = 1e-5 * maxDiag; B->ni = 2; B->nbad = 0;
+    }
+    double rho = 0;
+    int qmax = 0;
+    const int nx = 6 * B->nA + 3 * B->nL;
+    se3 *pose_bak = (se3 *)malloc(sizeof(se3) * (B->nA > 0 ? B->nA : 1));
+    double *pt_bak = (double *)malloc(sizeof(double) * 3 * (B->nL > 0 ? B->nL : 1));
+    do {
+        for (int i = 0; i < B->nA; i++) pose_bak[i] = B->pose[B->map_pose[i]];            /* push */
+        for (int l = 0; l < B->nL; l++) memcpy(&pt_bak[3 * l], &B->pt[3 * B->map_pt[l]], 3 * sizeof(double));
+        const int ok2 = ba_solve(B);
+        ba_update(B);
+        ba_compute_active_errors(B);
+        tempChi = ba_active_robust_chi2(B);
+        if (!ok2) tempChi = DBL_MAX;
+        rho = currentChi - tempChi;
+        double scale = 0.;                                   /* computeScale, :182-189 */
+        for (int j = 0; j < nx; j++) {
+            const double bj = j < 6 * B->nA ? B->bp[j] : B->bl[j - 6 * B->nA];
+            scale += B->x[j] * (B->lambda * B->x[j] + bj);
+        }
+        scale += 1e-3;
+        rho /= scale;
+        if (rho > 0 && isfinite(tempChi)) {
+            double alpha = 1. - pow((2 * rho - 1), 3);
+            alpha = fmin(alpha, 2. / 3.);
+            const double sf = fmax(1. / 3., alpha);
+            B->lambda *= sf; B->ni = 2; currentChi = tempChi;
+        } else {
+            B->lambda *= B->ni; B->ni *= 2;
+            for (int i = 0; i < B->nA; i++) B->pose[B->map_pose[i]] = pose_bak[i];        /* pop */
+            for (int l = 0; l < B->nL; l++) memcpy(&B->pt[3 * B->map_pt[l]], &pt_bak[3 * l], 3 * sizeof(double));
+        }
+        qmax++;
+        B->lm_trials_done++;
+    } while (rho < 0 && qmax < 10 && !ba_terminate(B));
+    free(pose_bak); free(pt_bak);
+    B->lm_iterations_done++;
+    if (qmax == 10 || rho == 0) return LM_TERMINATE;
+    if ((iniChi - currentChi) * 1e3 < iniChi) B->nbad++; else B->nbad = 0;
+    if (B->nbad >= 3) return LM_TERMINATE;
+    return LM_OK;
+}
+
+/* SparseOptimizer::optimize, sparse_optimizer.cpp:354-419 */
+static int ba_optimize(ba_t *B, int iterations)
+{
+    if (B->nA + B->nL == 0) return -1;
+    int done = 0;
+    for (int i = 0; i < iterations && !ba_terminate(B); i++) {
+        const int res = ba_lm_iteration(B, i);
+        done++;
+        if (res != LM_OK) break;
+    }
+    return done;
+}
+
+static void ba_alloc(ba_t *B)
+{
+    const int K = B->K, P = B->P > 0 ? B->P : 1, E = B->E > 0 ? B->E : 1;
+    B->pose_idx = (int *)malloc(sizeof(int) * K); B->pt_idx = (int *)malloc(sizeof(int) * P);
+    B->map_pose = (int *)malloc(sizeof(int) * K); B->map_pt = (int *)malloc(sizeof(int) * P);
+    B->act_edges = (int *)malloc(sizeof(int) * E);
+    B->Hpp = (double *)malloc(sizeof(double) * 36 * K); B->bp = (double *)malloc(sizeof(double) * 6 * K);
+    B->Hll = (double *)malloc(sizeof(double) * 9 * P); B->bl = (double *)malloc(sizeof(double) * 3 * P);
+    B->Hpl = (double *)malloc(sizeof(double) * 18 * E);
+    B->x = (double *)calloc((size_t)6 * K + 3 * P, sizeof(double));
+    B->S = (double *)malloc(sizeof(double) * 36 * (size_t)K * K); B->bs = (double *)malloc(sizeof(double) * 6 * K);
+    B->first = (int *)malloc(sizeof(int) * 6 * K);
+    B->lm_iterations_done = B->lm_trials_done = 0;
+}
+static void ba_free(ba_t *B)
+{
+    free(B->pose_idx); free(B->pt_idx); free(B->map_pose); free(B->map_pt); free(B->act_edges);
+    free(B->Hpp); free(B->bp); free(B->Hll); free(B->bl); free(B->Hpl); free(B->x); free(B->S); free(B->bs); free(B->first);
+}
+
+/* ---------------------------------------------------------------------------------------- */
+/* Optimizer::PoseOptimization, Optimizer.cc:262-474 (monocular edges).
+ * Tcw: in/out row-major 4x4 f32.  Xw f32[M,3], obs f32[M,2] (kpUn.pt), inv_sigma2 f32[M], K4 fx fy cx cy (float).
+ * outlier u8[M] out.  Returns nInitialCorrespondences - nBad (0 if < 3 correspondences). */
+int oracle_pose_optimization(float *Tcw, int M, const float *Xw, const float *obs, const float *inv_sigma2,
+                             const float *K4, uint8_t *outlier)
+{
+    if (M < 3) return 0;                                      /* :387-388 */
+    ba_t B; memset(&B, 0, sizeof B);
+    B.K = 1; B.P = M; B.E = M; B.pt_fixed_all = 1;
+    se3 pose; uint8_t fixed = 0;
+    double intr[4] = {K4[0], K4[1], K4[2], K4[3]};
+    B.pose = &pose; B.pose_fixed = &fixed; B.intr = intr;
+    double *pt = (double *)malloc(sizeof(double) * 3 * M), *o = (double *)malloc(sizeof(double) * 2 * M), *w = (double *)malloc(sizeof(double) * M);
+    int *ekf = (int *)calloc(M, sizeof(int)), *ept = (int *)malloc(sizeof(int) * M), *lvl = (int *)calloc(M, sizeof(int));
+    uint8_t *rob = (uint8_t *)malloc(M); double *err = (double *)calloc(2 * M, sizeof(double));
+    for (int i = 0; i < M; i++) {
+        for (int c = 0; c < 3; c++) pt[3 * i + c] = Xw[3 * i + c];
+        o[2 * i] = obs[2 * i]; o[2 * i + 1] = obs[2 * i + 1];
+        w[i] = inv_sigma2[i]; ept[i] = i; rob[i] = 1; outlier[i] = 0;
+    }
+    B.pt = pt; B.e_kf = ekf; B.e_pt = ept; B.e_obs = o; B.e_w = w; B.e_level = lvl; B.e_robust = rob; B.e_err = err;
+    const float deltaMono = sqrtf(5.991f);                    /* const float deltaMono = sqrt(5.991) */
+    B.delta = (double)(float)sqrt(5.991); (void)deltaMono;
+    B.dsqr = B.delta * B.delta;
+    ba_alloc(&B);
+    const float chi2Mono[4] = {5.991f, 5.991f, 5.991f, 5.991f};
+    int nBad = 0;
+    for (int it = 0; it < 4; it++) {
+        se3_from_Tcw_f32(Tcw, &pose);                         /* reset to the initial pose every round, :400 */
+        ba_init_active(&B);
+        ba_optimize(&B, 10);
+        nBad = 0;
+        for (int i = 0; i < M; i++) {
+            if (outlier[i]) ba_compute_error(&B, i);
+            const float chi2 = (float)ba_chi2(&B, i);
+            if (chi2 > chi2Mono[it]) { outlier[i] = 1; lvl[i] = 1; nBad++; }
+            else { outlier[i] = 0; lvl[i] = 0; }
+            if (it == 2) rob[i] = 0;
+        }
+        if (M < 10) break;                                    /* optimizer.edges().size()<10, :463 */
+    }
+    se3_to_Tcw_f32(&pose, Tcw);
+    ba_free(&B);
+    free(pt); free(o); free(w); free(ekf); free(ept); free(lvl); free(rob); free(err);
+    return M - nBad;
+}
+
+/* ---------------------------------------------------------------------------------------- */
+/* Bundle adjustment over flat arrays: LocalBundleAdjustment (Optimizer.cc:476-801) when two_stage != 0
+ * (its0 robust iterations, chi2/depth gating, its1 non-robust iterations) and BundleAdjustment (:68-260) when
+ * two_stage == 0 (its0 iterations, robust flag).  poses [K,16] f32 in/out, fixed u8[K], intr f64[K,4],
+ * points [P,3] f32 in/out, edges kf/pt i32[E], uv f32[E,2], inv_sigma2 f32[E].
+ * e_chi2 f64[E] / e_depth_ok u8[E] / e_outlier u8[E] out: the reference's final check (:734-766).
+ * stats (optional, 2 ints): LM iterations and trials executed. */
+int oracle_bundle_adjust(int K, float *poses, const uint8_t *fixed, const double *intr, int P, float *points,
+                         int E, const int *e_kf, const int *e_pt, const float *e_uv, const float *e_inv_sigma2,
+                         int two_stage, int its0, int its1, int robust, const volatile int *stop,
+                         double *e_chi2, uint8_t *e_depth_ok, uint8_t *e_outlier, int *stats)
+{
+    ba_t B; memset(&B, 0, sizeof B);
+    B.K = K; B.P = P; B.E = E; B.pt_fixed_all = 0; B.stop = stop;
+    se3 *pose = (se3 *)malloc(sizeof(se3) * K);
+    uint8_t *fx = (uint8_t *)malloc(K);
+    for (int k = 0; k < K; k++) { se3_from_Tcw_f32(poses + 16 * k, &pose[k]); fx[k] = fixed[k]; }
+    double *pt = (double *)malloc(sizeof(double) * 3 * (P > 0 ? P : 1));
+    for (int i = 0; i < 3 * P; i++) pt[i] = points[i];
+    double *o = (double *)malloc(sizeof(double) * 2 * (E > 0 ? E : 1)), *w = (double *)malloc(sizeof(double) * (E > 0 ? E : 1));
+    int *lvl = (int *)calloc(E > 0 ? E : 1, sizeof(int));
+    uint8_t *rob = (uint8_t *)malloc(E > 0 ? E : 1); double *err = (double *)calloc(2 * (E > 0 ? E : 1), sizeof(double));
+    for (int e = 0; e < E; e++) { o[2 * e] = e_uv[2 * e]; o[2 * e + 1] = e_uv[2 * e + 1]; w[e] = e_inv_sigma2[e]; rob[e] = (uint8_t)(two_stage ? 1 : robust); }
+    B.pose = pose; B.pose_fixed = fx; B.intr = intr; B.pt = pt; B.e_kf = e_kf; B.e_pt = e_pt; B.e_obs = o; B.e_w = w;
+    B.e_level = lvl; B.e_robust = rob; B.e_err = err;
+    B.delta = (double)(float)sqrt(5.991); B.dsqr = B.delta * B.delta;
+    ba_alloc(&B);
+    int do_more = 1;
+    if (stop && *stop) {                                      /* :678-680: return before touching anything */
+        ba_free(&B);
+        free(pose); free(fx); free(pt); free(o); free(w); free(lvl); free(rob); free(err);
+        return 1;
+    }
+    {
+        ba_init_active(&B);
+        ba_optimize(&B, its0);
+        if (two_stage) {
+            if (stop && *stop) do_more = 0;
+            if (do_more) {
+                for (int e = 0; e < E; e++) {                 /* :691-705 */
+                    if (ba_chi2(&B, e) > 5.991 || !ba_depth_positive(&B, e)) lvl[e] = 1;
+                    rob[e] = 0;
+                }
+                ba_init_active(&B);
+                ba_optimize(&B, its1);
+            }
+        }
+    }
+    for (int e = 0; e < E; e++) {                             /* :734-766 */
+        const double c = ba_chi2(&B, e); const int d = ba_depth_positive(&B, e);
+        if (e_chi2) e_chi2[e] = c;
+        if (e_depth_ok) e_depth_ok[e] = (uint8_t)d;
+        if (e_outlier) e_outlier[e] = (uint8_t)(c > 5.991 || !d);
+    }
+    /* every local KF (free, or fixed because mnId==0: fixed[k]==1) is written back through the SE3Quat round trip,
+     * :785-791; fixed cameras outside the local window (fixed[k]==2) are never touched */
+    for (int k = 0; k < K; k++) if (fixed[k] != 2) se3_to_Tcw_f32(&pose[k], poses + 16 * k);
+    for (int i = 0; i < 3 * P; i++) points[i] = (float)pt[i];
+    if (stats) { stats[0] = B.lm_iterations_done; stats[1] = B.lm_trials_done; }
+    ba_free(&B);
+    free(pose); free(fx); free(pt); free(o); free(w); free(lvl); free(rob); free(err);
+    return 0;
+}

@@ -117,13 +117,17 @@ def ba_graph(K=100, P=10000, seed=42, cam=KITTI, min_obs=3, max_obs=9, outlier_f
     # perturbed initial state
     poses = np.zeros((K, 4, 4), np.float32)
     for k in range(K):
-        dR = _rodrigues(rng.normal(0, np.deg2rad(0.5), 3)) if k else np.eye(3)
-        dt = rng.normal(0, 0.05, 3) if k else np.zeros(3)
+        dR = _rodrigues(rng.normal(0, np.deg2rad(0.5), 3)) if k > 1 else np.eye(3)
+        dt = rng.normal(0, 0.05, 3) if k > 1 else np.zeros(3)
         poses[k, :3, :3] = (dR @ Rcw[k]).astype(np.float32)
         poses[k, :3, 3] = (dR @ tcw[k] + dt).astype(np.float32)
         poses[k, 3, 3] = 1
     points = (Xw + rng.normal(0, 0.10, (P, 3))).astype(np.float32)
+    # KF 0 is fixed because mnId==0 (written back); KF 1 plays a fixed camera outside the local window: together
+    # they pin the monocular scale gauge like lFixedCameras does in the reference (Optimizer.cc:512-527)
     fixed = np.zeros(K, np.uint8); fixed[0] = 1
+    if K > 2:
+        fixed[1] = 2
     gt_poses = np.zeros((K, 4, 4)); gt_poses[:, :3, :3] = Rcw; gt_poses[:, :3, 3] = tcw; gt_poses[:, 3, 3] = 1
     return dict(poses=poses, fixed=fixed, intr=np.array([fx, fy, cx, cy], np.float64), points=points,
                 kf=kf, pt=pt, uv=uv.astype(np.float32), inv_sigma2=inv_sigma2.astype(np.float32),
