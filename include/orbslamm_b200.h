@@ -117,6 +117,62 @@ int orbx_synchronize(orbx_handle *h);
 /* number of kernels this handle has launched since creation (bench bookkeeping) */
 long long orbx_kernel_launches(const orbx_handle *h);
 
+/* ------------------------------------------------------------------ */
+/* ORB matcher  (replaces S/src/ORBmatcher.cc + the Frame grid it searches) */
+typedef struct orbm_handle orbm_handle;
+
+#define ORBS_MEM_HOST 0     /* the array arguments are host pointers (copied in/out, call blocks) */
+#define ORBS_MEM_DEVICE 1   /* the array arguments are device pointers (asynchronous on the handle's stream) */
+#define ORBM_TH_HIGH 100    /* ORBmatcher::TH_HIGH / TH_LOW / HISTO_LENGTH, ORBmatcher.cc:37-39 */
+#define ORBM_TH_LOW 50
+#define ORBM_HISTO_LENGTH 30
+
+int orbm_create(orbm_handle **out, int device);
+int orbm_destroy(orbm_handle *h);
+void *orbm_stream(orbm_handle *h);
+int orbm_synchronize(orbm_handle *h);
+long long orbm_kernel_launches(const orbm_handle *h);
+
+/* ORBmatcher::DescriptorDistance (ORBmatcher.cc:1649-1665) for all pairs: out[i*m + j] = Hamming(a[i], b[j]).
+ * a u8[n,32], b u8[m,32], out i32[n,m]. */
+int orbm_descriptor_distance(orbm_handle *h, const uint8_t *a, int n, const uint8_t *b, int m, int32_t *out, int memspace);
+
+/* Projection block of SearchByProjection(CurrentFrame, LastFrame, th, bMono=true), ORBmatcher.cc:1336-1391:
+ * per frame f and last-frame slot i (valid[i] != 0: the slot holds a non-outlier map point) project Xw with the
+ * current pose, keep it if the depth is positive and (u, v) lies inside the image bounds, and emit the search
+ * window.  fp32 arithmetic restated from OpenCV's small gemm (sequential fp32, no FMA).
+ *   K4 f32[4] = fx fy cx cy and bounds4 f32[4] = mnMinX mnMinY mnMaxX mnMaxY are always HOST pointers;
+ *   Tcw f32[n_frames,16] row-major;
+ *   scale_factors f32[nlevels]; Xw f32[n_frames*q_slab,3]; last_octave i32[.]; q_counts i32[n_frames];
+ *   q_valid u8[.] in/out; q_uv f32[.,2], q_radius f32[.], q_minl/q_maxl i32[.] out (octave-1 / octave+1). */
+int orbm_project_last_frame(orbm_handle *h, int n_frames, const float *Tcw, const float *K4, const float *bounds4,
+                            const float *scale_factors, int nlevels, const float *Xw, const int32_t *last_octave,
+                            const int32_t *q_counts, int q_slab, float th, uint8_t *q_valid, float *q_uv,
+                            float *q_radius, int32_t *q_minl, int32_t *q_maxl, int memspace);
+
+/* The search loop shared by SearchByProjection(Frame&, vector<MapPoint*>&, th) (ORBmatcher.cc:45-129: ratio > 0,
+ * check_ori = 0) and SearchByProjection(Cur, Last, th, mono) (ORBmatcher.cc:1353-1467: ratio <= 0, check_ori = 1),
+ * for n_frames independent frames.  Per frame the 64x48 grid of Frame::AssignFeaturesToGrid is rebuilt on the
+ * device, every valid query visits Frame::GetFeaturesInArea(u, v, r, minLevel, maxLevel), skips features that
+ * already hold a map point, takes the best (and second best) Hamming distance, accepts it if best <= th_dist
+ * (and, with ratio > 0, unless both are on the same level and best > ratio * second), and claims the feature.
+ * The reference's loop is sequential (an accepted query hides its feature from all later queries); the result
+ * here is identical to that sequential order.  With check_ori the 30-bin rotation histogram keeps the three
+ * dominant bins (ComputeThreeMaxima, ORBmatcher.cc:1603-1644).
+ *   features: f_xy f32[n_frames*f_slab,2] (mvKeysUn.pt), f_octave i32, f_angle f32, f_desc u8[.,32], f_counts i32[n_frames]
+ *   queries:  q_valid u8[n_frames*q_slab], q_uv f32[.,2], q_radius f32, q_minl/q_maxl i32, q_angle f32, q_desc u8[.,32],
+ *             q_counts i32[n_frames]
+ *   feat_match i32[n_frames*f_slab] in/out: in  < 0 = free, >= 0 = feature already holds a map point (skipped);
+ *                                            out = index of the query now assigned to the feature (Frame::mvpMapPoints)
+ *   nmatches i32[n_frames] out (the function's return value per frame). */
+int orbm_search_by_projection(orbm_handle *h, int n_frames, const float *bounds4,
+                              const float *f_xy, const int32_t *f_octave, const float *f_angle, const uint8_t *f_desc,
+                              const int32_t *f_counts, int f_slab,
+                              const uint8_t *q_valid, const float *q_uv, const float *q_radius, const int32_t *q_minl,
+                              const int32_t *q_maxl, const float *q_angle, const uint8_t *q_desc, const int32_t *q_counts,
+                              int q_slab, int th_dist, float ratio, int check_ori,
+                              int32_t *feat_match, int32_t *nmatches, int memspace);
+
 #ifdef __cplusplus
 }
 #endif

@@ -199,3 +199,86 @@ class ORBextractor:
 def _empty():
     z = np.zeros(0, np.float32)
     return dict(x=z, y=z, angle=z, response=z, octave=np.zeros(0, np.int32), size=z, desc=np.zeros((0, 32), np.uint8))
+
+
+def _dp(a):
+    """host ndarray -> pointer, int -> device pointer, None -> NULL"""
+    if a is None:
+        return None
+    if isinstance(a, (int, np.integer)):
+        return ctypes.c_void_p(int(a))
+    return a.ctypes.data
+
+
+class ORBmatcher:
+    """Mirror of iORB_SLAM::ORBmatcher (reference S/include/ORBmatcher.h:37-102) over flat arrays.
+
+    nnratio / checkOri as in the reference constructor (ORBmatcher.cc:41-43).  Frames are described by SoA
+    arrays instead of Frame objects; see include/orbslamm_b200.h for the layouts."""
+
+    TH_LOW, TH_HIGH, HISTO_LENGTH = 50, 100, 30
+
+    def __init__(self, nnratio=0.6, checkOri=True, device=0):
+        self._L = load()
+        self._h = ctypes.c_void_p()
+        _check(self._L.orbm_create(ctypes.byref(self._h), int(device)))
+        self.mfNNratio = float(nnratio)
+        self.mbCheckOrientation = bool(checkOri)
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            self._L.orbm_destroy(h)
+
+    @property
+    def handle(self): return self._h
+    def stream(self): return self._L.orbm_stream(self._h)
+    def synchronize(self): _check(self._L.orbm_synchronize(self._h))
+    def kernel_launches(self): return int(self._L.orbm_kernel_launches(self._h))
+
+    def DescriptorDistance(self, a, b):
+        """All-pairs Hamming distances of descriptor rows a [n,32] and b [m,32] (ORBmatcher.cc:1649-1665)."""
+        a = np.ascontiguousarray(a, np.uint8).reshape(-1, 32); b = np.ascontiguousarray(b, np.uint8).reshape(-1, 32)
+        out = np.zeros((len(a), len(b)), np.int32)
+        _check(self._L.orbm_descriptor_distance(self._h, _ptr(a), len(a), _ptr(b), len(b), _ptr(out), 0))
+        return out
+
+    def project_last_frame(self, Tcw, K4, bounds4, scale_factors, Xw, last_octave, q_counts, th, q_valid):
+        """Projection block of SearchByProjection(Cur, Last) for n_frames frames (host arrays, slab layout)."""
+        Tcw = np.ascontiguousarray(Tcw, np.float32).reshape(-1, 16); nfr = len(Tcw)
+        K4 = np.ascontiguousarray(K4, np.float32); b4 = np.ascontiguousarray(bounds4, np.float32)
+        sf = np.ascontiguousarray(scale_factors, np.float32)
+        Xw = np.ascontiguousarray(Xw, np.float32).reshape(nfr, -1, 3); slab = Xw.shape[1]
+        lo = np.ascontiguousarray(last_octave, np.int32).reshape(nfr, slab)
+        qc = np.ascontiguousarray(q_counts, np.int32)
+        qv = np.ascontiguousarray(q_valid, np.uint8).reshape(nfr, slab).copy()
+        uv = np.zeros((nfr, slab, 2), np.float32); rad = np.zeros((nfr, slab), np.float32)
+        mn = np.zeros((nfr, slab), np.int32); mx = np.zeros((nfr, slab), np.int32)
+        _check(self._L.orbm_project_last_frame(self._h, nfr, _ptr(Tcw), _ptr(K4), _ptr(b4), _ptr(sf), len(sf), _ptr(Xw), _ptr(lo),
+                                               _ptr(qc), slab, float(th), _ptr(qv), _ptr(uv), _ptr(rad), _ptr(mn), _ptr(mx), 0))
+        return qv, uv, rad, mn, mx
+
+    def SearchByProjection(self, bounds4, f_xy, f_octave, f_angle, f_desc, f_counts, q_valid, q_uv, q_radius, q_minl,
+                           q_maxl, q_angle, q_desc, q_counts, th_dist=100, use_ratio=False, feat_match=None):
+        """Generic projection search for n_frames frames (host arrays in slab layout [n_frames, slab, ...]).
+        use_ratio=False: the (Cur, Last) variant (orientation check per mbCheckOrientation);
+        use_ratio=True: the (Frame, MapPoints) variant with mfNNratio and no orientation check.
+        Returns (nmatches[n_frames], feat_match[n_frames, f_slab])."""
+        f_xy = np.ascontiguousarray(f_xy, np.float32); nfr, fs = f_xy.shape[0], f_xy.shape[1]
+        f_octave = np.ascontiguousarray(f_octave, np.int32); f_angle = np.ascontiguousarray(f_angle, np.float32)
+        f_desc = np.ascontiguousarray(f_desc, np.uint8); f_counts = np.ascontiguousarray(f_counts, np.int32)
+        q_valid = np.ascontiguousarray(q_valid, np.uint8); qs = q_valid.shape[1]
+        q_uv = np.ascontiguousarray(q_uv, np.float32); q_radius = np.ascontiguousarray(q_radius, np.float32)
+        q_minl = np.ascontiguousarray(q_minl, np.int32); q_maxl = np.ascontiguousarray(q_maxl, np.int32)
+        q_angle = np.ascontiguousarray(q_angle, np.float32); q_desc = np.ascontiguousarray(q_desc, np.uint8)
+        q_counts = np.ascontiguousarray(q_counts, np.int32)
+        fm = np.full((nfr, fs), -1, np.int32) if feat_match is None else np.ascontiguousarray(feat_match, np.int32).copy()
+        nm = np.zeros(nfr, np.int32)
+        b4 = np.ascontiguousarray(bounds4, np.float32)
+        ratio = self.mfNNratio if use_ratio else 0.0
+        ori = (not use_ratio) and self.mbCheckOrientation
+        _check(self._L.orbm_search_by_projection(self._h, nfr, _ptr(b4), _ptr(f_xy), _ptr(f_octave), _ptr(f_angle), _ptr(f_desc),
+                                                 _ptr(f_counts), fs, _ptr(q_valid), _ptr(q_uv), _ptr(q_radius), _ptr(q_minl),
+                                                 _ptr(q_maxl), _ptr(q_angle), _ptr(q_desc), _ptr(q_counts), qs, int(th_dist),
+                                                 float(ratio), int(ori), _ptr(fm), _ptr(nm), 0))
+        return nm, fm

@@ -1,0 +1,483 @@
+// matcher.cu -- ORBmatcher hot path on sm_100a (orbm_*): Hamming distance, last-frame projection, and the
+// grid-cell projection search with the reference's sequential claim semantics.
+//
+// Replaces S/src/ORBmatcher.cc:45-137, 1330-1472, 1603-1665 and S/src/Frame.cc:230-245, 327-392.
+// Pure integer work (XOR + POPC over 8 x u32) plus fp32 window arithmetic with explicit rounding.
+#include <vector>
+#include <mutex>
+#include "common.cuh"
+
+namespace orbs {
+
+constexpr int kGridCols = ORBS_FRAME_GRID_COLS, kGridRows = ORBS_FRAME_GRID_ROWS, kGridCells = kGridCols * kGridRows;
+constexpr int kHisto = ORBM_HISTO_LENGTH;
+
+struct GridParams { float min_x, min_y, max_x, max_y, w_inv, h_inv; };
+
+__device__ __forceinline__ int hamming256(const uint4 a0, const uint4 a1, const uint4 b0, const uint4 b1)
+{
+    return __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) +
+           __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
+}
+
+// all-pairs DescriptorDistance: one thread per (i, j)
+__global__ void __launch_bounds__(256)
+k_hamming_pairs(const uint4 *__restrict__ a, int n, const uint4 *__restrict__ b, int m, int *__restrict__ out)
+{
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (size_t)n * m) return;
+    const int i = (int)(t / m), j = (int)(t - (size_t)i * m);
+    out[t] = hamming256(__ldg(&a[2 * i]), __ldg(&a[2 * i + 1]), __ldg(&b[2 * j]), __ldg(&b[2 * j + 1]));
+}
+
+// ORBmatcher.cc:1354-1391, one thread per (frame, last-frame slot)
+__global__ void __launch_bounds__(256)
+k_project_last(int q_slab, const float *__restrict__ Tcw, float fx, float fy, float cx, float cy, GridParams g,
+               const float *__restrict__ scale_factors, int nlevels, const float *__restrict__ Xw,
+               const int *__restrict__ last_octave, const int *__restrict__ q_counts, float th,
+               uint8_t *__restrict__ q_valid, float2 *__restrict__ q_uv, float *__restrict__ q_radius,
+               int *__restrict__ q_minl, int *__restrict__ q_maxl)
+{
+    const int f = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= q_counts[f]) return;
+    const size_t q = (size_t)f * q_slab + i;
+    if (!q_valid[q]) return;
+    const float *T = Tcw + 16 * f;
+    const float X = Xw[3 * q], Y = Xw[3 * q + 1], Z = Xw[3 * q + 2];
+    float xc[3];
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+        float s = __fmul_rn(T[4 * r], X);
+        s = __fadd_rn(s, __fmul_rn(T[4 * r + 1], Y));
+        s = __fadd_rn(s, __fmul_rn(T[4 * r + 2], Z));
+        xc[r] = __fadd_rn(s, T[4 * r + 3]);
+    }
+    const float invzc = __double2float_rn(__ddiv_rn(1.0, (double)xc[2]));
+    bool ok = !(invzc < 0);
+    const float u = __fadd_rn(__fmul_rn(__fmul_rn(fx, xc[0]), invzc), cx);
+    const float v = __fadd_rn(__fmul_rn(__fmul_rn(fy, xc[1]), invzc), cy);
+    if (u < g.min_x || u > g.max_x) ok = false;
+    if (v < g.min_y || v > g.max_y) ok = false;
+    int oct = last_octave[q];
+    if (ok) {
+        oct = min(max(oct, 0), nlevels - 1);
+        q_uv[q] = make_float2(u, v);
+        q_radius[q] = __fmul_rn(th, scale_factors[oct]);
+        q_minl[q] = oct - 1;
+        q_maxl[q] = oct + 1;
+    }
+    q_valid[q] = ok ? 1 : 0;
+}
+
+// Frame::AssignFeaturesToGrid / PosInGrid: CSR per frame, cell = ix * 48 + iy.  Order inside a cell is not
+// preserved; the search re-creates the reference's visiting order through an explicit (ix, iy, index) key.
+__global__ void __launch_bounds__(512)
+k_grid_build(int f_slab, GridParams g, const float2 *__restrict__ f_xy, const int *__restrict__ f_counts,
+             int *__restrict__ cell_start /*[n_frames, cells+1]*/, int *__restrict__ cell_items /*[n_frames, f_slab]*/)
+{
+    __shared__ int cnt[kGridCells];
+    __shared__ int warp_tot[16];
+    const int f = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+    const int N = f_counts[f];
+    const float2 *xy = f_xy + (size_t)f * f_slab;
+    for (int c = tid; c < kGridCells; c += nt) cnt[c] = 0;
+    __syncthreads();
+    for (int i = tid; i < N; i += nt) {
+        const float2 p = xy[i];
+        const int px = (int)roundf(__fmul_rn(__fsub_rn(p.x, g.min_x), g.w_inv));
+        const int py = (int)roundf(__fmul_rn(__fsub_rn(p.y, g.min_y), g.h_inv));
+        if (px >= 0 && px < kGridCols && py >= 0 && py < kGridRows) atomicAdd(&cnt[px * kGridRows + py], 1);
+    }
+    __syncthreads();
+    // exclusive scan of 3072 counts: 6 per thread (512 threads)
+    constexpr int PER = kGridCells / 512;
+    int loc[PER], sum = 0;
+#pragma unroll
+    for (int k = 0; k < PER; k++) { loc[k] = cnt[tid * PER + k]; sum += loc[k]; }
+    int inc = sum;
+    const int lane = tid & 31, wid = tid >> 5;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += o; }
+    if (lane == 31) warp_tot[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        int v = lane < 16 ? warp_tot[lane] : 0, w = v;
+#pragma unroll
+        for (int d = 1; d < 16; d <<= 1) { const int o = __shfl_up_sync(0xffffffffu, w, d); if (lane >= d) w += o; }
+        if (lane < 16) warp_tot[lane] = w - v;
+    }
+    __syncthreads();
+    int run = warp_tot[wid] + inc - sum;
+    int *cs = cell_start + (size_t)f * (kGridCells + 1);
+#pragma unroll
+    for (int k = 0; k < PER; k++) { cs[tid * PER + k] = run; cnt[tid * PER + k] = run; run += loc[k]; }
+    if (tid == nt - 1) cs[kGridCells] = run;
+    __syncthreads();
+    int *items = cell_items + (size_t)f * f_slab;
+    for (int i = tid; i < N; i += nt) {
+        const float2 p = xy[i];
+        const int px = (int)roundf(__fmul_rn(__fsub_rn(p.x, g.min_x), g.w_inv));
+        const int py = (int)roundf(__fmul_rn(__fsub_rn(p.y, g.min_y), g.h_inv));
+        if (px >= 0 && px < kGridCols && py >= 0 && py < kGridRows) items[atomicAdd(&cnt[px * kGridRows + py], 1)] = i;
+    }
+}
+
+// One CTA per frame.  The reference loop is sequential over queries: an accepted query claims its feature and
+// later queries skip it.  Equivalent fixed point: query i may take feature k unless a query j < i took it.
+// Rounds: every query proposes its best feature among those not owned by a lower-index query (ownership from
+// the previous round); ownership = lowest proposing query; repeat until no proposal changes.  After round r the
+// first r queries are final, so the loop terminates with exactly the sequential result.
+struct SearchArgs {
+    int f_slab, q_slab;
+    GridParams g;
+    const float2 *f_xy; const int *f_octave; const float *f_angle; const uint4 *f_desc; const int *f_counts;
+    const uint8_t *q_valid; const float2 *q_uv; const float *q_radius; const int *q_minl; const int *q_maxl;
+    const float *q_angle; const uint4 *q_desc; const int *q_counts;
+    const int *cell_start; const int *cell_items;
+    int th_dist; float ratio; int check_ori;
+    int *feat_match; int *nmatches;
+    int *prop;      // [n_frames, q_slab] proposal of every query (feature index or -1)
+    int *owner;     // [n_frames, 2, f_slab]
+};
+
+constexpr unsigned long long kNoKey = ~0ull;
+
+__global__ void __launch_bounds__(512)
+k_search_projection(const SearchArgs A)
+{
+    __shared__ int s_changed;
+    __shared__ int s_hist[kHisto];
+    __shared__ int s_keep[3];
+    __shared__ int s_removed, s_accepted;
+    const int f = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+    const int lane = tid & 31, wid = tid >> 5, nwarps = nt >> 5;
+    const int N = A.f_counts[f], M = A.q_counts[f];
+    const size_t fo = (size_t)f * A.f_slab, qo = (size_t)f * A.q_slab;
+    const float2 *f_xy = A.f_xy + fo; const int *f_octave = A.f_octave + fo; const uint4 *f_desc = A.f_desc + 2 * fo;
+    const int *cs = A.cell_start + (size_t)f * (kGridCells + 1); const int *items = A.cell_items + fo;
+    int *fm = A.feat_match + fo;
+    int *prop = A.prop + qo;
+    int *owner[2] = {A.owner + 2 * fo, A.owner + 2 * fo + A.f_slab};
+    const GridParams g = A.g;
+
+    // features that already hold a map point are owned by "query -1": every query skips them
+    for (int k = tid; k < N; k += nt) { const int o = fm[k] >= 0 ? -1 : 0x7fffffff; owner[0][k] = o; owner[1][k] = o; }
+    for (int i = tid; i < M; i += nt) prop[i] = -2;
+    __syncthreads();
+
+    int cur = 0;
+    for (int round = 0; round <= M; round++) {
+        if (tid == 0) s_changed = 0;
+        __syncthreads();
+        const int *own_prev = owner[cur];
+        int *own_next = owner[cur ^ 1];
+        for (int i = wid; i < M; i += nwarps) {
+            int choice = -1;
+            if (A.q_valid[qo + i]) {
+                const float2 uv = A.q_uv[qo + i];
+                const float r = A.q_radius[qo + i];
+                const int minl = A.q_minl[qo + i], maxl = A.q_maxl[qo + i];
+                // Frame::GetFeaturesInArea, Frame.cc:327-380
+                int c0 = (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(uv.x, g.min_x), r), g.w_inv));
+                int c1 = (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(uv.x, g.min_x), r), g.w_inv));
+                int r0 = (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(uv.y, g.min_y), r), g.h_inv));
+                int r1 = (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(uv.y, g.min_y), r), g.h_inv));
+                c0 = max(c0, 0); r0 = max(r0, 0); c1 = min(c1, kGridCols - 1); r1 = min(r1, kGridRows - 1);
+                const bool empty = c0 >= kGridCols || c1 < 0 || r0 >= kGridRows || r1 < 0;
+                const bool check = (minl > 0) || (maxl >= 0);
+                unsigned long long k1 = kNoKey, k2 = kNoKey;       // two smallest (dist, visit order) keys of this lane
+                if (!empty) {
+                    const uint4 qa = __ldg(&A.q_desc[2 * (qo + i)]), qb = __ldg(&A.q_desc[2 * (qo + i) + 1]);
+                    const int ncx = c1 - c0 + 1, ncy = r1 - r0 + 1;
+                    for (int c = lane; c < ncx * ncy; c += 32) {
+                        const int ix = c0 + c / ncy, iy = r0 + c % ncy;
+                        const int cell = ix * kGridRows + iy;
+                        for (int j = cs[cell]; j < cs[cell + 1]; j++) {
+                            const int k = items[j];
+                            if (check) {
+                                const int o = f_octave[k];
+                                if (o < minl) continue;
+                                if (maxl >= 0 && o > maxl) continue;
+                            }
+                            const float2 p = f_xy[k];
+                            if (!(fabsf(__fsub_rn(p.x, uv.x)) < r && fabsf(__fsub_rn(p.y, uv.y)) < r)) continue;
+                            if (own_prev[k] < i) continue;             // claimed by an earlier query
+                            const int d = hamming256(qa, qb, __ldg(&f_desc[2 * k]), __ldg(&f_desc[2 * k + 1]));
+                            const unsigned long long key = ((unsigned long long)d << 32) | ((unsigned long long)ix << 26) |
+                                                           ((unsigned long long)iy << 20) | (unsigned long long)k;
+                            if (key < k1) { k2 = k1; k1 = key; } else if (key < k2) k2 = key;
+                        }
+                    }
+                }
+                // warp: best and second best keys
+                unsigned long long b1 = k1;
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) { const unsigned long long o = __shfl_xor_sync(0xffffffffu, b1, d); b1 = o < b1 ? o : b1; }
+                if (b1 != kNoKey) {
+                    unsigned long long b2 = (k1 == b1) ? k2 : k1;
+#pragma unroll
+                    for (int d = 16; d > 0; d >>= 1) { const unsigned long long o = __shfl_xor_sync(0xffffffffu, b2, d); b2 = o < b2 ? o : b2; }
+                    const int best = (int)(b1 >> 32), bidx = (int)(b1 & 0xfffff);
+                    if (best <= A.th_dist) {
+                        bool acc = true;
+                        if (A.ratio > 0.f) {
+                            const int best2 = b2 == kNoKey ? 256 : (int)(b2 >> 32);
+                            const int lvl1 = f_octave[bidx], lvl2 = b2 == kNoKey ? -1 : f_octave[(int)(b2 & 0xfffff)];
+                            if (lvl1 == lvl2 && (float)best > __fmul_rn(A.ratio, (float)best2)) acc = false;
+                        }
+                        if (acc) choice = bidx;
+                    }
+                }
+            }
+            if (lane == 0) {
+                if (prop[i] != choice) { prop[i] = choice; s_changed = 1; }
+            }
+        }
+        __syncthreads();
+        if (!s_changed) break;
+        for (int k = tid; k < N; k += nt) own_next[k] = fm[k] >= 0 ? -1 : 0x7fffffff;
+        __syncthreads();
+        for (int i = tid; i < M; i += nt) { const int k = prop[i]; if (k >= 0) atomicMin(&own_next[k], i); }
+        __syncthreads();
+        cur ^= 1;
+    }
+
+    // commit + rotation consistency (ORBmatcher.cc:1421-1468)
+    if (tid < kHisto) s_hist[tid] = 0;
+    if (tid == 0) { s_removed = 0; s_accepted = 0; }
+    __syncthreads();
+    const float factor = 1.0f / kHisto;
+    int my_acc = 0;
+    for (int i = tid; i < M; i += nt) {
+        const int k = prop[i];
+        if (k < 0) continue;
+        fm[k] = i;
+        my_acc++;
+        if (A.check_ori) {
+            float rot = __fsub_rn(A.q_angle[qo + i], A.f_angle[fo + k]);
+            if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+            int bin = (int)roundf(__fmul_rn(rot, factor));
+            if (bin == kHisto) bin = 0;
+            bin = min(max(bin, 0), kHisto - 1);
+            atomicAdd(&s_hist[bin], 1);
+            prop[i] = k | (bin << 24);
+        }
+    }
+    atomicAdd(&s_accepted, my_acc);
+    __syncthreads();
+    if (A.check_ori) {
+        if (tid == 0) {                       // ComputeThreeMaxima, ORBmatcher.cc:1603-1644
+            int max1 = 0, max2 = 0, max3 = 0, i1 = -1, i2 = -1, i3 = -1;
+            for (int i = 0; i < kHisto; i++) {
+                const int s = s_hist[i];
+                if (s > max1) { max3 = max2; max2 = max1; max1 = s; i3 = i2; i2 = i1; i1 = i; }
+                else if (s > max2) { max3 = max2; max2 = s; i3 = i2; i2 = i; }
+                else if (s > max3) { max3 = s; i3 = i; }
+            }
+            if ((float)max2 < __fmul_rn(0.1f, (float)max1)) { i2 = -1; i3 = -1; }
+            else if ((float)max3 < __fmul_rn(0.1f, (float)max1)) { i3 = -1; }
+            s_keep[0] = i1; s_keep[1] = i2; s_keep[2] = i3;
+        }
+        __syncthreads();
+        int my_rm = 0;
+        for (int i = tid; i < M; i += nt) {
+            const int v = prop[i];
+            if (v < 0) continue;
+            const int bin = v >> 24, k = v & 0xffffff;
+            if (bin != s_keep[0] && bin != s_keep[1] && bin != s_keep[2]) { fm[k] = -1; my_rm++; }
+        }
+        atomicAdd(&s_removed, my_rm);
+        __syncthreads();
+    }
+    if (tid == 0) A.nmatches[f] = s_accepted - s_removed;
+}
+
+}  // namespace orbs
+
+using namespace orbs;
+
+struct orbm_handle {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    long long launches = 0;
+    std::mutex mu;
+    DevBuf cell_start, cell_items, prop, owner, fm_init;
+    DevBuf stage[24];
+    int stage_used = 0;
+};
+
+namespace {
+// host<->device staging for ORBS_MEM_HOST calls
+struct Stager {
+    orbm_handle *h; int memspace; int rc = ORBS_OK;
+    struct Out { void *host; void *dev; size_t bytes; };
+    std::vector<Out> outs;
+    Stager(orbm_handle *hh, int ms) : h(hh), memspace(ms) { h->stage_used = 0; }
+    template <typename T> const T *in(const T *p, size_t n)
+    {
+        if (memspace == ORBS_MEM_DEVICE || !p || rc) return p;
+        DevBuf &b = h->stage[h->stage_used++];
+        if ((rc = b.reserve(n * sizeof(T) + 16))) return nullptr;
+        cudaError_t e = cudaMemcpyAsync(b.p, p, n * sizeof(T), cudaMemcpyHostToDevice, h->stream);
+        if (e != cudaSuccess) { rc = cuda_fail(e, "stage in", __FILE__, __LINE__); return nullptr; }
+        return b.as<T>();
+    }
+    template <typename T> T *inout(T *p, size_t n, bool copy_in = true)
+    {
+        if (memspace == ORBS_MEM_DEVICE || !p || rc) return p;
+        DevBuf &b = h->stage[h->stage_used++];
+        if ((rc = b.reserve(n * sizeof(T) + 16))) return nullptr;
+        if (copy_in) {
+            cudaError_t e = cudaMemcpyAsync(b.p, p, n * sizeof(T), cudaMemcpyHostToDevice, h->stream);
+            if (e != cudaSuccess) { rc = cuda_fail(e, "stage inout", __FILE__, __LINE__); return nullptr; }
+        }
+        outs.push_back({p, b.p, n * sizeof(T)});
+        return b.as<T>();
+    }
+    int finish()
+    {
+        if (rc) return rc;
+        if (memspace == ORBS_MEM_DEVICE) return ORBS_OK;
+        for (auto &o : outs) ORBS_CUDA(cudaMemcpyAsync(o.host, o.dev, o.bytes, cudaMemcpyDeviceToHost, h->stream));
+        ORBS_CUDA(cudaStreamSynchronize(h->stream));
+        return ORBS_OK;
+    }
+};
+
+GridParams make_grid(const float *b4)
+{
+    GridParams g;
+    g.min_x = b4[0]; g.min_y = b4[1]; g.max_x = b4[2]; g.max_y = b4[3];
+    g.w_inv = (float)kGridCols / (g.max_x - g.min_x);          // Frame.cc:101-102
+    g.h_inv = (float)kGridRows / (g.max_y - g.min_y);
+    return g;
+}
+}  // namespace
+
+extern "C" {
+
+int orbm_create(orbm_handle **out, int device)
+{
+    ORBS_REQUIRE(out, ORBS_E_INVALID, "orbm_create: null out pointer");
+    *out = nullptr;
+    ORBS_CUDA(cudaSetDevice(device));
+    orbm_handle *h = new orbm_handle();
+    h->device = device;
+    cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete h; return cuda_fail(e, "cudaStreamCreate", __FILE__, __LINE__); }
+    *out = h;
+    return ORBS_OK;
+}
+
+int orbm_destroy(orbm_handle *h)
+{
+    if (!h) return ORBS_OK;
+    cudaSetDevice(h->device);
+    if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
+    h->cell_start.release(); h->cell_items.release(); h->prop.release(); h->owner.release(); h->fm_init.release();
+    for (auto &b : h->stage) b.release();
+    delete h;
+    return ORBS_OK;
+}
+
+void *orbm_stream(orbm_handle *h) { return h ? (void *)h->stream : nullptr; }
+int orbm_synchronize(orbm_handle *h)
+{
+    ORBS_REQUIRE(h, ORBS_E_INVALID, "null handle");
+    ORBS_CUDA(cudaSetDevice(h->device));
+    ORBS_CUDA(cudaStreamSynchronize(h->stream));
+    return ORBS_OK;
+}
+long long orbm_kernel_launches(const orbm_handle *h) { return h ? h->launches : 0; }
+
+int orbm_descriptor_distance(orbm_handle *h, const uint8_t *a, int n, const uint8_t *b, int m, int32_t *out, int memspace)
+{
+    ORBS_REQUIRE(h && a && b && out, ORBS_E_INVALID, "null argument");
+    ORBS_REQUIRE(n >= 0 && m >= 0, ORBS_E_INVALID, "negative size");
+    if (n == 0 || m == 0) return ORBS_OK;
+    std::lock_guard<std::mutex> lk(h->mu);
+    ORBS_CUDA(cudaSetDevice(h->device));
+    Stager S(h, memspace);
+    const uint8_t *da = S.in(a, (size_t)n * 32), *db = S.in(b, (size_t)m * 32);
+    int32_t *dout = S.inout(out, (size_t)n * m, false);
+    if (S.rc) return S.rc;
+    ORBS_REQUIRE(((uintptr_t)da % 16 == 0) && ((uintptr_t)db % 16 == 0), ORBS_E_INVALID, "descriptor arrays must be 16-byte aligned");
+    const size_t total = (size_t)n * m;
+    k_hamming_pairs<<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>((const uint4 *)da, n, (const uint4 *)db, m, dout);
+    h->launches++;
+    ORBS_CUDA(cudaGetLastError());
+    return S.finish();
+}
+
+int orbm_project_last_frame(orbm_handle *h, int n_frames, const float *Tcw, const float *K4, const float *bounds4,
+                            const float *scale_factors, int nlevels, const float *Xw, const int32_t *last_octave,
+                            const int32_t *q_counts, int q_slab, float th, uint8_t *q_valid, float *q_uv,
+                            float *q_radius, int32_t *q_minl, int32_t *q_maxl, int memspace)
+{
+    ORBS_REQUIRE(h && Tcw && K4 && bounds4 && scale_factors && Xw && last_octave && q_counts && q_valid && q_uv && q_radius && q_minl && q_maxl,
+                 ORBS_E_INVALID, "null argument");
+    ORBS_REQUIRE(n_frames > 0 && q_slab > 0 && nlevels > 0, ORBS_E_INVALID, "non-positive size");
+    std::lock_guard<std::mutex> lk(h->mu);
+    ORBS_CUDA(cudaSetDevice(h->device));
+    Stager S(h, memspace);
+    const size_t nq = (size_t)n_frames * q_slab;
+    // K4 / bounds4 are tiny host-side parameter blocks in both memory spaces
+    const float *dT = S.in(Tcw, (size_t)n_frames * 16), *dsf = S.in(scale_factors, nlevels), *dX = S.in(Xw, nq * 3);
+    const int32_t *doct = S.in(last_octave, nq), *dqc = S.in(q_counts, n_frames);
+    uint8_t *dval = S.inout(q_valid, nq);
+    float *duv = S.inout(q_uv, nq * 2, false), *drad = S.inout(q_radius, nq, false);
+    int32_t *dmn = S.inout(q_minl, nq, false), *dmx = S.inout(q_maxl, nq, false);
+    if (S.rc) return S.rc;
+    k_project_last<<<dim3((q_slab + 255) / 256, n_frames), 256, 0, h->stream>>>(q_slab, dT, K4[0], K4[1], K4[2], K4[3], make_grid(bounds4), dsf,
+                                                                               nlevels, dX, doct, dqc, th, dval, (float2 *)duv, drad, dmn, dmx);
+    h->launches++;
+    ORBS_CUDA(cudaGetLastError());
+    return S.finish();
+}
+
+int orbm_search_by_projection(orbm_handle *h, int n_frames, const float *bounds4,
+                              const float *f_xy, const int32_t *f_octave, const float *f_angle, const uint8_t *f_desc,
+                              const int32_t *f_counts, int f_slab,
+                              const uint8_t *q_valid, const float *q_uv, const float *q_radius, const int32_t *q_minl,
+                              const int32_t *q_maxl, const float *q_angle, const uint8_t *q_desc, const int32_t *q_counts,
+                              int q_slab, int th_dist, float ratio, int check_ori,
+                              int32_t *feat_match, int32_t *nmatches, int memspace)
+{
+    ORBS_REQUIRE(h && bounds4 && f_xy && f_octave && f_desc && f_counts && q_valid && q_uv && q_radius && q_minl && q_maxl && q_desc && q_counts &&
+                 feat_match && nmatches, ORBS_E_INVALID, "null argument");
+    ORBS_REQUIRE(!check_ori || (f_angle && q_angle), ORBS_E_INVALID, "orientation check needs the angles");
+    ORBS_REQUIRE(n_frames > 0 && f_slab > 0 && q_slab > 0, ORBS_E_INVALID, "non-positive size");
+    ORBS_REQUIRE(f_slab < (1 << 20) && q_slab < (1 << 24), ORBS_E_INVALID, "slab too large (features < 2^20, queries < 2^24 per frame)");
+    ORBS_REQUIRE(bounds4[2] > bounds4[0] && bounds4[3] > bounds4[1], ORBS_E_INVALID, "empty image bounds");
+    std::lock_guard<std::mutex> lk(h->mu);
+    ORBS_CUDA(cudaSetDevice(h->device));
+    Stager S(h, memspace);
+    const size_t nf = (size_t)n_frames * f_slab, nq = (size_t)n_frames * q_slab;
+    SearchArgs A;
+    A.f_slab = f_slab; A.q_slab = q_slab; A.g = make_grid(bounds4);
+    A.f_xy = (const float2 *)S.in(f_xy, nf * 2); A.f_octave = S.in(f_octave, nf);
+    A.f_angle = f_angle ? S.in(f_angle, nf) : nullptr; A.f_desc = (const uint4 *)S.in(f_desc, nf * 32);
+    A.f_counts = S.in(f_counts, n_frames);
+    A.q_valid = S.in(q_valid, nq); A.q_uv = (const float2 *)S.in(q_uv, nq * 2); A.q_radius = S.in(q_radius, nq);
+    A.q_minl = S.in(q_minl, nq); A.q_maxl = S.in(q_maxl, nq); A.q_angle = q_angle ? S.in(q_angle, nq) : nullptr;
+    A.q_desc = (const uint4 *)S.in(q_desc, nq * 32); A.q_counts = S.in(q_counts, n_frames);
+    A.feat_match = S.inout(feat_match, nf); A.nmatches = S.inout(nmatches, n_frames, false);
+    if (S.rc) return S.rc;
+    ORBS_REQUIRE(((uintptr_t)A.f_desc % 16 == 0) && ((uintptr_t)A.q_desc % 16 == 0) && ((uintptr_t)A.f_xy % 8 == 0) && ((uintptr_t)A.q_uv % 8 == 0),
+                 ORBS_E_INVALID, "descriptor arrays must be 16-byte aligned, coordinate arrays 8-byte aligned");
+    int rc;
+    if ((rc = h->cell_start.reserve((size_t)n_frames * (kGridCells + 1) * sizeof(int)))) return rc;
+    if ((rc = h->cell_items.reserve(nf * sizeof(int)))) return rc;
+    if ((rc = h->prop.reserve(nq * sizeof(int)))) return rc;
+    if ((rc = h->owner.reserve(2 * nf * sizeof(int)))) return rc;
+    A.cell_start = h->cell_start.as<int>(); A.cell_items = h->cell_items.as<int>();
+    A.prop = h->prop.as<int>(); A.owner = h->owner.as<int>();
+    A.th_dist = th_dist; A.ratio = ratio; A.check_ori = check_ori ? 1 : 0;
+    k_grid_build<<<n_frames, 512, 0, h->stream>>>(f_slab, A.g, A.f_xy, A.f_counts, h->cell_start.as<int>(), h->cell_items.as<int>());
+    k_search_projection<<<n_frames, 512, 0, h->stream>>>(A);
+    h->launches += 2;
+    ORBS_CUDA(cudaGetLastError());
+    return S.finish();
+}
+
+}  // extern "C"
