@@ -1,0 +1,391 @@
+#!/usr/bin/env python3
+"""bench.py -- ORBSLAMM hot-path benchmark on B200 (contract: see DESIGN.md "Measurement").
+
+    python bench.py --gpus N --steps K --warmup W [--workload frontend|ba] [--impl reference]
+
+frontend (default, BASELINE.json metric "ORB extract+match fps @1241x376"):
+    one step = one new 1241x376 frame for each of `--streams` independent synthetic camera streams:
+    ORB extraction (pyramid, FAST, quad-tree, orientation, rBRIEF) + SearchByProjection(Cur, Last) against the
+    stream's previous frame (+ PoseOptimization once enabled).  value = frames/s with the images already in HBM;
+    e2e = the same through the host-buffer C-ABI calls (H2D of the images, D2H of keypoints/descriptors/matches).
+ba (metric "LocalBA LM iters/s @500KF/50k pts"): see bench_ba() below.
+
+--impl reference times the CPU oracle (cv2 primitives + restated reference code) on all host cores.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from orbslamm_b200 import synth  # noqa: E402
+
+CAM = synth.KITTI
+TH_PROJ = 15.0          # Tracking.cc:925-930 (mono)
+N_POOL = 5              # distinct frames per stream (steps cycle over frame pairs 1..N_POOL-1)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                pass
+        sm = [int(r[0]) for r in self.rows if r and r[0].isdigit()]
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for n, v in zip(names, r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": int(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+def frontend_workload(n_streams, rank):
+    """Synthetic streams: images [N_POOL, B, H, W] u8 and per-frame known shifts."""
+    w, h = CAM["w"], CAM["h"]
+    imgs = np.empty((N_POOL, n_streams, h, w), np.uint8)
+    shifts = np.zeros((N_POOL, n_streams, 2), np.int32)
+    for b in range(n_streams):
+        fr, sh = synth.stream(w, h, N_POOL, stream_id=rank * 1000 + b)
+        for t in range(N_POOL):
+            imgs[t, b] = fr[t]; shifts[t, b] = sh[t]
+    return imgs, shifts
+
+
+def build_queries(feats, shifts_next, rng):
+    """Last-frame 'map points' for one stream frame: keypoints lifted to depth U(5, 50) m so that they project onto
+    their shifted position in the next frame under the next frame's pose (identity here)."""
+    fx, fy, cx, cy = CAM["fx"], CAM["fy"], CAM["cx"], CAM["cy"]
+    n = len(feats["x"])
+    z = rng.uniform(5, 50, n)
+    dx, dy = shifts_next
+    Xw = np.stack([(feats["x"] + dx - cx) * z / fx, (feats["y"] + dy - cy) * z / fy, z], 1).astype(np.float32)
+    return Xw
+
+
+def bench_frontend(args, rank, world):
+    import torch
+    import orbslamm_b200 as ob
+    from orbslamm_b200 import build as obuild
+    obuild.build()
+    dev = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(dev)
+    B = args.streams
+    w, h = CAM["w"], CAM["h"]
+    imgs, shifts = frontend_workload(B, rank)
+    ex = ob.ORBextractor(CAM["nfeatures"], 1.2, 8, 20, 7, device=dev)
+    mt = ob.ORBmatcher(0.9, True, device=dev)
+    mt.set_stream(ex.stream())
+    L = ob.load()
+    slab = ex.max_keypoints(w, h)
+    sf = ex.GetScaleFactors()
+    K4 = np.array([CAM["fx"], CAM["fy"], CAM["cx"], CAM["cy"]], np.float32)
+    bounds = np.array([0, 0, w, h], np.float32)
+
+    # ---- untimed pre-pass: extract every pool frame once to build the per-frame map-point queries
+    rng = np.random.default_rng(1234 + rank)
+    pitch = (w + 63) // 64 * 64
+    d_imgs = torch.zeros((N_POOL, B, h, pitch), dtype=torch.uint8, device="cuda")
+    d_imgs[:, :, :, :w] = torch.from_numpy(imgs).cuda()
+    torch.cuda.synchronize()
+    q_Xw = np.zeros((N_POOL, B, slab, 3), np.float32); q_oct = np.zeros((N_POOL, B, slab), np.int32)
+    q_ang = np.zeros((N_POOL, B, slab), np.float32); q_desc = np.zeros((N_POOL, B, slab, 32), np.uint8)
+    q_valid = np.zeros((N_POOL, B, slab), np.uint8); q_cnt = np.zeros((N_POOL, B), np.int32)
+    host_feats = []
+    for t in range(N_POOL):
+        ex.extract_device(d_imgs[t].data_ptr(), B, w, h, pitch, h * pitch)
+        r = ex.download(B, slab)
+        host_feats.append(r)
+        for b in range(B):
+            n = int(r["counts"][b]); q_cnt[t, b] = n
+            nxt = shifts[t + 1, b] if t + 1 < N_POOL else (0, 0)
+            feats = dict(x=r["xy"][b, :n, 0], y=r["xy"][b, :n, 1])
+            q_Xw[t, b, :n] = build_queries(feats, nxt, rng)
+            q_oct[t, b, :n] = r["octave"][b, :n]; q_ang[t, b, :n] = r["angle"][b, :n]; q_desc[t, b, :n] = r["desc"][b, :n]
+            q_valid[t, b, :n] = 1
+    to_dev = lambda a: torch.from_numpy(a).cuda()
+    dq = dict(Xw=to_dev(q_Xw), oct=to_dev(q_oct), ang=to_dev(q_ang), desc=to_dev(q_desc), valid=to_dev(q_valid), cnt=to_dev(q_cnt))
+    Tcw = np.tile(np.eye(4, dtype=np.float32).reshape(1, 16), (B, 1))
+    d_Tcw = to_dev(Tcw); d_sf = to_dev(sf)
+    d_qvalid = torch.zeros((B, slab), dtype=torch.uint8, device="cuda")
+    d_quv = torch.zeros((B, slab, 2), dtype=torch.float32, device="cuda"); d_qrad = torch.zeros((B, slab), dtype=torch.float32, device="cuda")
+    d_qmn = torch.zeros((B, slab), dtype=torch.int32, device="cuda"); d_qmx = torch.zeros((B, slab), dtype=torch.int32, device="cuda")
+    d_fm = torch.zeros((B, slab), dtype=torch.int32, device="cuda"); d_nm = torch.zeros(B, dtype=torch.int32, device="cuda")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    stream = torch.cuda.ExternalStream(ex.stream(), device=dev)
+    torch.cuda.synchronize()
+    vp = ctypes.c_void_p
+
+    def step_device(t):
+        """extract frame t of every stream, match against frame t-1's map points -- all on ex.stream(), no host sync"""
+        ex.extract_device(d_imgs[t].data_ptr(), B, w, h, pitch, h * pitch)
+        v = ex.device_view()
+        with torch.cuda.stream(stream):
+            d_qvalid.copy_(dq["valid"][t - 1], non_blocking=True)
+            d_fm.fill_(-1)
+        ob._check(L.orbm_project_last_frame(mt.handle, B, vp(d_Tcw.data_ptr()), K4.ctypes.data, bounds.ctypes.data, vp(d_sf.data_ptr()), len(sf),
+                                            vp(dq["Xw"][t - 1].data_ptr()), vp(dq["oct"][t - 1].data_ptr()), vp(dq["cnt"][t - 1].data_ptr()), slab,
+                                            TH_PROJ, vp(d_qvalid.data_ptr()), vp(d_quv.data_ptr()), vp(d_qrad.data_ptr()), vp(d_qmn.data_ptr()),
+                                            vp(d_qmx.data_ptr()), 1))
+        ob._check(L.orbm_search_by_projection(mt.handle, B, bounds.ctypes.data, vp(v.kp_xy), vp(v.kp_octave), vp(v.kp_angle), vp(v.desc), vp(v.counts),
+                                              slab, vp(d_qvalid.data_ptr()), vp(d_quv.data_ptr()), vp(d_qrad.data_ptr()), vp(d_qmn.data_ptr()),
+                                              vp(d_qmx.data_ptr()), vp(dq["ang"][t - 1].data_ptr()), vp(dq["desc"][t - 1].data_ptr()),
+                                              vp(dq["cnt"][t - 1].data_ptr()), slab, 100, 0.0, 1, vp(d_fm.data_ptr()), vp(d_nm.data_ptr()), 1))
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing
+    for i in range(args.warmup):
+        step_device(1 + i % (N_POOL - 1))
+    barrier()
+    l0 = ex.kernel_launches() + mt.kernel_launches()
+    ex.set_profiling(True)
+    sampler = ClockSampler(dev); sampler.start()
+    total_ms = 0.0
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    t_wall = time.time()
+    for i in range(args.steps):
+        flush.fill_(i & 0xff)                       # L2 flush between timed iterations (untimed, torch's stream)
+        torch.cuda.synchronize()
+        evs[i][0].record(stream)
+        step_device(1 + i % (N_POOL - 1))
+        evs[i][1].record(stream)
+    barrier()
+    wall = time.time() - t_wall
+    total_ms = sum(a.elapsed_time(b) for a, b in evs)
+    clocks = sampler.stop()
+    launches = ex.kernel_launches() + mt.kernel_launches() - l0
+    ktimes = ex.kernel_times()
+    ex.set_profiling(False)
+    nmatch = d_nm.cpu().numpy()
+    if world > 1:
+        tt = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
+        torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.MAX)
+        total_ms = float(tt.item())
+    fps = world * B * args.steps / (total_ms * 1e-3)
+
+    # ---- end-to-end through the host-buffer C-ABI (pinned host images in, host results out)
+    h_imgs = torch.from_numpy(imgs).pin_memory()
+    o_xy = torch.empty((B, slab, 2), dtype=torch.float32).pin_memory(); o_ang = torch.empty((B, slab), dtype=torch.float32).pin_memory()
+    o_resp = torch.empty((B, slab), dtype=torch.float32).pin_memory(); o_oct = torch.empty((B, slab), dtype=torch.int32).pin_memory()
+    o_size = torch.empty((B, slab), dtype=torch.float32).pin_memory(); o_desc = torch.empty((B, slab, 32), dtype=torch.uint8).pin_memory()
+    o_cnt = torch.zeros(B, dtype=torch.int32).pin_memory()
+    hq_valid = np.zeros((B, slab), np.uint8); hq_uv = np.zeros((B, slab, 2), np.float32); hq_rad = np.zeros((B, slab), np.float32)
+    hq_mn = np.zeros((B, slab), np.int32); hq_mx = np.zeros((B, slab), np.int32)
+    h_fm = np.zeros((B, slab), np.int32); h_nm = np.zeros(B, np.int32)
+    P = lambda tns: vp(tns.data_ptr())
+    A = lambda arr: arr.ctypes.data
+
+    def step_host(t):
+        ob._check(L.orbx_extract(ex.handle, P(h_imgs[t]), B, w, h, w, w * h, P(o_xy), P(o_ang), P(o_resp), P(o_oct), P(o_size), P(o_desc), slab, P(o_cnt)))
+        hq_valid[:] = q_valid[t - 1]
+        h_fm.fill(-1)
+        ob._check(L.orbm_project_last_frame(mt.handle, B, A(Tcw), A(K4), A(bounds), A(sf), len(sf), A(q_Xw[t - 1]), A(q_oct[t - 1]), A(q_cnt[t - 1]), slab,
+                                            TH_PROJ, A(hq_valid), A(hq_uv), A(hq_rad), A(hq_mn), A(hq_mx), 0))
+        ob._check(L.orbm_search_by_projection(mt.handle, B, A(bounds), P(o_xy), P(o_oct), P(o_ang), P(o_desc), P(o_cnt), slab, A(hq_valid), A(hq_uv),
+                                              A(hq_rad), A(hq_mn), A(hq_mx), A(q_ang[t - 1]), A(q_desc[t - 1]), A(q_cnt[t - 1]), slab, 100, 0.0, 1,
+                                              A(h_fm), A(h_nm), 0))
+
+    for i in range(min(args.warmup, 3)):
+        step_host(1 + i % (N_POOL - 1))
+    barrier()
+    e2e_steps = max(3, min(args.steps, 20))
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        step_host(1 + i % (N_POOL - 1))
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        tt = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+        torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.MAX)
+        e2e_s = float(tt.item())
+    e2e_fps = world * B * e2e_steps / e2e_s
+    nkp = int(np.mean(o_cnt.numpy()))
+    se = B * slab                                   # slab entries per step
+    h2d = (B * w * h                                # images
+           + B * 64 + 32 + se * (12 + 4 + 1) + B * 4          # project: Tcw, scale factors, Xw, octave, valid, counts
+           + se * (8 + 4 + 4 + 32) + B * 4 + se * (1 + 8 + 4 + 4 + 4 + 4 + 32) + B * 4 + se * 4)   # search: features, queries, feat_match
+    d2h = (B * nkp * (8 + 4 * 4 + 32) + B * 4       # keypoints + descriptors + counts
+           + se * (1 + 8 + 4 + 4 + 4)               # projected windows
+           + se * 4 + B * 4)                        # feat_match + nmatches
+
+    # ---- roofline of the dominant kernel
+    hbm, how = peaks()
+    lw = ctypes.c_int(); lh = ctypes.c_int(); px = []
+    for l in range(8):
+        L.orbx_level_size(ex.handle, w, h, l, ctypes.byref(lw), ctypes.byref(lh)); px.append(lw.value * lh.value)
+    sum_px = sum(px)
+    ncand = sum(len(ex.candidates(0, l)) for l in range(8))
+    alg = {"resize_level": (sum_px - px[-1]) + (sum_px - px[0]),        # read levels 0..6, write levels 1..7 (all 7 launches)
+           "fast_cells": sum_px + 8 * ncand, "blur7": 2 * sum_px, "octree": 8 * ncand + 8 * nkp,
+           "orient_describe": nkp * (709 + 512 + 60)}
+    dom = max(ktimes, key=lambda k: ktimes[k][0])
+    dom_ms, dom_n = ktimes[dom]
+    per_launch_ms = dom_ms / max(dom_n, 1) * (7 if dom == "resize_level" else 1)
+    achieved = alg[dom] * B / (per_launch_ms * 1e-3) / 1e9
+    roofline = {"kernel": dom, "bound": "hbm", "achieved": round(achieved, 2), "peak": hbm, "unit": "GB/s", "frac": round(achieved / hbm, 5),
+                "traffic": None, "peak_source": how, "algorithmic_bytes_per_launch": int(alg[dom] * B),
+                "avg_launch_ms": round(per_launch_ms, 4),
+                "kernel_share_of_step": {k: round(v[0] / max(total_ms, 1e-9), 4) for k, v in ktimes.items()}}
+
+    out = {"metric": "ORB extract+match fps @1241x376", "value": round(fps, 1), "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": round(total_ms / args.steps, 4), "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+           "config": {"workload": "KITTI-shape 1241x376 synthetic streams, nFeatures=2000: extract + SearchByProjection(Cur,Last) per frame",
+                      "streams_per_gpu": B, "frames_per_step": B * world, "l2": "256 MiB flush buffer written between timed steps (untimed)",
+                      "keypoints_per_frame": nkp, "matches_per_frame": float(np.mean(nmatch)), "parallelism": f"streams x{world}"},
+           "e2e": {"value": round(e2e_fps, 1), "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps},
+           "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "wall_s": round(wall, 3)}
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_frontend_frames(stream_id, n_frames):
+    """Reference-faithful CPU front end for one stream (cv2 primitives + restated reference code), 1 thread."""
+    import cv2
+    import oracle
+    from oracle import orb_cv2
+    cv2.setNumThreads(1)
+    frames, shifts = synth.stream(CAM["w"], CAM["h"], n_frames + 1, stream_id=stream_id)
+    P = oracle.orb_params(CAM["nfeatures"], 1.2, 8, 20, 7)
+    g = oracle.grid_params(0, 0, CAM["w"], CAM["h"])
+    sf = np.array(list(P.scale)[:8], np.float32)
+    K4 = np.array([CAM["fx"], CAM["fy"], CAM["cx"], CAM["cy"]], np.float32)
+    rng = np.random.default_rng(stream_id)
+    last = orb_cv2.extract(P, frames[0])
+    t0 = time.perf_counter()
+    for t in range(1, n_frames + 1):
+        cur = orb_cv2.extract(P, frames[t])
+        Xw = build_queries(last, shifts[t], rng)
+        qv, uv, rad, mn, mx = oracle.project_last_frame(np.eye(4, dtype=np.float32), K4, g, sf, Xw, last["octave"], TH_PROJ,
+                                                         np.ones(len(Xw), np.uint8))
+        oracle.search_by_projection(g, np.stack([cur["x"], cur["y"]], 1), cur["octave"], cur["angle"], cur["desc"], qv, uv, rad, mn, mx,
+                                    last["angle"], last["desc"], 100, 0.0, True)
+        last = cur
+    return n_frames, time.perf_counter() - t0
+
+
+def _cpu_worker(a):
+    return cpu_frontend_frames(*a)
+
+
+def cpu_baseline_frontend(cores, frames_per_core):
+    import multiprocessing as mp
+    if cores == 1:
+        n, s = cpu_frontend_frames(900, frames_per_core)
+        return n / s, s
+    with mp.get_context("fork").Pool(cores) as pool:
+        t0 = time.perf_counter()
+        res = pool.map(_cpu_worker, [(900 + i, frames_per_core) for i in range(cores)])
+        wall = time.perf_counter() - t0
+    # throughput of the parallel phase: every worker times its own loop; use the slowest
+    n = sum(r[0] for r in res); s = max(r[1] for r in res)
+    return n / s, wall
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--streams", type=int, default=64, help="independent camera streams per GPU (frames per step per GPU)")
+    ap.add_argument("--workload", default="frontend", choices=["frontend", "ba"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-frames", type=int, default=100, help="bounded CPU-baseline sample (frames)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1))
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        if args.workload == "ba":
+            from bench_ba import reference_line
+            print(json.dumps(reference_line(args)), flush=True)
+            return
+        cores = os.cpu_count() or 1
+        per = max(4, args.cpu_frames // cores)
+        t0 = time.time()
+        fps, wall = cpu_baseline_frontend(cores, per)
+        line = {"impl": "reference", "metric": "ORB extract+match fps @1241x376", "value": round(fps, 2), "unit": "frames/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 / fps, 3), "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                "config": {"workload": "KITTI-shape 1241x376 synthetic streams, nFeatures=2000: extract + SearchByProjection(Cur,Last) per frame",
+                           "note": "the reference C++ cannot be built here (needs OpenCV C++/Eigen headers); this is the oracle: cv2 4.13 primitives "
+                                   "(FAST/resize/GaussianBlur) + restated reference code, one independent stream per core"},
+                "cpu_baseline": {"value": round(fps, 2), "unit": "frames/s", "cores": cores, "kind": "port",
+                                 "sample": f"{per} frames x {cores} streams (one per core), {wall:.1f} s"},
+                "e2e": {"value": round(fps, 2), "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line), flush=True)
+        return
+
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))
+        dist.init_process_group("nccl")
+    if args.workload == "ba":
+        from bench_ba import bench_ba
+        out = bench_ba(args, rank, world)
+    else:
+        out = bench_frontend(args, rank, world)
+        if rank == 0:
+            fps1, wall1 = cpu_baseline_frontend(1, max(10, args.cpu_frames))
+            out["cpu_baseline"] = {"value": round(fps1, 2), "unit": "frames/s", "cores": 1, "kind": "port",
+                                   "sample": f"{max(10, args.cpu_frames)} frames of one stream, {wall1:.1f} s; cv2 4.13 primitives + restated reference code "
+                                             "(reference front end is single-threaded per stream)"}
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

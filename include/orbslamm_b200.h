@@ -113,9 +113,15 @@ int orbx_get_candidates(orbx_handle *h, int frame, int level, int32_t *xys, int 
 
 /* The CUDA stream (cudaStream_t) this handle launches on, for event timing. */
 void *orbx_stream(orbx_handle *h);
+/* Launch on a caller-owned stream instead (so that several handles can be chained without events). */
+int orbx_set_stream(orbx_handle *h, void *cuda_stream);
 int orbx_synchronize(orbx_handle *h);
 /* number of kernels this handle has launched since creation (bench bookkeeping) */
 long long orbx_kernel_launches(const orbx_handle *h);
+/* Per-kernel CUDA-event timing on the handle's stream (bench roofline).  Kernel ids: 0 resize_level,
+ * 1 fast_cells, 2 blur7, 3 octree, 4 orient_describe.  set_profiling(1) resets the accumulators. */
+int orbx_set_profiling(orbx_handle *h, int enabled);
+int orbx_get_kernel_times(orbx_handle *h, double *total_ms, long long *counts, int n);
 
 /* ------------------------------------------------------------------ */
 /* ORB matcher  (replaces S/src/ORBmatcher.cc + the Frame grid it searches) */
@@ -130,6 +136,7 @@ typedef struct orbm_handle orbm_handle;
 int orbm_create(orbm_handle **out, int device);
 int orbm_destroy(orbm_handle *h);
 void *orbm_stream(orbm_handle *h);
+int orbm_set_stream(orbm_handle *h, void *cuda_stream);
 int orbm_synchronize(orbm_handle *h);
 long long orbm_kernel_launches(const orbm_handle *h);
 

@@ -191,7 +191,24 @@ class ORBextractor:
         _check(self._L.orbx_get_candidates(self._h, frame, level, _ptr(out), len(out), ctypes.byref(n)))
         return out[:n.value]
 
+    KERNELS = ("resize_level", "fast_cells", "blur7", "octree", "orient_describe")
+
+    def set_profiling(self, on):
+        self._L.orbx_set_profiling.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        _check(self._L.orbx_set_profiling(self._h, int(bool(on))))
+
+    def kernel_times(self):
+        """{kernel: (total_ms, launches)} since set_profiling(True)."""
+        ms = np.zeros(len(self.KERNELS)); cnt = np.zeros(len(self.KERNELS), np.int64)
+        self._L.orbx_get_kernel_times.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+        _check(self._L.orbx_get_kernel_times(self._h, _ptr(ms), _ptr(cnt), len(ms)))
+        return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(self.KERNELS)}
+
     def stream(self): return self._L.orbx_stream(self._h)
+
+    def set_stream(self, cuda_stream):
+        self._L.orbx_set_stream.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        _check(self._L.orbx_set_stream(self._h, ctypes.c_void_p(cuda_stream)))
     def synchronize(self): _check(self._L.orbx_synchronize(self._h))
     def kernel_launches(self): return int(self._L.orbx_kernel_launches(self._h))
 
@@ -233,6 +250,10 @@ class ORBmatcher:
     @property
     def handle(self): return self._h
     def stream(self): return self._L.orbm_stream(self._h)
+
+    def set_stream(self, cuda_stream):
+        self._L.orbm_set_stream.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        _check(self._L.orbm_set_stream(self._h, ctypes.c_void_p(cuda_stream)))
     def synchronize(self): _check(self._L.orbm_synchronize(self._h))
     def kernel_launches(self): return int(self._L.orbm_kernel_launches(self._h))
 

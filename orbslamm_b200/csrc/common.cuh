@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
+#include <vector>
 #include "../../include/orbslamm_b200.h"
 
 namespace orbs {
@@ -55,6 +56,41 @@ struct PinnedBuf {
     }
     void release() { if (p) cudaFreeHost(p); p = nullptr; bytes = 0; }
     template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+// Optional per-kernel CUDA-event timing on the launching stream (bench roofline numbers).
+struct KernelTimer {
+    static constexpr int kMaxKernels = 16;
+    bool enabled = false;
+    struct Rec { cudaEvent_t a, b; int id; };
+    std::vector<Rec> recs;
+    size_t used = 0;
+    double total_ms[kMaxKernels] = {0};
+    long long count[kMaxKernels] = {0};
+    void begin(int id, cudaStream_t st)
+    {
+        if (!enabled) return;
+        if (used == recs.size()) { Rec r; cudaEventCreate(&r.a); cudaEventCreate(&r.b); r.id = id; recs.push_back(r); }
+        recs[used].id = id;
+        cudaEventRecord(recs[used].a, st);
+    }
+    void end(cudaStream_t st)
+    {
+        if (!enabled) return;
+        cudaEventRecord(recs[used].b, st);
+        used++;
+    }
+    // call after the stream is synchronised
+    void collect()
+    {
+        for (size_t i = 0; i < used; i++) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, recs[i].a, recs[i].b) == cudaSuccess) { total_ms[recs[i].id] += ms; count[recs[i].id]++; }
+        }
+        used = 0;
+    }
+    void reset() { used = 0; for (int i = 0; i < kMaxKernels; i++) { total_ms[i] = 0; count[i] = 0; } }
+    void release() { for (auto &r : recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); } recs.clear(); used = 0; }
 };
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }

@@ -122,11 +122,20 @@ k_grid_build(int f_slab, GridParams g, const float2 *__restrict__ f_xy, const in
     }
 }
 
-// One CTA per frame.  The reference loop is sequential over queries: an accepted query claims its feature and
-// later queries skip it.  Equivalent fixed point: query i may take feature k unless a query j < i took it.
-// Rounds: every query proposes its best feature among those not owned by a lower-index query (ownership from
-// the previous round); ownership = lowest proposing query; repeat until no proposal changes.  After round r the
-// first r queries are final, so the loop terminates with exactly the sequential result.
+// Projection search in two kernels.
+//
+// The reference loop is sequential over queries: an accepted query claims its feature and later queries skip
+// it.  Equivalent fixed point: query i may take feature k unless a query j < i took it.
+//   k_search_candidates  (one warp per query, whole chip): the kTop best candidates of every query in the
+//       reference's comparison order (distance, then GetFeaturesInArea visiting order = (ix, iy, index)).
+//   k_search_resolve     (one CTA per frame): rounds -- every query proposes the first feature of its list that
+//       is not owned by a lower-index query (ownership from the previous round); ownership = lowest proposing
+//       query; repeat until no proposal changes.  After round r the first r queries are final, so the loop ends
+//       with exactly the sequential result.  A query whose list is exhausted although it had more than kTop
+//       candidates rescans its window (rare).  Then commit + rotation histogram.
+constexpr int kTop = 8;
+constexpr unsigned long long kNoKey = ~0ull;
+
 struct SearchArgs {
     int f_slab, q_slab;
     GridParams g;
@@ -136,29 +145,141 @@ struct SearchArgs {
     const int *cell_start; const int *cell_items;
     int th_dist; float ratio; int check_ori;
     int *feat_match; int *nmatches;
+    unsigned *top;  // [n_frames, q_slab, kTop]  dist << 20 | feature index, ascending in comparison order; 0xffffffff = none
+    int *ncand;     // [n_frames, q_slab] number of candidates in the window
     int *prop;      // [n_frames, q_slab] proposal of every query (feature index or -1)
     int *owner;     // [n_frames, 2, f_slab]
 };
 
-constexpr unsigned long long kNoKey = ~0ull;
+struct Window { int c0, c1, r0, r1; bool empty, check; };
 
-__global__ void __launch_bounds__(512)
-k_search_projection(const SearchArgs A)
+__device__ __forceinline__ Window make_window(const GridParams &g, float2 uv, float r, int minl, int maxl)
+{
+    // Frame::GetFeaturesInArea, Frame.cc:327-380
+    Window w;
+    w.c0 = (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(uv.x, g.min_x), r), g.w_inv));
+    w.c1 = (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(uv.x, g.min_x), r), g.w_inv));
+    w.r0 = (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(uv.y, g.min_y), r), g.h_inv));
+    w.r1 = (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(uv.y, g.min_y), r), g.h_inv));
+    w.c0 = max(w.c0, 0); w.r0 = max(w.r0, 0); w.c1 = min(w.c1, kGridCols - 1); w.r1 = min(w.r1, kGridRows - 1);
+    w.empty = w.c0 >= kGridCols || w.c1 < 0 || w.r0 >= kGridRows || w.r1 < 0;
+    w.check = (minl > 0) || (maxl >= 0);
+    return w;
+}
+
+__device__ __forceinline__ bool in_window(const Window &w, int minl, int maxl, float2 uv, float r, int oct, float2 p)
+{
+    if (w.check) {
+        if (oct < minl) return false;
+        if (maxl >= 0 && oct > maxl) return false;
+    }
+    return fabsf(__fsub_rn(p.x, uv.x)) < r && fabsf(__fsub_rn(p.y, uv.y)) < r;
+}
+
+__device__ __forceinline__ unsigned long long make_key(int d, int ix, int iy, int k)
+{
+    return ((unsigned long long)d << 32) | ((unsigned long long)ix << 26) | ((unsigned long long)iy << 20) | (unsigned long long)k;
+}
+
+__global__ void __launch_bounds__(256)
+k_search_candidates(const SearchArgs A)
+{
+    const int f = blockIdx.y, lane = threadIdx.x & 31;
+    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (i >= A.q_counts[f]) return;
+    const size_t fo = (size_t)f * A.f_slab, qo = (size_t)f * A.q_slab;
+    unsigned *top = A.top + (qo + i) * kTop;
+    if (!A.q_valid[qo + i]) { if (lane == 0) A.ncand[qo + i] = 0; return; }
+    const float2 *f_xy = A.f_xy + fo; const int *f_octave = A.f_octave + fo; const uint4 *f_desc = A.f_desc + 2 * fo;
+    const int *cs = A.cell_start + (size_t)f * (kGridCells + 1); const int *items = A.cell_items + fo;
+    const float2 uv = A.q_uv[qo + i];
+    const float r = A.q_radius[qo + i];
+    const int minl = A.q_minl[qo + i], maxl = A.q_maxl[qo + i];
+    const Window w = make_window(A.g, uv, r, minl, maxl);
+    unsigned long long loc[kTop];            // this lane's sorted best keys
+#pragma unroll
+    for (int t = 0; t < kTop; t++) loc[t] = kNoKey;
+    int n = 0;
+    if (!w.empty) {
+        const uint4 qa = __ldg(&A.q_desc[2 * (qo + i)]), qb = __ldg(&A.q_desc[2 * (qo + i) + 1]);
+        const int ncy = w.r1 - w.r0 + 1, ncells = (w.c1 - w.c0 + 1) * ncy;
+        for (int c = lane; c < ncells; c += 32) {
+            const int ix = w.c0 + c / ncy, iy = w.r0 + c % ncy;
+            const int cell = ix * kGridRows + iy;
+            const int je = cs[cell + 1];
+            for (int j = cs[cell]; j < je; j++) {
+                const int k = items[j];
+                if (!in_window(w, minl, maxl, uv, r, f_octave[k], f_xy[k])) continue;
+                n++;
+                unsigned long long key = make_key(hamming256(qa, qb, __ldg(&f_desc[2 * k]), __ldg(&f_desc[2 * k + 1])), ix, iy, k);
+#pragma unroll
+                for (int t = 0; t < kTop; t++) {                   // sorted insert
+                    const unsigned long long cur = loc[t];
+                    const bool lt = key < cur;
+                    loc[t] = lt ? key : cur;
+                    key = lt ? cur : key;
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) n += __shfl_xor_sync(0xffffffffu, n, d);
+    // merge the 32 sorted lists: kTop rounds of warp-min + pop
+#pragma unroll
+    for (int t = 0; t < kTop; t++) {
+        unsigned long long m = loc[0];
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) { const unsigned long long o = __shfl_xor_sync(0xffffffffu, m, d); m = o < m ? o : m; }
+        if (m != kNoKey && loc[0] == m) {
+#pragma unroll
+            for (int u = 0; u < kTop - 1; u++) loc[u] = loc[u + 1];
+            loc[kTop - 1] = kNoKey;
+        }
+        if (lane == 0) top[t] = m == kNoKey ? 0xffffffffu : ((unsigned)(m >> 32) << 20) | (unsigned)(m & 0xfffff);
+    }
+    if (lane == 0) A.ncand[qo + i] = n;
+}
+
+// slow path: full rescan of one query's window by one thread; best and second-best free candidates
+__device__ void rescan_window(const SearchArgs &A, int f, int i, const int *own_prev, unsigned long long &b1, unsigned long long &b2)
+{
+    const size_t fo = (size_t)f * A.f_slab, qo = (size_t)f * A.q_slab;
+    const float2 *f_xy = A.f_xy + fo; const int *f_octave = A.f_octave + fo; const uint4 *f_desc = A.f_desc + 2 * fo;
+    const int *cs = A.cell_start + (size_t)f * (kGridCells + 1); const int *items = A.cell_items + fo;
+    const float2 uv = A.q_uv[qo + i];
+    const float r = A.q_radius[qo + i];
+    const int minl = A.q_minl[qo + i], maxl = A.q_maxl[qo + i];
+    const Window w = make_window(A.g, uv, r, minl, maxl);
+    b1 = kNoKey; b2 = kNoKey;
+    if (w.empty) return;
+    const uint4 qa = __ldg(&A.q_desc[2 * (qo + i)]), qb = __ldg(&A.q_desc[2 * (qo + i) + 1]);
+    for (int ix = w.c0; ix <= w.c1; ix++)
+        for (int iy = w.r0; iy <= w.r1; iy++) {
+            const int cell = ix * kGridRows + iy;
+            for (int j = cs[cell]; j < cs[cell + 1]; j++) {
+                const int k = items[j];
+                if (!in_window(w, minl, maxl, uv, r, f_octave[k], f_xy[k])) continue;
+                if (own_prev[k] < i) continue;
+                const unsigned long long key = make_key(hamming256(qa, qb, __ldg(&f_desc[2 * k]), __ldg(&f_desc[2 * k + 1])), ix, iy, k);
+                if (key < b1) { b2 = b1; b1 = key; } else if (key < b2) b2 = key;
+            }
+        }
+}
+
+__global__ void __launch_bounds__(1024)
+k_search_resolve(const SearchArgs A)
 {
     __shared__ int s_changed;
     __shared__ int s_hist[kHisto];
     __shared__ int s_keep[3];
     __shared__ int s_removed, s_accepted;
     const int f = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
-    const int lane = tid & 31, wid = tid >> 5, nwarps = nt >> 5;
     const int N = A.f_counts[f], M = A.q_counts[f];
     const size_t fo = (size_t)f * A.f_slab, qo = (size_t)f * A.q_slab;
-    const float2 *f_xy = A.f_xy + fo; const int *f_octave = A.f_octave + fo; const uint4 *f_desc = A.f_desc + 2 * fo;
-    const int *cs = A.cell_start + (size_t)f * (kGridCells + 1); const int *items = A.cell_items + fo;
+    const int *f_octave = A.f_octave + fo;
     int *fm = A.feat_match + fo;
     int *prop = A.prop + qo;
     int *owner[2] = {A.owner + 2 * fo, A.owner + 2 * fo + A.f_slab};
-    const GridParams g = A.g;
 
     // features that already hold a map point are owned by "query -1": every query skips them
     for (int k = tid; k < N; k += nt) { const int o = fm[k] >= 0 ? -1 : 0x7fffffff; owner[0][k] = o; owner[1][k] = o; }
@@ -171,67 +292,41 @@ k_search_projection(const SearchArgs A)
         __syncthreads();
         const int *own_prev = owner[cur];
         int *own_next = owner[cur ^ 1];
-        for (int i = wid; i < M; i += nwarps) {
+        for (int i = tid; i < M; i += nt) {
             int choice = -1;
-            if (A.q_valid[qo + i]) {
-                const float2 uv = A.q_uv[qo + i];
-                const float r = A.q_radius[qo + i];
-                const int minl = A.q_minl[qo + i], maxl = A.q_maxl[qo + i];
-                // Frame::GetFeaturesInArea, Frame.cc:327-380
-                int c0 = (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(uv.x, g.min_x), r), g.w_inv));
-                int c1 = (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(uv.x, g.min_x), r), g.w_inv));
-                int r0 = (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(uv.y, g.min_y), r), g.h_inv));
-                int r1 = (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(uv.y, g.min_y), r), g.h_inv));
-                c0 = max(c0, 0); r0 = max(r0, 0); c1 = min(c1, kGridCols - 1); r1 = min(r1, kGridRows - 1);
-                const bool empty = c0 >= kGridCols || c1 < 0 || r0 >= kGridRows || r1 < 0;
-                const bool check = (minl > 0) || (maxl >= 0);
-                unsigned long long k1 = kNoKey, k2 = kNoKey;       // two smallest (dist, visit order) keys of this lane
-                if (!empty) {
-                    const uint4 qa = __ldg(&A.q_desc[2 * (qo + i)]), qb = __ldg(&A.q_desc[2 * (qo + i) + 1]);
-                    const int ncx = c1 - c0 + 1, ncy = r1 - r0 + 1;
-                    for (int c = lane; c < ncx * ncy; c += 32) {
-                        const int ix = c0 + c / ncy, iy = r0 + c % ncy;
-                        const int cell = ix * kGridRows + iy;
-                        for (int j = cs[cell]; j < cs[cell + 1]; j++) {
-                            const int k = items[j];
-                            if (check) {
-                                const int o = f_octave[k];
-                                if (o < minl) continue;
-                                if (maxl >= 0 && o > maxl) continue;
-                            }
-                            const float2 p = f_xy[k];
-                            if (!(fabsf(__fsub_rn(p.x, uv.x)) < r && fabsf(__fsub_rn(p.y, uv.y)) < r)) continue;
-                            if (own_prev[k] < i) continue;             // claimed by an earlier query
-                            const int d = hamming256(qa, qb, __ldg(&f_desc[2 * k]), __ldg(&f_desc[2 * k + 1]));
-                            const unsigned long long key = ((unsigned long long)d << 32) | ((unsigned long long)ix << 26) |
-                                                           ((unsigned long long)iy << 20) | (unsigned long long)k;
-                            if (key < k1) { k2 = k1; k1 = key; } else if (key < k2) k2 = key;
-                        }
-                    }
+            const int nc = A.ncand[qo + i];
+            if (nc > 0) {
+                const unsigned *top = A.top + (qo + i) * kTop;
+                // first and second free entries of the sorted list
+                unsigned e1 = 0xffffffffu, e2 = 0xffffffffu;
+                int seen = 0;
+#pragma unroll
+                for (int t = 0; t < kTop; t++) {
+                    const unsigned e = top[t];
+                    if (e == 0xffffffffu) continue;
+                    seen++;
+                    if (own_prev[e & 0xfffff] < i) continue;
+                    if (e1 == 0xffffffffu) e1 = e; else if (e2 == 0xffffffffu) e2 = e;
                 }
-                // warp: best and second best keys
-                unsigned long long b1 = k1;
-#pragma unroll
-                for (int d = 16; d > 0; d >>= 1) { const unsigned long long o = __shfl_xor_sync(0xffffffffu, b1, d); b1 = o < b1 ? o : b1; }
-                if (b1 != kNoKey) {
-                    unsigned long long b2 = (k1 == b1) ? k2 : k1;
-#pragma unroll
-                    for (int d = 16; d > 0; d >>= 1) { const unsigned long long o = __shfl_xor_sync(0xffffffffu, b2, d); b2 = o < b2 ? o : b2; }
-                    const int best = (int)(b1 >> 32), bidx = (int)(b1 & 0xfffff);
-                    if (best <= A.th_dist) {
-                        bool acc = true;
-                        if (A.ratio > 0.f) {
-                            const int best2 = b2 == kNoKey ? 256 : (int)(b2 >> 32);
-                            const int lvl1 = f_octave[bidx], lvl2 = b2 == kNoKey ? -1 : f_octave[(int)(b2 & 0xfffff)];
-                            if (lvl1 == lvl2 && (float)best > __fmul_rn(A.ratio, (float)best2)) acc = false;
-                        }
-                        if (acc) choice = bidx;
-                    }
+                int best = -1, bidx = -1, best2 = 256, lvl2 = -1;
+                const bool list_complete = nc <= kTop;
+                const bool need2 = A.ratio > 0.f;
+                if ((e1 == 0xffffffffu || (need2 && e2 == 0xffffffffu)) && !list_complete) {
+                    unsigned long long b1, b2;
+                    rescan_window(A, f, i, own_prev, b1, b2);
+                    if (b1 != kNoKey) { best = (int)(b1 >> 32); bidx = (int)(b1 & 0xfffff); }
+                    if (b2 != kNoKey) { best2 = (int)(b2 >> 32); lvl2 = f_octave[(int)(b2 & 0xfffff)]; }
+                } else {
+                    if (e1 != 0xffffffffu) { best = (int)(e1 >> 20); bidx = (int)(e1 & 0xfffff); }
+                    if (e2 != 0xffffffffu) { best2 = (int)(e2 >> 20); lvl2 = f_octave[e2 & 0xfffff]; }
+                }
+                if (bidx >= 0 && best <= A.th_dist) {
+                    bool acc = true;
+                    if (need2 && f_octave[bidx] == lvl2 && (float)best > __fmul_rn(A.ratio, (float)best2)) acc = false;
+                    if (acc) choice = bidx;
                 }
             }
-            if (lane == 0) {
-                if (prop[i] != choice) { prop[i] = choice; s_changed = 1; }
-            }
+            if (prop[i] != choice) { prop[i] = choice; s_changed = 1; }
         }
         __syncthreads();
         if (!s_changed) break;
@@ -263,7 +358,7 @@ k_search_projection(const SearchArgs A)
             prop[i] = k | (bin << 24);
         }
     }
-    atomicAdd(&s_accepted, my_acc);
+    if (my_acc) atomicAdd(&s_accepted, my_acc);
     __syncthreads();
     if (A.check_ori) {
         if (tid == 0) {                       // ComputeThreeMaxima, ORBmatcher.cc:1603-1644
@@ -286,7 +381,7 @@ k_search_projection(const SearchArgs A)
             const int bin = v >> 24, k = v & 0xffffff;
             if (bin != s_keep[0] && bin != s_keep[1] && bin != s_keep[2]) { fm[k] = -1; my_rm++; }
         }
-        atomicAdd(&s_removed, my_rm);
+        if (my_rm) atomicAdd(&s_removed, my_rm);
         __syncthreads();
     }
     if (tid == 0) A.nmatches[f] = s_accepted - s_removed;
@@ -299,9 +394,10 @@ using namespace orbs;
 struct orbm_handle {
     int device = 0;
     cudaStream_t stream = nullptr;
+    bool own_stream = true;
     long long launches = 0;
     std::mutex mu;
-    DevBuf cell_start, cell_items, prop, owner, fm_init;
+    DevBuf cell_start, cell_items, prop, owner, top, ncand;
     DevBuf stage[24];
     int stage_used = 0;
 };
@@ -373,10 +469,22 @@ int orbm_destroy(orbm_handle *h)
 {
     if (!h) return ORBS_OK;
     cudaSetDevice(h->device);
-    if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
-    h->cell_start.release(); h->cell_items.release(); h->prop.release(); h->owner.release(); h->fm_init.release();
+    if (h->stream && h->own_stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
+    else cudaDeviceSynchronize();
+    h->cell_start.release(); h->cell_items.release(); h->prop.release(); h->owner.release(); h->top.release(); h->ncand.release();
     for (auto &b : h->stage) b.release();
     delete h;
+    return ORBS_OK;
+}
+
+int orbm_set_stream(orbm_handle *h, void *stream)
+{
+    ORBS_REQUIRE(h, ORBS_E_INVALID, "null handle");
+    std::lock_guard<std::mutex> lk(h->mu);
+    ORBS_CUDA(cudaSetDevice(h->device));
+    ORBS_CUDA(cudaStreamSynchronize(h->stream));
+    if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+    h->stream = (cudaStream_t)stream; h->own_stream = false;
     return ORBS_OK;
 }
 
@@ -470,12 +578,15 @@ int orbm_search_by_projection(orbm_handle *h, int n_frames, const float *bounds4
     if ((rc = h->cell_items.reserve(nf * sizeof(int)))) return rc;
     if ((rc = h->prop.reserve(nq * sizeof(int)))) return rc;
     if ((rc = h->owner.reserve(2 * nf * sizeof(int)))) return rc;
+    if ((rc = h->top.reserve(nq * kTop * sizeof(unsigned)))) return rc;
+    if ((rc = h->ncand.reserve(nq * sizeof(int)))) return rc;
     A.cell_start = h->cell_start.as<int>(); A.cell_items = h->cell_items.as<int>();
-    A.prop = h->prop.as<int>(); A.owner = h->owner.as<int>();
+    A.prop = h->prop.as<int>(); A.owner = h->owner.as<int>(); A.top = h->top.as<unsigned>(); A.ncand = h->ncand.as<int>();
     A.th_dist = th_dist; A.ratio = ratio; A.check_ori = check_ori ? 1 : 0;
     k_grid_build<<<n_frames, 512, 0, h->stream>>>(f_slab, A.g, A.f_xy, A.f_counts, h->cell_start.as<int>(), h->cell_items.as<int>());
-    k_search_projection<<<n_frames, 512, 0, h->stream>>>(A);
-    h->launches += 2;
+    k_search_candidates<<<dim3((q_slab + 7) / 8, n_frames), 256, 0, h->stream>>>(A);
+    k_search_resolve<<<n_frames, 1024, 0, h->stream>>>(A);
+    h->launches += 3;
     ORBS_CUDA(cudaGetLastError());
     return S.finish();
 }

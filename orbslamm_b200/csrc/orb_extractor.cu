@@ -34,6 +34,7 @@ using namespace orbs;
 struct orbx_handle {
     int device = 0;
     cudaStream_t stream = nullptr;
+    bool own_stream = true;
     // parameters and tables (ORBextractor.cc:410-470)
     int nfeatures = 0, nlevels = 0, ini_th = 0, min_th = 0;
     double scale_factor = 0;
@@ -58,6 +59,7 @@ struct orbx_handle {
     int last_pitch0 = 0;
     size_t last_frame0 = 0;
     long long launches = 0;
+    KernelTimer timer;   // ids: 0 resize, 1 fast_cells, 2 blur7, 3 octree, 4 orient_describe
     std::mutex mu;
 };
 
@@ -233,21 +235,31 @@ static int launch_pipeline(orbx_handle *h, const uint8_t *d_img0, int n, int pit
         if (l == 1) { src = d_img0; spitch = pitch0; sframe = frame0; }
         else { src = pyr + S.pyr_off; spitch = S.pitch; sframe = P.pyr_frame_bytes; }
         dim3 grid((D.w + 63) / 64, (D.h + 3) / 4, n);
+        h->timer.begin(0, st);
         k_resize_level<<<grid, 256, 0, st>>>(src, S.w, S.h, spitch, sframe, pyr + D.pyr_off, D.w, D.h, D.pitch, P.pyr_frame_bytes,
                                               h->d_rs_tab.as<int2>() + D.rs_x_off, h->d_rs_tab.as<int2>() + D.rs_y_off);
+        h->timer.end(st);
         h->launches++;
     }
     if (P.total_cells > 0) {
+        h->timer.begin(1, st);
         k_fast_cells<<<dim3(P.total_cells, n), 128, 0, st>>>(P, h->d_cells.as<CellDesc>(), d_img0, pitch0, frame0, pyr,
                                                              h->d_cand.as<uint2>(), cand_count_ptr(h), err_ptr(h, nb));
+        h->timer.end(st);
+        h->timer.begin(2, st);
         k_blur7<<<dim3(P.total_tiles, n), 256, 0, st>>>(P, h->d_tiles.as<TileDesc>(), d_img0, pitch0, frame0, pyr, h->d_blur.as<uint8_t>());
+        h->timer.end(st);
+        h->timer.begin(3, st);
         k_octree<<<dim3(P.nlevels, n), 512, h->octree_smem, st>>>(P, h->d_cand.as<uint2>(), cand_count_ptr(h), h->d_knode.as<unsigned>(),
                                                                  h->d_lvl_kp.as<uint2>(), lvl_count_ptr(h, nb), err_ptr(h, nb));
+        h->timer.end(st);
         const int warps_per_block = 8;
+        h->timer.begin(4, st);
         k_orient_describe<<<dim3((P.kp_slab + warps_per_block - 1) / warps_per_block, n), warps_per_block * 32, 0, st>>>(
             P, d_img0, pitch0, frame0, pyr, h->d_blur.as<uint8_t>(), h->d_lvl_kp.as<uint2>(), lvl_count_ptr(h, nb),
             h->d_kp_xy.as<float2>(), h->d_kp_angle.as<float>(), h->d_kp_resp.as<float>(), h->d_kp_oct.as<int>(),
             h->d_kp_size.as<float>(), h->d_desc.as<uint8_t>(), counts_ptr(h, nb));
+        h->timer.end(st);
         h->launches += 4;
     }
     ORBS_CUDA(cudaGetLastError());
@@ -346,11 +358,13 @@ int orbx_destroy(orbx_handle *h)
 {
     if (!h) return ORBS_OK;
     cudaSetDevice(h->device);
-    if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
+    if (h->stream && h->own_stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
+    else cudaDeviceSynchronize();
     DevBuf *bufs[] = {&h->d_cells, &h->d_tiles, &h->d_rs_tab, &h->d_stage, &h->d_pyr, &h->d_blur, &h->d_cand, &h->d_knode, &h->d_lvl_kp,
                       &h->d_counts, &h->d_kp_xy, &h->d_kp_angle, &h->d_kp_resp, &h->d_kp_oct, &h->d_kp_size, &h->d_desc};
     for (DevBuf *b : bufs) b->release();
     h->h_counts.release();
+    h->timer.release();
     delete h;
     return ORBS_OK;
 }
@@ -508,6 +522,17 @@ int orbx_get_candidates(orbx_handle *h, int frame, int level, int32_t *xys, int 
     return ORBS_OK;
 }
 
+int orbx_set_stream(orbx_handle *h, void *stream)
+{
+    ORBS_REQUIRE(h, ORBS_E_INVALID, "null handle");
+    std::lock_guard<std::mutex> lk(h->mu);
+    ORBS_CUDA(cudaSetDevice(h->device));
+    ORBS_CUDA(cudaStreamSynchronize(h->stream));
+    if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+    h->stream = (cudaStream_t)stream; h->own_stream = false;
+    return ORBS_OK;
+}
+
 void *orbx_stream(orbx_handle *h) { return h ? (void *)h->stream : nullptr; }
 int orbx_synchronize(orbx_handle *h)
 {
@@ -517,5 +542,28 @@ int orbx_synchronize(orbx_handle *h)
     return ORBS_OK;
 }
 long long orbx_kernel_launches(const orbx_handle *h) { return h ? h->launches : 0; }
+
+int orbx_set_profiling(orbx_handle *h, int enabled)
+{
+    ORBS_REQUIRE(h, ORBS_E_INVALID, "null handle");
+    std::lock_guard<std::mutex> lk(h->mu);
+    ORBS_CUDA(cudaSetDevice(h->device));
+    ORBS_CUDA(cudaStreamSynchronize(h->stream));
+    h->timer.collect();
+    h->timer.enabled = enabled != 0;
+    if (enabled) h->timer.reset();
+    return ORBS_OK;
+}
+
+int orbx_get_kernel_times(orbx_handle *h, double *total_ms, long long *counts, int n)
+{
+    ORBS_REQUIRE(h && total_ms && counts && n > 0, ORBS_E_INVALID, "bad argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    ORBS_CUDA(cudaSetDevice(h->device));
+    ORBS_CUDA(cudaStreamSynchronize(h->stream));
+    h->timer.collect();
+    for (int i = 0; i < n && i < KernelTimer::kMaxKernels; i++) { total_ms[i] = h->timer.total_ms[i]; counts[i] = h->timer.count[i]; }
+    return ORBS_OK;
+}
 
 }  // extern "C"
