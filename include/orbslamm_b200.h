@@ -180,6 +180,44 @@ int orbm_search_by_projection(orbm_handle *h, int n_frames, const float *bounds4
                               int q_slab, int th_dist, float ratio, int check_ori,
                               int32_t *feat_match, int32_t *nmatches, int memspace);
 
+/* ------------------------------------------------------------------ */
+/* Optimizer  (replaces S/src/Optimizer.cc and the g2o LM / Schur / LDLT stack it drives; all fp64 inside,
+ * float32 poses and points at the boundary like cv::Mat / Converter.cc)                                      */
+typedef struct orbo_handle orbo_handle;
+
+int orbo_create(orbo_handle **out, int device);
+int orbo_destroy(orbo_handle *h);
+void *orbo_stream(orbo_handle *h);
+int orbo_set_stream(orbo_handle *h, void *cuda_stream);
+int orbo_synchronize(orbo_handle *h);
+long long orbo_kernel_launches(const orbo_handle *h);
+
+/* Optimizer::PoseOptimization(Frame*), Optimizer.cc:262-474 (monocular edges), for n_frames independent frames:
+ * 4 rounds x 10 LM iterations on EdgeSE3ProjectXYZOnlyPose edges, Huber sqrt(5.991), chi2 gating after each
+ * round, pose reset to the initial estimate at the start of every round.
+ *   Tcw f32[n_frames,16] in/out (row-major 4x4); K4 f32[4] HOST pointer (fx fy cx cy);
+ *   per frame slab of `slab` correspondences, counts i32[n_frames]:
+ *   Xw f32[.,3] (MapPoint::GetWorldPos), obs f32[.,2] (mvKeysUn.pt), inv_sigma2 f32[.] (mvInvLevelSigma2[octave]);
+ *   outlier u8[.] out (Frame::mvbOutlier); n_inliers i32[n_frames] out (the return value; 0 if < 3 correspondences). */
+int orbo_pose_optimization(orbo_handle *h, int n_frames, float *Tcw, const float *K4, const float *Xw, const float *obs,
+                           const float *inv_sigma2, const int32_t *counts, int slab, uint8_t *outlier, int32_t *n_inliers,
+                           int memspace);
+
+/* Optimizer::LocalBundleAdjustment (Optimizer.cc:476-801; two_stage = 1: its0 robust iterations, chi2 / depth gating,
+ * its1 non-robust iterations) and Optimizer::BundleAdjustment (Optimizer.cc:68-260; two_stage = 0: its0 iterations
+ * with `robust`) over flat arrays (HOST pointers):
+ *   poses f32[K,16] in/out; fixed u8[K]: 0 free, 1 fixed but written back (mnId == 0), 2 fixed camera (never written);
+ *   intr f64[K,4] fx fy cx cy per keyframe; points f32[P,3] in/out;
+ *   edges: e_kf i32[E], e_pt i32[E], e_uv f32[E,2], e_inv_sigma2 f32[E];
+ *   stop_flag: optional host flag polled between iterations and LM trials (mbAbortBA / mbStopGBA);
+ *   outputs (optional): e_chi2 f64[E], e_depth_ok u8[E], e_outlier u8[E] = the final check of Optimizer.cc:734-766;
+ *   stats i32[4]: LM iterations, LM trials, Cholesky failures, 1 if aborted before the first iteration.
+ * Returns ORBS_OK, or 1 if the stop flag was already set on entry (nothing touched, Optimizer.cc:678-680). */
+int orbo_bundle_adjust(orbo_handle *h, int K, float *poses, const uint8_t *fixed, const double *intr, int P, float *points,
+                       int E, const int32_t *e_kf, const int32_t *e_pt, const float *e_uv, const float *e_inv_sigma2,
+                       int two_stage, int its0, int its1, int robust, const volatile int *stop_flag,
+                       double *e_chi2, uint8_t *e_depth_ok, uint8_t *e_outlier, int32_t *stats);
+
 #ifdef __cplusplus
 }
 #endif

@@ -493,8 +493,9 @@ static void inv3(const double *A, double *I)                  /* Matrix3d::inver
 }
 
 /* profile LDL^T of the dense symmetric n x n matrix S (row-major, lower part used), in place.
- * returns 0 on a zero pivot (SimplicialLDLT's NumericalIssue). */
-static int ldlt_solve(double *S, int n, const int *first, const double *b, double *x)
+ * returns 0 on a zero pivot (SimplicialLDLT's NumericalIssue), or on a negative one when require_positive
+ * (LinearSolverDense's isPositive() gate, linear_solver_dense.h:107-112). */
+static int ldlt_solve(double *S, int n, const int *first, const double *b, double *x, int require_positive)
 {
     for (int i = 0; i < n; i++) {
         for (int j = first[i]; j <= i; j++) {
@@ -502,7 +503,7 @@ static int ldlt_solve(double *S, int n, const int *first, const double *b, doubl
             const int k0 = first[i] > first[j] ? first[i] : first[j];
             for (int k = k0; k < j; k++) s -= S[(size_t)i * n + k] * S[(size_t)j * n + k] * S[(size_t)k * n + k];
             if (j < i) S[(size_t)i * n + j] = s / S[(size_t)j * n + j];
-            else { if (s == 0.0 || !(s == s)) return 0; S[(size_t)i * n + i] = s; }
+            else { if (s == 0.0 || !(s == s) || (require_positive && s < 0.0)) return 0; S[(size_t)i * n + i] = s; }
         }
     }
     for (int i = 0; i < n; i++) { double s = b[i]; for (int k = first[i]; k < i; k++) s -= S[(size_t)i * n + k] * x[k]; x[i] = s; }
@@ -576,7 +577,8 @@ static int ba_solve(ba_t *B)
         }
     }
     double *xp = B->x;
-    const int ok = n > 0 ? ldlt_solve(S, n, B->first, bs, xp) : 1;
+    /* pose-only problems use LinearSolverDense (Eigen LDLT + isPositive gate), BA uses LinearSolverEigen (zero pivot only) */
+    const int ok = n > 0 ? ldlt_solve(S, n, B->first, bs, xp, B->pt_fixed_all) : 1;
     if (ok && nL) {
         /* x_l = Dinv (b_l - Hpl^T x_p), block_solver.hpp:463-487 */
         dbl = (double *)malloc(sizeof(double) * 3 * nL);

@@ -303,3 +303,68 @@ class ORBmatcher:
                                                  _ptr(q_maxl), _ptr(q_angle), _ptr(q_desc), _ptr(q_counts), qs, int(th_dist),
                                                  float(ratio), int(ori), _ptr(fm), _ptr(nm), 0))
         return nm, fm
+
+
+class Optimizer:
+    """Mirror of iORB_SLAM::Optimizer (reference S/include/Optimizer.h:37-68) over flat arrays: the static functions
+    PoseOptimization / LocalBundleAdjustment / BundleAdjustment become methods of a handle that owns the device
+    workspaces (the reference's statics are re-entrant; create one Optimizer per calling thread)."""
+
+    def __init__(self, device=0):
+        self._L = load()
+        self._h = ctypes.c_void_p()
+        _check(self._L.orbo_create(ctypes.byref(self._h), int(device)))
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            self._L.orbo_destroy(h)
+
+    @property
+    def handle(self): return self._h
+    def stream(self): return self._L.orbo_stream(self._h)
+    def set_stream(self, s): _check(self._L.orbo_set_stream(self._h, ctypes.c_void_p(s)))
+    def synchronize(self): _check(self._L.orbo_synchronize(self._h))
+    def kernel_launches(self): return int(self._L.orbo_kernel_launches(self._h))
+
+    def PoseOptimization(self, Tcw, K4, Xw, obs, inv_sigma2, counts):
+        """Batched Optimizer::PoseOptimization.  Tcw [n,4,4]; Xw [n,slab,3]; obs [n,slab,2]; inv_sigma2 [n,slab];
+        counts [n].  Returns (Tcw_out [n,4,4], outlier u8[n,slab], n_inliers i32[n])."""
+        T = np.ascontiguousarray(Tcw, np.float32).reshape(-1, 16).copy(); n = len(T)
+        K4 = np.ascontiguousarray(K4, np.float32)
+        Xw = np.ascontiguousarray(Xw, np.float32).reshape(n, -1, 3); slab = Xw.shape[1]
+        obs = np.ascontiguousarray(obs, np.float32).reshape(n, slab, 2)
+        w = np.ascontiguousarray(inv_sigma2, np.float32).reshape(n, slab)
+        counts = np.ascontiguousarray(counts, np.int32)
+        outl = np.zeros((n, slab), np.uint8); ninl = np.zeros(n, np.int32)
+        _check(self._L.orbo_pose_optimization(self._h, n, _ptr(T), _ptr(K4), _ptr(Xw), _ptr(obs), _ptr(w), _ptr(counts), slab,
+                                              _ptr(outl), _ptr(ninl), 0))
+        return T.reshape(n, 4, 4), outl, ninl
+
+    def _ba(self, poses, fixed, intr, points, e_kf, e_pt, e_uv, e_inv_sigma2, two_stage, its0, its1, robust, stop_flag=None):
+        poses = np.ascontiguousarray(poses, np.float32).reshape(-1, 16).copy(); K = len(poses)
+        fixed = np.ascontiguousarray(fixed, np.uint8)
+        intr = np.ascontiguousarray(intr, np.float64)
+        if intr.ndim == 1:
+            intr = np.tile(intr, (K, 1))
+        intr = np.ascontiguousarray(intr)
+        points = np.ascontiguousarray(points, np.float32).reshape(-1, 3).copy(); P = len(points)
+        e_kf = np.ascontiguousarray(e_kf, np.int32); e_pt = np.ascontiguousarray(e_pt, np.int32); E = len(e_kf)
+        e_uv = np.ascontiguousarray(e_uv, np.float32); w = np.ascontiguousarray(e_inv_sigma2, np.float32)
+        chi2 = np.zeros(E); dok = np.zeros(E, np.uint8); outl = np.zeros(E, np.uint8); stats = np.zeros(4, np.int32)
+        sp = None if stop_flag is None else stop_flag.ctypes.data
+        rc = self._L.orbo_bundle_adjust(self._h, K, _ptr(poses), _ptr(fixed), _ptr(intr), P, _ptr(points), E, _ptr(e_kf), _ptr(e_pt),
+                                        _ptr(e_uv), _ptr(w), int(two_stage), int(its0), int(its1), int(robust), sp, _ptr(chi2),
+                                        _ptr(dok), _ptr(outl), _ptr(stats))
+        if rc < 0:
+            _check(rc)
+        return dict(poses=poses.reshape(K, 4, 4), points=points, chi2=chi2, depth_ok=dok, outlier=outl,
+                    lm_iterations=int(stats[0]), lm_trials=int(stats[1]), chol_failures=int(stats[2]), aborted=bool(rc == 1))
+
+    def LocalBundleAdjustment(self, poses, fixed, intr, points, e_kf, e_pt, e_uv, e_inv_sigma2, stop_flag=None):
+        """Optimizer::LocalBundleAdjustment schedule: 5 robust LM iterations, chi2/depth gating, 10 non-robust."""
+        return self._ba(poses, fixed, intr, points, e_kf, e_pt, e_uv, e_inv_sigma2, True, 5, 10, True, stop_flag)
+
+    def BundleAdjustment(self, poses, fixed, intr, points, e_kf, e_pt, e_uv, e_inv_sigma2, nIterations=5, bRobust=True, stop_flag=None):
+        """Optimizer::BundleAdjustment (GlobalBundleAdjustemnt / MMGlobalBundleAdjustemnt core)."""
+        return self._ba(poses, fixed, intr, points, e_kf, e_pt, e_uv, e_inv_sigma2, False, nIterations, 0, bRobust, stop_flag)

@@ -17,6 +17,16 @@ def declare(L):
     L.orbm_descriptor_distance.argtypes = [vp, vp, i, vp, i, vp, i]
     L.orbm_project_last_frame.argtypes = [vp, i, vp, vp, vp, vp, i, vp, vp, vp, i, f, vp, vp, vp, vp, vp, i]
     L.orbm_search_by_projection.argtypes = [vp, i, vp, vp, vp, vp, vp, vp, i, vp, vp, vp, vp, vp, vp, vp, vp, i, i, f, i, vp, vp, i]
+    L.orbo_create.argtypes = [c.POINTER(vp), i]
+    L.orbo_destroy.argtypes = [vp]
+    L.orbo_stream.argtypes = [vp]; L.orbo_stream.restype = vp
+    L.orbo_set_stream.argtypes = [vp, vp]
+    L.orbo_synchronize.argtypes = [vp]
+    L.orbo_kernel_launches.argtypes = [vp]; L.orbo_kernel_launches.restype = c.c_longlong
+    L.orbo_pose_optimization.argtypes = [vp, i, vp, vp, vp, vp, vp, vp, i, vp, vp, i]
+    L.orbo_bundle_adjust.argtypes = [vp, i, vp, vp, vp, i, vp, i, vp, vp, vp, vp, i, i, i, i, vp, vp, vp, vp, vp]
+    for n in ("orbo_create", "orbo_destroy", "orbo_set_stream", "orbo_synchronize", "orbo_pose_optimization", "orbo_bundle_adjust"):
+        getattr(L, n).restype = c.c_int
     for n in ("orbm_create", "orbm_destroy", "orbm_synchronize", "orbm_descriptor_distance", "orbm_project_last_frame",
               "orbm_search_by_projection"):
         getattr(L, n).restype = c.c_int

@@ -1,0 +1,547 @@
+// ba_kernels.cuh -- bundle-adjustment kernels (Optimizer::LocalBundleAdjustment / BundleAdjustment on g2o's
+// BlockSolver_6_3 + Levenberg, restated).  All fp64.  Edges are stored grouped by map point (CSR), which makes
+// the per-point work (Hll, b_l, Schur complement, back-substitution) a warp-level job without atomics; pose
+// blocks are built by a second CSR (by keyframe).  Only the scatter of the Schur complement into the dense
+// reduced system uses fp64 atomics.
+//
+//   k_ba_errors        computeActiveErrors + activeRobustChi2          sparse_optimizer.cpp:61-114
+//   k_ba_build_points  linearizeOplus + constructQuadraticForm (Hll, b_l, Hpl)   block_solver.hpp:506-564,
+//   k_ba_build_poses   ... (Hpp, b_p)                                  base_binary_edge.hpp:55-120
+//   k_ba_schur_init/k_ba_schur   setLambda + Schur complement           block_solver.hpp:371-436,568-593
+//   k_chol_* / k_trs_*  dense Cholesky + triangular solves of the reduced system (replaces LinearSolverEigen)
+//   k_ba_backsub       x_l = Dinv (b_l - Hpl^T x_p) + computeScale     block_solver.hpp:463-487, levenberg.cpp:182-189
+//   k_ba_update/restore  oplus (exp(dx) * T, X += dx) with push/pop     sparse_optimizer.cpp:422-435
+#pragma once
+#include "common.cuh"
+#include "se3.cuh"
+
+namespace orbs {
+
+struct BaDev {
+    int K, P, E;
+    int nA;                       // free active poses (reduced system has n = 6 nA unknowns)
+    int n;                        // 6 * nA
+    int ld;                       // leading dimension of S (n rounded up to the tile size)
+    // state
+    Se3 *pose, *pose_bak;         // [K]
+    double *pt, *pt_bak;          // [P*3]
+    const double *intr;           // [K*4]
+    // edges grouped by point
+    const int *pt_start;          // [P+1]
+    const int *e_kf;              // [E]
+    const double *e_obs;          // [E*2]
+    const double *e_w;            // [E]
+    uint8_t *e_level;             // [E] 0 = active, 1 = outlier (setLevel(1))
+    double *e_err;                // [E*2] stored _error
+    double *e_W;                  // [E*18] Hpl block of the edge (6x3), valid for active edges with a free pose
+    // edges grouped by pose
+    const int *pose_start;        // [K+1]
+    const int *pose_edges;        // [E] -> edge index (point-grouped order)
+    const int *e_point;           // [E] point of an edge (point-grouped order)
+    // index mapping
+    const int *pose_idx;          // [K] hessian index or -1 (fixed / inactive)
+    const uint8_t *pt_active;     // [P]
+    // system
+    double *Hpp, *bp;             // [nA*36], [nA*6]
+    double *Hll, *bl;             // [P*9], [P*3]
+    double *x;                    // [n + 3P]  (poses by hessian index, points by point id)
+    double *S, *bs;               // [ld*ld] lower triangle used, [ld]
+    double *partial;              // [blocks] reduction scratch
+    double *scalars;              // [8]: 0 chi2, 1 scale (points), 2 scale (poses), 3 max diagonal
+    int *flags;                   // [4]: 0 cholesky failure
+    double delta, dsqr;
+    int robust;
+};
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    return v;
+}
+
+__device__ __forceinline__ double edge_chi2(double e0, double e1, double w) { return e0 * (w * e0 + 0.0 * e1) + e1 * (0.0 * e0 + w * e1); }
+
+// errors of all active edges at the current estimate + robust chi2 (per-block partial sums, fixed order)
+__global__ void __launch_bounds__(256)
+k_ba_errors(const BaDev B)
+{
+    __shared__ double s_w[8];
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    double chi = 0;
+    if (e < B.E && B.e_level[e] == 0) {
+        const int kf = B.e_kf[e], p = B.e_point[e];
+        double Xc[3], er[2];
+        se3_map(B.pose[kf], &B.pt[3 * p], Xc);
+        reproj_error(Xc, &B.intr[4 * kf], B.e_obs[2 * e], B.e_obs[2 * e + 1], er);
+        B.e_err[2 * e] = er[0]; B.e_err[2 * e + 1] = er[1];
+        const double c = edge_chi2(er[0], er[1], B.e_w[e]);
+        double r0 = c, r1 = 1;
+        if (B.robust) huber(c, B.delta, B.dsqr, r0, r1);
+        chi = r0;
+    }
+    chi = warp_sum(chi);
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = chi;
+    __syncthreads();
+    if (threadIdx.x == 0) { double s = 0; for (int w = 0; w < 8; w++) s += s_w[w]; B.partial[blockIdx.x] = s; }
+}
+
+// sum partial[0..n) in fixed order into scalars[slot]
+__global__ void __launch_bounds__(256)
+k_reduce_partials(const double *__restrict__ partial, int n, double *__restrict__ scalars, int slot, int use_max)
+{
+    __shared__ double s[256];
+    double a = 0;
+    for (int i = threadIdx.x; i < n; i += 256) a = use_max ? fmax(a, partial[i]) : a + partial[i];
+    s[threadIdx.x] = a;
+    __syncthreads();
+    for (int d = 128; d > 0; d >>= 1) {
+        if (threadIdx.x < d) s[threadIdx.x] = use_max ? fmax(s[threadIdx.x], s[threadIdx.x + d]) : s[threadIdx.x] + s[threadIdx.x + d];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) scalars[slot] = s[0];
+}
+
+// warp per point: Hll, b_l and the per-edge Hpl blocks
+__global__ void __launch_bounds__(256)
+k_ba_build_points(const BaDev B)
+{
+    const int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (p >= B.P || !B.pt_active[p]) return;
+    double H[6] = {0, 0, 0, 0, 0, 0}, b[3] = {0, 0, 0};
+    const double X[3] = {B.pt[3 * p], B.pt[3 * p + 1], B.pt[3 * p + 2]};
+    for (int e = B.pt_start[p] + lane; e < B.pt_start[p + 1]; e += 32) {
+        if (B.e_level[e]) continue;
+        const int kf = B.e_kf[e];
+        const Se3 T = B.pose[kf];
+        double Xc[3], R[9], Jl[6], Jp[12];
+        se3_map(T, X, Xc);
+        quat_to_R(T.q, R);
+        jac_binary(Xc, R, B.intr[4 * kf], B.intr[4 * kf + 1], Jl, Jp);
+        const double e0 = B.e_err[2 * e], e1 = B.e_err[2 * e + 1], w = B.e_w[e];
+        double rw = 1.0, r0u;
+        if (B.robust) huber(edge_chi2(e0, e1, w), B.delta, B.dsqr, r0u, rw);
+        const double wo = rw * w;
+        const double r0 = -w * e0 * rw, r1 = -w * e1 * rw;          // omega_r = -omega e rho'
+        H[0] += Jl[0] * wo * Jl[0] + Jl[3] * wo * Jl[3];
+        H[1] += Jl[0] * wo * Jl[1] + Jl[3] * wo * Jl[4];
+        H[2] += Jl[0] * wo * Jl[2] + Jl[3] * wo * Jl[5];
+        H[3] += Jl[1] * wo * Jl[1] + Jl[4] * wo * Jl[4];
+        H[4] += Jl[1] * wo * Jl[2] + Jl[4] * wo * Jl[5];
+        H[5] += Jl[2] * wo * Jl[2] + Jl[5] * wo * Jl[5];
+        b[0] += Jl[0] * r0 + Jl[3] * r1; b[1] += Jl[1] * r0 + Jl[4] * r1; b[2] += Jl[2] * r0 + Jl[5] * r1;
+        if (B.pose_idx[kf] >= 0) {
+            double *W = &B.e_W[18 * (size_t)e];
+#pragma unroll
+            for (int a = 0; a < 6; a++)
+#pragma unroll
+                for (int c = 0; c < 3; c++) W[3 * a + c] = Jp[a] * wo * Jl[c] + Jp[6 + a] * wo * Jl[3 + c];
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 6; i++) H[i] = warp_sum(H[i]);
+#pragma unroll
+    for (int i = 0; i < 3; i++) b[i] = warp_sum(b[i]);
+    if (lane == 0) {
+        double *Ho = &B.Hll[9 * (size_t)p];
+        Ho[0] = H[0]; Ho[1] = H[1]; Ho[2] = H[2]; Ho[3] = H[1]; Ho[4] = H[3]; Ho[5] = H[4]; Ho[6] = H[2]; Ho[7] = H[4]; Ho[8] = H[5];
+        B.bl[3 * p] = b[0]; B.bl[3 * p + 1] = b[1]; B.bl[3 * p + 2] = b[2];
+    }
+}
+
+// warp per free pose: Hpp (full 6x6) and b_p; also per-pose max |diag| candidates are taken later on the host side kernel
+__global__ void __launch_bounds__(256)
+k_ba_build_poses(const BaDev B)
+{
+    const int kf = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (kf >= B.K) return;
+    const int ip = B.pose_idx[kf];
+    if (ip < 0) return;
+    double acc[27];
+#pragma unroll
+    for (int i = 0; i < 27; i++) acc[i] = 0;
+    const Se3 T = B.pose[kf];
+    const double fx = B.intr[4 * kf], fy = B.intr[4 * kf + 1];
+    for (int j = B.pose_start[kf] + lane; j < B.pose_start[kf + 1]; j += 32) {
+        const int e = B.pose_edges[j];
+        if (B.e_level[e]) continue;
+        const int p = B.e_point[e];
+        double Xc[3], Jp[12];
+        se3_map(T, &B.pt[3 * p], Xc);
+        {   // pose Jacobian of EdgeSE3ProjectXYZ (division form)
+            const double x = Xc[0], y = Xc[1], z = Xc[2], z_2 = z * z;
+            Jp[0] = x * y / z_2 * fx; Jp[1] = -(1 + (x * x / z_2)) * fx; Jp[2] = y / z * fx;
+            Jp[3] = -1. / z * fx; Jp[4] = 0; Jp[5] = x / z_2 * fx;
+            Jp[6] = (1 + y * y / z_2) * fy; Jp[7] = -x * y / z_2 * fy; Jp[8] = -x / z * fy;
+            Jp[9] = 0; Jp[10] = -1. / z * fy; Jp[11] = y / z_2 * fy;
+        }
+        const double e0 = B.e_err[2 * e], e1 = B.e_err[2 * e + 1], w = B.e_w[e];
+        double rw = 1.0, r0u;
+        if (B.robust) huber(edge_chi2(e0, e1, w), B.delta, B.dsqr, r0u, rw);
+        const double wo = rw * w;
+        const double r0 = -w * e0 * rw, r1 = -w * e1 * rw;
+        int q = 0;
+#pragma unroll
+        for (int a = 0; a < 6; a++) {
+            acc[21 + a] += Jp[a] * r0 + Jp[6 + a] * r1;
+#pragma unroll
+            for (int c = a; c < 6; c++) { acc[q] += Jp[a] * wo * Jp[c] + Jp[6 + a] * wo * Jp[6 + c]; q++; }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 27; i++) acc[i] = warp_sum(acc[i]);
+    if (lane == 0) {
+        double *H = &B.Hpp[36 * (size_t)ip];
+        int q = 0;
+        for (int a = 0; a < 6; a++) for (int c = a; c < 6; c++) { H[6 * a + c] = acc[q]; H[6 * c + a] = acc[q]; q++; }
+        for (int a = 0; a < 6; a++) B.bp[6 * ip + a] = acc[21 + a];
+    }
+}
+
+// max |diagonal| of the free blocks (computeLambdaInit, levenberg.cpp:166-180): per-block partial maxima
+__global__ void __launch_bounds__(256)
+k_ba_max_diag(const BaDev B)
+{
+    __shared__ double s_w[8];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double m = 0;
+    if (i < B.nA) for (int j = 0; j < 6; j++) m = fmax(m, fabs(B.Hpp[36 * (size_t)i + 7 * j]));
+    const int p = i - B.nA;
+    if (p >= 0 && p < B.P && B.pt_active[p]) for (int j = 0; j < 3; j++) m = fmax(m, fabs(B.Hll[9 * (size_t)p + 4 * j]));
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, d));
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) { double s = 0; for (int w = 0; w < 8; w++) s = fmax(s, s_w[w]); B.partial[blockIdx.x] = s; }
+}
+
+// S (lower triangle, ld x ld, zeroed by a memset before) <- diag blocks Hpp + lambda I ; bs <- bp ; padding diag = 1
+__global__ void __launch_bounds__(256)
+k_ba_schur_init(const BaDev B, double lambda)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < B.nA * 36) {
+        const int i = t / 36, a = (t % 36) / 6, c = t % 6;
+        if (c <= a) B.S[(size_t)(6 * i + a) * B.ld + 6 * i + c] = B.Hpp[t] + (a == c ? lambda : 0.0);
+    }
+    if (t < B.ld) {
+        B.bs[t] = t < B.n ? B.bp[t] : 0.0;
+        if (t >= B.n) B.S[(size_t)t * B.ld + t] = 1.0;
+    }
+}
+
+// warp per point: Dinv = (Hll + lambda I)^-1, then for every pair of its free-pose edges the 6x6 block
+// W_row Dinv W_col^T is subtracted from the lower triangle of S, and W Dinv b_l from bs.
+__global__ void __launch_bounds__(256)
+k_ba_schur(const BaDev B, double lambda)
+{
+    const int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (p >= B.P || !B.pt_active[p]) return;
+    double D[9], Di[9];
+#pragma unroll
+    for (int i = 0; i < 9; i++) D[i] = B.Hll[9 * (size_t)p + i];
+    D[0] += lambda; D[4] += lambda; D[8] += lambda;
+    inv3(D, Di);
+    const double b0 = B.bl[3 * p], b1 = B.bl[3 * p + 1], b2 = B.bl[3 * p + 2];
+    const double db[3] = {Di[0] * b0 + Di[1] * b1 + Di[2] * b2, Di[3] * b0 + Di[4] * b1 + Di[5] * b2, Di[6] * b0 + Di[7] * b1 + Di[8] * b2};
+    const int e0 = B.pt_start[p], m = B.pt_start[p + 1] - e0;
+    // bs part: one edge per lane
+    for (int u = lane; u < m; u += 32) {
+        const int e = e0 + u;
+        if (B.e_level[e]) continue;
+        const int i1 = B.pose_idx[B.e_kf[e]];
+        if (i1 < 0) continue;
+        const double *W = &B.e_W[18 * (size_t)e];
+#pragma unroll
+        for (int a = 0; a < 6; a++) atomicAdd(&B.bs[6 * i1 + a], -(W[3 * a] * db[0] + W[3 * a + 1] * db[1] + W[3 * a + 2] * db[2]));
+    }
+    // pair part: pairs (u, v), u <= v, linearised
+    const int npairs = m * (m + 1) / 2;
+    for (int t = lane; t < npairs; t += 32) {
+        // invert t = v (v + 1) / 2 + u
+        int v = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+        while (v * (v + 1) / 2 > t) v--;
+        while ((v + 1) * (v + 2) / 2 <= t) v++;
+        const int u = t - v * (v + 1) / 2;
+        const int eu = e0 + u, ev = e0 + v;
+        if (B.e_level[eu] || B.e_level[ev]) continue;
+        const int iu = B.pose_idx[B.e_kf[eu]], iv = B.pose_idx[B.e_kf[ev]];
+        if (iu < 0 || iv < 0) continue;
+        // block (row = larger index, col = smaller index) = W_row Dinv W_col^T
+        const bool swap = iu > iv;
+        const double *Wr = &B.e_W[18 * (size_t)(swap ? eu : ev)], *Wc = &B.e_W[18 * (size_t)(swap ? ev : eu)];
+        const int ir = swap ? iu : iv, ic = swap ? iv : iu;
+        double BD[18];
+#pragma unroll
+        for (int a = 0; a < 6; a++)
+#pragma unroll
+            for (int c = 0; c < 3; c++) BD[3 * a + c] = Wr[3 * a] * Di[c] + Wr[3 * a + 1] * Di[3 + c] + Wr[3 * a + 2] * Di[6 + c];
+        double *Sb = &B.S[(size_t)(6 * ir) * B.ld + 6 * ic];
+#pragma unroll
+        for (int a = 0; a < 6; a++)
+#pragma unroll
+            for (int c = 0; c < 6; c++) {
+                if (ir == ic && c > a) continue;                   // diagonal block: lower part only
+                const double val = BD[3 * a] * Wc[3 * c] + BD[3 * a + 1] * Wc[3 * c + 1] + BD[3 * a + 2] * Wc[3 * c + 2];
+                atomicAdd(&Sb[(size_t)a * B.ld + c], -val);
+            }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Dense Cholesky S = L L^T on the lower triangle, tile size NB, right-looking.  Replaces
+// LinearSolverEigen::solve (SimplicialLDLT); a non-positive pivot raises flags[0] (solve() == false).
+constexpr int NB = 64;
+constexpr int kCholSmem = 2 * NB * (NB + 1) * (int)sizeof(double);   // dynamic shared memory of k_chol_trsm / k_chol_update
+
+__global__ void __launch_bounds__(256)
+k_chol_potrf(double *__restrict__ S, int ld, int k, int *__restrict__ flags)
+{
+    __shared__ double T[NB][NB + 1];
+    double *A = S + (size_t)(k * NB) * ld + k * NB;
+    const int tid = threadIdx.x;
+    for (int i = tid; i < NB * NB; i += 256) { const int r = i / NB, c = i % NB; T[r][c] = c <= r ? A[(size_t)r * ld + c] : 0.0; }
+    __syncthreads();
+    for (int j = 0; j < NB; j++) {
+        if (tid == 0) {
+            const double d = T[j][j];
+            if (!(d > 0.0)) { flags[0] = 1; T[j][j] = 1.0; } else T[j][j] = sqrt(d);
+        }
+        __syncthreads();
+        const double dj = T[j][j];
+        for (int r = j + 1 + tid; r < NB; r += 256) T[r][j] /= dj;
+        __syncthreads();
+        // trailing update of the tile: T[r][c] -= T[r][j] * T[c][j]  for j < c <= r
+        for (int i = tid; i < NB * NB; i += 256) {
+            const int r = i / NB, c = i % NB;
+            if (c > j && c <= r) T[r][c] -= T[r][j] * T[c][j];
+        }
+        __syncthreads();
+    }
+    for (int i = tid; i < NB * NB; i += 256) { const int r = i / NB, c = i % NB; if (c <= r) A[(size_t)r * ld + c] = T[r][c]; }
+}
+
+// A[i][k] <- A[i][k] * L[k][k]^-T   for tile rows i > k (one CTA per tile)
+__global__ void __launch_bounds__(256)
+k_chol_trsm(double *__restrict__ S, int ld, int k)
+{
+    extern __shared__ double smem_d[];
+    double (*L)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(smem_d);
+    double (*X)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(smem_d + NB * (NB + 1));
+    const int i = k + 1 + blockIdx.x, tid = threadIdx.x;
+    const double *Lk = S + (size_t)(k * NB) * ld + k * NB;
+    double *A = S + (size_t)(i * NB) * ld + k * NB;
+    for (int t = tid; t < NB * NB; t += 256) { const int r = t / NB, c = t % NB; L[r][c] = Lk[(size_t)r * ld + c]; X[r][c] = A[(size_t)r * ld + c]; }
+    __syncthreads();
+    // each thread owns rows r = tid / 4 .. (4 threads per row would need sync); use one thread per row, 64 rows
+    if (tid < NB) {
+        const int r = tid;
+        for (int c = 0; c < NB; c++) {
+            double s = X[r][c];
+            for (int q = 0; q < c; q++) s -= X[r][q] * L[c][q];
+            X[r][c] = s / L[c][c];
+        }
+    }
+    __syncthreads();
+    for (int t = tid; t < NB * NB; t += 256) { const int r = t / NB, c = t % NB; A[(size_t)r * ld + c] = X[r][c]; }
+}
+
+// A[i][j] -= A[i][k] * A[j][k]^T   for k < j <= i  (one CTA per (i, j) tile; 4x4 register blocking)
+__global__ void __launch_bounds__(256)
+k_chol_update(double *__restrict__ S, int ld, int k, int nt)
+{
+    extern __shared__ double smem_d[];
+    double (*Ai)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(smem_d);
+    double (*Aj)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(smem_d + NB * (NB + 1));
+    // linear tile index -> (i, j) with k < j <= i < nt
+    const int m = nt - k - 1;
+    int t = blockIdx.x;
+    int ii = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+    while (ii * (ii + 1) / 2 > t) ii--;
+    while ((ii + 1) * (ii + 2) / 2 <= t) ii++;
+    const int jj = t - ii * (ii + 1) / 2;
+    if (ii >= m) return;
+    const int i = k + 1 + ii, j = k + 1 + jj, tid = threadIdx.x;
+    const double *Pi = S + (size_t)(i * NB) * ld + k * NB, *Pj = S + (size_t)(j * NB) * ld + k * NB;
+    for (int q = tid; q < NB * NB; q += 256) { const int r = q / NB, c = q % NB; Ai[r][c] = Pi[(size_t)r * ld + c]; Aj[r][c] = Pj[(size_t)r * ld + c]; }
+    __syncthreads();
+    const int tr = (tid / 16) * 4, tc = (tid % 16) * 4;
+    double acc[4][4] = {};
+    for (int q = 0; q < NB; q++) {
+        double a[4], b[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) { a[u] = Ai[tr + u][q]; b[u] = Aj[tc + u][q]; }
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+#pragma unroll
+            for (int v = 0; v < 4; v++) acc[u][v] = fma(a[u], b[v], acc[u][v]);
+    }
+    double *C = S + (size_t)(i * NB) * ld + j * NB;
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+#pragma unroll
+        for (int v = 0; v < 4; v++)
+            if (i != j || tc + v <= tr + u) C[(size_t)(tr + u) * ld + tc + v] -= acc[u][v];
+}
+
+// triangular solves, tile by tile.  forward: y_k = L_kk^-1 (b_k);  then b_i -= L_ik y_k (i > k)
+__global__ void __launch_bounds__(NB)
+k_trs_diag(const double *__restrict__ S, int ld, int k, double *__restrict__ b, int transpose)
+{
+    __shared__ double L[NB][NB + 1];
+    __shared__ double y[NB];
+    const double *Lk = S + (size_t)(k * NB) * ld + k * NB;
+    const int tid = threadIdx.x;
+    for (int t = tid; t < NB * NB; t += NB) { const int r = t / NB, c = t % NB; L[r][c] = Lk[(size_t)r * ld + c]; }
+    y[tid] = b[k * NB + tid];
+    __syncthreads();
+    if (!transpose) {
+        for (int j = 0; j < NB; j++) {
+            if (tid == j) y[j] /= L[j][j];
+            __syncthreads();
+            if (tid > j) y[tid] -= L[tid][j] * y[j];
+            __syncthreads();
+        }
+    } else {
+        for (int j = NB - 1; j >= 0; j--) {
+            if (tid == j) y[j] /= L[j][j];
+            __syncthreads();
+            if (tid < j) y[tid] -= L[j][tid] * y[j];
+            __syncthreads();
+        }
+    }
+    b[k * NB + tid] = y[tid];
+}
+
+// forward: for tile rows i > k: b_i -= L_ik y_k.  backward (transpose): for tile rows j < k: b_j -= L_kj^T x_k.
+__global__ void __launch_bounds__(NB)
+k_trs_update(const double *__restrict__ S, int ld, int k, double *__restrict__ b, int transpose)
+{
+    __shared__ double yk[NB];
+    const int tid = threadIdx.x;
+    yk[tid] = b[k * NB + tid];
+    __syncthreads();
+    if (!transpose) {
+        const int i = k + 1 + blockIdx.x;
+        const double *Lik = S + (size_t)(i * NB) * ld + k * NB;
+        double s = 0;
+        for (int c = 0; c < NB; c++) s += Lik[(size_t)tid * ld + c] * yk[c];
+        b[i * NB + tid] -= s;
+    } else {
+        const int j = blockIdx.x;
+        const double *Lkj = S + (size_t)(k * NB) * ld + j * NB;
+        double s = 0;
+        for (int r = 0; r < NB; r++) s += Lkj[(size_t)r * ld + tid] * yk[r];
+        b[j * NB + tid] -= s;
+    }
+}
+
+// copy the pose part of the solution; pose part of computeScale
+__global__ void __launch_bounds__(256)
+k_ba_take_xp(const BaDev B, double lambda)
+{
+    __shared__ double s_w[8];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double sc = 0;
+    if (i < B.n) { const double x = B.bs[i]; B.x[i] = x; sc = x * (lambda * x + B.bp[i]); }
+    sc = warp_sum(sc);
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = sc;
+    __syncthreads();
+    if (threadIdx.x == 0) { double s = 0; for (int w = 0; w < 8; w++) s += s_w[w]; B.partial[blockIdx.x] = s; }
+}
+
+// warp per point: x_l = Dinv (b_l - sum_i Hpl_i^T x_i); point part of computeScale (per-block partials)
+__global__ void __launch_bounds__(256)
+k_ba_backsub(const BaDev B, double lambda)
+{
+    __shared__ double s_w[8];
+    const int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    double sc = 0;
+    if (p < B.P && B.pt_active[p]) {
+        double c[3] = {0, 0, 0};
+        for (int e = B.pt_start[p] + lane; e < B.pt_start[p + 1]; e += 32) {
+            if (B.e_level[e]) continue;
+            const int i1 = B.pose_idx[B.e_kf[e]];
+            if (i1 < 0) continue;
+            const double *W = &B.e_W[18 * (size_t)e];
+            const double *xp = &B.x[6 * i1];
+#pragma unroll
+            for (int a = 0; a < 6; a++) { c[0] -= W[3 * a] * xp[a]; c[1] -= W[3 * a + 1] * xp[a]; c[2] -= W[3 * a + 2] * xp[a]; }
+        }
+        c[0] = warp_sum(c[0]); c[1] = warp_sum(c[1]); c[2] = warp_sum(c[2]);
+        if (lane == 0) {
+            double D[9], Di[9];
+            for (int i = 0; i < 9; i++) D[i] = B.Hll[9 * (size_t)p + i];
+            D[0] += lambda; D[4] += lambda; D[8] += lambda;
+            inv3(D, Di);
+            const double bl[3] = {B.bl[3 * p], B.bl[3 * p + 1], B.bl[3 * p + 2]};
+            c[0] += bl[0]; c[1] += bl[1]; c[2] += bl[2];
+            double *xl = &B.x[B.n + 3 * (size_t)p];
+            for (int a = 0; a < 3; a++) {
+                xl[a] = Di[3 * a] * c[0] + Di[3 * a + 1] * c[1] + Di[3 * a + 2] * c[2];
+                sc += xl[a] * (lambda * xl[a] + bl[a]);
+            }
+        }
+    }
+    if (lane == 0) s_w[threadIdx.x >> 5] = sc;
+    __syncthreads();
+    if (threadIdx.x == 0) { double s = 0; for (int w = 0; w < 8; w++) s += s_w[w]; B.partial[blockIdx.x] = s; }
+}
+
+// push + oplus
+__global__ void __launch_bounds__(256)
+k_ba_update(const BaDev B)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < B.K) {
+        const int ip = B.pose_idx[i];
+        if (ip >= 0) {
+            const Se3 T = B.pose[i];
+            B.pose_bak[i] = T;
+            Se3 d, r;
+            se3_exp(&B.x[6 * ip], d);
+            se3_mul(d, T, r);
+            B.pose[i] = r;
+        }
+    }
+    const int p = i - B.K;
+    if (p >= 0 && p < B.P && B.pt_active[p]) {
+        for (int a = 0; a < 3; a++) { const double v = B.pt[3 * p + a]; B.pt_bak[3 * p + a] = v; B.pt[3 * p + a] = v + B.x[B.n + 3 * (size_t)p + a]; }
+    }
+}
+
+// pop
+__global__ void __launch_bounds__(256)
+k_ba_restore(const BaDev B)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < B.K && B.pose_idx[i] >= 0) B.pose[i] = B.pose_bak[i];
+    const int p = i - B.K;
+    if (p >= 0 && p < B.P && B.pt_active[p]) for (int a = 0; a < 3; a++) B.pt[3 * p + a] = B.pt_bak[3 * p + a];
+}
+
+// stored chi2 and current depth sign of every edge (Optimizer.cc:691-705, 734-766)
+__global__ void __launch_bounds__(256)
+k_ba_edge_check(const BaDev B, double *__restrict__ chi2, uint8_t *__restrict__ depth_ok)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= B.E) return;
+    chi2[e] = edge_chi2(B.e_err[2 * e], B.e_err[2 * e + 1], B.e_w[e]);
+    double Xc[3];
+    se3_map(B.pose[B.e_kf[e]], &B.pt[3 * B.e_point[e]], Xc);
+    depth_ok[e] = Xc[2] > 0.0;
+}
+
+__global__ void k_ba_import_poses(int K, const float *__restrict__ T, Se3 *__restrict__ pose)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < K) { Se3 s; se3_from_Tcw(T + 16 * i, s); pose[i] = s; }
+}
+
+__global__ void k_ba_export_poses(int K, const Se3 *__restrict__ pose, const uint8_t *__restrict__ fixed, float *__restrict__ T)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < K && fixed[i] != 2) se3_to_Tcw(pose[i], T + 16 * i);
+}
+
+}  // namespace orbs

@@ -93,6 +93,62 @@ struct KernelTimer {
     void release() { for (auto &r : recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); } recs.clear(); used = 0; }
 };
 
+// host<->device staging for ORBS_MEM_HOST calls: inputs are copied to pooled device buffers, outputs copied back in finish()
+struct StagePool {
+    static constexpr int kSlots = 40;
+    DevBuf buf[kSlots];
+    void release() { for (auto &b : buf) b.release(); }
+};
+
+struct Stager {
+    StagePool *pool; cudaStream_t stream; int memspace; int rc = ORBS_OK; int used = 0;
+    struct Out { void *host; void *dev; size_t bytes; };
+    std::vector<Out> outs;
+    Stager(StagePool *p, cudaStream_t st, int ms) : pool(p), stream(st), memspace(ms) {}
+    DevBuf *next(size_t bytes)
+    {
+        if (used >= StagePool::kSlots) { set_last_error("internal: staging pool exhausted"); rc = ORBS_E_INVALID; return nullptr; }
+        DevBuf &b = pool->buf[used++];
+        if ((rc = b.reserve(bytes + 16))) return nullptr;
+        return &b;
+    }
+    template <typename T> const T *in(const T *p, size_t n)
+    {
+        if (memspace == ORBS_MEM_DEVICE || !p || rc) return p;
+        DevBuf *b = next(n * sizeof(T));
+        if (!b) return nullptr;
+        cudaError_t e = cudaMemcpyAsync(b->p, p, n * sizeof(T), cudaMemcpyHostToDevice, stream);
+        if (e != cudaSuccess) { rc = cuda_fail(e, "stage in", __FILE__, __LINE__); return nullptr; }
+        return b->as<T>();
+    }
+    template <typename T> T *inout(T *p, size_t n, bool copy_in = true)
+    {
+        if (memspace == ORBS_MEM_DEVICE || !p || rc) return p;
+        DevBuf *b = next(n * sizeof(T));
+        if (!b) return nullptr;
+        if (copy_in) {
+            cudaError_t e = cudaMemcpyAsync(b->p, p, n * sizeof(T), cudaMemcpyHostToDevice, stream);
+            if (e != cudaSuccess) { rc = cuda_fail(e, "stage inout", __FILE__, __LINE__); return nullptr; }
+        }
+        outs.push_back({p, b->p, n * sizeof(T)});
+        return b->as<T>();
+    }
+    template <typename T> T *scratch(size_t n)      // device-only scratch in both memory spaces
+    {
+        if (rc) return nullptr;
+        DevBuf *b = next(n * sizeof(T));
+        return b ? b->as<T>() : nullptr;
+    }
+    int finish()
+    {
+        if (rc) return rc;
+        if (memspace == ORBS_MEM_DEVICE) return ORBS_OK;
+        for (auto &o : outs) ORBS_CUDA(cudaMemcpyAsync(o.host, o.dev, o.bytes, cudaMemcpyDeviceToHost, stream));
+        ORBS_CUDA(cudaStreamSynchronize(stream));
+        return ORBS_OK;
+    }
+};
+
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 }  // namespace orbs

@@ -398,48 +398,10 @@ struct orbm_handle {
     long long launches = 0;
     std::mutex mu;
     DevBuf cell_start, cell_items, prop, owner, top, ncand;
-    DevBuf stage[24];
-    int stage_used = 0;
+    StagePool pool;
 };
 
 namespace {
-// host<->device staging for ORBS_MEM_HOST calls
-struct Stager {
-    orbm_handle *h; int memspace; int rc = ORBS_OK;
-    struct Out { void *host; void *dev; size_t bytes; };
-    std::vector<Out> outs;
-    Stager(orbm_handle *hh, int ms) : h(hh), memspace(ms) { h->stage_used = 0; }
-    template <typename T> const T *in(const T *p, size_t n)
-    {
-        if (memspace == ORBS_MEM_DEVICE || !p || rc) return p;
-        DevBuf &b = h->stage[h->stage_used++];
-        if ((rc = b.reserve(n * sizeof(T) + 16))) return nullptr;
-        cudaError_t e = cudaMemcpyAsync(b.p, p, n * sizeof(T), cudaMemcpyHostToDevice, h->stream);
-        if (e != cudaSuccess) { rc = cuda_fail(e, "stage in", __FILE__, __LINE__); return nullptr; }
-        return b.as<T>();
-    }
-    template <typename T> T *inout(T *p, size_t n, bool copy_in = true)
-    {
-        if (memspace == ORBS_MEM_DEVICE || !p || rc) return p;
-        DevBuf &b = h->stage[h->stage_used++];
-        if ((rc = b.reserve(n * sizeof(T) + 16))) return nullptr;
-        if (copy_in) {
-            cudaError_t e = cudaMemcpyAsync(b.p, p, n * sizeof(T), cudaMemcpyHostToDevice, h->stream);
-            if (e != cudaSuccess) { rc = cuda_fail(e, "stage inout", __FILE__, __LINE__); return nullptr; }
-        }
-        outs.push_back({p, b.p, n * sizeof(T)});
-        return b.as<T>();
-    }
-    int finish()
-    {
-        if (rc) return rc;
-        if (memspace == ORBS_MEM_DEVICE) return ORBS_OK;
-        for (auto &o : outs) ORBS_CUDA(cudaMemcpyAsync(o.host, o.dev, o.bytes, cudaMemcpyDeviceToHost, h->stream));
-        ORBS_CUDA(cudaStreamSynchronize(h->stream));
-        return ORBS_OK;
-    }
-};
-
 GridParams make_grid(const float *b4)
 {
     GridParams g;
@@ -472,7 +434,7 @@ int orbm_destroy(orbm_handle *h)
     if (h->stream && h->own_stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
     else cudaDeviceSynchronize();
     h->cell_start.release(); h->cell_items.release(); h->prop.release(); h->owner.release(); h->top.release(); h->ncand.release();
-    for (auto &b : h->stage) b.release();
+    h->pool.release();
     delete h;
     return ORBS_OK;
 }
@@ -505,7 +467,7 @@ int orbm_descriptor_distance(orbm_handle *h, const uint8_t *a, int n, const uint
     if (n == 0 || m == 0) return ORBS_OK;
     std::lock_guard<std::mutex> lk(h->mu);
     ORBS_CUDA(cudaSetDevice(h->device));
-    Stager S(h, memspace);
+    Stager S(&h->pool, h->stream, memspace);
     const uint8_t *da = S.in(a, (size_t)n * 32), *db = S.in(b, (size_t)m * 32);
     int32_t *dout = S.inout(out, (size_t)n * m, false);
     if (S.rc) return S.rc;
@@ -527,7 +489,7 @@ int orbm_project_last_frame(orbm_handle *h, int n_frames, const float *Tcw, cons
     ORBS_REQUIRE(n_frames > 0 && q_slab > 0 && nlevels > 0, ORBS_E_INVALID, "non-positive size");
     std::lock_guard<std::mutex> lk(h->mu);
     ORBS_CUDA(cudaSetDevice(h->device));
-    Stager S(h, memspace);
+    Stager S(&h->pool, h->stream, memspace);
     const size_t nq = (size_t)n_frames * q_slab;
     // K4 / bounds4 are tiny host-side parameter blocks in both memory spaces
     const float *dT = S.in(Tcw, (size_t)n_frames * 16), *dsf = S.in(scale_factors, nlevels), *dX = S.in(Xw, nq * 3);
@@ -559,7 +521,7 @@ int orbm_search_by_projection(orbm_handle *h, int n_frames, const float *bounds4
     ORBS_REQUIRE(bounds4[2] > bounds4[0] && bounds4[3] > bounds4[1], ORBS_E_INVALID, "empty image bounds");
     std::lock_guard<std::mutex> lk(h->mu);
     ORBS_CUDA(cudaSetDevice(h->device));
-    Stager S(h, memspace);
+    Stager S(&h->pool, h->stream, memspace);
     const size_t nf = (size_t)n_frames * f_slab, nq = (size_t)n_frames * q_slab;
     SearchArgs A;
     A.f_slab = f_slab; A.q_slab = q_slab; A.g = make_grid(bounds4);

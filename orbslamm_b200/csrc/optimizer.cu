@@ -1,0 +1,391 @@
+// optimizer.cu -- host driver and C-ABI of the optimizer (orbo_*): PoseOptimization (device-resident LM, one CTA
+// per frame) and Local / Global bundle adjustment (host-driven Levenberg-Marquardt over CUDA kernels: per-point
+// Schur complement, dense Cholesky of the reduced pose system, back-substitution).
+//
+// Replaces S/src/Optimizer.cc:68-260, 262-474, 476-801 and the g2o stack behind it.
+#include <math.h>
+#include <string.h>
+#include <algorithm>
+#include <mutex>
+#include <vector>
+#include "common.cuh"
+#include "pose_opt.cuh"
+#include "ba_kernels.cuh"
+
+using namespace orbs;
+
+struct orbo_handle {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = true;
+    long long launches = 0;
+    std::mutex mu;
+    StagePool pool;          // pose optimisation staging
+    StagePool ba_pool;       // bundle adjustment buffers
+    PinnedBuf h_scalars;
+};
+
+extern "C" {
+
+int orbo_create(orbo_handle **out, int device)
+{
+    ORBS_REQUIRE(out, ORBS_E_INVALID, "orbo_create: null out pointer");
+    *out = nullptr;
+    ORBS_CUDA(cudaSetDevice(device));
+    orbo_handle *h = new orbo_handle();
+    h->device = device;
+    cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete h; return cuda_fail(e, "cudaStreamCreate", __FILE__, __LINE__); }
+    if (int rc = h->h_scalars.reserve(256)) { orbo_destroy(h); return rc; }
+    cudaFuncSetAttribute(k_chol_trsm, cudaFuncAttributeMaxDynamicSharedMemorySize, kCholSmem);
+    cudaFuncSetAttribute(k_chol_update, cudaFuncAttributeMaxDynamicSharedMemorySize, kCholSmem);
+    *out = h;
+    return ORBS_OK;
+}
+
+int orbo_destroy(orbo_handle *h)
+{
+    if (!h) return ORBS_OK;
+    cudaSetDevice(h->device);
+    if (h->stream && h->own_stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
+    else cudaDeviceSynchronize();
+    h->pool.release(); h->ba_pool.release(); h->h_scalars.release();
+    delete h;
+    return ORBS_OK;
+}
+
+void *orbo_stream(orbo_handle *h) { return h ? (void *)h->stream : nullptr; }
+
+int orbo_set_stream(orbo_handle *h, void *stream)
+{
+    ORBS_REQUIRE(h, ORBS_E_INVALID, "null handle");
+    std::lock_guard<std::mutex> lk(h->mu);
+    ORBS_CUDA(cudaSetDevice(h->device));
+    ORBS_CUDA(cudaStreamSynchronize(h->stream));
+    if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+    h->stream = (cudaStream_t)stream; h->own_stream = false;
+    return ORBS_OK;
+}
+
+int orbo_synchronize(orbo_handle *h)
+{
+    ORBS_REQUIRE(h, ORBS_E_INVALID, "null handle");
+    ORBS_CUDA(cudaSetDevice(h->device));
+    ORBS_CUDA(cudaStreamSynchronize(h->stream));
+    return ORBS_OK;
+}
+
+long long orbo_kernel_launches(const orbo_handle *h) { return h ? h->launches : 0; }
+
+int orbo_pose_optimization(orbo_handle *h, int n_frames, float *Tcw, const float *K4, const float *Xw, const float *obs,
+                           const float *inv_sigma2, const int32_t *counts, int slab, uint8_t *outlier, int32_t *n_inliers,
+                           int memspace)
+{
+    ORBS_REQUIRE(h && Tcw && K4 && Xw && obs && inv_sigma2 && counts && outlier && n_inliers, ORBS_E_INVALID, "null argument");
+    ORBS_REQUIRE(n_frames > 0 && slab > 0, ORBS_E_INVALID, "non-positive size");
+    std::lock_guard<std::mutex> lk(h->mu);
+    ORBS_CUDA(cudaSetDevice(h->device));
+    Stager S(&h->pool, h->stream, memspace);
+    const size_t ne = (size_t)n_frames * slab;
+    PoseArgs A;
+    A.slab = slab;
+    A.fx = K4[0]; A.fy = K4[1]; A.cx = K4[2]; A.cy = K4[3];          // float members of Frame, promoted to double by the edge
+    A.Tcw = S.inout(Tcw, (size_t)n_frames * 16);
+    A.Xw = S.in(Xw, ne * 3); A.obs = S.in(obs, ne * 2); A.w = S.in(inv_sigma2, ne);
+    A.counts = S.in(counts, n_frames);
+    A.outlier = S.inout(outlier, ne, false); A.n_inliers = S.inout(n_inliers, n_frames, false);
+    A.err = S.scratch<double>(ne * 2);
+    if (S.rc) return S.rc;
+    k_pose_optimization<<<n_frames, kPoseThreads, 0, h->stream>>>(A);
+    h->launches++;
+    ORBS_CUDA(cudaGetLastError());
+    return S.finish();
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------
+// Bundle adjustment driver
+namespace {
+
+struct BaHost {
+    orbo_handle *h;
+    cudaStream_t st;
+    BaDev B;
+    int ntiles = 0;
+    int err_blocks = 0, pt_blocks = 0, pose_blocks = 0, diag_blocks = 0, xp_blocks = 0;
+    double lambda = 0, ni = 2;
+    int nbad = 0;
+    const volatile int *stop = nullptr;
+    int lm_iterations = 0, lm_trials = 0, chol_failures = 0;
+    double *h_scal = nullptr;     // pinned [16]
+    int *h_flag = nullptr;        // pinned
+
+    bool terminate() const { return stop && *stop; }
+    void count(int n = 1) { h->launches += n; }
+
+    int read_scalars()
+    {
+        ORBS_CUDA(cudaMemcpyAsync(h_scal, B.scalars, 8 * sizeof(double), cudaMemcpyDeviceToHost, st));
+        ORBS_CUDA(cudaMemcpyAsync(h_flag, B.flags, sizeof(int), cudaMemcpyDeviceToHost, st));
+        ORBS_CUDA(cudaStreamSynchronize(st));
+        return ORBS_OK;
+    }
+
+    // computeActiveErrors + activeRobustChi2 -> scalars[0]
+    void errors()
+    {
+        k_ba_errors<<<err_blocks, 256, 0, st>>>(B);
+        k_reduce_partials<<<1, 256, 0, st>>>(B.partial, err_blocks, B.scalars, 0, 0);
+        count(2);
+    }
+
+    void build_system()
+    {
+        k_ba_build_points<<<pt_blocks, 256, 0, st>>>(B);
+        if (pose_blocks) k_ba_build_poses<<<pose_blocks, 256, 0, st>>>(B);
+        count(2);
+    }
+
+    // setLambda + Schur + factor + solve + back-substitution; scalars[1] (+ scalars[2]) = computeScale
+    int solve()
+    {
+        const int ld = B.ld;
+        ORBS_CUDA(cudaMemsetAsync(B.flags, 0, 4 * sizeof(int), st));
+        if (B.n > 0) {
+            ORBS_CUDA(cudaMemsetAsync(B.S, 0, (size_t)ld * ld * sizeof(double), st));
+            const int t = std::max(B.nA * 36, ld);
+            k_ba_schur_init<<<(t + 255) / 256, 256, 0, st>>>(B, lambda);
+            k_ba_schur<<<pt_blocks, 256, 0, st>>>(B, lambda);
+            count(2);
+            for (int k = 0; k < ntiles; k++) {
+                k_chol_potrf<<<1, 256, 0, st>>>(B.S, ld, k, B.flags);
+                const int m = ntiles - k - 1;
+                if (m > 0) {
+                    k_chol_trsm<<<m, 256, kCholSmem, st>>>(B.S, ld, k);
+                    k_chol_update<<<m * (m + 1) / 2, 256, kCholSmem, st>>>(B.S, ld, k, ntiles);
+                    count(2);
+                }
+                count(1);
+            }
+            for (int k = 0; k < ntiles; k++) {
+                k_trs_diag<<<1, NB, 0, st>>>(B.S, ld, k, B.bs, 0);
+                if (ntiles - k - 1 > 0) { k_trs_update<<<ntiles - k - 1, NB, 0, st>>>(B.S, ld, k, B.bs, 0); count(1); }
+                count(1);
+            }
+            for (int k = ntiles - 1; k >= 0; k--) {
+                k_trs_diag<<<1, NB, 0, st>>>(B.S, ld, k, B.bs, 1);
+                if (k > 0) { k_trs_update<<<k, NB, 0, st>>>(B.S, ld, k, B.bs, 1); count(1); }
+                count(1);
+            }
+            k_ba_take_xp<<<xp_blocks, 256, 0, st>>>(B, lambda);
+            k_reduce_partials<<<1, 256, 0, st>>>(B.partial, xp_blocks, B.scalars, 2, 0);
+            count(2);
+        } else {
+            ORBS_CUDA(cudaMemsetAsync(B.scalars + 2, 0, sizeof(double), st));
+        }
+        k_ba_backsub<<<pt_blocks, 256, 0, st>>>(B, lambda);
+        k_reduce_partials<<<1, 256, 0, st>>>(B.partial, pt_blocks, B.scalars, 1, 0);
+        count(2);
+        return ORBS_OK;
+    }
+
+    enum { LM_OK = 0, LM_TERMINATE = 1, LM_ERROR = 2 };
+
+    // OptimizationAlgorithmLevenberg::solve, optimization_algorithm_levenberg.cpp:61-164
+    int lm_iteration(int iteration)
+    {
+        errors();
+        build_system();
+        if (iteration == 0) {
+            k_ba_max_diag<<<diag_blocks, 256, 0, st>>>(B);
+            k_reduce_partials<<<1, 256, 0, st>>>(B.partial, diag_blocks, B.scalars, 3, 1);
+            count(2);
+        }
+        if (read_scalars()) return LM_ERROR;
+        double currentChi = h_scal[0];
+        const double iniChi = currentChi;
+        if (iteration == 0) { lambda = 1e-5 * h_scal[3]; ni = 2; nbad = 0; }
+        double rho = 0;
+        int qmax = 0;
+        const int upd_blocks = (B.K + B.P + 255) / 256;
+        do {
+            if (solve()) return LM_ERROR;
+            k_ba_update<<<upd_blocks, 256, 0, st>>>(B);
+            count(1);
+            errors();
+            if (read_scalars()) return LM_ERROR;
+            const bool ok2 = *h_flag == 0;
+            if (!ok2) chol_failures++;
+            double tempChi = h_scal[0];
+            if (!ok2) tempChi = 1.7976931348623157e308;
+            rho = currentChi - tempChi;
+            double scale = h_scal[1] + h_scal[2];
+            scale += 1e-3;
+            rho /= scale;
+            if (rho > 0 && std::isfinite(tempChi)) {
+                double alpha = 1. - pow((2 * rho - 1), 3);
+                alpha = std::min(alpha, 2. / 3.);
+                lambda *= std::max(1. / 3., alpha);
+                ni = 2;
+                currentChi = tempChi;
+            } else {
+                lambda *= ni; ni *= 2;
+                k_ba_restore<<<upd_blocks, 256, 0, st>>>(B);
+                count(1);
+            }
+            qmax++;
+            lm_trials++;
+        } while (rho < 0 && qmax < 10 && !terminate());
+        lm_iterations++;
+        if (qmax == 10 || rho == 0) return LM_TERMINATE;
+        if ((iniChi - currentChi) * 1e3 < iniChi) nbad++; else nbad = 0;
+        if (nbad >= 3) return LM_TERMINATE;
+        return LM_OK;
+    }
+
+    // SparseOptimizer::optimize, sparse_optimizer.cpp:354-419
+    int optimize(int iterations, bool any_active)
+    {
+        if (!any_active) return ORBS_OK;
+        for (int i = 0; i < iterations && !terminate(); i++) {
+            const int r = lm_iteration(i);
+            if (r == LM_ERROR) return ORBS_E_CUDA;
+            if (r != LM_OK) break;
+        }
+        return ORBS_OK;
+    }
+};
+
+}  // namespace
+
+extern "C" int orbo_bundle_adjust(orbo_handle *h, int K, float *poses, const uint8_t *fixed, const double *intr, int P, float *points,
+                                  int E, const int32_t *e_kf, const int32_t *e_pt, const float *e_uv, const float *e_inv_sigma2,
+                                  int two_stage, int its0, int its1, int robust, const volatile int *stop_flag,
+                                  double *e_chi2, uint8_t *e_depth_ok, uint8_t *e_outlier, int32_t *stats)
+{
+    ORBS_REQUIRE(h && poses && fixed && intr && points && e_kf && e_pt && e_uv && e_inv_sigma2, ORBS_E_INVALID, "null argument");
+    ORBS_REQUIRE(K > 0 && P > 0 && E > 0, ORBS_E_INVALID, "empty graph");
+    if (stats) stats[0] = stats[1] = stats[2] = stats[3] = 0;
+    if (stop_flag && *stop_flag) { if (stats) stats[3] = 1; return 1; }           // Optimizer.cc:678-680
+    for (int e = 0; e < E; e++)
+        ORBS_REQUIRE(e_kf[e] >= 0 && e_kf[e] < K && e_pt[e] >= 0 && e_pt[e] < P, ORBS_E_INVALID, "edge references a vertex out of range");
+    std::lock_guard<std::mutex> lk(h->mu);
+    ORBS_CUDA(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+
+    // ---- host-side graph layout: edges grouped by point (stable), second CSR by pose
+    std::vector<int> pt_start(P + 1, 0), order(E), pose_start(K + 1, 0), pose_edges(E), kf_s(E), pt_s(E);
+    for (int e = 0; e < E; e++) pt_start[e_pt[e] + 1]++;
+    for (int p = 0; p < P; p++) pt_start[p + 1] += pt_start[p];
+    { std::vector<int> fill(pt_start.begin(), pt_start.end() - 1); for (int e = 0; e < E; e++) order[fill[e_pt[e]]++] = e; }
+    std::vector<double> obs_s(2 * (size_t)E), w_s(E);
+    for (int j = 0; j < E; j++) {
+        const int e = order[j];
+        kf_s[j] = e_kf[e]; pt_s[j] = e_pt[e];
+        obs_s[2 * j] = e_uv[2 * e]; obs_s[2 * j + 1] = e_uv[2 * e + 1]; w_s[j] = e_inv_sigma2[e];
+        pose_start[e_kf[e] + 1]++;
+    }
+    for (int k = 0; k < K; k++) pose_start[k + 1] += pose_start[k];
+    { std::vector<int> fill(pose_start.begin(), pose_start.end() - 1); for (int j = 0; j < E; j++) pose_edges[fill[kf_s[j]]++] = j; }
+    std::vector<uint8_t> level(E, 0);
+    std::vector<double> pts_d(3 * (size_t)P);
+    for (size_t i = 0; i < pts_d.size(); i++) pts_d[i] = points[i];
+
+    // ---- device buffers
+    Stager S(&h->ba_pool, st, ORBS_MEM_HOST);
+    BaHost D;
+    D.h = h; D.st = st; D.stop = stop_flag;
+    D.h_scal = h->h_scalars.as<double>(); D.h_flag = (int *)(D.h_scal + 16);
+    BaDev &B = D.B;
+    memset(&B, 0, sizeof B);
+    B.K = K; B.P = P; B.E = E;
+    const float *d_T = S.in(poses, (size_t)K * 16);
+    const uint8_t *d_fixed = S.in(fixed, K);
+    B.intr = S.in(intr, (size_t)K * 4);
+    B.pt = const_cast<double *>(S.in(pts_d.data(), pts_d.size()));
+    B.pt_bak = S.scratch<double>(pts_d.size());
+    B.pose = S.scratch<Se3>(K); B.pose_bak = S.scratch<Se3>(K);
+    B.pt_start = S.in(pt_start.data(), pt_start.size()); B.e_kf = S.in(kf_s.data(), E); B.e_point = S.in(pt_s.data(), E);
+    B.e_obs = S.in(obs_s.data(), obs_s.size()); B.e_w = S.in(w_s.data(), E);
+    B.e_level = S.scratch<uint8_t>(E); B.e_err = S.scratch<double>(2 * (size_t)E); B.e_W = S.scratch<double>(18 * (size_t)E);
+    B.pose_start = S.in(pose_start.data(), pose_start.size()); B.pose_edges = S.in(pose_edges.data(), E);
+    int *d_pose_idx = S.scratch<int>(K); uint8_t *d_pt_active = S.scratch<uint8_t>(P);
+    B.pose_idx = d_pose_idx; B.pt_active = d_pt_active;
+    B.Hpp = S.scratch<double>(36 * (size_t)K); B.bp = S.scratch<double>(6 * (size_t)K + NB);
+    B.Hll = S.scratch<double>(9 * (size_t)P); B.bl = S.scratch<double>(3 * (size_t)P);
+    B.x = S.scratch<double>(6 * (size_t)K + 3 * (size_t)P);
+    const int ld_max = (int)align_up(6 * (size_t)K, NB);
+    B.S = S.scratch<double>((size_t)ld_max * ld_max); B.bs = S.scratch<double>(ld_max);
+    const int max_blocks = std::max({(E + 255) / 256, (P + 7) / 8, (K + P + 255) / 256, (6 * K + 255) / 256}) + 1;
+    B.partial = S.scratch<double>(max_blocks); B.scalars = S.scratch<double>(8); B.flags = S.scratch<int>(4);
+    double *d_chi2 = S.scratch<double>(E); uint8_t *d_depth = S.scratch<uint8_t>(E);
+    float *d_Tout = S.scratch<float>((size_t)K * 16);
+    if (S.rc) return S.rc;
+    B.delta = (double)(float)sqrt(5.991); B.dsqr = B.delta * B.delta;              // thHuberMono, Optimizer.cc:591
+    ORBS_CUDA(cudaMemsetAsync(B.e_level, 0, E, st));
+    ORBS_CUDA(cudaMemsetAsync(B.e_err, 0, 2 * (size_t)E * sizeof(double), st));
+    ORBS_CUDA(cudaMemsetAsync(B.scalars, 0, 8 * sizeof(double), st));
+    k_ba_import_poses<<<(K + 255) / 256, 256, 0, st>>>(K, d_T, B.pose);
+    ORBS_CUDA(cudaMemcpyAsync(d_Tout, d_T, (size_t)K * 16 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    h->launches++;
+    D.err_blocks = (E + 255) / 256; D.pt_blocks = (P + 7) / 8; D.pose_blocks = (K + 7) / 8;
+
+    // initializeOptimization(level 0) + buildIndexMapping, sparse_optimizer.cpp:166-267
+    std::vector<int> pose_idx(K);
+    std::vector<uint8_t> pt_active(P);
+    auto init_active = [&]() -> int {
+        std::vector<uint8_t> pose_act(K, 0);
+        std::fill(pt_active.begin(), pt_active.end(), 0);
+        bool any = false;
+        for (int j = 0; j < E; j++) if (!level[j]) { pose_act[kf_s[j]] = 1; pt_active[pt_s[j]] = 1; any = true; }
+        int nA = 0;
+        for (int k = 0; k < K; k++) pose_idx[k] = (pose_act[k] && !fixed[k]) ? nA++ : -1;
+        B.nA = nA; B.n = 6 * nA; B.ld = (int)align_up((size_t)B.n, NB); D.ntiles = B.ld / NB;
+        D.diag_blocks = (nA + P + 255) / 256; D.xp_blocks = std::max(1, (B.n + 255) / 256);
+        ORBS_CUDA(cudaMemcpyAsync(d_pose_idx, pose_idx.data(), K * sizeof(int), cudaMemcpyHostToDevice, st));
+        ORBS_CUDA(cudaMemcpyAsync(d_pt_active, pt_active.data(), P, cudaMemcpyHostToDevice, st));
+        ORBS_CUDA(cudaStreamSynchronize(st));
+        return any ? 1 : 0;
+    };
+
+    int any = init_active();
+    if (any < 0) return any;
+    B.robust = two_stage ? 1 : (robust ? 1 : 0);
+    int rc = D.optimize(its0, any == 1);
+    if (rc) return rc;
+    std::vector<double> chi2_s(E);
+    std::vector<uint8_t> depth_s(E);
+    auto edge_check = [&]() -> int {
+        k_ba_edge_check<<<(E + 255) / 256, 256, 0, st>>>(B, d_chi2, d_depth);
+        h->launches++;
+        ORBS_CUDA(cudaMemcpyAsync(chi2_s.data(), d_chi2, E * sizeof(double), cudaMemcpyDeviceToHost, st));
+        ORBS_CUDA(cudaMemcpyAsync(depth_s.data(), d_depth, E, cudaMemcpyDeviceToHost, st));
+        ORBS_CUDA(cudaStreamSynchronize(st));
+        return ORBS_OK;
+    };
+    if (two_stage && !(stop_flag && *stop_flag)) {
+        if ((rc = edge_check())) return rc;
+        for (int j = 0; j < E; j++) if (chi2_s[j] > 5.991 || !depth_s[j]) level[j] = 1;      // Optimizer.cc:691-705
+        ORBS_CUDA(cudaMemcpyAsync(B.e_level, level.data(), E, cudaMemcpyHostToDevice, st));
+        B.robust = 0;
+        any = init_active();
+        if (any < 0) return any;
+        if ((rc = D.optimize(its1, any == 1))) return rc;
+    }
+    if ((rc = edge_check())) return rc;
+    for (int j = 0; j < E; j++) {                                                         // Optimizer.cc:734-766
+        const int e = order[j];
+        if (e_chi2) e_chi2[e] = chi2_s[j];
+        if (e_depth_ok) e_depth_ok[e] = depth_s[j];
+        if (e_outlier) e_outlier[e] = (uint8_t)(chi2_s[j] > 5.991 || !depth_s[j]);
+    }
+    k_ba_export_poses<<<(K + 255) / 256, 256, 0, st>>>(K, B.pose, d_fixed, d_Tout);
+    h->launches++;
+    ORBS_CUDA(cudaMemcpyAsync(poses, d_Tout, (size_t)K * 16 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    ORBS_CUDA(cudaMemcpyAsync(pts_d.data(), B.pt, pts_d.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+    ORBS_CUDA(cudaStreamSynchronize(st));
+    for (size_t i = 0; i < pts_d.size(); i++) points[i] = (float)pts_d[i];
+    if (stats) { stats[0] = D.lm_iterations; stats[1] = D.lm_trials; stats[2] = D.chol_failures; stats[3] = 0; }
+    return ORBS_OK;
+}

@@ -1,0 +1,236 @@
+// pose_opt.cuh -- Optimizer::PoseOptimization (Optimizer.cc:262-474) as one persistent CTA per frame.
+// The whole 4 x 10 Levenberg-Marquardt schedule of the reference (g2o OptimizationAlgorithmLevenberg on a single
+// VertexSE3Expmap with unary EdgeSE3ProjectXYZOnlyPose edges, LinearSolverDense 6x6) runs on the device with no
+// host round trip; block-level reductions are fixed-order (deterministic).
+#pragma once
+#include "common.cuh"
+#include "se3.cuh"
+
+namespace orbs {
+
+struct PoseArgs {
+    int slab;
+    double fx, fy, cx, cy;
+    float *Tcw;                 // [n_frames, 16] in/out
+    const float *Xw, *obs, *w;  // [n_frames*slab, 3|2|1]
+    const int *counts;
+    uint8_t *outlier;           // [n_frames*slab]
+    int *n_inliers;             // [n_frames]
+    double *err;                // scratch [n_frames*slab, 2]: the stored _error of every edge
+};
+
+constexpr int kPoseThreads = 256;
+constexpr int kPoseNV = 28;      // 21 (upper H) + 6 (b) + 1 (chi2)
+
+// fixed-order block reduction of NV doubles per thread; result valid in out[0..NV) for all threads after return
+template <int NV>
+__device__ __forceinline__ void block_reduce_vec(double (&acc)[NV], double *warp_buf /*[nwarps*NV]*/, double *out /*[NV]*/)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+    for (int v = 0; v < NV; v++) {
+        double x = acc[v];
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) x += __shfl_down_sync(0xffffffffu, x, d);
+        if (lane == 0) warp_buf[wid * NV + v] = x;
+    }
+    __syncthreads();
+    if (threadIdx.x < NV) {
+        double s = 0;
+        for (int w = 0; w < nw; w++) s += warp_buf[w * NV + threadIdx.x];
+        out[threadIdx.x] = s;
+    }
+    __syncthreads();
+}
+
+// LDL^T solve of the 6x6 system (H + lambda I) x = b; H given by its upper triangle (row-major packed 21).
+// LinearSolverDense: fails unless the factorisation is positive (linear_solver_dense.h:107-112).
+__device__ inline bool solve6(const double *Hu, const double *b, double lambda, double *x)
+{
+    double A[36];
+    int p = 0;
+    for (int r = 0; r < 6; r++) for (int c = r; c < 6; c++) { A[6 * r + c] = Hu[p]; A[6 * c + r] = Hu[p]; p++; }
+    for (int i = 0; i < 6; i++) A[7 * i] += lambda;
+    for (int i = 0; i < 6; i++)
+        for (int j = 0; j <= i; j++) {
+            double s = A[6 * i + j];
+            for (int k = 0; k < j; k++) s -= A[6 * i + k] * A[6 * j + k] * A[7 * k];
+            if (j < i) A[6 * i + j] = s / A[7 * j];
+            else { if (!(s > 0.0)) return false; A[7 * i] = s; }
+        }
+    for (int i = 0; i < 6; i++) { double s = b[i]; for (int k = 0; k < i; k++) s -= A[6 * i + k] * x[k]; x[i] = s; }
+    for (int i = 0; i < 6; i++) x[i] /= A[7 * i];
+    for (int i = 5; i >= 0; i--) { const double xi = x[i]; for (int k = 0; k < i; k++) x[k] -= A[6 * i + k] * xi; }
+    return true;
+}
+
+__global__ void __launch_bounds__(kPoseThreads)
+k_pose_optimization(const PoseArgs A)
+{
+    __shared__ double s_warp[(kPoseThreads / 32) * kPoseNV];
+    __shared__ double s_red[kPoseNV];
+    __shared__ Se3 s_pose, s_backup;
+    __shared__ double s_lambda, s_ni, s_cur_chi, s_x[6];
+    __shared__ int s_nbad_lm, s_flag, s_ok2;
+    __shared__ double s_rho;
+    const int f = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+    const int M = A.counts[f];
+    const size_t o = (size_t)f * A.slab;
+    const float *Xw = A.Xw + 3 * o, *obs = A.obs + 2 * o, *wgt = A.w + o;
+    uint8_t *outlier = A.outlier + o;
+    double *err = A.err + 2 * o;
+    const double in[4] = {A.fx, A.fy, A.cx, A.cy};
+    const double delta = (double)(float)sqrt(5.991), dsqr = delta * delta;   // const float deltaMono = sqrt(5.991), Optimizer.cc:295
+    for (int i = tid; i < M; i += nt) outlier[i] = 0;
+    if (tid < 6) s_x[tid] = 0.0;
+    if (M < 3) { if (tid == 0) A.n_inliers[f] = 0; return; }                 // Optimizer.cc:387-388
+    __syncthreads();
+    int n_bad_total = 0;
+    bool robust = true;
+    for (int it = 0; it < 4; it++) {
+        if (tid == 0) se3_from_Tcw(A.Tcw + 16 * f, s_pose);                  // reset to the initial pose, Optimizer.cc:400
+        __syncthreads();
+        // any active edge?  (initializeOptimization(0): level-0 edges only)
+        int my_act = 0;
+        for (int i = tid; i < M; i += nt) my_act += !outlier[i];
+        const int n_act = __syncthreads_count(my_act > 0);
+        if (n_act > 0) {
+            for (int iter = 0; iter < 10; iter++) {
+                // computeActiveErrors + activeRobustChi2 + buildSystem
+                double acc[kPoseNV];
+#pragma unroll
+                for (int v = 0; v < kPoseNV; v++) acc[v] = 0;
+                const Se3 pose = s_pose;
+                for (int i = tid; i < M; i += nt) {
+                    if (outlier[i]) continue;
+                    const double X[3] = {(double)Xw[3 * i], (double)Xw[3 * i + 1], (double)Xw[3 * i + 2]};
+                    double Xc[3], e[2], Jp[12];
+                    se3_map(pose, X, Xc);
+                    reproj_error(Xc, in, (double)obs[2 * i], (double)obs[2 * i + 1], e);
+                    err[2 * i] = e[0]; err[2 * i + 1] = e[1];
+                    const double w = (double)wgt[i];
+                    const double chi2 = e[0] * (w * e[0] + 0.0 * e[1]) + e[1] * (0.0 * e[0] + w * e[1]);
+                    double rho0 = chi2, rho1 = 1.0;
+                    if (robust) huber(chi2, delta, dsqr, rho0, rho1);
+                    acc[27] += rho0;
+                    jac_pose_only(Xc, A.fx, A.fy, Jp);
+                    const double wo = rho1 * w;
+                    const double r0 = rho1 * w * e[0], r1 = rho1 * w * e[1];         // b -= rho' A^T omega e
+                    int p = 0;
+#pragma unroll
+                    for (int a = 0; a < 6; a++) {
+                        acc[21 + a] -= Jp[a] * r0 + Jp[6 + a] * r1;
+#pragma unroll
+                        for (int c = a; c < 6; c++) { acc[p] += Jp[a] * wo * Jp[c] + Jp[6 + a] * wo * Jp[6 + c]; p++; }
+                    }
+                }
+                block_reduce_vec<kPoseNV>(acc, s_warp, s_red);
+                if (tid == 0) {
+                    s_cur_chi = s_red[27];
+                    if (iter == 0) {                                                 // computeLambdaInit
+                        double mx = 0.;
+                        int p = 0;
+                        for (int a = 0; a < 6; a++) { mx = fmax(fabs(s_red[p]), mx); p += 6 - a; }
+                        s_lambda = 1e-5 * mx; s_ni = 2; s_nbad_lm = 0;
+                    }
+                }
+                __syncthreads();
+                const double ini_chi = s_cur_chi;
+                int qmax = 0;
+                double rho = 0;
+                do {
+                    if (tid == 0) {
+                        s_backup = s_pose;
+                        s_ok2 = solve6(s_red, s_red + 21, s_lambda, s_x) ? 1 : 0;
+                        Se3 d, r;
+                        se3_exp(s_x, d);
+                        se3_mul(d, s_pose, r);
+                        s_pose = r;
+                    }
+                    __syncthreads();
+                    const Se3 np = s_pose;
+                    double chi[1] = {0};
+                    for (int i = tid; i < M; i += nt) {
+                        if (outlier[i]) continue;
+                        const double X[3] = {(double)Xw[3 * i], (double)Xw[3 * i + 1], (double)Xw[3 * i + 2]};
+                        double Xc[3], e[2];
+                        se3_map(np, X, Xc);
+                        reproj_error(Xc, in, (double)obs[2 * i], (double)obs[2 * i + 1], e);
+                        err[2 * i] = e[0]; err[2 * i + 1] = e[1];
+                        const double w = (double)wgt[i];
+                        const double chi2 = e[0] * (w * e[0] + 0.0 * e[1]) + e[1] * (0.0 * e[0] + w * e[1]);
+                        double rho0 = chi2, rho1 = 1.0;
+                        if (robust) huber(chi2, delta, dsqr, rho0, rho1);
+                        chi[0] += rho0;
+                    }
+                    __shared__ double s_chi_out[1];
+                    block_reduce_vec<1>(chi, s_warp, s_chi_out);
+                    if (tid == 0) {
+                        double temp_chi = s_chi_out[0];
+                        if (!s_ok2) temp_chi = 1.7976931348623157e308;
+                        double r = s_cur_chi - temp_chi;
+                        double scale = 0.;
+                        for (int j = 0; j < 6; j++) scale += s_x[j] * (s_lambda * s_x[j] + s_red[21 + j]);
+                        scale += 1e-3;
+                        r /= scale;
+                        if (r > 0 && isfinite(temp_chi)) {
+                            double alpha = 1. - pow((2 * r - 1), 3.0);
+                            alpha = fmin(alpha, 2. / 3.);
+                            s_lambda *= fmax(1. / 3., alpha);
+                            s_ni = 2; s_cur_chi = temp_chi;
+                        } else {
+                            s_lambda *= s_ni; s_ni *= 2;
+                            s_pose = s_backup;
+                        }
+                        s_rho = r;
+                    }
+                    __syncthreads();
+                    rho = s_rho;
+                    qmax++;
+                    __syncthreads();
+                } while (rho < 0 && qmax < 10);
+                bool terminate = (qmax == 10 || rho == 0);
+                if (!terminate) {
+                    if (tid == 0) {
+                        if ((ini_chi - s_cur_chi) * 1e3 < ini_chi) s_nbad_lm++; else s_nbad_lm = 0;
+                        s_flag = s_nbad_lm >= 3;
+                    }
+                    __syncthreads();
+                    terminate = s_flag != 0;
+                    __syncthreads();
+                }
+                if (terminate) break;
+            }
+        }
+        // classify (Optimizer.cc:405-432)
+        const Se3 pose = s_pose;
+        int my_bad = 0;
+        for (int i = tid; i < M; i += nt) {
+            if (outlier[i]) {
+                const double X[3] = {(double)Xw[3 * i], (double)Xw[3 * i + 1], (double)Xw[3 * i + 2]};
+                double Xc[3], e[2];
+                se3_map(pose, X, Xc);
+                reproj_error(Xc, in, (double)obs[2 * i], (double)obs[2 * i + 1], e);
+                err[2 * i] = e[0]; err[2 * i + 1] = e[1];
+            }
+            const double e0 = err[2 * i], e1 = err[2 * i + 1], w = (double)wgt[i];
+            const float chi2 = (float)(e0 * (w * e0 + 0.0 * e1) + e1 * (0.0 * e0 + w * e1));
+            if (chi2 > 5.991f) { outlier[i] = 1; my_bad++; } else outlier[i] = 0;
+        }
+        if (it == 2) robust = false;
+        __shared__ int s_bad;
+        if (tid == 0) s_bad = 0;
+        __syncthreads();
+        if (my_bad) atomicAdd(&s_bad, my_bad);
+        __syncthreads();
+        n_bad_total = s_bad;
+        __syncthreads();
+        if (M < 10) break;                                                            // optimizer.edges().size()<10
+    }
+    if (tid == 0) {
+        se3_to_Tcw(s_pose, A.Tcw + 16 * f);
+        A.n_inliers[f] = M - n_bad_total;
+    }
+}
+
+}  // namespace orbs

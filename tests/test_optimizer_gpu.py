@@ -1,0 +1,81 @@
+"""GPU parity: PoseOptimization and Local / Global bundle adjustment vs the fp64 oracle (1e-5 relative)."""
+import numpy as np
+import pytest
+
+import oracle
+from orbslamm_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5      # north_star: pose/point updates match the reference g2o path to 1e-5 relative
+
+
+def _rel(a, b):
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-12)
+
+
+def _pose_cases(n, seed=0):
+    g = synth.ba_graph(K=24, P=1500, seed=seed, min_obs=5, max_obs=12)
+    K4 = np.array(g["intr"], np.float32)
+    cases = []
+    for k in range(2, 2 + n):
+        m = g["kf"] == k
+        Xw = g["gt_points"][g["pt"][m]].astype(np.float32)
+        cases.append(dict(T=g["poses"][k], Xw=Xw, obs=g["uv"][m], w=g["inv_sigma2"][m]))
+    return K4, cases
+
+
+def test_pose_optimization_matches_oracle(lib):
+    import orbslamm_b200 as ob
+    from helpers import slab
+    K4, cases = _pose_cases(12)
+    cases.append(dict(T=cases[0]["T"], Xw=cases[0]["Xw"][:2], obs=cases[0]["obs"][:2], w=cases[0]["w"][:2]))    # < 3 correspondences
+    cases.append(dict(T=cases[1]["T"], Xw=cases[1]["Xw"][:8], obs=cases[1]["obs"][:8], w=cases[1]["w"][:8]))    # < 10 edges: one round
+    n = len(cases); S = max(len(c["Xw"]) for c in cases)
+    opt = ob.Optimizer()
+    T, outl, ninl = opt.PoseOptimization(np.stack([c["T"] for c in cases]), K4, slab([c["Xw"] for c in cases], S, np.float32, (3,)),
+                                         slab([c["obs"] for c in cases], S, np.float32, (2,)), slab([c["w"] for c in cases], S, np.float32),
+                                         np.array([len(c["Xw"]) for c in cases], np.int32))
+    for i, c in enumerate(cases):
+        Tr, outr, nr = oracle.pose_optimization(c["T"], c["Xw"], c["obs"], c["w"], K4)
+        m = len(c["Xw"])
+        assert ninl[i] == nr, f"case {i}: inliers {ninl[i]} vs {nr}"
+        assert np.array_equal(outl[i, :m], outr), f"case {i}: outlier flags differ"
+        if m >= 3:
+            assert _rel(T[i], Tr) < RTOL, f"case {i}: pose rel err {_rel(T[i], Tr)}"
+        else:
+            assert np.array_equal(T[i], c["T"])
+
+
+@pytest.mark.parametrize("K,P", [(10, 200), (40, 2500), (100, 10000)])
+def test_local_ba_matches_oracle(lib, K, P):
+    import orbslamm_b200 as ob
+    g = synth.ba_graph(K=K, P=P, seed=42)
+    opt = ob.Optimizer()
+    got = opt.LocalBundleAdjustment(g["poses"], g["fixed"], g["intr"], g["points"], g["kf"], g["pt"], g["uv"], g["inv_sigma2"])
+    ref = oracle.bundle_adjust(g["poses"], g["fixed"], g["intr"], g["points"], g["kf"], g["pt"], g["uv"], g["inv_sigma2"], True, 5, 10, True)
+    assert got["lm_iterations"] == ref["lm_iterations"] and got["lm_trials"] == ref["lm_trials"]
+    assert got["chol_failures"] == 0
+    assert _rel(got["poses"], ref["poses"]) < RTOL
+    assert _rel(got["points"], ref["points"]) < RTOL
+    # the update itself (what BA changed) to 1e-5 relative as well
+    dp_ref = ref["points"] - g["points"]
+    assert np.abs((got["points"] - g["points"]) - dp_ref).max() < RTOL * max(np.abs(dp_ref).max(), 1e-12) + 2e-6
+    near = np.abs(ref["chi2"] - 5.991) < 1e-6
+    assert np.array_equal(got["outlier"][~near], ref["outlier"][~near])
+    assert np.allclose(got["chi2"], ref["chi2"], rtol=1e-6, atol=1e-9)
+    # fixed cameras outside the window are never written, KF 0 goes through the SE3Quat round trip
+    assert np.array_equal(got["poses"][1], g["poses"][1])
+
+
+def test_global_ba_and_abort(lib):
+    import orbslamm_b200 as ob
+    g = synth.ba_graph(K=30, P=1500, seed=7)
+    opt = ob.Optimizer()
+    got = opt.BundleAdjustment(g["poses"], g["fixed"], g["intr"], g["points"], g["kf"], g["pt"], g["uv"], g["inv_sigma2"], 20, False)
+    ref = oracle.bundle_adjust(g["poses"], g["fixed"], g["intr"], g["points"], g["kf"], g["pt"], g["uv"], g["inv_sigma2"], False, 20, 0, False)
+    assert got["lm_iterations"] == ref["lm_iterations"]
+    assert _rel(got["poses"], ref["poses"]) < RTOL and _rel(got["points"], ref["points"]) < RTOL
+    stop = np.ones(1, np.int32)
+    ab = opt.LocalBundleAdjustment(g["poses"], g["fixed"], g["intr"], g["points"], g["kf"], g["pt"], g["uv"], g["inv_sigma2"], stop_flag=stop)
+    assert ab["aborted"] and np.array_equal(ab["poses"], g["poses"]) and np.array_equal(ab["points"], g["points"])
