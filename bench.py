@@ -337,6 +337,8 @@ def main():
     ap.add_argument("--workload", default="frontend", choices=["frontend", "ba"])
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-frames", type=int, default=100, help="bounded CPU-baseline sample (frames)")
+    ap.add_argument("--ba-kf", type=int, default=500)
+    ap.add_argument("--ba-pts", type=int, default=50000)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1))

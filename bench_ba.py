@@ -1,0 +1,134 @@
+"""BA leg of bench.py: LocalBA LM iterations/s on the synthetic 500-KF / 50k-point covisibility graph.
+
+One "step" = one Optimizer::LocalBundleAdjustment call on the graph (reference schedule: 5 robust + 10 non-robust LM
+iterations; each iteration = errors -> linearise -> Schur -> dense Cholesky -> back-substitute -> update -> errors).
+value = LM iterations / second inside the LM loops with the graph resident in HBM (orbo_last_ba_timing);
+e2e   = LM iterations / second of the whole host-buffer C-ABI call (graph layout on the host, H2D, LM, D2H).
+"""
+import json
+import os
+import time
+
+import numpy as np
+
+from orbslamm_b200 import synth
+
+BA_K, BA_P = 500, 50000
+
+
+def _alg_bytes(K, P, E, ld):
+    # 3 edge passes x 20 B + 2 x (88 B K + 24 B P) + write+read of the dense reduced system
+    return 3 * 20 * E + 2 * (88 * K + 24 * P) + 2 * 8 * ld * ld
+
+
+def bench_ba(args, rank, world):
+    import torch
+    import orbslamm_b200 as ob
+    from orbslamm_b200 import build as obuild
+    from bench import ClockSampler, peaks
+    obuild.build()
+    dev = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(dev)
+    K, P = args.ba_kf, args.ba_pts
+    g = synth.ba_graph(K=K, P=P, seed=42 + rank)
+    E = len(g["kf"])
+    opt = ob.Optimizer(device=dev)
+    run = lambda: opt.LocalBundleAdjustment(g["poses"], g["fixed"], g["intr"], g["points"], g["kf"], g["pt"], g["uv"], g["inv_sigma2"])
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        run()
+    barrier()
+    l0 = opt.kernel_launches()
+    opt.set_profiling(True)
+    sampler = ClockSampler(dev); sampler.start()
+    loop_s = total_s = 0.0
+    iters = trials = 0
+    t_wall = time.time()
+    for i in range(args.steps):
+        flush.fill_(i & 0xff)
+        torch.cuda.synchronize()
+        r = run()
+        tm = opt.last_ba_timing()
+        loop_s += tm["lm_loop_s"]; total_s += tm["total_s"]
+        iters += r["lm_iterations"]; trials += r["lm_trials"]
+        ld = tm["ld"]
+    barrier()
+    wall = time.time() - t_wall
+    clocks = sampler.stop()
+    ktimes = opt.kernel_times()
+    opt.set_profiling(False)
+    launches = opt.kernel_launches() - l0
+    if world > 1:
+        tt = torch.tensor([loop_s, total_s], device="cuda", dtype=torch.float64)
+        torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.MAX)
+        loop_s, total_s = float(tt[0]), float(tt[1])
+    its = world * iters / loop_s
+    e2e = world * iters / total_s
+    hbm, how = peaks()
+    # dominant kernel by device time; algorithmic bytes per launch
+    dom = max(ktimes, key=lambda k: ktimes[k][0])
+    dom_ms, dom_n = ktimes[dom]
+    alg = {"errors": 20 * E + 88 * K + 24 * P + 16 * E, "build_points": 20 * E + 88 * K + 24 * P + 144 * E + 96 * P,
+           "build_poses": 20 * E + 88 * K + 24 * P + 336 * K, "schur": 144 * E + 96 * P + 8 * 36 * 3.5 * E,
+           "chol_potrf": 2 * 8 * 64 * 64, "chol_trsm": None, "chol_update": None, "tri_solves": 8 * ld * ld,
+           "backsub": 144 * E + 96 * P + 24 * P, "update": 2 * (56 * K + 24 * P) * 2, "memset_S": 8 * ld * ld}
+    # tiled Cholesky: one update launch at step k touches (m(m+1)/2) C tiles (read+write) + their A panels
+    nt = ld // 64
+    per_launch_ms = dom_ms / max(dom_n, 1)
+    if dom in ("chol_update", "chol_trsm"):
+        # average over the nt-1 launches of one factorisation: sum_k tiles_k * 64*64*8 * (2 C + 2 A) / (nt - 1)
+        tiles = sum((nt - k - 1) * (nt - k) // 2 for k in range(nt)) if dom == "chol_update" else sum(nt - k - 1 for k in range(nt))
+        alg_bytes = tiles * 64 * 64 * 8 * (4 if dom == "chol_update" else 3) / max(nt - 1, 1)
+    else:
+        alg_bytes = alg[dom]
+    achieved = alg_bytes / (per_launch_ms * 1e-3) / 1e9
+    lm_total_ms = loop_s * 1e3
+    roofline = {"kernel": dom, "bound": "hbm", "achieved": round(achieved, 2), "peak": hbm, "unit": "GB/s", "frac": round(achieved / hbm, 5),
+                "traffic": None, "peak_source": how, "algorithmic_bytes_per_launch": int(alg_bytes), "avg_launch_ms": round(per_launch_ms, 5),
+                "kernel_share_of_step": {k: round(v[0] / max(lm_total_ms, 1e-9), 4) for k, v in ktimes.items()},
+                "whole_iteration": {"algorithmic_bytes": int(_alg_bytes(K, P, E, ld)),
+                                    "achieved_GBps": round(_alg_bytes(K, P, E, ld) * iters / loop_s / 1e9, 2)}}
+    graph_bytes = K * 64 + K + K * 32 + P * 12 + E * (4 + 4 + 8 + 4)
+    out = {"metric": "LocalBA LM iters/s @500KF/50k pts", "value": round(its, 2), "unit": "LM iterations/s", "n_gpus": world, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": round(loop_s * 1e3 / args.steps, 3), "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": f"synthetic covisibility graph {K} KF / {P} points / {E} observations, LocalBA schedule 5 robust + 10 non-robust LM its",
+                      "lm_iterations_per_step": iters / args.steps, "lm_trials_per_step": trials / args.steps,
+                      "l2": "256 MiB flush buffer written between timed steps (untimed)", "reduced_system": f"{ld}x{ld} fp64 dense",
+                      "parallelism": f"independent graphs x{world}" if world > 1 else "1 GPU"},
+           "e2e": {"value": round(e2e, 2), "unit": "LM iterations/s", "h2d_bytes_per_step": int(graph_bytes), "d2h_bytes_per_step": int(K * 64 + P * 12 + E * 10)},
+           "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "wall_s": round(wall, 3)}
+    if rank == 0:
+        out["cpu_baseline"] = cpu_baseline_ba(K, P, 1)
+    return out
+
+
+def cpu_baseline_ba(K, P, repeats):
+    import oracle
+    g = synth.ba_graph(K=K, P=P, seed=42)
+    t0 = time.perf_counter()
+    iters = 0
+    for _ in range(repeats):
+        r = oracle.bundle_adjust(g["poses"], g["fixed"], g["intr"], g["points"], g["kf"], g["pt"], g["uv"], g["inv_sigma2"], True, 5, 10, True)
+        iters += r["lm_iterations"]
+    s = time.perf_counter() - t0
+    return {"value": round(iters / s, 3), "unit": "LM iterations/s", "cores": 1, "kind": "port",
+            "sample": f"{repeats} LocalBA call(s) on the same {K} KF / {P} pt graph ({iters} LM iterations, {s:.1f} s); fp64 restatement of the "
+                      "g2o path with a profile LDLT of the reduced system, 1 thread (g2o OpenMP is off in the reference)"}
+
+
+def reference_line(args):
+    K, P = args.ba_kf, args.ba_pts
+    cb = cpu_baseline_ba(K, P, 2)
+    return {"impl": "reference", "metric": "LocalBA LM iters/s @500KF/50k pts", "value": cb["value"], "unit": "LM iterations/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(15e3 / cb["value"], 2), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"synthetic covisibility graph {K} KF / {P} points, LocalBA schedule 5 robust + 10 non-robust LM its",
+                       "note": "reference C++ (g2o + Eigen) cannot be built here; this is the oracle port, single thread like the reference"},
+            "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "LM iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}

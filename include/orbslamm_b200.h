@@ -218,6 +218,14 @@ int orbo_bundle_adjust(orbo_handle *h, int K, float *poses, const uint8_t *fixed
                        int two_stage, int its0, int its1, int robust, const volatile int *stop_flag,
                        double *e_chi2, uint8_t *e_depth_ok, uint8_t *e_outlier, int32_t *stats);
 
+/* Bench bookkeeping for the last orbo_bundle_adjust call: out4 = { seconds inside the LM loops (graph resident on the
+ * device), seconds of the whole call, seconds of host graph layout + H2D, leading dimension of the reduced system }. */
+int orbo_last_ba_timing(orbo_handle *h, double *out4);
+/* Per-kernel CUDA-event timing of the BA kernels.  ids: 0 errors, 1 build_points, 2 build_poses, 3 schur, 4 chol_potrf,
+ * 5 chol_trsm, 6 chol_update, 7 triangular solves, 8 backsub, 9 update, 10 memset of the reduced system. */
+int orbo_set_profiling(orbo_handle *h, int enabled);
+int orbo_get_kernel_times(orbo_handle *h, double *total_ms, long long *counts, int n);
+
 #ifdef __cplusplus
 }
 #endif

@@ -361,6 +361,25 @@ class Optimizer:
         return dict(poses=poses.reshape(K, 4, 4), points=points, chi2=chi2, depth_ok=dok, outlier=outl,
                     lm_iterations=int(stats[0]), lm_trials=int(stats[1]), chol_failures=int(stats[2]), aborted=bool(rc == 1))
 
+    KERNELS = ("errors", "build_points", "build_poses", "schur", "chol_potrf", "chol_trsm", "chol_update", "tri_solves",
+               "backsub", "update", "memset_S")
+
+    def set_profiling(self, on):
+        self._L.orbo_set_profiling.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        _check(self._L.orbo_set_profiling(self._h, int(bool(on))))
+
+    def kernel_times(self):
+        ms = np.zeros(len(self.KERNELS)); cnt = np.zeros(len(self.KERNELS), np.int64)
+        self._L.orbo_get_kernel_times.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+        _check(self._L.orbo_get_kernel_times(self._h, _ptr(ms), _ptr(cnt), len(ms)))
+        return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(self.KERNELS)}
+
+    def last_ba_timing(self):
+        out = np.zeros(4)
+        self._L.orbo_last_ba_timing.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        _check(self._L.orbo_last_ba_timing(self._h, _ptr(out)))
+        return dict(lm_loop_s=float(out[0]), total_s=float(out[1]), setup_s=float(out[2]), ld=int(out[3]))
+
     def LocalBundleAdjustment(self, poses, fixed, intr, points, e_kf, e_pt, e_uv, e_inv_sigma2, stop_flag=None):
         """Optimizer::LocalBundleAdjustment schedule: 5 robust LM iterations, chi2/depth gating, 10 non-robust."""
         return self._ba(poses, fixed, intr, points, e_kf, e_pt, e_uv, e_inv_sigma2, True, 5, 10, True, stop_flag)

@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <mutex>
 #include <vector>
+#include <chrono>
 #include "common.cuh"
 #include "pose_opt.cuh"
 #include "ba_kernels.cuh"
@@ -23,7 +24,11 @@ struct orbo_handle {
     StagePool pool;          // pose optimisation staging
     StagePool ba_pool;       // bundle adjustment buffers
     PinnedBuf h_scalars;
+    KernelTimer timer;       // BA kernels, ids = BaK
+    double ba_timing[4] = {0, 0, 0, 0};   // last BA call: LM-loop seconds, total seconds, setup (layout + H2D) seconds, Schur bytes
 };
+
+enum BaK { BK_ERRORS = 0, BK_BUILD_POINTS, BK_BUILD_POSES, BK_SCHUR, BK_POTRF, BK_TRSM, BK_SYRK, BK_TRS, BK_BACKSUB, BK_UPDATE, BK_MEMSET, BK_COUNT };
 
 extern "C" {
 
@@ -49,7 +54,7 @@ int orbo_destroy(orbo_handle *h)
     cudaSetDevice(h->device);
     if (h->stream && h->own_stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
     else cudaDeviceSynchronize();
-    h->pool.release(); h->ba_pool.release(); h->h_scalars.release();
+    h->pool.release(); h->ba_pool.release(); h->h_scalars.release(); h->timer.release();
     delete h;
     return ORBS_OK;
 }
@@ -122,6 +127,7 @@ struct BaHost {
     int *h_flag = nullptr;        // pinned
 
     bool terminate() const { return stop && *stop; }
+    KernelTimer &T() { return h->timer; }
     void count(int n = 1) { h->launches += n; }
 
     int read_scalars()
@@ -135,15 +141,21 @@ struct BaHost {
     // computeActiveErrors + activeRobustChi2 -> scalars[0]
     void errors()
     {
+        T().begin(BK_ERRORS, st);
         k_ba_errors<<<err_blocks, 256, 0, st>>>(B);
         k_reduce_partials<<<1, 256, 0, st>>>(B.partial, err_blocks, B.scalars, 0, 0);
+        T().end(st);
         count(2);
     }
 
     void build_system()
     {
+        T().begin(BK_BUILD_POINTS, st);
         k_ba_build_points<<<pt_blocks, 256, 0, st>>>(B);
+        T().end(st);
+        T().begin(BK_BUILD_POSES, st);
         if (pose_blocks) k_ba_build_poses<<<pose_blocks, 256, 0, st>>>(B);
+        T().end(st);
         count(2);
     }
 
@@ -153,21 +165,32 @@ struct BaHost {
         const int ld = B.ld;
         ORBS_CUDA(cudaMemsetAsync(B.flags, 0, 4 * sizeof(int), st));
         if (B.n > 0) {
+            T().begin(BK_MEMSET, st);
             ORBS_CUDA(cudaMemsetAsync(B.S, 0, (size_t)ld * ld * sizeof(double), st));
+            T().end(st);
             const int t = std::max(B.nA * 36, ld);
+            T().begin(BK_SCHUR, st);
             k_ba_schur_init<<<(t + 255) / 256, 256, 0, st>>>(B, lambda);
             k_ba_schur<<<pt_blocks, 256, 0, st>>>(B, lambda);
+            T().end(st);
             count(2);
             for (int k = 0; k < ntiles; k++) {
+                T().begin(BK_POTRF, st);
                 k_chol_potrf<<<1, 256, 0, st>>>(B.S, ld, k, B.flags);
+                T().end(st);
                 const int m = ntiles - k - 1;
                 if (m > 0) {
+                    T().begin(BK_TRSM, st);
                     k_chol_trsm<<<m, 256, kCholSmem, st>>>(B.S, ld, k);
+                    T().end(st);
+                    T().begin(BK_SYRK, st);
                     k_chol_update<<<m * (m + 1) / 2, 256, kCholSmem, st>>>(B.S, ld, k, ntiles);
+                    T().end(st);
                     count(2);
                 }
                 count(1);
             }
+            T().begin(BK_TRS, st);
             for (int k = 0; k < ntiles; k++) {
                 k_trs_diag<<<1, NB, 0, st>>>(B.S, ld, k, B.bs, 0);
                 if (ntiles - k - 1 > 0) { k_trs_update<<<ntiles - k - 1, NB, 0, st>>>(B.S, ld, k, B.bs, 0); count(1); }
@@ -178,14 +201,17 @@ struct BaHost {
                 if (k > 0) { k_trs_update<<<k, NB, 0, st>>>(B.S, ld, k, B.bs, 1); count(1); }
                 count(1);
             }
+            T().end(st);
             k_ba_take_xp<<<xp_blocks, 256, 0, st>>>(B, lambda);
             k_reduce_partials<<<1, 256, 0, st>>>(B.partial, xp_blocks, B.scalars, 2, 0);
             count(2);
         } else {
             ORBS_CUDA(cudaMemsetAsync(B.scalars + 2, 0, sizeof(double), st));
         }
+        T().begin(BK_BACKSUB, st);
         k_ba_backsub<<<pt_blocks, 256, 0, st>>>(B, lambda);
         k_reduce_partials<<<1, 256, 0, st>>>(B.partial, pt_blocks, B.scalars, 1, 0);
+        T().end(st);
         count(2);
         return ORBS_OK;
     }
@@ -211,7 +237,9 @@ struct BaHost {
         const int upd_blocks = (B.K + B.P + 255) / 256;
         do {
             if (solve()) return LM_ERROR;
+            T().begin(BK_UPDATE, st);
             k_ba_update<<<upd_blocks, 256, 0, st>>>(B);
+            T().end(st);
             count(1);
             errors();
             if (read_scalars()) return LM_ERROR;
@@ -273,6 +301,7 @@ extern "C" int orbo_bundle_adjust(orbo_handle *h, int K, float *poses, const uin
     std::lock_guard<std::mutex> lk(h->mu);
     ORBS_CUDA(cudaSetDevice(h->device));
     cudaStream_t st = h->stream;
+    const auto t_begin = std::chrono::steady_clock::now();
 
     // ---- host-side graph layout: edges grouped by point (stable), second CSR by pose
     std::vector<int> pt_start(P + 1, 0), order(E), pose_start(K + 1, 0), pose_edges(E), kf_s(E), pt_s(E);
@@ -351,6 +380,7 @@ extern "C" int orbo_bundle_adjust(orbo_handle *h, int K, float *poses, const uin
 
     int any = init_active();
     if (any < 0) return any;
+    const auto t_loop = std::chrono::steady_clock::now();
     B.robust = two_stage ? 1 : (robust ? 1 : 0);
     int rc = D.optimize(its0, any == 1);
     if (rc) return rc;
@@ -374,6 +404,7 @@ extern "C" int orbo_bundle_adjust(orbo_handle *h, int K, float *poses, const uin
         if ((rc = D.optimize(its1, any == 1))) return rc;
     }
     if ((rc = edge_check())) return rc;
+    const auto t_loop_end = std::chrono::steady_clock::now();
     for (int j = 0; j < E; j++) {                                                         // Optimizer.cc:734-766
         const int e = order[j];
         if (e_chi2) e_chi2[e] = chi2_s[j];
@@ -386,6 +417,42 @@ extern "C" int orbo_bundle_adjust(orbo_handle *h, int K, float *poses, const uin
     ORBS_CUDA(cudaMemcpyAsync(pts_d.data(), B.pt, pts_d.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
     ORBS_CUDA(cudaStreamSynchronize(st));
     for (size_t i = 0; i < pts_d.size(); i++) points[i] = (float)pts_d[i];
+    {
+        const auto t_end = std::chrono::steady_clock::now();
+        auto sec = [](auto a, auto b) { return std::chrono::duration<double>(b - a).count(); };
+        h->ba_timing[0] = sec(t_loop, t_loop_end); h->ba_timing[1] = sec(t_begin, t_end); h->ba_timing[2] = sec(t_begin, t_loop);
+        h->ba_timing[3] = (double)B.ld;
+    }
     if (stats) { stats[0] = D.lm_iterations; stats[1] = D.lm_trials; stats[2] = D.chol_failures; stats[3] = 0; }
+    return ORBS_OK;
+}
+
+extern "C" int orbo_last_ba_timing(orbo_handle *h, double *out4)
+{
+    ORBS_REQUIRE(h && out4, ORBS_E_INVALID, "null argument");
+    for (int i = 0; i < 4; i++) out4[i] = h->ba_timing[i];
+    return ORBS_OK;
+}
+
+extern "C" int orbo_set_profiling(orbo_handle *h, int enabled)
+{
+    ORBS_REQUIRE(h, ORBS_E_INVALID, "null handle");
+    std::lock_guard<std::mutex> lk(h->mu);
+    ORBS_CUDA(cudaSetDevice(h->device));
+    ORBS_CUDA(cudaStreamSynchronize(h->stream));
+    h->timer.collect();
+    h->timer.enabled = enabled != 0;
+    if (enabled) h->timer.reset();
+    return ORBS_OK;
+}
+
+extern "C" int orbo_get_kernel_times(orbo_handle *h, double *total_ms, long long *counts, int n)
+{
+    ORBS_REQUIRE(h && total_ms && counts && n > 0, ORBS_E_INVALID, "bad argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    ORBS_CUDA(cudaSetDevice(h->device));
+    ORBS_CUDA(cudaStreamSynchronize(h->stream));
+    h->timer.collect();
+    for (int i = 0; i < n && i < KernelTimer::kMaxKernels; i++) { total_ms[i] = h->timer.total_ms[i]; counts[i] = h->timer.count[i]; }
     return ORBS_OK;
 }

@@ -86,26 +86,27 @@ def ba_graph(K=100, P=10000, seed=42, cam=KITTI, min_obs=3, max_obs=9, outlier_f
     anchor = rng.integers(0, K, P)
     local = np.stack([rng.uniform(-20, 20, P), rng.uniform(-3, 3, P), rng.uniform(4, 40, P)], 1)
     Xw = pos[anchor] + np.einsum("pij,pj->pi", Rwc[anchor], local)
-    kf_l, pt_l, uv_l, oct_l = [], [], [], []
     nobs_target = rng.integers(min_obs, max_obs + 1, P)
-    for p in range(P):
-        d = np.abs(np.arange(K) - anchor[p])
-        order = np.argsort(d, kind="stable")
-        got = 0
-        for k in order[: 4 * max_obs]:
-            Xc = Rcw[k] @ Xw[p] + tcw[k]
-            if Xc[2] <= 0.5:
-                continue
-            u, v = fx * Xc[0] / Xc[2] + cx, fy * Xc[1] / Xc[2] + cy
-            if not (0 <= u < w and 0 <= v < h):
-                continue
-            kf_l.append(k); pt_l.append(p); uv_l.append((u, v))
-            got += 1
-            if got >= nobs_target[p]:
-                break
-    E = len(kf_l)
-    kf = np.array(kf_l, np.int32); pt = np.array(pt_l, np.int32)
-    uv = np.array(uv_l, np.float64)
+    # candidate keyframes of a point: anchor, anchor-1, anchor+1, anchor-2, ... (nearest first); keep the first
+    # nobs_target of them that see the point in front of the camera and inside the image
+    C = 4 * max_obs
+    offs = np.zeros(C, np.int64)
+    offs[1::2] = -(np.arange(1, C, 2) // 2 + 1)
+    offs[2::2] = np.arange(2, C, 2) // 2
+    cand = anchor[:, None] + offs[None, :]                                   # [P, C]
+    inside = (cand >= 0) & (cand < K)
+    ck = np.clip(cand, 0, K - 1)
+    Xc = np.einsum("pcij,pj->pci", Rcw[ck], Xw) + tcw[ck]
+    z = Xc[..., 2]
+    zs = np.where(z > 0.5, z, 1.0)
+    u = fx * Xc[..., 0] / zs + cx
+    v = fy * Xc[..., 1] / zs + cy
+    vis = inside & (z > 0.5) & (u >= 0) & (u < w) & (v >= 0) & (v < h)
+    take = vis & (np.cumsum(vis, 1) <= nobs_target[:, None])
+    pi, ci = np.nonzero(take)
+    kf = ck[pi, ci].astype(np.int32); pt = pi.astype(np.int32)
+    uv = np.stack([u[pi, ci], v[pi, ci]], 1)
+    E = len(kf)
     octave = rng.integers(0, 8, E)
     sig = 1.2 ** octave
     uv += rng.normal(0, 1.0, (E, 2)) * sig[:, None]
