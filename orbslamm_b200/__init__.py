@@ -3,7 +3,7 @@
 Python here is only a thin ctypes binding over the C-ABI in include/orbslamm_b200.h
 (the product is liborbslamm_b200.so: hand-written CUDA + a C++ host driver).  There is
 no CPU fallback: if the shared library is missing or no CUDA device is usable, the calls
-raise.  The oracle/ package is never imported from here.
+raise.  The CPU checker package (tests only) is never imported from here.
 """
 import ctypes
 import os

@@ -1,0 +1,55 @@
+"""The C-ABI library loads without a GPU and exports every symbol include/orbslamm_b200.h declares."""
+import ctypes
+import os
+import re
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "orbslamm_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(orb[smxo]_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_every_declared_symbol_is_exported(lib):
+    names = _declared()
+    assert len(names) >= 30
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/orbslamm_b200.h but not exported"
+
+
+def test_no_compute_without_gpu_but_clean_errors(lib):
+    import orbslamm_b200 as ob
+    assert lib.orbs_version() >= 100
+    if lib.orbs_device_count() > 0:
+        return
+    # no CUDA device here: creating any handle must fail loudly with ORBS_E_CUDA (no CPU fallback exists)
+    for ctor in (lambda: ob.ORBextractor(1000, 1.2, 8, 20, 7), lambda: ob.ORBmatcher(0.9, True), lambda: ob.Optimizer()):
+        try:
+            ctor()
+        except ob.OrbsError as e:
+            assert e.code == -2
+        else:
+            raise AssertionError("handle creation succeeded without a GPU")
+
+
+def test_argument_validation_needs_no_gpu(lib):
+    h = ctypes.c_void_p()
+    assert lib.orbx_create(ctypes.byref(h), 0, 1.2, 8, 20, 7, 0) == -1          # nfeatures must be positive
+    assert lib.orbx_create(ctypes.byref(h), 1000, 1.2, 17, 20, 7, 0) == -1      # nlevels <= 16
+    assert lib.orbx_create(ctypes.byref(h), 1000, 1.2, 8, 0, 7, 0) == -1        # thresholds >= 1
+    assert b"" != lib.orbs_last_error()
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "orbslamm_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                code = "\n".join(l for l in txt.splitlines() if not l.lstrip().startswith(("#", "//", "*", '"')))
+                assert not re.search(r"^\s*(import oracle|from oracle)", code, flags=re.M), f
+                assert "liboracle" not in code and "oracle." not in code, f

@@ -1,0 +1,38 @@
+"""The oracle reproduces the committed golden vectors (guards the checker itself against drift)."""
+import os
+
+import numpy as np
+
+import oracle
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def test_extractor_golden():
+    d = np.load(os.path.join(G, "extract_400x300.npz"))
+    P = oracle.orb_params(int(d["params"][0]), float(d["scale_factor"]), int(d["params"][1]), int(d["params"][2]), int(d["params"][3]))
+    for i in (0, 1):
+        r = oracle.orb_extract(P, d[f"frame{i}"])
+        for k in ("x", "y", "angle", "response", "octave", "size", "desc"):
+            assert np.array_equal(r[k], d[f"f{i}_{k}"]), (i, k)
+
+
+def test_matcher_golden():
+    e = np.load(os.path.join(G, "extract_400x300.npz")); d = np.load(os.path.join(G, "match_400x300.npz"))
+    g = oracle.grid_params(*d["bounds"])
+    qv, uv, rad, mn, mx = oracle.project_last_frame(d["Tcw"], d["K4"], g, d["scale_factors"], d["Xw"], e["f0_octave"], 15.0, d["valid"])
+    assert np.array_equal(qv, d["q_valid"]) and np.array_equal(uv[qv > 0], d["q_uv"][qv > 0]) and np.array_equal(rad[qv > 0], d["q_radius"][qv > 0])
+    fxy = np.stack([e["f1_x"], e["f1_y"]], 1)
+    n1, fm1 = oracle.search_by_projection(g, fxy, e["f1_octave"], e["f1_angle"], e["f1_desc"], qv, uv, rad, mn, mx, e["f0_angle"], e["f0_desc"], 100, 0.0, True)
+    assert n1 == int(d["n_frames"]) and np.array_equal(fm1, d["fm_frames"])
+    n2, fm2 = oracle.search_by_projection(g, fxy, e["f1_octave"], e["f1_angle"], e["f1_desc"], qv, uv, rad * 2, mn, mx - 1, e["f0_angle"], e["f0_desc"], 100, 0.8, False)
+    assert n2 == int(d["n_local"]) and np.array_equal(fm2, d["fm_local"])
+
+
+def test_optimizer_golden():
+    d = np.load(os.path.join(G, "optimize_small.npz"))
+    T, outl, n = oracle.pose_optimization(d["po_T0"], d["po_Xw"], d["po_obs"], d["po_w"], d["po_K4"])
+    assert n == int(d["po_ninl"]) and np.array_equal(outl, d["po_outlier"]) and np.allclose(T, d["po_T"], rtol=0, atol=1e-7)
+    r = oracle.bundle_adjust(d["ba_poses0"], d["ba_fixed"], d["ba_intr"], d["ba_points0"], d["ba_kf"], d["ba_pt"], d["ba_uv"], d["ba_w"], True, 5, 10, True)
+    assert [r["lm_iterations"], r["lm_trials"]] == d["ba_iters"].tolist()
+    assert np.allclose(r["poses"], d["ba_poses"], rtol=0, atol=1e-7) and np.allclose(r["points"], d["ba_points"], rtol=0, atol=1e-6)

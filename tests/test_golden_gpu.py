@@ -1,0 +1,46 @@
+"""CUDA path (through the C-ABI) against the committed golden vectors."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def test_extractor_and_matcher_golden(lib):
+    import orbslamm_b200 as ob
+    e = np.load(os.path.join(G, "extract_400x300.npz")); d = np.load(os.path.join(G, "match_400x300.npz"))
+    ex = ob.ORBextractor(int(e["params"][0]), float(e["scale_factor"]), int(e["params"][1]), int(e["params"][2]), int(e["params"][3]))
+    outs = ex.extract_batch(np.stack([e["frame0"], e["frame1"]]))
+    for i in (0, 1):
+        for k in ("x", "y", "angle", "response", "octave", "size", "desc"):
+            assert np.array_equal(outs[i][k], e[f"f{i}_{k}"]), (i, k)
+    # public pyramid (mvImagePyramid) incl. the 19-px reflect-101 border
+    lvl = ex.pyramid_level(1, 2, 400, 300, border=True)
+    assert lvl.shape == (208 + 38, 278 + 38) and np.array_equal(lvl[19:-19, 19:-19], ex.pyramid_level(1, 2, 400, 300))
+    assert np.array_equal(lvl[0, 19:-19], lvl[38, 19:-19]) and np.array_equal(lvl[19:-19, 0], lvl[19:-19, 38])
+    m = ob.ORBmatcher(0.8, True)
+    n = len(e["f0_x"])
+    qv, uv, rad, mn, mx = m.project_last_frame(d["Tcw"][None], d["K4"], d["bounds"], d["scale_factors"], d["Xw"][None], e["f0_octave"][None],
+                                               np.array([n], np.int32), 15.0, d["valid"][None])
+    assert np.array_equal(qv[0], d["q_valid"]) and np.array_equal(uv[0][qv[0] > 0], d["q_uv"][d["q_valid"] > 0])
+    cur = outs[1]
+    args = (d["bounds"], np.stack([cur["x"], cur["y"]], 1)[None], cur["octave"][None], cur["angle"][None], cur["desc"][None], np.array([len(cur["x"])], np.int32))
+    nm, fm = m.SearchByProjection(*args, qv, uv, rad, mn, mx, e["f0_angle"][None], e["f0_desc"][None], np.array([n], np.int32), 100)
+    assert nm[0] == int(d["n_frames"]) and np.array_equal(fm[0], d["fm_frames"])
+    nm, fm = m.SearchByProjection(*args, qv, uv, rad * 2, mn, mx - 1, e["f0_angle"][None], e["f0_desc"][None], np.array([n], np.int32), 100, use_ratio=True)
+    assert nm[0] == int(d["n_local"]) and np.array_equal(fm[0], d["fm_local"])
+
+
+def test_optimizer_golden(lib):
+    import orbslamm_b200 as ob
+    d = np.load(os.path.join(G, "optimize_small.npz"))
+    opt = ob.Optimizer()
+    T, outl, n = opt.PoseOptimization(d["po_T0"][None], d["po_K4"], d["po_Xw"][None], d["po_obs"][None], d["po_w"][None], np.array([len(d["po_w"])], np.int32))
+    assert n[0] == int(d["po_ninl"]) and np.array_equal(outl[0], d["po_outlier"])
+    assert np.abs(T[0] - d["po_T"]).max() < 1e-5 * np.abs(d["po_T"]).max()
+    r = opt.LocalBundleAdjustment(d["ba_poses0"], d["ba_fixed"], d["ba_intr"], d["ba_points0"], d["ba_kf"], d["ba_pt"], d["ba_uv"], d["ba_w"])
+    assert [r["lm_iterations"], r["lm_trials"]] == d["ba_iters"].tolist()
+    assert np.abs(r["poses"] - d["ba_poses"]).max() < 1e-5 * np.abs(d["ba_poses"]).max()
+    assert np.abs(r["points"] - d["ba_points"]).max() < 1e-5 * np.abs(d["ba_points"]).max()

@@ -1,0 +1,106 @@
+"""Known-answer tests of the oracle (the vectors the reference never had) + config-1 plumbing."""
+import ctypes
+
+import numpy as np
+import pytest
+
+import oracle
+from orbslamm_b200 import synth
+
+
+def test_extractor_tables_match_reference_constants():
+    P = oracle.orb_params(1000, 1.2, 8, 20, 7)                 # TUM1.yaml
+    assert list(P.features_per_level)[:8] == [217, 181, 151, 126, 105, 87, 73, 60]
+    P2 = oracle.orb_params(2000, 1.2, 8, 20, 7)                # KITTI00-02.yaml
+    assert list(P2.features_per_level)[:8] == [434, 362, 302, 251, 209, 175, 145, 122]
+    assert list(P.umax) == [15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3]
+    assert [oracle.level_size(P2, 1241, 376, l) for l in range(8)] == [(1241, 376), (1034, 313), (862, 261), (718, 218), (598, 181),
+                                                                         (499, 151), (416, 126), (346, 105)]
+    assert [oracle.level_size(P, 640, 480, l) for l in range(8)] == [(640, 480), (533, 400), (444, 333), (370, 278), (309, 231),
+                                                                       (257, 193), (214, 161), (179, 134)]
+    assert np.float32(P.scale[1]) == np.float32(1.2) and np.float32(P.scale[2]) == np.float32(np.float32(1.2) * np.float64(np.float32(1.2)))
+
+
+def test_config1_plumbing_640x480():
+    """BASELINE.json configs[0]: one 640x480 frame, 1000 features, oracle path."""
+    P = oracle.orb_params(1000, 1.2, 8, 20, 7)
+    img = synth.base_image(640, 480, 1)
+    a, b = oracle.orb_extract(P, img), oracle.orb_extract(P, img)
+    for k in a:
+        assert np.array_equal(a[k], b[k])                      # deterministic
+    for l in range(8):
+        assert a["level_counts"][l] <= P.features_per_level[l] + 3
+    assert a["desc"].shape == (len(a["x"]), 32) and a["desc"].dtype == np.uint8
+    assert a["x"].min() >= 19 and a["x"].max() < 640 - 19 + 1e-3 and (a["angle"] >= 0).all() and (a["angle"] < 360).all()
+    e = oracle.orb_extract(P, np.zeros((0, 0), np.uint8))
+    assert len(e["x"]) == 0                                      # empty image -> silent return
+    flat = oracle.orb_extract(P, np.full((480, 640), 128, np.uint8))
+    assert len(flat["x"]) == 0                                   # no corners anywhere
+
+
+def test_hamming_kat():
+    z = np.zeros(32, np.uint8); f = np.full(32, 255, np.uint8)
+    assert oracle.descriptor_distance(z, z) == 0 and oracle.descriptor_distance(z, f) == 256
+    a = z.copy(); a[0] = 0b10110000; a[31] = 1
+    assert oracle.descriptor_distance(a, z) == 4
+    rng = np.random.default_rng(0)
+    for _ in range(50):
+        x, y = rng.integers(0, 256, 32, dtype=np.uint8), rng.integers(0, 256, 32, dtype=np.uint8)
+        assert oracle.descriptor_distance(x, y) == int(np.unpackbits(x ^ y).sum())
+
+
+def test_ic_angle_gradient_patch():
+    P = oracle.orb_params()
+    yy, xx = np.mgrid[0:64, 0:64]
+    assert oracle.ic_moments(P, (xx * 3).astype(np.uint8), 32, 32)[0] == 0           # horizontal ramp: m01 = 0
+    m01, m10 = oracle.ic_moments(P, (xx * 3).astype(np.uint8), 32, 32)
+    assert m10 > 0 and oracle.fast_atan2(m01, m10) == 0.0
+    m01, m10 = oracle.ic_moments(P, (yy * 3).astype(np.uint8), 32, 32)
+    assert m10 == 0 and m01 > 0 and abs(oracle.fast_atan2(m01, m10) - 90.0) < 1e-4
+    m01, m10 = oracle.ic_moments(P, np.full((64, 64), 9, np.uint8), 32, 32)
+    assert (m01, m10) == (0, 0)
+
+
+def test_octree_picks_best_per_node_and_respects_quota():
+    rng = np.random.default_rng(5)
+    n = 3000
+    cands = np.stack([rng.integers(3, 597, n), rng.integers(3, 437, n), rng.integers(7, 200, n)], 1).astype(np.float32)
+    cands = cands[np.sort(np.unique(cands[:, :2], axis=0, return_index=True)[1])]        # distinct positions, original order
+    for N in (1, 7, 60, 217, 500, 5000):
+        sel = oracle.distribute_octree(cands, 16, 616, 16, 456, N)
+        assert len(set(sel.tolist())) == len(sel)
+        assert len(sel) <= max(N + 3, 4) and (len(sel) >= min(N, len(cands)) or N > len(cands))
+    sel = oracle.distribute_octree(cands, 16, 616, 16, 456, 100000)
+    assert len(sel) == len(cands)                                # every point ends in its own node
+
+
+def test_three_maxima_and_rot_hist_via_search():
+    # two features, two queries with a 180 deg rotation between them: both land in one bin and survive
+    g = oracle.grid_params(0, 0, 640, 480)
+    f_xy = np.array([[100, 100], [300, 200]], np.float32); f_oct = np.zeros(2, np.int32)
+    f_ang = np.array([10, 20], np.float32); d = np.zeros((2, 32), np.uint8); d[1] = 255
+    n, fm = oracle.search_by_projection(g, f_xy, f_oct, f_ang, d, np.ones(2, np.uint8), f_xy + 1, np.full(2, 15, np.float32),
+                                        np.full(2, -1, np.int32), np.full(2, 1, np.int32), f_ang + 180, d, 100, 0.0, True)
+    assert n == 2 and fm.tolist() == [0, 1]
+    # a taken feature is skipped; the query falls back to nothing
+    n, fm = oracle.search_by_projection(g, f_xy, f_oct, f_ang, d, np.ones(2, np.uint8), f_xy + 1, np.full(2, 15, np.float32),
+                                        np.full(2, -1, np.int32), np.full(2, 1, np.int32), f_ang, d, 100, 0.0, False,
+                                        feat_match=np.array([5, -1], np.int32))
+    assert n == 1 and fm.tolist() == [5, 1]
+
+
+def test_se3_and_huber_kats():
+    L = oracle.lib()
+    # pose optimisation on exact data returns the exact pose and no outliers
+    g = synth.ba_graph(K=6, P=300, seed=3, outlier_frac=0.0)
+    k = 3; m = g["kf"] == k
+    Xw = g["gt_points"][g["pt"][m]].astype(np.float32)
+    T = g["gt_poses"][k]
+    Xc = (T[:3, :3] @ Xw.T.astype(np.float64)).T + T[:3, 3]
+    obs = np.stack([g["intr"][0] * Xc[:, 0] / Xc[:, 2] + g["intr"][2], g["intr"][1] * Xc[:, 1] / Xc[:, 2] + g["intr"][3]], 1).astype(np.float32)
+    To, out, n = oracle.pose_optimization(g["poses"][k], Xw, obs, np.ones(len(Xw), np.float32), np.array(g["intr"], np.float32))
+    assert n == len(Xw) and out.sum() == 0
+    assert np.abs(To - T).max() < 2e-4
+    # fewer than 3 correspondences -> 0, pose untouched
+    To, out, n = oracle.pose_optimization(g["poses"][k], Xw[:2], obs[:2], np.ones(2, np.float32), np.array(g["intr"], np.float32))
+    assert n == 0 and np.array_equal(To, g["poses"][k])

@@ -1,0 +1,59 @@
+#!/usr/bin/env python3
+"""Generate tests/golden/*.npz: small known-answer vectors for the hot path.
+
+The reference repository ships no golden vectors, and its C++ cannot be built here, so these come
+from the oracle.  At generation time the extractor vector is produced TWICE -- by orb_oracle.c and by the cv2-primitive
+twin (the OpenCV calls the reference makes) -- and the script refuses to write if they disagree.
+    python tools/make_golden.py
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import oracle                      # noqa: E402
+from oracle import orb_cv2         # noqa: E402
+from orbslamm_b200 import synth    # noqa: E402
+from helpers import make_tracking_case  # noqa: E402
+
+out = os.path.join(ROOT, "tests", "golden")
+os.makedirs(out, exist_ok=True)
+
+# 1. extractor: two consecutive 400x300 frames, 400 features
+cam = dict(synth.TUM); cam.update(w=400, h=300, nfeatures=400, cx=200.0, cy=150.0)
+case = make_tracking_case(cam, 21)
+P = case["P"]
+for img, feats in ((case["frames"][0], case["last"]), (case["frames"][1], case["cur"])):
+    b = orb_cv2.extract(P, img)
+    for k in ("x", "y", "angle", "response", "octave", "size", "desc"):
+        assert np.array_equal(feats[k], b[k]), f"oracle and cv2 twin disagree on {k}"
+ex = {f"f{i}_{k}": v for i, f in enumerate((case["last"], case["cur"])) for k, v in f.items()}
+np.savez_compressed(os.path.join(out, "extract_400x300.npz"), frame0=case["frames"][0], frame1=case["frames"][1],
+                    params=np.array([400, 8, 20, 7]), scale_factor=np.float32(1.2), **ex)
+
+# 2. matcher: projection + both search variants on those frames
+g = oracle.grid_params(*case["bounds"])
+sf = np.array(list(P.scale)[:8], np.float32)
+qv, uv, rad, mn, mx = oracle.project_last_frame(case["Tcw"], case["K4"], g, sf, case["Xw"], case["last"]["octave"], 15.0, case["valid"])
+cur, last = case["cur"], case["last"]
+fxy = np.stack([cur["x"], cur["y"]], 1)
+n1, fm1 = oracle.search_by_projection(g, fxy, cur["octave"], cur["angle"], cur["desc"], qv, uv, rad, mn, mx, last["angle"], last["desc"], 100, 0.0, True)
+n2, fm2 = oracle.search_by_projection(g, fxy, cur["octave"], cur["angle"], cur["desc"], qv, uv, rad * 2, mn, mx - 1, last["angle"], last["desc"], 100, 0.8, False)
+np.savez_compressed(os.path.join(out, "match_400x300.npz"), Tcw=case["Tcw"], K4=case["K4"], bounds=case["bounds"], Xw=case["Xw"], valid=case["valid"],
+                    scale_factors=sf, q_valid=qv, q_uv=uv, q_radius=rad, q_minl=mn, q_maxl=mx, n_frames=n1, fm_frames=fm1, n_local=n2, fm_local=fm2)
+
+# 3. optimizer: pose optimisation on the accepted matches + a 10 KF / 200 point LocalBA
+m = fm1 >= 0
+Xw_m = case["Xw"][fm1[m]]; obs_m = fxy[m]; w_m = np.array(list(P.inv_sigma2)[:8], np.float32)[cur["octave"][m]]
+T0 = case["Tcw"].copy(); T0[:3, 3] += np.array([0.05, -0.03, 0.08], np.float32)
+Tp, outl, ninl = oracle.pose_optimization(T0, Xw_m, obs_m, w_m, case["K4"])
+gb = synth.ba_graph(K=10, P=200, seed=42)
+rb = oracle.bundle_adjust(gb["poses"], gb["fixed"], gb["intr"], gb["points"], gb["kf"], gb["pt"], gb["uv"], gb["inv_sigma2"], True, 5, 10, True)
+np.savez_compressed(os.path.join(out, "optimize_small.npz"), po_T0=T0, po_Xw=Xw_m, po_obs=obs_m, po_w=w_m, po_K4=case["K4"], po_T=Tp, po_outlier=outl,
+                    po_ninl=ninl, ba_poses0=gb["poses"], ba_fixed=gb["fixed"], ba_intr=gb["intr"], ba_points0=gb["points"], ba_kf=gb["kf"], ba_pt=gb["pt"],
+                    ba_uv=gb["uv"], ba_w=gb["inv_sigma2"], ba_poses=rb["poses"], ba_points=rb["points"], ba_chi2=rb["chi2"], ba_outlier=rb["outlier"],
+                    ba_iters=np.array([rb["lm_iterations"], rb["lm_trials"]]))
+for f in sorted(os.listdir(out)):
+    print(f, os.path.getsize(os.path.join(out, f)))
