@@ -1,0 +1,16 @@
+#pragma once
+#include <mutex>
+#include "KeyFrame.h"
+
+namespace iORB_SLAM
+{
+class Map
+{
+public:
+    std::vector<KeyFrame *> GetAllKeyFrames() { return mvKFs; }
+    std::vector<MapPoint *> GetAllMapPoints() { return mvMPs; }
+    std::mutex mMutexMapUpdate;
+    std::vector<KeyFrame *> mvKFs;
+    std::vector<MapPoint *> mvMPs;
+};
+}  // namespace iORB_SLAM

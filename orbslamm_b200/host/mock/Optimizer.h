@@ -1,0 +1,19 @@
+// Mock of S/include/Optimizer.h:37-68 restricted to the functions the accelerated path defines.
+#pragma once
+#include "Frame.h"
+#include "KeyFrame.h"
+#include "Map.h"
+
+namespace iORB_SLAM
+{
+class Optimizer
+{
+public:
+    void static BundleAdjustment(const std::vector<KeyFrame *> &vpKF, const std::vector<MapPoint *> &vpMP, int nIterations = 5,
+                                 bool *pbStopFlag = NULL, const unsigned long nLoopKF = 0, const bool bRobust = true);
+    void static GlobalBundleAdjustemnt(Map *pMap, int nIterations = 5, bool *pbStopFlag = NULL, const unsigned long nLoopKF = 0,
+                                       const bool bRobust = true);
+    void static LocalBundleAdjustment(KeyFrame *pKF, bool *pbStopFlag, Map *pMap);
+    int static PoseOptimization(Frame *pFrame);
+};
+}  // namespace iORB_SLAM

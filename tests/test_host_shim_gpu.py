@@ -1,0 +1,86 @@
+"""The C++ drop-in classes (reference signatures, orbslamm_b200/host/) driven end to end and compared with the oracle."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle
+from orbslamm_b200 import synth
+from helpers import make_tracking_case
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HOST = os.path.join(ROOT, "orbslamm_b200", "host")
+
+
+def build_host_test(out_dir):
+    exe = os.path.join(out_dir, "host_shim_test")
+    srcs = [os.path.join(HOST, f) for f in ("ORBextractor_b200.cc", "ORBmatcher_b200.cc", "Optimizer_b200.cc", "mock/slam_statics.cc",
+                                            "test/host_shim_test.cc")]
+    cmd = ["g++", "-std=c++14", "-O2", "-I" + os.path.join(HOST, "mock"), "-I" + HOST, "-I" + os.path.join(ROOT, "include")] + srcs + \
+          ["-L" + os.path.join(ROOT, "orbslamm_b200"), "-lorbslamm_b200", "-Wl,-rpath," + os.path.join(ROOT, "orbslamm_b200"), "-lpthread", "-o", exe]
+    subprocess.check_call(cmd)
+    return exe
+
+
+def test_cpp_dropin_classes(lib, tmp_path):
+    d = str(tmp_path)
+    exe = build_host_test(d)
+    cam = dict(synth.TUM); cam.update(w=480, h=360, nfeatures=600, cx=240.0, cy=180.0)
+    case = make_tracking_case(cam, 31)
+    w = lambda name, a: np.ascontiguousarray(a).tofile(os.path.join(d, name))
+    w("dims.bin", np.array([cam["w"], cam["h"], cam["nfeatures"]], np.int32))
+    w("frame0.bin", case["frames"][0]); w("frame1.bin", case["frames"][1])
+    w("K4.bin", case["K4"]); w("bounds.bin", case["bounds"]); w("Tcw.bin", case["Tcw"]); w("Xw.bin", case["Xw"]); w("valid.bin", case["valid"])
+    T0 = case["Tcw"].copy(); T0[:3, 3] += np.array([0.04, -0.02, 0.06], np.float32)
+    w("T0.bin", T0)
+    g = synth.ba_graph(K=8, P=150, seed=3)
+    octs = np.rint(-np.log(g["inv_sigma2"].astype(np.float64)) / (2 * np.log(1.2))).astype(np.int32)
+    P = case["P"]
+    inv_s2 = np.array(list(P.inv_sigma2)[:8], np.float32)
+    w("ba_dims.bin", np.array([8, 150, len(g["kf"])], np.int32)); w("ba_poses.bin", g["poses"]); w("ba_points.bin", g["points"])
+    w("ba_uv.bin", g["uv"]); w("ba_w.bin", inv_s2[octs]); w("ba_kf.bin", g["kf"]); w("ba_pt.bin", g["pt"]); w("ba_oct.bin", octs)
+    w("ba_intr.bin", g["intr"])
+    out = subprocess.run([exe, d], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    r = lambda name, dt: np.fromfile(os.path.join(d, name), dt)
+    # extractor through the class
+    for tag, ref in (("last", case["last"]), ("cur", case["cur"])):
+        kp = r(tag + "_kp.bin", np.float32).reshape(-1, 5)
+        assert np.array_equal(kp[:, 0], ref["x"]) and np.array_equal(kp[:, 1], ref["y"]) and np.array_equal(kp[:, 2], ref["angle"])
+        assert np.array_equal(kp[:, 3], ref["response"]) and np.array_equal(kp[:, 4], ref["size"])
+        assert np.array_equal(r(tag + "_oct.bin", np.int32), ref["octave"]) and np.array_equal(r(tag + "_desc.bin", np.uint8).reshape(-1, 32), ref["desc"])
+    assert np.array_equal(r("pyr3.bin", np.uint8), oracle.pyramid(P, case["frames"][1])[3].ravel())
+    # matcher + pose optimisation through the classes
+    gp = oracle.grid_params(*case["bounds"]); sf = np.array(list(P.scale)[:8], np.float32)
+    cur, last = case["cur"], case["last"]
+    q = oracle.project_last_frame(case["Tcw"], case["K4"], gp, sf, case["Xw"], last["octave"], 15.0, case["valid"])
+    fxy = np.stack([cur["x"], cur["y"]], 1)
+    n_ref, fm_ref = oracle.search_by_projection(gp, fxy, cur["octave"], cur["angle"], cur["desc"], q[0], q[1], q[2], q[3], q[4], last["angle"], last["desc"], 100, 0.0, True)
+    counts = r("counts.bin", np.int32)
+    assert counts[0] == n_ref and np.array_equal(r("fm.bin", np.int32), fm_ref)
+    assert counts[2] == oracle.descriptor_distance(cur["desc"][0], cur["desc"][1])
+    m = fm_ref >= 0
+    Tp, outl, ninl = oracle.pose_optimization(T0, case["Xw"][fm_ref[m]], fxy[m], inv_s2[cur["octave"][m]], case["K4"])
+    assert counts[1] == ninl
+    out_flags = r("outlier.bin", np.uint8)
+    assert np.array_equal(out_flags[m], outl) and out_flags[~m].sum() == 0
+    assert np.abs(r("Tpose.bin", np.float32).reshape(4, 4) - Tp).max() < 1e-5 * np.abs(Tp).max()
+    # local BA through the class: fixed flags follow the reference's construction (KF 0: mnId==0, KF 1: fixed camera)
+    fixed = np.zeros(8, np.uint8); fixed[0] = 1; fixed[1] = 2
+    # the shim orders keyframes as [current, covisibles..., fixed cameras] and points by first appearance; the result is
+    # order independent up to rounding, so compare against the oracle on the original ordering
+    ref = oracle.bundle_adjust(g["poses"], fixed, g["intr"], g["points"], g["kf"], g["pt"], g["uv"], inv_s2[octs], True, 5, 10, True)
+    got_p = r("ba_out_poses.bin", np.float32).reshape(8, 4, 4); got_x = r("ba_out_points.bin", np.float32).reshape(-1, 3)
+    # local map points = points seen by a local keyframe (everything but the fixed camera KF 1); points seen only by KF 1
+    # are not part of the window and must stay untouched (Optimizer.cc:494-509)
+    seen = np.bincount(g["pt"][g["kf"] != 1], minlength=150) > 0
+    only_fixed = (np.bincount(g["pt"], minlength=150) > 0) & ~seen
+    assert np.array_equal(got_x[~seen], g["points"][~seen])
+    keep = ~only_fixed[g["pt"]]
+    ref = oracle.bundle_adjust(g["poses"], fixed, g["intr"], g["points"], g["kf"][keep], g["pt"][keep], g["uv"][keep], inv_s2[octs][keep], True, 5, 10, True)
+    assert np.abs(got_p - ref["poses"]).max() < 2e-5 * np.abs(ref["poses"]).max()
+    assert np.abs(got_x[seen] - ref["points"][seen]).max() < 2e-5 * np.abs(ref["points"]).max()
+    nobs = np.bincount(g["pt"], minlength=150) - np.bincount(g["pt"][keep][ref["outlier"] > 0], minlength=150)
+    assert np.abs(r("ba_out_nobs.bin", np.int32) - nobs).sum() <= 2          # erased observations (ties at the chi2 gate aside)
