@@ -93,6 +93,12 @@ def frontend_workload(n_streams, rank):
     return imgs, shifts
 
 
+def predicted_pose():
+    T = np.eye(4, dtype=np.float32)
+    T[:3, 3] = [0.02, -0.01, 0.03]
+    return T
+
+
 def build_queries(feats, shifts_next, rng):
     """Last-frame 'map points' for one stream frame: keypoints lifted to depth U(5, 50) m so that they project onto
     their shifted position in the next frame under the next frame's pose (identity here)."""
@@ -117,6 +123,8 @@ def bench_frontend(args, rank, world):
     ex = ob.ORBextractor(CAM["nfeatures"], 1.2, 8, 20, 7, device=dev)
     mt = ob.ORBmatcher(0.9, True, device=dev)
     mt.set_stream(ex.stream())
+    po = ob.Optimizer(device=dev)
+    po.set_stream(ex.stream())
     L = ob.load()
     slab = ex.max_keypoints(w, h)
     sf = ex.GetScaleFactors()
@@ -146,8 +154,10 @@ def bench_frontend(args, rank, world):
             q_valid[t, b, :n] = 1
     to_dev = lambda a: torch.from_numpy(a).cuda()
     dq = dict(Xw=to_dev(q_Xw), oct=to_dev(q_oct), ang=to_dev(q_ang), desc=to_dev(q_desc), valid=to_dev(q_valid), cnt=to_dev(q_cnt))
-    Tcw = np.tile(np.eye(4, dtype=np.float32).reshape(1, 16), (B, 1))
-    d_Tcw = to_dev(Tcw); d_sf = to_dev(sf)
+    Tcw = np.tile(predicted_pose().reshape(1, 16), (B, 1))     # motion-model prediction: slightly off the true (identity) pose
+    d_Tcw0 = to_dev(Tcw); d_Tcw = to_dev(Tcw.copy()); d_sf = to_dev(sf)
+    ils = ex.GetInverseScaleSigmaSquares(); d_ils = to_dev(ils)
+    d_fout = torch.zeros((B, slab), dtype=torch.uint8, device="cuda"); d_ninl = torch.zeros(B, dtype=torch.int32, device="cuda")
     d_qvalid = torch.zeros((B, slab), dtype=torch.uint8, device="cuda")
     d_quv = torch.zeros((B, slab, 2), dtype=torch.float32, device="cuda"); d_qrad = torch.zeros((B, slab), dtype=torch.float32, device="cuda")
     d_qmn = torch.zeros((B, slab), dtype=torch.int32, device="cuda"); d_qmx = torch.zeros((B, slab), dtype=torch.int32, device="cuda")
@@ -164,6 +174,7 @@ def bench_frontend(args, rank, world):
         with torch.cuda.stream(stream):
             d_qvalid.copy_(dq["valid"][t - 1], non_blocking=True)
             d_fm.fill_(-1)
+            d_Tcw.copy_(d_Tcw0, non_blocking=True)
         ob._check(L.orbm_project_last_frame(mt.handle, B, vp(d_Tcw.data_ptr()), K4.ctypes.data, bounds.ctypes.data, vp(d_sf.data_ptr()), len(sf),
                                             vp(dq["Xw"][t - 1].data_ptr()), vp(dq["oct"][t - 1].data_ptr()), vp(dq["cnt"][t - 1].data_ptr()), slab,
                                             TH_PROJ, vp(d_qvalid.data_ptr()), vp(d_quv.data_ptr()), vp(d_qrad.data_ptr()), vp(d_qmn.data_ptr()),
@@ -172,6 +183,9 @@ def bench_frontend(args, rank, world):
                                               slab, vp(d_qvalid.data_ptr()), vp(d_quv.data_ptr()), vp(d_qrad.data_ptr()), vp(d_qmn.data_ptr()),
                                               vp(d_qmx.data_ptr()), vp(dq["ang"][t - 1].data_ptr()), vp(dq["desc"][t - 1].data_ptr()),
                                               vp(dq["cnt"][t - 1].data_ptr()), slab, 100, 0.0, 1, vp(d_fm.data_ptr()), vp(d_nm.data_ptr()), 1))
+        ob._check(L.orbo_pose_optimization_matched(po.handle, B, vp(d_Tcw.data_ptr()), K4.ctypes.data, vp(v.kp_xy), vp(v.kp_octave), vp(v.counts), slab,
+                                                   vp(d_fm.data_ptr()), vp(dq["Xw"][t - 1].data_ptr()), vp(dq["cnt"][t - 1].data_ptr()), slab,
+                                                   vp(d_ils.data_ptr()), len(ils), vp(d_fout.data_ptr()), vp(d_ninl.data_ptr()), None, 1))
 
     def barrier():
         if world > 1:
@@ -182,7 +196,7 @@ def bench_frontend(args, rank, world):
     for i in range(args.warmup):
         step_device(1 + i % (N_POOL - 1))
     barrier()
-    l0 = ex.kernel_launches() + mt.kernel_launches()
+    l0 = ex.kernel_launches() + mt.kernel_launches() + po.kernel_launches()
     ex.set_profiling(True)
     sampler = ClockSampler(dev); sampler.start()
     total_ms = 0.0
@@ -199,7 +213,8 @@ def bench_frontend(args, rank, world):
     wall = time.time() - t_wall
     total_ms = sum(a.elapsed_time(b) for a, b in evs)
     clocks = sampler.stop()
-    launches = ex.kernel_launches() + mt.kernel_launches() - l0
+    launches = ex.kernel_launches() + mt.kernel_launches() + po.kernel_launches() - l0
+    ninl = d_ninl.cpu().numpy()
     ktimes = ex.kernel_times()
     ex.set_profiling(False)
     nmatch = d_nm.cpu().numpy()
@@ -218,6 +233,7 @@ def bench_frontend(args, rank, world):
     hq_valid = np.zeros((B, slab), np.uint8); hq_uv = np.zeros((B, slab, 2), np.float32); hq_rad = np.zeros((B, slab), np.float32)
     hq_mn = np.zeros((B, slab), np.int32); hq_mx = np.zeros((B, slab), np.int32)
     h_fm = np.zeros((B, slab), np.int32); h_nm = np.zeros(B, np.int32)
+    h_T = Tcw.copy(); h_fout = np.zeros((B, slab), np.uint8); h_ninl = np.zeros(B, np.int32)
     P = lambda tns: vp(tns.data_ptr())
     A = lambda arr: arr.ctypes.data
 
@@ -230,6 +246,9 @@ def bench_frontend(args, rank, world):
         ob._check(L.orbm_search_by_projection(mt.handle, B, A(bounds), P(o_xy), P(o_oct), P(o_ang), P(o_desc), P(o_cnt), slab, A(hq_valid), A(hq_uv),
                                               A(hq_rad), A(hq_mn), A(hq_mx), A(q_ang[t - 1]), A(q_desc[t - 1]), A(q_cnt[t - 1]), slab, 100, 0.0, 1,
                                               A(h_fm), A(h_nm), 0))
+        h_T[:] = Tcw
+        ob._check(L.orbo_pose_optimization_matched(po.handle, B, A(h_T), A(K4), P(o_xy), P(o_oct), P(o_cnt), slab, A(h_fm), A(q_Xw[t - 1]), A(q_cnt[t - 1]), slab,
+                                                   A(ils), len(ils), A(h_fout), A(h_ninl), None, 0))
 
     for i in range(min(args.warmup, 3)):
         step_host(1 + i % (N_POOL - 1))
@@ -249,10 +268,12 @@ def bench_frontend(args, rank, world):
     se = B * slab                                   # slab entries per step
     h2d = (B * w * h                                # images
            + B * 64 + 32 + se * (12 + 4 + 1) + B * 4          # project: Tcw, scale factors, Xw, octave, valid, counts
-           + se * (8 + 4 + 4 + 32) + B * 4 + se * (1 + 8 + 4 + 4 + 4 + 4 + 32) + B * 4 + se * 4)   # search: features, queries, feat_match
+           + se * (8 + 4 + 4 + 32) + B * 4 + se * (1 + 8 + 4 + 4 + 4 + 4 + 32) + B * 4 + se * 4    # search: features, queries, feat_match
+           + B * 64 + se * (8 + 4 + 4 + 12) + B * 8 + 32)  # pose optimisation: pose, features, matches, map points
     d2h = (B * nkp * (8 + 4 * 4 + 32) + B * 4       # keypoints + descriptors + counts
            + se * (1 + 8 + 4 + 4 + 4)               # projected windows
-           + se * 4 + B * 4)                        # feat_match + nmatches
+           + se * 4 + B * 4                         # feat_match + nmatches
+           + B * 64 + se + B * 4)                   # optimised pose, outlier flags, inlier count
 
     # ---- roofline of the dominant kernel
     hbm, how = peaks()
@@ -276,9 +297,9 @@ def bench_frontend(args, rank, world):
     out = {"metric": "ORB extract+match fps @1241x376", "value": round(fps, 1), "unit": "frames/s", "n_gpus": world, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": round(total_ms / args.steps, 4), "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-           "config": {"workload": "KITTI-shape 1241x376 synthetic streams, nFeatures=2000: extract + SearchByProjection(Cur,Last) per frame",
+           "config": {"workload": "KITTI-shape 1241x376 synthetic streams, nFeatures=2000: extract + SearchByProjection(Cur,Last) + PoseOptimization per frame",
                       "streams_per_gpu": B, "frames_per_step": B * world, "l2": "256 MiB flush buffer written between timed steps (untimed)",
-                      "keypoints_per_frame": nkp, "matches_per_frame": float(np.mean(nmatch)), "parallelism": f"streams x{world}"},
+                      "keypoints_per_frame": nkp, "matches_per_frame": float(np.mean(nmatch)), "pose_inliers_per_frame": float(np.mean(ninl)), "parallelism": f"streams x{world}"},
            "e2e": {"value": round(e2e_fps, 1), "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps},
            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "wall_s": round(wall, 3)}
     return out
@@ -297,15 +318,20 @@ def cpu_frontend_frames(stream_id, n_frames):
     sf = np.array(list(P.scale)[:8], np.float32)
     K4 = np.array([CAM["fx"], CAM["fy"], CAM["cx"], CAM["cy"]], np.float32)
     rng = np.random.default_rng(stream_id)
+    ils = np.array(list(P.inv_sigma2)[:8], np.float32)
+    T_pred = predicted_pose()
     last = orb_cv2.extract(P, frames[0])
     t0 = time.perf_counter()
     for t in range(1, n_frames + 1):
         cur = orb_cv2.extract(P, frames[t])
         Xw = build_queries(last, shifts[t], rng)
-        qv, uv, rad, mn, mx = oracle.project_last_frame(np.eye(4, dtype=np.float32), K4, g, sf, Xw, last["octave"], TH_PROJ,
+        qv, uv, rad, mn, mx = oracle.project_last_frame(T_pred, K4, g, sf, Xw, last["octave"], TH_PROJ,
                                                          np.ones(len(Xw), np.uint8))
-        oracle.search_by_projection(g, np.stack([cur["x"], cur["y"]], 1), cur["octave"], cur["angle"], cur["desc"], qv, uv, rad, mn, mx,
-                                    last["angle"], last["desc"], 100, 0.0, True)
+        fxy = np.stack([cur["x"], cur["y"]], 1)
+        _, fm = oracle.search_by_projection(g, fxy, cur["octave"], cur["angle"], cur["desc"], qv, uv, rad, mn, mx,
+                                            last["angle"], last["desc"], 100, 0.0, True)
+        m = fm >= 0
+        oracle.pose_optimization(T_pred, Xw[fm[m]], fxy[m], ils[cur["octave"][m]], K4)
         last = cur
     return n_frames, time.perf_counter() - t0
 
@@ -357,7 +383,7 @@ def main():
         line = {"impl": "reference", "metric": "ORB extract+match fps @1241x376", "value": round(fps, 2), "unit": "frames/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 / fps, 3), "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-                "config": {"workload": "KITTI-shape 1241x376 synthetic streams, nFeatures=2000: extract + SearchByProjection(Cur,Last) per frame",
+                "config": {"workload": "KITTI-shape 1241x376 synthetic streams, nFeatures=2000: extract + SearchByProjection(Cur,Last) + PoseOptimization per frame",
                            "note": "the reference C++ cannot be built here (needs OpenCV C++/Eigen headers); this is the oracle: cv2 4.13 primitives "
                                    "(FAST/resize/GaussianBlur) + restated reference code, one independent stream per core"},
                 "cpu_baseline": {"value": round(fps, 2), "unit": "frames/s", "cores": cores, "kind": "port",

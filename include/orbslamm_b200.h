@@ -203,6 +203,16 @@ int orbo_pose_optimization(orbo_handle *h, int n_frames, float *Tcw, const float
                            const float *inv_sigma2, const int32_t *counts, int slab, uint8_t *outlier, int32_t *n_inliers,
                            int memspace);
 
+/* Same optimisation, but the correspondences are gathered on the device from a matcher result exactly like the edge
+ * construction loop of Optimizer.cc:303-384: feature i of frame f contributes an edge iff feat_match[i] >= 0 (it holds
+ * map point / query feat_match[i]), with obs = f_xy[i], Xw = q_Xw[feat_match[i]], information = inv_level_sigma2[octave].
+ *   f_outlier u8[n_frames*f_slab] out (Frame::mvbOutlier, 0 for features without a map point); n_inliers i32[n_frames];
+ *   n_edges i32[n_frames] optional out (nInitialCorrespondences).  K4 and inv_level_sigma2... K4 is a HOST pointer. */
+int orbo_pose_optimization_matched(orbo_handle *h, int n_frames, float *Tcw, const float *K4, const float *f_xy,
+                                   const int32_t *f_octave, const int32_t *f_counts, int f_slab, const int32_t *feat_match,
+                                   const float *q_Xw, const int32_t *q_counts, int q_slab, const float *inv_level_sigma2,
+                                   int nlevels, uint8_t *f_outlier, int32_t *n_inliers, int32_t *n_edges, int memspace);
+
 /* Optimizer::LocalBundleAdjustment (Optimizer.cc:476-801; two_stage = 1: its0 robust iterations, chi2 / depth gating,
  * its1 non-robust iterations) and Optimizer::BundleAdjustment (Optimizer.cc:68-260; two_stage = 0: its0 iterations
  * with `robust`) over flat arrays (HOST pointers):

@@ -341,6 +341,21 @@ class Optimizer:
                                               _ptr(outl), _ptr(ninl), 0))
         return T.reshape(n, 4, 4), outl, ninl
 
+    def PoseOptimizationMatched(self, Tcw, K4, f_xy, f_octave, f_counts, feat_match, q_Xw, q_counts, inv_level_sigma2):
+        """PoseOptimization with the edges gathered on the device from a SearchByProjection result (host arrays here).
+        Returns (Tcw_out, outlier u8[n, f_slab], n_inliers, n_edges)."""
+        T = np.ascontiguousarray(Tcw, np.float32).reshape(-1, 16).copy(); n = len(T)
+        K4 = np.ascontiguousarray(K4, np.float32)
+        f_xy = np.ascontiguousarray(f_xy, np.float32); fs = f_xy.shape[1]
+        f_octave = np.ascontiguousarray(f_octave, np.int32); f_counts = np.ascontiguousarray(f_counts, np.int32)
+        fm = np.ascontiguousarray(feat_match, np.int32)
+        q_Xw = np.ascontiguousarray(q_Xw, np.float32).reshape(n, -1, 3); qs = q_Xw.shape[1]
+        q_counts = np.ascontiguousarray(q_counts, np.int32); ils = np.ascontiguousarray(inv_level_sigma2, np.float32)
+        outl = np.zeros((n, fs), np.uint8); ninl = np.zeros(n, np.int32); ne = np.zeros(n, np.int32)
+        _check(self._L.orbo_pose_optimization_matched(self._h, n, _ptr(T), _ptr(K4), _ptr(f_xy), _ptr(f_octave), _ptr(f_counts), fs, _ptr(fm),
+                                                      _ptr(q_Xw), _ptr(q_counts), qs, _ptr(ils), len(ils), _ptr(outl), _ptr(ninl), _ptr(ne), 0))
+        return T.reshape(n, 4, 4), outl, ninl, ne
+
     def _ba(self, poses, fixed, intr, points, e_kf, e_pt, e_uv, e_inv_sigma2, two_stage, its0, its1, robust, stop_flag=None):
         poses = np.ascontiguousarray(poses, np.float32).reshape(-1, 16).copy(); K = len(poses)
         fixed = np.ascontiguousarray(fixed, np.uint8)

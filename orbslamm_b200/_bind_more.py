@@ -24,6 +24,8 @@ def declare(L):
     L.orbo_synchronize.argtypes = [vp]
     L.orbo_kernel_launches.argtypes = [vp]; L.orbo_kernel_launches.restype = c.c_longlong
     L.orbo_pose_optimization.argtypes = [vp, i, vp, vp, vp, vp, vp, vp, i, vp, vp, i]
+    L.orbo_pose_optimization_matched.argtypes = [vp, i, vp, vp, vp, vp, vp, i, vp, vp, vp, i, vp, i, vp, vp, vp, i]
+    L.orbo_pose_optimization_matched.restype = c.c_int
     L.orbo_bundle_adjust.argtypes = [vp, i, vp, vp, vp, i, vp, i, vp, vp, vp, vp, i, i, i, i, vp, vp, vp, vp, vp]
     for n in ("orbo_create", "orbo_destroy", "orbo_set_stream", "orbo_synchronize", "orbo_pose_optimization", "orbo_bundle_adjust"):
         getattr(L, n).restype = c.c_int

@@ -107,6 +107,45 @@ int orbo_pose_optimization(orbo_handle *h, int n_frames, float *Tcw, const float
     return S.finish();
 }
 
+int orbo_pose_optimization_matched(orbo_handle *h, int n_frames, float *Tcw, const float *K4, const float *f_xy, const int32_t *f_octave,
+                                   const int32_t *f_counts, int f_slab, const int32_t *feat_match, const float *q_Xw, const int32_t *q_counts,
+                                   int q_slab, const float *inv_level_sigma2, int nlevels, uint8_t *f_outlier, int32_t *n_inliers,
+                                   int32_t *n_edges, int memspace)
+{
+    ORBS_REQUIRE(h && Tcw && K4 && f_xy && f_octave && f_counts && feat_match && q_Xw && q_counts && inv_level_sigma2 && f_outlier && n_inliers,
+                 ORBS_E_INVALID, "null argument");
+    ORBS_REQUIRE(n_frames > 0 && f_slab > 0 && q_slab > 0 && nlevels > 0, ORBS_E_INVALID, "non-positive size");
+    std::lock_guard<std::mutex> lk(h->mu);
+    ORBS_CUDA(cudaSetDevice(h->device));
+    Stager S(&h->pool, h->stream, memspace);
+    const size_t nf = (size_t)n_frames * f_slab, nq = (size_t)n_frames * q_slab;
+    PoseGatherArgs G;
+    G.f_slab = f_slab; G.q_slab = q_slab; G.nlevels = nlevels;
+    G.f_xy = (const float2 *)S.in(f_xy, nf * 2); G.f_octave = S.in(f_octave, nf); G.f_counts = S.in(f_counts, n_frames);
+    G.feat_match = S.in(feat_match, nf); G.q_Xw = S.in(q_Xw, nq * 3); G.q_counts = S.in(q_counts, n_frames);
+    G.inv_level_sigma2 = S.in(inv_level_sigma2, nlevels);
+    G.Xw = S.scratch<float>(nf * 3); G.obs = S.scratch<float>(nf * 2); G.w = S.scratch<float>(nf); G.edge_feat = S.scratch<int>(nf);
+    int32_t *d_nedges = n_edges ? S.inout(n_edges, n_frames, false) : S.scratch<int32_t>(n_frames);
+    G.counts = d_nedges;
+    PoseArgs A;
+    A.slab = f_slab;
+    A.fx = K4[0]; A.fy = K4[1]; A.cx = K4[2]; A.cy = K4[3];
+    A.Tcw = S.inout(Tcw, (size_t)n_frames * 16);
+    A.Xw = G.Xw; A.obs = G.obs; A.w = G.w; A.counts = d_nedges;
+    uint8_t *d_eout = S.scratch<uint8_t>(nf);
+    A.outlier = d_eout; A.n_inliers = S.inout(n_inliers, n_frames, false);
+    A.err = S.scratch<double>(nf * 2);
+    uint8_t *d_fout = S.inout(f_outlier, nf, false);
+    if (S.rc) return S.rc;
+    ORBS_CUDA(cudaMemsetAsync(d_fout, 0, nf, h->stream));
+    k_pose_gather<<<n_frames, 256, 0, h->stream>>>(G);
+    k_pose_optimization<<<n_frames, kPoseThreads, 0, h->stream>>>(A);
+    k_pose_scatter<<<dim3((f_slab + 255) / 256, n_frames), 256, 0, h->stream>>>(f_slab, d_nedges, G.edge_feat, d_eout, d_fout);
+    h->launches += 3;
+    ORBS_CUDA(cudaGetLastError());
+    return S.finish();
+}
+
 }  // extern "C"
 
 // ---------------------------------------------------------------------------------------------------------

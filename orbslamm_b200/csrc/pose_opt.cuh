@@ -233,4 +233,58 @@ k_pose_optimization(const PoseArgs A)
     }
 }
 
+
+// Frame -> edge list, in feature order like the loop of Optimizer.cc:303-384: every feature that holds a map point
+// (feat_match >= 0) becomes one EdgeSE3ProjectXYZOnlyPose.  One CTA per frame, stable compaction by block scan.
+struct PoseGatherArgs {
+    int f_slab, q_slab, nlevels;
+    const float2 *f_xy; const int *f_octave; const int *f_counts; const int *feat_match;
+    const float *q_Xw; const int *q_counts; const float *inv_level_sigma2;
+    float *Xw, *obs, *w; int *edge_feat; int *counts;      // outputs, slab = f_slab
+};
+
+__global__ void __launch_bounds__(256)
+k_pose_gather(const PoseGatherArgs A)
+{
+    __shared__ int s_warp[8];
+    __shared__ int s_base;
+    const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int N = A.f_counts[f], M = A.q_counts[f];
+    const size_t fo = (size_t)f * A.f_slab, qo = (size_t)f * A.q_slab;
+    if (tid == 0) s_base = 0;
+    __syncthreads();
+    for (int base = 0; base < N; base += 256) {
+        const int i = base + tid;
+        int q = -1;
+        if (i < N) { q = A.feat_match[fo + i]; if (q >= M) q = -1; }
+        const unsigned bal = __ballot_sync(0xffffffffu, q >= 0);
+        if (lane == 0) s_warp[wid] = __popc(bal);
+        __syncthreads();
+        int off = s_base;
+        for (int w = 0; w < wid; w++) off += s_warp[w];
+        if (q >= 0) {
+            const int e = off + __popc(bal & ((1u << lane) - 1));
+            const float2 p = A.f_xy[fo + i];
+            A.obs[2 * (fo + e)] = p.x; A.obs[2 * (fo + e) + 1] = p.y;
+            A.Xw[3 * (fo + e)] = A.q_Xw[3 * (qo + q)]; A.Xw[3 * (fo + e) + 1] = A.q_Xw[3 * (qo + q) + 1]; A.Xw[3 * (fo + e) + 2] = A.q_Xw[3 * (qo + q) + 2];
+            A.w[fo + e] = A.inv_level_sigma2[min(max(A.f_octave[fo + i], 0), A.nlevels - 1)];
+            A.edge_feat[fo + e] = i;
+        }
+        __syncthreads();
+        if (tid == 0) { int t = 0; for (int w = 0; w < 8; w++) t += s_warp[w]; s_base += t; }
+        __syncthreads();
+    }
+    if (tid == 0) A.counts[f] = s_base;
+}
+
+// edge outlier flags -> per-feature flags (Frame::mvbOutlier); f_outlier is zeroed beforehand
+__global__ void __launch_bounds__(256)
+k_pose_scatter(int f_slab, const int *__restrict__ e_counts, const int *__restrict__ edge_feat,
+               const uint8_t *__restrict__ e_outlier, uint8_t *__restrict__ f_outlier)
+{
+    const int f = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t fo = (size_t)f * f_slab;
+    if (i < e_counts[f]) f_outlier[fo + edge_feat[fo + i]] = e_outlier[fo + i];
+}
+
 }  // namespace orbs

@@ -79,3 +79,34 @@ def test_global_ba_and_abort(lib):
     stop = np.ones(1, np.int32)
     ab = opt.LocalBundleAdjustment(g["poses"], g["fixed"], g["intr"], g["points"], g["kf"], g["pt"], g["uv"], g["inv_sigma2"], stop_flag=stop)
     assert ab["aborted"] and np.array_equal(ab["poses"], g["poses"]) and np.array_equal(ab["points"], g["points"])
+
+
+def test_pose_optimization_from_matches(lib):
+    """Device-side edge gathering (Optimizer.cc:303-384) + PoseOptimization == oracle on the host-gathered edges."""
+    import orbslamm_b200 as ob
+    from helpers import make_tracking_case, slab
+    cases = [make_tracking_case(synth.TUM, sid) for sid in (6, 7)]
+    P = cases[0]["P"]
+    sf = np.array(list(P.scale)[:8], np.float32); ils = np.array(list(P.inv_sigma2)[:8], np.float32)
+    g = oracle.grid_params(*cases[0]["bounds"])
+    nF = max(len(c["cur"]["x"]) for c in cases); nQ = max(len(c["last"]["x"]) for c in cases)
+    fms, T0s, refs = [], [], []
+    for c in cases:
+        cur, last = c["cur"], c["last"]
+        q = oracle.project_last_frame(c["Tcw"], c["K4"], g, sf, c["Xw"], last["octave"], 15.0, c["valid"])
+        fxy = np.stack([cur["x"], cur["y"]], 1)
+        _, fm = oracle.search_by_projection(g, fxy, cur["octave"], cur["angle"], cur["desc"], q[0], q[1], q[2], q[3], q[4], last["angle"], last["desc"], 100, 0.0, True)
+        T0 = c["Tcw"].copy(); T0[:3, 3] += np.array([0.05, 0.02, -0.04], np.float32)
+        m = fm >= 0
+        refs.append((m, oracle.pose_optimization(T0, c["Xw"][fm[m]], fxy[m], ils[cur["octave"][m]], c["K4"])))
+        fms.append(fm); T0s.append(T0)
+    opt = ob.Optimizer()
+    T, outl, ninl, ne = opt.PoseOptimizationMatched(np.stack(T0s), cases[0]["K4"], slab([np.stack([c["cur"]["x"], c["cur"]["y"]], 1) for c in cases], nF, np.float32, (2,)),
+                                                    slab([c["cur"]["octave"] for c in cases], nF, np.int32), np.array([len(c["cur"]["x"]) for c in cases], np.int32),
+                                                    slab(fms, nF, np.int32) + 0, slab([c["Xw"] for c in cases], nQ, np.float32, (3,)),
+                                                    np.array([len(c["last"]["x"]) for c in cases], np.int32), ils)
+    for i, (m, (Tr, outr, nr)) in enumerate(refs):
+        n = len(m)
+        assert ne[i] == m.sum() and ninl[i] == nr
+        assert np.array_equal(outl[i, :n][m], outr) and outl[i, :n][~m].sum() == 0
+        assert _rel(T[i], Tr) < RTOL
