@@ -292,68 +292,116 @@ k_ba_schur(const BaDev B, double lambda)
 // Dense Cholesky S = L L^T on the lower triangle, tile size NB, right-looking.  Replaces
 // LinearSolverEigen::solve (SimplicialLDLT); a non-positive pivot raises flags[0] (solve() == false).
 constexpr int NB = 64;
-constexpr int kCholSmem = 2 * NB * (NB + 1) * (int)sizeof(double);   // dynamic shared memory of k_chol_trsm / k_chol_update
 
-__global__ void __launch_bounds__(256)
-k_chol_potrf(double *__restrict__ S, int ld, int k, int *__restrict__ flags)
-{
-    __shared__ double T[NB][NB + 1];
-    double *A = S + (size_t)(k * NB) * ld + k * NB;
-    const int tid = threadIdx.x;
-    for (int i = tid; i < NB * NB; i += 256) { const int r = i / NB, c = i % NB; T[r][c] = c <= r ? A[(size_t)r * ld + c] : 0.0; }
-    __syncthreads();
-    for (int j = 0; j < NB; j++) {
-        if (tid == 0) {
-            const double d = T[j][j];
-            if (!(d > 0.0)) { flags[0] = 1; T[j][j] = 1.0; } else T[j][j] = sqrt(d);
-        }
-        __syncthreads();
-        const double dj = T[j][j];
-        for (int r = j + 1 + tid; r < NB; r += 256) T[r][j] /= dj;
-        __syncthreads();
-        // trailing update of the tile: T[r][c] -= T[r][j] * T[c][j]  for j < c <= r
-        for (int i = tid; i < NB * NB; i += 256) {
-            const int r = i / NB, c = i % NB;
-            if (c > j && c <= r) T[r][c] -= T[r][j] * T[c][j];
-        }
-        __syncthreads();
-    }
-    for (int i = tid; i < NB * NB; i += 256) { const int r = i / NB, c = i % NB; if (c <= r) A[(size_t)r * ld + c] = T[r][c]; }
-}
+// Panel step k: every CTA factors the diagonal tile A_kk redundantly in shared memory (64^3/3 flops -- cheaper than a
+// separate launch + dependency); CTA 0 writes L_kk back and stores its inverse (used by the triangular solves), CTA b >= 1
+// computes A_ik <- A_ik L_kk^-T for tile row i = k + b.  64 threads: one matrix row per thread.
+constexpr int kPanelSmem = 2 * NB * (NB + 1) * (int)sizeof(double);
 
-// A[i][k] <- A[i][k] * L[k][k]^-T   for tile rows i > k (one CTA per tile)
+// 256 threads: 4 threads per matrix row, each holding 16 consecutive columns of the row in registers.
 __global__ void __launch_bounds__(256)
-k_chol_trsm(double *__restrict__ S, int ld, int k)
+k_chol_panel(double *__restrict__ S, int ld, int k, double *__restrict__ Linv, int *__restrict__ flags)
 {
     extern __shared__ double smem_d[];
-    double (*L)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(smem_d);
-    double (*X)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(smem_d + NB * (NB + 1));
-    const int i = k + 1 + blockIdx.x, tid = threadIdx.x;
-    const double *Lk = S + (size_t)(k * NB) * ld + k * NB;
-    double *A = S + (size_t)(i * NB) * ld + k * NB;
-    for (int t = tid; t < NB * NB; t += 256) { const int r = t / NB, c = t % NB; L[r][c] = Lk[(size_t)r * ld + c]; X[r][c] = A[(size_t)r * ld + c]; }
+    double (*T)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(smem_d);                  // A_kk, then L_kk (lower)
+    double (*X)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(smem_d + NB * (NB + 1));  // the tile being solved
+    __shared__ double colbuf[2][NB];
+    __shared__ double invd[NB];
+    const int tid = threadIdx.x, r = tid >> 2, sub = tid & 3, lane = tid & 31;
+    double *A = S + (size_t)(k * NB) * ld + k * NB;
+    const int i = k + blockIdx.x;
+    for (int q = tid; q < NB * NB; q += 256) { const int rr = q >> 6, cc = q & 63; T[rr][cc] = cc <= rr ? A[(size_t)rr * ld + cc] : 0.0; }
+    if (blockIdx.x > 0) {
+        const double *P = S + (size_t)(i * NB) * ld + k * NB;
+        for (int q = tid; q < NB * NB; q += 256) { const int rr = q >> 6, cc = q & 63; X[rr][cc] = P[(size_t)rr * ld + cc]; }
+    }
     __syncthreads();
-    // each thread owns rows r = tid / 4 .. (4 threads per row would need sync); use one thread per row, 64 rows
-    if (tid < NB) {
-        const int r = tid;
-        for (int c = 0; c < NB; c++) {
-            double s = X[r][c];
-            for (int q = 0; q < c; q++) s -= X[r][q] * L[c][q];
-            X[r][c] = s / L[c][c];
+    double a[16];
+#pragma unroll
+    for (int u = 0; u < 16; u++) a[u] = T[r][16 * sub + u];
+    // right-looking Cholesky of the diagonal tile, one barrier per column
+#pragma unroll
+    for (int j = 0; j < NB; j++) {
+        const int js = j >> 4, ju = j & 15;
+        if (sub == js && r >= j) colbuf[j & 1][r] = a[ju];
+        __syncthreads();
+        double d = colbuf[j & 1][j];
+        if (!(d > 0.0)) { if (blockIdx.x == 0 && tid == 0) flags[0] = 1; d = 1.0; }
+        const double rinv = rsqrt(d), sd = d * rinv;
+        if (r >= j) {
+            const double l = (r == j) ? sd : colbuf[j & 1][r] * rinv;
+            if (sub == js) a[ju] = l;
+            const double lr = l * rinv;
+#pragma unroll
+            for (int u = 0; u < 16; u++) {
+                const int c = 16 * sub + u;
+                if (c > j && c <= r) a[u] = fma(-lr, colbuf[j & 1][c], a[u]);
+            }
         }
     }
     __syncthreads();
-    for (int t = tid; t < NB * NB; t += 256) { const int r = t / NB, c = t % NB; A[(size_t)r * ld + c] = X[r][c]; }
+#pragma unroll
+    for (int u = 0; u < 16; u++) { const int c = 16 * sub + u; T[r][c] = c <= r ? a[u] : 0.0; }
+    __syncthreads();
+    if (tid < NB) invd[tid] = 1.0 / T[tid][tid];
+    __syncthreads();
+    const unsigned full = 0xffffffffu;
+    double x[16];
+    if (blockIdx.x == 0) {
+        for (int q = tid; q < NB * NB; q += 256) { const int rr = q >> 6, cc = q & 63; if (cc <= rr) A[(size_t)rr * ld + cc] = T[rr][cc]; }
+        // inverse of the lower-triangular tile: the 4 threads of "row" c hold column c of L^-1 (rows 16 sub .. 16 sub + 15)
+        const int c = r;
+#pragma unroll
+        for (int u = 0; u < 16; u++) x[u] = (16 * sub + u == c) ? 1.0 : 0.0;
+#pragma unroll
+        for (int rr = 0; rr < NB; rr++) {
+            const int os = rr >> 4, ou = rr & 15;
+            const double mine = rr >= c ? x[ou] * invd[rr] : 0.0;
+            const double xr = __shfl_sync(full, mine, (lane & ~3) | os);
+            if (sub == os) x[ou] = xr;
+#pragma unroll
+            for (int u = 0; u < 16; u++) { const int q = 16 * sub + u; if (q > rr) x[u] = fma(-T[q][rr], xr, x[u]); }
+        }
+#pragma unroll
+        for (int u = 0; u < 16; u++) X[16 * sub + u][c] = x[u];
+        __syncthreads();
+        double *Li = Linv + (size_t)k * NB * NB;
+        for (int q = tid; q < NB * NB; q += 256) Li[q] = X[q >> 6][q & 63];
+    } else {
+        // row r of the tile: x L^T = a, right-looking along the row
+#pragma unroll
+        for (int u = 0; u < 16; u++) x[u] = X[r][16 * sub + u];
+#pragma unroll
+        for (int c = 0; c < NB; c++) {
+            const int os = c >> 4, ou = c & 15;
+            const double xc = __shfl_sync(full, x[ou] * invd[c], (lane & ~3) | os);
+            if (sub == os) x[ou] = xc;
+#pragma unroll
+            for (int u = 0; u < 16; u++) { const int q = 16 * sub + u; if (q > c) x[u] = fma(-xc, T[q][c], x[u]); }
+        }
+#pragma unroll
+        for (int u = 0; u < 16; u++) X[r][16 * sub + u] = x[u];
+        __syncthreads();
+        double *P = S + (size_t)(i * NB) * ld + k * NB;
+        for (int q = tid; q < NB * NB; q += 256) { const int rr = q >> 6, cc = q & 63; P[(size_t)rr * ld + cc] = X[rr][cc]; }
+    }
 }
 
-// A[i][j] -= A[i][k] * A[j][k]^T   for k < j <= i  (one CTA per (i, j) tile; 4x4 register blocking)
+// A[i][j] -= A[i][k] * A[j][k]^T   for k < j <= i.  One CTA per (i, j) tile; panels staged row-major with cp.async
+// (pitch 65 doubles: conflict-free for both operands), thread (ty, tx) owns the interleaved 4x4 micro-tile
+// C[ty + 16u][tx + 16v].
+__device__ __forceinline__ void cp_async8(void *smem, const void *gmem)
+{
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gmem));
+}
+
 __global__ void __launch_bounds__(256)
 k_chol_update(double *__restrict__ S, int ld, int k, int nt)
 {
     extern __shared__ double smem_d[];
-    double (*Ai)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(smem_d);
+    double (*Ai)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(smem_d);                 // [row][q]
     double (*Aj)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(smem_d + NB * (NB + 1));
-    // linear tile index -> (i, j) with k < j <= i < nt
     const int m = nt - k - 1;
     int t = blockIdx.x;
     int ii = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
@@ -363,77 +411,95 @@ k_chol_update(double *__restrict__ S, int ld, int k, int nt)
     if (ii >= m) return;
     const int i = k + 1 + ii, j = k + 1 + jj, tid = threadIdx.x;
     const double *Pi = S + (size_t)(i * NB) * ld + k * NB, *Pj = S + (size_t)(j * NB) * ld + k * NB;
-    for (int q = tid; q < NB * NB; q += 256) { const int r = q / NB, c = q % NB; Ai[r][c] = Pi[(size_t)r * ld + c]; Aj[r][c] = Pj[(size_t)r * ld + c]; }
+#pragma unroll 4
+    for (int q = tid; q < NB * NB; q += 256) {
+        const int r = q >> 6, c = q & 63;
+        cp_async8(&Ai[r][c], &Pi[(size_t)r * ld + c]);
+        cp_async8(&Aj[r][c], &Pj[(size_t)r * ld + c]);
+    }
+    asm volatile("cp.async.commit_group;\n" ::);
+    const int ty = tid >> 4, tx = tid & 15;
+    // prefetch the C micro-tile while the panels land
+    double *C = S + (size_t)(i * NB) * ld + j * NB;
+    double cval[4][4];
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+#pragma unroll
+        for (int v = 0; v < 4; v++) cval[u][v] = C[(size_t)(ty + 16 * u) * ld + tx + 16 * v];
+    asm volatile("cp.async.wait_group 0;\n" ::);
     __syncthreads();
-    const int tr = (tid / 16) * 4, tc = (tid % 16) * 4;
     double acc[4][4] = {};
+#pragma unroll 8
     for (int q = 0; q < NB; q++) {
         double a[4], b[4];
 #pragma unroll
-        for (int u = 0; u < 4; u++) { a[u] = Ai[tr + u][q]; b[u] = Aj[tc + u][q]; }
+        for (int u = 0; u < 4; u++) { a[u] = Ai[ty + 16 * u][q]; b[u] = Aj[tx + 16 * u][q]; }
 #pragma unroll
         for (int u = 0; u < 4; u++)
 #pragma unroll
             for (int v = 0; v < 4; v++) acc[u][v] = fma(a[u], b[v], acc[u][v]);
     }
-    double *C = S + (size_t)(i * NB) * ld + j * NB;
 #pragma unroll
     for (int u = 0; u < 4; u++)
 #pragma unroll
         for (int v = 0; v < 4; v++)
-            if (i != j || tc + v <= tr + u) C[(size_t)(tr + u) * ld + tc + v] -= acc[u][v];
+            if (i != j || tx + 16 * v <= ty + 16 * u) C[(size_t)(ty + 16 * u) * ld + tx + 16 * v] = cval[u][v] - acc[u][v];
 }
+constexpr int kUpdateSmem = 2 * NB * (NB + 1) * (int)sizeof(double);
 
-// triangular solves, tile by tile.  forward: y_k = L_kk^-1 (b_k);  then b_i -= L_ik y_k (i > k)
-__global__ void __launch_bounds__(NB)
-k_trs_diag(const double *__restrict__ S, int ld, int k, double *__restrict__ b, int transpose)
+// Triangular solves as two dataflow kernels (one CTA per tile row, all co-resident; dependencies always point to
+// lower block indices so that in-order block scheduling cannot deadlock):
+//   forward  (dir = 0): CTA i waits for y_0..y_{i-1}, accumulates L_ik y_k, then y_i = Linv_ii (b_i - acc)
+//   backward (dir = 1): CTA b handles tile j = nt-1-b, waits for x_{nt-1}..x_{j+1}, accumulates L_ij^T x_i, then
+//                       x_j = Linv_jj^T (y_j - acc)
+// v is solved in place; ready[] must be zero on entry.
+__global__ void __launch_bounds__(256)
+k_chol_solve(const double *__restrict__ S, int ld, int nt, const double *__restrict__ Linv, double *v, int *ready, int dir)
 {
-    __shared__ double L[NB][NB + 1];
-    __shared__ double y[NB];
-    const double *Lk = S + (size_t)(k * NB) * ld + k * NB;
-    const int tid = threadIdx.x;
-    for (int t = tid; t < NB * NB; t += NB) { const int r = t / NB, c = t % NB; L[r][c] = Lk[(size_t)r * ld + c]; }
-    y[tid] = b[k * NB + tid];
+    __shared__ double s_vec[NB];
+    __shared__ double s_part[4][NB];
+    __shared__ double s_acc[NB];
+    const int tid = threadIdx.x, lane64 = tid & 63, part = tid >> 6;
+    const int me = dir == 0 ? blockIdx.x : nt - 1 - blockIdx.x;
+    if (tid < NB) s_acc[tid] = 0.0;
     __syncthreads();
-    if (!transpose) {
-        for (int j = 0; j < NB; j++) {
-            if (tid == j) y[j] /= L[j][j];
-            __syncthreads();
-            if (tid > j) y[tid] -= L[tid][j] * y[j];
-            __syncthreads();
+    const int nsteps = dir == 0 ? me : nt - 1 - me;
+    for (int s = 0; s < nsteps; s++) {
+        const int o = dir == 0 ? s : nt - 1 - s;            // the tile whose solution we consume
+        if (tid == 0) { while (*((volatile int *)&ready[o]) == 0) { } __threadfence(); }
+        __syncthreads();
+        if (tid < NB) s_vec[tid] = *((volatile double *)&v[o * NB + tid]);
+        __syncthreads();
+        double sum = 0;
+        if (dir == 0) {
+            // acc[r] += sum_c L[me*64 + r][o*64 + c] * y_o[c]; thread (r = lane64, quarter = part)
+            const double *row = S + (size_t)(me * NB + lane64) * ld + o * NB + part * 16;
+#pragma unroll
+            for (int c = 0; c < 16; c++) sum = fma(row[c], s_vec[part * 16 + c], sum);
+        } else {
+            // acc[c] += sum_r L[o*64 + r][me*64 + c] * x_o[r]; thread (c = lane64, quarter = part)
+            const double *col = S + (size_t)(o * NB + part * 16) * ld + me * NB + lane64;
+#pragma unroll
+            for (int r = 0; r < 16; r++) sum = fma(col[(size_t)r * ld], s_vec[part * 16 + r], sum);
         }
-    } else {
-        for (int j = NB - 1; j >= 0; j--) {
-            if (tid == j) y[j] /= L[j][j];
-            __syncthreads();
-            if (tid < j) y[tid] -= L[j][tid] * y[j];
-            __syncthreads();
-        }
+        s_part[part][lane64] = sum;
+        __syncthreads();
+        if (tid < NB) s_acc[tid] += s_part[0][tid] + s_part[1][tid] + s_part[2][tid] + s_part[3][tid];
+        __syncthreads();
     }
-    b[k * NB + tid] = y[tid];
-}
-
-// forward: for tile rows i > k: b_i -= L_ik y_k.  backward (transpose): for tile rows j < k: b_j -= L_kj^T x_k.
-__global__ void __launch_bounds__(NB)
-k_trs_update(const double *__restrict__ S, int ld, int k, double *__restrict__ b, int transpose)
-{
-    __shared__ double yk[NB];
-    const int tid = threadIdx.x;
-    yk[tid] = b[k * NB + tid];
+    // diagonal tile through its explicit inverse
+    if (tid < NB) s_vec[tid] = v[me * NB + tid] - s_acc[tid];
     __syncthreads();
-    if (!transpose) {
-        const int i = k + 1 + blockIdx.x;
-        const double *Lik = S + (size_t)(i * NB) * ld + k * NB;
-        double s = 0;
-        for (int c = 0; c < NB; c++) s += Lik[(size_t)tid * ld + c] * yk[c];
-        b[i * NB + tid] -= s;
-    } else {
-        const int j = blockIdx.x;
-        const double *Lkj = S + (size_t)(k * NB) * ld + j * NB;
-        double s = 0;
-        for (int r = 0; r < NB; r++) s += Lkj[(size_t)r * ld + tid] * yk[r];
-        b[j * NB + tid] -= s;
-    }
+    const double *Li = Linv + (size_t)me * NB * NB;
+    double sum = 0;
+    if (dir == 0) { for (int c = part * 16; c < part * 16 + 16; c++) sum = fma(Li[lane64 * NB + c], s_vec[c], sum); }     // y = Linv r
+    else { for (int r = part * 16; r < part * 16 + 16; r++) sum = fma(Li[r * NB + lane64], s_vec[r], sum); }               // x = Linv^T r
+    s_part[part][lane64] = sum;
+    __syncthreads();
+    if (tid < NB) v[me * NB + tid] = s_part[0][tid] + s_part[1][tid] + s_part[2][tid] + s_part[3][tid];
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) { *((volatile int *)&ready[me]) = 1; }
 }
 
 // copy the pose part of the solution; pose part of computeScale

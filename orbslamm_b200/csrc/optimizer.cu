@@ -42,8 +42,8 @@ int orbo_create(orbo_handle **out, int device)
     cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete h; return cuda_fail(e, "cudaStreamCreate", __FILE__, __LINE__); }
     if (int rc = h->h_scalars.reserve(256)) { orbo_destroy(h); return rc; }
-    cudaFuncSetAttribute(k_chol_trsm, cudaFuncAttributeMaxDynamicSharedMemorySize, kCholSmem);
-    cudaFuncSetAttribute(k_chol_update, cudaFuncAttributeMaxDynamicSharedMemorySize, kCholSmem);
+    cudaFuncSetAttribute(k_chol_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPanelSmem);
+    cudaFuncSetAttribute(k_chol_update, cudaFuncAttributeMaxDynamicSharedMemorySize, kUpdateSmem);
     *out = h;
     return ORBS_OK;
 }
@@ -162,6 +162,8 @@ struct BaHost {
     int nbad = 0;
     const volatile int *stop = nullptr;
     int lm_iterations = 0, lm_trials = 0, chol_failures = 0;
+    double *Linv = nullptr;       // [ntiles][64*64] inverses of the diagonal Cholesky tiles
+    int *ready = nullptr;         // [2*ntiles] dataflow flags of the triangular solves
     double *h_scal = nullptr;     // pinned [16]
     int *h_flag = nullptr;        // pinned
 
@@ -214,32 +216,23 @@ struct BaHost {
             T().end(st);
             count(2);
             for (int k = 0; k < ntiles; k++) {
-                T().begin(BK_POTRF, st);
-                k_chol_potrf<<<1, 256, 0, st>>>(B.S, ld, k, B.flags);
-                T().end(st);
                 const int m = ntiles - k - 1;
-                if (m > 0) {
-                    T().begin(BK_TRSM, st);
-                    k_chol_trsm<<<m, 256, kCholSmem, st>>>(B.S, ld, k);
-                    T().end(st);
-                    T().begin(BK_SYRK, st);
-                    k_chol_update<<<m * (m + 1) / 2, 256, kCholSmem, st>>>(B.S, ld, k, ntiles);
-                    T().end(st);
-                    count(2);
-                }
+                T().begin(BK_POTRF, st);
+                k_chol_panel<<<m + 1, 256, kPanelSmem, st>>>(B.S, ld, k, Linv, B.flags);
+                T().end(st);
                 count(1);
+                if (m > 0) {
+                    T().begin(BK_SYRK, st);
+                    k_chol_update<<<m * (m + 1) / 2, 256, kUpdateSmem, st>>>(B.S, ld, k, ntiles);
+                    T().end(st);
+                    count(1);
+                }
             }
             T().begin(BK_TRS, st);
-            for (int k = 0; k < ntiles; k++) {
-                k_trs_diag<<<1, NB, 0, st>>>(B.S, ld, k, B.bs, 0);
-                if (ntiles - k - 1 > 0) { k_trs_update<<<ntiles - k - 1, NB, 0, st>>>(B.S, ld, k, B.bs, 0); count(1); }
-                count(1);
-            }
-            for (int k = ntiles - 1; k >= 0; k--) {
-                k_trs_diag<<<1, NB, 0, st>>>(B.S, ld, k, B.bs, 1);
-                if (k > 0) { k_trs_update<<<k, NB, 0, st>>>(B.S, ld, k, B.bs, 1); count(1); }
-                count(1);
-            }
+            ORBS_CUDA(cudaMemsetAsync(ready, 0, 2 * (size_t)ntiles * sizeof(int), st));
+            k_chol_solve<<<ntiles, 256, 0, st>>>(B.S, ld, ntiles, Linv, B.bs, ready, 0);
+            k_chol_solve<<<ntiles, 256, 0, st>>>(B.S, ld, ntiles, Linv, B.bs, ready + ntiles, 1);
+            count(2);
             T().end(st);
             k_ba_take_xp<<<xp_blocks, 256, 0, st>>>(B, lambda);
             k_reduce_partials<<<1, 256, 0, st>>>(B.partial, xp_blocks, B.scalars, 2, 0);
@@ -385,6 +378,8 @@ extern "C" int orbo_bundle_adjust(orbo_handle *h, int K, float *poses, const uin
     B.x = S.scratch<double>(6 * (size_t)K + 3 * (size_t)P);
     const int ld_max = (int)align_up(6 * (size_t)K, NB);
     B.S = S.scratch<double>((size_t)ld_max * ld_max); B.bs = S.scratch<double>(ld_max);
+    D.Linv = S.scratch<double>((size_t)ld_max * NB); D.ready = S.scratch<int>(2 * (size_t)(ld_max / NB) + 2);
+    ORBS_REQUIRE(ld_max / NB <= 140, ORBS_E_INVALID, "more than 1493 free keyframes: the dataflow triangular solve needs all tile rows co-resident");
     const int max_blocks = std::max({(E + 255) / 256, (P + 7) / 8, (K + P + 255) / 256, (6 * K + 255) / 256}) + 1;
     B.partial = S.scratch<double>(max_blocks); B.scalars = S.scratch<double>(8); B.flags = S.scratch<int>(4);
     double *d_chi2 = S.scratch<double>(E); uint8_t *d_depth = S.scratch<uint8_t>(E);
