@@ -228,6 +228,18 @@ int orbo_bundle_adjust(orbo_handle *h, int K, float *poses, const uint8_t *fixed
                        int two_stage, int its0, int its1, int robust, const volatile int *stop_flag,
                        double *e_chi2, uint8_t *e_depth_ok, uint8_t *e_outlier, int32_t *stats);
 
+/* Multi-GPU bundle adjustment: one process per GPU, keyframe poses replicated, MAP POINTS (with all
+ * their observations) sharded over the ranks.  After orbo_comm_init the handle's orbo_bundle_adjust becomes a
+ * collective: every rank passes ALL keyframes (same order, same poses) but only ITS points and edges; each rank builds
+ * its partial reduced pose system, one ncclAllReduce (fp64 sum over NVLink) per LM trial combines them, every rank
+ * factors the same system redundantly and back-substitutes its own points.  chi2 / gain-ratio scalars, the stop flag
+ * and the keyframe activity mask are reduced too, so that all ranks take identical LM decisions.  Poses come back
+ * identical on every rank; point / edge outputs are the rank's shard.
+ *   orbo_comm_unique_id: rank 0 creates the 128-byte NCCL id, the caller distributes it (MPI, torch.distributed, files);
+ *   orbo_comm_init: collective. */
+int orbo_comm_unique_id(uint8_t *id128);
+int orbo_comm_init(orbo_handle *h, int nranks, int rank, const uint8_t *id128);
+
 /* Bench bookkeeping for the last orbo_bundle_adjust call: out4 = { seconds inside the LM loops (graph resident on the
  * device), seconds of the whole call, seconds of host graph layout + H2D, leading dimension of the reduced system }. */
 int orbo_last_ba_timing(orbo_handle *h, double *out4);

@@ -327,6 +327,19 @@ class Optimizer:
     def synchronize(self): _check(self._L.orbo_synchronize(self._h))
     def kernel_launches(self): return int(self._L.orbo_kernel_launches(self._h))
 
+    @staticmethod
+    def comm_unique_id():
+        """128-byte NCCL unique id (create on rank 0, hand to every rank's comm_init)."""
+        out = np.zeros(128, np.uint8)
+        _check(load().orbo_comm_unique_id(_ptr(out)))
+        return out
+
+    def comm_init(self, nranks, rank, unique_id):
+        """Collective: afterwards LocalBundleAdjustment / BundleAdjustment run sharded over `nranks` GPUs (map points
+        sharded, poses replicated, one NCCL all-reduce of the reduced pose system per LM trial)."""
+        uid = np.ascontiguousarray(unique_id, np.uint8)
+        _check(self._L.orbo_comm_init(self._h, int(nranks), int(rank), _ptr(uid)))
+
     def PoseOptimization(self, Tcw, K4, Xw, obs, inv_sigma2, counts):
         """Batched Optimizer::PoseOptimization.  Tcw [n,4,4]; Xw [n,slab,3]; obs [n,slab,2]; inv_sigma2 [n,slab];
         counts [n].  Returns (Tcw_out [n,4,4], outlier u8[n,slab], n_inliers i32[n])."""

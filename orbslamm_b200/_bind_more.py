@@ -23,6 +23,8 @@ def declare(L):
     L.orbo_set_stream.argtypes = [vp, vp]
     L.orbo_synchronize.argtypes = [vp]
     L.orbo_kernel_launches.argtypes = [vp]; L.orbo_kernel_launches.restype = c.c_longlong
+    L.orbo_comm_unique_id.argtypes = [vp]; L.orbo_comm_unique_id.restype = c.c_int
+    L.orbo_comm_init.argtypes = [vp, i, i, vp]; L.orbo_comm_init.restype = c.c_int
     L.orbo_pose_optimization.argtypes = [vp, i, vp, vp, vp, vp, vp, vp, i, vp, vp, i]
     L.orbo_pose_optimization_matched.argtypes = [vp, i, vp, vp, vp, vp, vp, i, vp, vp, vp, i, vp, i, vp, vp, vp, i]
     L.orbo_pose_optimization_matched.restype = c.c_int

@@ -217,16 +217,18 @@ k_ba_max_diag(const BaDev B)
 
 // S (lower triangle, ld x ld, zeroed by a memset before) <- diag blocks Hpp + lambda I ; bs <- bp ; padding diag = 1
 __global__ void __launch_bounds__(256)
-k_ba_schur_init(const BaDev B, double lambda)
+k_ba_schur_init(const BaDev B, double lambda, int lead)
 {
+    // sharded solve: Hpp / bp are already summed over the ranks; they (and lambda, and the padding diagonal) enter through the
+    // lead rank only, the other ranks start from zero and contribute their points' Schur terms
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t < B.nA * 36) {
         const int i = t / 36, a = (t % 36) / 6, c = t % 6;
-        if (c <= a) B.S[(size_t)(6 * i + a) * B.ld + 6 * i + c] = B.Hpp[t] + (a == c ? lambda : 0.0);
+        if (c <= a && lead) B.S[(size_t)(6 * i + a) * B.ld + 6 * i + c] = B.Hpp[t] + (a == c ? lambda : 0.0);
     }
     if (t < B.ld) {
-        B.bs[t] = t < B.n ? B.bp[t] : 0.0;
-        if (t >= B.n) B.S[(size_t)t * B.ld + t] = 1.0;
+        B.bs[t] = (t < B.n && lead) ? B.bp[t] : 0.0;
+        if (t >= B.n && lead) B.S[(size_t)t * B.ld + t] = 1.0;
     }
 }
 
@@ -504,12 +506,12 @@ k_chol_solve(const double *__restrict__ S, int ld, int nt, const double *__restr
 
 // copy the pose part of the solution; pose part of computeScale
 __global__ void __launch_bounds__(256)
-k_ba_take_xp(const BaDev B, double lambda)
+k_ba_take_xp(const BaDev B, double lambda, int lead)
 {
     __shared__ double s_w[8];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     double sc = 0;
-    if (i < B.n) { const double x = B.bs[i]; B.x[i] = x; sc = x * (lambda * x + B.bp[i]); }
+    if (i < B.n) { const double x = B.bs[i]; B.x[i] = x; sc = lead ? x * (lambda * x + B.bp[i]) : 0.0; }   // pose part counted once (lead rank)
     sc = warp_sum(sc);
     if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = sc;
     __syncthreads();

@@ -9,11 +9,46 @@
 #include <mutex>
 #include <vector>
 #include <chrono>
+#include <dlfcn.h>
+#include <nccl.h>
 #include "common.cuh"
 #include "pose_opt.cuh"
 #include "ba_kernels.cuh"
 
 using namespace orbs;
+
+// NCCL is bound at run time (dlopen by soname) so that single-GPU users need no NCCL at all
+namespace {
+struct NcclApi {
+    void *lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*CommAbort)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    bool load()
+    {
+        if (lib) return true;
+        lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!lib) return false;
+        GetUniqueId = (decltype(GetUniqueId))dlsym(lib, "ncclGetUniqueId");
+        CommInitRank = (decltype(CommInitRank))dlsym(lib, "ncclCommInitRank");
+        CommDestroy = (decltype(CommDestroy))dlsym(lib, "ncclCommDestroy");
+        CommAbort = (decltype(CommAbort))dlsym(lib, "ncclCommAbort");
+        AllReduce = (decltype(AllReduce))dlsym(lib, "ncclAllReduce");
+        GetErrorString = (decltype(GetErrorString))dlsym(lib, "ncclGetErrorString");
+        return GetUniqueId && CommInitRank && CommDestroy && AllReduce && GetErrorString;
+    }
+};
+NcclApi g_nccl;
+}  // namespace
+
+#define ORBS_NCCL(call)                                                                        \
+    do {                                                                                       \
+        ncclResult_t _r = (call);                                                              \
+        if (_r != ncclSuccess) { set_last_error(std::string("NCCL error: ") + g_nccl.GetErrorString(_r) + " in " #call); return ORBS_E_CUDA; } \
+    } while (0)
 
 struct orbo_handle {
     int device = 0;
@@ -25,6 +60,8 @@ struct orbo_handle {
     StagePool ba_pool;       // bundle adjustment buffers
     PinnedBuf h_scalars;
     KernelTimer timer;       // BA kernels, ids = BaK
+    ncclComm_t comm = nullptr;   // set by orbo_comm_init: orbo_bundle_adjust becomes a collective over map-point shards
+    int nranks = 1, rank = 0;
     double ba_timing[4] = {0, 0, 0, 0};   // last BA call: LM-loop seconds, total seconds, setup (layout + H2D) seconds, Schur bytes
 };
 
@@ -54,6 +91,7 @@ int orbo_destroy(orbo_handle *h)
     cudaSetDevice(h->device);
     if (h->stream && h->own_stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
     else cudaDeviceSynchronize();
+    if (h->comm) { if (g_nccl.CommAbort) g_nccl.CommAbort(h->comm); else g_nccl.CommDestroy(h->comm); }   // abort: never block on a peer at teardown
     h->pool.release(); h->ba_pool.release(); h->h_scalars.release(); h->timer.release();
     delete h;
     return ORBS_OK;
@@ -81,6 +119,31 @@ int orbo_synchronize(orbo_handle *h)
 }
 
 long long orbo_kernel_launches(const orbo_handle *h) { return h ? h->launches : 0; }
+
+int orbo_comm_unique_id(uint8_t *id128)
+{
+    ORBS_REQUIRE(id128, ORBS_E_INVALID, "null argument");
+    ORBS_REQUIRE(g_nccl.load(), ORBS_E_CUDA, "libnccl.so.2 not found");
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    ncclUniqueId id;
+    ORBS_NCCL(g_nccl.GetUniqueId(&id));
+    memcpy(id128, &id, 128);
+    return ORBS_OK;
+}
+
+int orbo_comm_init(orbo_handle *h, int nranks, int rank, const uint8_t *id128)
+{
+    ORBS_REQUIRE(h && id128 && nranks >= 1 && rank >= 0 && rank < nranks, ORBS_E_INVALID, "bad argument");
+    ORBS_REQUIRE(g_nccl.load(), ORBS_E_CUDA, "libnccl.so.2 not found");
+    std::lock_guard<std::mutex> lk(h->mu);
+    ORBS_CUDA(cudaSetDevice(h->device));
+    if (h->comm) { g_nccl.CommDestroy(h->comm); h->comm = nullptr; }
+    ncclUniqueId id;
+    memcpy(&id, id128, 128);
+    ORBS_NCCL(g_nccl.CommInitRank(&h->comm, nranks, id, rank));
+    h->nranks = nranks; h->rank = rank;
+    return ORBS_OK;
+}
 
 int orbo_pose_optimization(orbo_handle *h, int n_frames, float *Tcw, const float *K4, const float *Xw, const float *obs,
                            const float *inv_sigma2, const int32_t *counts, int slab, uint8_t *outlier, int32_t *n_inliers,
@@ -167,12 +230,36 @@ struct BaHost {
     double *h_scal = nullptr;     // pinned [16]
     int *h_flag = nullptr;        // pinned
 
-    bool terminate() const { return stop && *stop; }
+    bool multi() const { return h->nranks > 1; }
+    int allreduce(void *buf, size_t n, ncclDataType_t t, ncclRedOp_t op)
+    {
+        if (!multi()) return ORBS_OK;
+        ORBS_NCCL(g_nccl.AllReduce(buf, buf, n, t, op, h->comm, st));
+        return ORBS_OK;
+    }
+    // the stop flag must lead to the same decision on every rank: reduce it (max) when sharded
+    int *d_stop = nullptr; int *h_stop = nullptr;
+    bool terminate()
+    {
+        int v = (stop && *stop) ? 1 : 0;
+        if (multi()) {
+            *h_stop = v;
+            if (cudaMemcpyAsync(d_stop, h_stop, sizeof(int), cudaMemcpyHostToDevice, st) != cudaSuccess) return true;
+            if (allreduce(d_stop, 1, ncclInt32, ncclMax)) return true;
+            if (cudaMemcpyAsync(h_stop, d_stop, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess) return true;
+            if (cudaStreamSynchronize(st) != cudaSuccess) return true;
+            v = *h_stop;
+        }
+        return v != 0;
+    }
     KernelTimer &T() { return h->timer; }
     void count(int n = 1) { h->launches += n; }
 
     int read_scalars()
     {
+        // sharded: chi2 and the two computeScale parts are sums over ranks, the diagonal maximum a max
+        if (int rc = allreduce(B.scalars, 3, ncclDouble, ncclSum)) return rc;
+        if (int rc = allreduce(B.scalars + 3, 1, ncclDouble, ncclMax)) return rc;
         ORBS_CUDA(cudaMemcpyAsync(h_scal, B.scalars, 8 * sizeof(double), cudaMemcpyDeviceToHost, st));
         ORBS_CUDA(cudaMemcpyAsync(h_flag, B.flags, sizeof(int), cudaMemcpyDeviceToHost, st));
         ORBS_CUDA(cudaStreamSynchronize(st));
@@ -189,7 +276,7 @@ struct BaHost {
         count(2);
     }
 
-    void build_system()
+    int build_system()
     {
         T().begin(BK_BUILD_POINTS, st);
         k_ba_build_points<<<pt_blocks, 256, 0, st>>>(B);
@@ -198,6 +285,13 @@ struct BaHost {
         if (pose_blocks) k_ba_build_poses<<<pose_blocks, 256, 0, st>>>(B);
         T().end(st);
         count(2);
+        // sharded: every rank saw only its shard's observations of a keyframe -> sum the pose blocks (42 doubles per keyframe);
+        // afterwards Hpp / b_p are complete on every rank and enter the reduced system through the lead rank only
+        if (multi() && B.nA > 0) {
+            if (int rc = allreduce(B.Hpp, (size_t)B.nA * 36, ncclDouble, ncclSum)) return rc;
+            if (int rc = allreduce(B.bp, (size_t)B.nA * 6, ncclDouble, ncclSum)) return rc;
+        }
+        return ORBS_OK;
     }
 
     // setLambda + Schur + factor + solve + back-substitution; scalars[1] (+ scalars[2]) = computeScale
@@ -211,9 +305,12 @@ struct BaHost {
             T().end(st);
             const int t = std::max(B.nA * 36, ld);
             T().begin(BK_SCHUR, st);
-            k_ba_schur_init<<<(t + 255) / 256, 256, 0, st>>>(B, lambda);
+            k_ba_schur_init<<<(t + 255) / 256, 256, 0, st>>>(B, lambda, h->rank == 0 ? 1 : 0);
             k_ba_schur<<<pt_blocks, 256, 0, st>>>(B, lambda);
             T().end(st);
+            // the one exchange step of the sharded solve: sum the partial reduced systems over the map-point shards
+            if (int rc = allreduce(B.S, (size_t)ld * ld, ncclDouble, ncclSum)) return rc;
+            if (int rc = allreduce(B.bs, (size_t)ld, ncclDouble, ncclSum)) return rc;
             count(2);
             for (int k = 0; k < ntiles; k++) {
                 const int m = ntiles - k - 1;
@@ -234,7 +331,7 @@ struct BaHost {
             k_chol_solve<<<ntiles, 256, 0, st>>>(B.S, ld, ntiles, Linv, B.bs, ready + ntiles, 1);
             count(2);
             T().end(st);
-            k_ba_take_xp<<<xp_blocks, 256, 0, st>>>(B, lambda);
+            k_ba_take_xp<<<xp_blocks, 256, 0, st>>>(B, lambda, h->rank == 0 ? 1 : 0);
             k_reduce_partials<<<1, 256, 0, st>>>(B.partial, xp_blocks, B.scalars, 2, 0);
             count(2);
         } else {
@@ -254,7 +351,7 @@ struct BaHost {
     int lm_iteration(int iteration)
     {
         errors();
-        build_system();
+        if (build_system()) return LM_ERROR;
         if (iteration == 0) {
             k_ba_max_diag<<<diag_blocks, 256, 0, st>>>(B);
             k_reduce_partials<<<1, 256, 0, st>>>(B.partial, diag_blocks, B.scalars, 3, 1);
@@ -327,7 +424,7 @@ extern "C" int orbo_bundle_adjust(orbo_handle *h, int K, float *poses, const uin
     ORBS_REQUIRE(h && poses && fixed && intr && points && e_kf && e_pt && e_uv && e_inv_sigma2, ORBS_E_INVALID, "null argument");
     ORBS_REQUIRE(K > 0 && P > 0 && E > 0, ORBS_E_INVALID, "empty graph");
     if (stats) stats[0] = stats[1] = stats[2] = stats[3] = 0;
-    if (stop_flag && *stop_flag) { if (stats) stats[3] = 1; return 1; }           // Optimizer.cc:678-680
+    if (h->nranks == 1 && stop_flag && *stop_flag) { if (stats) stats[3] = 1; return 1; }   // Optimizer.cc:678-680 (sharded: decided collectively below)
     for (int e = 0; e < E; e++)
         ORBS_REQUIRE(e_kf[e] >= 0 && e_kf[e] < K && e_pt[e] >= 0 && e_pt[e] < P, ORBS_E_INVALID, "edge references a vertex out of range");
     std::lock_guard<std::mutex> lk(h->mu);
@@ -383,6 +480,8 @@ extern "C" int orbo_bundle_adjust(orbo_handle *h, int K, float *poses, const uin
     const int max_blocks = std::max({(E + 255) / 256, (P + 7) / 8, (K + P + 255) / 256, (6 * K + 255) / 256}) + 1;
     B.partial = S.scratch<double>(max_blocks); B.scalars = S.scratch<double>(8); B.flags = S.scratch<int>(4);
     double *d_chi2 = S.scratch<double>(E); uint8_t *d_depth = S.scratch<uint8_t>(E);
+    D.d_stop = S.scratch<int>(4); D.h_stop = D.h_flag + 1;
+    int *d_pose_act = S.scratch<int>(K + 1);
     float *d_Tout = S.scratch<float>((size_t)K * 16);
     if (S.rc) return S.rc;
     B.delta = (double)(float)sqrt(5.991); B.dsqr = B.delta * B.delta;              // thHuberMono, Optimizer.cc:591
@@ -398,10 +497,16 @@ extern "C" int orbo_bundle_adjust(orbo_handle *h, int K, float *poses, const uin
     std::vector<int> pose_idx(K);
     std::vector<uint8_t> pt_active(P);
     auto init_active = [&]() -> int {
-        std::vector<uint8_t> pose_act(K, 0);
+        std::vector<int> pose_act(K + 1, 0);                   // [K] = any active edge at all
         std::fill(pt_active.begin(), pt_active.end(), 0);
-        bool any = false;
-        for (int j = 0; j < E; j++) if (!level[j]) { pose_act[kf_s[j]] = 1; pt_active[pt_s[j]] = 1; any = true; }
+        for (int j = 0; j < E; j++) if (!level[j]) { pose_act[kf_s[j]] = 1; pt_active[pt_s[j]] = 1; pose_act[K] = 1; }
+        if (D.multi()) {                                       // a keyframe is active if any rank's shard observes it
+            ORBS_CUDA(cudaMemcpyAsync(d_pose_act, pose_act.data(), (K + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
+            if (int rc = D.allreduce(d_pose_act, K + 1, ncclInt32, ncclMax)) return rc;
+            ORBS_CUDA(cudaMemcpyAsync(pose_act.data(), d_pose_act, (K + 1) * sizeof(int), cudaMemcpyDeviceToHost, st));
+            ORBS_CUDA(cudaStreamSynchronize(st));
+        }
+        const bool any = pose_act[K] != 0;
         int nA = 0;
         for (int k = 0; k < K; k++) pose_idx[k] = (pose_act[k] && !fixed[k]) ? nA++ : -1;
         B.nA = nA; B.n = 6 * nA; B.ld = (int)align_up((size_t)B.n, NB); D.ntiles = B.ld / NB;
@@ -412,6 +517,7 @@ extern "C" int orbo_bundle_adjust(orbo_handle *h, int K, float *poses, const uin
         return any ? 1 : 0;
     };
 
+    if (D.multi() && D.terminate()) { if (stats) stats[3] = 1; return 1; }
     int any = init_active();
     if (any < 0) return any;
     const auto t_loop = std::chrono::steady_clock::now();
@@ -428,7 +534,7 @@ extern "C" int orbo_bundle_adjust(orbo_handle *h, int K, float *poses, const uin
         ORBS_CUDA(cudaStreamSynchronize(st));
         return ORBS_OK;
     };
-    if (two_stage && !(stop_flag && *stop_flag)) {
+    if (two_stage && !D.terminate()) {
         if ((rc = edge_check())) return rc;
         for (int j = 0; j < E; j++) if (chi2_s[j] > 5.991 || !depth_s[j]) level[j] = 1;      // Optimizer.cc:691-705
         ORBS_CUDA(cudaMemcpyAsync(B.e_level, level.data(), E, cudaMemcpyHostToDevice, st));
