@@ -112,6 +112,8 @@ __device__ __forceinline__ unsigned fast_score_pair(const unsigned (&w)[7][3])
 // unordered; the reference's candidate order (cell row, cell col, y, x) is carried in the record
 // and only matters for response ties inside a quad-tree node.
 // record: .x = x | y << 16 (relative to minBorder, as vToDistributeKeys), .y = score | ci << 8 | cj << 18
+constexpr int kPixWords = kPixPitch / 4;   // 20 words per staged row
+
 __global__ void __launch_bounds__(128)
 k_fast_cells(const __grid_constant__ ExtractPlan plan, const CellDesc *__restrict__ cells,
              const uint8_t *__restrict__ img0, int pitch0, size_t frame0,
@@ -119,7 +121,8 @@ k_fast_cells(const __grid_constant__ ExtractPlan plan, const CellDesc *__restric
              int *__restrict__ err_flag)
 {
     __shared__ __align__(16) uint8_t pix[kPixRows * kPixPitch];
-    __shared__ __align__(16) uint8_t sc[kScRows * kScPitch];
+    __shared__ __align__(16) uint8_t sc[kScRows * kScPitch];      // scores, 1-px zero frame around the detection region
+    __shared__ __align__(16) uint8_t lm[kScRows * kScPitch];      // 1 = strict 3x3 local maximum inside the cell
     const CellDesc cell = cells[blockIdx.x];
     const int frame = blockIdx.y;
     const LevelPlan &L = plan.lv[cell.level];
@@ -130,21 +133,37 @@ k_fast_cells(const __grid_constant__ ExtractPlan plan, const CellDesc *__restric
     const int cw = cell.cw, ch = cell.ch;
     const int dw = cw - 6, dh = ch - 6;
     if (dw <= 0 || dh <= 0) return;
+    const int tid = threadIdx.x;
 
-    // stage the sub-image: pixel (x, y) of the sub-image lives at pix[y][x + 1]
-    for (int i = threadIdx.x; i < kPixRows * kPixPitch / 4; i += blockDim.x) reinterpret_cast<unsigned *>(pix)[i] = 0u;
-    for (int i = threadIdx.x; i < kScRows * kScPitch / 4; i += blockDim.x) reinterpret_cast<unsigned *>(sc)[i] = 0u;
-    __syncthreads();
-    const uint8_t *src = img + (size_t)cell.y0 * pitch + cell.x0;
-    for (int i = threadIdx.x; i < cw * ch; i += blockDim.x) {
-        const int y = i / cw, x = i - y * cw;
-        pix[y * kPixPitch + x + 1] = src[(size_t)y * pitch + x];
+    // ---- stage the sub-image with aligned 32-bit loads: pixel (x, y) of the sub-image lives at pix[y][x + 1].
+    // smem word w of row y holds sub-image bytes 4w-1 .. 4w+2, i.e. level bytes x0 + 4w - 1 ..; the two aligned global
+    // words around that address are funnel-shifted together.  Loads never pass the last byte of the level row.
+    {
+        const int nwords = (cw + 1 + 3) >> 2;                       // words that contain at least one sub-image byte
+        const uint8_t *row_end_word = nullptr;
+        for (int t = tid; t < ch * kPixWords; t += 128) {
+            const int y = t / kPixWords, w = t - y * kPixWords;
+            unsigned v = 0u;
+            if (w <= nwords) {
+                const uint8_t *rowp = img + (size_t)(cell.y0 + y) * pitch;
+                const uint8_t *last = rowp + L.w - 1;               // last valid byte of this level row
+                const uint8_t *p = rowp + cell.x0 + 4 * w - 1;      // first byte wanted
+                const uintptr_t a0 = (uintptr_t)p & ~(uintptr_t)3;
+                const uintptr_t amax = (uintptr_t)last & ~(uintptr_t)3;
+                const unsigned lo = *reinterpret_cast<const unsigned *>(a0 <= amax ? a0 : amax);
+                const unsigned hi = *reinterpret_cast<const unsigned *>(a0 + 4 <= amax ? a0 + 4 : amax);
+                v = __funnelshift_r(lo, hi, 8 * (unsigned)((uintptr_t)p & 3));
+            }
+            reinterpret_cast<unsigned *>(pix)[t] = v;
+            (void)row_end_word;
+        }
+        for (int t = tid; t < (dh + 2) * (kScPitch / 4); t += 128) { reinterpret_cast<unsigned *>(sc)[t] = 0u; reinterpret_cast<unsigned *>(lm)[t] = 0u; }
     }
     __syncthreads();
 
-    // scores of the detection region [3, cw-3) x [3, ch-3): groups of 4 pixels
+    // ---- scores of the detection region [3, cw-3) x [3, ch-3): groups of 4 pixels
     const int ngroups = (dw + 3) >> 2;
-    for (int t = threadIdx.x; t < ngroups * dh; t += blockDim.x) {
+    for (int t = tid; t < ngroups * dh; t += 128) {
         const int gy = t / ngroups, gx = t - gy * ngroups;
         const int y = 3 + gy;                 // sub-image row of the centre
         const int c = 4 + 4 * gx;             // smem column of the first centre pixel (x = c - 1)
@@ -156,56 +175,50 @@ k_fast_cells(const __grid_constant__ ExtractPlan plan, const CellDesc *__restric
         }
         const unsigned s01 = fast_score_pair<0>(w);
         const unsigned s23 = fast_score_pair<1>(w);
-        // detection pixel index dx = 4*gx + k  ->  sc[gy + 1][dx + 1]
-        uint8_t *o = sc + (gy + 1) * kScPitch + 4 * gx + 1;
+        // detection pixel index dx = 4*gx + k  ->  sc[gy + 1][dx + 1]; pixels beyond the region stay 0
         const int rem = dw - 4 * gx;
-        o[0] = (uint8_t)(s01 & 0xff);
-        if (rem > 1) o[1] = (uint8_t)(s01 >> 16);
-        if (rem > 2) o[2] = (uint8_t)(s23 & 0xff);
-        if (rem > 3) o[3] = (uint8_t)(s23 >> 16);
+        unsigned packed = (s01 & 0xff) | ((rem > 1 ? (s01 >> 16) & 0xff : 0u) << 8) | ((rem > 2 ? s23 & 0xff : 0u) << 16) |
+                          ((rem > 3 ? (s23 >> 16) & 0xff : 0u) << 24);
+        uint8_t *o = sc + (gy + 1) * kScPitch + 4 * gx + 1;       // byte address = 4*gx + 1 (mod 4 == 1): write bytes
+        o[0] = (uint8_t)packed; o[1] = (uint8_t)(packed >> 8); o[2] = (uint8_t)(packed >> 16); o[3] = (uint8_t)(packed >> 24);
     }
     __syncthreads();
 
-    // threshold of this cell: iniTh if cv::FAST(iniTh, nms) returns at least one keypoint, else minTh
-    // (ORBextractor.cc:808-816; the test is on the NMS survivors, so a plateau of equal scores >= iniTh
-    // that suppresses itself still triggers the fallback)
+    // ---- cell-local strict 3x3 maxima, once; threshold of this cell: iniTh if cv::FAST(iniTh, nms) would return at
+    // least one keypoint, else minTh (ORBextractor.cc:808-816; the test is on the NMS survivors, so a plateau of equal
+    // scores >= iniTh that suppresses itself still triggers the fallback)
     int any = 0;
-    for (int i = threadIdx.x; i < dw * dh; i += blockDim.x) {
-        const int y = i / dw, x = i - y * dw;
-        const uint8_t *p = sc + (y + 1) * kScPitch + x + 1;
-        const int s = p[0];
-        if (s >= plan.ini_th)
-            any |= s > p[-1] && s > p[1] && s > p[-kScPitch - 1] && s > p[-kScPitch] && s > p[-kScPitch + 1] &&
-                   s > p[kScPitch - 1] && s > p[kScPitch] && s > p[kScPitch + 1];
+    const int xq = tid & 63, yq = tid >> 6;                        // 64 columns x 2 rows per sweep
+    for (int y = yq; y < dh; y += 2) {
+        if (xq < dw) {
+            const uint8_t *p = sc + (y + 1) * kScPitch + xq + 1;
+            const int s = p[0];
+            if (s >= plan.min_th) {
+                const bool keep = s > p[-1] && s > p[1] && s > p[-kScPitch - 1] && s > p[-kScPitch] && s > p[-kScPitch + 1] &&
+                                  s > p[kScPitch - 1] && s > p[kScPitch] && s > p[kScPitch + 1];
+                if (keep) { lm[(y + 1) * kScPitch + xq + 1] = 1; any |= s >= plan.ini_th; }
+            }
+        }
     }
     const int th = __syncthreads_or(any) ? plan.ini_th : plan.min_th;
 
-    // cell-local 3x3 non-maximum suppression (strict), append survivors
+    // ---- append survivors
     int *counter = cand_count + frame * plan.nlevels + cell.level;
     uint2 *out = cand + (size_t)frame * plan.cand_frame_entries + L.cand_off;
-    const int npix = dw * dh;
-    for (int base = 0; base < npix; base += blockDim.x) {
-        const int i = base + threadIdx.x;
+    for (int y0 = 0; y0 < dh; y0 += 2) {
+        const int y = y0 + yq;
         bool keep = false;
-        int s = 0, x = 0, y = 0;
-        if (i < npix) {
-            y = i / dw; x = i - y * dw;
-            const uint8_t *p = sc + (y + 1) * kScPitch + x + 1;
-            s = p[0];
-            if (s >= th) {
-                keep = s > p[-1] && s > p[1] && s > p[-kScPitch - 1] && s > p[-kScPitch] && s > p[-kScPitch + 1] &&
-                       s > p[kScPitch - 1] && s > p[kScPitch] && s > p[kScPitch + 1];
-            }
-        }
+        int s = 0;
+        if (y < dh && xq < dw) { s = sc[(y + 1) * kScPitch + xq + 1]; keep = lm[(y + 1) * kScPitch + xq + 1] && s >= th; }
         const unsigned ballot = __ballot_sync(0xffffffffu, keep);
         if (ballot) {
-            const int lane = threadIdx.x & 31;
+            const int lane = tid & 31;
             int pos = 0;
             if (lane == 0) pos = atomicAdd(counter, __popc(ballot));
             pos = __shfl_sync(0xffffffffu, pos, 0) + __popc(ballot & ((1u << lane) - 1));
             if (keep) {
                 if (pos < L.cand_cap) {
-                    const unsigned kx = (unsigned)(x + 3 + cell.addx), ky = (unsigned)(y + 3 + cell.addy);
+                    const unsigned kx = (unsigned)(xq + 3 + cell.addx), ky = (unsigned)(y + 3 + cell.addy);
                     out[pos] = make_uint2(kx | (ky << 16), (unsigned)s | ((unsigned)cell.ci << 8) | ((unsigned)cell.cj << 18));
                 } else {
                     *err_flag = 1;
@@ -230,37 +243,57 @@ k_blur7(const __grid_constant__ ExtractPlan plan, const TileDesc *__restrict__ t
         const uint8_t *__restrict__ img0, int pitch0, size_t frame0,
         const uint8_t *__restrict__ pyr, uint8_t *__restrict__ blur)
 {
-    constexpr int IW = kBlurTW + 6, IH = kBlurTH + 6, IP = IW + 2;
-    __shared__ uint8_t tin[IH * IP];
-    __shared__ uint16_t mid[IH * kBlurTW];
+    constexpr int IW = kBlurTW + 6, IH = kBlurTH + 6, IP = 80;    // 70 x 38 input, 80-byte smem rows (word aligned)
+    __shared__ __align__(16) uint8_t tin[IH * IP];
+    __shared__ __align__(16) uint16_t mid[IH * kBlurTW];
     const TileDesc t = tiles[blockIdx.x];
-    const int frame = blockIdx.y;
+    const int frame = blockIdx.y, tid = threadIdx.x;
     const LevelPlan &L = plan.lv[t.level];
     const uint8_t *img;
     int pitch;
     if (t.level == 0) { img = img0 + (size_t)frame * frame0; pitch = pitch0; }
     else { img = pyr + (size_t)frame * plan.pyr_frame_bytes + L.pyr_off; pitch = L.pitch; }
-    for (int i = threadIdx.x; i < IW * IH; i += blockDim.x) {
-        const int y = i / IW, x = i - y * IW;
-        const int sx = reflect101(t.x0 + x - 3, L.w), sy = reflect101(t.y0 + y - 3, L.h);
-        tin[y * IP + x] = img[(size_t)sy * pitch + sx];
+    // stage: thread = (column, row phase); the reflected source column is computed once
+    {
+        const int x = tid % 80, ph = tid / 80;                    // 3 row phases, 240 active threads
+        if (ph < 3) {
+            const int sx = x < IW ? reflect101(t.x0 + x - 3, L.w) : 0;
+            for (int y = ph; y < IH; y += 3) {
+                const int sy = reflect101(t.y0 + y - 3, L.h);
+                tin[y * IP + x] = x < IW ? img[(size_t)sy * pitch + sx] : (uint8_t)0;
+            }
+        }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < IH * kBlurTW; i += blockDim.x) {
-        const int y = i / kBlurTW, x = i - y * kBlurTW;
-        const uint8_t *p = tin + y * IP + x;
-        mid[i] = (uint16_t)(18 * (p[0] + p[6]) + 34 * (p[1] + p[5]) + 48 * (p[2] + p[4]) + 56 * p[3]);
+    // horizontal pass, 4 outputs per thread: two dp4a per output on funnel-shifted words
+    constexpr unsigned c0 = 18u | (34u << 8) | (48u << 16) | (56u << 24), c1 = 48u | (34u << 8) | (18u << 16);
+    for (int i = tid; i < IH * (kBlurTW / 4); i += 256) {
+        const int y = i >> 4, g = i & 15;
+        const unsigned *row = reinterpret_cast<const unsigned *>(tin + y * IP) + g;
+        const unsigned w0 = row[0], w1 = row[1], w2 = row[2];
+        unsigned o[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const unsigned lo = __funnelshift_r(w0, w1, 8 * k), hi = __funnelshift_r(w1, w2, 8 * k);
+            o[k] = __dp4a(lo, c0, __dp4a(hi, c1, 0u));
+        }
+        uint2 pk = make_uint2(o[0] | (o[1] << 16), o[2] | (o[3] << 16));
+        *reinterpret_cast<uint2 *>(mid + y * kBlurTW + 4 * g) = pk;
     }
     __syncthreads();
+    // vertical pass, 2 adjacent outputs per thread (one 32-bit load of two u16 per tap)
     uint8_t *dst = blur + (size_t)frame * plan.pyr_frame_bytes + L.pyr_off;   // blurred slab has the same layout
-    for (int i = threadIdx.x; i < kBlurTH * kBlurTW; i += blockDim.x) {
-        const int y = i / kBlurTW, x = i - y * kBlurTW;
-        const int ox = t.x0 + x, oy = t.y0 + y;
-        if (ox < L.w && oy < L.h) {
-            const uint16_t *p = mid + y * kBlurTW + x;
-            const unsigned v = 18u * (p[0] + p[6 * kBlurTW]) + 34u * (p[kBlurTW] + p[5 * kBlurTW]) +
-                               48u * (p[2 * kBlurTW] + p[4 * kBlurTW]) + 56u * p[3 * kBlurTW];
-            dst[(size_t)oy * L.pitch + ox] = (uint8_t)((v + 32768u) >> 16);
+    for (int i = tid; i < kBlurTH * (kBlurTW / 2); i += 256) {
+        const int y = i >> 5, xp = (i & 31) * 2;
+        const unsigned *p = reinterpret_cast<const unsigned *>(mid + y * kBlurTW + xp);
+        constexpr int S = kBlurTW / 2;                            // row stride in 32-bit words
+        const unsigned m0 = p[0], m1 = p[S], m2 = p[2 * S], m3 = p[3 * S], m4 = p[4 * S], m5 = p[5 * S], m6 = p[6 * S];
+        const unsigned lo = 18u * ((m0 & 0xffff) + (m6 & 0xffff)) + 34u * ((m1 & 0xffff) + (m5 & 0xffff)) + 48u * ((m2 & 0xffff) + (m4 & 0xffff)) + 56u * (m3 & 0xffff);
+        const unsigned hi = 18u * ((m0 >> 16) + (m6 >> 16)) + 34u * ((m1 >> 16) + (m5 >> 16)) + 48u * ((m2 >> 16) + (m4 >> 16)) + 56u * (m3 >> 16);
+        const int ox = t.x0 + xp, oy = t.y0 + y;
+        if (oy < L.h) {
+            if (ox < L.w) dst[(size_t)oy * L.pitch + ox] = (uint8_t)((lo + 32768u) >> 16);
+            if (ox + 1 < L.w) dst[(size_t)oy * L.pitch + ox + 1] = (uint8_t)((hi + 32768u) >> 16);
         }
     }
 }
