@@ -224,31 +224,27 @@ def bench_frontend(args, rank, world):
         total_ms = float(tt.item())
     fps = world * B * args.steps / (total_ms * 1e-3)
 
-    # ---- end-to-end through the host-buffer C-ABI (pinned host images in, host results out)
-    h_imgs = torch.from_numpy(imgs).pin_memory()
+    # ---- end-to-end through the host-buffer C-ABI: one orbf_track_frames call per step (pinned host images and map points
+    # in; keypoints, descriptors, matches, poses and outlier flags out; the stages in between stay on the device)
+    fe = ob.FrontEnd(ex, mt, po, device=dev)
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    h_imgs = pin(imgs)
+    hq = dict(Xw=pin(q_Xw), oct=pin(q_oct), ang=pin(q_ang), desc=pin(q_desc), valid=pin(q_valid), cnt=pin(q_cnt))
     o_xy = torch.empty((B, slab, 2), dtype=torch.float32).pin_memory(); o_ang = torch.empty((B, slab), dtype=torch.float32).pin_memory()
     o_resp = torch.empty((B, slab), dtype=torch.float32).pin_memory(); o_oct = torch.empty((B, slab), dtype=torch.int32).pin_memory()
     o_size = torch.empty((B, slab), dtype=torch.float32).pin_memory(); o_desc = torch.empty((B, slab, 32), dtype=torch.uint8).pin_memory()
-    o_cnt = torch.zeros(B, dtype=torch.int32).pin_memory()
-    hq_valid = np.zeros((B, slab), np.uint8); hq_uv = np.zeros((B, slab, 2), np.float32); hq_rad = np.zeros((B, slab), np.float32)
-    hq_mn = np.zeros((B, slab), np.int32); hq_mx = np.zeros((B, slab), np.int32)
-    h_fm = np.zeros((B, slab), np.int32); h_nm = np.zeros(B, np.int32)
-    h_T = Tcw.copy(); h_fout = np.zeros((B, slab), np.uint8); h_ninl = np.zeros(B, np.int32)
+    o_cnt = torch.zeros(B, dtype=torch.int32).pin_memory(); o_fm = torch.empty((B, slab), dtype=torch.int32).pin_memory()
+    o_nm = torch.zeros(B, dtype=torch.int32).pin_memory(); o_out = torch.empty((B, slab), dtype=torch.uint8).pin_memory()
+    o_ninl = torch.zeros(B, dtype=torch.int32).pin_memory(); h_T = pin(Tcw.copy())
     P = lambda tns: vp(tns.data_ptr())
     A = lambda arr: arr.ctypes.data
 
     def step_host(t):
-        ob._check(L.orbx_extract(ex.handle, P(h_imgs[t]), B, w, h, w, w * h, P(o_xy), P(o_ang), P(o_resp), P(o_oct), P(o_size), P(o_desc), slab, P(o_cnt)))
-        hq_valid[:] = q_valid[t - 1]
-        h_fm.fill(-1)
-        ob._check(L.orbm_project_last_frame(mt.handle, B, A(Tcw), A(K4), A(bounds), A(sf), len(sf), A(q_Xw[t - 1]), A(q_oct[t - 1]), A(q_cnt[t - 1]), slab,
-                                            TH_PROJ, A(hq_valid), A(hq_uv), A(hq_rad), A(hq_mn), A(hq_mx), 0))
-        ob._check(L.orbm_search_by_projection(mt.handle, B, A(bounds), P(o_xy), P(o_oct), P(o_ang), P(o_desc), P(o_cnt), slab, A(hq_valid), A(hq_uv),
-                                              A(hq_rad), A(hq_mn), A(hq_mx), A(q_ang[t - 1]), A(q_desc[t - 1]), A(q_cnt[t - 1]), slab, 100, 0.0, 1,
-                                              A(h_fm), A(h_nm), 0))
-        h_T[:] = Tcw
-        ob._check(L.orbo_pose_optimization_matched(po.handle, B, A(h_T), A(K4), P(o_xy), P(o_oct), P(o_cnt), slab, A(h_fm), A(q_Xw[t - 1]), A(q_cnt[t - 1]), slab,
-                                                   A(ils), len(ils), A(h_fout), A(h_ninl), None, 0))
+        h_T.copy_(torch.from_numpy(Tcw))
+        ob._check(L.orbf_track_frames(fe.handle, P(h_imgs[t]), B, w, h, w, w * h, A(K4), A(sf), A(ils), len(sf), P(hq["Xw"][t - 1]), P(hq["oct"][t - 1]),
+                                      P(hq["ang"][t - 1]), P(hq["desc"][t - 1]), P(hq["valid"][t - 1]), P(hq["cnt"][t - 1]), slab, TH_PROJ, 100, 1,
+                                      P(h_T), P(o_xy), P(o_ang), P(o_resp), P(o_oct), P(o_size), P(o_desc), slab, P(o_cnt), P(o_fm), P(o_nm), P(o_out),
+                                      P(o_ninl)))
 
     for i in range(min(args.warmup, 3)):
         step_host(1 + i % (N_POOL - 1))
@@ -265,15 +261,10 @@ def bench_frontend(args, rank, world):
         e2e_s = float(tt.item())
     e2e_fps = world * B * e2e_steps / e2e_s
     nkp = int(np.mean(o_cnt.numpy()))
+    assert np.array_equal(o_nm.numpy(), nmatch) and np.array_equal(o_ninl.numpy(), ninl), "host-buffer path and device-resident path disagree"
     se = B * slab                                   # slab entries per step
-    h2d = (B * w * h                                # images
-           + B * 64 + 32 + se * (12 + 4 + 1) + B * 4          # project: Tcw, scale factors, Xw, octave, valid, counts
-           + se * (8 + 4 + 4 + 32) + B * 4 + se * (1 + 8 + 4 + 4 + 4 + 4 + 32) + B * 4 + se * 4    # search: features, queries, feat_match
-           + B * 64 + se * (8 + 4 + 4 + 12) + B * 8 + 32)  # pose optimisation: pose, features, matches, map points
-    d2h = (B * nkp * (8 + 4 * 4 + 32) + B * 4       # keypoints + descriptors + counts
-           + se * (1 + 8 + 4 + 4 + 4)               # projected windows
-           + se * 4 + B * 4                         # feat_match + nmatches
-           + B * 64 + se + B * 4)                   # optimised pose, outlier flags, inlier count
+    h2d = B * w * h + se * (12 + 4 + 4 + 32 + 1) + B * 4 + B * 64 + 64     # images, last-frame map points, counts, poses, tables
+    d2h = se * (8 + 4 * 4 + 32) + B * 4 + se * (4 + 1) + B * 8 + B * 64     # keypoints + descriptors (strided slabs), matches, flags, poses
 
     # ---- roofline of the dominant kernel
     hbm, how = peaks()

@@ -79,6 +79,11 @@ int orbx_extract(orbx_handle *h, const uint8_t *images, int n_frames, int width,
 int orbx_extract_device(orbx_handle *h, const uint8_t *d_images, int n_frames, int width,
                         int height, int stride, size_t frame_stride);
 
+/* HOST images in (uploaded in chunks, overlapped with the extraction), results stay on the device like
+ * orbx_extract_device.  Asynchronous: the host image buffer must stay valid until orbx_synchronize / orbx_download. */
+int orbx_extract_host_async(orbx_handle *h, const uint8_t *images, int n_frames, int width, int height,
+                            int stride, size_t frame_stride);
+
 /* Device-resident results of the last extract call.  slab = per-frame capacity (entries). */
 typedef struct {
     int n_frames, slab;
@@ -239,6 +244,26 @@ int orbo_bundle_adjust(orbo_handle *h, int K, float *poses, const uint8_t *fixed
  *   orbo_comm_init: collective. */
 int orbo_comm_unique_id(uint8_t *id128);
 int orbo_comm_init(orbo_handle *h, int nranks, int rank, const uint8_t *id128);
+
+/* ------------------------------------------------------------------ */
+/* Fused front end: what Tracking::TrackWithMotionModel (S/src/Tracking.cc:912-973) does per frame -- Frame ctor ->
+ * ORBextractor::operator(), ORBmatcher::SearchByProjection(Cur, Last, th, mono), Optimizer::PoseOptimization -- for
+ * n_frames independent streams in one HOST-buffer call.  The handle borrows the three handles (which keep working on
+ * their own) and puts them on one stream; intermediate results stay in HBM.
+ *   in : images (as orbx_extract); K4, scale_factors[nlevels], inv_level_sigma2[nlevels] (HOST);
+ *        last-frame map points per stream: q_Xw f32[.,3], q_octave, q_angle, q_desc u8[.,32], q_valid u8, q_counts, q_slab;
+ *        Tcw f32[n_frames,16]: predicted pose in, optimised pose out; image bounds are (0, 0, width, height).
+ *   out: keypoints / descriptors / counts (as orbx_extract, cap >= orbx_max_keypoints), feat_match i32[n_frames*cap]
+ *        (index of the last-frame slot matched to each feature or -1), nmatches, outlier u8[n_frames*cap], n_inliers. */
+typedef struct orbf_handle orbf_handle;
+int orbf_create(orbf_handle **out, orbx_handle *ex, orbm_handle *mt, orbo_handle *po, int device);
+int orbf_destroy(orbf_handle *h);
+int orbf_track_frames(orbf_handle *h, const uint8_t *images, int n_frames, int width, int height, int stride, size_t frame_stride,
+                      const float *K4, const float *scale_factors, const float *inv_level_sigma2, int nlevels,
+                      const float *q_Xw, const int32_t *q_octave, const float *q_angle, const uint8_t *q_desc, const uint8_t *q_valid,
+                      const int32_t *q_counts, int q_slab, float th_proj, int th_dist, int check_ori,
+                      float *Tcw, float *kp_xy, float *kp_angle, float *kp_response, int32_t *kp_octave, float *kp_size, uint8_t *desc,
+                      int cap, int32_t *counts, int32_t *feat_match, int32_t *nmatches, uint8_t *outlier, int32_t *n_inliers);
 
 /* Bench bookkeeping for the last orbo_bundle_adjust call: out4 = { seconds inside the LM loops (graph resident on the
  * device), seconds of the whole call, seconds of host graph layout + H2D, leading dimension of the reduced system }. */

@@ -415,3 +415,42 @@ class Optimizer:
     def BundleAdjustment(self, poses, fixed, intr, points, e_kf, e_pt, e_uv, e_inv_sigma2, nIterations=5, bRobust=True, stop_flag=None):
         """Optimizer::BundleAdjustment (GlobalBundleAdjustemnt / MMGlobalBundleAdjustemnt core)."""
         return self._ba(poses, fixed, intr, points, e_kf, e_pt, e_uv, e_inv_sigma2, False, nIterations, 0, bRobust, stop_flag)
+
+
+class FrontEnd:
+    """Fused per-frame front end over one extractor / matcher / optimizer triple (orbf_*): host images in,
+    keypoints + matches + optimised poses out, everything in between stays on the device."""
+
+    def __init__(self, extractor, matcher, optimizer, device=0):
+        self._L = load()
+        self.ex, self.mt, self.po = extractor, matcher, optimizer       # keep them alive
+        self._h = ctypes.c_void_p()
+        _check(self._L.orbf_create(ctypes.byref(self._h), extractor.handle, matcher.handle, optimizer.handle, int(device)))
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            self._L.orbf_destroy(h)
+
+    @property
+    def handle(self): return self._h
+
+    def track_frames(self, images, K4, Tcw, q_Xw, q_octave, q_angle, q_desc, q_valid, q_counts, th_proj=15.0, th_dist=100, check_ori=True):
+        images = np.ascontiguousarray(images, np.uint8); B, H, W = images.shape
+        cap = self.ex.max_keypoints(W, H)
+        K4 = np.ascontiguousarray(K4, np.float32); T = np.ascontiguousarray(Tcw, np.float32).reshape(B, 16).copy()
+        sf = self.ex.GetScaleFactors(); ils = self.ex.GetInverseScaleSigmaSquares()
+        q_Xw = np.ascontiguousarray(q_Xw, np.float32).reshape(B, -1, 3); qs = q_Xw.shape[1]
+        q_octave = np.ascontiguousarray(q_octave, np.int32); q_angle = np.ascontiguousarray(q_angle, np.float32)
+        q_desc = np.ascontiguousarray(q_desc, np.uint8); q_valid = np.ascontiguousarray(q_valid, np.uint8)
+        q_counts = np.ascontiguousarray(q_counts, np.int32)
+        xy = np.empty((B, cap, 2), np.float32); ang = np.empty((B, cap), np.float32); resp = np.empty((B, cap), np.float32)
+        octv = np.empty((B, cap), np.int32); size = np.empty((B, cap), np.float32); desc = np.empty((B, cap, 32), np.uint8)
+        counts = np.zeros(B, np.int32); fm = np.empty((B, cap), np.int32); nm = np.zeros(B, np.int32)
+        outl = np.empty((B, cap), np.uint8); ninl = np.zeros(B, np.int32)
+        _check(self._L.orbf_track_frames(self._h, _ptr(images), B, W, H, images.strides[1], images.strides[0], _ptr(K4), _ptr(sf), _ptr(ils), len(sf),
+                                         _ptr(q_Xw), _ptr(q_octave), _ptr(q_angle), _ptr(q_desc), _ptr(q_valid), _ptr(q_counts), qs, float(th_proj),
+                                         int(th_dist), int(bool(check_ori)), _ptr(T), _ptr(xy), _ptr(ang), _ptr(resp), _ptr(octv), _ptr(size),
+                                         _ptr(desc), cap, _ptr(counts), _ptr(fm), _ptr(nm), _ptr(outl), _ptr(ninl)))
+        return dict(Tcw=T.reshape(B, 4, 4), xy=xy, angle=ang, response=resp, octave=octv, size=size, desc=desc, counts=counts,
+                    feat_match=fm, nmatches=nm, outlier=outl, n_inliers=ninl)

@@ -31,6 +31,11 @@ def declare(L):
     L.orbo_bundle_adjust.argtypes = [vp, i, vp, vp, vp, i, vp, i, vp, vp, vp, vp, i, i, i, i, vp, vp, vp, vp, vp]
     for n in ("orbo_create", "orbo_destroy", "orbo_set_stream", "orbo_synchronize", "orbo_pose_optimization", "orbo_bundle_adjust"):
         getattr(L, n).restype = c.c_int
+    L.orbx_extract_host_async.argtypes = [vp, vp, i, i, i, i, c.c_size_t]; L.orbx_extract_host_async.restype = c.c_int
+    L.orbf_create.argtypes = [c.POINTER(vp), vp, vp, vp, i]; L.orbf_create.restype = c.c_int
+    L.orbf_destroy.argtypes = [vp]; L.orbf_destroy.restype = c.c_int
+    L.orbf_track_frames.argtypes = [vp, vp, i, i, i, i, c.c_size_t, vp, vp, vp, i, vp, vp, vp, vp, vp, vp, i, f, i, i, vp, vp, vp, vp, vp, vp, vp, i, vp, vp, vp, vp, vp]
+    L.orbf_track_frames.restype = c.c_int
     for n in ("orbm_create", "orbm_destroy", "orbm_synchronize", "orbm_descriptor_distance", "orbm_project_last_frame",
               "orbm_search_by_projection"):
         getattr(L, n).restype = c.c_int

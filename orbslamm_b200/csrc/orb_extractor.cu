@@ -8,6 +8,7 @@
 #include <string.h>
 #include <vector>
 #include <mutex>
+#include <algorithm>
 #include "orb_extractor.cuh"
 #include "orb_kernels.cuh"   // kernels live in this translation unit
 
@@ -33,8 +34,9 @@ using namespace orbs;
 
 struct orbx_handle {
     int device = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
     bool own_stream = true;
+    std::vector<cudaEvent_t> chunk_events;
     // parameters and tables (ORBextractor.cc:410-470)
     int nfeatures = 0, nlevels = 0, ini_th = 0, min_th = 0;
     double scale_factor = 0;
@@ -221,13 +223,29 @@ static inline int *lvl_count_ptr(orbx_handle *h, int n) { return h->d_counts.as<
 static inline int *counts_ptr(orbx_handle *h, int n) { return h->d_counts.as<int>() + (size_t)2 * h->plan.nlevels * n; }
 static inline int *err_ptr(orbx_handle *h, int n) { return counts_ptr(h, n) + n; }
 
-static int launch_pipeline(orbx_handle *h, const uint8_t *d_img0, int n, int pitch0, size_t frame0)
+static int reset_counts(orbx_handle *h)
+{
+    const int nb = h->batch_cap;
+    ORBS_CUDA(cudaMemsetAsync(h->d_counts.p, 0, ((size_t)2 * h->plan.nlevels * nb + nb + 16) * sizeof(int), h->stream));
+    return ORBS_OK;
+}
+
+// frames [f0, f0 + n) of the batch whose first image is d_img0_all; every per-frame workspace is addressed by frame index,
+// so chunks of one batch can be processed back to back (host path: chunk c+1 is uploaded while chunk c computes)
+static int launch_pipeline(orbx_handle *h, const uint8_t *d_img0_all, int f0, int n, int pitch0, size_t frame0)
 {
     const ExtractPlan &P = h->plan;
     cudaStream_t st = h->stream;
     const int nb = h->batch_cap;     // layout of d_counts uses the allocated capacity
-    ORBS_CUDA(cudaMemsetAsync(h->d_counts.p, 0, ((size_t)2 * P.nlevels * nb + nb + 16) * sizeof(int), st));
-    uint8_t *pyr = h->d_pyr.as<uint8_t>();
+    const uint8_t *d_img0 = d_img0_all + (size_t)f0 * frame0;
+    uint8_t *pyr = h->d_pyr.as<uint8_t>() + (size_t)f0 * P.pyr_frame_bytes;
+    uint8_t *blur = h->d_blur.as<uint8_t>() + (size_t)f0 * P.pyr_frame_bytes;
+    uint2 *cand = h->d_cand.as<uint2>() + (size_t)f0 * P.cand_frame_entries;
+    unsigned *knode = h->d_knode.as<unsigned>() + (size_t)f0 * P.cand_frame_entries;
+    uint2 *lvl_kp = h->d_lvl_kp.as<uint2>() + (size_t)f0 * P.lvl_slab;
+    int *cand_count = cand_count_ptr(h) + (size_t)f0 * P.nlevels, *lvl_count = lvl_count_ptr(h, nb) + (size_t)f0 * P.nlevels;
+    int *counts = counts_ptr(h, nb) + f0;
+    const size_t ko = (size_t)f0 * P.kp_slab;
     // pyramid chain
     for (int l = 1; l < P.nlevels; l++) {
         const LevelPlan &S = P.lv[l - 1], &D = P.lv[l];
@@ -243,27 +261,58 @@ static int launch_pipeline(orbx_handle *h, const uint8_t *d_img0, int n, int pit
     }
     if (P.total_cells > 0) {
         h->timer.begin(1, st);
-        k_fast_cells<<<dim3(P.total_cells, n), 128, 0, st>>>(P, h->d_cells.as<CellDesc>(), d_img0, pitch0, frame0, pyr,
-                                                             h->d_cand.as<uint2>(), cand_count_ptr(h), err_ptr(h, nb));
+        k_fast_cells<<<dim3(P.total_cells, n), 128, 0, st>>>(P, h->d_cells.as<CellDesc>(), d_img0, pitch0, frame0, pyr, cand, cand_count, err_ptr(h, nb));
         h->timer.end(st);
         h->timer.begin(2, st);
-        k_blur7<<<dim3(P.total_tiles, n), 256, 0, st>>>(P, h->d_tiles.as<TileDesc>(), d_img0, pitch0, frame0, pyr, h->d_blur.as<uint8_t>());
+        k_blur7<<<dim3(P.total_tiles, n), 256, 0, st>>>(P, h->d_tiles.as<TileDesc>(), d_img0, pitch0, frame0, pyr, blur);
         h->timer.end(st);
         h->timer.begin(3, st);
-        k_octree<<<dim3(P.nlevels, n), 512, h->octree_smem, st>>>(P, h->d_cand.as<uint2>(), cand_count_ptr(h), h->d_knode.as<unsigned>(),
-                                                                 h->d_lvl_kp.as<uint2>(), lvl_count_ptr(h, nb), err_ptr(h, nb));
+        k_octree<<<dim3(P.nlevels, n), 512, h->octree_smem, st>>>(P, cand, cand_count, knode, lvl_kp, lvl_count, err_ptr(h, nb));
         h->timer.end(st);
         const int warps_per_block = 8;
         h->timer.begin(4, st);
         k_orient_describe<<<dim3((P.kp_slab + warps_per_block - 1) / warps_per_block, n), warps_per_block * 32, 0, st>>>(
-            P, d_img0, pitch0, frame0, pyr, h->d_blur.as<uint8_t>(), h->d_lvl_kp.as<uint2>(), lvl_count_ptr(h, nb),
-            h->d_kp_xy.as<float2>(), h->d_kp_angle.as<float>(), h->d_kp_resp.as<float>(), h->d_kp_oct.as<int>(),
-            h->d_kp_size.as<float>(), h->d_desc.as<uint8_t>(), counts_ptr(h, nb));
+            P, d_img0, pitch0, frame0, pyr, blur, lvl_kp, lvl_count, h->d_kp_xy.as<float2>() + ko, h->d_kp_angle.as<float>() + ko,
+            h->d_kp_resp.as<float>() + ko, h->d_kp_oct.as<int>() + ko, h->d_kp_size.as<float>() + ko, h->d_desc.as<uint8_t>() + 32 * ko, counts);
         h->timer.end(st);
         h->launches += 4;
     }
     ORBS_CUDA(cudaGetLastError());
-    h->last_frames = n; h->last_img0 = d_img0; h->last_pitch0 = pitch0; h->last_frame0 = frame0;
+    h->last_frames = f0 + n; h->last_img0 = d_img0_all; h->last_pitch0 = pitch0; h->last_frame0 = frame0;
+    return ORBS_OK;
+}
+
+// host images -> staged device copy, uploaded in chunks on a copy stream so that the upload of chunk c+1 overlaps the
+// extraction of chunk c
+static int upload_and_extract(orbx_handle *h, const uint8_t *images, int n_frames, int width, int height, int stride, size_t frame_stride)
+{
+    const size_t pitch = align_up(width, 64), frame = pitch * height;
+    if (int rc = h->d_stage.reserve(frame * n_frames)) return rc;
+    if (!h->copy_stream) ORBS_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    if (int rc = reset_counts(h)) return rc;
+    const int chunk = n_frames > 16 ? 16 : n_frames;
+    const int nchunks = (n_frames + chunk - 1) / chunk;
+    while ((int)h->chunk_events.size() < nchunks + 1) { cudaEvent_t e; ORBS_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); h->chunk_events.push_back(e); }
+    // the copy stream must not overwrite the staging buffer while an earlier call still reads it
+    ORBS_CUDA(cudaEventRecord(h->chunk_events[nchunks], h->stream));
+    ORBS_CUDA(cudaStreamWaitEvent(h->copy_stream, h->chunk_events[nchunks], 0));
+    for (int c = 0; c < nchunks; c++) {
+        const int f0 = c * chunk, n = std::min(chunk, n_frames - f0);
+        if (frame_stride == (size_t)stride * height) {
+            ORBS_CUDA(cudaMemcpy2DAsync(h->d_stage.as<uint8_t>() + f0 * frame, pitch, images + f0 * frame_stride, stride, width, (size_t)height * n,
+                                        cudaMemcpyHostToDevice, h->copy_stream));
+        } else {
+            for (int f = f0; f < f0 + n; f++)
+                ORBS_CUDA(cudaMemcpy2DAsync(h->d_stage.as<uint8_t>() + f * frame, pitch, images + f * frame_stride, stride, width, height,
+                                            cudaMemcpyHostToDevice, h->copy_stream));
+        }
+        ORBS_CUDA(cudaEventRecord(h->chunk_events[c], h->copy_stream));
+    }
+    for (int c = 0; c < nchunks; c++) {
+        const int f0 = c * chunk, n = std::min(chunk, n_frames - f0);
+        ORBS_CUDA(cudaStreamWaitEvent(h->stream, h->chunk_events[c], 0));
+        if (int rc = launch_pipeline(h, h->d_stage.as<uint8_t>(), f0, n, (int)pitch, frame)) return rc;
+    }
     return ORBS_OK;
 }
 
@@ -286,16 +335,21 @@ static int download_results(orbx_handle *h, float *kp_xy, float *kp_angle, float
         counts[f] = c;
         if (c > cap) { set_last_error("output capacity too small; size with orbx_max_keypoints()"); return ORBS_E_CAPACITY; }
     }
-    for (int f = 0; f < n; f++) {
-        const size_t c = (size_t)hc[f];
-        if (!c) continue;
-        const size_t so = (size_t)f * P.kp_slab, d = (size_t)f * cap;
-        if (kp_xy) ORBS_CUDA(cudaMemcpyAsync(kp_xy + 2 * d, h->d_kp_xy.as<float>() + 2 * so, c * 8, cudaMemcpyDeviceToHost, st));
-        if (kp_angle) ORBS_CUDA(cudaMemcpyAsync(kp_angle + d, h->d_kp_angle.as<float>() + so, c * 4, cudaMemcpyDeviceToHost, st));
-        if (kp_response) ORBS_CUDA(cudaMemcpyAsync(kp_response + d, h->d_kp_resp.as<float>() + so, c * 4, cudaMemcpyDeviceToHost, st));
-        if (kp_octave) ORBS_CUDA(cudaMemcpyAsync(kp_octave + d, h->d_kp_oct.as<int>() + so, c * 4, cudaMemcpyDeviceToHost, st));
-        if (kp_size) ORBS_CUDA(cudaMemcpyAsync(kp_size + d, h->d_kp_size.as<float>() + so, c * 4, cudaMemcpyDeviceToHost, st));
-        if (desc) ORBS_CUDA(cudaMemcpyAsync(desc + 32 * d, h->d_desc.as<uint8_t>() + 32 * so, c * 32, cudaMemcpyDeviceToHost, st));
+    int maxc = 0;
+    for (int f = 0; f < n; f++) maxc = std::max(maxc, hc[f]);
+    if (maxc > 0) {
+        // one strided copy per array: rows = frames, row width = the largest keypoint count of the batch
+        auto copy2d = [&](void *dst, const void *src, size_t elem) -> int {
+            ORBS_CUDA(cudaMemcpy2DAsync(dst, (size_t)cap * elem, src, (size_t)P.kp_slab * elem, (size_t)maxc * elem, n, cudaMemcpyDeviceToHost, st));
+            return ORBS_OK;
+        };
+        int rc = ORBS_OK;
+        if (kp_xy && (rc = copy2d(kp_xy, h->d_kp_xy.p, 8))) return rc;
+        if (kp_angle && (rc = copy2d(kp_angle, h->d_kp_angle.p, 4))) return rc;
+        if (kp_response && (rc = copy2d(kp_response, h->d_kp_resp.p, 4))) return rc;
+        if (kp_octave && (rc = copy2d(kp_octave, h->d_kp_oct.p, 4))) return rc;
+        if (kp_size && (rc = copy2d(kp_size, h->d_kp_size.p, 4))) return rc;
+        if (desc && (rc = copy2d(desc, h->d_desc.p, 32))) return rc;
     }
     ORBS_CUDA(cudaStreamSynchronize(st));
     return ORBS_OK;
@@ -365,6 +419,8 @@ int orbx_destroy(orbx_handle *h)
     for (DevBuf *b : bufs) b->release();
     h->h_counts.release();
     h->timer.release();
+    for (cudaEvent_t e : h->chunk_events) cudaEventDestroy(e);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     delete h;
     return ORBS_OK;
 }
@@ -414,7 +470,8 @@ int orbx_extract_device(orbx_handle *h, const uint8_t *d_images, int n_frames, i
     ORBS_CUDA(cudaSetDevice(h->device));
     if (int rc = ensure_plan(h, width, height)) return rc;
     if (int rc = ensure_batch(h, n_frames)) return rc;
-    return launch_pipeline(h, d_images, n_frames, stride, frame_stride);
+    if (int rc = reset_counts(h)) return rc;
+    return launch_pipeline(h, d_images, 0, n_frames, stride, frame_stride);
 }
 
 int orbx_extract(orbx_handle *h, const uint8_t *images, int n_frames, int width, int height, int stride, size_t frame_stride,
@@ -432,18 +489,19 @@ int orbx_extract(orbx_handle *h, const uint8_t *images, int n_frames, int width,
     ORBS_CUDA(cudaSetDevice(h->device));
     if (int rc = ensure_plan(h, width, height)) return rc;
     if (int rc = ensure_batch(h, n_frames)) return rc;
-    // stage the frames (pitch multiple of 64 for aligned rows)
-    const size_t pitch = align_up(width, 64), frame = pitch * height;
-    if (int rc = h->d_stage.reserve(frame * n_frames)) return rc;
-    if (n_frames == 1 || frame_stride == (size_t)stride * height) {
-        ORBS_CUDA(cudaMemcpy2DAsync(h->d_stage.p, pitch, images, stride, width, (size_t)height * n_frames, cudaMemcpyHostToDevice, h->stream));
-    } else {
-        for (int f = 0; f < n_frames; f++)
-            ORBS_CUDA(cudaMemcpy2DAsync(h->d_stage.as<uint8_t>() + f * frame, pitch, images + f * frame_stride, stride, width, height,
-                                        cudaMemcpyHostToDevice, h->stream));
-    }
-    if (int rc = launch_pipeline(h, h->d_stage.as<uint8_t>(), n_frames, (int)pitch, frame)) return rc;
+    if (int rc = upload_and_extract(h, images, n_frames, width, height, stride, frame_stride)) return rc;
     return download_results(h, kp_xy, kp_angle, kp_response, kp_octave, kp_size, desc, cap, counts);
+}
+
+int orbx_extract_host_async(orbx_handle *h, const uint8_t *images, int n_frames, int width, int height, int stride, size_t frame_stride)
+{
+    ORBS_REQUIRE(h && images, ORBS_E_INVALID, "null argument");
+    ORBS_REQUIRE(n_frames > 0 && width > 0 && height > 0 && stride >= width, ORBS_E_INVALID, "bad image shape");
+    std::lock_guard<std::mutex> lk(h->mu);
+    ORBS_CUDA(cudaSetDevice(h->device));
+    if (int rc = ensure_plan(h, width, height)) return rc;
+    if (int rc = ensure_batch(h, n_frames)) return rc;
+    return upload_and_extract(h, images, n_frames, width, height, stride, frame_stride);
 }
 
 int orbx_device_results(orbx_handle *h, orbx_device_view *view)
