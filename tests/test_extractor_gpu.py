@@ -26,3 +26,19 @@ def test_extract_matches_oracle(lib, cam):
     outs = ex.extract_batch(np.stack(frames))
     for f, (img, got) in enumerate(zip(frames, outs)):
         _assert_same(got, oracle.orb_extract(P, img), f"{cam} frame {f}")
+
+
+def test_extract_matches_reference_object_code(lib):
+    """CUDA extractor vs the reference's own ORBextractor.cc object code (oracle/_ref, prebuilt in the build container; see
+    tests/test_oracle_vs_reference.py for what is and is not the reference's code in that library)."""
+    from oracle import ref_build
+    if not ref_build.available():
+        pytest.skip("oracle/_ref not built")
+    import orbslamm_b200 as ob
+    for cam, nf in (("KITTI", 2000), ("TUM", 1000)):
+        c = getattr(synth, cam)
+        frames, _ = synth.stream(c["w"], c["h"], 2, stream_id=9)
+        ex = ob.ORBextractor(nf, 1.2, 8, 20, 7)
+        R = ref_build.RefORBextractor(nf, 1.2, 8, 20, 7)
+        for f, (img, got) in enumerate(zip(frames, ex.extract_batch(np.stack(frames)))):
+            _assert_same(got, R(img), f"{cam} frame {f} vs reference")

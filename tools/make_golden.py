@@ -2,8 +2,9 @@
 """Generate tests/golden/*.npz: small known-answer vectors for the hot path.
 
 The reference repository ships no golden vectors, and its C++ cannot be built here, so these come
-from the oracle.  At generation time the extractor vector is produced TWICE -- by orb_oracle.c and by the cv2-primitive
-twin (the OpenCV calls the reference makes) -- and the script refuses to write if they disagree.
+from the oracle.  At generation time the extractor vector is produced THREE times -- by orb_oracle.c, by the cv2-primitive
+twin (the OpenCV calls the reference makes) and by the reference's own ORBextractor.cc object code (oracle/_ref, ascending-heap
+tie-break) -- and the script refuses to write if any two disagree.
     python tools/make_golden.py
 """
 import os
@@ -14,7 +15,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import oracle                      # noqa: E402
-from oracle import orb_cv2         # noqa: E402
+from oracle import orb_cv2, ref_build  # noqa: E402
 from orbslamm_b200 import synth    # noqa: E402
 from helpers import make_tracking_case  # noqa: E402
 
@@ -25,10 +26,15 @@ os.makedirs(out, exist_ok=True)
 cam = dict(synth.TUM); cam.update(w=400, h=300, nfeatures=400, cx=200.0, cy=150.0)
 case = make_tracking_case(cam, 21)
 P = case["P"]
+assert ref_build.build(), "oracle/_ref (the reference's own ORBextractor.cc) must be buildable to write golden vectors"
+R = ref_build.RefORBextractor(400, 1.2, 8, 20, 7)
 for img, feats in ((case["frames"][0], case["last"]), (case["frames"][1], case["cur"])):
     b = orb_cv2.extract(P, img)
     for k in ("x", "y", "angle", "response", "octave", "size", "desc"):
         assert np.array_equal(feats[k], b[k]), f"oracle and cv2 twin disagree on {k}"
+    r = R(img)
+    for k in ("x", "y", "angle", "response", "octave", "size", "desc"):
+        assert np.array_equal(feats[k], r[k]), f"oracle and the reference's object code disagree on {k}"
 ex = {f"f{i}_{k}": v for i, f in enumerate((case["last"], case["cur"])) for k, v in f.items()}
 np.savez_compressed(os.path.join(out, "extract_400x300.npz"), frame0=case["frames"][0], frame1=case["frames"][1],
                     params=np.array([400, 8, 20, 7]), scale_factor=np.float32(1.2), **ex)
