@@ -389,7 +389,7 @@ class Optimizer:
         return dict(poses=poses.reshape(K, 4, 4), points=points, chi2=chi2, depth_ok=dok, outlier=outl,
                     lm_iterations=int(stats[0]), lm_trials=int(stats[1]), chol_failures=int(stats[2]), aborted=bool(rc == 1))
 
-    KERNELS = ("errors", "build_points", "build_poses", "schur", "chol_potrf", "chol_trsm", "chol_update", "tri_solves",
+    KERNELS = ("errors", "build_points", "build_poses", "schur", "chol_factor", "unused5", "unused6", "tri_solves",
                "backsub", "update", "memset_S")
 
     def set_profiling(self, on):
@@ -406,7 +406,10 @@ class Optimizer:
         out = np.zeros(4)
         self._L.orbo_last_ba_timing.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
         _check(self._L.orbo_last_ba_timing(self._h, _ptr(out)))
-        return dict(lm_loop_s=float(out[0]), total_s=float(out[1]), setup_s=float(out[2]), ld=int(out[3]))
+        sk = np.zeros(2, np.int64)
+        self._L.orbo_last_ba_skyline.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        _check(self._L.orbo_last_ba_skyline(self._h, _ptr(sk)))
+        return dict(lm_loop_s=float(out[0]), total_s=float(out[1]), setup_s=float(out[2]), ld=int(out[3]), tile_rows=int(sk[0]), skyline_tiles=int(sk[1]))
 
     def LocalBundleAdjustment(self, poses, fixed, intr, points, e_kf, e_pt, e_uv, e_inv_sigma2, stop_flag=None):
         """Optimizer::LocalBundleAdjustment schedule: 5 robust LM iterations, chi2/depth gating, 10 non-robust."""

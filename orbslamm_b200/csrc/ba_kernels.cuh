@@ -291,44 +291,155 @@ k_ba_schur(const BaDev B, double lambda)
 }
 
 // ---------------------------------------------------------------------------------------------
-// Dense Cholesky S = L L^T on the lower triangle, tile size NB, right-looking.  Replaces
-// LinearSolverEigen::solve (SimplicialLDLT); a non-positive pivot raises flags[0] (solve() == false).
+// Block-skyline Cholesky S = L L^T on the lower triangle, tile size NB.  Replaces LinearSolverEigen::solve
+// (SimplicialLDLT, linear_solver_eigen.h:94-124); a non-positive pivot raises flags[0] (solve() == false).
+//
+// Structure: tfirst[i] = first tile column of tile row i that can be nonzero (from the covisibility of the free keyframes;
+// the envelope of a Cholesky factor equals the envelope of the matrix, so tiles left of tfirst[i] are never touched).
+// PR_k = { i > k : tfirst[i] <= k } are the tile rows with a structurally nonzero L_ik, stored as a CSR list
+// (pr_start / pr_rows, ascending).  For a trajectory-like graph PR_k holds a handful of rows; for a fully coupled
+// graph it is every row below k and the algorithm is the ordinary dense tiled factorisation.
+//
+// One launch per tile column k (k_chol_step) with two kinds of CTAs:
+//   * panel CTAs (1 + |PR_k|): bring column k up to date with the one update that is still missing (from column k-1,
+//     applied left-looking in shared memory: A_kk -= L_k,k-1 L_k,k-1^T and A_ik -= L_i,k-1 L_k,k-1^T), factor the diagonal
+//     tile (every panel CTA redundantly -- cheaper than a dependent launch), then CTA 0 stores inv(L_kk) for the triangular
+//     solves and CTA b >= 1 writes L_ik = A_ik L_kk^-T;
+//   * update CTAs: the right-looking update from column k-1 of every tile (i, j), j >= k+1, i, j in PR_{k-1}:
+//     A_ij -= L_i,k-1 L_j,k-1^T.
+// The diagonal tiles of L are not written back: after the factorisation only the off-diagonal tiles and inv(L_kk) are used.
 constexpr int NB = 64;
+constexpr int kTilePitch = NB + 1;                      // doubles; conflict-free for row- and column-wise access
+constexpr int kTileElems = NB * kTilePitch;
+constexpr int kStepSmem = 4 * kTileElems * (int)sizeof(double);
 
-// Panel step k: every CTA factors the diagonal tile A_kk redundantly in shared memory (64^3/3 flops -- cheaper than a
-// separate launch + dependency); CTA 0 writes L_kk back and stores its inverse (used by the triangular solves), CTA b >= 1
-// computes A_ik <- A_ik L_kk^-T for tile row i = k + b.  64 threads: one matrix row per thread.
-constexpr int kPanelSmem = 2 * NB * (NB + 1) * (int)sizeof(double);
+struct CholPlan {
+    const int *tfirst;      // [nt]
+    const int *pr_start;    // [nt + 1]
+    const int *pr_rows;     // [pr_start[nt]]
+};
 
-// 256 threads: 4 threads per matrix row, each holding 16 consecutive columns of the row in registers.
+__device__ __forceinline__ void cp_async8(void *smem, const void *gmem)
+{
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gmem));
+}
+
+typedef double (*TilePtr)[kTilePitch];
+
+__device__ __forceinline__ void tile_load_async(TilePtr dst, const double *src, int ld, int tid)
+{
+#pragma unroll 4
+    for (int q = tid; q < NB * NB; q += 256) { const int r = q >> 6, c = q & 63; cp_async8(&dst[r][c], &src[(size_t)r * ld + c]); }
+}
+
+// C -= A B^T on 64x64 tiles in shared memory; thread (ty, tx) owns the interleaved 4x4 micro-tile C[ty + 16u][tx + 16v]
+__device__ __forceinline__ void tile_gemm_nt_sub(TilePtr C, TilePtr A, TilePtr Bm, int tid)
+{
+    const int ty = tid >> 4, tx = tid & 15;
+    double acc[4][4] = {};
+#pragma unroll 8
+    for (int q = 0; q < NB; q++) {
+        double a[4], b[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) { a[u] = A[ty + 16 * u][q]; b[u] = Bm[tx + 16 * u][q]; }
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+#pragma unroll
+            for (int v = 0; v < 4; v++) acc[u][v] = fma(a[u], b[v], acc[u][v]);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+#pragma unroll
+        for (int v = 0; v < 4; v++) C[ty + 16 * u][tx + 16 * v] -= acc[u][v];
+}
+
+// 256 threads.  Panel part: 4 threads per matrix row, each holding 16 consecutive columns of the row in registers.
 __global__ void __launch_bounds__(256)
-k_chol_panel(double *__restrict__ S, int ld, int k, double *__restrict__ Linv, int *__restrict__ flags)
+k_chol_step(double *__restrict__ S, int ld, int k, const CholPlan plan, double *__restrict__ Linv, int *__restrict__ flags)
 {
     extern __shared__ double smem_d[];
-    double (*T)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(smem_d);                  // A_kk, then L_kk (lower)
-    double (*X)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(smem_d + NB * (NB + 1));  // the tile being solved
+    TilePtr T = reinterpret_cast<TilePtr>(smem_d);                      // A_kk, then L_kk (lower)
+    TilePtr X = reinterpret_cast<TilePtr>(smem_d + kTileElems);         // the tile being solved
+    TilePtr P1 = reinterpret_cast<TilePtr>(smem_d + 2 * kTileElems);    // L_k,k-1   (update part: L_i,k-1)
+    TilePtr P2 = reinterpret_cast<TilePtr>(smem_d + 3 * kTileElems);    // L_i,k-1   (update part: L_j,k-1)
     __shared__ double colbuf[2][NB];
     __shared__ double invd[NB];
-    const int tid = threadIdx.x, r = tid >> 2, sub = tid & 3, lane = tid & 31;
-    double *A = S + (size_t)(k * NB) * ld + k * NB;
-    const int i = k + blockIdx.x;
-    for (int q = tid; q < NB * NB; q += 256) { const int rr = q >> 6, cc = q & 63; T[rr][cc] = cc <= rr ? A[(size_t)rr * ld + cc] : 0.0; }
-    if (blockIdx.x > 0) {
-        const double *P = S + (size_t)(i * NB) * ld + k * NB;
-        for (int q = tid; q < NB * NB; q += 256) { const int rr = q >> 6, cc = q & 63; X[rr][cc] = P[(size_t)rr * ld + cc]; }
+    const int tid = threadIdx.x;
+    const int npanel = 1 + plan.pr_start[k + 1] - plan.pr_start[k];
+
+    if ((int)blockIdx.x >= npanel) {
+        // ---- right-looking update from column c = k-1 of tile (i, j); i >= j >= k+1, both in PR_c
+        const int c = k - 1;
+        int q0 = plan.pr_start[c];
+        const int q1 = plan.pr_start[c + 1];
+        if (q0 < q1 && plan.pr_rows[q0] == k) q0++;                     // row k itself is handled by the panel CTAs
+        const int t = blockIdx.x - npanel;
+        int ii = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+        while (ii * (ii + 1) / 2 > t) ii--;
+        while ((ii + 1) * (ii + 2) / 2 <= t) ii++;
+        const int jj = t - ii * (ii + 1) / 2;
+        if (q0 + ii >= q1) return;
+        const int i = plan.pr_rows[q0 + ii], j = plan.pr_rows[q0 + jj];
+        tile_load_async(P1, S + (size_t)(i * NB) * ld + c * NB, ld, tid);
+        tile_load_async(P2, S + (size_t)(j * NB) * ld + c * NB, ld, tid);
+        asm volatile("cp.async.commit_group;\n" ::);
+        const int ty = tid >> 4, tx = tid & 15;
+        double *C = S + (size_t)(i * NB) * ld + j * NB;
+        double cval[4][4];
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+#pragma unroll
+            for (int v = 0; v < 4; v++) cval[u][v] = C[(size_t)(ty + 16 * u) * ld + tx + 16 * v];
+        asm volatile("cp.async.wait_group 0;\n" ::);
+        __syncthreads();
+        double acc[4][4] = {};
+#pragma unroll 8
+        for (int q = 0; q < NB; q++) {
+            double a[4], b[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) { a[u] = P1[ty + 16 * u][q]; b[u] = P2[tx + 16 * u][q]; }
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+#pragma unroll
+                for (int v = 0; v < 4; v++) acc[u][v] = fma(a[u], b[v], acc[u][v]);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+#pragma unroll
+            for (int v = 0; v < 4; v++)
+                if (i != j || tx + 16 * v <= ty + 16 * u) C[(size_t)(ty + 16 * u) * ld + tx + 16 * v] = cval[u][v] - acc[u][v];
+        return;
     }
+
+    // ---- panel part
+    const int b = blockIdx.x;
+    const int i = b == 0 ? k : plan.pr_rows[plan.pr_start[k] + b - 1];
+    const bool prev_k = k > 0 && plan.tfirst[k] <= k - 1;               // L_k,k-1 structurally nonzero
+    const bool prev_i = b > 0 && prev_k && plan.tfirst[i] <= k - 1;     // and L_i,k-1 too
+    tile_load_async(T, S + (size_t)(k * NB) * ld + k * NB, ld, tid);
+    if (b > 0) tile_load_async(X, S + (size_t)(i * NB) * ld + k * NB, ld, tid);
+    if (prev_k) tile_load_async(P1, S + (size_t)(k * NB) * ld + (k - 1) * NB, ld, tid);
+    if (prev_i) tile_load_async(P2, S + (size_t)(i * NB) * ld + (k - 1) * NB, ld, tid);
+    asm volatile("cp.async.commit_group;\n" ::);
+    asm volatile("cp.async.wait_group 0;\n" ::);
     __syncthreads();
+    if (prev_k) tile_gemm_nt_sub(T, P1, P1, tid);
+    if (prev_i) tile_gemm_nt_sub(X, P2, P1, tid);
+    __syncthreads();
+
+    const int r = tid >> 2, sub = tid & 3, lane = tid & 31;
     double a[16];
 #pragma unroll
     for (int u = 0; u < 16; u++) a[u] = T[r][16 * sub + u];
-    // right-looking Cholesky of the diagonal tile, one barrier per column
+    // right-looking Cholesky of the diagonal tile (lower part only), one barrier per column
 #pragma unroll
     for (int j = 0; j < NB; j++) {
         const int js = j >> 4, ju = j & 15;
         if (sub == js && r >= j) colbuf[j & 1][r] = a[ju];
         __syncthreads();
         double d = colbuf[j & 1][j];
-        if (!(d > 0.0)) { if (blockIdx.x == 0 && tid == 0) flags[0] = 1; d = 1.0; }
+        if (!(d > 0.0)) { if (b == 0 && tid == 0) flags[0] = 1; d = 1.0; }
         const double rinv = rsqrt(d), sd = d * rinv;
         if (r >= j) {
             const double l = (r == j) ? sd : colbuf[j & 1][r] * rinv;
@@ -349,8 +460,7 @@ k_chol_panel(double *__restrict__ S, int ld, int k, double *__restrict__ Linv, i
     __syncthreads();
     const unsigned full = 0xffffffffu;
     double x[16];
-    if (blockIdx.x == 0) {
-        for (int q = tid; q < NB * NB; q += 256) { const int rr = q >> 6, cc = q & 63; if (cc <= rr) A[(size_t)rr * ld + cc] = T[rr][cc]; }
+    if (b == 0) {
         // inverse of the lower-triangular tile: the 4 threads of "row" c hold column c of L^-1 (rows 16 sub .. 16 sub + 15)
         const int c = r;
 #pragma unroll
@@ -389,74 +499,14 @@ k_chol_panel(double *__restrict__ S, int ld, int k, double *__restrict__ Linv, i
     }
 }
 
-// A[i][j] -= A[i][k] * A[j][k]^T   for k < j <= i.  One CTA per (i, j) tile; panels staged row-major with cp.async
-// (pitch 65 doubles: conflict-free for both operands), thread (ty, tx) owns the interleaved 4x4 micro-tile
-// C[ty + 16u][tx + 16v].
-__device__ __forceinline__ void cp_async8(void *smem, const void *gmem)
-{
-    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gmem));
-}
-
-__global__ void __launch_bounds__(256)
-k_chol_update(double *__restrict__ S, int ld, int k, int nt)
-{
-    extern __shared__ double smem_d[];
-    double (*Ai)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(smem_d);                 // [row][q]
-    double (*Aj)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(smem_d + NB * (NB + 1));
-    const int m = nt - k - 1;
-    int t = blockIdx.x;
-    int ii = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
-    while (ii * (ii + 1) / 2 > t) ii--;
-    while ((ii + 1) * (ii + 2) / 2 <= t) ii++;
-    const int jj = t - ii * (ii + 1) / 2;
-    if (ii >= m) return;
-    const int i = k + 1 + ii, j = k + 1 + jj, tid = threadIdx.x;
-    const double *Pi = S + (size_t)(i * NB) * ld + k * NB, *Pj = S + (size_t)(j * NB) * ld + k * NB;
-#pragma unroll 4
-    for (int q = tid; q < NB * NB; q += 256) {
-        const int r = q >> 6, c = q & 63;
-        cp_async8(&Ai[r][c], &Pi[(size_t)r * ld + c]);
-        cp_async8(&Aj[r][c], &Pj[(size_t)r * ld + c]);
-    }
-    asm volatile("cp.async.commit_group;\n" ::);
-    const int ty = tid >> 4, tx = tid & 15;
-    // prefetch the C micro-tile while the panels land
-    double *C = S + (size_t)(i * NB) * ld + j * NB;
-    double cval[4][4];
-#pragma unroll
-    for (int u = 0; u < 4; u++)
-#pragma unroll
-        for (int v = 0; v < 4; v++) cval[u][v] = C[(size_t)(ty + 16 * u) * ld + tx + 16 * v];
-    asm volatile("cp.async.wait_group 0;\n" ::);
-    __syncthreads();
-    double acc[4][4] = {};
-#pragma unroll 8
-    for (int q = 0; q < NB; q++) {
-        double a[4], b[4];
-#pragma unroll
-        for (int u = 0; u < 4; u++) { a[u] = Ai[ty + 16 * u][q]; b[u] = Aj[tx + 16 * u][q]; }
-#pragma unroll
-        for (int u = 0; u < 4; u++)
-#pragma unroll
-            for (int v = 0; v < 4; v++) acc[u][v] = fma(a[u], b[v], acc[u][v]);
-    }
-#pragma unroll
-    for (int u = 0; u < 4; u++)
-#pragma unroll
-        for (int v = 0; v < 4; v++)
-            if (i != j || tx + 16 * v <= ty + 16 * u) C[(size_t)(ty + 16 * u) * ld + tx + 16 * v] = cval[u][v] - acc[u][v];
-}
-constexpr int kUpdateSmem = 2 * NB * (NB + 1) * (int)sizeof(double);
-
 // Triangular solves as two dataflow kernels (one CTA per tile row, all co-resident; dependencies always point to
-// lower block indices so that in-order block scheduling cannot deadlock):
-//   forward  (dir = 0): CTA i waits for y_0..y_{i-1}, accumulates L_ik y_k, then y_i = Linv_ii (b_i - acc)
-//   backward (dir = 1): CTA b handles tile j = nt-1-b, waits for x_{nt-1}..x_{j+1}, accumulates L_ij^T x_i, then
+// lower block indices so that in-order block scheduling cannot deadlock), restricted to the skyline:
+//   forward  (dir = 0): CTA i waits for y_k, k = tfirst[i]..i-1, accumulates L_ik y_k, then y_i = Linv_ii (b_i - acc)
+//   backward (dir = 1): CTA b handles tile j = nt-1-b, waits for x_i, i in PR_j (descending), accumulates L_ij^T x_i, then
 //                       x_j = Linv_jj^T (y_j - acc)
 // v is solved in place; ready[] must be zero on entry.
 __global__ void __launch_bounds__(256)
-k_chol_solve(const double *__restrict__ S, int ld, int nt, const double *__restrict__ Linv, double *v, int *ready, int dir)
+k_chol_solve(const double *__restrict__ S, int ld, int nt, const CholPlan plan, const double *__restrict__ Linv, double *v, int *ready, int dir)
 {
     __shared__ double s_vec[NB];
     __shared__ double s_part[4][NB];
@@ -465,9 +515,10 @@ k_chol_solve(const double *__restrict__ S, int ld, int nt, const double *__restr
     const int me = dir == 0 ? blockIdx.x : nt - 1 - blockIdx.x;
     if (tid < NB) s_acc[tid] = 0.0;
     __syncthreads();
-    const int nsteps = dir == 0 ? me : nt - 1 - me;
+    const int f = plan.tfirst[me], p0 = plan.pr_start[me], p1 = plan.pr_start[me + 1];
+    const int nsteps = dir == 0 ? me - f : p1 - p0;
     for (int s = 0; s < nsteps; s++) {
-        const int o = dir == 0 ? s : nt - 1 - s;            // the tile whose solution we consume
+        const int o = dir == 0 ? f + s : plan.pr_rows[p1 - 1 - s];     // the tile whose solution we consume
         if (tid == 0) { while (*((volatile int *)&ready[o]) == 0) { } __threadfence(); }
         __syncthreads();
         if (tid < NB) s_vec[tid] = *((volatile double *)&v[o * NB + tid]);

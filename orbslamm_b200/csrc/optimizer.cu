@@ -9,6 +9,7 @@
 #include <mutex>
 #include <vector>
 #include <chrono>
+#include <climits>
 #include <dlfcn.h>
 #include <nccl.h>
 #include "common.cuh"
@@ -62,6 +63,7 @@ struct orbo_handle {
     KernelTimer timer;       // BA kernels, ids = BaK
     ncclComm_t comm = nullptr;   // set by orbo_comm_init: orbo_bundle_adjust becomes a collective over map-point shards
     int nranks = 1, rank = 0;
+    long long ba_skyline[2] = {0, 0};
     double ba_timing[4] = {0, 0, 0, 0};   // last BA call: LM-loop seconds, total seconds, setup (layout + H2D) seconds, Schur bytes
 };
 
@@ -79,8 +81,7 @@ int orbo_create(orbo_handle **out, int device)
     cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete h; return cuda_fail(e, "cudaStreamCreate", __FILE__, __LINE__); }
     if (int rc = h->h_scalars.reserve(256)) { orbo_destroy(h); return rc; }
-    cudaFuncSetAttribute(k_chol_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPanelSmem);
-    cudaFuncSetAttribute(k_chol_update, cudaFuncAttributeMaxDynamicSharedMemorySize, kUpdateSmem);
+    cudaFuncSetAttribute(k_chol_step, cudaFuncAttributeMaxDynamicSharedMemorySize, kStepSmem);
     *out = h;
     return ORBS_OK;
 }
@@ -226,6 +227,42 @@ struct BaHost {
     const volatile int *stop = nullptr;
     int lm_iterations = 0, lm_trials = 0, chol_failures = 0;
     double *Linv = nullptr;       // [ntiles][64*64] inverses of the diagonal Cholesky tiles
+    CholPlan plan = {};           // block skyline of the reduced system (device arrays)
+    int *d_plan = nullptr;        // [nt_max + (nt_max + 1) + nt_max (nt_max - 1) / 2] backing store of plan
+    int nt_max = 0;
+    std::vector<int> step_grid;   // CTAs of k_chol_step per tile column
+    long long skyline_tiles = 0;  // structurally nonzero tiles of L (incl. diagonal)
+
+    // tile-level skyline from the first coupled free pose of every free pose (first_pose[ip] <= ip)
+    int set_skyline(const std::vector<int> &first_pose)
+    {
+        const int nt = ntiles, nA = B.nA;
+        std::vector<int> tfirst(nt), pr_start(nt + 1, 0), pr_rows;
+        for (int i = 0; i < nt; i++) tfirst[i] = i;
+        for (int ip = 0; ip < nA; ip++) {
+            const int tc = (6 * first_pose[ip]) / NB;
+            for (int r = 6 * ip; r < 6 * ip + 6; r += 5) tfirst[r / NB] = std::min(tfirst[r / NB], tc);   // first and last row of the pose
+        }
+        skyline_tiles = 0;
+        for (int k = 0; k < nt; k++) {
+            for (int i = k + 1; i < nt; i++) if (tfirst[i] <= k) pr_rows.push_back(i);
+            pr_start[k + 1] = (int)pr_rows.size();
+        }
+        skyline_tiles = nt + (long long)pr_rows.size();
+        step_grid.assign(nt, 1);
+        for (int k = 0; k < nt; k++) {
+            int nq = 0;
+            if (k > 0) { nq = pr_start[k] - pr_start[k - 1]; if (nq > 0 && pr_rows[pr_start[k - 1]] == k) nq--; }
+            step_grid[k] = 1 + (pr_start[k + 1] - pr_start[k]) + nq * (nq + 1) / 2;
+        }
+        int *d_tfirst = d_plan, *d_start = d_plan + nt_max, *d_rows = d_plan + 2 * nt_max + 1;
+        ORBS_CUDA(cudaMemcpyAsync(d_tfirst, tfirst.data(), nt * sizeof(int), cudaMemcpyHostToDevice, st));
+        ORBS_CUDA(cudaMemcpyAsync(d_start, pr_start.data(), (nt + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
+        if (!pr_rows.empty()) ORBS_CUDA(cudaMemcpyAsync(d_rows, pr_rows.data(), pr_rows.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+        ORBS_CUDA(cudaStreamSynchronize(st));                  // the host vectors die here
+        plan.tfirst = d_tfirst; plan.pr_start = d_start; plan.pr_rows = d_rows;
+        return ORBS_OK;
+    }
     int *ready = nullptr;         // [2*ntiles] dataflow flags of the triangular solves
     double *h_scal = nullptr;     // pinned [16]
     int *h_flag = nullptr;        // pinned
@@ -312,23 +349,14 @@ struct BaHost {
             if (int rc = allreduce(B.S, (size_t)ld * ld, ncclDouble, ncclSum)) return rc;
             if (int rc = allreduce(B.bs, (size_t)ld, ncclDouble, ncclSum)) return rc;
             count(2);
-            for (int k = 0; k < ntiles; k++) {
-                const int m = ntiles - k - 1;
-                T().begin(BK_POTRF, st);
-                k_chol_panel<<<m + 1, 256, kPanelSmem, st>>>(B.S, ld, k, Linv, B.flags);
-                T().end(st);
-                count(1);
-                if (m > 0) {
-                    T().begin(BK_SYRK, st);
-                    k_chol_update<<<m * (m + 1) / 2, 256, kUpdateSmem, st>>>(B.S, ld, k, ntiles);
-                    T().end(st);
-                    count(1);
-                }
-            }
+            T().begin(BK_POTRF, st);
+            for (int k = 0; k < ntiles; k++) k_chol_step<<<step_grid[k], 256, kStepSmem, st>>>(B.S, ld, k, plan, Linv, B.flags);
+            T().end(st);
+            count(ntiles);
             T().begin(BK_TRS, st);
             ORBS_CUDA(cudaMemsetAsync(ready, 0, 2 * (size_t)ntiles * sizeof(int), st));
-            k_chol_solve<<<ntiles, 256, 0, st>>>(B.S, ld, ntiles, Linv, B.bs, ready, 0);
-            k_chol_solve<<<ntiles, 256, 0, st>>>(B.S, ld, ntiles, Linv, B.bs, ready + ntiles, 1);
+            k_chol_solve<<<ntiles, 256, 0, st>>>(B.S, ld, ntiles, plan, Linv, B.bs, ready, 0);
+            k_chol_solve<<<ntiles, 256, 0, st>>>(B.S, ld, ntiles, plan, Linv, B.bs, ready + ntiles, 1);
             count(2);
             T().end(st);
             k_ba_take_xp<<<xp_blocks, 256, 0, st>>>(B, lambda, h->rank == 0 ? 1 : 0);
@@ -476,6 +504,9 @@ extern "C" int orbo_bundle_adjust(orbo_handle *h, int K, float *poses, const uin
     const int ld_max = (int)align_up(6 * (size_t)K, NB);
     B.S = S.scratch<double>((size_t)ld_max * ld_max); B.bs = S.scratch<double>(ld_max);
     D.Linv = S.scratch<double>((size_t)ld_max * NB); D.ready = S.scratch<int>(2 * (size_t)(ld_max / NB) + 2);
+    D.nt_max = ld_max / NB;
+    D.d_plan = S.scratch<int>(2 * (size_t)D.nt_max + 1 + (size_t)D.nt_max * D.nt_max / 2 + 4);
+    int *d_first_pose = S.scratch<int>(K + 1);
     ORBS_REQUIRE(ld_max / NB <= 140, ORBS_E_INVALID, "more than 1493 free keyframes: the dataflow triangular solve needs all tile rows co-resident");
     const int max_blocks = std::max({(E + 255) / 256, (P + 7) / 8, (K + P + 255) / 256, (6 * K + 255) / 256}) + 1;
     B.partial = S.scratch<double>(max_blocks); B.scalars = S.scratch<double>(8); B.flags = S.scratch<int>(4);
@@ -514,6 +545,23 @@ extern "C" int orbo_bundle_adjust(orbo_handle *h, int K, float *poses, const uin
         ORBS_CUDA(cudaMemcpyAsync(d_pose_idx, pose_idx.data(), K * sizeof(int), cudaMemcpyHostToDevice, st));
         ORBS_CUDA(cudaMemcpyAsync(d_pt_active, pt_active.data(), P, cudaMemcpyHostToDevice, st));
         ORBS_CUDA(cudaStreamSynchronize(st));
+        // skyline of the reduced system: free poses i, j are coupled iff an active point is seen by both; first_pose[i] = the
+        // smallest hessian index coupled to i (edges are grouped by point).  Sharded: minimum over the ranks' shards.
+        std::vector<int> first_pose(std::max(nA, 1));
+        for (int i = 0; i < nA; i++) first_pose[i] = i;
+        for (int p = 0; p < P; p++) {
+            int mn = INT_MAX;
+            for (int j = pt_start[p]; j < pt_start[p + 1]; j++) if (!level[j] && pose_idx[kf_s[j]] >= 0) mn = std::min(mn, pose_idx[kf_s[j]]);
+            if (mn == INT_MAX) continue;
+            for (int j = pt_start[p]; j < pt_start[p + 1]; j++) if (!level[j] && pose_idx[kf_s[j]] >= 0) { int &f = first_pose[pose_idx[kf_s[j]]]; f = std::min(f, mn); }
+        }
+        if (D.multi() && nA > 0) {
+            ORBS_CUDA(cudaMemcpyAsync(d_first_pose, first_pose.data(), nA * sizeof(int), cudaMemcpyHostToDevice, st));
+            if (int rc = D.allreduce(d_first_pose, nA, ncclInt32, ncclMin)) return rc;
+            ORBS_CUDA(cudaMemcpyAsync(first_pose.data(), d_first_pose, nA * sizeof(int), cudaMemcpyDeviceToHost, st));
+            ORBS_CUDA(cudaStreamSynchronize(st));
+        }
+        if (D.set_skyline(first_pose)) return -1;
         return any ? 1 : 0;
     };
 
@@ -562,6 +610,7 @@ extern "C" int orbo_bundle_adjust(orbo_handle *h, int K, float *poses, const uin
         auto sec = [](auto a, auto b) { return std::chrono::duration<double>(b - a).count(); };
         h->ba_timing[0] = sec(t_loop, t_loop_end); h->ba_timing[1] = sec(t_begin, t_end); h->ba_timing[2] = sec(t_begin, t_loop);
         h->ba_timing[3] = (double)B.ld;
+        h->ba_skyline[0] = D.ntiles; h->ba_skyline[1] = D.skyline_tiles;
     }
     if (stats) { stats[0] = D.lm_iterations; stats[1] = D.lm_trials; stats[2] = D.chol_failures; stats[3] = 0; }
     return ORBS_OK;
@@ -571,6 +620,13 @@ extern "C" int orbo_last_ba_timing(orbo_handle *h, double *out4)
 {
     ORBS_REQUIRE(h && out4, ORBS_E_INVALID, "null argument");
     for (int i = 0; i < 4; i++) out4[i] = h->ba_timing[i];
+    return ORBS_OK;
+}
+
+extern "C" int orbo_last_ba_skyline(orbo_handle *h, long long *out2)
+{
+    ORBS_REQUIRE(h && out2, ORBS_E_INVALID, "null argument");
+    out2[0] = h->ba_skyline[0]; out2[1] = h->ba_skyline[1];
     return ORBS_OK;
 }
 

@@ -133,3 +133,17 @@ def ba_graph(K=100, P=10000, seed=42, cam=KITTI, min_obs=3, max_obs=9, outlier_f
     return dict(poses=poses, fixed=fixed, intr=np.array([fx, fy, cx, cy], np.float64), points=points,
                 kf=kf, pt=pt, uv=uv.astype(np.float32), inv_sigma2=inv_sigma2.astype(np.float32),
                 gt_poses=gt_poses, gt_points=Xw, is_outlier=out)
+
+
+def permute_keyframes(g, seed=0):
+    """Same problem with the keyframes renumbered at random: the reduced pose system loses its band structure (what a loop
+    closure / merged multi-robot map looks like to the solver)."""
+    rng = np.random.default_rng(seed)
+    K = len(g["poses"])
+    perm = rng.permutation(K)                  # new index of old keyframe k
+    inv = np.argsort(perm)
+    out = dict(g)
+    out["poses"] = g["poses"][inv].copy(); out["fixed"] = g["fixed"][inv].copy(); out["gt_poses"] = g["gt_poses"][inv].copy()
+    out["kf"] = perm[g["kf"]].astype(np.int32)
+    out["perm"] = perm
+    return out
