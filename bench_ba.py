@@ -80,11 +80,11 @@ def bench_ba(args, rank, world):
     hbm, how = peaks()
     # dominant kernel by device time; algorithmic bytes per launch
     ktimes = {k: v for k, v in ktimes.items() if not k.startswith("unused")}
-    sky = tm["skyline_tiles"]
+    sky = tm["l_tiles"]
     dom = max(ktimes, key=lambda k: ktimes[k][0])
     dom_ms, dom_n = ktimes[dom]
-    # chol_factor = all k_chol_step launches of one solve: every structurally nonzero 64x64 tile of L is read and written once
-    # (the compulsory traffic of a skyline factorisation; panel re-reads of neighbouring tiles come from L2)
+    # chol_factor = all k_chol_panel / k_chol_update launches of one solve: every structurally nonzero 64x64 tile of L is read and
+    # written once (the compulsory traffic of a sparse tiled factorisation; re-reads of neighbouring tiles come from L2)
     alg = {"errors": 20 * E + 88 * K + 24 * P + 16 * E, "build_points": 20 * E + 88 * K + 24 * P + 144 * E + 96 * P,
            "build_poses": 20 * E + 88 * K + 24 * P + 336 * K, "schur": 144 * E + 96 * P + 8 * 36 * 3.5 * E,
            "chol_factor": 2 * 8 * 64 * 64 * sky, "tri_solves": 2 * 8 * 64 * 64 * sky,
@@ -95,6 +95,7 @@ def bench_ba(args, rank, world):
     lm_total_ms = loop_s * 1e3
     roofline = {"kernel": dom, "bound": "hbm", "achieved": round(achieved, 2), "peak": hbm, "unit": "GB/s", "frac": round(achieved / hbm, 5),
                 "traffic": None, "peak_source": how, "algorithmic_bytes_per_launch": int(alg_bytes), "avg_launch_ms": round(per_launch_ms, 5),
+                "launch": "one timed region = one factorisation / one pair of triangular solves (several dependent kernel launches)" if dom in ("chol_factor", "tri_solves") else "one kernel launch",
                 "kernel_share_of_step": {k: round(v[0] / max(lm_total_ms, 1e-9), 4) for k, v in ktimes.items()},
                 "whole_iteration": {"algorithmic_bytes": int(_alg_bytes(K, P, E, ld)),
                                     "achieved_GBps": round(_alg_bytes(K, P, E, ld) * iters / loop_s / 1e9, 2)}}
@@ -104,7 +105,7 @@ def bench_ba(args, rank, world):
            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
            "config": {"workload": f"synthetic covisibility graph {K} KF / {P} points / {E} observations, LocalBA schedule 5 robust + 10 non-robust LM its",
                       "lm_iterations_per_step": iters / args.steps, "lm_trials_per_step": trials / args.steps,
-                      "l2": "256 MiB flush buffer written between timed steps (untimed)", "reduced_system": f"{ld}x{ld} fp64, block skyline: {sky} of {(ld // 64) * (ld // 64 + 1) // 2} lower 64x64 tiles structurally nonzero",
+                      "l2": "256 MiB flush buffer written between timed steps (untimed)", "reduced_system": f"{ld}x{ld} fp64 (10 keyframes per 64-row tile), nested-dissection tile order: {sky} of {(ld // 64) * (ld // 64 + 1) // 2} lower 64x64 tiles structurally nonzero in L, {tm['levels']} elimination levels",
                       "parallelism": f"map points sharded x{world}, poses replicated, NCCL all-reduce of the {ld}x{ld} reduced system per LM trial" if world > 1 else "1 GPU"},
            "e2e": {"value": round(e2e, 2), "unit": "LM iterations/s", "h2d_bytes_per_step": int(graph_bytes), "d2h_bytes_per_step": int(K * 64 + P * 12 + E * 10)},
            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "wall_s": round(wall, 3)}

@@ -268,11 +268,12 @@ int orbf_track_frames(orbf_handle *h, const uint8_t *images, int n_frames, int w
 /* Bench bookkeeping for the last orbo_bundle_adjust call: out4 = { seconds inside the LM loops (graph resident on the
  * device), seconds of the whole call, seconds of host graph layout + H2D, leading dimension of the reduced system }. */
 int orbo_last_ba_timing(orbo_handle *h, double *out4);
-/* Block skyline of the reduced system in the last orbo_bundle_adjust call (what LinearSolverEigen's sparse LDLT exploits in
- * the reference, linear_solver_eigen.h:94-124): out2 = { tile rows (64x64 tiles), structurally nonzero tiles of L }. */
-int orbo_last_ba_skyline(orbo_handle *h, long long *out2);
-/* Per-kernel CUDA-event timing of the BA kernels.  ids: 0 errors, 1 build_points, 2 build_poses, 3 schur, 4 the block-skyline
- * Cholesky factorisation (all k_chol_step launches of one solve), 5-6 unused, 7 triangular solves, 8 backsub, 9 update,
+/* Sparse structure of the reduced system in the last orbo_bundle_adjust call (what LinearSolverEigen's sparse LDLT with its
+ * fill-reducing ordering exploits in the reference, linear_solver_eigen.h:94-124): out3 = { tile rows (64x64 tiles, 10 keyframes
+ * each), structurally nonzero tiles of L after the nested-dissection tile ordering, levels of the elimination DAG }. */
+int orbo_last_ba_structure(orbo_handle *h, long long *out3);
+/* Per-kernel CUDA-event timing of the BA kernels.  ids: 0 errors, 1 build_points, 2 build_poses, 3 schur, 4 the sparse tiled
+ * Cholesky factorisation (all k_chol_panel / k_chol_update launches of one solve), 5-6 unused, 7 triangular solves, 8 backsub, 9 update,
  * 10 memset of the reduced system. */
 int orbo_set_profiling(orbo_handle *h, int enabled);
 int orbo_get_kernel_times(orbo_handle *h, double *total_ms, long long *counts, int n);

@@ -406,10 +406,11 @@ class Optimizer:
         out = np.zeros(4)
         self._L.orbo_last_ba_timing.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
         _check(self._L.orbo_last_ba_timing(self._h, _ptr(out)))
-        sk = np.zeros(2, np.int64)
-        self._L.orbo_last_ba_skyline.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
-        _check(self._L.orbo_last_ba_skyline(self._h, _ptr(sk)))
-        return dict(lm_loop_s=float(out[0]), total_s=float(out[1]), setup_s=float(out[2]), ld=int(out[3]), tile_rows=int(sk[0]), skyline_tiles=int(sk[1]))
+        sk = np.zeros(3, np.int64)
+        self._L.orbo_last_ba_structure.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        _check(self._L.orbo_last_ba_structure(self._h, _ptr(sk)))
+        return dict(lm_loop_s=float(out[0]), total_s=float(out[1]), setup_s=float(out[2]), ld=int(out[3]), tile_rows=int(sk[0]), l_tiles=int(sk[1]),
+                    levels=int(sk[2]))
 
     def LocalBundleAdjustment(self, poses, fixed, intr, points, e_kf, e_pt, e_uv, e_inv_sigma2, stop_flag=None):
         """Optimizer::LocalBundleAdjustment schedule: 5 robust LM iterations, chi2/depth gating, 10 non-robust."""

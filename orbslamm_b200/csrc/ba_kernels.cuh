@@ -40,6 +40,8 @@ struct BaDev {
     const int *e_point;           // [E] point of an edge (point-grouped order)
     // index mapping
     const int *pose_idx;          // [K] hessian index or -1 (fixed / inactive)
+    const int *rowbase;           // [nA] first row of a free keyframe's 6x6 block in the (tile-permuted) reduced system
+    const uint8_t *row_pad;       // [ld] 1 = identity padding row of the reduced system
     const uint8_t *pt_active;     // [P]
     // system
     double *Hpp, *bp;             // [nA*36], [nA*6]
@@ -224,12 +226,11 @@ k_ba_schur_init(const BaDev B, double lambda, int lead)
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t < B.nA * 36) {
         const int i = t / 36, a = (t % 36) / 6, c = t % 6;
-        if (c <= a && lead) B.S[(size_t)(6 * i + a) * B.ld + 6 * i + c] = B.Hpp[t] + (a == c ? lambda : 0.0);
+        const int rb = B.rowbase[i];
+        if (c <= a && lead) B.S[(size_t)(rb + a) * B.ld + rb + c] = B.Hpp[t] + (a == c ? lambda : 0.0);
     }
-    if (t < B.ld) {
-        B.bs[t] = (t < B.n && lead) ? B.bp[t] : 0.0;
-        if (t >= B.n && lead) B.S[(size_t)t * B.ld + t] = 1.0;
-    }
+    if (t < B.n) { const int i = t / 6, a = t % 6; B.bs[B.rowbase[i] + a] = lead ? B.bp[t] : 0.0; }
+    if (t < B.ld && B.row_pad[t]) { B.bs[t] = 0.0; if (lead) B.S[(size_t)t * B.ld + t] = 1.0; }
 }
 
 // warp per point: Dinv = (Hll + lambda I)^-1, then for every pair of its free-pose edges the 6x6 block
@@ -254,8 +255,9 @@ k_ba_schur(const BaDev B, double lambda)
         const int i1 = B.pose_idx[B.e_kf[e]];
         if (i1 < 0) continue;
         const double *W = &B.e_W[18 * (size_t)e];
+        const int rb = B.rowbase[i1];
 #pragma unroll
-        for (int a = 0; a < 6; a++) atomicAdd(&B.bs[6 * i1 + a], -(W[3 * a] * db[0] + W[3 * a + 1] * db[1] + W[3 * a + 2] * db[2]));
+        for (int a = 0; a < 6; a++) atomicAdd(&B.bs[rb + a], -(W[3 * a] * db[0] + W[3 * a + 1] * db[1] + W[3 * a + 2] * db[2]));
     }
     // pair part: pairs (u, v), u <= v, linearised
     const int npairs = m * (m + 1) / 2;
@@ -269,16 +271,17 @@ k_ba_schur(const BaDev B, double lambda)
         if (B.e_level[eu] || B.e_level[ev]) continue;
         const int iu = B.pose_idx[B.e_kf[eu]], iv = B.pose_idx[B.e_kf[ev]];
         if (iu < 0 || iv < 0) continue;
-        // block (row = larger index, col = smaller index) = W_row Dinv W_col^T
-        const bool swap = iu > iv;
+        // block (row = lower in the permuted system, col = the other) = W_row Dinv W_col^T
+        const int ru = B.rowbase[iu], rv = B.rowbase[iv];
+        const bool swap = ru > rv;
         const double *Wr = &B.e_W[18 * (size_t)(swap ? eu : ev)], *Wc = &B.e_W[18 * (size_t)(swap ? ev : eu)];
-        const int ir = swap ? iu : iv, ic = swap ? iv : iu;
+        const int ir = swap ? ru : rv, ic = swap ? rv : ru;
         double BD[18];
 #pragma unroll
         for (int a = 0; a < 6; a++)
 #pragma unroll
             for (int c = 0; c < 3; c++) BD[3 * a + c] = Wr[3 * a] * Di[c] + Wr[3 * a + 1] * Di[3 + c] + Wr[3 * a + 2] * Di[6 + c];
-        double *Sb = &B.S[(size_t)(6 * ir) * B.ld + 6 * ic];
+        double *Sb = &B.S[(size_t)ir * B.ld + ic];
 #pragma unroll
         for (int a = 0; a < 6; a++)
 #pragma unroll
@@ -291,32 +294,36 @@ k_ba_schur(const BaDev B, double lambda)
 }
 
 // ---------------------------------------------------------------------------------------------
-// Block-skyline Cholesky S = L L^T on the lower triangle, tile size NB.  Replaces LinearSolverEigen::solve
-// (SimplicialLDLT, linear_solver_eigen.h:94-124); a non-positive pivot raises flags[0] (solve() == false).
+// Sparse tiled Cholesky S = L L^T of the reduced pose system (lower triangle, 64x64 tiles).  Replaces
+// LinearSolverEigen::solve (SimplicialLDLT with a fill-reducing ordering, linear_solver_eigen.h:94-124); a non-positive pivot
+// raises flags[0] (solve() == false).
 //
-// Structure: tfirst[i] = first tile column of tile row i that can be nonzero (from the covisibility of the free keyframes;
-// the envelope of a Cholesky factor equals the envelope of the matrix, so tiles left of tfirst[i] are never touched).
-// PR_k = { i > k : tfirst[i] <= k } are the tile rows with a structurally nonzero L_ik, stored as a CSR list
-// (pr_start / pr_rows, ascending).  For a trajectory-like graph PR_k holds a handful of rows; for a fully coupled
-// graph it is every row below k and the algorithm is the ordinary dense tiled factorisation.
+// Layout: free keyframes are packed kPosesPerTile = 10 to a tile (60 rows + 4 identity padding rows), and the TILES are
+// permuted by a nested-dissection ordering of the keyframe covisibility graph (host, optimizer.cu: build_schedule): the
+// elimination DAG of a trajectory-like graph then has depth O(log) instead of one dependent step per tile column.
+// rowbase[hessian index] is the first row of a keyframe's 6x6 block.  The symbolic factorisation (tile level) gives, per
+// tile column k, rows(k) = { i > k : L_ik != 0 } and the elimination level of k; columns of one level are independent.
 //
-// One launch per tile column k (k_chol_step) with two kinds of CTAs:
-//   * panel CTAs (1 + |PR_k|): bring column k up to date with the one update that is still missing (from column k-1,
-//     applied left-looking in shared memory: A_kk -= L_k,k-1 L_k,k-1^T and A_ik -= L_i,k-1 L_k,k-1^T), factor the diagonal
-//     tile (every panel CTA redundantly -- cheaper than a dependent launch), then CTA 0 stores inv(L_kk) for the triangular
-//     solves and CTA b >= 1 writes L_ik = A_ik L_kk^-T;
-//   * update CTAs: the right-looking update from column k-1 of every tile (i, j), j >= k+1, i, j in PR_{k-1}:
-//     A_ij -= L_i,k-1 L_j,k-1^T.
-// The diagonal tiles of L are not written back: after the factorisation only the off-diagonal tiles and inv(L_kk) are used.
+// Two launches per level:
+//   k_chol_panel   one CTA per (k, i), i = k or i in rows(k): every CTA factors the diagonal tile A_kk redundantly in shared
+//                  memory (cheaper than a dependent launch); CTA (k, k) stores inv(L_kk) for the triangular solves, CTA (k, i)
+//                  writes L_ik = A_ik L_kk^-T.  The diagonal tiles of L are not written back (never read again).
+//   k_chol_update  one CTA per (k, i, j), i >= j in rows(k): A_ij -= L_ik L_jk^T (fp64 atomics only where two columns of the
+//                  same level update the same tile).
 constexpr int NB = 64;
+constexpr int kPosesPerTile = 10;
 constexpr int kTilePitch = NB + 1;                      // doubles; conflict-free for row- and column-wise access
 constexpr int kTileElems = NB * kTilePitch;
-constexpr int kStepSmem = 4 * kTileElems * (int)sizeof(double);
+constexpr int kPanelSmem = 2 * kTileElems * (int)sizeof(double);
+constexpr int kUpdateSmem = 2 * kTileElems * (int)sizeof(double);
 
 struct CholPlan {
-    const int *tfirst;      // [nt]
-    const int *pr_start;    // [nt + 1]
-    const int *pr_rows;     // [pr_start[nt]]
+    const int *rows_start;  // [nt + 1]  CSR by column: rows(k), ascending
+    const int *rows;
+    const int *cols_start;  // [nt + 1]  CSR by row: cols(i) = { k < i : L_ik != 0 }, ascending
+    const int *cols;
+    const int4 *panel;      // tasks {k, i, 0, 0}, grouped by level
+    const int4 *update;     // tasks {k, i, j, shared}, grouped by level
 };
 
 __device__ __forceinline__ void cp_async8(void *smem, const void *gmem)
@@ -333,99 +340,23 @@ __device__ __forceinline__ void tile_load_async(TilePtr dst, const double *src, 
     for (int q = tid; q < NB * NB; q += 256) { const int r = q >> 6, c = q & 63; cp_async8(&dst[r][c], &src[(size_t)r * ld + c]); }
 }
 
-// C -= A B^T on 64x64 tiles in shared memory; thread (ty, tx) owns the interleaved 4x4 micro-tile C[ty + 16u][tx + 16v]
-__device__ __forceinline__ void tile_gemm_nt_sub(TilePtr C, TilePtr A, TilePtr Bm, int tid)
-{
-    const int ty = tid >> 4, tx = tid & 15;
-    double acc[4][4] = {};
-#pragma unroll 8
-    for (int q = 0; q < NB; q++) {
-        double a[4], b[4];
-#pragma unroll
-        for (int u = 0; u < 4; u++) { a[u] = A[ty + 16 * u][q]; b[u] = Bm[tx + 16 * u][q]; }
-#pragma unroll
-        for (int u = 0; u < 4; u++)
-#pragma unroll
-            for (int v = 0; v < 4; v++) acc[u][v] = fma(a[u], b[v], acc[u][v]);
-    }
-#pragma unroll
-    for (int u = 0; u < 4; u++)
-#pragma unroll
-        for (int v = 0; v < 4; v++) C[ty + 16 * u][tx + 16 * v] -= acc[u][v];
-}
-
-// 256 threads.  Panel part: 4 threads per matrix row, each holding 16 consecutive columns of the row in registers.
+// 256 threads: 4 threads per matrix row, each holding 16 consecutive columns of the row in registers.
 __global__ void __launch_bounds__(256)
-k_chol_step(double *__restrict__ S, int ld, int k, const CholPlan plan, double *__restrict__ Linv, int *__restrict__ flags)
+k_chol_panel(double *__restrict__ S, int ld, const int4 *__restrict__ tasks, double *__restrict__ Linv, int *__restrict__ flags)
 {
     extern __shared__ double smem_d[];
     TilePtr T = reinterpret_cast<TilePtr>(smem_d);                      // A_kk, then L_kk (lower)
     TilePtr X = reinterpret_cast<TilePtr>(smem_d + kTileElems);         // the tile being solved
-    TilePtr P1 = reinterpret_cast<TilePtr>(smem_d + 2 * kTileElems);    // L_k,k-1   (update part: L_i,k-1)
-    TilePtr P2 = reinterpret_cast<TilePtr>(smem_d + 3 * kTileElems);    // L_i,k-1   (update part: L_j,k-1)
     __shared__ double colbuf[2][NB];
     __shared__ double invd[NB];
     const int tid = threadIdx.x;
-    const int npanel = 1 + plan.pr_start[k + 1] - plan.pr_start[k];
-
-    if ((int)blockIdx.x >= npanel) {
-        // ---- right-looking update from column c = k-1 of tile (i, j); i >= j >= k+1, both in PR_c
-        const int c = k - 1;
-        int q0 = plan.pr_start[c];
-        const int q1 = plan.pr_start[c + 1];
-        if (q0 < q1 && plan.pr_rows[q0] == k) q0++;                     // row k itself is handled by the panel CTAs
-        const int t = blockIdx.x - npanel;
-        int ii = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
-        while (ii * (ii + 1) / 2 > t) ii--;
-        while ((ii + 1) * (ii + 2) / 2 <= t) ii++;
-        const int jj = t - ii * (ii + 1) / 2;
-        if (q0 + ii >= q1) return;
-        const int i = plan.pr_rows[q0 + ii], j = plan.pr_rows[q0 + jj];
-        tile_load_async(P1, S + (size_t)(i * NB) * ld + c * NB, ld, tid);
-        tile_load_async(P2, S + (size_t)(j * NB) * ld + c * NB, ld, tid);
-        asm volatile("cp.async.commit_group;\n" ::);
-        const int ty = tid >> 4, tx = tid & 15;
-        double *C = S + (size_t)(i * NB) * ld + j * NB;
-        double cval[4][4];
-#pragma unroll
-        for (int u = 0; u < 4; u++)
-#pragma unroll
-            for (int v = 0; v < 4; v++) cval[u][v] = C[(size_t)(ty + 16 * u) * ld + tx + 16 * v];
-        asm volatile("cp.async.wait_group 0;\n" ::);
-        __syncthreads();
-        double acc[4][4] = {};
-#pragma unroll 8
-        for (int q = 0; q < NB; q++) {
-            double a[4], b[4];
-#pragma unroll
-            for (int u = 0; u < 4; u++) { a[u] = P1[ty + 16 * u][q]; b[u] = P2[tx + 16 * u][q]; }
-#pragma unroll
-            for (int u = 0; u < 4; u++)
-#pragma unroll
-                for (int v = 0; v < 4; v++) acc[u][v] = fma(a[u], b[v], acc[u][v]);
-        }
-#pragma unroll
-        for (int u = 0; u < 4; u++)
-#pragma unroll
-            for (int v = 0; v < 4; v++)
-                if (i != j || tx + 16 * v <= ty + 16 * u) C[(size_t)(ty + 16 * u) * ld + tx + 16 * v] = cval[u][v] - acc[u][v];
-        return;
-    }
-
-    // ---- panel part
-    const int b = blockIdx.x;
-    const int i = b == 0 ? k : plan.pr_rows[plan.pr_start[k] + b - 1];
-    const bool prev_k = k > 0 && plan.tfirst[k] <= k - 1;               // L_k,k-1 structurally nonzero
-    const bool prev_i = b > 0 && prev_k && plan.tfirst[i] <= k - 1;     // and L_i,k-1 too
+    const int4 task = tasks[blockIdx.x];
+    const int k = task.x, i = task.y;
+    const bool diag = i == k;
     tile_load_async(T, S + (size_t)(k * NB) * ld + k * NB, ld, tid);
-    if (b > 0) tile_load_async(X, S + (size_t)(i * NB) * ld + k * NB, ld, tid);
-    if (prev_k) tile_load_async(P1, S + (size_t)(k * NB) * ld + (k - 1) * NB, ld, tid);
-    if (prev_i) tile_load_async(P2, S + (size_t)(i * NB) * ld + (k - 1) * NB, ld, tid);
+    if (!diag) tile_load_async(X, S + (size_t)(i * NB) * ld + k * NB, ld, tid);
     asm volatile("cp.async.commit_group;\n" ::);
     asm volatile("cp.async.wait_group 0;\n" ::);
-    __syncthreads();
-    if (prev_k) tile_gemm_nt_sub(T, P1, P1, tid);
-    if (prev_i) tile_gemm_nt_sub(X, P2, P1, tid);
     __syncthreads();
 
     const int r = tid >> 2, sub = tid & 3, lane = tid & 31;
@@ -439,7 +370,7 @@ k_chol_step(double *__restrict__ S, int ld, int k, const CholPlan plan, double *
         if (sub == js && r >= j) colbuf[j & 1][r] = a[ju];
         __syncthreads();
         double d = colbuf[j & 1][j];
-        if (!(d > 0.0)) { if (b == 0 && tid == 0) flags[0] = 1; d = 1.0; }
+        if (!(d > 0.0)) { if (diag && tid == 0) flags[0] = 1; d = 1.0; }
         const double rinv = rsqrt(d), sd = d * rinv;
         if (r >= j) {
             const double l = (r == j) ? sd : colbuf[j & 1][r] * rinv;
@@ -460,7 +391,7 @@ k_chol_step(double *__restrict__ S, int ld, int k, const CholPlan plan, double *
     __syncthreads();
     const unsigned full = 0xffffffffu;
     double x[16];
-    if (b == 0) {
+    if (diag) {
         // inverse of the lower-triangular tile: the 4 threads of "row" c hold column c of L^-1 (rows 16 sub .. 16 sub + 15)
         const int c = r;
 #pragma unroll
@@ -499,10 +430,58 @@ k_chol_step(double *__restrict__ S, int ld, int k, const CholPlan plan, double *
     }
 }
 
-// Triangular solves as two dataflow kernels (one CTA per tile row, all co-resident; dependencies always point to
-// lower block indices so that in-order block scheduling cannot deadlock), restricted to the skyline:
-//   forward  (dir = 0): CTA i waits for y_k, k = tfirst[i]..i-1, accumulates L_ik y_k, then y_i = Linv_ii (b_i - acc)
-//   backward (dir = 1): CTA b handles tile j = nt-1-b, waits for x_i, i in PR_j (descending), accumulates L_ij^T x_i, then
+// A[i][j] -= A[i][k] * A[j][k]^T.  Panels staged row-major with cp.async (pitch 65 doubles: conflict-free for both operands),
+// thread (ty, tx) owns the interleaved 4x4 micro-tile C[ty + 16u][tx + 16v].
+__global__ void __launch_bounds__(256)
+k_chol_update(double *__restrict__ S, int ld, const int4 *__restrict__ tasks)
+{
+    extern __shared__ double smem_d[];
+    TilePtr Ai = reinterpret_cast<TilePtr>(smem_d);
+    TilePtr Aj = reinterpret_cast<TilePtr>(smem_d + kTileElems);
+    const int4 task = tasks[blockIdx.x];
+    const int k = task.x, i = task.y, j = task.z, tid = threadIdx.x;
+    const bool shared_target = task.w != 0;
+    tile_load_async(Ai, S + (size_t)(i * NB) * ld + k * NB, ld, tid);
+    if (i != j) tile_load_async(Aj, S + (size_t)(j * NB) * ld + k * NB, ld, tid);
+    asm volatile("cp.async.commit_group;\n" ::);
+    const int ty = tid >> 4, tx = tid & 15;
+    double *C = S + (size_t)(i * NB) * ld + j * NB;
+    double cval[4][4];
+    if (!shared_target) {
+        // prefetch the C micro-tile while the panels land
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+#pragma unroll
+            for (int v = 0; v < 4; v++) cval[u][v] = C[(size_t)(ty + 16 * u) * ld + tx + 16 * v];
+    }
+    asm volatile("cp.async.wait_group 0;\n" ::);
+    __syncthreads();
+    TilePtr Bj = i != j ? Aj : Ai;
+    double acc[4][4] = {};
+#pragma unroll 8
+    for (int q = 0; q < NB; q++) {
+        double a[4], b[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) { a[u] = Ai[ty + 16 * u][q]; b[u] = Bj[tx + 16 * u][q]; }
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+#pragma unroll
+            for (int v = 0; v < 4; v++) acc[u][v] = fma(a[u], b[v], acc[u][v]);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+#pragma unroll
+        for (int v = 0; v < 4; v++)
+            if (i != j || tx + 16 * v <= ty + 16 * u) {
+                double *dst = &C[(size_t)(ty + 16 * u) * ld + tx + 16 * v];
+                if (shared_target) atomicAdd(dst, -acc[u][v]); else *dst = cval[u][v] - acc[u][v];
+            }
+}
+
+// Triangular solves as two dataflow kernels (one CTA per tile row, all co-resident; forward dependencies point to lower tile
+// indices, backward ones to higher indices, and CTAs are numbered accordingly, so in-order block scheduling cannot deadlock):
+//   forward  (dir = 0): CTA i waits for y_k, k in cols(i), accumulates L_ik y_k, then y_i = Linv_ii (b_i - acc)
+//   backward (dir = 1): CTA b handles tile j = nt-1-b, waits for x_i, i in rows(j) (descending), accumulates L_ij^T x_i, then
 //                       x_j = Linv_jj^T (y_j - acc)
 // v is solved in place; ready[] must be zero on entry.
 __global__ void __launch_bounds__(256)
@@ -515,10 +494,9 @@ k_chol_solve(const double *__restrict__ S, int ld, int nt, const CholPlan plan, 
     const int me = dir == 0 ? blockIdx.x : nt - 1 - blockIdx.x;
     if (tid < NB) s_acc[tid] = 0.0;
     __syncthreads();
-    const int f = plan.tfirst[me], p0 = plan.pr_start[me], p1 = plan.pr_start[me + 1];
-    const int nsteps = dir == 0 ? me - f : p1 - p0;
-    for (int s = 0; s < nsteps; s++) {
-        const int o = dir == 0 ? f + s : plan.pr_rows[p1 - 1 - s];     // the tile whose solution we consume
+    const int p0 = dir == 0 ? plan.cols_start[me] : plan.rows_start[me], p1 = dir == 0 ? plan.cols_start[me + 1] : plan.rows_start[me + 1];
+    for (int s = 0; s < p1 - p0; s++) {
+        const int o = dir == 0 ? plan.cols[p0 + s] : plan.rows[p1 - 1 - s];     // the tile whose solution we consume
         if (tid == 0) { while (*((volatile int *)&ready[o]) == 0) { } __threadfence(); }
         __syncthreads();
         if (tid < NB) s_vec[tid] = *((volatile double *)&v[o * NB + tid]);
@@ -562,7 +540,7 @@ k_ba_take_xp(const BaDev B, double lambda, int lead)
     __shared__ double s_w[8];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     double sc = 0;
-    if (i < B.n) { const double x = B.bs[i]; B.x[i] = x; sc = lead ? x * (lambda * x + B.bp[i]) : 0.0; }   // pose part counted once (lead rank)
+    if (i < B.n) { const double x = B.bs[B.rowbase[i / 6] + i % 6]; B.x[i] = x; sc = lead ? x * (lambda * x + B.bp[i]) : 0.0; }   // pose part counted once (lead rank)
     sc = warp_sum(sc);
     if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = sc;
     __syncthreads();

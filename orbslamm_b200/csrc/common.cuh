@@ -95,7 +95,7 @@ struct KernelTimer {
 
 // host<->device staging for ORBS_MEM_HOST calls: inputs are copied to pooled device buffers, outputs copied back in finish()
 struct StagePool {
-    static constexpr int kSlots = 40;
+    static constexpr int kSlots = 64;
     DevBuf buf[kSlots];
     void release() { for (auto &b : buf) b.release(); }
 };

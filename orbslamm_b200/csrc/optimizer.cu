@@ -63,7 +63,7 @@ struct orbo_handle {
     KernelTimer timer;       // BA kernels, ids = BaK
     ncclComm_t comm = nullptr;   // set by orbo_comm_init: orbo_bundle_adjust becomes a collective over map-point shards
     int nranks = 1, rank = 0;
-    long long ba_skyline[2] = {0, 0};
+    long long ba_skyline[3] = {0, 0, 0};
     double ba_timing[4] = {0, 0, 0, 0};   // last BA call: LM-loop seconds, total seconds, setup (layout + H2D) seconds, Schur bytes
 };
 
@@ -81,7 +81,8 @@ int orbo_create(orbo_handle **out, int device)
     cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete h; return cuda_fail(e, "cudaStreamCreate", __FILE__, __LINE__); }
     if (int rc = h->h_scalars.reserve(256)) { orbo_destroy(h); return rc; }
-    cudaFuncSetAttribute(k_chol_step, cudaFuncAttributeMaxDynamicSharedMemorySize, kStepSmem);
+    cudaFuncSetAttribute(k_chol_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPanelSmem);
+    cudaFuncSetAttribute(k_chol_update, cudaFuncAttributeMaxDynamicSharedMemorySize, kUpdateSmem);
     *out = h;
     return ORBS_OK;
 }
@@ -227,45 +228,116 @@ struct BaHost {
     const volatile int *stop = nullptr;
     int lm_iterations = 0, lm_trials = 0, chol_failures = 0;
     double *Linv = nullptr;       // [ntiles][64*64] inverses of the diagonal Cholesky tiles
-    CholPlan plan = {};           // block skyline of the reduced system (device arrays)
-    int *d_plan = nullptr;        // [nt_max + (nt_max + 1) + nt_max (nt_max - 1) / 2] backing store of plan
-    int nt_max = 0;
-    std::vector<int> step_grid;   // CTAs of k_chol_step per tile column
-    long long skyline_tiles = 0;  // structurally nonzero tiles of L (incl. diagonal)
-
-    // tile-level skyline from the first coupled free pose of every free pose (first_pose[ip] <= ip)
-    int set_skyline(const std::vector<int> &first_pose)
-    {
-        const int nt = ntiles, nA = B.nA;
-        std::vector<int> tfirst(nt), pr_start(nt + 1, 0), pr_rows;
-        for (int i = 0; i < nt; i++) tfirst[i] = i;
-        for (int ip = 0; ip < nA; ip++) {
-            const int tc = (6 * first_pose[ip]) / NB;
-            for (int r = 6 * ip; r < 6 * ip + 6; r += 5) tfirst[r / NB] = std::min(tfirst[r / NB], tc);   // first and last row of the pose
-        }
-        skyline_tiles = 0;
-        for (int k = 0; k < nt; k++) {
-            for (int i = k + 1; i < nt; i++) if (tfirst[i] <= k) pr_rows.push_back(i);
-            pr_start[k + 1] = (int)pr_rows.size();
-        }
-        skyline_tiles = nt + (long long)pr_rows.size();
-        step_grid.assign(nt, 1);
-        for (int k = 0; k < nt; k++) {
-            int nq = 0;
-            if (k > 0) { nq = pr_start[k] - pr_start[k - 1]; if (nq > 0 && pr_rows[pr_start[k - 1]] == k) nq--; }
-            step_grid[k] = 1 + (pr_start[k + 1] - pr_start[k]) + nq * (nq + 1) / 2;
-        }
-        int *d_tfirst = d_plan, *d_start = d_plan + nt_max, *d_rows = d_plan + 2 * nt_max + 1;
-        ORBS_CUDA(cudaMemcpyAsync(d_tfirst, tfirst.data(), nt * sizeof(int), cudaMemcpyHostToDevice, st));
-        ORBS_CUDA(cudaMemcpyAsync(d_start, pr_start.data(), (nt + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
-        if (!pr_rows.empty()) ORBS_CUDA(cudaMemcpyAsync(d_rows, pr_rows.data(), pr_rows.size() * sizeof(int), cudaMemcpyHostToDevice, st));
-        ORBS_CUDA(cudaStreamSynchronize(st));                  // the host vectors die here
-        plan.tfirst = d_tfirst; plan.pr_start = d_start; plan.pr_rows = d_rows;
-        return ORBS_OK;
-    }
     int *ready = nullptr;         // [2*ntiles] dataflow flags of the triangular solves
     double *h_scal = nullptr;     // pinned [16]
     int *h_flag = nullptr;        // pinned
+    CholPlan plan = {};           // sparse tile structure + task lists of the reduced system (device arrays)
+    int nt_max = 0;
+    int *d_plan_i = nullptr;      // rows_start, rows, cols_start, cols  [2 (nt_max + 1) + nt_max (nt_max - 1)]
+    int4 *d_tasks = nullptr;      // panel tasks then update tasks
+    size_t task_cap = 0;
+    int *d_rowbase = nullptr; uint8_t *d_rowpad = nullptr;
+    std::vector<int> panel_lv, update_lv;   // per level: first task index (size nlevels + 1)
+    int nlevels = 0;
+    long long l_tiles = 0;        // structurally nonzero tiles of L (incl. diagonal)
+    size_t n_panel = 0;
+
+    // Nested-dissection order of the tile groups by recursive bisection of the natural (temporal) order: the separator of
+    // [lo, hi) is the run of groups right of the middle that the left half reaches; left and right halves are then
+    // independent and are eliminated in parallel, the separator after both.
+    static void nd_order(const std::vector<uint8_t> &adj, int ng, int lo, int hi, std::vector<int> &out)
+    {
+        const int n = hi - lo;
+        if (n <= 3) { for (int g = lo; g < hi; g++) out.push_back(g); return; }
+        const int mid = lo + n / 2;
+        int reach = mid - 1;
+        for (int g = lo; g < mid; g++)
+            for (int h2 = hi - 1; h2 > reach; h2--) if (adj[(size_t)g * ng + h2]) { reach = h2; break; }
+        const int w = reach - mid + 1;
+        if (w == 0) { nd_order(adj, ng, lo, mid, out); nd_order(adj, ng, mid, hi, out); return; }
+        if (2 * w >= n || mid + w >= hi) { for (int g = lo; g < hi; g++) out.push_back(g); return; }   // no useful separator
+        nd_order(adj, ng, lo, mid, out);
+        nd_order(adj, ng, mid + w, hi, out);
+        for (int g = mid; g < mid + w; g++) out.push_back(g);
+    }
+
+    // adj[ng x ng]: covisibility of the tile groups (kPosesPerTile consecutive free keyframes each)
+    int build_schedule(const std::vector<uint8_t> &adj, int ng)
+    {
+        const int nt = ng, nA = B.nA;
+        std::vector<int> order; order.reserve(nt);
+        nd_order(adj, ng, 0, ng, order);
+        std::vector<int> pos(ng);
+        for (int t = 0; t < nt; t++) pos[order[t]] = t;
+        // symbolic factorisation on the permuted tile pattern
+        std::vector<uint8_t> pat((size_t)nt * nt, 0);
+        for (int a = 0; a < ng; a++)
+            for (int b2 = 0; b2 < ng; b2++) if (a != b2 && adj[(size_t)a * ng + b2]) { const int i = std::max(pos[a], pos[b2]), j = std::min(pos[a], pos[b2]); pat[(size_t)i * nt + j] = 1; }
+        std::vector<int> rows_start(nt + 1, 0), rows, cols_start(nt + 1, 0), cols, level(nt, 0);
+        for (int k = 0; k < nt; k++) {
+            const size_t r0 = rows.size();
+            for (int i = k + 1; i < nt; i++) if (pat[(size_t)i * nt + k]) rows.push_back(i);
+            rows_start[k + 1] = (int)rows.size();
+            for (size_t x = r0; x < rows.size(); x++)
+                for (size_t y = r0; y < x; y++) pat[(size_t)rows[x] * nt + rows[y]] = 1;
+        }
+        nlevels = 0;
+        for (int i = 0; i < nt; i++) {
+            int lv = 0;
+            for (int k = 0; k < i; k++) if (pat[(size_t)i * nt + k]) { cols.push_back(k); lv = std::max(lv, level[k] + 1); }
+            cols_start[i + 1] = (int)cols.size();
+            level[i] = lv;
+            nlevels = std::max(nlevels, lv + 1);
+        }
+        l_tiles = nt + (long long)rows.size();
+        // task lists by level
+        std::vector<std::vector<int>> by_level(nlevels);
+        for (int k = 0; k < nt; k++) by_level[level[k]].push_back(k);
+        std::vector<int4> panel, update;
+        panel_lv.assign(nlevels + 1, 0); update_lv.assign(nlevels + 1, 0);
+        std::vector<int> hits((size_t)nt * nt, 0);
+        for (int l = 0; l < nlevels; l++) {
+            const size_t u0 = update.size();
+            for (int k : by_level[l]) {
+                panel.push_back(make_int4(k, k, 0, 0));
+                for (int x = rows_start[k]; x < rows_start[k + 1]; x++) panel.push_back(make_int4(k, rows[x], 0, 0));
+                for (int x = rows_start[k]; x < rows_start[k + 1]; x++)
+                    for (int y = rows_start[k]; y <= x; y++) { update.push_back(make_int4(k, rows[x], rows[y], 0)); hits[(size_t)rows[x] * nt + rows[y]]++; }
+            }
+            for (size_t t = u0; t < update.size(); t++) {
+                int &hcount = hits[(size_t)update[t].y * nt + update[t].z];
+                if (hcount > 1) update[t].w = 1;                  // several columns of this level update the tile: atomics
+            }
+            for (size_t t = u0; t < update.size(); t++) hits[(size_t)update[t].y * nt + update[t].z] = 0;
+            panel_lv[l + 1] = (int)panel.size(); update_lv[l + 1] = (int)update.size();
+        }
+        n_panel = panel.size();
+        if (panel.size() + update.size() > task_cap) { set_last_error("internal: Cholesky task list exceeds its capacity"); return ORBS_E_INVALID; }
+        // row map
+        std::vector<int> rowbase(std::max(nA, 1));
+        std::vector<uint8_t> rowpad((size_t)nt * NB, 1);
+        for (int ip = 0; ip < nA; ip++) {
+            rowbase[ip] = NB * pos[ip / kPosesPerTile] + 6 * (ip % kPosesPerTile);
+            for (int a2 = 0; a2 < 6; a2++) rowpad[rowbase[ip] + a2] = 0;
+        }
+        int *d_rows_start = d_plan_i, *d_cols_start = d_plan_i + (nt_max + 1), *d_rows = d_plan_i + 2 * (nt_max + 1);
+        int *d_cols = d_rows + (size_t)nt_max * (nt_max - 1) / 2 + 1;
+        ORBS_CUDA(cudaMemcpyAsync(d_rows_start, rows_start.data(), (nt + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
+        ORBS_CUDA(cudaMemcpyAsync(d_cols_start, cols_start.data(), (nt + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
+        if (!rows.empty()) {
+            ORBS_CUDA(cudaMemcpyAsync(d_rows, rows.data(), rows.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+            ORBS_CUDA(cudaMemcpyAsync(d_cols, cols.data(), cols.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+        }
+        ORBS_CUDA(cudaMemcpyAsync(d_tasks, panel.data(), panel.size() * sizeof(int4), cudaMemcpyHostToDevice, st));
+        if (!update.empty()) ORBS_CUDA(cudaMemcpyAsync(d_tasks + panel.size(), update.data(), update.size() * sizeof(int4), cudaMemcpyHostToDevice, st));
+        if (nA > 0) ORBS_CUDA(cudaMemcpyAsync(d_rowbase, rowbase.data(), nA * sizeof(int), cudaMemcpyHostToDevice, st));
+        ORBS_CUDA(cudaMemcpyAsync(d_rowpad, rowpad.data(), rowpad.size(), cudaMemcpyHostToDevice, st));
+        ORBS_CUDA(cudaStreamSynchronize(st));                  // the host vectors die here
+        plan.rows_start = d_rows_start; plan.rows = d_rows; plan.cols_start = d_cols_start; plan.cols = d_cols;
+        plan.panel = d_tasks; plan.update = d_tasks + panel.size();
+        B.rowbase = d_rowbase; B.row_pad = d_rowpad;
+        return ORBS_OK;
+    }
 
     bool multi() const { return h->nranks > 1; }
     int allreduce(void *buf, size_t n, ncclDataType_t t, ncclRedOp_t op)
@@ -350,9 +422,15 @@ struct BaHost {
             if (int rc = allreduce(B.bs, (size_t)ld, ncclDouble, ncclSum)) return rc;
             count(2);
             T().begin(BK_POTRF, st);
-            for (int k = 0; k < ntiles; k++) k_chol_step<<<step_grid[k], 256, kStepSmem, st>>>(B.S, ld, k, plan, Linv, B.flags);
+            for (int l = 0; l < nlevels; l++) {
+                k_chol_panel<<<panel_lv[l + 1] - panel_lv[l], 256, kPanelSmem, st>>>(B.S, ld, plan.panel + panel_lv[l], Linv, B.flags);
+                count(1);
+                if (update_lv[l + 1] > update_lv[l]) {
+                    k_chol_update<<<update_lv[l + 1] - update_lv[l], 256, kUpdateSmem, st>>>(B.S, ld, plan.update + update_lv[l]);
+                    count(1);
+                }
+            }
             T().end(st);
-            count(ntiles);
             T().begin(BK_TRS, st);
             ORBS_CUDA(cudaMemsetAsync(ready, 0, 2 * (size_t)ntiles * sizeof(int), st));
             k_chol_solve<<<ntiles, 256, 0, st>>>(B.S, ld, ntiles, plan, Linv, B.bs, ready, 0);
@@ -501,13 +579,16 @@ extern "C" int orbo_bundle_adjust(orbo_handle *h, int K, float *poses, const uin
     B.Hpp = S.scratch<double>(36 * (size_t)K); B.bp = S.scratch<double>(6 * (size_t)K + NB);
     B.Hll = S.scratch<double>(9 * (size_t)P); B.bl = S.scratch<double>(3 * (size_t)P);
     B.x = S.scratch<double>(6 * (size_t)K + 3 * (size_t)P);
-    const int ld_max = (int)align_up(6 * (size_t)K, NB);
+    const int ld_max = NB * ((K + kPosesPerTile - 1) / kPosesPerTile);      // 10 keyframes (60 rows + 4 padding rows) per 64-row tile
     B.S = S.scratch<double>((size_t)ld_max * ld_max); B.bs = S.scratch<double>(ld_max);
     D.Linv = S.scratch<double>((size_t)ld_max * NB); D.ready = S.scratch<int>(2 * (size_t)(ld_max / NB) + 2);
     D.nt_max = ld_max / NB;
-    D.d_plan = S.scratch<int>(2 * (size_t)D.nt_max + 1 + (size_t)D.nt_max * D.nt_max / 2 + 4);
-    int *d_first_pose = S.scratch<int>(K + 1);
-    ORBS_REQUIRE(ld_max / NB <= 140, ORBS_E_INVALID, "more than 1493 free keyframes: the dataflow triangular solve needs all tile rows co-resident");
+    D.d_plan_i = S.scratch<int>(2 * (size_t)(D.nt_max + 1) + (size_t)D.nt_max * D.nt_max + 8);
+    D.task_cap = (size_t)D.nt_max * (D.nt_max + 1) / 2 + (size_t)D.nt_max * (D.nt_max + 1) * (D.nt_max + 2) / 6 + 8;
+    D.d_tasks = S.scratch<int4>(D.task_cap);
+    D.d_rowbase = S.scratch<int>(K + 1); D.d_rowpad = S.scratch<uint8_t>(ld_max + 16);
+    int *d_adj = S.scratch<int>((size_t)D.nt_max * D.nt_max + 4);
+    ORBS_REQUIRE(ld_max / NB <= 140, ORBS_E_INVALID, "more than 1400 keyframes: the dataflow triangular solve needs all tile rows co-resident");
     const int max_blocks = std::max({(E + 255) / 256, (P + 7) / 8, (K + P + 255) / 256, (6 * K + 255) / 256}) + 1;
     B.partial = S.scratch<double>(max_blocks); B.scalars = S.scratch<double>(8); B.flags = S.scratch<int>(4);
     double *d_chi2 = S.scratch<double>(E); uint8_t *d_depth = S.scratch<uint8_t>(E);
@@ -540,28 +621,41 @@ extern "C" int orbo_bundle_adjust(orbo_handle *h, int K, float *poses, const uin
         const bool any = pose_act[K] != 0;
         int nA = 0;
         for (int k = 0; k < K; k++) pose_idx[k] = (pose_act[k] && !fixed[k]) ? nA++ : -1;
-        B.nA = nA; B.n = 6 * nA; B.ld = (int)align_up((size_t)B.n, NB); D.ntiles = B.ld / NB;
+        B.nA = nA; B.n = 6 * nA; D.ntiles = (nA + kPosesPerTile - 1) / kPosesPerTile; B.ld = NB * D.ntiles;
         D.diag_blocks = (nA + P + 255) / 256; D.xp_blocks = std::max(1, (B.n + 255) / 256);
         ORBS_CUDA(cudaMemcpyAsync(d_pose_idx, pose_idx.data(), K * sizeof(int), cudaMemcpyHostToDevice, st));
         ORBS_CUDA(cudaMemcpyAsync(d_pt_active, pt_active.data(), P, cudaMemcpyHostToDevice, st));
         ORBS_CUDA(cudaStreamSynchronize(st));
-        // skyline of the reduced system: free poses i, j are coupled iff an active point is seen by both; first_pose[i] = the
-        // smallest hessian index coupled to i (edges are grouped by point).  Sharded: minimum over the ranks' shards.
-        std::vector<int> first_pose(std::max(nA, 1));
-        for (int i = 0; i < nA; i++) first_pose[i] = i;
-        for (int p = 0; p < P; p++) {
-            int mn = INT_MAX;
-            for (int j = pt_start[p]; j < pt_start[p + 1]; j++) if (!level[j] && pose_idx[kf_s[j]] >= 0) mn = std::min(mn, pose_idx[kf_s[j]]);
-            if (mn == INT_MAX) continue;
-            for (int j = pt_start[p]; j < pt_start[p + 1]; j++) if (!level[j] && pose_idx[kf_s[j]] >= 0) { int &f = first_pose[pose_idx[kf_s[j]]]; f = std::min(f, mn); }
+        // tile-level structure of the reduced system: free poses i, j are coupled iff an active point is seen by both (edges are
+        // grouped by point); tiles = groups of kPosesPerTile consecutive hessian indices.  Sharded: union over the ranks' shards.
+        const int ng = D.ntiles;
+        std::vector<uint8_t> adj((size_t)ng * ng, 0);
+        {
+            int gs[64];
+            for (int p = 0; p < P; p++) {
+                int m = 0;
+                for (int j = pt_start[p]; j < pt_start[p + 1]; j++) {
+                    if (level[j] || pose_idx[kf_s[j]] < 0) continue;
+                    const int g = pose_idx[kf_s[j]] / kPosesPerTile;
+                    bool seen = false;
+                    for (int q = 0; q < m; q++) if (gs[q] == g) { seen = true; break; }
+                    if (!seen) {
+                        for (int q = 0; q < m; q++) { adj[(size_t)g * ng + gs[q]] = 1; adj[(size_t)gs[q] * ng + g] = 1; }
+                        if (m < 64) gs[m++] = g;
+                        else for (int q2 = 0; q2 < ng; q2++) { adj[(size_t)g * ng + q2] = 1; adj[(size_t)q2 * ng + g] = 1; }   // > 64 distinct groups: couple to all
+                    }
+                }
+            }
         }
-        if (D.multi() && nA > 0) {
-            ORBS_CUDA(cudaMemcpyAsync(d_first_pose, first_pose.data(), nA * sizeof(int), cudaMemcpyHostToDevice, st));
-            if (int rc = D.allreduce(d_first_pose, nA, ncclInt32, ncclMin)) return rc;
-            ORBS_CUDA(cudaMemcpyAsync(first_pose.data(), d_first_pose, nA * sizeof(int), cudaMemcpyDeviceToHost, st));
+        if (D.multi() && ng > 0) {
+            std::vector<int> a32(adj.begin(), adj.end());
+            ORBS_CUDA(cudaMemcpyAsync(d_adj, a32.data(), a32.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+            if (int rc = D.allreduce(d_adj, a32.size(), ncclInt32, ncclMax)) return rc;
+            ORBS_CUDA(cudaMemcpyAsync(a32.data(), d_adj, a32.size() * sizeof(int), cudaMemcpyDeviceToHost, st));
             ORBS_CUDA(cudaStreamSynchronize(st));
+            for (size_t q = 0; q < adj.size(); q++) adj[q] = (uint8_t)a32[q];
         }
-        if (D.set_skyline(first_pose)) return -1;
+        if (ng > 0 && D.build_schedule(adj, ng)) return -1;
         return any ? 1 : 0;
     };
 
@@ -610,7 +704,7 @@ extern "C" int orbo_bundle_adjust(orbo_handle *h, int K, float *poses, const uin
         auto sec = [](auto a, auto b) { return std::chrono::duration<double>(b - a).count(); };
         h->ba_timing[0] = sec(t_loop, t_loop_end); h->ba_timing[1] = sec(t_begin, t_end); h->ba_timing[2] = sec(t_begin, t_loop);
         h->ba_timing[3] = (double)B.ld;
-        h->ba_skyline[0] = D.ntiles; h->ba_skyline[1] = D.skyline_tiles;
+        h->ba_skyline[0] = D.ntiles; h->ba_skyline[1] = D.l_tiles; h->ba_skyline[2] = D.nlevels;
     }
     if (stats) { stats[0] = D.lm_iterations; stats[1] = D.lm_trials; stats[2] = D.chol_failures; stats[3] = 0; }
     return ORBS_OK;
@@ -623,10 +717,10 @@ extern "C" int orbo_last_ba_timing(orbo_handle *h, double *out4)
     return ORBS_OK;
 }
 
-extern "C" int orbo_last_ba_skyline(orbo_handle *h, long long *out2)
+extern "C" int orbo_last_ba_structure(orbo_handle *h, long long *out2)
 {
     ORBS_REQUIRE(h && out2, ORBS_E_INVALID, "null argument");
-    out2[0] = h->ba_skyline[0]; out2[1] = h->ba_skyline[1];
+    out2[0] = h->ba_skyline[0]; out2[1] = h->ba_skyline[1]; out2[2] = h->ba_skyline[2];
     return ORBS_OK;
 }
 

@@ -68,23 +68,23 @@ def test_local_ba_matches_oracle(lib, K, P):
     assert np.array_equal(got["poses"][1], g["poses"][1])
 
 
-def test_local_ba_block_skyline(lib):
-    """Trajectory graph over many tile rows: the factorisation touches only the block skyline, result == oracle."""
+def test_local_ba_sparse_tiles(lib):
+    """Trajectory graph over many tile rows: nested-dissection tile order, few nonzero tiles, shallow elimination DAG; result == oracle."""
     import orbslamm_b200 as ob
     g = synth.ba_graph(K=260, P=16000, seed=3)
     opt = ob.Optimizer()
     got = opt.LocalBundleAdjustment(g["poses"], g["fixed"], g["intr"], g["points"], g["kf"], g["pt"], g["uv"], g["inv_sigma2"])
     tm = opt.last_ba_timing()
     nt = tm["tile_rows"]
-    assert nt == (6 * 258 + 63) // 64 and nt <= tm["skyline_tiles"] < nt * (nt + 1) // 4
+    assert nt == (258 + 9) // 10 and nt <= tm["l_tiles"] < nt * (nt + 1) // 4 and tm["levels"] <= 10
     ref = oracle.bundle_adjust(g["poses"], g["fixed"], g["intr"], g["points"], g["kf"], g["pt"], g["uv"], g["inv_sigma2"], True, 5, 10, True)
     assert got["lm_iterations"] == ref["lm_iterations"] and got["lm_trials"] == ref["lm_trials"] and got["chol_failures"] == 0
     assert _rel(got["poses"], ref["poses"]) < RTOL and _rel(got["points"], ref["points"]) < RTOL
 
 
 def test_local_ba_shuffled_keyframes_is_dense(lib):
-    """Keyframes renumbered at random (loop-closure-like coupling): the skyline is (almost) the full lower triangle and the same
-    kernels run the dense tiled factorisation; result == oracle and == the unshuffled problem."""
+    """Keyframes renumbered at random (loop-closure-like coupling): no separator exists, the tile pattern is (almost) the full lower triangle and
+    the same kernels run the dense tiled factorisation; result == oracle and == the unshuffled problem."""
     import orbslamm_b200 as ob
     g0 = synth.ba_graph(K=100, P=10000, seed=42)
     g = synth.permute_keyframes(g0, seed=5)
@@ -92,7 +92,7 @@ def test_local_ba_shuffled_keyframes_is_dense(lib):
     got = opt.LocalBundleAdjustment(g["poses"], g["fixed"], g["intr"], g["points"], g["kf"], g["pt"], g["uv"], g["inv_sigma2"])
     tm = opt.last_ba_timing()
     nt = tm["tile_rows"]
-    assert tm["skyline_tiles"] > 0.8 * nt * (nt + 1) // 2
+    assert tm["l_tiles"] > 0.8 * nt * (nt + 1) // 2 and tm["levels"] == nt
     ref = oracle.bundle_adjust(g["poses"], g["fixed"], g["intr"], g["points"], g["kf"], g["pt"], g["uv"], g["inv_sigma2"], True, 5, 10, True)
     assert got["lm_iterations"] == ref["lm_iterations"] and got["lm_trials"] == ref["lm_trials"] and got["chol_failures"] == 0
     assert _rel(got["poses"], ref["poses"]) < RTOL and _rel(got["points"], ref["points"]) < RTOL
