@@ -249,7 +249,7 @@ def bench_frontend(args, rank, world):
     for i in range(min(args.warmup, 3)):
         step_host(1 + i % (N_POOL - 1))
     barrier()
-    e2e_steps = max(3, min(args.steps, 20))
+    e2e_steps = args.steps if args.steps <= 20 else 20 + (args.steps - 20) % (N_POOL - 1)   # ends on the same pool frame as the device loop
     t0 = time.perf_counter()
     for i in range(e2e_steps):
         step_host(1 + i % (N_POOL - 1))

@@ -67,6 +67,7 @@ struct orbx_handle {
 
 static int build_plan(orbx_handle *h, int width, int height)
 {
+
     ExtractPlan &P = h->plan;
     memset(&P, 0, sizeof P);
     P.nlevels = h->nlevels; P.width = width; P.height = height;
@@ -261,7 +262,10 @@ static int launch_pipeline(orbx_handle *h, const uint8_t *d_img0_all, int f0, in
     }
     if (P.total_cells > 0) {
         h->timer.begin(1, st);
-        k_fast_cells<<<dim3(P.total_cells, n), 128, 0, st>>>(P, h->d_cells.as<CellDesc>(), d_img0, pitch0, frame0, pyr, cand, cand_count, err_ptr(h, nb));
+        // pyramid levels >= 1 are always 64-byte aligned; level 0 goes through the TMA engine when the caller's buffer allows it
+        const bool l0_bulk = (((uintptr_t)d_img0 | (uintptr_t)pitch0 | (uintptr_t)frame0) & 15) == 0 && pitch0 >= (int)align_up(P.lv[0].w, 16);
+        const unsigned tma_levels = (l0_bulk ? 1u : 0u) | 0xfffffffeu;
+        k_fast_cells<<<dim3(P.total_cells, n), 128, 0, st>>>(P, tma_levels, h->d_cells.as<CellDesc>(), d_img0, pitch0, frame0, pyr, cand, cand_count, err_ptr(h, nb));
         h->timer.end(st);
         h->timer.begin(2, st);
         k_blur7<<<dim3(P.total_tiles, n), 256, 0, st>>>(P, h->d_tiles.as<TileDesc>(), d_img0, pitch0, frame0, pyr, blur);

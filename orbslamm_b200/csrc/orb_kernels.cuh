@@ -45,186 +45,254 @@ k_resize_level(const uint8_t *__restrict__ src, int sw, int sh, int spitch, size
 }
 
 // ---------------------------------------------------------------------------------------------
-// FAST-9/16 corner score on packed pairs of pixels.
+// FAST-9/16 on packed pairs of pixels.
 //
 // For a pixel v and ring p[0..15]:  score = max( max_arc min_arc(p - v), max_arc min_arc(v - p) ) - 1
 // over the 16 cyclic arcs of 9 pixels; the pixel is a corner at threshold t iff score >= t, and the
-// score is cv::FAST's response.  Two horizontally adjacent pixels are processed in the two 16-bit
-// lanes of a register: A[i] = 256 + v - p[i] per lane (no inter-lane borrow), then sliding min / max
-// of 9 with native u16x2 min/max.
-constexpr int kPixPitch = 80;    // bytes per smem pixel row (cell sub-images are <= 66 wide)
-constexpr int kPixRows = 66;
-constexpr int kScPitch = 64;     // detection region is <= 60 wide (+ 2 zero border)
-constexpr int kScRows = 62;
-
-__device__ __forceinline__ unsigned pack_pair(unsigned wa, unsigned wb, int o)
-{
-    // bytes o and o+1 of the 8-byte string (wa, wb) into the two 16-bit lanes, zero extended
-    const unsigned sel = o | (o << 4) | ((o + 1) << 8) | ((o + 1) << 12);
-    return __byte_perm(wa, wb, sel) & 0x00ff00ffu;
-}
-
-// w[r][0..2]: the 12 bytes of pixel row (y - 3 + r) covering columns c-4 .. c+7 (c = first pixel of the
-// 4-pixel group).  PAIR 0 = pixels c, c+1; PAIR 1 = pixels c+2, c+3.  Returns both lanes' scores
-// clamped to [0, 254] as lo | hi << 16.
-template <int PAIR>
-__device__ __forceinline__ unsigned fast_score_pair(const unsigned (&w)[7][3])
-{
-    // ring in cyclic order: (dx, dy)
-    constexpr int RDX[16] = {0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1};
-    constexpr int RDY[16] = {3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1, 0, 1, 2, 3};
-    unsigned A[16];
-    {
-        constexpr int ic = 4 + 2 * PAIR;             // byte index of the pair's first centre pixel
-        const unsigned V = pack_pair(w[3][ic / 4], w[3][ic / 4 + (ic / 4 < 2 ? 1 : 0)], ic % 4) | 0x01000100u;
-#pragma unroll
-        for (int k = 0; k < 16; k++) {
-            const int idx = 4 + 2 * PAIR + RDX[k];   // 1 .. 9
-            const int r = 3 + RDY[k];
-            const int wi = idx / 4;
-            const unsigned P = pack_pair(w[r][wi], w[r][wi < 2 ? wi + 1 : wi], idx % 4);
-            A[k] = V - P;                            // 256 + v - p per lane, in [1, 511]
-        }
-    }
-    unsigned mn2[16], mx2[16];
-#pragma unroll
-    for (int k = 0; k < 16; k++) { mn2[k] = __vminu2(A[k], A[(k + 1) & 15]); mx2[k] = __vmaxu2(A[k], A[(k + 1) & 15]); }
-    unsigned mn4[16], mx4[16];
-#pragma unroll
-    for (int k = 0; k < 16; k++) { mn4[k] = __vminu2(mn2[k], mn2[(k + 2) & 15]); mx4[k] = __vmaxu2(mx2[k], mx2[(k + 2) & 15]); }
-    unsigned best_mn = 0u, best_mx = 0xffffffffu;
-#pragma unroll
-    for (int k = 0; k < 16; k++) {
-        const unsigned mn8 = __vminu2(mn4[k], mn4[(k + 4) & 15]);
-        const unsigned mx8 = __vmaxu2(mx4[k], mx4[(k + 4) & 15]);
-        const unsigned mn9 = __vminu2(mn8, A[(k + 8) & 15]);
-        const unsigned mx9 = __vmaxu2(mx8, A[(k + 8) & 15]);
-        best_mn = __vmaxu2(best_mn, mn9);            // max over arcs of min (256 + v - p): darker ring
-        best_mx = __vminu2(best_mx, mx9);            // min over arcs of max (256 + v - p): brighter ring
-    }
-    // lane score = max(best_mn - 256, 256 - best_mx) - 1, clamped at 0
-    const int lo = max(max((int)(best_mn & 0xffff) - 256, 256 - (int)(best_mx & 0xffff)) - 1, 0);
-    const int hi = max(max((int)(best_mn >> 16) - 256, 256 - (int)(best_mx >> 16)) - 1, 0);
-    return (unsigned)lo | ((unsigned)hi << 16);
-}
-
-// One CTA per FAST cell (= one cv::FAST call of the reference).  Candidates are appended
-// unordered; the reference's candidate order (cell row, cell col, y, x) is carried in the record
+// score is cv::FAST's response.  Two horizontally adjacent pixels live in the two 16-bit lanes of a
+// register: A[i] = 256 + v - p[i] per lane (no inter-lane borrow); the sliding min / max of 9 is two levels of the native
+// 3-input u16x2 min / max (VIMNMX3.U16x2): m3[k] = min3(A[k..k+2]), m9[k] = min3(m3[k], m3[k+3], m3[k+6]).
+//
+// One CTA per FAST cell (= one cv::FAST call of the reference, ORBextractor.cc:808-815):
+//   0. the cell's sub-image (plus one pixel to its left) is fetched by the TMA engine: one 16-byte aligned bulk copy per image
+//      row (cp.async.bulk.shared.global -> UBLKCP), all completing on one mbarrier; no thread touches global pixels.
+//      (Tensor-map box loads, cp.async.bulk.tensor / UTMALDG, raise "illegal instruction" on the target boxes even for the
+//      CUDA programming guide's own example -- scratch/tma_ref.cu -- so the descriptor-free bulk form is used.)
+//   1. bytes are widened to one pixel per 16-bit lane (pix16), so that ring pixel pairs are 32-bit words (even dx) or one PRMT
+//      of two words (odd dx);
+//   2. every thread scores 4 adjacent pixels per step from 21 64-bit shared loads;
+//   3. cell-local strict 3x3 non-maximum suppression on the 16-bit score plane, the iniTh -> minTh fallback of the cell, and a
+//      warp-aggregated append of the survivors.
+// Candidates are appended unordered; the reference's candidate order (cell row, cell col, y, x) is carried in the record
 // and only matters for response ties inside a quad-tree node.
 // record: .x = x | y << 16 (relative to minBorder, as vToDistributeKeys), .y = score | ci << 8 | cj << 18
-constexpr int kPixWords = kPixPitch / 4;   // 20 words per staged row
+constexpr int kRawRows = 66;                 // cell sub-images are <= 66 x 66
+constexpr int kRawPitchMax = 96;             // bytes per staged row: 16-byte aligned start (<= 15 bytes early) + cw + 1, rounded to 16
+constexpr int kPixPitch16 = 96;              // u16 per pix16 row (48 words: consecutive rows start 16 banks apart)
+constexpr int kScPitch16 = 66;               // u16 per score row (33 words)
+constexpr int kScRows = 62;                  // detection region is <= 60 x 60 (+ zero frame)
 
-__global__ void __launch_bounds__(128)
-k_fast_cells(const __grid_constant__ ExtractPlan plan, const CellDesc *__restrict__ cells,
+__device__ __forceinline__ unsigned hi_lo(unsigned a, unsigned b) { return __byte_perm(a, b, 0x5432); }   // (a.hi, b.lo)
+
+// A[k] = 256 + v - p[k] per lane -> score per lane in [0, 254]
+__device__ __forceinline__ unsigned fast_score_lanes(const unsigned (&A)[16])
+{
+    unsigned n3[16], x3[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        n3[k] = __vimin3_u16x2(A[k], A[(k + 1) & 15], A[(k + 2) & 15]);
+        x3[k] = __vimax3_u16x2(A[k], A[(k + 1) & 15], A[(k + 2) & 15]);
+    }
+    unsigned bmn = 0u, bmx = 0xffffffffu;
+#pragma unroll
+    for (int k = 0; k < 16; k += 2) {
+        const unsigned na = __vimin3_u16x2(n3[k], n3[(k + 3) & 15], n3[(k + 6) & 15]);
+        const unsigned nb = __vimin3_u16x2(n3[k + 1], n3[(k + 4) & 15], n3[(k + 7) & 15]);
+        bmn = __vimax3_u16x2(bmn, na, nb);               // max over arcs of min (256 + v - p): darker ring
+        const unsigned xa = __vimax3_u16x2(x3[k], x3[(k + 3) & 15], x3[(k + 6) & 15]);
+        const unsigned xb = __vimax3_u16x2(x3[k + 1], x3[(k + 4) & 15], x3[(k + 7) & 15]);
+        bmx = __vimin3_u16x2(bmx, xa, xb);               // min over arcs of max (256 + v - p): brighter ring
+    }
+    // lane score = max(bmn - 256, 256 - bmx, 1) - 1
+    const unsigned c256 = 0x01000100u;
+    const unsigned d = __vmaxu2(bmn, c256) - c256;
+    const unsigned e = c256 - __vminu2(bmx, c256);
+    return __vimax3_u16x2(d, e, 0x00010001u) - 0x00010001u;
+}
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+// (row, col) of the linear index tid + 128 * it over a [rows x n] grid, advanced without divisions
+struct RowCol {
+    int row, col, drow, dcol, n;
+    __device__ __forceinline__ RowCol(int tid, int n_) : n(n_) { row = tid / n_; col = tid - row * n_; drow = 128 / n_; dcol = 128 - drow * n_; }
+    __device__ __forceinline__ void next() { row += drow; col += dcol; if (col >= n) { col -= n; row++; } }
+};
+
+__global__ void __launch_bounds__(128, 8)
+k_fast_cells(const __grid_constant__ ExtractPlan plan, const unsigned tma_levels, const CellDesc *__restrict__ cells,
              const uint8_t *__restrict__ img0, int pitch0, size_t frame0,
              const uint8_t *__restrict__ pyr, uint2 *__restrict__ cand, int *__restrict__ cand_count,
              int *__restrict__ err_flag)
 {
-    __shared__ __align__(16) uint8_t pix[kPixRows * kPixPitch];
-    __shared__ __align__(16) uint8_t sc[kScRows * kScPitch];      // scores, 1-px zero frame around the detection region
-    __shared__ __align__(16) uint8_t lm[kScRows * kScPitch];      // 1 = strict 3x3 local maximum inside the cell
+    __shared__ __align__(128) uint8_t raw[kRawRows * kRawPitchMax];
+    __shared__ __align__(16) uint16_t pix16[kRawRows * kPixPitch16];      // sub-image pixel (x, y) at pix16[y][x + 1]
+    __shared__ __align__(16) uint16_t sc16[kScRows * kScPitch16];         // score of detection pixel (d, gy) at sc16[gy + 1][d + 2]
+    __shared__ __align__(8) unsigned long long mbar;
     const CellDesc cell = cells[blockIdx.x];
     const int frame = blockIdx.y;
     const LevelPlan &L = plan.lv[cell.level];
-    const uint8_t *img;
-    int pitch;
-    if (cell.level == 0) { img = img0 + (size_t)frame * frame0; pitch = pitch0; }
-    else { img = pyr + (size_t)frame * plan.pyr_frame_bytes + L.pyr_off; pitch = L.pitch; }
     const int cw = cell.cw, ch = cell.ch;
     const int dw = cw - 6, dh = ch - 6;
     if (dw <= 0 || dh <= 0) return;
     const int tid = threadIdx.x;
+    const bool use_tma = (tma_levels >> cell.level) & 1u;
+    const uint8_t *img;
+    int pitch;
+    if (cell.level == 0) { img = img0 + (size_t)frame * frame0; pitch = pitch0; }
+    else { img = pyr + (size_t)frame * plan.pyr_frame_bytes + L.pyr_off; pitch = L.pitch; }
+    // staged row r: raw[r * rb + shift + j] = level pixel (x0 - 1 + j, y0 + r), j = 0 .. cw
+    const int xa = (cell.x0 - 1) & ~15, shift = (cell.x0 - 1) - xa;
+    const int rb = (shift + cw + 1 + 15) & ~15;
 
-    // ---- stage the sub-image with aligned 32-bit loads: pixel (x, y) of the sub-image lives at pix[y][x + 1].
-    // smem word w of row y holds sub-image bytes 4w-1 .. 4w+2, i.e. level bytes x0 + 4w - 1 ..; the two aligned global
-    // words around that address are funnel-shifted together.  Loads never pass the last byte of the level row.
+    // ---- 0. fetch the rows
+    if (use_tma) {
+        if (tid == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (tid < 32) {
+            if (tid == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&mbar)), "r"(ch * rb) : "memory");
+            __syncwarp();
+            const uint8_t *src = img + (size_t)cell.y0 * pitch + xa;
+            for (int r = tid; r < ch; r += 32)
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(smem_u32(raw + r * rb)), "l"(src + (size_t)r * pitch), "r"(rb), "r"(smem_u32(&mbar)) : "memory");
+        }
+    } else {
+        // level 0 handed over with a base / pitch that is not 16-byte aligned: plain byte loads
+        for (int t = tid; t < ch * rb; t += 128) {
+            const int y = t / rb, j = t - y * rb;
+            const int x = xa + j;
+            raw[t] = x < L.w ? img[(size_t)(cell.y0 + y) * pitch + x] : (uint8_t)0;
+        }
+    }
+    // zero frame of the score plane: rows 0 and dh + 1, left word (indices 0, 1) and the words from index dw + 2 on
     {
-        const int nwords = (cw + 1 + 3) >> 2;                       // words that contain at least one sub-image byte
-        const uint8_t *row_end_word = nullptr;
-        for (int t = tid; t < ch * kPixWords; t += 128) {
-            const int y = t / kPixWords, w = t - y * kPixWords;
-            unsigned v = 0u;
-            if (w <= nwords) {
-                const uint8_t *rowp = img + (size_t)(cell.y0 + y) * pitch;
-                const uint8_t *last = rowp + L.w - 1;               // last valid byte of this level row
-                const uint8_t *p = rowp + cell.x0 + 4 * w - 1;      // first byte wanted
-                const uintptr_t a0 = (uintptr_t)p & ~(uintptr_t)3;
-                const uintptr_t amax = (uintptr_t)last & ~(uintptr_t)3;
-                const unsigned lo = *reinterpret_cast<const unsigned *>(a0 <= amax ? a0 : amax);
-                const unsigned hi = *reinterpret_cast<const unsigned *>(a0 + 4 <= amax ? a0 + 4 : amax);
-                v = __funnelshift_r(lo, hi, 8 * (unsigned)((uintptr_t)p & 3));
-            }
-            reinterpret_cast<unsigned *>(pix)[t] = v;
-            (void)row_end_word;
+        unsigned *s32 = reinterpret_cast<unsigned *>(sc16);
+        constexpr int SW = kScPitch16 / 2;                                  // 33 words per row
+        for (int t = tid; t < SW; t += 128) { s32[t] = 0u; s32[(dh + 1) * SW + t] = 0u; }
+        const int wr = (dw + 2) >> 1;                                       // first word holding an index >= dw + 2 (or dw + 1 if dw is odd: rewritten by the scores)
+        for (int y = tid; y < dh; y += 128) { s32[(y + 1) * SW] = 0u; s32[(y + 1) * SW + wr] = 0u; if (wr + 1 < SW) s32[(y + 1) * SW + wr + 1] = 0u; }
+    }
+    if (use_tma) {
+        unsigned done = 0;
+        for (int spin = 0; !done && spin < (1 << 16); spin++)
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(smem_u32(&mbar)) : "memory");
+        if (!__syncthreads_and((int)done)) { if (tid == 0) *err_flag = 3; return; }      // never hang the device
+    } else {
+        __syncthreads();
+    }
+
+    // ---- 1. widen: bytes shift + 4q .. shift + 4q + 3 of staged row y -> pix16[y][4q .. 4q+3]
+    {
+        const int wq = (cw + 1 + 3) >> 2;                                   // groups of 4 holding sub-image bytes j = 0 .. cw
+        const int rw = rb >> 2, w0 = shift >> 2, sh = 8 * (shift & 3);
+        const unsigned *raw32 = reinterpret_cast<const unsigned *>(raw);
+        for (RowCol rc(tid, wq); rc.row < ch; rc.next()) {
+            const int y = rc.row, q = rc.col;
+            const int wi = y * rw + w0 + q;
+            const unsigned lo = raw32[wi], hi = raw32[min(wi + 1, y * rw + rw - 1)];
+            const unsigned v = __funnelshift_r(lo, hi, sh);
+            uint2 o;
+            o.x = __byte_perm(v, 0u, 0x4140);                               // (b0, b1) zero-extended
+            o.y = __byte_perm(v, 0u, 0x4342);                               // (b2, b3)
+            *reinterpret_cast<uint2 *>(pix16 + y * kPixPitch16 + 4 * q) = o;
         }
-        for (int t = tid; t < (dh + 2) * (kScPitch / 4); t += 128) { reinterpret_cast<unsigned *>(sc)[t] = 0u; reinterpret_cast<unsigned *>(lm)[t] = 0u; }
     }
     __syncthreads();
 
-    // ---- scores of the detection region [3, cw-3) x [3, ch-3): groups of 4 pixels
+    // ---- 2. scores: one step = 4 adjacent detection pixels d = 4g .. 4g+3 of row gy (centres at pix16 index 4 + 4g ..)
     const int ngroups = (dw + 3) >> 2;
-    for (int t = tid; t < ngroups * dh; t += 128) {
-        const int gy = t / ngroups, gx = t - gy * ngroups;
-        const int y = 3 + gy;                 // sub-image row of the centre
-        const int c = 4 + 4 * gx;             // smem column of the first centre pixel (x = c - 1)
-        unsigned w[7][3];
+    for (RowCol rc(tid, ngroups); rc.row < dh; rc.next()) {
+        const int gy = rc.row, g = rc.col;
+        // r[dy][0..5]: words W-2 .. W+3 of row (3 + gy + dy - 3), W = 2 + 2g (the first centre pair)
+        unsigned r[7][6];
 #pragma unroll
-        for (int r = 0; r < 7; r++) {
-            const unsigned *row = reinterpret_cast<const unsigned *>(pix + (y - 3 + r) * kPixPitch + c - 4);
-            w[r][0] = row[0]; w[r][1] = row[1]; w[r][2] = row[2];
+        for (int dy = 0; dy < 7; dy++) {
+            const uint2 *row = reinterpret_cast<const uint2 *>(pix16 + (gy + dy) * kPixPitch16 + 4 * g);
+            const uint2 a = row[0], b2 = row[1], c = row[2];
+            r[dy][0] = a.x; r[dy][1] = a.y; r[dy][2] = b2.x; r[dy][3] = b2.y; r[dy][4] = c.x; r[dy][5] = c.y;
         }
-        const unsigned s01 = fast_score_pair<0>(w);
-        const unsigned s23 = fast_score_pair<1>(w);
-        // detection pixel index dx = 4*gx + k  ->  sc[gy + 1][dx + 1]; pixels beyond the region stay 0
-        const int rem = dw - 4 * gx;
-        unsigned packed = (s01 & 0xff) | ((rem > 1 ? (s01 >> 16) & 0xff : 0u) << 8) | ((rem > 2 ? s23 & 0xff : 0u) << 16) |
-                          ((rem > 3 ? (s23 >> 16) & 0xff : 0u) << 24);
-        uint8_t *o = sc + (gy + 1) * kScPitch + 4 * gx + 1;       // byte address = 4*gx + 1 (mod 4 == 1): write bytes
-        o[0] = (uint8_t)packed; o[1] = (uint8_t)(packed >> 8); o[2] = (uint8_t)(packed >> 16); o[3] = (uint8_t)(packed >> 24);
+        // odd-offset pairs
+        unsigned t3m[3], t3p[3];            // rows dy = -3 / +3: (1,2), (2,3), (3,4)
+#pragma unroll
+        for (int i = 0; i < 3; i++) { t3m[i] = hi_lo(r[0][1 + i], r[0][2 + i]); t3p[i] = hi_lo(r[6][1 + i], r[6][2 + i]); }
+        unsigned s1m[4], s0[4], s1p[4];     // rows dy = -1, 0, +1: (0,1), (1,2), (3,4), (4,5)
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int lo = i < 2 ? i : i + 1;
+            s1m[i] = hi_lo(r[2][lo], r[2][lo + 1]); s0[i] = hi_lo(r[3][lo], r[3][lo + 1]); s1p[i] = hi_lo(r[4][lo], r[4][lo + 1]);
+        }
+        unsigned sc[2];
+#pragma unroll
+        for (int p = 0; p < 2; p++) {
+            const int c = 2 + p;
+            const unsigned V = r[3][c] | 0x01000100u;
+            unsigned A[16];
+            // ring in cyclic order (dx, dy): (0,3) (1,3) (2,2) (3,1) (3,0) (3,-1) (2,-2) (1,-3) (0,-3) (-1,-3) (-2,-2) (-3,-1) (-3,0) (-3,1) (-2,2) (-1,3)
+            A[0] = V - r[6][c];        A[1] = V - t3p[1 + p];     A[2] = V - r[5][c + 1];    A[3] = V - s1p[2 + p];
+            A[4] = V - s0[2 + p];      A[5] = V - s1m[2 + p];     A[6] = V - r[1][c + 1];    A[7] = V - t3m[1 + p];
+            A[8] = V - r[0][c];        A[9] = V - t3m[p];         A[10] = V - r[1][c - 1];   A[11] = V - s1m[p];
+            A[12] = V - s0[p];         A[13] = V - s1p[p];        A[14] = V - r[5][c - 1];   A[15] = V - t3p[p];
+            sc[p] = fast_score_lanes(A);
+        }
+        // pixels beyond the detection region score 0
+        const int rem = dw - 4 * g;
+        if (rem < 4) { if (rem < 3) sc[1] = 0u; else sc[1] &= 0xffffu; if (rem < 2) sc[0] &= 0xffffu; }
+        unsigned *so = reinterpret_cast<unsigned *>(sc16 + (gy + 1) * kScPitch16 + 4 * g + 2);      // 4-byte aligned only
+        so[0] = sc[0]; so[1] = sc[1];
     }
     __syncthreads();
 
-    // ---- cell-local strict 3x3 maxima, once; threshold of this cell: iniTh if cv::FAST(iniTh, nms) would return at
-    // least one keypoint, else minTh (ORBextractor.cc:808-816; the test is on the NMS survivors, so a plateau of equal
-    // scores >= iniTh that suppresses itself still triggers the fallback)
-    int any = 0;
-    const int xq = tid & 63, yq = tid >> 6;                        // 64 columns x 2 rows per sweep
-    for (int y = yq; y < dh; y += 2) {
-        if (xq < dw) {
-            const uint8_t *p = sc + (y + 1) * kScPitch + xq + 1;
-            const int s = p[0];
-            if (s >= plan.min_th) {
-                const bool keep = s > p[-1] && s > p[1] && s > p[-kScPitch - 1] && s > p[-kScPitch] && s > p[-kScPitch + 1] &&
-                                  s > p[kScPitch - 1] && s > p[kScPitch] && s > p[kScPitch + 1];
-                if (keep) { lm[(y + 1) * kScPitch + xq + 1] = 1; any |= s >= plan.ini_th; }
-            }
+    // ---- 3. cell-local strict 3x3 maxima; threshold of this cell: iniTh if cv::FAST(iniTh, nms) would return at least one
+    // keypoint, else minTh (ORBextractor.cc:808-816; the test is on the NMS survivors, so a plateau of equal scores >= iniTh
+    // that suppresses itself still triggers the fallback).  One step = one pixel pair; keep bits stay in a register.
+    const int npairs = (dw + 1) >> 1;
+    unsigned keepbits = 0u, strongbits = 0u;      // bit 2*it + lane: NMS survivor with score >= minTh / >= iniTh
+    {
+        const unsigned *s32 = reinterpret_cast<const unsigned *>(sc16);
+        constexpr int SW = kScPitch16 / 2;
+        const unsigned minth2 = (unsigned)plan.min_th * 0x00010001u, inith2 = (unsigned)plan.ini_th * 0x00010001u;
+        int it = 0;
+        for (RowCol rc(tid, npairs); rc.row < dh; rc.next(), it++) {
+            const unsigned *c = s32 + (rc.row + 1) * SW + rc.col + 1;       // word of detection pixels (2i, 2i+1)
+            const unsigned w0 = c[0];
+            if (w0 == 0u) continue;
+            const unsigned ul = c[-SW - 1], uc = c[-SW], ur = c[-SW + 1], ml = c[-1], mr = c[1], dl = c[SW - 1], dc = c[SW], dr = c[SW + 1];
+            const unsigned up = __vimax3_u16x2(hi_lo(ul, uc), uc, hi_lo(uc, ur));
+            const unsigned dn = __vimax3_u16x2(hi_lo(dl, dc), dc, hi_lo(dc, dr));
+            const unsigned nb = __vimax3_u16x2(up, dn, __vmaxu2(hi_lo(ml, w0), hi_lo(w0, mr)));
+            // per lane: w0 > nb (strict maximum) and w0 >= minTh -> 0xffff lane masks
+            const unsigned km = __vcmpgtu2(w0, nb) & __vcmpgeu2(w0, minth2);
+            const unsigned sm = km & __vcmpgeu2(w0, inith2);
+            keepbits |= ((km & 1u) | ((km >> 15) & 2u)) << (2 * it);
+            strongbits |= ((sm & 1u) | ((sm >> 15) & 2u)) << (2 * it);
         }
     }
-    const int th = __syncthreads_or(any) ? plan.ini_th : plan.min_th;
+    // threshold of the cell: iniTh if any survivor reaches it, else the minTh retry
+    const bool strong = __syncthreads_or(strongbits != 0u);
+    const int th = strong ? plan.ini_th : plan.min_th;
+    (void)th;
+    unsigned mine = strong ? strongbits : keepbits;
 
-    // ---- append survivors
-    int *counter = cand_count + frame * plan.nlevels + cell.level;
+    // ---- append survivors: one atomic per warp, then every thread writes its own (usually 0..2) records
+    const int lane = tid & 31;
+    const int cnt = __popc(mine);
+    int incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += o; }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    if (total == 0) return;
+    int base = 0;
+    if (lane == 31) base = atomicAdd(cand_count + frame * plan.nlevels + cell.level, total);
+    int pos = __shfl_sync(0xffffffffu, base, 31) + incl - cnt;
     uint2 *out = cand + (size_t)frame * plan.cand_frame_entries + L.cand_off;
-    for (int y0 = 0; y0 < dh; y0 += 2) {
-        const int y = y0 + yq;
-        bool keep = false;
-        int s = 0;
-        if (y < dh && xq < dw) { s = sc[(y + 1) * kScPitch + xq + 1]; keep = lm[(y + 1) * kScPitch + xq + 1] && s >= th; }
-        const unsigned ballot = __ballot_sync(0xffffffffu, keep);
-        if (ballot) {
-            const int lane = tid & 31;
-            int pos = 0;
-            if (lane == 0) pos = atomicAdd(counter, __popc(ballot));
-            pos = __shfl_sync(0xffffffffu, pos, 0) + __popc(ballot & ((1u << lane) - 1));
-            if (keep) {
-                if (pos < L.cand_cap) {
-                    const unsigned kx = (unsigned)(xq + 3 + cell.addx), ky = (unsigned)(y + 3 + cell.addy);
-                    out[pos] = make_uint2(kx | (ky << 16), (unsigned)s | ((unsigned)cell.ci << 8) | ((unsigned)cell.cj << 18));
-                } else {
-                    *err_flag = 1;
-                }
-            }
+    while (mine) {
+        const int b = __ffs(mine) - 1;
+        mine &= mine - 1;
+        const int t = tid + 128 * (b >> 1), e = b & 1;
+        const int gy = t / npairs, i = t - gy * npairs;
+        const unsigned w0 = reinterpret_cast<const unsigned *>(sc16)[(gy + 1) * (kScPitch16 / 2) + i + 1];
+        const unsigned sc = e ? (w0 >> 16) : (w0 & 0xffffu);
+        if (pos < L.cand_cap) {
+            const unsigned kx = (unsigned)(2 * i + e + 3 + cell.addx), ky = (unsigned)(gy + 3 + cell.addy);
+            out[pos] = make_uint2(kx | (ky << 16), sc | ((unsigned)cell.ci << 8) | ((unsigned)cell.cj << 18));
+        } else {
+            *err_flag = 1;
         }
+        pos++;
     }
 }
 
