@@ -50,7 +50,8 @@ struct orbx_handle {
     DevBuf d_cells, d_tiles, d_rs_tab;
     // per-batch workspaces
     int batch_cap = 0;
-    DevBuf d_stage;      // staged host images
+    DevBuf d_stage;      // staged host images (64-byte pitch)
+    DevBuf d_packed;     // host images as uploaded (flat DMA), re-pitched on the device
     size_t stage_pitch = 0, stage_frame = 0;
     DevBuf d_pyr, d_blur, d_cand, d_knode, d_lvl_kp, d_counts /* cand_count | lvl_count | counts | err */;
     DevBuf d_kp_xy, d_kp_angle, d_kp_resp, d_kp_oct, d_kp_size, d_desc;
@@ -300,11 +301,13 @@ static int upload_and_extract(orbx_handle *h, const uint8_t *images, int n_frame
     // the copy stream must not overwrite the staging buffer while an earlier call still reads it
     ORBS_CUDA(cudaEventRecord(h->chunk_events[nchunks], h->stream));
     ORBS_CUDA(cudaStreamWaitEvent(h->copy_stream, h->chunk_events[nchunks], 0));
+    // contiguous frames: one flat DMA per chunk into d_packed, re-pitched on the device (k_repitch) -- full PCIe rate
+    const bool flat = frame_stride == (size_t)stride * height;
+    if (flat) { if (int rc = h->d_packed.reserve(frame_stride * n_frames + 64)) return rc; }
     for (int c = 0; c < nchunks; c++) {
         const int f0 = c * chunk, n = std::min(chunk, n_frames - f0);
-        if (frame_stride == (size_t)stride * height) {
-            ORBS_CUDA(cudaMemcpy2DAsync(h->d_stage.as<uint8_t>() + f0 * frame, pitch, images + f0 * frame_stride, stride, width, (size_t)height * n,
-                                        cudaMemcpyHostToDevice, h->copy_stream));
+        if (flat) {
+            ORBS_CUDA(cudaMemcpyAsync(h->d_packed.as<uint8_t>() + f0 * frame_stride, images + f0 * frame_stride, frame_stride * n, cudaMemcpyHostToDevice, h->copy_stream));
         } else {
             for (int f = f0; f < f0 + n; f++)
                 ORBS_CUDA(cudaMemcpy2DAsync(h->d_stage.as<uint8_t>() + f * frame, pitch, images + f * frame_stride, stride, width, height,
@@ -315,6 +318,12 @@ static int upload_and_extract(orbx_handle *h, const uint8_t *images, int n_frame
     for (int c = 0; c < nchunks; c++) {
         const int f0 = c * chunk, n = std::min(chunk, n_frames - f0);
         ORBS_CUDA(cudaStreamWaitEvent(h->stream, h->chunk_events[c], 0));
+        if (flat) {
+            const int threads = (int)(pitch >> 4) * height;
+            k_repitch<<<dim3((threads + 255) / 256, n), 256, 0, h->stream>>>(h->d_packed.as<uint8_t>() + f0 * frame_stride, stride, frame_stride,
+                                                                             h->d_stage.as<uint8_t>() + f0 * frame, (int)pitch, frame, width, height);
+            h->launches++;
+        }
         if (int rc = launch_pipeline(h, h->d_stage.as<uint8_t>(), f0, n, (int)pitch, frame)) return rc;
     }
     return ORBS_OK;
@@ -333,7 +342,7 @@ static int download_results(orbx_handle *h, float *kp_xy, float *kp_angle, float
     int *herr = hc + n + 1;
     ORBS_CUDA(cudaMemcpyAsync(herr, err_ptr(h, nb), sizeof(int), cudaMemcpyDeviceToHost, st));
     ORBS_CUDA(cudaStreamSynchronize(st));
-    if (*herr != 0) { set_last_error(*herr == 1 ? "internal: FAST candidate buffer overflow" : "internal: quad-tree node capacity exceeded"); return ORBS_E_CAPACITY; }
+    if (*herr != 0) { set_last_error(*herr == 1 ? "internal: FAST candidate buffer overflow" : *herr == 3 ? "internal: bulk copy of a FAST cell did not complete" : "internal: quad-tree node capacity exceeded"); return ORBS_E_CAPACITY; }
     for (int f = 0; f < n; f++) {
         const int c = hc[f];
         counts[f] = c;
@@ -418,7 +427,7 @@ int orbx_destroy(orbx_handle *h)
     cudaSetDevice(h->device);
     if (h->stream && h->own_stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
     else cudaDeviceSynchronize();
-    DevBuf *bufs[] = {&h->d_cells, &h->d_tiles, &h->d_rs_tab, &h->d_stage, &h->d_pyr, &h->d_blur, &h->d_cand, &h->d_knode, &h->d_lvl_kp,
+    DevBuf *bufs[] = {&h->d_cells, &h->d_tiles, &h->d_rs_tab, &h->d_stage, &h->d_packed, &h->d_pyr, &h->d_blur, &h->d_cand, &h->d_knode, &h->d_lvl_kp,
                       &h->d_counts, &h->d_kp_xy, &h->d_kp_angle, &h->d_kp_resp, &h->d_kp_oct, &h->d_kp_size, &h->d_desc};
     for (DevBuf *b : bufs) b->release();
     h->h_counts.release();

@@ -757,6 +757,28 @@ k_orient_describe(const __grid_constant__ ExtractPlan plan,
     }
 }
 
+// packed host layout (row stride = any) -> 64-byte pitched level-0 buffer; one aligned 16-byte store per thread.
+// The upload itself is ONE flat DMA per chunk (a strided 2-D copy of 1241-byte rows runs at a fraction of PCIe speed).
+__global__ void __launch_bounds__(256)
+k_repitch(const uint8_t *__restrict__ src, int stride, size_t sframe, uint8_t *__restrict__ dst, int pitch, size_t dframe, int width, int height)
+{
+    const int segs = pitch >> 4;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= segs * height) return;
+    const int y = t / segs, sg = t - y * segs;
+    const int x = sg << 4;
+    uint4 o = make_uint4(0u, 0u, 0u, 0u);
+    if (x < width) {
+        const uint8_t *p = src + (size_t)blockIdx.y * sframe + (size_t)y * stride + x;
+        const uintptr_t a0 = (uintptr_t)p & ~(uintptr_t)3;
+        const unsigned sh = 8u * (unsigned)((uintptr_t)p & 3);
+        const unsigned *w = reinterpret_cast<const unsigned *>(a0);
+        const unsigned w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = sh ? w[4] : 0u;
+        o.x = __funnelshift_r(w0, w1, sh); o.y = __funnelshift_r(w1, w2, sh); o.z = __funnelshift_r(w2, w3, sh); o.w = __funnelshift_r(w3, w4, sh);
+    }
+    *reinterpret_cast<uint4 *>(dst + (size_t)blockIdx.y * dframe + (size_t)y * pitch + x) = o;
+}
+
 // reflect-101 bordered copy of one level (public mvImagePyramid, ORBextractor.cc:1122-1128)
 __global__ void k_border_copy(const uint8_t *__restrict__ src, int w, int h, int pitch, uint8_t *__restrict__ dst, int border)
 {
