@@ -266,9 +266,12 @@ __device__ void rescan_window(const SearchArgs &A, int f, int i, const int *own_
         }
 }
 
+// use_smem: the working set of the fixed-point rounds (candidate lists, ownership, proposals) is staged in shared memory
+// (88 KB at 2000 features); the rounds then cost barriers + smem traffic instead of L2 round trips.
 __global__ void __launch_bounds__(1024)
-k_search_resolve(const SearchArgs A)
+k_search_resolve(const SearchArgs A, const int use_smem)
 {
+    extern __shared__ __align__(16) unsigned char resolve_smem[];
     __shared__ int s_changed;
     __shared__ int s_hist[kHisto];
     __shared__ int s_keep[3];
@@ -280,6 +283,17 @@ k_search_resolve(const SearchArgs A)
     int *fm = A.feat_match + fo;
     int *prop = A.prop + qo;
     int *owner[2] = {A.owner + 2 * fo, A.owner + 2 * fo + A.f_slab};
+    const unsigned *top_all = A.top + qo * kTop;
+    const int *ncand = A.ncand + qo;
+    if (use_smem) {
+        unsigned *s_top = reinterpret_cast<unsigned *>(resolve_smem);
+        int *s_nc = reinterpret_cast<int *>(s_top + (size_t)A.q_slab * kTop);
+        int *s_prop = s_nc + A.q_slab;
+        int *s_own = s_prop + A.q_slab;
+        for (int t = tid; t < M * kTop; t += nt) s_top[t] = top_all[t];
+        for (int t = tid; t < M; t += nt) s_nc[t] = ncand[t];
+        top_all = s_top; ncand = s_nc; prop = s_prop; owner[0] = s_own; owner[1] = s_own + A.f_slab;
+    }
 
     // features that already hold a map point are owned by "query -1": every query skips them
     for (int k = tid; k < N; k += nt) { const int o = fm[k] >= 0 ? -1 : 0x7fffffff; owner[0][k] = o; owner[1][k] = o; }
@@ -294,9 +308,9 @@ k_search_resolve(const SearchArgs A)
         int *own_next = owner[cur ^ 1];
         for (int i = tid; i < M; i += nt) {
             int choice = -1;
-            const int nc = A.ncand[qo + i];
+            const int nc = ncand[i];
             if (nc > 0) {
-                const unsigned *top = A.top + (qo + i) * kTop;
+                const unsigned *top = top_all + (size_t)i * kTop;
                 // first and second free entries of the sorted list
                 unsigned e1 = 0xffffffffu, e2 = 0xffffffffu;
                 int seen = 0;
@@ -398,6 +412,7 @@ struct orbm_handle {
     long long launches = 0;
     std::mutex mu;
     DevBuf cell_start, cell_items, prop, owner, top, ncand;
+    size_t resolve_smem = 0;
     StagePool pool;
 };
 
@@ -547,7 +562,15 @@ int orbm_search_by_projection(orbm_handle *h, int n_frames, const float *bounds4
     A.th_dist = th_dist; A.ratio = ratio; A.check_ori = check_ori ? 1 : 0;
     k_grid_build<<<n_frames, 512, 0, h->stream>>>(f_slab, A.g, A.f_xy, A.f_counts, h->cell_start.as<int>(), h->cell_items.as<int>());
     k_search_candidates<<<dim3((q_slab + 7) / 8, n_frames), 256, 0, h->stream>>>(A);
-    k_search_resolve<<<n_frames, 1024, 0, h->stream>>>(A);
+    {
+        const size_t smem = ((size_t)q_slab * (kTop + 2) + 2 * (size_t)f_slab) * sizeof(int);
+        const int use_smem = smem <= 200 * 1024;
+        if (use_smem && smem > h->resolve_smem) {
+            ORBS_CUDA(cudaFuncSetAttribute(k_search_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            h->resolve_smem = smem;
+        }
+        k_search_resolve<<<n_frames, 1024, use_smem ? smem : 0, h->stream>>>(A, use_smem);
+    }
     h->launches += 3;
     ORBS_CUDA(cudaGetLastError());
     return S.finish();

@@ -269,7 +269,7 @@ static int launch_pipeline(orbx_handle *h, const uint8_t *d_img0_all, int f0, in
         k_fast_cells<<<dim3(P.total_cells, n), 128, 0, st>>>(P, tma_levels, h->d_cells.as<CellDesc>(), d_img0, pitch0, frame0, pyr, cand, cand_count, err_ptr(h, nb));
         h->timer.end(st);
         h->timer.begin(2, st);
-        k_blur7<<<dim3(P.total_tiles, n), 256, 0, st>>>(P, h->d_tiles.as<TileDesc>(), d_img0, pitch0, frame0, pyr, blur);
+        k_blur7<<<dim3(P.total_tiles, n), 256, 0, st>>>(P, tma_levels, h->d_tiles.as<TileDesc>(), d_img0, pitch0, frame0, pyr, blur);
         h->timer.end(st);
         h->timer.begin(3, st);
         k_octree<<<dim3(P.nlevels, n), 512, h->octree_smem, st>>>(P, cand, cand_count, knode, lvl_kp, lvl_count, err_ptr(h, nb));

@@ -306,14 +306,21 @@ __device__ __forceinline__ int reflect101(int p, int len)
     return p;
 }
 
+// Tile = 64 x 32 outputs.  Input rows (reflected at the top / bottom of the level) are fetched by the TMA engine, one aligned
+// bulk copy per row; the reflected columns of the left / right level border are patched in shared memory.  Horizontal pass:
+// 4 outputs per thread with dp4a on funnel-shifted words; vertical pass: 4 outputs per thread with dp2a on vertically packed
+// u16 pairs, one 32-bit store.
+constexpr int kBlurRP = 112;                  // staged row pitch: 16-byte left margin + up to 96 loaded bytes
+constexpr int kBlurIH = kBlurTH + 6;
+
 __global__ void __launch_bounds__(256)
-k_blur7(const __grid_constant__ ExtractPlan plan, const TileDesc *__restrict__ tiles,
+k_blur7(const __grid_constant__ ExtractPlan plan, const unsigned tma_levels, const TileDesc *__restrict__ tiles,
         const uint8_t *__restrict__ img0, int pitch0, size_t frame0,
         const uint8_t *__restrict__ pyr, uint8_t *__restrict__ blur)
 {
-    constexpr int IW = kBlurTW + 6, IH = kBlurTH + 6, IP = 80;    // 70 x 38 input, 80-byte smem rows (word aligned)
-    __shared__ __align__(16) uint8_t tin[IH * IP];
-    __shared__ __align__(16) uint16_t mid[IH * kBlurTW];
+    __shared__ __align__(128) uint8_t raw[kBlurIH * kBlurRP];     // raw[r][16 + x - xa] = level pixel (x, reflect(y0 - 3 + r))
+    __shared__ __align__(16) uint16_t mid[kBlurIH * kBlurTW];
+    __shared__ __align__(8) unsigned long long mbar;
     const TileDesc t = tiles[blockIdx.x];
     const int frame = blockIdx.y, tid = threadIdx.x;
     const LevelPlan &L = plan.lv[t.level];
@@ -321,48 +328,87 @@ k_blur7(const __grid_constant__ ExtractPlan plan, const TileDesc *__restrict__ t
     int pitch;
     if (t.level == 0) { img = img0 + (size_t)frame * frame0; pitch = pitch0; }
     else { img = pyr + (size_t)frame * plan.pyr_frame_bytes + L.pyr_off; pitch = L.pitch; }
-    // stage: thread = (column, row phase); the reflected source column is computed once
-    {
-        const int x = tid % 80, ph = tid / 80;                    // 3 row phases, 240 active threads
-        if (ph < 3) {
-            const int sx = x < IW ? reflect101(t.x0 + x - 3, L.w) : 0;
-            for (int y = ph; y < IH; y += 3) {
-                const int sy = reflect101(t.y0 + y - 3, L.h);
-                tin[y * IP + x] = x < IW ? img[(size_t)sy * pitch + sx] : (uint8_t)0;
-            }
+    const bool use_tma = (tma_levels >> t.level) & 1u;
+    const int xa = max(t.x0 - 16, 0);                             // first loaded column (16-byte aligned: x0 % 64 == 0)
+    const int need = t.x0 + kBlurTW + 3 - xa;                     // columns xa .. x0 + 66
+    const int rb = min((need + 15) & ~15, ((pitch - xa) & ~15));  // never past the row pitch
+    if (use_tma) {
+        if (tid == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
+        if (tid == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&mbar)), "r"(kBlurIH * rb) : "memory");
+        __syncthreads();                                          // barrier initialised and armed before any copy is issued
+        if (tid < kBlurIH) {
+            const int sy = reflect101(t.y0 + tid - 3, L.h);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(smem_u32(raw + tid * kBlurRP + 16)), "l"(img + (size_t)sy * pitch + xa), "r"(rb), "r"(smem_u32(&mbar)) : "memory");
+        }
+        unsigned done = 0;
+        for (int spin = 0; !done && spin < (1 << 16); spin++)
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(smem_u32(&mbar)) : "memory");
+        if (!__syncthreads_and((int)done)) return;                // cannot happen; never hang the device
+    } else {
+        for (int i = tid; i < kBlurIH * rb; i += 256) {
+            const int r = i / rb, j = i - r * rb;
+            raw[r * kBlurRP + 16 + j] = img[(size_t)reflect101(t.y0 + r - 3, L.h) * pitch + xa + j];
+        }
+        __syncthreads();
+    }
+    // reflected columns (BORDER_REFLECT_101): x = -1..-3 at the left border, x = w..w+2 at the right border
+    if (tid < kBlurIH * 3) {
+        const int r = tid / 3, k = tid - r * 3 + 1;
+        uint8_t *row = raw + r * kBlurRP + 16 - xa;               // row[x] = pixel x
+        if (t.x0 == 0) row[-k] = row[reflect101(-k, L.w)];
+        const int xr = L.w - 1 + k;
+        if (xr <= t.x0 + kBlurTW + 2 && xr >= t.x0 - 3) row[xr] = row[reflect101(xr, L.w)];
     }
     __syncthreads();
-    // horizontal pass, 4 outputs per thread: two dp4a per output on funnel-shifted words
+    // horizontal pass: outputs x0 + 4g .. x0 + 4g + 3 of row y need bytes s .. s + 9, s = 16 + x0 - xa - 3 + 4g  (s % 4 == 1)
     constexpr unsigned c0 = 18u | (34u << 8) | (48u << 16) | (56u << 24), c1 = 48u | (34u << 8) | (18u << 16);
-    for (int i = tid; i < IH * (kBlurTW / 4); i += 256) {
+    const int s0 = 16 + t.x0 - xa - 3;
+    for (int i = tid; i < kBlurIH * (kBlurTW / 4); i += 256) {
         const int y = i >> 4, g = i & 15;
-        const unsigned *row = reinterpret_cast<const unsigned *>(tin + y * IP) + g;
+        const unsigned *row = reinterpret_cast<const unsigned *>(raw + y * kBlurRP + ((s0 + 4 * g) & ~3));
         const unsigned w0 = row[0], w1 = row[1], w2 = row[2];
         unsigned o[4];
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            const unsigned lo = __funnelshift_r(w0, w1, 8 * k), hi = __funnelshift_r(w1, w2, 8 * k);
+            const unsigned lo = k < 3 ? __funnelshift_r(w0, w1, 8 * (k + 1)) : w1;
+            const unsigned hi = k < 3 ? __funnelshift_r(w1, w2, 8 * (k + 1)) : w2;
             o[k] = __dp4a(lo, c0, __dp4a(hi, c1, 0u));
         }
-        uint2 pk = make_uint2(o[0] | (o[1] << 16), o[2] | (o[3] << 16));
-        *reinterpret_cast<uint2 *>(mid + y * kBlurTW + 4 * g) = pk;
+        *reinterpret_cast<uint2 *>(mid + y * kBlurTW + 4 * g) = make_uint2(o[0] | (o[1] << 16), o[2] | (o[3] << 16));
     }
     __syncthreads();
-    // vertical pass, 2 adjacent outputs per thread (one 32-bit load of two u16 per tap)
+    // vertical pass: 4 adjacent outputs per thread; rows are packed in vertical pairs for dp2a (two taps per instruction)
     uint8_t *dst = blur + (size_t)frame * plan.pyr_frame_bytes + L.pyr_off;   // blurred slab has the same layout
-    for (int i = tid; i < kBlurTH * (kBlurTW / 2); i += 256) {
-        const int y = i >> 5, xp = (i & 31) * 2;
-        const unsigned *p = reinterpret_cast<const unsigned *>(mid + y * kBlurTW + xp);
-        constexpr int S = kBlurTW / 2;                            // row stride in 32-bit words
-        const unsigned m0 = p[0], m1 = p[S], m2 = p[2 * S], m3 = p[3 * S], m4 = p[4 * S], m5 = p[5 * S], m6 = p[6 * S];
-        const unsigned lo = 18u * ((m0 & 0xffff) + (m6 & 0xffff)) + 34u * ((m1 & 0xffff) + (m5 & 0xffff)) + 48u * ((m2 & 0xffff) + (m4 & 0xffff)) + 56u * (m3 & 0xffff);
-        const unsigned hi = 18u * ((m0 >> 16) + (m6 >> 16)) + 34u * ((m1 >> 16) + (m5 >> 16)) + 48u * ((m2 >> 16) + (m4 >> 16)) + 56u * (m3 >> 16);
-        const int ox = t.x0 + xp, oy = t.y0 + y;
-        if (oy < L.h) {
-            if (ox < L.w) dst[(size_t)oy * L.pitch + ox] = (uint8_t)((lo + 32768u) >> 16);
-            if (ox + 1 < L.w) dst[(size_t)oy * L.pitch + ox + 1] = (uint8_t)((hi + 32768u) >> 16);
+    constexpr unsigned k01 = 18u | (34u << 8), k23 = 48u | (56u << 8), k45 = 48u | (34u << 8), k6 = 18u;
+    for (int i = tid; i < kBlurTH * (kBlurTW / 4); i += 256) {
+        const int y = i >> 4, g = i & 15;
+        const int ox = t.x0 + 4 * g, oy = t.y0 + y;
+        if (oy >= L.h || ox >= L.w) continue;
+        const uint2 *p = reinterpret_cast<const uint2 *>(mid + y * kBlurTW + 4 * g);
+        constexpr int S = kBlurTW / 4;                            // row stride in uint2
+        uint2 m[7];
+#pragma unroll
+        for (int r = 0; r < 7; r++) m[r] = p[r * S];
+        unsigned out = 0u;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            unsigned w[7];
+#pragma unroll
+            for (int r = 0; r < 7; r++) w[r] = h ? m[r].y : m[r].x;
+            unsigned lo = __dp2a_lo(__byte_perm(w[0], w[1], 0x5410), k01, 32768u);
+            unsigned hi = __dp2a_lo(__byte_perm(w[0], w[1], 0x7632), k01, 32768u);
+            lo = __dp2a_lo(__byte_perm(w[2], w[3], 0x5410), k23, lo); hi = __dp2a_lo(__byte_perm(w[2], w[3], 0x7632), k23, hi);
+            lo = __dp2a_lo(__byte_perm(w[4], w[5], 0x5410), k45, lo); hi = __dp2a_lo(__byte_perm(w[4], w[5], 0x7632), k45, hi);
+            lo = __dp2a_lo(w[6] & 0xffffu, k6, lo);                hi = __dp2a_lo(w[6] >> 16, k6, hi);
+            out |= ((lo >> 16) | ((hi >> 16) << 8)) << (16 * h);
         }
+        uint8_t *q = dst + (size_t)oy * L.pitch + ox;
+        if (ox + 3 < L.w) *reinterpret_cast<unsigned *>(q) = out;
+        else { for (int k = 0; k < 4 && ox + k < L.w; k++) q[k] = (uint8_t)(out >> (8 * k)); }
     }
 }
 
