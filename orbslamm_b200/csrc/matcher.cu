@@ -240,8 +240,9 @@ k_search_candidates(const SearchArgs A)
     if (lane == 0) A.ncand[qo + i] = n;
 }
 
-// slow path: full rescan of one query's window by one thread; best and second-best free candidates
-__device__ void rescan_window(const SearchArgs &A, int f, int i, const int *own_prev, unsigned long long &b1, unsigned long long &b2)
+// slow path: full rescan of one query's window by one WARP (lanes over grid cells, like k_search_candidates); best and
+// second-best free candidates in the reference's comparison order, valid in every lane
+__device__ void rescan_window_warp(const SearchArgs &A, int f, int i, const int *own_prev, int lane, unsigned long long &b1, unsigned long long &b2)
 {
     const size_t fo = (size_t)f * A.f_slab, qo = (size_t)f * A.q_slab;
     const float2 *f_xy = A.f_xy + fo; const int *f_octave = A.f_octave + fo; const uint4 *f_desc = A.f_desc + 2 * fo;
@@ -253,17 +254,27 @@ __device__ void rescan_window(const SearchArgs &A, int f, int i, const int *own_
     b1 = kNoKey; b2 = kNoKey;
     if (w.empty) return;
     const uint4 qa = __ldg(&A.q_desc[2 * (qo + i)]), qb = __ldg(&A.q_desc[2 * (qo + i) + 1]);
-    for (int ix = w.c0; ix <= w.c1; ix++)
-        for (int iy = w.r0; iy <= w.r1; iy++) {
-            const int cell = ix * kGridRows + iy;
-            for (int j = cs[cell]; j < cs[cell + 1]; j++) {
-                const int k = items[j];
-                if (!in_window(w, minl, maxl, uv, r, f_octave[k], f_xy[k])) continue;
-                if (own_prev[k] < i) continue;
-                const unsigned long long key = make_key(hamming256(qa, qb, __ldg(&f_desc[2 * k]), __ldg(&f_desc[2 * k + 1])), ix, iy, k);
-                if (key < b1) { b2 = b1; b1 = key; } else if (key < b2) b2 = key;
-            }
+    const int ncy = w.r1 - w.r0 + 1, ncells = (w.c1 - w.c0 + 1) * ncy;
+    for (int c = lane; c < ncells; c += 32) {
+        const int ix = w.c0 + c / ncy, iy = w.r0 + c % ncy;
+        const int cell = ix * kGridRows + iy;
+        const int je = cs[cell + 1];
+        for (int j = cs[cell]; j < je; j++) {
+            const int k = items[j];
+            if (!in_window(w, minl, maxl, uv, r, f_octave[k], f_xy[k])) continue;
+            if (own_prev[k] < i) continue;
+            const unsigned long long key = make_key(hamming256(qa, qb, __ldg(&f_desc[2 * k]), __ldg(&f_desc[2 * k + 1])), ix, iy, k);
+            if (key < b1) { b2 = b1; b1 = key; } else if (key < b2) b2 = key;
         }
+    }
+    // warp minimum, then the minimum of what is left (keys are unique: they contain the feature index)
+    unsigned long long m1 = b1;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) { const unsigned long long o = __shfl_xor_sync(0xffffffffu, m1, d); m1 = o < m1 ? o : m1; }
+    unsigned long long m2 = (b1 == m1) ? b2 : b1;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) { const unsigned long long o = __shfl_xor_sync(0xffffffffu, m2, d); m2 = o < m2 ? o : m2; }
+    b1 = m1; b2 = m2;
 }
 
 // use_smem: the working set of the fixed-point rounds (candidate lists, ownership, proposals) is staged in shared memory
@@ -272,7 +283,7 @@ __global__ void __launch_bounds__(1024)
 k_search_resolve(const SearchArgs A, const int use_smem)
 {
     extern __shared__ __align__(16) unsigned char resolve_smem[];
-    __shared__ int s_changed;
+    __shared__ int s_changed, s_nqueue;
     __shared__ int s_hist[kHisto];
     __shared__ int s_keep[3];
     __shared__ int s_removed, s_accepted;
@@ -285,8 +296,10 @@ k_search_resolve(const SearchArgs A, const int use_smem)
     int *owner[2] = {A.owner + 2 * fo, A.owner + 2 * fo + A.f_slab};
     const unsigned *top_all = A.top + qo * kTop;
     const int *ncand = A.ncand + qo;
+    int *s_queue = reinterpret_cast<int *>(resolve_smem);                 // [q_slab] queries waiting for a window rescan
+    const bool need2 = A.ratio > 0.f;
     if (use_smem) {
-        unsigned *s_top = reinterpret_cast<unsigned *>(resolve_smem);
+        unsigned *s_top = reinterpret_cast<unsigned *>(resolve_smem) + A.q_slab;
         int *s_nc = reinterpret_cast<int *>(s_top + (size_t)A.q_slab * kTop);
         int *s_prop = s_nc + A.q_slab;
         int *s_own = s_prop + A.q_slab;
@@ -302,7 +315,7 @@ k_search_resolve(const SearchArgs A, const int use_smem)
 
     int cur = 0;
     for (int round = 0; round <= M; round++) {
-        if (tid == 0) s_changed = 0;
+        if (tid == 0) { s_changed = 0; s_nqueue = 0; }
         __syncthreads();
         const int *own_prev = owner[cur];
         int *own_next = owner[cur ^ 1];
@@ -313,27 +326,21 @@ k_search_resolve(const SearchArgs A, const int use_smem)
                 const unsigned *top = top_all + (size_t)i * kTop;
                 // first and second free entries of the sorted list
                 unsigned e1 = 0xffffffffu, e2 = 0xffffffffu;
-                int seen = 0;
 #pragma unroll
                 for (int t = 0; t < kTop; t++) {
                     const unsigned e = top[t];
                     if (e == 0xffffffffu) continue;
-                    seen++;
                     if (own_prev[e & 0xfffff] < i) continue;
                     if (e1 == 0xffffffffu) e1 = e; else if (e2 == 0xffffffffu) e2 = e;
                 }
                 int best = -1, bidx = -1, best2 = 256, lvl2 = -1;
                 const bool list_complete = nc <= kTop;
-                const bool need2 = A.ratio > 0.f;
                 if ((e1 == 0xffffffffu || (need2 && e2 == 0xffffffffu)) && !list_complete) {
-                    unsigned long long b1, b2;
-                    rescan_window(A, f, i, own_prev, b1, b2);
-                    if (b1 != kNoKey) { best = (int)(b1 >> 32); bidx = (int)(b1 & 0xfffff); }
-                    if (b2 != kNoKey) { best2 = (int)(b2 >> 32); lvl2 = f_octave[(int)(b2 & 0xfffff)]; }
-                } else {
-                    if (e1 != 0xffffffffu) { best = (int)(e1 >> 20); bidx = (int)(e1 & 0xfffff); }
-                    if (e2 != 0xffffffffu) { best2 = (int)(e2 >> 20); lvl2 = f_octave[e2 & 0xfffff]; }
+                    s_queue[atomicAdd(&s_nqueue, 1)] = i;          // rare: resolved by a whole warp below
+                    continue;
                 }
+                if (e1 != 0xffffffffu) { best = (int)(e1 >> 20); bidx = (int)(e1 & 0xfffff); }
+                if (e2 != 0xffffffffu) { best2 = (int)(e2 >> 20); lvl2 = f_octave[e2 & 0xfffff]; }
                 if (bidx >= 0 && best <= A.th_dist) {
                     bool acc = true;
                     if (need2 && f_octave[bidx] == lvl2 && (float)best > __fmul_rn(A.ratio, (float)best2)) acc = false;
@@ -341,6 +348,24 @@ k_search_resolve(const SearchArgs A, const int use_smem)
                 }
             }
             if (prop[i] != choice) { prop[i] = choice; s_changed = 1; }
+        }
+        __syncthreads();
+        // queries whose list is exhausted although their window holds more than kTop candidates: one warp each
+        for (int q = tid >> 5; q < s_nqueue; q += nt >> 5) {
+            const int i = s_queue[q];
+            unsigned long long b1, b2;
+            rescan_window_warp(A, f, i, own_prev, tid & 31, b1, b2);
+            if ((tid & 31) == 0) {
+                int choice = -1, best = -1, bidx = -1, best2 = 256, lvl2 = -1;
+                if (b1 != kNoKey) { best = (int)(b1 >> 32); bidx = (int)(b1 & 0xfffff); }
+                if (b2 != kNoKey) { best2 = (int)(b2 >> 32); lvl2 = f_octave[(int)(b2 & 0xfffff)]; }
+                if (bidx >= 0 && best <= A.th_dist) {
+                    bool acc = true;
+                    if (need2 && f_octave[bidx] == lvl2 && (float)best > __fmul_rn(A.ratio, (float)best2)) acc = false;
+                    if (acc) choice = bidx;
+                }
+                if (prop[i] != choice) { prop[i] = choice; s_changed = 1; }
+            }
         }
         __syncthreads();
         if (!s_changed) break;
@@ -563,13 +588,15 @@ int orbm_search_by_projection(orbm_handle *h, int n_frames, const float *bounds4
     k_grid_build<<<n_frames, 512, 0, h->stream>>>(f_slab, A.g, A.f_xy, A.f_counts, h->cell_start.as<int>(), h->cell_items.as<int>());
     k_search_candidates<<<dim3((q_slab + 7) / 8, n_frames), 256, 0, h->stream>>>(A);
     {
-        const size_t smem = ((size_t)q_slab * (kTop + 2) + 2 * (size_t)f_slab) * sizeof(int);
+        size_t smem = ((size_t)q_slab * (kTop + 3) + 2 * (size_t)f_slab) * sizeof(int);
         const int use_smem = smem <= 200 * 1024;
-        if (use_smem && smem > h->resolve_smem) {
+        if (!use_smem) smem = (size_t)q_slab * sizeof(int);                    // rescan queue only
+        ORBS_REQUIRE(smem <= 200 * 1024, ORBS_E_INVALID, "too many map points per frame for the projection search");
+        if (smem > h->resolve_smem) {
             ORBS_CUDA(cudaFuncSetAttribute(k_search_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             h->resolve_smem = smem;
         }
-        k_search_resolve<<<n_frames, 1024, use_smem ? smem : 0, h->stream>>>(A, use_smem);
+        k_search_resolve<<<n_frames, 1024, smem, h->stream>>>(A, use_smem);
     }
     h->launches += 3;
     ORBS_CUDA(cudaGetLastError());
