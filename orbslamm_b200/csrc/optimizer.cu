@@ -166,7 +166,7 @@ int orbo_pose_optimization(orbo_handle *h, int n_frames, float *Tcw, const float
     A.outlier = S.inout(outlier, ne, false); A.n_inliers = S.inout(n_inliers, n_frames, false);
     A.err = S.scratch<double>(ne * 2);
     if (S.rc) return S.rc;
-    k_pose_optimization<<<n_frames, kPoseThreads, 0, h->stream>>>(A);
+    ORBS_CUDA(launch_high_priority(k_pose_optimization, dim3(n_frames), dim3(kPoseThreads), 0, h->stream, A));
     h->launches++;
     ORBS_CUDA(cudaGetLastError());
     return S.finish();
@@ -203,8 +203,8 @@ int orbo_pose_optimization_matched(orbo_handle *h, int n_frames, float *Tcw, con
     uint8_t *d_fout = S.inout(f_outlier, nf, false);
     if (S.rc) return S.rc;
     ORBS_CUDA(cudaMemsetAsync(d_fout, 0, nf, h->stream));
-    k_pose_gather<<<n_frames, 256, 0, h->stream>>>(G);
-    k_pose_optimization<<<n_frames, kPoseThreads, 0, h->stream>>>(A);
+    ORBS_CUDA(launch_high_priority(k_pose_gather, dim3(n_frames), dim3(256), 0, h->stream, G));
+    ORBS_CUDA(launch_high_priority(k_pose_optimization, dim3(n_frames), dim3(kPoseThreads), 0, h->stream, A));
     k_pose_scatter<<<dim3((f_slab + 255) / 256, n_frames), 256, 0, h->stream>>>(f_slab, d_nedges, G.edge_feat, d_eout, d_fout);
     h->launches += 3;
     ORBS_CUDA(cudaGetLastError());
@@ -454,17 +454,24 @@ struct BaHost {
     enum { LM_OK = 0, LM_TERMINATE = 1, LM_ERROR = 2 };
 
     // OptimizationAlgorithmLevenberg::solve, optimization_algorithm_levenberg.cpp:61-164
+    // errors_current: the stored edge errors and chi2 belong to the current estimate (the last trial was accepted), so the
+    // computeActiveErrors at the top of the next iteration (levenberg.cpp:69-72) would reproduce them bit for bit: skipped,
+    // together with its host round trip.  After a rejected trial (estimate restored) they are recomputed, as in g2o.
+    bool errors_current = false;
+    double chi_current = 0;
+
     int lm_iteration(int iteration)
     {
-        errors();
+        if (iteration == 0) errors_current = false;
+        if (!errors_current) errors();
         if (build_system()) return LM_ERROR;
         if (iteration == 0) {
             k_ba_max_diag<<<diag_blocks, 256, 0, st>>>(B);
             k_reduce_partials<<<1, 256, 0, st>>>(B.partial, diag_blocks, B.scalars, 3, 1);
             count(2);
         }
-        if (read_scalars()) return LM_ERROR;
-        double currentChi = h_scal[0];
+        if (!errors_current || iteration == 0) { if (read_scalars()) return LM_ERROR; chi_current = h_scal[0]; }
+        double currentChi = chi_current;
         const double iniChi = currentChi;
         if (iteration == 0) { lambda = 1e-5 * h_scal[3]; ni = 2; nbad = 0; }
         double rho = 0;
@@ -492,10 +499,12 @@ struct BaHost {
                 lambda *= std::max(1. / 3., alpha);
                 ni = 2;
                 currentChi = tempChi;
+                errors_current = true; chi_current = tempChi;
             } else {
                 lambda *= ni; ni *= 2;
                 k_ba_restore<<<upd_blocks, 256, 0, st>>>(B);
                 count(1);
+                errors_current = false;
             }
             qmax++;
             lm_trials++;

@@ -147,6 +147,7 @@ static int build_plan(orbx_handle *h, int width, int height)
             const LevelPlan &S = P.lv[l - 1];
             for (int axis = 0; axis < 2; axis++) {
                 const int ssize = axis ? S.h : S.w, dsize = axis ? L.h : L.w;
+                while (rs.size() & 3) rs.push_back(make_int2(0, 0));        // 32-byte aligned tables: 4 entries per vector load
                 (axis ? L.rs_y_off : L.rs_x_off) = (int)rs.size();
                 const double inv = (double)dsize / ssize, sc = 1. / inv;
                 for (int d = 0; d < dsize; d++) {
@@ -254,7 +255,7 @@ static int launch_pipeline(orbx_handle *h, const uint8_t *d_img0_all, int f0, in
         const uint8_t *src; int spitch; size_t sframe;
         if (l == 1) { src = d_img0; spitch = pitch0; sframe = frame0; }
         else { src = pyr + S.pyr_off; spitch = S.pitch; sframe = P.pyr_frame_bytes; }
-        dim3 grid((D.w + 63) / 64, (D.h + 3) / 4, n);
+        dim3 grid((D.w + 255) / 256, (D.h + 3) / 4, n);                     // 64 x 4 threads, 4 output pixels per thread
         h->timer.begin(0, st);
         k_resize_level<<<grid, 256, 0, st>>>(src, S.w, S.h, spitch, sframe, pyr + D.pyr_off, D.w, D.h, D.pitch, P.pyr_frame_bytes,
                                               h->d_rs_tab.as<int2>() + D.rs_x_off, h->d_rs_tab.as<int2>() + D.rs_y_off);
@@ -272,7 +273,8 @@ static int launch_pipeline(orbx_handle *h, const uint8_t *d_img0_all, int f0, in
         k_blur7<<<dim3(P.total_tiles, n), 256, 0, st>>>(P, tma_levels, h->d_tiles.as<TileDesc>(), d_img0, pitch0, frame0, pyr, blur);
         h->timer.end(st);
         h->timer.begin(3, st);
-        k_octree<<<dim3(P.nlevels, n), 512, h->octree_smem, st>>>(P, cand, cand_count, knode, lvl_kp, lvl_count, err_ptr(h, nb));
+        ORBS_CUDA(launch_high_priority(k_octree, dim3(P.nlevels, n), dim3(512), (size_t)h->octree_smem, st, P, (const uint2 *)cand, (const int *)cand_count, knode, lvl_kp,
+                                       lvl_count, err_ptr(h, nb)));
         h->timer.end(st);
         const int warps_per_block = 8;
         h->timer.begin(4, st);

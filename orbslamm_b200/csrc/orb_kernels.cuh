@@ -26,22 +26,32 @@ k_resize_level(const uint8_t *__restrict__ src, int sw, int sh, int spitch, size
                uint8_t *__restrict__ dst, int dw, int dh, int dpitch, size_t dframe,
                const int2 *__restrict__ tab_x, const int2 *__restrict__ tab_y)
 {
-    const int x = blockIdx.x * 64 + (threadIdx.x & 63);
+    // 4 adjacent output pixels per thread: one pair of row pointers, vector table loads, one 32-bit store
+    const int x = (blockIdx.x * 64 + (threadIdx.x & 63)) * 4;
     const int y = blockIdx.y * 4 + (threadIdx.x >> 6);
     if (x >= dw || y >= dh) return;
     const uint8_t *s = src + (size_t)blockIdx.z * sframe;
-    const int2 tx = __ldg(&tab_x[x]);
     const int2 ty = __ldg(&tab_y[y]);
-    const int sx0 = tx.x, sx1 = min(sx0 + 1, sw - 1);
     const int sy0 = ty.x, sy1 = min(sy0 + 1, sh - 1);
-    const int a0 = tx.y & 0xffff, a1 = tx.y >> 16;
     const int b0 = ty.y & 0xffff, b1 = ty.y >> 16;
     const uint8_t *r0p = s + (size_t)sy0 * spitch, *r1p = s + (size_t)sy1 * spitch;
-    const int r0 = r0p[sx0] * a0 + r0p[sx1] * a1;
-    const int r1 = r1p[sx0] * a0 + r1p[sx1] * a1;
-    int v = (((b0 * (r0 >> 4)) >> 16) + ((b1 * (r1 >> 4)) >> 16) + 2) >> 2;
-    v = min(max(v, 0), 255);
-    dst[(size_t)blockIdx.z * dframe + (size_t)y * dpitch + x] = (uint8_t)v;
+    const int4 t01 = __ldg(reinterpret_cast<const int4 *>(tab_x + x)), t23 = __ldg(reinterpret_cast<const int4 *>(tab_x + x + 2));
+    const int sxs[4] = {t01.x, t01.z, t23.x, t23.z}, cf[4] = {t01.y, t01.w, t23.y, t23.w};
+    unsigned out = 0u;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        // entries beyond dw are table padding (0, 0) or the next table: harmless reads, masked below
+        const int sx0 = min(sxs[k], sw - 1), sx1 = min(sx0 + 1, sw - 1);
+        const int a0 = cf[k] & 0xffff, a1 = cf[k] >> 16;
+        const int r0 = r0p[sx0] * a0 + r0p[sx1] * a1;
+        const int r1 = r1p[sx0] * a0 + r1p[sx1] * a1;
+        int v = (((b0 * (r0 >> 4)) >> 16) + ((b1 * (r1 >> 4)) >> 16) + 2) >> 2;
+        v = min(max(v, 0), 255);
+        out |= (unsigned)v << (8 * k);
+    }
+    uint8_t *q = dst + (size_t)blockIdx.z * dframe + (size_t)y * dpitch + x;
+    if (x + 3 < dw) *reinterpret_cast<unsigned *>(q) = out;
+    else for (int k = 0; k < 4 && x + k < dw; k++) q[k] = (uint8_t)(out >> (8 * k));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -754,14 +764,15 @@ k_orient_describe(const __grid_constant__ ExtractPlan plan,
         const int u = lane - kHalfPatch;
         const uint8_t *c = img + (size_t)y * pitch + x + u;
         const int au = abs(u);
-#pragma unroll 1
-        for (int v = -kHalfPatch; v <= kHalfPatch; v++) {
-            if (au <= plan.umax[abs(v)]) {
-                const int val = c[(ptrdiff_t)v * pitch];
-                m10 += u * val;
-                m01 += v * val;
-            }
-        }
+        // all 31 row loads are issued before the first use (the loop is latency-bound otherwise)
+        int vals[2 * kHalfPatch + 1];
+#pragma unroll
+        for (int v = -kHalfPatch; v <= kHalfPatch; v++)
+            vals[v + kHalfPatch] = (au <= plan.umax[v < 0 ? -v : v]) ? (int)__ldg(c + (ptrdiff_t)v * pitch) : 0;
+        int sum = 0;
+#pragma unroll
+        for (int v = -kHalfPatch; v <= kHalfPatch; v++) { sum += vals[v + kHalfPatch]; m01 += v * vals[v + kHalfPatch]; }
+        m10 = u * sum;
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {
