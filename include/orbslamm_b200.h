@@ -149,6 +149,25 @@ long long orbm_kernel_launches(const orbm_handle *h);
  * a u8[n,32], b u8[m,32], out i32[n,m]. */
 int orbm_descriptor_distance(orbm_handle *h, const uint8_t *a, int n, const uint8_t *b, int m, int32_t *out, int memspace);
 
+/* Frame::UndistortKeyPoints (S/src/Frame.cc:404-434): cv::undistortPoints(pts, K, distCoef, R = I, P = K) with OpenCV's default
+ * criteria (5 fixed-point iterations in fp64); a copy when dist5[0] == 0 (Frame.cc:406-410).
+ *   kp_xy f32[n_frames*slab,2] (Frame::mvKeys[i].pt), counts i32[n_frames]; K4 f32[4] = fx fy cx cy and dist5 f32[5] = k1 k2 p1 p2 k3
+ *   are HOST pointers (k3 = 0 for the 4-entry DistCoef of the reference's YAML files); kp_xy_un out (Frame::mvKeysUn[i].pt). */
+int orbm_undistort_keypoints(orbm_handle *h, int n_frames, const float *kp_xy, const int32_t *counts, int slab, const float *K4,
+                             const float *dist5, float *kp_xy_un, int memspace);
+
+/* Frame::isInFrustum (S/src/Frame.cc:269-325) with MapPoint::PredictScale / Get{Min,Max}DistanceInvariance
+ * (S/src/MapPoint.cc:373-394) for counts[f] map points per frame: positive depth, projection inside the image bounds, distance
+ * inside [0.8 mfMinDistance, 1.2 mfMaxDistance], viewing cosine >= limit (0.5 in Tracking::SearchLocalPoints, Tracking.cc:1233).
+ *   Tcw f32[n_frames,16]; Ow f32[n_frames,3] = Frame::mOw; K4 / bounds4 (mnMinX mnMinY mnMaxX mnMaxY) HOST pointers;
+ *   Xw, normal f32[n_frames*slab,3]; mf_min_distance / mf_max_distance f32[.] = MapPoint::mfMinDistance / mfMaxDistance.
+ *   out: in_view u8[.] (mbTrackInView), proj_xy f32[.,2] (mTrackProjX/Y), pred_level i32[.] (mnTrackScaleLevel), view_cos f32[.]
+ *   (mTrackViewCos) -- written for points in view; these feed orbm_search_by_projection for the local-map search. */
+int orbm_is_in_frustum(orbm_handle *h, int n_frames, const float *Tcw, const float *Ow, const float *K4, const float *bounds4,
+                       float log_scale_factor, float viewing_cos_limit, const float *Xw, const float *normal,
+                       const float *mf_min_distance, const float *mf_max_distance, const int32_t *counts, int slab,
+                       uint8_t *in_view, float *proj_xy, int32_t *pred_level, float *view_cos, int memspace);
+
 /* Projection block of SearchByProjection(CurrentFrame, LastFrame, th, bMono=true), ORBmatcher.cc:1336-1391:
  * per frame f and last-frame slot i (valid[i] != 0: the slot holds a non-outlier map point) project Xw with the
  * current pose, keep it if the depth is positive and (u, v) lies inside the image bounds, and emit the search

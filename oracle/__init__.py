@@ -11,10 +11,13 @@ Pieces:
                    orb_oracle.c and as the reference-faithful CPU baseline.
 
 Parity status: the reference repository holds no golden vectors or tests for
-this path and cannot be compiled here (needs OpenCV C++/Eigen
-headers).  The extractor oracle is pinned against cv2 4.13.0 (same OpenCV
-primitives the reference calls); the optimizer oracle is pinned against an
-independent numpy/scipy twin.  Beyond that: "parity unpinned" by the reference.
+this path.  Extractor: PINNED -- orb_oracle.c equals the reference's
+own ORBextractor.cc compiled unmodified against an OpenCV stand-in (oracle/_ref,
+ref_build.py, tests/test_oracle_vs_reference.py) and its OpenCV primitives equal
+cv2 4.13.0 bit for bit.  Matcher / optimizer: ORBmatcher.cc and Optimizer.cc cannot be
+compiled here (data model -> DBoW2 / g2o -> Eigen headers absent); the optimizer oracle
+is pinned against an independent numpy/scipy twin, beyond that "parity unpinned" by
+the reference.
 """
 import ctypes
 import os
@@ -291,3 +294,28 @@ def bundle_adjust(poses, fixed, intr, points, e_kf, e_pt, e_uv, e_inv_sigma2, tw
                                     _p(chi2, _f64p), _p(dok, _u8p), _p(outl, _u8p), _p(stats, _i32p))
     return dict(poses=poses.reshape(K, 4, 4), points=points, chi2=chi2[:E], depth_ok=dok[:E], outlier=outl[:E],
                 lm_iterations=int(stats[0]), lm_trials=int(stats[1]), rc=rc)
+
+
+def undistort_points(K4, dist5, xy):
+    """Frame::UndistortKeyPoints (Frame.cc:404-434): cv::undistortPoints(pts, K, dist, R=I, P=K)."""
+    xy = np.ascontiguousarray(xy, np.float32).reshape(-1, 2)
+    out = np.empty_like(xy)
+    K4 = np.ascontiguousarray(K4, np.float32); d = np.zeros(5, np.float32); d[:len(dist5)] = dist5
+    lib().oracle_undistort_points(_p(K4, _f32p), _p(d, _f32p), len(xy), _p(xy, _f32p), _p(out, _f32p))
+    return out
+
+
+def is_in_frustum(Tcw, Ow, K4, bounds4, log_scale_factor, cos_limit, Xw, normal, mf_min_dist, mf_max_dist):
+    """Frame::isInFrustum (Frame.cc:269-325) over flat arrays -> (in_view u8[M], proj f32[M,2], level i32[M], view_cos f32[M])."""
+    Xw = np.ascontiguousarray(Xw, np.float32).reshape(-1, 3); M = len(Xw)
+    normal = np.ascontiguousarray(normal, np.float32).reshape(-1, 3)
+    T = np.ascontiguousarray(Tcw, np.float32).reshape(16); Ow = np.ascontiguousarray(Ow, np.float32)
+    K4 = np.ascontiguousarray(K4, np.float32); b = np.ascontiguousarray(bounds4, np.float32)
+    mn = np.ascontiguousarray(mf_min_dist, np.float32); mx = np.ascontiguousarray(mf_max_dist, np.float32)
+    iv = np.zeros(M, np.uint8); uv = np.zeros((M, 2), np.float32); lv = np.zeros(M, np.int32); vc = np.zeros(M, np.float32)
+    L = lib()
+    L.oracle_is_in_frustum.argtypes = [_f32p, _f32p, _f32p, _f32p, ctypes.c_float, ctypes.c_float, ctypes.c_int, _f32p, _f32p, _f32p, _f32p,
+                                       _u8p, _f32p, _i32p, _f32p]
+    L.oracle_is_in_frustum(_p(T, _f32p), _p(Ow, _f32p), _p(K4, _f32p), _p(b, _f32p), float(log_scale_factor), float(cos_limit), M, _p(Xw, _f32p),
+                           _p(normal, _f32p), _p(mn, _f32p), _p(mx, _f32p), _p(iv, _u8p), _p(uv, _f32p), _p(lv, _i32p), _p(vc, _f32p))
+    return iv, uv, lv, vc

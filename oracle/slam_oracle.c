@@ -812,3 +812,74 @@ int oracle_bundle_adjust(int K, float *poses, const uint8_t *fixed, const double
     free(pose); free(fx); free(pt); free(o); free(w); free(lvl); free(rob); free(err);
     return 0;
 }
+
+/* ------------------------------------------------------------------ */
+/* Frame::UndistortKeyPoints (Frame.cc:404-434) = cv::undistortPoints(pts, K, distCoef, R = I, P = K) with the default
+ * termination criteria (5 iterations, no epsilon test).  OpenCV is un-vendored; restated from cvUndistortPointsInternal and
+ * pinned against cv2.undistortPoints (tests/test_oracle_opencv_pin.py).  dist5 = k1, k2, p1, p2, k3 (k3 = 0 for the 4-entry
+ * DistCoef of the reference's YAML files).  When k1 == 0 the reference copies the keypoints (Frame.cc:406-410). */
+void oracle_undistort_points(const float *K4, const float *dist5, int n, const float *xy, float *xy_un)
+{
+    if (dist5[0] == 0.0f) { memcpy(xy_un, xy, sizeof(float) * 2 * (size_t)n); return; }
+    const double fx = K4[0], fy = K4[1], cx = K4[2], cy = K4[3];
+    const double ifx = 1. / fx, ify = 1. / fy;
+    const double k1 = dist5[0], k2 = dist5[1], p1 = dist5[2], p2 = dist5[3], k3 = dist5[4];
+    for (int i = 0; i < n; i++) {
+        double x = xy[2 * i], y = xy[2 * i + 1];
+        const double u = x, v = y;
+        x = (x - cx) * ifx; y = (y - cy) * ify;
+        const double x0 = x, y0 = y;
+        for (int j = 0; j < 5; j++) {
+            const double r2 = x * x + y * y;
+            const double icdist = (1 + ((0. * r2 + 0.) * r2 + 0.) * r2) / (1 + ((k3 * r2 + k2) * r2 + k1) * r2);
+            if (icdist < 0) { x = (u - cx) * ifx; y = (v - cy) * ify; break; }
+            const double dX = 2 * p1 * x * y + p2 * (r2 + 2 * x * x) + 0. * r2 + 0. * r2 * r2;
+            const double dY = p1 * (r2 + 2 * y * y) + 2 * p2 * x * y + 0. * r2 + 0. * r2 * r2;
+            x = (x0 - dX) * icdist; y = (y0 - dY) * icdist;
+        }
+        const double xx = fx * x + 0. * y + cx, yy = 0. * x + fy * y + cy, ww = 1. / (0. * x + 0. * y + 1.);
+        xy_un[2 * i] = (float)(xx * ww); xy_un[2 * i + 1] = (float)(yy * ww);
+    }
+}
+
+/* Frame::isInFrustum (Frame.cc:269-325) with MapPoint::PredictScale (MapPoint.cc:385-394) and
+ * Get{Min,Max}DistanceInvariance (MapPoint.cc:373-383) over flat arrays.  Ow = camera centre (Frame::mOw).
+ * bounds4 = mnMinX, mnMinY, mnMaxX, mnMaxY.  cv::Mat algebra: R*P+t as the small-gemm path (fp32, left to right);
+ * cv::norm and Mat::dot accumulate in double.  Outputs are written only for points in view (mbTrackInView). */
+void oracle_is_in_frustum(const float *Tcw, const float *Ow, const float *K4, const float *bounds4, float log_scale_factor, float cos_limit,
+                          int M, const float *Xw, const float *normal, const float *mf_min_dist, const float *mf_max_dist,
+                          uint8_t *in_view, float *proj_xy, int *pred_level, float *view_cos)
+{
+    for (int i = 0; i < M; i++) {
+        in_view[i] = 0;
+        const float *P = Xw + 3 * i;
+        float pc[3];
+        for (int r = 0; r < 3; r++) {
+            float s = Tcw[4 * r] * P[0];
+            s = s + Tcw[4 * r + 1] * P[1];
+            s = s + Tcw[4 * r + 2] * P[2];
+            pc[r] = s + Tcw[4 * r + 3];
+        }
+        if (pc[2] < 0.0f) continue;
+        const float invz = 1.0f / pc[2];
+        const float u = K4[0] * pc[0] * invz + K4[2];
+        const float v = K4[1] * pc[1] * invz + K4[3];
+        if (u < bounds4[0] || u > bounds4[2]) continue;
+        if (v < bounds4[1] || v > bounds4[3]) continue;
+        const float maxd = 1.2f * mf_max_dist[i], mind = 0.8f * mf_min_dist[i];
+        const float po[3] = {P[0] - Ow[0], P[1] - Ow[1], P[2] - Ow[2]};
+        double s2 = 0;
+        for (int k = 0; k < 3; k++) s2 += (double)po[k] * (double)po[k];
+        const float dist = (float)sqrt(s2);
+        if (dist < mind || dist > maxd) continue;
+        double dot = 0;
+        for (int k = 0; k < 3; k++) dot += (double)po[k] * (double)normal[3 * i + k];
+        const float vc = (float)(dot / dist);
+        if (vc < cos_limit) continue;
+        const float ratio = mf_max_dist[i] / dist;
+        in_view[i] = 1;
+        proj_xy[2 * i] = u; proj_xy[2 * i + 1] = v;
+        pred_level[i] = (int)ceilf(logf(ratio) / log_scale_factor);
+        view_cos[i] = vc;
+    }
+}

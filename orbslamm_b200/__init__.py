@@ -279,6 +279,31 @@ class ORBmatcher:
                                                _ptr(qc), slab, float(th), _ptr(qv), _ptr(uv), _ptr(rad), _ptr(mn), _ptr(mx), 0))
         return qv, uv, rad, mn, mx
 
+    def UndistortKeyPoints(self, kp_xy, counts, K4, dist_coef):
+        """Frame::UndistortKeyPoints (Frame.cc:404-434) for n_frames frames: kp_xy [n_frames, slab, 2] -> undistorted."""
+        xy = np.ascontiguousarray(kp_xy, np.float32); nfr, slab = xy.shape[0], xy.shape[1]
+        cnt = np.ascontiguousarray(counts, np.int32); K4 = np.ascontiguousarray(K4, np.float32)
+        d = np.zeros(5, np.float32); d[:len(dist_coef)] = np.asarray(dist_coef, np.float32).ravel()
+        out = np.zeros_like(xy)
+        _check(self._L.orbm_undistort_keypoints(self._h, nfr, _ptr(xy), _ptr(cnt), slab, _ptr(K4), _ptr(d), _ptr(out), 0))
+        return out
+
+    def isInFrustum(self, Tcw, Ow, K4, bounds4, log_scale_factor, Xw, normal, mf_min_distance, mf_max_distance, counts, viewing_cos_limit=0.5):
+        """Frame::isInFrustum (Frame.cc:269-325) for counts[f] map points of n_frames frames (slab layout).
+        Returns (in_view u8, proj_xy f32[.,2], pred_level i32, view_cos f32)."""
+        T = np.ascontiguousarray(Tcw, np.float32).reshape(-1, 16); nfr = len(T)
+        Ow = np.ascontiguousarray(Ow, np.float32).reshape(nfr, 3)
+        K4 = np.ascontiguousarray(K4, np.float32); b4 = np.ascontiguousarray(bounds4, np.float32)
+        Xw = np.ascontiguousarray(Xw, np.float32).reshape(nfr, -1, 3); slab = Xw.shape[1]
+        nrm = np.ascontiguousarray(normal, np.float32).reshape(nfr, slab, 3)
+        mn = np.ascontiguousarray(mf_min_distance, np.float32).reshape(nfr, slab); mx = np.ascontiguousarray(mf_max_distance, np.float32).reshape(nfr, slab)
+        cnt = np.ascontiguousarray(counts, np.int32)
+        iv = np.zeros((nfr, slab), np.uint8); uv = np.zeros((nfr, slab, 2), np.float32)
+        lv = np.zeros((nfr, slab), np.int32); vc = np.zeros((nfr, slab), np.float32)
+        _check(self._L.orbm_is_in_frustum(self._h, nfr, _ptr(T), _ptr(Ow), _ptr(K4), _ptr(b4), float(log_scale_factor), float(viewing_cos_limit),
+                                          _ptr(Xw), _ptr(nrm), _ptr(mn), _ptr(mx), _ptr(cnt), slab, _ptr(iv), _ptr(uv), _ptr(lv), _ptr(vc), 0))
+        return iv, uv, lv, vc
+
     def SearchByProjection(self, bounds4, f_xy, f_octave, f_angle, f_desc, f_counts, q_valid, q_uv, q_radius, q_minl,
                            q_maxl, q_angle, q_desc, q_counts, th_dist=100, use_ratio=False, feat_match=None):
         """Generic projection search for n_frames frames (host arrays in slab layout [n_frames, slab, ...]).

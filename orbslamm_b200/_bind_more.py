@@ -17,6 +17,8 @@ def declare(L):
     L.orbm_descriptor_distance.argtypes = [vp, vp, i, vp, i, vp, i]
     L.orbm_project_last_frame.argtypes = [vp, i, vp, vp, vp, vp, i, vp, vp, vp, i, f, vp, vp, vp, vp, vp, i]
     L.orbm_search_by_projection.argtypes = [vp, i, vp, vp, vp, vp, vp, vp, i, vp, vp, vp, vp, vp, vp, vp, vp, i, i, f, i, vp, vp, i]
+    L.orbm_undistort_keypoints.argtypes = [vp, i, vp, vp, i, vp, vp, vp, i]
+    L.orbm_is_in_frustum.argtypes = [vp, i, vp, vp, vp, vp, f, f, vp, vp, vp, vp, vp, i, vp, vp, vp, vp, i]
     L.orbo_create.argtypes = [c.POINTER(vp), i]
     L.orbo_destroy.argtypes = [vp]
     L.orbo_stream.argtypes = [vp]; L.orbo_stream.restype = vp

@@ -389,41 +389,34 @@ k_chol_panel(double *__restrict__ S, int ld, const int4 *__restrict__ tasks, dou
     __syncthreads();
     if (tid < NB) invd[tid] = 1.0 / T[tid][tid];
     __syncthreads();
+    // Solve X L^T = A row by row (left-looking): the 4 threads of row r own the entries x_q with q % 4 == sub; entry c needs
+    // sum_{q<c} x_q L[c][q] (L row c is a broadcast read), reduced over the 4 threads with two shuffles.  The diagonal CTA
+    // solves for A = I, i.e. X = L^-T, and stores its transpose L^-1 for the triangular solves.
     const unsigned full = 0xffffffffu;
-    double x[16];
+    double xo[16];
+#pragma unroll
+    for (int m = 0; m < 16; m++) { const int q = 4 * m + sub; xo[m] = diag ? (q == r ? 1.0 : 0.0) : X[r][q]; }
+#pragma unroll
+    for (int c = 0; c < NB; c++) {
+        double p0 = 0.0, p1 = 0.0;
+#pragma unroll
+        for (int m = 0; m < c / 4; m++) {
+            if (m & 1) p1 = fma(xo[m], T[c][4 * m + sub], p1); else p0 = fma(xo[m], T[c][4 * m + sub], p0);
+        }
+        if (sub < (c & 3)) p0 = fma(xo[c / 4], T[c][4 * (c / 4) + sub], p0);
+        double p = p0 + p1;
+        p += __shfl_xor_sync(full, p, 1);
+        p += __shfl_xor_sync(full, p, 2);
+        if (sub == (c & 3)) xo[c / 4] = (xo[c / 4] - p) * invd[c];
+    }
+    __syncthreads();
     if (diag) {
-        // inverse of the lower-triangular tile: the 4 threads of "row" c hold column c of L^-1 (rows 16 sub .. 16 sub + 15)
-        const int c = r;
-#pragma unroll
-        for (int u = 0; u < 16; u++) x[u] = (16 * sub + u == c) ? 1.0 : 0.0;
-#pragma unroll
-        for (int rr = 0; rr < NB; rr++) {
-            const int os = rr >> 4, ou = rr & 15;
-            const double mine = rr >= c ? x[ou] * invd[rr] : 0.0;
-            const double xr = __shfl_sync(full, mine, (lane & ~3) | os);
-            if (sub == os) x[ou] = xr;
-#pragma unroll
-            for (int u = 0; u < 16; u++) { const int q = 16 * sub + u; if (q > rr) x[u] = fma(-T[q][rr], xr, x[u]); }
-        }
-#pragma unroll
-        for (int u = 0; u < 16; u++) X[16 * sub + u][c] = x[u];
-        __syncthreads();
         double *Li = Linv + (size_t)k * NB * NB;
-        for (int q = tid; q < NB * NB; q += 256) Li[q] = X[q >> 6][q & 63];
+#pragma unroll
+        for (int m = 0; m < 16; m++) Li[(size_t)(4 * m + sub) * NB + r] = xo[m];          // L^-1[c][r] = X[r][c]
     } else {
-        // row r of the tile: x L^T = a, right-looking along the row
 #pragma unroll
-        for (int u = 0; u < 16; u++) x[u] = X[r][16 * sub + u];
-#pragma unroll
-        for (int c = 0; c < NB; c++) {
-            const int os = c >> 4, ou = c & 15;
-            const double xc = __shfl_sync(full, x[ou] * invd[c], (lane & ~3) | os);
-            if (sub == os) x[ou] = xc;
-#pragma unroll
-            for (int u = 0; u < 16; u++) { const int q = 16 * sub + u; if (q > c) x[u] = fma(-xc, T[q][c], x[u]); }
-        }
-#pragma unroll
-        for (int u = 0; u < 16; u++) X[r][16 * sub + u] = x[u];
+        for (int m = 0; m < 16; m++) X[r][4 * m + sub] = xo[m];
         __syncthreads();
         double *P = S + (size_t)(i * NB) * ld + k * NB;
         for (int q = tid; q < NB * NB; q += 256) { const int rr = q >> 6, cc = q & 63; P[(size_t)rr * ld + cc] = X[rr][cc]; }

@@ -69,6 +69,78 @@ k_project_last(int q_slab, const float *__restrict__ Tcw, float fx, float fy, fl
     q_valid[q] = ok ? 1 : 0;
 }
 
+// Frame::UndistortKeyPoints (Frame.cc:404-434) = cv::undistortPoints(pts, K, dist, R = I, P = K): 5 fixed-point iterations in
+// fp64 (cvUndistortPointsInternal, default criteria), result rounded to fp32.  One thread per keypoint.
+__global__ void __launch_bounds__(256)
+k_undistort(int slab, const int *__restrict__ counts, const float2 *__restrict__ xy, float2 *__restrict__ xy_un,
+            double fx, double fy, double cx, double cy, double k1, double k2, double p1, double p2, double k3)
+{
+    const int f = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= counts[f]) return;
+    const size_t q = (size_t)f * slab + i;
+    const float2 p = xy[q];
+    if (k1 == 0.0) { xy_un[q] = p; return; }                     // Frame.cc:406-410
+    const double ifx = 1. / fx, ify = 1. / fy;
+    double x = p.x, y = p.y;
+    const double u = x, v = y;
+    x = (x - cx) * ifx; y = (y - cy) * ify;
+    const double x0 = x, y0 = y;
+    for (int j = 0; j < 5; j++) {
+        const double r2 = x * x + y * y;
+        const double icdist = 1. / (1. + ((k3 * r2 + k2) * r2 + k1) * r2);
+        if (icdist < 0) { x = (u - cx) * ifx; y = (v - cy) * ify; break; }
+        const double dX = 2 * p1 * x * y + p2 * (r2 + 2 * x * x);
+        const double dY = p1 * (r2 + 2 * y * y) + 2 * p2 * x * y;
+        x = (x0 - dX) * icdist; y = (y0 - dY) * icdist;
+    }
+    xy_un[q] = make_float2((float)((fx * x + cx) * 1.0), (float)((fy * y + cy) * 1.0));
+}
+
+// Frame::isInFrustum (Frame.cc:269-325) + MapPoint::PredictScale (MapPoint.cc:385-394), one thread per map point.
+// cv::Mat algebra restated as in k_project_last (small gemm: fp32, left to right); cv::norm / Mat::dot accumulate in double.
+__global__ void __launch_bounds__(256)
+k_in_frustum(int slab, const int *__restrict__ counts, const float *__restrict__ Tcw, const float *__restrict__ Ow,
+             float fx, float fy, float cx, float cy, GridParams g, float log_sf, float cos_limit,
+             const float *__restrict__ Xw, const float *__restrict__ normal, const float *__restrict__ mf_min, const float *__restrict__ mf_max,
+             uint8_t *__restrict__ in_view, float2 *__restrict__ proj, int *__restrict__ level, float *__restrict__ view_cos)
+{
+    const int f = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= counts[f]) return;
+    const size_t q = (size_t)f * slab + i;
+    in_view[q] = 0;
+    const float *T = Tcw + 16 * f;
+    const float X = Xw[3 * q], Y = Xw[3 * q + 1], Z = Xw[3 * q + 2];
+    float pc[3];
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+        float s = __fmul_rn(T[4 * r], X);
+        s = __fadd_rn(s, __fmul_rn(T[4 * r + 1], Y));
+        s = __fadd_rn(s, __fmul_rn(T[4 * r + 2], Z));
+        pc[r] = __fadd_rn(s, T[4 * r + 3]);
+    }
+    if (pc[2] < 0.0f) return;
+    const float invz = __fdiv_rn(1.0f, pc[2]);
+    const float u = __fadd_rn(__fmul_rn(__fmul_rn(fx, pc[0]), invz), cx);
+    const float v = __fadd_rn(__fmul_rn(__fmul_rn(fy, pc[1]), invz), cy);
+    if (u < g.min_x || u > g.max_x) return;
+    if (v < g.min_y || v > g.max_y) return;
+    const float maxd = __fmul_rn(1.2f, mf_max[q]), mind = __fmul_rn(0.8f, mf_min[q]);
+    const float po[3] = {__fsub_rn(X, Ow[3 * f]), __fsub_rn(Y, Ow[3 * f + 1]), __fsub_rn(Z, Ow[3 * f + 2])};
+    double s2 = 0, dot = 0;
+#pragma unroll
+    for (int k = 0; k < 3; k++) { s2 = __dadd_rn(s2, __dmul_rn((double)po[k], (double)po[k])); dot = __dadd_rn(dot, __dmul_rn((double)po[k], (double)normal[3 * q + k])); }
+    const float dist = (float)sqrt(s2);
+    if (dist < mind || dist > maxd) return;
+    const float vc = (float)(dot / (double)dist);
+    if (vc < cos_limit) return;
+    const float ratio = __fdiv_rn(mf_max[q], dist);
+    in_view[q] = 1;
+    proj[q] = make_float2(u, v);
+    // std::log(float) / float, std::ceil(float): log evaluated in double and rounded to float (= a correctly rounded logf)
+    level[q] = (int)ceilf(__fdiv_rn((float)log((double)ratio), log_sf));
+    view_cos[q] = vc;
+}
+
 // Frame::AssignFeaturesToGrid / PosInGrid: CSR per frame, cell = ix * 48 + iy.  Order inside a cell is not
 // preserved; the search re-creates the reference's visiting order through an explicit (ix, iy, index) key.
 __global__ void __launch_bounds__(512)
@@ -540,6 +612,57 @@ int orbm_project_last_frame(orbm_handle *h, int n_frames, const float *Tcw, cons
     if (S.rc) return S.rc;
     k_project_last<<<dim3((q_slab + 255) / 256, n_frames), 256, 0, h->stream>>>(q_slab, dT, K4[0], K4[1], K4[2], K4[3], make_grid(bounds4), dsf,
                                                                                nlevels, dX, doct, dqc, th, dval, (float2 *)duv, drad, dmn, dmx);
+    h->launches++;
+    ORBS_CUDA(cudaGetLastError());
+    return S.finish();
+}
+
+int orbm_undistort_keypoints(orbm_handle *h, int n_frames, const float *kp_xy, const int32_t *counts, int slab, const float *K4,
+                             const float *dist5, float *kp_xy_un, int memspace)
+{
+    ORBS_REQUIRE(h && kp_xy && counts && K4 && dist5 && kp_xy_un, ORBS_E_INVALID, "null argument");
+    ORBS_REQUIRE(n_frames > 0 && slab > 0, ORBS_E_INVALID, "non-positive size");
+    std::lock_guard<std::mutex> lk(h->mu);
+    ORBS_CUDA(cudaSetDevice(h->device));
+    Stager S(&h->pool, h->stream, memspace);
+    const size_t n = (size_t)n_frames * slab;
+    const float *dxy = S.in(kp_xy, n * 2);
+    const int32_t *dc = S.in(counts, n_frames);
+    float *dun = S.inout(kp_xy_un, n * 2, false);
+    if (S.rc) return S.rc;
+    k_undistort<<<dim3((slab + 255) / 256, n_frames), 256, 0, h->stream>>>(slab, dc, (const float2 *)dxy, (float2 *)dun, (double)K4[0], (double)K4[1],
+                                                                           (double)K4[2], (double)K4[3], (double)dist5[0], (double)dist5[1],
+                                                                           (double)dist5[2], (double)dist5[3], (double)dist5[4]);
+    h->launches++;
+    ORBS_CUDA(cudaGetLastError());
+    return S.finish();
+}
+
+int orbm_is_in_frustum(orbm_handle *h, int n_frames, const float *Tcw, const float *Ow, const float *K4, const float *bounds4,
+                       float log_scale_factor, float viewing_cos_limit, const float *Xw, const float *normal,
+                       const float *mf_min_distance, const float *mf_max_distance, const int32_t *counts, int slab,
+                       uint8_t *in_view, float *proj_xy, int32_t *pred_level, float *view_cos, int memspace)
+{
+    ORBS_REQUIRE(h && Tcw && Ow && K4 && bounds4 && Xw && normal && mf_min_distance && mf_max_distance && counts && in_view && proj_xy && pred_level &&
+                 view_cos, ORBS_E_INVALID, "null argument");
+    ORBS_REQUIRE(n_frames > 0 && slab > 0, ORBS_E_INVALID, "non-positive size");
+    std::lock_guard<std::mutex> lk(h->mu);
+    ORBS_CUDA(cudaSetDevice(h->device));
+    Stager S(&h->pool, h->stream, memspace);
+    const size_t n = (size_t)n_frames * slab;
+    const float *dT = S.in(Tcw, (size_t)n_frames * 16), *dO = S.in(Ow, (size_t)n_frames * 3), *dX = S.in(Xw, n * 3), *dN = S.in(normal, n * 3);
+    const float *dmn = S.in(mf_min_distance, n), *dmx = S.in(mf_max_distance, n);
+    const int32_t *dc = S.in(counts, n_frames);
+    uint8_t *div = S.inout(in_view, n, false);
+    float *duv = S.inout(proj_xy, n * 2, false), *dvc = S.inout(view_cos, n, false);
+    int32_t *dlv = S.inout(pred_level, n, false);
+    if (S.rc) return S.rc;
+    if (memspace == ORBS_MEM_HOST) {       // slots beyond counts[f] and out-of-view points keep defined values on the host
+        ORBS_CUDA(cudaMemsetAsync(div, 0, n, h->stream)); ORBS_CUDA(cudaMemsetAsync(duv, 0, n * 8, h->stream));
+        ORBS_CUDA(cudaMemsetAsync(dvc, 0, n * 4, h->stream)); ORBS_CUDA(cudaMemsetAsync(dlv, 0, n * 4, h->stream));
+    }
+    k_in_frustum<<<dim3((slab + 255) / 256, n_frames), 256, 0, h->stream>>>(slab, dc, dT, dO, K4[0], K4[1], K4[2], K4[3], make_grid(bounds4), log_scale_factor,
+                                                                            viewing_cos_limit, dX, dN, dmn, dmx, div, (float2 *)duv, dlv, dvc);
     h->launches++;
     ORBS_CUDA(cudaGetLastError());
     return S.finish();

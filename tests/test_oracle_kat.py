@@ -104,3 +104,21 @@ def test_se3_and_huber_kats():
     # fewer than 3 correspondences -> 0, pose untouched
     To, out, n = oracle.pose_optimization(g["poses"][k], Xw[:2], obs[:2], np.ones(2, np.float32), np.array(g["intr"], np.float32))
     assert n == 0 and np.array_equal(To, g["poses"][k])
+
+
+def test_is_in_frustum_known_answers():
+    """Frame::isInFrustum (Frame.cc:269-325) on hand-checkable points: identity pose, fx = fy = 100, cx = cy = 50, 100 x 100 image."""
+    T = np.eye(4, dtype=np.float32); Ow = np.zeros(3, np.float32)
+    K4 = np.array([100, 100, 50, 50], np.float32); b = np.array([0, 0, 100, 100], np.float32)
+    X = np.array([[0, 0, 10],      # centre of the image, distance 10
+                  [0, 0, -1],      # behind the camera
+                  [6, 0, 10],      # u = 110: outside
+                  [0, 0, 30],      # beyond 1.2 * mfMaxDistance = 24
+                  [0, 0, 3],       # nearer than 0.8 * mfMinDistance = 4
+                  [0, 0, 10]], np.float32)
+    n = np.array([[0, 0, 1]] * 5 + [[1, 0, 0]], np.float32)          # last point: viewing ray orthogonal to the normal
+    mn = np.full(6, 5, np.float32); mx = np.full(6, 20, np.float32)
+    iv, uv, lv, vc = oracle.is_in_frustum(T, Ow, K4, b, np.log(np.float32(1.2)), 0.5, X, n, mn, mx)
+    assert iv.tolist() == [1, 0, 0, 0, 0, 0]
+    assert uv[0].tolist() == [50.0, 50.0] and vc[0] == 1.0
+    assert lv[0] == int(np.ceil(np.log(np.float32(2.0)) / np.log(np.float32(1.2))))          # PredictScale: ceil(log(20/10) / log 1.2) = 4

@@ -89,3 +89,25 @@ def test_full_extractor_c_equals_cv2_path(cam):
     lv, bordered = orb_cv2.compute_pyramid(P, img, with_border=True)
     for x, y in zip(oracle.pyramid(P, img), lv):
         assert np.array_equal(x, y)
+
+
+def test_undistort_points_matches_cv2():
+    """Frame::UndistortKeyPoints -> cv::undistortPoints(pts, K, dist, R=I, P=K) (Frame.cc:423): restated iteration == cv2, bit for bit."""
+    rng = np.random.default_rng(11)
+    K4 = np.array([517.306408, 516.469215, 318.643040, 255.313989], np.float32)
+    K = np.array([[K4[0], 0, K4[2]], [0, K4[1], K4[3]], [0, 0, 1]], np.float32)
+    for dist in (np.array([0.262383, -0.953104, -0.005358, 0.002628, 1.163314], np.float32),
+                 np.array([0.262383, -0.953104, -0.005358, 0.002628], np.float32), np.array([-0.28, 0.07, 0.0002, -0.0003], np.float32)):
+        xy = np.stack([rng.uniform(0, 640, 5000), rng.uniform(0, 480, 5000)], 1).astype(np.float32)
+        ref = cv2.undistortPoints(xy.reshape(-1, 1, 2), K, dist.reshape(-1, 1), None, K).reshape(-1, 2)
+        assert np.array_equal(oracle.undistort_points(K4, dist, xy), ref)
+    xy = rng.uniform(0, 400, (50, 2)).astype(np.float32)
+    assert np.array_equal(oracle.undistort_points(K4, np.zeros(4, np.float32), xy), xy)      # Frame.cc:406-410
+
+
+def test_norm_accumulates_in_double():
+    """cv::norm(PO) in Frame::isInFrustum (Frame.cc:300): L2 norm of a float 3-vector accumulated in double."""
+    rng = np.random.default_rng(12)
+    v = rng.normal(0, 10, (2000, 3)).astype(np.float32)
+    ref = np.array([np.float32(cv2.norm(x)) for x in v])
+    assert np.array_equal(ref, np.sqrt((v.astype(np.float64) ** 2).sum(1)).astype(np.float32))
