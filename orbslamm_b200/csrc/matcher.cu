@@ -253,9 +253,28 @@ __device__ __forceinline__ unsigned long long make_key(int d, int ix, int iy, in
     return ((unsigned long long)d << 32) | ((unsigned long long)ix << 26) | ((unsigned long long)iy << 20) | (unsigned long long)k;
 }
 
+// Key of a candidate in the reference's comparison order (distance, then GetFeaturesInArea visiting order = (ix, iy, index)).
+// K32: f_slab <= 2048 -> the whole key fits 32 bits (9 + 6 + 6 + 11) and the sorted insert / warp merge are single VIMNMX ops.
+template <bool K32> struct CandKey;
+template <> struct CandKey<true> {
+    typedef unsigned T;
+    static constexpr T none = 0xffffffffu;
+    static __device__ __forceinline__ T make(int d, int ix, int iy, int k) { return ((unsigned)d << 23) | ((unsigned)ix << 17) | ((unsigned)iy << 11) | (unsigned)k; }
+    static __device__ __forceinline__ unsigned pack(T m) { return ((m >> 23) << 20) | (m & 0x7ffu); }
+};
+template <> struct CandKey<false> {
+    typedef unsigned long long T;
+    static constexpr T none = ~0ull;
+    static __device__ __forceinline__ T make(int d, int ix, int iy, int k) { return make_key(d, ix, iy, k); }
+    static __device__ __forceinline__ unsigned pack(T m) { return ((unsigned)(m >> 32) << 20) | (unsigned)(m & 0xfffff); }
+};
+
+template <bool K32>
 __global__ void __launch_bounds__(256)
 k_search_candidates(const SearchArgs A)
 {
+    typedef CandKey<K32> CK;
+    typedef typename CK::T Key;
     const int f = blockIdx.y, lane = threadIdx.x & 31;
     const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (i >= A.q_counts[f]) return;
@@ -268,9 +287,9 @@ k_search_candidates(const SearchArgs A)
     const float r = A.q_radius[qo + i];
     const int minl = A.q_minl[qo + i], maxl = A.q_maxl[qo + i];
     const Window w = make_window(A.g, uv, r, minl, maxl);
-    unsigned long long loc[kTop];            // this lane's sorted best keys
+    Key loc[kTop];            // this lane's sorted best keys
 #pragma unroll
-    for (int t = 0; t < kTop; t++) loc[t] = kNoKey;
+    for (int t = 0; t < kTop; t++) loc[t] = CK::none;
     int n = 0;
     if (!w.empty) {
         const uint4 qa = __ldg(&A.q_desc[2 * (qo + i)]), qb = __ldg(&A.q_desc[2 * (qo + i) + 1]);
@@ -283,10 +302,10 @@ k_search_candidates(const SearchArgs A)
                 const int k = items[j];
                 if (!in_window(w, minl, maxl, uv, r, f_octave[k], f_xy[k])) continue;
                 n++;
-                unsigned long long key = make_key(hamming256(qa, qb, __ldg(&f_desc[2 * k]), __ldg(&f_desc[2 * k + 1])), ix, iy, k);
+                Key key = CK::make(hamming256(qa, qb, __ldg(&f_desc[2 * k]), __ldg(&f_desc[2 * k + 1])), ix, iy, k);
 #pragma unroll
                 for (int t = 0; t < kTop; t++) {                   // sorted insert
-                    const unsigned long long cur = loc[t];
+                    const Key cur = loc[t];
                     const bool lt = key < cur;
                     loc[t] = lt ? key : cur;
                     key = lt ? cur : key;
@@ -299,15 +318,15 @@ k_search_candidates(const SearchArgs A)
     // merge the 32 sorted lists: kTop rounds of warp-min + pop
 #pragma unroll
     for (int t = 0; t < kTop; t++) {
-        unsigned long long m = loc[0];
+        Key m = loc[0];
 #pragma unroll
-        for (int d = 16; d > 0; d >>= 1) { const unsigned long long o = __shfl_xor_sync(0xffffffffu, m, d); m = o < m ? o : m; }
-        if (m != kNoKey && loc[0] == m) {
+        for (int d = 16; d > 0; d >>= 1) { const Key o = __shfl_xor_sync(0xffffffffu, m, d); m = o < m ? o : m; }
+        if (m != CK::none && loc[0] == m) {
 #pragma unroll
             for (int u = 0; u < kTop - 1; u++) loc[u] = loc[u + 1];
-            loc[kTop - 1] = kNoKey;
+            loc[kTop - 1] = CK::none;
         }
-        if (lane == 0) top[t] = m == kNoKey ? 0xffffffffu : ((unsigned)(m >> 32) << 20) | (unsigned)(m & 0xfffff);
+        if (lane == 0) top[t] = m == CK::none ? 0xffffffffu : CK::pack(m);
     }
     if (lane == 0) A.ncand[qo + i] = n;
 }
@@ -709,7 +728,8 @@ int orbm_search_by_projection(orbm_handle *h, int n_frames, const float *bounds4
     A.prop = h->prop.as<int>(); A.owner = h->owner.as<int>(); A.top = h->top.as<unsigned>(); A.ncand = h->ncand.as<int>();
     A.th_dist = th_dist; A.ratio = ratio; A.check_ori = check_ori ? 1 : 0;
     ORBS_CUDA(launch_high_priority(k_grid_build, dim3(n_frames), dim3(512), 0, h->stream, f_slab, A.g, A.f_xy, A.f_counts, h->cell_start.as<int>(), h->cell_items.as<int>()));
-    k_search_candidates<<<dim3((q_slab + 7) / 8, n_frames), 256, 0, h->stream>>>(A);
+    if (f_slab <= 2048) k_search_candidates<true><<<dim3((q_slab + 7) / 8, n_frames), 256, 0, h->stream>>>(A);
+    else k_search_candidates<false><<<dim3((q_slab + 7) / 8, n_frames), 256, 0, h->stream>>>(A);
     {
         size_t smem = ((size_t)q_slab * (kTop + 3) + 2 * (size_t)f_slab) * sizeof(int);
         const int use_smem = smem <= 200 * 1024;
