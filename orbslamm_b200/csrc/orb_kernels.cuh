@@ -341,7 +341,8 @@ k_blur7(const __grid_constant__ ExtractPlan plan, const unsigned tma_levels, con
     const bool use_tma = (tma_levels >> t.level) & 1u;
     const int xa = max(t.x0 - 16, 0);                             // first loaded column (16-byte aligned: x0 % 64 == 0)
     const int need = t.x0 + kBlurTW + 3 - xa;                     // columns xa .. x0 + 66
-    const int rb = min((need + 15) & ~15, ((pitch - xa) & ~15));  // never past the row pitch
+    // never past the row pitch (bulk copies: whole 16-byte units, the pitch is a multiple of 16 on that path)
+    const int rb = use_tma ? min((need + 15) & ~15, (pitch - xa) & ~15) : min(need, pitch - xa);
     if (use_tma) {
         if (tid == 0) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)));
