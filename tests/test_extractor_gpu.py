@@ -71,3 +71,19 @@ def test_extract_device_resident_images(lib, pitch_kind):
         assert np.array_equal(r["xy"][f, :n, 0], ref["x"]) and np.array_equal(r["xy"][f, :n, 1], ref["y"])
         assert np.array_equal(r["angle"][f, :n], ref["angle"]) and np.array_equal(r["response"][f, :n], ref["response"])
         assert np.array_equal(r["octave"][f, :n], ref["octave"]) and np.array_equal(r["desc"][f, :n], ref["desc"])
+
+
+@pytest.mark.parametrize("shape,nf,levels,sf", [((97, 131), 100, 4, 1.2), ((241, 322), 500, 5, 1.5), ((120, 500), 200, 3, 1.3), ((480, 640), 1000, 8, 1.2)])
+def test_extract_other_shapes(lib, shape, nf, levels, sf):
+    """Small / wide images, other level counts and scale factors (large FAST cells on coarse levels, one-tile blur rows, ragged
+    batches through the chunked host path) == oracle."""
+    import orbslamm_b200 as ob
+    n = 19                                                     # not a multiple of the 16-frame upload chunk
+    frames = [synth.stream(shape[1], shape[0], 1, stream_id=100 + i)[0][0] for i in range(3)]
+    batch = np.stack([frames[i % 3] for i in range(n)])
+    ex = ob.ORBextractor(nf, sf, levels, 20, 7)
+    P = oracle.orb_params(nf, sf, levels, 20, 7)
+    refs = [oracle.orb_extract(P, f) for f in frames]
+    outs = ex.extract_batch(batch)
+    for i in range(n):
+        _assert_same(outs[i], refs[i % 3], f"{shape} frame {i}")

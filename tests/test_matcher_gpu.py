@@ -101,3 +101,26 @@ def test_search_by_projection_local_map(lib):
         assert n_ref > 50
         assert nm[i] == n_ref
         assert np.array_equal(fm[i, :fc[i]], fm_ref)
+
+
+def test_search_by_projection_4000_features(lib):
+    """The monocular initialisation extractor uses 2 x nFeatures (Tracking.cc:126): more than 2048 feature slots per frame -> 64-bit
+    candidate keys in k_search_candidates, many over-full windows (warp rescans in k_search_resolve)."""
+    import orbslamm_b200 as ob
+    k = make_tracking_case(synth.KITTI, 9, nfeatures=4000)
+    m = ob.ORBmatcher(0.9, True)
+    sf = np.array(list(k["P"].scale)[:8], np.float32)
+    g = oracle.grid_params(*k["bounds"])
+    cur, last = k["cur"], k["last"]
+    nF, nQ = len(cur["x"]), len(last["x"])
+    assert nF > 2048
+    r = oracle.project_last_frame(k["Tcw"], k["K4"], g, sf, k["Xw"], last["octave"], 15.0, k["valid"])
+    fxy = np.stack([cur["x"], cur["y"]], 1)
+    for th, ratio, ori, scale_r in ((100, 0.0, True, 1.0), (100, 0.8, False, 2.0)):
+        n_ref, fm_ref = oracle.search_by_projection(g, fxy, cur["octave"], cur["angle"], cur["desc"], r[0], r[1], r[2] * scale_r, r[3], r[4],
+                                                    last["angle"], last["desc"], th, ratio, ori)
+        mm = ob.ORBmatcher(ratio if ratio > 0 else 0.9, ori)
+        nm, fm = mm.SearchByProjection(k["bounds"], fxy[None], cur["octave"][None], cur["angle"][None], cur["desc"][None], np.array([nF], np.int32),
+                                       r[0][None], r[1][None], (r[2] * scale_r)[None], r[3][None], r[4][None], last["angle"][None], last["desc"][None],
+                                       np.array([nQ], np.int32), th, use_ratio=ratio > 0)
+        assert n_ref > 500 and int(nm[0]) == n_ref and np.array_equal(fm[0], fm_ref)
