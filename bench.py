@@ -66,7 +66,7 @@ class ClockSampler:
             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "20"], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
             self.proc = None
@@ -278,7 +278,6 @@ def bench_frontend(args, rank, world):
     barrier()
     wall = time.time() - t_wall
     total_ms = sum(a.elapsed_time(b) for a, b in evs)
-    clocks = sampler.stop()
     launches = sum(it.launches() for it in insts) - l0
     ninl = torch.cat([it.ninl for it in insts]).cpu().numpy()
     nmatch = torch.cat([it.nm for it in insts]).cpu().numpy()
@@ -374,6 +373,7 @@ def bench_frontend(args, rank, world):
     e2e_steps = args.steps if args.steps <= 20 else 20 + (args.steps - 20) % (N_POOL - 1)   # ends on the same pool frame as the device loop
     e2e_s = run_all(e2e_steps)
     barrier()
+    clocks = sampler.stop()                         # sampled over both timed regions (device-resident loop and e2e loop)
     if world > 1:
         tt = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
         torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.MAX)

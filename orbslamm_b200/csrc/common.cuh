@@ -24,21 +24,6 @@ int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
         if (!(cond)) { orbs::set_last_error(msg); return (code); }             \
     } while (0)
 
-// Launch with the highest execution priority of the device (cudaLaunchAttributePriority).  Used for the latency-bound
-// kernels that run one CTA per frame (quad-tree, match resolution, pose LM): when several handles work concurrently, their
-// few CTAs are placed as soon as any CTA of another handle's wide kernel retires instead of queueing behind its whole grid.
-template <typename... KArgs, typename... Args>
-static inline cudaError_t launch_high_priority(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args)
-{
-    static const int prio = []() { int lo = 0, hi = 0; cudaDeviceGetStreamPriorityRange(&lo, &hi); return hi; }();
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributePriority; attr[0].val.priority = prio;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
-}
-
 // growable device buffer
 struct DevBuf {
     void *p = nullptr;

@@ -727,7 +727,7 @@ int orbm_search_by_projection(orbm_handle *h, int n_frames, const float *bounds4
     A.cell_start = h->cell_start.as<int>(); A.cell_items = h->cell_items.as<int>();
     A.prop = h->prop.as<int>(); A.owner = h->owner.as<int>(); A.top = h->top.as<unsigned>(); A.ncand = h->ncand.as<int>();
     A.th_dist = th_dist; A.ratio = ratio; A.check_ori = check_ori ? 1 : 0;
-    ORBS_CUDA(launch_high_priority(k_grid_build, dim3(n_frames), dim3(512), 0, h->stream, f_slab, A.g, A.f_xy, A.f_counts, h->cell_start.as<int>(), h->cell_items.as<int>()));
+    k_grid_build<<<n_frames, 512, 0, h->stream>>>(f_slab, A.g, A.f_xy, A.f_counts, h->cell_start.as<int>(), h->cell_items.as<int>());
     if (f_slab <= 2048) k_search_candidates<true><<<dim3((q_slab + 7) / 8, n_frames), 256, 0, h->stream>>>(A);
     else k_search_candidates<false><<<dim3((q_slab + 7) / 8, n_frames), 256, 0, h->stream>>>(A);
     {
@@ -739,7 +739,7 @@ int orbm_search_by_projection(orbm_handle *h, int n_frames, const float *bounds4
             ORBS_CUDA(cudaFuncSetAttribute(k_search_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             h->resolve_smem = smem;
         }
-        ORBS_CUDA(launch_high_priority(k_search_resolve, dim3(n_frames), dim3(1024), smem, h->stream, A, use_smem));
+        k_search_resolve<<<n_frames, 1024, smem, h->stream>>>(A, use_smem);
     }
     h->launches += 3;
     ORBS_CUDA(cudaGetLastError());

@@ -166,7 +166,7 @@ int orbo_pose_optimization(orbo_handle *h, int n_frames, float *Tcw, const float
     A.outlier = S.inout(outlier, ne, false); A.n_inliers = S.inout(n_inliers, n_frames, false);
     A.err = S.scratch<double>(ne * 2);
     if (S.rc) return S.rc;
-    ORBS_CUDA(launch_high_priority(k_pose_optimization, dim3(n_frames), dim3(kPoseThreads), 0, h->stream, A));
+    k_pose_optimization<<<n_frames, kPoseThreads, 0, h->stream>>>(A);
     h->launches++;
     ORBS_CUDA(cudaGetLastError());
     return S.finish();
@@ -203,8 +203,8 @@ int orbo_pose_optimization_matched(orbo_handle *h, int n_frames, float *Tcw, con
     uint8_t *d_fout = S.inout(f_outlier, nf, false);
     if (S.rc) return S.rc;
     ORBS_CUDA(cudaMemsetAsync(d_fout, 0, nf, h->stream));
-    ORBS_CUDA(launch_high_priority(k_pose_gather, dim3(n_frames), dim3(256), 0, h->stream, G));
-    ORBS_CUDA(launch_high_priority(k_pose_optimization, dim3(n_frames), dim3(kPoseThreads), 0, h->stream, A));
+    k_pose_gather<<<n_frames, 256, 0, h->stream>>>(G);
+    k_pose_optimization<<<n_frames, kPoseThreads, 0, h->stream>>>(A);
     k_pose_scatter<<<dim3((f_slab + 255) / 256, n_frames), 256, 0, h->stream>>>(f_slab, d_nedges, G.edge_feat, d_eout, d_fout);
     h->launches += 3;
     ORBS_CUDA(cudaGetLastError());
