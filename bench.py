@@ -402,17 +402,17 @@ def bench_frontend(args, rank, world):
     per_launch_ms = dom_ms / max(dom_n, 1) * (7 if dom == "resize_level" else 1)
     achieved = alg[dom] * B / (per_launch_ms * 1e-3) / 1e9
     roofline = {"kernel": dom, "bound": "hbm", "achieved": round(achieved, 2), "peak": hbm, "unit": "GB/s", "frac": round(achieved / hbm, 5),
-                "traffic": ncu_traffic("frontend", dom, B), "traffic_source": "profiles/r1g_traffic.json (ncu --set full, 128 frames per launch, scaled to this batch)",
+                "traffic": ncu_traffic("frontend", dom, B) if w == 1241 else None, "traffic_source": "profiles/r1g_traffic.json (ncu --set full, 128 frames per launch, scaled to this batch)",
                 "peak_source": how, "algorithmic_bytes_per_launch": int(alg[dom] * B),
                 "note": "k_fast_cells is bound by the integer ALU pipe (ncu: alu pipe 73 % of peak, DRAM 2 %), not by HBM; frac is reported against the HBM roofline as the contract asks",
                 "avg_launch_ms": round(per_launch_ms, 4),
                 "kernel_share_of_step": {k: round(v[0] / max(prof_ms, 1e-9), 4) for k, v in ktimes.items()},
                 "measured_in": f"single-instance pass over all {B} streams ({prof_steps} steps, {round(prof_ms / prof_steps, 4)} ms/step), CUDA events around every launch"}
 
-    out = {"metric": "ORB extract+match fps @1241x376", "value": round(fps, 1), "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+    out = {"metric": f"ORB extract+match fps @{w}x{h}", "value": round(fps, 1), "unit": "frames/s", "n_gpus": world, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": round(total_ms / args.steps, 4), "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-           "config": {"workload": "KITTI-shape 1241x376 synthetic streams, nFeatures=2000: extract + SearchByProjection(Cur,Last) + PoseOptimization per frame",
+           "config": {"workload": f"{'KITTI' if w == 1241 else 'TUM'}-shape {w}x{h} synthetic streams, nFeatures={CAM['nfeatures']}: extract + SearchByProjection(Cur,Last) + PoseOptimization per frame",
                       "streams_per_gpu": B, "frames_per_step": B * world, "instances_per_gpu": nI, "l2": "256 MiB flush buffer written between timed steps (untimed)",
                       "keypoints_per_frame": nkp, "matches_per_frame": float(np.mean(nmatch)), "pose_inliers_per_frame": float(np.mean(ninl)), "parallelism": f"streams x{world}"},
            "e2e": {"value": round(e2e_fps, 1), "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
@@ -481,12 +481,15 @@ def main():
     ap.add_argument("--instances", type=int, default=1, help="independent extractor/matcher/optimizer triples (own CUDA stream) per GPU in the device-resident leg")
     ap.add_argument("--e2e-workers", type=int, default=4, help="independent front-end instances serving the streams of one GPU in the e2e leg")
     ap.add_argument("--workload", default="frontend", choices=["frontend", "ba"])
+    ap.add_argument("--camera", default="kitti", choices=["kitti", "tum"], help="kitti: 1241x376 / 2000 features (BASELINE.json metric); tum: 640x480 / 1000 features (configs[1])")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-frames", type=int, default=100, help="bounded CPU-baseline sample (frames)")
     ap.add_argument("--ba-kf", type=int, default=500)
     ap.add_argument("--ba-pts", type=int, default=50000)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    global CAM
+    CAM = synth.TUM if args.camera == "tum" else synth.KITTI
     rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1))
 
     if args.impl == "reference":
@@ -497,13 +500,13 @@ def main():
             print(json.dumps(reference_line(args)), flush=True)
             return
         cores = os.cpu_count() or 1
-        per = max(4, args.cpu_frames // cores)
+        per = max(20, args.steps + args.warmup)          # one step = one new frame on every core's stream; >= 20 frames per core
         t0 = time.time()
         fps, wall = cpu_baseline_frontend(cores, per)
-        line = {"impl": "reference", "metric": "ORB extract+match fps @1241x376", "value": round(fps, 2), "unit": "frames/s", "n_gpus": args.gpus,
+        line = {"impl": "reference", "metric": f"ORB extract+match fps @{CAM['w']}x{CAM['h']}", "value": round(fps, 2), "unit": "frames/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 / fps, 3), "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-                "config": {"workload": "KITTI-shape 1241x376 synthetic streams, nFeatures=2000: extract + SearchByProjection(Cur,Last) + PoseOptimization per frame",
+                "config": {"workload": f"{'KITTI' if CAM['w'] == 1241 else 'TUM'}-shape {CAM['w']}x{CAM['h']} synthetic streams, nFeatures={CAM['nfeatures']}: extract + SearchByProjection(Cur,Last) + PoseOptimization per frame",
                            "note": "the reference C++ cannot be built here (needs OpenCV C++/Eigen headers); this is the oracle: cv2 4.13 primitives "
                                    "(FAST/resize/GaussianBlur) + restated reference code, one independent stream per core"},
                 "cpu_baseline": {"value": round(fps, 2), "unit": "frames/s", "cores": cores, "kind": "port",
