@@ -14,10 +14,11 @@ Parity status: the reference repository holds no golden vectors or tests for
 this path.  Extractor: PINNED -- orb_oracle.c equals the reference's
 own ORBextractor.cc compiled unmodified against an OpenCV stand-in (oracle/_ref,
 ref_build.py, tests/test_oracle_vs_reference.py) and its OpenCV primitives equal
-cv2 4.13.0 bit for bit.  Matcher / optimizer: ORBmatcher.cc and Optimizer.cc cannot be
-compiled here (data model -> DBoW2 / g2o -> Eigen headers absent); the optimizer oracle
-is pinned against an independent numpy/scipy twin, beyond that "parity unpinned" by
-the reference.
+cv2 4.13.0 bit for bit.  Matcher: PINNED -- slam_oracle.c's search equals the reference's
+own ORBmatcher.cc compiled unmodified against a stand-in data model (oracle/slamshim,
+oracle/_ref/libref_orbmatcher.so).  Optimizer: Optimizer.cc + g2o cannot be compiled here
+(Eigen headers absent); the oracle is pinned against an independent numpy/scipy twin,
+beyond that "parity unpinned" by the reference.
 """
 import ctypes
 import os

@@ -82,3 +82,67 @@ class RefORBextractor:
         out = np.zeros((h.value, w.value), np.uint8)
         self.L.ref_orbx_pyramid_level(self.h, level, ctypes.byref(w), ctypes.byref(h), out.ctypes.data, w.value)
         return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the reference's own ORBmatcher.cc (oracle/_ref/libref_orbmatcher.so, built by the same Makefile against oracle/slamshim)
+_SOM = os.path.join(_HERE, "_ref", "libref_orbmatcher.so")
+_LIBM = None
+
+
+def matcher_available():
+    return os.path.exists(_SOM)
+
+
+def matcher_lib():
+    global _LIBM
+    if _LIBM is None:
+        L = ctypes.CDLL(_SOM)
+        f, i, vp = ctypes.c_float, ctypes.c_int, ctypes.c_void_p
+        L.ref_orbm_set_camera.argtypes = [f] * 8
+        L.ref_orbm_descriptor_distance.argtypes = [vp, vp]
+        L.ref_orbm_search_last_frame.argtypes = [f, i, f, vp, vp, i, i, vp, vp, vp, vp, i, vp, vp, vp, vp, vp, vp]
+        L.ref_orbm_search_local_points.argtypes = [f, f, vp, i, i, vp, vp, vp, vp, vp, i, vp, vp, vp, vp, vp, vp]
+        _LIBM = L
+    return _LIBM
+
+
+def _c(a, dt):
+    return np.ascontiguousarray(a, dt)
+
+
+def ref_descriptor_distance(a, b):
+    """ORBmatcher::DescriptorDistance (ORBmatcher.cc:1649-1665), reference object code."""
+    a = _c(a, np.uint8); b = _c(b, np.uint8)
+    return matcher_lib().ref_orbm_descriptor_distance(a.ctypes.data, b.ctypes.data)
+
+
+def ref_search_last_frame(K4, bounds4, Tcw, scale_factors, cur, last, Xw, valid, th=15.0, nnratio=0.9, check_ori=True):
+    """ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th, bMono=true) (ORBmatcher.cc:1330-1472), reference object code.
+    cur / last: dicts x, y, octave, angle, desc.  Returns (nmatches, feat_match[N] = last-frame slot or -1)."""
+    L = matcher_lib()
+    L.ref_orbm_set_camera(*[float(v) for v in K4], float(bounds4[0]), float(bounds4[1]), float(bounds4[2]), float(bounds4[3]))
+    T = _c(Tcw, np.float32).reshape(16); sf = _c(scale_factors, np.float32)
+    fxy = _c(np.stack([cur["x"], cur["y"]], 1), np.float32); N = len(fxy); M = len(last["x"])
+    fo = _c(cur["octave"], np.int32); fa = _c(cur["angle"], np.float32); fd = _c(cur["desc"], np.uint8)
+    v = _c(valid, np.uint8); X = _c(Xw, np.float32); lo = _c(last["octave"], np.int32); la = _c(last["angle"], np.float32); ld = _c(last["desc"], np.uint8)
+    fm = np.full(N, -1, np.int32)
+    n = L.ref_orbm_search_last_frame(float(nnratio), int(bool(check_ori)), float(th), T.ctypes.data, sf.ctypes.data, len(sf), N, fxy.ctypes.data, fo.ctypes.data,
+                                     fa.ctypes.data, fd.ctypes.data, M, v.ctypes.data, X.ctypes.data, lo.ctypes.data, la.ctypes.data, ld.ctypes.data, fm.ctypes.data)
+    return n, fm
+
+
+def ref_search_local_points(K4, bounds4, scale_factors, cur, in_view, proj_xy, level, view_cos, q_desc, th=1.0, nnratio=0.8, held=None):
+    """ORBmatcher::SearchByProjection(F, vpMapPoints, th) (ORBmatcher.cc:45-129), reference object code.
+    Returns (nmatches, feat_match[N] = map point index, -1 = free, -2 = feature that already held a map point)."""
+    L = matcher_lib()
+    L.ref_orbm_set_camera(*[float(v) for v in K4], float(bounds4[0]), float(bounds4[1]), float(bounds4[2]), float(bounds4[3]))
+    sf = _c(scale_factors, np.float32)
+    fxy = _c(np.stack([cur["x"], cur["y"]], 1), np.float32); N = len(fxy); M = len(in_view)
+    fo = _c(cur["octave"], np.int32); fa = _c(cur["angle"], np.float32); fd = _c(cur["desc"], np.uint8)
+    hv = _c(held if held is not None else np.zeros(N, np.uint8), np.uint8)
+    iv = _c(in_view, np.uint8); uv = _c(proj_xy, np.float32); lv = _c(level, np.int32); vc = _c(view_cos, np.float32); qd = _c(q_desc, np.uint8)
+    fm = np.full(N, -1, np.int32)
+    n = L.ref_orbm_search_local_points(float(nnratio), float(th), sf.ctypes.data, len(sf), N, fxy.ctypes.data, fo.ctypes.data, fa.ctypes.data, fd.ctypes.data,
+                                       hv.ctypes.data, M, iv.ctypes.data, uv.ctypes.data, lv.ctypes.data, vc.ctypes.data, qd.ctypes.data, fm.ctypes.data)
+    return n, fm

@@ -124,3 +124,24 @@ def test_search_by_projection_4000_features(lib):
                                        r[0][None], r[1][None], (r[2] * scale_r)[None], r[3][None], r[4][None], last["angle"][None], last["desc"][None],
                                        np.array([nQ], np.int32), th, use_ratio=ratio > 0)
         assert n_ref > 500 and int(nm[0]) == n_ref and np.array_equal(fm[0], fm_ref)
+
+
+def test_search_matches_reference_object_code(lib):
+    """CUDA projection search vs the reference's own ORBmatcher.cc object code (oracle/_ref/libref_orbmatcher.so, prebuilt; see
+    tests/test_oracle_vs_reference.py for what is and is not the reference's code in that library)."""
+    from oracle import ref_build
+    if not ref_build.matcher_available():
+        pytest.skip("oracle/_ref matcher not built")
+    import orbslamm_b200 as ob
+    k = make_tracking_case(synth.KITTI, 6)
+    sf = np.array(list(k["P"].scale)[:8], np.float32)
+    cur, last = k["cur"], k["last"]
+    nF, nQ = len(cur["x"]), len(last["x"])
+    m = ob.ORBmatcher(0.9, True)
+    qv, uv, rad, mn, mx = m.project_last_frame(k["Tcw"][None], k["K4"], k["bounds"], sf, k["Xw"][None], last["octave"][None], np.array([nQ], np.int32), 15.0,
+                                               k["valid"][None])
+    fxy = np.stack([cur["x"], cur["y"]], 1)
+    nm, fm = m.SearchByProjection(k["bounds"], fxy[None], cur["octave"][None], cur["angle"][None], cur["desc"][None], np.array([nF], np.int32), qv, uv, rad, mn, mx,
+                                  last["angle"][None], last["desc"][None], np.array([nQ], np.int32), 100)
+    n_r, fm_r = ref_build.ref_search_last_frame(k["K4"], k["bounds"], k["Tcw"], sf, cur, last, k["Xw"], k["valid"], 15.0, 0.9, True)
+    assert int(nm[0]) == n_r and n_r > 500 and np.array_equal(fm[0], fm_r)

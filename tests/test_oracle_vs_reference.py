@@ -80,3 +80,58 @@ def test_reference_is_allocator_dependent_only_in_tie_breaks():
         assert a["angle"][i] == b["angle"][j] and a["response"][i] == b["response"][j] and np.array_equal(a["desc"][i], b["desc"][j])
     for l in range(8):
         assert abs(int((a["octave"] == l).sum()) - int((b["octave"] == l).sum())) <= 3
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Matcher: oracle/_ref/libref_orbmatcher.so is /root/reference/SingleRobotScenario/src/ORBmatcher.cc compiled unmodified against the
+# stand-in data model oracle/slamshim (Frame / KeyFrame / MapPoint / cv::Mat with the member names the file uses).  The search loops,
+# TH_HIGH / ratio / level rules, the rotation histogram, ComputeThreeMaxima and DescriptorDistance run as the reference's object code;
+# Frame::GetFeaturesInArea and the cv::Mat algebra are the shim's (restated from Frame.cc:327-392, pinned against cv2.gemm).
+import sys
+import os
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from helpers import make_tracking_case  # noqa: E402
+
+needs_matcher = pytest.mark.skipif(not ref_build.matcher_available(), reason="oracle/_ref matcher not built (needs /root/reference)")
+
+
+@needs_matcher
+@pytest.mark.parametrize("cam,sid,nf", [("TUM", 1, None), ("KITTI", 2, None), ("KITTI", 9, 4000), ("TUM", 4, 300)])
+def test_matcher_oracle_equals_reference_object_code(cam, sid, nf):
+    k = make_tracking_case(getattr(synth, cam), sid, nfeatures=nf)
+    sf = np.array(list(k["P"].scale)[:8], np.float32)
+    g = oracle.grid_params(*k["bounds"])
+    cur, last = k["cur"], k["last"]
+    r = oracle.project_last_frame(k["Tcw"], k["K4"], g, sf, k["Xw"], last["octave"], 15.0, k["valid"])
+    fxy = np.stack([cur["x"], cur["y"]], 1)
+    # SearchByProjection(CurrentFrame, LastFrame, th = 15, mono), with and without the orientation check (ORBmatcher.cc:1330-1472)
+    for ori in (True, False):
+        n_o, fm_o = oracle.search_by_projection(g, fxy, cur["octave"], cur["angle"], cur["desc"], r[0], r[1], r[2], r[3], r[4], last["angle"], last["desc"],
+                                                100, 0.0, ori)
+        n_r, fm_r = ref_build.ref_search_last_frame(k["K4"], k["bounds"], k["Tcw"], sf, cur, last, k["Xw"], k["valid"], 15.0, 0.9, ori)
+        assert n_o == n_r and n_r > 50 and np.array_equal(fm_o, fm_r)
+    # SearchByProjection(F, vpMapPoints, th) (ORBmatcher.cc:45-129): predicted levels, both RadiusByViewingCos branches, features
+    # that already hold a map point, th == 1 (no factor) and th == 3
+    rng = np.random.default_rng(5)
+    iv = r[0].copy(); uv = r[1]
+    lv = np.clip(last["octave"] + rng.integers(-1, 2, len(iv)), 0, 7).astype(np.int32)
+    vc = np.where(rng.random(len(iv)) < 0.5, 0.9995, 0.99).astype(np.float32)
+    held = (rng.random(len(cur["x"])) < 0.1).astype(np.uint8)
+    for th in (1.0, 3.0):
+        rad = np.where(vc > 0.998, np.float32(2.5), np.float32(4.0)).astype(np.float32)
+        if th != 1.0:
+            rad = rad * np.float32(th)
+        rad = rad * sf[lv]
+        fm_in = np.where(held > 0, 10 ** 6, -1).astype(np.int32)
+        n_o, fm_o = oracle.search_by_projection(g, fxy, cur["octave"], cur["angle"], cur["desc"], iv, uv, rad, lv - 1, lv, last["angle"], last["desc"],
+                                                100, 0.8, False, fm_in)
+        n_r, fm_r = ref_build.ref_search_local_points(k["K4"], k["bounds"], sf, cur, iv, uv, lv, vc, last["desc"], th, 0.8, held)
+        assert n_o == n_r and n_r > 30 and np.array_equal(np.where(fm_o == 10 ** 6, -2, fm_o), fm_r)
+
+
+@needs_matcher
+def test_descriptor_distance_equals_reference_object_code():
+    rng = np.random.default_rng(2)
+    for _ in range(200):
+        a = rng.integers(0, 256, 32, dtype=np.uint8); b = rng.integers(0, 256, 32, dtype=np.uint8)
+        assert ref_build.ref_descriptor_distance(a, b) == oracle.descriptor_distance(a, b) == int(np.unpackbits(a ^ b).sum())
