@@ -34,9 +34,9 @@ N_POOL = 5              # distinct frames per stream (steps cycle over frame pai
 
 
 def ncu_traffic(group, kernel, scale_to=None):
-    """dram__bytes_read + dram__bytes_write of one launch from the committed ncu capture (profiles/r1g_traffic.json), scaled
+    """dram__bytes_read + dram__bytes_write of one launch from the committed ncu capture (profiles/r1h_traffic.json), scaled
     linearly to this run's frames per launch; None when the capture has no such kernel."""
-    p = os.path.join(ROOT, "profiles", "r1g_traffic.json")
+    p = os.path.join(ROOT, "profiles", "r1h_traffic.json")
     try:
         d = json.load(open(p))[group]
         v = d["kernels"][kernel][0]["dram_bytes"]
@@ -402,7 +402,7 @@ def bench_frontend(args, rank, world):
     per_launch_ms = dom_ms / max(dom_n, 1) * (7 if dom == "resize_level" else 1)
     achieved = alg[dom] * B / (per_launch_ms * 1e-3) / 1e9
     roofline = {"kernel": dom, "bound": "hbm", "achieved": round(achieved, 2), "peak": hbm, "unit": "GB/s", "frac": round(achieved / hbm, 5),
-                "traffic": ncu_traffic("frontend", dom, B) if w == 1241 else None, "traffic_source": "profiles/r1g_traffic.json (ncu --set full, 128 frames per launch, scaled to this batch)",
+                "traffic": ncu_traffic("frontend", dom, B) if w == 1241 else None, "traffic_source": "profiles/r1h_traffic.json (ncu --set full, 128 frames per launch, scaled to this batch)",
                 "peak_source": how, "algorithmic_bytes_per_launch": int(alg[dom] * B),
                 "note": "k_fast_cells is bound by the integer ALU pipe (ncu: alu pipe 73 % of peak, DRAM 2 %), not by HBM; frac is reported against the HBM roofline as the contract asks",
                 "avg_launch_ms": round(per_launch_ms, 4),

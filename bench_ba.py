@@ -96,7 +96,7 @@ def bench_ba(args, rank, world):
     roofline = {"kernel": dom, "bound": "hbm", "achieved": round(achieved, 2), "peak": hbm, "unit": "GB/s", "frac": round(achieved / hbm, 5),
                 "traffic": None, "peak_source": how, "algorithmic_bytes_per_launch": int(alg_bytes), "avg_launch_ms": round(per_launch_ms, 5),
                 "note": "the factorisation is a chain of dependent 64x64 fp64 tile steps (latency-bound: ncu shows fp64 pipe 8 % and DRAM < 1 % in k_chol_panel); "
-                        "per-kernel DRAM traffic of one capture is in profiles/r1g_traffic.json",
+                        "per-kernel DRAM traffic of one capture is in profiles/r1h_traffic.json",
                 "launch": "one timed region = one factorisation / one pair of triangular solves (several dependent kernel launches)" if dom in ("chol_factor", "tri_solves") else "one kernel launch",
                 "kernel_share_of_step": {k: round(v[0] / max(lm_total_ms, 1e-9), 4) for k, v in ktimes.items()},
                 "whole_iteration": {"algorithmic_bytes": int(_alg_bytes(K, P, E, ld)),

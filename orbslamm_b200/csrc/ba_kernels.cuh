@@ -471,10 +471,11 @@ k_chol_update(double *__restrict__ S, int ld, const int4 *__restrict__ tasks)
             }
 }
 
-// Triangular solves as two dataflow kernels (one CTA per tile row, all co-resident; forward dependencies point to lower tile
-// indices, backward ones to higher indices, and CTAs are numbered accordingly, so in-order block scheduling cannot deadlock):
-//   forward  (dir = 0): CTA i waits for y_k, k in cols(i), accumulates L_ik y_k, then y_i = Linv_ii (b_i - acc)
-//   backward (dir = 1): CTA b handles tile j = nt-1-b, waits for x_i, i in rows(j) (descending), accumulates L_ij^T x_i, then
+// Triangular solves as two dataflow kernels.  CTA b handles the tile rows b, b + G, b + 2G, ... (G = gridDim.x <= the number of
+// co-resident CTAs) in solve order; a row only waits for rows that come earlier in that order, and every CTA walks its rows in
+// that order, so the wait graph is acyclic for any number of tile rows.
+//   forward  (dir = 0): row i waits for y_k, k in cols(i), accumulates L_ik y_k, then y_i = Linv_ii (b_i - acc)
+//   backward (dir = 1): row j (visited in descending order) waits for x_i, i in rows(j), accumulates L_ij^T x_i, then
 //                       x_j = Linv_jj^T (y_j - acc)
 // v is solved in place; ready[] must be zero on entry.
 __global__ void __launch_bounds__(256)
@@ -484,46 +485,48 @@ k_chol_solve(const double *__restrict__ S, int ld, int nt, const CholPlan plan, 
     __shared__ double s_part[4][NB];
     __shared__ double s_acc[NB];
     const int tid = threadIdx.x, lane64 = tid & 63, part = tid >> 6;
-    const int me = dir == 0 ? blockIdx.x : nt - 1 - blockIdx.x;
-    if (tid < NB) s_acc[tid] = 0.0;
-    __syncthreads();
-    const int p0 = dir == 0 ? plan.cols_start[me] : plan.rows_start[me], p1 = dir == 0 ? plan.cols_start[me + 1] : plan.rows_start[me + 1];
-    for (int s = 0; s < p1 - p0; s++) {
-        const int o = dir == 0 ? plan.cols[p0 + s] : plan.rows[p1 - 1 - s];     // the tile whose solution we consume
-        if (tid == 0) { while (*((volatile int *)&ready[o]) == 0) { } __threadfence(); }
+    for (int ord = blockIdx.x; ord < nt; ord += gridDim.x) {
+        const int me = dir == 0 ? ord : nt - 1 - ord;
+        if (tid < NB) s_acc[tid] = 0.0;
         __syncthreads();
-        if (tid < NB) s_vec[tid] = *((volatile double *)&v[o * NB + tid]);
-        __syncthreads();
-        double sum = 0;
-        if (dir == 0) {
-            // acc[r] += sum_c L[me*64 + r][o*64 + c] * y_o[c]; thread (r = lane64, quarter = part)
-            const double *row = S + (size_t)(me * NB + lane64) * ld + o * NB + part * 16;
+        const int p0 = dir == 0 ? plan.cols_start[me] : plan.rows_start[me], p1 = dir == 0 ? plan.cols_start[me + 1] : plan.rows_start[me + 1];
+        for (int s = 0; s < p1 - p0; s++) {
+            const int o = dir == 0 ? plan.cols[p0 + s] : plan.rows[p1 - 1 - s];     // the tile whose solution we consume
+            if (tid == 0) { while (*((volatile int *)&ready[o]) == 0) { } __threadfence(); }
+            __syncthreads();
+            if (tid < NB) s_vec[tid] = *((volatile double *)&v[o * NB + tid]);
+            __syncthreads();
+            double sum = 0;
+            if (dir == 0) {
+                // acc[r] += sum_c L[me*64 + r][o*64 + c] * y_o[c]; thread (r = lane64, quarter = part)
+                const double *row = S + (size_t)(me * NB + lane64) * ld + o * NB + part * 16;
 #pragma unroll
-            for (int c = 0; c < 16; c++) sum = fma(row[c], s_vec[part * 16 + c], sum);
-        } else {
-            // acc[c] += sum_r L[o*64 + r][me*64 + c] * x_o[r]; thread (c = lane64, quarter = part)
-            const double *col = S + (size_t)(o * NB + part * 16) * ld + me * NB + lane64;
+                for (int c = 0; c < 16; c++) sum = fma(row[c], s_vec[part * 16 + c], sum);
+            } else {
+                // acc[c] += sum_r L[o*64 + r][me*64 + c] * x_o[r]; thread (c = lane64, quarter = part)
+                const double *col = S + (size_t)(o * NB + part * 16) * ld + me * NB + lane64;
 #pragma unroll
-            for (int r = 0; r < 16; r++) sum = fma(col[(size_t)r * ld], s_vec[part * 16 + r], sum);
+                for (int r = 0; r < 16; r++) sum = fma(col[(size_t)r * ld], s_vec[part * 16 + r], sum);
+            }
+            s_part[part][lane64] = sum;
+            __syncthreads();
+            if (tid < NB) s_acc[tid] += s_part[0][tid] + s_part[1][tid] + s_part[2][tid] + s_part[3][tid];
+            __syncthreads();
         }
+        // diagonal tile through its explicit inverse
+        if (tid < NB) s_vec[tid] = v[me * NB + tid] - s_acc[tid];
+        __syncthreads();
+        const double *Li = Linv + (size_t)me * NB * NB;
+        double sum = 0;
+        if (dir == 0) { for (int c = part * 16; c < part * 16 + 16; c++) sum = fma(Li[lane64 * NB + c], s_vec[c], sum); }     // y = Linv r
+        else { for (int r = part * 16; r < part * 16 + 16; r++) sum = fma(Li[r * NB + lane64], s_vec[r], sum); }               // x = Linv^T r
         s_part[part][lane64] = sum;
         __syncthreads();
-        if (tid < NB) s_acc[tid] += s_part[0][tid] + s_part[1][tid] + s_part[2][tid] + s_part[3][tid];
+        if (tid < NB) v[me * NB + tid] = s_part[0][tid] + s_part[1][tid] + s_part[2][tid] + s_part[3][tid];
+        __threadfence();
         __syncthreads();
+        if (tid == 0) { *((volatile int *)&ready[me]) = 1; }
     }
-    // diagonal tile through its explicit inverse
-    if (tid < NB) s_vec[tid] = v[me * NB + tid] - s_acc[tid];
-    __syncthreads();
-    const double *Li = Linv + (size_t)me * NB * NB;
-    double sum = 0;
-    if (dir == 0) { for (int c = part * 16; c < part * 16 + 16; c++) sum = fma(Li[lane64 * NB + c], s_vec[c], sum); }     // y = Linv r
-    else { for (int r = part * 16; r < part * 16 + 16; r++) sum = fma(Li[r * NB + lane64], s_vec[r], sum); }               // x = Linv^T r
-    s_part[part][lane64] = sum;
-    __syncthreads();
-    if (tid < NB) v[me * NB + tid] = s_part[0][tid] + s_part[1][tid] + s_part[2][tid] + s_part[3][tid];
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) { *((volatile int *)&ready[me]) = 1; }
 }
 
 // copy the pose part of the solution; pose part of computeScale

@@ -59,6 +59,7 @@ struct orbo_handle {
     std::mutex mu;
     StagePool pool;          // pose optimisation staging
     StagePool ba_pool;       // bundle adjustment buffers
+    DevBuf ba_tasks;         // panel / update task lists of the tiled Cholesky (sized by the symbolic factorisation)
     PinnedBuf h_scalars;
     KernelTimer timer;       // BA kernels, ids = BaK
     ncclComm_t comm = nullptr;   // set by orbo_comm_init: orbo_bundle_adjust becomes a collective over map-point shards
@@ -94,7 +95,7 @@ int orbo_destroy(orbo_handle *h)
     if (h->stream && h->own_stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
     else cudaDeviceSynchronize();
     if (h->comm) { if (g_nccl.CommAbort) g_nccl.CommAbort(h->comm); else g_nccl.CommDestroy(h->comm); }   // abort: never block on a peer at teardown
-    h->pool.release(); h->ba_pool.release(); h->h_scalars.release(); h->timer.release();
+    h->pool.release(); h->ba_pool.release(); h->ba_tasks.release(); h->h_scalars.release(); h->timer.release();
     delete h;
     return ORBS_OK;
 }
@@ -235,7 +236,6 @@ struct BaHost {
     int nt_max = 0;
     int *d_plan_i = nullptr;      // rows_start, rows, cols_start, cols  [2 (nt_max + 1) + nt_max (nt_max - 1)]
     int4 *d_tasks = nullptr;      // panel tasks then update tasks
-    size_t task_cap = 0;
     int *d_rowbase = nullptr; uint8_t *d_rowpad = nullptr;
     std::vector<int> panel_lv, update_lv;   // per level: first task index (size nlevels + 1)
     int nlevels = 0;
@@ -312,7 +312,9 @@ struct BaHost {
             panel_lv[l + 1] = (int)panel.size(); update_lv[l + 1] = (int)update.size();
         }
         n_panel = panel.size();
-        if (panel.size() + update.size() > task_cap) { set_last_error("internal: Cholesky task list exceeds its capacity"); return ORBS_E_INVALID; }
+        if (panel.size() + update.size() > ((size_t)1 << 26)) { set_last_error("reduced pose system too large / too dense for the tiled Cholesky (more than 2^26 tile tasks)"); return ORBS_E_INVALID; }
+        if (int rc = h->ba_tasks.reserve((panel.size() + update.size() + 1) * sizeof(int4))) return rc;
+        d_tasks = h->ba_tasks.as<int4>();
         // row map
         std::vector<int> rowbase(std::max(nA, 1));
         std::vector<uint8_t> rowpad((size_t)nt * NB, 1);
@@ -433,8 +435,9 @@ struct BaHost {
             T().end(st);
             T().begin(BK_TRS, st);
             ORBS_CUDA(cudaMemsetAsync(ready, 0, 2 * (size_t)ntiles * sizeof(int), st));
-            k_chol_solve<<<ntiles, 256, 0, st>>>(B.S, ld, ntiles, plan, Linv, B.bs, ready, 0);
-            k_chol_solve<<<ntiles, 256, 0, st>>>(B.S, ld, ntiles, plan, Linv, B.bs, ready + ntiles, 1);
+            const int solve_ctas = std::min(ntiles, 128);          // all co-resident (one 256-thread CTA per SM at most)
+            k_chol_solve<<<solve_ctas, 256, 0, st>>>(B.S, ld, ntiles, plan, Linv, B.bs, ready, 0);
+            k_chol_solve<<<solve_ctas, 256, 0, st>>>(B.S, ld, ntiles, plan, Linv, B.bs, ready + ntiles, 1);
             count(2);
             T().end(st);
             k_ba_take_xp<<<xp_blocks, 256, 0, st>>>(B, lambda, h->rank == 0 ? 1 : 0);
@@ -593,11 +596,9 @@ extern "C" int orbo_bundle_adjust(orbo_handle *h, int K, float *poses, const uin
     D.Linv = S.scratch<double>((size_t)ld_max * NB); D.ready = S.scratch<int>(2 * (size_t)(ld_max / NB) + 2);
     D.nt_max = ld_max / NB;
     D.d_plan_i = S.scratch<int>(2 * (size_t)(D.nt_max + 1) + (size_t)D.nt_max * D.nt_max + 8);
-    D.task_cap = (size_t)D.nt_max * (D.nt_max + 1) / 2 + (size_t)D.nt_max * (D.nt_max + 1) * (D.nt_max + 2) / 6 + 8;
-    D.d_tasks = S.scratch<int4>(D.task_cap);
     D.d_rowbase = S.scratch<int>(K + 1); D.d_rowpad = S.scratch<uint8_t>(ld_max + 16);
     int *d_adj = S.scratch<int>((size_t)D.nt_max * D.nt_max + 4);
-    ORBS_REQUIRE(ld_max / NB <= 140, ORBS_E_INVALID, "more than 1400 keyframes: the dataflow triangular solve needs all tile rows co-resident");
+    ORBS_REQUIRE(ld_max / NB <= 1024, ORBS_E_INVALID, "more than 10240 keyframes in one bundle adjustment");
     const int max_blocks = std::max({(E + 255) / 256, (P + 7) / 8, (K + P + 255) / 256, (6 * K + 255) / 256}) + 1;
     B.partial = S.scratch<double>(max_blocks); B.scalars = S.scratch<double>(8); B.flags = S.scratch<int>(4);
     double *d_chi2 = S.scratch<double>(E); uint8_t *d_depth = S.scratch<uint8_t>(E);

@@ -82,6 +82,33 @@ def test_local_ba_sparse_tiles(lib):
     assert _rel(got["poses"], ref["poses"]) < RTOL and _rel(got["points"], ref["points"]) < RTOL
 
 
+def test_local_ba_full_size(lib):
+    """BASELINE.json's BA configuration (500 keyframes / 50 000 points / ~292 k observations) against the oracle directly."""
+    import orbslamm_b200 as ob
+    g = synth.ba_graph(K=500, P=50000, seed=42)
+    opt = ob.Optimizer()
+    got = opt.LocalBundleAdjustment(g["poses"], g["fixed"], g["intr"], g["points"], g["kf"], g["pt"], g["uv"], g["inv_sigma2"])
+    ref = oracle.bundle_adjust(g["poses"], g["fixed"], g["intr"], g["points"], g["kf"], g["pt"], g["uv"], g["inv_sigma2"], True, 5, 10, True)
+    assert got["lm_iterations"] == ref["lm_iterations"] == 15 and got["lm_trials"] == ref["lm_trials"] and got["chol_failures"] == 0
+    assert _rel(got["poses"], ref["poses"]) < RTOL and _rel(got["points"], ref["points"]) < RTOL
+    near = np.abs(ref["chi2"] - 5.991) < 1e-6
+    assert np.array_equal(got["outlier"][~near], ref["outlier"][~near])
+    tm = opt.last_ba_timing()
+    assert tm["tile_rows"] == 50 and tm["levels"] <= 12
+
+
+def test_local_ba_many_keyframes(lib):
+    """1500 keyframes = 150 tile rows: more rows than co-resident CTAs of the dataflow triangular solves (each CTA walks several rows)."""
+    import orbslamm_b200 as ob
+    g = synth.ba_graph(K=1500, P=60000, seed=11)
+    opt = ob.Optimizer()
+    got = opt.LocalBundleAdjustment(g["poses"], g["fixed"], g["intr"], g["points"], g["kf"], g["pt"], g["uv"], g["inv_sigma2"])
+    ref = oracle.bundle_adjust(g["poses"], g["fixed"], g["intr"], g["points"], g["kf"], g["pt"], g["uv"], g["inv_sigma2"], True, 5, 10, True)
+    assert got["lm_iterations"] == ref["lm_iterations"] and got["lm_trials"] == ref["lm_trials"] and got["chol_failures"] == 0
+    assert _rel(got["poses"], ref["poses"]) < RTOL and _rel(got["points"], ref["points"]) < RTOL
+    assert opt.last_ba_timing()["tile_rows"] == 150
+
+
 def test_local_ba_shuffled_keyframes_is_dense(lib):
     """Keyframes renumbered at random (loop-closure-like coupling): no separator exists, the tile pattern is (almost) the full lower triangle and
     the same kernels run the dense tiled factorisation; result == oracle and == the unshuffled problem."""
