@@ -67,7 +67,7 @@ k_resize_level(const uint8_t *__restrict__ src, int sw, int sh, int spitch, size
 //   0. the cell's sub-image (plus one pixel to its left) is fetched by the TMA engine: one 16-byte aligned bulk copy per image
 //      row (cp.async.bulk.shared.global -> UBLKCP), all completing on one mbarrier; no thread touches global pixels.
 //      (Tensor-map box loads, cp.async.bulk.tensor / UTMALDG, raise "illegal instruction" on the target boxes even for the
-//      CUDA programming guide's own example -- scratch/tma_ref.cu -- so the descriptor-free bulk form is used.)
+//      CUDA programming guide's own example -- tools/tma_probe/tensor_map_load.cu -- so the descriptor-free bulk form is used.)
 //   1. bytes are widened to one pixel per 16-bit lane (pix16), so that ring pixel pairs are 32-bit words (even dx) or one PRMT
 //      of two words (odd dx);
 //   2. every thread scores 4 adjacent pixels per step from 21 64-bit shared loads;
