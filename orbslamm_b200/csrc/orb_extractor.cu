@@ -63,11 +63,71 @@ struct orbx_handle {
     size_t last_frame0 = 0;
     long long launches = 0;
     KernelTimer timer;   // ids: 0 resize, 1 fast_cells, 2 blur7, 3 octree, 4 orient_describe
+    // TMA descriptors: one (x, y, frame) u8 tensor map per pyramid level and consumer (the box size is part of the descriptor)
+    LevelTmaps tmaps_fast, tmaps_blur;
+    unsigned tmap_levels = 0;            // bit l: level l has valid tensor maps
+    const void *tmap_pyr_base = nullptr; int tmap_pyr_frames = 0;
+    const void *tmap_img0 = nullptr; int tmap_img0_pitch = 0, tmap_img0_frames = 0; size_t tmap_img0_frame = 0;
     std::mutex mu;
 };
 
+// cuTensorMapEncodeTiled through the runtime (no -lcuda): u8 tensor (x, y, frame), box (box_w, box_h, 1), no swizzle, zero fill
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn()
+{
+    static EncodeTiledFn fn = []() -> EncodeTiledFn {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) return nullptr;
+        return (EncodeTiledFn)p;
+    }();
+    return fn;
+}
+
+static bool encode_level_map(CUtensorMap *m, const void *base, int w, int h, size_t pitch, size_t frame_bytes, int nframes, int box_w, int box_h)
+{
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn || ((uintptr_t)base & 15) || (pitch & 15) || (frame_bytes & 15) || nframes <= 0 || box_w > 256 || box_h > 256 || (box_w & 15) || box_w <= 0 || box_h <= 0) return false;
+    const cuuint64_t dims[3] = {(cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)nframes};
+    const cuuint64_t strides[2] = {(cuuint64_t)pitch, (cuuint64_t)frame_bytes};
+    const cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 1u};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    return fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+constexpr int kBlurBoxW = 112, kBlurBoxH = kBlurTH + 6;      // blur tile box: 16-byte left margin + 96 columns, 38 rows
+
+// (re)encode the maps whose buffers changed: levels >= 1 live in d_pyr (batch_cap frames), level 0 is the caller's / staged image batch
+static void refresh_tmaps(orbx_handle *h, const uint8_t *d_img0_all, int pitch0, size_t frame0, int n_frames_total)
+{
+    const ExtractPlan &P = h->plan;
+    if (h->tmap_pyr_base != h->d_pyr.p || h->tmap_pyr_frames != h->batch_cap) {
+        h->tmap_levels &= 1u;
+        for (int l = 1; l < P.nlevels; l++) {
+            const LevelPlan &L = P.lv[l];
+            const uint8_t *base = h->d_pyr.as<uint8_t>() + L.pyr_off;
+            if (L.cell_count > 0 && encode_level_map(&h->tmaps_fast.m[l], base, L.w, L.h, L.pitch, P.pyr_frame_bytes, h->batch_cap, L.fast_box_w, L.fast_box_h) &&
+                encode_level_map(&h->tmaps_blur.m[l], base, L.w, L.h, L.pitch, P.pyr_frame_bytes, h->batch_cap, kBlurBoxW, kBlurBoxH))
+                h->tmap_levels |= 1u << l;
+        }
+        h->tmap_pyr_base = h->d_pyr.p; h->tmap_pyr_frames = h->batch_cap;
+    }
+    if (h->tmap_img0 != d_img0_all || h->tmap_img0_pitch != pitch0 || h->tmap_img0_frame != frame0 || h->tmap_img0_frames != n_frames_total) {
+        const LevelPlan &L = P.lv[0];
+        h->tmap_levels &= ~1u;
+        const size_t fb = n_frames_total > 1 ? frame0 : align_up((size_t)pitch0 * L.h, 16);
+        if (L.cell_count > 0 && pitch0 >= (int)align_up(L.w, 16) && encode_level_map(&h->tmaps_fast.m[0], d_img0_all, L.w, L.h, (size_t)pitch0, fb, n_frames_total, L.fast_box_w, L.fast_box_h) &&
+            encode_level_map(&h->tmaps_blur.m[0], d_img0_all, L.w, L.h, (size_t)pitch0, fb, n_frames_total, kBlurBoxW, kBlurBoxH))
+            h->tmap_levels |= 1u;
+        h->tmap_img0 = d_img0_all; h->tmap_img0_pitch = pitch0; h->tmap_img0_frame = frame0; h->tmap_img0_frames = n_frames_total;
+    }
+}
+
 static int build_plan(orbx_handle *h, int width, int height)
 {
+    h->tmap_pyr_base = nullptr; h->tmap_img0 = nullptr; h->tmap_levels = 0;
 
     ExtractPlan &P = h->plan;
     memset(&P, 0, sizeof P);
@@ -124,6 +184,14 @@ static int build_plan(orbx_handle *h, int width, int height)
             }
         }
         L.cell_count = (int)cells.size() - L.cell_first;
+        {   // TMA box of this level's FAST cells: widest 16-byte aligned row span x tallest cell
+            int mw = 16, mh = 1;
+            for (int c = L.cell_first; c < (int)cells.size(); c++) {
+                const int xa = (cells[c].x0 - 1) & ~15;
+                mw = std::max(mw, (int)align_up((size_t)(cells[c].x0 - 1 - xa) + cells[c].cw + 1, 16)); mh = std::max(mh, (int)cells[c].ch);
+            }
+            L.fast_box_w = mw; L.fast_box_h = mh;
+        }
         // quad-tree roots (ORBextractor.cc:542-545)
         if (L.cell_count > 0) {
             L.n_ini = (int)roundf((float)L.bw / (float)L.bh);
@@ -267,7 +335,8 @@ static int launch_pipeline(orbx_handle *h, const uint8_t *d_img0_all, int f0, in
         // pyramid levels >= 1 are always 64-byte aligned; level 0 goes through the TMA engine when the caller's buffer allows it
         const bool l0_bulk = (((uintptr_t)d_img0 | (uintptr_t)pitch0 | (uintptr_t)frame0) & 15) == 0 && pitch0 >= (int)align_up(P.lv[0].w, 16);
         const unsigned tma_levels = (l0_bulk ? 1u : 0u) | 0xfffffffeu;
-        k_fast_cells<<<dim3(P.total_cells, n), 128, 0, st>>>(P, tma_levels, h->d_cells.as<CellDesc>(), d_img0, pitch0, frame0, pyr, cand, cand_count, err_ptr(h, nb));
+        k_fast_cells<<<dim3(P.total_cells, n), 128, 0, st>>>(P, h->tmaps_fast, h->tmap_levels, f0, tma_levels, h->d_cells.as<CellDesc>(), d_img0, pitch0, frame0, pyr, cand,
+                                                             cand_count, err_ptr(h, nb));
         h->timer.end(st);
         h->timer.begin(2, st);
         k_blur7<<<dim3(P.total_tiles, n), 256, 0, st>>>(P, tma_levels, h->d_tiles.as<TileDesc>(), d_img0, pitch0, frame0, pyr, blur);
@@ -296,6 +365,7 @@ static int upload_and_extract(orbx_handle *h, const uint8_t *images, int n_frame
     if (int rc = h->d_stage.reserve(frame * n_frames)) return rc;
     if (!h->copy_stream) ORBS_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
     if (int rc = reset_counts(h)) return rc;
+    refresh_tmaps(h, h->d_stage.as<uint8_t>(), (int)pitch, frame, n_frames);
     const int chunk = n_frames > 16 ? 16 : n_frames;
     const int nchunks = (n_frames + chunk - 1) / chunk;
     while ((int)h->chunk_events.size() < nchunks + 1) { cudaEvent_t e; ORBS_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); h->chunk_events.push_back(e); }
@@ -485,6 +555,7 @@ int orbx_extract_device(orbx_handle *h, const uint8_t *d_images, int n_frames, i
     if (int rc = ensure_plan(h, width, height)) return rc;
     if (int rc = ensure_batch(h, n_frames)) return rc;
     if (int rc = reset_counts(h)) return rc;
+    refresh_tmaps(h, d_images, stride, frame_stride, n_frames);
     return launch_pipeline(h, d_images, 0, n_frames, stride, frame_stride);
 }
 

@@ -25,6 +25,7 @@ struct LevelPlan {
     unsigned long long cand_off;  // entry offset inside one frame's candidate slab
     int rs_x_off, rs_y_off;   // offsets (entries) of this level's resize tables
     int tile_first, tile_count; // blur tiles
+    int fast_box_w, fast_box_h; // TMA box of this level's FAST cells: widest aligned row span (multiple of 16) x tallest cell
 };
 
 struct ExtractPlan {

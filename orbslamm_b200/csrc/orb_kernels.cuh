@@ -10,6 +10,7 @@
 //
 // All arithmetic is integer / fixed point except the fp32 angle and rotation, which use
 // explicit round-to-nearest intrinsics so that no FMA contraction can change a bit.
+#include <cuda.h>
 #include "orb_extractor.cuh"
 
 namespace orbs {
@@ -64,10 +65,11 @@ k_resize_level(const uint8_t *__restrict__ src, int sw, int sh, int spitch, size
 // 3-input u16x2 min / max (VIMNMX3.U16x2): m3[k] = min3(A[k..k+2]), m9[k] = min3(m3[k], m3[k+3], m3[k+6]).
 //
 // One CTA per FAST cell (= one cv::FAST call of the reference, ORBextractor.cc:808-815):
-//   0. the cell's sub-image (plus one pixel to its left) is fetched by the TMA engine: one 16-byte aligned bulk copy per image
-//      row (cp.async.bulk.shared.global -> UBLKCP), all completing on one mbarrier; no thread touches global pixels.
-//      (Tensor-map box loads, cp.async.bulk.tensor / UTMALDG, raise "illegal instruction" on the target boxes even for the
-//      CUDA programming guide's own example -- tools/tma_probe/tensor_map_load.cu -- so the descriptor-free bulk form is used.)
+//   0. the cell's sub-image (from the 16-byte aligned column left of it) is fetched by ONE TMA box load
+//      (cp.async.bulk.tensor.3d -> UTMALDG) on a per-level (x, y, frame) tensor map, completing on an mbarrier; no thread touches
+//      global pixels.  The box must start on a 16-byte boundary in global memory (an unaligned x coordinate raises "illegal
+//      instruction", tools/tma_probe/), hence the aligned start + byte shift.  Fallbacks: one descriptor-free bulk copy per row
+//      (cp.async.bulk -> UBLKCP) when no tensor map could be encoded, plain loads when the caller's level-0 buffer is unaligned.
 //   1. bytes are widened to one pixel per 16-bit lane (pix16), so that ring pixel pairs are 32-bit words (even dx) or one PRMT
 //      of two words (odd dx);
 //   2. every thread scores 4 adjacent pixels per step from 21 64-bit shared loads;
@@ -81,6 +83,8 @@ constexpr int kRawPitchMax = 96;             // bytes per staged row: 16-byte al
 constexpr int kPixPitch16 = 96;              // u16 per pix16 row (48 words: consecutive rows start 16 banks apart)
 constexpr int kScPitch16 = 66;               // u16 per score row (33 words)
 constexpr int kScRows = 62;                  // detection region is <= 60 x 60 (+ zero frame)
+
+struct LevelTmaps { CUtensorMap m[ORBS_MAX_LEVELS]; };      // one (x, y, frame) u8 tensor map per pyramid level
 
 __device__ __forceinline__ unsigned hi_lo(unsigned a, unsigned b) { return __byte_perm(a, b, 0x5432); }   // (a.hi, b.lo)
 
@@ -120,7 +124,8 @@ struct RowCol {
 };
 
 __global__ void __launch_bounds__(128, 8)
-k_fast_cells(const __grid_constant__ ExtractPlan plan, const unsigned tma_levels, const CellDesc *__restrict__ cells,
+k_fast_cells(const __grid_constant__ ExtractPlan plan, const __grid_constant__ LevelTmaps tmaps, const unsigned tmap_levels, const int frame_base,
+             const unsigned tma_levels, const CellDesc *__restrict__ cells,
              const uint8_t *__restrict__ img0, int pitch0, size_t frame0,
              const uint8_t *__restrict__ pyr, uint2 *__restrict__ cand, int *__restrict__ cand_count,
              int *__restrict__ err_flag)
@@ -143,10 +148,22 @@ k_fast_cells(const __grid_constant__ ExtractPlan plan, const unsigned tma_levels
     else { img = pyr + (size_t)frame * plan.pyr_frame_bytes + L.pyr_off; pitch = L.pitch; }
     // staged row r: raw[r * rb + shift + j] = level pixel (x0 - 1 + j, y0 + r), j = 0 .. cw
     const int xa = (cell.x0 - 1) & ~15, shift = (cell.x0 - 1) - xa;
-    const int rb = (shift + cw + 1 + 15) & ~15;
+    const bool use_map = (tmap_levels >> cell.level) & 1u;
+    const int rb = use_map ? L.fast_box_w : (shift + cw + 1 + 15) & ~15;     // staged row pitch
 
     // ---- 0. fetch the rows
-    if (use_tma) {
+    if (use_map) {
+        if (tid == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&mbar)), "r"(L.fast_box_w * L.fast_box_h) : "memory");
+            asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                         ::"r"(smem_u32(raw)), "l"(reinterpret_cast<unsigned long long>(&tmaps.m[cell.level])), "r"(xa), "r"((int)cell.y0),
+                         "r"(frame_base + frame), "r"(smem_u32(&mbar)) : "memory");
+        }
+        __syncthreads();
+    } else if (use_tma) {
         if (tid == 0) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)));
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -176,7 +193,7 @@ k_fast_cells(const __grid_constant__ ExtractPlan plan, const unsigned tma_levels
         const int wr = (dw + 2) >> 1;                                       // first word holding an index >= dw + 2 (or dw + 1 if dw is odd: rewritten by the scores)
         for (int y = tid; y < dh; y += 128) { s32[(y + 1) * SW] = 0u; s32[(y + 1) * SW + wr] = 0u; if (wr + 1 < SW) s32[(y + 1) * SW + wr + 1] = 0u; }
     }
-    if (use_tma) {
+    if (use_map || use_tma) {
         unsigned done = 0;
         for (int spin = 0; !done && spin < (1 << 16); spin++)
             asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(smem_u32(&mbar)) : "memory");

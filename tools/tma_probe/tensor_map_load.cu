@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <cuda/barrier>
 #include <cstdio>
+#include <dlfcn.h>
 #include <cstdlib>
 #include <vector>
 #include <cstdint>
@@ -35,8 +36,12 @@ int main(int argc, char **argv)
     std::vector<uint8_t> img((size_t)pitch * h);
     for (size_t i = 0; i < img.size(); i++) img[i] = (uint8_t)(i * 2654435761u >> 13);
     uint8_t *d; cudaMalloc(&d, img.size()); cudaMemcpy(d, img.data(), img.size(), cudaMemcpyHostToDevice);
-    void *p = nullptr; cudaDriverEntryPointQueryResult q;
-    cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+    void *p = nullptr; cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSuccess;
+    const int how = argc > 2 ? atoi(argv[2]) : 0;          // 0: runtime default, 1: by version 12000, 2: dlsym(libcuda)
+    if (how == 0) cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+    else if (how == 1) cudaGetDriverEntryPointByVersion("cuTensorMapEncodeTiled", &p, 12000, cudaEnableDefault, &q);
+    else { cudaFree(0); void *lib = dlopen("libcuda.so.1", RTLD_NOW); p = lib ? dlsym(lib, "cuTensorMapEncodeTiled") : nullptr; }
+    printf("entry point how=%d p=%p\n", how, p);
     typedef CUresult (*Fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
     Fn fn = (Fn)p;
     CUtensorMap tm;
