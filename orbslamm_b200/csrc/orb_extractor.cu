@@ -339,7 +339,7 @@ static int launch_pipeline(orbx_handle *h, const uint8_t *d_img0_all, int f0, in
                                                              cand_count, err_ptr(h, nb));
         h->timer.end(st);
         h->timer.begin(2, st);
-        k_blur7<<<dim3(P.total_tiles, n), 256, 0, st>>>(P, tma_levels, h->d_tiles.as<TileDesc>(), d_img0, pitch0, frame0, pyr, blur);
+        k_blur7<<<dim3(P.total_tiles, n), 256, 0, st>>>(P, h->tmaps_blur, h->tmap_levels, f0, tma_levels, h->d_tiles.as<TileDesc>(), d_img0, pitch0, frame0, pyr, blur);
         h->timer.end(st);
         h->timer.begin(3, st);
         k_octree<<<dim3(P.nlevels, n), 512, h->octree_smem, st>>>(P, cand, cand_count, knode, lvl_kp, lvl_count, err_ptr(h, nb));

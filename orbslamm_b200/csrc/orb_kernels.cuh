@@ -341,7 +341,8 @@ constexpr int kBlurRP = 112;                  // staged row pitch: 16-byte left 
 constexpr int kBlurIH = kBlurTH + 6;
 
 __global__ void __launch_bounds__(256)
-k_blur7(const __grid_constant__ ExtractPlan plan, const unsigned tma_levels, const TileDesc *__restrict__ tiles,
+k_blur7(const __grid_constant__ ExtractPlan plan, const __grid_constant__ LevelTmaps tmaps, const unsigned tmap_levels, const int frame_base,
+        const unsigned tma_levels, const TileDesc *__restrict__ tiles,
         const uint8_t *__restrict__ img0, int pitch0, size_t frame0,
         const uint8_t *__restrict__ pyr, uint8_t *__restrict__ blur)
 {
@@ -360,7 +361,25 @@ k_blur7(const __grid_constant__ ExtractPlan plan, const unsigned tma_levels, con
     const int need = t.x0 + kBlurTW + 3 - xa;                     // columns xa .. x0 + 66
     // never past the row pitch (bulk copies: whole 16-byte units, the pitch is a multiple of 16 on that path)
     const int rb = use_tma ? min((need + 15) & ~15, (pitch - xa) & ~15) : min(need, pitch - xa);
-    if (use_tma) {
+    // interior tile rows (no vertical reflection) with a tensor map: ONE box load of 112 x 38 bytes starting 16 bytes left of xa
+    // (negative / beyond-the-level columns are zero-filled and patched below)
+    const bool use_map = ((tmap_levels >> t.level) & 1u) && t.y0 >= 3 && t.y0 + kBlurTH + 3 <= L.h;
+    if (use_map) {
+        if (tid == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&mbar)), "r"(kBlurIH * kBlurRP) : "memory");
+            asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                         ::"r"(smem_u32(raw)), "l"(reinterpret_cast<unsigned long long>(&tmaps.m[t.level])), "r"(xa - 16), "r"((int)t.y0 - 3),
+                         "r"(frame_base + frame), "r"(smem_u32(&mbar)) : "memory");
+        }
+        __syncthreads();
+        unsigned done = 0;
+        for (int spin = 0; !done && spin < (1 << 16); spin++)
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(smem_u32(&mbar)) : "memory");
+        if (!__syncthreads_and((int)done)) return;                // cannot happen; never hang the device
+    } else if (use_tma) {
         if (tid == 0) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)));
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
