@@ -361,9 +361,9 @@ k_blur7(const __grid_constant__ ExtractPlan plan, const __grid_constant__ LevelT
     const int need = t.x0 + kBlurTW + 3 - xa;                     // columns xa .. x0 + 66
     // never past the row pitch (bulk copies: whole 16-byte units, the pitch is a multiple of 16 on that path)
     const int rb = use_tma ? min((need + 15) & ~15, (pitch - xa) & ~15) : min(need, pitch - xa);
-    // interior tile rows (no vertical reflection) with a tensor map: ONE box load of 112 x 38 bytes starting 16 bytes left of xa
-    // (negative / beyond-the-level columns are zero-filled and patched below)
-    const bool use_map = ((tmap_levels >> t.level) & 1u) && t.y0 >= 3 && t.y0 + kBlurTH + 3 <= L.h;
+    // with a tensor map: ONE box load of 112 x 38 bytes starting 16 bytes left of xa and 3 rows above the tile; rows / columns
+    // outside the level arrive zero-filled and are patched below with their BORDER_REFLECT_101 sources, which lie inside the box
+    const bool use_map = (tmap_levels >> t.level) & 1u;
     if (use_map) {
         if (tid == 0) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)));
@@ -379,6 +379,17 @@ k_blur7(const __grid_constant__ ExtractPlan plan, const __grid_constant__ LevelT
         for (int spin = 0; !done && spin < (1 << 16); spin++)
             asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(smem_u32(&mbar)) : "memory");
         if (!__syncthreads_and((int)done)) return;                // cannot happen; never hang the device
+        // reflected rows: y = -1..-3 above the level (first tile row), y = h..h+2 below it
+        if (t.y0 == 0 || t.y0 + kBlurTH + 3 > L.h) {
+            if (tid < 6 * (kBlurRP / 4)) {
+                const int k = tid / (kBlurRP / 4), wq = tid - k * (kBlurRP / 4);
+                const int sy = k < 3 ? -1 - k : L.h + (k - 3);                     // row outside the level
+                const int r = sy - (t.y0 - 3), rs = reflect101(sy, L.h) - (t.y0 - 3);   // its box row and the box row of its source
+                if (r >= 0 && r < kBlurIH && rs >= 0 && rs < kBlurIH)
+                    reinterpret_cast<unsigned *>(raw + r * kBlurRP)[wq] = reinterpret_cast<const unsigned *>(raw + rs * kBlurRP)[wq];
+            }
+            __syncthreads();
+        }
     } else if (use_tma) {
         if (tid == 0) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)));
