@@ -204,6 +204,64 @@ int orbm_search_by_projection(orbm_handle *h, int n_frames, const float *bounds4
                               int q_slab, int th_dist, float ratio, int check_ori,
                               int32_t *feat_match, int32_t *nmatches, int memspace);
 
+/* ---- KeyFrame / Sim3 projection family (ORBmatcher.cc:292-405, 827-977, 979-1102, 1104-1328, 1474-1601) ----------------------
+ * These five members share one shape: transform every candidate map point into the target view, run the visibility tests,
+ * predict the pyramid level (MapPoint::PredictScale, MapPoint.cc:385-394), search the target's feature grid in a radius
+ * th * mvScaleFactors[level] and keep the best Hamming distance.  They differ in which tests they make; `flags` selects them. */
+#define ORBM_PROJ_TWO_STEP     0x01 /* x = R2 (R X + t) + t2   (SearchBySim3: R1w,t1w then sR21,t21; :1155-1156, :1235-1236) */
+#define ORBM_PROJ_NO_DEPTH     0x02 /* no "z < 0 -> skip" test (SearchByProjection(Frame&, KeyFrame*, ...), :1503-1511) */
+#define ORBM_PROJ_FRAME_BOUNDS 0x04 /* reject u < min || u > max (Frame, :1513-1516); default is KeyFrame::IsInImage
+                                       (x >= min && x < max, KeyFrame.cc:659-662) */
+#define ORBM_PROJ_FRAME_UV     0x08 /* u = fx*xc*invz + cx (:1510-1511); default x = xc*invz, u = fx*x + cx (:334-338) */
+#define ORBM_PROJ_DIST_CAMERA  0x10 /* distance = |x| in the target camera (SearchBySim3, :1179); default |X - Ow| */
+#define ORBM_PROJ_CHECK_NORMAL 0x20 /* reject PO.dot(Pn) < 0.5*dist (:355-358, :886-889, :1037-1040) */
+#define ORBM_PROJ_LEVEL_PLUS1  0x40 /* levels [l-1, l+1] (GetFeaturesInArea(u,v,r,l-1,l+1), :1532); default [l-1, l] */
+
+typedef struct orbm_projection {    /* one per target view; always a HOST array */
+    float R[9], t[3];               /* Rcw, tcw of the target (Scw's rotation / scale and translation / scale for the Sim3 variants) */
+    float R2[9], t2[3];             /* second transform (ORBM_PROJ_TWO_STEP) */
+    float Ow[3];                    /* camera centre (unused with ORBM_PROJ_DIST_CAMERA) */
+    float fx, fy, cx, cy;
+    float min_x, min_y, max_x, max_y; /* image bounds of the target: KeyFrame::mnMinX.. (ints) or Frame::mnMinX.. */
+    float log_scale_factor;         /* mfLogScaleFactor of the target */
+    float th;                       /* radius = th * scale_factors[level] */
+    int32_t flags;
+} orbm_projection;
+
+/* Projection half.  q_valid in: the map point is a candidate (not bad, not already found, ...); out: and it passed every test.
+ *   Xw f32[n_views*q_slab,3]; normal f32[.,3] (may be NULL without ORBM_PROJ_CHECK_NORMAL); mf_min_distance / mf_max_distance f32[.]
+ *   = MapPoint::mfMinDistance / mfMaxDistance (the 0.8 / 1.2 factors of Get{Min,Max}DistanceInvariance are applied inside);
+ *   out: q_uv f32[.,2], q_radius f32[.], q_minl / q_maxl i32[.], q_level i32[.] (may be NULL).
+ * A predicted level outside [0, nlevels) makes the reference index mvScaleFactors out of range (undefined behaviour, PredictScale
+ * is not clamped in this version); such points are dropped here. */
+int orbm_project_points(orbm_handle *h, int n_views, const orbm_projection *proj, const float *scale_factors, int nlevels,
+                        const float *Xw, const float *normal, const float *mf_min_distance, const float *mf_max_distance,
+                        const int32_t *q_counts, int q_slab, uint8_t *q_valid, float *q_uv, float *q_radius, int32_t *q_minl,
+                        int32_t *q_maxl, int32_t *q_level, int memspace);
+
+/* orbm_search_by_projection for a KeyFrame target: the feature grid was built by the Frame (float bounds grid_bounds4, Frame.cc:
+ * 230-245) but KeyFrame::GetFeaturesInArea offsets by the KeyFrame's INTEGER mnMinX / mnMinY (KeyFrame.h, KeyFrame.cc:618-657);
+ * win_origin2 = those two values (NULL = same as the grid).  Everything else as orbm_search_by_projection. */
+int orbm_search_by_projection_kf(orbm_handle *h, int n_frames, const float *grid_bounds4, const float *win_origin2,
+                                 const float *f_xy, const int32_t *f_octave, const float *f_angle, const uint8_t *f_desc,
+                                 const int32_t *f_counts, int f_slab,
+                                 const uint8_t *q_valid, const float *q_uv, const float *q_radius, const int32_t *q_minl,
+                                 const int32_t *q_maxl, const float *q_angle, const uint8_t *q_desc, const int32_t *q_counts,
+                                 int q_slab, int th_dist, float ratio, int check_ori,
+                                 int32_t *feat_match, int32_t *nmatches, int memspace);
+
+/* Search half without claims (Fuse :892-938 and :1052-1078, SearchBySim3 :1193-1224 / :1273-1304): every valid query takes the
+ * feature with the smallest Hamming distance in its window (first visited wins ties), independently of all other queries.
+ *   inv_level_sigma2 f32[nlevels] (HOST, may be NULL): with it a candidate is skipped when
+ *   ((u-kpx)^2 + (v-kpy)^2) * inv_level_sigma2[octave] > chi2_gate   (Fuse, monocular branch :918-928, chi2_gate = 5.99)
+ *   out: q_best_idx i32[.] = feature index or -1 when the window is empty / best distance > th_dist; q_best_dist i32[.]. */
+int orbm_search_best_in_window(orbm_handle *h, int n_frames, const float *grid_bounds4, const float *win_origin2,
+                               const float *f_xy, const int32_t *f_octave, const uint8_t *f_desc, const int32_t *f_counts, int f_slab,
+                               const uint8_t *q_valid, const float *q_uv, const float *q_radius, const int32_t *q_minl,
+                               const int32_t *q_maxl, const uint8_t *q_desc, const int32_t *q_counts, int q_slab, int th_dist,
+                               const float *inv_level_sigma2, int nlevels, float chi2_gate,
+                               int32_t *q_best_idx, int32_t *q_best_dist, int memspace);
+
 /* ------------------------------------------------------------------ */
 /* Optimizer  (replaces S/src/Optimizer.cc and the g2o LM / Schur / LDLT stack it drives; all fp64 inside,
  * float32 poses and points at the boundary like cv::Mat / Converter.cc)                                      */

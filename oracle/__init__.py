@@ -320,3 +320,91 @@ def is_in_frustum(Tcw, Ow, K4, bounds4, log_scale_factor, cos_limit, Xw, normal,
     L.oracle_is_in_frustum(_p(T, _f32p), _p(Ow, _f32p), _p(K4, _f32p), _p(b, _f32p), float(log_scale_factor), float(cos_limit), M, _p(Xw, _f32p),
                            _p(normal, _f32p), _p(mn, _f32p), _p(mx, _f32p), _p(iv, _u8p), _p(uv, _f32p), _p(lv, _i32p), _p(vc, _f32p))
     return iv, uv, lv, vc
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# KeyFrame / Sim3 projection family (slam_oracle.c: oracle_project_points, oracle_search_best_in_window, oracle_search_by_projection_kf)
+PROJ_TWO_STEP, PROJ_NO_DEPTH, PROJ_FRAME_BOUNDS, PROJ_FRAME_UV, PROJ_DIST_CAMERA, PROJ_CHECK_NORMAL, PROJ_LEVEL_PLUS1 = 1, 2, 4, 8, 16, 32, 64
+
+
+class Projection(ctypes.Structure):
+    """= oracle_projection = orbm_projection (include/orbslamm_b200.h)"""
+    _fields_ = [("R", ctypes.c_float * 9), ("t", ctypes.c_float * 3), ("R2", ctypes.c_float * 9), ("t2", ctypes.c_float * 3),
+                ("Ow", ctypes.c_float * 3), ("fx", ctypes.c_float), ("fy", ctypes.c_float), ("cx", ctypes.c_float), ("cy", ctypes.c_float),
+                ("min_x", ctypes.c_float), ("min_y", ctypes.c_float), ("max_x", ctypes.c_float), ("max_y", ctypes.c_float),
+                ("log_scale_factor", ctypes.c_float), ("th", ctypes.c_float), ("flags", ctypes.c_int32)]
+
+
+def make_projection(R, t, K4, bounds4, log_scale_factor, th, flags, Ow=None, R2=None, t2=None):
+    V = Projection()
+    V.R[:] = [float(x) for x in np.asarray(R, np.float32).ravel()]; V.t[:] = [float(x) for x in np.asarray(t, np.float32).ravel()]
+    if R2 is not None:
+        V.R2[:] = [float(x) for x in np.asarray(R2, np.float32).ravel()]; V.t2[:] = [float(x) for x in np.asarray(t2, np.float32).ravel()]
+    if Ow is not None:
+        V.Ow[:] = [float(x) for x in np.asarray(Ow, np.float32).ravel()]
+    V.fx, V.fy, V.cx, V.cy = [float(x) for x in np.asarray(K4, np.float32)]
+    V.min_x, V.min_y, V.max_x, V.max_y = [float(x) for x in np.asarray(bounds4, np.float32)]
+    V.log_scale_factor = float(np.float32(log_scale_factor)); V.th = float(np.float32(th)); V.flags = int(flags)
+    return V
+
+
+def project_points(V, scale_factors, Xw, normal, mf_min, mf_max, valid):
+    """Returns (valid, uv, radius, minl, maxl, level)."""
+    sf = np.ascontiguousarray(scale_factors, np.float32)
+    Xw = np.ascontiguousarray(Xw, np.float32).reshape(-1, 3); M = len(Xw)
+    nrm = None if normal is None else np.ascontiguousarray(normal, np.float32).reshape(M, 3)
+    mn = np.ascontiguousarray(mf_min, np.float32); mx = np.ascontiguousarray(mf_max, np.float32)
+    qv = np.ascontiguousarray(valid, np.uint8).copy()
+    uv = np.zeros((M, 2), np.float32); rad = np.zeros(M, np.float32)
+    l0 = np.zeros(M, np.int32); l1 = np.zeros(M, np.int32); lv = np.zeros(M, np.int32)
+    L = lib()
+    L.oracle_project_points.restype = None
+    L.oracle_project_points.argtypes = [ctypes.c_void_p, _f32p, ctypes.c_int, ctypes.c_int, _f32p, ctypes.c_void_p, _f32p, _f32p, _u8p, _f32p, _f32p,
+                                        _i32p, _i32p, _i32p]
+    L.oracle_project_points(ctypes.byref(V), _p(sf, _f32p), len(sf), M, _p(Xw, _f32p), None if nrm is None else nrm.ctypes.data, _p(mn, _f32p),
+                            _p(mx, _f32p), _p(qv, _u8p), _p(uv, _f32p), _p(rad, _f32p), _p(l0, _i32p), _p(l1, _i32p), _p(lv, _i32p))
+    return qv, uv, rad, l0, l1, lv
+
+
+def search_best_in_window(g, win_origin2, f_xy, f_octave, f_desc, q_valid, q_uv, q_radius, q_minl, q_maxl, q_desc, th_dist,
+                          inv_level_sigma2=None, chi2_gate=5.99):
+    """Returns (best_idx, best_dist) per query (Fuse / SearchBySim3 candidate loop)."""
+    f_xy = np.ascontiguousarray(f_xy, np.float32).reshape(-1, 2); N = len(f_xy)
+    f_octave = np.ascontiguousarray(f_octave, np.int32); f_desc = np.ascontiguousarray(f_desc, np.uint8)
+    q_valid = np.ascontiguousarray(q_valid, np.uint8); M = len(q_valid)
+    q_uv = np.ascontiguousarray(q_uv, np.float32); q_radius = np.ascontiguousarray(q_radius, np.float32)
+    q_minl = np.ascontiguousarray(q_minl, np.int32); q_maxl = np.ascontiguousarray(q_maxl, np.int32); q_desc = np.ascontiguousarray(q_desc, np.uint8)
+    wo = None if win_origin2 is None else np.ascontiguousarray(win_origin2, np.float32)
+    inv = None if inv_level_sigma2 is None else np.ascontiguousarray(inv_level_sigma2, np.float32)
+    bi = np.zeros(M, np.int32); bd = np.zeros(M, np.int32)
+    L = lib()
+    L.oracle_search_best_in_window.restype = None
+    L.oracle_search_best_in_window.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, _f32p, _i32p, _u8p, ctypes.c_int, _u8p, _f32p, _f32p,
+                                               _i32p, _i32p, _u8p, ctypes.c_int, ctypes.c_void_p, ctypes.c_double, _i32p, _i32p]
+    L.oracle_search_best_in_window(ctypes.byref(g), None if wo is None else wo.ctypes.data, N, _p(f_xy, _f32p), _p(f_octave, _i32p), _p(f_desc, _u8p),
+                                   M, _p(q_valid, _u8p), _p(q_uv, _f32p), _p(q_radius, _f32p), _p(q_minl, _i32p), _p(q_maxl, _i32p), _p(q_desc, _u8p),
+                                   int(th_dist), None if inv is None else inv.ctypes.data, float(chi2_gate), _p(bi, _i32p), _p(bd, _i32p))
+    return bi, bd
+
+
+def search_by_projection_kf(g, win_origin2, f_xy, f_octave, f_angle, f_desc, q_valid, q_uv, q_radius, q_minl, q_maxl, q_angle,
+                            q_desc, th_dist=100, ratio=0.0, check_ori=True, feat_match=None):
+    """search_by_projection with a KeyFrame's integer window origin (None = the grid's)."""
+    f_xy = np.ascontiguousarray(f_xy, np.float32).reshape(-1, 2); N = len(f_xy)
+    f_octave = np.ascontiguousarray(f_octave, np.int32); f_angle = np.ascontiguousarray(f_angle, np.float32)
+    f_desc = np.ascontiguousarray(f_desc, np.uint8)
+    q_valid = np.ascontiguousarray(q_valid, np.uint8); M = len(q_valid)
+    q_uv = np.ascontiguousarray(q_uv, np.float32); q_radius = np.ascontiguousarray(q_radius, np.float32)
+    q_minl = np.ascontiguousarray(q_minl, np.int32); q_maxl = np.ascontiguousarray(q_maxl, np.int32)
+    q_angle = np.ascontiguousarray(q_angle, np.float32); q_desc = np.ascontiguousarray(q_desc, np.uint8)
+    wo = None if win_origin2 is None else np.ascontiguousarray(win_origin2, np.float32)
+    fm = np.full(N, -1, np.int32) if feat_match is None else np.ascontiguousarray(feat_match, np.int32).copy()
+    L = lib()
+    L.oracle_search_by_projection_kf.restype = ctypes.c_int
+    L.oracle_search_by_projection_kf.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, _f32p, _i32p, _f32p, _u8p, ctypes.c_int, _u8p, _f32p,
+                                                 _f32p, _i32p, _i32p, _f32p, _u8p, ctypes.c_int, ctypes.c_float, ctypes.c_int, _i32p]
+    n = L.oracle_search_by_projection_kf(ctypes.byref(g), None if wo is None else wo.ctypes.data, N, _p(f_xy, _f32p), _p(f_octave, _i32p),
+                                         _p(f_angle, _f32p), _p(f_desc, _u8p), M, _p(q_valid, _u8p), _p(q_uv, _f32p), _p(q_radius, _f32p),
+                                         _p(q_minl, _i32p), _p(q_maxl, _i32p), _p(q_angle, _f32p), _p(q_desc, _u8p), int(th_dist), float(ratio),
+                                         int(bool(check_ori)), _p(fm, _i32p))
+    return n, fm

@@ -146,3 +146,85 @@ def ref_search_local_points(K4, bounds4, scale_factors, cur, in_view, proj_xy, l
     n = L.ref_orbm_search_local_points(float(nnratio), float(th), sf.ctypes.data, len(sf), N, fxy.ctypes.data, fo.ctypes.data, fa.ctypes.data, fd.ctypes.data,
                                        hv.ctypes.data, M, iv.ctypes.data, uv.ctypes.data, lv.ctypes.data, vc.ctypes.data, qd.ctypes.data, fm.ctypes.data)
     return n, fm
+
+
+# ---- KeyFrame / Sim3 projection family (reference object code; see oracle/ref_matcher_capi.cc) -------------------------------------------
+class _RefKF(ctypes.Structure):
+    _fields_ = [("N", ctypes.c_int), ("xy", ctypes.c_void_p), ("octave", ctypes.c_void_p), ("angle", ctypes.c_void_p), ("desc", ctypes.c_void_p),
+                ("scale_factors", ctypes.c_void_p), ("inv_level_sigma2", ctypes.c_void_p), ("nlevels", ctypes.c_int),
+                ("K4", ctypes.c_void_p), ("grid_bounds4", ctypes.c_void_p), ("Tcw", ctypes.c_void_p)]
+
+
+def _refkf(kf):
+    """kf: dict xy [N,2], octave, angle, desc, scale_factors, inv_level_sigma2, K4, grid_bounds4, Tcw (optional).  Returns (struct, keepalive)."""
+    keep = dict(xy=_c(kf["xy"], np.float32), octave=_c(kf["octave"], np.int32), angle=_c(kf["angle"], np.float32), desc=_c(kf["desc"], np.uint8),
+                sf=_c(kf["scale_factors"], np.float32), inv=_c(kf["inv_level_sigma2"], np.float32), K4=_c(kf["K4"], np.float32),
+                gb=_c(kf["grid_bounds4"], np.float32), T=_c(kf.get("Tcw", np.eye(4)), np.float32).reshape(16))
+    s = _RefKF(len(keep["xy"]), keep["xy"].ctypes.data, keep["octave"].ctypes.data, keep["angle"].ctypes.data, keep["desc"].ctypes.data,
+               keep["sf"].ctypes.data, keep["inv"].ctypes.data, len(keep["sf"]), keep["K4"].ctypes.data, keep["gb"].ctypes.data, keep["T"].ctypes.data)
+    return s, keep
+
+
+def _pts(pts):
+    """pts: dict Xw [M,3], normal [M,3], mf_min, mf_max, desc [M,32]"""
+    return (_c(pts["Xw"], np.float32), _c(pts["normal"], np.float32), _c(pts["mf_min"], np.float32), _c(pts["mf_max"], np.float32), _c(pts["desc"], np.uint8))
+
+
+def ref_search_kf_sim3(kf, Scw, th, pts, skip, held):
+    """ORBmatcher::SearchByProjection(pKF, Scw, vpPoints, vpMatched, th) (ORBmatcher.cc:292-405). Returns (n, feat_match[N])."""
+    L = matcher_lib(); s, keep = _refkf(kf); X, nr, mn, mx, qd = _pts(pts)
+    S = _c(Scw, np.float32).reshape(16); sk = _c(skip, np.uint8); hd = _c(held, np.uint8); fm = np.full(s.N, -1, np.int32)
+    L.ref_orbm_search_kf_sim3.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 8
+    n = L.ref_orbm_search_kf_sim3(ctypes.byref(s), S.ctypes.data, int(th), len(X), sk.ctypes.data, X.ctypes.data, nr.ctypes.data, mn.ctypes.data,
+                                  mx.ctypes.data, qd.ctypes.data, hd.ctypes.data, fm.ctypes.data)
+    return n, fm
+
+
+def ref_fuse_kf(kf, th, pts, skip, occupied):
+    """ORBmatcher::Fuse(pKF, vpMapPoints, th) (ORBmatcher.cc:827-977).  kf['Tcw'] is the keyframe pose.  Returns (nFused, slot[M])."""
+    L = matcher_lib(); s, keep = _refkf(kf); X, nr, mn, mx, qd = _pts(pts)
+    sk = _c(skip, np.uint8); oc = _c(occupied, np.uint8); slot = np.full(len(X), -1, np.int32)
+    L.ref_orbm_fuse_kf.argtypes = [ctypes.c_void_p, ctypes.c_float, ctypes.c_int] + [ctypes.c_void_p] * 8
+    n = L.ref_orbm_fuse_kf(ctypes.byref(s), float(th), len(X), sk.ctypes.data, X.ctypes.data, nr.ctypes.data, mn.ctypes.data, mx.ctypes.data,
+                           qd.ctypes.data, oc.ctypes.data, slot.ctypes.data)
+    return n, slot
+
+
+def ref_fuse_sim3(kf, Scw, th, pts, skip, occupied):
+    """ORBmatcher::Fuse(pKF, Scw, vpPoints, th, vpReplacePoint) (ORBmatcher.cc:979-1102).  Returns (nFused, slot[M])."""
+    L = matcher_lib(); s, keep = _refkf(kf); X, nr, mn, mx, qd = _pts(pts)
+    S = _c(Scw, np.float32).reshape(16); sk = _c(skip, np.uint8); oc = _c(occupied, np.uint8); slot = np.full(len(X), -1, np.int32)
+    L.ref_orbm_fuse_sim3.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_float, ctypes.c_int] + [ctypes.c_void_p] * 8
+    n = L.ref_orbm_fuse_sim3(ctypes.byref(s), S.ctypes.data, float(th), len(X), sk.ctypes.data, X.ctypes.data, nr.ctypes.data, mn.ctypes.data,
+                             mx.ctypes.data, qd.ctypes.data, oc.ctypes.data, slot.ctypes.data)
+    return n, slot
+
+
+def ref_search_by_sim3(kf1, kf2, s12, R12, t12, th, has1, pts1, has2, pts2, matches12):
+    """ORBmatcher::SearchBySim3 (ORBmatcher.cc:1104-1328).  pts1 / pts2 are indexed like the keyframes' features.  Returns (nFound, matches12)."""
+    L = matcher_lib(); a, k1 = _refkf(kf1); b, k2 = _refkf(kf2)
+    X1, _, mn1, mx1, d1 = _pts(pts1); X2, _, mn2, mx2, d2 = _pts(pts2)
+    R = _c(R12, np.float32).reshape(9); t = _c(t12, np.float32).reshape(3); h1 = _c(has1, np.uint8); h2 = _c(has2, np.uint8)
+    m = _c(matches12, np.int32).copy()
+    L.ref_orbm_search_by_sim3.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_float] + [ctypes.c_void_p] * 11
+    n = L.ref_orbm_search_by_sim3(ctypes.byref(a), ctypes.byref(b), float(s12), R.ctypes.data, t.ctypes.data, float(th), h1.ctypes.data, X1.ctypes.data,
+                                  mn1.ctypes.data, mx1.ctypes.data, d1.ctypes.data, h2.ctypes.data, X2.ctypes.data, mn2.ctypes.data, mx2.ctypes.data,
+                                  d2.ctypes.data, m.ctypes.data)
+    return n, m
+
+
+def ref_search_frame_kf(K4, bounds4, Tcw, scale_factors, cur, held, has, skip, pts, kf_angle, th, orb_dist, check_ori=True):
+    """ORBmatcher::SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, ORBdist) (ORBmatcher.cc:1474-1601).  Returns (n, feat_match[N])."""
+    L = matcher_lib()
+    L.ref_orbm_set_camera(*[float(v) for v in K4], float(bounds4[0]), float(bounds4[1]), float(bounds4[2]), float(bounds4[3]))
+    T = _c(Tcw, np.float32).reshape(16); sf = _c(scale_factors, np.float32)
+    fxy = _c(np.stack([cur["x"], cur["y"]], 1), np.float32); N = len(fxy)
+    fo = _c(cur["octave"], np.int32); fa = _c(cur["angle"], np.float32); fd = _c(cur["desc"], np.uint8); hd = _c(held, np.uint8)
+    X, _, mn, mx, qd = _pts(pts); hs = _c(has, np.uint8); sk = _c(skip, np.uint8); ka = _c(kf_angle, np.float32)
+    fm = np.full(N, -1, np.int32)
+    L.ref_orbm_search_frame_kf.argtypes = [ctypes.c_int, ctypes.c_float, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int] + \
+        [ctypes.c_void_p] * 5 + [ctypes.c_int] + [ctypes.c_void_p] * 8
+    n = L.ref_orbm_search_frame_kf(int(bool(check_ori)), float(th), int(orb_dist), T.ctypes.data, sf.ctypes.data, len(sf), N, fxy.ctypes.data, fo.ctypes.data,
+                                   fa.ctypes.data, fd.ctypes.data, hd.ctypes.data, len(X), hs.ctypes.data, sk.ctypes.data, X.ctypes.data, mn.ctypes.data,
+                                   mx.ctypes.data, ka.ctypes.data, qd.ctypes.data, fm.ctypes.data)
+    return n, fm

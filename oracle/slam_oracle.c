@@ -7,6 +7,8 @@
  *   S/src/ORBmatcher.cc:45-137     SearchByProjection(Frame&, vector<MapPoint*>&, th)
  *   S/src/ORBmatcher.cc:1330-1472  SearchByProjection(Frame& Cur, const Frame& Last, th, bMono)
  *   S/src/ORBmatcher.cc:1603-1665  ComputeThreeMaxima, DescriptorDistance
+ *   S/src/ORBmatcher.cc:292-405, 827-977, 979-1102, 1104-1328, 1474-1601  the KeyFrame / Sim3 projection family
+ *       (SearchByProjection(KF, Scw), Fuse x2, SearchBySim3, SearchByProjection(Frame, KF)); S/src/KeyFrame.cc:618-662
  *   S/src/Frame.cc:230-245,327-392 AssignFeaturesToGrid, GetFeaturesInArea, PosInGrid
  * over flat arrays instead of Frame/MapPoint objects (monocular only: mvuRight < 0, every map point
  * has Observations() > 0).  cv::Mat float algebra (Rcw*x3Dw+tcw) is restated as OpenCV 4.13's small
@@ -164,12 +166,31 @@ static void three_maxima(const int *hist, int L, int *i1, int *i2, int *i3)   /*
  * feat_match[N]: in = -1 or an id >= 0 for features that already hold a map point (they are skipped);
  *                out = index of the query assigned to the feature.
  * Returns nmatches. */
+int oracle_search_by_projection_kf(const oracle_grid_params *g, const float *win_origin2, int N, const float *f_xy, const int *f_octave,
+                                   const float *f_angle, const uint8_t *f_desc,
+                                   int M, const uint8_t *q_valid, const float *q_uv, const float *q_radius,
+                                   const int *q_minl, const int *q_maxl, const float *q_angle, const uint8_t *q_desc,
+                                   int th_dist, float ratio, int check_ori, int *feat_match);
 int oracle_search_by_projection(const oracle_grid_params *g, int N, const float *f_xy, const int *f_octave,
                                 const float *f_angle, const uint8_t *f_desc,
                                 int M, const uint8_t *q_valid, const float *q_uv, const float *q_radius,
                                 const int *q_minl, const int *q_maxl, const float *q_angle, const uint8_t *q_desc,
                                 int th_dist, float ratio, int check_ori, int *feat_match)
 {
+    return oracle_search_by_projection_kf(g, NULL, N, f_xy, f_octave, f_angle, f_desc, M, q_valid, q_uv, q_radius, q_minl, q_maxl, q_angle, q_desc,
+                                          th_dist, ratio, check_ori, feat_match);
+}
+
+/* win_origin2 != NULL: the target is a KeyFrame, whose GetFeaturesInArea (KeyFrame.cc:618-657) offsets by its integer mnMinX / mnMinY
+ * while the grid was filled by the Frame with its float bounds (the claim loops of :292-405 and :1474-1601 use this form). */
+int oracle_search_by_projection_kf(const oracle_grid_params *g, const float *win_origin2, int N, const float *f_xy, const int *f_octave,
+                                   const float *f_angle, const uint8_t *f_desc,
+                                   int M, const uint8_t *q_valid, const float *q_uv, const float *q_radius,
+                                   const int *q_minl, const int *q_maxl, const float *q_angle, const uint8_t *q_desc,
+                                   int th_dist, float ratio, int check_ori, int *feat_match)
+{
+    oracle_grid_params gw = *g;
+    if (win_origin2) { gw.min_x = win_origin2[0]; gw.min_y = win_origin2[1]; }
     const int nc = GRID_COLS * GRID_ROWS;
     int *cell_start = (int *)malloc(sizeof(int) * (nc + 1));
     int *cell_items = (int *)malloc(sizeof(int) * (N > 0 ? N : 1));
@@ -183,7 +204,7 @@ int oracle_search_by_projection(const oracle_grid_params *g, int N, const float 
     int nmatches = 0;
     for (int i = 0; i < M; i++) {
         if (!q_valid[i]) continue;
-        const int nc_i = oracle_features_in_area(g, cell_start, cell_items, f_xy, f_octave, q_uv[2 * i], q_uv[2 * i + 1],
+        const int nc_i = oracle_features_in_area(&gw, cell_start, cell_items, f_xy, f_octave, q_uv[2 * i], q_uv[2 * i + 1],
                                                  q_radius[i], q_minl[i], q_maxl[i], cands);
         if (nc_i == 0) continue;
         int best = 256, best2 = 256, best_level = -1, best_level2 = -1, best_idx = -1;
@@ -218,6 +239,122 @@ int oracle_search_by_projection(const oracle_grid_params *g, int N, const float 
     }
     free(cell_start); free(cell_items); free(cands); free(rot_bin);
     return nmatches;
+}
+
+/* ---------------------------------------------------------------------------------------- */
+/* KeyFrame / Sim3 projection family.  The five members (ORBmatcher.cc:292-405 SearchByProjection(KF, Scw, ...), :827-977 Fuse(KF,
+ * vpMapPoints, th), :979-1102 Fuse(KF, Scw, ...), :1104-1328 SearchBySim3, :1474-1601 SearchByProjection(Frame, KF, ...)) share a
+ * projection block that differs only in which tests are made; the flags name the differences (values = ORBM_PROJ_* of
+ * include/orbslamm_b200.h). */
+#define PROJ_TWO_STEP 0x01
+#define PROJ_NO_DEPTH 0x02
+#define PROJ_FRAME_BOUNDS 0x04
+#define PROJ_FRAME_UV 0x08
+#define PROJ_DIST_CAMERA 0x10
+#define PROJ_CHECK_NORMAL 0x20
+#define PROJ_LEVEL_PLUS1 0x40
+
+typedef struct {
+    float R[9], t[3], R2[9], t2[3], Ow[3];
+    float fx, fy, cx, cy, min_x, min_y, max_x, max_y, log_scale_factor, th;
+    int32_t flags;
+} oracle_projection;
+
+static void rt_apply(const float *R, const float *t, const float *x, float *out)   /* cv::Mat R*x + t: small gemm, then add */
+{
+    for (int r = 0; r < 3; r++) {
+        float s = R[3 * r] * x[0];
+        s = s + R[3 * r + 1] * x[1];
+        s = s + R[3 * r + 2] * x[2];
+        out[r] = s + t[r];
+    }
+}
+
+void oracle_project_points(const oracle_projection *V, const float *scale_factors, int nlevels, int M, const float *Xw, const float *normal,
+                           const float *mf_min_dist, const float *mf_max_dist, uint8_t *q_valid, float *q_uv, float *q_radius,
+                           int *q_minl, int *q_maxl, int *q_level)
+{
+    for (int i = 0; i < M; i++) {
+        if (!q_valid[i]) continue;
+        q_valid[i] = 0;
+        const float *X = Xw + 3 * i;
+        float pc[3];
+        rt_apply(V->R, V->t, X, pc);                                       /* :326 / :850 / :1017 / :1155 / :1503 */
+        if (V->flags & PROJ_TWO_STEP) { float p1[3] = {pc[0], pc[1], pc[2]}; rt_apply(V->R2, V->t2, p1, pc); }   /* :1156, :1236 */
+        if (!(V->flags & PROJ_NO_DEPTH) && pc[2] < 0.0f) continue;         /* :329, :853, :1020, :1159 */
+        const float invz = 1.0f / pc[2];
+        float u, v;
+        if (V->flags & PROJ_FRAME_UV) {                                    /* :1510-1511 */
+            u = V->fx * pc[0] * invz + V->cx;
+            v = V->fy * pc[1] * invz + V->cy;
+        } else {                                                           /* :333-338 */
+            const float x = pc[0] * invz, y = pc[1] * invz;
+            u = V->fx * x + V->cx;
+            v = V->fy * y + V->cy;
+        }
+        if (V->flags & PROJ_FRAME_BOUNDS) {                                /* :1513-1516 */
+            if (u < V->min_x || u > V->max_x) continue;
+            if (v < V->min_y || v > V->max_y) continue;
+        } else if (!(u >= V->min_x && u < V->max_x && v >= V->min_y && v < V->max_y)) continue;   /* KeyFrame::IsInImage */
+        const float maxd = 1.2f * mf_max_dist[i], mind = 0.8f * mf_min_dist[i];   /* MapPoint.cc:373-383 */
+        float po[3];
+        if (V->flags & PROJ_DIST_CAMERA) { po[0] = pc[0]; po[1] = pc[1]; po[2] = pc[2]; }          /* :1179 */
+        else { po[0] = X[0] - V->Ow[0]; po[1] = X[1] - V->Ow[1]; po[2] = X[2] - V->Ow[2]; }        /* :347 */
+        double s2 = 0;
+        for (int k = 0; k < 3; k++) s2 += (double)po[k] * (double)po[k];
+        const float dist = (float)sqrt(s2);
+        if (dist < mind || dist > maxd) continue;
+        if (V->flags & PROJ_CHECK_NORMAL) {                                /* :355-358 */
+            double dot = 0;
+            for (int k = 0; k < 3; k++) dot += (double)po[k] * (double)normal[3 * i + k];
+            if (dot < 0.5 * dist) continue;
+        }
+        const float ratio = mf_max_dist[i] / dist;                         /* MapPoint::PredictScale */
+        const int level = (int)ceilf(logf(ratio) / V->log_scale_factor);
+        if (level < 0 || level >= nlevels) continue;                       /* reference: out-of-range index into mvScaleFactors (undefined) */
+        q_uv[2 * i] = u; q_uv[2 * i + 1] = v;
+        q_radius[i] = V->th * scale_factors[level];
+        q_minl[i] = level - 1;
+        q_maxl[i] = (V->flags & PROJ_LEVEL_PLUS1) ? level + 1 : level;
+        if (q_level) q_level[i] = level;
+        q_valid[i] = 1;
+    }
+}
+
+/* The candidate loop of Fuse (:892-938, :1052-1078) and SearchBySim3 (:1193-1224, :1273-1304): best Hamming distance in the window,
+ * no claims.  win_origin2 (may be NULL): KeyFrame::GetFeaturesInArea subtracts the KeyFrame's integer mnMinX / mnMinY while the grid
+ * itself was filled by the Frame with its float bounds.  inv_level_sigma2 (may be NULL): the monocular chi-square gate of Fuse. */
+void oracle_search_best_in_window(const oracle_grid_params *g, const float *win_origin2, int N, const float *f_xy, const int *f_octave,
+                                  const uint8_t *f_desc, int M, const uint8_t *q_valid, const float *q_uv, const float *q_radius,
+                                  const int *q_minl, const int *q_maxl, const uint8_t *q_desc, int th_dist,
+                                  const float *inv_level_sigma2, double chi2_gate, int *q_best_idx, int *q_best_dist)
+{
+    const int nc = GRID_COLS * GRID_ROWS;
+    int *cell_start = (int *)malloc(sizeof(int) * (nc + 1));
+    int *cell_items = (int *)malloc(sizeof(int) * (N > 0 ? N : 1));
+    int *cands = (int *)malloc(sizeof(int) * (N > 0 ? N : 1));
+    oracle_grid_build(g, N, f_xy, cell_start, cell_items);
+    oracle_grid_params gw = *g;
+    if (win_origin2) { gw.min_x = win_origin2[0]; gw.min_y = win_origin2[1]; }
+    for (int i = 0; i < M; i++) {
+        q_best_idx[i] = -1; q_best_dist[i] = -1;
+        if (!q_valid[i]) continue;
+        const float u = q_uv[2 * i], v = q_uv[2 * i + 1];
+        const int n = oracle_features_in_area(&gw, cell_start, cell_items, f_xy, f_octave, u, v, q_radius[i], q_minl[i], q_maxl[i], cands);
+        int best = 0x7fffffff, best_idx = -1;
+        for (int c = 0; c < n; c++) {
+            const int k = cands[c];
+            if (inv_level_sigma2) {
+                const float ex = u - f_xy[2 * k], ey = v - f_xy[2 * k + 1];
+                const float e2 = ex * ex + ey * ey;
+                if (e2 * inv_level_sigma2[f_octave[k]] > chi2_gate) continue;     /* float product against the double 5.99 (:927) */
+            }
+            const int d = oracle_descriptor_distance(q_desc + 32 * (size_t)i, f_desc + 32 * (size_t)k);
+            if (d < best) { best = d; best_idx = k; }
+        }
+        if (best_idx >= 0) { q_best_dist[i] = best; if (best <= th_dist) q_best_idx[i] = best_idx; }
+    }
+    free(cell_start); free(cell_items); free(cands);
 }
 
 /* ======================================================================================== */

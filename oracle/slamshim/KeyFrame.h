@@ -1,5 +1,6 @@
-/* oracle/slamshim/KeyFrame.h -- data-only stand-in for iORB_SLAM::KeyFrame (S/include/KeyFrame.h) so that the KeyFrame variants in
- * ORBmatcher.cc compile; they are not exercised by the parity tests.  TEST INFRASTRUCTURE ONLY. */
+/* oracle/slamshim/KeyFrame.h -- data-only stand-in for iORB_SLAM::KeyFrame (S/include/KeyFrame.h) with the members the KeyFrame variants
+ * of ORBmatcher.cc use.  The grid is the Frame's (KeyFrame.cc:54-60 copies F.mGrid and the cell sizes) while mnMinX.. are INTEGERS
+ * (S/include/KeyFrame.h) and GetFeaturesInArea / IsInImage follow KeyFrame.cc:618-662.  TEST INFRASTRUCTURE ONLY. */
 #pragma once
 #include <set>
 #include "MapPoint.h"
@@ -18,9 +19,26 @@ public:
     bool IsInImage(const float &x, const float &y) const { return (x >= mnMinX && x < mnMaxX && y >= mnMinY && y < mnMaxY); }
     std::vector<size_t> GetFeaturesInArea(const float &x, const float &y, const float &r) const
     {
-        std::vector<size_t> v;
-        for (size_t i = 0; i < mvKeysUn.size(); i++) if (std::fabs(mvKeysUn[i].pt.x - x) < r && std::fabs(mvKeysUn[i].pt.y - y) < r) v.push_back(i);
-        return v;
+        std::vector<size_t> vIndices;
+        vIndices.reserve(N);
+        const int nMinCellX = std::max(0, (int)floor((x - mnMinX - r) * mfGridElementWidthInv));
+        if (nMinCellX >= mnGridCols) return vIndices;
+        const int nMaxCellX = std::min((int)mnGridCols - 1, (int)ceil((x - mnMinX + r) * mfGridElementWidthInv));
+        if (nMaxCellX < 0) return vIndices;
+        const int nMinCellY = std::max(0, (int)floor((y - mnMinY - r) * mfGridElementHeightInv));
+        if (nMinCellY >= mnGridRows) return vIndices;
+        const int nMaxCellY = std::min((int)mnGridRows - 1, (int)ceil((y - mnMinY + r) * mfGridElementHeightInv));
+        if (nMaxCellY < 0) return vIndices;
+        for (int ix = nMinCellX; ix <= nMaxCellX; ix++)
+            for (int iy = nMinCellY; iy <= nMaxCellY; iy++) {
+                const std::vector<size_t> vCell = mGrid[ix][iy];
+                for (size_t j = 0, jend = vCell.size(); j < jend; j++) {
+                    const cv::KeyPoint &kpUn = mvKeysUn[vCell[j]];
+                    const float distx = kpUn.pt.x - x, disty = kpUn.pt.y - y;
+                    if (fabs(distx) < r && fabs(disty) < r) vIndices.push_back(vCell[j]);
+                }
+            }
+        return vIndices;
     }
     long unsigned int mnId;
     int N;
@@ -33,6 +51,9 @@ public:
     std::vector<float> mvScaleFactors, mvLevelSigma2, mvInvLevelSigma2;
     int mnMinX, mnMinY, mnMaxX, mnMaxY;
     cv::Mat Tcw, Ow;
+    int mnGridCols = 64, mnGridRows = 48;
+    float mfGridElementWidthInv = 0, mfGridElementHeightInv = 0;
+    std::vector<std::vector<std::vector<size_t>>> mGrid;
     std::vector<MapPoint *> mvpMapPoints;
 };
 }

@@ -330,6 +330,75 @@ class ORBmatcher:
         return nm, fm
 
 
+    # ---- KeyFrame / Sim3 projection family (ORBmatcher.cc:292-405, 827-977, 979-1102, 1104-1328, 1474-1601) -----------------------
+    PROJ_TWO_STEP, PROJ_NO_DEPTH, PROJ_FRAME_BOUNDS, PROJ_FRAME_UV, PROJ_DIST_CAMERA, PROJ_CHECK_NORMAL, PROJ_LEVEL_PLUS1 = 1, 2, 4, 8, 16, 32, 64
+
+    def project_points(self, views, scale_factors, Xw, normal, mf_min_distance, mf_max_distance, q_counts, q_valid):
+        """orbm_project_points for len(views) target views (slab layout [n_views, slab, ...]); views: list of Projection.
+        Returns (valid, uv, radius, minl, maxl, level)."""
+        nv = len(views)
+        arr = (Projection * nv)(*views)
+        sf = np.ascontiguousarray(scale_factors, np.float32)
+        Xw = np.ascontiguousarray(Xw, np.float32).reshape(nv, -1, 3); slab = Xw.shape[1]
+        nrm = None if normal is None else np.ascontiguousarray(normal, np.float32).reshape(nv, slab, 3)
+        mn = np.ascontiguousarray(mf_min_distance, np.float32).reshape(nv, slab); mx = np.ascontiguousarray(mf_max_distance, np.float32).reshape(nv, slab)
+        qc = np.ascontiguousarray(q_counts, np.int32)
+        qv = np.ascontiguousarray(q_valid, np.uint8).reshape(nv, slab).copy()
+        uv = np.zeros((nv, slab, 2), np.float32); rad = np.zeros((nv, slab), np.float32)
+        l0 = np.zeros((nv, slab), np.int32); l1 = np.zeros((nv, slab), np.int32); lv = np.zeros((nv, slab), np.int32)
+        _check(self._L.orbm_project_points(self._h, nv, ctypes.cast(arr, ctypes.c_void_p), _ptr(sf), len(sf), _ptr(Xw), None if nrm is None else _ptr(nrm),
+                                           _ptr(mn), _ptr(mx), _ptr(qc), slab, _ptr(qv), _ptr(uv), _ptr(rad), _ptr(l0), _ptr(l1), _ptr(lv), 0))
+        return qv, uv, rad, l0, l1, lv
+
+    def search_best_in_window(self, grid_bounds4, win_origin2, f_xy, f_octave, f_desc, f_counts, q_valid, q_uv, q_radius, q_minl, q_maxl, q_desc,
+                              q_counts, th_dist, inv_level_sigma2=None, chi2_gate=5.99):
+        """orbm_search_best_in_window (candidate loop of Fuse / SearchBySim3): returns (best_idx, best_dist) [n_frames, q_slab]."""
+        f_xy = np.ascontiguousarray(f_xy, np.float32); nfr, fs = f_xy.shape[0], f_xy.shape[1]
+        f_octave = np.ascontiguousarray(f_octave, np.int32); f_desc = np.ascontiguousarray(f_desc, np.uint8); f_counts = np.ascontiguousarray(f_counts, np.int32)
+        q_valid = np.ascontiguousarray(q_valid, np.uint8); qs = q_valid.shape[1]
+        q_uv = np.ascontiguousarray(q_uv, np.float32); q_radius = np.ascontiguousarray(q_radius, np.float32)
+        q_minl = np.ascontiguousarray(q_minl, np.int32); q_maxl = np.ascontiguousarray(q_maxl, np.int32)
+        q_desc = np.ascontiguousarray(q_desc, np.uint8); q_counts = np.ascontiguousarray(q_counts, np.int32)
+        gb = np.ascontiguousarray(grid_bounds4, np.float32)
+        wo = None if win_origin2 is None else np.ascontiguousarray(win_origin2, np.float32)
+        inv = None if inv_level_sigma2 is None else np.ascontiguousarray(inv_level_sigma2, np.float32)
+        bi = np.zeros((nfr, qs), np.int32); bd = np.zeros((nfr, qs), np.int32)
+        _check(self._L.orbm_search_best_in_window(self._h, nfr, _ptr(gb), None if wo is None else _ptr(wo), _ptr(f_xy), _ptr(f_octave), _ptr(f_desc),
+                                                  _ptr(f_counts), fs, _ptr(q_valid), _ptr(q_uv), _ptr(q_radius), _ptr(q_minl), _ptr(q_maxl), _ptr(q_desc),
+                                                  _ptr(q_counts), qs, int(th_dist), None if inv is None else _ptr(inv), 0 if inv is None else len(inv),
+                                                  float(chi2_gate), _ptr(bi), _ptr(bd), 0))
+        return bi, bd
+
+    def SearchByProjectionKF(self, grid_bounds4, win_origin2, f_xy, f_octave, f_angle, f_desc, f_counts, q_valid, q_uv, q_radius, q_minl,
+                             q_maxl, q_angle, q_desc, q_counts, th_dist=50, ratio=0.0, check_ori=False, feat_match=None):
+        """orbm_search_by_projection_kf: the claim loop against a KeyFrame target (integer window origin)."""
+        f_xy = np.ascontiguousarray(f_xy, np.float32); nfr, fs = f_xy.shape[0], f_xy.shape[1]
+        f_octave = np.ascontiguousarray(f_octave, np.int32); f_angle = np.ascontiguousarray(f_angle, np.float32)
+        f_desc = np.ascontiguousarray(f_desc, np.uint8); f_counts = np.ascontiguousarray(f_counts, np.int32)
+        q_valid = np.ascontiguousarray(q_valid, np.uint8); qs = q_valid.shape[1]
+        q_uv = np.ascontiguousarray(q_uv, np.float32); q_radius = np.ascontiguousarray(q_radius, np.float32)
+        q_minl = np.ascontiguousarray(q_minl, np.int32); q_maxl = np.ascontiguousarray(q_maxl, np.int32)
+        q_angle = np.ascontiguousarray(q_angle, np.float32); q_desc = np.ascontiguousarray(q_desc, np.uint8)
+        q_counts = np.ascontiguousarray(q_counts, np.int32)
+        fm = np.full((nfr, fs), -1, np.int32) if feat_match is None else np.ascontiguousarray(feat_match, np.int32).copy()
+        nm = np.zeros(nfr, np.int32)
+        gb = np.ascontiguousarray(grid_bounds4, np.float32)
+        wo = None if win_origin2 is None else np.ascontiguousarray(win_origin2, np.float32)
+        _check(self._L.orbm_search_by_projection_kf(self._h, nfr, _ptr(gb), None if wo is None else _ptr(wo), _ptr(f_xy), _ptr(f_octave), _ptr(f_angle),
+                                                    _ptr(f_desc), _ptr(f_counts), fs, _ptr(q_valid), _ptr(q_uv), _ptr(q_radius), _ptr(q_minl),
+                                                    _ptr(q_maxl), _ptr(q_angle), _ptr(q_desc), _ptr(q_counts), qs, int(th_dist),
+                                                    float(ratio), int(bool(check_ori)), _ptr(fm), _ptr(nm), 0))
+        return nm, fm
+
+
+class Projection(ctypes.Structure):
+    """= orbm_projection (include/orbslamm_b200.h)"""
+    _fields_ = [("R", ctypes.c_float * 9), ("t", ctypes.c_float * 3), ("R2", ctypes.c_float * 9), ("t2", ctypes.c_float * 3),
+                ("Ow", ctypes.c_float * 3), ("fx", ctypes.c_float), ("fy", ctypes.c_float), ("cx", ctypes.c_float), ("cy", ctypes.c_float),
+                ("min_x", ctypes.c_float), ("min_y", ctypes.c_float), ("max_x", ctypes.c_float), ("max_y", ctypes.c_float),
+                ("log_scale_factor", ctypes.c_float), ("th", ctypes.c_float), ("flags", ctypes.c_int32)]
+
+
 class Optimizer:
     """Mirror of iORB_SLAM::Optimizer (reference S/include/Optimizer.h:37-68) over flat arrays: the static functions
     PoseOptimization / LocalBundleAdjustment / BundleAdjustment become methods of a handle that owns the device

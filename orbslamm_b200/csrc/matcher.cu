@@ -12,7 +12,8 @@ namespace orbs {
 constexpr int kGridCols = ORBS_FRAME_GRID_COLS, kGridRows = ORBS_FRAME_GRID_ROWS, kGridCells = kGridCols * kGridRows;
 constexpr int kHisto = ORBM_HISTO_LENGTH;
 
-struct GridParams { float min_x, min_y, max_x, max_y, w_inv, h_inv; };
+// win_x / win_y: origin GetFeaturesInArea subtracts (= min_x / min_y for a Frame; a KeyFrame's integer mnMinX / mnMinY, KeyFrame.cc:623-635)
+struct GridParams { float min_x, min_y, max_x, max_y, w_inv, h_inv, win_x, win_y; };
 
 __device__ __forceinline__ int hamming256(const uint4 a0, const uint4 a1, const uint4 b0, const uint4 b1)
 {
@@ -141,6 +142,85 @@ k_in_frustum(int slab, const int *__restrict__ counts, const float *__restrict__
     view_cos[q] = vc;
 }
 
+// Projection half of the KeyFrame / Sim3 search family (ORBmatcher.cc:292-405, 827-977, 979-1102, 1104-1328, 1474-1601), one thread per
+// (view, map point).  cv::Mat algebra as in k_project_last (small gemm: fp32, left to right, no FMA); cv::norm / Mat::dot in double.
+struct ProjView {            // = orbm_projection (include/orbslamm_b200.h)
+    float R[9], t[3], R2[9], t2[3], Ow[3];
+    float fx, fy, cx, cy, min_x, min_y, max_x, max_y, log_sf, th;
+    int flags;
+};
+static_assert(sizeof(ProjView) == sizeof(orbm_projection), "ProjView must mirror orbm_projection");
+
+__device__ __forceinline__ void rt_apply(const float *R, const float *t, const float *x, float *out)
+{
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+        float s = __fmul_rn(R[3 * r], x[0]);
+        s = __fadd_rn(s, __fmul_rn(R[3 * r + 1], x[1]));
+        s = __fadd_rn(s, __fmul_rn(R[3 * r + 2], x[2]));
+        out[r] = __fadd_rn(s, t[r]);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_project_points(int q_slab, const ProjView *__restrict__ views, const float *__restrict__ scale_factors, int nlevels,
+                 const float *__restrict__ Xw, const float *__restrict__ normal, const float *__restrict__ mf_min, const float *__restrict__ mf_max,
+                 const int *__restrict__ q_counts, uint8_t *__restrict__ q_valid, float2 *__restrict__ q_uv, float *__restrict__ q_radius,
+                 int *__restrict__ q_minl, int *__restrict__ q_maxl, int *__restrict__ q_level)
+{
+    __shared__ ProjView V;
+    const int f = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+    for (int k = threadIdx.x; k < (int)(sizeof(ProjView) / 4); k += blockDim.x) reinterpret_cast<int *>(&V)[k] = reinterpret_cast<const int *>(views + f)[k];
+    __syncthreads();
+    if (i >= q_counts[f]) return;
+    const size_t q = (size_t)f * q_slab + i;
+    if (!q_valid[q]) return;
+    q_valid[q] = 0;
+    const int flags = V.flags;
+    const float X[3] = {Xw[3 * q], Xw[3 * q + 1], Xw[3 * q + 2]};
+    float pc[3];
+    rt_apply(V.R, V.t, X, pc);
+    if (flags & ORBM_PROJ_TWO_STEP) { float p1[3] = {pc[0], pc[1], pc[2]}; rt_apply(V.R2, V.t2, p1, pc); }
+    if (!(flags & ORBM_PROJ_NO_DEPTH) && pc[2] < 0.0f) return;
+    const float invz = __fdiv_rn(1.0f, pc[2]);          // 1/z in float == (float)(1.0/z) in double: division is innocuous under double rounding
+    float u, v;
+    if (flags & ORBM_PROJ_FRAME_UV) {
+        u = __fadd_rn(__fmul_rn(__fmul_rn(V.fx, pc[0]), invz), V.cx);
+        v = __fadd_rn(__fmul_rn(__fmul_rn(V.fy, pc[1]), invz), V.cy);
+    } else {
+        u = __fadd_rn(__fmul_rn(V.fx, __fmul_rn(pc[0], invz)), V.cx);
+        v = __fadd_rn(__fmul_rn(V.fy, __fmul_rn(pc[1], invz)), V.cy);
+    }
+    if (flags & ORBM_PROJ_FRAME_BOUNDS) {
+        if (u < V.min_x || u > V.max_x) return;
+        if (v < V.min_y || v > V.max_y) return;
+    } else if (!(u >= V.min_x && u < V.max_x && v >= V.min_y && v < V.max_y)) return;
+    const float maxd = __fmul_rn(1.2f, mf_max[q]), mind = __fmul_rn(0.8f, mf_min[q]);
+    float po[3];
+    if (flags & ORBM_PROJ_DIST_CAMERA) { po[0] = pc[0]; po[1] = pc[1]; po[2] = pc[2]; }
+    else { po[0] = __fsub_rn(X[0], V.Ow[0]); po[1] = __fsub_rn(X[1], V.Ow[1]); po[2] = __fsub_rn(X[2], V.Ow[2]); }
+    double s2 = 0;
+#pragma unroll
+    for (int k = 0; k < 3; k++) s2 = __dadd_rn(s2, __dmul_rn((double)po[k], (double)po[k]));
+    const float dist = (float)sqrt(s2);
+    if (dist < mind || dist > maxd) return;
+    if (flags & ORBM_PROJ_CHECK_NORMAL) {
+        double dot = 0;
+#pragma unroll
+        for (int k = 0; k < 3; k++) dot = __dadd_rn(dot, __dmul_rn((double)po[k], (double)normal[3 * q + k]));
+        if (dot < __dmul_rn(0.5, (double)dist)) return;
+    }
+    const float ratio = __fdiv_rn(mf_max[q], dist);
+    const int level = (int)ceilf(__fdiv_rn((float)log((double)ratio), V.log_sf));
+    if (level < 0 || level >= nlevels) return;       // the reference indexes mvScaleFactors out of range here (undefined)
+    q_uv[q] = make_float2(u, v);
+    q_radius[q] = __fmul_rn(V.th, scale_factors[level]);
+    q_minl[q] = level - 1;
+    q_maxl[q] = (flags & ORBM_PROJ_LEVEL_PLUS1) ? level + 1 : level;
+    if (q_level) q_level[q] = level;
+    q_valid[q] = 1;
+}
+
 // Frame::AssignFeaturesToGrid / PosInGrid: CSR per frame, cell = ix * 48 + iy.  Order inside a cell is not
 // preserved; the search re-creates the reference's visiting order through an explicit (ix, iy, index) key.
 __global__ void __launch_bounds__(512)
@@ -229,10 +309,10 @@ __device__ __forceinline__ Window make_window(const GridParams &g, float2 uv, fl
 {
     // Frame::GetFeaturesInArea, Frame.cc:327-380
     Window w;
-    w.c0 = (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(uv.x, g.min_x), r), g.w_inv));
-    w.c1 = (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(uv.x, g.min_x), r), g.w_inv));
-    w.r0 = (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(uv.y, g.min_y), r), g.h_inv));
-    w.r1 = (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(uv.y, g.min_y), r), g.h_inv));
+    w.c0 = (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(uv.x, g.win_x), r), g.w_inv));
+    w.c1 = (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(uv.x, g.win_x), r), g.w_inv));
+    w.r0 = (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(uv.y, g.win_y), r), g.h_inv));
+    w.r1 = (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(uv.y, g.win_y), r), g.h_inv));
     w.c0 = max(w.c0, 0); w.r0 = max(w.r0, 0); w.c1 = min(w.c1, kGridCols - 1); w.r1 = min(w.r1, kGridRows - 1);
     w.empty = w.c0 >= kGridCols || w.c1 < 0 || w.r0 >= kGridRows || w.r1 < 0;
     w.check = (minl > 0) || (maxl >= 0);
@@ -329,6 +409,65 @@ k_search_candidates(const SearchArgs A)
         if (lane == 0) top[t] = m == CK::none ? 0xffffffffu : CK::pack(m);
     }
     if (lane == 0) A.ncand[qo + i] = n;
+}
+
+// Search half without claims (Fuse, SearchBySim3): one warp per query, lanes over the grid cells of the window; the minimum of
+// (distance, visiting order) is the feature the reference's "dist < bestDist" loop ends with.
+struct BestArgs {
+    int f_slab, q_slab;
+    GridParams g;
+    const float2 *f_xy; const int *f_octave; const uint4 *f_desc; const int *f_counts;
+    const uint8_t *q_valid; const float2 *q_uv; const float *q_radius; const int *q_minl; const int *q_maxl; const uint4 *q_desc; const int *q_counts;
+    const int *cell_start; const int *cell_items;
+    int th_dist, use_gate, nlevels; float chi2_gate; float inv_sigma2[32];
+    int *best_idx; int *best_dist;
+};
+
+__global__ void __launch_bounds__(256)
+k_search_best(const BestArgs A)
+{
+    const int f = blockIdx.y, lane = threadIdx.x & 31;
+    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (i >= A.q_counts[f]) return;
+    const size_t fo = (size_t)f * A.f_slab, qo = (size_t)f * A.q_slab;
+    unsigned long long best = kNoKey;
+    if (A.q_valid[qo + i]) {
+        const float2 *f_xy = A.f_xy + fo; const int *f_octave = A.f_octave + fo; const uint4 *f_desc = A.f_desc + 2 * fo;
+        const int *cs = A.cell_start + (size_t)f * (kGridCells + 1); const int *items = A.cell_items + fo;
+        const float2 uv = A.q_uv[qo + i];
+        const float r = A.q_radius[qo + i];
+        const int minl = A.q_minl[qo + i], maxl = A.q_maxl[qo + i];
+        const Window w = make_window(A.g, uv, r, minl, maxl);
+        if (!w.empty) {
+            const uint4 qa = __ldg(&A.q_desc[2 * (qo + i)]), qb = __ldg(&A.q_desc[2 * (qo + i) + 1]);
+            const int ncy = w.r1 - w.r0 + 1, ncells = (w.c1 - w.c0 + 1) * ncy;
+            for (int c = lane; c < ncells; c += 32) {
+                const int ix = w.c0 + c / ncy, iy = w.r0 + c % ncy;
+                const int cell = ix * kGridRows + iy;
+                const int je = cs[cell + 1];
+                for (int j = cs[cell]; j < je; j++) {
+                    const int k = items[j];
+                    const int oct = f_octave[k];
+                    const float2 p = f_xy[k];
+                    if (!in_window(w, minl, maxl, uv, r, oct, p)) continue;
+                    if (A.use_gate) {                              // ORBmatcher.cc:918-928
+                        const float ex = __fsub_rn(uv.x, p.x), ey = __fsub_rn(uv.y, p.y);
+                        const float e2 = __fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey));
+                        if (__fmul_rn(e2, A.inv_sigma2[min(max(oct, 0), A.nlevels - 1)]) > A.chi2_gate) continue;
+                    }
+                    const unsigned long long key = make_key(hamming256(qa, qb, __ldg(&f_desc[2 * k]), __ldg(&f_desc[2 * k + 1])), ix, iy, k);
+                    best = key < best ? key : best;
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) { const unsigned long long o = __shfl_xor_sync(0xffffffffu, best, d); best = o < best ? o : best; }
+    if (lane == 0) {
+        const int dist = best == kNoKey ? -1 : (int)(best >> 32);
+        A.best_dist[qo + i] = dist;
+        A.best_idx[qo + i] = (dist >= 0 && dist <= A.th_dist) ? (int)(best & 0xfffff) : -1;
+    }
 }
 
 // slow path: full rescan of one query's window by one WARP (lanes over grid cells, like k_search_candidates); best and
@@ -539,6 +678,7 @@ GridParams make_grid(const float *b4)
     g.min_x = b4[0]; g.min_y = b4[1]; g.max_x = b4[2]; g.max_y = b4[3];
     g.w_inv = (float)kGridCols / (g.max_x - g.min_x);          // Frame.cc:101-102
     g.h_inv = (float)kGridRows / (g.max_y - g.min_y);
+    g.win_x = g.min_x; g.win_y = g.min_y;
     return g;
 }
 }  // namespace
@@ -695,6 +835,18 @@ int orbm_search_by_projection(orbm_handle *h, int n_frames, const float *bounds4
                               int q_slab, int th_dist, float ratio, int check_ori,
                               int32_t *feat_match, int32_t *nmatches, int memspace)
 {
+    return orbm_search_by_projection_kf(h, n_frames, bounds4, nullptr, f_xy, f_octave, f_angle, f_desc, f_counts, f_slab, q_valid, q_uv, q_radius,
+                                        q_minl, q_maxl, q_angle, q_desc, q_counts, q_slab, th_dist, ratio, check_ori, feat_match, nmatches, memspace);
+}
+
+int orbm_search_by_projection_kf(orbm_handle *h, int n_frames, const float *bounds4, const float *win_origin2,
+                                 const float *f_xy, const int32_t *f_octave, const float *f_angle, const uint8_t *f_desc,
+                                 const int32_t *f_counts, int f_slab,
+                                 const uint8_t *q_valid, const float *q_uv, const float *q_radius, const int32_t *q_minl,
+                                 const int32_t *q_maxl, const float *q_angle, const uint8_t *q_desc, const int32_t *q_counts,
+                                 int q_slab, int th_dist, float ratio, int check_ori,
+                                 int32_t *feat_match, int32_t *nmatches, int memspace)
+{
     ORBS_REQUIRE(h && bounds4 && f_xy && f_octave && f_desc && f_counts && q_valid && q_uv && q_radius && q_minl && q_maxl && q_desc && q_counts &&
                  feat_match && nmatches, ORBS_E_INVALID, "null argument");
     ORBS_REQUIRE(!check_ori || (f_angle && q_angle), ORBS_E_INVALID, "orientation check needs the angles");
@@ -707,6 +859,7 @@ int orbm_search_by_projection(orbm_handle *h, int n_frames, const float *bounds4
     const size_t nf = (size_t)n_frames * f_slab, nq = (size_t)n_frames * q_slab;
     SearchArgs A;
     A.f_slab = f_slab; A.q_slab = q_slab; A.g = make_grid(bounds4);
+    if (win_origin2) { A.g.win_x = win_origin2[0]; A.g.win_y = win_origin2[1]; }
     A.f_xy = (const float2 *)S.in(f_xy, nf * 2); A.f_octave = S.in(f_octave, nf);
     A.f_angle = f_angle ? S.in(f_angle, nf) : nullptr; A.f_desc = (const uint4 *)S.in(f_desc, nf * 32);
     A.f_counts = S.in(f_counts, n_frames);
@@ -742,6 +895,85 @@ int orbm_search_by_projection(orbm_handle *h, int n_frames, const float *bounds4
         k_search_resolve<<<n_frames, 1024, smem, h->stream>>>(A, use_smem);
     }
     h->launches += 3;
+    ORBS_CUDA(cudaGetLastError());
+    return S.finish();
+}
+
+int orbm_project_points(orbm_handle *h, int n_views, const orbm_projection *proj, const float *scale_factors, int nlevels,
+                        const float *Xw, const float *normal, const float *mf_min_distance, const float *mf_max_distance,
+                        const int32_t *q_counts, int q_slab, uint8_t *q_valid, float *q_uv, float *q_radius, int32_t *q_minl,
+                        int32_t *q_maxl, int32_t *q_level, int memspace)
+{
+    ORBS_REQUIRE(h && proj && scale_factors && Xw && mf_min_distance && mf_max_distance && q_counts && q_valid && q_uv && q_radius && q_minl && q_maxl,
+                 ORBS_E_INVALID, "null argument");
+    ORBS_REQUIRE(n_views > 0 && q_slab > 0 && nlevels > 0, ORBS_E_INVALID, "non-positive size");
+    for (int f = 0; f < n_views; f++)
+        ORBS_REQUIRE(normal || !(proj[f].flags & ORBM_PROJ_CHECK_NORMAL), ORBS_E_INVALID, "ORBM_PROJ_CHECK_NORMAL needs the normals");
+    std::lock_guard<std::mutex> lk(h->mu);
+    ORBS_CUDA(cudaSetDevice(h->device));
+    Stager S(&h->pool, h->stream, memspace);
+    const size_t nq = (size_t)n_views * q_slab;
+    ProjView *dviews = S.scratch<ProjView>(n_views);                       // the parameter blocks are host arrays in both memory spaces
+    if (S.rc) return S.rc;
+    ORBS_CUDA(cudaMemcpyAsync(dviews, proj, sizeof(ProjView) * (size_t)n_views, cudaMemcpyHostToDevice, h->stream));
+    const float *dsf = S.in(scale_factors, nlevels), *dX = S.in(Xw, nq * 3), *dN = normal ? S.in(normal, nq * 3) : nullptr;
+    const float *dmn = S.in(mf_min_distance, nq), *dmx = S.in(mf_max_distance, nq);
+    const int32_t *dqc = S.in(q_counts, n_views);
+    uint8_t *dval = S.inout(q_valid, nq);
+    float *duv = S.inout(q_uv, nq * 2, false), *drad = S.inout(q_radius, nq, false);
+    int32_t *dl0 = S.inout(q_minl, nq, false), *dl1 = S.inout(q_maxl, nq, false), *dlv = q_level ? S.inout(q_level, nq, false) : nullptr;
+    if (S.rc) return S.rc;
+    if (memspace == ORBS_MEM_HOST) {       // rejected points keep defined values on the host
+        ORBS_CUDA(cudaMemsetAsync(duv, 0, nq * 8, h->stream)); ORBS_CUDA(cudaMemsetAsync(drad, 0, nq * 4, h->stream));
+        ORBS_CUDA(cudaMemsetAsync(dl0, 0, nq * 4, h->stream)); ORBS_CUDA(cudaMemsetAsync(dl1, 0, nq * 4, h->stream));
+        if (dlv) ORBS_CUDA(cudaMemsetAsync(dlv, 0, nq * 4, h->stream));
+    }
+    k_project_points<<<dim3((q_slab + 255) / 256, n_views), 256, 0, h->stream>>>(q_slab, dviews, dsf, nlevels, dX, dN, dmn, dmx, dqc, dval, (float2 *)duv,
+                                                                                 drad, dl0, dl1, dlv);
+    h->launches++;
+    ORBS_CUDA(cudaGetLastError());
+    if (memspace == ORBS_MEM_DEVICE) ORBS_CUDA(cudaStreamSynchronize(h->stream));   // proj is a host array the caller may reuse
+    return S.finish();
+}
+
+int orbm_search_best_in_window(orbm_handle *h, int n_frames, const float *grid_bounds4, const float *win_origin2,
+                               const float *f_xy, const int32_t *f_octave, const uint8_t *f_desc, const int32_t *f_counts, int f_slab,
+                               const uint8_t *q_valid, const float *q_uv, const float *q_radius, const int32_t *q_minl,
+                               const int32_t *q_maxl, const uint8_t *q_desc, const int32_t *q_counts, int q_slab, int th_dist,
+                               const float *inv_level_sigma2, int nlevels, float chi2_gate,
+                               int32_t *q_best_idx, int32_t *q_best_dist, int memspace)
+{
+    ORBS_REQUIRE(h && grid_bounds4 && f_xy && f_octave && f_desc && f_counts && q_valid && q_uv && q_radius && q_minl && q_maxl && q_desc && q_counts &&
+                 q_best_idx && q_best_dist, ORBS_E_INVALID, "null argument");
+    ORBS_REQUIRE(n_frames > 0 && f_slab > 0 && q_slab > 0, ORBS_E_INVALID, "non-positive size");
+    ORBS_REQUIRE(f_slab < (1 << 20), ORBS_E_INVALID, "slab too large (features < 2^20 per frame)");
+    ORBS_REQUIRE(!inv_level_sigma2 || (nlevels > 0 && nlevels <= 32), ORBS_E_INVALID, "1..32 pyramid levels");
+    ORBS_REQUIRE(grid_bounds4[2] > grid_bounds4[0] && grid_bounds4[3] > grid_bounds4[1], ORBS_E_INVALID, "empty image bounds");
+    std::lock_guard<std::mutex> lk(h->mu);
+    ORBS_CUDA(cudaSetDevice(h->device));
+    Stager S(&h->pool, h->stream, memspace);
+    const size_t nf = (size_t)n_frames * f_slab, nq = (size_t)n_frames * q_slab;
+    BestArgs A;
+    A.f_slab = f_slab; A.q_slab = q_slab; A.g = make_grid(grid_bounds4);
+    if (win_origin2) { A.g.win_x = win_origin2[0]; A.g.win_y = win_origin2[1]; }
+    A.f_xy = (const float2 *)S.in(f_xy, nf * 2); A.f_octave = S.in(f_octave, nf); A.f_desc = (const uint4 *)S.in(f_desc, nf * 32);
+    A.f_counts = S.in(f_counts, n_frames);
+    A.q_valid = S.in(q_valid, nq); A.q_uv = (const float2 *)S.in(q_uv, nq * 2); A.q_radius = S.in(q_radius, nq);
+    A.q_minl = S.in(q_minl, nq); A.q_maxl = S.in(q_maxl, nq); A.q_desc = (const uint4 *)S.in(q_desc, nq * 32); A.q_counts = S.in(q_counts, n_frames);
+    A.best_idx = S.inout(q_best_idx, nq, false); A.best_dist = S.inout(q_best_dist, nq, false);
+    if (S.rc) return S.rc;
+    ORBS_REQUIRE(((uintptr_t)A.f_desc % 16 == 0) && ((uintptr_t)A.q_desc % 16 == 0) && ((uintptr_t)A.f_xy % 8 == 0) && ((uintptr_t)A.q_uv % 8 == 0),
+                 ORBS_E_INVALID, "descriptor arrays must be 16-byte aligned, coordinate arrays 8-byte aligned");
+    int rc;
+    if ((rc = h->cell_start.reserve((size_t)n_frames * (kGridCells + 1) * sizeof(int)))) return rc;
+    if ((rc = h->cell_items.reserve(nf * sizeof(int)))) return rc;
+    A.cell_start = h->cell_start.as<int>(); A.cell_items = h->cell_items.as<int>();
+    A.th_dist = th_dist; A.use_gate = inv_level_sigma2 ? 1 : 0; A.nlevels = inv_level_sigma2 ? nlevels : 1; A.chi2_gate = chi2_gate;
+    for (int l = 0; l < 32; l++) A.inv_sigma2[l] = (inv_level_sigma2 && l < nlevels) ? inv_level_sigma2[l] : 0.f;
+    if (memspace == ORBS_MEM_HOST) { ORBS_CUDA(cudaMemsetAsync(A.best_idx, 0xff, nq * 4, h->stream)); ORBS_CUDA(cudaMemsetAsync(A.best_dist, 0xff, nq * 4, h->stream)); }
+    k_grid_build<<<n_frames, 512, 0, h->stream>>>(f_slab, A.g, A.f_xy, A.f_counts, h->cell_start.as<int>(), h->cell_items.as<int>());
+    k_search_best<<<dim3((q_slab + 7) / 8, n_frames), 256, 0, h->stream>>>(A);
+    h->launches += 2;
     ORBS_CUDA(cudaGetLastError());
     return S.finish();
 }

@@ -1,0 +1,278 @@
+"""The KeyFrame / Sim3 members of ORBmatcher composed from the two C-ABI halves (projection, window search) exactly like the C++ drop-in
+(orbslamm_b200/host/ORBmatcher_b200.cc) composes them; parametrised by a backend so that the same composition runs on the oracle
+(CPU tests, against the reference's object code) and on the CUDA library (GPU tests).
+
+Reference: S/src/ORBmatcher.cc:292-405 (SearchByProjection(KF, Scw)), :827-977 and :979-1102 (Fuse), :1104-1328 (SearchBySim3),
+:1474-1601 (SearchByProjection(Frame, KF)).  The host-side cv::Mat algebra that precedes the loops (Scw decomposition, sR12 / sR21 / t21)
+is restated here in numpy float32 with OpenCV's evaluation order (Mat / scalar = multiply by the double reciprocal; small gemm)."""
+import numpy as np
+
+import oracle
+from orbslamm_b200 import synth
+
+F32 = np.float32
+TH_LOW, TH_HIGH = 50, 100
+
+
+# ------------------------------------------------------------------ cv::Mat algebra on the host
+def gemm32(A, B):
+    """OpenCV small-matrix product: fp32 products added left to right."""
+    A = np.asarray(A, F32); B = np.asarray(B, F32)
+    out = np.zeros((A.shape[0], B.shape[1]), F32)
+    for i in range(A.shape[0]):
+        for j in range(B.shape[1]):
+            s = F32(A[i, 0] * B[0, j])
+            for k in range(1, A.shape[1]):
+                s = F32(s + F32(A[i, k] * B[k, j]))
+            out[i, j] = s
+    return out
+
+
+def scale32(A, s):
+    """Mat * double -> float"""
+    return (np.asarray(A, F32).astype(np.float64) * np.float64(s)).astype(F32)
+
+
+def decompose_scw(Scw):
+    """ORBmatcher.cc:300-305"""
+    Scw = np.asarray(Scw, F32).reshape(4, 4)
+    sR = Scw[:3, :3]
+    r0 = sR[0].astype(np.float64)
+    scw = F32(np.sqrt(r0[0] * r0[0] + r0[1] * r0[1] + r0[2] * r0[2]))
+    Rcw = scale32(sR, 1.0 / np.float64(scw))
+    tcw = scale32(Scw[:3, 3:4], 1.0 / np.float64(scw))
+    Ow = gemm32(-(Rcw.T.copy()), tcw)
+    return Rcw, tcw.ravel(), Ow.ravel()
+
+
+def camera_centre(Tcw):
+    Tcw = np.asarray(Tcw, F32).reshape(4, 4)
+    return gemm32(-(Tcw[:3, :3].T.copy()), Tcw[:3, 3:4]).ravel()
+
+
+# ------------------------------------------------------------------ backends
+class OracleBackend:
+    P = oracle
+
+    def project(self, R, t, K4, bounds4, log_sf, th, flags, sf, pts, valid, Ow=None, R2=None, t2=None, use_normal=True):
+        V = oracle.make_projection(R, t, K4, bounds4, log_sf, th, flags, Ow=Ow, R2=R2, t2=t2)
+        return oracle.project_points(V, sf, pts["Xw"], pts["normal"] if use_normal else None, pts["mf_min"], pts["mf_max"], valid)
+
+    def best(self, kf, qv, uv, rad, l0, l1, q_desc, th_dist, gate=False):
+        g = oracle.grid_params(*[float(x) for x in kf["grid_bounds4"]])
+        return oracle.search_best_in_window(g, kf["win_origin2"], kf["xy"], kf["octave"], kf["desc"], qv, uv, rad, l0, l1, q_desc, th_dist,
+                                            kf["inv_level_sigma2"] if gate else None, 5.99)
+
+    def claim(self, kf, qv, uv, rad, l0, l1, q_angle, q_desc, th_dist, ori, fm_in, frame=False):
+        g = oracle.grid_params(*[float(x) for x in kf["grid_bounds4"]])
+        return oracle.search_by_projection_kf(g, None if frame else kf["win_origin2"], kf["xy"], kf["octave"], kf["angle"], kf["desc"], qv, uv, rad,
+                                              l0, l1, q_angle, q_desc, th_dist, 0.0, ori, fm_in)
+
+
+class CudaBackend:
+    def __init__(self):
+        import orbslamm_b200 as ob
+        self.ob = ob
+        self.m = ob.ORBmatcher(0.75, True)
+
+    def project(self, R, t, K4, bounds4, log_sf, th, flags, sf, pts, valid, Ow=None, R2=None, t2=None, use_normal=True):
+        o = oracle.make_projection(R, t, K4, bounds4, log_sf, th, flags, Ow=Ow, R2=R2, t2=t2)
+        V = self.ob.Projection.from_buffer_copy(bytes(o))
+        M = len(valid)
+        r = self.m.project_points([V], sf, pts["Xw"][None], pts["normal"][None] if use_normal else None, pts["mf_min"][None], pts["mf_max"][None],
+                                  np.array([M], np.int32), np.asarray(valid, np.uint8)[None])
+        return tuple(a[0] for a in r)
+
+    def best(self, kf, qv, uv, rad, l0, l1, q_desc, th_dist, gate=False):
+        N, M = len(kf["xy"]), len(qv)
+        bi, bd = self.m.search_best_in_window(kf["grid_bounds4"], kf["win_origin2"], kf["xy"][None], kf["octave"][None], kf["desc"][None],
+                                              np.array([N], np.int32), qv[None], uv[None], rad[None], l0[None], l1[None], q_desc[None],
+                                              np.array([M], np.int32), th_dist, kf["inv_level_sigma2"] if gate else None, 5.99)
+        return bi[0], bd[0]
+
+    def claim(self, kf, qv, uv, rad, l0, l1, q_angle, q_desc, th_dist, ori, fm_in, frame=False):
+        N, M = len(kf["xy"]), len(qv)
+        nm, fm = self.m.SearchByProjectionKF(kf["grid_bounds4"], None if frame else kf["win_origin2"], kf["xy"][None], kf["octave"][None],
+                                             kf["angle"][None], kf["desc"][None], np.array([N], np.int32), qv[None], uv[None], rad[None], l0[None],
+                                             l1[None], np.asarray(q_angle, F32)[None], q_desc[None], np.array([M], np.int32), th_dist, 0.0, ori,
+                                             None if fm_in is None else fm_in[None])
+        return int(nm[0]), fm[0]
+
+
+# ------------------------------------------------------------------ the five members
+P = oracle
+
+
+def kf_bounds(kf):
+    """KeyFrame::mnMinX.. are ints (KeyFrame.h); IsInImage and GetFeaturesInArea use them"""
+    return np.trunc(np.asarray(kf["grid_bounds4"], F32)).astype(F32)
+
+
+def search_kf_sim3(B, kf, Scw, th, pts, skip, held):
+    """SearchByProjection(pKF, Scw, vpPoints, vpMatched, th): returns (nmatches, feat_match[N]: point index, -2 held, -1 none)."""
+    Rcw, tcw, Ow = decompose_scw(Scw)
+    qv, uv, rad, l0, l1, _ = B.project(Rcw, tcw, kf["K4"], kf_bounds(kf), kf["log_sf"], F32(int(th)), P.PROJ_CHECK_NORMAL, kf["scale_factors"], pts,
+                                       1 - np.asarray(skip, np.uint8), Ow=Ow)
+    fm_in = np.where(np.asarray(held) > 0, 1 << 30, -1).astype(np.int32)
+    n, fm = B.claim(kf, qv, uv, rad, l0, l1, np.zeros(len(qv), F32), pts["desc"], TH_LOW, False, fm_in)
+    return n, np.where(fm == 1 << 30, -2, fm)
+
+
+def fuse_search(B, kf, th, pts, skip, Scw=None):
+    """Search half of Fuse: slot[i] = the keyframe feature the point would be fused into, or -1."""
+    if Scw is None:
+        T = np.asarray(kf["Tcw"], F32).reshape(4, 4)
+        Rcw, tcw, Ow = T[:3, :3], T[:3, 3], camera_centre(T)
+    else:
+        Rcw, tcw, Ow = decompose_scw(Scw)
+    qv, uv, rad, l0, l1, _ = B.project(Rcw, tcw, kf["K4"], kf_bounds(kf), kf["log_sf"], F32(th), P.PROJ_CHECK_NORMAL, kf["scale_factors"], pts,
+                                       1 - np.asarray(skip, np.uint8), Ow=Ow)
+    bi, _ = B.best(kf, qv, uv, rad, l0, l1, pts["desc"], TH_LOW, gate=Scw is None)
+    return bi
+
+
+def search_by_sim3(B, kf1, kf2, s12, R12, t12, th, has1, pts1, has2, pts2, matches12):
+    """SearchBySim3: returns (nFound, matches12 updated)."""
+    R12 = np.asarray(R12, F32).reshape(3, 3); t12 = np.asarray(t12, F32).reshape(3, 1)
+    sR12 = scale32(R12, np.float64(F32(s12)))
+    sR21 = scale32(R12.T.copy(), 1.0 / np.float64(F32(s12)))
+    t21 = gemm32(-sR21, t12)
+    T1 = np.asarray(kf1["Tcw"], F32).reshape(4, 4); T2 = np.asarray(kf2["Tcw"], F32).reshape(4, 4)
+    m12 = np.asarray(matches12, np.int32).copy()
+    N1, N2 = len(kf1["xy"]), len(kf2["xy"])
+    done1 = m12 >= 0
+    done2 = np.zeros(N2, bool); done2[m12[done1]] = True        # GetIndexInKeyFrame(pKF2) of an existing match = its feature index
+    flags = P.PROJ_TWO_STEP | P.PROJ_DIST_CAMERA
+    v1 = ((np.asarray(has1) > 0) & ~done1).astype(np.uint8)
+    qv, uv, rad, l0, l1, _ = B.project(T1[:3, :3], T1[:3, 3], kf1["K4"], kf_bounds(kf2), kf2["log_sf"], F32(th), flags, kf2["scale_factors"], pts1, v1,
+                                       R2=sR21, t2=t21.ravel(), use_normal=False)
+    match1, _ = B.best(kf2, qv, uv, rad, l0, l1, pts1["desc"], TH_HIGH)
+    v2 = ((np.asarray(has2) > 0) & ~done2).astype(np.uint8)
+    qv, uv, rad, l0, l1, _ = B.project(T2[:3, :3], T2[:3, 3], kf1["K4"], kf_bounds(kf1), kf1["log_sf"], F32(th), flags, kf1["scale_factors"], pts2, v2,
+                                       R2=sR12, t2=t12.ravel(), use_normal=False)
+    match2, _ = B.best(kf1, qv, uv, rad, l0, l1, pts2["desc"], TH_HIGH)
+    n = 0
+    for i1 in range(N1):
+        j = match1[i1]
+        if j >= 0 and match2[j] == i1:
+            m12[i1] = j; n += 1
+    return n, m12
+
+
+def search_frame_kf(B, cur, Tcw, K4, bounds4, log_sf, sf, held, has, skip, pts, kf_angle, th, orb_dist, check_ori):
+    """SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, ORBdist): returns (nmatches, feat_match[N])."""
+    T = np.asarray(Tcw, F32).reshape(4, 4)
+    Ow = camera_centre(T)
+    flags = P.PROJ_NO_DEPTH | P.PROJ_FRAME_BOUNDS | P.PROJ_FRAME_UV | P.PROJ_LEVEL_PLUS1
+    v = ((np.asarray(has) > 0) & ~(np.asarray(skip) > 0)).astype(np.uint8)
+    qv, uv, rad, l0, l1, _ = B.project(T[:3, :3], T[:3, 3], K4, bounds4, log_sf, F32(th), flags, sf, pts, v, Ow=Ow, use_normal=False)
+    fm_in = np.where(np.asarray(held) > 0, 1 << 30, -1).astype(np.int32)
+    n, fm = B.claim(cur, qv, uv, rad, l0, l1, kf_angle, pts["desc"], orb_dist, check_ori, fm_in, frame=True)
+    return n, np.where(fm == 1 << 30, -2, fm)
+
+
+# ------------------------------------------------------------------ synthetic cases
+def make_case(cam, stream_id, distorted_bounds=False, seed=0):
+    """Two synthetic frames: the current frame's features act as the target keyframe (pose Tcw), the last frame's keypoints as map points
+    with the MapPoint members the family reads (normal, mfMinDistance, mfMaxDistance)."""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from helpers import make_tracking_case
+    k = make_tracking_case(cam, stream_id)
+    rng = np.random.default_rng(100 + seed + stream_id)
+    cur, last = k["cur"], k["last"]
+    sf = np.array(list(k["P"].scale)[:8], F32); inv2 = np.array(list(k["P"].inv_sigma2)[:8], F32)
+    gb = np.array([-27.3, -20.7, cam["w"] + 25.6, cam["h"] + 18.2], F32) if distorted_bounds else k["bounds"].astype(F32)
+    kf = dict(xy=np.stack([cur["x"], cur["y"]], 1).astype(F32), octave=cur["octave"].astype(np.int32), angle=cur["angle"].astype(F32),
+              desc=np.ascontiguousarray(cur["desc"]), scale_factors=sf, inv_level_sigma2=inv2, K4=k["K4"], grid_bounds4=gb, Tcw=k["Tcw"],
+              log_sf=F32(np.log(sf[1])))
+    kf["win_origin2"] = kf_bounds(kf)[:2].copy()
+    M = len(last["x"])
+    Xw = k["Xw"]
+    # reference keyframe of every point = the identity-pose camera; mfMaxDistance = dist * scale[level], mfMinDistance = max / scale[nlevels-1]
+    # (MapPoint::UpdateNormalAndDepth, MapPoint.cc:331-371); normal = mean viewing direction, perturbed so that a few fail the 60 degree test
+    d = np.linalg.norm(Xw, axis=1)
+    lvl = last["octave"]
+    mf_max = (d * sf[lvl] * rng.uniform(0.8, 1.25, M)).astype(F32)
+    # MapPoint::PredictScale is not clamped in this version of the reference: a level outside [0, 8) indexes mvScaleFactors out of range
+    # (undefined behaviour, whatever the heap holds).  Keep the predicted level of every point inside the pyramid.
+    Tk = k["Tcw"].astype(np.float64)
+    dt = np.linalg.norm(Xw - (-Tk[:3, :3].T @ Tk[:3, 3]), axis=1)
+    lv = np.ceil(np.log(mf_max / dt) / np.log(1.2))
+    bad = (lv < 0.001) | (lv > 6.999)
+    mf_max = np.where(bad, dt * 1.2 ** (np.clip(lvl, 1, 7) - 0.5), mf_max).astype(F32)
+    mf_min = (mf_max / sf[7]).astype(F32)
+    nrm = Xw / d[:, None] + rng.normal(0, 0.45, (M, 3))
+    nrm = (nrm / np.linalg.norm(nrm, axis=1)[:, None]).astype(F32)
+    pts = dict(Xw=Xw.astype(F32), normal=nrm, mf_min=mf_min, mf_max=mf_max, desc=np.ascontiguousarray(last["desc"]))
+    skip = (rng.random(M) < 0.1).astype(np.uint8)
+    held = (rng.random(len(cur["x"])) < 0.15).astype(np.uint8)
+    return dict(k=k, kf=kf, pts=pts, skip=skip, held=held, sf=sf, last=last, cur=cur)
+
+
+def sim3_of(Tcw, s):
+    S = np.asarray(Tcw, F32).reshape(4, 4).copy()
+    S[:3, :3] = (S[:3, :3].astype(np.float64) * s).astype(F32)
+    S[:3, 3] = (S[:3, 3].astype(np.float64) * s).astype(F32)
+    return S
+
+
+def make_sim3_pair(cam, stream_id, s12=1.02):
+    """KF1 = last frame, KF2 = current frame of a synthetic stream whose frames differ by an integer image shift: a fronto-parallel plane at
+    depth z0 seen from two cameras that differ by a translation parallel to it reproduces the shift exactly.  KF2 lives in its own map,
+    1 / s12 the size of KF1's.  Returns everything SearchBySim3 reads."""
+    c = make_case(cam, stream_id)
+    k, last, cur = c["k"], c["last"], c["cur"]
+    rng = np.random.default_rng(7 + stream_id)
+    sf, inv2 = c["sf"], c["kf"]["inv_level_sigma2"]
+    fx, fy, cx, cy = [float(v) for v in k["K4"]]
+    dx, dy = k["shift"]
+    z0 = 20.0
+    a = np.deg2rad(11.0)
+    R1 = np.array([[np.cos(a), 0, np.sin(a)], [0, 1, 0], [-np.sin(a), 0, np.cos(a)]]); t1 = np.array([0.4, -0.2, 1.1])
+    T1 = np.eye(4); T1[:3, :3] = R1; T1[:3, 3] = t1
+    Tsh = np.eye(4); Tsh[:3, 3] = [dx * z0 / fx, dy * z0 / fy, 0.0]
+    T2 = Tsh @ T1                                                   # camera 2 from world (KF1's scale)
+
+    def backproject(f, T, noise):
+        n = len(f["x"])
+        z = z0 + rng.normal(0, noise, n)
+        Xc = np.stack([(f["x"] - cx) * z / fx, (f["y"] - cy) * z / fy, z], 1)
+        return (Xc - T[:3, 3]) @ T[:3, :3]
+
+    def points(f, X, T, desc, metric):
+        # T: the camera the points get projected INTO (the other keyframe); metric: its map scale relative to KF1's.  The predicted level
+        # stays inside the pyramid (see make_case): level = octave or octave - 1
+        n = len(X)
+        d = np.linalg.norm(X @ T[:3, :3].T + T[:3, 3], axis=1) * metric
+        o = f["octave"].astype(np.float64)
+        u = np.where(o > 0, rng.uniform(-1.4, -0.1, n), rng.uniform(-0.9, -0.1, n))
+        mf_max = (d * 1.2 ** (o + u)).astype(F32)
+        return dict(Xw=X.astype(F32), normal=np.zeros((n, 3), F32), mf_min=(mf_max / sf[7]).astype(F32), mf_max=mf_max, desc=np.ascontiguousarray(desc))
+
+    def keyframe(f, T):
+        kf = dict(xy=np.stack([f["x"], f["y"]], 1).astype(F32), octave=f["octave"].astype(np.int32), angle=f["angle"].astype(F32),
+                  desc=np.ascontiguousarray(f["desc"]), scale_factors=sf, inv_level_sigma2=inv2, K4=k["K4"], grid_bounds4=c["kf"]["grid_bounds4"],
+                  Tcw=T.astype(F32), log_sf=c["kf"]["log_sf"])
+        kf["win_origin2"] = kf_bounds(kf)[:2].copy()
+        return kf
+
+    X1 = backproject(last, T1, 0.05); X2 = backproject(cur, T2, 0.05)
+    pts1 = points(last, X1, T2, last["desc"], 1.0 / float(s12))    # PredictScale sees |p| in the target camera, in the target's metric
+    pts2 = points(cur, X2, T1, cur["desc"], 1.0)
+    pts2["Xw"] = (X2 / float(s12)).astype(F32)
+    T2s = T2.copy(); T2s[:3, 3] = T2[:3, 3] / float(s12)            # pose of KF2 in its own map: p2 = (R2 X + t2) / s12
+    kf1, kf2 = keyframe(last, T1), keyframe(cur, T2s)
+    has1 = (rng.random(len(last["x"])) < 0.9).astype(np.uint8); has2 = (rng.random(len(cur["x"])) < 0.9).astype(np.uint8)
+    # S12: p1 = s12 R12 p2 + t12 with T12 = T1 T2^-1 = Tsh^-1 (in KF1's metric)
+    T12 = T1 @ np.linalg.inv(T2)
+    R12 = T12[:3, :3].astype(F32); t12 = T12[:3, 3].astype(F32)
+    m12 = np.full(len(last["x"]), -1, np.int32)
+    # a few matches that already exist on entry (vpMatches12): nearest shifted keypoint pairs
+    used = set()
+    for i in range(0, len(last["x"]), 40):
+        dd = np.abs(cur["x"] - last["x"][i] - dx) + np.abs(cur["y"] - last["y"][i] - dy)
+        j = int(np.argmin(dd))
+        if dd[j] < 1.5 and has1[i] and has2[j] and j not in used:
+            m12[i] = j; used.add(j)
+    return dict(kf1=kf1, kf2=kf2, pts1=pts1, pts2=pts2, has1=has1, has2=has2, s12=F32(s12), R12=R12, t12=t12, m12=m12)

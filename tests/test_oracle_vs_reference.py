@@ -135,3 +135,49 @@ def test_descriptor_distance_equals_reference_object_code():
     for _ in range(200):
         a = rng.integers(0, 256, 32, dtype=np.uint8); b = rng.integers(0, 256, 32, dtype=np.uint8)
         assert ref_build.ref_descriptor_distance(a, b) == oracle.descriptor_distance(a, b) == int(np.unpackbits(a ^ b).sum())
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# KeyFrame / Sim3 projection family: SearchByProjection(KF, Scw) :292-405, Fuse :827-977 / :979-1102, SearchBySim3 :1104-1328,
+# SearchByProjection(Frame, KF) :1474-1601 -- the reference's object code against the oracle's two halves composed as the drop-in does.
+import kf_family as kff  # noqa: E402
+
+
+@needs_matcher
+@pytest.mark.parametrize("cam,sid,dist", [("TUM", 1, False), ("KITTI", 2, False), ("TUM", 3, True)])
+def test_kf_family_oracle_equals_reference_object_code(cam, sid, dist):
+    c = kff.make_case(getattr(synth, cam), sid, distorted_bounds=dist)
+    B = kff.OracleBackend()
+    kf, pts, skip, held = c["kf"], c["pts"], c["skip"], c["held"]
+    # SearchByProjection(pKF, Scw, vpPoints, vpMatched, th = 10)  (LoopClosing.cc:245 / MultiMapper.cc:352)
+    Scw = kff.sim3_of(kf["Tcw"], 1.37)
+    n_r, fm_r = ref_build.ref_search_kf_sim3(kf, Scw, 10, pts, skip, held)
+    n_o, fm_o = kff.search_kf_sim3(B, kf, Scw, 10, pts, skip, held)
+    assert n_r > 30 and n_o == n_r and np.array_equal(fm_o, fm_r)
+    # Fuse(pKF, vpMapPoints, th = 3)  (LocalMapping.cc:483 ff.) with occupied and free slots, and Fuse(pKF, Scw, vpPoints, th = 4, vpReplace)
+    for th in (3.0, 6.0):
+        n_r, slot_r = ref_build.ref_fuse_kf(kf, th, pts, skip, held)
+        slot_o = kff.fuse_search(B, kf, th, pts, skip)
+        assert n_r > 30 and np.array_equal(slot_o, slot_r) and int((slot_o >= 0).sum()) == n_r
+    n_r, slot_r = ref_build.ref_fuse_sim3(kf, Scw, 4.0, pts, skip, held)
+    slot_o = kff.fuse_search(B, kf, 4.0, pts, skip, Scw=Scw)
+    assert n_r > 30 and np.array_equal(slot_o, slot_r) and int((slot_o >= 0).sum()) == n_r
+    # SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, ORBdist)  (Tracking.cc:1454 / :1482: th 10 / 3, ORBdist 100 / 64)
+    k = c["k"]
+    has = (np.random.default_rng(3).random(len(skip)) < 0.85).astype(np.uint8)
+    cur = dict(kf); cur["grid_bounds4"] = k["bounds"].astype(np.float32)
+    for th, od, ori in ((10.0, 100, True), (3.0, 64, True), (10.0, 100, False)):
+        n_r, fm_r = ref_build.ref_search_frame_kf(k["K4"], k["bounds"], k["Tcw"], c["sf"], c["cur"], held, has, skip, pts, c["last"]["angle"], th, od, ori)
+        n_o, fm_o = kff.search_frame_kf(B, cur, k["Tcw"], k["K4"], k["bounds"], kf["log_sf"], c["sf"], held, has, skip, pts, c["last"]["angle"], th, od, ori)
+        assert n_r > 20 and n_o == n_r and np.array_equal(fm_o, fm_r)
+
+
+@needs_matcher
+@pytest.mark.parametrize("cam,sid", [("TUM", 1), ("KITTI", 2)])
+def test_search_by_sim3_oracle_equals_reference_object_code(cam, sid):
+    p = kff.make_sim3_pair(getattr(synth, cam), sid)
+    for th in (7.5, 3.0):
+        n_r, m_r = ref_build.ref_search_by_sim3(p["kf1"], p["kf2"], p["s12"], p["R12"], p["t12"], th, p["has1"], p["pts1"], p["has2"], p["pts2"], p["m12"])
+        n_o, m_o = kff.search_by_sim3(kff.OracleBackend(), p["kf1"], p["kf2"], p["s12"], p["R12"], p["t12"], th, p["has1"], p["pts1"], p["has2"], p["pts2"],
+                                      p["m12"])
+        assert n_r > 20 and n_o == n_r and np.array_equal(m_o, m_r)
