@@ -23,5 +23,6 @@ public:
     std::vector<bool> mvbOutlier;
     cv::Mat mTcw;
     std::vector<float> mvScaleFactors, mvInvLevelSigma2;
+    float mfLogScaleFactor = 0;
 };
 }  // namespace iORB_SLAM

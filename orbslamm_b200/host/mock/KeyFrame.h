@@ -1,4 +1,5 @@
 #pragma once
+#include <set>
 #include "MapPoint.h"
 
 namespace iORB_SLAM
@@ -14,9 +15,32 @@ public:
     std::vector<KeyFrame *> GetVectorCovisibleKeyFrames() { return mvpOrderedConnectedKeyFrames; }
     std::vector<MapPoint *> GetMapPointMatches() { return mvpMapPoints; }
     void EraseMapPointMatch(MapPoint *pMP) { for (auto &p : mvpMapPoints) if (p == pMP) p = nullptr; }
+    void EraseMapPointMatch(const size_t &idx) { mvpMapPoints[idx] = nullptr; }
+    void ReplaceMapPointMatch(const size_t &idx, MapPoint *pMP) { mvpMapPoints[idx] = pMP; }
+    MapPoint *GetMapPoint(const size_t &idx) { return mvpMapPoints[idx]; }
+    void AddMapPoint(MapPoint *pMP, const size_t &idx) { mvpMapPoints[idx] = pMP; }
+    std::set<MapPoint *> GetMapPoints() { std::set<MapPoint *> s; for (MapPoint *p : mvpMapPoints) if (p && !p->isBad()) s.insert(p); return s; }
+    cv::Mat GetRotation() { cv::Mat R(3, 3, CV_32F); for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) R.at<float>(r, c) = Tcw.at<float>(r, c); return R; }
+    cv::Mat GetTranslation() { cv::Mat t(3, 1, CV_32F); for (int r = 0; r < 3; r++) t.at<float>(r) = Tcw.at<float>(r, 3); return t; }
+    cv::Mat GetCameraCenter()          // Ow = -Rcw^T tcw (KeyFrame::SetPose, KeyFrame.cc:72-76), OpenCV small-gemm order
+    {
+        cv::Mat O(3, 1, CV_32F);
+        for (int r = 0; r < 3; r++) {
+            float s = -Tcw.at<float>(0, r) * Tcw.at<float>(0, 3);
+            s = s + -Tcw.at<float>(1, r) * Tcw.at<float>(1, 3);
+            s = s + -Tcw.at<float>(2, r) * Tcw.at<float>(2, 3);
+            O.at<float>(r) = s;
+        }
+        return O;
+    }
 
     long unsigned int mnId = 0, mnBALocalForKF = ~0ul, mnBAFixedForKF = ~0ul, mnBAGlobalForKF = 0;
     float fx = 0, fy = 0, cx = 0, cy = 0;
+    int N = 0;
+    int mnMinX = 0, mnMinY = 0, mnMaxX = 0, mnMaxY = 0;           // ints in S/include/KeyFrame.h
+    float mfGridElementWidthInv = 0, mfGridElementHeightInv = 0, mfLogScaleFactor = 0;
+    std::vector<float> mvScaleFactors;
+    cv::Mat mDescriptors;
     std::vector<cv::KeyPoint> mvKeysUn;
     std::vector<float> mvuRight, mvInvLevelSigma2;
     std::vector<MapPoint *> mvpMapPoints;

@@ -84,3 +84,77 @@ def test_cpp_dropin_classes(lib, tmp_path):
     assert np.abs(got_x[seen] - ref["points"][seen]).max() < 2e-5 * np.abs(ref["points"]).max()
     nobs = np.bincount(g["pt"], minlength=150) - np.bincount(g["pt"][keep][ref["outlier"] > 0], minlength=150)
     assert np.abs(r("ba_out_nobs.bin", np.int32) - nobs).sum() <= 2          # erased observations (ties at the chi2 gate aside)
+
+
+def test_cpp_dropin_kf_family(lib, tmp_path):
+    """ORBmatcher::SearchByProjection(KF, Scw) / Fuse x2 / SearchByProjection(Frame, KF) / SearchBySim3 through the C++ drop-in class on the mock
+    data model: search results equal the oracle composition (= the reference's object code, tests/test_oracle_vs_reference.py) and the map
+    updates of Fuse follow the reference's rules (ORBmatcher.cc:940-972, 1080-1097)."""
+    import kf_family as kff
+    d = str(tmp_path)
+    exe = os.path.join(d, "host_kf_family_test")
+    srcs = [os.path.join(HOST, f) for f in ("ORBmatcher_b200.cc", "mock/slam_statics.cc", "test/host_kf_family_test.cc")]
+    subprocess.check_call(["g++", "-std=c++14", "-O2", "-I" + os.path.join(HOST, "mock"), "-I" + HOST, "-I" + os.path.join(ROOT, "include")] + srcs +
+                          ["-L" + os.path.join(ROOT, "orbslamm_b200"), "-lorbslamm_b200", "-Wl,-rpath," + os.path.join(ROOT, "orbslamm_b200"), "-lpthread", "-o", exe])
+    c = kff.make_case(synth.TUM, 3, distorted_bounds=True)
+    kf, pts, skip, held, k = c["kf"], c["pts"], c["skip"], c["held"], c["k"]
+    Scw = kff.sim3_of(kf["Tcw"], 1.37)
+    w = lambda name, a: np.ascontiguousarray(a).tofile(os.path.join(d, name))
+
+    def w_kf(tag, kf):
+        w(tag + "_xy.bin", kf["xy"]); w(tag + "_angle.bin", kf["angle"]); w(tag + "_octave.bin", kf["octave"]); w(tag + "_desc.bin", kf["desc"]); w(tag + "_Tcw.bin", kf["Tcw"])
+
+    def w_pts(tag, p):
+        w(tag + "_Xw.bin", p["Xw"]); w(tag + "_normal.bin", p["normal"]); w(tag + "_mfmin.bin", p["mf_min"]); w(tag + "_mfmax.bin", p["mf_max"]); w(tag + "_desc.bin", p["desc"])
+
+    w("sf.bin", c["sf"]); w("inv2.bin", kf["inv_level_sigma2"]); w("K4.bin", kf["K4"]); w("grid_bounds.bin", kf["grid_bounds4"]); w("frame_bounds.bin", k["bounds"].astype(np.float32))
+    w("skip.bin", skip); w("held.bin", held); w("Scw.bin", Scw); w_kf("kf", kf); w_pts("pts", pts)
+    has = (np.random.default_rng(3).random(len(skip)) < 0.85).astype(np.uint8)
+    w("has.bin", has); w("kf_angle.bin", c["last"]["angle"].astype(np.float32))
+    p = kff.make_sim3_pair(synth.TUM, 1)
+    w("s3_grid_bounds.bin", p["kf1"]["grid_bounds4"]); w_kf("s3_kf1", p["kf1"]); w_kf("s3_kf2", p["kf2"]); w_pts("s3_pts1", p["pts1"]); w_pts("s3_pts2", p["pts2"])
+    w("s3_has1.bin", p["has1"]); w("s3_has2.bin", p["has2"]); w("s3_m12.bin", p["m12"])
+    w("s3_srt.bin", np.concatenate([[p["s12"]], p["R12"].ravel(), p["t12"].ravel()]).astype(np.float32))
+    out = subprocess.run([exe, d], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    r = lambda name: np.fromfile(os.path.join(d, name), np.int32)
+    Bo = kff.OracleBackend()
+    N, M = len(kf["xy"]), len(skip)
+    # claim searches
+    n_o, fm_o = kff.search_kf_sim3(Bo, kf, Scw, 10, pts, skip, held)
+    got = r("out_search_kf_sim3.bin")
+    assert n_o > 30 and got[N] == n_o and np.array_equal(got[:N], fm_o)
+    cur = dict(kf); cur["grid_bounds4"] = k["bounds"].astype(np.float32)
+    n_o, fm_o = kff.search_frame_kf(Bo, cur, k["Tcw"], k["K4"], k["bounds"], kf["log_sf"], c["sf"], held, has, skip, pts, c["last"]["angle"], 10.0, 100, True)
+    got = r("out_search_frame_kf.bin")
+    assert n_o > 20 and got[N] == n_o and np.array_equal(got[:N], fm_o)
+    # Fuse: emulate the reference's map updates from the oracle's search result
+    for name, th, S in (("out_fuse_kf.bin", 3.0, None), ("out_fuse_sim3.bin", 4.0, Scw)):
+        slot = kff.fuse_search(Bo, kf, th, pts, skip, Scw=S)
+        got = r(name)
+        per = got[:4 * M].reshape(M, 4); kf_mp = got[4 * M:4 * M + N]; n = got[4 * M + N]
+        in_kf = np.where(held > 0, 1000000 + np.arange(N), -1)           # map point id per keyframe slot
+        bad = skip.astype(bool).copy(); repl_by = np.full(M, -1); idx_in = np.full(M, -1); vrep = np.full(M, -1); nobs = np.ones(M, int)
+        nf = 0
+        for i in range(M):
+            s = slot[i]
+            if s < 0 or (S is None and (bad[i] or idx_in[i] >= 0)):
+                continue
+            o = in_kf[s]
+            if o >= 0:
+                if S is not None:
+                    vrep[i] = o
+                elif o >= 1000000 or nobs[o] > nobs[i]:                   # holders have 1000 observations
+                    bad[i] = True; repl_by[i] = o
+                else:                                                     # pMPinKF->Replace(pMP): pMP takes over the slot
+                    bad[o] = True; repl_by[o] = i; idx_in[i] = idx_in[o]; idx_in[o] = -1; in_kf[s] = i; nobs[i] += 1
+            else:
+                in_kf[s] = i; idx_in[i] = s; nobs[i] += 1
+            nf += 1
+        assert n == nf and nf > 30
+        assert np.array_equal(per[:, 0], bad.astype(np.int32)) and np.array_equal(per[:, 1], repl_by) and np.array_equal(per[:, 2], idx_in) and np.array_equal(per[:, 3], vrep)
+        assert np.array_equal(kf_mp, in_kf)
+    # SearchBySim3
+    n_o, m_o = kff.search_by_sim3(Bo, p["kf1"], p["kf2"], p["s12"], p["R12"], p["t12"], 7.5, p["has1"], p["pts1"], p["has2"], p["pts2"], p["m12"])
+    got = r("out_search_by_sim3.bin")
+    assert n_o > 20 and got[-1] == n_o and np.array_equal(got[:-1], m_o)
