@@ -310,6 +310,21 @@ int orbo_bundle_adjust(orbo_handle *h, int K, float *poses, const uint8_t *fixed
                        int two_stage, int its0, int its1, int robust, const volatile int *stop_flag,
                        double *e_chi2, uint8_t *e_depth_ok, uint8_t *e_outlier, int32_t *stats);
 
+/* Optimizer::OptimizeSim3(pKF1, pKF2, vpMatches1, g2oS12, th2, bFixScale) (S/src/Optimizer.cc:1348-1543) for n_pairs independent keyframe
+ * pairs: one VertexSim3Expmap against fixed points, EdgeSim3ProjectXYZ (x1 = S12 X2) + EdgeInverseSim3ProjectXYZ (x2 = S21 X1) per
+ * correspondence with Huber kernels (delta = sqrt(th2)), g2o Levenberg on the dense 7x7 system, numeric Jacobians (central differences,
+ * delta = 1e-9, base_binary_edge.hpp:131-205): 5 iterations, drop pairs with chi2 > th2 on either edge, 10 (5 if none dropped) more.
+ *   sim3 f64[n_pairs,8] in/out = g2o::Sim3 members r (x y z w), t, s of g2oS12 -- left untouched when fewer than 10 correspondences
+ *     survive the first pass (the reference returns 0 there, :1497-1498);
+ *   valid u8[n_pairs*slab]: slot i is a correspondence (vpMatches1[i] set, both points good, :1398-1433); P1c / P2c f32[.,3]: the two map
+ *     points in their own camera frames (R1w*P3D1w+t1w, float, :1411-1424); obs1 / obs2 f32[.,2] = kpUn.pt in KF1 / KF2; inv_sigma2_1/2
+ *     f32[.] = mvInvLevelSigma2[octave]; K1 / K2 f32[n_pairs,4] = fx fy cx cy; counts i32[n_pairs];
+ *   out: inlier u8[.] (vpMatches1[i] stays set), n_inliers i32[n_pairs] (the return value), lm_stats i32[n_pairs,2] (may be NULL):
+ *     LM iterations and trials executed. */
+int orbo_optimize_sim3(orbo_handle *h, int n_pairs, double *sim3, const uint8_t *valid, const float *P1c, const float *P2c, const float *obs1,
+                       const float *obs2, const float *inv_sigma2_1, const float *inv_sigma2_2, const float *K1, const float *K2, const int32_t *counts,
+                       int slab, float th2, int fix_scale, uint8_t *inlier, int32_t *n_inliers, int32_t *lm_stats, int memspace);
+
 /* Multi-GPU bundle adjustment: one process per GPU, keyframe poses replicated, MAP POINTS (with all
  * their observations) sharded over the ranks.  After orbo_comm_init the handle's orbo_bundle_adjust becomes a
  * collective: every rank passes ALL keyframes (same order, same poses) but only ITS points and edges; each rank builds

@@ -408,3 +408,17 @@ def search_by_projection_kf(g, win_origin2, f_xy, f_octave, f_angle, f_desc, q_v
                                          _p(q_minl, _i32p), _p(q_maxl, _i32p), _p(q_angle, _f32p), _p(q_desc, _u8p), int(th_dist), float(ratio),
                                          int(bool(check_ori)), _p(fm, _i32p))
     return n, fm
+
+
+def optimize_sim3(sim3, valid, P1c, P2c, obs1, obs2, w1, w2, K1, K2, th2=10.0, fix_scale=False):
+    """Optimizer::OptimizeSim3 (Optimizer.cc:1348-1543).  sim3 = (qx, qy, qz, qw, tx, ty, tz, s) of g2oS12.
+    Returns dict(sim3, inlier u8[N], n_in, lm_iterations, lm_trials)."""
+    S = np.ascontiguousarray(sim3, np.float64).copy()
+    v = np.ascontiguousarray(valid, np.uint8); N = len(v)
+    a = [np.ascontiguousarray(x, np.float32) for x in (P1c, P2c, obs1, obs2, w1, w2, K1, K2)]
+    inl = np.zeros(N, np.uint8); st = np.zeros(2, np.int32)
+    L = lib()
+    L.oracle_optimize_sim3.restype = ctypes.c_int
+    L.oracle_optimize_sim3.argtypes = [_f64p, ctypes.c_int, _u8p] + [_f32p] * 8 + [ctypes.c_float, ctypes.c_int, _u8p, _i32p]
+    n = L.oracle_optimize_sim3(_p(S, _f64p), N, _p(v, _u8p), *[_p(x, _f32p) for x in a], float(th2), int(bool(fix_scale)), _p(inl, _u8p), _p(st, _i32p))
+    return dict(sim3=S, inlier=inl, n_in=int(n), lm_iterations=int(st[0]), lm_trials=int(st[1]))

@@ -1020,3 +1020,261 @@ void oracle_is_in_frustum(const float *Tcw, const float *Ow, const float *K4, co
         view_cos[i] = vc;
     }
 }
+
+/* ======================================================================================== */
+/* Optimizer::OptimizeSim3, Optimizer.cc:1348-1543: one VertexSim3Expmap against fixed points, EdgeSim3ProjectXYZ (x1 = S12 X2) and
+ * EdgeInverseSim3ProjectXYZ (x2 = S21 X1) with Huber kernels, BlockSolverX + LinearSolverDense (7x7 LDLT), g2o's Levenberg.  The
+ * edges have no analytic Jacobian in this g2o (types_seven_dof_expmap.h:147,169): BaseBinaryEdge::linearizeOplus differentiates
+ * numerically, central differences with delta = 1e-9 through oplusImpl (base_binary_edge.hpp:131-205).
+ *   g2o::Sim3 (types/sim3.h): r quaternion (x y z w), t, s; exp map :45-104; map :106-108; inverse :184-187; operator* :214-220.
+ *   VertexSim3Expmap::oplusImpl (types_seven_dof_expmap.h:54-63): update[6] = 0 when _fix_scale; estimate <- Sim3(update) * estimate. */
+typedef struct { double q[4]; double t[3]; double s; } sim3;
+
+static void sim3_exp(const double u[7], sim3 *out)                 /* Sim3(const Vector7d&), sim3.h:45-104 */
+{
+    const double w[3] = {u[0], u[1], u[2]}, sigma = u[6];
+    const double theta = sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+    const double O[9] = {0, -w[2], w[1], w[2], 0, -w[0], -w[1], w[0], 0};
+    double O2[9], R[9], W[9];
+    mat3_mul(O, O, O2);
+    const double s = exp(sigma), eps = 0.00001;
+    double A, Bc, C;
+    if (fabs(sigma) < eps) {
+        C = 1;
+        if (theta < eps) {
+            A = 1. / 2.; Bc = 1. / 6.;
+            for (int i = 0; i < 9; i++) R[i] = (i % 4 == 0 ? 1.0 : 0.0) + O[i] + O2[i];
+        } else {
+            const double theta2 = theta * theta;
+            A = (1 - cos(theta)) / (theta2);
+            Bc = (theta - sin(theta)) / (theta2 * theta);
+            for (int i = 0; i < 9; i++) R[i] = (i % 4 == 0 ? 1.0 : 0.0) + sin(theta) / theta * O[i] + (1 - cos(theta)) / (theta * theta) * O2[i];
+        }
+    } else {
+        C = (s - 1) / sigma;
+        if (theta < eps) {
+            const double sigma2 = sigma * sigma;
+            A = ((sigma - 1) * s + 1) / sigma2;
+            Bc = ((0.5 * sigma2 - sigma + 1) * s) / (sigma2 * sigma);
+            for (int i = 0; i < 9; i++) R[i] = (i % 4 == 0 ? 1.0 : 0.0) + O[i] + O2[i];
+        } else {
+            for (int i = 0; i < 9; i++) R[i] = (i % 4 == 0 ? 1.0 : 0.0) + sin(theta) / theta * O[i] + (1 - cos(theta)) / (theta * theta) * O2[i];
+            const double a = s * sin(theta), b = s * cos(theta), theta2 = theta * theta, sigma2 = sigma * sigma, c = theta2 + sigma2;
+            A = (a * sigma + (1 - b) * theta) / (theta * c);
+            Bc = (C - ((b - 1) * sigma + a * theta) / (c)) * 1. / (theta2);
+        }
+    }
+    quat_from_R(R, out->q);
+    for (int i = 0; i < 9; i++) W[i] = A * O[i] + Bc * O2[i] + C * (i % 4 == 0 ? 1.0 : 0.0);
+    for (int r = 0; r < 3; r++) out->t[r] = W[3 * r] * u[3] + W[3 * r + 1] * u[4] + W[3 * r + 2] * u[5];
+    out->s = s;
+}
+
+static void sim3_map(const sim3 *S, const double x[3], double out[3])          /* s*(r*xyz) + t */
+{
+    double rx[3];
+    quat_rotate(S->q, x, rx);
+    for (int k = 0; k < 3; k++) out[k] = S->s * rx[k] + S->t[k];
+}
+
+static void sim3_inverse(const sim3 *S, sim3 *out)                              /* Sim3(r.conjugate(), r.conjugate()*((-1./s)*t), 1./s) */
+{
+    const double qc[4] = {-S->q[0], -S->q[1], -S->q[2], S->q[3]};
+    const double f = -1. / S->s, st[3] = {f * S->t[0], f * S->t[1], f * S->t[2]};
+    quat_rotate(qc, st, out->t);
+    memcpy(out->q, qc, sizeof qc);
+    out->s = 1. / S->s;
+}
+
+static void sim3_mul(const sim3 *a, const sim3 *b, sim3 *o)                     /* operator*, sim3.h:214-220 */
+{
+    sim3 r;
+    quat_mul(a->q, b->q, r.q);
+    double rt[3];
+    quat_rotate(a->q, b->t, rt);
+    for (int k = 0; k < 3; k++) r.t[k] = a->s * rt[k] + a->t[k];
+    r.s = a->s * b->s;
+    *o = r;
+}
+
+typedef struct {
+    int N; const float *P1c, *P2c, *obs1, *obs2, *w1, *w2; double K1[4], K2[4];
+    int fix_scale; double delta, dsqr;
+    uint8_t *active;             /* per correspondence: both edges still in the graph */
+    double *err;                 /* [N,4]: stored _error of e12 and e21 */
+} s3_t;
+
+static void s3_errors(const s3_t *B, const sim3 *S, int i, double e[4])
+{
+    sim3 Si;
+    double X2[3] = {B->P2c[3 * i], B->P2c[3 * i + 1], B->P2c[3 * i + 2]}, X1[3] = {B->P1c[3 * i], B->P1c[3 * i + 1], B->P1c[3 * i + 2]}, p[3];
+    sim3_map(S, X2, p);                                             /* EdgeSim3ProjectXYZ::computeError */
+    e[0] = (double)B->obs1[2 * i] - (p[0] / p[2] * B->K1[0] + B->K1[2]);
+    e[1] = (double)B->obs1[2 * i + 1] - (p[1] / p[2] * B->K1[1] + B->K1[3]);
+    sim3_inverse(S, &Si);                                           /* EdgeInverseSim3ProjectXYZ::computeError */
+    sim3_map(&Si, X1, p);
+    e[2] = (double)B->obs2[2 * i] - (p[0] / p[2] * B->K2[0] + B->K2[2]);
+    e[3] = (double)B->obs2[2 * i + 1] - (p[1] / p[2] * B->K2[1] + B->K2[3]);
+}
+
+static void s3_oplus(const s3_t *B, const sim3 *S, const double *upd, sim3 *out)
+{
+    double u[7];
+    memcpy(u, upd, sizeof u);
+    if (B->fix_scale) u[6] = 0;
+    sim3 d;
+    sim3_exp(u, &d);
+    sim3_mul(&d, S, out);
+}
+
+static double s3_chi2(double e0, double e1, double w) { return e0 * (w * e0 + 0.0 * e1) + e1 * (0.0 * e0 + w * e1); }
+
+static double s3_active_errors(s3_t *B, const sim3 *S)             /* computeActiveErrors + activeRobustChi2 */
+{
+    double chi = 0;
+    for (int i = 0; i < B->N; i++) {
+        if (!B->active[i]) continue;
+        double *e = &B->err[4 * i];
+        s3_errors(B, S, i, e);
+        for (int k = 0; k < 2; k++) {
+            const double c = s3_chi2(e[2 * k], e[2 * k + 1], (double)(k ? B->w2[i] : B->w1[i]));
+            double rho[3];
+            if (c <= B->dsqr) { rho[0] = c; } else { rho[0] = 2 * sqrt(c) * B->delta - B->dsqr; }
+            chi += rho[0];
+        }
+    }
+    return chi;
+}
+
+static int ldlt7(const double *H, const double *b, double lambda, double *x)    /* LinearSolverDense: Eigen LDLT + isPositive */
+{
+    double A[49];
+    memcpy(A, H, sizeof A);
+    for (int i = 0; i < 7; i++) A[8 * i] += lambda;
+    for (int i = 0; i < 7; i++)
+        for (int j = 0; j <= i; j++) {
+            double s = A[7 * i + j];
+            for (int k = 0; k < j; k++) s -= A[7 * i + k] * A[7 * j + k] * A[8 * k];
+            if (j < i) A[7 * i + j] = s / A[8 * j];
+            else { if (!(s > 0.0)) return 0; A[8 * i] = s; }
+        }
+    for (int i = 0; i < 7; i++) { double s = b[i]; for (int k = 0; k < i; k++) s -= A[7 * i + k] * x[k]; x[i] = s; }
+    for (int i = 0; i < 7; i++) x[i] /= A[8 * i];
+    for (int i = 6; i >= 0; i--) { const double xi = x[i]; for (int k = 0; k < i; k++) x[k] -= A[7 * i + k] * xi; }
+    return 1;
+}
+
+/* SparseOptimizer::optimize(iterations) with OptimizationAlgorithmLevenberg::solve on the single Sim3 vertex */
+static void s3_optimize(s3_t *B, sim3 *S, int iterations, int *stats)
+{
+    int any = 0;
+    for (int i = 0; i < B->N; i++) any |= B->active[i];
+    if (!any) return;
+    double lambda = 0, ni = 2;
+    int nbad = 0;
+    for (int it = 0; it < iterations; it++) {
+        double currentChi = s3_active_errors(B, S), tempChi;
+        const double iniChi = currentChi;
+        double H[49], b[7], x[7];
+        memset(H, 0, sizeof H); memset(b, 0, sizeof b);
+        for (int i = 0; i < B->N; i++) {                            /* buildSystem: linearizeOplus (numeric) + constructQuadraticForm */
+            if (!B->active[i]) continue;
+            double J[4][7];
+            const double delta = 1e-9, scalar = 1.0 / (2 * delta);
+            for (int d = 0; d < 7; d++) {
+                double add[7] = {0, 0, 0, 0, 0, 0, 0}, ep[4], em[4];
+                sim3 Sp;
+                add[d] = delta; s3_oplus(B, S, add, &Sp); s3_errors(B, &Sp, i, ep);
+                add[d] = -delta; s3_oplus(B, S, add, &Sp); s3_errors(B, &Sp, i, em);
+                for (int r = 0; r < 4; r++) J[r][d] = scalar * (ep[r] - em[r]);
+            }
+            const double *e = &B->err[4 * i];
+            for (int k = 0; k < 2; k++) {
+                const double w = (double)(k ? B->w2[i] : B->w1[i]);
+                const double e0 = e[2 * k], e1 = e[2 * k + 1];
+                const double c = s3_chi2(e0, e1, w);
+                double rho1 = 1.;
+                if (c > B->dsqr) rho1 = B->delta / sqrt(c);
+                const double wo = rho1 * w, r0 = rho1 * w * e0, r1 = rho1 * w * e1;
+                const double *J0 = J[2 * k], *J1 = J[2 * k + 1];
+                for (int a = 0; a < 7; a++) {
+                    b[a] -= J0[a] * r0 + J1[a] * r1;
+                    for (int cc = a; cc < 7; cc++) { const double v = J0[a] * wo * J0[cc] + J1[a] * wo * J1[cc]; H[7 * a + cc] += v; if (cc != a) H[7 * cc + a] += v; }
+                }
+            }
+        }
+        if (it == 0) {                                              /* computeLambdaInit */
+            double mx = 0;
+            for (int a = 0; a < 7; a++) mx = fmax(fabs(H[8 * a]), mx);
+            lambda = 1e-5 * mx; ni = 2; nbad = 0;
+        }
+        double rho = 0;
+        int qmax = 0;
+        do {
+            const sim3 backup = *S;
+            const int ok2 = ldlt7(H, b, lambda, x);
+            sim3 Sn;
+            s3_oplus(B, S, x, &Sn);
+            *S = Sn;
+            tempChi = s3_active_errors(B, S);
+            if (!ok2) tempChi = DBL_MAX;
+            rho = currentChi - tempChi;
+            double scale = 0.;
+            for (int j = 0; j < 7; j++) scale += x[j] * (lambda * x[j] + b[j]);
+            scale += 1e-3;
+            rho /= scale;
+            if (rho > 0 && isfinite(tempChi)) {
+                double alpha = 1. - pow((2 * rho - 1), 3);
+                alpha = fmin(alpha, 2. / 3.);
+                lambda *= fmax(1. / 3., alpha); ni = 2; currentChi = tempChi;
+            } else { lambda *= ni; ni *= 2; *S = backup; }
+            qmax++;
+            if (stats) stats[1]++;
+        } while (rho < 0 && qmax < 10);
+        if (stats) stats[0]++;
+        if (qmax == 10 || rho == 0) break;
+        if ((iniChi - currentChi) * 1e3 < iniChi) nbad++; else nbad = 0;
+        if (nbad >= 3) break;
+    }
+}
+
+/* sim3_io: r (x y z w), t, s of g2oS12 in/out.  P1c / P2c f32[N,3]: the matched map points in their own camera frames (R1w*P3D1w+t1w,
+ * Optimizer.cc:1411-1424, float as cv::Mat computes them); valid u8[N]: the pair makes a correspondence (:1398-1433); obs1 / obs2 f32[N,2]:
+ * kpUn.pt in KF1 / KF2; w1 / w2: mvInvLevelSigma2 of the keypoint octaves.  inlier u8[N] out: vpMatches1[i] is kept.
+ * Returns nIn (0 with g2oS12 untouched when fewer than 10 correspondences survive the first pass, :1497-1498).  stats: LM iterations, trials. */
+int oracle_optimize_sim3(double *sim3_io, int N, const uint8_t *valid, const float *P1c, const float *P2c, const float *obs1, const float *obs2,
+                         const float *w1, const float *w2, const float *K1, const float *K2, float th2, int fix_scale, uint8_t *inlier, int *stats)
+{
+    s3_t B; memset(&B, 0, sizeof B);
+    B.N = N; B.P1c = P1c; B.P2c = P2c; B.obs1 = obs1; B.obs2 = obs2; B.w1 = w1; B.w2 = w2; B.fix_scale = fix_scale;
+    for (int k = 0; k < 4; k++) { B.K1[k] = K1[k]; B.K2[k] = K2[k]; }
+    const float deltaHuber = sqrtf(th2);                            /* const float deltaHuber = sqrt(th2) */
+    B.delta = deltaHuber; B.dsqr = B.delta * B.delta;
+    B.active = (uint8_t *)malloc(N > 0 ? N : 1); B.err = (double *)calloc(4 * (size_t)(N > 0 ? N : 1), sizeof(double));
+    if (stats) stats[0] = stats[1] = 0;
+    sim3 S;
+    memcpy(S.q, sim3_io, 4 * sizeof(double)); memcpy(S.t, sim3_io + 4, 3 * sizeof(double)); S.s = sim3_io[7];
+    int nCorr = 0;
+    for (int i = 0; i < N; i++) { B.active[i] = valid[i] ? 1 : 0; inlier[i] = B.active[i]; nCorr += B.active[i]; }
+    s3_optimize(&B, &S, 5, stats);
+    int nBad = 0;
+    for (int i = 0; i < N; i++) {
+        if (!B.active[i]) continue;
+        const double *e = &B.err[4 * i];
+        if (s3_chi2(e[0], e[1], (double)w1[i]) > th2 || s3_chi2(e[2], e[3], (double)w2[i]) > th2) { B.active[i] = 0; inlier[i] = 0; nBad++; }
+    }
+    const int more = nBad > 0 ? 10 : 5;
+    int nIn = 0;
+    if (nCorr - nBad >= 10) {
+        s3_optimize(&B, &S, more, stats);
+        for (int i = 0; i < N; i++) {
+            if (!B.active[i]) continue;
+            const double *e = &B.err[4 * i];
+            if (s3_chi2(e[0], e[1], (double)w1[i]) > th2 || s3_chi2(e[2], e[3], (double)w2[i]) > th2) inlier[i] = 0;
+            else nIn++;
+        }
+        memcpy(sim3_io, S.q, 4 * sizeof(double)); memcpy(sim3_io + 4, S.t, 3 * sizeof(double)); sim3_io[7] = S.s;
+    }
+    free(B.active); free(B.err);
+    return nIn;
+}

@@ -463,6 +463,19 @@ class Optimizer:
                                                       _ptr(q_Xw), _ptr(q_counts), qs, _ptr(ils), len(ils), _ptr(outl), _ptr(ninl), _ptr(ne), 0))
         return T.reshape(n, 4, 4), outl, ninl, ne
 
+    def OptimizeSim3(self, sim3, valid, P1c, P2c, obs1, obs2, inv_sigma2_1, inv_sigma2_2, K1, K2, counts, th2=10.0, bFixScale=False):
+        """Optimizer::OptimizeSim3 (Optimizer.cc:1348-1543) for n_pairs keyframe pairs (slab layout [n_pairs, slab, ...]).
+        sim3 [n_pairs, 8] = r (x y z w), t, s of g2oS12.  Returns (sim3, inlier u8, n_inliers, lm_stats [n_pairs, 2])."""
+        S = np.ascontiguousarray(sim3, np.float64).reshape(-1, 8).copy(); n = len(S)
+        v = np.ascontiguousarray(valid, np.uint8).reshape(n, -1); slab = v.shape[1]
+        a = [np.ascontiguousarray(x, np.float32) for x in (P1c, P2c, obs1, obs2, inv_sigma2_1, inv_sigma2_2)]
+        K1 = np.ascontiguousarray(K1, np.float32).reshape(n, 4); K2 = np.ascontiguousarray(K2, np.float32).reshape(n, 4)
+        cnt = np.ascontiguousarray(counts, np.int32)
+        inl = np.zeros((n, slab), np.uint8); nin = np.zeros(n, np.int32); st = np.zeros((n, 2), np.int32)
+        _check(self._L.orbo_optimize_sim3(self._h, n, _ptr(S), _ptr(v), *[_ptr(x) for x in a], _ptr(K1), _ptr(K2), _ptr(cnt), slab, float(th2),
+                                          int(bool(bFixScale)), _ptr(inl), _ptr(nin), _ptr(st), 0))
+        return S, inl, nin, st
+
     def _ba(self, poses, fixed, intr, points, e_kf, e_pt, e_uv, e_inv_sigma2, two_stage, its0, its1, robust, stop_flag=None):
         poses = np.ascontiguousarray(poses, np.float32).reshape(-1, 16).copy(); K = len(poses)
         fixed = np.ascontiguousarray(fixed, np.uint8)

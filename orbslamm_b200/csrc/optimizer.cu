@@ -14,6 +14,7 @@
 #include <nccl.h>
 #include "common.cuh"
 #include "pose_opt.cuh"
+#include "sim3_opt.cuh"
 #include "ba_kernels.cuh"
 
 using namespace orbs;
@@ -208,6 +209,35 @@ int orbo_pose_optimization_matched(orbo_handle *h, int n_frames, float *Tcw, con
     k_pose_optimization<<<n_frames, kPoseThreads, 0, h->stream>>>(A);
     k_pose_scatter<<<dim3((f_slab + 255) / 256, n_frames), 256, 0, h->stream>>>(f_slab, d_nedges, G.edge_feat, d_eout, d_fout);
     h->launches += 3;
+    ORBS_CUDA(cudaGetLastError());
+    return S.finish();
+}
+
+int orbo_optimize_sim3(orbo_handle *h, int n_pairs, double *sim3, const uint8_t *valid, const float *P1c, const float *P2c, const float *obs1,
+                       const float *obs2, const float *inv_sigma2_1, const float *inv_sigma2_2, const float *K1, const float *K2, const int32_t *counts,
+                       int slab, float th2, int fix_scale, uint8_t *inlier, int32_t *n_inliers, int32_t *lm_stats, int memspace)
+{
+    ORBS_REQUIRE(h && sim3 && valid && P1c && P2c && obs1 && obs2 && inv_sigma2_1 && inv_sigma2_2 && K1 && K2 && counts && inlier && n_inliers,
+                 ORBS_E_INVALID, "null argument");
+    ORBS_REQUIRE(n_pairs > 0 && slab > 0, ORBS_E_INVALID, "non-positive size");
+    std::lock_guard<std::mutex> lk(h->mu);
+    ORBS_CUDA(cudaSetDevice(h->device));
+    Stager S(&h->pool, h->stream, memspace);
+    const size_t ne = (size_t)n_pairs * slab;
+    Sim3Args A;
+    A.slab = slab;
+    A.sim3 = S.inout(sim3, (size_t)n_pairs * 8);
+    A.valid = S.in(valid, ne); A.P1c = S.in(P1c, ne * 3); A.P2c = S.in(P2c, ne * 3); A.obs1 = S.in(obs1, ne * 2); A.obs2 = S.in(obs2, ne * 2);
+    A.w1 = S.in(inv_sigma2_1, ne); A.w2 = S.in(inv_sigma2_2, ne); A.K1 = S.in(K1, (size_t)n_pairs * 4); A.K2 = S.in(K2, (size_t)n_pairs * 4);
+    A.counts = S.in(counts, n_pairs);
+    A.th2 = th2; A.fix_scale = fix_scale ? 1 : 0;
+    A.inlier = S.inout(inlier, ne, false); A.n_inliers = S.inout(n_inliers, n_pairs, false);
+    A.stats = lm_stats ? S.inout(lm_stats, (size_t)n_pairs * 2, false) : nullptr;
+    A.err = S.scratch<double>(ne * 4); A.active = S.scratch<uint8_t>(ne);
+    if (S.rc) return S.rc;
+    if (memspace == ORBS_MEM_HOST) ORBS_CUDA(cudaMemsetAsync(A.inlier, 0, ne, h->stream));
+    k_optimize_sim3<<<n_pairs, kSim3Threads, 0, h->stream>>>(A);
+    h->launches++;
     ORBS_CUDA(cudaGetLastError());
     return S.finish();
 }

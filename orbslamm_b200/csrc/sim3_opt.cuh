@@ -1,0 +1,343 @@
+// sim3_opt.cuh -- Optimizer::OptimizeSim3 (Optimizer.cc:1348-1543) as one persistent CTA per keyframe pair.
+// One VertexSim3Expmap against fixed points, EdgeSim3ProjectXYZ (x1 = S12 X2) and EdgeInverseSim3ProjectXYZ (x2 = S21 X1) with Huber
+// kernels, g2o's Levenberg on a dense 7x7 system (BlockSolverX + LinearSolverDense).  The edges have no analytic Jacobian in this g2o
+// (types_seven_dof_expmap.h:147,169): BaseBinaryEdge::linearizeOplus differentiates numerically, central differences with delta = 1e-9
+// through oplusImpl (base_binary_edge.hpp:131-205).  The 14 perturbed transforms depend only on the current estimate, so they (and
+// their inverses) are built once per linearisation in shared memory and every correspondence evaluates its two edges against them.
+// Whole 5 + (5 | 10) iteration schedule on the device, no host round trip; fixed-order block reductions.
+#pragma once
+#include "common.cuh"
+#include "pose_opt.cuh"
+
+namespace orbs {
+
+struct Sim3 { double q[4]; double t[3]; double s; };
+
+__device__ inline void sim3_exp(const double u[7], Sim3 &out)                  // Sim3(const Vector7d&), types/sim3.h:45-104
+{
+    const double w[3] = {u[0], u[1], u[2]}, sigma = u[6];
+    const double theta = sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+    const double O[9] = {0, -w[2], w[1], w[2], 0, -w[0], -w[1], w[0], 0};
+    double O2[9], R[9];
+    for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) O2[3 * r + c] = O[3 * r] * O[c] + O[3 * r + 1] * O[3 + c] + O[3 * r + 2] * O[6 + c];
+    const double s = exp(sigma), eps = 0.00001;
+    double A, B, C;
+    if (fabs(sigma) < eps) {
+        C = 1;
+        if (theta < eps) {
+            A = 1. / 2.; B = 1. / 6.;
+            for (int i = 0; i < 9; i++) R[i] = (i % 4 == 0 ? 1.0 : 0.0) + O[i] + O2[i];
+        } else {
+            const double theta2 = theta * theta;
+            A = (1 - cos(theta)) / (theta2);
+            B = (theta - sin(theta)) / (theta2 * theta);
+            for (int i = 0; i < 9; i++) R[i] = (i % 4 == 0 ? 1.0 : 0.0) + sin(theta) / theta * O[i] + (1 - cos(theta)) / (theta * theta) * O2[i];
+        }
+    } else {
+        C = (s - 1) / sigma;
+        if (theta < eps) {
+            const double sigma2 = sigma * sigma;
+            A = ((sigma - 1) * s + 1) / sigma2;
+            B = ((0.5 * sigma2 - sigma + 1) * s) / (sigma2 * sigma);
+            for (int i = 0; i < 9; i++) R[i] = (i % 4 == 0 ? 1.0 : 0.0) + O[i] + O2[i];
+        } else {
+            for (int i = 0; i < 9; i++) R[i] = (i % 4 == 0 ? 1.0 : 0.0) + sin(theta) / theta * O[i] + (1 - cos(theta)) / (theta * theta) * O2[i];
+            const double a = s * sin(theta), b = s * cos(theta), theta2 = theta * theta, sigma2 = sigma * sigma, c = theta2 + sigma2;
+            A = (a * sigma + (1 - b) * theta) / (theta * c);
+            B = (C - ((b - 1) * sigma + a * theta) / (c)) * 1. / (theta2);
+        }
+    }
+    quat_from_R(R, out.q);
+    for (int r = 0; r < 3; r++) {
+        const double W0 = A * O[3 * r] + B * O2[3 * r] + C * (r == 0 ? 1.0 : 0.0), W1 = A * O[3 * r + 1] + B * O2[3 * r + 1] + C * (r == 1 ? 1.0 : 0.0),
+                     W2 = A * O[3 * r + 2] + B * O2[3 * r + 2] + C * (r == 2 ? 1.0 : 0.0);
+        out.t[r] = W0 * u[3] + W1 * u[4] + W2 * u[5];
+    }
+    out.s = s;
+}
+
+__device__ __forceinline__ void sim3_map(const Sim3 &S, const double x[3], double out[3])       // s*(r*xyz) + t
+{
+    double rx[3];
+    quat_rotate(S.q, x, rx);
+#pragma unroll
+    for (int k = 0; k < 3; k++) out[k] = S.s * rx[k] + S.t[k];
+}
+
+__device__ inline void sim3_inverse(const Sim3 &S, Sim3 &out)                  // Sim3(r.conjugate(), r.conjugate()*((-1./s)*t), 1./s)
+{
+    const double qc[4] = {-S.q[0], -S.q[1], -S.q[2], S.q[3]};
+    const double f = -1. / S.s, st[3] = {f * S.t[0], f * S.t[1], f * S.t[2]};
+    quat_rotate(qc, st, out.t);
+    out.q[0] = qc[0]; out.q[1] = qc[1]; out.q[2] = qc[2]; out.q[3] = qc[3];
+    out.s = 1. / S.s;
+}
+
+__device__ inline void sim3_mul(const Sim3 &a, const Sim3 &b, Sim3 &o)         // operator*, sim3.h:214-220 (no renormalisation)
+{
+    Sim3 r;
+    quat_mul(a.q, b.q, r.q);
+    double rt[3];
+    quat_rotate(a.q, b.t, rt);
+    for (int k = 0; k < 3; k++) r.t[k] = a.s * rt[k] + a.t[k];
+    r.s = a.s * b.s;
+    o = r;
+}
+
+// VertexSim3Expmap::oplusImpl, types_seven_dof_expmap.h:54-63
+__device__ inline void sim3_oplus(const Sim3 &S, const double *upd, bool fix_scale, Sim3 &out)
+{
+    double u[7];
+    for (int k = 0; k < 7; k++) u[k] = upd[k];
+    if (fix_scale) u[6] = 0;
+    Sim3 d;
+    sim3_exp(u, d);
+    sim3_mul(d, S, out);
+}
+
+struct Sim3Args {
+    int slab;
+    double *sim3;                // [n_pairs, 8] in/out: r (x y z w), t, s
+    const uint8_t *valid;        // [n_pairs*slab]
+    const float *P1c, *P2c, *obs1, *obs2, *w1, *w2;
+    const float *K1, *K2;        // [n_pairs, 4]
+    const int *counts;
+    float th2; int fix_scale;
+    uint8_t *inlier;             // [n_pairs*slab] out
+    int *n_inliers;              // [n_pairs] out
+    double *err;                 // scratch [n_pairs*slab, 4]: stored _error of e12 / e21
+    uint8_t *active;             // scratch [n_pairs*slab]
+    int *stats;                  // optional [n_pairs, 2]: LM iterations, trials
+};
+
+constexpr int kSim3Threads = 128;
+constexpr int kSim3NV = 36;      // 28 (upper H) + 7 (b) + 1 (chi2)
+
+template <int N>
+__device__ inline bool solve_ldlt(const double *Hu /*upper packed*/, const double *b, double lambda, double *x)
+{
+    double A[N * N];
+    int p = 0;
+    for (int r = 0; r < N; r++) for (int c = r; c < N; c++) { A[N * r + c] = Hu[p]; A[N * c + r] = Hu[p]; p++; }
+    for (int i = 0; i < N; i++) A[(N + 1) * i] += lambda;
+    for (int i = 0; i < N; i++)
+        for (int j = 0; j <= i; j++) {
+            double s = A[N * i + j];
+            for (int k = 0; k < j; k++) s -= A[N * i + k] * A[N * j + k] * A[(N + 1) * k];
+            if (j < i) A[N * i + j] = s / A[(N + 1) * j];
+            else { if (!(s > 0.0)) return false; A[(N + 1) * i] = s; }
+        }
+    for (int i = 0; i < N; i++) { double s = b[i]; for (int k = 0; k < i; k++) s -= A[N * i + k] * x[k]; x[i] = s; }
+    for (int i = 0; i < N; i++) x[i] /= A[(N + 1) * i];
+    for (int i = N - 1; i >= 0; i--) { const double xi = x[i]; for (int k = 0; k < i; k++) x[k] -= A[N * i + k] * xi; }
+    return true;
+}
+
+__device__ __forceinline__ void sim3_edge_errors(const Sim3 &S, const Sim3 &Si, const double X1[3], const double X2[3], const double o[4], const double K1[4],
+                                                 const double K2[4], double e[4])
+{
+    double p[3];
+    sim3_map(S, X2, p);                                            // EdgeSim3ProjectXYZ::computeError
+    e[0] = o[0] - (p[0] / p[2] * K1[0] + K1[2]);
+    e[1] = o[1] - (p[1] / p[2] * K1[1] + K1[3]);
+    sim3_map(Si, X1, p);                                           // EdgeInverseSim3ProjectXYZ::computeError
+    e[2] = o[2] - (p[0] / p[2] * K2[0] + K2[2]);
+    e[3] = o[3] - (p[1] / p[2] * K2[1] + K2[3]);
+}
+
+__device__ __forceinline__ double chi2_iso(double e0, double e1, double w) { return e0 * (w * e0 + 0.0 * e1) + e1 * (0.0 * e0 + w * e1); }
+
+__global__ void __launch_bounds__(kSim3Threads)
+k_optimize_sim3(const Sim3Args A)
+{
+    __shared__ double s_warp[(kSim3Threads / 32) * kSim3NV];
+    __shared__ double s_red[kSim3NV];
+    __shared__ Sim3 s_S, s_Si, s_backup, s_pert[14], s_perti[14];
+    __shared__ double s_lambda, s_ni, s_cur_chi, s_x[7], s_rho, s_chi_out[1];
+    __shared__ int s_nbad_lm, s_flag, s_ok2, s_cnt;
+    const int f = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+    const int M = A.counts[f];
+    const size_t o = (size_t)f * A.slab;
+    const float *P1c = A.P1c + 3 * o, *P2c = A.P2c + 3 * o, *obs1 = A.obs1 + 2 * o, *obs2 = A.obs2 + 2 * o, *w1 = A.w1 + o, *w2 = A.w2 + o;
+    uint8_t *active = A.active + o, *inlier = A.inlier + o;
+    double *err = A.err + 4 * o;
+    double K1[4], K2[4];
+    for (int k = 0; k < 4; k++) { K1[k] = (double)A.K1[4 * f + k]; K2[k] = (double)A.K2[4 * f + k]; }
+    const double th2 = (double)A.th2;
+    const double delta = (double)sqrtf(A.th2), dsqr = delta * delta;       // const float deltaHuber = sqrt(th2), Optimizer.cc:1395
+    const bool fix_scale = A.fix_scale != 0;
+    int my = 0;
+    for (int i = tid; i < M; i += nt) { const uint8_t v = A.valid[o + i] ? 1 : 0; active[i] = v; inlier[i] = v; my += v; }
+    if (tid == 0) {
+        for (int k = 0; k < 4; k++) s_S.q[k] = A.sim3[8 * f + k];
+        for (int k = 0; k < 3; k++) s_S.t[k] = A.sim3[8 * f + 4 + k];
+        s_S.s = A.sim3[8 * f + 7];
+        s_cnt = 0;
+        if (A.stats) { A.stats[2 * f] = 0; A.stats[2 * f + 1] = 0; }
+    }
+    __syncthreads();
+    if (my) atomicAdd(&s_cnt, my);
+    __syncthreads();
+    const int n_corr = s_cnt;
+    int n_bad = 0, n_in = 0;
+
+    for (int pass = 0; pass < 2; pass++) {
+        const int iterations = pass == 0 ? 5 : (n_bad > 0 ? 10 : 5);
+        const int n_act = n_corr - n_bad;
+        if (pass == 1 && n_act < 10) break;                                   // Optimizer.cc:1497-1498: return 0, g2oS12 untouched
+        if (n_act > 0) {
+            for (int iter = 0; iter < iterations; iter++) {
+                // the 14 perturbed estimates of the numeric Jacobian and the inverse of the current one
+                if (tid < 14) {
+                    double add[7] = {0, 0, 0, 0, 0, 0, 0};
+                    add[tid >> 1] = (tid & 1) ? -1e-9 : 1e-9;
+                    Sim3 sp, spi;
+                    sim3_oplus(s_S, add, fix_scale, sp);
+                    sim3_inverse(sp, spi);
+                    s_pert[tid] = sp; s_perti[tid] = spi;
+                } else if (tid == 32) { Sim3 si; sim3_inverse(s_S, si); s_Si = si; }
+                __syncthreads();
+                // computeActiveErrors + activeRobustChi2 + buildSystem
+                double acc[kSim3NV];
+#pragma unroll
+                for (int v = 0; v < kSim3NV; v++) acc[v] = 0;
+                for (int i = tid; i < M; i += nt) {
+                    if (!active[i]) continue;
+                    const double X1[3] = {(double)P1c[3 * i], (double)P1c[3 * i + 1], (double)P1c[3 * i + 2]};
+                    const double X2[3] = {(double)P2c[3 * i], (double)P2c[3 * i + 1], (double)P2c[3 * i + 2]};
+                    const double ob[4] = {(double)obs1[2 * i], (double)obs1[2 * i + 1], (double)obs2[2 * i], (double)obs2[2 * i + 1]};
+                    double e[4], J[4][7];
+                    sim3_edge_errors(s_S, s_Si, X1, X2, ob, K1, K2, e);
+                    err[4 * i] = e[0]; err[4 * i + 1] = e[1]; err[4 * i + 2] = e[2]; err[4 * i + 3] = e[3];
+                    const double scalar = 1.0 / (2 * 1e-9);
+#pragma unroll
+                    for (int d = 0; d < 7; d++) {
+                        double ep[4], em[4];
+                        sim3_edge_errors(s_pert[2 * d], s_perti[2 * d], X1, X2, ob, K1, K2, ep);
+                        sim3_edge_errors(s_pert[2 * d + 1], s_perti[2 * d + 1], X1, X2, ob, K1, K2, em);
+#pragma unroll
+                        for (int r = 0; r < 4; r++) J[r][d] = scalar * (ep[r] - em[r]);
+                    }
+#pragma unroll
+                    for (int k = 0; k < 2; k++) {
+                        const double w = (double)(k ? w2[i] : w1[i]);
+                        const double e0 = e[2 * k], e1 = e[2 * k + 1];
+                        const double c = chi2_iso(e0, e1, w);
+                        double rho0 = c, rho1 = 1.0;
+                        huber(c, delta, dsqr, rho0, rho1);
+                        acc[35] += rho0;
+                        const double wo = rho1 * w, r0 = rho1 * w * e0, r1 = rho1 * w * e1;
+                        int p = 0;
+#pragma unroll
+                        for (int a = 0; a < 7; a++) {
+                            acc[28 + a] -= J[2 * k][a] * r0 + J[2 * k + 1][a] * r1;
+#pragma unroll
+                            for (int cc = a; cc < 7; cc++) { acc[p] += J[2 * k][a] * wo * J[2 * k][cc] + J[2 * k + 1][a] * wo * J[2 * k + 1][cc]; p++; }
+                        }
+                    }
+                }
+                block_reduce_vec<kSim3NV>(acc, s_warp, s_red);
+                if (tid == 0) {
+                    s_cur_chi = s_red[35];
+                    if (iter == 0) {                                              // computeLambdaInit
+                        double mx = 0.;
+                        int p = 0;
+                        for (int a = 0; a < 7; a++) { mx = fmax(fabs(s_red[p]), mx); p += 7 - a; }
+                        s_lambda = 1e-5 * mx; s_ni = 2; s_nbad_lm = 0;
+                    }
+                }
+                __syncthreads();
+                const double ini_chi = s_cur_chi;
+                int qmax = 0;
+                double rho = 0;
+                do {
+                    if (tid == 0) {
+                        s_backup = s_S;
+                        s_ok2 = solve_ldlt<7>(s_red, s_red + 28, s_lambda, s_x) ? 1 : 0;
+                        Sim3 r, ri;
+                        sim3_oplus(s_S, s_x, fix_scale, r);
+                        sim3_inverse(r, ri);
+                        s_S = r; s_Si = ri;
+                    }
+                    __syncthreads();
+                    double chi[1] = {0};
+                    for (int i = tid; i < M; i += nt) {
+                        if (!active[i]) continue;
+                        const double X1[3] = {(double)P1c[3 * i], (double)P1c[3 * i + 1], (double)P1c[3 * i + 2]};
+                        const double X2[3] = {(double)P2c[3 * i], (double)P2c[3 * i + 1], (double)P2c[3 * i + 2]};
+                        const double ob[4] = {(double)obs1[2 * i], (double)obs1[2 * i + 1], (double)obs2[2 * i], (double)obs2[2 * i + 1]};
+                        double e[4];
+                        sim3_edge_errors(s_S, s_Si, X1, X2, ob, K1, K2, e);
+                        err[4 * i] = e[0]; err[4 * i + 1] = e[1]; err[4 * i + 2] = e[2]; err[4 * i + 3] = e[3];
+#pragma unroll
+                        for (int k = 0; k < 2; k++) {
+                            const double c = chi2_iso(e[2 * k], e[2 * k + 1], (double)(k ? w2[i] : w1[i]));
+                            double rho0 = c, rho1 = 1.0;
+                            huber(c, delta, dsqr, rho0, rho1);
+                            chi[0] += rho0;
+                        }
+                    }
+                    block_reduce_vec<1>(chi, s_warp, s_chi_out);
+                    if (tid == 0) {
+                        double temp_chi = s_chi_out[0];
+                        if (!s_ok2) temp_chi = 1.7976931348623157e308;
+                        double r = s_cur_chi - temp_chi;
+                        double scale = 0.;
+                        for (int j = 0; j < 7; j++) scale += s_x[j] * (s_lambda * s_x[j] + s_red[28 + j]);
+                        scale += 1e-3;
+                        r /= scale;
+                        if (r > 0 && isfinite(temp_chi)) {
+                            double alpha = 1. - pow((2 * r - 1), 3.0);
+                            alpha = fmin(alpha, 2. / 3.);
+                            s_lambda *= fmax(1. / 3., alpha);
+                            s_ni = 2; s_cur_chi = temp_chi;
+                        } else {
+                            s_lambda *= s_ni; s_ni *= 2;
+                            s_S = s_backup;
+                        }
+                        s_rho = r;
+                        if (A.stats) A.stats[2 * f + 1]++;
+                    }
+                    __syncthreads();
+                    rho = s_rho;
+                    qmax++;
+                    __syncthreads();
+                } while (rho < 0 && qmax < 10);
+                if (tid == 0 && A.stats) A.stats[2 * f]++;
+                bool terminate = (qmax == 10 || rho == 0);
+                if (!terminate) {
+                    if (tid == 0) {
+                        if ((ini_chi - s_cur_chi) * 1e3 < ini_chi) s_nbad_lm++; else s_nbad_lm = 0;
+                        s_flag = s_nbad_lm >= 3;
+                    }
+                    __syncthreads();
+                    terminate = s_flag != 0;
+                    __syncthreads();
+                }
+                if (terminate) break;
+            }
+        }
+        // inlier check on the stored errors (Optimizer.cc:1469-1486, 1506-1520)
+        if (tid == 0) s_cnt = 0;
+        __syncthreads();
+        int cnt = 0;
+        for (int i = tid; i < M; i += nt) {
+            if (!active[i]) continue;
+            const bool bad = chi2_iso(err[4 * i], err[4 * i + 1], (double)w1[i]) > th2 || chi2_iso(err[4 * i + 2], err[4 * i + 3], (double)w2[i]) > th2;
+            if (pass == 0) { if (bad) { active[i] = 0; inlier[i] = 0; cnt++; } }
+            else { if (bad) inlier[i] = 0; else cnt++; }
+        }
+        if (cnt) atomicAdd(&s_cnt, cnt);
+        __syncthreads();
+        if (pass == 0) n_bad = s_cnt; else n_in = s_cnt;
+        __syncthreads();
+        if (pass == 1 && tid == 0) {
+            for (int k = 0; k < 4; k++) A.sim3[8 * f + k] = s_S.q[k];
+            for (int k = 0; k < 3; k++) A.sim3[8 * f + 4 + k] = s_S.t[k];
+            A.sim3[8 * f + 7] = s_S.s;
+        }
+    }
+    if (tid == 0) A.n_inliers[f] = n_in;
+}
+
+}  // namespace orbs

@@ -1,6 +1,6 @@
 // Optimizer_b200.cc -- GPU-backed definitions of Optimizer::PoseOptimization / LocalBundleAdjustment /
 // BundleAdjustment / GlobalBundleAdjustemnt.  In the reference tree these replace the same-named functions of
-// S/src/Optimizer.cc (:60-65, :68-260, :262-474, :476-801); OptimizeSim3 and the essential-graph optimisers stay on
+// S/src/Optimizer.cc (:60-65, :68-260, :262-474, :476-801) and OptimizeSim3 (:1348-1543); the essential-graph optimisers stay on
 // g2o ("next" rows of SURVEY.md 8(f)).  The graph *construction* below follows the reference line by line (which
 // keyframes are local / fixed, which observations become edges, which locks are taken); only the numerical solve is
 // delegated to orbo_* (include/orbslamm_b200.h).  Monocular observations only (mvuRight < 0).
@@ -241,6 +241,52 @@ void Optimizer::LocalBundleAdjustment(KeyFrame *pKF, bool *pbStopFlag, Map *pMap
         mps[p]->SetWorldPos(X);
         mps[p]->UpdateNormalAndDepth();
     }
+}
+
+// LoopClosing::ComputeSim3 / MultiMapper -> Optimizer::OptimizeSim3(mpCurrentKF, pKF, vpMapPointMatches, gScm, 10, mbFixScale)   (LoopClosing.cc:332)
+int Optimizer::OptimizeSim3(KeyFrame *pKF1, KeyFrame *pKF2, std::vector<MapPoint *> &vpMatches1, g2o::Sim3 &g2oS12, const float th2, const bool bFixScale)
+{
+    const int32_t N = (int32_t)vpMatches1.size();
+    if (!N) return 0;
+    float R1w[9], t1w[3], R2w[9], t2w[3];
+    {
+        const cv::Mat R1 = pKF1->GetRotation(), T1 = pKF1->GetTranslation(), R2 = pKF2->GetRotation(), T2 = pKF2->GetTranslation();
+        for (int r = 0; r < 3; r++) { for (int c = 0; c < 3; c++) { R1w[3 * r + c] = R1.at<float>(r, c); R2w[3 * r + c] = R2.at<float>(r, c); } t1w[r] = T1.at<float>(r); t2w[r] = T2.at<float>(r); }
+    }
+    const std::vector<MapPoint *> vpMapPoints1 = pKF1->GetMapPointMatches();
+    std::vector<uint8_t> valid(N, 0), inlier(N, 0);
+    std::vector<float> P1c(3 * (size_t)N, 0.f), P2c(3 * (size_t)N, 0.f), obs1(2 * (size_t)N, 0.f), obs2(2 * (size_t)N, 0.f), w1(N, 0.f), w2(N, 0.f);
+    auto to_camera = [](const float *R, const float *t, const cv::Mat &X, float *out) {   // R*P3Dw + t: cv::Mat small gemm (fp32, left to right), then add
+        for (int r = 0; r < 3; r++) {
+            float s = R[3 * r] * X.at<float>(0);
+            s = s + R[3 * r + 1] * X.at<float>(1);
+            s = s + R[3 * r + 2] * X.at<float>(2);
+            out[r] = s + t[r];
+        }
+    };
+    for (int i = 0; i < N; i++) {                                               // Optimizer.cc:1398-1463
+        if (!vpMatches1[i]) continue;
+        MapPoint *pMP1 = vpMapPoints1[i], *pMP2 = vpMatches1[i];
+        const int i2 = pMP2->GetIndexInKeyFrame(pKF2);
+        if (!pMP1 || !pMP2) continue;
+        if (pMP1->isBad() || pMP2->isBad() || i2 < 0) continue;
+        to_camera(R1w, t1w, pMP1->GetWorldPos(), &P1c[3 * i]);
+        to_camera(R2w, t2w, pMP2->GetWorldPos(), &P2c[3 * i]);
+        const cv::KeyPoint &kpUn1 = pKF1->mvKeysUn[i], &kpUn2 = pKF2->mvKeysUn[i2];
+        obs1[2 * i] = kpUn1.pt.x; obs1[2 * i + 1] = kpUn1.pt.y; obs2[2 * i] = kpUn2.pt.x; obs2[2 * i + 1] = kpUn2.pt.y;
+        w1[i] = pKF1->mvInvLevelSigma2[kpUn1.octave]; w2[i] = pKF2->mvInvLevelSigma2[kpUn2.octave];
+        valid[i] = 1;
+    }
+    double S[8] = {g2oS12.rotation().x(), g2oS12.rotation().y(), g2oS12.rotation().z(), g2oS12.rotation().w(),
+                   g2oS12.translation()[0], g2oS12.translation()[1], g2oS12.translation()[2], g2oS12.scale()};
+    const float K1[4] = {pKF1->fx, pKF1->fy, pKF1->cx, pKF1->cy}, K2[4] = {pKF2->fx, pKF2->fy, pKF2->cx, pKF2->cy};   // mK(0,0), (1,1), (0,2), (1,2)
+    int32_t nIn = 0;
+    check(orbo_optimize_sim3(handle(), 1, S, valid.data(), P1c.data(), P2c.data(), obs1.data(), obs2.data(), w1.data(), w2.data(), K1, K2, &N, N, th2,
+                             bFixScale ? 1 : 0, inlier.data(), &nIn, nullptr, ORBS_MEM_HOST), "orbo_optimize_sim3");
+    for (int i = 0; i < N; i++) if (valid[i] && !inlier[i]) vpMatches1[i] = static_cast<MapPoint *>(NULL);          // :1476, :1516
+    g2oS12.rotation().x() = S[0]; g2oS12.rotation().y() = S[1]; g2oS12.rotation().z() = S[2]; g2oS12.rotation().w() = S[3];
+    g2oS12.translation()[0] = S[4]; g2oS12.translation()[1] = S[5]; g2oS12.translation()[2] = S[6]; g2oS12.scale() = S[7];
+    return nIn;
 }
 
 }  // namespace iORB_SLAM

@@ -3,6 +3,7 @@
 #include "Frame.h"
 #include "KeyFrame.h"
 #include "Map.h"
+#include "Thirdparty/g2o/g2o/types/sim3.h"
 
 namespace iORB_SLAM
 {
@@ -15,5 +16,6 @@ public:
                                        const bool bRobust = true);
     void static LocalBundleAdjustment(KeyFrame *pKF, bool *pbStopFlag, Map *pMap);
     int static PoseOptimization(Frame *pFrame);
+    static int OptimizeSim3(KeyFrame *pKF1, KeyFrame *pKF2, std::vector<MapPoint *> &vpMatches1, g2o::Sim3 &g2oS12, const float th2, const bool bFixScale);
 };
 }  // namespace iORB_SLAM

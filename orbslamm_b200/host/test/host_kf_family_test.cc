@@ -8,6 +8,7 @@
 #include <string>
 #include <vector>
 #include "ORBmatcher.h"
+#include "Optimizer.h"
 
 using namespace iORB_SLAM;
 
@@ -120,7 +121,7 @@ int main(int argc, char **argv)
         for (int k = 0; k < F.N; k++) if (held[k]) F.mvpMapPoints[k] = &holder;
         std::vector<MapPoint> mps; load_points(mps, "pts", 0);
         const std::vector<unsigned char> has = rd<unsigned char>(D + "/has.bin");
-        const std::vector<float> kang = rd<float>(D + "/kf_angle.bin");
+        const std::vector<float> kang = rd<float>(D + "/reloc_angle.bin");
         KeyFrame K; K.N = M; K.mvKeysUn.resize(M); K.mvpMapPoints.assign(M, nullptr);
         std::set<MapPoint *> found;
         for (int i = 0; i < M; i++) { K.mvKeysUn[i].angle = kang[i]; if (has[i]) K.mvpMapPoints[i] = &mps[i]; if (skip[i]) found.insert(&mps[i]); }
@@ -152,6 +153,16 @@ int main(int argc, char **argv)
         for (int i = 0; i < K1.N; i++) out[i] = vm[i] ? (int)(vm[i]->mnId - 100000) : -1;
         out[K1.N] = n;
         wr(D + "/out_search_by_sim3.bin", out);
+        // Optimizer::OptimizeSim3 on those matches (LoopClosing::ComputeSim3 runs the two back to back)
+        const std::vector<double> s0 = rd<double>(D + "/s3_init.bin");
+        g2o::Sim3 g;
+        g.rotation().x() = s0[0]; g.rotation().y() = s0[1]; g.rotation().z() = s0[2]; g.rotation().w() = s0[3];
+        g.translation()[0] = s0[4]; g.translation()[1] = s0[5]; g.translation()[2] = s0[6]; g.scale() = s0[7];
+        const int nin = Optimizer::OptimizeSim3(&K1, &K2, vm, g, 10.f, false);
+        std::vector<double> so = {g.rotation().x(), g.rotation().y(), g.rotation().z(), g.rotation().w(), g.translation()[0], g.translation()[1],
+                                  g.translation()[2], g.scale(), (double)nin};
+        for (int i = 0; i < K1.N; i++) so.push_back(vm[i] ? (double)(vm[i]->mnId - 100000) : -1.0);
+        wr(D + "/out_optimize_sim3.bin", so);
     }
     printf("kf family host shim ok\n");
     return 0;

@@ -276,3 +276,46 @@ def make_sim3_pair(cam, stream_id, s12=1.02):
         if dd[j] < 1.5 and has1[i] and has2[j] and j not in used:
             m12[i] = j; used.add(j)
     return dict(kf1=kf1, kf2=kf2, pts1=pts1, pts2=pts2, has1=has1, has2=has2, s12=F32(s12), R12=R12, t12=t12, m12=m12)
+
+
+def quat_of(R):
+    """Eigen::Quaterniond(Matrix3d) for a proper rotation (w > 0 branch or not), x y z w"""
+    from scipy.spatial.transform import Rotation
+    q = Rotation.from_matrix(np.asarray(R, np.float64)).as_quat()
+    return q if q[3] >= 0 else -q
+
+
+def make_sim3_opt_case(cam, stream_id, n_outliers=12, s12=1.02, seed=0):
+    """Correspondences for Optimizer::OptimizeSim3 from the SearchBySim3 pair: true feature pairs (nearest shifted keypoints), a few wrong
+    pairs, camera-frame points in float as the reference computes them, and a perturbed initial Sim3."""
+    p = make_sim3_pair(cam, stream_id, s12=s12)
+    kf1, kf2 = p["kf1"], p["kf2"]
+    rng = np.random.default_rng(11 + seed + stream_id)
+    x1, x2 = kf1["xy"], kf2["xy"]
+    T1, T2 = kf1["Tcw"], kf2["Tcw"]
+    P1c_all = np.stack([gemm32(T1[:3, :3], X.reshape(3, 1)).ravel() + T1[:3, 3] for X in p["pts1"]["Xw"]]).astype(F32)
+    P2c_all = np.stack([gemm32(T2[:3, :3], X.reshape(3, 1)).ravel() + T2[:3, 3] for X in p["pts2"]["Xw"]]).astype(F32)
+    # true correspondences: project P1c into KF2 with the true S21 and take the nearest KF2 keypoint
+    fx, fy, cx, cy = [float(v) for v in kf1["K4"]]
+    R12 = p["R12"].astype(np.float64); t12 = p["t12"].astype(np.float64); s = float(p["s12"])
+    q2 = (P1c_all.astype(np.float64) - t12) @ R12 / s
+    u2 = np.stack([fx * q2[:, 0] / q2[:, 2] + cx, fy * q2[:, 1] / q2[:, 2] + cy], 1)
+    N1 = len(x1)
+    pair = np.full(N1, -1)
+    for i in range(0, N1, 3):
+        d = np.abs(x2 - u2[i]).sum(1)
+        j = int(np.argmin(d))
+        if d[j] < 1.0:
+            pair[i] = j
+    idx = np.where(pair >= 0)[0]
+    bad = rng.choice(idx, size=min(n_outliers, len(idx) // 4), replace=False)
+    pair[bad] = rng.integers(0, len(x2), len(bad))
+    valid = (pair >= 0).astype(np.uint8)
+    j = np.where(pair >= 0, pair, 0)
+    inv2 = kf1["inv_level_sigma2"]
+    case = dict(valid=valid, P1c=P1c_all, P2c=P2c_all[j], obs1=x1, obs2=x2[j], w1=inv2[kf1["octave"]], w2=inv2[kf2["octave"][j]], K1=kf1["K4"], K2=kf2["K4"],
+                true=np.concatenate([quat_of(R12), t12, [s]]), bad=bad)
+    from scipy.spatial.transform import Rotation
+    dR = Rotation.from_rotvec(rng.normal(0, 0.004, 3)).as_matrix()
+    case["init"] = np.concatenate([quat_of(dR @ R12), t12 + rng.normal(0, 0.02, 3), [s * 1.01]])
+    return case

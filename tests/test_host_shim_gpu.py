@@ -93,7 +93,7 @@ def test_cpp_dropin_kf_family(lib, tmp_path):
     import kf_family as kff
     d = str(tmp_path)
     exe = os.path.join(d, "host_kf_family_test")
-    srcs = [os.path.join(HOST, f) for f in ("ORBmatcher_b200.cc", "mock/slam_statics.cc", "test/host_kf_family_test.cc")]
+    srcs = [os.path.join(HOST, f) for f in ("ORBmatcher_b200.cc", "Optimizer_b200.cc", "mock/slam_statics.cc", "test/host_kf_family_test.cc")]
     subprocess.check_call(["g++", "-std=c++14", "-O2", "-I" + os.path.join(HOST, "mock"), "-I" + HOST, "-I" + os.path.join(ROOT, "include")] + srcs +
                           ["-L" + os.path.join(ROOT, "orbslamm_b200"), "-lorbslamm_b200", "-Wl,-rpath," + os.path.join(ROOT, "orbslamm_b200"), "-lpthread", "-o", exe])
     c = kff.make_case(synth.TUM, 3, distorted_bounds=True)
@@ -110,11 +110,15 @@ def test_cpp_dropin_kf_family(lib, tmp_path):
     w("sf.bin", c["sf"]); w("inv2.bin", kf["inv_level_sigma2"]); w("K4.bin", kf["K4"]); w("grid_bounds.bin", kf["grid_bounds4"]); w("frame_bounds.bin", k["bounds"].astype(np.float32))
     w("skip.bin", skip); w("held.bin", held); w("Scw.bin", Scw); w_kf("kf", kf); w_pts("pts", pts)
     has = (np.random.default_rng(3).random(len(skip)) < 0.85).astype(np.uint8)
-    w("has.bin", has); w("kf_angle.bin", c["last"]["angle"].astype(np.float32))
+    w("has.bin", has); w("reloc_angle.bin", c["last"]["angle"].astype(np.float32))
     p = kff.make_sim3_pair(synth.TUM, 1)
     w("s3_grid_bounds.bin", p["kf1"]["grid_bounds4"]); w_kf("s3_kf1", p["kf1"]); w_kf("s3_kf2", p["kf2"]); w_pts("s3_pts1", p["pts1"]); w_pts("s3_pts2", p["pts2"])
     w("s3_has1.bin", p["has1"]); w("s3_has2.bin", p["has2"]); w("s3_m12.bin", p["m12"])
     w("s3_srt.bin", np.concatenate([[p["s12"]], p["R12"].ravel(), p["t12"].ravel()]).astype(np.float32))
+    from scipy.spatial.transform import Rotation
+    s_init = np.concatenate([kff.quat_of(Rotation.from_rotvec([0.003, -0.002, 0.004]).as_matrix() @ p["R12"].astype(np.float64)),
+                             p["t12"].astype(np.float64) + [0.02, -0.01, 0.015], [float(p["s12"]) * 1.01]])
+    w("s3_init.bin", s_init)
     out = subprocess.run([exe, d], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
     r = lambda name: np.fromfile(os.path.join(d, name), np.int32)
@@ -158,3 +162,14 @@ def test_cpp_dropin_kf_family(lib, tmp_path):
     n_o, m_o = kff.search_by_sim3(Bo, p["kf1"], p["kf2"], p["s12"], p["R12"], p["t12"], 7.5, p["has1"], p["pts1"], p["has2"], p["pts2"], p["m12"])
     got = r("out_search_by_sim3.bin")
     assert n_o > 20 and got[-1] == n_o and np.array_equal(got[:-1], m_o)
+    # Optimizer::OptimizeSim3 on the SearchBySim3 matches
+    kf1, kf2 = p["kf1"], p["kf2"]
+    valid = (m_o >= 0).astype(np.uint8); j = np.where(m_o >= 0, m_o, 0)
+    cam = lambda T, X: np.stack([kff.gemm32(T[:3, :3], x.reshape(3, 1)).ravel() + T[:3, 3] for x in X]).astype(np.float32)
+    inv2 = kf1["inv_level_sigma2"]
+    ro = oracle.optimize_sim3(s_init, valid, cam(kf1["Tcw"], p["pts1"]["Xw"]), cam(kf2["Tcw"], p["pts2"]["Xw"])[j], kf1["xy"], kf2["xy"][j],
+                              inv2[kf1["octave"]], inv2[kf2["octave"][j]], kf1["K4"], kf2["K4"], 10.0, False)
+    got = np.fromfile(os.path.join(d, "out_optimize_sim3.bin"), np.float64)
+    assert ro["n_in"] > 20 and int(got[8]) == ro["n_in"]
+    assert np.abs(got[:8] - ro["sim3"]).max() < 1e-5 * np.abs(ro["sim3"]).max()
+    assert np.array_equal(got[9:].astype(np.int64), np.where(ro["inlier"] > 0, m_o, -1))

@@ -169,3 +169,34 @@ def test_pose_optimization_from_matches(lib):
         assert ne[i] == m.sum() and ninl[i] == nr
         assert np.array_equal(outl[i, :n][m], outr) and outl[i, :n][~m].sum() == 0
         assert _rel(T[i], Tr) < RTOL
+
+
+@pytest.mark.parametrize("fix_scale", [False, True])
+def test_optimize_sim3_matches_oracle(lib, fix_scale):
+    """Optimizer::OptimizeSim3 (Optimizer.cc:1348-1543): several keyframe pairs per launch (ragged), against the oracle: identical inlier
+    sets, inlier counts and LM iteration / trial counts, Sim3 to 1e-5 relative (north_star tolerance for the g2o paths); a pair with too few
+    correspondences returns 0 and leaves g2oS12 untouched (:1497-1498)."""
+    import orbslamm_b200 as ob
+    import kf_family as kff
+    from helpers import slab
+    cases = [kff.make_sim3_opt_case(synth.TUM, 1), kff.make_sim3_opt_case(synth.KITTI, 2), kff.make_sim3_opt_case(synth.TUM, 4, n_outliers=0)]
+    few = kff.make_sim3_opt_case(synth.TUM, 2)
+    few["valid"] = few["valid"].copy(); few["valid"][np.where(few["valid"])[0][9:]] = 0           # 9 correspondences
+    cases.append(few)
+    W = max(len(c["valid"]) for c in cases) + 3
+    o = ob.Optimizer()
+    S, inl, nin, st = o.OptimizeSim3(np.stack([c["init"] for c in cases]), slab([c["valid"] for c in cases], W, np.uint8),
+                                     slab([c["P1c"] for c in cases], W, np.float32, (3,)), slab([c["P2c"] for c in cases], W, np.float32, (3,)),
+                                     slab([c["obs1"] for c in cases], W, np.float32, (2,)), slab([c["obs2"] for c in cases], W, np.float32, (2,)),
+                                     slab([c["w1"] for c in cases], W, np.float32), slab([c["w2"] for c in cases], W, np.float32),
+                                     np.stack([c["K1"] for c in cases]), np.stack([c["K2"] for c in cases]), [len(c["valid"]) for c in cases], 10.0, fix_scale)
+    for k, c in enumerate(cases):
+        r = oracle.optimize_sim3(c["init"], c["valid"], c["P1c"], c["P2c"], c["obs1"], c["obs2"], c["w1"], c["w2"], c["K1"], c["K2"], 10.0, fix_scale)
+        n = len(c["valid"])
+        assert nin[k] == r["n_in"] and np.array_equal(inl[k, :n], r["inlier"]) and not inl[k, n:].any()
+        assert st[k, 0] == r["lm_iterations"] and st[k, 1] == r["lm_trials"]
+        assert np.abs(S[k] - r["sim3"]).max() < 1e-5 * np.abs(r["sim3"]).max()
+        if k < 3:
+            assert r["n_in"] > 40 and r["inlier"][c["bad"]].sum() <= 1 and np.abs(r["sim3"] - c["true"]).max() < np.abs(c["init"] - c["true"]).max()
+        else:
+            assert r["n_in"] == 0 and np.array_equal(S[k], c["init"])
