@@ -262,6 +262,46 @@ int orbm_search_best_in_window(orbm_handle *h, int n_frames, const float *grid_b
                                const float *inv_level_sigma2, int nlevels, float chi2_gate,
                                int32_t *q_best_idx, int32_t *q_best_dist, int memspace);
 
+/* ---- vocabulary-bucket matchers: SearchByBoW(KeyFrame*, Frame&, ..) ORBmatcher.cc:159-290, SearchByBoW(KeyFrame*, KeyFrame*, ..) :524-657,
+ * SearchForTriangulation :659-825 ---------------------------------------------------------------------------------------------------------
+ * A DBoW2::FeatureVector (std::map<NodeId, std::vector<unsigned>>, Frame::mFeatVec / KeyFrame::mFeatVec) is passed as CSR per keyframe:
+ *   fv_nodes i32[n_pairs, fv_slab] ascending node ids, fv_start i32[n_pairs, fv_slab + 1] offsets into fv_items, fv_items i32[n_pairs, slab]
+ *   feature indices in the order the map's vectors hold them, fv_counts i32[n_pairs] number of nodes.
+ * Side 1 is the keyframe whose features are walked (the reference's outer loop), side 2 the one searched.
+ *   ORBM_BOW_MATCH: elig1[i] / elig2[i] = the feature takes part (side 1: holds a good map point; side 2: all features for the Frame variant,
+ *     holds a good map point for the KeyFrame variant).  Best and second best Hamming distance over the still unclaimed side-2 features of
+ *     the node; accepted if best <= TH_LOW and (float)best < ratio * (float)second; the accepted feature is claimed.
+ *   ORBM_BOW_TRIANGULATION (monocular keyframes, bOnlyStereo = false): elig = the feature holds NO map point; no claims (the reference never
+ *     sets vbMatched2); smallest distance <= TH_LOW among the candidates that pass the epipole-distance gate (:747-753) and
+ *     CheckDistEpipolarLine (:140-157), the last one winning ties (:742).  Needs `epi`.
+ * With check_ori the rotation histogram keeps the three dominant bins.  Out: match12 i32[n_pairs*slab1] = side-2 feature index or -1,
+ * nmatches i32[n_pairs]. */
+#define ORBM_BOW_MATCH 0
+#define ORBM_BOW_TRIANGULATION 1
+typedef struct orbm_epipolar {       /* array members follow `memspace`; scale_factors2 / level_sigma2_2 are HOST arrays of nlevels floats */
+    const float *xy1, *xy2;          /* mvKeysUn.pt of side 1 [n_pairs*slab1,2] / side 2 [n_pairs*slab2,2] */
+    const int32_t *octave2;          /* [n_pairs*slab2] */
+    const float *F12;                /* [n_pairs,9] row-major fundamental matrix (LocalMapping::ComputeF12) */
+    const float *epipole;            /* [n_pairs,2] ex, ey: camera centre of keyframe 1 projected into keyframe 2 (:665-673) */
+    const float *scale_factors2, *level_sigma2_2;
+    int32_t nlevels;
+} orbm_epipolar;
+int orbm_search_by_bow(orbm_handle *h, int n_pairs, int mode,
+                       const uint8_t *desc1, const float *angle1, const uint8_t *elig1, const int32_t *counts1, int slab1,
+                       const int32_t *fv1_nodes, const int32_t *fv1_start, const int32_t *fv1_items, const int32_t *fv1_counts, int fv1_slab,
+                       const uint8_t *desc2, const float *angle2, const uint8_t *elig2, const int32_t *counts2, int slab2,
+                       const int32_t *fv2_nodes, const int32_t *fv2_start, const int32_t *fv2_items, const int32_t *fv2_counts, int fv2_slab,
+                       float ratio, int check_ori, const orbm_epipolar *epi, int32_t *match12, int32_t *nmatches, int memspace);
+
+/* ORBmatcher::SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize) (ORBmatcher.cc:407-522) for n_pairs frame pairs: the
+ * level-0 keypoints of F1 search GetFeaturesInArea(prev.x, prev.y, windowSize, 0, 0) of F2; best / second best with the ratio test; a feature
+ * of F2 already matched with a smaller-or-equal distance is skipped, a better match steals it (:471-476); rotation histogram (:497-512).
+ *   prev_matched f32[n_pairs*slab1,2] in/out (updated with the matched keypoint positions, :517-519); matches12 i32[n_pairs*slab1] out. */
+int orbm_search_for_initialization(orbm_handle *h, int n_pairs, const float *bounds4,
+                                   const int32_t *octave1, const float *angle1, const uint8_t *desc1, const int32_t *counts1, int slab1,
+                                   const float *xy2, const int32_t *octave2, const float *angle2, const uint8_t *desc2, const int32_t *counts2, int slab2,
+                                   float *prev_matched, int window, float ratio, int check_ori, int32_t *matches12, int32_t *nmatches, int memspace);
+
 /* ------------------------------------------------------------------ */
 /* Optimizer  (replaces S/src/Optimizer.cc and the g2o LM / Schur / LDLT stack it drives; all fp64 inside,
  * float32 poses and points at the boundary like cv::Mat / Converter.cc)                                      */

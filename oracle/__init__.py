@@ -422,3 +422,68 @@ def optimize_sim3(sim3, valid, P1c, P2c, obs1, obs2, w1, w2, K1, K2, th2=10.0, f
     L.oracle_optimize_sim3.argtypes = [_f64p, ctypes.c_int, _u8p] + [_f32p] * 8 + [ctypes.c_float, ctypes.c_int, _u8p, _i32p]
     n = L.oracle_optimize_sim3(_p(S, _f64p), N, _p(v, _u8p), *[_p(x, _f32p) for x in a], float(th2), int(bool(fix_scale)), _p(inl, _u8p), _p(st, _i32p))
     return dict(sim3=S, inlier=inl, n_in=int(n), lm_iterations=int(st[0]), lm_trials=int(st[1]))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# vocabulary-bucket matchers and SearchForInitialization
+class FeatVec(ctypes.Structure):
+    _fields_ = [("n_nodes", ctypes.c_int), ("nodes", ctypes.c_void_p), ("start", ctypes.c_void_p), ("items", ctypes.c_void_p)]
+
+
+class Epipolar(ctypes.Structure):
+    _fields_ = [("xy1", ctypes.c_void_p), ("xy2", ctypes.c_void_p), ("octave2", ctypes.c_void_p), ("F12", ctypes.c_void_p), ("ex", ctypes.c_float),
+                ("ey", ctypes.c_float), ("scale_factors2", ctypes.c_void_p), ("level_sigma2_2", ctypes.c_void_p)]
+
+
+def feature_vector(node_of_feature):
+    """DBoW2::FeatureVector as CSR from the node id of every feature (-1 = none): ascending node ids, features in index order."""
+    n = np.asarray(node_of_feature, np.int64)
+    idx = np.where(n >= 0)[0]
+    order = idx[np.argsort(n[idx], kind="stable")]
+    nodes, counts = np.unique(n[order], return_counts=True)
+    start = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+    return dict(nodes=nodes.astype(np.int32), start=start, items=order.astype(np.int32))
+
+
+def _fv(fv):
+    keep = [np.ascontiguousarray(fv[k], np.int32) for k in ("nodes", "start", "items")]
+    return FeatVec(len(keep[0]), keep[0].ctypes.data, keep[1].ctypes.data, keep[2].ctypes.data), keep
+
+
+def search_by_bow(mode, desc1, angle1, elig1, fv1, desc2, angle2, elig2, fv2, ratio, check_ori, epi=None):
+    """mode 0: SearchByBoW (both variants); mode 1: SearchForTriangulation (epi = dict xy1, xy2, octave2, F12, ex, ey, scale_factors2, level_sigma2_2).
+    Returns (nmatches, match12[N1])."""
+    d1 = np.ascontiguousarray(desc1, np.uint8); d2 = np.ascontiguousarray(desc2, np.uint8)
+    a1 = np.ascontiguousarray(angle1, np.float32); a2 = np.ascontiguousarray(angle2, np.float32)
+    e1 = np.ascontiguousarray(elig1, np.uint8); e2 = np.ascontiguousarray(elig2, np.uint8)
+    f1, k1 = _fv(fv1); f2, k2 = _fv(fv2)
+    m = np.full(len(d1), -1, np.int32)
+    ep = None
+    if epi is not None:
+        ka = [np.ascontiguousarray(epi["xy1"], np.float32), np.ascontiguousarray(epi["xy2"], np.float32), np.ascontiguousarray(epi["octave2"], np.int32),
+              np.ascontiguousarray(epi["F12"], np.float32), np.ascontiguousarray(epi["scale_factors2"], np.float32), np.ascontiguousarray(epi["level_sigma2_2"], np.float32)]
+        ep = Epipolar(ka[0].ctypes.data, ka[1].ctypes.data, ka[2].ctypes.data, ka[3].ctypes.data, float(epi["ex"]), float(epi["ey"]), ka[4].ctypes.data, ka[5].ctypes.data)
+    L = lib()
+    L.oracle_search_by_bow.restype = ctypes.c_int
+    L.oracle_search_by_bow.argtypes = [ctypes.c_int, ctypes.c_int, _u8p, _f32p, _u8p, ctypes.c_void_p, ctypes.c_int, _u8p, _f32p, _u8p, ctypes.c_void_p,
+                                       ctypes.c_float, ctypes.c_int, ctypes.c_void_p, _i32p]
+    n = L.oracle_search_by_bow(int(mode), len(d1), _p(d1, _u8p), _p(a1, _f32p), _p(e1, _u8p), ctypes.byref(f1), len(d2), _p(d2, _u8p), _p(a2, _f32p),
+                               _p(e2, _u8p), ctypes.byref(f2), float(ratio), int(bool(check_ori)), None if ep is None else ctypes.byref(ep), _p(m, _i32p))
+    return n, m
+
+
+def search_for_initialization(g, f1, f2, prev_matched, window=100, ratio=0.9, check_ori=True):
+    """f1 / f2: dicts x, y, octave, angle, desc.  Returns (nmatches, matches12, prev_matched updated)."""
+    xy1 = np.ascontiguousarray(np.stack([f1["x"], f1["y"]], 1), np.float32); xy2 = np.ascontiguousarray(np.stack([f2["x"], f2["y"]], 1), np.float32)
+    o1 = np.ascontiguousarray(f1["octave"], np.int32); o2 = np.ascontiguousarray(f2["octave"], np.int32)
+    a1 = np.ascontiguousarray(f1["angle"], np.float32); a2 = np.ascontiguousarray(f2["angle"], np.float32)
+    d1 = np.ascontiguousarray(f1["desc"], np.uint8); d2 = np.ascontiguousarray(f2["desc"], np.uint8)
+    pm = np.ascontiguousarray(prev_matched, np.float32).copy()
+    m = np.full(len(xy1), -1, np.int32)
+    L = lib()
+    L.oracle_search_for_initialization.restype = ctypes.c_int
+    L.oracle_search_for_initialization.argtypes = [ctypes.c_void_p, ctypes.c_int, _f32p, _i32p, _f32p, _u8p, ctypes.c_int, _f32p, _i32p, _f32p, _u8p, _f32p,
+                                                   ctypes.c_int, ctypes.c_float, ctypes.c_int, _i32p]
+    n = L.oracle_search_for_initialization(ctypes.byref(g), len(xy1), _p(xy1, _f32p), _p(o1, _i32p), _p(a1, _f32p), _p(d1, _u8p), len(xy2), _p(xy2, _f32p),
+                                           _p(o2, _i32p), _p(a2, _f32p), _p(d2, _u8p), _p(pm, _f32p), int(window), float(ratio), int(bool(check_ori)), _p(m, _i32p))
+    return n, m, pm

@@ -228,3 +228,62 @@ def ref_search_frame_kf(K4, bounds4, Tcw, scale_factors, cur, held, has, skip, p
                                    fa.ctypes.data, fd.ctypes.data, hd.ctypes.data, len(X), hs.ctypes.data, sk.ctypes.data, X.ctypes.data, mn.ctypes.data,
                                    mx.ctypes.data, ka.ctypes.data, qd.ctypes.data, fm.ctypes.data)
     return n, fm
+
+
+# ---- vocabulary-bucket matchers and SearchForInitialization (reference object code) ----------------------------------------------------
+def _fvargs(fv):
+    k = [_c(fv["nodes"], np.int32), _c(fv["start"], np.int32), _c(fv["items"], np.int32)]
+    return k, [len(k[0]), k[0].ctypes.data, k[1].ctypes.data, k[2].ctypes.data]
+
+
+def ref_search_by_bow_kf_frame(kf, has1, fv1, f_angle, f_desc, fv2, nnratio=0.7, check_ori=True):
+    """ORBmatcher::SearchByBoW(pKF, F, vpMapPointMatches) (ORBmatcher.cc:159-290).  Returns (n, match[N_frame] = keyframe feature or -1)."""
+    L = matcher_lib(); s, keep = _refkf(kf)
+    h = _c(has1, np.uint8); k1, a1 = _fvargs(fv1); k2, a2 = _fvargs(fv2); fa = _c(f_angle, np.float32); fd = _c(f_desc, np.uint8)
+    m = np.full(len(fa), -1, np.int32)
+    vp, i = ctypes.c_void_p, ctypes.c_int
+    L.ref_orbm_search_by_bow_kf_frame.argtypes = [ctypes.c_float, i, vp, vp, i, vp, vp, vp, i, vp, vp, i, vp, vp, vp, vp]
+    n = L.ref_orbm_search_by_bow_kf_frame(float(nnratio), int(bool(check_ori)), ctypes.byref(s), h.ctypes.data, *a1, len(fa), fa.ctypes.data, fd.ctypes.data, *a2,
+                                          m.ctypes.data)
+    return n, m
+
+
+def ref_search_by_bow_kf_kf(kf1, has1, fv1, kf2, has2, fv2, nnratio=0.75, check_ori=True):
+    """ORBmatcher::SearchByBoW(pKF1, pKF2, vpMatches12) (ORBmatcher.cc:524-657).  Returns (n, match12[N1])."""
+    L = matcher_lib(); a, ka = _refkf(kf1); b, kb = _refkf(kf2)
+    h1 = _c(has1, np.uint8); h2 = _c(has2, np.uint8); k1, a1 = _fvargs(fv1); k2, a2 = _fvargs(fv2)
+    m = np.full(a.N, -1, np.int32)
+    vp, i = ctypes.c_void_p, ctypes.c_int
+    L.ref_orbm_search_by_bow_kf_kf.argtypes = [ctypes.c_float, i, vp, vp, i, vp, vp, vp, vp, vp, i, vp, vp, vp, vp]
+    n = L.ref_orbm_search_by_bow_kf_kf(float(nnratio), int(bool(check_ori)), ctypes.byref(a), h1.ctypes.data, *a1, ctypes.byref(b), h2.ctypes.data, *a2, m.ctypes.data)
+    return n, m
+
+
+def ref_search_for_triangulation(kf1, has1, fv1, kf2, has2, fv2, level_sigma2, F12, nnratio=0.6, check_ori=False):
+    """ORBmatcher::SearchForTriangulation(pKF1, pKF2, F12, vMatchedPairs, false) (ORBmatcher.cc:659-825).  Returns (n, match12[N1])."""
+    L = matcher_lib(); a, ka = _refkf(kf1); b, kb = _refkf(kf2)
+    h1 = _c(has1, np.uint8); h2 = _c(has2, np.uint8); k1, a1 = _fvargs(fv1); k2, a2 = _fvargs(fv2)
+    ls = _c(level_sigma2, np.float32); F = _c(F12, np.float32).reshape(9)
+    m = np.full(a.N, -1, np.int32)
+    vp, i = ctypes.c_void_p, ctypes.c_int
+    L.ref_orbm_search_for_triangulation.argtypes = [ctypes.c_float, i, vp, vp, i, vp, vp, vp, vp, vp, i, vp, vp, vp, vp, vp, vp]
+    n = L.ref_orbm_search_for_triangulation(float(nnratio), int(bool(check_ori)), ctypes.byref(a), h1.ctypes.data, *a1, ctypes.byref(b), h2.ctypes.data, *a2,
+                                            ls.ctypes.data, F.ctypes.data, m.ctypes.data)
+    return n, m
+
+
+def ref_search_for_initialization(K4, bounds4, scale_factors, f1, f2, prev_matched, window=100, nnratio=0.9, check_ori=True):
+    """ORBmatcher::SearchForInitialization (ORBmatcher.cc:407-522).  Returns (n, matches12, prev_matched updated)."""
+    L = matcher_lib()
+    L.ref_orbm_set_camera(*[float(v) for v in K4], float(bounds4[0]), float(bounds4[1]), float(bounds4[2]), float(bounds4[3]))
+    sf = _c(scale_factors, np.float32)
+    arr = []
+    for f in (f1, f2):
+        arr += [_c(np.stack([f["x"], f["y"]], 1), np.float32), _c(f["octave"], np.int32), _c(f["angle"], np.float32), _c(f["desc"], np.uint8)]
+    pm = _c(prev_matched, np.float32).copy(); m = np.full(len(arr[0]), -1, np.int32)
+    vp, i = ctypes.c_void_p, ctypes.c_int
+    L.ref_orbm_search_for_initialization.argtypes = [ctypes.c_float, i, i, vp, i, i, vp, vp, vp, vp, i, vp, vp, vp, vp, vp, vp]
+    n = L.ref_orbm_search_for_initialization(float(nnratio), int(bool(check_ori)), int(window), sf.ctypes.data, len(sf), len(arr[0]), arr[0].ctypes.data,
+                                             arr[1].ctypes.data, arr[2].ctypes.data, arr[3].ctypes.data, len(arr[4]), arr[4].ctypes.data, arr[5].ctypes.data,
+                                             arr[6].ctypes.data, arr[7].ctypes.data, pm.ctypes.data, m.ctypes.data)
+    return n, m, pm

@@ -288,4 +288,94 @@ int ref_orbm_search_frame_kf(int check_ori, float th, int orb_dist, const float 
     return n;
 }
 
+
+/* ---- vocabulary-bucket matchers and SearchForInitialization -------------------------------------------------------------------------- */
+static void fill_featvec(DBoW2::FeatureVector &fv, int n_nodes, const int *nodes, const int *start, const int *items)
+{
+    for (int a = 0; a < n_nodes; a++) {
+        std::vector<unsigned int> &v = fv[(unsigned)nodes[a]];
+        for (int u = start[a]; u < start[a + 1]; u++) v.push_back((unsigned)items[u]);
+    }
+}
+
+/* ORBmatcher::SearchByBoW(pKF, F, vpMapPointMatches), ORBmatcher.cc:159-290.  has1[i]: keyframe feature i holds a good map point.
+ * match[k] (per FRAME feature) = keyframe feature whose map point was assigned, or -1. */
+int ref_orbm_search_by_bow_kf_frame(float nnratio, int check_ori, const RefKF *kf, const unsigned char *has1, int nn1, const int *nodes1, const int *start1,
+                                    const int *items1, int N2, const float *f_angle, const unsigned char *f_desc, int nn2, const int *nodes2, const int *start2,
+                                    const int *items2, int *match)
+{
+    KeyFrame K; fill_keyframe(K, *kf);
+    fill_featvec(K.mFeatVec, nn1, nodes1, start1, items1);
+    std::vector<MapPoint> mps(K.N);
+    for (int i = 0; i < K.N; i++) if (has1[i]) K.mvpMapPoints[i] = &mps[i];
+    Frame F;
+    std::vector<float> xy(2 * (size_t)(N2 > 0 ? N2 : 1), 0.f); std::vector<int> oct(N2 > 0 ? N2 : 1, 0);
+    const float eye[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+    fill_frame(F, N2, xy.data(), oct.data(), f_angle, f_desc, eye, kf->scale_factors, kf->nlevels);
+    fill_featvec(F.mFeatVec, nn2, nodes2, start2, items2);
+    std::vector<MapPoint *> out;
+    ORBmatcher matcher(nnratio, check_ori != 0);
+    const int n = matcher.SearchByBoW(&K, F, out);
+    for (int k = 0; k < N2; k++) match[k] = out[k] ? (int)(out[k] - mps.data()) : -1;
+    return n;
+}
+
+/* ORBmatcher::SearchByBoW(pKF1, pKF2, vpMatches12), ORBmatcher.cc:524-657.  match12[i1] = feature of KF2 whose map point was matched, or -1. */
+int ref_orbm_search_by_bow_kf_kf(float nnratio, int check_ori, const RefKF *kf1, const unsigned char *has1, int nn1, const int *nodes1, const int *start1,
+                                 const int *items1, const RefKF *kf2, const unsigned char *has2, int nn2, const int *nodes2, const int *start2,
+                                 const int *items2, int *match12)
+{
+    KeyFrame K1, K2; fill_keyframe(K1, *kf1); fill_keyframe(K2, *kf2);
+    fill_featvec(K1.mFeatVec, nn1, nodes1, start1, items1); fill_featvec(K2.mFeatVec, nn2, nodes2, start2, items2);
+    std::vector<MapPoint> p1(K1.N), p2(K2.N);
+    for (int i = 0; i < K1.N; i++) if (has1[i]) K1.mvpMapPoints[i] = &p1[i];
+    for (int i = 0; i < K2.N; i++) if (has2[i]) K2.mvpMapPoints[i] = &p2[i];
+    std::vector<MapPoint *> out;
+    ORBmatcher matcher(nnratio, check_ori != 0);
+    const int n = matcher.SearchByBoW(&K1, &K2, out);
+    for (int i = 0; i < K1.N; i++) match12[i] = out[i] ? (int)(out[i] - p2.data()) : -1;
+    return n;
+}
+
+/* ORBmatcher::SearchForTriangulation(pKF1, pKF2, F12, vMatchedPairs, bOnlyStereo = false), ORBmatcher.cc:659-825 (monocular keyframes).
+ * has1 / has2: the feature already holds a map point (skipped).  match12[i1] = i2 or -1 (the pairs). */
+int ref_orbm_search_for_triangulation(float nnratio, int check_ori, const RefKF *kf1, const unsigned char *has1, int nn1, const int *nodes1, const int *start1,
+                                      const int *items1, const RefKF *kf2, const unsigned char *has2, int nn2, const int *nodes2, const int *start2,
+                                      const int *items2, const float *level_sigma2, const float *F12, int *match12)
+{
+    KeyFrame K1, K2; fill_keyframe(K1, *kf1); fill_keyframe(K2, *kf2);
+    K2.mvLevelSigma2.assign(level_sigma2, level_sigma2 + kf2->nlevels); K1.mvLevelSigma2 = K2.mvLevelSigma2;
+    fill_featvec(K1.mFeatVec, nn1, nodes1, start1, items1); fill_featvec(K2.mFeatVec, nn2, nodes2, start2, items2);
+    MapPoint holder;
+    for (int i = 0; i < K1.N; i++) if (has1[i]) K1.mvpMapPoints[i] = &holder;
+    for (int i = 0; i < K2.N; i++) if (has2[i]) K2.mvpMapPoints[i] = &holder;
+    cv::Mat F(3, 3, CV_32F);
+    std::memcpy(F.data, F12, 9 * sizeof(float));
+    std::vector<std::pair<size_t, size_t>> pairs;
+    ORBmatcher matcher(nnratio, check_ori != 0);
+    const int n = matcher.SearchForTriangulation(&K1, &K2, F, pairs, false);
+    for (int i = 0; i < K1.N; i++) match12[i] = -1;
+    for (auto &pr : pairs) match12[pr.first] = (int)pr.second;
+    return n;
+}
+
+/* ORBmatcher::SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize), ORBmatcher.cc:407-522 */
+int ref_orbm_search_for_initialization(float nnratio, int check_ori, int window, const float *scale_factors, int nlevels,
+                                       int N1, const float *xy1, const int *oct1, const float *ang1, const unsigned char *desc1,
+                                       int N2, const float *xy2, const int *oct2, const float *ang2, const unsigned char *desc2,
+                                       float *prev_matched, int *matches12)
+{
+    Frame F1, F2;
+    const float eye[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+    fill_frame(F1, N1, xy1, oct1, ang1, desc1, eye, scale_factors, nlevels);
+    fill_frame(F2, N2, xy2, oct2, ang2, desc2, eye, scale_factors, nlevels);
+    std::vector<cv::Point2f> prev(N1);
+    for (int i = 0; i < N1; i++) { prev[i].x = prev_matched[2 * i]; prev[i].y = prev_matched[2 * i + 1]; }
+    std::vector<int> m12;
+    ORBmatcher matcher(nnratio, check_ori != 0);
+    const int n = matcher.SearchForInitialization(F1, F2, prev, m12, window);
+    for (int i = 0; i < N1; i++) { matches12[i] = m12[i]; prev_matched[2 * i] = prev[i].x; prev_matched[2 * i + 1] = prev[i].y; }
+    return n;
+}
+
 }

@@ -1278,3 +1278,150 @@ int oracle_optimize_sim3(double *sim3_io, int N, const uint8_t *valid, const flo
     free(B.active); free(B.err);
     return nIn;
 }
+
+/* ======================================================================================== */
+/* Vocabulary-bucket matchers and SearchForInitialization (matcher, continued)              */
+/* A DBoW2::FeatureVector (std::map<NodeId, vector<unsigned>>) is passed as CSR: ascending node ids, start offsets, feature indices in
+ * push order.  The three bucket matchers walk the two maps like a merge join (ORBmatcher.cc:176-269, :548-634, :695-790) and only ever
+ * compare features of equal node id, so the restatement iterates over the common nodes.
+ *   mode 0: SearchByBoW(KeyFrame*, Frame&, ..) :159-290 and SearchByBoW(KeyFrame*, KeyFrame*, ..) :524-657 -- best / second best over the
+ *           still unclaimed side-2 features of the bucket, accept if best <= TH_LOW and (float)best < ratio * (float)second, claim.
+ *   mode 1: SearchForTriangulation :659-825 (monocular: mvuRight < 0, bOnlyStereo = false) -- no claims (vbMatched2 is never set), best
+ *           distance <= TH_LOW with the LAST candidate winning ties (dist > bestDist -> skip), epipole-distance and epipolar-line gates.
+ * elig1 / elig2: the feature takes part (has a good map point for mode 0 / has none for mode 1).  match12[idx1] = idx2 or -1. */
+typedef struct { int n_nodes; const int *nodes; const int *start; const int *items; } oracle_featvec;
+typedef struct { const float *xy1, *xy2; const int *octave2; const float *F12; float ex, ey; const float *scale_factors2, *level_sigma2_2; } oracle_epipolar;
+
+static int check_dist_epipolar_line(const float *p1, const float *p2, const float *F12, float sigma2)     /* ORBmatcher.cc:140-157 */
+{
+    const float a = p1[0] * F12[0] + p1[1] * F12[3] + F12[6];
+    const float b = p1[0] * F12[1] + p1[1] * F12[4] + F12[7];
+    const float c = p1[0] * F12[2] + p1[1] * F12[5] + F12[8];
+    const float num = a * p2[0] + b * p2[1] + c;
+    const float den = a * a + b * b;
+    if (den == 0) return 0;
+    const float dsqr = num * num / den;
+    return dsqr < 3.84 * sigma2;
+}
+
+int oracle_search_by_bow(int mode, int N1, const uint8_t *desc1, const float *angle1, const uint8_t *elig1, const oracle_featvec *fv1,
+                         int N2, const uint8_t *desc2, const float *angle2, const uint8_t *elig2, const oracle_featvec *fv2,
+                         float ratio, int check_ori, const oracle_epipolar *ep, int *match12)
+{
+    uint8_t *matched2 = (uint8_t *)calloc(N2 > 0 ? N2 : 1, 1);
+    int *rot_bin = (int *)malloc(sizeof(int) * (N1 > 0 ? N1 : 1));
+    int hist[HISTO_LENGTH];
+    memset(hist, 0, sizeof hist);
+    for (int i = 0; i < N1; i++) { match12[i] = -1; rot_bin[i] = -1; }
+    const float factor = 1.0f / HISTO_LENGTH;
+    int nmatches = 0, a = 0, b = 0;
+    while (a < fv1->n_nodes && b < fv2->n_nodes) {
+        if (fv1->nodes[a] < fv2->nodes[b]) { a++; continue; }           /* lower_bound on the other map */
+        if (fv1->nodes[a] > fv2->nodes[b]) { b++; continue; }
+        for (int u = fv1->start[a]; u < fv1->start[a + 1]; u++) {
+            const int idx1 = fv1->items[u];
+            if (!elig1[idx1]) continue;
+            int best1 = mode == 0 ? 256 : TH_LOW, best2 = 256, best_idx = -1;
+            for (int v = fv2->start[b]; v < fv2->start[b + 1]; v++) {
+                const int idx2 = fv2->items[v];
+                if (mode == 0) {
+                    if (matched2[idx2] || !elig2[idx2]) continue;
+                    const int d = oracle_descriptor_distance(desc1 + 32 * (size_t)idx1, desc2 + 32 * (size_t)idx2);
+                    if (d < best1) { best2 = best1; best1 = d; best_idx = idx2; }
+                    else if (d < best2) best2 = d;
+                } else {
+                    if (matched2[idx2] || !elig2[idx2]) continue;
+                    const int d = oracle_descriptor_distance(desc1 + 32 * (size_t)idx1, desc2 + 32 * (size_t)idx2);
+                    if (d > TH_LOW || d > best1) continue;
+                    const float distex = ep->ex - ep->xy2[2 * idx2], distey = ep->ey - ep->xy2[2 * idx2 + 1];
+                    if (distex * distex + distey * distey < 100 * ep->scale_factors2[ep->octave2[idx2]]) continue;
+                    if (check_dist_epipolar_line(ep->xy1 + 2 * idx1, ep->xy2 + 2 * idx2, ep->F12, ep->level_sigma2_2[ep->octave2[idx2]])) { best_idx = idx2; best1 = d; }
+                }
+            }
+            int accept;
+            if (mode == 0) accept = best1 <= TH_LOW && (float)best1 < ratio * (float)best2;
+            else accept = best_idx >= 0;
+            if (!accept) continue;
+            match12[idx1] = best_idx;
+            if (mode == 0) matched2[best_idx] = 1;
+            nmatches++;
+            if (check_ori) {
+                float rot = angle1[idx1] - angle2[best_idx];
+                if (rot < 0.0) rot += 360.0f;
+                int bin = (int)roundf(rot * factor);
+                if (bin == HISTO_LENGTH) bin = 0;
+                rot_bin[idx1] = bin; hist[bin]++;
+            }
+        }
+        a++; b++;
+    }
+    if (check_ori) {
+        int i1, i2, i3;
+        three_maxima(hist, HISTO_LENGTH, &i1, &i2, &i3);
+        for (int i = 0; i < N1; i++) { const int bn = rot_bin[i]; if (bn >= 0 && bn != i1 && bn != i2 && bn != i3) { match12[i] = -1; nmatches--; } }
+    }
+    free(matched2); free(rot_bin);
+    return nmatches;
+}
+
+/* ORBmatcher::SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize), ORBmatcher.cc:407-522: level-0 keypoints of F1 search a
+ * window around their previous match in F2 (GetFeaturesInArea(x, y, windowSize, 0, 0)); a candidate already matched with a smaller-or-equal
+ * distance is skipped, a better one is stolen (its former owner loses the match but stays in the rotation histogram, :471-476, :497-505).
+ * prev_matched f32[N1,2] in/out (:517-519).  Returns nmatches. */
+int oracle_search_for_initialization(const oracle_grid_params *g, int N1, const float *xy1_unused, const int *octave1, const float *angle1, const uint8_t *desc1,
+                                     int N2, const float *xy2, const int *octave2, const float *angle2, const uint8_t *desc2,
+                                     float *prev_matched, int window, float ratio, int check_ori, int *matches12)
+{
+    (void)xy1_unused;
+    const int nc = GRID_COLS * GRID_ROWS;
+    int *cell_start = (int *)malloc(sizeof(int) * (nc + 1));
+    int *cell_items = (int *)malloc(sizeof(int) * (N2 > 0 ? N2 : 1)), *cands = (int *)malloc(sizeof(int) * (N2 > 0 ? N2 : 1));
+    int *matched_dist = (int *)malloc(sizeof(int) * (N2 > 0 ? N2 : 1)), *matches21 = (int *)malloc(sizeof(int) * (N2 > 0 ? N2 : 1));
+    int *rot_bin = (int *)malloc(sizeof(int) * (N1 > 0 ? N1 : 1));
+    int hist[HISTO_LENGTH];
+    memset(hist, 0, sizeof hist);
+    oracle_grid_build(g, N2, xy2, cell_start, cell_items);
+    for (int i = 0; i < N2; i++) { matched_dist[i] = 0x7fffffff; matches21[i] = -1; }
+    for (int i = 0; i < N1; i++) { matches12[i] = -1; rot_bin[i] = -1; }
+    const float factor = 1.0f / HISTO_LENGTH;
+    int nmatches = 0;
+    for (int i1 = 0; i1 < N1; i1++) {
+        const int level1 = octave1[i1];
+        if (level1 > 0) continue;
+        const int n = oracle_features_in_area(g, cell_start, cell_items, xy2, octave2, prev_matched[2 * i1], prev_matched[2 * i1 + 1], (float)window, level1, level1, cands);
+        if (n == 0) continue;
+        int best = 0x7fffffff, best2 = 0x7fffffff, best_idx = -1;
+        for (int c = 0; c < n; c++) {
+            const int i2 = cands[c];
+            const int d = oracle_descriptor_distance(desc1 + 32 * (size_t)i1, desc2 + 32 * (size_t)i2);
+            if (matched_dist[i2] <= d) continue;
+            if (d < best) { best2 = best; best = d; best_idx = i2; }
+            else if (d < best2) best2 = d;
+        }
+        if (best <= TH_LOW) {
+            if (best < (float)best2 * ratio) {
+                if (matches21[best_idx] >= 0) { matches12[matches21[best_idx]] = -1; nmatches--; }
+                matches12[i1] = best_idx; matches21[best_idx] = i1; matched_dist[best_idx] = best;
+                nmatches++;
+                if (check_ori) {
+                    float rot = angle1[i1] - angle2[best_idx];
+                    if (rot < 0.0) rot += 360.0f;
+                    int bin = (int)roundf(rot * factor);
+                    if (bin == HISTO_LENGTH) bin = 0;
+                    rot_bin[i1] = bin; hist[bin]++;
+                }
+            }
+        }
+    }
+    if (check_ori) {
+        int i1, i2, i3;
+        three_maxima(hist, HISTO_LENGTH, &i1, &i2, &i3);
+        for (int i = 0; i < N1; i++) {
+            const int bn = rot_bin[i];
+            if (bn >= 0 && bn != i1 && bn != i2 && bn != i3 && matches12[i] >= 0) { matches12[i] = -1; nmatches--; }
+        }
+    }
+    for (int i = 0; i < N1; i++) if (matches12[i] >= 0) { prev_matched[2 * i] = xy2[2 * matches12[i]]; prev_matched[2 * i + 1] = xy2[2 * matches12[i] + 1]; }
+    free(cell_start); free(cell_items); free(cands); free(matched_dist); free(matches21); free(rot_bin);
+    return nmatches;
+}

@@ -391,6 +391,58 @@ class ORBmatcher:
         return nm, fm
 
 
+    # ---- vocabulary-bucket matchers (ORBmatcher.cc:159-290, 524-657, 659-825) and SearchForInitialization (:407-522) ----------------------
+    @staticmethod
+    def _fv_slabs(fvs, slab):
+        """list of CSR FeatureVectors (dicts nodes, start, items) -> slab arrays (nodes, start, items, counts, node_slab)"""
+        n = len(fvs); ns = max(1, max(len(f["nodes"]) for f in fvs))
+        nodes = np.zeros((n, ns), np.int32); start = np.zeros((n, ns + 1), np.int32); items = np.zeros((n, slab), np.int32); cnt = np.zeros(n, np.int32)
+        for i, f in enumerate(fvs):
+            k = len(f["nodes"]); cnt[i] = k
+            nodes[i, :k] = f["nodes"]; start[i, :k + 1] = f["start"]; items[i, :len(f["items"])] = f["items"]
+        return nodes, start, items, cnt, ns
+
+    def SearchByBoW(self, desc1, angle1, elig1, counts1, fvs1, desc2, angle2, elig2, counts2, fvs2, triangulation=None):
+        """orbm_search_by_bow for n_pairs keyframe pairs (slab layout).  fvs1 / fvs2: lists of CSR FeatureVectors.  triangulation: None for
+        SearchByBoW (mfNNratio, mbCheckOrientation), or dict(xy1, xy2, octave2, F12 [n,9], epipole [n,2], scale_factors2, level_sigma2_2) for
+        SearchForTriangulation.  Returns (nmatches [n_pairs], match12 [n_pairs, slab1])."""
+        d1 = np.ascontiguousarray(desc1, np.uint8); d2 = np.ascontiguousarray(desc2, np.uint8); n, s1, s2 = d1.shape[0], d1.shape[1], d2.shape[1]
+        a1 = np.ascontiguousarray(angle1, np.float32); a2 = np.ascontiguousarray(angle2, np.float32)
+        e1 = np.ascontiguousarray(elig1, np.uint8); e2 = np.ascontiguousarray(elig2, np.uint8)
+        c1 = np.ascontiguousarray(counts1, np.int32); c2 = np.ascontiguousarray(counts2, np.int32)
+        n1, st1, it1, nc1, ns1 = self._fv_slabs(fvs1, s1); n2, st2, it2, nc2, ns2 = self._fv_slabs(fvs2, s2)
+        m = np.zeros((n, s1), np.int32); nm = np.zeros(n, np.int32)
+        ep = None; keep = []
+        if triangulation is not None:
+            t = triangulation
+            keep = [np.ascontiguousarray(t["xy1"], np.float32), np.ascontiguousarray(t["xy2"], np.float32), np.ascontiguousarray(t["octave2"], np.int32),
+                    np.ascontiguousarray(t["F12"], np.float32), np.ascontiguousarray(t["epipole"], np.float32),
+                    np.ascontiguousarray(t["scale_factors2"], np.float32), np.ascontiguousarray(t["level_sigma2_2"], np.float32)]
+            ep = Epipolar(*[k.ctypes.data for k in keep], len(keep[5]))
+        _check(self._L.orbm_search_by_bow(self._h, n, 0 if ep is None else 1, _ptr(d1), _ptr(a1), _ptr(e1), _ptr(c1), s1, _ptr(n1), _ptr(st1), _ptr(it1), _ptr(nc1),
+                                          ns1, _ptr(d2), _ptr(a2), _ptr(e2), _ptr(c2), s2, _ptr(n2), _ptr(st2), _ptr(it2), _ptr(nc2), ns2, self.mfNNratio,
+                                          int(self.mbCheckOrientation), None if ep is None else ctypes.byref(ep), _ptr(m), _ptr(nm), 0))
+        return nm, m
+
+    def SearchForInitialization(self, bounds4, octave1, angle1, desc1, counts1, xy2, octave2, angle2, desc2, counts2, prev_matched, windowSize=10):
+        """ORBmatcher::SearchForInitialization for n_pairs frame pairs (slab layout).  Returns (nmatches, matches12, prev_matched updated)."""
+        o1 = np.ascontiguousarray(octave1, np.int32); n, s1 = o1.shape
+        a1 = np.ascontiguousarray(angle1, np.float32); d1 = np.ascontiguousarray(desc1, np.uint8); c1 = np.ascontiguousarray(counts1, np.int32)
+        x2 = np.ascontiguousarray(xy2, np.float32); s2 = x2.shape[1]
+        o2 = np.ascontiguousarray(octave2, np.int32); a2 = np.ascontiguousarray(angle2, np.float32); d2 = np.ascontiguousarray(desc2, np.uint8)
+        c2 = np.ascontiguousarray(counts2, np.int32); pm = np.ascontiguousarray(prev_matched, np.float32).copy(); b4 = np.ascontiguousarray(bounds4, np.float32)
+        m = np.zeros((n, s1), np.int32); nm = np.zeros(n, np.int32)
+        _check(self._L.orbm_search_for_initialization(self._h, n, _ptr(b4), _ptr(o1), _ptr(a1), _ptr(d1), _ptr(c1), s1, _ptr(x2), _ptr(o2), _ptr(a2), _ptr(d2),
+                                                      _ptr(c2), s2, _ptr(pm), int(windowSize), self.mfNNratio, int(self.mbCheckOrientation), _ptr(m), _ptr(nm), 0))
+        return nm, m, pm
+
+
+class Epipolar(ctypes.Structure):
+    """= orbm_epipolar (include/orbslamm_b200.h)"""
+    _fields_ = [("xy1", ctypes.c_void_p), ("xy2", ctypes.c_void_p), ("octave2", ctypes.c_void_p), ("F12", ctypes.c_void_p), ("epipole", ctypes.c_void_p),
+                ("scale_factors2", ctypes.c_void_p), ("level_sigma2_2", ctypes.c_void_p), ("nlevels", ctypes.c_int32)]
+
+
 class Projection(ctypes.Structure):
     """= orbm_projection (include/orbslamm_b200.h)"""
     _fields_ = [("R", ctypes.c_float * 9), ("t", ctypes.c_float * 3), ("R2", ctypes.c_float * 9), ("t2", ctypes.c_float * 3),

@@ -24,6 +24,10 @@ def declare(L):
     L.orbm_search_best_in_window.argtypes = [vp, i, vp, vp, vp, vp, vp, vp, i, vp, vp, vp, vp, vp, vp, vp, i, i, vp, i, f, vp, vp, i]
     for n in ("orbm_project_points", "orbm_search_by_projection_kf", "orbm_search_best_in_window"):
         getattr(L, n).restype = c.c_int
+    L.orbm_search_by_bow.argtypes = [vp, i, i, vp, vp, vp, vp, i, vp, vp, vp, vp, i, vp, vp, vp, vp, i, vp, vp, vp, vp, i, f, i, vp, vp, vp, i]
+    L.orbm_search_by_bow.restype = c.c_int
+    L.orbm_search_for_initialization.argtypes = [vp, i, vp, vp, vp, vp, vp, i, vp, vp, vp, vp, vp, i, vp, i, f, i, vp, vp, i]
+    L.orbm_search_for_initialization.restype = c.c_int
     L.orbo_create.argtypes = [c.POINTER(vp), i]
     L.orbo_destroy.argtypes = [vp]
     L.orbo_stream.argtypes = [vp]; L.orbo_stream.restype = vp

@@ -656,6 +656,233 @@ k_search_resolve(const SearchArgs A, const int use_smem)
     if (tid == 0) A.nmatches[f] = s_accepted - s_removed;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------------------
+// Vocabulary-bucket matchers: SearchByBoW(KeyFrame*, Frame&) :159-290, SearchByBoW(KeyFrame*, KeyFrame*) :524-657 (mode 0) and
+// SearchForTriangulation :659-825 (mode 1).  Features are only compared inside a vocabulary node, and a claim never leaves its node, so
+// the nodes are independent: ONE WARP PER COMMON NODE walks the side-1 features of the node in the reference's order (the claim chain),
+// the 32 lanes scan the node's side-2 features (XOR + POPC) and a warp reduction yields best / second best in the reference's comparison
+// order.  The merge join over the two std::map<NodeId, ...> is a binary search of the side-1 node id in side 2's sorted node list.
+struct BowArgs {
+    int mode, slab1, slab2, nslab1, nslab2;
+    const uint4 *desc1, *desc2; const float *angle1, *angle2; const uint8_t *elig1, *elig2;
+    const int *counts1;
+    const int *nodes1, *start1, *items1, *ncount1;      // [n_pairs, nslab1], [n_pairs, nslab1 + 1], [n_pairs, slab1], [n_pairs]
+    const int *nodes2, *start2, *items2, *ncount2;
+    float ratio; int check_ori;
+    const float2 *xy1, *xy2; const int *octave2; const float *F12, *epipole; float scale_factors2[32], level_sigma2_2[32]; int nlevels;   // mode 1
+    uint8_t *matched2;                                  // scratch [n_pairs, slab2], zeroed
+    int *match12; int *rot_bin;                         // [n_pairs, slab1]
+    int *nmatches;                                      // [n_pairs]
+};
+
+__device__ __forceinline__ int rot_hist_bin(float a1, float a2)
+{
+    float rot = __fsub_rn(a1, a2);
+    if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+    int bin = (int)roundf(__fmul_rn(rot, 1.0f / kHisto));
+    if (bin == kHisto) bin = 0;
+    return min(max(bin, 0), kHisto - 1);
+}
+
+__global__ void __launch_bounds__(256)
+k_bow_match(const BowArgs A)
+{
+    const int f = blockIdx.y, lane = threadIdx.x & 31;
+    const int a = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (a >= A.ncount1[f]) return;
+    const int *nodes2 = A.nodes2 + (size_t)f * A.nslab2;
+    const int node = A.nodes1[(size_t)f * A.nslab1 + a];
+    int lo = 0, hi = A.ncount2[f];
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (nodes2[mid] < node) lo = mid + 1; else hi = mid; }
+    if (lo >= A.ncount2[f] || nodes2[lo] != node) return;
+    const size_t o1 = (size_t)f * A.slab1, o2 = (size_t)f * A.slab2;
+    const int *st1 = A.start1 + (size_t)f * (A.nslab1 + 1), *st2 = A.start2 + (size_t)f * (A.nslab2 + 1);
+    const int *items1 = A.items1 + o1, *items2 = A.items2 + o2;
+    const int u0 = st1[a], u1 = st1[a + 1], v0 = st2[lo], v1 = st2[lo + 1];
+    uint8_t *matched2 = A.matched2 + o2;
+    float F[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, ex = 0, ey = 0;
+    if (A.mode == 1) { for (int k = 0; k < 9; k++) F[k] = A.F12[9 * f + k]; ex = A.epipole[2 * f]; ey = A.epipole[2 * f + 1]; }
+    for (int u = u0; u < u1; u++) {
+        const int idx1 = items1[u];
+        if (!A.elig1[o1 + idx1]) continue;
+        const uint4 qa = __ldg(&A.desc1[2 * (o1 + idx1)]), qb = __ldg(&A.desc1[2 * (o1 + idx1) + 1]);
+        // key = distance << 20 | position in the node (mode 0: first minimum wins; mode 1: last minimum wins -> position inverted)
+        unsigned b1 = 0xffffffffu, b2 = 0xffffffffu;
+        float la = 0, lb = 0, lc = 0;
+        if (A.mode == 1) {                                  // epipolar line of kp1 in image 2 (CheckDistEpipolarLine, :140-146)
+            const float2 p1 = A.xy1[o1 + idx1];
+            la = __fadd_rn(__fadd_rn(__fmul_rn(p1.x, F[0]), __fmul_rn(p1.y, F[3])), F[6]);
+            lb = __fadd_rn(__fadd_rn(__fmul_rn(p1.x, F[1]), __fmul_rn(p1.y, F[4])), F[7]);
+            lc = __fadd_rn(__fadd_rn(__fmul_rn(p1.x, F[2]), __fmul_rn(p1.y, F[5])), F[8]);
+        }
+        for (int v = v0 + lane; v < v1; v += 32) {
+            const int idx2 = items2[v];
+            if (matched2[idx2] || !A.elig2[o2 + idx2]) continue;
+            const int d = hamming256(qa, qb, __ldg(&A.desc2[2 * (o2 + idx2)]), __ldg(&A.desc2[2 * (o2 + idx2) + 1]));
+            unsigned key;
+            if (A.mode == 0) key = ((unsigned)d << 20) | (unsigned)(v - v0);
+            else {
+                if (d > ORBM_TH_LOW) continue;
+                const float2 p2 = A.xy2[o2 + idx2];
+                const int oct = min(max(A.octave2[o2 + idx2], 0), A.nlevels - 1);
+                const float dx = __fsub_rn(ex, p2.x), dy = __fsub_rn(ey, p2.y);
+                if (__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)) < __fmul_rn(100.0f, A.scale_factors2[oct])) continue;      // :747-753
+                const float num = __fadd_rn(__fadd_rn(__fmul_rn(la, p2.x), __fmul_rn(lb, p2.y)), lc);
+                const float den = __fadd_rn(__fmul_rn(la, la), __fmul_rn(lb, lb));
+                if (den == 0) continue;
+                const float dsqr = __fdiv_rn(__fmul_rn(num, num), den);
+                if (!((double)dsqr < 3.84 * (double)A.level_sigma2_2[oct])) continue;
+                key = ((unsigned)d << 20) | (unsigned)(0xfffff - (v - v0));
+            }
+            if (key < b1) { b2 = b1; b1 = key; } else if (key < b2) b2 = key;
+        }
+        unsigned m1 = b1;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) m1 = min(m1, __shfl_xor_sync(0xffffffffu, m1, d));
+        unsigned m2 = (b1 == m1) ? b2 : b1;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) m2 = min(m2, __shfl_xor_sync(0xffffffffu, m2, d));
+        if (m1 == 0xffffffffu) continue;
+        const int best1 = (int)(m1 >> 20), best2 = m2 == 0xffffffffu ? 256 : (int)(m2 >> 20);
+        bool accept;
+        int idx2;
+        if (A.mode == 0) { accept = best1 <= ORBM_TH_LOW && (float)best1 < __fmul_rn(A.ratio, (float)best2); idx2 = items2[v0 + (int)(m1 & 0xfffff)]; }
+        else { accept = true; idx2 = items2[v0 + (0xfffff - (int)(m1 & 0xfffff))]; }
+        if (!accept) continue;
+        if (lane == 0) {
+            A.match12[o1 + idx1] = idx2;
+            if (A.mode == 0) matched2[idx2] = 1;
+            if (A.check_ori) A.rot_bin[o1 + idx1] = rot_hist_bin(A.angle1[o1 + idx1], A.angle2[o2 + idx2]);
+        }
+        __syncwarp();
+    }
+}
+
+__device__ inline void three_maxima_dev(const int *hist, int *keep)        // ComputeThreeMaxima, ORBmatcher.cc:1603-1644
+{
+    int max1 = 0, max2 = 0, max3 = 0, i1 = -1, i2 = -1, i3 = -1;
+    for (int i = 0; i < kHisto; i++) {
+        const int s = hist[i];
+        if (s > max1) { max3 = max2; max2 = max1; max1 = s; i3 = i2; i2 = i1; i1 = i; }
+        else if (s > max2) { max3 = max2; max2 = s; i3 = i2; i2 = i; }
+        else if (s > max3) { max3 = s; i3 = i; }
+    }
+    if ((float)max2 < __fmul_rn(0.1f, (float)max1)) { i2 = -1; i3 = -1; }
+    else if ((float)max3 < __fmul_rn(0.1f, (float)max1)) { i3 = -1; }
+    keep[0] = i1; keep[1] = i2; keep[2] = i3;
+}
+
+// rotation-consistency filter + match count of one pair (one CTA per pair)
+__global__ void __launch_bounds__(256)
+k_bow_finish(int slab1, const int *__restrict__ counts1, int check_ori, int *__restrict__ match12, const int *__restrict__ rot_bin, int *__restrict__ nmatches)
+{
+    __shared__ int s_hist[kHisto], s_keep[3], s_n;
+    const int f = blockIdx.x, tid = threadIdx.x, N = counts1[f];
+    int *m = match12 + (size_t)f * slab1;
+    const int *rb = rot_bin + (size_t)f * slab1;
+    if (tid < kHisto) s_hist[tid] = 0;
+    if (tid == 0) s_n = 0;
+    __syncthreads();
+    if (check_ori) {
+        for (int i = tid; i < N; i += blockDim.x) if (m[i] >= 0) atomicAdd(&s_hist[rb[i]], 1);
+        __syncthreads();
+        if (tid == 0) three_maxima_dev(s_hist, s_keep);
+        __syncthreads();
+    }
+    int cnt = 0;
+    for (int i = tid; i < N; i += blockDim.x) {
+        if (m[i] < 0) continue;
+        if (check_ori) { const int b = rb[i]; if (b != s_keep[0] && b != s_keep[1] && b != s_keep[2]) { m[i] = -1; continue; } }
+        cnt++;
+    }
+    if (cnt) atomicAdd(&s_n, cnt);
+    __syncthreads();
+    if (tid == 0) nmatches[f] = s_n;
+}
+
+// ORBmatcher::SearchForInitialization (:407-522): one warp per frame pair walks the level-0 keypoints of F1 in order (a later keypoint may
+// steal a feature of F2 from an earlier one, so the loop is a chain); the lanes scan the grid cells of the window.
+struct InitArgs {
+    int slab1, slab2;
+    GridParams g;
+    const int *octave1; const float *angle1; const uint4 *desc1; const int *counts1;
+    const float2 *xy2; const int *octave2; const float *angle2; const uint4 *desc2; const int *counts2;
+    const int *cell_start, *cell_items;
+    float2 *prev_matched;                 // [n_pairs, slab1] in/out
+    float window, ratio; int check_ori;
+    int *matched_dist, *matches21;        // scratch [n_pairs, slab2]
+    int *matches12, *rot_bin;             // [n_pairs, slab1]
+    int *nmatches;
+};
+
+__global__ void __launch_bounds__(32)
+k_search_init(const InitArgs A)
+{
+    __shared__ int s_hist[kHisto], s_keep[3];
+    const int f = blockIdx.x, lane = threadIdx.x;
+    const int N1 = A.counts1[f], N2 = A.counts2[f];
+    const size_t o1 = (size_t)f * A.slab1, o2 = (size_t)f * A.slab2;
+    int *matched_dist = A.matched_dist + o2, *matches21 = A.matches21 + o2, *matches12 = A.matches12 + o1, *rot_bin = A.rot_bin + o1;
+    const float2 *xy2 = A.xy2 + o2; const int *octave2 = A.octave2 + o2; const uint4 *desc2 = A.desc2 + 2 * o2;
+    const int *cs = A.cell_start + (size_t)f * (kGridCells + 1); const int *items = A.cell_items + o2;
+    for (int i = lane; i < N2; i += 32) { matched_dist[i] = 0x7fffffff; matches21[i] = -1; }
+    for (int i = lane; i < N1; i += 32) { matches12[i] = -1; rot_bin[i] = -1; }
+    if (lane < kHisto) s_hist[lane] = 0;
+    __syncwarp();
+    int nmatches = 0;
+    for (int i1 = 0; i1 < N1; i1++) {
+        if (A.octave1[o1 + i1] > 0) continue;
+        const float2 uv = A.prev_matched[o1 + i1];
+        const Window w = make_window(A.g, uv, A.window, 0, 0);
+        if (w.empty) continue;
+        const uint4 qa = __ldg(&A.desc1[2 * (o1 + i1)]), qb = __ldg(&A.desc1[2 * (o1 + i1) + 1]);
+        unsigned long long b1 = kNoKey, b2 = kNoKey;
+        const int ncy = w.r1 - w.r0 + 1, ncells = (w.c1 - w.c0 + 1) * ncy;
+        for (int c = lane; c < ncells; c += 32) {
+            const int ix = w.c0 + c / ncy, iy = w.r0 + c % ncy;
+            const int cell = ix * kGridRows + iy;
+            const int je = cs[cell + 1];
+            for (int j = cs[cell]; j < je; j++) {
+                const int k = items[j];
+                if (!in_window(w, 0, 0, uv, A.window, octave2[k], xy2[k])) continue;
+                const int d = hamming256(qa, qb, __ldg(&desc2[2 * k]), __ldg(&desc2[2 * k + 1]));
+                if (matched_dist[k] <= d) continue;
+                const unsigned long long key = make_key(d, ix, iy, k);
+                if (key < b1) { b2 = b1; b1 = key; } else if (key < b2) b2 = key;
+            }
+        }
+        unsigned long long m1 = b1;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) { const unsigned long long o = __shfl_xor_sync(0xffffffffu, m1, d); m1 = o < m1 ? o : m1; }
+        unsigned long long m2 = (b1 == m1) ? b2 : b1;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) { const unsigned long long o = __shfl_xor_sync(0xffffffffu, m2, d); m2 = o < m2 ? o : m2; }
+        if (m1 == kNoKey) continue;
+        const int best = (int)(m1 >> 32), bidx = (int)(m1 & 0xfffff);
+        const float best2f = m2 == kNoKey ? 2147483648.0f : (float)(int)(m2 >> 32);          // (float)INT_MAX
+        if (best <= ORBM_TH_LOW && (float)best < __fmul_rn(best2f, A.ratio)) {
+            if (lane == 0) {
+                const int prev = matches21[bidx];
+                if (prev >= 0) matches12[prev] = -1;
+                matches12[i1] = bidx; matches21[bidx] = i1; matched_dist[bidx] = best;
+                if (A.check_ori) { const int bin = rot_hist_bin(A.angle1[o1 + i1], A.angle2[o2 + bidx]); rot_bin[i1] = bin; s_hist[bin]++; }
+            }
+            __syncwarp();
+        }
+    }
+    __syncwarp();
+    if (A.check_ori) {
+        if (lane == 0) three_maxima_dev(s_hist, s_keep);
+        __syncwarp();
+        for (int i = lane; i < N1; i += 32) { const int b = rot_bin[i]; if (b >= 0 && b != s_keep[0] && b != s_keep[1] && b != s_keep[2]) matches12[i] = -1; }
+        __syncwarp();
+    }
+    for (int i = lane; i < N1; i += 32) if (matches12[i] >= 0) { nmatches++; A.prev_matched[o1 + i] = xy2[matches12[i]]; }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) nmatches += __shfl_xor_sync(0xffffffffu, nmatches, d);
+    if (lane == 0) A.nmatches[f] = nmatches;
+}
+
 }  // namespace orbs
 
 using namespace orbs;
@@ -973,6 +1200,95 @@ int orbm_search_best_in_window(orbm_handle *h, int n_frames, const float *grid_b
     if (memspace == ORBS_MEM_HOST) { ORBS_CUDA(cudaMemsetAsync(A.best_idx, 0xff, nq * 4, h->stream)); ORBS_CUDA(cudaMemsetAsync(A.best_dist, 0xff, nq * 4, h->stream)); }
     k_grid_build<<<n_frames, 512, 0, h->stream>>>(f_slab, A.g, A.f_xy, A.f_counts, h->cell_start.as<int>(), h->cell_items.as<int>());
     k_search_best<<<dim3((q_slab + 7) / 8, n_frames), 256, 0, h->stream>>>(A);
+    h->launches += 2;
+    ORBS_CUDA(cudaGetLastError());
+    return S.finish();
+}
+
+int orbm_search_by_bow(orbm_handle *h, int n_pairs, int mode,
+                       const uint8_t *desc1, const float *angle1, const uint8_t *elig1, const int32_t *counts1, int slab1,
+                       const int32_t *fv1_nodes, const int32_t *fv1_start, const int32_t *fv1_items, const int32_t *fv1_counts, int fv1_slab,
+                       const uint8_t *desc2, const float *angle2, const uint8_t *elig2, const int32_t *counts2, int slab2,
+                       const int32_t *fv2_nodes, const int32_t *fv2_start, const int32_t *fv2_items, const int32_t *fv2_counts, int fv2_slab,
+                       float ratio, int check_ori, const orbm_epipolar *epi, int32_t *match12, int32_t *nmatches, int memspace)
+{
+    ORBS_REQUIRE(h && desc1 && elig1 && counts1 && fv1_nodes && fv1_start && fv1_items && fv1_counts && desc2 && elig2 && counts2 && fv2_nodes && fv2_start &&
+                 fv2_items && fv2_counts && match12 && nmatches, ORBS_E_INVALID, "null argument");
+    ORBS_REQUIRE(mode == ORBM_BOW_MATCH || mode == ORBM_BOW_TRIANGULATION, ORBS_E_INVALID, "unknown mode");
+    ORBS_REQUIRE(!check_ori || (angle1 && angle2), ORBS_E_INVALID, "orientation check needs the angles");
+    ORBS_REQUIRE(mode != ORBM_BOW_TRIANGULATION || (epi && epi->xy1 && epi->xy2 && epi->octave2 && epi->F12 && epi->epipole && epi->scale_factors2 &&
+                 epi->level_sigma2_2 && epi->nlevels > 0 && epi->nlevels <= 32), ORBS_E_INVALID, "triangulation mode needs the epipolar block (1..32 levels)");
+    ORBS_REQUIRE(n_pairs > 0 && slab1 > 0 && slab2 > 0 && fv1_slab > 0 && fv2_slab > 0, ORBS_E_INVALID, "non-positive size");
+    ORBS_REQUIRE(slab2 < (1 << 20), ORBS_E_INVALID, "slab too large (features < 2^20 per keyframe)");
+    std::lock_guard<std::mutex> lk(h->mu);
+    ORBS_CUDA(cudaSetDevice(h->device));
+    Stager S(&h->pool, h->stream, memspace);
+    const size_t n1 = (size_t)n_pairs * slab1, n2 = (size_t)n_pairs * slab2;
+    BowArgs A;
+    A.mode = mode; A.slab1 = slab1; A.slab2 = slab2; A.nslab1 = fv1_slab; A.nslab2 = fv2_slab;
+    A.desc1 = (const uint4 *)S.in(desc1, n1 * 32); A.desc2 = (const uint4 *)S.in(desc2, n2 * 32);
+    A.angle1 = angle1 ? S.in(angle1, n1) : nullptr; A.angle2 = angle2 ? S.in(angle2, n2) : nullptr;
+    A.elig1 = S.in(elig1, n1); A.elig2 = S.in(elig2, n2); A.counts1 = S.in(counts1, n_pairs);
+    A.nodes1 = S.in(fv1_nodes, (size_t)n_pairs * fv1_slab); A.start1 = S.in(fv1_start, (size_t)n_pairs * (fv1_slab + 1)); A.items1 = S.in(fv1_items, n1);
+    A.ncount1 = S.in(fv1_counts, n_pairs);
+    A.nodes2 = S.in(fv2_nodes, (size_t)n_pairs * fv2_slab); A.start2 = S.in(fv2_start, (size_t)n_pairs * (fv2_slab + 1)); A.items2 = S.in(fv2_items, n2);
+    A.ncount2 = S.in(fv2_counts, n_pairs);
+    A.ratio = ratio; A.check_ori = check_ori ? 1 : 0;
+    A.xy1 = A.xy2 = nullptr; A.octave2 = nullptr; A.F12 = A.epipole = nullptr; A.nlevels = 1;
+    for (int l = 0; l < 32; l++) { A.scale_factors2[l] = 0.f; A.level_sigma2_2[l] = 0.f; }
+    if (mode == ORBM_BOW_TRIANGULATION) {
+        A.xy1 = (const float2 *)S.in(epi->xy1, n1 * 2); A.xy2 = (const float2 *)S.in(epi->xy2, n2 * 2); A.octave2 = S.in(epi->octave2, n2);
+        A.F12 = S.in(epi->F12, (size_t)n_pairs * 9); A.epipole = S.in(epi->epipole, (size_t)n_pairs * 2);
+        A.nlevels = epi->nlevels;
+        for (int l = 0; l < epi->nlevels; l++) { A.scale_factors2[l] = epi->scale_factors2[l]; A.level_sigma2_2[l] = epi->level_sigma2_2[l]; }
+    }
+    A.matched2 = S.scratch<uint8_t>(n2); A.rot_bin = S.scratch<int>(n1);
+    A.match12 = S.inout(match12, n1, false); A.nmatches = S.inout(nmatches, n_pairs, false);
+    if (S.rc) return S.rc;
+    ORBS_REQUIRE(((uintptr_t)A.desc1 % 16 == 0) && ((uintptr_t)A.desc2 % 16 == 0), ORBS_E_INVALID, "descriptor arrays must be 16-byte aligned");
+    ORBS_CUDA(cudaMemsetAsync(A.matched2, 0, n2, h->stream));
+    ORBS_CUDA(cudaMemsetAsync(A.match12, 0xff, n1 * sizeof(int), h->stream));
+    k_bow_match<<<dim3((fv1_slab + 7) / 8, n_pairs), 256, 0, h->stream>>>(A);
+    k_bow_finish<<<n_pairs, 256, 0, h->stream>>>(slab1, A.counts1, A.check_ori, A.match12, A.rot_bin, A.nmatches);
+    h->launches += 2;
+    ORBS_CUDA(cudaGetLastError());
+    return S.finish();
+}
+
+int orbm_search_for_initialization(orbm_handle *h, int n_pairs, const float *bounds4,
+                                   const int32_t *octave1, const float *angle1, const uint8_t *desc1, const int32_t *counts1, int slab1,
+                                   const float *xy2, const int32_t *octave2, const float *angle2, const uint8_t *desc2, const int32_t *counts2, int slab2,
+                                   float *prev_matched, int window, float ratio, int check_ori, int32_t *matches12, int32_t *nmatches, int memspace)
+{
+    ORBS_REQUIRE(h && bounds4 && octave1 && desc1 && counts1 && xy2 && octave2 && desc2 && counts2 && prev_matched && matches12 && nmatches, ORBS_E_INVALID,
+                 "null argument");
+    ORBS_REQUIRE(!check_ori || (angle1 && angle2), ORBS_E_INVALID, "orientation check needs the angles");
+    ORBS_REQUIRE(n_pairs > 0 && slab1 > 0 && slab2 > 0, ORBS_E_INVALID, "non-positive size");
+    ORBS_REQUIRE(slab2 < (1 << 20), ORBS_E_INVALID, "slab too large (features < 2^20 per frame)");
+    ORBS_REQUIRE(bounds4[2] > bounds4[0] && bounds4[3] > bounds4[1], ORBS_E_INVALID, "empty image bounds");
+    std::lock_guard<std::mutex> lk(h->mu);
+    ORBS_CUDA(cudaSetDevice(h->device));
+    Stager S(&h->pool, h->stream, memspace);
+    const size_t n1 = (size_t)n_pairs * slab1, n2 = (size_t)n_pairs * slab2;
+    InitArgs A;
+    A.slab1 = slab1; A.slab2 = slab2; A.g = make_grid(bounds4);
+    A.octave1 = S.in(octave1, n1); A.angle1 = angle1 ? S.in(angle1, n1) : nullptr; A.desc1 = (const uint4 *)S.in(desc1, n1 * 32); A.counts1 = S.in(counts1, n_pairs);
+    A.xy2 = (const float2 *)S.in(xy2, n2 * 2); A.octave2 = S.in(octave2, n2); A.angle2 = angle2 ? S.in(angle2, n2) : nullptr;
+    A.desc2 = (const uint4 *)S.in(desc2, n2 * 32); A.counts2 = S.in(counts2, n_pairs);
+    A.prev_matched = (float2 *)S.inout(prev_matched, n1 * 2);
+    A.window = (float)window; A.ratio = ratio; A.check_ori = check_ori ? 1 : 0;
+    A.matched_dist = S.scratch<int>(n2); A.matches21 = S.scratch<int>(n2); A.rot_bin = S.scratch<int>(n1);
+    A.matches12 = S.inout(matches12, n1, false); A.nmatches = S.inout(nmatches, n_pairs, false);
+    if (S.rc) return S.rc;
+    ORBS_REQUIRE(((uintptr_t)A.desc1 % 16 == 0) && ((uintptr_t)A.desc2 % 16 == 0) && ((uintptr_t)A.xy2 % 8 == 0) && ((uintptr_t)A.prev_matched % 8 == 0),
+                 ORBS_E_INVALID, "descriptor arrays must be 16-byte aligned, coordinate arrays 8-byte aligned");
+    int rc;
+    if ((rc = h->cell_start.reserve((size_t)n_pairs * (kGridCells + 1) * sizeof(int)))) return rc;
+    if ((rc = h->cell_items.reserve(n2 * sizeof(int)))) return rc;
+    A.cell_start = h->cell_start.as<int>(); A.cell_items = h->cell_items.as<int>();
+    if (memspace == ORBS_MEM_HOST) ORBS_CUDA(cudaMemsetAsync(A.matches12, 0xff, n1 * sizeof(int), h->stream));
+    k_grid_build<<<n_pairs, 512, 0, h->stream>>>(slab2, A.g, A.xy2, A.counts2, h->cell_start.as<int>(), h->cell_items.as<int>());
+    k_search_init<<<n_pairs, 32, 0, h->stream>>>(A);
     h->launches += 2;
     ORBS_CUDA(cudaGetLastError());
     return S.finish();

@@ -319,3 +319,47 @@ def make_sim3_opt_case(cam, stream_id, n_outliers=12, s12=1.02, seed=0):
     dR = Rotation.from_rotvec(rng.normal(0, 0.004, 3)).as_matrix()
     case["init"] = np.concatenate([quat_of(dR @ R12), t12 + rng.normal(0, 0.02, 3), [s * 1.01]])
     return case
+
+
+# ------------------------------------------------------------------ vocabulary-bucket matchers
+def synthetic_nodes(desc, n_bits=6):
+    """Stand-in for the vocabulary node of a descriptor (DBoW2 transform at levelsup): one bit per 5-byte group = 'more than half of its
+    bits set'.  Descriptors that differ in a few bits mostly share the node, like neighbours in the vocabulary tree."""
+    d = np.ascontiguousarray(desc, np.uint8)
+    bits = np.unpackbits(d, axis=1)
+    node = np.zeros(len(d), np.int64)
+    for k in range(n_bits):
+        node |= (bits[:, 40 * k:40 * k + 40].sum(1) > 20).astype(np.int64) << k
+    return node * 3 + 7            # node ids are sparse in the real tree
+
+
+def epipole_and_F(kf1, kf2):
+    """Epipole of camera 1 in image 2 as SearchForTriangulation computes it (:665-673) and F12 = K1^-T [t12]x R12 K2^-1 (LocalMapping::ComputeF12)."""
+    T1 = np.asarray(kf1["Tcw"], F32).reshape(4, 4); T2 = np.asarray(kf2["Tcw"], F32).reshape(4, 4)
+    Cw = camera_centre(T1)
+    C2 = (gemm32(T2[:3, :3], Cw.reshape(3, 1)).ravel() + T2[:3, 3]).astype(F32)
+    invz = F32(1.0) / C2[2]
+    fx, fy, cx, cy = [F32(v) for v in kf2["K4"]]
+    ex = F32(F32(F32(fx * C2[0]) * invz) + cx); ey = F32(F32(F32(fy * C2[1]) * invz) + cy)
+    R1, t1, R2, t2 = T1[:3, :3].astype(np.float64), T1[:3, 3].astype(np.float64), T2[:3, :3].astype(np.float64), T2[:3, 3].astype(np.float64)
+    R12 = R1 @ R2.T; t12 = -R12 @ t2 + t1
+    tx = np.array([[0, -t12[2], t12[1]], [t12[2], 0, -t12[0]], [-t12[1], t12[0], 0]])
+    K = lambda k: np.array([[k[0], 0, k[2]], [0, k[1], k[3]], [0, 0, 1]], np.float64)
+    F12 = np.linalg.inv(K(kf1["K4"])).T @ tx @ R12 @ np.linalg.inv(K(kf2["K4"]))
+    return ex, ey, F12.astype(F32)
+
+
+def make_bow_case(cam, stream_id, perturb=False):
+    """Two keyframes with synthetic vocabulary nodes, map-point masks and (for SearchForTriangulation) F12 / epipole.  perturb: the second pose
+    used for F12 is moved off the true one, which gives a finite epipole and makes the epipolar gates reject part of the candidates."""
+    p = make_sim3_pair(cam, stream_id, s12=1.0)
+    kf1, kf2 = dict(p["kf1"]), dict(p["kf2"])
+    rng = np.random.default_rng(23 + stream_id)
+    if perturb:
+        T = kf2["Tcw"].copy(); T[2, 3] += F32(0.35); T[0, 3] += F32(0.05)
+        kf2["Tcw"] = T
+    fv1 = oracle.feature_vector(synthetic_nodes(kf1["desc"])); fv2 = oracle.feature_vector(synthetic_nodes(kf2["desc"]))
+    ex, ey, F12 = epipole_and_F(kf1, kf2)
+    ls2 = (kf1["scale_factors"].astype(np.float64) ** 2).astype(F32)
+    tri1 = (rng.random(len(kf1["xy"])) < 0.55).astype(np.uint8); tri2 = (rng.random(len(kf2["xy"])) < 0.55).astype(np.uint8)   # features WITH a map point
+    return dict(kf1=kf1, kf2=kf2, fv1=fv1, fv2=fv2, has1=p["has1"], has2=p["has2"], tri1=tri1, tri2=tri2, ex=ex, ey=ey, F12=F12, ls2=ls2)

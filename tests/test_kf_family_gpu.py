@@ -105,3 +105,75 @@ def test_kf_family_batched_views_and_edge_cases(lib):
                                      cases[0]["kf"]["inv_level_sigma2"], 5.99)
     so = kff.fuse_search(Bo, cases[0]["kf"], 3.0, cases[0]["pts"], cases[0]["skip"])
     assert np.array_equal(bi[0, :qc[0]], so) and (bi[1, :qc[1]] == -1).all() and (bd[1, :qc[1]] == -1).all()
+
+
+@pytest.mark.parametrize("ori", [True, False])
+def test_bow_family_cuda_equals_oracle_and_reference(lib, ori):
+    """SearchByBoW (both variants) and SearchForTriangulation: three keyframe pairs per launch (ragged), exact match arrays and counts."""
+    import orbslamm_b200 as ob
+    cases = [kff.make_bow_case(synth.TUM, 1, False), kff.make_bow_case(synth.KITTI, 2, True), kff.make_bow_case(synth.TUM, 4, True)]
+    n = len(cases)
+    s1 = max(len(b["kf1"]["desc"]) for b in cases) + 2; s2 = max(len(b["kf2"]["desc"]) for b in cases) + 5
+    d1 = slab([b["kf1"]["desc"] for b in cases], s1, np.uint8, (32,)); d2 = slab([b["kf2"]["desc"] for b in cases], s2, np.uint8, (32,))
+    a1 = slab([b["kf1"]["angle"] for b in cases], s1, np.float32); a2 = slab([b["kf2"]["angle"] for b in cases], s2, np.float32)
+    c1 = [len(b["kf1"]["desc"]) for b in cases]; c2 = [len(b["kf2"]["desc"]) for b in cases]
+    fv1 = [b["fv1"] for b in cases]; fv2 = [b["fv2"] for b in cases]
+    # SearchByBoW(KF, KF)
+    m = ob.ORBmatcher(0.75, ori)
+    nm, mt = m.SearchByBoW(d1, a1, slab([b["has1"] for b in cases], s1, np.uint8), c1, fv1, d2, a2, slab([b["has2"] for b in cases], s2, np.uint8), c2, fv2)
+    for k, b in enumerate(cases):
+        n_o, m_o = oracle.search_by_bow(0, b["kf1"]["desc"], b["kf1"]["angle"], b["has1"], b["fv1"], b["kf2"]["desc"], b["kf2"]["angle"], b["has2"], b["fv2"], 0.75, ori)
+        assert n_o > 100 and nm[k] == n_o and np.array_equal(mt[k, :c1[k]], m_o)
+        if HAVE_REF:
+            n_r, m_r = ref_build.ref_search_by_bow_kf_kf(b["kf1"], b["has1"], b["fv1"], b["kf2"], b["has2"], b["fv2"], 0.75, ori)
+            assert nm[k] == n_r and np.array_equal(mt[k, :c1[k]], m_r)
+    # SearchByBoW(KF, Frame): every frame feature is a candidate
+    m = ob.ORBmatcher(0.7, ori)
+    nm, mt = m.SearchByBoW(d1, a1, slab([b["has1"] for b in cases], s1, np.uint8), c1, fv1, d2, a2, np.ones((n, s2), np.uint8), c2, fv2)
+    for k, b in enumerate(cases):
+        n_o, m_o = oracle.search_by_bow(0, b["kf1"]["desc"], b["kf1"]["angle"], b["has1"], b["fv1"], b["kf2"]["desc"], b["kf2"]["angle"], np.ones(c2[k], np.uint8),
+                                        b["fv2"], 0.7, ori)
+        assert nm[k] == n_o and np.array_equal(mt[k, :c1[k]], m_o)
+        if HAVE_REF:
+            n_r, m_r = ref_build.ref_search_by_bow_kf_frame(b["kf1"], b["has1"], b["fv1"], b["kf2"]["angle"], b["kf2"]["desc"], b["fv2"], 0.7, ori)
+            inv = np.full(c2[k], -1, np.int32); g = mt[k, :c1[k]]; inv[g[g >= 0]] = np.where(g >= 0)[0]
+            assert nm[k] == n_r and np.array_equal(inv, m_r)
+    # SearchForTriangulation
+    m = ob.ORBmatcher(0.6, ori)
+    tri = dict(xy1=slab([b["kf1"]["xy"] for b in cases], s1, np.float32, (2,)), xy2=slab([b["kf2"]["xy"] for b in cases], s2, np.float32, (2,)),
+               octave2=slab([b["kf2"]["octave"] for b in cases], s2, np.int32), F12=np.stack([b["F12"].ravel() for b in cases]),
+               epipole=np.array([[b["ex"], b["ey"]] for b in cases], np.float32), scale_factors2=cases[0]["kf2"]["scale_factors"], level_sigma2_2=cases[0]["ls2"])
+    nm, mt = m.SearchByBoW(d1, a1, slab([1 - b["tri1"] for b in cases], s1, np.uint8), c1, fv1, d2, a2, slab([1 - b["tri2"] for b in cases], s2, np.uint8), c2, fv2, tri)
+    for k, b in enumerate(cases):
+        epi = dict(xy1=b["kf1"]["xy"], xy2=b["kf2"]["xy"], octave2=b["kf2"]["octave"], F12=b["F12"], ex=b["ex"], ey=b["ey"], scale_factors2=b["kf2"]["scale_factors"],
+                   level_sigma2_2=b["ls2"])
+        n_o, m_o = oracle.search_by_bow(1, b["kf1"]["desc"], b["kf1"]["angle"], 1 - b["tri1"], b["fv1"], b["kf2"]["desc"], b["kf2"]["angle"], 1 - b["tri2"], b["fv2"],
+                                        0.6, ori, epi)
+        assert n_o > 5 and nm[k] == n_o and np.array_equal(mt[k, :c1[k]], m_o)
+        if HAVE_REF:
+            n_r, m_r = ref_build.ref_search_for_triangulation(b["kf1"], b["tri1"], b["fv1"], b["kf2"], b["tri2"], b["fv2"], b["ls2"], b["F12"], 0.6, ori)
+            assert nm[k] == n_r and np.array_equal(mt[k, :c1[k]], m_r)
+
+
+def test_search_for_initialization_cuda_equals_oracle_and_reference(lib):
+    import orbslamm_b200 as ob
+    from helpers import make_tracking_case
+    cases = [make_tracking_case(synth.TUM, 1), make_tracking_case(synth.TUM, 6), make_tracking_case(synth.TUM, 9, nfeatures=2000)]
+    s1 = max(len(k["last"]["x"]) for k in cases) + 1; s2 = max(len(k["cur"]["x"]) for k in cases) + 4
+    g = oracle.grid_params(*cases[0]["bounds"]); sf = np.array(list(cases[0]["P"].scale)[:8], np.float32)
+    for win, ori in ((100, True), (100, False), (20, True)):
+        m = ob.ORBmatcher(0.9, ori)
+        pm = slab([np.stack([k["last"]["x"], k["last"]["y"]], 1) for k in cases], s1, np.float32, (2,))
+        nm, mt, pm2 = m.SearchForInitialization(cases[0]["bounds"], slab([k["last"]["octave"] for k in cases], s1, np.int32),
+                                                slab([k["last"]["angle"] for k in cases], s1, np.float32), slab([k["last"]["desc"] for k in cases], s1, np.uint8, (32,)),
+                                                [len(k["last"]["x"]) for k in cases],
+                                                slab([np.stack([k["cur"]["x"], k["cur"]["y"]], 1) for k in cases], s2, np.float32, (2,)),
+                                                slab([k["cur"]["octave"] for k in cases], s2, np.int32), slab([k["cur"]["angle"] for k in cases], s2, np.float32),
+                                                slab([k["cur"]["desc"] for k in cases], s2, np.uint8, (32,)), [len(k["cur"]["x"]) for k in cases], pm, win)
+        for i, k in enumerate(cases):
+            n1 = len(k["last"]["x"])
+            a = oracle.search_for_initialization(g, k["last"], k["cur"], pm[i, :n1], win, 0.9, ori)
+            assert a[0] > 50 and nm[i] == a[0] and np.array_equal(mt[i, :n1], a[1]) and np.array_equal(pm2[i, :n1], a[2])
+            if HAVE_REF:
+                b = ref_build.ref_search_for_initialization(k["K4"], k["bounds"], sf, k["last"], k["cur"], pm[i, :n1], win, 0.9, ori)
+                assert nm[i] == b[0] and np.array_equal(mt[i, :n1], b[1]) and np.array_equal(pm2[i, :n1], b[2])

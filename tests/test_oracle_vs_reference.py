@@ -181,3 +181,40 @@ def test_search_by_sim3_oracle_equals_reference_object_code(cam, sid):
         n_o, m_o = kff.search_by_sim3(kff.OracleBackend(), p["kf1"], p["kf2"], p["s12"], p["R12"], p["t12"], th, p["has1"], p["pts1"], p["has2"], p["pts2"],
                                       p["m12"])
         assert n_r > 20 and n_o == n_r and np.array_equal(m_o, m_r)
+
+
+@needs_matcher
+@pytest.mark.parametrize("cam,sid,perturb", [("TUM", 1, False), ("KITTI", 2, True), ("TUM", 4, True)])
+def test_bow_family_oracle_equals_reference_object_code(cam, sid, perturb):
+    """SearchByBoW(KF, Frame) :159-290, SearchByBoW(KF, KF) :524-657, SearchForTriangulation :659-825 on synthetic vocabulary nodes."""
+    b = kff.make_bow_case(getattr(synth, cam), sid, perturb)
+    kf1, kf2, fv1, fv2 = b["kf1"], b["kf2"], b["fv1"], b["fv2"]
+    all2 = np.ones(len(kf2["desc"]), np.uint8)
+    for ori in (True, False):
+        n_o, m_o = oracle.search_by_bow(0, kf1["desc"], kf1["angle"], b["has1"], fv1, kf2["desc"], kf2["angle"], b["has2"], fv2, 0.75, ori)
+        n_r, m_r = ref_build.ref_search_by_bow_kf_kf(kf1, b["has1"], fv1, kf2, b["has2"], fv2, 0.75, ori)
+        assert n_r > 100 and n_o == n_r and np.array_equal(m_o, m_r)
+        n_o, m_o = oracle.search_by_bow(0, kf1["desc"], kf1["angle"], b["has1"], fv1, kf2["desc"], kf2["angle"], all2, fv2, 0.7, ori)
+        n_r, m_r = ref_build.ref_search_by_bow_kf_frame(kf1, b["has1"], fv1, kf2["angle"], kf2["desc"], fv2, 0.7, ori)
+        inv = np.full(len(all2), -1, np.int32); inv[m_o[m_o >= 0]] = np.where(m_o >= 0)[0]          # the reference indexes the result by frame feature
+        assert n_r > 100 and n_o == n_r and np.array_equal(inv, m_r)
+        epi = dict(xy1=kf1["xy"], xy2=kf2["xy"], octave2=kf2["octave"], F12=b["F12"], ex=b["ex"], ey=b["ey"], scale_factors2=kf2["scale_factors"], level_sigma2_2=b["ls2"])
+        n_o, m_o = oracle.search_by_bow(1, kf1["desc"], kf1["angle"], 1 - b["tri1"], fv1, kf2["desc"], kf2["angle"], 1 - b["tri2"], fv2, 0.6, ori, epi)
+        n_r, m_r = ref_build.ref_search_for_triangulation(kf1, b["tri1"], fv1, kf2, b["tri2"], fv2, b["ls2"], b["F12"], 0.6, ori)
+        assert n_r > (5 if perturb else 40) and n_o == n_r and np.array_equal(m_o, m_r)
+
+
+@needs_matcher
+@pytest.mark.parametrize("cam,sid", [("TUM", 1), ("KITTI", 2)])
+def test_search_for_initialization_oracle_equals_reference_object_code(cam, sid):
+    k = make_tracking_case(getattr(synth, cam), sid)
+    g = oracle.grid_params(*k["bounds"]); sf = np.array(list(k["P"].scale)[:8], np.float32)
+    pm = np.stack([k["last"]["x"], k["last"]["y"]], 1)
+    for win, ori in ((100, True), (100, False), (20, True)):
+        a = oracle.search_for_initialization(g, k["last"], k["cur"], pm, win, 0.9, ori)
+        b = ref_build.ref_search_for_initialization(k["K4"], k["bounds"], sf, k["last"], k["cur"], pm, win, 0.9, ori)
+        assert b[0] > 50 and a[0] == b[0] and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+    # second call of the initialiser: windows centred on the updated previous matches
+    a2 = oracle.search_for_initialization(g, k["last"], k["cur"], a[2], 100, 0.9, True)
+    b2 = ref_build.ref_search_for_initialization(k["K4"], k["bounds"], sf, k["last"], k["cur"], b[2], 100, 0.9, True)
+    assert a2[0] == b2[0] and np.array_equal(a2[1], b2[1])
