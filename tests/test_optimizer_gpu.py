@@ -199,6 +199,10 @@ def test_optimize_sim3_matches_oracle(lib, fix_scale):
         assert abs(int(st[k, 0]) - r["lm_iterations"]) <= 1 and abs(int(st[k, 1]) - r["lm_trials"]) <= 2
         assert np.abs(S[k] - r["sim3"]).max() < 1e-5 * np.abs(r["sim3"]).max()
         if k < 3:
-            assert r["n_in"] > 40 and r["inlier"][c["bad"]].sum() <= 1 and np.abs(r["sim3"] - c["true"]).max() < np.abs(c["init"] - c["true"]).max()
+            assert r["n_in"] > 40 and r["inlier"][c["bad"]].sum() <= 1
+            if fix_scale:
+                assert r["sim3"][7] == c["init"][7] and S[k, 7] == c["init"][7]
+            else:
+                assert np.abs(r["sim3"] - c["true"]).max() < np.abs(c["init"] - c["true"]).max()
         else:
             assert r["n_in"] == 0 and np.array_equal(S[k], c["init"])
