@@ -1,8 +1,9 @@
 // ORBmatcher_b200.cc -- GPU-backed definitions of the ORBmatcher members on the tracking hot path and of the KeyFrame / Sim3
 // projection family.  In the reference tree these replace the same-named functions of S/src/ORBmatcher.cc (:41-43 ctor, :45-129
 // and :1330-1472 SearchByProjection, :131-137 RadiusByViewingCos, :1649-1665 DescriptorDistance, :292-405 SearchByProjection(KF, Scw),
-// :827-977 and :979-1102 Fuse, :1104-1328 SearchBySim3, :1474-1601 SearchByProjection(Frame, KF)); the BoW members (SearchByBoW,
-// SearchForTriangulation) and SearchForInitialization stay in ORBmatcher.cc -- "next" rows of SURVEY.md 8(f).
+// :827-977 and :979-1102 Fuse, :1104-1328 SearchBySim3, :1474-1601 SearchByProjection(Frame, KF), :159-290 and :524-657 SearchByBoW,
+// :407-522 SearchForInitialization, :659-825 SearchForTriangulation) -- every member of the class: ORBmatcher.cc leaves the build.
+// (ComputeThreeMaxima and CheckDistEpipolarLine, the two protected helpers, run inside the kernels.)
 //
 // The shim only marshals: Frame/MapPoint fields -> flat arrays -> orbm_* (include/orbslamm_b200.h) -> pointers written
 // back into Frame::mvpMapPoints.  ORBmatcher objects are stack-constructed from several threads in the reference, so
@@ -426,6 +427,135 @@ int ORBmatcher::SearchBySim3(KeyFrame *pKF1, KeyFrame *pKF2, std::vector<MapPoin
         if (idx2 >= 0 && vnMatch2[idx2] == i1) { vpMatches12[i1] = vpMapPoints2[idx2]; nFound++; }
     }
     return nFound;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------------------
+// Vocabulary-bucket matchers and SearchForInitialization
+namespace
+{
+struct FeatVecCSR {
+    std::vector<int32_t> nodes, start, items; int32_t n = 0;
+    FeatVecCSR(const DBoW2::FeatureVector &fv, size_t n_features)
+    {
+        items.reserve(n_features + 1);
+        start.push_back(0);
+        for (DBoW2::FeatureVector::const_iterator it = fv.begin(); it != fv.end(); ++it) {
+            nodes.push_back((int32_t)it->first);
+            for (size_t k = 0; k < it->second.size(); k++) items.push_back((int32_t)it->second[k]);
+            start.push_back((int32_t)items.size());
+        }
+        n = (int32_t)nodes.size();
+        if (nodes.empty()) { nodes.push_back(0); start.push_back(0); }
+        items.resize(n_features + 1, 0);
+    }
+};
+struct DescAngles {
+    std::vector<uint64_t> desc64; std::vector<float> angle; std::vector<uint8_t> elig; int32_t n = 0;
+    DescAngles(const cv::Mat &D, const std::vector<cv::KeyPoint> &keys, int N) : desc64(4 * (size_t)N + 2), angle(N + 1, 0.f), elig(N + 1, 0), n(N)
+    {
+        for (int i = 0; i < N; i++) { std::memcpy(desc() + 32 * (size_t)i, D.ptr(i), 32); angle[i] = keys[i].angle; }
+    }
+    uint8_t *desc() { return (uint8_t *)(((uintptr_t)desc64.data() + 15) & ~(uintptr_t)15); }
+};
+int bow_call(int mode, DescAngles &A, FeatVecCSR &fa, DescAngles &B, FeatVecCSR &fb, float ratio, bool ori, const orbm_epipolar *epi, std::vector<int32_t> &match12)
+{
+    match12.assign(A.n + 1, -1);
+    if (!A.n || !B.n || !fa.n || !fb.n) return 0;
+    int32_t nmatches = 0;
+    check(orbm_search_by_bow(handle(), 1, mode, A.desc(), A.angle.data(), A.elig.data(), &A.n, A.n, fa.nodes.data(), fa.start.data(), fa.items.data(), &fa.n,
+                             (int)fa.nodes.size(), B.desc(), B.angle.data(), B.elig.data(), &B.n, B.n, fb.nodes.data(), fb.start.data(), fb.items.data(), &fb.n,
+                             (int)fb.nodes.size(), ratio, ori ? 1 : 0, epi, match12.data(), &nmatches, ORBS_MEM_HOST), "orbm_search_by_bow");
+    return nmatches;
+}
+}  // namespace
+
+// Tracking::TrackReferenceKeyFrame / Relocalization -> matcher.SearchByBoW(mpReferenceKF, mCurrentFrame, vpMapPointMatches)   (Tracking.cc:809, 1415)
+int ORBmatcher::SearchByBoW(KeyFrame *pKF, Frame &F, std::vector<MapPoint *> &vpMapPointMatches)
+{
+    const std::vector<MapPoint *> vpMapPointsKF = pKF->GetMapPointMatches();
+    vpMapPointMatches = std::vector<MapPoint *>(F.N, static_cast<MapPoint *>(NULL));
+    DescAngles A(pKF->mDescriptors, pKF->mvKeysUn, (int)vpMapPointsKF.size()), B(F.mDescriptors, F.mvKeys, F.N);      // kp.angle - F.mvKeys[..].angle (:243)
+    for (int i = 0; i < A.n; i++) { MapPoint *p = vpMapPointsKF[i]; A.elig[i] = (p && !p->isBad()) ? 1 : 0; }
+    for (int i = 0; i < B.n; i++) B.elig[i] = 1;
+    FeatVecCSR fa(pKF->mFeatVec, A.n), fb(F.mFeatVec, B.n);
+    std::vector<int32_t> m;
+    const int n = bow_call(ORBM_BOW_MATCH, A, fa, B, fb, mfNNratio, mbCheckOrientation, nullptr, m);
+    for (int i = 0; i < A.n; i++) if (m[i] >= 0) vpMapPointMatches[m[i]] = vpMapPointsKF[i];
+    return n;
+}
+
+// LoopClosing::ComputeSim3 / MultiMapper -> matcher.SearchByBoW(mpCurrentKF, pKF, vvpMapPointMatches[i])   (LoopClosing.cc:245 ff.)
+int ORBmatcher::SearchByBoW(KeyFrame *pKF1, KeyFrame *pKF2, std::vector<MapPoint *> &vpMatches12)
+{
+    const std::vector<MapPoint *> vpMapPoints1 = pKF1->GetMapPointMatches(), vpMapPoints2 = pKF2->GetMapPointMatches();
+    vpMatches12 = std::vector<MapPoint *>(vpMapPoints1.size(), static_cast<MapPoint *>(NULL));
+    DescAngles A(pKF1->mDescriptors, pKF1->mvKeysUn, (int)vpMapPoints1.size()), B(pKF2->mDescriptors, pKF2->mvKeysUn, (int)vpMapPoints2.size());
+    for (int i = 0; i < A.n; i++) { MapPoint *p = vpMapPoints1[i]; A.elig[i] = (p && !p->isBad()) ? 1 : 0; }
+    for (int i = 0; i < B.n; i++) { MapPoint *p = vpMapPoints2[i]; B.elig[i] = (p && !p->isBad()) ? 1 : 0; }
+    FeatVecCSR fa(pKF1->mFeatVec, A.n), fb(pKF2->mFeatVec, B.n);
+    std::vector<int32_t> m;
+    const int n = bow_call(ORBM_BOW_MATCH, A, fa, B, fb, mfNNratio, mbCheckOrientation, nullptr, m);
+    for (int i = 0; i < A.n; i++) if (m[i] >= 0) vpMatches12[i] = vpMapPoints2[m[i]];
+    return n;
+}
+
+// LocalMapping::CreateNewMapPoints -> matcher.SearchForTriangulation(mpCurrentKeyFrame, pKF2, F12, vMatchedIndices, false)   (LocalMapping.cc:215 ff.)
+int ORBmatcher::SearchForTriangulation(KeyFrame *pKF1, KeyFrame *pKF2, cv::Mat F12, std::vector<std::pair<size_t, size_t>> &vMatchedPairs, const bool bOnlyStereo)
+{
+    if (bOnlyStereo) throw std::runtime_error("orbslamm_b200: only the monocular SearchForTriangulation is accelerated");
+    // epipole of camera 1 in image 2 (:665-673), cv::Mat algebra in OpenCV's order
+    float R2w[9], t2w[3], Cw[3], C2[3];
+    mat33(pKF2->GetRotation(), R2w); vec3(pKF2->GetTranslation(), t2w); vec3(pKF1->GetCameraCenter(), Cw);
+    for (int r = 0; r < 3; r++) {
+        float s = R2w[3 * r] * Cw[0];
+        s = s + R2w[3 * r + 1] * Cw[1];
+        s = s + R2w[3 * r + 2] * Cw[2];
+        C2[r] = s + t2w[r];
+    }
+    const float invz = 1.0f / C2[2];
+    const float epipole[2] = {pKF2->fx * C2[0] * invz + pKF2->cx, pKF2->fy * C2[1] * invz + pKF2->cy};
+    DescAngles A(pKF1->mDescriptors, pKF1->mvKeysUn, pKF1->N), B(pKF2->mDescriptors, pKF2->mvKeysUn, pKF2->N);
+    std::vector<float> xy1(2 * (size_t)A.n + 2), xy2(2 * (size_t)B.n + 2); std::vector<int32_t> oct2(B.n + 1);
+    for (int i = 0; i < A.n; i++) {
+        if (!(pKF1->mvuRight[i] < 0)) throw std::runtime_error("orbslamm_b200: stereo keyframes are not supported");
+        A.elig[i] = pKF1->GetMapPoint(i) ? 0 : 1; xy1[2 * i] = pKF1->mvKeysUn[i].pt.x; xy1[2 * i + 1] = pKF1->mvKeysUn[i].pt.y;
+    }
+    for (int i = 0; i < B.n; i++) {
+        if (!(pKF2->mvuRight[i] < 0)) throw std::runtime_error("orbslamm_b200: stereo keyframes are not supported");
+        B.elig[i] = pKF2->GetMapPoint(i) ? 0 : 1; xy2[2 * i] = pKF2->mvKeysUn[i].pt.x; xy2[2 * i + 1] = pKF2->mvKeysUn[i].pt.y; oct2[i] = pKF2->mvKeysUn[i].octave;
+    }
+    float F[9];
+    mat33(F12, F);
+    orbm_epipolar epi;
+    epi.xy1 = xy1.data(); epi.xy2 = xy2.data(); epi.octave2 = oct2.data(); epi.F12 = F; epi.epipole = epipole;
+    epi.scale_factors2 = pKF2->mvScaleFactors.data(); epi.level_sigma2_2 = pKF2->mvLevelSigma2.data(); epi.nlevels = (int32_t)pKF2->mvScaleFactors.size();
+    FeatVecCSR fa(pKF1->mFeatVec, A.n), fb(pKF2->mFeatVec, B.n);
+    std::vector<int32_t> m;
+    const int n = bow_call(ORBM_BOW_TRIANGULATION, A, fa, B, fb, mfNNratio, mbCheckOrientation, &epi, m);
+    vMatchedPairs.clear();
+    vMatchedPairs.reserve(n);
+    for (int i = 0; i < A.n; i++) if (m[i] >= 0) vMatchedPairs.push_back(std::make_pair((size_t)i, (size_t)m[i]));
+    return n;
+}
+
+// Tracking::MonocularInitialization -> matcher.SearchForInitialization(mInitialFrame, mCurrentFrame, mvbPrevMatched, mvIniMatches, 100)   (Tracking.cc:639)
+int ORBmatcher::SearchForInitialization(Frame &F1, Frame &F2, std::vector<cv::Point2f> &vbPrevMatched, std::vector<int> &vnMatches12, int windowSize)
+{
+    const int32_t N1 = (int32_t)F1.mvKeysUn.size(), N2 = (int32_t)F2.mvKeysUn.size();
+    vnMatches12 = std::vector<int>(N1, -1);
+    if (!N1 || !N2) return 0;
+    DescAngles A(F1.mDescriptors, F1.mvKeysUn, N1), B(F2.mDescriptors, F2.mvKeysUn, N2);
+    std::vector<int32_t> oct1(N1), oct2(N2), m(N1, -1);
+    std::vector<float> xy2(2 * (size_t)N2), prev(2 * (size_t)N1);
+    for (int i = 0; i < N1; i++) { oct1[i] = F1.mvKeysUn[i].octave; prev[2 * i] = vbPrevMatched[i].x; prev[2 * i + 1] = vbPrevMatched[i].y; }
+    for (int i = 0; i < N2; i++) { oct2[i] = F2.mvKeysUn[i].octave; xy2[2 * i] = F2.mvKeysUn[i].pt.x; xy2[2 * i + 1] = F2.mvKeysUn[i].pt.y; }
+    const float bounds[4] = {Frame::mnMinX, Frame::mnMinY, Frame::mnMaxX, Frame::mnMaxY};
+    int32_t nmatches = 0;
+    check(orbm_search_for_initialization(handle(), 1, bounds, oct1.data(), A.angle.data(), A.desc(), &N1, N1, xy2.data(), oct2.data(), B.angle.data(), B.desc(), &N2, N2,
+                                         prev.data(), windowSize, mfNNratio, mbCheckOrientation ? 1 : 0, m.data(), &nmatches, ORBS_MEM_HOST),
+          "orbm_search_for_initialization");
+    for (int i = 0; i < N1; i++) { vnMatches12[i] = m[i]; vbPrevMatched[i].x = prev[2 * i]; vbPrevMatched[i].y = prev[2 * i + 1]; }
+    return nmatches;
 }
 
 }  // namespace iORB_SLAM

@@ -1,5 +1,6 @@
 #pragma once
 #include "MapPoint.h"
+#include "Thirdparty/DBoW2/DBoW2/FeatureVector.h"
 
 #define FRAME_GRID_ROWS 48
 #define FRAME_GRID_COLS 64
@@ -24,5 +25,6 @@ public:
     cv::Mat mTcw;
     std::vector<float> mvScaleFactors, mvInvLevelSigma2;
     float mfLogScaleFactor = 0;
+    DBoW2::FeatureVector mFeatVec;
 };
 }  // namespace iORB_SLAM

@@ -1,6 +1,7 @@
 #pragma once
 #include <set>
 #include "MapPoint.h"
+#include "Thirdparty/DBoW2/DBoW2/FeatureVector.h"
 
 namespace iORB_SLAM
 {
@@ -39,7 +40,8 @@ public:
     int N = 0;
     int mnMinX = 0, mnMinY = 0, mnMaxX = 0, mnMaxY = 0;           // ints in S/include/KeyFrame.h
     float mfGridElementWidthInv = 0, mfGridElementHeightInv = 0, mfLogScaleFactor = 0;
-    std::vector<float> mvScaleFactors;
+    std::vector<float> mvScaleFactors, mvLevelSigma2;
+    DBoW2::FeatureVector mFeatVec;
     cv::Mat mDescriptors;
     std::vector<cv::KeyPoint> mvKeysUn;
     std::vector<float> mvuRight, mvInvLevelSigma2;

@@ -164,6 +164,70 @@ int main(int argc, char **argv)
         for (int i = 0; i < K1.N; i++) so.push_back(vm[i] ? (double)(vm[i]->mnId - 100000) : -1.0);
         wr(D + "/out_optimize_sim3.bin", so);
     }
+    {   // SearchByBoW x2, SearchForTriangulation on a keyframe pair with vocabulary nodes per feature
+        wr(D + "/grid_bounds.bin", rd<float>(D + "/bow_grid_bounds.bin"));
+        const std::vector<int> node1 = rd<int>(D + "/bow_node1.bin"), node2 = rd<int>(D + "/bow_node2.bin");
+        const std::vector<unsigned char> has1 = rd<unsigned char>(D + "/bow_has1.bin"), has2 = rd<unsigned char>(D + "/bow_has2.bin"),
+                                         tri1 = rd<unsigned char>(D + "/bow_tri1.bin"), tri2 = rd<unsigned char>(D + "/bow_tri2.bin");
+        const std::vector<float> F12 = rd<float>(D + "/bow_F12.bin"), ls2 = rd<float>(D + "/bow_ls2.bin");
+        for (int ori = 0; ori < 2; ori++) {
+            KeyFrame K1, K2; load_kf(K1, "bow_kf1"); load_kf(K2, "bow_kf2");
+            K1.mvLevelSigma2 = ls2; K2.mvLevelSigma2 = ls2; K1.mvuRight.assign(K1.N, -1.f); K2.mvuRight.assign(K2.N, -1.f);
+            for (int i = 0; i < K1.N; i++) K1.mFeatVec.addFeature((unsigned)node1[i], (unsigned)i);
+            for (int i = 0; i < K2.N; i++) K2.mFeatVec.addFeature((unsigned)node2[i], (unsigned)i);
+            std::vector<MapPoint> p1(K1.N), p2(K2.N);
+            for (int i = 0; i < K1.N; i++) { p1[i].mnId = i; if (has1[i]) K1.mvpMapPoints[i] = &p1[i]; }
+            for (int i = 0; i < K2.N; i++) { p2[i].mnId = i; if (has2[i]) K2.mvpMapPoints[i] = &p2[i]; }
+            std::vector<int> out;
+            {   // keyframe - keyframe
+                std::vector<MapPoint *> m12;
+                ORBmatcher matcher(0.75, ori != 0);
+                const int n = matcher.SearchByBoW(&K1, &K2, m12);
+                for (int i = 0; i < K1.N; i++) out.push_back(m12[i] ? (int)m12[i]->mnId : -1);
+                out.push_back(n);
+            }
+            {   // keyframe - frame (the frame has keyframe 2's features)
+                Frame F;
+                F.N = K2.N; F.mvKeys = K2.mvKeysUn; F.mvKeysUn = K2.mvKeysUn; F.mDescriptors = K2.mDescriptors; F.mFeatVec = K2.mFeatVec;
+                std::vector<MapPoint *> mf;
+                ORBmatcher matcher(0.7, ori != 0);
+                const int n = matcher.SearchByBoW(&K1, F, mf);
+                for (int k = 0; k < F.N; k++) out.push_back(mf[k] ? (int)mf[k]->mnId : -1);
+                out.push_back(n);
+            }
+            {   // triangulation candidates: features without a map point
+                for (int i = 0; i < K1.N; i++) K1.mvpMapPoints[i] = tri1[i] ? &p1[i] : nullptr;
+                for (int i = 0; i < K2.N; i++) K2.mvpMapPoints[i] = tri2[i] ? &p2[i] : nullptr;
+                cv::Mat F(3, 3, CV_32F);
+                memcpy(F.data, F12.data(), 36);
+                std::vector<std::pair<size_t, size_t>> pairs;
+                ORBmatcher matcher(0.6, ori != 0);
+                const int n = matcher.SearchForTriangulation(&K1, &K2, F, pairs, false);
+                std::vector<int> m(K1.N, -1);
+                for (auto &pr : pairs) m[pr.first] = (int)pr.second;
+                out.insert(out.end(), m.begin(), m.end());
+                out.push_back(n);
+            }
+            wr(D + (ori ? "/out_bow_ori1.bin" : "/out_bow_ori0.bin"), out);
+        }
+    }
+    {   // SearchForInitialization, called twice like the initialiser does (the second call starts from the updated vbPrevMatched)
+        wr(D + "/grid_bounds.bin", rd<float>(D + "/init_bounds.bin"));
+        KeyFrame A, B; load_kf(A, "init_f1"); load_kf(B, "init_f2");
+        Frame F1, F2;
+        F1.N = A.N; F1.mvKeysUn = A.mvKeysUn; F1.mvKeys = A.mvKeysUn; F1.mDescriptors = A.mDescriptors;
+        F2.N = B.N; F2.mvKeysUn = B.mvKeysUn; F2.mvKeys = B.mvKeysUn; F2.mDescriptors = B.mDescriptors;
+        std::vector<cv::Point2f> prev(F1.N);
+        for (int i = 0; i < F1.N; i++) prev[i] = F1.mvKeysUn[i].pt;
+        std::vector<int> out, m12;
+        ORBmatcher matcher(0.9, true);
+        for (int call = 0; call < 2; call++) {
+            const int n = matcher.SearchForInitialization(F1, F2, prev, m12, 100);
+            out.insert(out.end(), m12.begin(), m12.end());
+            out.push_back(n);
+        }
+        wr(D + "/out_init.bin", out);
+    }
     printf("kf family host shim ok\n");
     return 0;
 }

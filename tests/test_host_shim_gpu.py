@@ -119,6 +119,13 @@ def test_cpp_dropin_kf_family(lib, tmp_path):
     s_init = np.concatenate([kff.quat_of(Rotation.from_rotvec([0.003, -0.002, 0.004]).as_matrix() @ p["R12"].astype(np.float64)),
                              p["t12"].astype(np.float64) + [0.02, -0.01, 0.015], [float(p["s12"]) * 1.01]])
     w("s3_init.bin", s_init)
+    b = kff.make_bow_case(synth.TUM, 4, True)
+    w("bow_grid_bounds.bin", b["kf1"]["grid_bounds4"]); w_kf("bow_kf1", b["kf1"]); w_kf("bow_kf2", b["kf2"])
+    w("bow_node1.bin", kff.synthetic_nodes(b["kf1"]["desc"]).astype(np.int32)); w("bow_node2.bin", kff.synthetic_nodes(b["kf2"]["desc"]).astype(np.int32))
+    w("bow_has1.bin", b["has1"]); w("bow_has2.bin", b["has2"]); w("bow_tri1.bin", b["tri1"]); w("bow_tri2.bin", b["tri2"]); w("bow_F12.bin", b["F12"]); w("bow_ls2.bin", b["ls2"])
+    ki = make_tracking_case(synth.TUM, 6)
+    as_kf = lambda f: dict(xy=np.stack([f["x"], f["y"]], 1).astype(np.float32), angle=f["angle"], octave=f["octave"], desc=f["desc"], Tcw=np.eye(4, dtype=np.float32))
+    w("init_bounds.bin", ki["bounds"].astype(np.float32)); w_kf("init_f1", as_kf(ki["last"])); w_kf("init_f2", as_kf(ki["cur"]))
     out = subprocess.run([exe, d], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
     r = lambda name: np.fromfile(os.path.join(d, name), np.int32)
@@ -173,3 +180,23 @@ def test_cpp_dropin_kf_family(lib, tmp_path):
     assert ro["n_in"] > 20 and int(got[8]) == ro["n_in"]
     assert np.abs(got[:8] - ro["sim3"]).max() < 1e-5 * np.abs(ro["sim3"]).max()
     assert np.array_equal(got[9:].astype(np.int64), np.where(ro["inlier"] > 0, m_o, -1))
+    # SearchByBoW x2 and SearchForTriangulation
+    kf1, kf2 = b["kf1"], b["kf2"]; N1, N2 = len(kf1["desc"]), len(kf2["desc"])
+    epi = dict(xy1=kf1["xy"], xy2=kf2["xy"], octave2=kf2["octave"], F12=b["F12"], ex=b["ex"], ey=b["ey"], scale_factors2=kf2["scale_factors"], level_sigma2_2=b["ls2"])
+    for ori in (0, 1):
+        got = r("out_bow_ori%d.bin" % ori)
+        n_o, m_o = oracle.search_by_bow(0, kf1["desc"], kf1["angle"], b["has1"], b["fv1"], kf2["desc"], kf2["angle"], b["has2"], b["fv2"], 0.75, ori)
+        assert n_o > 100 and got[N1] == n_o and np.array_equal(got[:N1], m_o)
+        got = got[N1 + 1:]
+        n_o, m_o = oracle.search_by_bow(0, kf1["desc"], kf1["angle"], b["has1"], b["fv1"], kf2["desc"], kf2["angle"], np.ones(N2, np.uint8), b["fv2"], 0.7, ori)
+        inv = np.full(N2, -1, np.int32); inv[m_o[m_o >= 0]] = np.where(m_o >= 0)[0]
+        assert got[N2] == n_o and np.array_equal(got[:N2], inv)
+        got = got[N2 + 1:]
+        n_o, m_o = oracle.search_by_bow(1, kf1["desc"], kf1["angle"], 1 - b["tri1"], b["fv1"], kf2["desc"], kf2["angle"], 1 - b["tri2"], b["fv2"], 0.6, ori, epi)
+        assert n_o > 5 and got[N1] == n_o and np.array_equal(got[:N1], m_o)
+    # SearchForInitialization, two calls
+    g = oracle.grid_params(*ki["bounds"])
+    got = r("out_init.bin"); n1 = len(ki["last"]["x"])
+    a1 = oracle.search_for_initialization(g, ki["last"], ki["cur"], np.stack([ki["last"]["x"], ki["last"]["y"]], 1), 100, 0.9, True)
+    a2 = oracle.search_for_initialization(g, ki["last"], ki["cur"], a1[2], 100, 0.9, True)
+    assert a1[0] > 50 and got[n1] == a1[0] and np.array_equal(got[:n1], a1[1]) and got[2 * n1 + 1] == a2[0] and np.array_equal(got[n1 + 1:2 * n1 + 1], a2[1])
