@@ -168,6 +168,21 @@ int orbm_is_in_frustum(orbm_handle *h, int n_frames, const float *Tcw, const flo
                        const float *mf_min_distance, const float *mf_max_distance, const int32_t *counts, int slab,
                        uint8_t *in_view, float *proj_xy, int32_t *pred_level, float *view_cos, int memspace);
 
+/* Frame::AssignFeaturesToGrid (S/src/Frame.cc:230-245, PosInGrid :382-392): the 64x48 feature grid of n_frames frames as CSR,
+ *   cell = ix * 48 + iy; cell_start i32[n_frames, 64*48 + 1]; cell_items i32[n_frames, f_slab] feature indices, ascending inside a cell
+ *   (the order of the reference's mGrid[ix][iy] vectors).  Features that fall outside the grid are in no cell. */
+int orbm_assign_features_to_grid(orbm_handle *h, int n_frames, const float *bounds4, const float *f_xy, const int32_t *f_counts, int f_slab,
+                                 int32_t *cell_start, int32_t *cell_items, int memspace);
+
+/* Frame::GetFeaturesInArea(x, y, r, minLevel, maxLevel) (S/src/Frame.cc:327-380) / KeyFrame::GetFeaturesInArea(x, y, r) (S/src/KeyFrame.cc:
+ * 618-657; pass win_origin2 = the keyframe's integer mnMinX, mnMinY and no level arrays) for q_counts[f] queries per frame.
+ *   q_xyr f32[n_frames*q_slab,3] = x, y, r; q_minl / q_maxl i32[.] (may be NULL = -1, -1); f_octave may be NULL without level limits.
+ *   out_idx i32[n_frames*q_slab, cap]: the indices in the reference's order (cells ix-major, ascending index inside a cell), truncated
+ *   at cap; out_count i32[.]: the full size of the returned vector. */
+int orbm_get_features_in_area(orbm_handle *h, int n_frames, const float *bounds4, const float *win_origin2, const float *f_xy, const int32_t *f_octave,
+                              const int32_t *f_counts, int f_slab, const float *q_xyr, const int32_t *q_minl, const int32_t *q_maxl,
+                              const int32_t *q_counts, int q_slab, int cap, int32_t *out_idx, int32_t *out_count, int memspace);
+
 /* Projection block of SearchByProjection(CurrentFrame, LastFrame, th, bMono=true), ORBmatcher.cc:1336-1391:
  * per frame f and last-frame slot i (valid[i] != 0: the slot holds a non-outlier map point) project Xw with the
  * current pose, keep it if the depth is positive and (u, v) lies inside the image bounds, and emit the search

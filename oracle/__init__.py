@@ -487,3 +487,27 @@ def search_for_initialization(g, f1, f2, prev_matched, window=100, ratio=0.9, ch
     n = L.oracle_search_for_initialization(ctypes.byref(g), len(xy1), _p(xy1, _f32p), _p(o1, _i32p), _p(a1, _f32p), _p(d1, _u8p), len(xy2), _p(xy2, _f32p),
                                            _p(o2, _i32p), _p(a2, _f32p), _p(d2, _u8p), _p(pm, _f32p), int(window), float(ratio), int(bool(check_ori)), _p(m, _i32p))
     return n, m, pm
+
+
+def grid_build(g, f_xy):
+    """Frame::AssignFeaturesToGrid: (cell_start[3073], cell_items[N]) with cell = ix * 48 + iy, ascending index inside a cell."""
+    xy = np.ascontiguousarray(f_xy, np.float32).reshape(-1, 2); N = len(xy)
+    cs = np.zeros(64 * 48 + 1, np.int32); ci = np.full(max(N, 1), -1, np.int32)
+    L = lib()
+    L.oracle_grid_build.restype = None
+    L.oracle_grid_build.argtypes = [ctypes.c_void_p, ctypes.c_int, _f32p, _i32p, _i32p]
+    L.oracle_grid_build(ctypes.byref(g), N, _p(xy, _f32p), _p(cs, _i32p), _p(ci, _i32p))
+    return cs, ci[:N]
+
+
+def features_in_area(g, cell_start, cell_items, f_xy, f_octave, x, y, r, min_level=-1, max_level=-1):
+    """Frame::GetFeaturesInArea: indices in the reference's visiting order."""
+    xy = np.ascontiguousarray(f_xy, np.float32).reshape(-1, 2); oc = np.ascontiguousarray(f_octave, np.int32)
+    cs = np.ascontiguousarray(cell_start, np.int32); ci = np.ascontiguousarray(cell_items, np.int32)
+    out = np.zeros(max(len(xy), 1), np.int32)
+    L = lib()
+    L.oracle_features_in_area.restype = ctypes.c_int
+    L.oracle_features_in_area.argtypes = [ctypes.c_void_p, _i32p, _i32p, _f32p, _i32p, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_int, ctypes.c_int, _i32p]
+    n = L.oracle_features_in_area(ctypes.byref(g), _p(cs, _i32p), _p(ci, _i32p), _p(xy, _f32p), _p(oc, _i32p), float(x), float(y), float(r), int(min_level),
+                                  int(max_level), _p(out, _i32p))
+    return out[:n].copy()

@@ -304,6 +304,27 @@ class ORBmatcher:
                                           _ptr(Xw), _ptr(nrm), _ptr(mn), _ptr(mx), _ptr(cnt), slab, _ptr(iv), _ptr(uv), _ptr(lv), _ptr(vc), 0))
         return iv, uv, lv, vc
 
+    def AssignFeaturesToGrid(self, bounds4, f_xy, f_counts):
+        """Frame::AssignFeaturesToGrid (Frame.cc:230-245): returns (cell_start [n, 3073], cell_items [n, f_slab]) with cell = ix * 48 + iy."""
+        xy = np.ascontiguousarray(f_xy, np.float32); n, fs = xy.shape[0], xy.shape[1]
+        cnt = np.ascontiguousarray(f_counts, np.int32); b4 = np.ascontiguousarray(bounds4, np.float32)
+        cs = np.zeros((n, 64 * 48 + 1), np.int32); ci = np.zeros((n, fs), np.int32)
+        _check(self._L.orbm_assign_features_to_grid(self._h, n, _ptr(b4), _ptr(xy), _ptr(cnt), fs, _ptr(cs), _ptr(ci), 0))
+        return cs, ci
+
+    def GetFeaturesInArea(self, bounds4, f_xy, f_octave, f_counts, q_xyr, q_minl, q_maxl, q_counts, cap=256, win_origin2=None):
+        """Frame / KeyFrame::GetFeaturesInArea for q_counts[f] queries per frame: returns (idx [n, q_slab, cap], count [n, q_slab])."""
+        xy = np.ascontiguousarray(f_xy, np.float32); n, fs = xy.shape[0], xy.shape[1]
+        oc = None if f_octave is None else np.ascontiguousarray(f_octave, np.int32)
+        cnt = np.ascontiguousarray(f_counts, np.int32); b4 = np.ascontiguousarray(bounds4, np.float32)
+        q = np.ascontiguousarray(q_xyr, np.float32); qs = q.shape[1]
+        mn = None if q_minl is None else np.ascontiguousarray(q_minl, np.int32); mx = None if q_maxl is None else np.ascontiguousarray(q_maxl, np.int32)
+        qc = np.ascontiguousarray(q_counts, np.int32); wo = None if win_origin2 is None else np.ascontiguousarray(win_origin2, np.float32)
+        idx = np.zeros((n, qs, cap), np.int32); out_n = np.zeros((n, qs), np.int32)
+        _check(self._L.orbm_get_features_in_area(self._h, n, _ptr(b4), _ptr(wo), _ptr(xy), _ptr(oc), _ptr(cnt), fs, _ptr(q), _ptr(mn), _ptr(mx), _ptr(qc), qs, int(cap),
+                                                 _ptr(idx), _ptr(out_n), 0))
+        return idx, out_n
+
     def SearchByProjection(self, bounds4, f_xy, f_octave, f_angle, f_desc, f_counts, q_valid, q_uv, q_radius, q_minl,
                            q_maxl, q_angle, q_desc, q_counts, th_dist=100, use_ratio=False, feat_match=None):
         """Generic projection search for n_frames frames (host arrays in slab layout [n_frames, slab, ...]).

@@ -28,6 +28,8 @@ def declare(L):
     L.orbm_search_by_bow.restype = c.c_int
     L.orbm_search_for_initialization.argtypes = [vp, i, vp, vp, vp, vp, vp, i, vp, vp, vp, vp, vp, i, vp, i, f, i, vp, vp, i]
     L.orbm_search_for_initialization.restype = c.c_int
+    L.orbm_assign_features_to_grid.argtypes = [vp, i, vp, vp, vp, i, vp, vp, i]; L.orbm_assign_features_to_grid.restype = c.c_int
+    L.orbm_get_features_in_area.argtypes = [vp, i, vp, vp, vp, vp, vp, i, vp, vp, vp, vp, i, i, vp, vp, i]; L.orbm_get_features_in_area.restype = c.c_int
     L.orbo_create.argtypes = [c.POINTER(vp), i]
     L.orbo_destroy.argtypes = [vp]
     L.orbo_stream.argtypes = [vp]; L.orbo_stream.restype = vp

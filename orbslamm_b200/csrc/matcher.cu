@@ -328,6 +328,58 @@ __device__ __forceinline__ bool in_window(const Window &w, int minl, int maxl, f
     return fabsf(__fsub_rn(p.x, uv.x)) < r && fabsf(__fsub_rn(p.y, uv.y)) < r;
 }
 
+// Frame::AssignFeaturesToGrid / GetFeaturesInArea as stand-alone entry points (Frame.cc:230-245, 327-380; KeyFrame.cc:618-657).
+// The reference's cells hold their features in ascending index order (push_back in a loop over i); k_grid_build appends unordered, so the
+// exported grid is sorted per cell.
+__global__ void __launch_bounds__(256)
+k_grid_sort_cells(int f_slab, const int *__restrict__ cell_start, int *__restrict__ cell_items)
+{
+    const int f = blockIdx.y, c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= kGridCells) return;
+    const int *cs = cell_start + (size_t)f * (kGridCells + 1);
+    int *it = cell_items + (size_t)f * f_slab;
+    const int b = cs[c], e = cs[c + 1];
+    for (int i = b + 1; i < e; i++) {
+        const int v = it[i];
+        int j = i - 1;
+        while (j >= b && it[j] > v) { it[j + 1] = it[j]; j--; }
+        it[j + 1] = v;
+    }
+}
+
+// one warp per query; cells in the reference's order (ix outer, iy inner), the features of a cell in ascending index, appended in order
+__global__ void __launch_bounds__(256)
+k_features_in_area(int f_slab, int q_slab, int cap, GridParams g, const float2 *__restrict__ f_xy, const int *__restrict__ f_octave,
+                   const int *__restrict__ cell_start, const int *__restrict__ cell_items, const float *__restrict__ q_xyr, const int *__restrict__ q_minl,
+                   const int *__restrict__ q_maxl, const int *__restrict__ q_counts, int *__restrict__ out_idx, int *__restrict__ out_count)
+{
+    const int f = blockIdx.y, lane = threadIdx.x & 31;
+    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (i >= q_counts[f]) return;
+    const size_t fo = (size_t)f * f_slab, q = (size_t)f * q_slab + i;
+    const float2 uv = make_float2(q_xyr[3 * q], q_xyr[3 * q + 1]);
+    const float r = q_xyr[3 * q + 2];
+    const int minl = q_minl ? q_minl[q] : -1, maxl = q_maxl ? q_maxl[q] : -1;
+    const Window w = make_window(g, uv, r, minl, maxl);
+    const int *cs = cell_start + (size_t)f * (kGridCells + 1); const int *items = cell_items + fo;
+    int *out = out_idx + q * cap;
+    int n = 0;
+    if (!w.empty)
+        for (int ix = w.c0; ix <= w.c1; ix++)
+            for (int iy = w.r0; iy <= w.r1; iy++) {
+                const int cell = ix * kGridRows + iy, je = cs[cell + 1];
+                for (int j0 = cs[cell]; j0 < je; j0 += 32) {
+                    const int j = j0 + lane;
+                    bool hit = false; int k = -1;
+                    if (j < je) { k = items[j]; hit = in_window(w, minl, maxl, uv, r, f_octave ? f_octave[fo + k] : 0, f_xy[fo + k]); }
+                    const unsigned bal = __ballot_sync(0xffffffffu, hit);
+                    if (hit) { const int pos = n + __popc(bal & ((1u << lane) - 1)); if (pos < cap) out[pos] = k; }
+                    n += __popc(bal);
+                }
+            }
+    if (lane == 0) out_count[q] = n;
+}
+
 __device__ __forceinline__ unsigned long long make_key(int d, int ix, int iy, int k)
 {
     return ((unsigned long long)d << 32) | ((unsigned long long)ix << 26) | ((unsigned long long)iy << 20) | (unsigned long long)k;
@@ -1290,6 +1342,61 @@ int orbm_search_for_initialization(orbm_handle *h, int n_pairs, const float *bou
     k_grid_build<<<n_pairs, 512, 0, h->stream>>>(slab2, A.g, A.xy2, A.counts2, h->cell_start.as<int>(), h->cell_items.as<int>());
     k_search_init<<<n_pairs, 32, 0, h->stream>>>(A);
     h->launches += 2;
+    ORBS_CUDA(cudaGetLastError());
+    return S.finish();
+}
+
+int orbm_assign_features_to_grid(orbm_handle *h, int n_frames, const float *bounds4, const float *f_xy, const int32_t *f_counts, int f_slab,
+                                 int32_t *cell_start, int32_t *cell_items, int memspace)
+{
+    ORBS_REQUIRE(h && bounds4 && f_xy && f_counts && cell_start && cell_items, ORBS_E_INVALID, "null argument");
+    ORBS_REQUIRE(n_frames > 0 && f_slab > 0, ORBS_E_INVALID, "non-positive size");
+    ORBS_REQUIRE(bounds4[2] > bounds4[0] && bounds4[3] > bounds4[1], ORBS_E_INVALID, "empty image bounds");
+    std::lock_guard<std::mutex> lk(h->mu);
+    ORBS_CUDA(cudaSetDevice(h->device));
+    Stager S(&h->pool, h->stream, memspace);
+    const size_t nf = (size_t)n_frames * f_slab;
+    const float2 *dxy = (const float2 *)S.in(f_xy, nf * 2);
+    const int32_t *dc = S.in(f_counts, n_frames);
+    int32_t *dcs = S.inout(cell_start, (size_t)n_frames * (kGridCells + 1), false), *dci = S.inout(cell_items, nf, false);
+    if (S.rc) return S.rc;
+    if (memspace == ORBS_MEM_HOST) ORBS_CUDA(cudaMemsetAsync(dci, 0xff, nf * sizeof(int), h->stream));
+    k_grid_build<<<n_frames, 512, 0, h->stream>>>(f_slab, make_grid(bounds4), dxy, dc, dcs, dci);
+    k_grid_sort_cells<<<dim3((kGridCells + 255) / 256, n_frames), 256, 0, h->stream>>>(f_slab, dcs, dci);
+    h->launches += 2;
+    ORBS_CUDA(cudaGetLastError());
+    return S.finish();
+}
+
+int orbm_get_features_in_area(orbm_handle *h, int n_frames, const float *bounds4, const float *win_origin2, const float *f_xy, const int32_t *f_octave,
+                              const int32_t *f_counts, int f_slab, const float *q_xyr, const int32_t *q_minl, const int32_t *q_maxl,
+                              const int32_t *q_counts, int q_slab, int cap, int32_t *out_idx, int32_t *out_count, int memspace)
+{
+    ORBS_REQUIRE(h && bounds4 && f_xy && f_counts && q_xyr && q_counts && out_idx && out_count, ORBS_E_INVALID, "null argument");
+    ORBS_REQUIRE(f_octave || (!q_minl && !q_maxl), ORBS_E_INVALID, "level limits need the feature octaves");
+    ORBS_REQUIRE(n_frames > 0 && f_slab > 0 && q_slab > 0 && cap > 0, ORBS_E_INVALID, "non-positive size");
+    ORBS_REQUIRE(bounds4[2] > bounds4[0] && bounds4[3] > bounds4[1], ORBS_E_INVALID, "empty image bounds");
+    std::lock_guard<std::mutex> lk(h->mu);
+    ORBS_CUDA(cudaSetDevice(h->device));
+    Stager S(&h->pool, h->stream, memspace);
+    const size_t nf = (size_t)n_frames * f_slab, nq = (size_t)n_frames * q_slab;
+    GridParams g = make_grid(bounds4);
+    if (win_origin2) { g.win_x = win_origin2[0]; g.win_y = win_origin2[1]; }
+    const float2 *dxy = (const float2 *)S.in(f_xy, nf * 2);
+    const int32_t *doct = f_octave ? S.in(f_octave, nf) : nullptr, *dc = S.in(f_counts, n_frames);
+    const float *dq = S.in(q_xyr, nq * 3);
+    const int32_t *dmn = q_minl ? S.in(q_minl, nq) : nullptr, *dmx = q_maxl ? S.in(q_maxl, nq) : nullptr, *dqc = S.in(q_counts, n_frames);
+    int32_t *dout = S.inout(out_idx, nq * cap, false), *dcnt = S.inout(out_count, nq, false);
+    if (S.rc) return S.rc;
+    int rc;
+    if ((rc = h->cell_start.reserve((size_t)n_frames * (kGridCells + 1) * sizeof(int)))) return rc;
+    if ((rc = h->cell_items.reserve(nf * sizeof(int)))) return rc;
+    if (memspace == ORBS_MEM_HOST) { ORBS_CUDA(cudaMemsetAsync(dout, 0xff, nq * cap * sizeof(int), h->stream)); ORBS_CUDA(cudaMemsetAsync(dcnt, 0, nq * sizeof(int), h->stream)); }
+    k_grid_build<<<n_frames, 512, 0, h->stream>>>(f_slab, g, dxy, dc, h->cell_start.as<int>(), h->cell_items.as<int>());
+    k_grid_sort_cells<<<dim3((kGridCells + 255) / 256, n_frames), 256, 0, h->stream>>>(f_slab, h->cell_start.as<int>(), h->cell_items.as<int>());
+    k_features_in_area<<<dim3((q_slab + 7) / 8, n_frames), 256, 0, h->stream>>>(f_slab, q_slab, cap, g, dxy, doct, h->cell_start.as<int>(), h->cell_items.as<int>(),
+                                                                              dq, dmn, dmx, dqc, dout, dcnt);
+    h->launches += 3;
     ORBS_CUDA(cudaGetLastError());
     return S.finish();
 }

@@ -75,6 +75,26 @@ void Optimizer::GlobalBundleAdjustemnt(Map *pMap, int nIterations, bool *pbStopF
     BundleAdjustment(vpKFs, vpMP, nIterations, pbStopFlag, nLoopKF, bRobust);
 }
 
+#ifdef ORBSLAMM_MULTI_ROBOT
+// MultipleRobotsScenario/src/Optimizer.cc:40-57: the map plus every map attached to it by MultiMapper, one bundle adjustment over the union
+void Optimizer::MMGlobalBundleAdjustemnt(Map *pMap, int nIterations, bool *pbStopFlag, const unsigned long nLoopKF, const bool bRobust)
+{
+    std::vector<KeyFrame *> vpKFs = pMap->GetAllKeyFrames();
+    std::vector<MapPoint *> vpMPs = pMap->GetAllMapPoints();
+    if (pMap->isAttached()) {
+        std::vector<Map *> vpAttachedMaps = pMap->getAttachedMaps();
+        for (std::vector<Map *>::iterator it = vpAttachedMaps.begin(), itend = vpAttachedMaps.end(); it != itend; it++) {
+            Map *pmMap = *it;
+            std::vector<KeyFrame *> vpAttachedKFs = pmMap->GetAllKeyFrames();
+            std::vector<MapPoint *> vpAttachedMPs = pmMap->GetAllMapPoints();
+            vpKFs.insert(vpKFs.end(), vpAttachedKFs.begin(), vpAttachedKFs.end());
+            vpMPs.insert(vpMPs.end(), vpAttachedMPs.begin(), vpAttachedMPs.end());
+        }
+    }
+    BundleAdjustment(vpKFs, vpMPs, nIterations, pbStopFlag, nLoopKF, bRobust);
+}
+#endif
+
 namespace
 {
 // bool* stop flag of the reference -> the int flag the C-ABI polls
@@ -98,7 +118,11 @@ void Optimizer::BundleAdjustment(const std::vector<KeyFrame *> &vpKFs, const std
         kfIndex[pKF] = (int)kfs.size(); kfs.push_back(pKF);
         poses.resize(poses.size() + 16);
         pose_to_flat(pKF->GetPose(), &poses[poses.size() - 16]);
-        fixed.push_back(pKF->mnId == 0 ? 1 : 0);
+#ifdef ORBSLAMM_MULTI_ROBOT
+        fixed.push_back((pKF->mnId == 0 && !pKF->isNotFixed()) ? 1 : 0);        // M/src/Optimizer.cc:99: the first keyframe of an attached map is free
+#else
+        fixed.push_back(pKF->mnId == 0 ? 1 : 0);                                 // S/src/Optimizer.cc:100
+#endif
         intr.push_back(pKF->fx); intr.push_back(pKF->fy); intr.push_back(pKF->cx); intr.push_back(pKF->cy);
     }
     std::vector<MapPoint *> mps;

@@ -62,3 +62,43 @@ def test_is_in_frustum_matches_oracle(lib):
         assert np.array_equal(uv[f, :n][k], r_uv[k]) and np.array_equal(vc[f, :n][k], r_vc[k]) and np.array_equal(lv[f, :n][k], r_lv[k])
         assert not iv[f, n:].any()
     assert 200 < seen < counts.sum() - 200          # the case exercises both outcomes
+
+
+def test_assign_features_to_grid_and_get_features_in_area(lib):
+    """Frame::AssignFeaturesToGrid (Frame.cc:230-245) and GetFeaturesInArea (Frame.cc:327-380, KeyFrame.cc:618-657) as stand-alone calls:
+    the grid equals the oracle's cell by cell, the returned index lists are identical including their order; distorted (non-integer) bounds,
+    a keyframe's integer window origin, level limits, truncation at cap and windows outside the image are covered."""
+    import orbslamm_b200 as ob
+    from helpers import make_tracking_case, slab
+    cases = [make_tracking_case(synth.TUM, 2), make_tracking_case(synth.KITTI, 3)]
+    m = ob.ORBmatcher()
+    rng = np.random.default_rng(4)
+    for bounds in (np.array([0, 0, 1241, 480], np.float32), np.array([-27.3, -20.7, 1266.6, 498.2], np.float32)):
+        g = oracle.grid_params(*[float(b) for b in bounds])
+        fs = max(len(k["cur"]["x"]) for k in cases) + 3
+        fxy = slab([np.stack([k["cur"]["x"], k["cur"]["y"]], 1) for k in cases], fs, np.float32, (2,))
+        foc = slab([k["cur"]["octave"] for k in cases], fs, np.int32)
+        fc = np.array([len(k["cur"]["x"]) for k in cases], np.int32)
+        cs, ci = m.AssignFeaturesToGrid(bounds, fxy, fc)
+        Q = 300
+        q = np.zeros((2, Q, 3), np.float32)
+        q[:, :, 0] = rng.uniform(bounds[0] - 30, bounds[2] + 30, (2, Q)); q[:, :, 1] = rng.uniform(bounds[1] - 30, bounds[3] + 30, (2, Q))
+        q[:, :, 2] = rng.choice([2.5, 7.5, 15.0, 40.0, 100.0], (2, Q))
+        lv = rng.integers(0, 8, (2, Q)).astype(np.int32)
+        mn = np.where(rng.random((2, Q)) < 0.3, -1, lv - 1).astype(np.int32); mx = np.where(mn < 0, -1, lv + rng.integers(0, 2, (2, Q))).astype(np.int32)
+        idx, cnt = m.GetFeaturesInArea(bounds, fxy, foc, fc, q, mn, mx, [Q, Q - 7], cap=64)
+        wo = np.trunc(bounds[:2]).astype(np.float32)
+        idx_k, cnt_k = m.GetFeaturesInArea(bounds, fxy, None, fc, q, None, None, [Q, Q - 7], cap=512, win_origin2=wo)
+        gw = oracle.grid_params(*[float(b) for b in bounds]); gw.min_x, gw.min_y = float(wo[0]), float(wo[1])
+        for f, k in enumerate(cases):
+            n = fc[f]
+            ocs, oci = oracle.grid_build(g, fxy[f, :n])
+            assert np.array_equal(cs[f], ocs) and np.array_equal(ci[f, :ocs[-1]], oci[:ocs[-1]])
+            nq = [Q, Q - 7][f]
+            for i in range(nq):
+                ref = oracle.features_in_area(g, ocs, oci, fxy[f, :n], foc[f, :n], q[f, i, 0], q[f, i, 1], q[f, i, 2], mn[f, i], mx[f, i])
+                assert cnt[f, i] == len(ref) and np.array_equal(idx[f, i, :min(len(ref), 64)], ref[:64])
+                ref = oracle.features_in_area(gw, ocs, oci, fxy[f, :n], foc[f, :n], q[f, i, 0], q[f, i, 1], q[f, i, 2], -1, -1)
+                assert cnt_k[f, i] == len(ref) and np.array_equal(idx_k[f, i, :len(ref)], ref)
+            assert (cnt[f, nq:] == 0).all()
+        assert cnt.max() > 64                                     # truncation exercised
