@@ -318,6 +318,32 @@ int orbm_search_for_initialization(orbm_handle *h, int n_pairs, const float *bou
                                    float *prev_matched, int window, float ratio, int check_ori, int32_t *matches12, int32_t *nmatches, int memspace);
 
 /* ------------------------------------------------------------------ */
+/* DBoW2 vocabulary transform  (replaces S/Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1127-1262 transform, BowVector.cpp:34-84,
+ * FORB.cpp:81-101, as called by Frame::ComputeBoW / KeyFrame::ComputeBoW, S/src/Frame.cc:395-402: transform(descs, mBowVec, mFeatVec, 4)) */
+typedef struct orbv_handle orbv_handle;
+
+/* The vocabulary tree as flat HOST arrays (copied to HBM once): node 0 is the root; node_desc u8[n_nodes,32]; the children of node i are
+ * child_ids[child_start[i] .. child_start[i+1]) in the order of Node::children (file order of ORBvoc.txt, TemplatedVocabulary.h:1370-1419);
+ * a node without children is a word with id word_id[i] and weight weight[i] (the idf part; TF_IDF weighting, L1 scoring as ORBSLAMM
+ * loads it).  k, L as in the file header. */
+int orbv_create(orbv_handle **out, int device, int k, int L, int n_nodes, const uint8_t *node_desc, const int32_t *child_start,
+                const int32_t *child_ids, const int32_t *word_id, const double *weight);
+int orbv_destroy(orbv_handle *h);
+long long orbv_kernel_launches(const orbv_handle *h);
+
+/* transform(features, v, fv, levelsup) for n_frames frames: every descriptor walks the tree (at each level the child with the smallest
+ * Hamming distance, the first one on ties); words with weight 0 are stopped and contribute to neither vector.
+ *   desc u8[n_frames*slab,32], counts i32[n_frames];
+ *   out: word_of_feature / node_of_feature i32[n_frames*slab] (may be NULL; -1 = stopped);
+ *        BowVector: bow_ids i32[n_frames*slab] ascending word ids, bow_vals f64[.] (sum of the word weight over its features in feature
+ *        order, then divided by the L1 norm taken in ascending word order -- the std::map loops of the reference), bow_counts i32[n_frames];
+ *        FeatureVector as the CSR orbm_search_by_bow takes: fv_nodes i32[n_frames*slab], fv_start i32[n_frames*(slab+1)],
+ *        fv_items i32[n_frames*slab] (feature indices, ascending inside a node), fv_counts i32[n_frames]. */
+int orbv_transform(orbv_handle *h, int n_frames, const uint8_t *desc, const int32_t *counts, int slab, int levelsup,
+                   int32_t *word_of_feature, int32_t *node_of_feature, int32_t *bow_ids, double *bow_vals, int32_t *bow_counts,
+                   int32_t *fv_nodes, int32_t *fv_start, int32_t *fv_items, int32_t *fv_counts, int memspace);
+
+/* ------------------------------------------------------------------ */
 /* Optimizer  (replaces S/src/Optimizer.cc and the g2o LM / Schur / LDLT stack it drives; all fp64 inside,
  * float32 poses and points at the boundary like cv::Mat / Converter.cc)                                      */
 typedef struct orbo_handle orbo_handle;

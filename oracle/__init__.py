@@ -511,3 +511,25 @@ def features_in_area(g, cell_start, cell_items, f_xy, f_octave, x, y, r, min_lev
     n = L.oracle_features_in_area(ctypes.byref(g), _p(cs, _i32p), _p(ci, _i32p), _p(xy, _f32p), _p(oc, _i32p), float(x), float(y), float(r), int(min_level),
                                   int(max_level), _p(out, _i32p))
     return out[:n].copy()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# DBoW2 vocabulary transform
+def vocab_transform(vocab, desc, levelsup=4):
+    """vocab: dict L, node_desc [n,32] u8, child_start [n+1], child_ids [n-1], word_id [n], weight [n] f64 (orbslamm_b200.vocabulary format).
+    Returns dict(word_of, node_of, bow_ids, bow_vals, fv=dict(nodes, start, items))."""
+    d = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32); N = len(d)
+    nd = np.ascontiguousarray(vocab["node_desc"], np.uint8); cs = np.ascontiguousarray(vocab["child_start"], np.int32)
+    ci = np.ascontiguousarray(vocab["child_ids"], np.int32); wi = np.ascontiguousarray(vocab["word_id"], np.int32); ww = np.ascontiguousarray(vocab["weight"], np.float64)
+    M = max(N, 1)
+    wo = np.zeros(M, np.int32); no = np.zeros(M, np.int32); bi = np.zeros(M, np.int32); bv = np.zeros(M, np.float64)
+    fn = np.zeros(M, np.int32); fs = np.zeros(M + 1, np.int32); fi = np.zeros(M, np.int32); fc = ctypes.c_int(0)
+    L = lib()
+    L.oracle_vocab_transform.restype = ctypes.c_int
+    L.oracle_vocab_transform.argtypes = [ctypes.c_int, _u8p, _i32p, _i32p, _i32p, _f64p, ctypes.c_int, _u8p, ctypes.c_int, _i32p, _i32p, _i32p, _f64p, _i32p, _i32p,
+                                         _i32p, ctypes.POINTER(ctypes.c_int)]
+    nb = L.oracle_vocab_transform(int(vocab["L"]), _p(nd, _u8p), _p(cs, _i32p), _p(ci, _i32p), _p(wi, _i32p), _p(ww, _f64p), N, _p(d, _u8p), int(levelsup),
+                                  _p(wo, _i32p), _p(no, _i32p), _p(bi, _i32p), _p(bv, _f64p), _p(fn, _i32p), _p(fs, _i32p), _p(fi, _i32p), ctypes.byref(fc))
+    nf = fc.value
+    return dict(word_of=wo[:N], node_of=no[:N], bow_ids=bi[:nb].copy(), bow_vals=bv[:nb].copy(),
+                fv=dict(nodes=fn[:nf].copy(), start=fs[:nf + 1].copy(), items=fi[:fs[nf]].copy()))

@@ -1425,3 +1425,65 @@ int oracle_search_for_initialization(const oracle_grid_params *g, int N1, const 
     free(cell_start); free(cell_items); free(cands); free(matched_dist); free(matches21); free(rot_bin);
     return nmatches;
 }
+
+/* ======================================================================================== */
+/* DBoW2 vocabulary transform: TemplatedVocabulary<TDescriptor,F>::transform(features, v, fv, levelsup), S/Thirdparty/DBoW2/DBoW2/
+ * TemplatedVocabulary.h:1127-1177 (TF_IDF weighting, L1 norm: the only configuration ORBSLAMM loads) with the per-feature tree walk
+ * :1217-1262, BowVector::addWeight / normalize (BowVector.cpp:34-84) and FORB::distance (FORB.cpp:81-101 = the same bit-hack Hamming).
+ * The tree is given flat: children of node i = child_ids[child_start[i] .. child_start[i+1]) in Node::children order; leaves carry
+ * word_id / weight.  Outputs: per-feature word / node (-1 = stopped word), the BowVector as ascending (word, value) pairs and the
+ * FeatureVector as CSR.  Returns the number of words in the BowVector. */
+int oracle_vocab_transform(int L, const uint8_t *node_desc, const int *child_start, const int *child_ids, const int *word_id, const double *weight,
+                           int N, const uint8_t *desc, int levelsup, int *word_of, int *node_of, int *bow_ids, double *bow_vals,
+                           int *fv_nodes, int *fv_start, int *fv_items, int *fv_count)
+{
+    const int nid_level = L - levelsup;
+    int nb = 0, nf = 0;
+    for (int i = 0; i < N; i++) {
+        const uint8_t *f = desc + 32 * (size_t)i;
+        int nid = 0, final_id = 0, level = 0;                      /* transform(feature, id, w, &nid, levelsup), :1217-1262 */
+        do {
+            ++level;
+            const int c0 = child_start[final_id], c1 = child_start[final_id + 1];
+            final_id = child_ids[c0];
+            double best_d = oracle_descriptor_distance(f, node_desc + 32 * (size_t)final_id);
+            for (int c = c0 + 1; c < c1; c++) {
+                const int id = child_ids[c];
+                const double d = oracle_descriptor_distance(f, node_desc + 32 * (size_t)id);
+                if (d < best_d) { best_d = d; final_id = id; }
+            }
+            if (level == nid_level) nid = final_id;
+        } while (child_start[final_id] != child_start[final_id + 1]);
+        const double w = weight[final_id];
+        word_of[i] = -1; node_of[i] = -1;
+        if (!(w > 0)) continue;                                    /* stopped word */
+        word_of[i] = word_id[final_id]; node_of[i] = nid;
+        {   /* v.addWeight(id, w): std::map lower_bound, += or insert (BowVector.cpp:34-46) */
+            int lo = 0, hi = nb;
+            while (lo < hi) { const int mid = (lo + hi) / 2; if (bow_ids[mid] < word_of[i]) lo = mid + 1; else hi = mid; }
+            if (lo < nb && bow_ids[lo] == word_of[i]) bow_vals[lo] += w;
+            else {
+                memmove(bow_ids + lo + 1, bow_ids + lo, sizeof(int) * (nb - lo)); memmove(bow_vals + lo + 1, bow_vals + lo, sizeof(double) * (nb - lo));
+                bow_ids[lo] = word_of[i]; bow_vals[lo] = w; nb++;
+            }
+        }
+        {   /* fv.addFeature(nid, i): node list kept ascending, the feature lists are rebuilt below */
+            int lo = 0, hi = nf;
+            while (lo < hi) { const int mid = (lo + hi) / 2; if (fv_nodes[mid] < nid) lo = mid + 1; else hi = mid; }
+            if (!(lo < nf && fv_nodes[lo] == nid)) { memmove(fv_nodes + lo + 1, fv_nodes + lo, sizeof(int) * (nf - lo)); fv_nodes[lo] = nid; nf++; }
+        }
+    }
+    /* feature lists per node in push order (= ascending feature index) */
+    int pos = 0;
+    for (int a = 0; a < nf; a++) {
+        fv_start[a] = pos;
+        for (int i = 0; i < N; i++) if (node_of[i] == fv_nodes[a]) fv_items[pos++] = i;
+    }
+    fv_start[nf] = pos;
+    *fv_count = nf;
+    /* must = mustNormalize(L1) -> v.normalize(L1), BowVector.cpp:62-84 */
+    double norm = 0.0;
+    for (int a = 0; a < nb; a++) norm += fabs(bow_vals[a]);
+    if (norm > 0.0) for (int a = 0; a < nb; a++) bow_vals[a] /= norm;
+    return nb;
+}

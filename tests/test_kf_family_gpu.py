@@ -177,3 +177,36 @@ def test_search_for_initialization_cuda_equals_oracle_and_reference(lib):
             if HAVE_REF:
                 b = ref_build.ref_search_for_initialization(k["K4"], k["bounds"], sf, k["last"], k["cur"], pm[i, :n1], win, 0.9, ori)
                 assert nm[i] == b[0] and np.array_equal(mt[i, :n1], b[1]) and np.array_equal(pm2[i, :n1], b[2])
+
+
+def test_vocabulary_transform_cuda_equals_oracle(lib):
+    """orbv_transform (Frame::ComputeBoW): per-feature words / nodes, BowVector (ids exact, fp64 values bit-exact: same summation order) and
+    FeatureVector for a ragged batch of frames; stopped words, sibling ties and levelsup variants; the FeatureVector feeds SearchByBoW."""
+    import orbslamm_b200 as ob
+    from orbslamm_b200 import vocabulary as V
+    from helpers import make_tracking_case
+    v = V.synthetic(10, 4, seed=3)
+    voc = V.ORBVocabulary(v)
+    rng = np.random.default_rng(2)
+    leaves = np.where(v["word_id"] >= 0)[0]
+    k = make_tracking_case(synth.TUM, 5)
+    frames = [k["cur"]["desc"], k["last"]["desc"],
+              v["node_desc"][rng.choice(leaves, 700)] ^ np.packbits(rng.random((700, 256)) < 0.06, axis=1), np.zeros((0, 32), np.uint8)]
+    W = max(len(f) for f in frames) + 9
+    for levelsup in (4, 2, 0, 7):
+        out = voc.transform(slab(frames, W, np.uint8, (32,)), [len(f) for f in frames], levelsup)
+        for f, o in zip(frames, out):
+            r = oracle.vocab_transform(v, f, levelsup)
+            assert np.array_equal(o["word_of"], r["word_of"]) and np.array_equal(o["node_of"], r["node_of"])
+            assert np.array_equal(o["bow_ids"], r["bow_ids"]) and np.array_equal(o["bow_vals"], r["bow_vals"])
+            for key in ("nodes", "start", "items"):
+                assert np.array_equal(o["fv"][key], r["fv"][key])
+    # the device FeatureVectors drive SearchByBoW (Tracking::TrackReferenceKeyFrame: ComputeBoW, then SearchByBoW(KF, F))
+    out = voc.transform(slab(frames[:2], W, np.uint8, (32,)), [len(frames[0]), len(frames[1])], 2)
+    m = ob.ORBmatcher(0.7, True)
+    has = (rng.random(len(frames[1])) < 0.9).astype(np.uint8)
+    nm, mt = m.SearchByBoW(frames[1][None], k["last"]["angle"][None], has[None], [len(frames[1])], [out[1]["fv"]],
+                           frames[0][None], k["cur"]["angle"][None], np.ones((1, len(frames[0])), np.uint8), [len(frames[0])], [out[0]["fv"]])
+    n_o, m_o = oracle.search_by_bow(0, frames[1], k["last"]["angle"], has, out[1]["fv"], frames[0], k["cur"]["angle"], np.ones(len(frames[0]), np.uint8), out[0]["fv"],
+                                    0.7, True)
+    assert n_o > 20 and nm[0] == n_o and np.array_equal(mt[0], m_o)

@@ -146,3 +146,45 @@ def test_optimize_sim3_oracle_properties():
     v = c["valid"].copy(); v[np.where(v)[0][9:]] = 0
     r3 = oracle.optimize_sim3(c["init"], v, *args[1:], 10.0, False)
     assert r3["n_in"] == 0 and np.array_equal(r3["sim3"], c["init"])
+
+
+def test_vocab_transform_known_answers():
+    """DBoW2 transform restatement (TemplatedVocabulary.h:1127-1262) on a hand-built 2-ary tree of depth 2:
+           root -> A(0x00..) -> words w0 (0x00.., weight 2), w1 (0x0f.., weight 3)
+                -> B(0xff..) -> words w2 (0xff.., weight 0 = stopped), w3 (0xf0.., weight 5)
+    plus a random-tree check of the first-minimum rule, the std::map ordering and the L1 normalisation."""
+    from orbslamm_b200 import vocabulary as V
+    full = lambda b: np.full(32, b, np.uint8)
+    parent = [0, 0, 1, 1, 0, 4, 4]           # file (depth-first) order: A, w0, w1, B, w2, w3
+    leaf = [False, False, True, True, False, True, True]
+    desc = np.stack([full(0), full(0x00), full(0x00), full(0x0f), full(0xff), full(0xff), full(0xf0)])
+    v = V.from_nodes(2, 2, parent, leaf, desc, [0, 0, 2.0, 3.0, 0, 0.0, 5.0])
+    assert v["child_ids"].tolist() == [1, 4, 2, 3, 5, 6] and v["word_id"].tolist() == [-1, -1, 0, 1, -1, 2, 3]
+    feats = np.stack([full(0x01), full(0x0f), full(0x0e), full(0xfe), full(0xf1), full(0x00)])
+    r = oracle.vocab_transform(v, feats, levelsup=1)
+    assert r["word_of"].tolist() == [0, 1, 1, -1, 3, 0]                    # feature 3 falls on the stopped word
+    assert r["node_of"].tolist() == [1, 1, 1, -1, 4, 1]                    # level L - levelsup = 1: A or B
+    assert r["bow_ids"].tolist() == [0, 1, 3] and np.allclose(r["bow_vals"], np.array([4.0, 6.0, 5.0]) / 15.0, rtol=0, atol=1e-16)
+    assert r["fv"]["nodes"].tolist() == [1, 4] and r["fv"]["start"].tolist() == [0, 4, 5] and r["fv"]["items"].tolist() == [0, 1, 2, 5, 4]
+    r0 = oracle.vocab_transform(v, feats, levelsup=2)                       # nid_level <= 0: every feature under the root
+    assert r0["fv"]["nodes"].tolist() == [0] and r0["fv"]["items"].tolist() == [0, 1, 2, 4, 5]
+    # a tie between siblings: the first child wins
+    v2 = V.from_nodes(2, 1, [0, 0, 0], [False, True, True], np.stack([full(0), full(0x0f), full(0xf0)]), [0, 1.0, 1.0])
+    assert oracle.vocab_transform(v2, full(0xff)[None], 0)["word_of"].tolist() == [0]
+    # random tree: brute-force numpy walk
+    v3 = V.synthetic(10, 3, seed=5)
+    rng = np.random.default_rng(1)
+    leaves = np.where(v3["word_id"] >= 0)[0]
+    d = v3["node_desc"][rng.choice(leaves, 300)] ^ np.packbits(rng.random((300, 256)) < 0.1, axis=1)
+    r3 = oracle.vocab_transform(v3, d, levelsup=2)
+    for i in range(300):
+        node, lvl, nid = 0, 0, 0
+        while v3["child_start"][node] != v3["child_start"][node + 1]:
+            ch = v3["child_ids"][v3["child_start"][node]:v3["child_start"][node + 1]]
+            dist = np.unpackbits(v3["node_desc"][ch] ^ d[i], axis=1).sum(1)
+            node = int(ch[int(np.argmin(dist))]); lvl += 1
+            if lvl == 1:
+                nid = node
+        w = v3["weight"][node]
+        assert r3["word_of"][i] == (v3["word_id"][node] if w > 0 else -1) and r3["node_of"][i] == (nid if w > 0 else -1)
+    assert np.all(np.diff(r3["bow_ids"]) > 0) and abs(r3["bow_vals"].sum() - 1.0) < 1e-12
