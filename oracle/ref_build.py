@@ -287,3 +287,45 @@ def ref_search_for_initialization(K4, bounds4, scale_factors, f1, f2, prev_match
                                              arr[1].ctypes.data, arr[2].ctypes.data, arr[3].ctypes.data, len(arr[4]), arr[4].ctypes.data, arr[5].ctypes.data,
                                              arr[6].ctypes.data, arr[7].ctypes.data, pm.ctypes.data, m.ctypes.data)
     return n, m, pm
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the reference's own DBoW2 (oracle/_ref/libref_dbow2.so: TemplatedVocabulary / FORB / BowVector / FeatureVector / ScoringObject unmodified)
+_SOD = os.path.join(_HERE, "_ref", "libref_dbow2.so")
+_LIBD = None
+
+
+def dbow2_available():
+    return os.path.exists(_SOD)
+
+
+class RefVocabulary:
+    """ORBVocabulary of the reference: loadFromTextFile + transform(features, BowVector, FeatureVector, levelsup), reference object code."""
+
+    def __init__(self, path):
+        global _LIBD
+        if _LIBD is None:
+            _LIBD = ctypes.CDLL(_SOD)
+            _LIBD.ref_dbow2_load_text.restype = ctypes.c_void_p; _LIBD.ref_dbow2_load_text.argtypes = [ctypes.c_char_p]
+            _LIBD.ref_dbow2_destroy.argtypes = [ctypes.c_void_p]; _LIBD.ref_dbow2_size.argtypes = [ctypes.c_void_p]
+            _LIBD.ref_dbow2_transform.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int] + [ctypes.c_void_p] * 6
+        self.L = _LIBD
+        self.h = self.L.ref_dbow2_load_text(path.encode())
+        if not self.h:
+            raise RuntimeError("reference loadFromTextFile failed: " + path)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.ref_dbow2_destroy(self.h); self.h = None
+
+    def size(self):
+        return self.L.ref_dbow2_size(self.h)
+
+    def transform(self, desc, levelsup=4):
+        d = _c(desc, np.uint8).reshape(-1, 32); N = len(d); M = max(N, 1)
+        bi = np.zeros(M, np.int32); bv = np.zeros(M, np.float64); fn = np.zeros(M, np.int32); fs = np.zeros(M + 1, np.int32); fi = np.zeros(M, np.int32)
+        fc = ctypes.c_int(0)
+        nb = self.L.ref_dbow2_transform(self.h, N, d.ctypes.data, int(levelsup), bi.ctypes.data, bv.ctypes.data, fn.ctypes.data, fs.ctypes.data, fi.ctypes.data,
+                                        ctypes.addressof(fc))
+        nf = fc.value
+        return dict(bow_ids=bi[:nb].copy(), bow_vals=bv[:nb].copy(), fv=dict(nodes=fn[:nf].copy(), start=fs[:nf + 1].copy(), items=fi[:fs[nf]].copy()))

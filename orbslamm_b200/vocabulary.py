@@ -20,7 +20,18 @@ def from_nodes(k, L, parent, is_leaf, node_desc, weight):
     leaf = np.asarray(is_leaf, bool).copy(); leaf[0] = False
     word_id = np.full(n, -1, np.int32); word_id[leaf] = np.arange(int(leaf.sum()), dtype=np.int32)
     return dict(k=int(k), L=int(L), node_desc=np.ascontiguousarray(node_desc, np.uint8), child_start=child_start, child_ids=order.astype(np.int32),
-                word_id=word_id, weight=np.ascontiguousarray(weight, np.float64))
+                word_id=word_id, weight=np.ascontiguousarray(weight, np.float64), parent=parent.astype(np.int32), is_leaf=leaf)
+
+
+def save_text(vocab, path):
+    """Write the ORBvoc.txt format (TemplatedVocabulary::saveToTextFile, TemplatedVocabulary.h:1422-1447).  No trailing newline: the reference's
+    loader reads one more (empty) node line after a final newline (`while(!f.eof()) getline`, :1377-1380)."""
+    n = len(vocab["word_id"])
+    lines = ["%d %d 0 0" % (vocab["k"], vocab["L"])]
+    for i in range(1, n):
+        lines.append("%d %d %s %.17g" % (vocab["parent"][i], 1 if vocab["is_leaf"][i] else 0, " ".join(str(int(b)) for b in vocab["node_desc"][i]), vocab["weight"][i]))
+    with open(path, "w") as f:
+        f.write("\n".join(lines))
 
 
 def load_text(path):

@@ -201,6 +201,17 @@ def test_vocabulary_transform_cuda_equals_oracle(lib):
             assert np.array_equal(o["bow_ids"], r["bow_ids"]) and np.array_equal(o["bow_vals"], r["bow_vals"])
             for key in ("nodes", "start", "items"):
                 assert np.array_equal(o["fv"][key], r["fv"][key])
+    if ref_build.dbow2_available():                      # and directly against the reference's own DBoW2 object code
+        import tempfile, os
+        path = os.path.join(tempfile.mkdtemp(), "voc.txt")
+        V.save_text(v, path)
+        R = ref_build.RefVocabulary(path)
+        out = voc.transform(slab(frames, W, np.uint8, (32,)), [len(f) for f in frames], 4)
+        for f, o in zip(frames, out):
+            r = R.transform(f, 4)
+            assert np.array_equal(o["bow_ids"], r["bow_ids"]) and np.array_equal(o["bow_vals"], r["bow_vals"])
+            for key in ("nodes", "start", "items"):
+                assert np.array_equal(o["fv"][key], r["fv"][key])
     # the device FeatureVectors drive SearchByBoW (Tracking::TrackReferenceKeyFrame: ComputeBoW, then SearchByBoW(KF, F))
     out = voc.transform(slab(frames[:2], W, np.uint8, (32,)), [len(frames[0]), len(frames[1])], 2)
     m = ob.ORBmatcher(0.7, True)

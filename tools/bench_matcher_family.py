@@ -19,7 +19,7 @@ import kf_family as kff  # noqa: E402
 from helpers import slab  # noqa: E402
 
 B = int(os.environ.get("PAIRS", "32"))
-REP = 5
+REP = int(os.environ.get("REP", "5"))
 HAVE_REF = ref_build.matcher_available()
 
 
