@@ -73,59 +73,95 @@ __device__ void block_bitonic_sort(unsigned long long *keys, int n_pow2)
         }
 }
 
-// BowVector (v.addWeight in feature order, then L1 normalisation in ascending word order) and FeatureVector (fv.addFeature) of one frame
+// exclusive prefix sum of one int per thread over the block (<= 1024 threads); returns the thread's offset, *total = block sum
+__device__ __forceinline__ int block_exclusive_scan(int v, int *s_warp /*[32]*/, int *total)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    int inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += o; }
+    if (lane == 31) s_warp[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        int w = lane < nw ? s_warp[lane] : 0, x = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(0xffffffffu, x, d); if (lane >= d) x += o; }
+        s_warp[lane] = x - w;
+        if (lane == 31) *total = x;
+    }
+    __syncthreads();
+    const int off = s_warp[wid] + inc - v;
+    __syncthreads();
+    return off;
+}
+
+// BowVector (v.addWeight in feature order, then L1 normalisation in ascending word order) and FeatureVector (fv.addFeature) of one frame.
+// After the sort every word / node is a run of keys: the run heads are numbered by a block scan, each head thread sums its run in feature
+// order (runs are independent std::map entries), and only the L1 norm -- one fp64 sum over the ascending words -- stays sequential.
 __global__ void __launch_bounds__(1024)
 k_vocab_assemble(int slab, int n_pow2, const int *__restrict__ counts, const int *__restrict__ word_of, const int *__restrict__ node_of,
                  const double *__restrict__ weight_of, int *__restrict__ bow_ids, double *__restrict__ bow_vals, int *__restrict__ bow_counts,
                  int *__restrict__ fv_nodes, int *__restrict__ fv_start, int *__restrict__ fv_items, int *__restrict__ fv_counts)
 {
     extern __shared__ __align__(16) unsigned long long s_keys[];
-    __shared__ int s_n;
-    const int f = blockIdx.x, tid = threadIdx.x, N = counts[f];
+    __shared__ int s_warp[32], s_total, s_valid;
+    __shared__ double s_norm;
+    const int f = blockIdx.x, tid = threadIdx.x, nt = blockDim.x, N = counts[f];
     const size_t o = (size_t)f * slab;
+    const int per = (n_pow2 + nt - 1) / nt;                                   // contiguous keys per thread
     for (int pass = 0; pass < 2; pass++) {
         const int *key_of = pass == 0 ? word_of : node_of;
-        for (int t = tid; t < n_pow2; t += blockDim.x) {
+        for (int t = tid; t < n_pow2; t += nt) {
             unsigned long long k = ~0ull;
             if (t < N && key_of[o + t] >= 0) k = ((unsigned long long)(unsigned)key_of[o + t] << 32) | (unsigned)t;
             s_keys[t] = k;
         }
         __syncthreads();
         block_bitonic_sort(s_keys, n_pow2);
-        if (tid == 0) {
-            int n_out = 0;
+        // run heads in this thread's chunk
+        const int t0 = tid * per, t1 = min(t0 + per, n_pow2);
+        int heads = 0, valid = 0;
+        for (int t = t0; t < t1; t++) {
+            const unsigned long long k = s_keys[t];
+            if (k == ~0ull) break;
+            valid++;
+            if (t == 0 || (unsigned)(s_keys[t - 1] >> 32) != (unsigned)(k >> 32)) heads++;
+        }
+        int out = block_exclusive_scan(heads, s_warp, &s_total);
+        const int n_out = s_total;
+        block_exclusive_scan(valid, s_warp, &s_valid);
+        const int n_valid = s_valid;
+        int *st = fv_start + (size_t)f * (slab + 1);
+        for (int t = t0; t < t1; t++) {
+            const unsigned long long k = s_keys[t];
+            if (k == ~0ull) break;
+            const unsigned id = (unsigned)(k >> 32);
+            if (t != 0 && (unsigned)(s_keys[t - 1] >> 32) == id) continue;
             if (pass == 0) {
-                int t = 0;
-                while (t < n_pow2 && s_keys[t] != ~0ull) {
-                    const unsigned word = (unsigned)(s_keys[t] >> 32);
-                    double v = 0;
-                    bool first = true;
-                    while (t < n_pow2 && s_keys[t] != ~0ull && (unsigned)(s_keys[t] >> 32) == word) {
-                        const double w = weight_of[o + (unsigned)(s_keys[t] & 0xffffffffu)];
-                        v = first ? w : __dadd_rn(v, w);                // insert, then "vit->second += v" in feature order
-                        first = false; t++;
-                    }
-                    bow_ids[o + n_out] = (int)word; bow_vals[o + n_out] = v; n_out++;
-                }
-                double norm = 0.0;                                      // BowVector::normalize(L1), BowVector.cpp:62-84
-                for (int a = 0; a < n_out; a++) norm = __dadd_rn(norm, fabs(bow_vals[o + a]));
-                if (norm > 0.0) for (int a = 0; a < n_out; a++) bow_vals[o + a] = __ddiv_rn(bow_vals[o + a], norm);
-                bow_counts[f] = n_out;
-            } else {
-                int t = 0;
-                int *st = fv_start + (size_t)f * (slab + 1);
-                while (t < n_pow2 && s_keys[t] != ~0ull) {
-                    const unsigned node = (unsigned)(s_keys[t] >> 32);
-                    fv_nodes[o + n_out] = (int)node; st[n_out] = t; n_out++;
-                    while (t < n_pow2 && s_keys[t] != ~0ull && (unsigned)(s_keys[t] >> 32) == node) t++;
-                }
-                st[n_out] = t;
-                fv_counts[f] = n_out;
-                s_n = t;
-            }
+                double v = weight_of[o + (unsigned)(k & 0xffffffffu)];       // insert, then "vit->second += v" in feature order
+                for (int u = t + 1; u < n_pow2 && s_keys[u] != ~0ull && (unsigned)(s_keys[u] >> 32) == id; u++)
+                    v = __dadd_rn(v, weight_of[o + (unsigned)(s_keys[u] & 0xffffffffu)]);
+                bow_ids[o + out] = (int)id; bow_vals[o + out] = v;
+            } else { fv_nodes[o + out] = (int)id; st[out] = t; }
+            out++;
         }
         __syncthreads();
-        if (pass == 1) for (int t = tid; t < s_n; t += blockDim.x) fv_items[o + t] = (int)(s_keys[t] & 0xffffffffu);
+        if (pass == 0) {
+            double *s_vals = reinterpret_cast<double *>(s_keys);             // the keys of this pass are no longer needed
+            for (int a = tid; a < n_out; a += nt) s_vals[a] = bow_vals[o + a];
+            __syncthreads();
+            if (tid == 0) {                                                  // BowVector::normalize(L1), BowVector.cpp:62-84: one sum in ascending word order
+                double norm = 0.0;
+                for (int a = 0; a < n_out; a++) norm = __dadd_rn(norm, fabs(s_vals[a]));
+                s_norm = norm; bow_counts[f] = n_out;
+            }
+            __syncthreads();
+            const double norm = s_norm;
+            if (norm > 0.0) for (int a = tid; a < n_out; a += nt) bow_vals[o + a] = __ddiv_rn(s_vals[a], norm);
+        } else {
+            if (tid == 0) { st[n_out] = n_valid; fv_counts[f] = n_out; }
+            for (int t = tid; t < n_valid; t += nt) fv_items[o + t] = (int)(s_keys[t] & 0xffffffffu);
+        }
         __syncthreads();
     }
 }

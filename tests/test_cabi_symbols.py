@@ -11,12 +11,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def _declared():
     src = open(os.path.join(ROOT, "include", "orbslamm_b200.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(orb[smxo]_[a-z0-9_]+)\s*\(", src)))
+    return sorted(set(re.findall(r"\b(orb[smxofv]_[a-z0-9_]+)\s*\(", src)))
 
 
 def test_every_declared_symbol_is_exported(lib):
     names = _declared()
-    assert len(names) >= 30
+    assert len(names) >= 55 and "orbv_transform" in names and "orbf_track_frames" in names and "orbm_search_by_bow" in names
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/orbslamm_b200.h but not exported"
 
@@ -42,6 +42,12 @@ def test_argument_validation_needs_no_gpu(lib):
     assert lib.orbx_create(ctypes.byref(h), 1000, 1.2, 17, 20, 7, 0) == -1      # nlevels <= 16
     assert lib.orbx_create(ctypes.byref(h), 1000, 1.2, 8, 0, 7, 0) == -1        # thresholds >= 1
     assert b"" != lib.orbs_last_error()
+    lib.orbv_create.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 5
+    assert lib.orbv_create(ctypes.byref(h), 0, 10, 6, 100, None, None, None, None, None) == -1     # vocabulary arrays are required
+    cs = np.array([0, 1, 1], np.int32); z = np.zeros(64, np.uint8); w = np.zeros(2, np.float64); ids = np.zeros(2, np.int32)
+    assert lib.orbv_create(ctypes.byref(h), 0, 10, 6, 1, z.ctypes.data, cs.ctypes.data, ids.ctypes.data, ids.ctypes.data, w.ctypes.data) == -1   # a root alone is no tree
+    assert lib.orbv_create(ctypes.byref(h), 0, 10, 6, 2, z.ctypes.data, np.array([0, 2, 2], np.int32).ctypes.data, ids.ctypes.data, ids.ctypes.data,
+                           w.ctypes.data) == -1                                                                                  # child lists must cover n - 1 nodes
 
 
 def test_product_never_imports_the_oracle():

@@ -221,3 +221,33 @@ def test_vocabulary_transform_cuda_equals_oracle(lib):
     n_o, m_o = oracle.search_by_bow(0, frames[1], k["last"]["angle"], has, out[1]["fv"], frames[0], k["cur"]["angle"], np.ones(len(frames[0]), np.uint8), out[0]["fv"],
                                     0.7, True)
     assert n_o > 20 and nm[0] == n_o and np.array_equal(mt[0], m_o)
+
+
+def test_new_entry_points_reject_bad_arguments(lib):
+    """No exception crosses the C boundary: null pointers, missing optional blocks and oversize slabs return ORBS_E_INVALID with a message."""
+    import ctypes
+    import orbslamm_b200 as ob
+    m = ob.ORBmatcher()
+    h = m.handle
+    L = lib
+    z = np.zeros(64, np.int32)
+    assert L.orbm_project_points(h, 1, None, None, 8, None, None, None, None, None, 4, None, None, None, None, None, None, 0) == -1
+    assert L.orbm_search_best_in_window(h, 1, None, None, None, None, None, None, 4, None, None, None, None, None, None, None, 4, 50, None, 0, 5.99, None, None, 0) == -1
+    assert L.orbm_search_by_bow(h, 1, 7, *([None] * 4), 4, *([None] * 4), 4, *([None] * 4), 4, *([None] * 4), 4, 0.7, 0, None, None, None, 0) == -1
+    assert L.orbm_search_for_initialization(h, 0, *([None] * 5), 4, *([None] * 5), 4, None, 100, 0.9, 1, None, None, 0) == -1
+    assert L.orbm_get_features_in_area(h, 1, None, None, None, None, None, 4, None, None, None, None, 4, 0, None, None, 0) == -1
+    assert L.orbm_assign_features_to_grid(h, 1, None, None, None, 4, None, None, 0) == -1
+    o = ob.Optimizer()
+    assert L.orbo_optimize_sim3(o.handle, 1, *([None] * 12), 4, 10.0, 0, None, None, None, 0) == -1
+    assert b"" != L.orbs_last_error()
+    # triangulation mode without the epipolar block
+    d = np.zeros((4, 32), np.uint8); e = np.ones(4, np.uint8); c = np.array([4], np.int32); nodes = np.array([1], np.int32); st = np.array([0, 4], np.int32)
+    it = np.arange(4, dtype=np.int32); out = np.zeros(4, np.int32); nm = np.zeros(1, np.int32)
+    p = lambda a: a.ctypes.data
+    assert L.orbm_search_by_bow(h, 1, 1, p(d), None, p(e), p(c), 4, p(nodes), p(st), p(it), p(c), 1, p(d), None, p(e), p(c), 4, p(nodes), p(st), p(it), p(c), 1,
+                                0.6, 0, None, p(out), p(nm), 0) == -1
+    # ... and a well-formed minimal call succeeds (identical descriptors in one node: best == second -> the ratio test rejects)
+    nc = np.array([1], np.int32)
+    assert L.orbm_search_by_bow(h, 1, 0, p(d), None, p(e), p(c), 4, p(nodes), p(st), p(it), p(nc), 1, p(d), None, p(e), p(c), 4, p(nodes), p(st), p(it), p(nc), 1,
+                                0.6, 0, None, p(out), p(nm), 0) == 0
+    assert nm[0] == 0 and (out == -1).all()
