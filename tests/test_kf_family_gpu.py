@@ -238,7 +238,7 @@ def test_new_entry_points_reject_bad_arguments(lib):
     assert L.orbm_get_features_in_area(h, 1, None, None, None, None, None, 4, None, None, None, None, 4, 0, None, None, 0) == -1
     assert L.orbm_assign_features_to_grid(h, 1, None, None, None, 4, None, None, 0) == -1
     o = ob.Optimizer()
-    assert L.orbo_optimize_sim3(o.handle, 1, *([None] * 12), 4, 10.0, 0, None, None, None, 0) == -1
+    assert L.orbo_optimize_sim3(o.handle, 1, *([None] * 11), 4, 10.0, 0, None, None, None, 0) == -1
     assert b"" != L.orbs_last_error()
     # triangulation mode without the epipolar block
     d = np.zeros((4, 32), np.uint8); e = np.ones(4, np.uint8); c = np.array([4], np.int32); nodes = np.array([1], np.int32); st = np.array([0, 4], np.int32)
@@ -251,3 +251,62 @@ def test_new_entry_points_reject_bad_arguments(lib):
     assert L.orbm_search_by_bow(h, 1, 0, p(d), None, p(e), p(c), 4, p(nodes), p(st), p(it), p(nc), 1, p(d), None, p(e), p(c), 4, p(nodes), p(st), p(it), p(nc), 1,
                                 0.6, 0, None, p(out), p(nm), 0) == 0
     assert nm[0] == 0 and (out == -1).all()
+
+
+def test_device_resident_chain_equals_host_path(lib):
+    """ORBS_MEM_DEVICE: orbm_project_points -> orbm_search_best_in_window and orbv_transform -> orbm_search_by_bow chained on device buffers (no host
+    copies between the calls, one stream) give exactly what the host-buffer calls give."""
+    import ctypes
+    import torch
+    import orbslamm_b200 as ob
+    from orbslamm_b200 import vocabulary as V
+    c = kff.make_case(synth.KITTI, 2)
+    kf, pts, skip = c["kf"], c["pts"], c["skip"]
+    Bc = kff.CudaBackend()
+    host = kff.fuse_search(Bc, kf, 3.0, pts, skip)                          # host-buffer path (already checked against the oracle)
+    m = ob.ORBmatcher()
+    h, L = m.handle, lib
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    ptr = lambda t: ctypes.c_void_p(t.data_ptr())
+    N, M = len(kf["xy"]), len(skip)
+    T = kf["Tcw"]
+    view = ob.Projection.from_buffer_copy(bytes(oracle.make_projection(T[:3, :3], T[:3, 3], kf["K4"], kff.kf_bounds(kf), kf["log_sf"], 3.0, oracle.PROJ_CHECK_NORMAL,
+                                                                         Ow=kff.camera_centre(T))))
+    d_sf, d_X, d_N, d_mn, d_mx = dev(c["sf"]), dev(pts["Xw"]), dev(pts["normal"]), dev(pts["mf_min"]), dev(pts["mf_max"])
+    d_qc, d_fc = dev(np.array([M], np.int32)), dev(np.array([N], np.int32))
+    d_val = dev((1 - skip).astype(np.uint8))
+    d_uv = torch.zeros(M, 2, dtype=torch.float32, device="cuda"); d_rad = torch.zeros(M, dtype=torch.float32, device="cuda")
+    d_l0 = torch.zeros(M, dtype=torch.int32, device="cuda"); d_l1 = torch.zeros(M, dtype=torch.int32, device="cuda")
+    d_fxy, d_foc, d_fd, d_qd = dev(kf["xy"]), dev(kf["octave"]), dev(kf["desc"]), dev(pts["desc"])
+    d_bi = torch.zeros(M, dtype=torch.int32, device="cuda"); d_bd = torch.zeros(M, dtype=torch.int32, device="cuda")
+    gb = np.ascontiguousarray(kf["grid_bounds4"], np.float32); wo = np.ascontiguousarray(kf["win_origin2"], np.float32)
+    inv = np.ascontiguousarray(kf["inv_level_sigma2"], np.float32)
+    assert L.orbm_project_points(h, 1, ctypes.byref(view), ptr(d_sf), 8, ptr(d_X), ptr(d_N), ptr(d_mn), ptr(d_mx), ptr(d_qc), M, ptr(d_val), ptr(d_uv), ptr(d_rad),
+                                 ptr(d_l0), ptr(d_l1), None, 1) == 0
+    assert L.orbm_search_best_in_window(h, 1, gb.ctypes.data, wo.ctypes.data, ptr(d_fxy), ptr(d_foc), ptr(d_fd), ptr(d_fc), N, ptr(d_val), ptr(d_uv), ptr(d_rad),
+                                        ptr(d_l0), ptr(d_l1), ptr(d_qd), ptr(d_qc), M, 50, inv.ctypes.data, 8, 5.99, ptr(d_bi), ptr(d_bd), 1) == 0
+    m.synchronize()
+    assert np.array_equal(d_bi.cpu().numpy(), host)
+    # vocabulary transform of two frames on the device, its FeatureVectors straight into SearchByBoW
+    v = V.synthetic(10, 3, seed=8)
+    voc = V.ORBVocabulary(v)
+    b = kff.make_bow_case(synth.TUM, 1)
+    k1, k2 = b["kf1"], b["kf2"]
+    S = max(len(k1["desc"]), len(k2["desc"]))
+    desc = slab([k1["desc"], k2["desc"]], S, np.uint8, (32,)); cnt = np.array([len(k1["desc"]), len(k2["desc"])], np.int32)
+    ho = voc.transform(desc, cnt, 2)                                         # host-buffer path
+    d_desc, d_cnt = dev(desc), dev(cnt)
+    i32 = lambda *s: torch.zeros(*s, dtype=torch.int32, device="cuda")
+    d_bi2, d_bc, d_fn, d_fs, d_fi, d_fcn = i32(2, S), i32(2), i32(2, S), i32(2, S + 1), i32(2, S), i32(2)
+    d_bv = torch.zeros(2, S, dtype=torch.float64, device="cuda")
+    assert L.orbv_transform(voc._h, 2, ptr(d_desc), ptr(d_cnt), S, 2, None, None, ptr(d_bi2), ptr(d_bv), ptr(d_bc), ptr(d_fn), ptr(d_fs), ptr(d_fi), ptr(d_fcn), 1) == 0
+    torch.cuda.synchronize()
+    ang = dev(slab([k1["angle"], k2["angle"]], S, np.float32)); el = dev(slab([b["has1"], np.ones(len(k2["desc"]), np.uint8)], S, np.uint8))
+    d_m = i32(S); d_nm = i32(1)
+    # the vocabulary handle has its own stream: the matcher call is issued after the synchronise above
+    assert L.orbm_search_by_bow(h, 1, 0, ptr(d_desc[0]), ptr(ang[0]), ptr(el[0]), ptr(d_cnt[0:1]), S, ptr(d_fn[0]), ptr(d_fs[0]), ptr(d_fi[0]), ptr(d_fcn[0:1]), S,
+                                ptr(d_desc[1]), ptr(ang[1]), ptr(el[1]), ptr(d_cnt[1:2]), S, ptr(d_fn[1]), ptr(d_fs[1]), ptr(d_fi[1]), ptr(d_fcn[1:2]), S,
+                                0.7, 1, None, ptr(d_m), ptr(d_nm), 1) == 0
+    m.synchronize()
+    n_o, m_o = oracle.search_by_bow(0, k1["desc"], k1["angle"], b["has1"], ho[0]["fv"], k2["desc"], k2["angle"], np.ones(len(k2["desc"]), np.uint8), ho[1]["fv"], 0.7, True)
+    assert n_o > 50 and int(d_nm.cpu()[0]) == n_o and np.array_equal(d_m.cpu().numpy()[:len(k1["desc"])], m_o)
