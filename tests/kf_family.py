@@ -363,3 +363,73 @@ def make_bow_case(cam, stream_id, perturb=False):
     ls2 = (kf1["scale_factors"].astype(np.float64) ** 2).astype(F32)
     tri1 = (rng.random(len(kf1["xy"])) < 0.55).astype(np.uint8); tri2 = (rng.random(len(kf2["xy"])) < 0.55).astype(np.uint8)   # features WITH a map point
     return dict(kf1=kf1, kf2=kf2, fv1=fv1, fv2=fv2, has1=p["has1"], has2=p["has2"], tri1=tri1, tri2=tri2, ex=ex, ey=ey, F12=F12, ls2=ls2)
+
+
+# ------------------------------------------------------------------ golden vectors (tools/make_golden.py, tests/test_golden_*.py)
+GOLDEN_CAM = dict(synth.TUM); GOLDEN_CAM.update(w=400, h=300, nfeatures=400, cx=200.0, cy=150.0)
+
+
+def _bow(B, mode, d1, a1, e1, fv1, d2, a2, e2, fv2, ratio, ori, epi=None):
+    if isinstance(B, OracleBackend):
+        return oracle.search_by_bow(mode, d1, a1, e1, fv1, d2, a2, e2, fv2, ratio, ori, epi)
+    m = B.ob.ORBmatcher(ratio, ori)
+    tri = None
+    if epi is not None:
+        tri = dict(xy1=epi["xy1"][None], xy2=epi["xy2"][None], octave2=epi["octave2"][None], F12=np.asarray(epi["F12"], F32).reshape(1, 9),
+                   epipole=np.array([[epi["ex"], epi["ey"]]], F32), scale_factors2=epi["scale_factors2"], level_sigma2_2=epi["level_sigma2_2"])
+    nm, mt = m.SearchByBoW(d1[None], a1[None], np.asarray(e1, np.uint8)[None], [len(d1)], [fv1], d2[None], a2[None], np.asarray(e2, np.uint8)[None], [len(d2)], [fv2], tri)
+    return int(nm[0]), mt[0]
+
+
+def golden_outputs(B):
+    """Every member of the widened path on one 400x300 / 400-feature case, for backend B (oracle or CUDA): a flat dict of arrays."""
+    from orbslamm_b200 import vocabulary as V
+    out = {}
+    c = make_case(GOLDEN_CAM, 21, distorted_bounds=True)
+    kf, pts, skip, held, k = c["kf"], c["pts"], c["skip"], c["held"], c["k"]
+    Scw = sim3_of(kf["Tcw"], 1.21)
+    n, fm = search_kf_sim3(B, kf, Scw, 10, pts, skip, held)
+    out["search_kf_sim3"] = np.concatenate([fm, [n]])
+    out["fuse_kf"] = fuse_search(B, kf, 3.0, pts, skip)
+    out["fuse_sim3"] = fuse_search(B, kf, 4.0, pts, skip, Scw=Scw)
+    has = (np.random.default_rng(3).random(len(skip)) < 0.85).astype(np.uint8)
+    cur = dict(kf); cur["grid_bounds4"] = k["bounds"].astype(F32)
+    n, fm = search_frame_kf(B, cur, k["Tcw"], k["K4"], k["bounds"], kf["log_sf"], c["sf"], held, has, skip, pts, c["last"]["angle"], 10.0, 100, True)
+    out["search_frame_kf"] = np.concatenate([fm, [n]])
+    p = make_sim3_pair(GOLDEN_CAM, 21)
+    n, m12 = search_by_sim3(B, p["kf1"], p["kf2"], p["s12"], p["R12"], p["t12"], 7.5, p["has1"], p["pts1"], p["has2"], p["pts2"], p["m12"])
+    out["search_by_sim3"] = np.concatenate([m12, [n]])
+    b = make_bow_case(GOLDEN_CAM, 21, True)
+    k1, k2 = b["kf1"], b["kf2"]
+    n, m = _bow(B, 0, k1["desc"], k1["angle"], b["has1"], b["fv1"], k2["desc"], k2["angle"], b["has2"], b["fv2"], 0.75, True)
+    out["bow_kf_kf"] = np.concatenate([m, [n]])
+    epi = dict(xy1=k1["xy"], xy2=k2["xy"], octave2=k2["octave"], F12=b["F12"], ex=b["ex"], ey=b["ey"], scale_factors2=k2["scale_factors"], level_sigma2_2=b["ls2"])
+    n, m = _bow(B, 1, k1["desc"], k1["angle"], 1 - b["tri1"], b["fv1"], k2["desc"], k2["angle"], 1 - b["tri2"], b["fv2"], 0.6, False, epi)
+    out["triangulation"] = np.concatenate([m, [n]])
+    l, cu = k["last"], k["cur"]
+    pm = np.stack([l["x"], l["y"]], 1).astype(F32)
+    if isinstance(B, OracleBackend):
+        n, m, pm2 = oracle.search_for_initialization(oracle.grid_params(*k["bounds"]), l, cu, pm, 100, 0.9, True)
+    else:
+        mi = B.ob.ORBmatcher(0.9, True)
+        nm, mt, pmo = mi.SearchForInitialization(k["bounds"], l["octave"][None], l["angle"][None], l["desc"][None], [len(l["x"])],
+                                                 np.stack([cu["x"], cu["y"]], 1).astype(F32)[None], cu["octave"][None], cu["angle"][None], cu["desc"][None], [len(cu["x"])],
+                                                 pm[None], 100)
+        n, m, pm2 = int(nm[0]), mt[0], pmo[0]
+    out["init"] = np.concatenate([m, [n]]); out["init_prev"] = pm2
+    voc = V.synthetic(6, 3, seed=9)
+    if isinstance(B, OracleBackend):
+        t = oracle.vocab_transform(voc, cu["desc"], 2)
+    else:
+        t = V.ORBVocabulary(voc).transform(cu["desc"][None], [len(cu["desc"])], 2)[0]
+    out["voc_bow_ids"], out["voc_bow_vals"] = t["bow_ids"], t["bow_vals"]
+    out["voc_fv_nodes"], out["voc_fv_start"], out["voc_fv_items"] = t["fv"]["nodes"], t["fv"]["start"], t["fv"]["items"]
+    s = make_sim3_opt_case(GOLDEN_CAM, 21, n_outliers=6)
+    if isinstance(B, OracleBackend):
+        r = oracle.optimize_sim3(s["init"], s["valid"], s["P1c"], s["P2c"], s["obs1"], s["obs2"], s["w1"], s["w2"], s["K1"], s["K2"], 10.0, False)
+        out["sim3"], out["sim3_inlier"] = r["sim3"], np.concatenate([r["inlier"], [r["n_in"]]])
+    else:
+        S, inl, nin, _ = B.ob.Optimizer().OptimizeSim3(s["init"][None], s["valid"][None], s["P1c"][None], s["P2c"][None], s["obs1"][None], s["obs2"][None], s["w1"][None],
+                                                       s["w2"][None], s["K1"][None], s["K2"][None], [len(s["valid"])], 10.0, False)
+        out["sim3"], out["sim3_inlier"] = S[0], np.concatenate([inl[0], [nin[0]]])
+    return out

@@ -36,3 +36,20 @@ def test_optimizer_golden():
     r = oracle.bundle_adjust(d["ba_poses0"], d["ba_fixed"], d["ba_intr"], d["ba_points0"], d["ba_kf"], d["ba_pt"], d["ba_uv"], d["ba_w"], True, 5, 10, True)
     assert [r["lm_iterations"], r["lm_trials"]] == d["ba_iters"].tolist()
     assert np.allclose(r["poses"], d["ba_poses"], rtol=0, atol=1e-7) and np.allclose(r["points"], d["ba_points"], rtol=0, atol=1e-6)
+
+
+def test_kf_family_golden():
+    """The widened rows (rest of ORBmatcher, OptimizeSim3, DBoW2 transform): the oracle reproduces tests/golden/kf_family_400x300.npz, which was
+    written only after the reference's own object code (oracle/_ref) agreed with it member by member (tools/make_golden.py)."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import kf_family as kff
+    d = np.load(os.path.join(G, "kf_family_400x300.npz"))
+    got = kff.golden_outputs(kff.OracleBackend())
+    assert set(got) == set(d.files)
+    for k in d.files:
+        if k == "sim3":
+            assert np.allclose(got[k], d[k], rtol=0, atol=1e-9), k
+        else:
+            assert np.array_equal(got[k], d[k]), k
+    assert d["search_kf_sim3"][-1] > 10 and d["fuse_kf"].max() >= 0 and d["bow_kf_kf"][-1] > 20 and d["init"][-1] > 20 and d["sim3_inlier"][-1] >= 10

@@ -44,3 +44,18 @@ def test_optimizer_golden(lib):
     assert [r["lm_iterations"], r["lm_trials"]] == d["ba_iters"].tolist()
     assert np.abs(r["poses"] - d["ba_poses"]).max() < 1e-5 * np.abs(d["ba_poses"]).max()
     assert np.abs(r["points"] - d["ba_points"]).max() < 1e-5 * np.abs(d["ba_points"]).max()
+
+
+def test_kf_family_golden_gpu(lib):
+    """CUDA path against tests/golden/kf_family_400x300.npz (rest of ORBmatcher, OptimizeSim3, DBoW2 transform): exact, Sim3 to 1e-5 relative."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import kf_family as kff
+    d = np.load(os.path.join(G, "kf_family_400x300.npz"))
+    got = kff.golden_outputs(kff.CudaBackend())
+    assert set(got) == set(d.files)
+    for k in d.files:
+        if k == "sim3":
+            assert np.abs(got[k] - d[k]).max() < 1e-5 * np.abs(d[k]).max(), k
+        else:
+            assert np.array_equal(got[k], d[k]), k

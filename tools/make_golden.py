@@ -63,3 +63,35 @@ np.savez_compressed(os.path.join(out, "optimize_small.npz"), po_T0=T0, po_Xw=Xw_
                     ba_iters=np.array([rb["lm_iterations"], rb["lm_trials"]]))
 for f in sorted(os.listdir(out)):
     print(f, os.path.getsize(os.path.join(out, f)))
+
+# 4. the widened rows (rest of ORBmatcher, OptimizeSim3, DBoW2 transform) on a 400x300 case: outputs only -- the inputs are regenerated from the seeded
+#    synthetic stream through the (golden-checked) oracle extractor.  Written only if the reference's object code agrees where it exists.
+import kf_family as kff  # noqa: E402
+gold = kff.golden_outputs(kff.OracleBackend())
+assert ref_build.matcher_available() and ref_build.dbow2_available(), "oracle/_ref matcher / DBoW2 must be built to write these golden vectors"
+c = kff.make_case(kff.GOLDEN_CAM, 21, distorted_bounds=True)
+Scw = kff.sim3_of(c["kf"]["Tcw"], 1.21)
+n, fm = ref_build.ref_search_kf_sim3(c["kf"], Scw, 10, c["pts"], c["skip"], c["held"])
+assert np.array_equal(np.concatenate([fm, [n]]), gold["search_kf_sim3"])
+assert np.array_equal(ref_build.ref_fuse_kf(c["kf"], 3.0, c["pts"], c["skip"], c["held"])[1], gold["fuse_kf"])
+assert np.array_equal(ref_build.ref_fuse_sim3(c["kf"], Scw, 4.0, c["pts"], c["skip"], c["held"])[1], gold["fuse_sim3"])
+p = kff.make_sim3_pair(kff.GOLDEN_CAM, 21)
+n, m12 = ref_build.ref_search_by_sim3(p["kf1"], p["kf2"], p["s12"], p["R12"], p["t12"], 7.5, p["has1"], p["pts1"], p["has2"], p["pts2"], p["m12"])
+assert np.array_equal(np.concatenate([m12, [n]]), gold["search_by_sim3"])
+b = kff.make_bow_case(kff.GOLDEN_CAM, 21, True)
+n, m = ref_build.ref_search_by_bow_kf_kf(b["kf1"], b["has1"], b["fv1"], b["kf2"], b["has2"], b["fv2"], 0.75, True)
+assert np.array_equal(np.concatenate([m, [n]]), gold["bow_kf_kf"])
+n, m = ref_build.ref_search_for_triangulation(b["kf1"], b["tri1"], b["fv1"], b["kf2"], b["tri2"], b["fv2"], b["ls2"], b["F12"], 0.6, False)
+assert np.array_equal(np.concatenate([m, [n]]), gold["triangulation"])
+k = c["k"]
+n, m, pm = ref_build.ref_search_for_initialization(k["K4"], k["bounds"], c["sf"], k["last"], k["cur"], np.stack([k["last"]["x"], k["last"]["y"]], 1), 100, 0.9, True)
+assert np.array_equal(np.concatenate([m, [n]]), gold["init"]) and np.array_equal(pm, gold["init_prev"])
+import tempfile  # noqa: E402
+from orbslamm_b200 import vocabulary as V  # noqa: E402
+vp = os.path.join(tempfile.mkdtemp(), "voc.txt")
+V.save_text(V.synthetic(6, 3, seed=9), vp)
+t = ref_build.RefVocabulary(vp).transform(k["cur"]["desc"], 2)
+assert np.array_equal(t["bow_ids"], gold["voc_bow_ids"]) and np.array_equal(t["bow_vals"], gold["voc_bow_vals"]) and np.array_equal(t["fv"]["items"], gold["voc_fv_items"])
+np.savez_compressed(os.path.join(out, "kf_family_400x300.npz"), **gold)
+for f in sorted(os.listdir(out)):
+    print(f, os.path.getsize(os.path.join(out, f)))
