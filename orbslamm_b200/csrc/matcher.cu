@@ -852,8 +852,8 @@ k_bow_finish(int slab1, const int *__restrict__ counts1, int check_ori, int *__r
     if (tid == 0) nmatches[f] = s_n;
 }
 
-// ORBmatcher::SearchForInitialization (:407-522): one warp per frame pair walks the level-0 keypoints of F1 in order (a later keypoint may
-// steal a feature of F2 from an earlier one, so the loop is a chain); the lanes scan the grid cells of the window.
+// ORBmatcher::SearchForInitialization (:407-522): one CTA per frame pair walks the level-0 keypoints of F1 in order (a later keypoint may
+// steal a feature of F2 from an earlier one, so the loop is a chain); the threads scan the grid cells of the window.
 struct InitArgs {
     int slab1, slab2;
     GridParams g;
@@ -867,21 +867,25 @@ struct InitArgs {
     int *nmatches;
 };
 
-__global__ void __launch_bounds__(32)
+constexpr int kInitThreads = 256;
+
+__global__ void __launch_bounds__(kInitThreads)
 k_search_init(const InitArgs A)
 {
     __shared__ int s_hist[kHisto], s_keep[3];
-    const int f = blockIdx.x, lane = threadIdx.x;
+    __shared__ unsigned long long s_b1[kInitThreads / 32], s_b2[kInitThreads / 32];
+    __shared__ int s_cnt;
+    const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nt = blockDim.x;
     const int N1 = A.counts1[f], N2 = A.counts2[f];
     const size_t o1 = (size_t)f * A.slab1, o2 = (size_t)f * A.slab2;
     int *matched_dist = A.matched_dist + o2, *matches21 = A.matches21 + o2, *matches12 = A.matches12 + o1, *rot_bin = A.rot_bin + o1;
     const float2 *xy2 = A.xy2 + o2; const int *octave2 = A.octave2 + o2; const uint4 *desc2 = A.desc2 + 2 * o2;
     const int *cs = A.cell_start + (size_t)f * (kGridCells + 1); const int *items = A.cell_items + o2;
-    for (int i = lane; i < N2; i += 32) { matched_dist[i] = 0x7fffffff; matches21[i] = -1; }
-    for (int i = lane; i < N1; i += 32) { matches12[i] = -1; rot_bin[i] = -1; }
-    if (lane < kHisto) s_hist[lane] = 0;
-    __syncwarp();
-    int nmatches = 0;
+    for (int i = tid; i < N2; i += nt) { matched_dist[i] = 0x7fffffff; matches21[i] = -1; }
+    for (int i = tid; i < N1; i += nt) { matches12[i] = -1; rot_bin[i] = -1; }
+    if (tid < kHisto) s_hist[tid] = 0;
+    if (tid == 0) s_cnt = 0;
+    __syncthreads();
     for (int i1 = 0; i1 < N1; i1++) {
         if (A.octave1[o1 + i1] > 0) continue;
         const float2 uv = A.prev_matched[o1 + i1];
@@ -890,7 +894,7 @@ k_search_init(const InitArgs A)
         const uint4 qa = __ldg(&A.desc1[2 * (o1 + i1)]), qb = __ldg(&A.desc1[2 * (o1 + i1) + 1]);
         unsigned long long b1 = kNoKey, b2 = kNoKey;
         const int ncy = w.r1 - w.r0 + 1, ncells = (w.c1 - w.c0 + 1) * ncy;
-        for (int c = lane; c < ncells; c += 32) {
+        for (int c = tid; c < ncells; c += nt) {
             const int ix = w.c0 + c / ncy, iy = w.r0 + c % ncy;
             const int cell = ix * kGridRows + iy;
             const int je = cs[cell + 1];
@@ -903,36 +907,44 @@ k_search_init(const InitArgs A)
                 if (key < b1) { b2 = b1; b1 = key; } else if (key < b2) b2 = key;
             }
         }
+        // block-wide smallest and second smallest key (keys are unique: they contain the feature index)
         unsigned long long m1 = b1;
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) { const unsigned long long o = __shfl_xor_sync(0xffffffffu, m1, d); m1 = o < m1 ? o : m1; }
         unsigned long long m2 = (b1 == m1) ? b2 : b1;
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) { const unsigned long long o = __shfl_xor_sync(0xffffffffu, m2, d); m2 = o < m2 ? o : m2; }
-        if (m1 == kNoKey) continue;
-        const int best = (int)(m1 >> 32), bidx = (int)(m1 & 0xfffff);
-        const float best2f = m2 == kNoKey ? 2147483648.0f : (float)(int)(m2 >> 32);          // (float)INT_MAX
-        if (best <= ORBM_TH_LOW && (float)best < __fmul_rn(best2f, A.ratio)) {
-            if (lane == 0) {
+        if (lane == 0) { s_b1[wid] = m1; s_b2[wid] = m2; }
+        __syncthreads();
+        m1 = kNoKey; m2 = kNoKey;
+#pragma unroll
+        for (int q = 0; q < kInitThreads / 32; q++) {
+            const unsigned long long x1 = s_b1[q], x2 = s_b2[q];
+            if (x1 < m1) { m2 = m1 < x2 ? m1 : x2; m1 = x1; } else { m2 = x1 < m2 ? x1 : m2; }
+        }
+        if (m1 != kNoKey) {
+            const int best = (int)(m1 >> 32), bidx = (int)(m1 & 0xfffff);
+            const float best2f = m2 == kNoKey ? 2147483648.0f : (float)(int)(m2 >> 32);          // (float)INT_MAX
+            if (best <= ORBM_TH_LOW && (float)best < __fmul_rn(best2f, A.ratio) && tid == 0) {
                 const int prev = matches21[bidx];
                 if (prev >= 0) matches12[prev] = -1;
                 matches12[i1] = bidx; matches21[bidx] = i1; matched_dist[bidx] = best;
                 if (A.check_ori) { const int bin = rot_hist_bin(A.angle1[o1 + i1], A.angle2[o2 + bidx]); rot_bin[i1] = bin; s_hist[bin]++; }
             }
-            __syncwarp();
         }
+        __syncthreads();          // the update is visible to every thread of the next step; s_b1 / s_b2 may be rewritten
     }
-    __syncwarp();
     if (A.check_ori) {
-        if (lane == 0) three_maxima_dev(s_hist, s_keep);
-        __syncwarp();
-        for (int i = lane; i < N1; i += 32) { const int b = rot_bin[i]; if (b >= 0 && b != s_keep[0] && b != s_keep[1] && b != s_keep[2]) matches12[i] = -1; }
-        __syncwarp();
+        if (tid == 0) three_maxima_dev(s_hist, s_keep);
+        __syncthreads();
+        for (int i = tid; i < N1; i += nt) { const int b = rot_bin[i]; if (b >= 0 && b != s_keep[0] && b != s_keep[1] && b != s_keep[2]) matches12[i] = -1; }
+        __syncthreads();
     }
-    for (int i = lane; i < N1; i += 32) if (matches12[i] >= 0) { nmatches++; A.prev_matched[o1 + i] = xy2[matches12[i]]; }
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) nmatches += __shfl_xor_sync(0xffffffffu, nmatches, d);
-    if (lane == 0) A.nmatches[f] = nmatches;
+    int nmatches = 0;
+    for (int i = tid; i < N1; i += nt) if (matches12[i] >= 0) { nmatches++; A.prev_matched[o1 + i] = xy2[matches12[i]]; }
+    if (nmatches) atomicAdd(&s_cnt, nmatches);
+    __syncthreads();
+    if (tid == 0) A.nmatches[f] = s_cnt;
 }
 
 }  // namespace orbs
@@ -1340,7 +1352,7 @@ int orbm_search_for_initialization(orbm_handle *h, int n_pairs, const float *bou
     A.cell_start = h->cell_start.as<int>(); A.cell_items = h->cell_items.as<int>();
     if (memspace == ORBS_MEM_HOST) ORBS_CUDA(cudaMemsetAsync(A.matches12, 0xff, n1 * sizeof(int), h->stream));
     k_grid_build<<<n_pairs, 512, 0, h->stream>>>(slab2, A.g, A.xy2, A.counts2, h->cell_start.as<int>(), h->cell_items.as<int>());
-    k_search_init<<<n_pairs, 32, 0, h->stream>>>(A);
+    k_search_init<<<n_pairs, kInitThreads, 0, h->stream>>>(A);
     h->launches += 2;
     ORBS_CUDA(cudaGetLastError());
     return S.finish();

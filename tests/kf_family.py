@@ -338,9 +338,9 @@ def epipole_and_F(kf1, kf2):
     T1 = np.asarray(kf1["Tcw"], F32).reshape(4, 4); T2 = np.asarray(kf2["Tcw"], F32).reshape(4, 4)
     Cw = camera_centre(T1)
     C2 = (gemm32(T2[:3, :3], Cw.reshape(3, 1)).ravel() + T2[:3, 3]).astype(F32)
-    invz = F32(1.0) / C2[2]
-    fx, fy, cx, cy = [F32(v) for v in kf2["K4"]]
-    ex = F32(F32(F32(fx * C2[0]) * invz) + cx); ey = F32(F32(F32(fy * C2[1]) * invz) + cy)
+    with np.errstate(divide="ignore", invalid="ignore"):          # cameras that differ by an in-plane translation: the epipole is at infinity, as in the reference
+        invz = F32(1.0) / C2[2]
+        ex = F32(F32(F32(F32(kf2["K4"][0]) * C2[0]) * invz) + F32(kf2["K4"][2])); ey = F32(F32(F32(F32(kf2["K4"][1]) * C2[1]) * invz) + F32(kf2["K4"][3]))
     R1, t1, R2, t2 = T1[:3, :3].astype(np.float64), T1[:3, 3].astype(np.float64), T2[:3, :3].astype(np.float64), T2[:3, 3].astype(np.float64)
     R12 = R1 @ R2.T; t12 = -R12 @ t2 + t1
     tx = np.array([[0, -t12[2], t12[1]], [t12[2], 0, -t12[0]], [-t12[1], t12[0], 0]])

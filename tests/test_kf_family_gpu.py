@@ -310,3 +310,34 @@ def test_device_resident_chain_equals_host_path(lib):
     m.synchronize()
     n_o, m_o = oracle.search_by_bow(0, k1["desc"], k1["angle"], b["has1"], ho[0]["fv"], k2["desc"], k2["angle"], np.ones(len(k2["desc"]), np.uint8), ho[1]["fv"], 0.7, True)
     assert n_o > 50 and int(d_nm.cpu()[0]) == n_o and np.array_equal(d_m.cpu().numpy()[:len(k1["desc"])], m_o)
+
+
+def test_degenerate_inputs(lib):
+    """Empty and disjoint inputs: keyframes without features or without common vocabulary nodes, frames without level-0 keypoints, a vocabulary
+    transform of zero descriptors -- every call succeeds and reports zero matches."""
+    import orbslamm_b200 as ob
+    from orbslamm_b200 import vocabulary as V
+    rng = np.random.default_rng(0)
+    d1 = rng.integers(0, 256, (2, 40, 32), dtype=np.uint8); d2 = rng.integers(0, 256, (2, 50, 32), dtype=np.uint8)
+    a1 = np.zeros((2, 40), np.float32); a2 = np.zeros((2, 50), np.float32)
+    fvA = oracle.feature_vector(np.arange(40) % 4 * 2)              # nodes 0, 2, 4, 6
+    fvB = oracle.feature_vector(np.arange(50) % 5 * 2 + 1)          # nodes 1, 3, 5, 7, 9: nothing in common
+    empty = dict(nodes=np.zeros(0, np.int32), start=np.zeros(1, np.int32), items=np.zeros(0, np.int32))
+    m = ob.ORBmatcher(0.9, True)
+    nm, mt = m.SearchByBoW(d1, a1, np.ones((2, 40), np.uint8), [40, 0], [fvA, empty], d2, a2, np.ones((2, 50), np.uint8), [50, 50], [fvB, fvB])
+    assert nm.tolist() == [0, 0] and (mt == -1).all()
+    # same nodes on both sides but nothing eligible on side 1
+    nm, mt = m.SearchByBoW(d1[:1], a1[:1], np.zeros((1, 40), np.uint8), [40], [fvA], d1[:1], a1[:1], np.ones((1, 40), np.uint8), [40], [fvA])
+    assert nm.tolist() == [0] and (mt == -1).all()
+    # identical keyframes: every feature matches itself (distance 0 < ratio * second best)
+    nm, mt = m.SearchByBoW(d1[:1], a1[:1], np.ones((1, 40), np.uint8), [40], [fvA], d1[:1], a1[:1], np.ones((1, 40), np.uint8), [40], [fvA])
+    n_o, m_o = oracle.search_by_bow(0, d1[0], a1[0], np.ones(40, np.uint8), fvA, d1[0], a1[0], np.ones(40, np.uint8), fvA, 0.9, True)
+    assert nm[0] == n_o == 40 and np.array_equal(mt[0], m_o) and np.array_equal(m_o, np.arange(40))
+    # SearchForInitialization: no level-0 keypoints in F1 / an empty F2
+    oc1 = np.ones((2, 40), np.int32); oc1[1] = 0
+    xy2 = rng.uniform(10, 300, (2, 50, 2)).astype(np.float32)
+    nm, mt, pm = m.SearchForInitialization([0, 0, 400, 300], oc1, a1, d1, [40, 40], xy2, np.zeros((2, 50), np.int32), a2, d2, [50, 0], xy2[:, :40].copy(), 100)
+    assert nm.tolist() == [0, 0] and (mt == -1).all() and np.array_equal(pm, xy2[:, :40])
+    voc = V.ORBVocabulary(V.synthetic(4, 2, seed=1))
+    t = voc.transform(np.zeros((1, 8, 32), np.uint8), [0], 4)[0]
+    assert len(t["bow_ids"]) == 0 and len(t["fv"]["nodes"]) == 0 and t["fv"]["start"].tolist() == [0]
