@@ -391,6 +391,21 @@ int orbo_bundle_adjust(orbo_handle *h, int K, float *poses, const uint8_t *fixed
                        int two_stage, int its0, int its1, int robust, const volatile int *stop_flag,
                        double *e_chi2, uint8_t *e_depth_ok, uint8_t *e_outlier, int32_t *stats);
 
+/* Sim3Solver (S/src/Sim3Solver.cc), the data-parallel part of the RANSAC.  ComputeSim3 (Horn's closed form on three points, :226-338) stays with
+ * the caller: the random index triples do not depend on the inlier counts, so all hypotheses of a solver (<= mRansacMaxIts = 300) can be
+ * generated first and checked in ONE call; the caller then walks the counts in order and applies the rule of iterate() (:176-194) unchanged.
+ *   orbo_sim3_prepare: the constructor's per-correspondence data for one keyframe (:84-103, :419-437): max_err i32[N] = (size_t)(9.210 *
+ *     mvLevelSigma2[octave]) -- the reference stores the thresholds in std::vector<size_t>, i.e. truncated -- and p2d f32[N,2] =
+ *     FromCameraToImage(X3Dc, K).  level_sigma2 f32[nlevels] and K4 are HOST arrays.
+ *   orbo_sim3_check_inliers: CheckInliers (:340-365) with Project (:392-417) for n_hyp hypotheses: T12 / T21 f32[n_hyp,16] (mT12i / mT21i,
+ *     row-major), X3Dc1 / X3Dc2 f32[N,3] (mvX3Dc1 / 2), P1im1 / P2im2 f32[N,2], K1 / K2 f32[4] HOST.
+ *     out: inliers u8[n_hyp,N] (mvbInliersi per hypothesis), n_inliers i32[n_hyp] (mnInliersi). */
+int orbo_sim3_prepare(orbo_handle *h, int N, const float *X3Dc, const int32_t *octave, const float *level_sigma2, int nlevels, const float *K4,
+                      int32_t *max_err, float *p2d, int memspace);
+int orbo_sim3_check_inliers(orbo_handle *h, int n_hyp, const float *T12, const float *T21, int N, const float *X3Dc1, const float *X3Dc2, const float *P1im1,
+                            const float *P2im2, const int32_t *max_err1, const int32_t *max_err2, const float *K1, const float *K2, uint8_t *inliers,
+                            int32_t *n_inliers, int memspace);
+
 /* Optimizer::OptimizeSim3(pKF1, pKF2, vpMatches1, g2oS12, th2, bFixScale) (S/src/Optimizer.cc:1348-1543) for n_pairs independent keyframe
  * pairs: one VertexSim3Expmap against fixed points, EdgeSim3ProjectXYZ (x1 = S12 X2) + EdgeInverseSim3ProjectXYZ (x2 = S21 X1) per
  * correspondence with Huber kernels (delta = sqrt(th2)), g2o Levenberg on the dense 7x7 system, numeric Jacobians (central differences,

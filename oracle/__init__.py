@@ -533,3 +533,29 @@ def vocab_transform(vocab, desc, levelsup=4):
     nf = fc.value
     return dict(word_of=wo[:N], node_of=no[:N], bow_ids=bi[:nb].copy(), bow_vals=bv[:nb].copy(),
                 fv=dict(nodes=fn[:nf].copy(), start=fs[:nf + 1].copy(), items=fi[:fs[nf]].copy()))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Sim3Solver: thresholds, FromCameraToImage, CheckInliers over a batch of RANSAC hypotheses
+def sim3_prepare(X3Dc1, X3Dc2, oct1, oct2, level_sigma2, K1, K2):
+    """The constructor's per-correspondence data: (max_err1, max_err2 i32[N], P1im1, P2im2 f32[N,2])."""
+    X1 = np.ascontiguousarray(X3Dc1, np.float32); X2 = np.ascontiguousarray(X3Dc2, np.float32); N = len(X1)
+    o1 = np.ascontiguousarray(oct1, np.int32); o2 = np.ascontiguousarray(oct2, np.int32); ls = np.ascontiguousarray(level_sigma2, np.float32)
+    k1 = np.ascontiguousarray(K1, np.float32); k2 = np.ascontiguousarray(K2, np.float32)
+    m1 = np.zeros(N, np.int32); m2 = np.zeros(N, np.int32); p1 = np.zeros((N, 2), np.float32); p2 = np.zeros((N, 2), np.float32)
+    L = lib()
+    L.oracle_sim3_max_error(N, _p(o1, _i32p), _p(ls, _f32p), _p(m1, _i32p)); L.oracle_sim3_max_error(N, _p(o2, _i32p), _p(ls, _f32p), _p(m2, _i32p))
+    L.oracle_sim3_from_camera_to_image(N, _p(X1, _f32p), _p(k1, _f32p), _p(p1, _f32p)); L.oracle_sim3_from_camera_to_image(N, _p(X2, _f32p), _p(k2, _f32p), _p(p2, _f32p))
+    return m1, m2, p1, p2
+
+
+def sim3_check_inliers(T12, T21, X3Dc1, X3Dc2, P1im1, P2im2, max_err1, max_err2, K1, K2):
+    """Sim3Solver::CheckInliers for n_hyp hypotheses: returns (inliers u8[n_hyp, N], n_inliers i32[n_hyp])."""
+    a = [np.ascontiguousarray(x, np.float32) for x in (T12, T21, X3Dc1, X3Dc2, P1im1, P2im2)]
+    nh = a[0].reshape(-1, 16).shape[0]; N = len(a[2])
+    m1 = np.ascontiguousarray(max_err1, np.int32); m2 = np.ascontiguousarray(max_err2, np.int32)
+    k1 = np.ascontiguousarray(K1, np.float32); k2 = np.ascontiguousarray(K2, np.float32)
+    inl = np.zeros((nh, N), np.uint8); n = np.zeros(nh, np.int32)
+    lib().oracle_sim3_check_inliers(nh, _p(a[0], _f32p), _p(a[1], _f32p), N, _p(a[2], _f32p), _p(a[3], _f32p), _p(a[4], _f32p), _p(a[5], _f32p), _p(m1, _i32p),
+                                    _p(m2, _i32p), _p(k1, _f32p), _p(k2, _f32p), _p(inl, _u8p), _p(n, _i32p))
+    return inl, n

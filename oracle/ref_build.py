@@ -329,3 +329,27 @@ class RefVocabulary:
                                         ctypes.addressof(fc))
         nf = fc.value
         return dict(bow_ids=bi[:nb].copy(), bow_vals=bv[:nb].copy(), fv=dict(nodes=fn[:nf].copy(), start=fs[:nf + 1].copy(), items=fi[:fs[nf]].copy()))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the reference's own Sim3Solver.cc (oracle/_ref/libref_sim3solver.so): constructor bookkeeping, FromCameraToImage, Project, CheckInliers
+_SOS = os.path.join(_HERE, "_ref", "libref_sim3solver.so")
+
+
+def sim3solver_available():
+    return os.path.exists(_SOS)
+
+
+def ref_sim3_check_inliers(X3Dc1, X3Dc2, oct1, oct2, level_sigma2, K1, K2, T12, T21):
+    """Returns (inliers u8[n_hyp, N], n_inliers, max_err1, max_err2, P1im1, P2im2) from the reference's object code."""
+    L = ctypes.CDLL(_SOS)
+    X1 = _c(X3Dc1, np.float32); X2 = _c(X3Dc2, np.float32); N = len(X1)
+    o1 = _c(oct1, np.int32); o2 = _c(oct2, np.int32); ls = _c(level_sigma2, np.float32); k1 = _c(K1, np.float32); k2 = _c(K2, np.float32)
+    a = _c(T12, np.float32).reshape(-1, 16); b = _c(T21, np.float32).reshape(-1, 16); nh = len(a)
+    inl = np.zeros((nh, N), np.uint8); n = np.zeros(nh, np.int32); m1 = np.zeros(N, np.int32); m2 = np.zeros(N, np.int32)
+    p1 = np.zeros((N, 2), np.float32); p2 = np.zeros((N, 2), np.float32)
+    vp, i = ctypes.c_void_p, ctypes.c_int
+    L.ref_sim3_check_inliers.argtypes = [i, vp, vp, vp, vp, vp, i, vp, vp, i, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.ref_sim3_check_inliers(N, X1.ctypes.data, X2.ctypes.data, o1.ctypes.data, o2.ctypes.data, ls.ctypes.data, len(ls), k1.ctypes.data, k2.ctypes.data, nh,
+                             a.ctypes.data, b.ctypes.data, inl.ctypes.data, n.ctypes.data, m1.ctypes.data, m2.ctypes.data, p1.ctypes.data, p2.ctypes.data)
+    return inl, n, m1, m2, p1, p2

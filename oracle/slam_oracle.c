@@ -1487,3 +1487,58 @@ int oracle_vocab_transform(int L, const uint8_t *node_desc, const int *child_sta
     if (norm > 0.0) for (int a = 0; a < nb; a++) bow_vals[a] /= norm;
     return nb;
 }
+
+/* ======================================================================================== */
+/* Sim3Solver (S/src/Sim3Solver.cc): the data-parallel part of the RANSAC -- FromCameraToImage (:419-437), Project (:392-417) and CheckInliers
+ * (:340-365) -- for n_hyp hypotheses (T12, T21 as produced by ComputeSim3, row-major 4x4 float) over N correspondences.  All float; cv::Mat R*P+t
+ * = small gemm then add; Mat::dot accumulates in double and the result is stored in a float; the error thresholds are the reference's
+ * std::vector<size_t> entries, i.e. 9.210 * sigma^2 TRUNCATED to an integer (:88-89, Sim3Solver.h:78-79). */
+void oracle_sim3_max_error(int N, const int *octave, const float *level_sigma2, int *max_err)
+{
+    for (int i = 0; i < N; i++) max_err[i] = (int)(size_t)(9.210 * level_sigma2[octave[i]]);
+}
+
+void oracle_sim3_from_camera_to_image(int N, const float *X3Dc, const float *K4, float *p2d)
+{
+    for (int i = 0; i < N; i++) {
+        const float invz = 1 / (X3Dc[3 * i + 2]);
+        const float x = X3Dc[3 * i] * invz, y = X3Dc[3 * i + 1] * invz;
+        p2d[2 * i] = K4[0] * x + K4[2]; p2d[2 * i + 1] = K4[1] * y + K4[3];
+    }
+}
+
+static void sim3_project(const float *T, const float *K4, const float *P, float *uv)
+{
+    float pc[3];
+    for (int r = 0; r < 3; r++) {
+        float s = T[4 * r] * P[0];
+        s = s + T[4 * r + 1] * P[1];
+        s = s + T[4 * r + 2] * P[2];
+        pc[r] = s + T[4 * r + 3];
+    }
+    const float invz = 1 / (pc[2]);
+    const float x = pc[0] * invz, y = pc[1] * invz;
+    uv[0] = K4[0] * x + K4[2]; uv[1] = K4[1] * y + K4[3];
+}
+
+void oracle_sim3_check_inliers(int n_hyp, const float *T12, const float *T21, int N, const float *X3Dc1, const float *X3Dc2, const float *P1im1,
+                               const float *P2im2, const int *max_err1, const int *max_err2, const float *K1, const float *K2,
+                               uint8_t *inliers, int *n_inliers)
+{
+    for (int h = 0; h < n_hyp; h++) {
+        int n = 0;
+        for (int i = 0; i < N; i++) {
+            float p2im1[2], p1im2[2];
+            sim3_project(T12 + 16 * h, K1, X3Dc2 + 3 * i, p2im1);          /* Project(mvX3Dc2, vP2im1, mT12i, mK1) */
+            sim3_project(T21 + 16 * h, K2, X3Dc1 + 3 * i, p1im2);          /* Project(mvX3Dc1, vP1im2, mT21i, mK2) */
+            const float d1[2] = {P1im1[2 * i] - p2im1[0], P1im1[2 * i + 1] - p2im1[1]};
+            const float d2[2] = {p1im2[0] - P2im2[2 * i], p1im2[1] - P2im2[2 * i + 1]};
+            const float err1 = (float)((double)d1[0] * (double)d1[0] + (double)d1[1] * (double)d1[1]);
+            const float err2 = (float)((double)d2[0] * (double)d2[0] + (double)d2[1] * (double)d2[1]);
+            const int in = err1 < (float)max_err1[i] && err2 < (float)max_err2[i];
+            inliers[(size_t)h * N + i] = (uint8_t)in;
+            n += in;
+        }
+        n_inliers[h] = n;
+    }
+}

@@ -50,7 +50,7 @@ public:
     int mnScaleLevels; float mfLogScaleFactor;
     std::vector<float> mvScaleFactors, mvLevelSigma2, mvInvLevelSigma2;
     int mnMinX, mnMinY, mnMaxX, mnMaxY;
-    cv::Mat Tcw, Ow;
+    cv::Mat Tcw, Ow, mK;
     int mnGridCols = 64, mnGridRows = 48;
     float mfGridElementWidthInv = 0, mfGridElementHeightInv = 0;
     std::vector<std::vector<std::vector<size_t>>> mGrid;

@@ -40,11 +40,20 @@ struct KeyPoint {
     KeyPoint() : size(0), angle(-1), response(0), octave(0), class_id(-1) {}
 };
 
+struct Size { int width, height; Size() : width(0), height(0) {} Size(int w, int h) : width(w), height(h) {} };
+
 class Mat {
 public:
     int rows, cols;
     Mat() : rows(0), cols(0), type_(CV_32F), step_(0), data(nullptr) {}
     Mat(int r, int c, int type) { alloc(r, c, type); }
+    Mat(Size sz, int type) { alloc(sz.height, sz.width, type); }
+    Size size() const { return Size(cols, rows); }
+    void create(int r, int c, int type) { if (data && rows == r && cols == c && type_ == type) return; alloc(r, c, type); }
+    /* assignment: an lvalue rebinds (cv::Mat header semantics); a temporary view (P.col(i) = expr, OpenCV's MatExpr assignment) is written through */
+    Mat(const Mat &) = default;
+    Mat &operator=(const Mat &o) & { rows = o.rows; cols = o.cols; type_ = o.type_; step_ = o.step_; data = o.data; buf = o.buf; return *this; }
+    Mat &operator=(const Mat &o) && { write_from(o); return *this; }
     static Mat zeros(int r, int c, int type) { Mat m(r, c, type); std::memset(m.data, 0, m.step_ * r); return m; }
     static Mat eye(int r, int c, int type) { Mat m = zeros(r, c, type); for (int i = 0; i < std::min(r, c); i++) m.at<float>(i, i) = 1.f; return m; }
     int type() const { return type_; }
@@ -61,7 +70,9 @@ public:
     Mat row(int i) const { return rowRange(i, i + 1); }
     Mat col(int j) const { return colRange(j, j + 1); }
     Mat clone() const { Mat m(rows, cols, type_); for (int i = 0; i < rows; i++) std::memcpy(m.data + (size_t)i * m.step_, data + (size_t)i * step_, (size_t)cols * elem()); return m; }
-    void copyTo(Mat &o) const { o = clone(); }
+    void copyTo(Mat &o) const { if (o.data && o.rows == rows && o.cols == cols && o.type_ == type_) o.write_from(*this); else o = clone(); }
+    void copyTo(Mat &&o) const { o.write_from(*this); }                       /* into a view: sR.copyTo(T.rowRange(0,3).colRange(0,3)) */
+    void write_from(const Mat &o) { assert(rows == o.rows && cols == o.cols); for (int i = 0; i < rows; i++) std::memcpy(data + (size_t)i * step_, o.data + (size_t)i * o.step_, (size_t)cols * elem()); }
     Mat t() const { Mat m(cols, rows, type_); for (int i = 0; i < rows; i++) for (int j = 0; j < cols; j++) m.at<float>(j, i) = at<float>(i, j); return m; }
     double dot(const Mat &o) const
     {
@@ -105,6 +116,74 @@ static inline double norm(const Mat &a)
     double s = 0;
     for (int i = 0; i < a.rows; i++) for (int j = 0; j < a.cols; j++) { const double v = a.at<float>(i, j); s += v * v; }
     return std::sqrt(s);
+}
+
+/* cv::Mat_<float>(r, c) << a, b, ...  (MatCommaInitializer_) */
+template <typename T> class Mat_;
+template <typename T> struct MatCommaInitializer_ {
+    Mat m; int k;
+    MatCommaInitializer_(const Mat &mm, T first) : m(mm), k(0) { put(first); }
+    void put(T v) { m.at<T>(k / m.cols, k % m.cols) = v; k++; }
+    MatCommaInitializer_ &operator,(double v) { put((T)v); return *this; }
+    operator Mat() const { return m; }
+};
+template <typename T> class Mat_ : public Mat {
+public:
+    Mat_(int r, int c) : Mat(r, c, CV_32F) {}
+    MatCommaInitializer_<T> operator<<(double v) const { return MatCommaInitializer_<T>(*this, (T)v); }
+};
+
+#define CV_REDUCE_SUM 0
+/* The four functions below exist so that the reference's Sim3Solver.cc compiles; ComputeSim3, the only caller, is NOT part of what oracle/_ref pins
+ * (the pinned members are CheckInliers / Project / FromCameraToImage and the constructor), so these are plain double-precision stand-ins, not
+ * restatements of OpenCV's float algorithms. */
+static inline void reduce(const Mat &src, Mat &dst, int dim, int)
+{
+    assert(dim == 1);
+    dst = Mat(src.rows, 1, CV_32F);
+    for (int i = 0; i < src.rows; i++) { float s = src.at<float>(i, 0); for (int j = 1; j < src.cols; j++) s = s + src.at<float>(i, j); dst.at<float>(i, 0) = s; }
+}
+static inline void pow(const Mat &src, double p, Mat &dst)
+{
+    Mat m(src.rows, src.cols, CV_32F);
+    for (int i = 0; i < src.rows; i++) for (int j = 0; j < src.cols; j++) m.at<float>(i, j) = (float)std::pow((double)src.at<float>(i, j), p);
+    dst = m;
+}
+static inline bool eigen(const Mat &A, Mat &evals, Mat &evecs)      /* symmetric Jacobi in double, eigenvalues descending, eigenvectors as rows */
+{
+    const int n = A.rows;
+    std::vector<double> a((size_t)n * n), v((size_t)n * n, 0.0);
+    for (int i = 0; i < n; i++) { for (int j = 0; j < n; j++) a[(size_t)i * n + j] = A.at<float>(i, j); v[(size_t)i * n + i] = 1; }
+    for (int sweep = 0; sweep < 64; sweep++) {
+        double off = 0;
+        for (int i = 0; i < n; i++) for (int j = i + 1; j < n; j++) off += a[(size_t)i * n + j] * a[(size_t)i * n + j];
+        if (off < 1e-300) break;
+        for (int p = 0; p < n; p++) for (int q = p + 1; q < n; q++) {
+            if (a[(size_t)p * n + q] == 0) continue;
+            const double th = (a[(size_t)q * n + q] - a[(size_t)p * n + p]) / (2 * a[(size_t)p * n + q]);
+            const double t = (th >= 0 ? 1 : -1) / (std::fabs(th) + std::sqrt(th * th + 1)), c = 1 / std::sqrt(t * t + 1), s = t * c;
+            for (int k = 0; k < n; k++) { const double x = a[(size_t)k * n + p], y = a[(size_t)k * n + q]; a[(size_t)k * n + p] = c * x - s * y; a[(size_t)k * n + q] = s * x + c * y; }
+            for (int k = 0; k < n; k++) { const double x = a[(size_t)p * n + k], y = a[(size_t)q * n + k]; a[(size_t)p * n + k] = c * x - s * y; a[(size_t)q * n + k] = s * x + c * y; }
+            for (int k = 0; k < n; k++) { const double x = v[(size_t)p * n + k], y = v[(size_t)q * n + k]; v[(size_t)p * n + k] = c * x - s * y; v[(size_t)q * n + k] = s * x + c * y; }
+        }
+    }
+    std::vector<int> order(n);
+    for (int i = 0; i < n; i++) order[i] = i;
+    std::sort(order.begin(), order.end(), [&](int x, int y) { return a[(size_t)x * n + x] > a[(size_t)y * n + y]; });
+    evals = Mat(n, 1, CV_32F); evecs = Mat(n, n, CV_32F);
+    for (int i = 0; i < n; i++) { evals.at<float>(i, 0) = (float)a[(size_t)order[i] * n + order[i]]; for (int k = 0; k < n; k++) evecs.at<float>(i, k) = (float)v[(size_t)order[i] * n + k]; }
+    return true;
+}
+static inline void Rodrigues(const Mat &rvec, Mat &R)
+{
+    const double r[3] = {rvec.at<float>(0), rvec.at<float>(1), rvec.at<float>(2)};
+    const double theta = std::sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+    R = Mat::eye(3, 3, CV_32F);
+    if (theta < 2.220446049250313e-16) return;
+    const double c = std::cos(theta), s = std::sin(theta), c1 = 1 - c, x = r[0] / theta, y = r[1] / theta, z = r[2] / theta;
+    const double M[9] = {c + c1 * x * x, c1 * x * y - s * z, c1 * x * z + s * y, c1 * x * y + s * z, c + c1 * y * y, c1 * y * z - s * x,
+                         c1 * x * z - s * y, c1 * y * z + s * x, c + c1 * z * z};
+    for (int i = 0; i < 9; i++) R.at<float>(i / 3, i % 3) = (float)M[i];
 }
 
 }  // namespace cv

@@ -549,6 +549,25 @@ class Optimizer:
                                           int(bool(bFixScale)), _ptr(inl), _ptr(nin), _ptr(st), 0))
         return S, inl, nin, st
 
+    def Sim3Prepare(self, X3Dc, octave, level_sigma2, K4):
+        """Sim3Solver constructor data for one keyframe: (max_err i32[N], p2d f32[N,2])."""
+        X = np.ascontiguousarray(X3Dc, np.float32); N = len(X)
+        o = np.ascontiguousarray(octave, np.int32); ls = np.ascontiguousarray(level_sigma2, np.float32); K = np.ascontiguousarray(K4, np.float32)
+        me = np.zeros(N, np.int32); p = np.zeros((N, 2), np.float32)
+        _check(self._L.orbo_sim3_prepare(self._h, N, _ptr(X), _ptr(o), _ptr(ls), len(ls), _ptr(K), _ptr(me), _ptr(p), 0))
+        return me, p
+
+    def Sim3CheckInliers(self, T12, T21, X3Dc1, X3Dc2, P1im1, P2im2, max_err1, max_err2, K1, K2):
+        """Sim3Solver::CheckInliers for a batch of RANSAC hypotheses: (inliers u8[n_hyp, N], n_inliers i32[n_hyp])."""
+        a = [np.ascontiguousarray(x, np.float32) for x in (T12, T21, X3Dc1, X3Dc2, P1im1, P2im2)]
+        nh = a[0].reshape(-1, 16).shape[0]; N = len(a[2])
+        m1 = np.ascontiguousarray(max_err1, np.int32); m2 = np.ascontiguousarray(max_err2, np.int32)
+        k1 = np.ascontiguousarray(K1, np.float32); k2 = np.ascontiguousarray(K2, np.float32)
+        inl = np.zeros((nh, N), np.uint8); n = np.zeros(nh, np.int32)
+        _check(self._L.orbo_sim3_check_inliers(self._h, nh, _ptr(a[0]), _ptr(a[1]), N, _ptr(a[2]), _ptr(a[3]), _ptr(a[4]), _ptr(a[5]), _ptr(m1), _ptr(m2), _ptr(k1),
+                                               _ptr(k2), _ptr(inl), _ptr(n), 0))
+        return inl, n
+
     def _ba(self, poses, fixed, intr, points, e_kf, e_pt, e_uv, e_inv_sigma2, two_stage, its0, its1, robust, stop_flag=None):
         poses = np.ascontiguousarray(poses, np.float32).reshape(-1, 16).copy(); K = len(poses)
         fixed = np.ascontiguousarray(fixed, np.uint8)

@@ -242,6 +242,52 @@ int orbo_optimize_sim3(orbo_handle *h, int n_pairs, double *sim3, const uint8_t 
     return S.finish();
 }
 
+int orbo_sim3_prepare(orbo_handle *h, int N, const float *X3Dc, const int32_t *octave, const float *level_sigma2, int nlevels, const float *K4,
+                      int32_t *max_err, float *p2d, int memspace)
+{
+    ORBS_REQUIRE(h && X3Dc && octave && level_sigma2 && K4 && max_err && p2d, ORBS_E_INVALID, "null argument");
+    ORBS_REQUIRE(N > 0 && nlevels > 0, ORBS_E_INVALID, "non-positive size");
+    std::lock_guard<std::mutex> lk(h->mu);
+    ORBS_CUDA(cudaSetDevice(h->device));
+    Stager S(&h->pool, h->stream, memspace);
+    const float *dX = S.in(X3Dc, (size_t)N * 3);
+    const int32_t *doct = S.in(octave, N);
+    float *dls = S.scratch<float>(nlevels);                              // level_sigma2 is a host array in both memory spaces
+    int32_t *dme = S.inout(max_err, N, false);
+    float *dp = S.inout(p2d, (size_t)N * 2, false);
+    if (S.rc) return S.rc;
+    ORBS_CUDA(cudaMemcpyAsync(dls, level_sigma2, sizeof(float) * nlevels, cudaMemcpyHostToDevice, h->stream));
+    k_sim3_prepare<<<(N + 255) / 256, 256, 0, h->stream>>>(N, dX, doct, dls, nlevels, K4[0], K4[1], K4[2], K4[3], dme, dp);
+    h->launches++;
+    ORBS_CUDA(cudaGetLastError());
+    if (memspace == ORBS_MEM_DEVICE) ORBS_CUDA(cudaStreamSynchronize(h->stream));
+    return S.finish();
+}
+
+int orbo_sim3_check_inliers(orbo_handle *h, int n_hyp, const float *T12, const float *T21, int N, const float *X3Dc1, const float *X3Dc2, const float *P1im1,
+                            const float *P2im2, const int32_t *max_err1, const int32_t *max_err2, const float *K1, const float *K2, uint8_t *inliers,
+                            int32_t *n_inliers, int memspace)
+{
+    ORBS_REQUIRE(h && T12 && T21 && X3Dc1 && X3Dc2 && P1im1 && P2im2 && max_err1 && max_err2 && K1 && K2 && inliers && n_inliers, ORBS_E_INVALID, "null argument");
+    ORBS_REQUIRE(n_hyp > 0 && n_hyp <= 65535 && N > 0, ORBS_E_INVALID, "1..65535 hypotheses, at least one correspondence");
+    std::lock_guard<std::mutex> lk(h->mu);
+    ORBS_CUDA(cudaSetDevice(h->device));
+    Stager S(&h->pool, h->stream, memspace);
+    Sim3CheckArgs A;
+    A.n_hyp = n_hyp; A.N = N;
+    A.T12 = S.in(T12, (size_t)n_hyp * 16); A.T21 = S.in(T21, (size_t)n_hyp * 16);
+    A.X1 = S.in(X3Dc1, (size_t)N * 3); A.X2 = S.in(X3Dc2, (size_t)N * 3); A.P1im1 = S.in(P1im1, (size_t)N * 2); A.P2im2 = S.in(P2im2, (size_t)N * 2);
+    A.max_err1 = S.in(max_err1, N); A.max_err2 = S.in(max_err2, N);
+    for (int k = 0; k < 4; k++) { A.K1[k] = K1[k]; A.K2[k] = K2[k]; }
+    A.inliers = S.inout(inliers, (size_t)n_hyp * N, false); A.n_inliers = S.inout(n_inliers, n_hyp, false);
+    if (S.rc) return S.rc;
+    ORBS_CUDA(cudaMemsetAsync(A.n_inliers, 0, sizeof(int) * n_hyp, h->stream));
+    k_sim3_check_inliers<<<dim3((N + 255) / 256, n_hyp), 256, 0, h->stream>>>(A);
+    h->launches++;
+    ORBS_CUDA(cudaGetLastError());
+    return S.finish();
+}
+
 }  // extern "C"
 
 // ---------------------------------------------------------------------------------------------------------

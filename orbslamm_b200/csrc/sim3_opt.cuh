@@ -340,4 +340,75 @@ k_optimize_sim3(const Sim3Args A)
     if (tid == 0) A.n_inliers[f] = n_in;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------------------
+// Sim3Solver (S/src/Sim3Solver.cc): the data-parallel part of the RANSAC.  ComputeSim3 (Horn's closed form on 3 points, a handful of OpenCV
+// small-matrix calls) stays with the caller; what costs time in the reference is CheckInliers -- two cv::Mat projections per correspondence and
+// hypothesis, each through freshly allocated 3x1 / 2x1 matrices (:392-417) -- and that is one thread per (hypothesis, correspondence) here.
+struct Sim3CheckArgs {
+    int n_hyp, N;
+    const float *T12, *T21;            // [n_hyp, 16]
+    const float *X1, *X2, *P1im1, *P2im2;
+    const int *max_err1, *max_err2;    // the reference's std::vector<size_t>: 9.210 * sigma^2 truncated
+    float K1[4], K2[4];
+    uint8_t *inliers;                  // [n_hyp, N]
+    int *n_inliers;                    // [n_hyp], zeroed
+};
+
+__device__ __forceinline__ void sim3_project_f32(const float *T, const float *K, const float *P, float &u, float &v)   // Project, :392-417
+{
+    float pc[3];
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+        float s = __fmul_rn(T[4 * r], P[0]);
+        s = __fadd_rn(s, __fmul_rn(T[4 * r + 1], P[1]));
+        s = __fadd_rn(s, __fmul_rn(T[4 * r + 2], P[2]));
+        pc[r] = __fadd_rn(s, T[4 * r + 3]);
+    }
+    const float invz = __fdiv_rn(1.0f, pc[2]);
+    u = __fadd_rn(__fmul_rn(K[0], __fmul_rn(pc[0], invz)), K[2]);
+    v = __fadd_rn(__fmul_rn(K[1], __fmul_rn(pc[1], invz)), K[3]);
+}
+
+__global__ void __launch_bounds__(256)
+k_sim3_check_inliers(const Sim3CheckArgs A)
+{
+    __shared__ float s_T[32];
+    __shared__ int s_n;
+    const int h = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (threadIdx.x < 16) s_T[threadIdx.x] = A.T12[16 * h + threadIdx.x];
+    else if (threadIdx.x < 32) s_T[threadIdx.x] = A.T21[16 * h + threadIdx.x - 16];
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    bool in = false;
+    if (i < A.N) {
+        const float X1[3] = {A.X1[3 * i], A.X1[3 * i + 1], A.X1[3 * i + 2]}, X2[3] = {A.X2[3 * i], A.X2[3 * i + 1], A.X2[3 * i + 2]};
+        float u21, v21, u12, v12;
+        sim3_project_f32(s_T, A.K1, X2, u21, v21);                  // Project(mvX3Dc2, vP2im1, mT12i, mK1)
+        sim3_project_f32(s_T + 16, A.K2, X1, u12, v12);             // Project(mvX3Dc1, vP1im2, mT21i, mK2)
+        const float d1x = __fsub_rn(A.P1im1[2 * i], u21), d1y = __fsub_rn(A.P1im1[2 * i + 1], v21);
+        const float d2x = __fsub_rn(u12, A.P2im2[2 * i]), d2y = __fsub_rn(v12, A.P2im2[2 * i + 1]);
+        const float err1 = (float)__dadd_rn(__dmul_rn((double)d1x, (double)d1x), __dmul_rn((double)d1y, (double)d1y));   // Mat::dot: double accumulation
+        const float err2 = (float)__dadd_rn(__dmul_rn((double)d2x, (double)d2x), __dmul_rn((double)d2y, (double)d2y));
+        in = err1 < (float)A.max_err1[i] && err2 < (float)A.max_err2[i];
+        A.inliers[(size_t)h * A.N + i] = in ? 1 : 0;
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, in);
+    if ((threadIdx.x & 31) == 0 && bal) atomicAdd(&s_n, __popc(bal));
+    __syncthreads();
+    if (threadIdx.x == 0 && s_n) atomicAdd(&A.n_inliers[h], s_n);
+}
+
+// the constructor's per-correspondence data: integer-truncated thresholds (:88-89) and FromCameraToImage (:419-437)
+__global__ void __launch_bounds__(256)
+k_sim3_prepare(int N, const float *__restrict__ X3Dc, const int *__restrict__ octave, const float *__restrict__ level_sigma2, int nlevels, float fx, float fy,
+               float cx, float cy, int *__restrict__ max_err, float *__restrict__ p2d)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const float invz = __fdiv_rn(1.0f, X3Dc[3 * i + 2]);
+    p2d[2 * i] = __fadd_rn(__fmul_rn(fx, __fmul_rn(X3Dc[3 * i], invz)), cx);
+    p2d[2 * i + 1] = __fadd_rn(__fmul_rn(fy, __fmul_rn(X3Dc[3 * i + 1], invz)), cy);
+    max_err[i] = (int)(unsigned long long)__dmul_rn(9.210, (double)level_sigma2[min(max(octave[i], 0), nlevels - 1)]);
+}
+
 }  // namespace orbs

@@ -433,3 +433,26 @@ def golden_outputs(B):
                                                        s["w2"][None], s["K1"][None], s["K2"][None], [len(s["valid"])], 10.0, False)
         out["sim3"], out["sim3_inlier"] = S[0], np.concatenate([inl[0], [nin[0]]])
     return out
+
+
+# ------------------------------------------------------------------ Sim3Solver RANSAC hypotheses
+def make_sim3_ransac_case(cam, stream_id, n_hyp=300, seed=0):
+    """Correspondences of make_sim3_opt_case plus n_hyp hypotheses (T12, T21) spread around the true Sim3 from exact to far off, as a RANSAC produces
+    them; built in double and rounded to float like ComputeSim3's outputs."""
+    from scipy.spatial.transform import Rotation
+    s = make_sim3_opt_case(cam, stream_id)
+    v = s["valid"] > 0
+    p = make_sim3_pair(cam, stream_id)
+    rng = np.random.default_rng(31 + seed + stream_id)
+    R12 = p["R12"].astype(np.float64); t12 = p["t12"].astype(np.float64); s12 = float(p["s12"])
+    T12 = np.zeros((n_hyp, 4, 4), F32); T21 = np.zeros((n_hyp, 4, 4), F32)
+    for h in range(n_hyp):
+        mag = [0.0, 1e-4, 1e-3, 5e-3, 2e-2, 0.1][h % 6]
+        R = Rotation.from_rotvec(rng.normal(0, mag, 3)).as_matrix() @ R12
+        t = t12 + rng.normal(0, 4 * mag, 3); sc = s12 * (1 + rng.normal(0, mag))
+        A = np.eye(4); A[:3, :3] = sc * R; A[:3, 3] = t
+        T12[h] = A.astype(F32); T21[h] = np.linalg.inv(A).astype(F32)
+    oct1 = np.rint(-np.log(s["w1"][v].astype(np.float64)) / (2 * np.log(1.2))).astype(np.int32)
+    oct2 = np.rint(-np.log(s["w2"][v].astype(np.float64)) / (2 * np.log(1.2))).astype(np.int32)
+    ls2 = (p["kf1"]["scale_factors"].astype(np.float64) ** 2).astype(F32)
+    return dict(X1=s["P1c"][v], X2=s["P2c"][v], oct1=oct1, oct2=oct2, ls2=ls2, K1=s["K1"], K2=s["K2"], T12=T12, T21=T21)

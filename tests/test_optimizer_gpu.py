@@ -206,3 +206,26 @@ def test_optimize_sim3_matches_oracle(lib, fix_scale):
                 assert np.abs(r["sim3"] - c["true"]).max() < np.abs(c["init"] - c["true"]).max()
         else:
             assert r["n_in"] == 0 and np.array_equal(S[k], c["init"])
+
+
+@pytest.mark.parametrize("cam,sid", [("TUM", 1), ("KITTI", 2)])
+def test_sim3_solver_check_inliers(lib, cam, sid):
+    """Sim3Solver's data-parallel part (constructor thresholds, FromCameraToImage, Project, CheckInliers) for 300 RANSAC hypotheses in one call:
+    exact against the oracle and, where oracle/_ref travelled, against the reference's own Sim3Solver.cc object code."""
+    import orbslamm_b200 as ob
+    import kf_family as kff
+    from oracle import ref_build
+    r = kff.make_sim3_ransac_case(getattr(synth, cam), sid)
+    o = ob.Optimizer()
+    m1, p1 = o.Sim3Prepare(r["X1"], r["oct1"], r["ls2"], r["K1"]); m2, p2 = o.Sim3Prepare(r["X2"], r["oct2"], r["ls2"], r["K2"])
+    om1, om2, op1, op2 = oracle.sim3_prepare(r["X1"], r["X2"], r["oct1"], r["oct2"], r["ls2"], r["K1"], r["K2"])
+    assert np.array_equal(m1, om1) and np.array_equal(m2, om2) and np.array_equal(p1, op1) and np.array_equal(p2, op2)
+    inl, n = o.Sim3CheckInliers(r["T12"], r["T21"], r["X1"], r["X2"], p1, p2, m1, m2, r["K1"], r["K2"])
+    oi, on = oracle.sim3_check_inliers(r["T12"], r["T21"], r["X1"], r["X2"], op1, op2, om1, om2, r["K1"], r["K2"])
+    assert np.array_equal(inl, oi) and np.array_equal(n, on) and np.array_equal(n, inl.sum(1)) and len(np.unique(n)) > 20
+    if ref_build.sim3solver_available():
+        ri, rn, rm1, rm2, rp1, rp2 = ref_build.ref_sim3_check_inliers(r["X1"], r["X2"], r["oct1"], r["oct2"], r["ls2"], r["K1"], r["K2"], r["T12"], r["T21"])
+        assert np.array_equal(inl, ri) and np.array_equal(n, rn) and np.array_equal(m1, rm1) and np.array_equal(p2, rp2)
+    # a single hypothesis and a single correspondence
+    i1, n1 = o.Sim3CheckInliers(r["T12"][:1], r["T21"][:1], r["X1"][:1], r["X2"][:1], p1[:1], p2[:1], m1[:1], m2[:1], r["K1"], r["K2"])
+    assert i1.shape == (1, 1) and n1[0] == oi[0, 0]

@@ -282,3 +282,22 @@ def test_vocab_transform_on_the_real_orbvoc():
             assert np.array_equal(a["bow_ids"], r["bow_ids"]) and np.array_equal(a["bow_vals"], r["bow_vals"])
             for key in ("nodes", "start", "items"):
                 assert np.array_equal(a["fv"][key], r["fv"][key])
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Sim3Solver: oracle/_ref/libref_sim3solver.so is the reference's own Sim3Solver.cc compiled unmodified against oracle/slamshim.  Pinned: the
+# constructor's bookkeeping (integer-truncated thresholds), FromCameraToImage, Project and CheckInliers -- the data-parallel part of the RANSAC.
+needs_sim3solver = pytest.mark.skipif(not ref_build.sim3solver_available(), reason="oracle/_ref Sim3Solver not built (needs /root/reference)")
+
+
+@needs_sim3solver
+@pytest.mark.parametrize("cam,sid", [("TUM", 1), ("KITTI", 2)])
+def test_sim3_check_inliers_oracle_equals_reference_object_code(cam, sid):
+    r = kff.make_sim3_ransac_case(getattr(synth, cam), sid)
+    inl_r, n_r, m1_r, m2_r, p1_r, p2_r = ref_build.ref_sim3_check_inliers(r["X1"], r["X2"], r["oct1"], r["oct2"], r["ls2"], r["K1"], r["K2"], r["T12"], r["T21"])
+    m1, m2, p1, p2 = oracle.sim3_prepare(r["X1"], r["X2"], r["oct1"], r["oct2"], r["ls2"], r["K1"], r["K2"])
+    assert np.array_equal(m1, m1_r) and np.array_equal(m2, m2_r) and np.array_equal(p1, p1_r) and np.array_equal(p2, p2_r)
+    assert m1.min() == 9 and (m1 == np.floor(9.210 * r["ls2"][r["oct1"]].astype(np.float64))).all()           # size_t truncation of 9.210 * sigma^2
+    inl, n = oracle.sim3_check_inliers(r["T12"], r["T21"], r["X1"], r["X2"], p1, p2, m1, m2, r["K1"], r["K2"])
+    assert np.array_equal(inl, inl_r) and np.array_equal(n, n_r)
+    assert n.max() > 0.8 * len(r["X1"]) and n.min() < 0.3 * len(r["X1"]) and len(np.unique(n)) > 20               # exact to far-off hypotheses
