@@ -47,7 +47,7 @@ public:
     std::vector<float> mvuRight, mvInvLevelSigma2;
     std::vector<MapPoint *> mvpMapPoints;
     std::vector<KeyFrame *> mvpOrderedConnectedKeyFrames;
-    cv::Mat Tcw, mTcwGBA;
+    cv::Mat Tcw, mTcwGBA, mK;
     bool mbBad = false;
 };
 }  // namespace iORB_SLAM

@@ -200,3 +200,33 @@ def test_cpp_dropin_kf_family(lib, tmp_path):
     a1 = oracle.search_for_initialization(g, ki["last"], ki["cur"], np.stack([ki["last"]["x"], ki["last"]["y"]], 1), 100, 0.9, True)
     a2 = oracle.search_for_initialization(g, ki["last"], ki["cur"], a1[2], 100, 0.9, True)
     assert a1[0] > 50 and got[n1] == a1[0] and np.array_equal(got[:n1], a1[1]) and got[2 * n1 + 1] == a2[0] and np.array_equal(got[n1 + 1:2 * n1 + 1], a2[1])
+
+
+def test_cpp_dropin_sim3solver(lib, tmp_path):
+    """Sim3Solver::iterate through the C++ drop-in (hypotheses of a call generated first, CheckInliers of all of them in one device call) against a
+    reference-style sequential loop with the same seed, the same ComputeSim3 and the CPU oracle's CheckInliers: same returned transform, inlier
+    flags, inlier count, iteration and call counts -- for a run that succeeds after a few failed hypotheses (chunks of 5 and of 1) and for a run
+    that never succeeds and consumes every iteration."""
+    import kf_family as kff
+    d = str(tmp_path)
+    exe = os.path.join(d, "host_sim3solver_test")
+    srcs = [os.path.join(HOST, f) for f in ("Sim3Solver_b200.cc", "mock/Sim3Solver_rest.cc", "mock/slam_statics.cc", "test/host_sim3solver_test.cc")]
+    odir = os.path.dirname(oracle.build())
+    subprocess.check_call(["g++", "-std=c++14", "-O2", "-I" + os.path.join(HOST, "mock"), "-I" + HOST, "-I" + os.path.join(ROOT, "include")] + srcs +
+                          ["-L" + os.path.join(ROOT, "orbslamm_b200"), "-lorbslamm_b200", "-Wl,-rpath," + os.path.join(ROOT, "orbslamm_b200"), "-L" + odir, "-loracle",
+                           "-Wl,-rpath," + odir, "-lpthread", "-o", exe])
+    s = kff.make_sim3_opt_case(synth.TUM, 1, n_outliers=60)
+    v = s["valid"] > 0
+    p = kff.make_sim3_pair(synth.TUM, 1)
+    w = lambda name, a: np.ascontiguousarray(a).tofile(os.path.join(d, name))
+    oct_of = lambda ww: np.rint(-np.log(ww.astype(np.float64)) / (2 * np.log(1.2))).astype(np.int32)
+    w("s3r_X1.bin", s["P1c"][v]); w("s3r_X2.bin", s["P2c"][v]); w("s3r_K1.bin", s["K1"]); w("s3r_K2.bin", s["K2"])
+    w("s3r_oct1.bin", oct_of(s["w1"][v])); w("s3r_oct2.bin", oct_of(s["w2"][v]))
+    w("s3r_ls2.bin", (p["kf1"]["scale_factors"].astype(np.float64) ** 2).astype(np.float32))
+    out = subprocess.run([exe, d], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    rows = [dict(zip(l.split()[0::2], l.split()[1::2])) for l in open(os.path.join(d, "out_sim3solver.txt"))]
+    assert len(rows) == 3 and all(r["same"] == "1" for r in rows)
+    n = int(v.sum())
+    assert int(rows[0]["nInliers"]) > 20 and int(rows[1]["nInliers"]) > 20 and int(rows[1]["calls"]) == int(rows[1]["iterations"])
+    assert int(rows[2]["nInliers"]) == 0 and int(rows[2]["iterations"]) >= 1 and int(rows[2]["best"]) > 20 and int(rows[2]["N"]) == n
