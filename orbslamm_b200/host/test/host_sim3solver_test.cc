@@ -100,7 +100,7 @@ int main(int argc, char **argv)
     const int N = (int)o1.size();
     int bad = 0;
     FILE *out = fopen((d + "/out_sim3solver.txt").c_str(), "w");
-    for (int scenario = 0; scenario < 3; scenario++) {          // 0: succeeds early (chunks of 5); 1: chunks of 1; 2: never succeeds, all iterations consumed
+    for (int scenario = 0; scenario < 3; scenario++) {          // 0: succeeds after a few failed hypotheses (chunks of 5); 1: the same in chunks of 1; 2: the inlier bar is out of reach, every iteration is consumed
         Result res[2];
         for (int device = 0; device < 2; device++) {
             KeyFrame A, B;
@@ -115,6 +115,7 @@ int main(int argc, char **argv)
                 mp[s].assign(N, MapPoint());
                 for (int i = 0; i < N; i++) {
                     K.mvKeysUn[i].octave = oc[i];
+                    mp[s][i].mWorldPos = cv::Mat(3, 1, CV_32F);            // vector::assign copied the header: give every point its own storage
                     for (int k = 0; k < 3; k++) mp[s][i].mWorldPos.at<float>(k) = X[3 * i + k];
                     mp[s][i].mObservations[&K] = i; K.mvpMapPoints[i] = &mp[s][i];
                 }
@@ -122,12 +123,17 @@ int main(int argc, char **argv)
             std::vector<MapPoint *> matched(N);
             for (int i = 0; i < N; i++) matched[i] = &mp[1][i];
             Probe solver(&A, &B, matched, false);
-            srand(1234 + scenario);
-            res[device] = solver.run(device != 0, scenario == 2 ? N : 20, scenario == 1 ? 1 : 5);
+            DUtils::Random::SeedRand(scenario == 2 ? 99 : 1235);
+            res[device] = solver.run(device != 0, scenario == 2 ? (4 * N) / 5 + 3 : 20, scenario == 1 ? 1 : 5);
         }
         const bool same = res[0].T == res[1].T && res[0].nInliers == res[1].nInliers && res[0].iterations == res[1].iterations && res[0].calls == res[1].calls &&
                           res[0].best == res[1].best && res[0].inl == res[1].inl;
-        if (!same) bad++;
+        if (!same) {
+            bad++;
+            for (int k = 0; k < 2; k++)
+                printf("scenario %d %s: nInliers %d iterations %d calls %d best %d T[3]=%g T[0]=%g ninl_flags %d\n", scenario, k ? "device" : "sequential", res[k].nInliers,
+                       res[k].iterations, res[k].calls, res[k].best, res[k].T[3], res[k].T[0], (int)res[k].inl.size());
+        }
         fprintf(out, "scenario %d same %d nInliers %d iterations %d calls %d best %d N %d\n", scenario, same ? 1 : 0, res[1].nInliers, res[1].iterations, res[1].calls, res[1].best, N);
     }
     fclose(out);
