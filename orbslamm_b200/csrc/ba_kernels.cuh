@@ -326,6 +326,20 @@ struct CholPlan {
     const int4 *update;     // tasks {k, i, j, shared}, grouped by level
 };
 
+// Sharded solve: only the structurally nonzero tiles of the reduced system travel over NVLink.  The panel task list names exactly the tiles
+// (i, k) of the lower triangle that S or its factor can touch; pack them into one contiguous buffer for the all-reduce and scatter them back.
+__global__ void __launch_bounds__(256)
+k_tiles_pack(const double *__restrict__ S, int ld, const int4 *__restrict__ tiles, double *__restrict__ packed, int to_packed)
+{
+    const int4 t = tiles[blockIdx.x];                 // {k, i, 0, 0}: tile row i, tile column k
+    double *tile = const_cast<double *>(S) + (size_t)t.y * 64 * ld + (size_t)t.x * 64;
+    double *buf = packed + (size_t)blockIdx.x * 4096;
+    for (int q = threadIdx.x; q < 4096; q += 256) {
+        const int r = q >> 6, c = q & 63;
+        if (to_packed) buf[q] = tile[(size_t)r * ld + c]; else tile[(size_t)r * ld + c] = buf[q];
+    }
+}
+
 __device__ __forceinline__ void cp_async8(void *smem, const void *gmem)
 {
     const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);

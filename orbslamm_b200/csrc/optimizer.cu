@@ -61,6 +61,7 @@ struct orbo_handle {
     StagePool pool;          // pose optimisation staging
     StagePool ba_pool;       // bundle adjustment buffers
     DevBuf ba_tasks;         // panel / update task lists of the tiled Cholesky (sized by the symbolic factorisation)
+    DevBuf ba_packed;        // sharded solve: the structurally nonzero tiles of the reduced system, contiguous, for the all-reduce
     PinnedBuf h_scalars;
     KernelTimer timer;       // BA kernels, ids = BaK
     ncclComm_t comm = nullptr;   // set by orbo_comm_init: orbo_bundle_adjust becomes a collective over map-point shards
@@ -96,7 +97,7 @@ int orbo_destroy(orbo_handle *h)
     if (h->stream && h->own_stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
     else cudaDeviceSynchronize();
     if (h->comm) { if (g_nccl.CommAbort) g_nccl.CommAbort(h->comm); else g_nccl.CommDestroy(h->comm); }   // abort: never block on a peer at teardown
-    h->pool.release(); h->ba_pool.release(); h->ba_tasks.release(); h->h_scalars.release(); h->timer.release();
+    h->pool.release(); h->ba_pool.release(); h->ba_tasks.release(); h->ba_packed.release(); h->h_scalars.release(); h->timer.release();
     delete h;
     return ORBS_OK;
 }
@@ -496,8 +497,16 @@ struct BaHost {
             k_ba_schur<<<pt_blocks, 256, 0, st>>>(B, lambda);
             T().end(st);
             // the one exchange step of the sharded solve: sum the partial reduced systems over the map-point shards
-            if (int rc = allreduce(B.S, (size_t)ld * ld, ncclDouble, ncclSum)) return rc;
-            if (int rc = allreduce(B.bs, (size_t)ld, ncclDouble, ncclSum)) return rc;
+            if (multi()) {
+                // all-reduce the structurally nonzero tiles only (148 of 1275 at 500 keyframes: 4.8 MB instead of the 82 MB ld x ld array)
+                if (int rc = h->ba_packed.reserve(n_panel * 4096 * sizeof(double))) return rc;
+                double *packed = h->ba_packed.as<double>();
+                k_tiles_pack<<<(unsigned)n_panel, 256, 0, st>>>(B.S, ld, plan.panel, packed, 1);
+                if (int rc = allreduce(packed, n_panel * 4096, ncclDouble, ncclSum)) return rc;
+                k_tiles_pack<<<(unsigned)n_panel, 256, 0, st>>>(B.S, ld, plan.panel, packed, 0);
+                if (int rc = allreduce(B.bs, (size_t)ld, ncclDouble, ncclSum)) return rc;
+                count(2);
+            }
             count(2);
             T().begin(BK_POTRF, st);
             for (int l = 0; l < nlevels; l++) {
