@@ -472,7 +472,26 @@ def cpu_baseline_frontend(cores, frames_per_core):
     return n / s, wall
 
 
+_REAL_STDOUT = None
+
+
+def _own_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner on communicator creation), so file
+    descriptor 1 is pointed at stderr for the whole run and the result line goes to the saved descriptor."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, (json.dumps(line) + "\n").encode())
+
+
 def main():
+    _own_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -497,7 +516,7 @@ def main():
             return
         if args.workload == "ba":
             from bench_ba import reference_line
-            print(json.dumps(reference_line(args)), flush=True)
+            emit(reference_line(args))
             return
         cores = os.cpu_count() or 1
         per = max(20, args.steps + args.warmup)          # one step = one new frame on every core's stream; >= 20 frames per core
@@ -514,7 +533,7 @@ def main():
                 "cpu_baseline": {"value": round(fps, 2), "unit": "frames/s", "cores": cores, "kind": "port",
                                  "sample": f"{per} frames x {cores} streams (one per core), {wall:.1f} s"},
                 "e2e": {"value": round(fps, 2), "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line), flush=True)
+        emit(line)
         return
 
     if world > 1:
@@ -533,7 +552,7 @@ def main():
                                    "sample": f"{max(10, args.cpu_frames)} frames of one stream, {wall1:.1f} s; cv2 4.13 primitives + restated reference code "
                                              "(reference front end is single-threaded per stream)"}
     if rank == 0:
-        print(json.dumps(out), flush=True)
+        emit(out)
     if world > 1:
         import torch.distributed as dist
         dist.barrier()
