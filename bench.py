@@ -475,6 +475,19 @@ def cpu_baseline_frontend(cores, frames_per_core):
 _REAL_STDOUT = None
 
 
+def cpu_model():
+    """CPU model and logical core count of the box the baseline ran on (SURVEY.md 8d asks for both next to the CPU number)."""
+    name = "unknown"
+    try:
+        for l in open("/proc/cpuinfo"):
+            if l.lower().startswith("model name"):
+                name = l.split(":", 1)[1].strip()
+                break
+    except OSError:
+        pass
+    return f"{name} ({os.cpu_count()} logical cores)"
+
+
 def _own_stdout():
     """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner on communicator creation), so file
     descriptor 1 is pointed at stderr for the whole run and the result line goes to the saved descriptor."""
@@ -530,7 +543,7 @@ def main():
                                    "code, one independent stream per core.  oracle/_ref holds the reference's own ORBextractor.cc / ORBmatcher.cc as object code, but over "
                                    "scalar restatements of those primitives (OpenCV C++ headers are not in the image; 175 vs 99 ms per 1241x376 extraction), and "
                                    "Optimizer.cc cannot be built at all (Eigen): the faster port is the fairer baseline"},
-                "cpu_baseline": {"value": round(fps, 2), "unit": "frames/s", "cores": cores, "kind": "port",
+                "cpu_baseline": {"value": round(fps, 2), "unit": "frames/s", "cores": cores, "kind": "port", "cpu": cpu_model(),
                                  "sample": f"{per} frames x {cores} streams (one per core), {wall:.1f} s"},
                 "e2e": {"value": round(fps, 2), "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         emit(line)
@@ -548,7 +561,7 @@ def main():
         out = bench_frontend(args, rank, world)
         if rank == 0:
             fps1, wall1 = cpu_baseline_frontend(1, max(10, args.cpu_frames))
-            out["cpu_baseline"] = {"value": round(fps1, 2), "unit": "frames/s", "cores": 1, "kind": "port",
+            out["cpu_baseline"] = {"value": round(fps1, 2), "unit": "frames/s", "cores": 1, "kind": "port", "cpu": cpu_model(),
                                    "sample": f"{max(10, args.cpu_frames)} frames of one stream, {wall1:.1f} s; cv2 4.13 primitives + restated reference code "
                                              "(reference front end is single-threaded per stream)"}
     if rank == 0:

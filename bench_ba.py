@@ -125,7 +125,8 @@ def cpu_baseline_ba(K, P, repeats):
         r = oracle.bundle_adjust(g["poses"], g["fixed"], g["intr"], g["points"], g["kf"], g["pt"], g["uv"], g["inv_sigma2"], True, 5, 10, True)
         iters += r["lm_iterations"]
     s = time.perf_counter() - t0
-    return {"value": round(iters / s, 3), "unit": "LM iterations/s", "cores": 1, "kind": "port",
+    from bench import cpu_model
+    return {"value": round(iters / s, 3), "unit": "LM iterations/s", "cores": 1, "kind": "port", "cpu": cpu_model(),
             "sample": f"{repeats} LocalBA call(s) on the same {K} KF / {P} pt graph ({iters} LM iterations, {s:.1f} s); fp64 restatement of the "
                       "g2o path with a profile LDLT of the reduced system, 1 thread (g2o OpenMP is off in the reference)"}
 
