@@ -34,3 +34,24 @@ def test_ba_reduces_reprojection_error_and_flags_outliers():
     assert ref["outlier"][g["is_outlier"]].mean() > 0.97
     # fixed camera untouched, KF 0 only through the float round trip
     assert np.array_equal(ref["poses"][1], g["poses"][1]) and np.abs(ref["poses"][0] - g["poses"][0]).max() < 1e-6
+
+
+def test_optimize_sim3_oracle_equals_twin():
+    """oracle_optimize_sim3 against the independent matrix-exponential twin (tests/sim3_twin.py): same inlier sets and counts, the optimised Sim3 equal
+    to 1e-6 (the two use different Jacobian steps, so the last LM trials differ at the noise floor), for free and fixed scale."""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import kf_family as kff
+    import sim3_twin
+    for cam, sid in ((synth.TUM, 1), (synth.KITTI, 2)):
+        c = kff.make_sim3_opt_case(cam, sid)
+        for fix in (False, True):
+            args = (c["valid"], c["P1c"], c["P2c"], c["obs1"], c["obs2"], c["w1"], c["w2"], c["K1"], c["K2"])
+            r = oracle.optimize_sim3(c["init"], *args, 10.0, fix)
+            T, inl, n_in = sim3_twin.Twin(c["init"], *args, 10.0, fix).run()
+            assert n_in == r["n_in"] and np.array_equal(inl, r["inlier"] > 0)
+            To = sim3_twin.to_matrix(r["sim3"])
+            assert np.abs(T - To).max() < 1e-6 * np.abs(To).max(), np.abs(T - To).max()
+    # fewer than 10 correspondences after the first pass: both return 0 inliers and no estimate
+    v = c["valid"].copy(); v[np.where(v)[0][9:]] = 0
+    assert sim3_twin.Twin(c["init"], v, *args[1:], 10.0, False).run()[2] == 0 and oracle.optimize_sim3(c["init"], v, *args[1:], 10.0, False)["n_in"] == 0
