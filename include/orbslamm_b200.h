@@ -391,6 +391,16 @@ int orbo_bundle_adjust(orbo_handle *h, int K, float *poses, const uint8_t *fixed
                        int two_stage, int its0, int its1, int robust, const volatile int *stop_flag,
                        double *e_chi2, uint8_t *e_depth_ok, uint8_t *e_outlier, int32_t *stats);
 
+/* Numeric core of Optimizer::OptimizeEssentialGraph / MMOptimizeEssentialGraph (S/src/Optimizer.cc:804-1067, 1069-1346): Levenberg over K
+ * VertexSim3Expmap vertices and E EdgeSim3 edges (error = log(Sji * Siw * Sjw^-1), identity information, numeric Jacobians with delta = 1e-9 for
+ * both vertices), lambda_init = 1e-16 and 20 iterations in the reference; the normal equations go through the tiled sparse Cholesky.
+ * HOST pointers.  sim3 f64[K,8] in/out = r (x y z w), t, s of every vertex (CorrectedSim3 or Sim3(Rcw, tcw, 1), :845-869); fixed u8[K] (the loop
+ * keyframe, :866-867); edge e joins vertex[0] = e_i[e] and vertex[1] = e_j[e] with measurement e_meas f64[E,8] = Sji (:895-905; the caller builds the
+ * loop / spanning-tree / loop-edge / covisibility edge set of :880-1000); fix_scale = bFixScale; lambda_init <= 0 selects g2o's default
+ * (1e-5 * max diagonal).  stats i32[3] (may be NULL): LM iterations, LM trials, failed factorisations. */
+int orbo_optimize_pose_graph(orbo_handle *h, int K, double *sim3, const uint8_t *fixed, int E, const int32_t *e_i, const int32_t *e_j,
+                             const double *e_meas, int fix_scale, int iterations, double lambda_init, int32_t *stats);
+
 /* Sim3Solver (S/src/Sim3Solver.cc), the data-parallel part of the RANSAC.  ComputeSim3 (Horn's closed form on three points, :226-338) stays with
  * the caller: the random index triples do not depend on the inlier counts, so all hypotheses of a solver (<= mRansacMaxIts = 300) can be
  * generated first and checked in ONE call; the caller then walks the counts in order and applies the rule of iterate() (:176-194) unchanged.

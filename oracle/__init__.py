@@ -559,3 +559,17 @@ def sim3_check_inliers(T12, T21, X3Dc1, X3Dc2, P1im1, P2im2, max_err1, max_err2,
     lib().oracle_sim3_check_inliers(nh, _p(a[0], _f32p), _p(a[1], _f32p), N, _p(a[2], _f32p), _p(a[3], _f32p), _p(a[4], _f32p), _p(a[5], _f32p), _p(m1, _i32p),
                                     _p(m2, _i32p), _p(k1, _f32p), _p(k2, _f32p), _p(inl, _u8p), _p(n, _i32p))
     return inl, n
+
+
+def optimize_pose_graph(sim3, fixed, e_i, e_j, e_meas, fix_scale=False, iterations=20, lambda_init=1e-16):
+    """Numeric core of Optimizer::OptimizeEssentialGraph (Optimizer.cc:804-1067).  sim3 [K,8], e_meas [E,8] = (qx qy qz qw tx ty tz s).
+    Returns dict(sim3, lm_iterations, lm_trials, chol_failures)."""
+    S = np.ascontiguousarray(sim3, np.float64).reshape(-1, 8).copy(); K = len(S)
+    fx = np.ascontiguousarray(fixed, np.uint8); ei = np.ascontiguousarray(e_i, np.int32); ej = np.ascontiguousarray(e_j, np.int32)
+    em = np.ascontiguousarray(e_meas, np.float64).reshape(-1, 8); st = np.zeros(3, np.int32)
+    L = lib()
+    L.oracle_optimize_pose_graph.restype = ctypes.c_int
+    L.oracle_optimize_pose_graph.argtypes = [ctypes.c_int, _f64p, _u8p, ctypes.c_int, _i32p, _i32p, _f64p, ctypes.c_int, ctypes.c_int, ctypes.c_double, _i32p]
+    L.oracle_optimize_pose_graph(K, _p(S, _f64p), _p(fx, _u8p), len(ei), _p(ei, _i32p), _p(ej, _i32p), _p(em, _f64p), int(bool(fix_scale)), int(iterations),
+                                 float(lambda_init), _p(st, _i32p))
+    return dict(sim3=S, lm_iterations=int(st[0]), lm_trials=int(st[1]), chol_failures=int(st[2]))

@@ -1542,3 +1542,177 @@ void oracle_sim3_check_inliers(int n_hyp, const float *T12, const float *T21, in
         n_inliers[h] = n;
     }
 }
+
+/* ======================================================================================== */
+/* Optimizer::OptimizeEssentialGraph / MMOptimizeEssentialGraph, numeric core (S/src/Optimizer.cc:804-1067, 1069-1346): a pose graph of
+ * VertexSim3Expmap vertices and EdgeSim3 edges (error = log(Sji * Siw * Sjw^-1), identity information, no robust kernel; g2o/types/
+ * types_seven_dof_expmap.h:64-84, sim3.h:110-181), numeric Jacobians for both vertices (base_binary_edge.hpp:131-205, delta = 1e-9), g2o's
+ * Levenberg with setUserLambdaInit(1e-16) and 20 iterations, BlockSolver_7_3 + LinearSolverEigen (a direct sparse Cholesky; here a dense LDLT,
+ * equal up to fp64 rounding).  The graph assembly (which keyframes, which edges) is the shim's / caller's job. */
+static void lu3_solve(const double A[9], const double b[3], double x[3])          /* Eigen PartialPivLU 3x3 */
+{
+    double M[3][4] = {{A[0], A[1], A[2], b[0]}, {A[3], A[4], A[5], b[1]}, {A[6], A[7], A[8], b[2]}};
+    for (int c = 0; c < 3; c++) {
+        int p = c;
+        for (int r = c + 1; r < 3; r++) if (fabs(M[r][c]) > fabs(M[p][c])) p = r;
+        if (p != c) for (int k = 0; k < 4; k++) { const double t = M[c][k]; M[c][k] = M[p][k]; M[p][k] = t; }
+        for (int r = c + 1; r < 3; r++) { const double f = M[r][c] / M[c][c]; for (int k = c; k < 4; k++) M[r][k] -= f * M[c][k]; }
+    }
+    for (int r = 2; r >= 0; r--) { double s = M[r][3]; for (int k = r + 1; k < 3; k++) s -= M[r][k] * x[k]; x[r] = s / M[r][r]; }
+}
+
+static void sim3_log(const sim3 *S, double res[7])                                 /* Sim3::log, sim3.h:110-181 */
+{
+    const double sigma = log(S->s);
+    double R[9], omega[3], O[9], O2[9], W[9];
+    quat_to_R(S->q, R);
+    const double d = 0.5 * (R[0] + R[4] + R[8] - 1), eps = 0.00001;
+    const double dR[3] = {R[7] - R[5], R[2] - R[6], R[3] - R[1]};                  /* deltaR(R) */
+    double A, B, C;
+    if (fabs(sigma) < eps) {
+        C = 1;
+        if (d > 1 - eps) { for (int k = 0; k < 3; k++) omega[k] = 0.5 * dR[k]; A = 1. / 2.; B = 1. / 6.; }
+        else {
+            const double theta = acos(d), theta2 = theta * theta;
+            for (int k = 0; k < 3; k++) omega[k] = theta / (2 * sqrt(1 - d * d)) * dR[k];
+            A = (1 - cos(theta)) / (theta2); B = (theta - sin(theta)) / (theta2 * theta);
+        }
+    } else {
+        C = (S->s - 1) / sigma;
+        if (d > 1 - eps) {
+            const double sigma2 = sigma * sigma;
+            for (int k = 0; k < 3; k++) omega[k] = 0.5 * dR[k];
+            A = ((sigma - 1) * S->s + 1) / (sigma2); B = ((0.5 * sigma2 - sigma + 1) * S->s) / (sigma2 * sigma);
+        } else {
+            const double theta = acos(d);
+            for (int k = 0; k < 3; k++) omega[k] = theta / (2 * sqrt(1 - d * d)) * dR[k];
+            const double theta2 = theta * theta, a = S->s * sin(theta), b = S->s * cos(theta), c = theta2 + sigma * sigma;
+            A = (a * sigma + (1 - b) * theta) / (theta * c); B = (C - ((b - 1) * sigma + a * theta) / (c)) * 1. / (theta2);
+        }
+    }
+    O[0] = 0; O[1] = -omega[2]; O[2] = omega[1]; O[3] = omega[2]; O[4] = 0; O[5] = -omega[0]; O[6] = -omega[1]; O[7] = omega[0]; O[8] = 0;
+    mat3_mul(O, O, O2);
+    for (int i = 0; i < 9; i++) W[i] = A * O[i] + B * O2[i] + C * (i % 4 == 0 ? 1.0 : 0.0);
+    double ups[3];
+    lu3_solve(W, S->t, ups);
+    for (int k = 0; k < 3; k++) { res[k] = omega[k]; res[k + 3] = ups[k]; }
+    res[6] = sigma;
+}
+
+static void pg_edge_error(const sim3 *meas, const sim3 *Si, const sim3 *Sj, double e[7])      /* EdgeSim3::computeError */
+{
+    sim3 Sjinv, a, b;
+    sim3_inverse(Sj, &Sjinv);
+    sim3_mul(meas, Si, &a);
+    sim3_mul(&a, &Sjinv, &b);
+    sim3_log(&b, e);
+}
+
+static void pg_oplus(const sim3 *S, const double *upd, int fix_scale, sim3 *out)
+{
+    double u[7];
+    memcpy(u, upd, sizeof u);
+    if (fix_scale) u[6] = 0;
+    sim3 d;
+    sim3_exp(u, &d);
+    sim3_mul(&d, S, out);
+}
+
+static int ldlt_dense(double *A, int n, const double *b, double *x)              /* unpivoted LDL^T, zero pivot -> failure */
+{
+    for (int i = 0; i < n; i++)
+        for (int j = 0; j <= i; j++) {
+            double s = A[(size_t)i * n + j];
+            for (int k = 0; k < j; k++) s -= A[(size_t)i * n + k] * A[(size_t)j * n + k] * A[(size_t)k * n + k];
+            if (j < i) A[(size_t)i * n + j] = s / A[(size_t)j * n + j];
+            else { if (s == 0.0 || !isfinite(s)) return 0; A[(size_t)i * n + i] = s; }
+        }
+    for (int i = 0; i < n; i++) { double s = b[i]; for (int k = 0; k < i; k++) s -= A[(size_t)i * n + k] * x[k]; x[i] = s; }
+    for (int i = 0; i < n; i++) x[i] /= A[(size_t)i * n + i];
+    for (int i = n - 1; i >= 0; i--) { const double xi = x[i]; for (int k = 0; k < i; k++) x[k] -= A[(size_t)i * n + k] * xi; }
+    return 1;
+}
+
+/* sim3 [K,8] in/out (r xyzw, t, s), fixed u8[K]; edges: vertex[0] = e_i, vertex[1] = e_j, measurement e_meas [E,8] (= Sji).
+ * stats (may be NULL): LM iterations, LM trials, failed factorisations.  Returns the number of iterations executed. */
+int oracle_optimize_pose_graph(int K, double *sim3_io, const uint8_t *fixed, int E, const int *e_i, const int *e_j, const double *e_meas, int fix_scale,
+                               int iterations, double lambda_init, int *stats)
+{
+    sim3 *V = (sim3 *)malloc(sizeof(sim3) * (K > 0 ? K : 1)), *bak = (sim3 *)malloc(sizeof(sim3) * (K > 0 ? K : 1)), *M = (sim3 *)malloc(sizeof(sim3) * (E > 0 ? E : 1));
+    int *hidx = (int *)malloc(sizeof(int) * (K > 0 ? K : 1));
+    int nA = 0;
+    for (int k = 0; k < K; k++) { memcpy(V[k].q, sim3_io + 8 * k, 32); memcpy(V[k].t, sim3_io + 8 * k + 4, 24); V[k].s = sim3_io[8 * k + 7]; hidx[k] = fixed[k] ? -1 : nA++; }
+    for (int e = 0; e < E; e++) { memcpy(M[e].q, e_meas + 8 * e, 32); memcpy(M[e].t, e_meas + 8 * e + 4, 24); M[e].s = e_meas[8 * e + 7]; }
+    const int n = 7 * nA;
+    double *H = (double *)malloc(sizeof(double) * (size_t)(n > 0 ? n : 1) * (n > 0 ? n : 1)), *Hw = (double *)malloc(sizeof(double) * (size_t)(n > 0 ? n : 1) * (n > 0 ? n : 1));
+    double *b = (double *)malloc(sizeof(double) * (n > 0 ? n : 1)), *x = (double *)calloc(n > 0 ? n : 1, sizeof(double)), *err = (double *)malloc(sizeof(double) * 7 * (E > 0 ? E : 1));
+    int its = 0, trials = 0, fails = 0, nbad = 0;
+    double lambda = 0, ni = 2;
+#define PG_ACTIVE(e) (hidx[e_i[e]] >= 0 || hidx[e_j[e]] >= 0)
+#define PG_CHI2(out) do { out = 0; for (int e = 0; e < E; e++) { if (!PG_ACTIVE(e)) continue; pg_edge_error(&M[e], &V[e_i[e]], &V[e_j[e]], &err[7 * e]); for (int k = 0; k < 7; k++) out += err[7 * e + k] * err[7 * e + k]; } } while (0)
+    for (int it = 0; it < iterations && n > 0; it++) {
+        double currentChi, tempChi;
+        PG_CHI2(currentChi);
+        const double iniChi = currentChi;
+        memset(H, 0, sizeof(double) * (size_t)n * n); memset(b, 0, sizeof(double) * n);
+        for (int e = 0; e < E; e++) {
+            if (!PG_ACTIVE(e)) continue;
+            double J[2][7][7];                                                   /* [vertex][row][col] */
+            const int vid[2] = {e_i[e], e_j[e]};
+            for (int s = 0; s < 2; s++) {
+                if (hidx[vid[s]] < 0) continue;
+                for (int d = 0; d < 7; d++) {
+                    double add[7] = {0, 0, 0, 0, 0, 0, 0}, ep[7], em[7];
+                    sim3 P;
+                    add[d] = 1e-9; pg_oplus(&V[vid[s]], add, fix_scale, &P);
+                    pg_edge_error(&M[e], s == 0 ? &P : &V[vid[0]], s == 1 ? &P : &V[vid[1]], ep);
+                    add[d] = -1e-9; pg_oplus(&V[vid[s]], add, fix_scale, &P);
+                    pg_edge_error(&M[e], s == 0 ? &P : &V[vid[0]], s == 1 ? &P : &V[vid[1]], em);
+                    for (int r = 0; r < 7; r++) J[s][r][d] = (1.0 / (2 * 1e-9)) * (ep[r] - em[r]);
+                }
+            }
+            for (int s = 0; s < 2; s++) {
+                const int hs = hidx[vid[s]];
+                if (hs < 0) continue;
+                for (int a = 0; a < 7; a++) { double g = 0; for (int r = 0; r < 7; r++) g += J[s][r][a] * err[7 * e + r]; b[7 * hs + a] -= g; }
+                for (int t = 0; t < 2; t++) {
+                    const int ht = hidx[vid[t]];
+                    if (ht < 0) continue;
+                    for (int a = 0; a < 7; a++) for (int c = 0; c < 7; c++) { double g = 0; for (int r = 0; r < 7; r++) g += J[s][r][a] * J[t][r][c]; H[(size_t)(7 * hs + a) * n + 7 * ht + c] += g; }
+                }
+            }
+        }
+        if (it == 0) { lambda = lambda_init > 0 ? lambda_init : 0; if (!(lambda_init > 0)) { double mx = 0; for (int a = 0; a < n; a++) mx = fmax(fabs(H[(size_t)a * n + a]), mx); lambda = 1e-5 * mx; } ni = 2; nbad = 0; }
+        double rho = 0;
+        int qmax = 0;
+        do {
+            memcpy(bak, V, sizeof(sim3) * K);
+            memcpy(Hw, H, sizeof(double) * (size_t)n * n);
+            for (int a = 0; a < n; a++) Hw[(size_t)a * n + a] += lambda;
+            const int ok2 = ldlt_dense(Hw, n, b, x);
+            if (!ok2) fails++;
+            for (int k = 0; k < K; k++) if (hidx[k] >= 0) { sim3 nv; pg_oplus(&V[k], &x[7 * hidx[k]], fix_scale, &nv); V[k] = nv; }
+            PG_CHI2(tempChi);
+            if (!ok2) tempChi = DBL_MAX;
+            rho = currentChi - tempChi;
+            double scale = 0.;
+            for (int a = 0; a < n; a++) scale += x[a] * (lambda * x[a] + b[a]);
+            scale += 1e-3;
+            rho /= scale;
+            if (rho > 0 && isfinite(tempChi)) {
+                double alpha = 1. - pow((2 * rho - 1), 3);
+                alpha = fmin(alpha, 2. / 3.);
+                lambda *= fmax(1. / 3., alpha); ni = 2; currentChi = tempChi;
+            } else { lambda *= ni; ni *= 2; memcpy(V, bak, sizeof(sim3) * K); }
+            qmax++; trials++;
+        } while (rho < 0 && qmax < 10);
+        its++;
+        if (qmax == 10 || rho == 0) break;
+        if ((iniChi - currentChi) * 1e3 < iniChi) nbad++; else nbad = 0;
+        if (nbad >= 3) break;
+    }
+    for (int k = 0; k < K; k++) { memcpy(sim3_io + 8 * k, V[k].q, 32); memcpy(sim3_io + 8 * k + 4, V[k].t, 24); sim3_io[8 * k + 7] = V[k].s; }
+    if (stats) { stats[0] = its; stats[1] = trials; stats[2] = fails; }
+    free(V); free(bak); free(M); free(hidx); free(H); free(Hw); free(b); free(x); free(err);
+    return its;
+}

@@ -568,6 +568,16 @@ class Optimizer:
                                                _ptr(k2), _ptr(inl), _ptr(n), 0))
         return inl, n
 
+    def OptimizePoseGraph(self, sim3, fixed, e_i, e_j, e_meas, bFixScale=False, iterations=20, lambda_init=1e-16):
+        """Numeric core of Optimizer::OptimizeEssentialGraph (Optimizer.cc:804-1067): sim3 [K,8], e_meas [E,8] = Sji.  Returns dict(sim3, lm_iterations,
+        lm_trials, chol_failures)."""
+        S = np.ascontiguousarray(sim3, np.float64).reshape(-1, 8).copy()
+        fx = np.ascontiguousarray(fixed, np.uint8); ei = np.ascontiguousarray(e_i, np.int32); ej = np.ascontiguousarray(e_j, np.int32)
+        em = np.ascontiguousarray(e_meas, np.float64).reshape(-1, 8); st = np.zeros(3, np.int32)
+        _check(self._L.orbo_optimize_pose_graph(self._h, len(S), _ptr(S), _ptr(fx), len(ei), _ptr(ei), _ptr(ej), _ptr(em), int(bool(bFixScale)), int(iterations),
+                                                float(lambda_init), _ptr(st)))
+        return dict(sim3=S, lm_iterations=int(st[0]), lm_trials=int(st[1]), chol_failures=int(st[2]))
+
     def _ba(self, poses, fixed, intr, points, e_kf, e_pt, e_uv, e_inv_sigma2, two_stage, its0, its1, robust, stop_flag=None):
         poses = np.ascontiguousarray(poses, np.float32).reshape(-1, 16).copy(); K = len(poses)
         fixed = np.ascontiguousarray(fixed, np.uint8)

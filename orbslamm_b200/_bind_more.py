@@ -44,6 +44,7 @@ def declare(L):
     L.orbo_optimize_sim3.argtypes = [vp, i, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i, f, i, vp, vp, vp, i]; L.orbo_optimize_sim3.restype = c.c_int
     L.orbo_sim3_prepare.argtypes = [vp, i, vp, vp, vp, i, vp, vp, vp, i]; L.orbo_sim3_prepare.restype = c.c_int
     L.orbo_sim3_check_inliers.argtypes = [vp, i, vp, vp, i, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i]; L.orbo_sim3_check_inliers.restype = c.c_int
+    L.orbo_optimize_pose_graph.argtypes = [vp, i, vp, vp, i, vp, vp, vp, i, i, c.c_double, vp]; L.orbo_optimize_pose_graph.restype = c.c_int
     L.orbo_bundle_adjust.argtypes = [vp, i, vp, vp, vp, i, vp, i, vp, vp, vp, vp, i, i, i, i, vp, vp, vp, vp, vp]
     for n in ("orbo_create", "orbo_destroy", "orbo_set_stream", "orbo_synchronize", "orbo_pose_optimization", "orbo_bundle_adjust"):
         getattr(L, n).restype = c.c_int

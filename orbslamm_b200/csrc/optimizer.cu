@@ -15,6 +15,7 @@
 #include "common.cuh"
 #include "pose_opt.cuh"
 #include "sim3_opt.cuh"
+#include "pose_graph.cuh"
 #include "ba_kernels.cuh"
 
 using namespace orbs;
@@ -839,5 +840,241 @@ extern "C" int orbo_get_kernel_times(orbo_handle *h, double *total_ms, long long
     ORBS_CUDA(cudaStreamSynchronize(h->stream));
     h->timer.collect();
     for (int i = 0; i < n && i < KernelTimer::kMaxKernels; i++) { total_ms[i] = h->timer.total_ms[i]; counts[i] = h->timer.count[i]; }
+    return ORBS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Essential-graph (Sim3 pose graph) optimisation: host-driven Levenberg over the kernels of pose_graph.cuh, normal equations factored by
+// the tiled sparse Cholesky of the BA (same kernels, own schedule: 9 vertices per 64-row tile)
+namespace {
+
+struct PgHost {
+    orbo_handle *h; cudaStream_t st; PgDev P;
+    DevBuf bufs[16]; int nbuf = 0;
+    int nt = 0, nlevels = 0; size_t n_panel = 0;
+    std::vector<int> panel_lv, update_lv;
+    CholPlan plan = {};
+    double *Linv = nullptr, *packed = nullptr; int *ready = nullptr, *flags = nullptr;
+    int eblocks = 0;
+    ~PgHost() { for (int i = 0; i < nbuf; i++) bufs[i].release(); }
+    template <typename T> T *alloc(size_t n, int *rc) { if (*rc) return nullptr; if (nbuf >= 16) { *rc = ORBS_E_INVALID; return nullptr; } *rc = bufs[nbuf].reserve(std::max<size_t>(n, 1) * sizeof(T)); return bufs[nbuf++].as<T>(); }
+
+    // tile groups of kPgPerTile consecutive free vertices; adjacency from the edges; nested dissection; symbolic factorisation; task lists
+    int schedule(int K, const std::vector<int> &hidx, int E, const int32_t *e_i, const int32_t *e_j)
+    {
+        const int nA = P.nA;
+        nt = (nA + kPgPerTile - 1) / kPgPerTile;
+        const int ng = nt;
+        std::vector<uint8_t> adj((size_t)ng * ng, 0);
+        for (int e = 0; e < E; e++) {
+            const int a = hidx[e_i[e]], b = hidx[e_j[e]];
+            if (a < 0 || b < 0) continue;
+            adj[(size_t)(a / kPgPerTile) * ng + b / kPgPerTile] = 1; adj[(size_t)(b / kPgPerTile) * ng + a / kPgPerTile] = 1;
+        }
+        std::vector<int> order; order.reserve(nt);
+        BaHost::nd_order(adj, ng, 0, ng, order);
+        std::vector<int> pos(ng);
+        for (int t = 0; t < nt; t++) pos[order[t]] = t;
+        std::vector<uint8_t> pat((size_t)nt * nt, 0);
+        for (int a = 0; a < ng; a++)
+            for (int b = 0; b < ng; b++) if (a != b && adj[(size_t)a * ng + b]) { const int i = std::max(pos[a], pos[b]), j = std::min(pos[a], pos[b]); pat[(size_t)i * nt + j] = 1; }
+        std::vector<int> rows_start(nt + 1, 0), rows, cols_start(nt + 1, 0), cols, level(nt, 0);
+        for (int k = 0; k < nt; k++) {
+            const size_t r0 = rows.size();
+            for (int i = k + 1; i < nt; i++) if (pat[(size_t)i * nt + k]) rows.push_back(i);
+            rows_start[k + 1] = (int)rows.size();
+            for (size_t x = r0; x < rows.size(); x++) for (size_t y = r0; y < x; y++) pat[(size_t)rows[x] * nt + rows[y]] = 1;
+        }
+        nlevels = 0;
+        for (int i = 0; i < nt; i++) {
+            int lv = 0;
+            for (int k = 0; k < i; k++) if (pat[(size_t)i * nt + k]) { cols.push_back(k); lv = std::max(lv, level[k] + 1); }
+            cols_start[i + 1] = (int)cols.size();
+            level[i] = lv; nlevels = std::max(nlevels, lv + 1);
+        }
+        std::vector<std::vector<int>> by_level(nlevels);
+        for (int k = 0; k < nt; k++) by_level[level[k]].push_back(k);
+        std::vector<int4> panel, update;
+        panel_lv.assign(nlevels + 1, 0); update_lv.assign(nlevels + 1, 0);
+        std::vector<int> hits((size_t)nt * nt, 0);
+        for (int l = 0; l < nlevels; l++) {
+            const size_t u0 = update.size();
+            for (int k : by_level[l]) {
+                panel.push_back(make_int4(k, k, 0, 0));
+                for (int x = rows_start[k]; x < rows_start[k + 1]; x++) panel.push_back(make_int4(k, rows[x], 0, 0));
+                for (int x = rows_start[k]; x < rows_start[k + 1]; x++)
+                    for (int y = rows_start[k]; y <= x; y++) { update.push_back(make_int4(k, rows[x], rows[y], 0)); hits[(size_t)rows[x] * nt + rows[y]]++; }
+            }
+            for (size_t t = u0; t < update.size(); t++) if (hits[(size_t)update[t].y * nt + update[t].z] > 1) update[t].w = 1;
+            for (size_t t = u0; t < update.size(); t++) hits[(size_t)update[t].y * nt + update[t].z] = 0;
+            panel_lv[l + 1] = (int)panel.size(); update_lv[l + 1] = (int)update.size();
+        }
+        n_panel = panel.size();
+        ORBS_REQUIRE(panel.size() + update.size() <= ((size_t)1 << 26), ORBS_E_INVALID, "pose graph too large / too dense for the tiled Cholesky");
+        std::vector<int> rowbase(std::max(nA, 1));
+        std::vector<uint8_t> rowpad((size_t)nt * NB, 1);
+        for (int ip = 0; ip < nA; ip++) {
+            rowbase[ip] = NB * pos[ip / kPgPerTile] + 7 * (ip % kPgPerTile);
+            for (int a = 0; a < 7; a++) rowpad[rowbase[ip] + a] = 0;
+        }
+        int rc = ORBS_OK;
+        int *d_rs = alloc<int>(nt + 1, &rc), *d_cs = alloc<int>(nt + 1, &rc), *d_rows = alloc<int>(rows.size(), &rc), *d_cols = alloc<int>(cols.size(), &rc);
+        int4 *d_tasks = alloc<int4>(panel.size() + update.size(), &rc);
+        int *d_rowbase = alloc<int>(nA, &rc); uint8_t *d_rowpad = alloc<uint8_t>(rowpad.size(), &rc);
+        if (rc) return rc;
+        ORBS_CUDA(cudaMemcpyAsync(d_rs, rows_start.data(), (nt + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
+        ORBS_CUDA(cudaMemcpyAsync(d_cs, cols_start.data(), (nt + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
+        if (!rows.empty()) { ORBS_CUDA(cudaMemcpyAsync(d_rows, rows.data(), rows.size() * sizeof(int), cudaMemcpyHostToDevice, st)); ORBS_CUDA(cudaMemcpyAsync(d_cols, cols.data(), cols.size() * sizeof(int), cudaMemcpyHostToDevice, st)); }
+        ORBS_CUDA(cudaMemcpyAsync(d_tasks, panel.data(), panel.size() * sizeof(int4), cudaMemcpyHostToDevice, st));
+        if (!update.empty()) ORBS_CUDA(cudaMemcpyAsync(d_tasks + panel.size(), update.data(), update.size() * sizeof(int4), cudaMemcpyHostToDevice, st));
+        ORBS_CUDA(cudaMemcpyAsync(d_rowbase, rowbase.data(), std::max(nA, 1) * sizeof(int), cudaMemcpyHostToDevice, st));
+        ORBS_CUDA(cudaMemcpyAsync(d_rowpad, rowpad.data(), rowpad.size(), cudaMemcpyHostToDevice, st));
+        ORBS_CUDA(cudaStreamSynchronize(st));
+        plan.rows_start = d_rs; plan.rows = d_rows; plan.cols_start = d_cs; plan.cols = d_cols; plan.panel = d_tasks; plan.update = d_tasks + panel.size();
+        P.rowbase = d_rowbase; P.row_pad = d_rowpad; P.ld = nt * NB;
+        return ORBS_OK;
+    }
+
+    int chi2(double *out)
+    {
+        k_pg_errors<<<eblocks, 128, 0, st>>>(P);
+        k_pg_sum<<<1, 32, 0, st>>>(P.partial, eblocks, P.scalars);
+        h->launches += 2;
+        ORBS_CUDA(cudaMemcpyAsync(out, P.scalars, sizeof(double), cudaMemcpyDeviceToHost, st));
+        ORBS_CUDA(cudaStreamSynchronize(st));
+        return ORBS_OK;
+    }
+    // S <- H (packed copy of the structurally nonzero tiles) + lambda I, factor, solve; ok = the factorisation succeeded
+    int solve(double lambda, bool *ok)
+    {
+        const int ld = P.ld;
+        ORBS_CUDA(cudaMemsetAsync(flags, 0, 4 * sizeof(int), st));
+        k_tiles_pack<<<(unsigned)n_panel, 256, 0, st>>>(P.S, ld, plan.panel, packed, 0);
+        k_pg_prepare<<<(ld + 255) / 256, 256, 0, st>>>(P, lambda);
+        h->launches += 2;
+        for (int l = 0; l < nlevels; l++) {
+            k_chol_panel<<<panel_lv[l + 1] - panel_lv[l], 256, kPanelSmem, st>>>(P.S, ld, plan.panel + panel_lv[l], Linv, flags);
+            h->launches++;
+            if (update_lv[l + 1] > update_lv[l]) { k_chol_update<<<update_lv[l + 1] - update_lv[l], 256, kUpdateSmem, st>>>(P.S, ld, plan.update + update_lv[l]); h->launches++; }
+        }
+        ORBS_CUDA(cudaMemsetAsync(ready, 0, 2 * (size_t)nt * sizeof(int), st));
+        const int ctas = std::min(nt, 128);
+        k_chol_solve<<<ctas, 256, 0, st>>>(P.S, ld, nt, plan, Linv, P.v, ready, 0);
+        k_chol_solve<<<ctas, 256, 0, st>>>(P.S, ld, nt, plan, Linv, P.v, ready + nt, 1);
+        h->launches += 2;
+        int f = 0;
+        ORBS_CUDA(cudaMemcpyAsync(&f, flags, sizeof(int), cudaMemcpyDeviceToHost, st));
+        ORBS_CUDA(cudaStreamSynchronize(st));
+        *ok = f == 0;
+        return ORBS_OK;
+    }
+};
+
+}  // namespace
+
+extern "C" int orbo_optimize_pose_graph(orbo_handle *h, int K, double *sim3, const uint8_t *fixed, int E, const int32_t *e_i, const int32_t *e_j,
+                                        const double *e_meas, int fix_scale, int iterations, double lambda_init, int32_t *stats)
+{
+    ORBS_REQUIRE(h && sim3 && fixed && e_i && e_j && e_meas, ORBS_E_INVALID, "null argument");
+    ORBS_REQUIRE(K > 0 && E > 0 && iterations >= 0, ORBS_E_INVALID, "non-positive size");
+    for (int e = 0; e < E; e++) ORBS_REQUIRE(e_i[e] >= 0 && e_i[e] < K && e_j[e] >= 0 && e_j[e] < K && e_i[e] != e_j[e], ORBS_E_INVALID, "edge endpoint out of range");
+    std::lock_guard<std::mutex> lk(h->mu);
+    ORBS_CUDA(cudaSetDevice(h->device));
+    if (stats) { stats[0] = stats[1] = stats[2] = 0; }
+    PgHost G; G.h = h; G.st = h->stream;
+    PgDev &P = G.P;
+    std::vector<int> hidx(K);
+    int nA = 0;
+    for (int k = 0; k < K; k++) hidx[k] = fixed[k] ? -1 : nA++;
+    if (nA == 0) return ORBS_OK;
+    P.K = K; P.E = E; P.nA = nA; P.fix_scale = fix_scale ? 1 : 0;
+    static_assert(sizeof(Sim3) == 8 * sizeof(double), "Sim3 must be 8 packed doubles (r xyzw, t, s)");
+    int rc = ORBS_OK;
+    if ((rc = G.schedule(K, hidx, E, e_i, e_j))) return rc;
+    const int ld = P.ld, nt = G.nt;
+    ORBS_REQUIRE((size_t)ld * ld * sizeof(double) <= ((size_t)24 << 30), ORBS_E_INVALID, "pose graph too large for one GPU");
+    G.eblocks = (E + 127) / 128;
+    P.verts = G.alloc<Sim3>(K, &rc); P.backup = G.alloc<Sim3>(K, &rc);
+    int *d_hidx = G.alloc<int>(K, &rc), *d_ei = G.alloc<int>(E, &rc), *d_ej = G.alloc<int>(E, &rc);
+    Sim3 *d_meas = G.alloc<Sim3>(E, &rc);
+    P.err = G.alloc<double>((size_t)7 * E, &rc);
+    // one buffer: S | b | v | partial | scalars | Linv | packed | ready | flags
+    const size_t nS = (size_t)ld * ld, nLinv = (size_t)nt * NB * NB, nPacked = G.n_panel * 4096;
+    double *big = G.alloc<double>(nS + 2 * (size_t)ld + G.eblocks + 8 + nLinv + nPacked + (size_t)nt + 8, &rc);
+    if (rc) return rc;
+    P.S = big; P.b = big + nS; P.v = P.b + ld; P.partial = P.v + ld; P.scalars = P.partial + G.eblocks; G.Linv = P.scalars + 8; G.packed = G.Linv + nLinv;
+    G.ready = reinterpret_cast<int *>(G.packed + nPacked); G.flags = G.ready + 2 * nt;
+    P.hidx = d_hidx; P.e_i = d_ei; P.e_j = d_ej; P.meas = d_meas;
+    cudaStream_t st = h->stream;
+    ORBS_CUDA(cudaMemcpyAsync(P.verts, sim3, sizeof(Sim3) * K, cudaMemcpyHostToDevice, st));
+    ORBS_CUDA(cudaMemcpyAsync(d_hidx, hidx.data(), sizeof(int) * K, cudaMemcpyHostToDevice, st));
+    ORBS_CUDA(cudaMemcpyAsync(d_ei, e_i, sizeof(int) * E, cudaMemcpyHostToDevice, st));
+    ORBS_CUDA(cudaMemcpyAsync(d_ej, e_j, sizeof(int) * E, cudaMemcpyHostToDevice, st));
+    ORBS_CUDA(cudaMemcpyAsync(d_meas, e_meas, sizeof(Sim3) * E, cudaMemcpyHostToDevice, st));
+    std::vector<double> hb(ld), hx(ld);
+    std::vector<uint8_t> rowpad(ld);
+    ORBS_CUDA(cudaMemcpyAsync(rowpad.data(), P.row_pad, ld, cudaMemcpyDeviceToHost, st));
+    ORBS_CUDA(cudaStreamSynchronize(st));
+    double lambda = 0, ni = 2;
+    int nbad = 0, its = 0, trials = 0, fails = 0;
+    // OptimizationAlgorithmLevenberg::solve (optimization_algorithm_levenberg.cpp:61-164) per iteration, SparseOptimizer::optimize around it
+    for (int it = 0; it < iterations; it++) {
+        double currentChi = 0, tempChi = 0;
+        if ((rc = G.chi2(&currentChi))) return rc;
+        const double iniChi = currentChi;
+        ORBS_CUDA(cudaMemsetAsync(P.S, 0, nS * sizeof(double), st));
+        ORBS_CUDA(cudaMemsetAsync(P.b, 0, (size_t)ld * sizeof(double), st));
+        k_pg_build<<<(E + 63) / 64, 64, 0, st>>>(P);
+        k_tiles_pack<<<(unsigned)G.n_panel, 256, 0, st>>>(P.S, ld, G.plan.panel, G.packed, 1);        // keep H: the factorisation overwrites S
+        h->launches += 2;
+        ORBS_CUDA(cudaMemcpyAsync(hb.data(), P.b, sizeof(double) * ld, cudaMemcpyDeviceToHost, st));
+        ORBS_CUDA(cudaStreamSynchronize(st));
+        if (it == 0) {
+            if (lambda_init > 0) lambda = lambda_init;                                                   // setUserLambdaInit
+            else {                                                                                       // computeLambdaInit: 1e-5 * max diagonal
+                std::vector<double> diag(ld);
+                ORBS_CUDA(cudaMemcpy2DAsync(diag.data(), sizeof(double), P.S, ((size_t)ld + 1) * sizeof(double), sizeof(double), ld, cudaMemcpyDeviceToHost, st));
+                ORBS_CUDA(cudaStreamSynchronize(st));
+                double mx = 0;
+                for (int t = 0; t < ld; t++) if (!rowpad[t]) mx = std::max(mx, std::fabs(diag[t]));
+                lambda = 1e-5 * mx;
+            }
+            ni = 2; nbad = 0;
+        }
+        double rho = 0;
+        int qmax = 0;
+        do {
+            bool ok2 = true;
+            if ((rc = G.solve(lambda, &ok2))) return rc;
+            if (!ok2) fails++;
+            ORBS_CUDA(cudaMemcpyAsync(hx.data(), P.v, sizeof(double) * ld, cudaMemcpyDeviceToHost, st));
+            k_pg_update<<<(K + 127) / 128, 128, 0, st>>>(P);
+            h->launches++;
+            if ((rc = G.chi2(&tempChi))) return rc;
+            if (!ok2) tempChi = 1.7976931348623157e308;
+            rho = currentChi - tempChi;
+            double scale = 0.;
+            for (int t = 0; t < ld; t++) if (!rowpad[t]) scale += hx[t] * (lambda * hx[t] + hb[t]);
+            scale += 1e-3;
+            rho /= scale;
+            if (rho > 0 && std::isfinite(tempChi)) {
+                double alpha = 1. - std::pow((2 * rho - 1), 3);
+                alpha = std::min(alpha, 2. / 3.);
+                lambda *= std::max(1. / 3., alpha); ni = 2; currentChi = tempChi;
+            } else {
+                lambda *= ni; ni *= 2;
+                k_pg_restore<<<(K + 127) / 128, 128, 0, st>>>(P);
+                h->launches++;
+            }
+            qmax++; trials++;
+        } while (rho < 0 && qmax < 10);
+        its++;
+        if (qmax == 10 || rho == 0) break;
+        if ((iniChi - currentChi) * 1e3 < iniChi) nbad++; else nbad = 0;
+        if (nbad >= 3) break;
+    }
+    ORBS_CUDA(cudaMemcpyAsync(sim3, P.verts, sizeof(Sim3) * K, cudaMemcpyDeviceToHost, st));
+    ORBS_CUDA(cudaStreamSynchronize(st));
+    if (stats) { stats[0] = its; stats[1] = trials; stats[2] = fails; }
     return ORBS_OK;
 }

@@ -456,3 +456,54 @@ def make_sim3_ransac_case(cam, stream_id, n_hyp=300, seed=0):
     oct2 = np.rint(-np.log(s["w2"][v].astype(np.float64)) / (2 * np.log(1.2))).astype(np.int32)
     ls2 = (p["kf1"]["scale_factors"].astype(np.float64) ** 2).astype(F32)
     return dict(X1=s["P1c"][v], X2=s["P2c"][v], oct1=oct1, oct2=oct2, ls2=ls2, K1=s["K1"], K2=s["K2"], T12=T12, T21=T21)
+
+
+# ------------------------------------------------------------------ essential graph (Sim3 pose graph)
+def sim3_compose(a, b):
+    """g2o::Sim3 product on (qx qy qz qw tx ty tz s) rows, double"""
+    from scipy.spatial.transform import Rotation
+    Ra, Rb = Rotation.from_quat(a[:4]), Rotation.from_quat(b[:4])
+    q = (Ra * Rb).as_quat()
+    return np.concatenate([q if q[3] >= 0 else -q, a[7] * Ra.apply(b[4:7]) + a[4:7], [a[7] * b[7]]])
+
+
+def sim3_inverse(a):
+    from scipy.spatial.transform import Rotation
+    Ri = Rotation.from_quat(a[:4]).inv()
+    q = Ri.as_quat()
+    return np.concatenate([q if q[3] >= 0 else -q, Ri.apply(-a[4:7] / a[7]), [1.0 / a[7]]])
+
+
+def make_pose_graph(K=60, seed=0, n_loops=8, scale_drift=0.01):
+    """A loop-closure situation like the one OptimizeEssentialGraph sees: K keyframes on a closed trajectory, their odometry edges (spanning tree +
+    covisibility to the next but one) measured from drifted poses, a few loop edges measured from the true poses; vertices start at the drifted
+    poses; keyframe 0 is fixed.  Returns (sim3 [K,8], fixed, e_i, e_j, e_meas [E,8], true [K,8])."""
+    from scipy.spatial.transform import Rotation
+    rng = np.random.default_rng(seed)
+    true = []
+    for k in range(K):
+        a = 2 * np.pi * k / K
+        Rwc = Rotation.from_euler("y", -a + np.pi / 2) * Rotation.from_rotvec(rng.normal(0, 0.02, 3))
+        C = np.array([10 * np.cos(a), 0.2 * np.sin(3 * a), 10 * np.sin(a)])
+        Rcw = Rwc.inv()
+        q = Rcw.as_quat()
+        true.append(np.concatenate([q if q[3] >= 0 else -q, -Rcw.apply(C), [1.0]]))
+    true = np.array(true)
+    drift = [true[0].copy()]                       # Siw with accumulated drift (rotation, translation and scale)
+    for k in range(1, K):
+        rel = sim3_compose(true[k], sim3_inverse(true[k - 1]))                # S_k,k-1
+        noise = np.concatenate([Rotation.from_rotvec(rng.normal(0, 0.004, 3)).as_quat(), rng.normal(0, 0.02, 3), [1 + rng.normal(0, scale_drift)]])
+        drift.append(sim3_compose(sim3_compose(noise, rel), drift[k - 1]))
+    drift = np.array(drift)
+    ei, ej, meas = [], [], []
+    def edge(i, j, src):                            # vertex[0] = i, vertex[1] = j, measurement Sji = Sjw * Swi (Optimizer.cc:895-905)
+        ei.append(i); ej.append(j); meas.append(sim3_compose(src[j], sim3_inverse(src[i])))
+    for k in range(1, K):
+        edge(k, k - 1, drift)
+        if k >= 2:
+            edge(k, k - 2, drift)
+    for _ in range(n_loops):                        # loop edges between the end and the start of the trajectory, from the true poses
+        i = int(rng.integers(K - 8, K)); j = int(rng.integers(0, max(1, min(6, K - 8))))
+        edge(i, j, true)
+    fixed = np.zeros(K, np.uint8); fixed[0] = 1
+    return drift, fixed, np.array(ei, np.int32), np.array(ej, np.int32), np.array(meas), true

@@ -229,3 +229,25 @@ def test_sim3_solver_check_inliers(lib, cam, sid):
     # a single hypothesis and a single correspondence
     i1, n1 = o.Sim3CheckInliers(r["T12"][:1], r["T21"][:1], r["X1"][:1], r["X2"][:1], p1[:1], p2[:1], m1[:1], m2[:1], r["K1"], r["K2"])
     assert i1.shape == (1, 1) and n1[0] == oi[0, 0]
+
+
+@pytest.mark.parametrize("K,fix_scale", [(60, False), (60, True), (200, False), (12, False)])
+def test_optimize_pose_graph_matches_oracle(lib, K, fix_scale):
+    """Numeric core of Optimizer::OptimizeEssentialGraph (Sim3 pose graph, numeric Jacobians, LM from lambda = 1e-16, tiled sparse Cholesky with 9
+    vertices per tile): vertices equal to the oracle's to 1e-5 relative (north_star tolerance for the g2o paths), the loop is closed, the fixed vertex is
+    untouched.  K = 12 fits two tiles, K = 200 spans 23."""
+    import orbslamm_b200 as ob
+    import kf_family as kff
+    S, fixed, ei, ej, em, true = kff.make_pose_graph(K, seed=K)
+    o = ob.Optimizer()
+    got = o.OptimizePoseGraph(S, fixed, ei, ej, em, fix_scale, 20, 1e-16)
+    ref = oracle.optimize_pose_graph(S, fixed, ei, ej, em, fix_scale, 20, 1e-16)
+    assert got["chol_failures"] == 0 and ref["chol_failures"] == 0
+    assert abs(got["lm_iterations"] - ref["lm_iterations"]) <= 1                 # trials at the noise floor of the 1e-9 numeric Jacobians may differ
+    assert np.abs(got["sim3"] - ref["sim3"]).max() < 1e-5 * np.abs(ref["sim3"]).max()
+    assert np.array_equal(got["sim3"][0], S[0])
+    cam = lambda A: -A[:, 4:7] / A[:, 7:8]                                         # not the camera centre, but a pose-dependent point that must move towards the truth
+    if not fix_scale:
+        assert np.abs(cam(got["sim3"]) - cam(true)).max() < 0.95 * np.abs(cam(S) - cam(true)).max()
+    if fix_scale:
+        assert np.allclose(got["sim3"][:, 7], S[:, 7], rtol=0, atol=1e-12)

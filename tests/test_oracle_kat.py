@@ -188,3 +188,22 @@ def test_vocab_transform_known_answers():
         w = v3["weight"][node]
         assert r3["word_of"][i] == (v3["word_id"][node] if w > 0 else -1) and r3["node_of"][i] == (nid if w > 0 else -1)
     assert np.all(np.diff(r3["bow_ids"]) > 0) and abs(r3["bow_vals"].sum() - 1.0) < 1e-12
+
+
+def test_pose_graph_oracle_properties():
+    """OptimizeEssentialGraph's numeric core: Sim3 log is the inverse of the exponential (through one LM-free check: a consistent graph is a fixed point),
+    a drifted loop is pulled towards the truth, the fixed vertex and -- with bFixScale -- the scales do not move."""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import kf_family as kff
+    S, fixed, ei, ej, em, true = kff.make_pose_graph(40, seed=3)
+    # measurements taken from the vertices themselves: zero error, nothing moves
+    em0 = np.array([kff.sim3_compose(S[j], kff.sim3_inverse(S[i])) for i, j in zip(ei, ej)])
+    r0 = oracle.optimize_pose_graph(S, fixed, ei, ej, em0, False, 20, 1e-16)
+    assert np.abs(r0["sim3"] - S).max() < 1e-7
+    r = oracle.optimize_pose_graph(S, fixed, ei, ej, em, False, 20, 1e-16)
+    cam = lambda A: -A[:, 4:7] / A[:, 7:8]
+    assert np.abs(cam(r["sim3"]) - cam(true)).max() < 0.6 * np.abs(cam(S) - cam(true)).max()
+    assert np.array_equal(r["sim3"][0], S[0]) and r["chol_failures"] == 0 and 1 <= r["lm_iterations"] <= 20
+    rf = oracle.optimize_pose_graph(S, fixed, ei, ej, em, True, 20, 1e-16)
+    assert np.allclose(rf["sim3"][:, 7], S[:, 7], rtol=0, atol=1e-12)
