@@ -1,10 +1,12 @@
 // Optimizer_b200.cc -- GPU-backed definitions of Optimizer::PoseOptimization / LocalBundleAdjustment /
 // BundleAdjustment / GlobalBundleAdjustemnt.  In the reference tree these replace the same-named functions of
-// S/src/Optimizer.cc (:60-65, :68-260, :262-474, :476-801) and OptimizeSim3 (:1348-1543); the essential-graph optimisers stay on
-// g2o ("next" rows of SURVEY.md 8(f)).  The graph *construction* below follows the reference line by line (which
+// S/src/Optimizer.cc (:60-65, :68-260, :262-474, :476-801) OptimizeSim3 (:1348-1543) and (MM)OptimizeEssentialGraph (:804-1067, M: :1069-1346):
+// every member of the class.  The graph *construction* below follows the reference line by line (which
 // keyframes are local / fixed, which observations become edges, which locks are taken); only the numerical solve is
 // delegated to orbo_* (include/orbslamm_b200.h).  Monocular observations only (mvuRight < 0).
+#include <cmath>
 #include <list>
+#include <set>
 #include <map>
 #include <mutex>
 #include <stdexcept>
@@ -312,5 +314,209 @@ int Optimizer::OptimizeSim3(KeyFrame *pKF1, KeyFrame *pKF2, std::vector<MapPoint
     g2oS12.translation()[0] = S[4]; g2oS12.translation()[1] = S[5]; g2oS12.translation()[2] = S[6]; g2oS12.scale() = S[7];
     return nIn;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------------------------
+// Essential graph.  The graph assembly below follows Optimizer.cc:820-1000 line by line (which keyframes become vertices, which edges are
+// inserted and with which measurement); the solve is orbo_optimize_pose_graph.  g2o::Sim3 values are read and written through rotation() /
+// translation() / scale(); the Sim3 products / inverses of the assembly are the formulas of g2o/types/sim3.h on plain doubles.
+namespace
+{
+struct S8 { double v[8]; };          // r (x y z w), t, s
+void q_rot(const double *q, const double *x, double *o)          // Eigen::Quaterniond * Vector3d (_transformVector)
+{
+    double uv[3] = {q[1] * x[2] - q[2] * x[1], q[2] * x[0] - q[0] * x[2], q[0] * x[1] - q[1] * x[0]};
+    uv[0] += uv[0]; uv[1] += uv[1]; uv[2] += uv[2];
+    o[0] = x[0] + q[3] * uv[0] + (q[1] * uv[2] - q[2] * uv[1]);
+    o[1] = x[1] + q[3] * uv[1] + (q[2] * uv[0] - q[0] * uv[2]);
+    o[2] = x[2] + q[3] * uv[2] + (q[0] * uv[1] - q[1] * uv[0]);
+}
+S8 s8_mul(const S8 &a, const S8 &b)                               // Sim3::operator*, sim3.h:214-220
+{
+    S8 r;
+    const double *p = a.v, *q = b.v;
+    r.v[3] = p[3] * q[3] - p[0] * q[0] - p[1] * q[1] - p[2] * q[2];
+    r.v[0] = p[3] * q[0] + p[0] * q[3] + p[1] * q[2] - p[2] * q[1];
+    r.v[1] = p[3] * q[1] + p[1] * q[3] + p[2] * q[0] - p[0] * q[2];
+    r.v[2] = p[3] * q[2] + p[2] * q[3] + p[0] * q[1] - p[1] * q[0];
+    double rt[3];
+    q_rot(a.v, b.v + 4, rt);
+    for (int k = 0; k < 3; k++) r.v[4 + k] = a.v[7] * rt[k] + a.v[4 + k];
+    r.v[7] = a.v[7] * b.v[7];
+    return r;
+}
+S8 s8_inv(const S8 &a)                                            // Sim3::inverse, sim3.h:184-187
+{
+    S8 r;
+    r.v[0] = -a.v[0]; r.v[1] = -a.v[1]; r.v[2] = -a.v[2]; r.v[3] = a.v[3];
+    const double f = -1. / a.v[7], st[3] = {f * a.v[4], f * a.v[5], f * a.v[6]};
+    q_rot(r.v, st, r.v + 4);
+    r.v[7] = 1. / a.v[7];
+    return r;
+}
+void s8_map(const S8 &a, const double *x, double *o) { double r[3]; q_rot(a.v, x, r); for (int k = 0; k < 3; k++) o[k] = a.v[7] * r[k] + a.v[4 + k]; }   // s*(r*xyz) + t
+S8 s8_of(g2o::Sim3 s) { S8 r; r.v[0] = s.rotation().x(); r.v[1] = s.rotation().y(); r.v[2] = s.rotation().z(); r.v[3] = s.rotation().w();
+                        for (int k = 0; k < 3; k++) r.v[4 + k] = s.translation()[k]; r.v[7] = s.scale(); return r; }
+S8 s8_of_pose(KeyFrame *pKF)                                      // g2o::Sim3 Siw(Converter::toMatrix3d(Rcw), Converter::toVector3d(tcw), 1.0): Quaterniond(Matrix3d)
+{
+    const cv::Mat Rm = pKF->GetRotation(), tm = pKF->GetTranslation();
+    double R[9];
+    for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) R[3 * r + c] = Rm.at<float>(r, c);
+    S8 o;
+    double *q = o.v, t = R[0] + R[4] + R[8];
+    if (t > 0) { t = std::sqrt(t + 1.0); q[3] = 0.5 * t; t = 0.5 / t; q[0] = (R[7] - R[5]) * t; q[1] = (R[2] - R[6]) * t; q[2] = (R[3] - R[1]) * t; }
+    else {
+        int i = 0;
+        if (R[4] > R[0]) i = 1;
+        if (R[8] > R[4 * i]) i = 2;
+        const int j = (i + 1) % 3, k = (j + 1) % 3;
+        t = std::sqrt(R[4 * i] - R[4 * j] - R[4 * k] + 1.0);
+        q[i] = 0.5 * t; t = 0.5 / t;
+        q[3] = (R[3 * k + j] - R[3 * j + k]) * t; q[j] = (R[3 * j + i] + R[3 * i + j]) * t; q[k] = (R[3 * k + i] + R[3 * i + k]) * t;
+    }
+    for (int k = 0; k < 3; k++) o.v[4 + k] = tm.at<float>(k);
+    o.v[7] = 1.0;
+    return o;
+}
+
+void essential_graph(const std::vector<KeyFrame *> &vpKFs, const std::vector<MapPoint *> &vpMPs, Map *pMap, KeyFrame *pLoopKF, KeyFrame *pCurKF,
+                     const LoopClosing::KeyFrameAndPose &NonCorrectedSim3, const LoopClosing::KeyFrameAndPose &CorrectedSim3,
+                     const std::map<KeyFrame *, std::set<KeyFrame *>> &LoopConnections, const bool &bFixScale)
+{
+    const int minFeat = 100;
+    std::map<KeyFrame *, int> vid;                       // keyframe -> vertex (the reference indexes arrays by mnId)
+    std::vector<S8> vScw;
+    std::vector<uint8_t> fixed;
+    for (size_t i = 0, iend = vpKFs.size(); i < iend; i++) {                    // vertices, :829-862
+        KeyFrame *pKF = vpKFs[i];
+        if (pKF->isBad()) continue;
+        LoopClosing::KeyFrameAndPose::const_iterator it = CorrectedSim3.find(pKF);
+        vid[pKF] = (int)vScw.size();
+        vScw.push_back(it != CorrectedSim3.end() ? s8_of(it->second) : s8_of_pose(pKF));
+        fixed.push_back(pKF == pLoopKF ? 1 : 0);
+    }
+    std::vector<int32_t> ei, ej;
+    std::vector<double> meas;
+    auto add_edge = [&](KeyFrame *a, KeyFrame *b, const S8 &Sba) {             // vertex[0] = a, vertex[1] = b, measurement Sba
+        if (!vid.count(a) || !vid.count(b)) return;                             // g2o refuses an edge with a missing vertex
+        ei.push_back(vid[a]); ej.push_back(vid[b]);
+        meas.insert(meas.end(), Sba.v, Sba.v + 8);
+    };
+    auto non_corrected = [&](KeyFrame *pKF) -> S8 {                             // NonCorrectedSim3 if present, else the vertex estimate
+        LoopClosing::KeyFrameAndPose::const_iterator it = NonCorrectedSim3.find(pKF);
+        if (it != NonCorrectedSim3.end()) return s8_of(it->second);
+        return vid.count(pKF) ? vScw[vid[pKF]] : s8_of_pose(pKF);
+    };
+    std::set<std::pair<long unsigned int, long unsigned int>> sInsertedEdges;
+    for (std::map<KeyFrame *, std::set<KeyFrame *>>::const_iterator mit = LoopConnections.begin(), mend = LoopConnections.end(); mit != mend; mit++) {   // loop edges, :868-893
+        KeyFrame *pKF = mit->first;
+        if (!vid.count(pKF)) continue;
+        const long unsigned int nIDi = pKF->mnId;
+        const S8 Swi = s8_inv(vScw[vid[pKF]]);
+        for (std::set<KeyFrame *>::const_iterator sit = mit->second.begin(), send = mit->second.end(); sit != send; sit++) {
+            const long unsigned int nIDj = (*sit)->mnId;
+            if ((nIDi != pCurKF->mnId || nIDj != pLoopKF->mnId) && pKF->GetWeight(*sit) < minFeat) continue;
+            if (!vid.count(*sit)) continue;
+            add_edge(pKF, *sit, s8_mul(vScw[vid[*sit]], Swi));
+            sInsertedEdges.insert(std::make_pair(std::min(nIDi, nIDj), std::max(nIDi, nIDj)));
+        }
+    }
+    for (size_t i = 0, iend = vpKFs.size(); i < iend; i++) {                    // normal edges, :896-993
+        KeyFrame *pKF = vpKFs[i];
+        if (!vid.count(pKF)) continue;
+        const S8 Swi = s8_inv(non_corrected(pKF));
+        KeyFrame *pParentKF = pKF->GetParent();
+        if (pParentKF) add_edge(pKF, pParentKF, s8_mul(non_corrected(pParentKF), Swi));                              // spanning tree
+        const std::set<KeyFrame *> sLoopEdges = pKF->GetLoopEdges();
+        for (std::set<KeyFrame *>::const_iterator sit = sLoopEdges.begin(), send = sLoopEdges.end(); sit != send; sit++) {   // earlier loop closures
+            KeyFrame *pLKF = *sit;
+            if (pLKF->mnId < pKF->mnId) add_edge(pKF, pLKF, s8_mul(non_corrected(pLKF), Swi));
+        }
+        const std::vector<KeyFrame *> vpConnectedKFs = pKF->GetCovisiblesByWeight(minFeat);                           // strong covisibility
+        for (std::vector<KeyFrame *>::const_iterator vit = vpConnectedKFs.begin(); vit != vpConnectedKFs.end(); vit++) {
+            KeyFrame *pKFn = *vit;
+            if (pKFn && pKFn != pParentKF && !pKF->hasChild(pKFn) && !sLoopEdges.count(pKFn)) {
+                if (!pKFn->isBad() && pKFn->mnId < pKF->mnId) {
+                    if (sInsertedEdges.count(std::make_pair(std::min(pKF->mnId, pKFn->mnId), std::max(pKF->mnId, pKFn->mnId)))) continue;
+                    add_edge(pKF, pKFn, s8_mul(non_corrected(pKFn), Swi));
+                }
+            }
+        }
+    }
+    const int32_t K = (int32_t)vScw.size(), E = (int32_t)ei.size();
+    std::vector<double> est(8 * (size_t)std::max(K, 1));
+    for (int k = 0; k < K; k++) for (int c = 0; c < 8; c++) est[8 * (size_t)k + c] = vScw[k].v[c];
+    if (K > 0 && E > 0)                                                                                               // optimizer.optimize(20), lambda init 1e-16 (:812, :996-997)
+        check(orbo_optimize_pose_graph(handle(), K, est.data(), fixed.data(), E, ei.data(), ej.data(), meas.data(), bFixScale ? 1 : 0, 20, 1e-16, nullptr),
+              "orbo_optimize_pose_graph");
+
+    std::unique_lock<std::mutex> lock(pMap->mMutexMapUpdate);                                                         // :999
+    std::vector<S8> vCorrectedSwc(K);
+    for (size_t i = 0; i < vpKFs.size(); i++) {                                 // SE3 pose recovering: Sim3 [sR t; 0 1] -> SE3 [R t/s; 0 1], :1002-1018
+        KeyFrame *pKFi = vpKFs[i];
+        if (!vid.count(pKFi)) continue;
+        const int k = vid[pKFi];
+        S8 C;
+        for (int c = 0; c < 8; c++) C.v[c] = est[8 * (size_t)k + c];
+        vCorrectedSwc[k] = s8_inv(C);
+        const double *q = C.v;                                                  // Quaterniond::toRotationMatrix
+        const double tx = 2 * q[0], ty = 2 * q[1], tz = 2 * q[2], twx = tx * q[3], twy = ty * q[3], twz = tz * q[3], txx = tx * q[0], txy = ty * q[0], txz = tz * q[0],
+                     tyy = ty * q[1], tyz = tz * q[1], tzz = tz * q[2];
+        const double R[9] = {1 - (tyy + tzz), txy - twz, txz + twy, txy + twz, 1 - (txx + tzz), tyz - twx, txz - twy, tyz + twx, 1 - (txx + tyy)};
+        const double is = 1. / C.v[7];
+        cv::Mat Tiw = cv::Mat::eye(4, 4, CV_32F);                               // Converter::toCvSE3
+        for (int r = 0; r < 3; r++) { for (int c = 0; c < 3; c++) Tiw.at<float>(r, c) = (float)R[3 * r + c]; Tiw.at<float>(r, 3) = (float)(C.v[4 + r] * is); }
+        pKFi->SetPose(Tiw);
+    }
+    for (size_t i = 0, iend = vpMPs.size(); i < iend; i++) {                    // map points: corrected by their reference keyframe, :1021-1045
+        MapPoint *pMP = vpMPs[i];
+        if (pMP->isBad()) continue;
+        int k = -1;
+        if (pMP->mnCorrectedByKF == pCurKF->mnId) {
+            for (std::map<KeyFrame *, int>::const_iterator it = vid.begin(); it != vid.end(); ++it) if (it->first->mnId == pMP->mnCorrectedReference) { k = it->second; break; }
+        } else {
+            KeyFrame *pRefKF = pMP->GetReferenceKeyFrame();
+            if (vid.count(pRefKF)) k = vid[pRefKF];
+        }
+        if (k < 0) continue;
+        cv::Mat P3Dw = pMP->GetWorldPos();
+        const double X[3] = {P3Dw.at<float>(0), P3Dw.at<float>(1), P3Dw.at<float>(2)};
+        double Xr[3], Xc[3];
+        s8_map(vScw[k], X, Xr);
+        s8_map(vCorrectedSwc[k], Xr, Xc);
+        cv::Mat out(3, 1, CV_32F);
+        for (int c = 0; c < 3; c++) out.at<float>(c) = (float)Xc[c];
+        pMP->SetWorldPos(out);
+        pMP->UpdateNormalAndDepth();
+    }
+}
+}  // namespace
+
+void Optimizer::OptimizeEssentialGraph(Map *pMap, KeyFrame *pLoopKF, KeyFrame *pCurKF, const LoopClosing::KeyFrameAndPose &NonCorrectedSim3,
+                                       const LoopClosing::KeyFrameAndPose &CorrectedSim3, const std::map<KeyFrame *, std::set<KeyFrame *>> &LoopConnections,
+                                       const bool &bFixScale)
+{
+    essential_graph(pMap->GetAllKeyFrames(), pMap->GetAllMapPoints(), pMap, pLoopKF, pCurKF, NonCorrectedSim3, CorrectedSim3, LoopConnections, bFixScale);
+}
+
+#ifdef ORBSLAMM_MULTI_ROBOT
+// MultipleRobotsScenario/src/Optimizer.cc:1069-1346: the same optimisation over the map and every map attached to it by MultiMapper
+void Optimizer::MMOptimizeEssentialGraph(Map *pMap, KeyFrame *pLoopKF, KeyFrame *pCurKF, const LoopClosing::KeyFrameAndPose &NonCorrectedSim3,
+                                         const LoopClosing::KeyFrameAndPose &CorrectedSim3, const std::map<KeyFrame *, std::set<KeyFrame *>> &LoopConnections,
+                                         const bool &bFixScale)
+{
+    std::vector<KeyFrame *> vpKFs = pMap->GetAllKeyFrames();
+    std::vector<MapPoint *> vpMPs = pMap->GetAllMapPoints();
+    if (pMap->isAttached()) {
+        std::vector<Map *> vpAttachedMaps = pMap->getAttachedMaps();
+        for (std::vector<Map *>::iterator it = vpAttachedMaps.begin(), itend = vpAttachedMaps.end(); it != itend; it++) {
+            std::vector<KeyFrame *> vpAttachedKFs = (*it)->GetAllKeyFrames();
+            std::vector<MapPoint *> vpAttachedMPs = (*it)->GetAllMapPoints();
+            vpKFs.insert(vpKFs.end(), vpAttachedKFs.begin(), vpAttachedKFs.end());
+            vpMPs.insert(vpMPs.end(), vpAttachedMPs.begin(), vpAttachedMPs.end());
+        }
+    }
+    essential_graph(vpKFs, vpMPs, pMap, pLoopKF, pCurKF, NonCorrectedSim3, CorrectedSim3, LoopConnections, bFixScale);
+}
+#endif
 
 }  // namespace iORB_SLAM

@@ -1,4 +1,6 @@
 #pragma once
+#include <algorithm>
+#include <map>
 #include <set>
 #include "MapPoint.h"
 #include "Thirdparty/DBoW2/DBoW2/FeatureVector.h"
@@ -12,6 +14,19 @@ public:
     cv::Mat GetPose() { return Tcw.clone(); }
     void SetPose(const cv::Mat &T) { Tcw = T.clone(); }
     bool isBad() { return mbBad; }
+    KeyFrame *GetParent() { return mpParent; }
+    bool hasChild(KeyFrame *pKF) { return mspChildrens.count(pKF) != 0; }
+    std::set<KeyFrame *> GetLoopEdges() { return mspLoopEdges; }
+    int GetWeight(KeyFrame *pKF) { return mConnectedKeyFrameWeights.count(pKF) ? mConnectedKeyFrameWeights[pKF] : 0; }
+    std::vector<KeyFrame *> GetCovisiblesByWeight(const int &w)     // KeyFrame.cc:208-225: ordered by weight, descending
+    {
+        std::vector<std::pair<int, KeyFrame *>> v;
+        for (auto &kv : mConnectedKeyFrameWeights) if (kv.second >= w) v.push_back(std::make_pair(kv.second, kv.first));
+        std::stable_sort(v.begin(), v.end(), [](const std::pair<int, KeyFrame *> &a, const std::pair<int, KeyFrame *> &b) { return a.first > b.first; });
+        std::vector<KeyFrame *> out;
+        for (auto &x : v) out.push_back(x.second);
+        return out;
+    }
     bool isNotFixed() { return false; }                          // M/include/KeyFrame.h:113-115 (multi-robot tree)
     std::vector<KeyFrame *> GetVectorCovisibleKeyFrames() { return mvpOrderedConnectedKeyFrames; }
     std::vector<MapPoint *> GetMapPointMatches() { return mvpMapPoints; }
@@ -47,6 +62,9 @@ public:
     std::vector<float> mvuRight, mvInvLevelSigma2;
     std::vector<MapPoint *> mvpMapPoints;
     std::vector<KeyFrame *> mvpOrderedConnectedKeyFrames;
+    KeyFrame *mpParent = nullptr;
+    std::set<KeyFrame *> mspChildrens, mspLoopEdges;
+    std::map<KeyFrame *, int> mConnectedKeyFrameWeights;
     cv::Mat Tcw, mTcwGBA, mK;
     bool mbBad = false;
 };

@@ -39,7 +39,9 @@ public:
     float mTrackProjX = 0, mTrackProjY = 0, mTrackViewCos = 1;
     bool mbTrackInView = false;
     int mnTrackScaleLevel = 0;
-    long unsigned int mnBALocalForKF = ~0ul, mnBAGlobalForKF = 0;
+    long unsigned int mnBALocalForKF = ~0ul, mnBAGlobalForKF = 0, mnCorrectedByKF = ~0ul, mnCorrectedReference = 0;
+    KeyFrame *GetReferenceKeyFrame() { return mpRefKF; }
+    KeyFrame *mpRefKF = nullptr;
     cv::Mat mPosGBA;
     static std::mutex mGlobalMutex;
 

@@ -507,3 +507,85 @@ def make_pose_graph(K=60, seed=0, n_loops=8, scale_drift=0.01):
         edge(i, j, true)
     fixed = np.zeros(K, np.uint8); fixed[0] = 1
     return drift, fixed, np.array(ei, np.int32), np.array(ej, np.int32), np.array(meas), true
+
+
+# ------------------------------------------------------------------ essential graph through the C++ drop-in (tests/test_host_shim_gpu.py)
+def make_essential_graph_scene(K=40, seed=4):
+    """A mock map for Optimizer::OptimizeEssentialGraph: keyframe SE3 poses with drift, spanning tree k -> k-1, covisibility weights, one earlier loop
+    edge, the loop connections and corrected / non-corrected Sim3 of the current keyframe and its two neighbours, map points with reference keyframes."""
+    from scipy.spatial.transform import Rotation
+    S, fixed, _, _, _, true = make_pose_graph(K, seed=seed, scale_drift=0.0)
+    S = S.copy(); S[:, 7] = 1.0                                   # keyframe poses are SE3
+    rng = np.random.default_rng(seed)
+    def T_of(s):
+        T = np.eye(4, dtype=F32); T[:3, :3] = Rotation.from_quat(s[:4]).as_matrix().astype(F32); T[:3, 3] = s[4:7].astype(F32); return T
+    poses = np.stack([T_of(s) for s in S])
+    parent = np.arange(-1, K - 1, dtype=np.int32)
+    cov = []
+    for k in range(1, K):
+        cov += [k, k - 1, 200]
+        if k >= 2: cov += [k, k - 2, 150]
+        if k >= 3: cov += [k, k - 3, 90]
+    cur, loop = K - 1, 0
+    cov += [cur, 1, 120, cur, 0, 30, K - 2, 0, 50]
+    loopedges = [K // 2, 5]
+    loopconn = [cur, 0, cur, 1, K - 2, 0]
+    corr_idx = [cur, K - 2, K - 3]
+    corr = np.stack([np.concatenate([true[i][:7] * np.array([1, 1, 1, 1, 1.05, 1.05, 1.05]), [1.05]]) for i in corr_idx])     # [sR st] with s = 1.05
+    noncorr = np.stack([S[i] for i in corr_idx])
+    P = 3 * K
+    pref = np.repeat(np.arange(K), 3).astype(np.int32)
+    pts = rng.uniform(-12, 12, (P, 3)).astype(F32)
+    pcorr = np.full(P, -1, np.int32); pcorr[-3:] = K - 2          # points already corrected by the current keyframe (mnCorrectedByKF / mnCorrectedReference)
+    return dict(K=K, loop=loop, cur=cur, poses=poses, parent=parent, cov=np.array(cov, np.int32), loopedges=np.array(loopedges, np.int32),
+                loopconn=np.array(loopconn, np.int32), corr_idx=np.array(corr_idx, np.int32), corr=corr, noncorr=noncorr, pref=pref, pts=pts, pcorr=pcorr)
+
+
+def essential_graph_expected(sc, fix_scale, backend):
+    """The reference's assembly (Optimizer.cc:820-1000) on the scene + backend(sim3, fixed, ei, ej, meas, fix_scale) -> corrected poses [K,4,4] f32, points f32."""
+    from scipy.spatial.transform import Rotation
+    K = sc["K"]
+    def s_of_pose(T):
+        q = Rotation.from_matrix(T[:3, :3].astype(np.float64)).as_quat()
+        return np.concatenate([q if q[3] >= 0 else -q, T[:3, 3].astype(np.float64), [1.0]])
+    corr = {int(i): sc["corr"][n] for n, i in enumerate(sc["corr_idx"])}; nonc = {int(i): sc["noncorr"][n] for n, i in enumerate(sc["corr_idx"])}
+    vScw = np.stack([corr[k] if k in corr else s_of_pose(sc["poses"][k]) for k in range(K)])
+    w = {}
+    for a, b, ww in sc["cov"].reshape(-1, 3): w[(int(a), int(b))] = int(ww); w[(int(b), int(a))] = int(ww)
+    ledge = {k: set() for k in range(K)}
+    for a, b in sc["loopedges"].reshape(-1, 2): ledge[int(a)].add(int(b)); ledge[int(b)].add(int(a))
+    conn = {}
+    for a, b in sc["loopconn"].reshape(-1, 2): conn.setdefault(int(a), set()).add(int(b))
+    ei, ej, meas = [], [], []
+    inserted = set()
+    for i in sorted(conn):                                         # std::map over KeyFrame*: the mock keyframes live in one array, so pointer order = index order
+        Swi = sim3_inverse(vScw[i])
+        for j in sorted(conn[i]):
+            if (i != sc["cur"] or j != sc["loop"]) and w.get((i, j), 0) < 100: continue
+            ei.append(i); ej.append(j); meas.append(sim3_compose(vScw[j], Swi)); inserted.add((min(i, j), max(i, j)))
+    nc = lambda k: nonc[k] if k in nonc else vScw[k]
+    for i in range(K):
+        Swi = sim3_inverse(nc(i))
+        p = int(sc["parent"][i])
+        if p >= 0:
+            ei.append(i); ej.append(p); meas.append(sim3_compose(nc(p), Swi))
+        for l in sorted(ledge[i]):
+            if l < i: ei.append(i); ej.append(l); meas.append(sim3_compose(nc(l), Swi))
+        neigh = sorted([(ww, j) for (a, j), ww in w.items() if a == i and ww >= 100], key=lambda x: -x[0])
+        children = {k for k in range(K) if int(sc["parent"][k]) == i}
+        for ww, j in neigh:
+            if j != p and j not in children and j not in ledge[i] and j < i and (min(i, j), max(i, j)) not in inserted:
+                ei.append(i); ej.append(j); meas.append(sim3_compose(nc(j), Swi))
+    fixed = np.zeros(K, np.uint8); fixed[sc["loop"]] = 1
+    est = backend(vScw, fixed, np.array(ei, np.int32), np.array(ej, np.int32), np.array(meas), fix_scale)
+    poses = np.zeros((K, 4, 4), F32)
+    for k in range(K):
+        T = np.eye(4); T[:3, :3] = Rotation.from_quat(est[k][:4]).as_matrix(); T[:3, 3] = est[k][4:7] / est[k][7]
+        poses[k] = T.astype(F32)
+    pts = sc["pts"].astype(np.float64).copy()
+    for p in range(len(pts)):
+        r = int(sc["pcorr"][p]) if sc["pcorr"][p] >= 0 else int(sc["pref"][p])
+        Srw, Swr = vScw[r], sim3_inverse(est[r])
+        x = Srw[7] * Rotation.from_quat(Srw[:4]).apply(pts[p]) + Srw[4:7]
+        pts[p] = Swr[7] * Rotation.from_quat(Swr[:4]).apply(x) + Swr[4:7]
+    return poses, pts.astype(F32), len(ei)

@@ -231,3 +231,31 @@ def test_cpp_dropin_sim3solver(lib, tmp_path):
     assert int(rows[0]["nInliers"]) > 20 and int(rows[0]["iterations"]) > 1 and int(rows[0]["nInliers"]) == int(rows[1]["nInliers"])
     assert int(rows[1]["calls"]) == int(rows[1]["iterations"]) == int(rows[0]["iterations"]) and int(rows[0]["calls"]) == -(-int(rows[0]["iterations"]) // 5)
     assert int(rows[2]["nInliers"]) == 0 and int(rows[2]["iterations"]) > 3 and int(rows[2]["best"]) > 20 and int(rows[2]["N"]) == n
+
+
+@pytest.mark.parametrize("fix_scale", [False, True])
+def test_cpp_dropin_essential_graph(lib, tmp_path, fix_scale):
+    """Optimizer::OptimizeEssentialGraph through the C++ drop-in on a mock map (spanning tree, covisibility >= 100, an earlier loop edge, loop
+    connections with the weight rule, corrected / non-corrected Sim3, map points incl. ones already corrected by the current keyframe): the corrected
+    keyframe poses and map points equal an independent Python assembly of the same graph solved by the oracle."""
+    import kf_family as kff
+    d = str(tmp_path)
+    exe = os.path.join(d, "host_essential_graph_test")
+    srcs = [os.path.join(HOST, f) for f in ("Optimizer_b200.cc", "mock/slam_statics.cc", "test/host_essential_graph_test.cc")]
+    subprocess.check_call(["g++", "-std=c++14", "-O2", "-I" + os.path.join(HOST, "mock"), "-I" + HOST, "-I" + os.path.join(ROOT, "include")] + srcs +
+                          ["-L" + os.path.join(ROOT, "orbslamm_b200"), "-lorbslamm_b200", "-Wl,-rpath," + os.path.join(ROOT, "orbslamm_b200"), "-lpthread", "-o", exe])
+    sc = kff.make_essential_graph_scene(40, 4)
+    w = lambda name, a: np.ascontiguousarray(a).tofile(os.path.join(d, name))
+    w("eg_hdr.bin", np.array([sc["K"], sc["loop"], sc["cur"], int(fix_scale)], np.int32)); w("eg_poses.bin", sc["poses"]); w("eg_points.bin", sc["pts"])
+    w("eg_parent.bin", sc["parent"]); w("eg_cov.bin", sc["cov"]); w("eg_loopedges.bin", sc["loopedges"]); w("eg_loopconn.bin", sc["loopconn"])
+    w("eg_corr_idx.bin", sc["corr_idx"]); w("eg_corr.bin", sc["corr"].astype(np.float64)); w("eg_noncorr.bin", sc["noncorr"].astype(np.float64))
+    w("eg_point_ref.bin", sc["pref"]); w("eg_point_corr.bin", sc["pcorr"])
+    out = subprocess.run([exe, d], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    got_p = np.fromfile(os.path.join(d, "eg_out_poses.bin"), np.float32).reshape(-1, 4, 4); got_x = np.fromfile(os.path.join(d, "eg_out_points.bin"), np.float32).reshape(-1, 3)
+    backend = lambda S, fx, ei, ej, m, fs: oracle.optimize_pose_graph(S, fx, ei, ej, m, fs, 20, 1e-16)["sim3"]
+    ep, ex, ne = kff.essential_graph_expected(sc, fix_scale, backend)
+    assert ne == 80                                               # 3 loop-connection edges pass the weight rule... plus tree, earlier loop edge and covisibility edges
+    assert np.abs(got_p - ep).max() < 1e-5 * np.abs(ep).max() + 2e-5 and np.abs(got_x - ex).max() < 1e-5 * np.abs(ex).max() + 5e-5
+    assert np.abs(got_p - sc["poses"]).max() > 0.1 and np.abs(got_x - sc["pts"]).max() > 0.1         # the loop correction really moved the map
+    assert np.abs(got_p[sc["loop"]] - sc["poses"][sc["loop"]]).max() < 1e-6                             # the loop keyframe is fixed
