@@ -59,3 +59,17 @@ def test_product_never_imports_the_oracle():
                 code = "\n".join(l for l in txt.splitlines() if not l.lstrip().startswith(("#", "//", "*", '"')))
                 assert not re.search(r"^\s*(import oracle|from oracle)", code, flags=re.M), f
                 assert "liboracle" not in code and "oracle." not in code, f
+
+
+def test_host_shims_compile_for_both_trees():
+    """The C++ drop-in sources compile against the mock data model for the single-robot tree and, with -DORBSLAMM_MULTI_ROBOT, for the multi-robot
+    tree (MMGlobalBundleAdjustemnt, MMOptimizeEssentialGraph, the isNotFixed() rule) -- no GPU needed; running them is tests/test_host_shim_gpu.py."""
+    import subprocess
+    host = os.path.join(ROOT, "orbslamm_b200", "host")
+    srcs = [os.path.join(host, f) for f in ("ORBextractor_b200.cc", "ORBmatcher_b200.cc", "Optimizer_b200.cc", "Sim3Solver_b200.cc", "mock/slam_statics.cc",
+                                            "mock/Sim3Solver_rest.cc", "test/host_shim_test.cc", "test/host_kf_family_test.cc", "test/host_sim3solver_test.cc",
+                                            "test/host_essential_graph_test.cc")]
+    base = ["g++", "-std=c++14", "-fsyntax-only", "-I" + os.path.join(host, "mock"), "-I" + host, "-I" + os.path.join(ROOT, "include")]
+    for extra in ([], ["-DORBSLAMM_MULTI_ROBOT"]):
+        out = subprocess.run(base + extra + srcs, capture_output=True, text=True)
+        assert out.returncode == 0, out.stderr[-3000:]
