@@ -120,6 +120,19 @@ def main():
     res["DBoW2 transform (ComputeBoW), 2000 features, k=10 L=6"] = {
         "gpu_ms_per_call": 1e3 * timed(lambda: vh.transform(fr, [2000] * B, 4)), "calls_cover_frames": B,
         "cpu_ms_per_frame_oracle_port": 1e3 * timed(lambda: oracle.vocab_transform(voc, fr[0], 4), 3)}
+    # Sim3Solver: 300 RANSAC hypotheses of one solver in one call (reference: one CheckInliers per hypothesis)
+    r3 = kff.make_sim3_ransac_case(synth.KITTI, 2, n_hyp=300)
+    m1, p1 = o.Sim3Prepare(r3["X1"], r3["oct1"], r3["ls2"], r3["K1"]); m2, p2 = o.Sim3Prepare(r3["X2"], r3["oct2"], r3["ls2"], r3["K2"])
+    res["Sim3Solver::CheckInliers, 300 hypotheses x %d correspondences" % len(r3["X1"])] = {
+        "gpu_ms_per_call": 1e3 * timed(lambda: o.Sim3CheckInliers(r3["T12"], r3["T21"], r3["X1"], r3["X2"], p1, p2, m1, m2, r3["K1"], r3["K2"])), "calls_cover_hypotheses": 300}
+    if ref_build.sim3solver_available():
+        res[list(res)[-1]]["cpu_ms_300_hypotheses_reference_object_code"] = 1e3 * timed(
+            lambda: ref_build.ref_sim3_check_inliers(r3["X1"], r3["X2"], r3["oct1"], r3["oct2"], r3["ls2"], r3["K1"], r3["K2"], r3["T12"], r3["T21"]), 3)
+    # essential graph: 500-keyframe loop
+    Sg, fxg, eig, ejg, emg, _ = kff.make_pose_graph(500, seed=1)
+    res["OptimizeEssentialGraph core, 500 keyframes / %d edges" % len(eig)] = {
+        "gpu_ms_per_call": 1e3 * timed(lambda: o.OptimizePoseGraph(Sg, fxg, eig, ejg, emg, False, 20, 1e-16), 3),
+        "cpu_ms_oracle_port_dense_ldlt": 1e3 * timed(lambda: oracle.optimize_pose_graph(Sg, fxg, eig, ejg, emg, False, 20, 1e-16), 1)}
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "matcher_family.json"), "w") as f:
         json.dump(res, f, indent=1)
