@@ -53,3 +53,14 @@ def test_kf_family_golden():
         else:
             assert np.array_equal(got[k], d[k]), k
     assert d["search_kf_sim3"][-1] > 10 and d["fuse_kf"].max() >= 0 and d["bow_kf_kf"][-1] > 20 and d["init"][-1] > 20 and d["sim3_inlier"][-1] >= 10
+
+
+def test_sim3_chain_golden():
+    """Sim3Solver inlier check (exact; the file was written only after the reference's Sim3Solver.cc object code agreed) and the fixed-scale essential-graph core."""
+    d = np.load(os.path.join(G, "sim3_chain_small.npz"))
+    m1, m2, p1, p2 = oracle.sim3_prepare(d["X1"], d["X2"], d["oct1"], d["oct2"], d["ls2"], d["K1"], d["K2"])
+    assert np.array_equal(m1, d["max_err1"]) and np.array_equal(m2, d["max_err2"]) and np.array_equal(p1, d["p1im1"]) and np.array_equal(p2, d["p2im2"])
+    inl, n = oracle.sim3_check_inliers(d["T12"], d["T21"], d["X1"], d["X2"], p1, p2, m1, m2, d["K1"], d["K2"])
+    assert np.array_equal(np.packbits(inl, axis=1), d["inliers"]) and np.array_equal(n, d["n_inliers"]) and n.max() > 20
+    r = oracle.optimize_pose_graph(d["pg_sim3"], d["pg_fixed"], d["pg_ei"], d["pg_ej"], d["pg_meas"], True, 20, 1e-16)
+    assert [r["lm_iterations"], r["lm_trials"]] == d["pg_iters"].tolist() and np.allclose(r["sim3"], d["pg_out"], rtol=0, atol=1e-9)

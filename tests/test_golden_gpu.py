@@ -59,3 +59,16 @@ def test_kf_family_golden_gpu(lib):
             assert np.abs(got[k] - d[k]).max() < 1e-5 * np.abs(d[k]).max(), k
         else:
             assert np.array_equal(got[k], d[k]), k
+
+
+def test_sim3_chain_golden_gpu(lib):
+    """CUDA path against tests/golden/sim3_chain_small.npz: the Sim3Solver inlier check exactly, the fixed-scale essential-graph core to 1e-5 relative."""
+    import orbslamm_b200 as ob
+    d = np.load(os.path.join(G, "sim3_chain_small.npz"))
+    o = ob.Optimizer()
+    m1, p1 = o.Sim3Prepare(d["X1"], d["oct1"], d["ls2"], d["K1"]); m2, p2 = o.Sim3Prepare(d["X2"], d["oct2"], d["ls2"], d["K2"])
+    assert np.array_equal(m1, d["max_err1"]) and np.array_equal(m2, d["max_err2"]) and np.array_equal(p1, d["p1im1"]) and np.array_equal(p2, d["p2im2"])
+    inl, n = o.Sim3CheckInliers(d["T12"], d["T21"], d["X1"], d["X2"], p1, p2, m1, m2, d["K1"], d["K2"])
+    assert np.array_equal(np.packbits(inl, axis=1), d["inliers"]) and np.array_equal(n, d["n_inliers"])
+    r = o.OptimizePoseGraph(d["pg_sim3"], d["pg_fixed"], d["pg_ei"], d["pg_ej"], d["pg_meas"], True, 20, 1e-16)
+    assert np.abs(r["sim3"] - d["pg_out"]).max() < 1e-5 * np.abs(d["pg_out"]).max()

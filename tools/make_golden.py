@@ -95,3 +95,18 @@ assert np.array_equal(t["bow_ids"], gold["voc_bow_ids"]) and np.array_equal(t["b
 np.savez_compressed(os.path.join(out, "kf_family_400x300.npz"), **gold)
 for f in sorted(os.listdir(out)):
     print(f, os.path.getsize(os.path.join(out, f)))
+
+# 5. Sim3Solver inlier check (exact; written only if the reference's Sim3Solver.cc object code agrees) and the essential-graph core (oracle output)
+assert ref_build.sim3solver_available(), "oracle/_ref Sim3Solver must be built to write these golden vectors"
+r3 = kff.make_sim3_ransac_case(kff.GOLDEN_CAM, 21, n_hyp=60)
+m1, m2, p1, p2 = oracle.sim3_prepare(r3["X1"], r3["X2"], r3["oct1"], r3["oct2"], r3["ls2"], r3["K1"], r3["K2"])
+inl, n = oracle.sim3_check_inliers(r3["T12"], r3["T21"], r3["X1"], r3["X2"], p1, p2, m1, m2, r3["K1"], r3["K2"])
+ri, rn, rm1, rm2, rp1, rp2 = ref_build.ref_sim3_check_inliers(r3["X1"], r3["X2"], r3["oct1"], r3["oct2"], r3["ls2"], r3["K1"], r3["K2"], r3["T12"], r3["T21"])
+assert np.array_equal(inl, ri) and np.array_equal(n, rn) and np.array_equal(m1, rm1) and np.array_equal(p2, rp2)
+Sg, fxg, eig, ejg, emg, _ = kff.make_pose_graph(16, seed=2, n_loops=3)
+pg = oracle.optimize_pose_graph(Sg, fxg, eig, ejg, emg, True, 20, 1e-16)
+np.savez_compressed(os.path.join(out, "sim3_chain_small.npz"), X1=r3["X1"], X2=r3["X2"], oct1=r3["oct1"], oct2=r3["oct2"], ls2=r3["ls2"], K1=r3["K1"], K2=r3["K2"],
+                    T12=r3["T12"], T21=r3["T21"], max_err1=m1, max_err2=m2, p1im1=p1, p2im2=p2, inliers=np.packbits(inl, axis=1), n_inliers=n,
+                    pg_sim3=Sg, pg_fixed=fxg, pg_ei=eig, pg_ej=ejg, pg_meas=emg, pg_out=pg["sim3"], pg_iters=np.array([pg["lm_iterations"], pg["lm_trials"]]))
+for f in sorted(os.listdir(out)):
+    print(f, os.path.getsize(os.path.join(out, f)))
