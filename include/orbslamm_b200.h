@@ -11,9 +11,14 @@
  * Reference interfaces replaced (paths relative to the reference checkout,
  * S/ = SingleRobotScenario/):
  *   orbx_*     S/include/ORBextractor.h:45-111   (ctor, operator(), getters, mvImagePyramid)
- *   orbm_*     S/include/ORBmatcher.h:37-102     (DescriptorDistance, SearchByProjection)
- *              S/src/Frame.cc:230-245,327-392    (AssignFeaturesToGrid / GetFeaturesInArea / PosInGrid)
- *   orbo_*     S/include/Optimizer.h:37-68       (PoseOptimization, LocalBundleAdjustment, BundleAdjustment)
+ *   orbm_*     S/include/ORBmatcher.h:37-102     (every member: DescriptorDistance, SearchByProjection x4, SearchByBoW x2,
+ *                                                 SearchForInitialization, SearchForTriangulation, SearchBySim3, Fuse x2)
+ *              S/src/Frame.cc:230-245,269-325,327-392,404-434  (AssignFeaturesToGrid, isInFrustum, GetFeaturesInArea / PosInGrid, UndistortKeyPoints)
+ *   orbv_*     S/Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1127-1262  (transform, as called by Frame::ComputeBoW, S/src/Frame.cc:395-402)
+ *   orbo_*     S/include/Optimizer.h:37-68       (every member: PoseOptimization, LocalBundleAdjustment, BundleAdjustment, OptimizeSim3,
+ *                                                 OptimizeEssentialGraph; M/: MMGlobalBundleAdjustemnt, MMOptimizeEssentialGraph)
+ *              S/include/Sim3Solver.h:33-129     (CheckInliers / Project / FromCameraToImage of the RANSAC)
+ *   orbf_*     the fused per-frame front end (extract -> project -> search -> pose optimisation) used by the e2e path
  */
 #ifndef ORBSLAMM_B200_H
 #define ORBSLAMM_B200_H
