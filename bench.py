@@ -512,7 +512,8 @@ def main():
     ap.add_argument("--streams", type=int, default=128, help="independent camera streams per GPU (frames per step per GPU)")
     ap.add_argument("--instances", type=int, default=1, help="independent extractor/matcher/optimizer triples (own CUDA stream) per GPU in the device-resident leg")
     ap.add_argument("--e2e-workers", type=int, default=4, help="independent front-end instances serving the streams of one GPU in the e2e leg")
-    ap.add_argument("--workload", default="frontend", choices=["frontend", "ba"])
+    ap.add_argument("--workload", default="all", choices=["all", "frontend", "ba"],
+                    help="all (default): the front-end line with the LocalBA leg as its \"ba\" sub-record -- both halves of BASELINE.json's metric")
     ap.add_argument("--camera", default="kitti", choices=["kitti", "tum"], help="kitti: 1241x376 / 2000 features (BASELINE.json metric); tum: 640x480 / 1000 features (configs[1])")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-frames", type=int, default=100, help="bounded CPU-baseline sample (frames)")
@@ -535,6 +536,10 @@ def main():
         per = max(20, args.steps + args.warmup)          # one step = one new frame on every core's stream; >= 20 frames per core
         t0 = time.time()
         fps, wall = cpu_baseline_frontend(cores, per)
+        ba_ref = None
+        if args.workload == "all":
+            from bench_ba import reference_line
+            ba_ref = reference_line(args)
         line = {"impl": "reference", "metric": f"ORB extract+match fps @{CAM['w']}x{CAM['h']}", "value": round(fps, 2), "unit": "frames/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 / fps, 3), "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "u8", "data": "synthetic",
@@ -546,6 +551,8 @@ def main():
                 "cpu_baseline": {"value": round(fps, 2), "unit": "frames/s", "cores": cores, "kind": "port", "cpu": cpu_model(),
                                  "sample": f"{per} frames x {cores} streams (one per core), {wall:.1f} s"},
                 "e2e": {"value": round(fps, 2), "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        if ba_ref is not None:
+            line["ba"] = ba_ref
         emit(line)
         return
 
@@ -559,11 +566,19 @@ def main():
         out = bench_ba(args, rank, world)
     else:
         out = bench_frontend(args, rank, world)
+        ba = None
+        if args.workload == "all":
+            # second half of BASELINE.json's metric: LocalBA LM iterations/s on the 500 KF / 50k point graph (sharded over the ranks at N > 1);
+            # runs before rank 0's CPU baseline so that the other ranks do not wait in a collective for it
+            from bench_ba import bench_ba
+            ba = bench_ba(args, rank, world)
         if rank == 0:
             fps1, wall1 = cpu_baseline_frontend(1, max(10, args.cpu_frames))
             out["cpu_baseline"] = {"value": round(fps1, 2), "unit": "frames/s", "cores": 1, "kind": "port", "cpu": cpu_model(),
                                    "sample": f"{max(10, args.cpu_frames)} frames of one stream, {wall1:.1f} s; cv2 4.13 primitives + restated reference code "
                                              "(reference front end is single-threaded per stream)"}
+            if ba is not None:
+                out["ba"] = ba
     if rank == 0:
         emit(out)
     if world > 1:

@@ -33,6 +33,12 @@ def bench_ba(args, rank, world):
     g = synth.ba_graph(K=K, P=P, seed=42)
     E = len(g["kf"])
     opt = ob.Optimizer(device=dev)
+    steps = max(10, args.steps) if getattr(args, "workload", "ba") == "all" else args.steps
+    sharded_parity = None
+    full = g
+    if world > 1:
+        # the single-GPU answer first (every rank solves the whole graph on its own GPU: ~20 ms), the sharded one is checked against it below
+        single = ob.Optimizer(device=dev).LocalBundleAdjustment(g["poses"], g["fixed"], g["intr"], g["points"], g["kf"], g["pt"], g["uv"], g["inv_sigma2"])
     if world > 1:
         # one graph, map points sharded over the ranks, poses replicated; one NCCL all-reduce of the reduced pose system per LM trial
         from orbslamm_b200 import sharding
@@ -41,6 +47,16 @@ def bench_ba(args, rank, world):
         opt.comm_init(world, rank, uid[0])
         g = sharding.shard_graph(g, world, rank)
     run = lambda: opt.LocalBundleAdjustment(g["poses"], g["fixed"], g["intr"], g["points"], g["kf"], g["pt"], g["uv"], g["inv_sigma2"])
+    if world > 1:
+        # parity gate BEFORE timing: the sharded solve must reproduce the single-GPU poses (replicated) and this rank's points to 1e-6 relative
+        r = run()
+        rel = lambda a, b: float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+        ok = (r["lm_iterations"] == single["lm_iterations"] and rel(r["poses"], single["poses"]) < 1e-6
+              and rel(r["points"], single["points"][g["local_points"]]) < 1e-6)
+        tt = torch.tensor([1 if ok else 0], device="cuda", dtype=torch.int32)
+        torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.MIN)
+        sharded_parity = bool(int(tt.item()))
+        assert sharded_parity, "sharded LocalBA differs from the single-GPU result (poses / points beyond 1e-6 relative or different LM iteration count)"
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
     def barrier():
@@ -57,7 +73,7 @@ def bench_ba(args, rank, world):
     loop_s = total_s = 0.0
     iters = trials = 0
     t_wall = time.time()
-    for i in range(args.steps):
+    for i in range(steps):
         flush.fill_(i & 0xff)
         torch.cuda.synchronize()
         r = run()
@@ -102,15 +118,18 @@ def bench_ba(args, rank, world):
                 "whole_iteration": {"algorithmic_bytes": int(_alg_bytes(K, P, E, ld)),
                                     "achieved_GBps": round(_alg_bytes(K, P, E, ld) * iters / loop_s / 1e9, 2)}}
     graph_bytes = K * 64 + K + K * 32 + P * 12 + E * (4 + 4 + 8 + 4)
-    out = {"metric": "LocalBA LM iters/s @500KF/50k pts", "value": round(its, 2), "unit": "LM iterations/s", "n_gpus": world, "steps": args.steps,
-           "warmup": args.warmup, "ms_per_step": round(loop_s * 1e3 / args.steps, 3), "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
+    out = {"metric": "LocalBA LM iters/s @500KF/50k pts", "value": round(its, 2), "unit": "LM iterations/s", "n_gpus": world, "steps": steps,
+           "warmup": args.warmup, "ms_per_step": round(loop_s * 1e3 / steps, 3), "ms_per_lm_iteration": round(loop_s * 1e3 / max(iters, 1), 4), "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
            "config": {"workload": f"synthetic covisibility graph {K} KF / {P} points / {E} observations, LocalBA schedule 5 robust + 10 non-robust LM its",
-                      "lm_iterations_per_step": iters / args.steps, "lm_trials_per_step": trials / args.steps,
+                      "lm_iterations_per_step": iters / steps, "lm_trials_per_step": trials / steps,
                       "l2": "256 MiB flush buffer written between timed steps (untimed)", "reduced_system": f"{ld}x{ld} fp64 (10 keyframes per 64-row tile), nested-dissection tile order: {sky} of {(ld // 64) * (ld // 64 + 1) // 2} lower 64x64 tiles structurally nonzero in L, {tm['levels']} elimination levels",
                       "parallelism": f"map points sharded x{world}, poses replicated, NCCL all-reduce of the {ld}x{ld} reduced system per LM trial" if world > 1 else "1 GPU"},
            "e2e": {"value": round(e2e, 2), "unit": "LM iterations/s", "h2d_bytes_per_step": int(graph_bytes), "d2h_bytes_per_step": int(K * 64 + P * 12 + E * 10)},
            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "wall_s": round(wall, 3)}
+    out["lm_iterations"] = int(iters)
+    if sharded_parity is not None:
+        out["sharded_parity"] = sharded_parity
     if rank == 0:
         out["cpu_baseline"] = cpu_baseline_ba(K, P, 1)
     return out

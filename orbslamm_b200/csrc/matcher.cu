@@ -958,7 +958,6 @@ struct orbm_handle {
     long long launches = 0;
     std::mutex mu;
     DevBuf cell_start, cell_items, prop, owner, top, ncand;
-    size_t resolve_smem = 0;
     StagePool pool;
 };
 
@@ -985,6 +984,9 @@ int orbm_create(orbm_handle **out, int device)
     h->device = device;
     cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete h; return cuda_fail(e, "cudaStreamCreate", __FILE__, __LINE__); }
+    // per-device function attribute, shared by all handles (the drop-in creates one per calling thread): always the static bound
+    e = cudaFuncSetAttribute(k_search_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) { cudaStreamDestroy(h->stream); delete h; return cuda_fail(e, "cudaFuncSetAttribute(k_search_resolve)", __FILE__, __LINE__); }
     *out = h;
     return ORBS_OK;
 }
@@ -1179,10 +1181,8 @@ int orbm_search_by_projection_kf(orbm_handle *h, int n_frames, const float *boun
         const int use_smem = smem <= 200 * 1024;
         if (!use_smem) smem = (size_t)q_slab * sizeof(int);                    // rescan queue only
         ORBS_REQUIRE(smem <= 200 * 1024, ORBS_E_INVALID, "too many map points per frame for the projection search");
-        if (smem > h->resolve_smem) {
-            ORBS_CUDA(cudaFuncSetAttribute(k_search_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            h->resolve_smem = smem;
-        }
+        // the opt-in limit is a per-device attribute of the FUNCTION, not of a handle: it is raised once, to the static upper
+        // bound, in orbm_create and never lowered (handles of different sizes share it)
         k_search_resolve<<<n_frames, 1024, smem, h->stream>>>(A, use_smem);
     }
     h->launches += 3;

@@ -239,7 +239,9 @@ static int build_plan(orbx_handle *h, int width, int height)
     // octree shared memory: 64 B per node + scan scratch
     h->octree_smem = max_node_cap * 64 + (512 + 1) * 4 + 64;
     ORBS_REQUIRE(h->octree_smem <= 220 * 1024, ORBS_E_INVALID, "nfeatures too large for the on-chip quad-tree (per-level quota > ~3400)");
-    ORBS_CUDA(cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, h->octree_smem));
+    // the opt-in limit is per device and per FUNCTION (shared by every extractor handle, e.g. Tracking's mpIniORBextractor with
+    // 2 * nFeatures next to mpORBextractorLeft): always the static upper bound, so a smaller handle never lowers it
+    ORBS_CUDA(cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     if (!cells.empty()) {
         if (int rc = h->d_cells.reserve(cells.size() * sizeof(CellDesc))) return rc;
         ORBS_CUDA(cudaMemcpyAsync(h->d_cells.p, cells.data(), cells.size() * sizeof(CellDesc), cudaMemcpyHostToDevice, h->stream));

@@ -178,8 +178,9 @@ struct orbv_handle {
     int k = 0, L = 0, n_nodes = 0;
     DevBuf desc, child_start, child_ids, word_id, weight;
     StagePool pool;
-    size_t assemble_smem = 0;
 };
+
+constexpr size_t kAssembleSmemMax = 128 * 1024;      // 16384 (word, feature) keys
 
 extern "C" {
 
@@ -210,6 +211,10 @@ int orbv_create(orbv_handle **out, int device, int k, int L, int n_nodes, const 
         if (e == cudaSuccess) e = cudaMemcpyAsync(h->weight.p, weight, (size_t)n_nodes * 8, cudaMemcpyHostToDevice, h->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
         if (e != cudaSuccess) rc = cuda_fail(e, "vocabulary upload", __FILE__, __LINE__);
+    }
+    if (!rc) {   // per-device function attribute shared by every vocabulary handle: the static bound, never lowered
+        e = cudaFuncSetAttribute(k_vocab_assemble, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAssembleSmemMax);
+        if (e != cudaSuccess) rc = cuda_fail(e, "cudaFuncSetAttribute(k_vocab_assemble)", __FILE__, __LINE__);
     }
     if (rc) { orbv_destroy(h); return rc; }
     *out = h;
@@ -263,10 +268,7 @@ int orbv_transform(orbv_handle *h, int n_frames, const uint8_t *desc, const int3
     int n_pow2 = 1;
     while (n_pow2 < slab) n_pow2 <<= 1;
     const size_t smem = (size_t)n_pow2 * sizeof(unsigned long long);
-    if (smem > h->assemble_smem) {
-        ORBS_CUDA(cudaFuncSetAttribute(k_vocab_assemble, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        h->assemble_smem = smem;
-    }
+    ORBS_REQUIRE(smem <= kAssembleSmemMax, ORBS_E_INVALID, "too many features per frame for the on-chip BoW assembly (slab > 16384)");
     k_vocab_assemble<<<n_frames, 1024, smem, h->stream>>>(slab, n_pow2, dc, dword, dnode, dw, dbi, dbv, dbc, dfn, dfs, dfi, dfc);
     h->launches += 2;
     ORBS_CUDA(cudaGetLastError());
