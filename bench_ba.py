@@ -101,19 +101,21 @@ def bench_ba(args, rank, world):
     dom_ms, dom_n = ktimes[dom]
     # chol_factor = all k_chol_panel / k_chol_update launches of one solve: every structurally nonzero 64x64 tile of L is read and
     # written once (the compulsory traffic of a sparse tiled factorisation; re-reads of neighbouring tiles come from L2)
+    # algorithmic bytes per launch: edges E, points P, keyframes K, `sky` structurally nonzero 64x64 tiles, `ntile` tile rows
+    ntile = ld // 64
     alg = {"errors": 20 * E + 88 * K + 24 * P + 16 * E, "build_points": 20 * E + 88 * K + 24 * P + 144 * E + 96 * P,
-           "build_poses": 20 * E + 88 * K + 24 * P + 336 * K, "schur": 144 * E + 96 * P + 8 * 36 * 3.5 * E,
-           "chol_factor": 2 * 8 * 64 * 64 * sky, "tri_solves": 2 * 8 * 64 * 64 * sky,
-           "backsub": 144 * E + 96 * P + 24 * P, "update": 2 * (56 * K + 24 * P) * 2, "memset_S": 8 * ld * ld}
+           "build_poses": 20 * E + 88 * K + 24 * P + 336 * K, "point_prep": 2 * 144 * E + 96 * P + 72 * P,
+           "schur": 144 * E + 8 * 4096 * sky + 16 * 3.5 * E, "reduced_solve": 2 * 8 * 4096 * sky + 8 * 4096 * ntile,
+           "backsub": 144 * E + 72 * P + 24 * P, "update": 2 * (56 * K + 24 * P) * 2, "lm_decide": 8 * (E // 256 + P // 32)}
     per_launch_ms = dom_ms / max(dom_n, 1)
     alg_bytes = alg[dom]
     achieved = alg_bytes / (per_launch_ms * 1e-3) / 1e9
     lm_total_ms = loop_s * 1e3
     roofline = {"kernel": dom, "bound": "hbm", "achieved": round(achieved, 2), "peak": hbm, "unit": "GB/s", "frac": round(achieved / hbm, 5),
                 "traffic": None, "peak_source": how, "algorithmic_bytes_per_launch": int(alg_bytes), "avg_launch_ms": round(per_launch_ms, 5),
-                "note": "the factorisation is a chain of dependent 64x64 fp64 tile steps (latency-bound: ncu shows fp64 pipe 8 % and DRAM < 1 % in k_chol_panel); "
-                        "per-kernel DRAM traffic of one capture is in profiles/r1h_traffic.json",
-                "launch": "one timed region = one factorisation / one pair of triangular solves (several dependent kernel launches)" if dom in ("chol_factor", "tri_solves") else "one kernel launch",
+                "note": "reduced_solve = ONE persistent dataflow kernel (left-looking tiled Cholesky on DMMA + both triangular solves): a chain of dependent 64x64 fp64 "
+                        "tile tasks, latency-bound by construction; schur = memset of the packed tiles + lambda + one warp per target 6x6 block",
+                "launch": "one timed region per LM trial (reduced_solve: 1 launch; schur: memset + 2 launches)",
                 "kernel_share_of_step": {k: round(v[0] / max(lm_total_ms, 1e-9), 4) for k, v in ktimes.items()},
                 "whole_iteration": {"algorithmic_bytes": int(_alg_bytes(K, P, E, ld)),
                                     "achieved_GBps": round(_alg_bytes(K, P, E, ld) * iters / loop_s / 1e9, 2)}}
@@ -123,8 +125,8 @@ def bench_ba(args, rank, world):
            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
            "config": {"workload": f"synthetic covisibility graph {K} KF / {P} points / {E} observations, LocalBA schedule 5 robust + 10 non-robust LM its",
                       "lm_iterations_per_step": iters / steps, "lm_trials_per_step": trials / steps,
-                      "l2": "256 MiB flush buffer written between timed steps (untimed)", "reduced_system": f"{ld}x{ld} fp64 (10 keyframes per 64-row tile), nested-dissection tile order: {sky} of {(ld // 64) * (ld // 64 + 1) // 2} lower 64x64 tiles structurally nonzero in L, {tm['levels']} elimination levels",
-                      "parallelism": f"map points sharded x{world}, poses replicated, NCCL all-reduce of the {ld}x{ld} reduced system per LM trial" if world > 1 else "1 GPU"},
+                      "l2": "256 MiB flush buffer written between timed steps (untimed)", "reduced_system": f"{ld}x{ld} fp64 (10 keyframes per 64-row tile), nested-dissection tile order: {sky} of {(ld // 64) * (ld // 64 + 1) // 2} lower 64x64 tiles structurally nonzero in L (only those are stored), {tm['levels']} elimination levels",
+                      "parallelism": f"map points sharded x{world}, poses replicated, ONE NCCL all-reduce of the {sky} packed tiles + rhs ({(sky * 4096 + ld) * 8 / 1e6:.1f} MB) per LM trial + a 5-scalar all-reduce for the LM decision" if world > 1 else "1 GPU"},
            "e2e": {"value": round(e2e, 2), "unit": "LM iterations/s", "h2d_bytes_per_step": int(graph_bytes), "d2h_bytes_per_step": int(K * 64 + P * 12 + E * 10)},
            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "wall_s": round(wall, 3)}
     out["lm_iterations"] = int(iters)

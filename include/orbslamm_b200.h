@@ -387,13 +387,15 @@ int orbo_pose_optimization_matched(orbo_handle *h, int n_frames, float *Tcw, con
  *   poses f32[K,16] in/out; fixed u8[K]: 0 free, 1 fixed but written back (mnId == 0), 2 fixed camera (never written);
  *   intr f64[K,4] fx fy cx cy per keyframe; points f32[P,3] in/out;
  *   edges: e_kf i32[E], e_pt i32[E], e_uv f32[E,2], e_inv_sigma2 f32[E];
- *   stop_flag: optional host flag polled between iterations and LM trials (mbAbortBA / mbStopGBA);
+ *   stop_flag: optional host flag, ONE BYTE (a C++ `bool *` such as &mbAbortBA / &mbStopGBA is passed as is), watched by the
+ *              calling thread while the LM slots run on the device and seen by the device before every trial decision
+ *              (g2o: terminate() per iteration and per trial, sparse_optimizer.h:188, levenberg.cpp:149);
  *   outputs (optional): e_chi2 f64[E], e_depth_ok u8[E], e_outlier u8[E] = the final check of Optimizer.cc:734-766;
  *   stats i32[4]: LM iterations, LM trials, Cholesky failures, 1 if aborted before the first iteration.
  * Returns ORBS_OK, or 1 if the stop flag was already set on entry (nothing touched, Optimizer.cc:678-680). */
 int orbo_bundle_adjust(orbo_handle *h, int K, float *poses, const uint8_t *fixed, const double *intr, int P, float *points,
                        int E, const int32_t *e_kf, const int32_t *e_pt, const float *e_uv, const float *e_inv_sigma2,
-                       int two_stage, int its0, int its1, int robust, const volatile int *stop_flag,
+                       int two_stage, int its0, int its1, int robust, const volatile uint8_t *stop_flag,
                        double *e_chi2, uint8_t *e_depth_ok, uint8_t *e_outlier, int32_t *stats);
 
 /* Numeric core of Optimizer::OptimizeEssentialGraph / MMOptimizeEssentialGraph (S/src/Optimizer.cc:804-1067, 1069-1346): Levenberg over K
@@ -439,9 +441,11 @@ int orbo_optimize_sim3(orbo_handle *h, int n_pairs, double *sim3, const uint8_t 
 /* Multi-GPU bundle adjustment: one process per GPU, keyframe poses replicated, MAP POINTS (with all
  * their observations) sharded over the ranks.  After orbo_comm_init the handle's orbo_bundle_adjust becomes a
  * collective: every rank passes ALL keyframes (same order, same poses) but only ITS points and edges; each rank builds
- * its partial reduced pose system, one ncclAllReduce (fp64 sum over NVLink) per LM trial combines them, every rank
- * factors the same system redundantly and back-substitutes its own points.  chi2 / gain-ratio scalars, the stop flag
- * and the keyframe activity mask are reduced too, so that all ranks take identical LM decisions.  Poses come back
+ * its partial reduced pose system as packed nonzero tiles + right-hand side in ONE buffer, one ncclAllReduce (fp64 sum over
+ * NVLink) per LM trial combines them, every rank factors the same system redundantly and back-substitutes its own points.
+ * Five scalars (chi2, the two gain-ratio parts, stop flag, Cholesky failure) are summed after the trial so that all ranks take
+ * identical LM decisions on their device-resident control blocks; the keyframe activity mask and the tile adjacency are
+ * reduced once per call.  Poses come back
  * identical on every rank; point / edge outputs are the rank's shard.
  *   orbo_comm_unique_id: rank 0 creates the 128-byte NCCL id, the caller distributes it (MPI, torch.distributed, files);
  *   orbo_comm_init: collective. */

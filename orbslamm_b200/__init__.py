@@ -589,6 +589,8 @@ class Optimizer:
         e_kf = np.ascontiguousarray(e_kf, np.int32); e_pt = np.ascontiguousarray(e_pt, np.int32); E = len(e_kf)
         e_uv = np.ascontiguousarray(e_uv, np.float32); w = np.ascontiguousarray(e_inv_sigma2, np.float32)
         chi2 = np.zeros(E); dok = np.zeros(E, np.uint8); outl = np.zeros(E, np.uint8); stats = np.zeros(4, np.int32)
+        if stop_flag is not None:
+            assert stop_flag.dtype == np.uint8, "stop_flag is one byte (C++ bool)"
         sp = None if stop_flag is None else stop_flag.ctypes.data
         rc = self._L.orbo_bundle_adjust(self._h, K, _ptr(poses), _ptr(fixed), _ptr(intr), P, _ptr(points), E, _ptr(e_kf), _ptr(e_pt),
                                         _ptr(e_uv), _ptr(w), int(two_stage), int(its0), int(its1), int(robust), sp, _ptr(chi2),
@@ -598,8 +600,7 @@ class Optimizer:
         return dict(poses=poses.reshape(K, 4, 4), points=points, chi2=chi2, depth_ok=dok, outlier=outl,
                     lm_iterations=int(stats[0]), lm_trials=int(stats[1]), chol_failures=int(stats[2]), aborted=bool(rc == 1))
 
-    KERNELS = ("errors", "build_points", "build_poses", "schur", "chol_factor", "unused5", "unused6", "tri_solves",
-               "backsub", "update", "memset_S")
+    KERNELS = ("errors", "build_points", "build_poses", "point_prep", "schur", "reduced_solve", "backsub", "update", "lm_decide")
 
     def set_profiling(self, on):
         self._L.orbo_set_profiling.argtypes = [ctypes.c_void_p, ctypes.c_int]

@@ -96,7 +96,7 @@ struct KernelTimer {
 
 // host<->device staging for ORBS_MEM_HOST calls: inputs are copied to pooled device buffers, outputs copied back in finish()
 struct StagePool {
-    static constexpr int kSlots = 64;
+    static constexpr int kSlots = 96;
     DevBuf buf[kSlots];
     void release() { for (auto &b : buf) b.release(); }
 };

@@ -16,6 +16,7 @@
 #include "pose_opt.cuh"
 #include "sim3_opt.cuh"
 #include "pose_graph.cuh"
+#include <cub/cub.cuh>
 #include "ba_kernels.cuh"
 
 using namespace orbs;
@@ -61,9 +62,15 @@ struct orbo_handle {
     std::mutex mu;
     StagePool pool;          // pose optimisation staging
     StagePool ba_pool;       // bundle adjustment buffers
-    DevBuf ba_tasks;         // panel / update task lists of the tiled Cholesky (sized by the symbolic factorisation)
-    DevBuf ba_packed;        // sharded solve: the structurally nonzero tiles of the reduced system, contiguous, for the all-reduce
-    PinnedBuf h_scalars;
+    DevBuf ba_tasks;         // task / dependency lists of the tiled solver (sized by the symbolic factorisation)
+    DevBuf ba_sys;           // reduced system: [A tiles | rhs] (contiguous: the one all-reduce of the sharded solve), L, Linv, y, x
+    DevBuf ba_flags;         // dataflow epoch flags + ticket counters of k_rs_solve
+    DevBuf ba_cub;           // cub temp storage (pair sort, scans)
+    PinnedBuf h_scalars;     // LmCtl copies + the mirrored stop flag
+    static constexpr int kCtlCopies = 4;
+    cudaEvent_t slot_done[kCtlCopies] = {nullptr, nullptr, nullptr, nullptr};
+    int rs_epoch = 0;
+    int sm_count = 148;
     KernelTimer timer;       // BA kernels, ids = BaK
     ncclComm_t comm = nullptr;   // set by orbo_comm_init: orbo_bundle_adjust becomes a collective over map-point shards
     int nranks = 1, rank = 0;
@@ -71,7 +78,7 @@ struct orbo_handle {
     double ba_timing[4] = {0, 0, 0, 0};   // last BA call: LM-loop seconds, total seconds, setup (layout + H2D) seconds, Schur bytes
 };
 
-enum BaK { BK_ERRORS = 0, BK_BUILD_POINTS, BK_BUILD_POSES, BK_SCHUR, BK_POTRF, BK_TRSM, BK_SYRK, BK_TRS, BK_BACKSUB, BK_UPDATE, BK_MEMSET, BK_COUNT };
+enum BaK { BK_ERRORS = 0, BK_BUILD_POINTS, BK_BUILD_POSES, BK_PREP, BK_SCHUR, BK_SOLVE, BK_BACKSUB, BK_UPDATE, BK_DECIDE, BK_COUNT };
 
 extern "C" {
 
@@ -84,9 +91,11 @@ int orbo_create(orbo_handle **out, int device)
     h->device = device;
     cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete h; return cuda_fail(e, "cudaStreamCreate", __FILE__, __LINE__); }
-    if (int rc = h->h_scalars.reserve(256)) { orbo_destroy(h); return rc; }
-    cudaFuncSetAttribute(k_chol_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPanelSmem);
-    cudaFuncSetAttribute(k_chol_update, cudaFuncAttributeMaxDynamicSharedMemorySize, kUpdateSmem);
+    if (int rc = h->h_scalars.reserve(orbo_handle::kCtlCopies * sizeof(LmCtl) + 256)) { orbo_destroy(h); return rc; }
+    for (auto &ev : h->slot_done) { e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming); if (e != cudaSuccess) { orbo_destroy(h); return cuda_fail(e, "cudaEventCreate", __FILE__, __LINE__); } }
+    { int v = 0; if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && v > 0) h->sm_count = v; }
+    // opt-in shared memory limits are per-device function attributes: set once, to the static sizes
+    cudaFuncSetAttribute(k_rs_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, kRsSmemBytes);
     *out = h;
     return ORBS_OK;
 }
@@ -98,7 +107,9 @@ int orbo_destroy(orbo_handle *h)
     if (h->stream && h->own_stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
     else cudaDeviceSynchronize();
     if (h->comm) { if (g_nccl.CommAbort) g_nccl.CommAbort(h->comm); else g_nccl.CommDestroy(h->comm); }   // abort: never block on a peer at teardown
-    h->pool.release(); h->ba_pool.release(); h->ba_tasks.release(); h->ba_packed.release(); h->h_scalars.release(); h->timer.release();
+    h->pool.release(); h->ba_pool.release(); h->ba_tasks.release(); h->ba_sys.release(); h->ba_flags.release(); h->ba_cub.release();
+    h->h_scalars.release(); h->timer.release();
+    for (auto &ev : h->slot_done) if (ev) cudaEventDestroy(ev);
     delete h;
     return ORBS_OK;
 }
@@ -293,131 +304,41 @@ int orbo_sim3_check_inliers(orbo_handle *h, int n_hyp, const float *T12, const f
 }  // extern "C"
 
 // ---------------------------------------------------------------------------------------------------------
-// Bundle adjustment driver
+// Bundle adjustment driver: the graph layout on the host, the structure of the reduced system (tile adjacency -> nested-dissection
+// order -> symbolic factorisation -> task list; Schur pairs sorted by target block) once per call, then LM "slots" enqueued
+// back to back.  Every slot is the same kernel sequence; what it does is decided by the device control block (LmCtl):
+//     [state == BUILD]  linearise (Hll, b_l, Hpl | Hpp, b_p), first time: lambda init
+//     [state != DONE]   per-point G, Z | zero + lambda | Schur blocks | (sharded: ONE all-reduce of the packed tiles + rhs) |
+//                       factor + solves (one persistent kernel) | back-substitution | push + oplus | errors | reduce |
+//                       (sharded: 5 scalars) | decide | pop if rejected
+// The host never waits for a decision: it reads a pinned copy of the control block two slots later and stops enqueueing.
 namespace {
 
-struct BaHost {
-    orbo_handle *h;
-    cudaStream_t st;
+struct BaRun {
+    orbo_handle *h = nullptr;
+    cudaStream_t st = nullptr;
+    Stager *S = nullptr;
     BaDev B;
-    int ntiles = 0;
-    int err_blocks = 0, pt_blocks = 0, pose_blocks = 0, diag_blocks = 0, xp_blocks = 0;
-    double lambda = 0, ni = 2;
-    int nbad = 0;
-    const volatile int *stop = nullptr;
-    int lm_iterations = 0, lm_trials = 0, chol_failures = 0;
-    double *Linv = nullptr;       // [ntiles][64*64] inverses of the diagonal Cholesky tiles
-    int *ready = nullptr;         // [2*ntiles] dataflow flags of the triangular solves
-    double *h_scal = nullptr;     // pinned [16]
-    int *h_flag = nullptr;        // pinned
-    CholPlan plan = {};           // sparse tile structure + task lists of the reduced system (device arrays)
+    TilePlanHost plan;
+    RsPlan rsplan = {};
+    RsBuf rsbuf = {};
+    const volatile uint8_t *stop = nullptr;
+    int *h_stop = nullptr;                 // pinned, read by k_lm_reduce through the unified address space
+    LmCtl *h_ctl = nullptr;                // pinned [kCtlCopies]
+    double *diag6 = nullptr;               // [6 nA | nranks] first-iteration diagonal exchange
+    int err_blocks = 0, pt_blocks = 0, diag_blocks = 0, xp_blocks = 0, upd_blocks = 0;
+    int solve_ctas = 0, n_seg = 0;
+    std::vector<int> pose_idx;
+    const uint8_t *fixed = nullptr;
+    // device scratch that build_structure needs
+    int *d_pose_idx = nullptr, *d_rowbase = nullptr, *d_slot_of = nullptr, *d_tile_pose = nullptr, *d_pose_act = nullptr;
+    uint8_t *d_adj = nullptr;
+    long long pair_cap = 0;
+    int *d_pair_cnt = nullptr, *d_pair_start = nullptr, *d_head = nullptr, *d_scan = nullptr, *d_seg_start = nullptr, *d_nseg = nullptr;
+    unsigned long long *d_key[2] = {nullptr, nullptr}, *d_val[2] = {nullptr, nullptr};
+    void *d_cub = nullptr; size_t cub_bytes = 0;
+    RsTask *d_tasks = nullptr; int2 *d_deps = nullptr; size_t tasks_cap = 0, deps_cap = 0;
     int nt_max = 0;
-    int *d_plan_i = nullptr;      // rows_start, rows, cols_start, cols  [2 (nt_max + 1) + nt_max (nt_max - 1)]
-    int4 *d_tasks = nullptr;      // panel tasks then update tasks
-    int *d_rowbase = nullptr; uint8_t *d_rowpad = nullptr;
-    std::vector<int> panel_lv, update_lv;   // per level: first task index (size nlevels + 1)
-    int nlevels = 0;
-    long long l_tiles = 0;        // structurally nonzero tiles of L (incl. diagonal)
-    size_t n_panel = 0;
-
-    // Nested-dissection order of the tile groups by recursive bisection of the natural (temporal) order: the separator of
-    // [lo, hi) is the run of groups right of the middle that the left half reaches; left and right halves are then
-    // independent and are eliminated in parallel, the separator after both.
-    static void nd_order(const std::vector<uint8_t> &adj, int ng, int lo, int hi, std::vector<int> &out)
-    {
-        const int n = hi - lo;
-        if (n <= 3) { for (int g = lo; g < hi; g++) out.push_back(g); return; }
-        const int mid = lo + n / 2;
-        int reach = mid - 1;
-        for (int g = lo; g < mid; g++)
-            for (int h2 = hi - 1; h2 > reach; h2--) if (adj[(size_t)g * ng + h2]) { reach = h2; break; }
-        const int w = reach - mid + 1;
-        if (w == 0) { nd_order(adj, ng, lo, mid, out); nd_order(adj, ng, mid, hi, out); return; }
-        if (2 * w >= n || mid + w >= hi) { for (int g = lo; g < hi; g++) out.push_back(g); return; }   // no useful separator
-        nd_order(adj, ng, lo, mid, out);
-        nd_order(adj, ng, mid + w, hi, out);
-        for (int g = mid; g < mid + w; g++) out.push_back(g);
-    }
-
-    // adj[ng x ng]: covisibility of the tile groups (kPosesPerTile consecutive free keyframes each)
-    int build_schedule(const std::vector<uint8_t> &adj, int ng)
-    {
-        const int nt = ng, nA = B.nA;
-        std::vector<int> order; order.reserve(nt);
-        nd_order(adj, ng, 0, ng, order);
-        std::vector<int> pos(ng);
-        for (int t = 0; t < nt; t++) pos[order[t]] = t;
-        // symbolic factorisation on the permuted tile pattern
-        std::vector<uint8_t> pat((size_t)nt * nt, 0);
-        for (int a = 0; a < ng; a++)
-            for (int b2 = 0; b2 < ng; b2++) if (a != b2 && adj[(size_t)a * ng + b2]) { const int i = std::max(pos[a], pos[b2]), j = std::min(pos[a], pos[b2]); pat[(size_t)i * nt + j] = 1; }
-        std::vector<int> rows_start(nt + 1, 0), rows, cols_start(nt + 1, 0), cols, level(nt, 0);
-        for (int k = 0; k < nt; k++) {
-            const size_t r0 = rows.size();
-            for (int i = k + 1; i < nt; i++) if (pat[(size_t)i * nt + k]) rows.push_back(i);
-            rows_start[k + 1] = (int)rows.size();
-            for (size_t x = r0; x < rows.size(); x++)
-                for (size_t y = r0; y < x; y++) pat[(size_t)rows[x] * nt + rows[y]] = 1;
-        }
-        nlevels = 0;
-        for (int i = 0; i < nt; i++) {
-            int lv = 0;
-            for (int k = 0; k < i; k++) if (pat[(size_t)i * nt + k]) { cols.push_back(k); lv = std::max(lv, level[k] + 1); }
-            cols_start[i + 1] = (int)cols.size();
-            level[i] = lv;
-            nlevels = std::max(nlevels, lv + 1);
-        }
-        l_tiles = nt + (long long)rows.size();
-        // task lists by level
-        std::vector<std::vector<int>> by_level(nlevels);
-        for (int k = 0; k < nt; k++) by_level[level[k]].push_back(k);
-        std::vector<int4> panel, update;
-        panel_lv.assign(nlevels + 1, 0); update_lv.assign(nlevels + 1, 0);
-        std::vector<int> hits((size_t)nt * nt, 0);
-        for (int l = 0; l < nlevels; l++) {
-            const size_t u0 = update.size();
-            for (int k : by_level[l]) {
-                panel.push_back(make_int4(k, k, 0, 0));
-                for (int x = rows_start[k]; x < rows_start[k + 1]; x++) panel.push_back(make_int4(k, rows[x], 0, 0));
-                for (int x = rows_start[k]; x < rows_start[k + 1]; x++)
-                    for (int y = rows_start[k]; y <= x; y++) { update.push_back(make_int4(k, rows[x], rows[y], 0)); hits[(size_t)rows[x] * nt + rows[y]]++; }
-            }
-            for (size_t t = u0; t < update.size(); t++) {
-                int &hcount = hits[(size_t)update[t].y * nt + update[t].z];
-                if (hcount > 1) update[t].w = 1;                  // several columns of this level update the tile: atomics
-            }
-            for (size_t t = u0; t < update.size(); t++) hits[(size_t)update[t].y * nt + update[t].z] = 0;
-            panel_lv[l + 1] = (int)panel.size(); update_lv[l + 1] = (int)update.size();
-        }
-        n_panel = panel.size();
-        if (panel.size() + update.size() > ((size_t)1 << 26)) { set_last_error("reduced pose system too large / too dense for the tiled Cholesky (more than 2^26 tile tasks)"); return ORBS_E_INVALID; }
-        if (int rc = h->ba_tasks.reserve((panel.size() + update.size() + 1) * sizeof(int4))) return rc;
-        d_tasks = h->ba_tasks.as<int4>();
-        // row map
-        std::vector<int> rowbase(std::max(nA, 1));
-        std::vector<uint8_t> rowpad((size_t)nt * NB, 1);
-        for (int ip = 0; ip < nA; ip++) {
-            rowbase[ip] = NB * pos[ip / kPosesPerTile] + 6 * (ip % kPosesPerTile);
-            for (int a2 = 0; a2 < 6; a2++) rowpad[rowbase[ip] + a2] = 0;
-        }
-        int *d_rows_start = d_plan_i, *d_cols_start = d_plan_i + (nt_max + 1), *d_rows = d_plan_i + 2 * (nt_max + 1);
-        int *d_cols = d_rows + (size_t)nt_max * (nt_max - 1) / 2 + 1;
-        ORBS_CUDA(cudaMemcpyAsync(d_rows_start, rows_start.data(), (nt + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
-        ORBS_CUDA(cudaMemcpyAsync(d_cols_start, cols_start.data(), (nt + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
-        if (!rows.empty()) {
-            ORBS_CUDA(cudaMemcpyAsync(d_rows, rows.data(), rows.size() * sizeof(int), cudaMemcpyHostToDevice, st));
-            ORBS_CUDA(cudaMemcpyAsync(d_cols, cols.data(), cols.size() * sizeof(int), cudaMemcpyHostToDevice, st));
-        }
-        ORBS_CUDA(cudaMemcpyAsync(d_tasks, panel.data(), panel.size() * sizeof(int4), cudaMemcpyHostToDevice, st));
-        if (!update.empty()) ORBS_CUDA(cudaMemcpyAsync(d_tasks + panel.size(), update.data(), update.size() * sizeof(int4), cudaMemcpyHostToDevice, st));
-        if (nA > 0) ORBS_CUDA(cudaMemcpyAsync(d_rowbase, rowbase.data(), nA * sizeof(int), cudaMemcpyHostToDevice, st));
-        ORBS_CUDA(cudaMemcpyAsync(d_rowpad, rowpad.data(), rowpad.size(), cudaMemcpyHostToDevice, st));
-        ORBS_CUDA(cudaStreamSynchronize(st));                  // the host vectors die here
-        plan.rows_start = d_rows_start; plan.rows = d_rows; plan.cols_start = d_cols_start; plan.cols = d_cols;
-        plan.panel = d_tasks; plan.update = d_tasks + panel.size();
-        B.rowbase = d_rowbase; B.row_pad = d_rowpad;
-        return ORBS_OK;
-    }
 
     bool multi() const { return h->nranks > 1; }
     int allreduce(void *buf, size_t n, ncclDataType_t t, ncclRedOp_t op)
@@ -426,194 +347,221 @@ struct BaHost {
         ORBS_NCCL(g_nccl.AllReduce(buf, buf, n, t, op, h->comm, st));
         return ORBS_OK;
     }
-    // the stop flag must lead to the same decision on every rank: reduce it (max) when sharded
-    int *d_stop = nullptr; int *h_stop = nullptr;
-    bool terminate()
-    {
-        int v = (stop && *stop) ? 1 : 0;
-        if (multi()) {
-            *h_stop = v;
-            if (cudaMemcpyAsync(d_stop, h_stop, sizeof(int), cudaMemcpyHostToDevice, st) != cudaSuccess) return true;
-            if (allreduce(d_stop, 1, ncclInt32, ncclMax)) return true;
-            if (cudaMemcpyAsync(h_stop, d_stop, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess) return true;
-            if (cudaStreamSynchronize(st) != cudaSuccess) return true;
-            v = *h_stop;
-        }
-        return v != 0;
-    }
     KernelTimer &T() { return h->timer; }
     void count(int n = 1) { h->launches += n; }
 
-    int read_scalars()
+    // pose activity from the device (after a level change) -> hessian indices; returns 1 if any edge is active, < 0 on error
+    int read_activity(bool *changed)
     {
-        // sharded: chi2 and the two computeScale parts are sums over ranks, the diagonal maximum a max
-        if (int rc = allreduce(B.scalars, 3, ncclDouble, ncclSum)) return rc;
-        if (int rc = allreduce(B.scalars + 3, 1, ncclDouble, ncclMax)) return rc;
-        ORBS_CUDA(cudaMemcpyAsync(h_scal, B.scalars, 8 * sizeof(double), cudaMemcpyDeviceToHost, st));
-        ORBS_CUDA(cudaMemcpyAsync(h_flag, B.flags, sizeof(int), cudaMemcpyDeviceToHost, st));
+        ORBS_CUDA(cudaMemsetAsync(d_pose_act, 0, (B.K + 1) * sizeof(int), st));
+        k_ba_activity<<<(B.P + 255) / 256, 256, 0, st>>>(B, d_pose_act);
+        count();
+        if (int rc = allreduce(d_pose_act, B.K + 1, ncclInt32, ncclMax)) return -1 - 0 * rc;
+        std::vector<int> act(B.K + 1);
+        ORBS_CUDA(cudaMemcpyAsync(act.data(), d_pose_act, (B.K + 1) * sizeof(int), cudaMemcpyDeviceToHost, st));
         ORBS_CUDA(cudaStreamSynchronize(st));
+        std::vector<int> idx(B.K);
+        int nA = 0;
+        for (int k = 0; k < B.K; k++) idx[k] = (act[k] && !fixed[k]) ? nA++ : -1;
+        *changed = idx != pose_idx;
+        pose_idx.swap(idx);
+        B.nA = nA; B.n = 6 * nA;
+        return act[B.K] ? 1 : 0;
+    }
+
+    // structure of the reduced system for the current pose_idx / edge levels
+    int build_structure()
+    {
+        const int nA = B.nA, ng = (nA + kPosesPerTile - 1) / kPosesPerTile;
+        B.nt = ng;
+        ORBS_CUDA(cudaMemcpyAsync(d_pose_idx, pose_idx.data(), B.K * sizeof(int), cudaMemcpyHostToDevice, st));
+        if (ng == 0) { B.ns = 0; n_seg = 0; return ORBS_OK; }
+        ORBS_CUDA(cudaMemsetAsync(d_adj, 0, (size_t)ng * ng, st));
+        k_ba_tile_adj<<<(B.P + 255) / 256, 256, 0, st>>>(B, d_adj, ng);
+        count();
+        if (int rc = allreduce(d_adj, (size_t)ng * ng, ncclUint8, ncclMax)) return rc;
+        std::vector<uint8_t> adj((size_t)ng * ng);
+        ORBS_CUDA(cudaMemcpyAsync(adj.data(), d_adj, adj.size(), cudaMemcpyDeviceToHost, st));
+        ORBS_CUDA(cudaStreamSynchronize(st));
+        plan.build(adj, ng);
+        B.ns = plan.ns;
+        ORBS_REQUIRE(plan.ns < (1 << 24), ORBS_E_INVALID, "reduced pose system too large / too dense for the tiled Cholesky (more than 2^24 tiles)");
+        std::vector<int> rowbase(std::max(nA, 1)), tile_pose((size_t)ng * kPosesPerTile, -1);
+        for (int ip = 0; ip < nA; ip++) {
+            const int t = plan.pos[ip / kPosesPerTile];
+            rowbase[ip] = TS * t + 6 * (ip % kPosesPerTile);
+            tile_pose[(size_t)t * kPosesPerTile + ip % kPosesPerTile] = ip;
+        }
+        if (plan.tasks.size() > tasks_cap || plan.deps.size() + 1 > deps_cap) {
+            tasks_cap = plan.tasks.size() + 64; deps_cap = plan.deps.size() + 256;
+            if (int rc = h->ba_tasks.reserve(tasks_cap * sizeof(RsTask) + deps_cap * sizeof(int2))) return rc;
+        }
+        d_tasks = h->ba_tasks.as<RsTask>(); d_deps = reinterpret_cast<int2 *>(d_tasks + tasks_cap);
+        ORBS_CUDA(cudaMemcpyAsync(d_tasks, plan.tasks.data(), plan.tasks.size() * sizeof(RsTask), cudaMemcpyHostToDevice, st));
+        if (!plan.deps.empty()) ORBS_CUDA(cudaMemcpyAsync(d_deps, plan.deps.data(), plan.deps.size() * sizeof(int2), cudaMemcpyHostToDevice, st));
+        ORBS_CUDA(cudaMemcpyAsync(d_rowbase, rowbase.data(), std::max(nA, 1) * sizeof(int), cudaMemcpyHostToDevice, st));
+        ORBS_CUDA(cudaMemcpyAsync(d_slot_of, plan.slot_of.data(), plan.slot_of.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+        ORBS_CUDA(cudaMemcpyAsync(d_tile_pose, tile_pose.data(), tile_pose.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+        rsplan.tasks = d_tasks; rsplan.ntasks = (int)plan.tasks.size(); rsplan.deps = d_deps; rsplan.nt = ng; rsplan.ns = plan.ns;
+        solve_ctas = std::min(rsplan.ntasks, h->sm_count);
+        // reduced-system storage depends on ns: [A | bs] contiguous (one all-reduce), L, Linv, b/y/x vectors, flags
+        {
+            const size_t nA_t = (size_t)plan.ns * TS2, nv = (size_t)ng * TS;
+            if (int rc = h->ba_sys.reserve((2 * nA_t + (size_t)ng * TS2 + 3 * nv + 16) * sizeof(double))) return rc;
+            double *base = h->ba_sys.as<double>();
+            B.A = base; B.bs = base + nA_t;
+            rsbuf.A = B.A; rsbuf.b = B.bs; rsbuf.L = B.bs + nv; rsbuf.Linv = rsbuf.L + nA_t; rsbuf.y = rsbuf.Linv + (size_t)ng * TS2; rsbuf.x = rsbuf.y + nv;
+            B.x = rsbuf.x;
+            const size_t nflags = (size_t)plan.ns + 2 * (size_t)ng + 8;
+            const bool fresh = nflags * sizeof(int) > h->ba_flags.bytes;
+            if (int rc = h->ba_flags.reserve(nflags * sizeof(int))) return rc;
+            if (fresh) { ORBS_CUDA(cudaMemsetAsync(h->ba_flags.p, 0, h->ba_flags.bytes, st)); }
+            int *f = h->ba_flags.as<int>();
+            rsbuf.counters = f; rsbuf.flags = f + 4; rsbuf.done_slot = f + 8; rsbuf.done_y = rsbuf.done_slot + plan.ns; rsbuf.done_x = rsbuf.done_y + ng;
+            B.flags = rsbuf.flags;
+            ORBS_CUDA(cudaMemsetAsync(f, 0, 8 * sizeof(int), st));
+        }
+        xp_blocks = std::max(1, (B.n + 255) / 256); B.n_xp = xp_blocks;
+        diag_blocks = (nA + B.P + 255) / 256; B.n_diag = diag_blocks;
+        // Schur pairs, sorted by target block
+        k_ba_pair_count<<<(B.P + 255) / 256, 256, 0, st>>>(B, d_pair_cnt);
+        ORBS_CUDA(cudaMemsetAsync(d_pair_cnt + B.P, 0, sizeof(int), st));
+        size_t need = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, need, d_pair_cnt, d_pair_start, B.P + 1, st);
+        size_t need2 = 0;
+        const int end_bit = 32 + 7 + std::max(1, 32 - __builtin_clz((unsigned)std::max(plan.ns, 1)));
+        cub::DeviceRadixSort::SortPairs(nullptr, need2, d_key[0], d_key[1], d_val[0], d_val[1], (int)pair_cap, 0, std::min(end_bit, 64), st);
+        size_t need3 = 0;
+        cub::DeviceScan::InclusiveSum(nullptr, need3, d_head, d_scan, (int)pair_cap, st);
+        need = std::max({need, need2, need3});
+        if (int rc = h->ba_cub.reserve(need + 256)) return rc;
+        d_cub = h->ba_cub.p; cub_bytes = h->ba_cub.bytes;
+        cub::DeviceScan::ExclusiveSum(d_cub, cub_bytes, d_pair_cnt, d_pair_start, B.P + 1, st);
+        ORBS_CUDA(cudaMemsetAsync(d_key[0], 0xff, (size_t)pair_cap * sizeof(unsigned long long), st));
+        k_ba_pair_emit<<<(B.P + 256) / 256, 256, 0, st>>>(B, d_pair_start, d_key[0], d_val[0]);
+        cub::DeviceRadixSort::SortPairs(d_cub, cub_bytes, d_key[0], d_key[1], d_val[0], d_val[1], (int)pair_cap, 0, std::min(end_bit, 64), st);
+        k_ba_seg_heads<<<(unsigned)((pair_cap + 255) / 256), 256, 0, st>>>(d_key[1], d_pair_start + B.P, d_head, (int)pair_cap);
+        cub::DeviceScan::InclusiveSum(d_cub, cub_bytes, d_head, d_scan, (int)pair_cap, st);
+        k_ba_seg_starts<<<(unsigned)((pair_cap + 255) / 256), 256, 0, st>>>(d_head, d_scan, d_pair_start + B.P, d_seg_start, d_nseg, (int)pair_cap);
+        count(8);
+        ORBS_CUDA(cudaGetLastError());
+        ORBS_CUDA(cudaMemcpyAsync(&n_seg, d_nseg, sizeof(int), cudaMemcpyDeviceToHost, st));
+        ORBS_CUDA(cudaStreamSynchronize(st));
+        B.pair_key = d_key[1]; B.pair_val = d_val[1]; B.seg_start = d_seg_start; B.n_seg = d_nseg;
         return ORBS_OK;
     }
 
-    // computeActiveErrors + activeRobustChi2 -> scalars[0]
     void errors()
     {
         T().begin(BK_ERRORS, st);
         k_ba_errors<<<err_blocks, 256, 0, st>>>(B);
-        k_reduce_partials<<<1, 256, 0, st>>>(B.partial, err_blocks, B.scalars, 0, 0);
         T().end(st);
-        count(2);
+        count();
     }
 
-    int build_system()
+    // one LM slot (see the header comment); `first`: slot 0 of an optimize() call carries the lambda initialisation
+    int enqueue_slot(bool first)
     {
         T().begin(BK_BUILD_POINTS, st);
         k_ba_build_points<<<pt_blocks, 256, 0, st>>>(B);
         T().end(st);
         T().begin(BK_BUILD_POSES, st);
-        if (pose_blocks) k_ba_build_poses<<<pose_blocks, 256, 0, st>>>(B);
+        k_ba_build_poses<<<B.K, 128, 0, st>>>(B);
         T().end(st);
         count(2);
-        // sharded: every rank saw only its shard's observations of a keyframe -> sum the pose blocks (42 doubles per keyframe);
-        // afterwards Hpp / b_p are complete on every rank and enter the reduced system through the lead rank only
-        if (multi() && B.nA > 0) {
-            if (int rc = allreduce(B.Hpp, (size_t)B.nA * 36, ncclDouble, ncclSum)) return rc;
-            if (int rc = allreduce(B.bp, (size_t)B.nA * 6, ncclDouble, ncclSum)) return rc;
+        if (first) {
+            k_ba_max_diag<<<diag_blocks, 256, 0, st>>>(B, diag6);
+            k_ba_max_diag_finish<<<1, 256, 0, st>>>(B, diag6 + B.n);
+            count(2);
+            if (int rc = allreduce(diag6, (size_t)B.n + h->nranks, ncclDouble, ncclSum)) return rc;
         }
-        return ORBS_OK;
-    }
-
-    // setLambda + Schur + factor + solve + back-substitution; scalars[1] (+ scalars[2]) = computeScale
-    int solve()
-    {
-        const int ld = B.ld;
-        ORBS_CUDA(cudaMemsetAsync(B.flags, 0, 4 * sizeof(int), st));
+        k_lm_iter_begin<<<1, 1, 0, st>>>(B, diag6, diag6 + B.n);
+        T().begin(BK_PREP, st);
+        k_ba_point_prep<<<pt_blocks, 256, 0, st>>>(B);
+        T().end(st);
+        count(2);
         if (B.n > 0) {
-            T().begin(BK_MEMSET, st);
-            ORBS_CUDA(cudaMemsetAsync(B.S, 0, (size_t)ld * ld * sizeof(double), st));
-            T().end(st);
-            const int t = std::max(B.nA * 36, ld);
             T().begin(BK_SCHUR, st);
-            k_ba_schur_init<<<(t + 255) / 256, 256, 0, st>>>(B, lambda, h->rank == 0 ? 1 : 0);
-            k_ba_schur<<<pt_blocks, 256, 0, st>>>(B, lambda);
+            ORBS_CUDA(cudaMemsetAsync(B.A, 0, ((size_t)B.ns * TS2 + (size_t)B.nt * TS) * sizeof(double), st));
+            k_ba_diag_init<<<(B.nt * TS + 255) / 256, 256, 0, st>>>(B);
+            if (n_seg > 0) k_ba_schur_seg<<<(n_seg + 7) / 8, 256, 0, st>>>(B);
             T().end(st);
-            // the one exchange step of the sharded solve: sum the partial reduced systems over the map-point shards
-            if (multi()) {
-                // all-reduce the structurally nonzero tiles only (148 of 1275 at 500 keyframes: 4.8 MB instead of the 82 MB ld x ld array)
-                if (int rc = h->ba_packed.reserve(n_panel * 4096 * sizeof(double))) return rc;
-                double *packed = h->ba_packed.as<double>();
-                k_tiles_pack<<<(unsigned)n_panel, 256, 0, st>>>(B.S, ld, plan.panel, packed, 1);
-                if (int rc = allreduce(packed, n_panel * 4096, ncclDouble, ncclSum)) return rc;
-                k_tiles_pack<<<(unsigned)n_panel, 256, 0, st>>>(B.S, ld, plan.panel, packed, 0);
-                if (int rc = allreduce(B.bs, (size_t)ld, ncclDouble, ncclSum)) return rc;
-                count(2);
-            }
             count(2);
-            T().begin(BK_POTRF, st);
-            for (int l = 0; l < nlevels; l++) {
-                k_chol_panel<<<panel_lv[l + 1] - panel_lv[l], 256, kPanelSmem, st>>>(B.S, ld, plan.panel + panel_lv[l], Linv, B.flags);
-                count(1);
-                if (update_lv[l + 1] > update_lv[l]) {
-                    k_chol_update<<<update_lv[l + 1] - update_lv[l], 256, kUpdateSmem, st>>>(B.S, ld, plan.update + update_lv[l]);
-                    count(1);
-                }
-            }
+            // the one exchange step of the sharded solve: the structurally nonzero tiles of the reduced system and its right-hand side, summed over the map-point shards
+            if (int rc = allreduce(B.A, (size_t)B.ns * TS2 + (size_t)B.nt * TS, ncclDouble, ncclSum)) return rc;
+            T().begin(BK_SOLVE, st);
+            k_rs_solve<<<solve_ctas, 256, kRsSmemBytes, st>>>(rsplan, rsbuf, B.ctl, ++h->rs_epoch);
             T().end(st);
-            T().begin(BK_TRS, st);
-            ORBS_CUDA(cudaMemsetAsync(ready, 0, 2 * (size_t)ntiles * sizeof(int), st));
-            const int solve_ctas = std::min(ntiles, 128);          // all co-resident (one 256-thread CTA per SM at most)
-            k_chol_solve<<<solve_ctas, 256, 0, st>>>(B.S, ld, ntiles, plan, Linv, B.bs, ready, 0);
-            k_chol_solve<<<solve_ctas, 256, 0, st>>>(B.S, ld, ntiles, plan, Linv, B.bs, ready + ntiles, 1);
-            count(2);
-            T().end(st);
-            k_ba_take_xp<<<xp_blocks, 256, 0, st>>>(B, lambda, h->rank == 0 ? 1 : 0);
-            k_reduce_partials<<<1, 256, 0, st>>>(B.partial, xp_blocks, B.scalars, 2, 0);
-            count(2);
-        } else {
-            ORBS_CUDA(cudaMemsetAsync(B.scalars + 2, 0, sizeof(double), st));
+            count();
         }
         T().begin(BK_BACKSUB, st);
-        k_ba_backsub<<<pt_blocks, 256, 0, st>>>(B, lambda);
-        k_reduce_partials<<<1, 256, 0, st>>>(B.partial, pt_blocks, B.scalars, 1, 0);
+        k_ba_take_xp<<<xp_blocks, 256, 0, st>>>(B);
+        k_ba_backsub<<<pt_blocks, 256, 0, st>>>(B);
         T().end(st);
-        count(2);
+        T().begin(BK_UPDATE, st);
+        k_ba_update<<<upd_blocks, 256, 0, st>>>(B);
+        T().end(st);
+        count(3);
+        errors();
+        T().begin(BK_DECIDE, st);
+        k_lm_reduce<<<1, 256, 0, st>>>(B, h_stop, 1);
+        if (int rc = allreduce(B.scalars, 5, ncclDouble, ncclSum)) return rc;
+        k_lm_decide<<<1, 1, 0, st>>>(B);
+        k_ba_restore<<<upd_blocks, 256, 0, st>>>(B);
+        T().end(st);
+        count(3);
+        ORBS_CUDA(cudaGetLastError());
         return ORBS_OK;
     }
 
-    enum { LM_OK = 0, LM_TERMINATE = 1, LM_ERROR = 2 };
+    void poll_stop() { if (stop && *stop) *h_stop = 1; }
 
-    // OptimizationAlgorithmLevenberg::solve, optimization_algorithm_levenberg.cpp:61-164
-    // errors_current: the stored edge errors and chi2 belong to the current estimate (the last trial was accepted), so the
-    // computeActiveErrors at the top of the next iteration (levenberg.cpp:69-72) would reproduce them bit for bit: skipped,
-    // together with its host round trip.  After a rejected trial (estimate restored) they are recomputed, as in g2o.
-    bool errors_current = false;
-    double chi_current = 0;
-
-    int lm_iteration(int iteration)
+    // SparseOptimizer::optimize(iterations), sparse_optimizer.cpp:354-419
+    int optimize(int iterations, bool any_active, LmCtl *final_ctl)
     {
-        if (iteration == 0) errors_current = false;
-        if (!errors_current) errors();
-        if (build_system()) return LM_ERROR;
-        if (iteration == 0) {
-            k_ba_max_diag<<<diag_blocks, 256, 0, st>>>(B);
-            k_reduce_partials<<<1, 256, 0, st>>>(B.partial, diag_blocks, B.scalars, 3, 1);
-            count(2);
-        }
-        if (!errors_current || iteration == 0) { if (read_scalars()) return LM_ERROR; chi_current = h_scal[0]; }
-        double currentChi = chi_current;
-        const double iniChi = currentChi;
-        if (iteration == 0) { lambda = 1e-5 * h_scal[3]; ni = 2; nbad = 0; }
-        double rho = 0;
-        int qmax = 0;
-        const int upd_blocks = (B.K + B.P + 255) / 256;
-        do {
-            if (solve()) return LM_ERROR;
-            T().begin(BK_UPDATE, st);
-            k_ba_update<<<upd_blocks, 256, 0, st>>>(B);
-            T().end(st);
-            count(1);
+        LmCtl c0;
+        ORBS_CUDA(cudaMemcpyAsync(&c0, B.ctl, sizeof(LmCtl), cudaMemcpyDeviceToHost, st));
+        ORBS_CUDA(cudaStreamSynchronize(st));
+        poll_stop();
+        const bool run = any_active && iterations > 0 && !*h_stop;
+        c0.state = run ? LM_BUILD : LM_DONE; c0.iteration = 0; c0.max_iterations = iterations; c0.qmax = 0; c0.nbad = 0; c0.first = 1; c0.last_rejected = 0;
+        ORBS_CUDA(cudaMemcpyAsync(B.ctl, &c0, sizeof(LmCtl), cudaMemcpyHostToDevice, st));
+        ORBS_CUDA(cudaStreamSynchronize(st));                       // c0 lives on this stack frame
+        if (run) {
+            // computeActiveErrors + activeRobustChi2 of the starting estimate (levenberg.cpp:69-72); later iterations inherit them from the accepted trial
             errors();
-            if (read_scalars()) return LM_ERROR;
-            const bool ok2 = *h_flag == 0;
-            if (!ok2) chol_failures++;
-            double tempChi = h_scal[0];
-            if (!ok2) tempChi = 1.7976931348623157e308;
-            rho = currentChi - tempChi;
-            double scale = h_scal[1] + h_scal[2];
-            scale += 1e-3;
-            rho /= scale;
-            if (rho > 0 && std::isfinite(tempChi)) {
-                double alpha = 1. - pow((2 * rho - 1), 3);
-                alpha = std::min(alpha, 2. / 3.);
-                lambda *= std::max(1. / 3., alpha);
-                ni = 2;
-                currentChi = tempChi;
-                errors_current = true; chi_current = tempChi;
-            } else {
-                lambda *= ni; ni *= 2;
-                k_ba_restore<<<upd_blocks, 256, 0, st>>>(B);
-                count(1);
-                errors_current = false;
+            k_lm_reduce<<<1, 256, 0, st>>>(B, h_stop, 0);
+            count();
+            if (int rc = allreduce(B.scalars, 5, ncclDouble, ncclSum)) return rc;
+            constexpr int kLag = 2;
+            bool done = false;
+            int slot = 0;
+            for (; slot < iterations && !done; slot++) {
+                poll_stop();
+                if (int rc = enqueue_slot(slot == 0)) return rc;
+                ORBS_CUDA(cudaMemcpyAsync(&h_ctl[slot % orbo_handle::kCtlCopies], B.ctl, sizeof(LmCtl), cudaMemcpyDeviceToHost, st));
+                ORBS_CUDA(cudaEventRecord(h->slot_done[slot % orbo_handle::kCtlCopies], st));
+                if (slot >= kLag) {
+                    const int q = (slot - kLag) % orbo_handle::kCtlCopies;
+                    while (cudaEventQuery(h->slot_done[q]) == cudaErrorNotReady) poll_stop();
+                    if (h_ctl[q].state == LM_DONE) done = true;     // early stop (nbad rule, stop flag, failed trials): the slots already enqueued are no-ops
+                }
             }
-            qmax++;
-            lm_trials++;
-        } while (rho < 0 && qmax < 10 && !terminate());
-        lm_iterations++;
-        if (qmax == 10 || rho == 0) return LM_TERMINATE;
-        if ((iniChi - currentChi) * 1e3 < iniChi) nbad++; else nbad = 0;
-        if (nbad >= 3) return LM_TERMINATE;
-        return LM_OK;
-    }
-
-    // SparseOptimizer::optimize, sparse_optimizer.cpp:354-419
-    int optimize(int iterations, bool any_active)
-    {
-        if (!any_active) return ORBS_OK;
-        for (int i = 0; i < iterations && !terminate(); i++) {
-            const int r = lm_iteration(i);
-            if (r == LM_ERROR) return ORBS_E_CUDA;
-            if (r != LM_OK) break;
+            // the common case ends here: `iterations` accepted trials.  Rejected trials need further slots, one at a time.
+            for (int guard = 0; guard < 10 * iterations + 4; guard++) {
+                const int q = (slot - 1) % orbo_handle::kCtlCopies;
+                while (cudaEventQuery(h->slot_done[q]) == cudaErrorNotReady) poll_stop();
+                if (h_ctl[q].state == LM_DONE) break;
+                poll_stop();
+                if (int rc = enqueue_slot(false)) return rc;
+                ORBS_CUDA(cudaMemcpyAsync(&h_ctl[slot % orbo_handle::kCtlCopies], B.ctl, sizeof(LmCtl), cudaMemcpyDeviceToHost, st));
+                ORBS_CUDA(cudaEventRecord(h->slot_done[slot % orbo_handle::kCtlCopies], st));
+                slot++;
+            }
         }
+        ORBS_CUDA(cudaMemcpyAsync(&h_ctl[0], B.ctl, sizeof(LmCtl), cudaMemcpyDeviceToHost, st));
+        ORBS_CUDA(cudaStreamSynchronize(st));
+        *final_ctl = h_ctl[0];
         return ORBS_OK;
     }
 };
@@ -622,7 +570,7 @@ struct BaHost {
 
 extern "C" int orbo_bundle_adjust(orbo_handle *h, int K, float *poses, const uint8_t *fixed, const double *intr, int P, float *points,
                                   int E, const int32_t *e_kf, const int32_t *e_pt, const float *e_uv, const float *e_inv_sigma2,
-                                  int two_stage, int its0, int its1, int robust, const volatile int *stop_flag,
+                                  int two_stage, int its0, int its1, int robust, const volatile uint8_t *stop_flag,
                                   double *e_chi2, uint8_t *e_depth_ok, uint8_t *e_outlier, int32_t *stats)
 {
     ORBS_REQUIRE(h && poses && fixed && intr && points && e_kf && e_pt && e_uv && e_inv_sigma2, ORBS_E_INVALID, "null argument");
@@ -639,7 +587,10 @@ extern "C" int orbo_bundle_adjust(orbo_handle *h, int K, float *poses, const uin
     // ---- host-side graph layout: edges grouped by point (stable), second CSR by pose
     std::vector<int> pt_start(P + 1, 0), order(E), pose_start(K + 1, 0), pose_edges(E), kf_s(E), pt_s(E);
     for (int e = 0; e < E; e++) pt_start[e_pt[e] + 1]++;
-    for (int p = 0; p < P; p++) pt_start[p + 1] += pt_start[p];
+    long long pair_cap = 0;
+    for (int p = 0; p < P; p++) { const long long m = pt_start[p + 1]; pair_cap += m * (m + 1) / 2; pt_start[p + 1] += pt_start[p]; }
+    ORBS_REQUIRE(pair_cap < (1ll << 31), ORBS_E_INVALID, "too many co-observations for one bundle adjustment (2^31 keyframe pairs)");
+    pair_cap = std::max(pair_cap, 1ll);
     { std::vector<int> fill(pt_start.begin(), pt_start.end() - 1); for (int e = 0; e < E; e++) order[fill[e_pt[e]]++] = e; }
     std::vector<double> obs_s(2 * (size_t)E), w_s(E);
     for (int j = 0; j < E; j++) {
@@ -650,18 +601,19 @@ extern "C" int orbo_bundle_adjust(orbo_handle *h, int K, float *poses, const uin
     }
     for (int k = 0; k < K; k++) pose_start[k + 1] += pose_start[k];
     { std::vector<int> fill(pose_start.begin(), pose_start.end() - 1); for (int j = 0; j < E; j++) pose_edges[fill[kf_s[j]]++] = j; }
-    std::vector<uint8_t> level(E, 0);
     std::vector<double> pts_d(3 * (size_t)P);
     for (size_t i = 0; i < pts_d.size(); i++) pts_d[i] = points[i];
 
     // ---- device buffers
     Stager S(&h->ba_pool, st, ORBS_MEM_HOST);
-    BaHost D;
-    D.h = h; D.st = st; D.stop = stop_flag;
-    D.h_scal = h->h_scalars.as<double>(); D.h_flag = (int *)(D.h_scal + 16);
+    BaRun D;
+    D.h = h; D.st = st; D.S = &S; D.stop = stop_flag; D.fixed = fixed;
+    D.h_ctl = h->h_scalars.as<LmCtl>(); D.h_stop = reinterpret_cast<int *>(D.h_ctl + orbo_handle::kCtlCopies);
+    *D.h_stop = 0;
     BaDev &B = D.B;
     memset(&B, 0, sizeof B);
     B.K = K; B.P = P; B.E = E;
+    B.nranks = h->nranks; B.rank = h->rank; B.lead = h->rank == 0 ? 1 : 0;
     const float *d_T = S.in(poses, (size_t)K * 16);
     const uint8_t *d_fixed = S.in(fixed, K);
     B.intr = S.in(intr, (size_t)K * 4);
@@ -670,139 +622,106 @@ extern "C" int orbo_bundle_adjust(orbo_handle *h, int K, float *poses, const uin
     B.pose = S.scratch<Se3>(K); B.pose_bak = S.scratch<Se3>(K);
     B.pt_start = S.in(pt_start.data(), pt_start.size()); B.e_kf = S.in(kf_s.data(), E); B.e_point = S.in(pt_s.data(), E);
     B.e_obs = S.in(obs_s.data(), obs_s.size()); B.e_w = S.in(w_s.data(), E);
-    B.e_level = S.scratch<uint8_t>(E); B.e_err = S.scratch<double>(2 * (size_t)E); B.e_W = S.scratch<double>(18 * (size_t)E);
+    B.e_level = S.scratch<uint8_t>(E); B.e_err = S.scratch<double>(2 * (size_t)E);
+    B.e_W = S.scratch<double>(18 * (size_t)E); B.e_Z = S.scratch<double>(18 * (size_t)E);
     B.pose_start = S.in(pose_start.data(), pose_start.size()); B.pose_edges = S.in(pose_edges.data(), E);
-    int *d_pose_idx = S.scratch<int>(K); uint8_t *d_pt_active = S.scratch<uint8_t>(P);
-    B.pose_idx = d_pose_idx; B.pt_active = d_pt_active;
-    B.Hpp = S.scratch<double>(36 * (size_t)K); B.bp = S.scratch<double>(6 * (size_t)K + NB);
+    D.d_pose_idx = S.scratch<int>(K); B.pose_idx = D.d_pose_idx;
+    B.pt_active = S.scratch<uint8_t>(P);
+    B.Hpp = S.scratch<double>(36 * (size_t)K); B.bp = S.scratch<double>(6 * (size_t)K + 8);
     B.Hll = S.scratch<double>(9 * (size_t)P); B.bl = S.scratch<double>(3 * (size_t)P);
-    B.x = S.scratch<double>(6 * (size_t)K + 3 * (size_t)P);
-    const int ld_max = NB * ((K + kPosesPerTile - 1) / kPosesPerTile);      // 10 keyframes (60 rows + 4 padding rows) per 64-row tile
-    B.S = S.scratch<double>((size_t)ld_max * ld_max); B.bs = S.scratch<double>(ld_max);
-    D.Linv = S.scratch<double>((size_t)ld_max * NB); D.ready = S.scratch<int>(2 * (size_t)(ld_max / NB) + 2);
-    D.nt_max = ld_max / NB;
-    D.d_plan_i = S.scratch<int>(2 * (size_t)(D.nt_max + 1) + (size_t)D.nt_max * D.nt_max + 8);
-    D.d_rowbase = S.scratch<int>(K + 1); D.d_rowpad = S.scratch<uint8_t>(ld_max + 16);
-    int *d_adj = S.scratch<int>((size_t)D.nt_max * D.nt_max + 4);
-    ORBS_REQUIRE(ld_max / NB <= 1024, ORBS_E_INVALID, "more than 10240 keyframes in one bundle adjustment");
-    const int max_blocks = std::max({(E + 255) / 256, (P + 7) / 8, (K + P + 255) / 256, (6 * K + 255) / 256}) + 1;
-    B.partial = S.scratch<double>(max_blocks); B.scalars = S.scratch<double>(8); B.flags = S.scratch<int>(4);
+    B.ptG = S.scratch<double>(6 * (size_t)P); B.ptg = S.scratch<double>(3 * (size_t)P); B.xl = S.scratch<double>(3 * (size_t)P);
+    D.nt_max = (K + kPosesPerTile - 1) / kPosesPerTile;
+    ORBS_REQUIRE(D.nt_max <= 1024, ORBS_E_INVALID, "more than 10240 keyframes in one bundle adjustment");
+    D.d_rowbase = S.scratch<int>(K + 1); B.rowbase = D.d_rowbase;
+    D.d_slot_of = S.scratch<int>((size_t)D.nt_max * D.nt_max + 4); B.slot_of = D.d_slot_of;
+    D.d_tile_pose = S.scratch<int>((size_t)D.nt_max * kPosesPerTile + 4); B.tile_pose = D.d_tile_pose;
+    D.d_adj = S.scratch<uint8_t>((size_t)D.nt_max * D.nt_max + 16);
+    D.d_pose_act = S.scratch<int>(K + 2);
+    D.err_blocks = (E + 255) / 256; D.pt_blocks = (P + 31) / 32; D.upd_blocks = (K + P + 255) / 256;
+    B.n_chi = D.err_blocks; B.n_pt = D.pt_blocks;
+    B.p_chi = S.scratch<double>(D.err_blocks + (size_t)D.pt_blocks + (6 * (size_t)K + 255) / 256 + 1 + ((size_t)K + P + 255) / 256 + 1);
+    B.p_pt = B.p_chi + D.err_blocks; B.p_xp = B.p_pt + D.pt_blocks; B.p_diag = B.p_xp + (6 * (size_t)K + 255) / 256 + 1;
+    B.scalars = S.scratch<double>(16 + sizeof(LmCtl) / sizeof(double) + 2);
+    B.ctl = reinterpret_cast<LmCtl *>(B.scalars + 16);
+    D.diag6 = S.scratch<double>(6 * (size_t)K + 64);
+    D.pair_cap = pair_cap;
+    D.d_pair_cnt = S.scratch<int>(P + 2); D.d_pair_start = S.scratch<int>(P + 2);
+    D.d_key[0] = S.scratch<unsigned long long>(pair_cap); D.d_key[1] = S.scratch<unsigned long long>(pair_cap);
+    D.d_val[0] = S.scratch<unsigned long long>(pair_cap); D.d_val[1] = S.scratch<unsigned long long>(pair_cap);
+    D.d_head = S.scratch<int>(pair_cap); D.d_scan = S.scratch<int>(pair_cap); D.d_seg_start = S.scratch<int>(pair_cap + 2); D.d_nseg = S.scratch<int>(4);
     double *d_chi2 = S.scratch<double>(E); uint8_t *d_depth = S.scratch<uint8_t>(E);
-    D.d_stop = S.scratch<int>(4); D.h_stop = D.h_flag + 1;
-    int *d_pose_act = S.scratch<int>(K + 1);
-    float *d_Tout = S.scratch<float>((size_t)K * 16);
+    float *d_Tout = S.scratch<float>((size_t)K * 16); float *d_pts_out = S.scratch<float>(3 * (size_t)P);
     if (S.rc) return S.rc;
     B.delta = (double)(float)sqrt(5.991); B.dsqr = B.delta * B.delta;              // thHuberMono, Optimizer.cc:591
     ORBS_CUDA(cudaMemsetAsync(B.e_level, 0, E, st));
     ORBS_CUDA(cudaMemsetAsync(B.e_err, 0, 2 * (size_t)E * sizeof(double), st));
-    ORBS_CUDA(cudaMemsetAsync(B.scalars, 0, 8 * sizeof(double), st));
+    ORBS_CUDA(cudaMemsetAsync(B.scalars, 0, (16 + sizeof(LmCtl) / sizeof(double) + 2) * sizeof(double), st));
     k_ba_import_poses<<<(K + 255) / 256, 256, 0, st>>>(K, d_T, B.pose);
     ORBS_CUDA(cudaMemcpyAsync(d_Tout, d_T, (size_t)K * 16 * sizeof(float), cudaMemcpyDeviceToDevice, st));
     h->launches++;
-    D.err_blocks = (E + 255) / 256; D.pt_blocks = (P + 7) / 8; D.pose_blocks = (K + 7) / 8;
 
-    // initializeOptimization(level 0) + buildIndexMapping, sparse_optimizer.cpp:166-267
-    std::vector<int> pose_idx(K);
-    std::vector<uint8_t> pt_active(P);
-    auto init_active = [&]() -> int {
-        std::vector<int> pose_act(K + 1, 0);                   // [K] = any active edge at all
-        std::fill(pt_active.begin(), pt_active.end(), 0);
-        for (int j = 0; j < E; j++) if (!level[j]) { pose_act[kf_s[j]] = 1; pt_active[pt_s[j]] = 1; pose_act[K] = 1; }
-        if (D.multi()) {                                       // a keyframe is active if any rank's shard observes it
-            ORBS_CUDA(cudaMemcpyAsync(d_pose_act, pose_act.data(), (K + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
-            if (int rc = D.allreduce(d_pose_act, K + 1, ncclInt32, ncclMax)) return rc;
-            ORBS_CUDA(cudaMemcpyAsync(pose_act.data(), d_pose_act, (K + 1) * sizeof(int), cudaMemcpyDeviceToHost, st));
-            ORBS_CUDA(cudaStreamSynchronize(st));
-        }
-        const bool any = pose_act[K] != 0;
-        int nA = 0;
-        for (int k = 0; k < K; k++) pose_idx[k] = (pose_act[k] && !fixed[k]) ? nA++ : -1;
-        B.nA = nA; B.n = 6 * nA; D.ntiles = (nA + kPosesPerTile - 1) / kPosesPerTile; B.ld = NB * D.ntiles;
-        D.diag_blocks = (nA + P + 255) / 256; D.xp_blocks = std::max(1, (B.n + 255) / 256);
-        ORBS_CUDA(cudaMemcpyAsync(d_pose_idx, pose_idx.data(), K * sizeof(int), cudaMemcpyHostToDevice, st));
-        ORBS_CUDA(cudaMemcpyAsync(d_pt_active, pt_active.data(), P, cudaMemcpyHostToDevice, st));
+    // sharded: the stop decision is collective (every rank must take it or none)
+    if (D.multi()) {
+        int v = (stop_flag && *stop_flag) ? 1 : 0;
+        ORBS_CUDA(cudaMemcpyAsync(D.d_pose_act, &v, sizeof(int), cudaMemcpyHostToDevice, st));
+        if (int rc = D.allreduce(D.d_pose_act, 1, ncclInt32, ncclMax)) return rc;
+        ORBS_CUDA(cudaMemcpyAsync(&v, D.d_pose_act, sizeof(int), cudaMemcpyDeviceToHost, st));
         ORBS_CUDA(cudaStreamSynchronize(st));
-        // tile-level structure of the reduced system: free poses i, j are coupled iff an active point is seen by both (edges are
-        // grouped by point); tiles = groups of kPosesPerTile consecutive hessian indices.  Sharded: union over the ranks' shards.
-        const int ng = D.ntiles;
-        std::vector<uint8_t> adj((size_t)ng * ng, 0);
-        {
-            int gs[64];
-            for (int p = 0; p < P; p++) {
-                int m = 0;
-                for (int j = pt_start[p]; j < pt_start[p + 1]; j++) {
-                    if (level[j] || pose_idx[kf_s[j]] < 0) continue;
-                    const int g = pose_idx[kf_s[j]] / kPosesPerTile;
-                    bool seen = false;
-                    for (int q = 0; q < m; q++) if (gs[q] == g) { seen = true; break; }
-                    if (!seen) {
-                        for (int q = 0; q < m; q++) { adj[(size_t)g * ng + gs[q]] = 1; adj[(size_t)gs[q] * ng + g] = 1; }
-                        if (m < 64) gs[m++] = g;
-                        else for (int q2 = 0; q2 < ng; q2++) { adj[(size_t)g * ng + q2] = 1; adj[(size_t)q2 * ng + g] = 1; }   // > 64 distinct groups: couple to all
-                    }
-                }
-            }
-        }
-        if (D.multi() && ng > 0) {
-            std::vector<int> a32(adj.begin(), adj.end());
-            ORBS_CUDA(cudaMemcpyAsync(d_adj, a32.data(), a32.size() * sizeof(int), cudaMemcpyHostToDevice, st));
-            if (int rc = D.allreduce(d_adj, a32.size(), ncclInt32, ncclMax)) return rc;
-            ORBS_CUDA(cudaMemcpyAsync(a32.data(), d_adj, a32.size() * sizeof(int), cudaMemcpyDeviceToHost, st));
-            ORBS_CUDA(cudaStreamSynchronize(st));
-            for (size_t q = 0; q < adj.size(); q++) adj[q] = (uint8_t)a32[q];
-        }
-        if (ng > 0 && D.build_schedule(adj, ng)) return -1;
-        return any ? 1 : 0;
-    };
-
-    if (D.multi() && D.terminate()) { if (stats) stats[3] = 1; return 1; }
-    int any = init_active();
-    if (any < 0) return any;
+        if (v) { if (stats) stats[3] = 1; return 1; }
+    }
+    // initializeOptimization(level 0) + buildIndexMapping, sparse_optimizer.cpp:166-267
+    D.pose_idx.assign(K, -2);
+    bool changed = false;
+    int any = D.read_activity(&changed);
+    if (any < 0) return ORBS_E_CUDA;
+    int rc = D.build_structure();
+    if (rc) return rc;
     const auto t_loop = std::chrono::steady_clock::now();
     B.robust = two_stage ? 1 : (robust ? 1 : 0);
-    int rc = D.optimize(its0, any == 1);
-    if (rc) return rc;
-    std::vector<double> chi2_s(E);
-    std::vector<uint8_t> depth_s(E);
-    auto edge_check = [&]() -> int {
-        k_ba_edge_check<<<(E + 255) / 256, 256, 0, st>>>(B, d_chi2, d_depth);
+    LmCtl fin;
+    memset(&fin, 0, sizeof fin);
+    if ((rc = D.optimize(its0, any == 1, &fin))) return rc;
+    std::vector<double> chi2_s;
+    std::vector<uint8_t> depth_s;
+    const bool want_edges = e_chi2 || e_depth_ok || e_outlier;
+    if (two_stage && !*D.h_stop) {
+        // chi2 / depth gating (Optimizer.cc:691-705) on the device; the structure is rebuilt only if a keyframe lost all its observations
+        k_ba_edge_check<<<(E + 255) / 256, 256, 0, st>>>(B, d_chi2, d_depth, 1);
         h->launches++;
+        B.robust = 0;
+        any = D.read_activity(&changed);
+        if (any < 0) return ORBS_E_CUDA;
+        if (changed && (rc = D.build_structure())) return rc;
+        if ((rc = D.optimize(its1, any == 1, &fin))) return rc;
+    }
+    k_ba_edge_check<<<(E + 255) / 256, 256, 0, st>>>(B, d_chi2, d_depth, 0);
+    k_ba_export_poses<<<(K + 255) / 256, 256, 0, st>>>(K, B.pose, d_fixed, d_Tout);
+    k_ba_export_points<<<(3 * P + 255) / 256, 256, 0, st>>>(P, B.pt, d_pts_out);
+    h->launches += 3;
+    if (want_edges) {
+        chi2_s.resize(E); depth_s.resize(E);
         ORBS_CUDA(cudaMemcpyAsync(chi2_s.data(), d_chi2, E * sizeof(double), cudaMemcpyDeviceToHost, st));
         ORBS_CUDA(cudaMemcpyAsync(depth_s.data(), d_depth, E, cudaMemcpyDeviceToHost, st));
-        ORBS_CUDA(cudaStreamSynchronize(st));
-        return ORBS_OK;
-    };
-    if (two_stage && !D.terminate()) {
-        if ((rc = edge_check())) return rc;
-        for (int j = 0; j < E; j++) if (chi2_s[j] > 5.991 || !depth_s[j]) level[j] = 1;      // Optimizer.cc:691-705
-        ORBS_CUDA(cudaMemcpyAsync(B.e_level, level.data(), E, cudaMemcpyHostToDevice, st));
-        B.robust = 0;
-        any = init_active();
-        if (any < 0) return any;
-        if ((rc = D.optimize(its1, any == 1))) return rc;
     }
-    if ((rc = edge_check())) return rc;
-    const auto t_loop_end = std::chrono::steady_clock::now();
-    for (int j = 0; j < E; j++) {                                                         // Optimizer.cc:734-766
-        const int e = order[j];
-        if (e_chi2) e_chi2[e] = chi2_s[j];
-        if (e_depth_ok) e_depth_ok[e] = depth_s[j];
-        if (e_outlier) e_outlier[e] = (uint8_t)(chi2_s[j] > 5.991 || !depth_s[j]);
-    }
-    k_ba_export_poses<<<(K + 255) / 256, 256, 0, st>>>(K, B.pose, d_fixed, d_Tout);
-    h->launches++;
     ORBS_CUDA(cudaMemcpyAsync(poses, d_Tout, (size_t)K * 16 * sizeof(float), cudaMemcpyDeviceToHost, st));
-    ORBS_CUDA(cudaMemcpyAsync(pts_d.data(), B.pt, pts_d.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+    ORBS_CUDA(cudaMemcpyAsync(points, d_pts_out, 3 * (size_t)P * sizeof(float), cudaMemcpyDeviceToHost, st));
     ORBS_CUDA(cudaStreamSynchronize(st));
-    for (size_t i = 0; i < pts_d.size(); i++) points[i] = (float)pts_d[i];
+    const auto t_loop_end = std::chrono::steady_clock::now();
+    if (want_edges)
+        for (int j = 0; j < E; j++) {                                                         // Optimizer.cc:734-766
+            const int e = order[j];
+            if (e_chi2) e_chi2[e] = chi2_s[j];
+            if (e_depth_ok) e_depth_ok[e] = depth_s[j];
+            if (e_outlier) e_outlier[e] = (uint8_t)(chi2_s[j] > 5.991 || !depth_s[j]);
+        }
     {
         const auto t_end = std::chrono::steady_clock::now();
         auto sec = [](auto a, auto b) { return std::chrono::duration<double>(b - a).count(); };
         h->ba_timing[0] = sec(t_loop, t_loop_end); h->ba_timing[1] = sec(t_begin, t_end); h->ba_timing[2] = sec(t_begin, t_loop);
-        h->ba_timing[3] = (double)B.ld;
-        h->ba_skyline[0] = D.ntiles; h->ba_skyline[1] = D.l_tiles; h->ba_skyline[2] = D.nlevels;
+        h->ba_timing[3] = (double)B.nt * TS;
+        h->ba_skyline[0] = B.nt; h->ba_skyline[1] = B.ns; h->ba_skyline[2] = D.plan.nlevels;
     }
-    if (stats) { stats[0] = D.lm_iterations; stats[1] = D.lm_trials; stats[2] = D.chol_failures; stats[3] = 0; }
+    if (stats) { stats[0] = fin.lm_iterations; stats[1] = fin.lm_trials; stats[2] = fin.chol_failures; stats[3] = 0; }
     return ORBS_OK;
 }
 
@@ -844,94 +763,79 @@ extern "C" int orbo_get_kernel_times(orbo_handle *h, double *total_ms, long long
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Essential-graph (Sim3 pose graph) optimisation: host-driven Levenberg over the kernels of pose_graph.cuh, normal equations factored by
-// the tiled sparse Cholesky of the BA (same kernels, own schedule: 9 vertices per 64-row tile)
+// Essential-graph (Sim3 pose graph) optimisation: host-driven Levenberg over the kernels of pose_graph.cuh, normal equations solved by
+// the tiled sparse solver of the BA (tile_solver.cuh; own symbolic factorisation: 9 Sim3 vertices per 64-row tile)
 namespace {
 
 struct PgHost {
     orbo_handle *h; cudaStream_t st; PgDev P;
-    DevBuf bufs[16]; int nbuf = 0;
-    int nt = 0, nlevels = 0; size_t n_panel = 0;
-    std::vector<int> panel_lv, update_lv;
-    CholPlan plan = {};
-    double *Linv = nullptr, *packed = nullptr; int *ready = nullptr, *flags = nullptr;
-    int eblocks = 0;
+    DevBuf bufs[24]; int nbuf = 0;
+    TilePlanHost plan;
+    RsPlan rsplan = {}; RsBuf rsbuf = {};
+    int eblocks = 0, solve_ctas = 1;
     ~PgHost() { for (int i = 0; i < nbuf; i++) bufs[i].release(); }
-    template <typename T> T *alloc(size_t n, int *rc) { if (*rc) return nullptr; if (nbuf >= 16) { *rc = ORBS_E_INVALID; return nullptr; } *rc = bufs[nbuf].reserve(std::max<size_t>(n, 1) * sizeof(T)); return bufs[nbuf++].as<T>(); }
+    template <typename T> T *alloc(size_t n, int *rc) { if (*rc) return nullptr; if (nbuf >= 24) { *rc = ORBS_E_INVALID; return nullptr; } *rc = bufs[nbuf].reserve(std::max<size_t>(n, 1) * sizeof(T)); return bufs[nbuf++].as<T>(); }
 
-    // tile groups of kPgPerTile consecutive free vertices; adjacency from the edges; nested dissection; symbolic factorisation; task lists
+    // tile groups of kPgPerTile consecutive free vertices; adjacency from the edges; elimination order + symbolic factorisation + tasks;
+    // the per-target-block contribution lists of the normal equations (sorted: deterministic accumulation)
     int schedule(int K, const std::vector<int> &hidx, int E, const int32_t *e_i, const int32_t *e_j)
     {
         const int nA = P.nA;
-        nt = (nA + kPgPerTile - 1) / kPgPerTile;
-        const int ng = nt;
+        const int ng = (nA + kPgPerTile - 1) / kPgPerTile;
         std::vector<uint8_t> adj((size_t)ng * ng, 0);
         for (int e = 0; e < E; e++) {
             const int a = hidx[e_i[e]], b = hidx[e_j[e]];
             if (a < 0 || b < 0) continue;
             adj[(size_t)(a / kPgPerTile) * ng + b / kPgPerTile] = 1; adj[(size_t)(b / kPgPerTile) * ng + a / kPgPerTile] = 1;
         }
-        std::vector<int> order; order.reserve(nt);
-        BaHost::nd_order(adj, ng, 0, ng, order);
-        std::vector<int> pos(ng);
-        for (int t = 0; t < nt; t++) pos[order[t]] = t;
-        std::vector<uint8_t> pat((size_t)nt * nt, 0);
-        for (int a = 0; a < ng; a++)
-            for (int b = 0; b < ng; b++) if (a != b && adj[(size_t)a * ng + b]) { const int i = std::max(pos[a], pos[b]), j = std::min(pos[a], pos[b]); pat[(size_t)i * nt + j] = 1; }
-        std::vector<int> rows_start(nt + 1, 0), rows, cols_start(nt + 1, 0), cols, level(nt, 0);
-        for (int k = 0; k < nt; k++) {
-            const size_t r0 = rows.size();
-            for (int i = k + 1; i < nt; i++) if (pat[(size_t)i * nt + k]) rows.push_back(i);
-            rows_start[k + 1] = (int)rows.size();
-            for (size_t x = r0; x < rows.size(); x++) for (size_t y = r0; y < x; y++) pat[(size_t)rows[x] * nt + rows[y]] = 1;
-        }
-        nlevels = 0;
-        for (int i = 0; i < nt; i++) {
-            int lv = 0;
-            for (int k = 0; k < i; k++) if (pat[(size_t)i * nt + k]) { cols.push_back(k); lv = std::max(lv, level[k] + 1); }
-            cols_start[i + 1] = (int)cols.size();
-            level[i] = lv; nlevels = std::max(nlevels, lv + 1);
-        }
-        std::vector<std::vector<int>> by_level(nlevels);
-        for (int k = 0; k < nt; k++) by_level[level[k]].push_back(k);
-        std::vector<int4> panel, update;
-        panel_lv.assign(nlevels + 1, 0); update_lv.assign(nlevels + 1, 0);
-        std::vector<int> hits((size_t)nt * nt, 0);
-        for (int l = 0; l < nlevels; l++) {
-            const size_t u0 = update.size();
-            for (int k : by_level[l]) {
-                panel.push_back(make_int4(k, k, 0, 0));
-                for (int x = rows_start[k]; x < rows_start[k + 1]; x++) panel.push_back(make_int4(k, rows[x], 0, 0));
-                for (int x = rows_start[k]; x < rows_start[k + 1]; x++)
-                    for (int y = rows_start[k]; y <= x; y++) { update.push_back(make_int4(k, rows[x], rows[y], 0)); hits[(size_t)rows[x] * nt + rows[y]]++; }
-            }
-            for (size_t t = u0; t < update.size(); t++) if (hits[(size_t)update[t].y * nt + update[t].z] > 1) update[t].w = 1;
-            for (size_t t = u0; t < update.size(); t++) hits[(size_t)update[t].y * nt + update[t].z] = 0;
-            panel_lv[l + 1] = (int)panel.size(); update_lv[l + 1] = (int)update.size();
-        }
-        n_panel = panel.size();
-        ORBS_REQUIRE(panel.size() + update.size() <= ((size_t)1 << 26), ORBS_E_INVALID, "pose graph too large / too dense for the tiled Cholesky");
+        plan.build(adj, ng);
+        const int nt = plan.nt;
+        P.nt = nt; P.ns = plan.ns;
         std::vector<int> rowbase(std::max(nA, 1));
-        std::vector<uint8_t> rowpad((size_t)nt * NB, 1);
+        std::vector<uint8_t> rowpad((size_t)nt * TS, 1);
         for (int ip = 0; ip < nA; ip++) {
-            rowbase[ip] = NB * pos[ip / kPgPerTile] + 7 * (ip % kPgPerTile);
+            rowbase[ip] = TS * plan.pos[ip / kPgPerTile] + 7 * (ip % kPgPerTile);
             for (int a = 0; a < 7; a++) rowpad[rowbase[ip] + a] = 0;
         }
+        // contributions: (row global row, col global row, edge, side_row, side_col), sorted
+        struct C { int rr, rc, e, sr, sc; };
+        std::vector<C> cs; cs.reserve((size_t)E * 3);
+        for (int e = 0; e < E; e++) {
+            const int hs[2] = {hidx[e_i[e]], hidx[e_j[e]]};
+            for (int s = 0; s < 2; s++) if (hs[s] >= 0) cs.push_back({rowbase[hs[s]], rowbase[hs[s]], e, s, s});
+            if (hs[0] >= 0 && hs[1] >= 0) {
+                const int r0 = rowbase[hs[0]], r1 = rowbase[hs[1]];
+                if (r0 > r1) cs.push_back({r0, r1, e, 0, 1}); else cs.push_back({r1, r0, e, 1, 0});
+            }
+        }
+        std::stable_sort(cs.begin(), cs.end(), [](const C &a, const C &b) { return a.rr != b.rr ? a.rr < b.rr : a.rc < b.rc; });
+        std::vector<PgBlock> blocks; std::vector<PgEntry> entries(cs.size());
+        for (size_t q = 0; q < cs.size(); q++) {
+            entries[q] = {cs[q].e, cs[q].sr, cs[q].sc, 0};
+            if (q == 0 || cs[q].rr != cs[q - 1].rr || cs[q].rc != cs[q - 1].rc) {
+                PgBlock b = {};
+                b.slot = plan.slot_of[(size_t)(cs[q].rr >> 6) * nt + (cs[q].rc >> 6)];
+                b.r0 = cs[q].rr & 63; b.c0 = cs[q].rc & 63; b.diag = cs[q].rr == cs[q].rc; b.start = (int)q; b.n = 0; b.rs = cs[q].rr;
+                blocks.push_back(b);
+            }
+            blocks.back().n++;
+        }
+        P.n_blocks = (int)blocks.size();
         int rc = ORBS_OK;
-        int *d_rs = alloc<int>(nt + 1, &rc), *d_cs = alloc<int>(nt + 1, &rc), *d_rows = alloc<int>(rows.size(), &rc), *d_cols = alloc<int>(cols.size(), &rc);
-        int4 *d_tasks = alloc<int4>(panel.size() + update.size(), &rc);
+        RsTask *d_tasks = alloc<RsTask>(plan.tasks.size(), &rc); int2 *d_deps = alloc<int2>(plan.deps.size(), &rc);
         int *d_rowbase = alloc<int>(nA, &rc); uint8_t *d_rowpad = alloc<uint8_t>(rowpad.size(), &rc);
+        PgBlock *d_blocks = alloc<PgBlock>(blocks.size(), &rc); PgEntry *d_entries = alloc<PgEntry>(entries.size(), &rc);
         if (rc) return rc;
-        ORBS_CUDA(cudaMemcpyAsync(d_rs, rows_start.data(), (nt + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
-        ORBS_CUDA(cudaMemcpyAsync(d_cs, cols_start.data(), (nt + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
-        if (!rows.empty()) { ORBS_CUDA(cudaMemcpyAsync(d_rows, rows.data(), rows.size() * sizeof(int), cudaMemcpyHostToDevice, st)); ORBS_CUDA(cudaMemcpyAsync(d_cols, cols.data(), cols.size() * sizeof(int), cudaMemcpyHostToDevice, st)); }
-        ORBS_CUDA(cudaMemcpyAsync(d_tasks, panel.data(), panel.size() * sizeof(int4), cudaMemcpyHostToDevice, st));
-        if (!update.empty()) ORBS_CUDA(cudaMemcpyAsync(d_tasks + panel.size(), update.data(), update.size() * sizeof(int4), cudaMemcpyHostToDevice, st));
+        ORBS_CUDA(cudaMemcpyAsync(d_tasks, plan.tasks.data(), plan.tasks.size() * sizeof(RsTask), cudaMemcpyHostToDevice, st));
+        if (!plan.deps.empty()) ORBS_CUDA(cudaMemcpyAsync(d_deps, plan.deps.data(), plan.deps.size() * sizeof(int2), cudaMemcpyHostToDevice, st));
         ORBS_CUDA(cudaMemcpyAsync(d_rowbase, rowbase.data(), std::max(nA, 1) * sizeof(int), cudaMemcpyHostToDevice, st));
         ORBS_CUDA(cudaMemcpyAsync(d_rowpad, rowpad.data(), rowpad.size(), cudaMemcpyHostToDevice, st));
-        ORBS_CUDA(cudaStreamSynchronize(st));
-        plan.rows_start = d_rs; plan.rows = d_rows; plan.cols_start = d_cs; plan.cols = d_cols; plan.panel = d_tasks; plan.update = d_tasks + panel.size();
-        P.rowbase = d_rowbase; P.row_pad = d_rowpad; P.ld = nt * NB;
+        if (!blocks.empty()) ORBS_CUDA(cudaMemcpyAsync(d_blocks, blocks.data(), blocks.size() * sizeof(PgBlock), cudaMemcpyHostToDevice, st));
+        if (!entries.empty()) ORBS_CUDA(cudaMemcpyAsync(d_entries, entries.data(), entries.size() * sizeof(PgEntry), cudaMemcpyHostToDevice, st));
+        ORBS_CUDA(cudaStreamSynchronize(st));                  // the host vectors die here
+        rsplan.tasks = d_tasks; rsplan.ntasks = (int)plan.tasks.size(); rsplan.deps = d_deps; rsplan.nt = nt; rsplan.ns = plan.ns;
+        solve_ctas = std::max(1, std::min(rsplan.ntasks, h->sm_count));
+        P.rowbase = d_rowbase; P.row_pad = d_rowpad; P.blocks = d_blocks; P.entries = d_entries;
         return ORBS_OK;
     }
 
@@ -944,26 +848,16 @@ struct PgHost {
         ORBS_CUDA(cudaStreamSynchronize(st));
         return ORBS_OK;
     }
-    // S <- H (packed copy of the structurally nonzero tiles) + lambda I, factor, solve; ok = the factorisation succeeded
+    // A <- H + lambda I, factor, solve; ok = the factorisation succeeded
     int solve(double lambda, bool *ok)
     {
-        const int ld = P.ld;
-        ORBS_CUDA(cudaMemsetAsync(flags, 0, 4 * sizeof(int), st));
-        k_tiles_pack<<<(unsigned)n_panel, 256, 0, st>>>(P.S, ld, plan.panel, packed, 0);
-        k_pg_prepare<<<(ld + 255) / 256, 256, 0, st>>>(P, lambda);
-        h->launches += 2;
-        for (int l = 0; l < nlevels; l++) {
-            k_chol_panel<<<panel_lv[l + 1] - panel_lv[l], 256, kPanelSmem, st>>>(P.S, ld, plan.panel + panel_lv[l], Linv, flags);
-            h->launches++;
-            if (update_lv[l + 1] > update_lv[l]) { k_chol_update<<<update_lv[l + 1] - update_lv[l], 256, kUpdateSmem, st>>>(P.S, ld, plan.update + update_lv[l]); h->launches++; }
-        }
-        ORBS_CUDA(cudaMemsetAsync(ready, 0, 2 * (size_t)nt * sizeof(int), st));
-        const int ctas = std::min(nt, 128);
-        k_chol_solve<<<ctas, 256, 0, st>>>(P.S, ld, nt, plan, Linv, P.v, ready, 0);
-        k_chol_solve<<<ctas, 256, 0, st>>>(P.S, ld, nt, plan, Linv, P.v, ready + nt, 1);
+        ORBS_CUDA(cudaMemsetAsync(rsbuf.flags, 0, 4 * sizeof(int), st));
+        ORBS_CUDA(cudaMemcpyAsync(P.A, P.H, (size_t)P.ns * TS2 * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        k_pg_prepare<<<(P.nt * TS + 255) / 256, 256, 0, st>>>(P, lambda);
+        k_rs_solve<<<solve_ctas, 256, kRsSmemBytes, st>>>(rsplan, rsbuf, nullptr, ++h->rs_epoch);
         h->launches += 2;
         int f = 0;
-        ORBS_CUDA(cudaMemcpyAsync(&f, flags, sizeof(int), cudaMemcpyDeviceToHost, st));
+        ORBS_CUDA(cudaMemcpyAsync(&f, rsbuf.flags, sizeof(int), cudaMemcpyDeviceToHost, st));
         ORBS_CUDA(cudaStreamSynchronize(st));
         *ok = f == 0;
         return ORBS_OK;
@@ -983,6 +877,7 @@ extern "C" int orbo_optimize_pose_graph(orbo_handle *h, int K, double *sim3, con
     if (stats) { stats[0] = stats[1] = stats[2] = 0; }
     PgHost G; G.h = h; G.st = h->stream;
     PgDev &P = G.P;
+    memset(&P, 0, sizeof P);
     std::vector<int> hidx(K);
     int nA = 0;
     for (int k = 0; k < K; k++) hidx[k] = fixed[k] ? -1 : nA++;
@@ -991,21 +886,26 @@ extern "C" int orbo_optimize_pose_graph(orbo_handle *h, int K, double *sim3, con
     static_assert(sizeof(Sim3) == 8 * sizeof(double), "Sim3 must be 8 packed doubles (r xyzw, t, s)");
     int rc = ORBS_OK;
     if ((rc = G.schedule(K, hidx, E, e_i, e_j))) return rc;
-    const int ld = P.ld, nt = G.nt;
-    ORBS_REQUIRE((size_t)ld * ld * sizeof(double) <= ((size_t)24 << 30), ORBS_E_INVALID, "pose graph too large for one GPU");
+    const int nt = P.nt, ns = P.ns, ld = nt * TS;
+    ORBS_REQUIRE((size_t)ns * TS2 * sizeof(double) * 3 <= ((size_t)64 << 30), ORBS_E_INVALID, "pose graph too large for one GPU");
     G.eblocks = (E + 127) / 128;
     P.verts = G.alloc<Sim3>(K, &rc); P.backup = G.alloc<Sim3>(K, &rc);
     int *d_hidx = G.alloc<int>(K, &rc), *d_ei = G.alloc<int>(E, &rc), *d_ej = G.alloc<int>(E, &rc);
     Sim3 *d_meas = G.alloc<Sim3>(E, &rc);
     P.err = G.alloc<double>((size_t)7 * E, &rc);
-    // one buffer: S | b | v | partial | scalars | Linv | packed | ready | flags
-    const size_t nS = (size_t)ld * ld, nLinv = (size_t)nt * NB * NB, nPacked = G.n_panel * 4096;
-    double *big = G.alloc<double>(nS + 2 * (size_t)ld + G.eblocks + 8 + nLinv + nPacked + (size_t)nt + 8, &rc);
+    P.eJ = G.alloc<double>((size_t)98 * E, &rc);
+    // one buffer: H | A | L | Linv | b | y | x | partial | scalars, then the dataflow flags
+    const size_t nT = (size_t)ns * TS2;
+    double *big = G.alloc<double>(3 * nT + (size_t)nt * TS2 + 3 * (size_t)ld + G.eblocks + 8, &rc);
+    int *flg = G.alloc<int>((size_t)ns + 2 * (size_t)nt + 8, &rc);
     if (rc) return rc;
-    P.S = big; P.b = big + nS; P.v = P.b + ld; P.partial = P.v + ld; P.scalars = P.partial + G.eblocks; G.Linv = P.scalars + 8; G.packed = G.Linv + nLinv;
-    G.ready = reinterpret_cast<int *>(G.packed + nPacked); G.flags = G.ready + 2 * nt;
+    P.H = big; P.A = big + nT; G.rsbuf.L = P.A + nT; G.rsbuf.Linv = G.rsbuf.L + nT; P.b = G.rsbuf.Linv + (size_t)nt * TS2;
+    G.rsbuf.y = P.b + ld; P.x = G.rsbuf.y + ld; P.partial = P.x + ld; P.scalars = P.partial + G.eblocks;
+    G.rsbuf.A = P.A; G.rsbuf.b = P.b; G.rsbuf.x = P.x;
+    G.rsbuf.counters = flg; G.rsbuf.flags = flg + 4; G.rsbuf.done_slot = flg + 8; G.rsbuf.done_y = G.rsbuf.done_slot + ns; G.rsbuf.done_x = G.rsbuf.done_y + nt;
     P.hidx = d_hidx; P.e_i = d_ei; P.e_j = d_ej; P.meas = d_meas;
     cudaStream_t st = h->stream;
+    ORBS_CUDA(cudaMemsetAsync(flg, 0, ((size_t)ns + 2 * (size_t)nt + 8) * sizeof(int), st));
     ORBS_CUDA(cudaMemcpyAsync(P.verts, sim3, sizeof(Sim3) * K, cudaMemcpyHostToDevice, st));
     ORBS_CUDA(cudaMemcpyAsync(d_hidx, hidx.data(), sizeof(int) * K, cudaMemcpyHostToDevice, st));
     ORBS_CUDA(cudaMemcpyAsync(d_ei, e_i, sizeof(int) * E, cudaMemcpyHostToDevice, st));
@@ -1022,10 +922,10 @@ extern "C" int orbo_optimize_pose_graph(orbo_handle *h, int K, double *sim3, con
         double currentChi = 0, tempChi = 0;
         if ((rc = G.chi2(&currentChi))) return rc;
         const double iniChi = currentChi;
-        ORBS_CUDA(cudaMemsetAsync(P.S, 0, nS * sizeof(double), st));
+        ORBS_CUDA(cudaMemsetAsync(P.H, 0, nT * sizeof(double), st));
         ORBS_CUDA(cudaMemsetAsync(P.b, 0, (size_t)ld * sizeof(double), st));
-        k_pg_build<<<(E + 63) / 64, 64, 0, st>>>(P);
-        k_tiles_pack<<<(unsigned)G.n_panel, 256, 0, st>>>(P.S, ld, G.plan.panel, G.packed, 1);        // keep H: the factorisation overwrites S
+        k_pg_jac<<<(E * 14 + 127) / 128, 128, 0, st>>>(P);
+        k_pg_accum<<<(P.n_blocks + 7) / 8, 256, 0, st>>>(P);
         h->launches += 2;
         ORBS_CUDA(cudaMemcpyAsync(hb.data(), P.b, sizeof(double) * ld, cudaMemcpyDeviceToHost, st));
         ORBS_CUDA(cudaStreamSynchronize(st));
@@ -1033,7 +933,8 @@ extern "C" int orbo_optimize_pose_graph(orbo_handle *h, int K, double *sim3, con
             if (lambda_init > 0) lambda = lambda_init;                                                   // setUserLambdaInit
             else {                                                                                       // computeLambdaInit: 1e-5 * max diagonal
                 std::vector<double> diag(ld);
-                ORBS_CUDA(cudaMemcpy2DAsync(diag.data(), sizeof(double), P.S, ((size_t)ld + 1) * sizeof(double), sizeof(double), ld, cudaMemcpyDeviceToHost, st));
+                for (int t = 0; t < nt; t++)
+                    ORBS_CUDA(cudaMemcpy2DAsync(diag.data() + (size_t)t * TS, sizeof(double), P.H + (size_t)t * TS2, (TS + 1) * sizeof(double), sizeof(double), TS, cudaMemcpyDeviceToHost, st));
                 ORBS_CUDA(cudaStreamSynchronize(st));
                 double mx = 0;
                 for (int t = 0; t < ld; t++) if (!rowpad[t]) mx = std::max(mx, std::fabs(diag[t]));
@@ -1047,7 +948,7 @@ extern "C" int orbo_optimize_pose_graph(orbo_handle *h, int K, double *sim3, con
             bool ok2 = true;
             if ((rc = G.solve(lambda, &ok2))) return rc;
             if (!ok2) fails++;
-            ORBS_CUDA(cudaMemcpyAsync(hx.data(), P.v, sizeof(double) * ld, cudaMemcpyDeviceToHost, st));
+            ORBS_CUDA(cudaMemcpyAsync(hx.data(), P.x, sizeof(double) * ld, cudaMemcpyDeviceToHost, st));
             k_pg_update<<<(K + 127) / 128, 128, 0, st>>>(P);
             h->launches++;
             if ((rc = G.chi2(&tempChi))) return rc;

@@ -1,11 +1,13 @@
 // pose_graph.cuh -- numeric core of Optimizer::OptimizeEssentialGraph / MMOptimizeEssentialGraph (S/src/Optimizer.cc:804-1067, 1069-1346): a pose
 // graph of VertexSim3Expmap vertices and EdgeSim3 edges, error = log(Sji * Siw * Sjw^-1) (types_seven_dof_expmap.h:64-84, sim3.h:110-181), identity
 // information, numeric Jacobians for both vertices (base_binary_edge.hpp:131-205, delta = 1e-9), g2o's Levenberg from lambda = 1e-16.
-// The 7K x 7K normal equations are as sparse as the reduced BA system, so they go through the same tiled sparse Cholesky (ba_kernels.cuh:
-// k_chol_panel / k_chol_update / k_chol_solve, nested-dissection tile order): 9 vertices per 64-row tile (63 rows + 1 identity row).
+// The 7K x 7K normal equations are as sparse as the reduced BA system, so they go through the same tiled sparse solver (tile_solver.cuh:
+// packed nonzero 64x64 tiles, nested-dissection tile order, one persistent dataflow kernel): 9 vertices per 64-row tile (63 rows + 1
+// identity row).  The normal equations are assembled per TARGET 7x7 block in a fixed order (no atomics): results are bit-reproducible.
 #pragma once
 #include "common.cuh"
 #include "sim3_opt.cuh"
+#include "tile_solver.cuh"
 
 namespace orbs {
 
@@ -71,17 +73,23 @@ __device__ inline void pg_edge_error(const Sim3 &meas, const Sim3 &Si, const Sim
     sim3_log(b, e);
 }
 
+struct PgBlock { int slot, r0, c0, diag, start, n, rs, pad; };   // target block: tile slot, offsets inside the tile, entries [start, start + n), rs = global row (diag: b)
+struct PgEntry { int e, s_row, s_col, pad; };                      // contribution J[e][s_row]^T J[e][s_col]
+
 struct PgDev {
-    int K, E, nA, ld, fix_scale;
+    int K, E, nA, nt, ns, fix_scale, n_blocks;
     Sim3 *verts; Sim3 *backup;        // [K]
     const int *hidx;                  // [K] hessian index or -1 (fixed)
     const int *rowbase;               // [nA] first row of the vertex's 7x7 block in the permuted tile layout
-    const uint8_t *row_pad;           // [ld] 1 = identity padding row
+    const uint8_t *row_pad;           // [nt*64] 1 = identity padding row
     const int *e_i, *e_j; const Sim3 *meas;
     double *err;                      // [E,7] stored _error
-    double *S;                        // [ld, ld] lower triangle, tiles
-    double *b;                        // [ld] right-hand side (kept), v = working copy solved in place
-    double *v;
+    double *eJ;                       // [E,2,49] numeric Jacobians of both vertices (row-major 7x7: J[r][d])
+    const PgBlock *blocks; const PgEntry *entries;
+    double *H;                        // [ns][4096] normal equations, packed tiles (kept: every LM trial factors H + lambda I)
+    double *A;                        // [ns][4096] H + lambda I
+    double *b;                        // [nt*64] right-hand side
+    double *x;                        // [nt*64] solution
     double *partial;                  // per-block chi2 partials
     double *scalars;                  // [4]: chi2
 };
@@ -114,58 +122,66 @@ __global__ void k_pg_sum(const double *__restrict__ partial, int n, double *__re
     if (threadIdx.x == 0 && blockIdx.x == 0) { double s = 0; for (int i = 0; i < n; i++) s += partial[i]; out[0] = s; }
 }
 
-// buildSystem: numeric linearizeOplus for both vertices + constructQuadraticForm, one thread per edge; 7x7 blocks are added into the lower
-// triangle of S (fp64 atomics: several edges share a vertex) and into b
-__global__ void __launch_bounds__(64)
-k_pg_build(const PgDev P)
+// numeric linearizeOplus for both vertices (base_binary_edge.hpp:131-205, central differences, delta = 1e-9): thread per (edge, side, column)
+__global__ void __launch_bounds__(128)
+k_pg_jac(const PgDev P)
 {
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= P.E) return;
-    const int vid[2] = {P.e_i[e], P.e_j[e]};
-    const int hs[2] = {P.hidx[vid[0]], P.hidx[vid[1]]};
-    if (hs[0] < 0 && hs[1] < 0) return;
-    const Sim3 Sv[2] = {P.verts[vid[0]], P.verts[vid[1]]};
-    const Sim3 M = P.meas[e];
-    double J[2][7][7];
-    for (int s = 0; s < 2; s++) {
-        if (hs[s] < 0) continue;
-        for (int d = 0; d < 7; d++) {
-            double add[7] = {0, 0, 0, 0, 0, 0, 0}, ep[7], em[7];
-            Sim3 Pp;
-            add[d] = 1e-9; sim3_oplus(Sv[s], add, P.fix_scale != 0, Pp);
-            pg_edge_error(M, s == 0 ? Pp : Sv[0], s == 1 ? Pp : Sv[1], ep);
-            add[d] = -1e-9; sim3_oplus(Sv[s], add, P.fix_scale != 0, Pp);
-            pg_edge_error(M, s == 0 ? Pp : Sv[0], s == 1 ? Pp : Sv[1], em);
-            for (int r = 0; r < 7; r++) J[s][r][d] = (1.0 / (2 * 1e-9)) * (ep[r] - em[r]);
-        }
-    }
-    const double *er = P.err + 7 * (size_t)e;
-    for (int s = 0; s < 2; s++) {
-        if (hs[s] < 0) continue;
-        const int rs = P.rowbase[hs[s]];
-        for (int a = 0; a < 7; a++) { double g = 0; for (int r = 0; r < 7; r++) g += J[s][r][a] * er[r]; atomicAdd(&P.b[rs + a], -g); }
-        for (int t = 0; t < 2; t++) {
-            if (hs[t] < 0) continue;
-            const int rt = P.rowbase[hs[t]];
-            if (rt > rs) continue;                                     // lower triangle only: block row >= block column
-            for (int a = 0; a < 7; a++)
-                for (int c = 0; c < 7; c++) {
-                    if (s == t && c > a) continue;                     // diagonal block: its lower part
-                    double g = 0;
-                    for (int r = 0; r < 7; r++) g += J[s][r][a] * J[t][r][c];
-                    atomicAdd(&P.S[(size_t)(rs + a) * P.ld + rt + c], g);
-                }
-        }
-    }
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= P.E * 14) return;
+    const int e = t / 14, s = (t % 14) / 7, d = t % 7;
+    const int vi = P.e_i[e], vj = P.e_j[e];
+    if (P.hidx[s == 0 ? vi : vj] < 0) return;
+    const Sim3 Si = P.verts[vi], Sj = P.verts[vj], M = P.meas[e];
+    double add[7] = {0, 0, 0, 0, 0, 0, 0}, ep[7], em[7];
+    Sim3 Pp;
+    add[d] = 1e-9; sim3_oplus(s == 0 ? Si : Sj, add, P.fix_scale != 0, Pp);
+    pg_edge_error(M, s == 0 ? Pp : Si, s == 1 ? Pp : Sj, ep);
+    add[d] = -1e-9; sim3_oplus(s == 0 ? Si : Sj, add, P.fix_scale != 0, Pp);
+    pg_edge_error(M, s == 0 ? Pp : Si, s == 1 ? Pp : Sj, em);
+    double *J = P.eJ + ((size_t)e * 2 + s) * 49;
+#pragma unroll
+    for (int r = 0; r < 7; r++) J[7 * r + d] = (1.0 / (2 * 1e-9)) * (ep[r] - em[r]);
 }
 
-// + lambda on the diagonal of the real rows, 1 on the padding rows; v <- b
+// constructQuadraticForm per target block (base_binary_edge.hpp:55-120): one warp sums the block's contributions J_row^T J_col in list order
+// (fixed = deterministic) and writes it once into the packed tile; diagonal blocks also give b = - sum J^T e
+__global__ void __launch_bounds__(256)
+k_pg_accum(const PgDev P)
+{
+    const int blk = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (blk >= P.n_blocks) return;
+    const PgBlock Bk = P.blocks[blk];
+    double g0 = 0, g1 = 0, gb = 0;                       // entries lane and lane + 32 of the 7x7 block; b entry lane (< 7)
+    const int q0 = lane, q1 = lane + 32;
+    const int a0 = q0 / 7, c0 = q0 % 7, a1 = q1 / 7, c1 = q1 % 7;
+    for (int t = 0; t < Bk.n; t++) {
+        const PgEntry en = P.entries[Bk.start + t];
+        const double *Jr = P.eJ + ((size_t)en.e * 2 + en.s_row) * 49, *Jc = P.eJ + ((size_t)en.e * 2 + en.s_col) * 49;
+        double s0 = 0, s1 = 0;
+#pragma unroll
+        for (int r = 0; r < 7; r++) { s0 += Jr[7 * r + a0] * Jc[7 * r + c0]; if (q1 < 49) s1 += Jr[7 * r + a1] * Jc[7 * r + c1]; }
+        g0 += s0; g1 += s1;
+        if (Bk.diag && lane < 7) {
+            const double *er = P.err + 7 * (size_t)en.e;
+            double s = 0;
+#pragma unroll
+            for (int r = 0; r < 7; r++) s += Jr[7 * r + lane] * er[r];
+            gb += s;
+        }
+    }
+    double *T = P.H + (size_t)Bk.slot * TS2 + Bk.r0 * TS + Bk.c0;
+    T[a0 * TS + c0] = g0;
+    if (q1 < 49) T[a1 * TS + c1] = g1;
+    if (Bk.diag && lane < 7) P.b[Bk.rs + lane] = -gb;
+}
+
+// A <- H + lambda on the diagonal of the real rows, 1 on the padding rows (A was copied from H)
 __global__ void k_pg_prepare(const PgDev P, double lambda)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= P.ld) return;
-    if (P.row_pad[t]) { P.S[(size_t)t * P.ld + t] = 1.0; P.v[t] = 0.0; }
-    else { P.S[(size_t)t * P.ld + t] += lambda; P.v[t] = P.b[t]; }
+    if (t >= P.nt * TS) return;
+    double *d = P.A + (size_t)(t >> 6) * TS2 + (t & 63) * TS + (t & 63);          // diagonal tile i is slot i
+    if (P.row_pad[t]) *d = 1.0; else *d += lambda;
 }
 
 // push + oplus: estimate <- exp(x) * estimate for the free vertices
@@ -178,7 +194,7 @@ __global__ void k_pg_update(const PgDev P)
     const int h = P.hidx[k];
     if (h < 0) return;
     double x[7];
-    for (int a = 0; a < 7; a++) x[a] = P.v[P.rowbase[h] + a];
+    for (int a = 0; a < 7; a++) x[a] = P.x[P.rowbase[h] + a];
     Sim3 nv;
     sim3_oplus(cur, x, P.fix_scale != 0, nv);
     P.verts[k] = nv;

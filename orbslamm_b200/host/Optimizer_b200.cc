@@ -100,10 +100,10 @@ void Optimizer::MMGlobalBundleAdjustemnt(Map *pMap, int nIterations, bool *pbSto
 namespace
 {
 // bool* stop flag of the reference -> the int flag the C-ABI polls
-struct StopBridge {
-    bool *src; volatile int flag = 0;
-    explicit StopBridge(bool *p) : src(p) { if (src && *src) flag = 1; }
-};
+// the reference's `bool *pbStopFlag` (mbAbortBA / mbStopGBA, raised by another thread while the optimisation runs) goes to the C-ABI as is:
+// the library watches that byte for the whole call
+static_assert(sizeof(bool) == 1, "the C-ABI stop flag is one byte");
+inline const volatile uint8_t *stop_ptr(bool *p) { return reinterpret_cast<const volatile uint8_t *>(p); }
 }  // namespace
 
 void Optimizer::BundleAdjustment(const std::vector<KeyFrame *> &vpKFs, const std::vector<MapPoint *> &vpMP, int nIterations, bool *pbStopFlag,
@@ -152,9 +152,8 @@ void Optimizer::BundleAdjustment(const std::vector<KeyFrame *> &vpKFs, const std
         points.push_back(X.at<float>(0)); points.push_back(X.at<float>(1)); points.push_back(X.at<float>(2));
     }
     if (kfs.empty() || mps.empty() || ekf.empty()) return;
-    StopBridge stop(pbStopFlag);
     const int rc = orbo_bundle_adjust(handle(), (int)kfs.size(), poses.data(), fixed.data(), intr.data(), (int)mps.size(), points.data(), (int)ekf.size(),
-                                      ekf.data(), ept.data(), uv.data(), w.data(), 0, nIterations, 0, bRobust ? 1 : 0, pbStopFlag ? &stop.flag : nullptr,
+                                      ekf.data(), ept.data(), uv.data(), w.data(), 0, nIterations, 0, bRobust ? 1 : 0, stop_ptr(pbStopFlag),
                                       nullptr, nullptr, nullptr, nullptr);
     check(rc, "orbo_bundle_adjust");
     for (size_t i = 0; i < kfs.size(); i++) {                                // Optimizer.cc:196-231
@@ -245,10 +244,9 @@ void Optimizer::LocalBundleAdjustment(KeyFrame *pKF, bool *pbStopFlag, Map *pMap
     }
     if (pbStopFlag && *pbStopFlag) return;                                   // Optimizer.cc:678-680
     if (mps.empty() || ekf.empty()) return;
-    StopBridge stop(pbStopFlag);
     std::vector<uint8_t> outlier(ekf.size());
     const int rc = orbo_bundle_adjust(handle(), (int)kfs.size(), poses.data(), fixed.data(), intr.data(), (int)mps.size(), points.data(), (int)ekf.size(),
-                                      ekf.data(), ept.data(), uv.data(), w.data(), 1, 5, 10, 1, pbStopFlag ? &stop.flag : nullptr, nullptr, nullptr,
+                                      ekf.data(), ept.data(), uv.data(), w.data(), 1, 5, 10, 1, stop_ptr(pbStopFlag), nullptr, nullptr,
                                       outlier.data(), nullptr);
     check(rc, "orbo_bundle_adjust");
     if (rc == 1) return;

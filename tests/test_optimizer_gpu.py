@@ -135,7 +135,7 @@ def test_global_ba_and_abort(lib):
     ref = oracle.bundle_adjust(g["poses"], g["fixed"], g["intr"], g["points"], g["kf"], g["pt"], g["uv"], g["inv_sigma2"], False, 20, 0, False)
     assert got["lm_iterations"] == ref["lm_iterations"]
     assert _rel(got["poses"], ref["poses"]) < RTOL and _rel(got["points"], ref["points"]) < RTOL
-    stop = np.ones(1, np.int32)
+    stop = np.ones(1, np.uint8)
     ab = opt.LocalBundleAdjustment(g["poses"], g["fixed"], g["intr"], g["points"], g["kf"], g["pt"], g["uv"], g["inv_sigma2"], stop_flag=stop)
     assert ab["aborted"] and np.array_equal(ab["poses"], g["poses"]) and np.array_equal(ab["points"], g["points"])
 
