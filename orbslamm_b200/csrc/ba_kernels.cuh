@@ -121,7 +121,18 @@ k_ba_errors(const BaDev B)
     block_partial(chi, B.p_chi);
 }
 
-// 8 lanes per point: Hll, b_l and the per-edge Hpl blocks
+// Hll + lambda I = G G^T (lower Cholesky of the 3x3 point block); returns the reciprocals of the diagonal
+__device__ __forceinline__ void point_chol(const double *H, double lambda, double (&G)[6], double (&inv)[3])
+{
+    G[0] = sqrt(H[0] + lambda); inv[0] = 1.0 / G[0];
+    G[1] = H[3] * inv[0]; G[3] = H[6] * inv[0];
+    G[2] = sqrt(H[4] + lambda - G[1] * G[1]); inv[1] = 1.0 / G[2];
+    G[4] = (H[7] - G[3] * G[1]) * inv[1];
+    G[5] = sqrt(H[8] + lambda - G[3] * G[3] - G[4] * G[4]); inv[2] = 1.0 / G[5];
+}
+
+// 8 lanes per point: Hll, b_l and the per-edge Hpl blocks.  When lambda is already known (every iteration but the first) and the
+// point has at most 8 observations, the per-trial quantities of k_ba_point_prep (G, g, Z = Hpl G^-T) are produced here from registers.
 __global__ void __launch_bounds__(256)
 k_ba_build_points(const BaDev B)
 {
@@ -129,9 +140,12 @@ k_ba_build_points(const BaDev B)
     const int p = blockIdx.x * 32 + (threadIdx.x >> 3), sub = threadIdx.x & 7;
     const bool live = p < B.P && B.pt_active[p];
     double H[6] = {0, 0, 0, 0, 0, 0}, b[3] = {0, 0, 0};
+    double W[18];
+    int my_e = -1;
+    const int e_begin = live ? B.pt_start[p] : 0, e_end = live ? B.pt_start[p + 1] : 0;
     if (live) {
         const double X[3] = {B.pt[3 * p], B.pt[3 * p + 1], B.pt[3 * p + 2]};
-        for (int e = B.pt_start[p] + sub; e < B.pt_start[p + 1]; e += 8) {
+        for (int e = e_begin + sub; e < e_end; e += 8) {
             if (B.e_level[e]) continue;
             const int kf = B.e_kf[e];
             const Se3 T = B.pose[kf];
@@ -152,11 +166,12 @@ k_ba_build_points(const BaDev B)
             H[5] += Jl[2] * wo * Jl[2] + Jl[5] * wo * Jl[5];
             b[0] += Jl[0] * r0 + Jl[3] * r1; b[1] += Jl[1] * r0 + Jl[4] * r1; b[2] += Jl[2] * r0 + Jl[5] * r1;
             if (B.pose_idx[kf] >= 0) {
-                double *W = &B.e_W[18 * (size_t)e];
+                double *Wg = &B.e_W[18 * (size_t)e];
 #pragma unroll
                 for (int a = 0; a < 6; a++)
 #pragma unroll
-                    for (int c = 0; c < 3; c++) W[3 * a + c] = Jp[a] * wo * Jl[c] + Jp[6 + a] * wo * Jl[3 + c];
+                    for (int c = 0; c < 3; c++) { W[3 * a + c] = Jp[a] * wo * Jl[c] + Jp[6 + a] * wo * Jl[3 + c]; Wg[3 * a + c] = W[3 * a + c]; }
+                my_e = e;
             }
         }
     }
@@ -164,10 +179,30 @@ k_ba_build_points(const BaDev B)
     for (int i = 0; i < 6; i++) H[i] = group8_sum(H[i]);
 #pragma unroll
     for (int i = 0; i < 3; i++) b[i] = group8_sum(b[i]);
-    if (live && sub == 0) {
+    if (!live) return;
+    if (sub == 0) {
         double *Ho = &B.Hll[9 * (size_t)p];
         Ho[0] = H[0]; Ho[1] = H[1]; Ho[2] = H[2]; Ho[3] = H[1]; Ho[4] = H[3]; Ho[5] = H[4]; Ho[6] = H[2]; Ho[7] = H[4]; Ho[8] = H[5];
         B.bl[3 * p] = b[0]; B.bl[3 * p + 1] = b[1]; B.bl[3 * p + 2] = b[2];
+    }
+    if (B.ctl->first || e_end - e_begin > 8) return;                    // lambda not known yet / more than one edge per lane: k_ba_point_prep
+    const double Hf[9] = {H[0], H[1], H[2], H[1], H[3], H[4], H[2], H[4], H[5]};
+    double G[6], inv[3];
+    point_chol(Hf, B.ctl->lambda, G, inv);
+    if (sub == 0) {
+        double *Go = &B.ptG[6 * (size_t)p];
+#pragma unroll
+        for (int i = 0; i < 6; i++) Go[i] = G[i];
+        const double y0 = b[0] * inv[0], y1 = (b[1] - G[1] * y0) * inv[1], y2 = (b[2] - G[3] * y0 - G[4] * y1) * inv[2];
+        B.ptg[3 * p] = y0; B.ptg[3 * p + 1] = y1; B.ptg[3 * p + 2] = y2;
+    }
+    if (my_e >= 0) {
+        double *Z = &B.e_Z[18 * (size_t)my_e];
+#pragma unroll
+        for (int a = 0; a < 6; a++) {
+            const double z0 = W[3 * a] * inv[0], z1 = (W[3 * a + 1] - z0 * G[1]) * inv[1], z2 = (W[3 * a + 2] - z0 * G[3] - z1 * G[4]) * inv[2];
+            Z[3 * a] = z0; Z[3 * a + 1] = z1; Z[3 * a + 2] = z2;
+        }
     }
 }
 
@@ -276,41 +311,44 @@ __global__ void k_lm_iter_begin(const BaDev B, const double *__restrict__ diag6,
         c->currentChi = B.scalars[0];
         c->lambda = 1e-5 * m; c->ni = 2; c->nbad = 0;
         c->first = 0;
-    }
+        c->fresh_first = 1;                                 // this slot linearised without lambda: k_ba_point_prep does all points
+    } else c->fresh_first = 0;
     c->iniChi = c->currentChi;
     c->qmax = 0;
     c->rho = 0;
 }
 
-// per trial, 8 lanes per point: Hll + lambda I = G G^T, g = G^-1 b_l, and per edge Z = Hpl G^-T  (so that Hpl Dinv Hpl'^T = Z Z'^T)
+// per trial, 8 lanes per point: Hll + lambda I = G G^T, g = G^-1 b_l, and per edge Z = Hpl G^-T  (so that Hpl Dinv Hpl'^T = Z Z'^T).
+// After an accepted trial k_ba_build_points has produced them already (same arithmetic); this kernel then only serves the first
+// iteration, retries with a larger lambda and points with more than 8 observations.
 __global__ void __launch_bounds__(256)
 k_ba_point_prep(const BaDev B)
 {
-    if (B.ctl->state == LM_DONE) return;
+    const int state = B.ctl->state;
+    if (state == LM_DONE) return;
     if (blockIdx.x == 0 && threadIdx.x < 4) B.flags[threadIdx.x] = 0;
     const int p = blockIdx.x * 32 + (threadIdx.x >> 3), sub = threadIdx.x & 7;
     if (p >= B.P || !B.pt_active[p]) return;
+    const int e_begin = B.pt_start[p], e_end = B.pt_start[p + 1];
+    if (state == LM_BUILD && !B.ctl->fresh_first && e_end - e_begin <= 8) return;       // done by k_ba_build_points
     const double lambda = B.ctl->lambda;
-    const double *H = &B.Hll[9 * (size_t)p];
-    const double g00 = sqrt(H[0] + lambda), i00 = 1.0 / g00;
-    const double g10 = H[3] * i00, g20 = H[6] * i00;
-    const double g11 = sqrt(H[4] + lambda - g10 * g10), i11 = 1.0 / g11;
-    const double g21 = (H[7] - g20 * g10) * i11;
-    const double g22 = sqrt(H[8] + lambda - g20 * g20 - g21 * g21), i22 = 1.0 / g22;
+    double G[6], inv[3];
+    point_chol(&B.Hll[9 * (size_t)p], lambda, G, inv);
     if (sub == 0) {
-        double *G = &B.ptG[6 * (size_t)p];
-        G[0] = g00; G[1] = g10; G[2] = g11; G[3] = g20; G[4] = g21; G[5] = g22;
+        double *Go = &B.ptG[6 * (size_t)p];
+#pragma unroll
+        for (int i = 0; i < 6; i++) Go[i] = G[i];
         const double b0 = B.bl[3 * p], b1 = B.bl[3 * p + 1], b2 = B.bl[3 * p + 2];
-        const double y0 = b0 * i00, y1 = (b1 - g10 * y0) * i11, y2 = (b2 - g20 * y0 - g21 * y1) * i22;
+        const double y0 = b0 * inv[0], y1 = (b1 - G[1] * y0) * inv[1], y2 = (b2 - G[3] * y0 - G[4] * y1) * inv[2];
         B.ptg[3 * p] = y0; B.ptg[3 * p + 1] = y1; B.ptg[3 * p + 2] = y2;
     }
-    for (int e = B.pt_start[p] + sub; e < B.pt_start[p + 1]; e += 8) {
+    for (int e = e_begin + sub; e < e_end; e += 8) {
         if (B.e_level[e] || B.pose_idx[B.e_kf[e]] < 0) continue;
         const double *W = &B.e_W[18 * (size_t)e];
         double *Z = &B.e_Z[18 * (size_t)e];
 #pragma unroll
         for (int a = 0; a < 6; a++) {
-            const double z0 = W[3 * a] * i00, z1 = (W[3 * a + 1] - z0 * g10) * i11, z2 = (W[3 * a + 2] - z0 * g20 - z1 * g21) * i22;
+            const double z0 = W[3 * a] * inv[0], z1 = (W[3 * a + 1] - z0 * G[1]) * inv[1], z2 = (W[3 * a + 2] - z0 * G[3] - z1 * G[4]) * inv[2];
             Z[3 * a] = z0; Z[3 * a + 1] = z1; Z[3 * a + 2] = z2;
         }
     }
@@ -328,76 +366,137 @@ k_ba_diag_init(const BaDev B)
     B.A[(size_t)t * TS2 + r * TS + r] = real ? B.ctl->lambda : 1.0;          // diagonal tile t is slot t
 }
 
-// One warp per target 6x6 block of the reduced system: block += [diag] Hpp - sum over its (row edge, col edge) pairs of Z_r Z_c^T,
-// lanes run over the pairs (fixed strided order + butterfly = deterministic); diagonal blocks also produce bs = bp - sum Z g.
-__global__ void __launch_bounds__(256)
-k_ba_schur_seg(const BaDev B)
+// ---- Schur complement, assembled per target 6x6 block from the sorted pair list ------------------------------------------
+// A block's pairs ("segment") are cut into work items of <= kItemPairs pairs; one 128-thread CTA per item:
+//   1. every thread loads the two Z records (6x3 fp64 = 144 B each) of ITS pair with 18 independent 16-byte loads and multiplies them
+//      (36 products; diagonal blocks: + Z g for the right-hand side).  (A variant that staged the records through shared memory with
+//      cooperative cp.async was slower: 203 vs 164 us -- the staging loop costs more instructions than the 32-line requests it saves.)
+//   2. the warp folds its 32 x 42 partial values with a multi-value butterfly (43 shuffles instead of 210), the four warps are summed
+//      in fixed order and the item's partial block goes to scratch.
+// k_ba_schur_finish (one warp per block) adds a block's items in item order: block += [diag] Hpp - sum, bs += b_p - sum Z g.
+constexpr int kItemPairs = 128;
+constexpr int kRecPitch = 19;           // doubles per staged record (odd: conflict-free 64-bit reads with one record per lane)
+constexpr int kSchurVals = 42;          // 36 block entries + 6 right-hand-side entries
+
+template <int N>
+__device__ __forceinline__ void mv_fold(double *v, int bit, int lane)
+{
+    constexpr int H = (N + 1) / 2;
+    const bool upper = (lane & bit) != 0;
+#pragma unroll
+    for (int i = 0; i < H; i++) {
+        const double lo = v[i], hi = (i + H < N) ? v[i + H] : 0.0;
+        const double send = upper ? lo : hi, keep = upper ? hi : lo;
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+    }
+}
+
+__global__ void __launch_bounds__(128)
+k_ba_schur_items(const BaDev B, const int *__restrict__ seg_item0, double *__restrict__ item_part)
 {
     if (B.ctl->state == LM_DONE) return;
-    const int seg = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (seg >= *B.n_seg) return;
-    const int s0 = B.seg_start[seg], s1 = B.seg_start[seg + 1];
-    const unsigned tgt = (unsigned)(B.pair_key[s0] >> 32);
-    const int slot = tgt >> 7, blk = tgt & 127, br = blk / kPosesPerTile, bc = blk % kPosesPerTile;
-    const bool diag = slot < B.nt && br == bc;
-    double acc[36], ab[6];
+    __shared__ int s_seg;
+    __shared__ double s_part[4][kSchurVals];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, item = blockIdx.x;
+    if (tid == 0) {                                            // the segment of this item: last seg with seg_item0[seg] <= item
+        int lo = 0, hi = *B.n_seg - 1;
+        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (seg_item0[mid] <= item) lo = mid; else hi = mid - 1; }
+        s_seg = lo;
+    }
+    __syncthreads();
+    const int seg = s_seg;
+    const int s0 = B.seg_start[seg] + (item - seg_item0[seg]) * kItemPairs, s1 = min(B.seg_start[seg + 1], s0 + kItemPairs);
+    const unsigned tgt = (unsigned)(B.pair_key[B.seg_start[seg]] >> 32);
+    const int slot = tgt >> 7, blk = tgt & 127;
+    const bool diag = slot < B.nt && blk / kPosesPerTile == blk % kPosesPerTile;
+    const int t = s0 + tid;
+    int er = -1, ec = -1;
+    if (t < s1) {
+        const unsigned long long pv = B.pair_val[t];
+        er = (int)(pv & 0xffffffffu); ec = (int)(pv >> 32);
+        if (B.e_level[er] | B.e_level[ec]) { er = -1; ec = -1; }          // gated out after the robust stage
+    }
+    double v[kSchurVals];
 #pragma unroll
-    for (int i = 0; i < 36; i++) acc[i] = 0;
+    for (int i = 0; i < kSchurVals; i++) v[i] = 0.0;
+    if (er >= 0) {
+        // every thread multiplies its own pair: 9 + 9 independent 16-byte loads in flight per thread
+        const double2 *pr = reinterpret_cast<const double2 *>(&B.e_Z[18 * (size_t)er]);
+        const double2 *pc = reinterpret_cast<const double2 *>(&B.e_Z[18 * (size_t)ec]);
+        double zr[18], zc[18];
 #pragma unroll
-    for (int i = 0; i < 6; i++) ab[i] = 0;
-    for (int t = s0 + lane; t < s1; t += 32) {
-        const unsigned long long v = B.pair_val[t];
-        const int er = (int)(v & 0xffffffffu), ec = (int)(v >> 32);
-        if (B.e_level[er] | B.e_level[ec]) continue;
-        double Zr[18], Zc[18];
-        const double2 *zr = reinterpret_cast<const double2 *>(&B.e_Z[18 * (size_t)er]);
-        const double2 *zc = reinterpret_cast<const double2 *>(&B.e_Z[18 * (size_t)ec]);
+        for (int i = 0; i < 9; i++) { const double2 q = pr[i]; zr[2 * i] = q.x; zr[2 * i + 1] = q.y; }
 #pragma unroll
-        for (int i = 0; i < 9; i++) { const double2 a = zr[i]; Zr[2 * i] = a.x; Zr[2 * i + 1] = a.y; }
-#pragma unroll
-        for (int i = 0; i < 9; i++) { const double2 a = zc[i]; Zc[2 * i] = a.x; Zc[2 * i + 1] = a.y; }
+        for (int i = 0; i < 9; i++) { const double2 q = pc[i]; zc[2 * i] = q.x; zc[2 * i + 1] = q.y; }
 #pragma unroll
         for (int a = 0; a < 6; a++)
 #pragma unroll
-            for (int c = 0; c < 6; c++) acc[6 * a + c] += Zr[3 * a] * Zc[3 * c] + Zr[3 * a + 1] * Zc[3 * c + 1] + Zr[3 * a + 2] * Zc[3 * c + 2];
+            for (int c = 0; c < 6; c++) v[6 * a + c] = zr[3 * a] * zc[3 * c] + zr[3 * a + 1] * zc[3 * c + 1] + zr[3 * a + 2] * zc[3 * c + 2];
         if (diag) {
             if (er == ec) {
                 const double *g = &B.ptg[3 * (size_t)B.e_point[er]];
                 const double g0 = g[0], g1 = g[1], g2 = g[2];
 #pragma unroll
-                for (int a = 0; a < 6; a++) ab[a] += Zr[3 * a] * g0 + Zr[3 * a + 1] * g1 + Zr[3 * a + 2] * g2;
+                for (int a = 0; a < 6; a++) v[36 + a] = zr[3 * a] * g0 + zr[3 * a + 1] * g1 + zr[3 * a + 2] * g2;
             } else {
                 // two observations of one point by the same keyframe (never produced by ORB-SLAM, legal for g2o): both cross terms
 #pragma unroll
                 for (int a = 0; a < 6; a++)
 #pragma unroll
-                    for (int c = 0; c < 6; c++) acc[6 * a + c] += Zc[3 * a] * Zr[3 * c] + Zc[3 * a + 1] * Zr[3 * c + 1] + Zc[3 * a + 2] * Zr[3 * c + 2];
+                    for (int c = a + 1; c < 6; c++) { const double sm = v[6 * a + c] + v[6 * c + a]; v[6 * a + c] = sm; v[6 * c + a] = sm; }
+#pragma unroll
+                for (int a = 0; a < 6; a++) v[7 * a] *= 2.0;
             }
         }
     }
+    // fold 32 lanes x 42 values: after the five steps a lane holds (at most) two fully summed values
+    mv_fold<42>(v, 16, lane); mv_fold<21>(v, 8, lane); mv_fold<11>(v, 4, lane); mv_fold<6>(v, 2, lane); mv_fold<3>(v, 1, lane);
 #pragma unroll
-    for (int i = 0; i < 36; i++) acc[i] = warp_sum(acc[i]);
-    // lane q owns entry (q / 6, q % 6) of the block, lanes 0..3 also entries 32..35
-    double mine = 0, mine2 = 0;
-#pragma unroll
-    for (int i = 0; i < 32; i++) if (lane == i) mine = acc[i];
-#pragma unroll
-    for (int i = 32; i < 36; i++) if (lane + 32 == i) mine2 = acc[i];
+    for (int f = 0; f < 2; f++) {
+        int i4 = f + ((lane & 1) ? 2 : 0); bool ok = i4 < 3;
+        int i3 = i4 + ((lane & 2) ? 3 : 0); ok = ok && i3 < 6;
+        int i2 = i3 + ((lane & 4) ? 6 : 0); ok = ok && i2 < 11;
+        int i1 = i2 + ((lane & 8) ? 11 : 0); ok = ok && i1 < 21;
+        int i0 = i1 + ((lane & 16) ? 21 : 0); ok = ok && i0 < 42;
+        if (ok) s_part[warp][i0] = v[f];
+    }
+    __syncthreads();
+    if (tid < kSchurVals) item_part[(size_t)item * kSchurVals + tid] = ((s_part[0][tid] + s_part[1][tid]) + s_part[2][tid]) + s_part[3][tid];
+}
+
+__global__ void __launch_bounds__(256)
+k_ba_schur_finish(const BaDev B, const int *__restrict__ seg_item0, const double *__restrict__ item_part)
+{
+    if (B.ctl->state == LM_DONE) return;
+    const int seg = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (seg >= *B.n_seg) return;
+    const unsigned tgt = (unsigned)(B.pair_key[B.seg_start[seg]] >> 32);
+    const int slot = tgt >> 7, blk = tgt & 127, br = blk / kPosesPerTile, bc = blk % kPosesPerTile;
+    const bool diag = slot < B.nt && br == bc;
+    double m1 = 0, m2 = 0;                                     // entries lane and lane + 32 (< 42)
+    for (int it = seg_item0[seg]; it < seg_item0[seg + 1]; it++) {
+        m1 += item_part[(size_t)it * kSchurVals + lane];
+        if (lane < kSchurVals - 32) m2 += item_part[(size_t)it * kSchurVals + 32 + lane];
+    }
     double *Ab = B.A + (size_t)slot * TS2 + (6 * br) * TS + 6 * bc;
     double h1 = 0, h2 = 0;
     if (diag) {
         const int ip = B.tile_pose[slot * kPosesPerTile + br];
         h1 = B.Hpp[36 * (size_t)ip + lane];
         if (lane < 4) h2 = B.Hpp[36 * (size_t)ip + 32 + lane];
-#pragma unroll
-        for (int i = 0; i < 6; i++) ab[i] = warp_sum(ab[i]);
-        double bmine = 0;
-#pragma unroll
-        for (int i = 0; i < 6; i++) if (lane == i) bmine = ab[i];
-        if (lane < 6) B.bs[slot * TS + 6 * br + lane] += B.bp[6 * ip + lane] - bmine;
+        if (lane >= 4 && lane < 10) B.bs[slot * TS + 6 * br + lane - 4] += B.bp[6 * ip + lane - 4] - m2;
     }
-    Ab[(lane / 6) * TS + lane % 6] += h1 - mine;
-    if (lane < 4) Ab[((32 + lane) / 6) * TS + (32 + lane) % 6] += h2 - mine2;
+    Ab[(lane / 6) * TS + lane % 6] += h1 - m1;
+    if (lane < 4) Ab[((32 + lane) / 6) * TS + (32 + lane) % 6] += h2 - m2;
+}
+
+// work items per segment (k_ba_schur_items)
+__global__ void __launch_bounds__(256)
+k_ba_seg_items(const int *__restrict__ seg_start, const int *__restrict__ n_seg, int *__restrict__ cnt, int n)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    cnt[s] = s < *n_seg ? (seg_start[s + 1] - seg_start[s] + kItemPairs - 1) / kItemPairs : 0;
 }
 
 // copy-free view of the pose solution: x lives in tile-permuted rows (B.x = solver output); pose part of computeScale

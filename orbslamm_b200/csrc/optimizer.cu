@@ -66,6 +66,7 @@ struct orbo_handle {
     DevBuf ba_sys;           // reduced system: [A tiles | rhs] (contiguous: the one all-reduce of the sharded solve), L, Linv, y, x
     DevBuf ba_flags;         // dataflow epoch flags + ticket counters of k_rs_solve
     DevBuf ba_cub;           // cub temp storage (pair sort, scans)
+    DevBuf ba_items;         // per-work-item partial blocks of the Schur assembly
     PinnedBuf h_scalars;     // LmCtl copies + the mirrored stop flag
     static constexpr int kCtlCopies = 4;
     cudaEvent_t slot_done[kCtlCopies] = {nullptr, nullptr, nullptr, nullptr};
@@ -107,7 +108,7 @@ int orbo_destroy(orbo_handle *h)
     if (h->stream && h->own_stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
     else cudaDeviceSynchronize();
     if (h->comm) { if (g_nccl.CommAbort) g_nccl.CommAbort(h->comm); else g_nccl.CommDestroy(h->comm); }   // abort: never block on a peer at teardown
-    h->pool.release(); h->ba_pool.release(); h->ba_tasks.release(); h->ba_sys.release(); h->ba_flags.release(); h->ba_cub.release();
+    h->pool.release(); h->ba_pool.release(); h->ba_tasks.release(); h->ba_sys.release(); h->ba_flags.release(); h->ba_cub.release(); h->ba_items.release();
     h->h_scalars.release(); h->timer.release();
     for (auto &ev : h->slot_done) if (ev) cudaEventDestroy(ev);
     delete h;
@@ -327,7 +328,7 @@ struct BaRun {
     LmCtl *h_ctl = nullptr;                // pinned [kCtlCopies]
     double *diag6 = nullptr;               // [6 nA | nranks] first-iteration diagonal exchange
     int err_blocks = 0, pt_blocks = 0, diag_blocks = 0, xp_blocks = 0, upd_blocks = 0;
-    int solve_ctas = 0, n_seg = 0;
+    int solve_ctas = 0, n_seg = 0, n_items = 0;
     std::vector<int> pose_idx;
     const uint8_t *fixed = nullptr;
     // device scratch that build_structure needs
@@ -407,17 +408,19 @@ struct BaRun {
         // reduced-system storage depends on ns: [A | bs] contiguous (one all-reduce), L, Linv, b/y/x vectors, flags
         {
             const size_t nA_t = (size_t)plan.ns * TS2, nv = (size_t)ng * TS;
-            if (int rc = h->ba_sys.reserve((2 * nA_t + (size_t)ng * TS2 + 3 * nv + 16) * sizeof(double))) return rc;
+            if (int rc = h->ba_sys.reserve((2 * nA_t + (size_t)ng * TS2 + 3 * nv + (size_t)plan.n_part * TS2 + 16) * sizeof(double))) return rc;
             double *base = h->ba_sys.as<double>();
             B.A = base; B.bs = base + nA_t;
             rsbuf.A = B.A; rsbuf.b = B.bs; rsbuf.L = B.bs + nv; rsbuf.Linv = rsbuf.L + nA_t; rsbuf.y = rsbuf.Linv + (size_t)ng * TS2; rsbuf.x = rsbuf.y + nv;
+            rsbuf.part = rsbuf.x + nv;
             B.x = rsbuf.x;
-            const size_t nflags = (size_t)plan.ns + 2 * (size_t)ng + 8;
+            const size_t nflags = (size_t)plan.ns + 2 * (size_t)ng + (size_t)plan.n_part + 8;
             const bool fresh = nflags * sizeof(int) > h->ba_flags.bytes;
             if (int rc = h->ba_flags.reserve(nflags * sizeof(int))) return rc;
             if (fresh) { ORBS_CUDA(cudaMemsetAsync(h->ba_flags.p, 0, h->ba_flags.bytes, st)); }
             int *f = h->ba_flags.as<int>();
             rsbuf.counters = f; rsbuf.flags = f + 4; rsbuf.done_slot = f + 8; rsbuf.done_y = rsbuf.done_slot + plan.ns; rsbuf.done_x = rsbuf.done_y + ng;
+            rsbuf.done_part = rsbuf.done_x + ng;
             B.flags = rsbuf.flags;
             ORBS_CUDA(cudaMemsetAsync(f, 0, 8 * sizeof(int), st));
         }
@@ -448,6 +451,16 @@ struct BaRun {
         ORBS_CUDA(cudaMemcpyAsync(&n_seg, d_nseg, sizeof(int), cudaMemcpyDeviceToHost, st));
         ORBS_CUDA(cudaStreamSynchronize(st));
         B.pair_key = d_key[1]; B.pair_val = d_val[1]; B.seg_start = d_seg_start; B.n_seg = d_nseg;
+        // work items of the Schur assembly: segments cut into pieces of kItemPairs pairs (d_head / d_scan are free again)
+        n_items = 0;
+        if (n_seg > 0) {
+            k_ba_seg_items<<<(n_seg + 256) / 256, 256, 0, st>>>(d_seg_start, d_nseg, d_head, n_seg + 1);
+            cub::DeviceScan::ExclusiveSum(d_cub, cub_bytes, d_head, d_scan, n_seg + 1, st);
+            count(2);
+            ORBS_CUDA(cudaMemcpyAsync(&n_items, d_scan + n_seg, sizeof(int), cudaMemcpyDeviceToHost, st));
+            ORBS_CUDA(cudaStreamSynchronize(st));
+            if (int rc = h->ba_items.reserve((size_t)std::max(n_items, 1) * kSchurVals * sizeof(double))) return rc;
+        }
         return ORBS_OK;
     }
 
@@ -484,9 +497,12 @@ struct BaRun {
             T().begin(BK_SCHUR, st);
             ORBS_CUDA(cudaMemsetAsync(B.A, 0, ((size_t)B.ns * TS2 + (size_t)B.nt * TS) * sizeof(double), st));
             k_ba_diag_init<<<(B.nt * TS + 255) / 256, 256, 0, st>>>(B);
-            if (n_seg > 0) k_ba_schur_seg<<<(n_seg + 7) / 8, 256, 0, st>>>(B);
+            if (n_items > 0) {
+                k_ba_schur_items<<<n_items, 128, 0, st>>>(B, d_scan, h->ba_items.as<double>());
+                k_ba_schur_finish<<<(n_seg + 7) / 8, 256, 0, st>>>(B, d_scan, h->ba_items.as<double>());
+            }
             T().end(st);
-            count(2);
+            count(3);
             // the one exchange step of the sharded solve: the structurally nonzero tiles of the reduced system and its right-hand side, summed over the map-point shards
             if (int rc = allreduce(B.A, (size_t)B.ns * TS2 + (size_t)B.nt * TS, ncclDouble, ncclSum)) return rc;
             T().begin(BK_SOLVE, st);
@@ -694,6 +710,25 @@ extern "C" int orbo_bundle_adjust(orbo_handle *h, int K, float *poses, const uin
         if (changed && (rc = D.build_structure())) return rc;
         if ((rc = D.optimize(its1, any == 1, &fin))) return rc;
     }
+    if (const char *tp = getenv("ORBS_RS_TRACE")) {
+        // profiling aid: one more solve of the last system with per-task timestamps, dumped as text (task type i j ndep t_start t_deps t_end sm)
+        const int ntk = D.rsplan.ntasks;
+        long long *d_tr = nullptr;
+        if (ntk > 0 && cudaMalloc(&d_tr, (size_t)ntk * 4 * sizeof(long long)) == cudaSuccess) {
+            cudaMemsetAsync(d_tr, 0, (size_t)ntk * 4 * sizeof(long long), st);
+            RsBuf rb = D.rsbuf; rb.trace = d_tr;
+            k_rs_solve<<<D.solve_ctas, 256, kRsSmemBytes, st>>>(D.rsplan, rb, nullptr, ++h->rs_epoch);
+            std::vector<long long> tr((size_t)ntk * 4);
+            cudaMemcpyAsync(tr.data(), d_tr, tr.size() * sizeof(long long), cudaMemcpyDeviceToHost, st);
+            cudaStreamSynchronize(st);
+            cudaFree(d_tr);
+            if (FILE *f = fopen(tp, "w")) {
+                for (int t = 0; t < ntk; t++) { const RsTask &k = D.plan.tasks[t]; fprintf(f, "%d %d %d %d %d %lld %lld %lld %lld\n", t, k.type, k.i, k.j, k.ndep, tr[4 * t], tr[4 * t + 1], tr[4 * t + 2], tr[4 * t + 3]); }
+                fclose(f);
+            }
+        }
+    }
+    const auto t_loop_end = std::chrono::steady_clock::now();          // optimize() returned after a stream synchronisation
     k_ba_edge_check<<<(E + 255) / 256, 256, 0, st>>>(B, d_chi2, d_depth, 0);
     k_ba_export_poses<<<(K + 255) / 256, 256, 0, st>>>(K, B.pose, d_fixed, d_Tout);
     k_ba_export_points<<<(3 * P + 255) / 256, 256, 0, st>>>(P, B.pt, d_pts_out);
@@ -706,7 +741,6 @@ extern "C" int orbo_bundle_adjust(orbo_handle *h, int K, float *poses, const uin
     ORBS_CUDA(cudaMemcpyAsync(poses, d_Tout, (size_t)K * 16 * sizeof(float), cudaMemcpyDeviceToHost, st));
     ORBS_CUDA(cudaMemcpyAsync(points, d_pts_out, 3 * (size_t)P * sizeof(float), cudaMemcpyDeviceToHost, st));
     ORBS_CUDA(cudaStreamSynchronize(st));
-    const auto t_loop_end = std::chrono::steady_clock::now();
     if (want_edges)
         for (int j = 0; j < E; j++) {                                                         // Optimizer.cc:734-766
             const int e = order[j];
@@ -896,16 +930,17 @@ extern "C" int orbo_optimize_pose_graph(orbo_handle *h, int K, double *sim3, con
     P.eJ = G.alloc<double>((size_t)98 * E, &rc);
     // one buffer: H | A | L | Linv | b | y | x | partial | scalars, then the dataflow flags
     const size_t nT = (size_t)ns * TS2;
-    double *big = G.alloc<double>(3 * nT + (size_t)nt * TS2 + 3 * (size_t)ld + G.eblocks + 8, &rc);
-    int *flg = G.alloc<int>((size_t)ns + 2 * (size_t)nt + 8, &rc);
+    double *big = G.alloc<double>(3 * nT + (size_t)nt * TS2 + 3 * (size_t)ld + G.eblocks + 12 + (size_t)G.plan.n_part * TS2, &rc);
+    const size_t n_flg = (size_t)ns + 2 * (size_t)nt + (size_t)G.plan.n_part + 8;
+    int *flg = G.alloc<int>(n_flg, &rc);
     if (rc) return rc;
     P.H = big; P.A = big + nT; G.rsbuf.L = P.A + nT; G.rsbuf.Linv = G.rsbuf.L + nT; P.b = G.rsbuf.Linv + (size_t)nt * TS2;
-    G.rsbuf.y = P.b + ld; P.x = G.rsbuf.y + ld; P.partial = P.x + ld; P.scalars = P.partial + G.eblocks;
+    G.rsbuf.y = P.b + ld; P.x = G.rsbuf.y + ld; P.partial = P.x + ld; P.scalars = P.partial + G.eblocks; G.rsbuf.part = big + ((3 * nT + (size_t)nt * TS2 + 3 * (size_t)ld + G.eblocks + 8 + 1) & ~(size_t)1);   // 16-byte aligned (double2 accesses)
     G.rsbuf.A = P.A; G.rsbuf.b = P.b; G.rsbuf.x = P.x;
-    G.rsbuf.counters = flg; G.rsbuf.flags = flg + 4; G.rsbuf.done_slot = flg + 8; G.rsbuf.done_y = G.rsbuf.done_slot + ns; G.rsbuf.done_x = G.rsbuf.done_y + nt;
+    G.rsbuf.counters = flg; G.rsbuf.flags = flg + 4; G.rsbuf.done_slot = flg + 8; G.rsbuf.done_y = G.rsbuf.done_slot + ns; G.rsbuf.done_x = G.rsbuf.done_y + nt; G.rsbuf.done_part = G.rsbuf.done_x + nt;
     P.hidx = d_hidx; P.e_i = d_ei; P.e_j = d_ej; P.meas = d_meas;
     cudaStream_t st = h->stream;
-    ORBS_CUDA(cudaMemsetAsync(flg, 0, ((size_t)ns + 2 * (size_t)nt + 8) * sizeof(int), st));
+    ORBS_CUDA(cudaMemsetAsync(flg, 0, n_flg * sizeof(int), st));
     ORBS_CUDA(cudaMemcpyAsync(P.verts, sim3, sizeof(Sim3) * K, cudaMemcpyHostToDevice, st));
     ORBS_CUDA(cudaMemcpyAsync(d_hidx, hidx.data(), sizeof(int) * K, cudaMemcpyHostToDevice, st));
     ORBS_CUDA(cudaMemcpyAsync(d_ei, e_i, sizeof(int) * E, cudaMemcpyHostToDevice, st));

@@ -37,10 +37,12 @@ struct LmCtl {
     int iteration, max_iterations, qmax, nbad, first;
     int lm_iterations, lm_trials, chol_failures;
     int last_rejected;         // the trial just decided was rejected: k_*_restore pops the estimate
-    int pad[2];
+    int fresh_first;           // the current slot linearised before lambda was known (first iteration)
+    int pad[1];
 };
 
-struct RsTask { int type, i, j, slot, dep0, ndep, diag, pad; };   // type 0: factor tile (i, j); 1: forward row i; 2: backward row j
+struct RsTask { int type, i, j, slot, dep0, ndep, diag, part0, npart, pad0, pad1, pad2; };
+// type 0: factor tile (i, j); 1: forward row i; 2: backward row j; 3: partial update sum of a chunk of a tile's dependencies (slot = partial tile)
 
 struct RsPlan {
     const RsTask *tasks; int ntasks;
@@ -55,9 +57,11 @@ struct RsBuf {
     const double *b;           // [nt*64] right-hand side
     double *y;                 // [nt*64] forward solution
     double *x;                 // [nt*64] solution
-    int *done_slot, *done_y, *done_x;   // epoch flags
+    double *part;              // [npart][4096] partial update sums of tiles with many dependencies (helper tasks)
+    int *done_slot, *done_y, *done_x, *done_part;   // epoch flags
     int *counters;             // [0] ticket, [1] exited
     int *flags;                // [0] non-positive pivot (solve() == false)
+    long long *trace;          // optional [ntasks][4]: globaltimer at task start / dependencies done / end, SM id (profiling builds of the caller)
 };
 
 __device__ __forceinline__ void rs_cp16(void *smem, const void *gmem)
@@ -104,11 +108,16 @@ __device__ __forceinline__ void rs_gemm_nt(double (&acc)[8][2], const double *Ao
     }
 }
 
-// Cholesky of the 64x64 tile in T (pitch 65, lower part valid) and its inverse.  256 threads: 4 threads per row, 16 columns each.
-// Returns through Linv_out (global, row-major): inv(L).  T holds L (lower, zero above) afterwards.
-__device__ __forceinline__ void rs_factor_invert(double *T, double *colbuf /*[2][64]*/, double *invd /*[64]*/, double *Linv_out, int *flags, int tid)
+// Cholesky of the 64x64 tile in T (pitch 65, lower part valid) and the inverse of its factor.
+//   factor : right-looking, 256 threads = 4 threads per row holding 16 columns each in registers, one barrier per pivot
+//            (the 64 dependent pivots -- rsqrt, scale, update -- are the floor of this step: ~20 us; an fp32-seeded Newton rsqrt was
+//            no faster than the library sequence);
+//   inverse: blocked 8 x 8 on DMMA: the eight diagonal 8x8 blocks are inverted by one warp each (forward substitution), then the
+//            off-diagonal blocks by block distance d = 1..7, X[i][j] = -inv(D_i) sum_{k=j..i-1} L[i][k] X[k][j], one warp per block.
+// Lb / Xi: operand-pitch (68) buffers for L and inv(L); Sw: [8][64] per-warp scratch.  Linv_out (global, row-major 64x64) = inv(L).
+__device__ __forceinline__ void rs_factor_invert(double *T, double *Lb, double *Xi, double *Sw, double *colbuf, double *Linv_out, int *flags, int tid)
 {
-    const int r = tid >> 2, sub = tid & 3;
+    const int r = tid >> 2, sub = tid & 3, warp = tid >> 5, lane = tid & 31;
     double a[16];
 #pragma unroll
     for (int u = 0; u < 16; u++) a[u] = T[r * kFacPitch + 16 * sub + u];
@@ -133,32 +142,49 @@ __device__ __forceinline__ void rs_factor_invert(double *T, double *colbuf /*[2]
         }
     }
     if (bad && tid == 0) flags[0] = 1;
+#pragma unroll
+    for (int u = 0; u < 16; u++) { const int c = 16 * sub + u; Lb[r * kOpPitch + c] = c <= r ? a[u] : 0.0; Xi[r * kOpPitch + c] = 0.0; }
     __syncthreads();
+    // ---- inverse, phase 1: warp w inverts diagonal block w; lane c < 8 solves column c of inv(D) by forward substitution
+    {
+        const double *D = Lb + (8 * warp) * kOpPitch + 8 * warp;
+        const int c = lane & 7;
+        double x[8];
 #pragma unroll
-    for (int u = 0; u < 16; u++) { const int c = 16 * sub + u; T[r * kFacPitch + c] = c <= r ? a[u] : 0.0; }
-    __syncthreads();
-    if (tid < TS) invd[tid] = 1.0 / T[tid * kFacPitch + tid];
-    __syncthreads();
-    // X L^T = I row by row: the 4 threads of row r own x_q with q % 4 == sub; X = L^-T, stored transposed = L^-1
-    const unsigned full = 0xffffffffu;
-    double xo[16];
+        for (int q = 0; q < 8; q++) {
+            double sacc = (q == c) ? 1.0 : 0.0;
 #pragma unroll
-    for (int m = 0; m < 16; m++) { const int q = 4 * m + sub; xo[m] = (q == r) ? 1.0 : 0.0; }
-#pragma unroll
-    for (int c = 0; c < TS; c++) {
-        double p0 = 0.0, p1 = 0.0;
-#pragma unroll
-        for (int m = 0; m < c / 4; m++) {
-            if (m & 1) p1 = fma(xo[m], T[c * kFacPitch + 4 * m + sub], p1); else p0 = fma(xo[m], T[c * kFacPitch + 4 * m + sub], p0);
+            for (int p2 = 0; p2 < q; p2++) sacc = fma(-D[q * kOpPitch + p2], x[p2], sacc);
+            x[q] = (q >= c) ? sacc / D[q * kOpPitch + q] : 0.0;
         }
-        if (sub < (c & 3)) p0 = fma(xo[c / 4], T[c * kFacPitch + 4 * (c / 4) + sub], p0);
-        double p = p0 + p1;
-        p += __shfl_xor_sync(full, p, 1);
-        p += __shfl_xor_sync(full, p, 2);
-        if (sub == (c & 3)) xo[c / 4] = (xo[c / 4] - p) * invd[c];
-    }
+        if (lane < 8) {
 #pragma unroll
-    for (int m = 0; m < 16; m++) Linv_out[(size_t)(4 * m + sub) * TS + r] = xo[m];          // L^-1[c][r] = X[r][c]
+            for (int q = 0; q < 8; q++) Xi[(8 * warp + q) * kOpPitch + 8 * warp + c] = x[q];
+        }
+    }
+    __syncthreads();
+    // ---- phase 2: off-diagonal blocks by distance
+    const int fr = lane >> 2, fk = lane & 3;
+    double *S = Sw + warp * 64;
+    for (int dist = 1; dist < 8; dist++) {
+        const int j = warp, i = warp + dist;
+        if (i < 8) {
+            double c0 = 0.0, c1 = 0.0;
+            for (int k = j; k < i; k++) {
+#pragma unroll
+                for (int k0 = 0; k0 < 8; k0 += 4)
+                    dmma884(c0, c1, Lb[(8 * i + fr) * kOpPitch + 8 * k + k0 + fk], Xi[(8 * k + k0 + fk) * kOpPitch + 8 * j + fr]);
+            }
+            S[fr * 8 + 2 * fk] = c0; S[fr * 8 + 2 * fk + 1] = c1;
+            __syncwarp();
+            double e0 = 0.0, e1 = 0.0;
+#pragma unroll
+            for (int k0 = 0; k0 < 8; k0 += 4) dmma884(e0, e1, Xi[(8 * i + fr) * kOpPitch + 8 * i + k0 + fk], S[(k0 + fk) * 8 + fr]);
+            Xi[(8 * i + fr) * kOpPitch + 8 * j + 2 * fk] = -e0; Xi[(8 * i + fr) * kOpPitch + 8 * j + 2 * fk + 1] = -e1;
+        }
+        __syncthreads();
+    }
+    for (int q = tid; q < TS * TS; q += 256) Linv_out[q] = Xi[(q >> 6) * kOpPitch + (q & 63)];
 }
 
 __global__ void __launch_bounds__(256, 1)
@@ -169,7 +195,7 @@ k_rs_solve(const RsPlan P, const RsBuf B, const LmCtl *__restrict__ ctl, int epo
     double *opA[2] = {rs_smem, rs_smem + 2 * TS * kOpPitch};
     double *opB[2] = {rs_smem + TS * kOpPitch, rs_smem + 3 * TS * kOpPitch};
     __shared__ int s_task, s_pref;
-    __shared__ double s_col[2 * TS], s_invd[TS], s_vec[TS], s_red[4 * TS];
+    __shared__ double s_vec[TS], s_red[4 * TS], s_col[2 * TS];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int fr = lane >> 2, fk = lane & 3;
 
@@ -180,13 +206,26 @@ k_rs_solve(const RsPlan P, const RsBuf B, const LmCtl *__restrict__ ctl, int epo
         const int t = s_task;
         if (t >= P.ntasks) break;
         const RsTask task = P.tasks[t];
-        if (task.type == 0) {
-            // ---- factor tile (i, j): acc = A_ij - sum_k L_ik L_jk^T
+        if (B.trace && tid == 0) { long long g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g)); B.trace[4 * t] = g; unsigned sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm)); B.trace[4 * t + 3] = sm; }
+        if (task.type == 0 || task.type == 3) {
+            // ---- factor tile (i, j): acc = A_ij - sum_k L_ik L_jk^T; tiles with many dependencies get their sum from helper tasks
+            // (type 3: partial sums of a chunk of the dependencies into a scratch tile), subtracted here in fixed order
+            const bool helper = task.type == 3;
             double acc[8][2];
-            {
+            if (helper) {
+#pragma unroll
+                for (int nb = 0; nb < 8; nb++) acc[nb][0] = acc[nb][1] = 0.0;
+            } else {
                 const double *At = B.A + (size_t)task.slot * TS2 + (8 * warp + fr) * TS + 2 * fk;
 #pragma unroll
                 for (int nb = 0; nb < 8; nb++) { const double2 v = __ldcg(reinterpret_cast<const double2 *>(At + 8 * nb)); acc[nb][0] = v.x; acc[nb][1] = v.y; }
+                for (int pp = 0; pp < task.npart; pp++) {
+                    if (tid == 0) { while (rs_ld_acquire(&B.done_part[task.part0 + pp]) != epoch) { } }
+                    __syncthreads();
+                    const double *Pt = B.part + (size_t)(task.part0 + pp) * TS2 + (8 * warp + fr) * TS + 2 * fk;
+#pragma unroll
+                    for (int nb = 0; nb < 8; nb++) { const double2 v = __ldcg(reinterpret_cast<const double2 *>(Pt + 8 * nb)); acc[nb][0] -= v.x; acc[nb][1] -= v.y; }
+                }
             }
             const bool diag = task.i == task.j;
             int staged = -1;                                   // dependency already in flight into buffer (staged & 1)
@@ -214,15 +253,27 @@ k_rs_solve(const RsPlan P, const RsBuf B, const LmCtl *__restrict__ ctl, int epo
                         staged = d + 1;
                     }
                 }
-                rs_gemm_nt<true>(acc, opA[buf], diag ? opA[buf] : opB[buf], warp, lane);
+                if (helper) rs_gemm_nt<false>(acc, opA[buf], diag ? opA[buf] : opB[buf], warp, lane);
+                else rs_gemm_nt<true>(acc, opA[buf], diag ? opA[buf] : opB[buf], warp, lane);
             }
             __syncthreads();
+            if (helper) {
+                double *Pt = B.part + (size_t)task.slot * TS2 + (8 * warp + fr) * TS + 2 * fk;
+#pragma unroll
+                for (int nb = 0; nb < 8; nb++) *reinterpret_cast<double2 *>(Pt + 8 * nb) = make_double2(acc[nb][0], acc[nb][1]);
+                __threadfence();
+                __syncthreads();
+                if (tid == 0) rs_st_release(&B.done_part[task.slot], epoch);
+                if (B.trace && tid == 0) { long long g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g)); B.trace[4 * t + 1] = g; B.trace[4 * t + 2] = g; }
+                continue;
+            }
+            if (B.trace && tid == 0) { long long g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g)); B.trace[4 * t + 1] = g; }
             if (diag) {
                 double *T = rs_smem;                                           // pitch 65 view of the operand area
 #pragma unroll
                 for (int nb = 0; nb < 8; nb++) { double *p = &T[(8 * warp + fr) * kFacPitch + 8 * nb + 2 * fk]; p[0] = acc[nb][0]; p[1] = acc[nb][1]; }
                 __syncthreads();
-                rs_factor_invert(T, s_col, s_invd, B.Linv + (size_t)task.i * TS2, B.flags, tid);
+                rs_factor_invert(T, rs_smem + TS * kFacPitch, rs_smem + TS * kFacPitch + TS * kOpPitch, rs_smem + TS * kFacPitch + 2 * TS * kOpPitch, s_col, B.Linv + (size_t)task.i * TS2, B.flags, tid);
             } else {
                 // L_ij = acc * inv(L_jj)^T
 #pragma unroll
@@ -305,6 +356,7 @@ k_rs_solve(const RsPlan P, const RsBuf B, const LmCtl *__restrict__ ctl, int epo
             __syncthreads();
             if (tid == 0) rs_st_release(&B.done_x[task.j], epoch);
         }
+        if (B.trace && tid == 0) { long long g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g)); B.trace[4 * t + 2] = g; }
     }
     if (tid == 0) {
         __threadfence();
@@ -316,7 +368,8 @@ k_rs_solve(const RsPlan P, const RsBuf B, const LmCtl *__restrict__ ctl, int epo
 // ---------------------------------------------------------------------------------------------------------
 // Host side: elimination order, symbolic factorisation, slots and the task list.
 struct TilePlanHost {
-    int nt = 0, ns = 0, nlevels = 0;
+    static constexpr int kChunk = 2, kMaxPart = 4096;      // helper tasks: dependencies per chunk, cap on scratch tiles (128 MB)
+    int nt = 0, ns = 0, nlevels = 0, n_part = 0;
     std::vector<int> pos;            // group -> tile row in elimination order
     std::vector<int> slot_of;        // [nt*nt] slot of tile (i, j), i >= j, or -1
     std::vector<int2> slot_tile;     // [ns] (i, j)
@@ -328,7 +381,7 @@ struct TilePlanHost {
     static void nd_order(const std::vector<uint8_t> &adj, int ng, int lo, int hi, std::vector<int> &out)
     {
         const int n = hi - lo;
-        if (n <= 3) { for (int g = lo; g < hi; g++) out.push_back(g); return; }
+        if (n <= 2) { for (int g = lo; g < hi; g++) out.push_back(g); return; }     // (three in natural order are a chain of three; middle-last is two levels)
         const int mid = lo + n / 2;
         int reach = mid - 1;
         for (int g = lo; g < mid; g++)
@@ -375,10 +428,21 @@ struct TilePlanHost {
         std::vector<int> by_level(nt);
         for (int k = 0; k < nt; k++) by_level[k] = k;
         std::stable_sort(by_level.begin(), by_level.end(), [&](int a, int b) { return level[a] < level[b]; });
+        n_part = 0;
         auto factor_task = [&](int i, int j) {
             RsTask t = {}; t.type = 0; t.i = i; t.j = j; t.slot = slot_of[(size_t)i * nt + j]; t.diag = j; t.dep0 = (int)deps.size();
             for (int k : cols[j]) if (pat[(size_t)i * nt + k] || i == j) deps.push_back(make_int2(slot_of[(size_t)i * nt + k], slot_of[(size_t)j * nt + k]));
             t.ndep = (int)deps.size() - t.dep0;
+            // a tile with many dependencies would serialise ~2 us GEMMs in one CTA (the root separator of the elimination tree): hand
+            // chunks of kChunk dependencies to helper tasks on other SMs, the owner subtracts their partial sums in chunk order
+            if (t.ndep > kChunk && n_part + (t.ndep + kChunk - 1) / kChunk <= kMaxPart) {
+                t.part0 = n_part;
+                for (int d0 = 0; d0 < t.ndep; d0 += kChunk) {
+                    RsTask hlp = {}; hlp.type = 3; hlp.i = i; hlp.j = j; hlp.slot = n_part++; hlp.diag = j; hlp.dep0 = t.dep0 + d0; hlp.ndep = std::min(kChunk, t.ndep - d0);
+                    tasks.push_back(hlp);
+                }
+                t.npart = n_part - t.part0; t.ndep = 0;
+            }
             tasks.push_back(t);
         };
         {   // per level: the diagonal tasks of its columns, then their panels
