@@ -109,9 +109,7 @@ __device__ __forceinline__ void rs_gemm_nt(double (&acc)[8][2], const double *Ao
 }
 
 // Cholesky of the 64x64 tile in T (pitch 65, lower part valid) and the inverse of its factor.
-//   factor : right-looking, 256 threads = 4 threads per row holding 16 columns each in registers, one barrier per pivot
-//            (the 64 dependent pivots -- rsqrt, scale, update -- are the floor of this step: ~20 us; an fp32-seeded Newton rsqrt was
-//            no faster than the library sequence);
+//   factor : right-looking, 256 threads = 4 threads per row holding 16 columns each in registers, one barrier per pivot;
 //   inverse: blocked 8 x 8 on DMMA: the eight diagonal 8x8 blocks are inverted by one warp each (forward substitution), then the
 //            off-diagonal blocks by block distance d = 1..7, X[i][j] = -inv(D_i) sum_{k=j..i-1} L[i][k] X[k][j], one warp per block.
 // Lb / Xi: operand-pitch (68) buffers for L and inv(L); Sw: [8][64] per-warp scratch.  Linv_out (global, row-major 64x64) = inv(L).
@@ -121,23 +119,28 @@ __device__ __forceinline__ void rs_factor_invert(double *T, double *Lb, double *
     double a[16];
 #pragma unroll
     for (int u = 0; u < 16; u++) a[u] = T[r * kFacPitch + 16 * sub + u];
+    // 64 dependent pivots.  The loop is unrolled by 16 only (the column a thread publishes must be a compile-time register index): fully
+    // unrolled, the 64 distinct step bodies are ~100 KB of straight-line SASS executed once each -- instruction-fetch bound.
     bool bad = false;
+#pragma unroll 1
+    for (int js = 0; js < 4; js++) {
 #pragma unroll
-    for (int j = 0; j < TS; j++) {
-        const int js = j >> 4, ju = j & 15;
-        if (sub == js && r >= j) colbuf[(j & 1) * TS + r] = a[ju];
-        __syncthreads();
-        double d = colbuf[(j & 1) * TS + j];
-        if (!(d > 0.0)) { bad = true; d = 1.0; }
-        const double rinv = rsqrt(d), sd = d * rinv;
-        if (r >= j) {
-            const double l = (r == j) ? sd : colbuf[(j & 1) * TS + r] * rinv;
-            if (sub == js) a[ju] = l;
-            const double lr = l * rinv;
+        for (int ju = 0; ju < 16; ju++) {
+            const int j = 16 * js + ju;
+            if (sub == js && r >= j) colbuf[(j & 1) * TS + r] = a[ju];
+            __syncthreads();
+            double d = colbuf[(j & 1) * TS + j];
+            if (!(d > 0.0)) { bad = true; d = 1.0; }
+            const double rinv = rsqrt(d), sd = d * rinv;
+            if (r >= j) {
+                const double l = (r == j) ? sd : colbuf[(j & 1) * TS + r] * rinv;
+                if (sub == js) a[ju] = l;
+                const double lr = l * rinv;
 #pragma unroll
-            for (int u = 0; u < 16; u++) {
-                const int c = 16 * sub + u;
-                if (c > j && c <= r) a[u] = fma(-lr, colbuf[(j & 1) * TS + c], a[u]);
+                for (int u = 0; u < 16; u++) {
+                    const int c = 16 * sub + u;
+                    if (c > j && c <= r) a[u] = fma(-lr, colbuf[(j & 1) * TS + c], a[u]);
+                }
             }
         }
     }
