@@ -558,22 +558,15 @@ static double ba_active_robust_chi2(const ba_t *B)            /* sparse_optimize
     return chi;
 }
 
-/* buildSystem: linearizeOplus + constructQuadraticForm per active edge, block_solver.hpp:506-564 */
-static void ba_build_system(ba_t *B)
+/* linearizeOplus of one edge: Jp (2x6, pose) and Jl (2x3, point; untouched for pose-only edges) */
+static void ba_edge_jacobians(const ba_t *B, int e, double Jp[12], double Jl[6])
 {
-    memset(B->Hpp, 0, sizeof(double) * 36 * (B->nA > 0 ? B->nA : 1));
-    memset(B->bp, 0, sizeof(double) * 6 * (B->nA > 0 ? B->nA : 1));
-    if (B->nL) { memset(B->Hll, 0, sizeof(double) * 9 * B->nL); memset(B->bl, 0, sizeof(double) * 3 * B->nL); }
-    for (int i = 0; i < B->nAE; i++) {
-        const int e = B->act_edges[i];
         const int kf = B->e_kf[e], p = B->e_pt[e];
-        const int ip = B->pose_idx[kf], il = B->pt_fixed_all ? -1 : B->pt_idx[p];
         const double *in = &B->intr[4 * kf];
         const double fx = in[0], fy = in[1];
         double Xc[3];
         se3_map(&B->pose[kf], &B->pt[3 * p], Xc);
         const double x = Xc[0], y = Xc[1], z = Xc[2];
-        double Jp[12], Jl[6];   /* 2x6 pose, 2x3 point */
         if (B->pt_fixed_all) {                      /* EdgeSE3ProjectXYZOnlyPose::linearizeOplus, .cpp:266-288 */
             const double invz = 1.0 / z, invz_2 = invz * invz;
             Jp[0] = x * y * invz_2 * fx; Jp[1] = -(1 + (x * x * invz_2)) * fx; Jp[2] = y * invz * fx;
@@ -595,6 +588,20 @@ static void ba_build_system(ba_t *B)
             Jp[6] = (1 + y * y / z_2) * fy; Jp[7] = -x * y / z_2 * fy; Jp[8] = -x / z * fy;
             Jp[9] = 0; Jp[10] = -1. / z * fy; Jp[11] = y / z_2 * fy;
         }
+}
+
+/* buildSystem: linearizeOplus + constructQuadraticForm per active edge, block_solver.hpp:506-564 */
+static void ba_build_system(ba_t *B)
+{
+    memset(B->Hpp, 0, sizeof(double) * 36 * (B->nA > 0 ? B->nA : 1));
+    memset(B->bp, 0, sizeof(double) * 6 * (B->nA > 0 ? B->nA : 1));
+    if (B->nL) { memset(B->Hll, 0, sizeof(double) * 9 * B->nL); memset(B->bl, 0, sizeof(double) * 3 * B->nL); }
+    for (int i = 0; i < B->nAE; i++) {
+        const int e = B->act_edges[i];
+        const int kf = B->e_kf[e], p = B->e_pt[e];
+        const int ip = B->pose_idx[kf], il = B->pt_fixed_all ? -1 : B->pt_idx[p];
+        double Jp[12], Jl[6];   /* 2x6 pose, 2x3 point */
+        ba_edge_jacobians(B, e, Jp, Jl);
         /* constructQuadraticForm, base_binary_edge.hpp:55-120 / base_unary_edge.hpp:43-72 */
         double w = B->e_w[e], rw = 1.0;
         if (B->e_robust[e]) { double rho[3]; huber(B, ba_chi2(B, e), rho); rw = rho[1]; }
@@ -862,7 +869,7 @@ int oracle_pose_optimization(float *Tcw, int M, const float *Xw, const float *ob
     B.pt = pt; B.e_kf = ekf; B.e_pt = ept; B.e_obs = o; B.e_w = w; B.e_level = lvl; B.e_robust = rob; B.e_err = err;
     const float deltaMono = sqrtf(5.991f);                    /* const float deltaMono = sqrt(5.991) */
     B.delta = (double)(float)sqrt(5.991); (void)deltaMono;
-    B.dsqr = B.delta * B.delta;
+    B.dsqr = (double)(float)(B.delta * B.delta);          /* RobustKernelHuber keeps delta^2 in a FLOAT member (robust_kernel_impl.h:84, set by setDelta, robust_kernel_impl.cpp:65-69) */
     ba_alloc(&B);
     const float chi2Mono[4] = {5.991f, 5.991f, 5.991f, 5.991f};
     int nBad = 0;
@@ -911,7 +918,9 @@ int oracle_bundle_adjust(int K, float *poses, const uint8_t *fixed, const double
     for (int e = 0; e < E; e++) { o[2 * e] = e_uv[2 * e]; o[2 * e + 1] = e_uv[2 * e + 1]; w[e] = e_inv_sigma2[e]; rob[e] = (uint8_t)(two_stage ? 1 : robust); }
     B.pose = pose; B.pose_fixed = fx; B.intr = intr; B.pt = pt; B.e_kf = e_kf; B.e_pt = e_pt; B.e_obs = o; B.e_w = w;
     B.e_level = lvl; B.e_robust = rob; B.e_err = err;
-    B.delta = (double)(float)sqrt(5.991); B.dsqr = B.delta * B.delta;
+    /* LocalBundleAdjustment: const float thHuberMono = sqrt(5.991) (Optimizer.cc:592); BundleAdjustment: const float thHuber2D = sqrt(5.99) (:106) */
+    B.delta = two_stage ? (double)(float)sqrt(5.991) : (double)(float)sqrt(5.99);
+    B.dsqr = (double)(float)(B.delta * B.delta);   /* RobustKernelHuber keeps delta^2 in a FLOAT member (robust_kernel_impl.h:84, set by setDelta, robust_kernel_impl.cpp:65-69) */
     ba_alloc(&B);
     int do_more = 1;
     if (stop && *stop) {                                      /* :678-680: return before touching anything */
@@ -1148,19 +1157,36 @@ static double s3_active_errors(s3_t *B, const sim3 *S)             /* computeAct
 
 static int ldlt7(const double *H, const double *b, double lambda, double *x)    /* LinearSolverDense: Eigen LDLT + isPositive */
 {
-    double A[49];
+    /* Eigen::LDLT (Eigen/src/Cholesky/LDLT.h, unblocked): symmetric pivoting on the largest remaining |diagonal|, then the rank-1 update of the
+     * trailing block; isPositive() = no negative pivot; solve = P^T L^-T D^-1 L^-1 P b */
+    double A[49], L[49], D[7], y[7];
+    int perm[7];
     memcpy(A, H, sizeof A);
-    for (int i = 0; i < 7; i++) A[8 * i] += lambda;
-    for (int i = 0; i < 7; i++)
-        for (int j = 0; j <= i; j++) {
-            double s = A[7 * i + j];
-            for (int k = 0; k < j; k++) s -= A[7 * i + k] * A[7 * j + k] * A[8 * k];
-            if (j < i) A[7 * i + j] = s / A[8 * j];
-            else { if (!(s > 0.0)) return 0; A[8 * i] = s; }
+    for (int i = 0; i < 7; i++) for (int j = i + 1; j < 7; j++) A[7 * i + j] = A[7 * j + i];      /* only the lower triangle is referenced */
+    for (int i = 0; i < 7; i++) { A[8 * i] += lambda; perm[i] = i; }
+    for (int i = 0; i < 49; i++) L[i] = (i % 8 == 0) ? 1.0 : 0.0;
+    int positive = 1;
+    for (int k = 0; k < 7; k++) {
+        int p = k;
+        for (int i = k + 1; i < 7; i++) if (fabs(A[8 * i]) > fabs(A[8 * p])) p = i;
+        if (p != k) {
+            for (int j = 0; j < 7; j++) { const double t = A[7 * k + j]; A[7 * k + j] = A[7 * p + j]; A[7 * p + j] = t; }
+            for (int i = 0; i < 7; i++) { const double t = A[7 * i + k]; A[7 * i + k] = A[7 * i + p]; A[7 * i + p] = t; }
+            for (int j = 0; j < k; j++) { const double t = L[7 * k + j]; L[7 * k + j] = L[7 * p + j]; L[7 * p + j] = t; }
+            const int t = perm[k]; perm[k] = perm[p]; perm[p] = t;
         }
-    for (int i = 0; i < 7; i++) { double s = b[i]; for (int k = 0; k < i; k++) s -= A[7 * i + k] * x[k]; x[i] = s; }
-    for (int i = 0; i < 7; i++) x[i] /= A[8 * i];
-    for (int i = 6; i >= 0; i--) { const double xi = x[i]; for (int k = 0; k < i; k++) x[k] -= A[7 * i + k] * xi; }
+        const double d = A[8 * k]; D[k] = d;
+        if (d < 0) positive = 0;
+        if (d == 0) continue;
+        for (int i = k + 1; i < 7; i++) L[7 * i + k] = A[7 * i + k] / d;
+        for (int i = k + 1; i < 7; i++) for (int j = k + 1; j < 7; j++) A[7 * i + j] -= L[7 * i + k] * A[7 * k + j];
+    }
+    if (!positive) return 0;
+    for (int i = 0; i < 7; i++) y[i] = b[perm[i]];
+    for (int i = 0; i < 7; i++) { double s = y[i]; for (int k = 0; k < i; k++) s -= L[7 * i + k] * y[k]; y[i] = s; }
+    for (int i = 0; i < 7; i++) y[i] = D[i] != 0 ? y[i] / D[i] : 0.0;
+    for (int i = 6; i >= 0; i--) { double s = y[i]; for (int k = i + 1; k < 7; k++) s -= L[7 * k + i] * y[k]; y[i] = s; }
+    for (int i = 0; i < 7; i++) x[perm[i]] = y[i];
     return 1;
 }
 
@@ -1195,11 +1221,14 @@ static void s3_optimize(s3_t *B, sim3 *S, int iterations, int *stats)
                 const double c = s3_chi2(e0, e1, w);
                 double rho1 = 1.;
                 if (c > B->dsqr) rho1 = B->delta / sqrt(c);
-                const double wo = rho1 * w, r0 = rho1 * w * e0, r1 = rho1 * w * e1;
+                /* constructQuadraticForm, base_binary_edge.hpp:55-120, in g2o's evaluation order: omega_r = -(information * error), then *= rho'; the FULL
+                 * block B^T (rho' information) B is accumulated entry by entry ((J_a w) J_c and (J_c w) J_a round differently; Eigen's LDLT reads the lower
+                 * triangle) -- pinned against the reference's object code */
+                const double wo = rho1 * w, r0 = -(w * e0) * rho1, r1 = -(w * e1) * rho1;
                 const double *J0 = J[2 * k], *J1 = J[2 * k + 1];
                 for (int a = 0; a < 7; a++) {
-                    b[a] -= J0[a] * r0 + J1[a] * r1;
-                    for (int cc = a; cc < 7; cc++) { const double v = J0[a] * wo * J0[cc] + J1[a] * wo * J1[cc]; H[7 * a + cc] += v; if (cc != a) H[7 * cc + a] += v; }
+                    b[a] += J0[a] * r0 + J1[a] * r1;
+                    for (int cc = 0; cc < 7; cc++) H[7 * a + cc] += J0[a] * wo * J0[cc] + J1[a] * wo * J1[cc];
                 }
             }
         }
@@ -1249,7 +1278,7 @@ int oracle_optimize_sim3(double *sim3_io, int N, const uint8_t *valid, const flo
     B.N = N; B.P1c = P1c; B.P2c = P2c; B.obs1 = obs1; B.obs2 = obs2; B.w1 = w1; B.w2 = w2; B.fix_scale = fix_scale;
     for (int k = 0; k < 4; k++) { B.K1[k] = K1[k]; B.K2[k] = K2[k]; }
     const float deltaHuber = sqrtf(th2);                            /* const float deltaHuber = sqrt(th2) */
-    B.delta = deltaHuber; B.dsqr = B.delta * B.delta;
+    B.delta = deltaHuber; B.dsqr = (double)(float)(B.delta * B.delta);   /* RobustKernelHuber keeps delta^2 in a FLOAT member (robust_kernel_impl.h:84, set by setDelta, robust_kernel_impl.cpp:65-69) */
     B.active = (uint8_t *)malloc(N > 0 ? N : 1); B.err = (double *)calloc(4 * (size_t)(N > 0 ? N : 1), sizeof(double));
     if (stats) stats[0] = stats[1] = 0;
     sim3 S;
@@ -1591,8 +1620,11 @@ static void sim3_log(const sim3 *S, double res[7])                              
         }
     }
     O[0] = 0; O[1] = -omega[2]; O[2] = omega[1]; O[3] = omega[2]; O[4] = 0; O[5] = -omega[0]; O[6] = -omega[1]; O[7] = omega[0]; O[8] = 0;
-    mat3_mul(O, O, O2);
-    for (int i = 0; i < 9; i++) W[i] = A * O[i] + B * O2[i] + C * (i % 4 == 0 ? 1.0 : 0.0);
+    /* W = A*Omega + B*Omega*Omega + C*I evaluates left to right: (B*Omega)*Omega -- pinned against the reference's object code (1 ulp apart from B*(Omega*Omega)) */
+    double BO[9];
+    for (int i = 0; i < 9; i++) BO[i] = B * O[i];
+    mat3_mul(BO, O, O2);
+    for (int i = 0; i < 9; i++) W[i] = A * O[i] + O2[i] + C * (i % 4 == 0 ? 1.0 : 0.0);
     double ups[3];
     lu3_solve(W, S->t, ups);
     for (int k = 0; k < 3; k++) { res[k] = omega[k]; res[k + 3] = ups[k]; }
@@ -1715,4 +1747,84 @@ int oracle_optimize_pose_graph(int K, double *sim3_io, const uint8_t *fixed, int
     if (stats) { stats[0] = its; stats[1] = trials; stats[2] = fails; }
     free(V); free(bak); free(M); free(hidx); free(H); free(Hw); free(b); free(x); free(err);
     return its;
+}
+
+/* ======================================================================================== */
+/* Probes: single primitives of the restatement, exported so that tests can compare them with the reference's own g2o object code
+ * (oracle/_ref/libref_optimizer.so, ref_g2o_* in oracle/ref_optimizer_capi.cc) on random inputs.                                   */
+static void probe_ba1(ba_t *B, se3 *pose, uint8_t *fixed, double *pt, int *ekf, int *ept, double *obs, double *w, double *err, const double *q, const double *t,
+                      const double *Xw, const double *o2, double weight, const double *K4, int only_pose)
+{
+    memset(B, 0, sizeof *B);
+    memcpy(pose->q, q, 4 * sizeof(double)); memcpy(pose->t, t, 3 * sizeof(double));
+    quat_normalize_pos(pose->q);                         /* SE3Quat(const Quaterniond&, const Vector3d&) normalises, se3quat.h:66-69 */
+    *fixed = 0; memcpy(pt, Xw, 3 * sizeof(double)); *ekf = 0; *ept = 0; obs[0] = o2[0]; obs[1] = o2[1]; *w = weight;
+    B->K = 1; B->P = 1; B->E = 1; B->pose = pose; B->pose_fixed = fixed; B->intr = K4; B->pt = pt; B->pt_fixed_all = (uint8_t)only_pose;
+    B->e_kf = ekf; B->e_pt = ept; B->e_obs = obs; B->e_w = w; B->e_err = err;
+}
+void oracle_probe_se3_exp(const double *u6, double *q, double *t) { se3 s; se3_exp(u6, &s); memcpy(q, s.q, 4 * sizeof(double)); memcpy(t, s.t, 3 * sizeof(double)); }
+void oracle_probe_se3_oplus(double *q, double *t, const double *u6)
+{
+    se3 T, d, r; memcpy(T.q, q, 4 * sizeof(double)); memcpy(T.t, t, 3 * sizeof(double));
+    quat_normalize_pos(T.q);                             /* the SE3Quat(q, t) constructor of the caller normalises */
+    se3_exp(u6, &d); se3_mul(&d, &T, &r);
+    memcpy(q, r.q, 4 * sizeof(double)); memcpy(t, r.t, 3 * sizeof(double));
+}
+void oracle_probe_converter_to_se3quat(const float *Tcw, double *q, double *t) { se3 s; se3_from_Tcw_f32(Tcw, &s); memcpy(q, s.q, 4 * sizeof(double)); memcpy(t, s.t, 3 * sizeof(double)); }
+void oracle_probe_converter_to_cvmat(const double *q, const double *t, float *Tcw) { se3 s; memcpy(s.q, q, 4 * sizeof(double)); memcpy(s.t, t, 3 * sizeof(double)); quat_normalize_pos(s.q); se3_to_Tcw_f32(&s, Tcw); }
+void oracle_probe_edge_se3(const double *q, const double *t, const double *Xw, const double *obs2, double inv_sigma2, const double *K4, int only_pose,
+                           double *err2, double *chi2, int *depth_ok, double *Jpoint6, double *Jpose12)
+{
+    ba_t B; se3 pose; uint8_t fixed; double pt[3], obs[2], w, err[2]; int ekf, ept;
+    probe_ba1(&B, &pose, &fixed, pt, &ekf, &ept, obs, &w, err, q, t, Xw, obs2, inv_sigma2, K4, only_pose);
+    ba_compute_error(&B, 0);
+    err2[0] = err[0]; err2[1] = err[1];
+    if (chi2) *chi2 = ba_chi2(&B, 0);
+    if (depth_ok) *depth_ok = ba_depth_positive(&B, 0);
+    double Jl[6] = {0, 0, 0, 0, 0, 0};
+    ba_edge_jacobians(&B, 0, Jpose12, Jl);
+    if (Jpoint6) memcpy(Jpoint6, Jl, sizeof Jl);
+}
+void oracle_probe_huber(double e2, double delta, double *rho3) { ba_t B; memset(&B, 0, sizeof B); B.delta = delta; B.dsqr = (double)(float)(delta * delta); huber(&B, e2, rho3); }
+static void probe_get_sim3(const double *s8, sim3 *S) { memcpy(S->q, s8, 4 * sizeof(double)); memcpy(S->t, s8 + 4, 3 * sizeof(double)); S->s = s8[7]; }
+static void probe_put_sim3(const sim3 *S, double *s8) { memcpy(s8, S->q, 4 * sizeof(double)); memcpy(s8 + 4, S->t, 3 * sizeof(double)); s8[7] = S->s; }
+void oracle_probe_sim3_exp(const double *u7, double *s8) { sim3 S; sim3_exp(u7, &S); probe_put_sim3(&S, s8); }
+void oracle_probe_sim3_log(const double *s8, double *u7) { sim3 S; probe_get_sim3(s8, &S); sim3_log(&S, u7); }
+void oracle_probe_sim3_inverse(const double *s8, double *o8) { sim3 S, O; probe_get_sim3(s8, &S); sim3_inverse(&S, &O); probe_put_sim3(&O, o8); }
+void oracle_probe_sim3_mul(const double *a8, const double *b8, double *o8) { sim3 A, Bm, O; probe_get_sim3(a8, &A); probe_get_sim3(b8, &Bm); sim3_mul(&A, &Bm, &O); probe_put_sim3(&O, o8); }
+void oracle_probe_sim3_map(const double *s8, const double *x3, double *o3) { sim3 S; probe_get_sim3(s8, &S); sim3_map(&S, x3, o3); }
+void oracle_probe_sim3_oplus(double *s8, const double *u7, int fix_scale) { sim3 S, O; probe_get_sim3(s8, &S); pg_oplus(&S, u7, fix_scale, &O); probe_put_sim3(&O, s8); }
+/* EdgeSim3: error and the numeric Jacobians of both vertices (central differences through oplus, delta = 1e-9), row-major 7x7 */
+void oracle_probe_edge_sim3(const double *meas8, const double *si8, const double *sj8, int fix_scale, double *err7, double *Ji49, double *Jj49)
+{
+    sim3 M, Sv[2];
+    probe_get_sim3(meas8, &M); probe_get_sim3(si8, &Sv[0]); probe_get_sim3(sj8, &Sv[1]);
+    pg_edge_error(&M, &Sv[0], &Sv[1], err7);
+    for (int s = 0; s < 2; s++)
+        for (int d = 0; d < 7; d++) {
+            double add[7] = {0, 0, 0, 0, 0, 0, 0}, ep[7], em[7];
+            sim3 Pp;
+            add[d] = 1e-9; pg_oplus(&Sv[s], add, fix_scale, &Pp); pg_edge_error(&M, s == 0 ? &Pp : &Sv[0], s == 1 ? &Pp : &Sv[1], ep);
+            add[d] = -1e-9; pg_oplus(&Sv[s], add, fix_scale, &Pp); pg_edge_error(&M, s == 0 ? &Pp : &Sv[0], s == 1 ? &Pp : &Sv[1], em);
+            for (int r = 0; r < 7; r++) (s == 0 ? Ji49 : Jj49)[7 * r + d] = (1.0 / (2 * 1e-9)) * (ep[r] - em[r]);
+        }
+}
+/* EdgeSim3ProjectXYZ (inverse = 0) / EdgeInverseSim3ProjectXYZ (inverse = 1) of OptimizeSim3: error and the numeric Jacobian wrt the Sim3 vertex (2x7) */
+void oracle_probe_edge_sim3_project(int inverse, const double *s8, const double *K1, const double *K2, const float *X3, const float *obs, int fix_scale,
+                                    double *err2, double *Jsim14)
+{
+    s3_t B; memset(&B, 0, sizeof B);
+    B.N = 1; B.P1c = X3; B.P2c = X3; B.obs1 = obs; B.obs2 = obs; B.fix_scale = fix_scale;
+    memcpy(B.K1, K1, sizeof B.K1); memcpy(B.K2, K2, sizeof B.K2);
+    sim3 S; probe_get_sim3(s8, &S);
+    double e[4];
+    s3_errors(&B, &S, 0, e);
+    err2[0] = e[2 * inverse]; err2[1] = e[2 * inverse + 1];
+    for (int d = 0; d < 7; d++) {
+        double add[7] = {0, 0, 0, 0, 0, 0, 0}, ep[4], em[4];
+        sim3 Sp;
+        add[d] = 1e-9; s3_oplus(&B, &S, add, &Sp); s3_errors(&B, &Sp, 0, ep);
+        add[d] = -1e-9; s3_oplus(&B, &S, add, &Sp); s3_errors(&B, &Sp, 0, em);
+        for (int r = 0; r < 2; r++) Jsim14[7 * r + d] = (1.0 / (2 * 1e-9)) * (ep[2 * inverse + r] - em[2 * inverse + r]);
+    }
 }

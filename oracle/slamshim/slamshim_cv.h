@@ -33,6 +33,8 @@ namespace cv {
 
 template <typename T> struct Point_ { T x, y; Point_() : x(0), y(0) {} Point_(T a, T b) : x(a), y(b) {} };
 typedef Point_<float> Point2f;
+template <typename T> struct Point3_ { T x, y, z; Point3_() : x(0), y(0), z(0) {} Point3_(T a, T b, T c) : x(a), y(b), z(c) {} };
+typedef Point3_<float> Point3f;
 typedef Point_<int> Point;
 
 struct KeyPoint {

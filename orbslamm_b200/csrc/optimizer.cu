@@ -668,7 +668,9 @@ extern "C" int orbo_bundle_adjust(orbo_handle *h, int K, float *poses, const uin
     double *d_chi2 = S.scratch<double>(E); uint8_t *d_depth = S.scratch<uint8_t>(E);
     float *d_Tout = S.scratch<float>((size_t)K * 16); float *d_pts_out = S.scratch<float>(3 * (size_t)P);
     if (S.rc) return S.rc;
-    B.delta = (double)(float)sqrt(5.991); B.dsqr = B.delta * B.delta;              // thHuberMono, Optimizer.cc:591
+    // LocalBundleAdjustment: const float thHuberMono = sqrt(5.991) (Optimizer.cc:592); BundleAdjustment: const float thHuber2D = sqrt(5.99) (:106)
+    B.delta = two_stage ? (double)(float)sqrt(5.991) : (double)(float)sqrt(5.99);
+    B.dsqr = (double)(float)(B.delta * B.delta);   // RobustKernelHuber keeps delta^2 in a FLOAT member (robust_kernel_impl.h:84): pinned against the reference's object code
     ORBS_CUDA(cudaMemsetAsync(B.e_level, 0, E, st));
     ORBS_CUDA(cudaMemsetAsync(B.e_err, 0, 2 * (size_t)E * sizeof(double), st));
     ORBS_CUDA(cudaMemsetAsync(B.scalars, 0, (16 + sizeof(LmCtl) / sizeof(double) + 2) * sizeof(double), st));

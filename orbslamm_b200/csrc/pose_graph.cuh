@@ -56,8 +56,11 @@ __device__ inline void sim3_log(const Sim3 &S, double res[7])                   
         }
     }
     O[0] = 0; O[1] = -omega[2]; O[2] = omega[1]; O[3] = omega[2]; O[4] = 0; O[5] = -omega[0]; O[6] = -omega[1]; O[7] = omega[0]; O[8] = 0;
-    for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) O2[3 * r + c] = O[3 * r] * O[c] + O[3 * r + 1] * O[3 + c] + O[3 * r + 2] * O[6 + c];
-    for (int i = 0; i < 9; i++) W[i] = A * O[i] + B * O2[i] + C * (i % 4 == 0 ? 1.0 : 0.0);
+    // W = A*Omega + B*Omega*Omega + C*I evaluates left to right, (B*Omega)*Omega (pinned against the reference's g2o object code)
+    double BO[9];
+    for (int i = 0; i < 9; i++) BO[i] = B * O[i];
+    for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) O2[3 * r + c] = BO[3 * r] * O[c] + BO[3 * r + 1] * O[3 + c] + BO[3 * r + 2] * O[6 + c];
+    for (int i = 0; i < 9; i++) W[i] = A * O[i] + O2[i] + C * (i % 4 == 0 ? 1.0 : 0.0);
     double ups[3];
     lu3_solve(W, S.t, ups);
     for (int k = 0; k < 3; k++) { res[k] = omega[k]; res[k + 3] = ups[k]; }

@@ -80,7 +80,7 @@ k_pose_optimization(const PoseArgs A)
     uint8_t *outlier = A.outlier + o;
     double *err = A.err + 2 * o;
     const double in[4] = {A.fx, A.fy, A.cx, A.cy};
-    const double delta = (double)(float)sqrt(5.991), dsqr = delta * delta;   // const float deltaMono = sqrt(5.991), Optimizer.cc:295
+    const double delta = (double)(float)sqrt(5.991), dsqr = (double)(float)(delta * delta);   // const float deltaMono = sqrt(5.991), Optimizer.cc:295; delta^2 is a float member of RobustKernelHuber
     for (int i = tid; i < M; i += nt) outlier[i] = 0;
     if (tid < 6) s_x[tid] = 0.0;
     if (M < 3) { if (tid == 0) A.n_inliers[f] = 0; return; }                 // Optimizer.cc:387-388

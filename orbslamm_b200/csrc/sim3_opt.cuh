@@ -164,7 +164,7 @@ k_optimize_sim3(const Sim3Args A)
     double K1[4], K2[4];
     for (int k = 0; k < 4; k++) { K1[k] = (double)A.K1[4 * f + k]; K2[k] = (double)A.K2[4 * f + k]; }
     const double th2 = (double)A.th2;
-    const double delta = (double)sqrtf(A.th2), dsqr = delta * delta;       // const float deltaHuber = sqrt(th2), Optimizer.cc:1395
+    const double delta = (double)sqrtf(A.th2), dsqr = (double)(float)(delta * delta);       // const float deltaHuber = sqrt(th2), Optimizer.cc:1395; delta^2 is a float member of RobustKernelHuber
     const bool fix_scale = A.fix_scale != 0;
     int my = 0;
     for (int i = tid; i < M; i += nt) { const uint8_t v = A.valid[o + i] ? 1 : 0; active[i] = v; inlier[i] = v; my += v; }
@@ -226,13 +226,15 @@ k_optimize_sim3(const Sim3Args A)
                         double rho0 = c, rho1 = 1.0;
                         huber(c, delta, dsqr, rho0, rho1);
                         acc[35] += rho0;
-                        const double wo = rho1 * w, r0 = rho1 * w * e0, r1 = rho1 * w * e1;
+                        // g2o's evaluation order (base_binary_edge.hpp:55-120, pinned against the reference's object code): omega_r = -(information * error),
+                        // then *= rho'; the block entry that Eigen's LDLT reads is the LOWER one, (J_cc w) J_a
+                        const double wo = rho1 * w, r0 = -(w * e0) * rho1, r1 = -(w * e1) * rho1;
                         int p = 0;
 #pragma unroll
                         for (int a = 0; a < 7; a++) {
-                            acc[28 + a] -= J[2 * k][a] * r0 + J[2 * k + 1][a] * r1;
+                            acc[28 + a] += J[2 * k][a] * r0 + J[2 * k + 1][a] * r1;
 #pragma unroll
-                            for (int cc = a; cc < 7; cc++) { acc[p] += J[2 * k][a] * wo * J[2 * k][cc] + J[2 * k + 1][a] * wo * J[2 * k + 1][cc]; p++; }
+                            for (int cc = a; cc < 7; cc++) { acc[p] += J[2 * k][cc] * wo * J[2 * k][a] + J[2 * k + 1][cc] * wo * J[2 * k + 1][a]; p++; }
                         }
                     }
                 }

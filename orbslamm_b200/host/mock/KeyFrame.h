@@ -51,7 +51,7 @@ public:
     }
 
     long unsigned int mnId = 0, mnBALocalForKF = ~0ul, mnBAFixedForKF = ~0ul, mnBAGlobalForKF = 0;
-    float fx = 0, fy = 0, cx = 0, cy = 0;
+    float fx = 0, fy = 0, cx = 0, cy = 0, mbf = 0;
     int N = 0;
     int mnMinX = 0, mnMinY = 0, mnMaxX = 0, mnMaxY = 0;           // ints in S/include/KeyFrame.h
     float mfGridElementWidthInv = 0, mfGridElementHeightInv = 0, mfLogScaleFactor = 0;

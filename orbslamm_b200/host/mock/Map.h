@@ -9,6 +9,7 @@ class Map
 public:
     std::vector<KeyFrame *> GetAllKeyFrames() { return mvKFs; }
     std::vector<MapPoint *> GetAllMapPoints() { return mvMPs; }
+    long unsigned int GetMaxKFid() { long unsigned int m = 0; for (KeyFrame *k : mvKFs) m = std::max(m, k->mnId); return m; }   // Map.cc:120-124 (mnMaxKFid)
     bool isAttached() { return !mvAttached.empty(); }                    // M/include/Map.h (MultiMapper)
     std::vector<Map *> getAttachedMaps() { return mvAttached; }
     std::vector<Map *> mvAttached;
