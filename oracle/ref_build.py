@@ -353,3 +353,80 @@ def ref_sim3_check_inliers(X3Dc1, X3Dc2, oct1, oct2, level_sigma2, K1, K2, T12, 
     L.ref_sim3_check_inliers(N, X1.ctypes.data, X2.ctypes.data, o1.ctypes.data, o2.ctypes.data, ls.ctypes.data, len(ls), k1.ctypes.data, k2.ctypes.data, nh,
                              a.ctypes.data, b.ctypes.data, inl.ctypes.data, n.ctypes.data, m1.ctypes.data, m2.ctypes.data, p1.ctypes.data, p2.ctypes.data)
     return inl, n, m1, m2, p1, p2
+
+
+# ------------------------------------------------------------------------------------------------
+# the reference's own Optimizer.cc + Converter.cc + vendored g2o (oracle/_ref/libref_optimizer.so, same Makefile: compiled unmodified against the Eigen
+# stand-in oracle/eigenshim, the data-model stand-in oracle/optshim and oracle/slamshim's cv::Mat); C API in oracle/ref_optimizer_capi.cc
+_OPT_SO = os.path.join(_HERE, "_ref", "libref_optimizer.so")
+_OPT_LIB = None
+
+
+def optimizer_available():
+    return os.path.exists(_OPT_SO)
+
+
+def optimizer_lib():
+    global _OPT_LIB
+    if _OPT_LIB is None:
+        _OPT_LIB = ctypes.CDLL(_OPT_SO)
+    return _OPT_LIB
+
+
+def _vp(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _ba_args(poses, fixed, intr, points, e_kf, e_pt, e_uv, e_w):
+    poses = np.ascontiguousarray(poses, np.float32).reshape(-1, 16).copy(); K = len(poses)
+    points = np.ascontiguousarray(points, np.float32).reshape(-1, 3).copy()
+    intr = np.ascontiguousarray(intr, np.float64)
+    if intr.ndim == 1:
+        intr = np.tile(intr, (K, 1))
+    return (poses, np.ascontiguousarray(fixed, np.uint8), np.ascontiguousarray(intr), points, np.ascontiguousarray(e_kf, np.int32), np.ascontiguousarray(e_pt, np.int32),
+            np.ascontiguousarray(e_uv, np.float32), np.ascontiguousarray(e_w, np.float32))
+
+
+def ref_local_ba(poses, fixed, intr, points, e_kf, e_pt, e_uv, e_inv_sigma2):
+    """Optimizer::LocalBundleAdjustment of the reference on the stand-in map of a flat graph (current keyframe = last free one).  Returns dict(poses [K,4,4],
+    points [P,3], nobs [P] = observations left per point after the reference erased its outliers)."""
+    p, fx, it, pt, kf, ept, uv, w = _ba_args(poses, fixed, intr, points, e_kf, e_pt, e_uv, e_inv_sigma2)
+    nobs = np.zeros(len(pt), np.int32)
+    optimizer_lib().ref_opt_local_ba(len(p), _vp(p), _vp(fx), _vp(it), len(pt), _vp(pt), len(kf), _vp(kf), _vp(ept), _vp(uv), _vp(w), _vp(nobs))
+    return dict(poses=p.reshape(-1, 4, 4), points=pt, nobs=nobs)
+
+
+def ref_bundle_adjust(poses, fixed, intr, points, e_kf, e_pt, e_uv, e_inv_sigma2, n_iterations=20, robust=False):
+    """Optimizer::BundleAdjustment of the reference (nLoopKF = 0).  Only the fixed == 1 (mnId == 0) keyframe is held."""
+    p, fx, it, pt, kf, ept, uv, w = _ba_args(poses, fixed, intr, points, e_kf, e_pt, e_uv, e_inv_sigma2)
+    optimizer_lib().ref_opt_bundle_adjust(len(p), _vp(p), _vp(fx), _vp(it), len(pt), _vp(pt), len(kf), _vp(kf), _vp(ept), _vp(uv), _vp(w), int(n_iterations), int(bool(robust)))
+    return dict(poses=p.reshape(-1, 4, 4), points=pt)
+
+
+def ref_pose_optimization(Tcw, Xw, obs, inv_sigma2, K4):
+    """Optimizer::PoseOptimization of the reference: (Tcw [4,4], outlier u8[N], n_inliers)."""
+    T = np.ascontiguousarray(Tcw, np.float32).reshape(16).copy()
+    Xw = np.ascontiguousarray(Xw, np.float32); obs = np.ascontiguousarray(obs, np.float32); w = np.ascontiguousarray(inv_sigma2, np.float32)
+    k4 = np.ascontiguousarray(K4, np.float32); out = np.zeros(len(w), np.uint8)
+    n = optimizer_lib().ref_opt_pose_optimization(_vp(T), _vp(k4), len(w), _vp(Xw), _vp(obs), _vp(w), _vp(out))
+    return T.reshape(4, 4), out, int(n)
+
+
+def ref_optimize_sim3(sim3, valid, P1c, P2c, obs1, obs2, w1, w2, K1, K2, th2=10.0, fix_scale=False):
+    """Optimizer::OptimizeSim3 of the reference; the keyframes sit at the identity, so the camera-frame points the reference computes (R*X + t in float) are
+    exactly the given ones.  Returns dict(sim3 [8], inlier u8[N], n_in)."""
+    f = lambda x: np.ascontiguousarray(x, np.float32)
+    I4 = np.eye(4, dtype=np.float32).reshape(16)
+    s = np.ascontiguousarray(sim3, np.float64).copy(); v = np.ascontiguousarray(valid, np.uint8); inl = np.zeros(len(v), np.uint8)
+    a = [f(K1), f(K2), f(P1c), f(P2c), f(obs1), f(obs2), f(w1), f(w2)]
+    n = optimizer_lib().ref_opt_optimize_sim3(_vp(I4), _vp(I4), _vp(a[0]), _vp(a[1]), len(v), _vp(v), _vp(a[2]), _vp(a[3]), _vp(a[4]), _vp(a[5]), _vp(a[6]), _vp(a[7]), _vp(s),
+                                              ctypes.c_float(th2), int(bool(fix_scale)), _vp(inl))
+    return dict(sim3=s, inlier=inl, n_in=int(n))
+
+
+def ref_pose_graph(sim3, fixed, e_i, e_j, e_meas, fix_scale=False, iterations=20):
+    """The g2o graph of Optimizer::OptimizeEssentialGraph (BlockSolver_7_3 / LinearSolverEigen / Levenberg, lambda init 1e-16) built by the reference's object code."""
+    s = np.ascontiguousarray(sim3, np.float64).reshape(-1, 8).copy()
+    fx = np.ascontiguousarray(fixed, np.uint8); ei = np.ascontiguousarray(e_i, np.int32); ej = np.ascontiguousarray(e_j, np.int32); em = np.ascontiguousarray(e_meas, np.float64)
+    its = optimizer_lib().ref_g2o_pose_graph(len(s), _vp(s), _vp(fx), len(ei), _vp(ei), _vp(ej), _vp(em), int(bool(fix_scale)), int(iterations))
+    return dict(sim3=s, lm_iterations=int(its))

@@ -243,16 +243,20 @@ def test_optimize_pose_graph_matches_oracle(lib, K, fix_scale):
     got = o.OptimizePoseGraph(S, fixed, ei, ej, em, fix_scale, 20, 1e-16)
     ref = oracle.optimize_pose_graph(S, fixed, ei, ej, em, fix_scale, 20, 1e-16)
     assert got["chol_failures"] == 0 and ref["chol_failures"] == 0
-    assert abs(got["lm_iterations"] - ref["lm_iterations"]) <= 1                 # trials at the noise floor of the 1e-9 numeric Jacobians may differ
-    close = np.abs(got["sim3"] - ref["sim3"]).max() < 1e-5 * np.abs(ref["sim3"]).max()
-    if fix_scale:
-        assert close
-    else:
-        # free scale: g2o's 1e-9 differentiation step leaves ~1e-6 noise in the Jacobians and the LM ends in a flat valley where single trials are accepted
-        # or rejected by rounding (the fp64 atomics of k_pg_build add in varying order); if the two stop at different trials they still reach the same chi2
-        import pose_graph_twin as pgt
-        chi = lambda A: pgt.Twin(A, fixed, ei, ej, em, fix_scale).chi2()
-        assert close or abs(chi(got["sim3"]) - chi(ref["sim3"])) < 1e-3 * chi(ref["sim3"])
+    # the normal equations are accumulated per target block in edge order (no atomics): same LM iterations as the oracle, and a second run is bit-identical
+    assert got["lm_iterations"] == ref["lm_iterations"]
+    again = o.OptimizePoseGraph(S, fixed, ei, ej, em, fix_scale, 20, 1e-16)
+    assert np.array_equal(again["sim3"], got["sim3"]) and again["lm_trials"] == got["lm_trials"]
+    rel = np.abs(got["sim3"] - ref["sim3"]).max() / np.abs(ref["sim3"]).max()
+    # free scale: north_star's 1e-5 with five decades to spare.  Fixed scale: the scale column of g2o's numeric Jacobians is pure differentiation noise and the
+    # REFERENCE'S OWN result moves by up to 7e-6 with the elimination order of its sparse LDL^T (measured on its object code, tests/test_reference_optimizer.py);
+    # the tiled Cholesky is one more such order
+    assert rel < (1e-9 if not fix_scale else 3e-5), rel
+    from oracle import ref_build
+    if ref_build.optimizer_available():
+        rr = ref_build.ref_pose_graph(S, fixed, ei, ej, em, fix_scale, 20)
+        assert rr["lm_iterations"] == got["lm_iterations"]
+        assert np.abs(got["sim3"] - rr["sim3"]).max() < (1e-9 if not fix_scale else 3e-5) * np.abs(rr["sim3"]).max()
     assert np.array_equal(got["sim3"][0], S[0])
     cam = lambda A: -A[:, 4:7] / A[:, 7:8]                                         # not the camera centre, but a pose-dependent point that must move towards the truth
     if not fix_scale:

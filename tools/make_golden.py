@@ -57,6 +57,14 @@ T0 = case["Tcw"].copy(); T0[:3, 3] += np.array([0.05, -0.03, 0.08], np.float32)
 Tp, outl, ninl = oracle.pose_optimization(T0, Xw_m, obs_m, w_m, case["K4"])
 gb = synth.ba_graph(K=10, P=200, seed=42)
 rb = oracle.bundle_adjust(gb["poses"], gb["fixed"], gb["intr"], gb["points"], gb["kf"], gb["pt"], gb["uv"], gb["inv_sigma2"], True, 5, 10, True)
+# ... written only if the reference's own Optimizer.cc + g2o object code (oracle/_ref/libref_optimizer.so) agrees: exact flags, values within one float32 step
+assert ref_build.optimizer_available(), "oracle/_ref/libref_optimizer.so (the reference's Optimizer.cc + g2o) must be built to write these golden vectors"
+_step = lambda a, b: float(np.abs(np.asarray(a, np.float64) - b).max() / np.spacing(np.float32(np.abs(b).max())))
+Tr_, outr_, nr_ = ref_build.ref_pose_optimization(T0, Xw_m, obs_m, w_m, case["K4"])
+assert nr_ == ninl and np.array_equal(outr_, outl) and _step(Tp, Tr_) <= 1.0, "oracle and the reference's object code disagree on PoseOptimization"
+rr_ = ref_build.ref_local_ba(gb["poses"], gb["fixed"], gb["intr"], gb["points"], gb["kf"], gb["pt"], gb["uv"], gb["inv_sigma2"])
+_inw = np.zeros(len(gb["points"]), bool); _inw[gb["pt"][(gb["fixed"] != 2)[gb["kf"]]]] = True
+assert _step(rb["poses"], rr_["poses"]) <= 1.0 and _step(rb["points"][_inw], rr_["points"][_inw]) <= 1.0, "oracle and the reference's object code disagree on LocalBA"
 np.savez_compressed(os.path.join(out, "optimize_small.npz"), po_T0=T0, po_Xw=Xw_m, po_obs=obs_m, po_w=w_m, po_K4=case["K4"], po_T=Tp, po_outlier=outl,
                     po_ninl=ninl, ba_poses0=gb["poses"], ba_fixed=gb["fixed"], ba_intr=gb["intr"], ba_points0=gb["points"], ba_kf=gb["kf"], ba_pt=gb["pt"],
                     ba_uv=gb["uv"], ba_w=gb["inv_sigma2"], ba_poses=rb["poses"], ba_points=rb["points"], ba_chi2=rb["chi2"], ba_outlier=rb["outlier"],
@@ -105,6 +113,14 @@ ri, rn, rm1, rm2, rp1, rp2 = ref_build.ref_sim3_check_inliers(r3["X1"], r3["X2"]
 assert np.array_equal(inl, ri) and np.array_equal(n, rn) and np.array_equal(m1, rm1) and np.array_equal(p2, rp2)
 Sg, fxg, eig, ejg, emg, _ = kff.make_pose_graph(16, seed=2, n_loops=3)
 pg = oracle.optimize_pose_graph(Sg, fxg, eig, ejg, emg, True, 20, 1e-16)
+_rpg = ref_build.ref_pose_graph(Sg, fxg, eig, ejg, emg, True, 20)          # same LM iterations; fixed-scale values within the reference's own order-of-elimination spread
+assert _rpg["lm_iterations"] == pg["lm_iterations"] and np.abs(_rpg["sim3"] - pg["sim3"]).max() < 2e-5 * np.abs(pg["sim3"]).max()
+for _cam, _sid in ((kff.GOLDEN_CAM, 1),):
+    _c = kff.make_sim3_opt_case(_cam, _sid)
+    for _fix in (False, True):
+        _a = (_c["init"], _c["valid"], _c["P1c"], _c["P2c"], _c["obs1"], _c["obs2"], _c["w1"], _c["w2"], _c["K1"], _c["K2"], 10.0, _fix)
+        _o, _r = oracle.optimize_sim3(*_a), ref_build.ref_optimize_sim3(*_a)
+        assert _o["n_in"] == _r["n_in"] and np.array_equal(_o["sim3"], _r["sim3"]), "oracle and the reference's object code disagree on OptimizeSim3"
 np.savez_compressed(os.path.join(out, "sim3_chain_small.npz"), X1=r3["X1"], X2=r3["X2"], oct1=r3["oct1"], oct2=r3["oct2"], ls2=r3["ls2"], K1=r3["K1"], K2=r3["K2"],
                     T12=r3["T12"], T21=r3["T21"], max_err1=m1, max_err2=m2, p1im1=p1, p2im2=p2, inliers=np.packbits(inl, axis=1), n_inliers=n,
                     pg_sim3=Sg, pg_fixed=fxg, pg_ei=eig, pg_ej=ejg, pg_meas=emg, pg_out=pg["sim3"], pg_iters=np.array([pg["lm_iterations"], pg["lm_trials"]]))
