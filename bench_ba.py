@@ -147,9 +147,37 @@ def cpu_baseline_ba(K, P, repeats):
         iters += r["lm_iterations"]
     s = time.perf_counter() - t0
     from bench import cpu_model
-    return {"value": round(iters / s, 3), "unit": "LM iterations/s", "cores": 1, "kind": "port", "cpu": cpu_model(),
-            "sample": f"{repeats} LocalBA call(s) on the same {K} KF / {P} pt graph ({iters} LM iterations, {s:.1f} s); fp64 restatement of the "
-                      "g2o path with a profile LDLT of the reduced system, 1 thread (g2o OpenMP is off in the reference)"}
+    out = {"value": round(iters / s, 3), "unit": "LM iterations/s", "cores": 1, "kind": "port", "cpu": cpu_model(),
+           "sample": f"{repeats} LocalBA call(s) on the same {K} KF / {P} pt graph ({iters} LM iterations, {s:.1f} s); fp64 restatement of the "
+                     "g2o path with a profile LDLT of the reduced system, 1 thread (g2o OpenMP is off in the reference)"}
+    ref = reference_object_code_ba(g)
+    if ref is not None:
+        out["reference_object_code"] = ref
+    return out
+
+
+def reference_object_code_ba(g):
+    """The reference's own Optimizer::LocalBundleAdjustment + vendored g2o, compiled unmodified into oracle/_ref/libref_optimizer.so (oracle/Makefile), on
+    the same graph.  Eigen is not in the image: the object code runs over oracle/eigenshim (scalar fixed-size algebra, its own SimplicialLDLT), so it
+    is slower than a build against real Eigen would be -- reported next to the faster port, which stays the headline CPU baseline."""
+    import ctypes
+    so = os.path.join(os.path.dirname(os.path.abspath(__file__)), "oracle", "_ref", "libref_optimizer.so")
+    if not os.path.exists(so):
+        return None
+    R = ctypes.CDLL(so)
+    K, P = len(g["poses"]), len(g["points"])
+    c = lambda a, dt: np.ascontiguousarray(a, dt).copy()
+    poses = c(g["poses"], np.float32).reshape(-1, 16); points = c(g["points"], np.float32); fixed = c(g["fixed"], np.uint8)
+    intr = np.tile(np.asarray(g["intr"], np.float64), (K, 1)).copy() if np.asarray(g["intr"]).ndim == 1 else c(g["intr"], np.float64)
+    kf = c(g["kf"], np.int32); pt = c(g["pt"], np.int32); uv = c(g["uv"], np.float32); w = c(g["inv_sigma2"], np.float32)
+    nobs = np.zeros(P, np.int32)
+    ptr = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    t0 = time.perf_counter()
+    R.ref_opt_local_ba(K, ptr(poses), ptr(fixed), ptr(intr), P, ptr(points), len(kf), ptr(kf), ptr(pt), ptr(uv), ptr(w), ptr(nobs))
+    s = time.perf_counter() - t0
+    return {"value": round(15 / s, 3), "unit": "LM iterations/s", "cores": 1, "kind": "reference",
+            "sample": f"1 Optimizer::LocalBundleAdjustment call of the reference's object code (Optimizer.cc + g2o unmodified, Eigen stand-in), graph construction "
+                      f"included, {s:.1f} s for the 5 + 10 iteration schedule"}
 
 
 def reference_line(args):

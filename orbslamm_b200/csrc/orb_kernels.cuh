@@ -15,7 +15,9 @@
 
 namespace orbs {
 
-__constant__ int8_t c_brief_pattern[1024] = {
+// 256 tests x (x0, y0, x1, y1) int8: lane l of a descriptor warp owns tests 8l .. 8l+7 = 32 contiguous bytes, fetched as two
+// 16-byte loads into registers (a __constant__ or byte-wise shared copy serialises: lane-varying addresses / 8-way bank conflicts)
+__device__ __align__(16) const int8_t g_brief_pattern[1024] = {
 #include "../../include/orb_brief_pattern.inc"
 };
 
@@ -783,9 +785,6 @@ k_orient_describe(const __grid_constant__ ExtractPlan plan,
                   int *__restrict__ kp_octave, float *__restrict__ kp_size, uint8_t *__restrict__ desc,
                   int *__restrict__ counts)
 {
-    __shared__ int8_t pat[1024];
-    for (int i = threadIdx.x; i < 1024; i += blockDim.x) pat[i] = c_brief_pattern[i];
-    __syncthreads();
     const int frame = blockIdx.y;
     const int lane = threadIdx.x & 31;
     const int o = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);     // output slot
@@ -835,14 +834,19 @@ k_orient_describe(const __grid_constant__ ExtractPlan plan,
     const float a = (float)cos((double)ang), b = (float)sin((double)ang);
     const uint8_t *bl = blur + (size_t)frame * plan.pyr_frame_bytes + L.pyr_off;
     const uint8_t *center = bl + (size_t)y * L.pitch + x;
-    const int8_t *pp = pat + lane * 32;
+    unsigned pw[8];
+    {
+        const uint4 *gp = reinterpret_cast<const uint4 *>(g_brief_pattern) + 2 * lane;
+        const uint4 q0 = __ldg(gp), q1 = __ldg(gp + 1);
+        pw[0] = q0.x; pw[1] = q0.y; pw[2] = q0.z; pw[3] = q0.w; pw[4] = q1.x; pw[5] = q1.y; pw[6] = q1.z; pw[7] = q1.w;
+    }
     int val = 0;
 #pragma unroll
     for (int t = 0; t < 8; t++) {
         int tv[2];
 #pragma unroll
         for (int e = 0; e < 2; e++) {
-            const float px = (float)pp[4 * t + 2 * e], py = (float)pp[4 * t + 2 * e + 1];
+            const float px = (float)(int)(int8_t)(pw[t] >> (16 * e)), py = (float)(int)(int8_t)(pw[t] >> (16 * e + 8));
             const int ry = __float2int_rn(__fadd_rn(__fmul_rn(px, b), __fmul_rn(py, a)));
             const int rx = __float2int_rn(__fsub_rn(__fmul_rn(px, a), __fmul_rn(py, b)));
             tv[e] = center[(ptrdiff_t)ry * L.pitch + rx];
