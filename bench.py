@@ -566,7 +566,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--streams", type=int, default=128, help="independent camera streams per GPU (frames per step per GPU)")
-    ap.add_argument("--instances", type=int, default=1, help="independent extractor/matcher/optimizer triples (own CUDA stream) per GPU in the device-resident leg")
+    ap.add_argument("--instances", type=int, default=2, help="independent extractor/matcher/optimizer triples (own CUDA stream) per GPU in the device-resident leg")
     ap.add_argument("--mode", default="pipeline", choices=["pipeline", "split"], help="how the device-resident leg uses --instances (see bench_frontend)")
     ap.add_argument("--e2e-workers", type=int, default=4, help="independent front-end instances serving the streams of one GPU in the e2e leg")
     ap.add_argument("--workload", default="all", choices=["all", "frontend", "ba"],

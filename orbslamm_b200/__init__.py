@@ -472,6 +472,25 @@ class Projection(ctypes.Structure):
                 ("log_scale_factor", ctypes.c_float), ("th", ctypes.c_float), ("flags", ctypes.c_int32)]
 
 
+# orbm_projection flags (include/orbslamm_b200.h)
+PROJ_TWO_STEP, PROJ_NO_DEPTH, PROJ_FRAME_BOUNDS, PROJ_FRAME_UV, PROJ_DIST_CAMERA, PROJ_CHECK_NORMAL, PROJ_LEVEL_PLUS1 = 1, 2, 4, 8, 16, 32, 64
+
+
+def make_projection(R, t, K4, bounds4, log_scale_factor, th, flags, Ow=None, R2=None, t2=None):
+    """Fill an orbm_projection: the view a batch of map points is projected into (rotation / translation, optional second transform, camera centre,
+    intrinsics, image bounds, log of the pyramid scale factor, window factor, PROJ_* flags)."""
+    V = Projection()
+    V.R[:] = [float(x) for x in np.asarray(R, np.float32).ravel()]; V.t[:] = [float(x) for x in np.asarray(t, np.float32).ravel()]
+    if R2 is not None:
+        V.R2[:] = [float(x) for x in np.asarray(R2, np.float32).ravel()]; V.t2[:] = [float(x) for x in np.asarray(t2, np.float32).ravel()]
+    if Ow is not None:
+        V.Ow[:] = [float(x) for x in np.asarray(Ow, np.float32).ravel()]
+    V.fx, V.fy, V.cx, V.cy = [float(x) for x in np.asarray(K4, np.float32)]
+    V.min_x, V.min_y, V.max_x, V.max_y = [float(x) for x in np.asarray(bounds4, np.float32)]
+    V.log_scale_factor = float(np.float32(log_scale_factor)); V.th = float(np.float32(th)); V.flags = int(flags)
+    return V
+
+
 class Optimizer:
     """Mirror of iORB_SLAM::Optimizer (reference S/include/Optimizer.h:37-68) over flat arrays: the static functions
     PoseOptimization / LocalBundleAdjustment / BundleAdjustment become methods of a handle that owns the device

@@ -22,6 +22,17 @@ def shard_graph(g, world, rank):
                 uv=g["uv"][le], inv_sigma2=g["inv_sigma2"][le], local_points=lp, local_edges=le)
 
 
+def shard_graph_by_owner(g, owner, rank):
+    """Shard with an explicit owner rank per map point (BASELINE.json configs[3]: after a map merge the points stay on the GPU of the robot whose map
+    they come from; keyframes are replicated).  owner: int [P]."""
+    owner = np.asarray(owner)
+    lp = np.nonzero(owner == rank)[0].astype(np.int64)
+    local_index = np.full(len(owner), -1, np.int64); local_index[lp] = np.arange(len(lp))
+    le = np.nonzero(owner[np.asarray(g["pt"])] == rank)[0]
+    return dict(poses=g["poses"], fixed=g["fixed"], intr=g["intr"], points=g["points"][lp], kf=g["kf"][le], pt=local_index[np.asarray(g["pt"])[le]].astype(np.int32),
+                uv=g["uv"][le], inv_sigma2=g["inv_sigma2"][le], local_points=lp, local_edges=le)
+
+
 def merge_points(n_points, shards):
     """shards: list over ranks of (local_point_ids, values [Pl, ...]) -> full array [n_points, ...]."""
     first = shards[0][1]

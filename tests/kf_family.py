@@ -7,8 +7,18 @@ Reference: S/src/ORBmatcher.cc:292-405 (SearchByProjection(KF, Scw)), :827-977 a
 is restated here in numpy float32 with OpenCV's evaluation order (Mat / scalar = multiply by the double reciprocal; small gemm)."""
 import numpy as np
 
-import oracle
+import orbslamm_b200 as _ob
 from orbslamm_b200 import synth
+
+
+class _LazyOracle:
+    """the CPU oracle is loaded on first use: the CUDA-only users of this module (bench.py's map-merge leg) never touch it"""
+    def __getattr__(self, name):
+        import oracle as o
+        return getattr(o, name)
+
+
+oracle = _LazyOracle()
 
 F32 = np.float32
 TH_LOW, TH_HIGH = 50, 100
@@ -52,7 +62,6 @@ def camera_centre(Tcw):
 
 # ------------------------------------------------------------------ backends
 class OracleBackend:
-    P = oracle
 
     def project(self, R, t, K4, bounds4, log_sf, th, flags, sf, pts, valid, Ow=None, R2=None, t2=None, use_normal=True):
         V = oracle.make_projection(R, t, K4, bounds4, log_sf, th, flags, Ow=Ow, R2=R2, t2=t2)
@@ -76,8 +85,7 @@ class CudaBackend:
         self.m = ob.ORBmatcher(0.75, True)
 
     def project(self, R, t, K4, bounds4, log_sf, th, flags, sf, pts, valid, Ow=None, R2=None, t2=None, use_normal=True):
-        o = oracle.make_projection(R, t, K4, bounds4, log_sf, th, flags, Ow=Ow, R2=R2, t2=t2)
-        V = self.ob.Projection.from_buffer_copy(bytes(o))
+        V = self.ob.make_projection(R, t, K4, bounds4, log_sf, th, flags, Ow=Ow, R2=R2, t2=t2)
         M = len(valid)
         r = self.m.project_points([V], sf, pts["Xw"][None], pts["normal"][None] if use_normal else None, pts["mf_min"][None], pts["mf_max"][None],
                                   np.array([M], np.int32), np.asarray(valid, np.uint8)[None])
@@ -100,7 +108,7 @@ class CudaBackend:
 
 
 # ------------------------------------------------------------------ the five members
-P = oracle
+P = _ob               # PROJ_* flags (include/orbslamm_b200.h; the oracle's values are the same and tests/test_cabi_symbols.py keeps them so)
 
 
 def kf_bounds(kf):

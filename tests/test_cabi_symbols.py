@@ -73,3 +73,16 @@ def test_host_shims_compile_for_both_trees():
     for extra in ([], ["-DORBSLAMM_MULTI_ROBOT"]):
         out = subprocess.run(base + extra + srcs, capture_output=True, text=True)
         assert out.returncode == 0, out.stderr[-3000:]
+
+
+def test_projection_flags_and_struct_match_the_oracle():
+    """orbm_projection and its PROJ_* flags are declared twice on the Python side (product: orbslamm_b200, checker: oracle): same values, same layout"""
+    import ctypes
+    import orbslamm_b200 as ob
+    import oracle
+    for n in ("PROJ_TWO_STEP", "PROJ_NO_DEPTH", "PROJ_FRAME_BOUNDS", "PROJ_FRAME_UV", "PROJ_DIST_CAMERA", "PROJ_CHECK_NORMAL", "PROJ_LEVEL_PLUS1"):
+        assert getattr(ob, n) == getattr(oracle, n)
+    assert ctypes.sizeof(ob.Projection) == ctypes.sizeof(oracle.Projection)
+    a = ob.make_projection(range(9), range(3), [1, 2, 3, 4], [5, 6, 7, 8], 0.18, 10, 33, Ow=[1, 2, 3], R2=range(9, 18), t2=[7, 8, 9])
+    b = oracle.make_projection(range(9), range(3), [1, 2, 3, 4], [5, 6, 7, 8], 0.18, 10, 33, Ow=[1, 2, 3], R2=range(9, 18), t2=[7, 8, 9])
+    assert bytes(a) == bytes(b)
