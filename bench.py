@@ -569,7 +569,7 @@ def main():
     ap.add_argument("--instances", type=int, default=2, help="independent extractor/matcher/optimizer triples (own CUDA stream) per GPU in the device-resident leg")
     ap.add_argument("--mode", default="pipeline", choices=["pipeline", "split"], help="how the device-resident leg uses --instances (see bench_frontend)")
     ap.add_argument("--e2e-workers", type=int, default=4, help="independent front-end instances serving the streams of one GPU in the e2e leg")
-    ap.add_argument("--workload", default="all", choices=["all", "frontend", "ba"],
+    ap.add_argument("--workload", default="all", choices=["all", "frontend", "ba", "merge"],
                     help="all (default): the front-end line with the LocalBA leg as its \"ba\" sub-record -- both halves of BASELINE.json's metric")
     ap.add_argument("--camera", default="kitti", choices=["kitti", "tum"], help="kitti: 1241x376 / 2000 features (BASELINE.json metric); tum: 640x480 / 1000 features (configs[1])")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
@@ -588,6 +588,10 @@ def main():
         if args.workload == "ba":
             from bench_ba import reference_line
             emit(reference_line(args))
+            return
+        if args.workload == "merge":
+            from bench_merge import reference_merge
+            emit(reference_merge(args))
             return
         cores = os.cpu_count() or 1
         per = max(20, args.steps + args.warmup)          # one step = one new frame on every core's stream; >= 20 frames per core
@@ -610,6 +614,8 @@ def main():
                 "e2e": {"value": round(fps, 2), "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         if ba_ref is not None:
             line["ba"] = ba_ref
+            from bench_merge import reference_merge
+            line["merge"] = reference_merge(args)
         emit(line)
         return
 
@@ -621,6 +627,9 @@ def main():
     if args.workload == "ba":
         from bench_ba import bench_ba
         out = bench_ba(args, rank, world)
+    elif args.workload == "merge":
+        from bench_merge import bench_merge
+        out = bench_merge(args, rank, world)
     else:
         out = bench_frontend(args, rank, world)
         ba = None
@@ -629,6 +638,9 @@ def main():
             # runs before rank 0's CPU baseline so that the other ranks do not wait in a collective for it
             from bench_ba import bench_ba
             ba = bench_ba(args, rank, world)
+            # configs[3]: two-map Sim3 merge + global BA of the merged map (points stay with their origin map's GPUs at N > 1)
+            from bench_merge import bench_merge
+            merge = bench_merge(args, rank, world)
         if rank == 0:
             fps1, wall1 = cpu_baseline_frontend(1, max(10, args.cpu_frames))
             out["cpu_baseline"] = {"value": round(fps1, 2), "unit": "frames/s", "cores": 1, "kind": "port", "cpu": cpu_model(),
@@ -636,6 +648,7 @@ def main():
                                              "(reference front end is single-threaded per stream)"}
             if ba is not None:
                 out["ba"] = ba
+                out["merge"] = merge
     if rank == 0:
         emit(out)
     if world > 1:

@@ -1,6 +1,7 @@
 // ORBextractor_b200.cc -- replaces S/src/ORBextractor.cc in libORBSLAMM.so: marshals cv::Mat / cv::KeyPoint to the
 // flat-array C-ABI (include/orbslamm_b200.h).  All arithmetic happens in liborbslamm_b200.so on the GPU.
 #include <cassert>
+#include <cstring>
 #include <stdexcept>
 #include <string>
 #include "ORBextractor.h"
@@ -50,7 +51,8 @@ void ORBextractor::operator()(cv::InputArray _image, cv::InputArray /*mask*/, st
     _keypoints.reserve(n);
     for (int i = 0; i < n; i++) _keypoints.push_back(cv::KeyPoint(mXY[2 * i], mXY[2 * i + 1], mSize[i], mAngle[i], mResponse[i], mOctave[i], -1));
     _descriptors.create(n, 32, CV_8U);                             // ORBextractor.cc:1068
-    for (int i = 0; i < n; i++) std::memcpy(_descriptors.ptr(i), desc.ptr(i), 32);
+    cv::Mat out = _descriptors.getMat();                           // (OutputArray is a proxy: no ptr() of its own)
+    for (int i = 0; i < n; i++) std::memcpy(out.ptr(i), desc.ptr(i), 32);
 }
 
 void ORBextractor::FetchImagePyramid()

@@ -8,6 +8,7 @@
 #include <list>
 #include <set>
 #include <map>
+#include <unordered_map>
 #include <mutex>
 #include <stdexcept>
 #include <string>
@@ -465,18 +466,23 @@ void essential_graph(const std::vector<KeyFrame *> &vpKFs, const std::vector<Map
         for (int r = 0; r < 3; r++) { for (int c = 0; c < 3; c++) Tiw.at<float>(r, c) = (float)R[3 * r + c]; Tiw.at<float>(r, 3) = (float)(C.v[4 + r] * is); }
         pKFi->SetPose(Tiw);
     }
+    std::unordered_map<unsigned long, int> vertex_of_id;                        // mnId -> vertex (the reference indexes vScw by mnId, :1032-1041)
+    vertex_of_id.reserve(vid.size());
+    for (std::map<KeyFrame *, int>::const_iterator it = vid.begin(); it != vid.end(); ++it) vertex_of_id[it->first->mnId] = it->second;
     for (size_t i = 0, iend = vpMPs.size(); i < iend; i++) {                    // map points: corrected by their reference keyframe, :1021-1045
         MapPoint *pMP = vpMPs[i];
         if (pMP->isBad()) continue;
-        int k = -1;
-        if (pMP->mnCorrectedByKF == pCurKF->mnId) {
-            for (std::map<KeyFrame *, int>::const_iterator it = vid.begin(); it != vid.end(); ++it) if (it->first->mnId == pMP->mnCorrectedReference) { k = it->second; break; }
-        } else {
-            KeyFrame *pRefKF = pMP->GetReferenceKeyFrame();
-            if (vid.count(pRefKF)) k = vid[pRefKF];
-        }
-        if (k < 0) continue;
+        const unsigned long nIDr = pMP->mnCorrectedByKF == pCurKF->mnId ? pMP->mnCorrectedReference : pMP->GetReferenceKeyFrame()->mnId;
+        const std::unordered_map<unsigned long, int>::const_iterator f = vertex_of_id.find(nIDr);
+        const int k = f == vertex_of_id.end() ? -1 : f->second;
         cv::Mat P3Dw = pMP->GetWorldPos();
+        if (k < 0) {
+            // the reference keyframe is not a vertex (bad keyframe): the reference reads default-constructed (identity) Sim3s from its mnId-indexed
+            // vectors, i.e. the position is kept but still re-set and the normal / depth refreshed
+            pMP->SetWorldPos(P3Dw);
+            pMP->UpdateNormalAndDepth();
+            continue;
+        }
         const double X[3] = {P3Dw.at<float>(0), P3Dw.at<float>(1), P3Dw.at<float>(2)};
         double Xr[3], Xc[3];
         s8_map(vScw[k], X, Xr);

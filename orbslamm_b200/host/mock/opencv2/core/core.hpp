@@ -59,7 +59,25 @@ private:
     std::shared_ptr<unsigned char> buf_;
 };
 
-typedef const Mat &InputArray;
-typedef Mat &OutputArray;
+// Proxy types like OpenCV's own (core/mat.hpp): InputArray / OutputArray are NOT cv::Mat -- no ptr(), no rows -- so that API misuse in the drop-in sources fails
+// in this mock build exactly as it would against real OpenCV.
+class _InputArray {
+public:
+    _InputArray() {}
+    _InputArray(const Mat &m) : m_(const_cast<Mat *>(&m)) {}
+    Mat getMat() const { return m_ ? *m_ : Mat(); }
+    bool empty() const { return !m_ || m_->empty(); }
+protected:
+    Mat *m_ = nullptr;
+};
+class _OutputArray : public _InputArray {
+public:
+    _OutputArray() {}
+    _OutputArray(Mat &m) : _InputArray(m) {}
+    void create(int r, int c, int type) const { if (m_) m_->create(r, c, type); }
+    void release() const { if (m_) m_->release(); }
+};
+typedef const _InputArray &InputArray;
+typedef const _OutputArray &OutputArray;
 
 }  // namespace cv

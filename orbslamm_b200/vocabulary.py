@@ -35,6 +35,11 @@ def save_text(vocab, path):
 
 
 def load_text(path):
+    """Reads the nodes the file lists.  Divergence from the reference's loader, kept on purpose: after a final newline `while(!f.eof()) getline`
+    (TemplatedVocabulary.h:1377-1410) appends one more node under the root whose leaf flag, weight and descriptor are whatever the failed stream
+    extractions leave behind (uninitialised memory in a real OpenCV build).  It cannot be reproduced; modelling it as a zero-descriptor, weight-0 node
+    was tried and DROPS 45 of 1956 words of a KITTI-shape frame on the shipped ORBvoc.txt, whereas the reference's own object code (oracle/_ref) gives
+    the same BowVector with and without the final newline -- which is what this loader gives (tests/test_oracle_vs_reference.py)."""
     with open(path) as f:
         k, L, n1, n2 = [int(x) for x in f.readline().split()[:4]]
         if n1 != 0 or n2 != 0:

@@ -272,8 +272,13 @@ def run_merge(scene, drive, check=None, out=None, gba_opt=None):
     run on the SAME inputs at every stage and asserted equal (integer stages exactly, fp64 stages to 1e-5 / identical flags).  Returns the merged graph and results."""
     A, Bm = scene["A"], scene["B"]
     out = {} if out is None else out
+    import time
+    timing = out.setdefault("stage_ms", {})
     def both(name, fn, cmp):
+        t0 = time.perf_counter()
         r = fn(drive)
+        key = name.split(" cand ")[0].split(" KF ")[0]
+        timing[key] = timing.get(key, 0.0) + (time.perf_counter() - t0) * 1e3
         if check is not None:
             cmp(name, fn(check), r)
         return r

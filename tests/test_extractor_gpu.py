@@ -87,3 +87,19 @@ def test_extract_other_shapes(lib, shape, nf, levels, sf):
     outs = ex.extract_batch(batch)
     for i in range(n):
         _assert_same(outs[i], refs[i % 3], f"{shape} frame {i}")
+
+
+def test_two_extractors_of_different_size_interleaved(lib):
+    """Monocular Tracking owns mpIniORBextractor(2 * nFeatures) and mpORBextractorLeft(nFeatures) (Tracking.cc:115-121) and uses them alternately after a tracking
+    loss; the opt-in shared-memory limits of the kernels are per-device function attributes, so a second, smaller handle must not lower what the first one needs."""
+    import orbslamm_b200 as ob
+    c = synth.KITTI
+    frames, _ = synth.stream(c["w"], c["h"], 2, stream_id=12)
+    big = ob.ORBextractor(2 * c["nfeatures"], 1.2, 8, 20, 7)
+    first = big(frames[0])
+    small = ob.ORBextractor(c["nfeatures"] // 4, 1.2, 8, 20, 7)
+    Pb, Ps = oracle.orb_params(2 * c["nfeatures"], 1.2, 8, 20, 7), oracle.orb_params(c["nfeatures"] // 4, 1.2, 8, 20, 7)
+    for rnd in range(2):
+        _assert_same(small(frames[rnd]), oracle.orb_extract(Ps, frames[rnd]), f"small extractor, round {rnd}")
+        _assert_same(big(frames[rnd]), oracle.orb_extract(Pb, frames[rnd]), f"big extractor after the small one, round {rnd}")
+    _assert_same(first, oracle.orb_extract(Pb, frames[0]), "big extractor, first call")
