@@ -401,12 +401,33 @@ template <> struct CandKey<false> {
     static __device__ __forceinline__ unsigned pack(T m) { return ((unsigned)(m >> 32) << 20) | (unsigned)(m & 0xfffff); }
 };
 
+// ascending bitonic sort of one key per lane across the warp (15 compare-exchange steps; the keys are unique, `none` sorts last)
+template <typename Key>
+__device__ __forceinline__ Key warp_sort_ascending(Key v, int lane)
+{
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            const Key o = __shfl_xor_sync(0xffffffffu, v, j);
+            const bool take_min = ((lane & k) == 0) == ((lane & j) == 0);
+            v = take_min ? (o < v ? o : v) : (o < v ? v : o);
+        }
+    }
+    return v;
+}
+
+// One warp per query.  The features of the window's grid cells are dealt to the lanes one by one (prefix sum of the cell populations + a 5-step
+// search for the owning cell), so a typical window -- 4 to 9 cells holding about a dozen features -- keeps a dozen lanes busy for ONE pass instead of
+// 4 to 9 lanes walking their cells serially.  Every batch of <= 32 candidate keys is sorted across the warp and merged into the running top-kTop list
+// (lanes 0 .. kTop-1) with a 16-lane bitonic merge.  Same result as a sequential scan: the kTop smallest keys in the reference's comparison order.
 template <bool K32>
 __global__ void __launch_bounds__(256)
 k_search_candidates(const SearchArgs A)
 {
     typedef CandKey<K32> CK;
     typedef typename CK::T Key;
+    constexpr unsigned full = 0xffffffffu;
     const int f = blockIdx.y, lane = threadIdx.x & 31;
     const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (i >= A.q_counts[f]) return;
@@ -419,49 +440,61 @@ k_search_candidates(const SearchArgs A)
     const float r = A.q_radius[qo + i];
     const int minl = A.q_minl[qo + i], maxl = A.q_maxl[qo + i];
     const Window w = make_window(A.g, uv, r, minl, maxl);
-    Key loc[kTop];            // this lane's sorted best keys
-#pragma unroll
-    for (int t = 0; t < kTop; t++) loc[t] = CK::none;
+    Key best = CK::none;      // lane t < kTop: the t-th smallest key so far
+    bool first = true;
     int n = 0;
     if (!w.empty) {
         const uint4 qa = __ldg(&A.q_desc[2 * (qo + i)]), qb = __ldg(&A.q_desc[2 * (qo + i) + 1]);
         const int ncy = w.r1 - w.r0 + 1, ncells = (w.c1 - w.c0 + 1) * ncy;
-        for (int c = lane; c < ncells; c += 32) {
-            const int ix = w.c0 + c / ncy, iy = w.r0 + c % ncy;
-            const int cell = ix * kGridRows + iy;
-            const int je = cs[cell + 1];
-            for (int j = cs[cell]; j < je; j++) {
-                const int k = items[j];
-                if (!in_window(w, minl, maxl, uv, r, f_octave[k], f_xy[k])) continue;
-                n++;
-                Key key = CK::make(hamming256(qa, qb, __ldg(&f_desc[2 * k]), __ldg(&f_desc[2 * k + 1])), ix, iy, k);
+        for (int cb = 0; cb < ncells; cb += 32) {
+            const int c = cb + lane;
+            int start = 0, cnt = 0, cxy = 0;
+            if (c < ncells) {
+                const int ix = w.c0 + c / ncy, iy = w.r0 + c % ncy;
+                const int cell = ix * kGridRows + iy;
+                start = cs[cell]; cnt = cs[cell + 1] - start; cxy = (ix << 8) | iy;
+            }
+            int incl = cnt;
 #pragma unroll
-                for (int t = 0; t < kTop; t++) {                   // sorted insert
-                    const Key cur = loc[t];
-                    const bool lt = key < cur;
-                    loc[t] = lt ? key : cur;
-                    key = lt ? cur : key;
+            for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(full, incl, d); if (lane >= d) incl += o; }
+            const int tot = __shfl_sync(full, incl, 31);
+            const int first_item = start - (incl - cnt);                   // items index of the cell's first feature minus its rank in the batch order
+            for (int t0 = 0; t0 < tot; t0 += 32) {
+                const int t = t0 + lane;
+                int lo = 0;                                                 // the cell that holds item t: number of lanes with incl <= t
+#pragma unroll
+                for (int sft = 16; sft > 0; sft >>= 1) { const int v = __shfl_sync(full, incl, lo + sft - 1); if (v <= t) lo += sft; }
+                const int o_first = __shfl_sync(full, first_item, lo), o_cxy = __shfl_sync(full, cxy, lo);
+                Key key = CK::none;
+                if (t < tot) {
+                    const int k = items[o_first + t];
+                    if (in_window(w, minl, maxl, uv, r, f_octave[k], f_xy[k])) {
+                        n++;
+                        key = CK::make(hamming256(qa, qb, __ldg(&f_desc[2 * k]), __ldg(&f_desc[2 * k + 1])), o_cxy >> 8, o_cxy & 0xff, k);
+                    }
+                }
+                key = warp_sort_ascending(key, lane);
+                if (first) { best = lane < kTop ? key : CK::none; first = false; }
+                else {
+                    // lanes 0..7: the list so far (ascending), lanes 8..15: the 8 smallest new keys, descending -> one bitonic sequence of 16
+                    const Key rev = __shfl_sync(full, key, (15 - lane) & 31);
+                    Key v = lane < kTop ? best : (lane < 2 * kTop ? rev : CK::none);
+#pragma unroll
+                    for (int j = kTop; j > 0; j >>= 1) {
+                        const Key o = __shfl_xor_sync(full, v, j);
+                        v = ((lane & j) == 0) ? (o < v ? o : v) : (o < v ? v : o);
+                    }
+                    best = lane < kTop ? v : CK::none;
                 }
             }
         }
     }
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) n += __shfl_xor_sync(0xffffffffu, n, d);
-    // merge the 32 sorted lists: kTop rounds of warp-min + pop
-#pragma unroll
-    for (int t = 0; t < kTop; t++) {
-        Key m = loc[0];
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) { const Key o = __shfl_xor_sync(0xffffffffu, m, d); m = o < m ? o : m; }
-        if (m != CK::none && loc[0] == m) {
-#pragma unroll
-            for (int u = 0; u < kTop - 1; u++) loc[u] = loc[u + 1];
-            loc[kTop - 1] = CK::none;
-        }
-        if (lane == 0) top[t] = m == CK::none ? 0xffffffffu : CK::pack(m);
-    }
+    for (int d = 16; d > 0; d >>= 1) n += __shfl_xor_sync(full, n, d);
+    if (lane < kTop) top[lane] = best == CK::none ? 0xffffffffu : CK::pack(best);
     if (lane == 0) A.ncand[qo + i] = n;
 }
+
 
 // Search half without claims (Fuse, SearchBySim3): one warp per query, lanes over the grid cells of the window; the minimum of
 // (distance, visiting order) is the feature the reference's "dist < bestDist" loop ends with.

@@ -83,7 +83,7 @@ k_resize_level(const uint8_t *__restrict__ src, int sw, int sh, int spitch, size
 constexpr int kRawRows = 66;                 // cell sub-images are <= 66 x 66
 constexpr int kRawPitchMax = 96;             // bytes per staged row: 16-byte aligned start (<= 15 bytes early) + cw + 1, rounded to 16
 constexpr int kPixPitch16 = 96;              // u16 per pix16 row (48 words: consecutive rows start 16 banks apart)
-constexpr int kScPitch16 = 66;               // u16 per score row (33 words)
+constexpr int kScPitch16 = 68;               // u16 per score row (34 words: every row starts 8-byte aligned for the 64-bit loads of the NMS pass)
 constexpr int kScRows = 62;                  // detection region is <= 60 x 60 (+ zero frame)
 
 struct LevelTmaps { CUtensorMap m[ORBS_MAX_LEVELS]; };      // one (x, y, frame) u8 tensor map per pyramid level
@@ -187,13 +187,14 @@ k_fast_cells(const __grid_constant__ ExtractPlan plan, const __grid_constant__ L
             raw[t] = x < L.w ? img[(size_t)(cell.y0 + y) * pitch + x] : (uint8_t)0;
         }
     }
-    // zero frame of the score plane: rows 0 and dh + 1, left word (indices 0, 1) and the words from index dw + 2 on
+    // zero frame of the score plane: rows 0 and dh + 1, the left word (indices 0, 1) and, right of the scores, every word up to the last one the NMS pass
+    // reads (word 2 * ngroups + 1; the first of them is rewritten by the scores if it holds a real pixel)
     {
         unsigned *s32 = reinterpret_cast<unsigned *>(sc16);
-        constexpr int SW = kScPitch16 / 2;                                  // 33 words per row
+        constexpr int SW = kScPitch16 / 2;                                  // 34 words per row
         for (int t = tid; t < SW; t += 128) { s32[t] = 0u; s32[(dh + 1) * SW + t] = 0u; }
-        const int wr = (dw + 2) >> 1;                                       // first word holding an index >= dw + 2 (or dw + 1 if dw is odd: rewritten by the scores)
-        for (int y = tid; y < dh; y += 128) { s32[(y + 1) * SW] = 0u; s32[(y + 1) * SW + wr] = 0u; if (wr + 1 < SW) s32[(y + 1) * SW + wr + 1] = 0u; }
+        const int wr = (dw + 2) >> 1, wl = 2 * ((dw + 3) >> 2) + 1;         // first word holding an index >= dw + 2 (or dw + 1 if dw is odd), last word read
+        for (int y = tid; y < dh; y += 128) { s32[(y + 1) * SW] = 0u; for (int w = wr; w <= wl; w++) s32[(y + 1) * SW + w] = 0u; }
     }
     if (use_map || use_tma) {
         unsigned done = 0;
@@ -267,27 +268,32 @@ k_fast_cells(const __grid_constant__ ExtractPlan plan, const __grid_constant__ L
 
     // ---- 3. cell-local strict 3x3 maxima; threshold of this cell: iniTh if cv::FAST(iniTh, nms) would return at least one
     // keypoint, else minTh (ORBextractor.cc:808-816; the test is on the NMS survivors, so a plateau of equal scores >= iniTh
-    // that suppresses itself still triggers the fallback).  One step = one pixel pair; keep bits stay in a register.
-    const int npairs = (dw + 1) >> 1;
-    unsigned keepbits = 0u, strongbits = 0u;      // bit 2*it + lane: NMS survivor with score >= minTh / >= iniTh
+    // that suppresses itself still triggers the fallback).  One step = the same 4 adjacent pixels as in the scoring pass: six 64-bit loads
+    // (three rows of words 2g .. 2g+3), the column maxima of the rows above / below shared by the two centre words; keep bits stay in a register.
+    unsigned keepbits = 0u, strongbits = 0u;      // bit 4*it + k: pixel 4g + k is an NMS survivor with score >= minTh / >= iniTh
     {
-        const unsigned *s32 = reinterpret_cast<const unsigned *>(sc16);
-        constexpr int SW = kScPitch16 / 2;
+        constexpr int SW2 = kScPitch16 / 4;                                 // row pitch in uint2
         const unsigned minth2 = (unsigned)plan.min_th * 0x00010001u, inith2 = (unsigned)plan.ini_th * 0x00010001u;
+        const unsigned bias2 = 0x80008000u - minth2;                        // lane + bias has bit 15 set iff lane >= minTh (scores <= 254: no carry between lanes)
         int it = 0;
-        for (RowCol rc(tid, npairs); rc.row < dh; rc.next(), it++) {
-            const unsigned *c = s32 + (rc.row + 1) * SW + rc.col + 1;       // word of detection pixels (2i, 2i+1)
-            const unsigned w0 = c[0];
-            if (w0 == 0u) continue;
-            const unsigned ul = c[-SW - 1], uc = c[-SW], ur = c[-SW + 1], ml = c[-1], mr = c[1], dl = c[SW - 1], dc = c[SW], dr = c[SW + 1];
-            const unsigned up = __vimax3_u16x2(hi_lo(ul, uc), uc, hi_lo(uc, ur));
-            const unsigned dn = __vimax3_u16x2(hi_lo(dl, dc), dc, hi_lo(dc, dr));
-            const unsigned nb = __vimax3_u16x2(up, dn, __vmaxu2(hi_lo(ml, w0), hi_lo(w0, mr)));
-            // per lane: w0 > nb (strict maximum) and w0 >= minTh -> 0xffff lane masks
-            const unsigned km = __vcmpgtu2(w0, nb) & __vcmpgeu2(w0, minth2);
-            const unsigned sm = km & __vcmpgeu2(w0, inith2);
-            keepbits |= ((km & 1u) | ((km >> 15) & 2u)) << (2 * it);
-            strongbits |= ((sm & 1u) | ((sm >> 15) & 2u)) << (2 * it);
+        for (RowCol rc(tid, ngroups); rc.row < dh; rc.next(), it++) {
+            const uint2 *up = reinterpret_cast<const uint2 *>(sc16 + rc.row * kScPitch16 + 4 * rc.col);      // score rows gy, gy + 1 (centre), gy + 2
+            const uint2 m0 = up[SW2], m1 = up[SW2 + 1];
+            const unsigned c1 = m0.y, c2 = m1.x;                            // pixels (4g, 4g+1) and (4g+2, 4g+3)
+            if (((__vmaxu2(c1, c2) + bias2) & 0x80008000u) == 0u) continue;
+            const uint2 u0 = up[0], u1 = up[1], d0 = up[2 * SW2], d1 = up[2 * SW2 + 1];
+            const unsigned v0 = __vmaxu2(u0.x, d0.x), v1 = __vmaxu2(u0.y, d0.y), v2 = __vmaxu2(u1.x, d1.x), v3 = __vmaxu2(u1.y, d1.y);
+            const unsigned v12 = hi_lo(v1, v2), m12 = hi_lo(c1, c2);
+            const unsigned nb1 = __vimax3_u16x2(__vimax3_u16x2(hi_lo(v0, v1), v1, v12), hi_lo(m0.x, c1), m12);
+            const unsigned nb2 = __vimax3_u16x2(__vimax3_u16x2(v12, v2, hi_lo(v2, v3)), m12, hi_lo(c2, m1.y));
+            // per lane: keep iff centre > all eight neighbours and centre >= th  <=>  max(neighbours + 1, th, centre) == centre.  The lane-wise difference
+            // (never negative, <= 255) plus 0x7fff sets bit 15 exactly where the lane differs.
+            const unsigned n1 = nb1 + 0x00010001u, n2 = nb2 + 0x00010001u;
+            const unsigned k1 = ~((__vimax3_u16x2(n1, minth2, c1) - c1) + 0x7fff7fffu) & 0x80008000u, k2 = ~((__vimax3_u16x2(n2, minth2, c2) - c2) + 0x7fff7fffu) & 0x80008000u;
+            const unsigned s1 = ~((__vimax3_u16x2(n1, inith2, c1) - c1) + 0x7fff7fffu) & 0x80008000u, s2 = ~((__vimax3_u16x2(n2, inith2, c2) - c2) + 0x7fff7fffu) & 0x80008000u;
+            const unsigned K = (k1 >> 15) | (k2 >> 13), S = (s1 >> 15) | (s2 >> 13);       // bits 0, 16 (pixels 4g, 4g+1) and 2, 18 (4g+2, 4g+3)
+            keepbits |= ((K & 5u) | ((K >> 15) & 10u)) << (4 * it);
+            strongbits |= ((S & 5u) | ((S >> 15) & 10u)) << (4 * it);
         }
     }
     // threshold of the cell: iniTh if any survivor reaches it, else the minTh retry
@@ -311,12 +317,11 @@ k_fast_cells(const __grid_constant__ ExtractPlan plan, const __grid_constant__ L
     while (mine) {
         const int b = __ffs(mine) - 1;
         mine &= mine - 1;
-        const int t = tid + 128 * (b >> 1), e = b & 1;
-        const int gy = t / npairs, i = t - gy * npairs;
-        const unsigned w0 = reinterpret_cast<const unsigned *>(sc16)[(gy + 1) * (kScPitch16 / 2) + i + 1];
-        const unsigned sc = e ? (w0 >> 16) : (w0 & 0xffffu);
+        const int t = tid + 128 * (b >> 2), e = b & 3;
+        const int gy = t / ngroups, d = 4 * (t - gy * ngroups) + e;
+        const unsigned sc = sc16[(gy + 1) * kScPitch16 + d + 2];
         if (pos < L.cand_cap) {
-            const unsigned kx = (unsigned)(2 * i + e + 3 + cell.addx), ky = (unsigned)(gy + 3 + cell.addy);
+            const unsigned kx = (unsigned)(d + 3 + cell.addx), ky = (unsigned)(gy + 3 + cell.addy);
             out[pos] = make_uint2(kx | (ky << 16), sc | ((unsigned)cell.ci << 8) | ((unsigned)cell.cj << 18));
         } else {
             *err_flag = 1;

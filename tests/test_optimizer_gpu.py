@@ -140,6 +140,31 @@ def test_global_ba_and_abort(lib):
     assert ab["aborted"] and np.array_equal(ab["poses"], g["poses"]) and np.array_equal(ab["points"], g["points"])
 
 
+def test_stop_flag_raised_by_another_thread_mid_run(lib):
+    """mbAbortBA (LocalMapping::InsertKeyFrame) / mbStopGBA are raised by another thread WHILE the optimisation runs and g2o's terminate() sees them at the next
+    iteration (sparse_optimizer.cpp:384-389).  The C-ABI polls the caller's byte during the run: a flag raised mid-run must cut the LM loop short."""
+    import threading
+    import time
+    import orbslamm_b200 as ob
+    g = synth.ba_graph(K=300, P=30000, seed=3)
+    opt = ob.Optimizer()
+    args = (g["poses"], g["fixed"], g["intr"], g["points"], g["kf"], g["pt"], g["uv"], g["inv_sigma2"])
+    full = opt.BundleAdjustment(*args, nIterations=60, bRobust=True)
+    assert full["lm_iterations"] >= 12 and not full["aborted"]
+    cut = None
+    for delay in (0.004, 0.008, 0.016, 0.002):                      # the flag has to fall inside the LM loop (after the graph setup, before the last iteration)
+        stop = np.zeros(1, np.uint8)
+        t = threading.Timer(delay, lambda: stop.__setitem__(0, 1))
+        t.start()
+        r = opt.BundleAdjustment(*args, nIterations=60, bRobust=True, stop_flag=stop)
+        t.join()
+        if 0 < r["lm_iterations"] < full["lm_iterations"]:
+            cut = r
+            break
+    assert cut is not None, "no run was cut short by a flag raised from another thread"
+    assert not np.array_equal(cut["poses"], g["poses"])            # the iterations that did run are kept, as in the reference
+
+
 def test_pose_optimization_from_matches(lib):
     """Device-side edge gathering (Optimizer.cc:303-384) + PoseOptimization == oracle on the host-gathered edges."""
     import orbslamm_b200 as ob
