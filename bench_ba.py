@@ -132,6 +132,22 @@ def bench_ba(args, rank, world):
     out["lm_iterations"] = int(iters)
     if sharded_parity is not None:
         out["sharded_parity"] = sharded_parity
+        # what the multi-robot system actually runs: one LocalBA per robot (LocalMapping per System) = N independent solves, one per GPU, no collective
+        solo = ob.Optimizer(device=dev)
+        run1 = lambda: solo.LocalBundleAdjustment(full["poses"], full["fixed"], full["intr"], full["points"], full["kf"], full["pt"], full["uv"], full["inv_sigma2"])
+        for _ in range(2):
+            run1()
+        barrier()
+        rl = 0.0; ri = 0
+        for i in range(steps):
+            flush.fill_(i & 0xff)
+            torch.cuda.synchronize()
+            r1 = run1()
+            rl += solo.last_ba_timing()["lm_loop_s"]; ri += r1["lm_iterations"]
+        tt = torch.tensor([rl], device="cuda", dtype=torch.float64)
+        torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.MAX)
+        out["replicas"] = {"value": round(world * ri / float(tt.item()), 2), "unit": "LM iterations/s", "scaling": "weak",
+                           "note": f"{world} independent 500 KF / 50k-point LocalBAs, one per GPU (one LocalMapping thread per robot), aggregate; max over ranks"}
     if rank == 0:
         out["cpu_baseline"] = cpu_baseline_ba(K, P, 1)
     return out

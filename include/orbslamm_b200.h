@@ -154,6 +154,14 @@ long long orbm_kernel_launches(const orbm_handle *h);
  * a u8[n,32], b u8[m,32], out i32[n,m]. */
 int orbm_descriptor_distance(orbm_handle *h, const uint8_t *a, int n, const uint8_t *b, int m, int32_t *out, int memspace);
 
+/* MapPoint::ComputeDistinctiveDescriptors (S/src/MapPoint.cc:242-307) for a batch of map points: point p owns the descriptor rows start[p] .. start[p+1]-1 of
+ * desc (its observations in std::map<KeyFrame*, size_t> order, bad keyframes left out); best_idx[p] = the row (relative to start[p]) with the least median
+ * Hamming distance to the point's rows (sorted row, element (int)(0.5 * (N - 1)), self distance 0 included; first row on ties), -1 for a point without rows.
+ * The reference calls the member once per map point from LocalMapping::ProcessNewKeyFrame / CreateNewMapPoints / SearchInNeighbors, LoopClosing and
+ * MultiMapper (O(N^2) DescriptorDistance calls each); the drop-in collects the points of one such loop and makes one call.
+ *   desc u8[start[n_points], 32] (16-byte aligned), start i32[n_points + 1], best_idx i32[n_points]. */
+int orbm_distinctive_descriptors(orbm_handle *h, int n_points, const uint8_t *desc, const int32_t *start, int32_t *best_idx, int memspace);
+
 /* Frame::UndistortKeyPoints (S/src/Frame.cc:404-434): cv::undistortPoints(pts, K, distCoef, R = I, P = K) with OpenCV's default
  * criteria (5 fixed-point iterations in fp64); a copy when dist5[0] == 0 (Frame.cc:406-410).
  *   kp_xy f32[n_frames*slab,2] (Frame::mvKeys[i].pt), counts i32[n_frames]; K4 f32[4] = fx fy cx cy and dist5 f32[5] = k1 k2 p1 p2 k3
@@ -407,6 +415,13 @@ int orbo_bundle_adjust(orbo_handle *h, int K, float *poses, const uint8_t *fixed
  * (1e-5 * max diagonal).  stats i32[3] (may be NULL): LM iterations, LM trials, failed factorisations. */
 int orbo_optimize_pose_graph(orbo_handle *h, int K, double *sim3, const uint8_t *fixed, int E, const int32_t *e_i, const int32_t *e_j,
                              const double *e_meas, int fix_scale, int iterations, double lambda_init, int32_t *stats);
+
+/* Sim3Solver::ComputeSim3 (S/src/Sim3Solver.cc:226-338: Horn's closed form on three point pairs) for n_hyp RANSAC min sets in one launch.
+ *   X1, X2 f32[n_hyp, 3, 3]: the three points (rows) of every min set in camera-1 / camera-2 coordinates (mvX3Dc1[idx], mvX3Dc2[idx]);
+ *   out: T12, T21 f32[n_hyp, 16] (mT12i, mT21i, row-major 4x4), Rts f32[n_hyp, 13] = mR12i (9), mt12i (3), ms12i -- may be NULL.
+ * Float arithmetic in OpenCV's evaluation order; cv::eigen is OpenCV-build dependent, so parity is a float tolerance (1e-4 relative on the matrices), not
+ * bit-exactness: the drop-in uses this entry only when built with -DORBSLAMM_DEVICE_COMPUTE_SIM3 and otherwise keeps the reference's host ComputeSim3. */
+int orbo_sim3_compute(orbo_handle *h, int n_hyp, const float *X1, const float *X2, int fix_scale, float *T12, float *T21, float *Rts, int memspace);
 
 /* Sim3Solver (S/src/Sim3Solver.cc), the data-parallel part of the RANSAC.  ComputeSim3 (Horn's closed form on three points, :226-338) stays with
  * the caller: the random index triples do not depend on the inlier counts, so all hypotheses of a solver (<= mRansacMaxIts = 300) can be

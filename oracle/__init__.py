@@ -228,6 +228,26 @@ def descriptor_distance(a, b):
     return int(lib().oracle_descriptor_distance(_p(a, _u8p), _p(b, _u8p)))
 
 
+def distinctive_descriptor(desc):
+    """MapPoint::ComputeDistinctiveDescriptors (S/src/MapPoint.cc:271-303) on the descriptors of one map point's observations, u8[N, 32]: the N x N
+    DescriptorDistance table (float entries, zero diagonal), every row sorted, its element (int)(0.5 * (N - 1)) = the median, the FIRST row with the
+    strictly smallest median wins.  Returns BestIdx (-1 for N = 0: the reference returns before choosing)."""
+    d = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32); N = len(d)
+    if N == 0:
+        return -1
+    D = np.zeros((N, N), np.float32)
+    for i in range(N):
+        for j in range(i + 1, N):
+            D[i, j] = D[j, i] = descriptor_distance(d[i], d[j])
+    best_median, best = 2 ** 31 - 1, 0
+    for i in range(N):
+        v = np.sort(D[i].astype(np.int32))
+        median = int(v[int(0.5 * (N - 1))])
+        if median < best_median:
+            best_median, best = median, i
+    return best
+
+
 def project_last_frame(Tcw, K4, g, scale_factors, Xw, last_octave, th, valid):
     """Projection block of SearchByProjection(Cur, Last).  Returns (valid, uv, radius, minl, maxl)."""
     Tcw = np.ascontiguousarray(Tcw, np.float32).reshape(16); K4 = np.ascontiguousarray(K4, np.float32)

@@ -264,6 +264,21 @@ class ORBmatcher:
         _check(self._L.orbm_descriptor_distance(self._h, _ptr(a), len(a), _ptr(b), len(b), _ptr(out), 0))
         return out
 
+    def ComputeDistinctiveDescriptors(self, desc_lists):
+        """MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:242-307) for a batch of map points: desc_lists[p] = u8[N_p, 32], the descriptors of the point's
+        observations in map order.  Returns best_idx i32[n_points] (-1 for an empty list)."""
+        n = len(desc_lists)
+        start = np.zeros(n + 1, np.int32)
+        for p, d in enumerate(desc_lists): start[p + 1] = start[p] + len(d)
+        flat = np.zeros((max(int(start[n]), 1), 32), np.uint8)
+        for p, d in enumerate(desc_lists):
+            if len(d): flat[start[p]:start[p + 1]] = np.asarray(d, np.uint8).reshape(-1, 32)
+        out = np.zeros(n, np.int32)
+        self._L.orbm_distinctive_descriptors.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+        self._L.orbm_distinctive_descriptors.restype = ctypes.c_int
+        _check(self._L.orbm_distinctive_descriptors(self._h, n, _ptr(flat), _ptr(start), _ptr(out), 0))
+        return out
+
     def project_last_frame(self, Tcw, K4, bounds4, scale_factors, Xw, last_octave, q_counts, th, q_valid):
         """Projection block of SearchByProjection(Cur, Last) for n_frames frames (host arrays, slab layout)."""
         Tcw = np.ascontiguousarray(Tcw, np.float32).reshape(-1, 16); nfr = len(Tcw)
@@ -575,6 +590,15 @@ class Optimizer:
         me = np.zeros(N, np.int32); p = np.zeros((N, 2), np.float32)
         _check(self._L.orbo_sim3_prepare(self._h, N, _ptr(X), _ptr(o), _ptr(ls), len(ls), _ptr(K), _ptr(me), _ptr(p), 0))
         return me, p
+
+    def Sim3Compute(self, X1, X2, bFixScale=False):
+        """Sim3Solver::ComputeSim3 for a batch of min sets: X1, X2 f32[n_hyp, 3, 3] (three points each).  Returns (T12, T21 [n_hyp,4,4], R12 [n_hyp,3,3], t12, s12)."""
+        a = np.ascontiguousarray(X1, np.float32).reshape(-1, 9); b = np.ascontiguousarray(X2, np.float32).reshape(-1, 9); n = len(a)
+        T12 = np.zeros((n, 16), np.float32); T21 = np.zeros((n, 16), np.float32); R = np.zeros((n, 13), np.float32)
+        self._L.orbo_sim3_compute.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+        self._L.orbo_sim3_compute.restype = ctypes.c_int
+        _check(self._L.orbo_sim3_compute(self._h, n, _ptr(a), _ptr(b), int(bool(bFixScale)), _ptr(T12), _ptr(T21), _ptr(R), 0))
+        return T12.reshape(n, 4, 4), T21.reshape(n, 4, 4), R[:, :9].reshape(n, 3, 3), R[:, 9:12], R[:, 12]
 
     def Sim3CheckInliers(self, T12, T21, X3Dc1, X3Dc2, P1im1, P2im2, max_err1, max_err2, K1, K2):
         """Sim3Solver::CheckInliers for a batch of RANSAC hypotheses: (inliers u8[n_hyp, N], n_inliers i32[n_hyp])."""

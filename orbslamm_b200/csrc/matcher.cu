@@ -3,6 +3,7 @@
 //
 // Replaces S/src/ORBmatcher.cc:45-137, 1330-1472, 1603-1665 and S/src/Frame.cc:230-245, 327-392.
 // Pure integer work (XOR + POPC over 8 x u32) plus fp32 window arithmetic with explicit rounding.
+#include <algorithm>
 #include <vector>
 #include <mutex>
 #include "common.cuh"
@@ -29,6 +30,35 @@ k_hamming_pairs(const uint4 *__restrict__ a, int n, const uint4 *__restrict__ b,
     if (t >= (size_t)n * m) return;
     const int i = (int)(t / m), j = (int)(t - (size_t)i * m);
     out[t] = hamming256(__ldg(&a[2 * i]), __ldg(&a[2 * i + 1]), __ldg(&b[2 * j]), __ldg(&b[2 * j + 1]));
+}
+
+// MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:242-307) for a batch of map points: the descriptor with the least MEDIAN distance to the point's other
+// observations (`vDists[0.5 * (N - 1)]` of the sorted row, the zero self-distance included; the first row wins ties).  One warp per point, lanes over the rows;
+// a row's median is found by bisection on the distance value (9 counting passes over the row: the smallest v with |{j : d_ij <= v}| >= k + 1), which needs no
+// per-row storage however many observations a point has.  The reference does this on the host with an N x N float array on the stack per call.
+__global__ void __launch_bounds__(256)
+k_distinctive(int n_points, const uint4 *__restrict__ desc, const int *__restrict__ start, int *__restrict__ best_idx)
+{
+    const int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (p >= n_points) return;
+    const int b = start[p], N = start[p + 1] - b;
+    if (N <= 0) { if (lane == 0) best_idx[p] = -1; return; }
+    const int kth = (N - 1) >> 1;                                          // (int)(0.5 * (N - 1))
+    unsigned best = 0xffffffffu;                                           // median << 16 | row: minimum = least median, first row
+    for (int i = lane; i < N; i += 32) {
+        const uint4 a0 = __ldg(&desc[2 * (size_t)(b + i)]), a1 = __ldg(&desc[2 * (size_t)(b + i) + 1]);
+        int lo = 0, hi = 256;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            int c = 0;
+            for (int j = 0; j < N; j++) c += hamming256(a0, a1, __ldg(&desc[2 * (size_t)(b + j)]), __ldg(&desc[2 * (size_t)(b + j) + 1])) <= mid;
+            if (c >= kth + 1) hi = mid; else lo = mid + 1;
+        }
+        best = min(best, ((unsigned)lo << 16) | (unsigned)min(i, 0xffff));
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, d));
+    if (lane == 0) best_idx[p] = (int)(best & 0xffffu);
 }
 
 // ORBmatcher.cc:1354-1391, one thread per (frame, last-frame slot)
@@ -1071,6 +1101,32 @@ int orbm_descriptor_distance(orbm_handle *h, const uint8_t *a, int n, const uint
     ORBS_REQUIRE(((uintptr_t)da % 16 == 0) && ((uintptr_t)db % 16 == 0), ORBS_E_INVALID, "descriptor arrays must be 16-byte aligned");
     const size_t total = (size_t)n * m;
     k_hamming_pairs<<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>((const uint4 *)da, n, (const uint4 *)db, m, dout);
+    h->launches++;
+    ORBS_CUDA(cudaGetLastError());
+    return S.finish();
+}
+
+int orbm_distinctive_descriptors(orbm_handle *h, int n_points, const uint8_t *desc, const int32_t *start, int32_t *best_idx, int memspace)
+{
+    ORBS_REQUIRE(h && desc && start && best_idx, ORBS_E_INVALID, "null argument");
+    ORBS_REQUIRE(n_points >= 0, ORBS_E_INVALID, "negative size");
+    if (n_points == 0) return ORBS_OK;
+    std::lock_guard<std::mutex> lk(h->mu);
+    ORBS_CUDA(cudaSetDevice(h->device));
+    int32_t total = 0;
+    if (memspace == ORBS_MEM_HOST) total = start[n_points];
+    else ORBS_CUDA(cudaMemcpy(&total, start + n_points, sizeof(int32_t), cudaMemcpyDeviceToHost));
+    ORBS_REQUIRE(total >= 0, ORBS_E_INVALID, "start[] must be non-decreasing from 0");
+    if (memspace == ORBS_MEM_HOST)
+        for (int p = 0; p < n_points; p++)
+            ORBS_REQUIRE(start[p + 1] >= start[p] && start[p + 1] - start[p] <= 65535, ORBS_E_INVALID, "a map point has a negative number or more than 65535 observations");
+    Stager S(&h->pool, h->stream, memspace);
+    const uint8_t *dd = S.in(desc, (size_t)std::max(total, 1) * 32);
+    const int32_t *ds = S.in(start, (size_t)n_points + 1);
+    int32_t *dout = S.inout(best_idx, (size_t)n_points, false);
+    if (S.rc) return S.rc;
+    ORBS_REQUIRE((uintptr_t)dd % 16 == 0, ORBS_E_INVALID, "descriptor array must be 16-byte aligned");
+    k_distinctive<<<(n_points + 7) / 8, 256, 0, h->stream>>>(n_points, (const uint4 *)dd, ds, dout);
     h->launches++;
     ORBS_CUDA(cudaGetLastError());
     return S.finish();

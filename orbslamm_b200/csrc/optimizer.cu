@@ -278,6 +278,23 @@ int orbo_sim3_prepare(orbo_handle *h, int N, const float *X3Dc, const int32_t *o
     return S.finish();
 }
 
+int orbo_sim3_compute(orbo_handle *h, int n_hyp, const float *X1, const float *X2, int fix_scale, float *T12, float *T21, float *Rts, int memspace)
+{
+    ORBS_REQUIRE(h && X1 && X2 && T12 && T21, ORBS_E_INVALID, "null argument");
+    ORBS_REQUIRE(n_hyp > 0, ORBS_E_INVALID, "at least one hypothesis");
+    std::lock_guard<std::mutex> lk(h->mu);
+    ORBS_CUDA(cudaSetDevice(h->device));
+    Stager S(&h->pool, h->stream, memspace);
+    const float *d1 = S.in(X1, (size_t)n_hyp * 9), *d2 = S.in(X2, (size_t)n_hyp * 9);
+    float *o12 = S.inout(T12, (size_t)n_hyp * 16, false), *o21 = S.inout(T21, (size_t)n_hyp * 16, false);
+    float *ort = Rts ? S.inout(Rts, (size_t)n_hyp * 13, false) : S.scratch<float>((size_t)n_hyp * 13);
+    if (S.rc) return S.rc;
+    k_sim3_compute<<<(n_hyp + 127) / 128, 128, 0, h->stream>>>(n_hyp, d1, d2, fix_scale ? 1 : 0, o12, o21, ort);
+    h->launches++;
+    ORBS_CUDA(cudaGetLastError());
+    return S.finish();
+}
+
 int orbo_sim3_check_inliers(orbo_handle *h, int n_hyp, const float *T12, const float *T21, int N, const float *X3Dc1, const float *X3Dc2, const float *P1im1,
                             const float *P2im2, const int32_t *max_err1, const int32_t *max_err2, const float *K1, const float *K2, uint8_t *inliers,
                             int32_t *n_inliers, int memspace)

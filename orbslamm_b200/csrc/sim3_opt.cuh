@@ -413,4 +413,144 @@ k_sim3_prepare(int N, const float *__restrict__ X3Dc, const int *__restrict__ oc
     max_err[i] = (int)(unsigned long long)__dmul_rn(9.210, (double)level_sigma2[min(max(octave[i], 0), nlevels - 1)]);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Sim3Solver::ComputeSim3 (Sim3Solver.cc:226-338; Horn 1987, closed form on three point pairs) for a batch of RANSAC hypotheses, one thread each.
+// The reference runs it through OpenCV float matrices; this restates the arithmetic with OpenCV's evaluation order and precisions where they are known:
+//   centroid     cv::reduce(SUM) in float, then `C / 3` = float(double(C) * (1.0 / 3))                          (MatExpr scale)
+//   M            Pr2 * Pr1.t(): a gemm with a transposed operand -> OpenCV's general path, double accumulation, rounded to float
+//   N            doubles from the float entries of M, stored as float (Mat_<float> <<)
+//   eigen        cv::eigen of a symmetric 4x4 float matrix = Jacobi rotations in float (JacobiImpl_: pivot = largest off-diagonal entry tracked per row /
+//                column, 30 n^2 sweeps at most, eigenvalues sorted descending); the quaternion is the first eigenvector
+//   angle-axis   norm() and atan2 in double; `2*ang*vec/norm(vec)` = float(double(v) * ((2 ang) * (1 / norm)))  (MatExpr scale)
+//   Rodrigues    in double (theta, c, s, c1, r / theta), rounded to float
+//   P3 = R Pr2   3x3 small-matrix gemm: float products summed left to right;  nom = Pr1.dot(P3) and den = sum(P3^2) accumulate in double
+//   t12, T12, T21  scaled small gemms: float(double(float dot) * alpha)
+// cv::eigen is build dependent (an OpenCV built with Eigen uses SelfAdjointEigenSolver instead of Jacobi) and the quaternion's sign is arbitrary, so this path is
+// pinned to a float TOLERANCE against the cv2-backed restatement (tests/test_sim3_compute_gpu.py), not bit for bit; the drop-in keeps the reference's own host
+// ComputeSim3 unless built with -DORBSLAMM_DEVICE_COMPUTE_SIM3.
+__device__ __forceinline__ float s3_hypotf(float a, float b)
+{
+    a = fabsf(a); b = fabsf(b);                                            // OpenCV's hypot(): scaled form
+    if (a > b) { b = __fdiv_rn(b, a); return __fmul_rn(a, sqrtf(__fadd_rn(1.f, __fmul_rn(b, b)))); }
+    if (b > 0) { a = __fdiv_rn(a, b); return __fmul_rn(b, sqrtf(__fadd_rn(1.f, __fmul_rn(a, a)))); }
+    return 0.f;
+}
+
+__device__ inline void s3_jacobi4(float (&A)[4][4], float (&W)[4], float (&V)[4][4])
+{
+    constexpr int n = 4;
+    const float eps = 1.1920929e-07f;
+    int indR[n], indC[n];
+    for (int i = 0; i < n; i++) { for (int j = 0; j < n; j++) V[i][j] = 0.f; V[i][i] = 1.f; }
+    for (int k = 0; k < n; k++) {
+        W[k] = A[k][k];
+        if (k < n - 1) { int m = k + 1; float mv = fabsf(A[k][m]); for (int i = k + 2; i < n; i++) { const float v = fabsf(A[k][i]); if (mv < v) { mv = v; m = i; } } indR[k] = m; }
+        if (k > 0) { int m = 0; float mv = fabsf(A[0][k]); for (int i = 1; i < k; i++) { const float v = fabsf(A[i][k]); if (mv < v) { mv = v; m = i; } } indC[k] = m; }
+    }
+    for (int iters = 0; iters < n * n * 30; iters++) {
+        int k = 0; float mv = fabsf(A[0][indR[0]]);
+        for (int i = 1; i < n - 1; i++) { const float v = fabsf(A[i][indR[i]]); if (mv < v) { mv = v; k = i; } }
+        int l = indR[k];
+        for (int i = 1; i < n; i++) { const float v = fabsf(A[indC[i]][i]); if (mv < v) { mv = v; k = indC[i]; l = i; } }
+        const float p = A[k][l];
+        if (fabsf(p) <= eps) break;
+        const float y = (float)(((double)__fsub_rn(W[l], W[k])) * 0.5);
+        float t = __fadd_rn(fabsf(y), s3_hypotf(p, y));
+        float sn = s3_hypotf(p, t);
+        const float c = __fdiv_rn(t, sn);
+        sn = __fdiv_rn(p, sn); t = __fmul_rn(__fdiv_rn(p, t), p);
+        if (y < 0) { sn = -sn; t = -t; }
+        A[k][l] = 0.f;
+        W[k] = __fsub_rn(W[k], t); W[l] = __fadd_rn(W[l], t);
+#define S3_ROT(v0, v1) { const float a0 = v0, b0 = v1; v0 = __fsub_rn(__fmul_rn(a0, c), __fmul_rn(b0, sn)); v1 = __fadd_rn(__fmul_rn(a0, sn), __fmul_rn(b0, c)); }
+        for (int i = 0; i < k; i++) S3_ROT(A[i][k], A[i][l]);
+        for (int i = k + 1; i < l; i++) S3_ROT(A[k][i], A[i][l]);
+        for (int i = l + 1; i < n; i++) S3_ROT(A[k][i], A[l][i]);
+        for (int i = 0; i < n; i++) S3_ROT(V[k][i], V[l][i]);
+#undef S3_ROT
+        for (int j = 0; j < 2; j++) {
+            const int idx = j == 0 ? k : l;
+            if (idx < n - 1) { int m = idx + 1; float mx = fabsf(A[idx][m]); for (int i = idx + 2; i < n; i++) { const float v = fabsf(A[idx][i]); if (mx < v) { mx = v; m = i; } } indR[idx] = m; }
+            if (idx > 0) { int m = 0; float mx = fabsf(A[0][idx]); for (int i = 1; i < idx; i++) { const float v = fabsf(A[i][idx]); if (mx < v) { mx = v; m = i; } } indC[idx] = m; }
+        }
+    }
+    for (int k = 0; k < n - 1; k++) {                                      // eigenvalues descending, eigenvectors in rows
+        int m = k;
+        for (int i = k + 1; i < n; i++) if (W[m] < W[i]) m = i;
+        if (k != m) { const float w = W[m]; W[m] = W[k]; W[k] = w; for (int i = 0; i < n; i++) { const float v = V[m][i]; V[m][i] = V[k][i]; V[k][i] = v; } }
+    }
+}
+
+// X1 / X2: f32[n_hyp, 3 points, 3 coordinates] (the min sets, camera-1 / camera-2 coordinates).  Out: T12, T21 f32[n_hyp, 16]; Rts f32[n_hyp, 13] = R12 (9), t12 (3), s12.
+__global__ void __launch_bounds__(128)
+k_sim3_compute(int n_hyp, const float *__restrict__ X1, const float *__restrict__ X2, int fix_scale, float *__restrict__ T12, float *__restrict__ T21, float *__restrict__ Rts)
+{
+    const int h = blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= n_hyp) return;
+    float P1[3][3], P2[3][3], O1[3], O2[3];                                // [coordinate][point]
+    for (int i = 0; i < 3; i++) for (int r = 0; r < 3; r++) { P1[r][i] = X1[9 * (size_t)h + 3 * i + r]; P2[r][i] = X2[9 * (size_t)h + 3 * i + r]; }
+    for (int r = 0; r < 3; r++) {
+        O1[r] = (float)__dmul_rn((double)__fadd_rn(__fadd_rn(P1[r][0], P1[r][1]), P1[r][2]), 1.0 / 3.0);
+        O2[r] = (float)__dmul_rn((double)__fadd_rn(__fadd_rn(P2[r][0], P2[r][1]), P2[r][2]), 1.0 / 3.0);
+        for (int i = 0; i < 3; i++) { P1[r][i] = __fsub_rn(P1[r][i], O1[r]); P2[r][i] = __fsub_rn(P2[r][i], O2[r]); }
+    }
+    float M[3][3];
+    for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) {
+        double a = 0;
+        for (int k = 0; k < 3; k++) a = __dadd_rn(a, __dmul_rn((double)P2[r][k], (double)P1[c][k]));
+        M[r][c] = (float)a;
+    }
+    const double m00 = M[0][0], m01 = M[0][1], m02 = M[0][2], m10 = M[1][0], m11 = M[1][1], m12 = M[1][2], m20 = M[2][0], m21 = M[2][1], m22 = M[2][2];
+    const float N11 = (float)(m00 + m11 + m22), N12 = (float)(m12 - m21), N13 = (float)(m20 - m02), N14 = (float)(m01 - m10), N22 = (float)(m00 - m11 - m22),
+                N23 = (float)(m01 + m10), N24 = (float)(m20 + m02), N33 = (float)(-m00 + m11 - m22), N34 = (float)(m12 + m21), N44 = (float)(-m00 - m11 + m22);
+    float A[4][4] = {{N11, N12, N13, N14}, {N12, N22, N23, N24}, {N13, N23, N33, N34}, {N14, N24, N34, N44}}, W[4], V[4][4];
+    s3_jacobi4(A, W, V);
+    const double vx = V[0][1], vy = V[0][2], vz = V[0][3];
+    const double nrm = sqrt(vx * vx + vy * vy + vz * vz);
+    const double ang = atan2(nrm, (double)V[0][0]);
+    const double alpha = (2 * ang) * (1.0 / nrm);
+    const float rv[3] = {(float)(vx * alpha), (float)(vy * alpha), (float)(vz * alpha)};
+    float R[3][3];
+    {   // cv::Rodrigues(vector -> matrix), double inside
+        const double rx0 = rv[0], ry0 = rv[1], rz0 = rv[2];
+        const double theta = sqrt(rx0 * rx0 + ry0 * ry0 + rz0 * rz0);
+        if (!(theta >= 2.220446049250313e-16)) { for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) R[r][c] = r == c ? 1.f : 0.f; }
+        else {
+            const double c = cos(theta), sn = sin(theta), c1 = 1. - c, it = 1. / theta;
+            const double rx = rx0 * it, ry = ry0 * it, rz = rz0 * it;
+            R[0][0] = (float)(c + c1 * rx * rx); R[0][1] = (float)(c1 * rx * ry - sn * rz); R[0][2] = (float)(c1 * rx * rz + sn * ry);
+            R[1][0] = (float)(c1 * rx * ry + sn * rz); R[1][1] = (float)(c + c1 * ry * ry); R[1][2] = (float)(c1 * ry * rz - sn * rx);
+            R[2][0] = (float)(c1 * rx * rz - sn * ry); R[2][1] = (float)(c1 * ry * rz + sn * rx); R[2][2] = (float)(c + c1 * rz * rz);
+        }
+    }
+    float s12 = 1.0f;
+    if (!fix_scale) {
+        double nom = 0, den = 0;
+        for (int r = 0; r < 3; r++) for (int i = 0; i < 3; i++) {
+            const float p3 = __fadd_rn(__fadd_rn(__fmul_rn(R[r][0], P2[0][i]), __fmul_rn(R[r][1], P2[1][i])), __fmul_rn(R[r][2], P2[2][i]));
+            nom = __dadd_rn(nom, __dmul_rn((double)P1[r][i], (double)p3));
+            den = __dadd_rn(den, (double)__fmul_rn(p3, p3));
+        }
+        s12 = (float)(nom / den);
+    }
+    float t12[3];
+    for (int r = 0; r < 3; r++) {
+        const float d = __fadd_rn(__fadd_rn(__fmul_rn(R[r][0], O2[0]), __fmul_rn(R[r][1], O2[1])), __fmul_rn(R[r][2], O2[2]));
+        t12[r] = __fsub_rn(O1[r], (float)__dmul_rn((double)d, (double)s12));
+    }
+    float *o12 = T12 + 16 * (size_t)h, *o21 = T21 + 16 * (size_t)h, *ort = Rts + 13 * (size_t)h;
+    float sRi[3][3];
+    const double is = 1.0 / (double)s12;
+    for (int r = 0; r < 3; r++) {
+        for (int c = 0; c < 3; c++) { o12[4 * r + c] = (float)__dmul_rn((double)R[r][c], (double)s12); sRi[r][c] = (float)__dmul_rn((double)R[c][r], is); o21[4 * r + c] = sRi[r][c]; ort[3 * r + c] = R[r][c]; }
+        o12[4 * r + 3] = t12[r]; ort[9 + r] = t12[r];
+    }
+    for (int r = 0; r < 3; r++) {
+        const float d = __fadd_rn(__fadd_rn(__fmul_rn(sRi[r][0], t12[0]), __fmul_rn(sRi[r][1], t12[1])), __fmul_rn(sRi[r][2], t12[2]));
+        o21[4 * r + 3] = (float)__dmul_rn((double)d, -1.0);
+    }
+    for (int c = 0; c < 3; c++) { o12[12 + c] = 0.f; o21[12 + c] = 0.f; }
+    o12[15] = 1.f; o21[15] = 1.f; ort[12] = s12;
+}
+
 }  // namespace orbs

@@ -76,6 +76,34 @@ int ORBmatcher::DescriptorDistance(const cv::Mat &a, const cv::Mat &b)
     return d;
 }
 
+// MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:242-307) for all the map points of one caller loop in ONE device call.  The reference calls the
+// member point by point (LocalMapping.cc:163, 436, 628; LoopClosing.cc:500; MultiMapper.cc:607), each call doing O(N^2) DescriptorDistance evaluations on the
+// host; the loops become `ORBmatcher::ComputeDistinctiveDescriptors(points)` after them.
+void ORBmatcher::ComputeDistinctiveDescriptors(const std::vector<MapPoint *> &vpMPs)
+{
+    std::vector<MapPoint *> pts;
+    std::vector<int32_t> start(1, 0);
+    std::vector<cv::Mat> rows;
+    for (size_t i = 0; i < vpMPs.size(); i++) {
+        MapPoint *pMP = vpMPs[i];
+        if (!pMP || pMP->isBad()) continue;                                      // MapPoint.cc:251-253
+        const std::map<KeyFrame *, size_t> observations = pMP->GetObservations();
+        const size_t before = rows.size();
+        for (std::map<KeyFrame *, size_t>::const_iterator mit = observations.begin(); mit != observations.end(); ++mit)
+            if (!mit->first->isBad()) rows.push_back(mit->first->mDescriptors.row((int)mit->second));
+        if (rows.size() == before) continue;                                     // :257-258, :269-270: nothing to choose from
+        pts.push_back(pMP); start.push_back((int32_t)rows.size());
+    }
+    if (pts.empty()) return;
+    std::vector<uint64_t> buf(rows.size() * 4 + 2);
+    uintptr_t a = ((uintptr_t)buf.data() + 15) & ~(uintptr_t)15;
+    uint8_t *flat = (uint8_t *)a;
+    for (size_t r = 0; r < rows.size(); r++) std::memcpy(flat + 32 * r, rows[r].ptr(0), 32);
+    std::vector<int32_t> best(pts.size(), 0);
+    check(orbm_distinctive_descriptors(handle(), (int)pts.size(), flat, start.data(), best.data(), ORBS_MEM_HOST), "orbm_distinctive_descriptors");
+    for (size_t p = 0; p < pts.size(); p++) pts[p]->SetDescriptor(rows[start[p] + best[p]].clone());
+}
+
 // Tracking::SearchLocalPoints -> ORBmatcher(0.8).SearchByProjection(mCurrentFrame, mvpLocalMapPoints, th)   (Tracking.cc:1249)
 int ORBmatcher::SearchByProjection(Frame &F, const std::vector<MapPoint *> &vpMapPoints, const float th)
 {

@@ -85,6 +85,9 @@ cv::Mat Sim3Solver::iterate(int nIterations, bool &bNoMore, std::vector<bool> &v
     std::vector<float> T12(16 * (size_t)nHyp), T21(16 * (size_t)nHyp);
     std::vector<size_t> vAvailableIndices;
     cv::Mat P3Dc1i(3, 3, CV_32F), P3Dc2i(3, 3, CV_32F);
+#ifdef ORBSLAMM_DEVICE_COMPUTE_SIM3
+    std::vector<float> minset1(9 * (size_t)nHyp + 1), minset2(9 * (size_t)nHyp + 1);
+#endif
     for (int h = 0; h < nHyp; h++) {
         vAvailableIndices = mvAllIndices;
         for (short i = 0; i < 3; ++i) {
@@ -94,10 +97,28 @@ cv::Mat Sim3Solver::iterate(int nIterations, bool &bNoMore, std::vector<bool> &v
             vAvailableIndices[idx] = vAvailableIndices.back();
             vAvailableIndices.pop_back();
         }
+#ifdef ORBSLAMM_DEVICE_COMPUTE_SIM3
+        for (int i = 0; i < 3; i++) for (int r = 0; r < 3; r++) { minset1[9 * (size_t)h + 3 * i + r] = P3Dc1i.at<float>(r, i); minset2[9 * (size_t)h + 3 * i + r] = P3Dc2i.at<float>(r, i); }
+#else
         ComputeSim3(P3Dc1i, P3Dc2i);
         hyp[h].T12 = mT12i.clone(); hyp[h].T21 = mT21i.clone(); hyp[h].R = mR12i.clone(); hyp[h].t = mt12i.clone(); hyp[h].s = ms12i;
         flat44(mT12i, &T12[16 * (size_t)h]); flat44(mT21i, &T21[16 * (size_t)h]);
+#endif
     }
+#ifdef ORBSLAMM_DEVICE_COMPUTE_SIM3
+    // optional: Horn's closed form for all min sets in one launch (orbo_sim3_compute).  Float-tolerance parity with cv::eigen / cv::Rodrigues, not bit-exactness
+    // (include/orbslamm_b200.h), which is why the default build keeps the reference's ComputeSim3 above.
+    if (nHyp > 0) {
+        std::vector<float> Rts(13 * (size_t)nHyp);
+        s3_check(orbo_sim3_compute(s3_handle(), nHyp, minset1.data(), minset2.data(), mbFixScale ? 1 : 0, T12.data(), T21.data(), Rts.data(), ORBS_MEM_HOST), "orbo_sim3_compute");
+        for (int h = 0; h < nHyp; h++) {
+            hyp[h].T12 = cv::Mat(4, 4, CV_32F); hyp[h].T21 = cv::Mat(4, 4, CV_32F); hyp[h].R = cv::Mat(3, 3, CV_32F); hyp[h].t = cv::Mat(3, 1, CV_32F);
+            for (int r = 0; r < 4; r++) for (int c = 0; c < 4; c++) { hyp[h].T12.at<float>(r, c) = T12[16 * (size_t)h + 4 * r + c]; hyp[h].T21.at<float>(r, c) = T21[16 * (size_t)h + 4 * r + c]; }
+            for (int r = 0; r < 3; r++) { for (int c = 0; c < 3; c++) hyp[h].R.at<float>(r, c) = Rts[13 * (size_t)h + 3 * r + c]; hyp[h].t.at<float>(r) = Rts[13 * (size_t)h + 9 + r]; }
+            hyp[h].s = Rts[13 * (size_t)h + 12];
+        }
+    }
+#endif
 
     // 2. CheckInliers of all of them in one device call
     std::vector<uint8_t> in((size_t)nHyp * N + 1);

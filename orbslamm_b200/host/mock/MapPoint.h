@@ -18,6 +18,8 @@ public:
     cv::Mat GetWorldPos() { return mWorldPos.clone(); }
     void SetWorldPos(const cv::Mat &p) { mWorldPos = p.clone(); }
     cv::Mat GetDescriptor() { return mDescriptor.clone(); }
+    // added by the drop-in (mDescriptor is protected in S/include/MapPoint.h and written under mMutexFeatures, MapPoint.cc:304-307): see INTEGRATION.md
+    void SetDescriptor(const cv::Mat &d) { mDescriptor = d.clone(); }
     bool isBad() { return mbBad; }
     int Observations() { return nObs; }
     std::map<KeyFrame *, size_t> GetObservations() { return mObservations; }

@@ -12,6 +12,8 @@ class ORBmatcher
 public:
     ORBmatcher(float nnratio = 0.6, bool checkOri = true);
     static int DescriptorDistance(const cv::Mat &a, const cv::Mat &b);
+    // added by the drop-in: MapPoint::ComputeDistinctiveDescriptors for a batch of map points in one device call
+    static void ComputeDistinctiveDescriptors(const std::vector<MapPoint *> &vpMPs);
     int SearchByProjection(Frame &F, const std::vector<MapPoint *> &vpMapPoints, const float th = 3);
     int SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, const float th, const bool bMono);
     int SearchByProjection(Frame &CurrentFrame, KeyFrame *pKF, const std::set<MapPoint *> &sAlreadyFound, const float th, const int ORBdist);

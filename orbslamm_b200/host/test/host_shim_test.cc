@@ -131,6 +131,23 @@ int main(int argc, char **argv)
     for (int k = 0; k < K; k++) for (int r = 0; r < 4; r++) for (int c = 0; c < 4; c++) oposes.push_back(kfs[k].Tcw.at<float>(r, c));
     for (int p = 0; p < P; p++) { for (int c = 0; c < 3; c++) opts.push_back(pts[p].mWorldPos.at<float>(c)); nobs.push_back(pts[p].nObs); }
     wr(d + "/ba_out_poses.bin", oposes); wr(d + "/ba_out_points.bin", opts); wr(d + "/ba_out_nobs.bin", nobs);
+    // MapPoint::ComputeDistinctiveDescriptors for the whole mock map in one call: keyframe descriptors from a file, one row per observation
+    {
+        const std::vector<unsigned char> kd = rd<unsigned char>(d + "/ba_desc.bin");      // [E, 32] in edge order
+        std::vector<size_t> row_of_edge(E);
+        std::vector<int> nrow(K, 0);
+        for (int e = 0; e < E; e++) row_of_edge[e] = nrow[bkf[e]]++;
+        for (int k = 0; k < K; k++) kfs[k].mDescriptors = cv::Mat(std::max(nrow[k], 1), 32, CV_8U);
+        for (int e = 0; e < E; e++) memcpy(kfs[bkf[e]].mDescriptors.ptr((int)row_of_edge[e]), &kd[32 * (size_t)e], 32);
+        kfs[2].mbBad = true;                                                              // observations in a bad keyframe are left out (MapPoint.cc:262-266)
+        pts[3].mbBad = true;                                                              // a bad point keeps its descriptor (:251-253)
+        std::vector<MapPoint *> all;
+        for (int p = 0; p < P; p++) { memset(pts[p].mDescriptor.ptr(0), 0xAB, 32); all.push_back(&pts[p]); }
+        ORBmatcher::ComputeDistinctiveDescriptors(all);
+        std::vector<unsigned char> chosen;
+        for (int p = 0; p < P; p++) chosen.insert(chosen.end(), pts[p].mDescriptor.ptr(0), pts[p].mDescriptor.ptr(0) + 32);
+        wr(d + "/distinctive.bin", chosen);
+    }
     printf("host shim ok: %d/%d keypoints, %d matches, %d inliers\n", Last.N, Cur.N, nmatches, ninl);
     return 0;
 }

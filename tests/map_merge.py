@@ -142,7 +142,7 @@ def compute_sim3(P1, P2):
         C = F.scale32(C, 1.0 / np.float64(P.shape[1]))
         return P - C, C
     Pr1, O1 = centroid(P1); Pr2, O2 = centroid(P2)
-    M = cv2.gemm(Pr2, Pr1.T.copy(), 1.0, None, 0.0)
+    M = cv2.gemm(Pr2, Pr1, 1.0, None, 0.0, flags=cv2.GEMM_2_T)          # Pr2 * Pr1.t(): a MatExpr gemm with a transposed operand
     m = lambda r, c: np.float64(M[r, c])
     N11 = m(0, 0) + m(1, 1) + m(2, 2); N12 = m(1, 2) - m(2, 1); N13 = m(2, 0) - m(0, 2); N14 = m(0, 1) - m(1, 0)
     N22 = m(0, 0) - m(1, 1) - m(2, 2); N23 = m(0, 1) + m(1, 0); N24 = m(2, 0) + m(0, 2)

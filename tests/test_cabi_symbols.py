@@ -70,7 +70,7 @@ def test_host_shims_compile_for_both_trees():
                                             "mock/Sim3Solver_rest.cc", "test/host_shim_test.cc", "test/host_kf_family_test.cc", "test/host_sim3solver_test.cc",
                                             "test/host_essential_graph_test.cc")]
     base = ["g++", "-std=c++14", "-fsyntax-only", "-I" + os.path.join(host, "mock"), "-I" + host, "-I" + os.path.join(ROOT, "include")]
-    for extra in ([], ["-DORBSLAMM_MULTI_ROBOT"]):
+    for extra in ([], ["-DORBSLAMM_MULTI_ROBOT"], ["-DORBSLAMM_DEVICE_COMPUTE_SIM3"]):
         out = subprocess.run(base + extra + srcs, capture_output=True, text=True)
         assert out.returncode == 0, out.stderr[-3000:]
 

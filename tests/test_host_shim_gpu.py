@@ -42,6 +42,12 @@ def test_cpp_dropin_classes(lib, tmp_path):
     w("ba_dims.bin", np.array([8, 150, len(g["kf"])], np.int32)); w("ba_poses.bin", g["poses"]); w("ba_points.bin", g["points"])
     w("ba_uv.bin", g["uv"]); w("ba_w.bin", inv_s2[octs]); w("ba_kf.bin", g["kf"]); w("ba_pt.bin", g["pt"]); w("ba_oct.bin", octs)
     w("ba_intr.bin", g["intr"])
+    rng = np.random.default_rng(5)
+    pt_desc = rng.integers(0, 256, (150, 32), dtype=np.uint8)                 # every observation = its point's descriptor with up to 40 flipped bits
+    ba_desc = pt_desc[g["pt"]].copy()
+    for e in range(len(ba_desc)):
+        for b in rng.integers(0, 256, int(rng.integers(0, 41))): ba_desc[e, b >> 3] ^= np.uint8(1 << (b & 7))
+    w("ba_desc.bin", ba_desc)
     out = subprocess.run([exe, d], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
     r = lambda name, dt: np.fromfile(os.path.join(d, name), dt)
@@ -84,6 +90,25 @@ def test_cpp_dropin_classes(lib, tmp_path):
     assert np.abs(got_x[seen] - ref["points"][seen]).max() < 2e-5 * np.abs(ref["points"]).max()
     nobs = np.bincount(g["pt"], minlength=150) - np.bincount(g["pt"][keep][ref["outlier"] > 0], minlength=150)
     assert np.abs(r("ba_out_nobs.bin", np.int32) - nobs).sum() <= 2          # erased observations (ties at the chi2 gate aside)
+    # batched MapPoint::ComputeDistinctiveDescriptors through the class: observations in std::map<KeyFrame*> order = keyframe index order (the mock keyframes
+    # live in one array), the observations LocalBA erased above are gone, keyframe 2 is bad, point 3 is bad
+    chosen = r("distinctive.bin", np.uint8).reshape(150, 32)
+    left = np.ones(len(g["kf"]), bool)
+    final_nobs = r("ba_out_nobs.bin", np.int32)
+    checked = 0
+    for p in range(150):
+        es = np.where(g["pt"] == p)[0]
+        if p == 3 or len(es) != final_nobs[p]:                                # bad point / LocalBA erased some of its observations (which ones is checked above)
+            if p == 3: assert (chosen[p] == 0xAB).all()
+            continue
+        es = es[np.argsort(g["kf"][es], kind="stable")]
+        es = es[g["kf"][es] != 2]
+        if len(es) == 0:
+            assert (chosen[p] == 0xAB).all()
+            continue
+        assert np.array_equal(chosen[p], ba_desc[es[oracle.distinctive_descriptor(ba_desc[es])]]), p
+        checked += 1
+    assert checked > 100
 
 
 def test_cpp_dropin_kf_family(lib, tmp_path):

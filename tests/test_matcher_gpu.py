@@ -145,3 +145,22 @@ def test_search_matches_reference_object_code(lib):
                                   last["angle"][None], last["desc"][None], np.array([nQ], np.int32), 100)
     n_r, fm_r = ref_build.ref_search_last_frame(k["K4"], k["bounds"], k["Tcw"], sf, cur, last, k["Xw"], k["valid"], 15.0, 0.9, True)
     assert int(nm[0]) == n_r and n_r > 500 and np.array_equal(fm[0], fm_r)
+
+
+def test_distinctive_descriptors_batch(lib):
+    """orbm_distinctive_descriptors == MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:242-307) per point: ragged batch incl. empty, single, pair (the
+    (int)(0.5 * (N - 1)) = 0 median of a pair is the zero self-distance: first row wins), more rows than lanes, exact duplicates (ties)."""
+    import orbslamm_b200 as ob
+    rng = np.random.default_rng(8)
+    lists = []
+    for n in [0, 1, 2, 3, 4, 7, 33, 70, 5, 0, 12] + [int(x) for x in rng.integers(1, 20, 300)]:
+        base = rng.integers(0, 256, 32, dtype=np.uint8)
+        d = np.tile(base, (n, 1))
+        for i in range(n):
+            for b in rng.integers(0, 256, int(rng.integers(0, 60))): d[i, b >> 3] ^= np.uint8(1 << (b & 7))
+        if n >= 4: d[n - 1] = d[1]                                          # a duplicate row
+        lists.append(d)
+    got = ob.ORBmatcher(0.6, True).ComputeDistinctiveDescriptors(lists)
+    ref = np.array([oracle.distinctive_descriptor(d) for d in lists], np.int32)
+    assert np.array_equal(got, ref)
+    assert got[0] == -1 and got[1] == 0 and got[2] == 0

@@ -207,3 +207,17 @@ def test_pose_graph_oracle_properties():
     assert np.array_equal(r["sim3"][0], S[0]) and r["chol_failures"] == 0 and 1 <= r["lm_iterations"] <= 20
     rf = oracle.optimize_pose_graph(S, fixed, ei, ej, em, True, 20, 1e-16)
     assert np.allclose(rf["sim3"][:, 7], S[:, 7], rtol=0, atol=1e-12)
+
+
+def test_distinctive_descriptor_known_answer():
+    """MapPoint.cc:271-303 by hand: rows a, b, c with d(a,b) = 8, d(a,c) = 16, d(b,c) = 8 -> sorted rows (0,8,16), (0,8,8), (0,8,16); element (int)(0.5*2) = 1 is
+    8 everywhere: the first row wins.  With a fourth row far from all, element (int)(0.5*3) = 1: a: (0,8,16,x) -> 8, b -> 8, c -> 8, far -> its nearest: still row 0;
+    moving c next to b makes b the strict minimum."""
+    a = np.zeros(32, np.uint8); b = a.copy(); b[0] = 0xff; c = b.copy(); c[1] = 0xff
+    assert oracle.descriptor_distance(a, b) == 8 and oracle.descriptor_distance(a, c) == 16
+    assert oracle.distinctive_descriptor(np.stack([a, b, c])) == 0
+    far = np.full(32, 0xff, np.uint8)
+    assert oracle.distinctive_descriptor(np.stack([a, b, c, far])) == 0
+    c2 = b.copy(); c2[1] = 0x01                                          # d(b,c2) = 1, d(a,c2) = 9
+    assert oracle.distinctive_descriptor(np.stack([a, b, c2])) == 1      # medians 8, 1, 1 -> first strict minimum is row 1
+    assert oracle.distinctive_descriptor(np.zeros((0, 32), np.uint8)) == -1 and oracle.distinctive_descriptor(a[None]) == 0
