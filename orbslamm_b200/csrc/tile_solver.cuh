@@ -23,7 +23,6 @@ namespace orbs {
 constexpr int TS = 64;                       // tile size
 constexpr int TS2 = TS * TS;
 constexpr int kOpPitch = 68;                 // operand tiles in smem: (68 r + c) -> DMMA fragment loads are conflict-free per half-warp
-constexpr int kFacPitch = 65;                // factorisation tile in smem (row / column walks)
 constexpr int kRsSmemBytes = 4 * TS * kOpPitch * (int)sizeof(double);   // two operand double-buffers
 
 enum { LM_BUILD = 0, LM_RETRY = 1, LM_DONE = 2 };
@@ -108,67 +107,113 @@ __device__ __forceinline__ void rs_gemm_nt(double (&acc)[8][2], const double *Ao
     }
 }
 
-// Cholesky of the 64x64 tile in T (pitch 65, lower part valid) and the inverse of its factor.
-//   factor : right-looking, 256 threads = 4 threads per row holding 16 columns each in registers, one barrier per pivot;
-//   inverse: blocked 8 x 8 on DMMA: the eight diagonal 8x8 blocks are inverted by one warp each (forward substitution), then the
-//            off-diagonal blocks by block distance d = 1..7, X[i][j] = -inv(D_i) sum_{k=j..i-1} L[i][k] X[k][j], one warp per block.
-// Lb / Xi: operand-pitch (68) buffers for L and inv(L); Sw: [8][64] per-warp scratch.  Linv_out (global, row-major 64x64) = inv(L).
-__device__ __forceinline__ void rs_factor_invert(double *T, double *Lb, double *Xi, double *Sw, double *colbuf, double *Linv_out, int *flags, int tid)
+// Cholesky of the 64x64 tile in T (operand pitch 68, lower part valid) and the inverse of its factor, blocked 8 x 8 on DMMA.
+//   for block column b = 0..7:
+//     panel    : warps 0..6-b   P_i = T(i,b) inv(D_b)^T                                  (one 8x8x8 DMMA product each)
+//     trailing : T(i,j) -= P_i P_j^T for b < j <= i; warp 0 takes block (b+1, b+1) FIRST and then factors + inverts it (8 pivots in registers, row r of the
+//                block in lanes r, r+8, r+16, r+24; column broadcasts by shuffle) while warps 1..7 do the rest of the trailing update (look-ahead: the
+//                serial 8-pivot chain of the next diagonal block runs beside the update instead of behind it)
+//   two barriers per block column (16 in all; the former right-looking scalar version needed one per pivot, 64, with every thread touching 16 columns each time:
+//   21 us per tile on the critical path of the elimination tree, measured with the task trace).
+//   inverse: the diagonal 8x8 inverses come out of the factor steps; off-diagonal blocks by block distance d = 1..7,
+//            X[i][j] = -inv(D_i) sum_{k=j..i-1} L[i][k] X[k][j], one warp per block.
+// T / Xi: operand-pitch (68) buffers, on return T = L (lower block triangle; diagonal blocks with zero upper part), Xi = inv(L);  Sw: [8][64] per-warp
+// scratch.  Linv_out (global, row-major 64x64) = inv(L).
+__device__ __forceinline__ void rs_factor8_invert(double *Tb, double *Xb, bool &bad, int lane)
 {
-    const int r = tid >> 2, sub = tid & 3, warp = tid >> 5, lane = tid & 31;
-    double a[16];
+    // Tb / Xb: the diagonal block in T and in Xi.  All 32 lanes run (lane l mirrors row l & 7) so that every shuffle is warp-uniform.
+    constexpr unsigned full = 0xffffffffu;
+    const int r = lane & 7;
+    // The inverse rides along: lane c also solves column c of inv(L) by forward substitution, x[q] = (delta_qc - sum_{p<q} L[q][p] x[p]) / L[q][q].  Its partial
+    // sums s[q] are advanced with the SAME column broadcasts the factor update needs (L[q][j] = lane q's `l`), one extra FMA per shuffle, off the critical path.
+    // Critical path per pivot: diagonal -> rsqrt -> scale -> FMA into the next diagonal.  Two things keep the shuffles OFF that path: (1) the column entries are
+    // broadcast UNSCALED (A[q][j], final since the previous pivot) while the rsqrt is still running, every lane scales them itself (same expression as the
+    // owning lane: bit-identical); (2) every lane tracks all eight running diagonals dd[q] = A[q][q] - sum_p L[q][p]^2 with the same FMAs as the owner.
+    double a[8], x[8], sx[8], dd[8];
+    const int c = r;
 #pragma unroll
-    for (int u = 0; u < 16; u++) a[u] = T[r * kFacPitch + 16 * sub + u];
-    // 64 dependent pivots.  The loop is unrolled by 16 only (the column a thread publishes must be a compile-time register index): fully
-    // unrolled, the 64 distinct step bodies are ~100 KB of straight-line SASS executed once each -- instruction-fetch bound.
+    for (int q = 0; q < 8; q++) { a[q] = Tb[r * kOpPitch + q]; sx[q] = 0.0; }
+#pragma unroll
+    for (int q = 0; q < 8; q++) dd[q] = __shfl_sync(full, a[q], q);
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        double u[8];
+#pragma unroll
+        for (int q = j + 1; q < 8; q++) u[q] = __shfl_sync(full, a[j], q);   // A[q][j] before scaling
+        double d = dd[j];
+        if (!(d > 0.0)) { bad = true; d = 1.0; }
+        const double rinv = rsqrt(d);
+        const double l = (r == j) ? d * rinv : a[j] * rinv;                // column j of the factor (rows >= j)
+        a[j] = l;
+        x[j] = (j >= c) ? ((j == c ? 1.0 : 0.0) - sx[j]) * rinv : 0.0;
+#pragma unroll
+        for (int q = j + 1; q < 8; q++) {
+            const double lq = u[q] * rinv;                                   // L[q][j]
+            if (q <= r) a[q] = fma(-l, lq, a[q]);
+            dd[q] = fma(-lq, lq, dd[q]);
+            sx[q] = fma(lq, x[j], sx[q]);
+        }
+    }
+    if (lane < 8) {
+#pragma unroll
+        for (int q = 0; q < 8; q++) { Tb[r * kOpPitch + q] = q <= r ? a[q] : 0.0; Xb[q * kOpPitch + c] = x[q]; }
+    }
+}
+
+__device__ __forceinline__ void rs_factor_invert(double *T, double *Xi, double *Sw, double *Linv_out, int *flags, int tid)
+{
+    const int warp = tid >> 5, lane = tid & 31, fr = lane >> 2, fk = lane & 3;
     bool bad = false;
-#pragma unroll 1
-    for (int js = 0; js < 4; js++) {
-#pragma unroll
-        for (int ju = 0; ju < 16; ju++) {
-            const int j = 16 * js + ju;
-            if (sub == js && r >= j) colbuf[(j & 1) * TS + r] = a[ju];
-            __syncthreads();
-            double d = colbuf[(j & 1) * TS + j];
-            if (!(d > 0.0)) { bad = true; d = 1.0; }
-            const double rinv = rsqrt(d), sd = d * rinv;
-            if (r >= j) {
-                const double l = (r == j) ? sd : colbuf[(j & 1) * TS + r] * rinv;
-                if (sub == js) a[ju] = l;
-                const double lr = l * rinv;
-#pragma unroll
-                for (int u = 0; u < 16; u++) {
-                    const int c = 16 * sub + u;
-                    if (c > j && c <= r) a[u] = fma(-lr, colbuf[(j & 1) * TS + c], a[u]);
+    // warp 0 factors the first diagonal block while the others clear Xi (everything but that block, which warp 0 writes in full)
+    if (warp == 0) rs_factor8_invert(T, Xi, bad, lane);
+    else for (int q = tid - 32; q < TS * kOpPitch; q += 224) { const int rr = q / kOpPitch, cc = q - rr * kOpPitch; if (rr >= 8 || cc >= 8) Xi[q] = 0.0; }
+    __syncthreads();
+    for (int b = 0; b < 8; b++) {
+        const int m = 7 - b;                                                 // block rows below the diagonal block
+        // ---- panel: P_i = T(i,b) inv(D_b)^T, i = b + 1 + warp
+        if (warp < m) {
+            const int i = b + 1 + warp;
+            double *Ab = T + (8 * i + fr) * kOpPitch + 8 * b;
+            const double *Db = Xi + (8 * b + fr) * kOpPitch + 8 * b;
+            const double a0 = Ab[fk], a1 = Ab[4 + fk];
+            double c0 = 0.0, c1 = 0.0;
+            dmma884(c0, c1, a0, Db[fk]);
+            dmma884(c0, c1, a1, Db[4 + fk]);
+            __syncwarp();
+            Ab[2 * fk] = c0; Ab[2 * fk + 1] = c1;
+        }
+        __syncthreads();
+        if (b == 7) break;
+        // ---- trailing update T(i,j) -= P_i P_j^T, b < j <= i <= 7; block (b+1, b+1) goes to warp 0, which then factors it (look-ahead)
+        if (warp == 0) {
+            const int i = b + 1;
+            double *Cb = T + (8 * i + fr) * kOpPitch + 8 * i + 2 * fk;
+            const double *Pi = T + (8 * i + fr) * kOpPitch + 8 * b;
+            double c0 = Cb[0], c1 = Cb[1];
+            dmma884(c0, c1, -Pi[fk], Pi[fk]);
+            dmma884(c0, c1, -Pi[4 + fk], Pi[4 + fk]);
+            Cb[0] = c0; Cb[1] = c1;
+            __syncwarp();
+            rs_factor8_invert(T + (8 * i) * kOpPitch + 8 * i, Xi + (8 * i) * kOpPitch + 8 * i, bad, lane);
+        } else {
+            int cnt = -1;                                                    // blocks after the first, dealt round-robin to warps 1..7
+            for (int i = b + 1; i < 8; i++)
+                for (int j = b + 1; j <= i; j++, cnt++) {
+                    if (cnt < 0 || cnt % 7 != warp - 1) continue;
+                    double *Cb = T + (8 * i + fr) * kOpPitch + 8 * j + 2 * fk;
+                    const double *Pi = T + (8 * i + fr) * kOpPitch + 8 * b, *Pj = T + (8 * j + fr) * kOpPitch + 8 * b;
+                    double c0 = Cb[0], c1 = Cb[1];
+                    dmma884(c0, c1, -Pi[fk], Pj[fk]);
+                    dmma884(c0, c1, -Pi[4 + fk], Pj[4 + fk]);
+                    Cb[0] = c0; Cb[1] = c1;
                 }
-            }
         }
+        __syncthreads();
     }
-    if (bad && tid == 0) flags[0] = 1;
-#pragma unroll
-    for (int u = 0; u < 16; u++) { const int c = 16 * sub + u; Lb[r * kOpPitch + c] = c <= r ? a[u] : 0.0; Xi[r * kOpPitch + c] = 0.0; }
-    __syncthreads();
-    // ---- inverse, phase 1: warp w inverts diagonal block w; lane c < 8 solves column c of inv(D) by forward substitution
-    {
-        const double *D = Lb + (8 * warp) * kOpPitch + 8 * warp;
-        const int c = lane & 7;
-        double x[8];
-#pragma unroll
-        for (int q = 0; q < 8; q++) {
-            double sacc = (q == c) ? 1.0 : 0.0;
-#pragma unroll
-            for (int p2 = 0; p2 < q; p2++) sacc = fma(-D[q * kOpPitch + p2], x[p2], sacc);
-            x[q] = (q >= c) ? sacc / D[q * kOpPitch + q] : 0.0;
-        }
-        if (lane < 8) {
-#pragma unroll
-            for (int q = 0; q < 8; q++) Xi[(8 * warp + q) * kOpPitch + 8 * warp + c] = x[q];
-        }
-    }
-    __syncthreads();
-    // ---- phase 2: off-diagonal blocks by distance
-    const int fr = lane >> 2, fk = lane & 3;
+    if (__syncthreads_or(bad) && tid == 0) flags[0] = 1;
+    // ---- inverse, off-diagonal blocks by distance (the diagonal blocks of Xi are in place)
     double *S = Sw + warp * 64;
+    const double *Lb = T;
     for (int dist = 1; dist < 8; dist++) {
         const int j = warp, i = warp + dist;
         if (i < 8) {
@@ -272,11 +317,11 @@ k_rs_solve(const RsPlan P, const RsBuf B, const LmCtl *__restrict__ ctl, int epo
             }
             if (B.trace && tid == 0) { long long g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g)); B.trace[4 * t + 1] = g; }
             if (diag) {
-                double *T = rs_smem;                                           // pitch 65 view of the operand area
+                double *T = rs_smem;                                           // operand-pitch view of the first buffer
 #pragma unroll
-                for (int nb = 0; nb < 8; nb++) { double *p = &T[(8 * warp + fr) * kFacPitch + 8 * nb + 2 * fk]; p[0] = acc[nb][0]; p[1] = acc[nb][1]; }
+                for (int nb = 0; nb < 8; nb++) { double *p = &T[(8 * warp + fr) * kOpPitch + 8 * nb + 2 * fk]; p[0] = acc[nb][0]; p[1] = acc[nb][1]; }
                 __syncthreads();
-                rs_factor_invert(T, rs_smem + TS * kFacPitch, rs_smem + TS * kFacPitch + TS * kOpPitch, rs_smem + TS * kFacPitch + 2 * TS * kOpPitch, s_col, B.Linv + (size_t)task.i * TS2, B.flags, tid);
+                rs_factor_invert(T, rs_smem + TS * kOpPitch, rs_smem + 2 * TS * kOpPitch, B.Linv + (size_t)task.i * TS2, B.flags, tid);
             } else {
                 // L_ij = acc * inv(L_jj)^T
 #pragma unroll
