@@ -606,9 +606,9 @@ def main():
                 "vs_baseline": None, "dtype": "u8", "data": "synthetic",
                 "config": {"workload": f"{'KITTI' if CAM['w'] == 1241 else 'TUM'}-shape {CAM['w']}x{CAM['h']} synthetic streams, nFeatures={CAM['nfeatures']}: extract + SearchByProjection(Cur,Last) + PoseOptimization per frame",
                            "note": "the oracle port: the REAL OpenCV primitives the reference calls (cv2 4.13 FAST / resize / GaussianBlur, SIMD) + restated reference "
-                                   "code, one independent stream per core.  oracle/_ref holds the reference's own ORBextractor.cc / ORBmatcher.cc as object code, but over "
-                                   "scalar restatements of those primitives (OpenCV C++ headers are not in the image; 175 vs 99 ms per 1241x376 extraction), and "
-                                   "Optimizer.cc cannot be built at all (Eigen): the faster port is the fairer baseline"},
+                                   "code, one independent stream per core.  oracle/_ref holds the reference's own ORBextractor.cc / ORBmatcher.cc / Optimizer.cc + g2o as object "
+                                   "code, but over scalar stand-ins for OpenCV / Eigen (headers absent from the image; 175 vs 99 ms per 1241x376 extraction, 1.5 vs 9.4 LM it/s): "
+                                   "the faster port is the fairer baseline; the BA record carries the object-code timing too"},
                 "cpu_baseline": {"value": round(fps, 2), "unit": "frames/s", "cores": cores, "kind": "port", "cpu": cpu_model(),
                                  "sample": f"{per} frames x {cores} streams (one per core), {wall:.1f} s"},
                 "e2e": {"value": round(fps, 2), "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}

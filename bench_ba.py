@@ -203,5 +203,5 @@ def reference_line(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(15e3 / cb["value"], 2), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"synthetic covisibility graph {K} KF / {P} points, LocalBA schedule 5 robust + 10 non-robust LM its",
-                       "note": "reference C++ (g2o + Eigen) cannot be built here; this is the oracle port, single thread like the reference"},
+                       "note": "value = the oracle port (fp64 restatement of the g2o path, 1 thread like the reference: g2o is built without OpenMP); cpu_baseline.reference_object_code = the reference's own Optimizer.cc + g2o over the Eigen stand-in (slower than a real-Eigen build)"},
             "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "LM iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}

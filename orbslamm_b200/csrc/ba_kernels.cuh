@@ -391,7 +391,7 @@ __device__ __forceinline__ void mv_fold(double *v, int bit, int lane)
     }
 }
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 4)
 k_ba_schur_items(const BaDev B, const int *__restrict__ seg_item0, double *__restrict__ item_part)
 {
     if (B.ctl->state == LM_DONE) return;
