@@ -30,13 +30,15 @@ from orbslamm_b200 import synth  # noqa: E402
 
 CAM = synth.KITTI
 TH_PROJ = 15.0          # Tracking.cc:925-930 (mono)
+TRAFFIC_JSON = "r2h_traffic.json"
 N_POOL = 5              # distinct frames per stream (steps cycle over frame pairs 1..N_POOL-1)
 
 
 def ncu_traffic(group, kernel, scale_to=None):
-    """dram__bytes_read + dram__bytes_write of one launch from the committed ncu capture (profiles/r1h_traffic.json), scaled
-    linearly to this run's frames per launch; None when the capture has no such kernel."""
-    p = os.path.join(ROOT, "profiles", "r1h_traffic.json")
+    """dram__bytes_read + dram__bytes_write of one launch from the committed ncu capture (profiles/r2h_traffic.json, written by
+    tools/ncu_summary.py traffic from the --set full capture of the final kernels), scaled linearly to this run's frames per launch; None when
+    the capture has no such kernel."""
+    p = os.path.join(ROOT, "profiles", TRAFFIC_JSON)
     try:
         d = json.load(open(p))[group]
         v = d["kernels"][kernel][0]["dram_bytes"]
@@ -453,9 +455,9 @@ def bench_frontend(args, rank, world):
     per_launch_ms = dom_ms / max(dom_n, 1) * (7 if dom == "resize_level" else 1)
     achieved = alg[dom] * B / (per_launch_ms * 1e-3) / 1e9
     roofline = {"kernel": dom, "bound": "hbm", "achieved": round(achieved, 2), "peak": hbm, "unit": "GB/s", "frac": round(achieved / hbm, 5),
-                "traffic": ncu_traffic("frontend", dom, B) if w == 1241 else None, "traffic_source": "profiles/r1h_traffic.json (ncu --set full, 128 frames per launch, scaled to this batch)",
+                "traffic": ncu_traffic("frontend", dom, B) if w == 1241 else None, "traffic_source": f"profiles/{TRAFFIC_JSON} (ncu --set full, 128 frames per launch, scaled to this batch)",
                 "peak_source": how, "algorithmic_bytes_per_launch": int(alg[dom] * B),
-                "note": "k_fast_cells is bound by the integer ALU pipe (ncu: alu pipe 73 % of peak, DRAM 2 %), not by HBM; frac is reported against the HBM roofline as the contract asks",
+                "note": "k_fast_cells is bound by instruction issue / the integer ALU pipe (ncu: issue ~73 %, alu pipe ~77 % of peak, DRAM ~3 %), not by HBM; frac is reported against the HBM roofline as the contract asks",
                 "avg_launch_ms": round(per_launch_ms, 4),
                 "kernel_share_of_step": {k: round(v[0] / max(prof_ms, 1e-9), 4) for k, v in ktimes.items()},
                 "measured_in": f"single-instance pass over all {B} streams ({prof_steps} steps, {round(prof_ms / prof_steps, 4)} ms/step), CUDA events around every launch"}
@@ -563,7 +565,7 @@ def main():
     _own_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--streams", type=int, default=128, help="independent camera streams per GPU (frames per step per GPU)")
     ap.add_argument("--instances", type=int, default=2, help="independent extractor/matcher/optimizer triples (own CUDA stream) per GPU in the device-resident leg")

@@ -112,7 +112,8 @@ def bench_ba(args, rank, world):
     achieved = alg_bytes / (per_launch_ms * 1e-3) / 1e9
     lm_total_ms = loop_s * 1e3
     roofline = {"kernel": dom, "bound": "hbm", "achieved": round(achieved, 2), "peak": hbm, "unit": "GB/s", "frac": round(achieved / hbm, 5),
-                "traffic": None, "peak_source": how, "algorithmic_bytes_per_launch": int(alg_bytes), "avg_launch_ms": round(per_launch_ms, 5),
+                "traffic": ncu_traffic("ba", {"reduced_solve": "rs_solve", "schur": "ba_schur_items", "build_points": "ba_build_points"}.get(dom, dom)) if (K, P) == (BA_K, BA_P) else None,
+                "peak_source": how, "algorithmic_bytes_per_launch": int(alg_bytes), "avg_launch_ms": round(per_launch_ms, 5),
                 "note": "reduced_solve = ONE persistent dataflow kernel (left-looking tiled Cholesky on DMMA + both triangular solves): a chain of dependent 64x64 fp64 "
                         "tile tasks, latency-bound by construction; schur = memset of the packed tiles + lambda + one warp per target 6x6 block",
                 "launch": "one timed region per LM trial (reduced_solve: 1 launch; schur: memset + 2 launches)",

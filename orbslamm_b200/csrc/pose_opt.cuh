@@ -68,10 +68,10 @@ __global__ void __launch_bounds__(kPoseThreads)
 k_pose_optimization(const PoseArgs A)
 {
     __shared__ double s_warp[(kPoseThreads / 32) * kPoseNV];
-    __shared__ double s_red[kPoseNV];
+    __shared__ double s_red[kPoseNV], s_sys[kPoseNV];
     __shared__ Se3 s_pose, s_backup;
     __shared__ double s_lambda, s_ni, s_cur_chi, s_x[6];
-    __shared__ int s_nbad_lm, s_flag, s_ok2;
+    __shared__ int s_nbad_lm, s_flag, s_ok2, s_accept;
     __shared__ double s_rho;
     const int f = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
     const int M = A.counts[f];
@@ -95,12 +95,15 @@ k_pose_optimization(const PoseArgs A)
         for (int i = tid; i < M; i += nt) my_act += !outlier[i];
         const int n_act = __syncthreads_count(my_act > 0);
         if (n_act > 0) {
-            for (int iter = 0; iter < 10; iter++) {
-                // computeActiveErrors + activeRobustChi2 + buildSystem
+            // One pass over the edges per LM TRIAL: errors, robust chi2 AND the normal equations at the pose it is given (computeActiveErrors +
+            // activeRobustChi2 + buildSystem).  g2o evaluates a trial with computeActiveErrors and, if it accepts, starts the next iteration with
+            // computeActiveErrors + buildSystem at that same pose: the trial pass already holds exactly that system, so it is kept (s_sys) instead of being
+            // rebuilt; a rejected trial keeps the previous system, as g2o does (only lambda changes).  Same loops, same summation order: bit-identical
+            // to building twice, at about 60 % of the work.
+            auto edge_pass = [&](const Se3 pose) {
                 double acc[kPoseNV];
 #pragma unroll
                 for (int v = 0; v < kPoseNV; v++) acc[v] = 0;
-                const Se3 pose = s_pose;
                 for (int i = tid; i < M; i += nt) {
                     if (outlier[i]) continue;
                     const double X[3] = {(double)Xw[3 * i], (double)Xw[3 * i + 1], (double)Xw[3 * i + 2]};
@@ -125,52 +128,38 @@ k_pose_optimization(const PoseArgs A)
                     }
                 }
                 block_reduce_vec<kPoseNV>(acc, s_warp, s_red);
-                if (tid == 0) {
-                    s_cur_chi = s_red[27];
-                    if (iter == 0) {                                                 // computeLambdaInit
-                        double mx = 0.;
-                        int p = 0;
-                        for (int a = 0; a < 6; a++) { mx = fmax(fabs(s_red[p]), mx); p += 6 - a; }
-                        s_lambda = 1e-5 * mx; s_ni = 2; s_nbad_lm = 0;
-                    }
-                }
-                __syncthreads();
+            };
+            edge_pass(s_pose);
+            if (tid < kPoseNV) s_sys[tid] = s_red[tid];
+            if (tid == 0) {
+                s_cur_chi = s_red[27];
+                double mx = 0.;                                                      // computeLambdaInit
+                int p = 0;
+                for (int a = 0; a < 6; a++) { mx = fmax(fabs(s_red[p]), mx); p += 6 - a; }
+                s_lambda = 1e-5 * mx; s_ni = 2; s_nbad_lm = 0;
+            }
+            __syncthreads();
+            for (int iter = 0; iter < 10; iter++) {
                 const double ini_chi = s_cur_chi;
                 int qmax = 0;
                 double rho = 0;
                 do {
                     if (tid == 0) {
                         s_backup = s_pose;
-                        s_ok2 = solve6(s_red, s_red + 21, s_lambda, s_x) ? 1 : 0;
+                        s_ok2 = solve6(s_sys, s_sys + 21, s_lambda, s_x) ? 1 : 0;
                         Se3 d, r;
                         se3_exp(s_x, d);
                         se3_mul(d, s_pose, r);
                         s_pose = r;
                     }
                     __syncthreads();
-                    const Se3 np = s_pose;
-                    double chi[1] = {0};
-                    for (int i = tid; i < M; i += nt) {
-                        if (outlier[i]) continue;
-                        const double X[3] = {(double)Xw[3 * i], (double)Xw[3 * i + 1], (double)Xw[3 * i + 2]};
-                        double Xc[3], e[2];
-                        se3_map(np, X, Xc);
-                        reproj_error(Xc, in, (double)obs[2 * i], (double)obs[2 * i + 1], e);
-                        err[2 * i] = e[0]; err[2 * i + 1] = e[1];
-                        const double w = (double)wgt[i];
-                        const double chi2 = e[0] * (w * e[0] + 0.0 * e[1]) + e[1] * (0.0 * e[0] + w * e[1]);
-                        double rho0 = chi2, rho1 = 1.0;
-                        if (robust) huber(chi2, delta, dsqr, rho0, rho1);
-                        chi[0] += rho0;
-                    }
-                    __shared__ double s_chi_out[1];
-                    block_reduce_vec<1>(chi, s_warp, s_chi_out);
+                    edge_pass(s_pose);
                     if (tid == 0) {
-                        double temp_chi = s_chi_out[0];
+                        double temp_chi = s_red[27];
                         if (!s_ok2) temp_chi = 1.7976931348623157e308;
                         double r = s_cur_chi - temp_chi;
                         double scale = 0.;
-                        for (int j = 0; j < 6; j++) scale += s_x[j] * (s_lambda * s_x[j] + s_red[21 + j]);
+                        for (int j = 0; j < 6; j++) scale += s_x[j] * (s_lambda * s_x[j] + s_sys[21 + j]);
                         scale += 1e-3;
                         r /= scale;
                         if (r > 0 && isfinite(temp_chi)) {
@@ -178,14 +167,17 @@ k_pose_optimization(const PoseArgs A)
                             alpha = fmin(alpha, 2. / 3.);
                             s_lambda *= fmax(1. / 3., alpha);
                             s_ni = 2; s_cur_chi = temp_chi;
+                            s_accept = 1;
                         } else {
                             s_lambda *= s_ni; s_ni *= 2;
                             s_pose = s_backup;
+                            s_accept = 0;
                         }
                         s_rho = r;
                     }
                     __syncthreads();
                     rho = s_rho;
+                    if (s_accept && tid < kPoseNV) s_sys[tid] = s_red[tid];          // the accepted trial's system is the next iteration's
                     qmax++;
                     __syncthreads();
                 } while (rho < 0 && qmax < 10);

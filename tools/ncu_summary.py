@@ -2,6 +2,7 @@
 """Summarise ncu outputs from gpurun_out/ into profiles/ (tracked).
   python tools/ncu_summary.py launches gpurun_out/launches_r1.csv profiles/r1_launches.txt
   python tools/ncu_summary.py kernel   gpurun_out/prof_fast_r1.ncu-rep profiles/r1_fast_cells.txt
+  python tools/ncu_summary.py traffic  gpurun_out/r2h_fe.ncu-rep gpurun_out/r2h_ba.ncu-rep profiles/r2h_traffic.json
 """
 import collections
 import csv
@@ -57,5 +58,31 @@ def kernel(src, dst):
     print(open(dst).read())
 
 
+def traffic(fe_rep, ba_rep, dst, frames_per_launch=128):
+    """dram__bytes_read + dram__bytes_write and duration per launch of every captured kernel -> the json bench.py reads for roofline.traffic"""
+    import json
+    out = {"source": f"ncu --set full --clock-control none ({fe_rep}, {ba_rep}); per launch"}
+    for group, rep in (("frontend", fe_rep), ("ba", ba_rep)):
+        txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        rows = list(csv.reader(txt.splitlines()))
+        h, units = rows[0], rows[1]
+        ik, ir, iw, it = h.index("Kernel Name"), h.index("dram__bytes_read.sum"), h.index("dram__bytes_write.sum"), h.index("gpu__time_duration.sum")
+        mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        tm = {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}
+        ks = collections.defaultdict(list)
+        for r in rows[2:]:
+            name = r[ik].split("(")[0].replace("void ", "").replace("orbs::", "")
+            name = name.split("<")[0]
+            if name.startswith("k_"): name = name[2:]
+            f = lambda v: float(v.replace(",", ""))
+            ks[name].append({"dram_bytes": int(f(r[ir]) * mult[units[ir]] + f(r[iw]) * mult[units[iw]]), "duration_us": round(f(r[it]) * tm[units[it]], 2)})
+        out[group] = {"frames_per_launch": frames_per_launch, "kernels": ks} if group == "frontend" else {"kernels": ks}
+    json.dump(out, open(dst, "w"), indent=1)
+    print(json.dumps({g: {k: v[0] for k, v in out[g]["kernels"].items()} for g in ("frontend", "ba")}, indent=1))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "kernel": kernel}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    if sys.argv[1] == "traffic":
+        traffic(sys.argv[2], sys.argv[3], sys.argv[4])
+    else:
+        {"launches": launches, "kernel": kernel}[sys.argv[1]](sys.argv[2], sys.argv[3])
