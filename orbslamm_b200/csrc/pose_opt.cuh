@@ -45,22 +45,45 @@ __device__ __forceinline__ void block_reduce_vec(double (&acc)[NV], double *warp
 
 // LDL^T solve of the 6x6 system (H + lambda I) x = b; H given by its upper triangle (row-major packed 21).
 // LinearSolverDense: fails unless the factorisation is positive (linear_solver_dense.h:107-112).
-__device__ inline bool solve6(const double *Hu, const double *b, double lambda, double *x)
+__device__ __forceinline__ bool solve6(const double *Hu, const double *b, double lambda, double *x)
 {
-    double A[36];
-    int p = 0;
-    for (int r = 0; r < 6; r++) for (int c = r; c < 6; c++) { A[6 * r + c] = Hu[p]; A[6 * c + r] = Hu[p]; p++; }
-    for (int i = 0; i < 6; i++) A[7 * i] += lambda;
+    // every loop fully unrolled: the 6x6 matrix lives in registers (with runtime loop bounds it went to local memory, and this runs on ONE thread while
+    // the other 255 wait -- it was the longest serial stretch of an LM trial)
+    double A[6][6];
+    {
+        int p = 0;
+#pragma unroll
+        for (int r = 0; r < 6; r++)
+#pragma unroll
+            for (int c = r; c < 6; c++) { A[r][c] = Hu[p]; A[c][r] = Hu[p]; p++; }
+    }
+#pragma unroll
+    for (int i = 0; i < 6; i++) A[i][i] += lambda;
+    bool ok = true;
+#pragma unroll
     for (int i = 0; i < 6; i++)
+#pragma unroll
         for (int j = 0; j <= i; j++) {
-            double s = A[6 * i + j];
-            for (int k = 0; k < j; k++) s -= A[6 * i + k] * A[6 * j + k] * A[7 * k];
-            if (j < i) A[6 * i + j] = s / A[7 * j];
-            else { if (!(s > 0.0)) return false; A[7 * i] = s; }
+            double s = A[i][j];
+#pragma unroll
+            for (int k = 0; k < j; k++) s -= A[i][k] * A[j][k] * A[k][k];
+            if (j < i) A[i][j] = s / A[j][j];
+            else { if (!(s > 0.0)) ok = false; A[i][i] = s; }
         }
-    for (int i = 0; i < 6; i++) { double s = b[i]; for (int k = 0; k < i; k++) s -= A[6 * i + k] * x[k]; x[i] = s; }
-    for (int i = 0; i < 6; i++) x[i] /= A[7 * i];
-    for (int i = 5; i >= 0; i--) { const double xi = x[i]; for (int k = 0; k < i; k++) x[k] -= A[6 * i + k] * xi; }
+    if (!ok) return false;
+    double y[6];
+#pragma unroll
+    for (int i = 0; i < 6; i++) { double s = b[i]; 
+#pragma unroll
+        for (int k = 0; k < i; k++) s -= A[i][k] * y[k]; y[i] = s; }
+#pragma unroll
+    for (int i = 0; i < 6; i++) y[i] /= A[i][i];
+#pragma unroll
+    for (int i = 5; i >= 0; i--) { const double xi = y[i]; 
+#pragma unroll
+        for (int k = 0; k < i; k++) y[k] -= A[i][k] * xi; }
+#pragma unroll
+    for (int i = 0; i < 6; i++) x[i] = y[i];
     return true;
 }
 
@@ -87,6 +110,7 @@ k_pose_optimization(const PoseArgs A)
     __syncthreads();
     int n_bad_total = 0;
     bool robust = true;
+#pragma unroll 1
     for (int it = 0; it < 4; it++) {
         if (tid == 0) se3_from_Tcw(A.Tcw + 16 * f, s_pose);                  // reset to the initial pose, Optimizer.cc:400
         __syncthreads();
@@ -139,6 +163,7 @@ k_pose_optimization(const PoseArgs A)
                 s_lambda = 1e-5 * mx; s_ni = 2; s_nbad_lm = 0;
             }
             __syncthreads();
+#pragma unroll 1
             for (int iter = 0; iter < 10; iter++) {
                 const double ini_chi = s_cur_chi;
                 int qmax = 0;

@@ -17,16 +17,24 @@ __host__ __device__ inline void quat_from_R(const double R[9], double q[4])     
         t = 0.5 / t;
         q[0] = (R[7] - R[5]) * t; q[1] = (R[2] - R[6]) * t; q[2] = (R[3] - R[1]) * t;
     } else {
+        // Eigen picks i = the largest diagonal entry, j = (i + 1) % 3, k = (j + 1) % 3; written out per case so that R and q are never indexed by a
+        // runtime value (which would put them in local memory on the device -- this sits on the one-thread stretch of every LM trial)
         int i = 0;
         if (R[4] > R[0]) i = 1;
-        if (R[8] > R[4 * i]) i = 2;
-        const int j = (i + 1) % 3, k = (j + 1) % 3;
-        t = sqrt(R[4 * i] - R[4 * j] - R[4 * k] + 1.0);
-        q[i] = 0.5 * t;
-        t = 0.5 / t;
-        q[3] = (R[3 * k + j] - R[3 * j + k]) * t;
-        q[j] = (R[3 * j + i] + R[3 * i + j]) * t;
-        q[k] = (R[3 * k + i] + R[3 * i + k]) * t;
+        if (R[8] > (i == 1 ? R[4] : R[0])) i = 2;
+        if (i == 0) {            // j = 1, k = 2
+            t = sqrt(R[0] - R[4] - R[8] + 1.0);
+            q[0] = 0.5 * t; t = 0.5 / t;
+            q[3] = (R[7] - R[5]) * t; q[1] = (R[3] + R[1]) * t; q[2] = (R[6] + R[2]) * t;
+        } else if (i == 1) {     // j = 2, k = 0
+            t = sqrt(R[4] - R[8] - R[0] + 1.0);
+            q[1] = 0.5 * t; t = 0.5 / t;
+            q[3] = (R[2] - R[6]) * t; q[2] = (R[7] + R[5]) * t; q[0] = (R[1] + R[3]) * t;
+        } else {                 // j = 0, k = 1
+            t = sqrt(R[8] - R[0] - R[4] + 1.0);
+            q[2] = 0.5 * t; t = 0.5 / t;
+            q[3] = (R[3] - R[1]) * t; q[0] = (R[2] + R[6]) * t; q[1] = (R[5] + R[7]) * t;
+        }
     }
 }
 
@@ -68,7 +76,8 @@ __host__ __device__ inline void quat_to_R(const double q[4], double R[9])       
 __host__ __device__ inline void se3_from_Tcw(const float *T, Se3 &s)                // Converter::toSE3Quat, Converter.cc:37-47
 {
     double R[9];
-    for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) R[3 * r + c] = (double)T[4 * r + c];
+    #pragma unroll
+    for (int i = 0; i < 9; i++) R[i] = (double)T[4 * (i / 3) + i % 3];
     quat_from_R(R, s.q);
     quat_normalize_pos(s.q);
     s.t[0] = T[3]; s.t[1] = T[7]; s.t[2] = T[11];
@@ -78,7 +87,10 @@ __host__ __device__ inline void se3_to_Tcw(const Se3 &s, float *T)              
 {
     double R[9];
     quat_to_R(s.q, R);
-    for (int r = 0; r < 3; r++) { for (int c = 0; c < 3; c++) T[4 * r + c] = (float)R[3 * r + c]; T[4 * r + 3] = (float)s.t[r]; }
+    #pragma unroll
+    for (int i = 0; i < 9; i++) T[4 * (i / 3) + i % 3] = (float)R[i];
+#pragma unroll
+    for (int r = 0; r < 3; r++) T[4 * r + 3] = (float)s.t[r];
     T[12] = T[13] = T[14] = 0.f; T[15] = 1.f;
 }
 
@@ -95,17 +107,21 @@ __host__ __device__ inline void se3_exp(const double u[6], Se3 &out)
     const double theta = sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
     const double O[9] = {0, -w[2], w[1], w[2], 0, -w[0], -w[1], w[0], 0};
     double O2[9], R[9], V[9];
-    for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) O2[3 * r + c] = O[3 * r] * O[c] + O[3 * r + 1] * O[3 + c] + O[3 * r + 2] * O[6 + c];
+    #pragma unroll
+    for (int i = 0; i < 9; i++) O2[i] = O[3 * (i / 3)] * O[i % 3] + O[3 * (i / 3) + 1] * O[3 + i % 3] + O[3 * (i / 3) + 2] * O[6 + i % 3];
     if (theta < 0.00001) {
+        #pragma unroll
         for (int i = 0; i < 9; i++) { R[i] = (i % 4 == 0 ? 1.0 : 0.0) + O[i] + O2[i]; V[i] = R[i]; }
     } else {
         const double a = sin(theta) / theta, b = (1 - cos(theta)) / (theta * theta), c = (theta - sin(theta)) / pow(theta, 3.0);
+        #pragma unroll
         for (int i = 0; i < 9; i++) {
             R[i] = (i % 4 == 0 ? 1.0 : 0.0) + a * O[i] + b * O2[i];
             V[i] = (i % 4 == 0 ? 1.0 : 0.0) + b * O[i] + c * O2[i];
         }
     }
     quat_from_R(R, out.q);
+    #pragma unroll
     for (int r = 0; r < 3; r++) out.t[r] = V[3 * r] * u[3] + V[3 * r + 1] * u[4] + V[3 * r + 2] * u[5];
     quat_normalize_pos(out.q);
 }
@@ -152,8 +168,10 @@ __host__ __device__ inline void jac_binary(const double Xc[3], const double R[9]
     const double x = Xc[0], y = Xc[1], z = Xc[2], z_2 = z * z;
     const double tmp[6] = {fx, 0, -x / z * fx, 0, fy, -y / z * fy};
     const double s = -1. / z;
+    #pragma unroll
     for (int r = 0; r < 2; r++) {
         const double st0 = s * tmp[3 * r], st1 = s * tmp[3 * r + 1], st2 = s * tmp[3 * r + 2];
+        #pragma unroll
         for (int c = 0; c < 3; c++) Jl[3 * r + c] = st0 * R[c] + st1 * R[3 + c] + st2 * R[6 + c];
     }
     Jp[0] = x * y / z_2 * fx; Jp[1] = -(1 + (x * x / z_2)) * fx; Jp[2] = y / z * fx;
