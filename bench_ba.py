@@ -95,9 +95,10 @@ def bench_ba(args, rank, world):
     e2e = iters / total_s
     hbm, how = peaks()
     # dominant kernel by device time; algorithmic bytes per launch
-    ktimes = {k: v for k, v in ktimes.items() if not k.startswith("unused")}
+    ktimes = {k: v for k, v in ktimes.items() if not k.startswith("unused") and (world > 1 or k != "exchange")}
+    comm_mode = {0: "single GPU", 1: "NCCL all-reduce", 2: "NVLink peer-memory kernels (reduce-scatter + all-gather over cudaIpc-mapped buffers)"}[opt.comm_mode()]
     sky = tm["l_tiles"]
-    dom = max(ktimes, key=lambda k: ktimes[k][0])
+    dom = max((k for k in ktimes if k != "exchange"), key=lambda k: ktimes[k][0])
     dom_ms, dom_n = ktimes[dom]
     # chol_factor = all k_chol_panel / k_chol_update launches of one solve: every structurally nonzero 64x64 tile of L is read and
     # written once (the compulsory traffic of a sparse tiled factorisation; re-reads of neighbouring tiles come from L2)
@@ -131,6 +132,7 @@ def bench_ba(args, rank, world):
            "e2e": {"value": round(e2e, 2), "unit": "LM iterations/s", "h2d_bytes_per_step": int(graph_bytes), "d2h_bytes_per_step": int(K * 64 + P * 12 + E * 10)},
            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "wall_s": round(wall, 3)}
     out["lm_iterations"] = int(iters)
+    out["config"]["exchange"] = comm_mode
     if sharded_parity is not None:
         out["sharded_parity"] = sharded_parity
         # what the multi-robot system actually runs: one LocalBA per robot (LocalMapping per System) = N independent solves, one per GPU, no collective

@@ -466,6 +466,9 @@ int orbo_optimize_sim3(orbo_handle *h, int n_pairs, double *sim3, const uint8_t 
  *   orbo_comm_init: collective. */
 int orbo_comm_unique_id(uint8_t *id128);
 int orbo_comm_init(orbo_handle *h, int nranks, int rank, const uint8_t *id128);
+/* how the sharded solve exchanges the reduced system: 0 = single GPU, 1 = NCCL all-reduce, 2 = NVLink peer-memory kernels (csrc/peer_reduce.cuh; chosen by
+ * orbo_comm_init when every rank can map every other rank's buffers through cudaIpc, ORBS_NO_PEER=1 keeps NCCL). */
+int orbo_comm_mode(const orbo_handle *h);
 
 /* ------------------------------------------------------------------ */
 /* Fused front end: what Tracking::TrackWithMotionModel (S/src/Tracking.cc:912-973) does per frame -- Frame ctor ->

@@ -643,7 +643,12 @@ class Optimizer:
         return dict(poses=poses.reshape(K, 4, 4), points=points, chi2=chi2, depth_ok=dok, outlier=outl,
                     lm_iterations=int(stats[0]), lm_trials=int(stats[1]), chol_failures=int(stats[2]), aborted=bool(rc == 1))
 
-    KERNELS = ("errors", "build_points", "build_poses", "point_prep", "schur", "reduced_solve", "backsub", "update", "lm_decide")
+    KERNELS = ("errors", "build_points", "build_poses", "point_prep", "schur", "reduced_solve", "backsub", "update", "lm_decide", "exchange")
+
+    def comm_mode(self):
+        """0 = single GPU, 1 = NCCL all-reduce, 2 = NVLink peer-memory exchange"""
+        self._L.orbo_comm_mode.argtypes = [ctypes.c_void_p]; self._L.orbo_comm_mode.restype = ctypes.c_int
+        return int(self._L.orbo_comm_mode(self._h))
 
     def set_profiling(self, on):
         self._L.orbo_set_profiling.argtypes = [ctypes.c_void_p, ctypes.c_int]

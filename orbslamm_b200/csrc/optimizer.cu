@@ -18,6 +18,7 @@
 #include "pose_graph.cuh"
 #include <cub/cub.cuh>
 #include "ba_kernels.cuh"
+#include "peer_reduce.cuh"
 
 using namespace orbs;
 
@@ -30,6 +31,7 @@ struct NcclApi {
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*CommAbort)(ncclComm_t) = nullptr;
     ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
     bool load()
     {
@@ -41,6 +43,7 @@ struct NcclApi {
         CommDestroy = (decltype(CommDestroy))dlsym(lib, "ncclCommDestroy");
         CommAbort = (decltype(CommAbort))dlsym(lib, "ncclCommAbort");
         AllReduce = (decltype(AllReduce))dlsym(lib, "ncclAllReduce");
+        AllGather = (decltype(AllGather))dlsym(lib, "ncclAllGather");
         GetErrorString = (decltype(GetErrorString))dlsym(lib, "ncclGetErrorString");
         return GetUniqueId && CommInitRank && CommDestroy && AllReduce && GetErrorString;
     }
@@ -75,11 +78,121 @@ struct orbo_handle {
     KernelTimer timer;       // BA kernels, ids = BaK
     ncclComm_t comm = nullptr;   // set by orbo_comm_init: orbo_bundle_adjust becomes a collective over map-point shards
     int nranks = 1, rank = 0;
+    // NVLink peer-memory exchange (peer_reduce.cuh): every rank's control block and packed system buffer mapped through cudaIpc handles
+    bool peer_on = false;
+    PeerDev peer = {};
+    size_t peer_sys_bytes = 0;
+    unsigned peer_epoch = 0, peer_sepoch = 0;
     long long ba_skyline[3] = {0, 0, 0};
     double ba_timing[4] = {0, 0, 0, 0};   // last BA call: LM-loop seconds, total seconds, setup (layout + H2D) seconds, Schur bytes
 };
 
-enum BaK { BK_ERRORS = 0, BK_BUILD_POINTS, BK_BUILD_POSES, BK_PREP, BK_SCHUR, BK_SOLVE, BK_BACKSUB, BK_UPDATE, BK_DECIDE, BK_COUNT };
+enum BaK { BK_ERRORS = 0, BK_BUILD_POINTS, BK_BUILD_POSES, BK_PREP, BK_SCHUR, BK_SOLVE, BK_BACKSUB, BK_UPDATE, BK_DECIDE, BK_EXCHANGE, BK_COUNT };
+
+
+namespace {
+// ---- NVLink peer-memory exchange: set-up (collective over the NCCL communicator) ----------------------------------------
+// Exchanges one cudaIpc handle per rank (all-gather of 64 bytes through NCCL) and maps the peers' allocations.  Returns the mapped pointers in out[] (own
+// pointer for own rank); false if anything fails on this rank.
+bool peer_exchange(orbo_handle *h, void *mine, void **out)
+{
+    cudaIpcMemHandle_t hm;
+    if (cudaIpcGetMemHandle(&hm, mine) != cudaSuccess) { cudaGetLastError(); return false; }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    uint8_t *d = nullptr;
+    if (cudaMalloc(&d, 64 * (size_t)(h->nranks + 1)) != cudaSuccess) { cudaGetLastError(); return false; }
+    bool ok = cudaMemcpyAsync(d, &hm, 64, cudaMemcpyHostToDevice, h->stream) == cudaSuccess;
+    ok = ok && g_nccl.AllGather(d, d + 64, 64, ncclChar, h->comm, h->stream) == ncclSuccess;
+    std::vector<cudaIpcMemHandle_t> all(h->nranks);
+    ok = ok && cudaMemcpyAsync(all.data(), d + 64, 64 * (size_t)h->nranks, cudaMemcpyDeviceToHost, h->stream) == cudaSuccess;
+    ok = ok && cudaStreamSynchronize(h->stream) == cudaSuccess;
+    cudaFree(d);
+    if (!ok) { cudaGetLastError(); return false; }
+    for (int r = 0; r < h->nranks; r++) {
+        if (r == h->rank) { out[r] = mine; continue; }
+        void *p = nullptr;
+        if (cudaIpcOpenMemHandle(&p, all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = false; p = nullptr; }
+        out[r] = p;
+    }
+    return ok;
+}
+
+// every rank must take the same path: agree on `ok` (1 only if it is 1 everywhere)
+bool peer_agree(orbo_handle *h, bool ok)
+{
+    int *d = nullptr, v = ok ? 1 : 0;
+    if (cudaMalloc(&d, sizeof(int)) != cudaSuccess) return false;
+    cudaMemcpyAsync(d, &v, sizeof(int), cudaMemcpyHostToDevice, h->stream);
+    const bool sent = g_nccl.AllReduce(d, d, 1, ncclInt32, ncclMin, h->comm, h->stream) == ncclSuccess;
+    cudaMemcpyAsync(&v, d, sizeof(int), cudaMemcpyDeviceToHost, h->stream);
+    cudaStreamSynchronize(h->stream);
+    cudaFree(d);
+    return sent && v == 1;
+}
+
+void peer_close(orbo_handle *h, bool sys_only)
+{
+    for (int r = 0; r < kMaxPeers; r++) {
+        if (r != h->rank && h->peer.sys[r]) cudaIpcCloseMemHandle(h->peer.sys[r]);
+        if (!sys_only && r != h->rank && h->peer.ctl[r]) cudaIpcCloseMemHandle(h->peer.ctl[r]);
+    }
+    if (h->peer.sys[h->rank]) cudaFree(h->peer.sys[h->rank]);
+    if (!sys_only && h->peer.ctl[h->rank]) cudaFree(h->peer.ctl[h->rank]);
+    for (int r = 0; r < kMaxPeers; r++) { h->peer.sys[r] = nullptr; if (!sys_only) h->peer.ctl[r] = nullptr; }
+    h->peer_sys_bytes = 0;
+    cudaGetLastError();
+}
+
+// control blocks: once per communicator.  ORBS_NO_PEER=1 keeps the NCCL path (A/B comparisons).
+void peer_setup(orbo_handle *h)
+{
+    h->peer_on = false;
+    h->peer = PeerDev{};
+    h->peer.n = h->nranks; h->peer.rank = h->rank;
+    h->peer_epoch = h->peer_sepoch = 0;
+    const char *off = getenv("ORBS_NO_PEER");
+    bool ok = h->nranks > 1 && h->nranks <= kMaxPeers && g_nccl.AllGather && !(off && off[0] == '1');
+    PeerCtlDev *mine = nullptr;
+    if (ok) ok = cudaMalloc(&mine, sizeof(PeerCtlDev)) == cudaSuccess && cudaMemset(mine, 0, sizeof(PeerCtlDev)) == cudaSuccess && cudaDeviceSynchronize() == cudaSuccess;
+    if (h->nranks > 1 && g_nccl.AllGather) {                        // the collective part runs on every rank or on none (nranks and the symbol are the same everywhere)
+        void *ptrs[kMaxPeers] = {};
+        const bool all_want = peer_agree(h, ok);
+        if (all_want) {
+            ok = peer_exchange(h, mine, ptrs);
+            for (int r = 0; r < h->nranks; r++) h->peer.ctl[r] = (PeerCtlDev *)ptrs[r];
+            ok = peer_agree(h, ok);
+        } else ok = false;
+    } else ok = false;
+    if (!ok) { if (mine) { h->peer.ctl[h->rank] = mine; } peer_close(h, false); return; }
+    h->peer_on = true;
+}
+
+// the packed system buffer in shareable memory: (re)allocated and re-mapped collectively when it has to grow (the size is the same on every rank)
+int peer_reserve_sys(orbo_handle *h, size_t bytes)
+{
+    if (bytes <= h->peer_sys_bytes) return ORBS_OK;
+    cudaStreamSynchronize(h->stream);
+    peer_close(h, true);
+    peer_agree(h, true);                                            // nobody frees while a peer still has the old buffer mapped ... and everybody has unmapped
+    const size_t want = bytes + bytes / 4 + 4096;
+    void *mine = nullptr;
+    bool ok = cudaMalloc(&mine, want) == cudaSuccess;
+    void *ptrs[kMaxPeers] = {};
+    if (peer_agree(h, ok)) {
+        ok = peer_exchange(h, mine, ptrs);
+        for (int r = 0; r < h->nranks; r++) h->peer.sys[r] = (double *)ptrs[r];
+        ok = peer_agree(h, ok);
+    } else ok = false;
+    if (!ok) {
+        if (mine && !h->peer.sys[h->rank]) h->peer.sys[h->rank] = (double *)mine;
+        peer_close(h, true);
+        h->peer_on = false;                                         // every rank lands here together: NCCL from now on
+        return ORBS_OK;
+    }
+    h->peer_sys_bytes = want;
+    return ORBS_OK;
+}
+}  // namespace
 
 extern "C" {
 
@@ -107,6 +220,7 @@ int orbo_destroy(orbo_handle *h)
     cudaSetDevice(h->device);
     if (h->stream && h->own_stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
     else cudaDeviceSynchronize();
+    if (h->peer.ctl[h->rank] || h->peer.sys[h->rank]) peer_close(h, false);
     if (h->comm) { if (g_nccl.CommAbort) g_nccl.CommAbort(h->comm); else g_nccl.CommDestroy(h->comm); }   // abort: never block on a peer at teardown
     h->pool.release(); h->ba_pool.release(); h->ba_tasks.release(); h->ba_sys.release(); h->ba_flags.release(); h->ba_cub.release(); h->ba_items.release();
     h->h_scalars.release(); h->timer.release();
@@ -158,8 +272,10 @@ int orbo_comm_init(orbo_handle *h, int nranks, int rank, const uint8_t *id128)
     if (h->comm) { g_nccl.CommDestroy(h->comm); h->comm = nullptr; }
     ncclUniqueId id;
     memcpy(&id, id128, 128);
+    if (h->peer_on || h->peer.ctl[h->rank]) { peer_close(h, false); h->peer_on = false; }
     ORBS_NCCL(g_nccl.CommInitRank(&h->comm, nranks, id, rank));
     h->nranks = nranks; h->rank = rank;
+    peer_setup(h);                                                  // NVLink peer-memory exchange where the ranks can map each other's memory, else NCCL only
     return ORBS_OK;
 }
 
@@ -365,6 +481,30 @@ struct BaRun {
         ORBS_NCCL(g_nccl.AllReduce(buf, buf, n, t, op, h->comm, st));
         return ORBS_OK;
     }
+    // the per-trial exchanges: NVLink peer memory (peer_reduce.cuh) when the ranks could map each other's buffers, NCCL otherwise
+    int exchange_system()
+    {
+        if (!multi()) return ORBS_OK;
+        const size_t n = (size_t)B.ns * TS2 + (size_t)B.nt * TS;
+        if (!h->peer_on) return allreduce(B.A, n, ncclDouble, ncclSum);
+        const unsigned ep = ++h->peer_epoch;
+        const int grid = std::max(8, std::min(h->sm_count, (int)(n / 2 / h->nranks / 512) + 1));
+        k_peer_reduce_scatter<<<grid, 256, 0, st>>>(h->peer, B.ctl, (long long)(n / 2), ep);
+        k_peer_all_gather<<<grid, 256, 0, st>>>(h->peer, B.ctl, (long long)(n / 2), ep);
+        k_peer_barrier<<<1, 32, 0, st>>>(h->peer, B.ctl, ep);
+        count(3);
+        ORBS_CUDA(cudaGetLastError());
+        return ORBS_OK;
+    }
+    int exchange_scalars()
+    {
+        if (!multi()) return ORBS_OK;
+        if (!h->peer_on) return allreduce(B.scalars, 5, ncclDouble, ncclSum);
+        k_peer_scalars<<<1, 32, 0, st>>>(h->peer, B.ctl, B.scalars, ++h->peer_sepoch);
+        count();
+        ORBS_CUDA(cudaGetLastError());
+        return ORBS_OK;
+    }
     KernelTimer &T() { return h->timer; }
     void count(int n = 1) { h->launches += n; }
 
@@ -428,7 +568,12 @@ struct BaRun {
             if (int rc = h->ba_sys.reserve((2 * nA_t + (size_t)ng * TS2 + 3 * nv + (size_t)plan.n_part * TS2 + 16) * sizeof(double))) return rc;
             double *base = h->ba_sys.as<double>();
             B.A = base; B.bs = base + nA_t;
-            rsbuf.A = B.A; rsbuf.b = B.bs; rsbuf.L = B.bs + nv; rsbuf.Linv = rsbuf.L + nA_t; rsbuf.y = rsbuf.Linv + (size_t)ng * TS2; rsbuf.x = rsbuf.y + nv;
+            if (multi() && h->peer_on) {
+                // [A | b] lives in the shareable buffer the peers have mapped (the first part of ba_sys stays unused)
+                if (int rc = peer_reserve_sys(h, (nA_t + nv) * sizeof(double))) return rc;
+                if (h->peer_on) { B.A = h->peer.sys[h->rank]; B.bs = B.A + nA_t; }
+            }
+            rsbuf.A = B.A; rsbuf.b = B.bs; rsbuf.L = base + nA_t + nv; rsbuf.Linv = rsbuf.L + nA_t; rsbuf.y = rsbuf.Linv + (size_t)ng * TS2; rsbuf.x = rsbuf.y + nv;
             rsbuf.part = rsbuf.x + nv;
             B.x = rsbuf.x;
             const size_t nflags = (size_t)plan.ns + 2 * (size_t)ng + (size_t)plan.n_part + 8;
@@ -521,7 +666,9 @@ struct BaRun {
             T().end(st);
             count(3);
             // the one exchange step of the sharded solve: the structurally nonzero tiles of the reduced system and its right-hand side, summed over the map-point shards
-            if (int rc = allreduce(B.A, (size_t)B.ns * TS2 + (size_t)B.nt * TS, ncclDouble, ncclSum)) return rc;
+            T().begin(BK_EXCHANGE, st);
+            if (int rc = exchange_system()) return rc;
+            T().end(st);
             T().begin(BK_SOLVE, st);
             k_rs_solve<<<solve_ctas, 256, kRsSmemBytes, st>>>(rsplan, rsbuf, B.ctl, ++h->rs_epoch);
             T().end(st);
@@ -538,7 +685,11 @@ struct BaRun {
         errors();
         T().begin(BK_DECIDE, st);
         k_lm_reduce<<<1, 256, 0, st>>>(B, h_stop, 1);
-        if (int rc = allreduce(B.scalars, 5, ncclDouble, ncclSum)) return rc;
+        T().end(st);
+        T().begin(BK_EXCHANGE, st);
+        if (int rc = exchange_scalars()) return rc;
+        T().end(st);
+        T().begin(BK_DECIDE, st);
         k_lm_decide<<<1, 1, 0, st>>>(B);
         k_ba_restore<<<upd_blocks, 256, 0, st>>>(B);
         T().end(st);
@@ -565,7 +716,7 @@ struct BaRun {
             errors();
             k_lm_reduce<<<1, 256, 0, st>>>(B, h_stop, 0);
             count();
-            if (int rc = allreduce(B.scalars, 5, ncclDouble, ncclSum)) return rc;
+            if (int rc = exchange_scalars()) return rc;
             constexpr int kLag = 2;
             bool done = false;
             int slot = 0;
@@ -775,7 +926,17 @@ extern "C" int orbo_bundle_adjust(orbo_handle *h, int K, float *poses, const uin
         h->ba_skyline[0] = B.nt; h->ba_skyline[1] = B.ns; h->ba_skyline[2] = D.plan.nlevels;
     }
     if (stats) { stats[0] = fin.lm_iterations; stats[1] = fin.lm_trials; stats[2] = fin.chol_failures; stats[3] = 0; }
+    if (D.multi() && h->peer_on) {
+        int perr = 0;
+        ORBS_CUDA(cudaMemcpy(&perr, &h->peer.ctl[h->rank]->error, sizeof(int), cudaMemcpyDeviceToHost));
+        ORBS_REQUIRE(perr == 0, ORBS_E_CUDA, "sharded bundle adjustment: a rank did not arrive at a peer-memory exchange (timed out waiting for its flag)");
+    }
     return ORBS_OK;
+}
+
+extern "C" int orbo_comm_mode(const orbo_handle *h)
+{
+    return !h || h->nranks <= 1 ? 0 : (h->peer_on ? 2 : 1);            // 0 single GPU, 1 NCCL all-reduce, 2 NVLink peer-memory exchange
 }
 
 extern "C" int orbo_last_ba_timing(orbo_handle *h, double *out4)
