@@ -15,7 +15,7 @@
 //   k_ba_point_prep    Hll + lambda I = G G^T per point, Z_e = Hpl_e G^-T, g = G^-1 b_l      block_solver.hpp:371-398
 //   k_ba_diag_init / k_ba_schur_seg   setLambda + Schur complement          block_solver.hpp:399-436, 568-593
 //   k_rs_solve         sparse tiled Cholesky + triangular solves (tile_solver.cuh; replaces LinearSolverEigen)
-//   k_ba_take_xp / k_ba_backsub   x_l = Dinv (b_l - Hpl^T x_p) + computeScale   block_solver.hpp:463-487, levenberg.cpp:182-189
+//   k_ba_backsub                  x_l = Dinv (b_l - Hpl^T x_p) + computeScale   block_solver.hpp:463-487, levenberg.cpp:182-189
 //   k_ba_update / k_ba_restore    push + oplus / pop                        sparse_optimizer.cpp:422-435
 //   k_lm_reduce / k_lm_decide     rho, lambda update, accept / reject, stop rules   levenberg.cpp:102-161
 #pragma once
@@ -499,20 +499,6 @@ k_ba_seg_items(const int *__restrict__ seg_start, const int *__restrict__ n_seg,
     cnt[s] = s < *n_seg ? (seg_start[s + 1] - seg_start[s] + kItemPairs - 1) / kItemPairs : 0;
 }
 
-// copy-free view of the pose solution: x lives in tile-permuted rows (B.x = solver output); pose part of computeScale
-__global__ void __launch_bounds__(256)
-k_ba_take_xp(const BaDev B)
-{
-    if (B.ctl->state == LM_DONE) return;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    double sc = 0;
-    if (i < B.n) {
-        const double x = B.x[B.rowbase[i / 6] + i % 6];
-        sc = x * ((B.lead ? B.ctl->lambda * x : 0.0) + B.bp[i]);      // sharded: lambda x^2 once (lead rank), bp is this rank's partial sum
-    }
-    block_partial(sc, B.p_xp);
-}
-
 // 8 lanes per point: x_l = G^-T (g - sum_e Z_e^T x_p(e)); point part of computeScale (per-block partials)
 __global__ void __launch_bounds__(256)
 k_ba_backsub(const BaDev B)
@@ -541,7 +527,18 @@ k_ba_backsub(const BaDev B)
         B.xl[3 * (size_t)p] = x0; B.xl[3 * (size_t)p + 1] = x1; B.xl[3 * (size_t)p + 2] = x2;
         sc = x0 * (lambda * x0 + B.bl[3 * p]) + x1 * (lambda * x1 + B.bl[3 * p + 1]) + x2 * (lambda * x2 + B.bl[3 * p + 2]);
     }
-    block_partial(sc, B.p_pt);
+    if ((int)blockIdx.x < B.n_pt) block_partial(sc, B.p_pt);
+    // pose part of computeScale (x lives in tile-permuted rows of the solver output): one partial per block for the first n_xp blocks
+    if ((int)blockIdx.x < B.n_xp) {
+        __syncthreads();
+        const int i = blockIdx.x * blockDim.x + threadIdx.x;
+        double sx = 0;
+        if (i < B.n) {
+            const double x = B.x[B.rowbase[i / 6] + i % 6];
+            sx = x * ((B.lead ? B.ctl->lambda * x : 0.0) + B.bp[i]);        // sharded: lambda x^2 once (lead rank), bp is this rank's partial sum
+        }
+        block_partial(sx, B.p_xp);
+    }
 }
 
 // push + oplus
@@ -578,11 +575,13 @@ k_ba_restore(const BaDev B)
     if (p >= 0 && p < B.P && B.pt_active[p]) for (int a = 0; a < 3; a++) B.pt[3 * p + a] = B.pt_bak[3 * p + a];
 }
 
+__device__ __forceinline__ void lm_decide(const BaDev &B);
+
 // fixed-order sums of the per-block partials of one trial -> scalars[0..4] (sharded: summed over the ranks before k_lm_decide)
 __global__ void __launch_bounds__(256)
 k_lm_reduce(const BaDev B, const volatile int *__restrict__ host_stop, int with_scale)
 {
-    if (B.ctl->state == LM_DONE) return;
+    if (B.ctl->state == LM_DONE) { if (with_scale == 2 && threadIdx.x == 0) B.ctl->last_rejected = 0; return; }
     __shared__ double s[3][256];
     double a0 = 0, a1 = 0, a2 = 0;
     for (int i = threadIdx.x; i < B.n_chi; i += 256) a0 += B.p_chi[i];
@@ -600,11 +599,12 @@ k_lm_reduce(const BaDev B, const volatile int *__restrict__ host_stop, int with_
         B.scalars[0] = s[0][0]; B.scalars[1] = s[1][0]; B.scalars[2] = s[2][0];
         B.scalars[3] = (host_stop && *host_stop) ? 1.0 : 0.0;
         B.scalars[4] = B.flags[0] ? 1.0 : 0.0;
+        if (with_scale == 2) lm_decide(B);                                  // single GPU: nothing to exchange, decide in the same launch
     }
 }
 
 // one LM trial decided on the device (levenberg.cpp:102-161 + the iteration loop of SparseOptimizer::optimize)
-__global__ void k_lm_decide(const BaDev B)
+__device__ __forceinline__ void lm_decide(const BaDev &B)
 {
     LmCtl *c = B.ctl;
     c->last_rejected = 0;
@@ -637,7 +637,14 @@ __global__ void k_lm_decide(const BaDev B)
     if ((c->iniChi - c->currentChi) * 1e3 < c->iniChi) c->nbad++; else c->nbad = 0;
     if (c->nbad >= 3 || c->iteration >= c->max_iterations || stop) { c->state = LM_DONE; return; }
     c->state = LM_BUILD;
+    // start of the next iteration (levenberg.cpp:69-100 without the first-iteration lambda initialisation, which k_lm_iter_begin does in slot 0)
+    c->fresh_first = 0;
+    c->iniChi = c->currentChi;
+    c->qmax = 0;
+    c->rho = 0;
 }
+
+__global__ void k_lm_decide(const BaDev B) { lm_decide(B); }
 
 // after the robust stage: edges with chi2 > 5.991 or non-positive depth leave the optimisation (setLevel(1), Optimizer.cc:691-705);
 // also reports chi2 / depth of every edge for the caller's outlier handling (Optimizer.cc:734-766)

@@ -650,7 +650,7 @@ struct BaRun {
             count(2);
             if (int rc = allreduce(diag6, (size_t)B.n + h->nranks, ncclDouble, ncclSum)) return rc;
         }
-        k_lm_iter_begin<<<1, 1, 0, st>>>(B, diag6, diag6 + B.n);
+        if (first) { k_lm_iter_begin<<<1, 1, 0, st>>>(B, diag6, diag6 + B.n); count(); }     // later iterations are prepared by the decide step of the previous one
         T().begin(BK_PREP, st);
         k_ba_point_prep<<<pt_blocks, 256, 0, st>>>(B);
         T().end(st);
@@ -675,25 +675,29 @@ struct BaRun {
             count();
         }
         T().begin(BK_BACKSUB, st);
-        k_ba_take_xp<<<xp_blocks, 256, 0, st>>>(B);
-        k_ba_backsub<<<pt_blocks, 256, 0, st>>>(B);
+        k_ba_backsub<<<std::max(pt_blocks, xp_blocks), 256, 0, st>>>(B);
         T().end(st);
         T().begin(BK_UPDATE, st);
         k_ba_update<<<upd_blocks, 256, 0, st>>>(B);
         T().end(st);
-        count(3);
+        count(2);
         errors();
         T().begin(BK_DECIDE, st);
-        k_lm_reduce<<<1, 256, 0, st>>>(B, h_stop, 1);
-        T().end(st);
-        T().begin(BK_EXCHANGE, st);
-        if (int rc = exchange_scalars()) return rc;
-        T().end(st);
-        T().begin(BK_DECIDE, st);
-        k_lm_decide<<<1, 1, 0, st>>>(B);
+        if (!multi()) {
+            k_lm_reduce<<<1, 256, 0, st>>>(B, h_stop, 2);                   // sums + decision in one launch
+        } else {
+            k_lm_reduce<<<1, 256, 0, st>>>(B, h_stop, 1);
+            T().end(st);
+            T().begin(BK_EXCHANGE, st);
+            if (int rc = exchange_scalars()) return rc;
+            T().end(st);
+            T().begin(BK_DECIDE, st);
+            k_lm_decide<<<1, 1, 0, st>>>(B);
+            count();
+        }
         k_ba_restore<<<upd_blocks, 256, 0, st>>>(B);
         T().end(st);
-        count(3);
+        count(2);
         ORBS_CUDA(cudaGetLastError());
         return ORBS_OK;
     }
