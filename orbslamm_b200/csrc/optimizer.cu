@@ -71,6 +71,8 @@ struct orbo_handle {
     DevBuf ba_cub;           // cub temp storage (pair sort, scans)
     DevBuf ba_items;         // per-work-item partial blocks of the Schur assembly
     PinnedBuf h_scalars;     // LmCtl copies + the mirrored stop flag
+    PinnedBuf ba_host;       // pinned arena of a BA call: the point-sorted graph arrays are laid out here and go to the device by DMA at PCIe speed
+                             // (from pageable std::vectors the 12 MB of a 500-keyframe graph took ~3 ms of a 13 ms call)
     static constexpr int kCtlCopies = 4;
     cudaEvent_t slot_done[kCtlCopies] = {nullptr, nullptr, nullptr, nullptr};
     int rs_epoch = 0;
@@ -223,7 +225,7 @@ int orbo_destroy(orbo_handle *h)
     if (h->peer.ctl[h->rank] || h->peer.sys[h->rank]) peer_close(h, false);
     if (h->comm) { if (g_nccl.CommAbort) g_nccl.CommAbort(h->comm); else g_nccl.CommDestroy(h->comm); }   // abort: never block on a peer at teardown
     h->pool.release(); h->ba_pool.release(); h->ba_tasks.release(); h->ba_sys.release(); h->ba_flags.release(); h->ba_cub.release(); h->ba_items.release();
-    h->h_scalars.release(); h->timer.release();
+    h->h_scalars.release(); h->ba_host.release(); h->timer.release();
     for (auto &ev : h->slot_done) if (ev) cudaEventDestroy(ev);
     delete h;
     return ORBS_OK;
@@ -772,15 +774,27 @@ extern "C" int orbo_bundle_adjust(orbo_handle *h, int K, float *poses, const uin
     cudaStream_t st = h->stream;
     const auto t_begin = std::chrono::steady_clock::now();
 
-    // ---- host-side graph layout: edges grouped by point (stable), second CSR by pose
-    std::vector<int> pt_start(P + 1, 0), order(E), pose_start(K + 1, 0), pose_edges(E), kf_s(E), pt_s(E);
+    // ---- host-side graph layout: edges grouped by point (stable), second CSR by pose; every array that goes to the device is carved out of one pinned arena
+    const bool want_edges = e_chi2 || e_depth_ok || e_outlier;
+    auto up = [](size_t b) { return (b + 63) & ~(size_t)63; };
+    const size_t arena = up((P + 1) * sizeof(int)) + 3 * up((size_t)E * sizeof(int)) + up((K + 1) * sizeof(int)) + up(2 * (size_t)E * sizeof(double)) +
+                         up((size_t)E * sizeof(double)) + up(3 * (size_t)P * sizeof(double)) + (want_edges ? up((size_t)E * sizeof(double)) + up((size_t)E) : 0) + 64;
+    if (int rc = h->ba_host.reserve(arena)) return rc;
+    uint8_t *ap = h->ba_host.as<uint8_t>();
+    auto carve = [&](size_t bytes) { uint8_t *p = ap; ap += up(bytes); return p; };
+    int *pt_start = (int *)carve((P + 1) * sizeof(int)), *kf_s = (int *)carve((size_t)E * sizeof(int)), *pt_s = (int *)carve((size_t)E * sizeof(int));
+    int *pose_edges = (int *)carve((size_t)E * sizeof(int)), *pose_start = (int *)carve((K + 1) * sizeof(int));
+    double *obs_s = (double *)carve(2 * (size_t)E * sizeof(double)), *w_s = (double *)carve((size_t)E * sizeof(double)), *pts_d = (double *)carve(3 * (size_t)P * sizeof(double));
+    double *chi2_s = want_edges ? (double *)carve((size_t)E * sizeof(double)) : nullptr;
+    uint8_t *depth_s = want_edges ? carve((size_t)E) : nullptr;
+    std::vector<int> order(E);
+    memset(pt_start, 0, (P + 1) * sizeof(int)); memset(pose_start, 0, (K + 1) * sizeof(int));
     for (int e = 0; e < E; e++) pt_start[e_pt[e] + 1]++;
     long long pair_cap = 0;
     for (int p = 0; p < P; p++) { const long long m = pt_start[p + 1]; pair_cap += m * (m + 1) / 2; pt_start[p + 1] += pt_start[p]; }
     ORBS_REQUIRE(pair_cap < (1ll << 31), ORBS_E_INVALID, "too many co-observations for one bundle adjustment (2^31 keyframe pairs)");
     pair_cap = std::max(pair_cap, 1ll);
-    { std::vector<int> fill(pt_start.begin(), pt_start.end() - 1); for (int e = 0; e < E; e++) order[fill[e_pt[e]]++] = e; }
-    std::vector<double> obs_s(2 * (size_t)E), w_s(E);
+    { std::vector<int> fill(pt_start, pt_start + P); for (int e = 0; e < E; e++) order[fill[e_pt[e]]++] = e; }
     for (int j = 0; j < E; j++) {
         const int e = order[j];
         kf_s[j] = e_kf[e]; pt_s[j] = e_pt[e];
@@ -788,9 +802,8 @@ extern "C" int orbo_bundle_adjust(orbo_handle *h, int K, float *poses, const uin
         pose_start[e_kf[e] + 1]++;
     }
     for (int k = 0; k < K; k++) pose_start[k + 1] += pose_start[k];
-    { std::vector<int> fill(pose_start.begin(), pose_start.end() - 1); for (int j = 0; j < E; j++) pose_edges[fill[kf_s[j]]++] = j; }
-    std::vector<double> pts_d(3 * (size_t)P);
-    for (size_t i = 0; i < pts_d.size(); i++) pts_d[i] = points[i];
+    { std::vector<int> fill(pose_start, pose_start + K); for (int j = 0; j < E; j++) pose_edges[fill[kf_s[j]]++] = j; }
+    for (size_t i = 0; i < 3 * (size_t)P; i++) pts_d[i] = points[i];
 
     // ---- device buffers
     Stager S(&h->ba_pool, st, ORBS_MEM_HOST);
@@ -805,14 +818,14 @@ extern "C" int orbo_bundle_adjust(orbo_handle *h, int K, float *poses, const uin
     const float *d_T = S.in(poses, (size_t)K * 16);
     const uint8_t *d_fixed = S.in(fixed, K);
     B.intr = S.in(intr, (size_t)K * 4);
-    B.pt = const_cast<double *>(S.in(pts_d.data(), pts_d.size()));
-    B.pt_bak = S.scratch<double>(pts_d.size());
+    B.pt = const_cast<double *>(S.in(pts_d, 3 * (size_t)P));
+    B.pt_bak = S.scratch<double>(3 * (size_t)P);
     B.pose = S.scratch<Se3>(K); B.pose_bak = S.scratch<Se3>(K);
-    B.pt_start = S.in(pt_start.data(), pt_start.size()); B.e_kf = S.in(kf_s.data(), E); B.e_point = S.in(pt_s.data(), E);
-    B.e_obs = S.in(obs_s.data(), obs_s.size()); B.e_w = S.in(w_s.data(), E);
+    B.pt_start = S.in(pt_start, (size_t)P + 1); B.e_kf = S.in(kf_s, E); B.e_point = S.in(pt_s, E);
+    B.e_obs = S.in(obs_s, 2 * (size_t)E); B.e_w = S.in(w_s, E);
     B.e_level = S.scratch<uint8_t>(E); B.e_err = S.scratch<double>(2 * (size_t)E);
     B.e_W = S.scratch<double>(18 * (size_t)E); B.e_Z = S.scratch<double>(18 * (size_t)E);
-    B.pose_start = S.in(pose_start.data(), pose_start.size()); B.pose_edges = S.in(pose_edges.data(), E);
+    B.pose_start = S.in(pose_start, (size_t)K + 1); B.pose_edges = S.in(pose_edges, E);
     D.d_pose_idx = S.scratch<int>(K); B.pose_idx = D.d_pose_idx;
     B.pt_active = S.scratch<uint8_t>(P);
     B.Hpp = S.scratch<double>(36 * (size_t)K); B.bp = S.scratch<double>(6 * (size_t)K + 8);
@@ -871,9 +884,6 @@ extern "C" int orbo_bundle_adjust(orbo_handle *h, int K, float *poses, const uin
     LmCtl fin;
     memset(&fin, 0, sizeof fin);
     if ((rc = D.optimize(its0, any == 1, &fin))) return rc;
-    std::vector<double> chi2_s;
-    std::vector<uint8_t> depth_s;
-    const bool want_edges = e_chi2 || e_depth_ok || e_outlier;
     if (two_stage && !*D.h_stop) {
         // chi2 / depth gating (Optimizer.cc:691-705) on the device; the structure is rebuilt only if a keyframe lost all its observations
         k_ba_edge_check<<<(E + 255) / 256, 256, 0, st>>>(B, d_chi2, d_depth, 1);
@@ -908,9 +918,8 @@ extern "C" int orbo_bundle_adjust(orbo_handle *h, int K, float *poses, const uin
     k_ba_export_points<<<(3 * P + 255) / 256, 256, 0, st>>>(P, B.pt, d_pts_out);
     h->launches += 3;
     if (want_edges) {
-        chi2_s.resize(E); depth_s.resize(E);
-        ORBS_CUDA(cudaMemcpyAsync(chi2_s.data(), d_chi2, E * sizeof(double), cudaMemcpyDeviceToHost, st));
-        ORBS_CUDA(cudaMemcpyAsync(depth_s.data(), d_depth, E, cudaMemcpyDeviceToHost, st));
+        ORBS_CUDA(cudaMemcpyAsync(chi2_s, d_chi2, E * sizeof(double), cudaMemcpyDeviceToHost, st));
+        ORBS_CUDA(cudaMemcpyAsync(depth_s, d_depth, E, cudaMemcpyDeviceToHost, st));
     }
     ORBS_CUDA(cudaMemcpyAsync(poses, d_Tout, (size_t)K * 16 * sizeof(float), cudaMemcpyDeviceToHost, st));
     ORBS_CUDA(cudaMemcpyAsync(points, d_pts_out, 3 * (size_t)P * sizeof(float), cudaMemcpyDeviceToHost, st));
