@@ -30,7 +30,7 @@ from orbslamm_b200 import synth  # noqa: E402
 
 CAM = synth.KITTI
 TH_PROJ = 15.0          # Tracking.cc:925-930 (mono)
-TRAFFIC_JSON = "r2h_traffic.json"
+TRAFFIC_JSON = "r2i_traffic.json"
 N_POOL = 5              # distinct frames per stream (steps cycle over frame pairs 1..N_POOL-1)
 
 

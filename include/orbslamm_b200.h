@@ -456,8 +456,9 @@ int orbo_optimize_sim3(orbo_handle *h, int n_pairs, double *sim3, const uint8_t 
 /* Multi-GPU bundle adjustment: one process per GPU, keyframe poses replicated, MAP POINTS (with all
  * their observations) sharded over the ranks.  After orbo_comm_init the handle's orbo_bundle_adjust becomes a
  * collective: every rank passes ALL keyframes (same order, same poses) but only ITS points and edges; each rank builds
- * its partial reduced pose system as packed nonzero tiles + right-hand side in ONE buffer, one ncclAllReduce (fp64 sum over
- * NVLink) per LM trial combines them, every rank factors the same system redundantly and back-substitutes its own points.
+ * its partial reduced pose system as packed nonzero tiles + right-hand side in ONE buffer, ONE exchange per LM trial sums them over
+ * the ranks (reduce-scatter + all-gather kernels over NVLink peer memory, csrc/peer_reduce.cuh; ncclAllReduce where the ranks cannot
+ * map each other's memory), every rank factors the same system redundantly and back-substitutes its own points.
  * Five scalars (chi2, the two gain-ratio parts, stop flag, Cholesky failure) are summed after the trial so that all ranks take
  * identical LM decisions on their device-resident control blocks; the keyframe activity mask and the tile adjacency are
  * reduced once per call.  Poses come back

@@ -1,6 +1,7 @@
-// optimizer.cu -- host driver and C-ABI of the optimizer (orbo_*): PoseOptimization (device-resident LM, one CTA
-// per frame) and Local / Global bundle adjustment (host-driven Levenberg-Marquardt over CUDA kernels: per-point
-// Schur complement, dense Cholesky of the reduced pose system, back-substitution).
+// optimizer.cu -- host driver and C-ABI of the optimizer (orbo_*): PoseOptimization and OptimizeSim3 (whole LM schedule on the device, one CTA per
+// frame / keyframe pair), Local / Global bundle adjustment (device-resident Levenberg-Marquardt control block, the host only enqueues trial "slots":
+// per-target Schur assembly, sparse tiled Cholesky of the reduced pose system in one persistent DMMA kernel, back-substitution; sharded over GPUs with
+// one exchange of the reduced system per trial), the Sim3Solver RANSAC pieces and the essential-graph optimisation.
 //
 // Replaces S/src/Optimizer.cc:68-260, 262-474, 476-801 and the g2o stack behind it.
 #include <math.h>
