@@ -154,6 +154,7 @@ __device__ __forceinline__ void rs_factor8_invert(double *Tb, double *Xb, bool &
             sx[q] = fma(lq, x[j], sx[q]);
         }
     }
+    __syncwarp();                                                        // the mirror lanes read the block above; lanes 0..7 overwrite it
     if (lane < 8) {
 #pragma unroll
         for (int q = 0; q < 8; q++) { Tb[r * kOpPitch + q] = q <= r ? a[q] : 0.0; Xb[q * kOpPitch + c] = x[q]; }
