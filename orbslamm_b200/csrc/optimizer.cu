@@ -491,11 +491,18 @@ struct BaRun {
         const size_t n = (size_t)B.ns * TS2 + (size_t)B.nt * TS;
         if (!h->peer_on) return allreduce(B.A, n, ncclDouble, ncclSum);
         const unsigned ep = ++h->peer_epoch;
-        const int grid = std::max(8, std::min(h->sm_count, (int)(n / 2 / h->nranks / 512) + 1));
-        k_peer_reduce_scatter<<<grid, 256, 0, st>>>(h->peer, B.ctl, (long long)(n / 2), ep);
-        k_peer_all_gather<<<grid, 256, 0, st>>>(h->peer, B.ctl, (long long)(n / 2), ep);
-        k_peer_barrier<<<1, 32, 0, st>>>(h->peer, B.ctl, ep);
-        count(3);
+        // the sums go to the private copy the solver reads (rsbuf.A / rsbuf.b); the shared buffer keeps this rank's partial until the next trial
+        double *out = const_cast<double *>(rsbuf.A);
+        if (h->nranks <= 4) {
+            const int grid = std::max(8, std::min(h->sm_count, (int)(n / 2 / 512) + 1));
+            k_peer_all_reduce<<<grid, 256, 0, st>>>(h->peer, B.ctl, (long long)(n / 2), ep, out);
+            count();
+        } else {
+            const int grid = std::max(8, std::min(h->sm_count, (int)(n / 2 / h->nranks / 256) + 1));
+            k_peer_reduce_scatter<<<grid, 256, 0, st>>>(h->peer, B.ctl, (long long)(n / 2), ep);
+            k_peer_all_gather<<<grid, 256, 0, st>>>(h->peer, B.ctl, (long long)(n / 2), ep, out);
+            count(2);
+        }
         ORBS_CUDA(cudaGetLastError());
         return ORBS_OK;
     }
@@ -576,7 +583,9 @@ struct BaRun {
                 if (int rc = peer_reserve_sys(h, (nA_t + nv) * sizeof(double))) return rc;
                 if (h->peer_on) { B.A = h->peer.sys[h->rank]; B.bs = B.A + nA_t; }
             }
-            rsbuf.A = B.A; rsbuf.b = B.bs; rsbuf.L = base + nA_t + nv; rsbuf.Linv = rsbuf.L + nA_t; rsbuf.y = rsbuf.Linv + (size_t)ng * TS2; rsbuf.x = rsbuf.y + nv;
+            rsbuf.A = B.A; rsbuf.b = B.bs;
+            if (multi() && h->peer_on) { rsbuf.A = base; rsbuf.b = base + nA_t; }       // peer exchange: the solver reads the summed copy in ba_sys
+            rsbuf.L = base + nA_t + nv; rsbuf.Linv = rsbuf.L + nA_t; rsbuf.y = rsbuf.Linv + (size_t)ng * TS2; rsbuf.x = rsbuf.y + nv;
             rsbuf.part = rsbuf.x + nv;
             B.x = rsbuf.x;
             const size_t nflags = (size_t)plan.ns + 2 * (size_t)ng + (size_t)plan.n_part + 8;

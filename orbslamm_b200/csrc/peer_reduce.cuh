@@ -3,10 +3,13 @@
 // The sharded solve (optimizer.cu) needs, once per LM trial, the SUM over the ranks of the packed reduced system (structurally nonzero 64x64 fp64 tiles +
 // right-hand side: 4.9 MB at 500 keyframes) and of five scalars.  NCCL does that in ~100 us + ~40 us at 8 GPUs, which is as long as everything else in
 // the trial but the factorisation.  Here every rank maps every other rank's buffers (cudaIpc handles, exchanged once through the NCCL communicator) and
-// the reduction is three tiny kernels on the BA stream:
-//   k_peer_reduce_scatter   rank r sums chunk r of all ranks' buffers, in rank order (bit-identical whoever computes it), into its own chunk
-//   k_peer_all_gather       every rank copies the other ranks' reduced chunks
-//   k_peer_barrier          nobody overwrites its buffer while a peer may still be reading it
+// the reduction is one or two small kernels on the BA stream:
+//   up to 4 ranks:  k_peer_all_reduce      every rank reads every rank's whole partial buffer and writes the sum, in rank order (bit-identical on every rank),
+//                                          into a private buffer the solver reads: ONE flag synchronisation
+//   more ranks:     k_peer_reduce_scatter  rank r sums chunk r of all ranks' buffers, in rank order, into its own chunk
+//                   k_peer_all_gather      every rank copies the other ranks' reduced chunks (into the private buffer)
+//   Nobody may overwrite its shared buffer while a peer still reads it: the scalar exchange that follows the solve in the same trial (k_peer_scalars: every
+//   rank signals after its own reduction kernels, in stream order, and waits for everybody) is that barrier, so no separate one is needed.
 // Synchronisation: per-phase epoch flags in peer memory (st.release.sys after __threadfence_system, ld.acquire.sys spins with a bound: a rank that never
 // arrives sets an error flag instead of hanging the device).  The epoch only grows, flags are never reset.
 #pragma once
@@ -84,7 +87,7 @@ k_peer_reduce_scatter(const PeerDev P, const LmCtl *__restrict__ ctl, long long 
 }
 
 __global__ void __launch_bounds__(256)
-k_peer_all_gather(const PeerDev P, const LmCtl *__restrict__ ctl, long long n2, unsigned epoch)
+k_peer_all_gather(const PeerDev P, const LmCtl *__restrict__ ctl, long long n2, unsigned epoch, double *__restrict__ out)
 {
     if (ctl->state == LM_DONE) return;
     const int lane = threadIdx.x & 31;
@@ -93,20 +96,30 @@ k_peer_all_gather(const PeerDev P, const LmCtl *__restrict__ ctl, long long n2, 
         peer_wait(P, 1, epoch, lane);
     }
     __syncthreads();
-    for (int q = 1; q < P.n; q++) {
-        const int p = (P.rank + q) % P.n;                          // start with the neighbour: the ranks do not all pull from rank 0 at once
+    for (int q = 0; q < P.n; q++) {
+        const int p = (P.rank + q) % P.n;                          // own chunk first, then the neighbours: the ranks do not all pull from rank 0 at once
         const long long c0 = p * n2 / P.n, c1 = (p + 1) * n2 / P.n;
         for (long long i = c0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < c1; i += (long long)gridDim.x * blockDim.x)
-            reinterpret_cast<double2 *>(P.sys[P.rank])[i] = peer_ld2(P.sys[p] + 2 * i);
+            reinterpret_cast<double2 *>(out)[i] = peer_ld2(P.sys[p] + 2 * i);
     }
 }
 
-// everybody finished reading everybody else's buffer: from here on the buffers may be overwritten
-__global__ void k_peer_barrier(const PeerDev P, const LmCtl *__restrict__ ctl, unsigned epoch)
+// one-shot all-reduce for a few ranks: out (private) = sum over the ranks of their shared partial buffers
+__global__ void __launch_bounds__(256)
+k_peer_all_reduce(const PeerDev P, const LmCtl *__restrict__ ctl, long long n2, unsigned epoch, double *__restrict__ out)
 {
     if (ctl->state == LM_DONE) return;
-    peer_signal(P, 2, epoch, threadIdx.x);
-    peer_wait(P, 2, epoch, threadIdx.x);
+    const int lane = threadIdx.x & 31;
+    if (threadIdx.x < 32) {
+        if (blockIdx.x == 0) peer_signal(P, 0, epoch, lane);
+        peer_wait(P, 0, epoch, lane);
+    }
+    __syncthreads();
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.x * blockDim.x) {
+        double2 s = make_double2(0.0, 0.0);
+        for (int p = 0; p < P.n; p++) { const double2 v = peer_ld2(P.sys[p] + 2 * i); s.x += v.x; s.y += v.y; }
+        reinterpret_cast<double2 *>(out)[i] = s;
+    }
 }
 
 // sum of `scalars[0..4]` over the ranks, in rank order on every rank: each rank writes its five values into everybody's slot table, then adds up its own table
