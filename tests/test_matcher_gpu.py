@@ -164,3 +164,25 @@ def test_distinctive_descriptors_batch(lib):
     ref = np.array([oracle.distinctive_descriptor(d) for d in lists], np.int32)
     assert np.array_equal(got, ref)
     assert got[0] == -1 and got[1] == 0 and got[2] == 0
+
+
+def test_search_by_projection_wide_windows_32bit_keys(lib):
+    """k_search_candidates with <= 2048 feature slots (32-bit keys) and windows three times the usual radius: more than 32 grid cells and more than 32 features
+    per window, i.e. several cell chunks and several sorted batches merged into the running top-8 per query -- must still equal the sequential scan."""
+    import orbslamm_b200 as ob
+    k = make_tracking_case(synth.TUM, 5)
+    sf = np.array(list(k["P"].scale)[:8], np.float32)
+    g = oracle.grid_params(*k["bounds"])
+    cur, last = k["cur"], k["last"]
+    nF, nQ = len(cur["x"]), len(last["x"])
+    assert nF <= 2048
+    r = oracle.project_last_frame(k["Tcw"], k["K4"], g, sf, k["Xw"], last["octave"], 15.0, k["valid"])
+    fxy = np.stack([cur["x"], cur["y"]], 1)
+    for scale_r, lvl in ((3.0, False), (6.0, True)):
+        mn, mx = (np.full_like(r[3], -1), np.full_like(r[4], -1)) if lvl else (r[3], r[4])       # lvl: no octave gate -> every feature of the window is a candidate
+        n_ref, fm_ref = oracle.search_by_projection(g, fxy, cur["octave"], cur["angle"], cur["desc"], r[0], r[1], r[2] * scale_r, mn, mx,
+                                                    last["angle"], last["desc"], 100, 0.0, True)
+        nm, fm = ob.ORBmatcher(0.9, True).SearchByProjection(k["bounds"], fxy[None], cur["octave"][None], cur["angle"][None], cur["desc"][None], np.array([nF], np.int32),
+                                                             r[0][None], r[1][None], (r[2] * scale_r)[None], mn[None], mx[None], last["angle"][None],
+                                                             last["desc"][None], np.array([nQ], np.int32), 100)
+        assert n_ref > 100 and int(nm[0]) == n_ref and np.array_equal(fm[0], fm_ref), (scale_r, lvl, n_ref, int(nm[0]))
