@@ -777,8 +777,6 @@ extern "C" int orbo_bundle_adjust(orbo_handle *h, int K, float *poses, const uin
     ORBS_REQUIRE(K > 0 && P > 0 && E > 0, ORBS_E_INVALID, "empty graph");
     if (stats) stats[0] = stats[1] = stats[2] = stats[3] = 0;
     if (h->nranks == 1 && stop_flag && *stop_flag) { if (stats) stats[3] = 1; return 1; }   // Optimizer.cc:678-680 (sharded: decided collectively below)
-    for (int e = 0; e < E; e++)
-        ORBS_REQUIRE(e_kf[e] >= 0 && e_kf[e] < K && e_pt[e] >= 0 && e_pt[e] < P, ORBS_E_INVALID, "edge references a vertex out of range");
     std::lock_guard<std::mutex> lk(h->mu);
     ORBS_CUDA(cudaSetDevice(h->device));
     cudaStream_t st = h->stream;
@@ -799,19 +797,29 @@ extern "C" int orbo_bundle_adjust(orbo_handle *h, int K, float *poses, const uin
     uint8_t *depth_s = want_edges ? carve((size_t)E) : nullptr;
     std::vector<int> order(E);
     memset(pt_start, 0, (P + 1) * sizeof(int)); memset(pose_start, 0, (K + 1) * sizeof(int));
-    for (int e = 0; e < E; e++) pt_start[e_pt[e] + 1]++;
+    // pass A: validate + count per point and per keyframe;  pass B: stable scatter into point order;  pass C: second CSR by keyframe
+    {
+        bool ok = true;
+        for (int e = 0; e < E; e++) {
+            const int kf = e_kf[e], pt = e_pt[e];
+            if ((unsigned)kf >= (unsigned)K || (unsigned)pt >= (unsigned)P) { ok = false; break; }
+            pt_start[pt + 1]++; pose_start[kf + 1]++;
+        }
+        ORBS_REQUIRE(ok, ORBS_E_INVALID, "edge references a vertex out of range");
+    }
     long long pair_cap = 0;
     for (int p = 0; p < P; p++) { const long long m = pt_start[p + 1]; pair_cap += m * (m + 1) / 2; pt_start[p + 1] += pt_start[p]; }
     ORBS_REQUIRE(pair_cap < (1ll << 31), ORBS_E_INVALID, "too many co-observations for one bundle adjustment (2^31 keyframe pairs)");
     pair_cap = std::max(pair_cap, 1ll);
-    { std::vector<int> fill(pt_start, pt_start + P); for (int e = 0; e < E; e++) order[fill[e_pt[e]]++] = e; }
-    for (int j = 0; j < E; j++) {
-        const int e = order[j];
-        kf_s[j] = e_kf[e]; pt_s[j] = e_pt[e];
-        obs_s[2 * j] = e_uv[2 * e]; obs_s[2 * j + 1] = e_uv[2 * e + 1]; w_s[j] = e_inv_sigma2[e];
-        pose_start[e_kf[e] + 1]++;
-    }
     for (int k = 0; k < K; k++) pose_start[k + 1] += pose_start[k];
+    {
+        std::vector<int> fill(pt_start, pt_start + P);
+        for (int e = 0; e < E; e++) {
+            const int pt = e_pt[e], j = fill[pt]++;
+            order[j] = e; kf_s[j] = e_kf[e]; pt_s[j] = pt;
+            obs_s[2 * j] = e_uv[2 * e]; obs_s[2 * j + 1] = e_uv[2 * e + 1]; w_s[j] = e_inv_sigma2[e];
+        }
+    }
     { std::vector<int> fill(pose_start, pose_start + K); for (int j = 0; j < E; j++) pose_edges[fill[kf_s[j]]++] = j; }
     for (size_t i = 0; i < 3 * (size_t)P; i++) pts_d[i] = points[i];
 
