@@ -71,6 +71,7 @@ struct orbo_handle {
     DevBuf ba_flags;         // dataflow epoch flags + ticket counters of k_rs_solve
     DevBuf ba_cub;           // cub temp storage (pair sort, scans)
     DevBuf ba_items;         // per-work-item partial blocks of the Schur assembly
+    DevBuf pg_bufs[24];      // essential-graph buffers, kept across calls (a cudaMalloc / cudaFree pair per buffer and call cost 5 - 200 ms in a busy process)
     PinnedBuf h_scalars;     // LmCtl copies + the mirrored stop flag
     PinnedBuf ba_host;       // pinned arena of a BA call: the point-sorted graph arrays are laid out here and go to the device by DMA at PCIe speed
                              // (from pageable std::vectors the 12 MB of a 500-keyframe graph took ~3 ms of a 13 ms call)
@@ -225,7 +226,7 @@ int orbo_destroy(orbo_handle *h)
     else cudaDeviceSynchronize();
     if (h->peer.ctl[h->rank] || h->peer.sys[h->rank]) peer_close(h, false);
     if (h->comm) { if (g_nccl.CommAbort) g_nccl.CommAbort(h->comm); else g_nccl.CommDestroy(h->comm); }   // abort: never block on a peer at teardown
-    h->pool.release(); h->ba_pool.release(); h->ba_tasks.release(); h->ba_sys.release(); h->ba_flags.release(); h->ba_cub.release(); h->ba_items.release();
+    h->pool.release(); h->ba_pool.release(); h->ba_tasks.release(); h->ba_sys.release(); h->ba_flags.release(); h->ba_cub.release(); h->ba_items.release(); for (auto &b : h->pg_bufs) b.release();
     h->h_scalars.release(); h->ba_host.release(); h->timer.release();
     for (auto &ev : h->slot_done) if (ev) cudaEventDestroy(ev);
     delete h;
@@ -1014,12 +1015,11 @@ namespace {
 
 struct PgHost {
     orbo_handle *h; cudaStream_t st; PgDev P;
-    DevBuf bufs[24]; int nbuf = 0;
+    int nbuf = 0;
     TilePlanHost plan;
     RsPlan rsplan = {}; RsBuf rsbuf = {};
     int eblocks = 0, solve_ctas = 1;
-    ~PgHost() { for (int i = 0; i < nbuf; i++) bufs[i].release(); }
-    template <typename T> T *alloc(size_t n, int *rc) { if (*rc) return nullptr; if (nbuf >= 24) { *rc = ORBS_E_INVALID; return nullptr; } *rc = bufs[nbuf].reserve(std::max<size_t>(n, 1) * sizeof(T)); return bufs[nbuf++].as<T>(); }
+    template <typename T> T *alloc(size_t n, int *rc) { if (*rc) return nullptr; if (nbuf >= 24) { *rc = ORBS_E_INVALID; return nullptr; } *rc = h->pg_bufs[nbuf].reserve(std::max<size_t>(n, 1) * sizeof(T)); return h->pg_bufs[nbuf++].as<T>(); }
 
     // tile groups of kPgPerTile consecutive free vertices; adjacency from the edges; elimination order + symbolic factorisation + tasks;
     // the per-target-block contribution lists of the normal equations (sorted: deterministic accumulation)
