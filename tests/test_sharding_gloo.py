@@ -63,3 +63,45 @@ def test_shard_partition_properties():
             seen_p.append(lp); seen_e.append(le)
         assert np.array_equal(np.sort(np.concatenate(seen_p)), np.arange(1000))
         assert np.array_equal(np.sort(np.concatenate(seen_e)), np.arange(7000))
+
+
+def _owner_worker(rank, world, port, ret):
+    """sharding by an explicit owner (configs[3]: points stay on the GPUs of their origin map): the per-keyframe observation counts -- a stand-in for the
+    partial Hpp blocks every rank contributes to the reduced system -- summed over the ranks equal the full graph's"""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = synth.ba_graph(K=14, P=333, seed=4)
+    origin = (np.arange(len(g["points"])) * 7 % 5 < 2).astype(np.int64)            # an uneven split into two "maps"
+    sh = sharding.shard_graph_by_owner(g, origin, rank)
+    assert np.all(origin[sh["local_points"]] == rank) and np.array_equal(sh["local_points"][sh["pt"]], g["pt"][sh["local_edges"]])
+    part = torch.from_numpy(np.bincount(sh["kf"], minlength=len(g["poses"])).astype(np.int64))
+    dist.all_reduce(part)
+    assert np.array_equal(part.numpy(), np.bincount(g["kf"], minlength=len(g["poses"])))
+    objs = [None] * world
+    dist.all_gather_object(objs, (sh["local_points"], sh["points"]))
+    assert np.array_equal(sharding.merge_points(len(g["points"]), objs), g["points"])
+    ret[rank] = 1
+    dist.destroy_process_group()
+
+
+def test_ba_sharding_by_owner_world2():
+    world = 2
+    mgr = mp.Manager(); ret = mgr.dict()
+    mp.spawn(_owner_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    assert sorted(ret.keys()) == [0, 1]
+
+
+def test_owner_by_origin_splits_the_gpus_between_the_two_maps():
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import map_merge as M
+    rng = np.random.default_rng(1)
+    origin = (rng.random(1000) < 0.4).astype(np.int64)
+    assert np.all(M.owner_by_origin(origin, 1) == 0)
+    for world in (2, 3, 4, 8):
+        own = M.owner_by_origin(origin, world)
+        half = world // 2
+        assert own[origin == 0].max() < half and own[origin == 1].min() >= half and own.max() < world
+        for o, lo, hi in ((0, 0, half), (1, half, world)):                           # round-robin inside a map's GPUs: balanced to within one point
+            c = np.bincount(own[origin == o], minlength=world)[lo:hi]
+            assert c.max() - c.min() <= 1
