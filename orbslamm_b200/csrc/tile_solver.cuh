@@ -244,7 +244,7 @@ k_rs_solve(const RsPlan P, const RsBuf B, const LmCtl *__restrict__ ctl, int epo
     double *opA[2] = {rs_smem, rs_smem + 2 * TS * kOpPitch};
     double *opB[2] = {rs_smem + TS * kOpPitch, rs_smem + 3 * TS * kOpPitch};
     __shared__ int s_task, s_pref;
-    __shared__ double s_vec[TS], s_red[4 * TS], s_col[2 * TS];
+    __shared__ double s_vec[TS], s_red[4 * TS];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int fr = lane >> 2, fk = lane & 3;
 
