@@ -43,6 +43,31 @@ def launches(src, dst):
     print(open(dst).read())
 
 
+def launches_batch(src, dst, n):
+    """the launch list restricted to the launches over batches of n frames (a grid dimension == n): the device-resident leg of bench.py, whose per-kernel
+    shares are what roofline.kernel_share_of_step reports (the whole-command list also holds the e2e leg's 32-frame batches and the single-frame latency calls)"""
+    n = str(int(n))
+    rows = [r for r in csv.reader(open(src)) if len(r) > 10]
+    h = rows[0]
+    ik, ig, iv, iu = h.index("Kernel Name"), h.index("Grid Size"), h.index("Metric Value"), h.index("Metric Unit")
+    agg = collections.defaultdict(lambda: [0, 0.0])
+    for r in rows[1:]:
+        dims = [d.strip() for d in r[ig].strip("()").split(",")]
+        if n not in dims or not r[ik].startswith(("orbs::", "void orbs::")):
+            continue
+        v = float(r[iv].replace(",", ""))
+        v = v / 1e3 if r[iu] == "ns" else v * 1e3 if r[iu] == "ms" else v
+        k = r[ik].split("(")[0]
+        agg[k][0] += 1; agg[k][1] += v
+    tot = sum(v[1] for v in agg.values())
+    with open(dst, "w") as f:
+        f.write(f"# ncu --metrics gpu__time_duration.sum --clock-control none  (source {src}); only launches over batches of {n} frames (the device-resident leg); cold-cache, serialised: compare SHARES\n")
+        f.write(f"{'kernel':70s} {'launches':>8s} {'total_us':>12s} {'share':>7s} {'avg_us':>10s}\n")
+        for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            f.write(f"{k[:70]:70s} {v[0]:8d} {v[1]:12.1f} {v[1] / tot:7.3f} {v[1] / v[0]:10.1f}\n")
+    print(open(dst).read())
+
+
 def kernel(src, dst):
     out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
@@ -82,7 +107,9 @@ def traffic(fe_rep, ba_rep, dst, frames_per_launch=128):
 
 
 if __name__ == "__main__":
-    if sys.argv[1] == "traffic":
+    if sys.argv[1] == "launches_batch":
+        launches_batch(sys.argv[2], sys.argv[3], sys.argv[4])
+    elif sys.argv[1] == "traffic":
         traffic(sys.argv[2], sys.argv[3], sys.argv[4])
     else:
         {"launches": launches, "kernel": kernel}[sys.argv[1]](sys.argv[2], sys.argv[3])
