@@ -64,3 +64,24 @@ def test_sim3_chain_golden():
     assert np.array_equal(np.packbits(inl, axis=1), d["inliers"]) and np.array_equal(n, d["n_inliers"]) and n.max() > 20
     r = oracle.optimize_pose_graph(d["pg_sim3"], d["pg_fixed"], d["pg_ei"], d["pg_ej"], d["pg_meas"], True, 20, 1e-16)
     assert [r["lm_iterations"], r["lm_trials"]] == d["pg_iters"].tolist() and np.allclose(r["sim3"], d["pg_out"], rtol=0, atol=1e-9)
+
+
+def test_round2_golden():
+    """tests/golden/round2_small.npz (tools/make_golden_r2.py): batched ComputeDistinctiveDescriptors, the OpenCV call sequence of ComputeSim3 through cv2, and every
+    decision + the merged poses of the two-map merge chain driven by the oracle."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import map_merge as M
+    d = np.load(os.path.join(G, "round2_small.npz"))
+    st = d["dd_start"]
+    best = [oracle.distinctive_descriptor(d["dd_flat"][st[p]:st[p + 1]]) for p in range(len(st) - 1)]
+    assert np.array_equal(best, d["dd_best"]) and d["dd_best"][0] == -1
+    for h in range(len(d["s3_X1"])):
+        T12, T21 = M.compute_sim3(d["s3_X1"][h].T.copy(), d["s3_X2"][h].T.copy())[:2]
+        assert np.array_equal(T12, d["s3_T12"][h]) and np.array_equal(T21, d["s3_T21"][h])            # same cv2 build as the generator (4.13): bit for bit
+    sc = M.make_scene(seed=0, Ka=10, Kb=10, n_world=1800)
+    out = M.run_merge(sc, M.Stages("oracle", sc["voc"]))
+    dec = out["candidates"] + out["bow_matches"] + list(out["ransac"][-1]) + list(out["sim3_inliers"][-1]) + [out["total_matches"], out["fused"], out["essential_edges"],
+                                                                                                           out["loop_connections"], out["gba"]["lm_iterations"]]
+    assert dec == d["mm_decisions"].tolist()
+    assert np.abs(out["poses"] - d["mm_poses"]).max() < 1e-6 * np.abs(d["mm_poses"]).max()

@@ -72,3 +72,26 @@ def test_sim3_chain_golden_gpu(lib):
     assert np.array_equal(np.packbits(inl, axis=1), d["inliers"]) and np.array_equal(n, d["n_inliers"])
     r = o.OptimizePoseGraph(d["pg_sim3"], d["pg_fixed"], d["pg_ei"], d["pg_ej"], d["pg_meas"], True, 20, 1e-16)
     assert np.abs(r["sim3"] - d["pg_out"]).max() < 1e-5 * np.abs(d["pg_out"]).max()
+
+
+def test_round2_golden_gpu(lib):
+    """CUDA path against tests/golden/round2_small.npz: distinctive descriptors exactly, ComputeSim3 to the float tolerance of its header comment, the two-map merge
+    chain with identical decisions and the merged poses to 1e-4."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import map_merge as M
+    import orbslamm_b200 as ob
+    d = np.load(os.path.join(G, "round2_small.npz"))
+    st = d["dd_start"]
+    got = ob.ORBmatcher(0.6, True).ComputeDistinctiveDescriptors([d["dd_flat"][st[p]:st[p + 1]] for p in range(len(st) - 1)])
+    assert np.array_equal(got, d["dd_best"])
+    T12, T21, _, _, _ = ob.Optimizer().Sim3Compute(d["s3_X1"], d["s3_X2"])
+    for h in range(len(T12)):
+        assert np.abs(T12[h] - d["s3_T12"][h]).max() < 1e-4 * max(np.abs(d["s3_T12"][h]).max(), 1.0)
+        assert np.abs(T21[h] - d["s3_T21"][h]).max() < 1e-4 * max(np.abs(d["s3_T21"][h]).max(), 1.0)
+    sc = M.make_scene(seed=0, Ka=10, Kb=10, n_world=1800)
+    out = M.run_merge(sc, M.Stages("cuda", sc["voc"]))
+    dec = out["candidates"] + out["bow_matches"] + list(out["ransac"][-1]) + list(out["sim3_inliers"][-1]) + [out["total_matches"], out["fused"], out["essential_edges"],
+                                                                                                           out["loop_connections"], out["gba"]["lm_iterations"]]
+    assert dec == d["mm_decisions"].tolist()
+    assert np.abs(out["poses"] - d["mm_poses"]).max() < 1e-4 * np.abs(d["mm_poses"]).max()
