@@ -51,6 +51,7 @@ struct orbx_handle {
     ExtractPlan plan;
     int octree_smem = 0;
     DevBuf d_cells, d_tiles, d_rs_tab;
+    bool rs_words[ORBS_MAX_LEVELS] = {};   // level l's resize may use k_resize_level<true> (the 4 source columns of every thread within 8 bytes of an aligned word)
     // per-batch workspaces
     int batch_cap = 0;
     DevBuf d_stage;      // staged host images (64-byte pitch)
@@ -230,6 +231,12 @@ static int build_plan(orbx_handle *h, int width, int height)
                     const int a0 = (short)cv_round_f((1.f - fx) * 2048.f), a1 = (short)cv_round_f(fx * 2048.f);
                     rs.push_back(make_int2(sx, (a1 << 16) | (a0 & 0xffff)));
                 }
+                if (axis == 0) {
+                    bool ok = true;
+                    const int2 *tx = rs.data() + L.rs_x_off;
+                    for (int d = 0; d < dsize && ok; d += 4) ok = tx[std::min(d + 3, dsize - 1)].x - (tx[d].x & ~3) <= 7;
+                    h->rs_words[l] = ok;
+                }
             }
         }
     }
@@ -330,8 +337,10 @@ static int launch_pipeline(orbx_handle *h, const uint8_t *d_img0_all, int f0, in
         else { src = pyr + S.pyr_off; spitch = S.pitch; sframe = P.pyr_frame_bytes; }
         dim3 grid((D.w + 255) / 256, (D.h + 3) / 4, n);                     // 64 x 4 threads, 4 output pixels per thread
         h->timer.begin(0, st);
-        k_resize_level<<<grid, 256, 0, st>>>(src, S.w, S.h, spitch, sframe, pyr + D.pyr_off, D.w, D.h, D.pitch, P.pyr_frame_bytes,
-                                              h->d_rs_tab.as<int2>() + D.rs_x_off, h->d_rs_tab.as<int2>() + D.rs_y_off);
+        // word loads need 4-byte aligned source rows (always true for pyramid levels; level 0 may be a caller-owned device buffer)
+        const bool words = h->rs_words[l] && ((((uintptr_t)src | (uintptr_t)spitch | (uintptr_t)sframe) & 3) == 0);
+        (words ? k_resize_level<true> : k_resize_level<false>)<<<grid, 256, 0, st>>>(src, S.w, S.h, spitch, sframe, pyr + D.pyr_off, D.w, D.h, D.pitch, P.pyr_frame_bytes,
+                                                                                      h->d_rs_tab.as<int2>() + D.rs_x_off, h->d_rs_tab.as<int2>() + D.rs_y_off);
         h->timer.end(st);
         h->launches++;
     }

@@ -24,6 +24,14 @@ __device__ __align__(16) const int8_t g_brief_pattern[1024] = {
 // ---------------------------------------------------------------------------------------------
 // Pyramid: level l from level l-1, OpenCV fixed-point bilinear (11-bit coefficients).
 // tab_x / tab_y entries: .x = source index, .y = (a1 << 16) | a0   (a0 + a1 = 2048)
+//
+// kWords (rows 4-byte aligned and the four source columns of a thread within 8 bytes of the aligned word left of the first one --
+// the host checks both, any scale factor <= ~2): each source row arrives as THREE aligned 32-bit loads; the byte pair
+// (p[sx], p[sx + 1]) of an output is one funnel shift of two of those words and the horizontal interpolation one dp2a against
+// the packed (a0, a1) of the table entry -- 6 loads and ~25 instructions per output pixel instead of 16 byte loads with 64-bit
+// address arithmetic each (~57).  Words past the row's last one are clamped to it: the bytes they would have held only ever
+// meet a1 = 0 (sx = sw - 1 has fx = 0 in the table, as in cv::resize).  !kWords: byte loads (unaligned caller-owned level 0).
+template <bool kWords>
 __global__ void __launch_bounds__(256)
 k_resize_level(const uint8_t *__restrict__ src, int sw, int sh, int spitch, size_t sframe,
                uint8_t *__restrict__ dst, int dw, int dh, int dpitch, size_t dframe,
@@ -41,16 +49,38 @@ k_resize_level(const uint8_t *__restrict__ src, int sw, int sh, int spitch, size
     const int4 t01 = __ldg(reinterpret_cast<const int4 *>(tab_x + x)), t23 = __ldg(reinterpret_cast<const int4 *>(tab_x + x + 2));
     const int sxs[4] = {t01.x, t01.z, t23.x, t23.z}, cf[4] = {t01.y, t01.w, t23.y, t23.w};
     unsigned out = 0u;
+    if (kWords) {
+        // entries beyond dw are table padding (0, 0) or the next table: they only select among registers already loaded, masked below
+        const int base = sxs[0] & ~3, lastw = (sw - 1) & ~3;
+        const int o0 = base, o1 = min(base + 4, lastw), o2 = min(base + 8, lastw);
+        const unsigned u0 = __ldg(reinterpret_cast<const unsigned *>(r0p + o0)), u1 = __ldg(reinterpret_cast<const unsigned *>(r0p + o1)),
+                       u2 = __ldg(reinterpret_cast<const unsigned *>(r0p + o2));
+        const unsigned v0 = __ldg(reinterpret_cast<const unsigned *>(r1p + o0)), v1 = __ldg(reinterpret_cast<const unsigned *>(r1p + o1)),
+                       v2 = __ldg(reinterpret_cast<const unsigned *>(r1p + o2));
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-        // entries beyond dw are table padding (0, 0) or the next table: harmless reads, masked below
-        const int sx0 = min(sxs[k], sw - 1), sx1 = min(sx0 + 1, sw - 1);
-        const int a0 = cf[k] & 0xffff, a1 = cf[k] >> 16;
-        const int r0 = r0p[sx0] * a0 + r0p[sx1] * a1;
-        const int r1 = r1p[sx0] * a0 + r1p[sx1] * a1;
-        int v = (((b0 * (r0 >> 4)) >> 16) + ((b1 * (r1 >> 4)) >> 16) + 2) >> 2;
-        v = min(max(v, 0), 255);
-        out |= (unsigned)v << (8 * k);
+        for (int k = 0; k < 4; k++) {
+            const int o = sxs[k] - base;                                     // 0 .. 7 for a valid output, 0 .. 3 for the first one
+            const bool up = k > 0 && o >= 4;
+            const unsigned sh8 = (unsigned)(o & 3) * 8u;
+            const unsigned p0 = __funnelshift_r(up ? u1 : u0, up ? u2 : u1, sh8);   // byte 0 = row0[sx], byte 1 = row0[sx + 1]
+            const unsigned p1 = __funnelshift_r(up ? v1 : v0, up ? v2 : v1, sh8);
+            const int r0 = (int)__dp2a_lo((unsigned)cf[k], p0, 0u);            // row0[sx] * a0 + row0[sx + 1] * a1
+            const int r1 = (int)__dp2a_lo((unsigned)cf[k], p1, 0u);
+            const int v = min((((b0 * (r0 >> 4)) >> 16) + ((b1 * (r1 >> 4)) >> 16) + 2) >> 2, 255);   // every term is >= 0
+            out |= (unsigned)v << (8 * k);
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            // entries beyond dw are table padding (0, 0) or the next table: harmless reads, masked below
+            const int sx0 = min(sxs[k], sw - 1), sx1 = min(sx0 + 1, sw - 1);
+            const int a0 = cf[k] & 0xffff, a1 = cf[k] >> 16;
+            const int r0 = r0p[sx0] * a0 + r0p[sx1] * a1;
+            const int r1 = r1p[sx0] * a0 + r1p[sx1] * a1;
+            int v = (((b0 * (r0 >> 4)) >> 16) + ((b1 * (r1 >> 4)) >> 16) + 2) >> 2;
+            v = min(max(v, 0), 255);
+            out |= (unsigned)v << (8 * k);
+        }
     }
     uint8_t *q = dst + (size_t)blockIdx.z * dframe + (size_t)y * dpitch + x;
     if (x + 3 < dw) *reinterpret_cast<unsigned *>(q) = out;

@@ -73,10 +73,12 @@ def test_extract_device_resident_images(lib, pitch_kind):
         assert np.array_equal(r["octave"][f, :n], ref["octave"]) and np.array_equal(r["desc"][f, :n], ref["desc"])
 
 
-@pytest.mark.parametrize("shape,nf,levels,sf", [((97, 131), 100, 4, 1.2), ((241, 322), 500, 5, 1.5), ((120, 500), 200, 3, 1.3), ((480, 640), 1000, 8, 1.2)])
+@pytest.mark.parametrize("shape,nf,levels,sf", [((97, 131), 100, 4, 1.2), ((241, 322), 500, 5, 1.5), ((120, 500), 200, 3, 1.3), ((480, 640), 1000, 8, 1.2),
+                                                 ((200, 300), 150, 3, 2.0)])
 def test_extract_other_shapes(lib, shape, nf, levels, sf):
     """Small / wide images, other level counts and scale factors (large FAST cells on coarse levels, one-tile blur rows, ragged
-    batches through the chunked host path) == oracle."""
+    batches through the chunked host path) == oracle.  Scale factor 2.0: the four source columns of a resize thread no longer fit
+    the three aligned words of k_resize_level<true>, the byte-load variant runs."""
     import orbslamm_b200 as ob
     n = 19                                                     # not a multiple of the 16-frame upload chunk
     frames = [synth.stream(shape[1], shape[0], 1, stream_id=100 + i)[0][0] for i in range(3)]
