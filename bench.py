@@ -466,13 +466,8 @@ def bench_frontend(args, rank, world):
     out = {"metric": f"ORB extract+match fps @{w}x{h}", "value": round(fps, 1), "unit": "frames/s", "n_gpus": world, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": round(total_ms / args.steps, 4), "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-           "config": {"workload": f"{'KITTI' if w == 1241 else 'TUM'}-shape {w}x{h} synthetic streams, nFeatures={CAM['nfeatures']}: extract + SearchByProjection(Cur,Last) + PoseOptimization per frame",
-                      "streams_per_gpu": B, "frames_per_step": B * world, "instances_per_gpu": nI,
-                      "instances": ("software pipeline: every instance serves all streams on alternating steps (extract of step i+1 overlaps match + pose of step i); the K steps are one timed region"
-                                    if pipelined else "streams split over the instances, fork-join per step"),
-                      "l2": ("inputs larger than L2: each step reads %.0f MB of new images from a %.0f MB pool and a %.2f GB working set; no flush inside the timed region" % (B * h * pitch / 1e6, N_POOL * B * h * pitch / 1e6, 2 * B * 1.444e6 / 1e9 + B * h * pitch / 1e9))
-                            if pipelined else "256 MiB flush buffer written between timed steps (untimed)",
-                      "keypoints_per_frame": nkp, "matches_per_frame": float(np.mean(nmatch)), "pose_inliers_per_frame": float(np.mean(ninl)), "parallelism": f"streams x{world}"},
+           "config": frontend_config(args, world),
+           "stats": {"keypoints_per_frame": nkp, "matches_per_frame": float(np.mean(nmatch)), "pose_inliers_per_frame": float(np.mean(ninl))},
            "e2e": {"value": round(e2e_fps, 1), "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
                    "workers": nW, "gpu_launches": int(launches_e2e),
                    "note": "orbf_track_frames on pinned host buffers; the GPU's streams are split over `workers` independent front-end instances "
@@ -480,6 +475,22 @@ def bench_frontend(args, rank, world):
            "latency_ms": latency,
            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "wall_s": round(wall, 3)}
     return out
+
+
+def frontend_config(args, world):
+    """The workload description both arms print verbatim (`--impl reference` runs on THIS config); measured per-frame counts live in `stats`."""
+    w, h = CAM["w"], CAM["h"]
+    B = args.streams
+    pitch = (w + 63) // 64 * 64
+    nI = max(1, min(args.instances, B))
+    pipelined = args.mode == "pipeline" and nI > 1
+    return {"workload": f"{'KITTI' if w == 1241 else 'TUM'}-shape {w}x{h} synthetic streams, nFeatures={CAM['nfeatures']}: extract + SearchByProjection(Cur,Last) + PoseOptimization per frame",
+            "streams_per_gpu": B, "frames_per_step": B * world, "instances_per_gpu": nI,
+            "instances": ("software pipeline: every instance serves all streams on alternating steps (extract of step i+1 overlaps match + pose of step i); the K steps are one timed region"
+                          if pipelined else "streams split over the instances, fork-join per step"),
+            "l2": ("inputs larger than L2: each step reads %.0f MB of new images from a %.0f MB pool and a %.2f GB working set; no flush inside the timed region" % (B * h * pitch / 1e6, N_POOL * B * h * pitch / 1e6, 2 * B * 1.444e6 / 1e9 + B * h * pitch / 1e9))
+                  if pipelined else "256 MiB flush buffer written between timed steps (untimed)",
+            "parallelism": f"streams x{world}"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -607,11 +618,11 @@ def main():
         line = {"impl": "reference", "metric": f"ORB extract+match fps @{CAM['w']}x{CAM['h']}", "value": round(fps, 2), "unit": "frames/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 / fps, 3), "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-                "config": {"workload": f"{'KITTI' if CAM['w'] == 1241 else 'TUM'}-shape {CAM['w']}x{CAM['h']} synthetic streams, nFeatures={CAM['nfeatures']}: extract + SearchByProjection(Cur,Last) + PoseOptimization per frame",
-                           "note": "the oracle port: the REAL OpenCV primitives the reference calls (cv2 4.13 FAST / resize / GaussianBlur, SIMD) + restated reference "
-                                   "code, one independent stream per core.  oracle/_ref holds the reference's own ORBextractor.cc / ORBmatcher.cc / Optimizer.cc + g2o as object "
-                                   "code, but over scalar stand-ins for OpenCV / Eigen (headers absent from the image; 175 vs 99 ms per 1241x376 extraction, 1.5 vs 9.4 LM it/s): "
-                                   "the faster port is the fairer baseline; the BA record carries the object-code timing too"},
+                "config": frontend_config(args, args.gpus),
+                "note": ("the oracle port: the REAL OpenCV primitives the reference calls (cv2 4.13 FAST / resize / GaussianBlur, SIMD) + restated reference "
+                         "code, one independent stream per core.  oracle/_ref holds the reference's own ORBextractor.cc / ORBmatcher.cc / Optimizer.cc + g2o as object "
+                         "code, but over scalar stand-ins for OpenCV / Eigen (headers absent from the image; 175 vs 99 ms per 1241x376 extraction, 1.5 vs 9.4 LM it/s): "
+                         "the faster port is the fairer baseline; the BA record carries the object-code timing too"),
                 "cpu_baseline": {"value": round(fps, 2), "unit": "frames/s", "cores": cores, "kind": "port", "cpu": cpu_model(),
                                  "sample": f"{per} frames x {cores} streams (one per core), {wall:.1f} s"},
                 "e2e": {"value": round(fps, 2), "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}

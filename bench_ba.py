@@ -135,14 +135,14 @@ def bench_ba(args, rank, world):
     out = {"metric": "LocalBA LM iters/s @500KF/50k pts", "value": round(its, 2), "unit": "LM iterations/s", "n_gpus": world, "steps": steps,
            "warmup": args.warmup, "ms_per_step": round(loop_s * 1e3 / steps, 3), "ms_per_lm_iteration": round(loop_s * 1e3 / max(iters, 1), 4), "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": {"workload": f"synthetic covisibility graph {K} KF / {P} points / {E} observations, LocalBA schedule 5 robust + 10 non-robust LM its",
-                      "lm_iterations_per_step": iters / steps, "lm_trials_per_step": trials / steps,
-                      "l2": "256 MiB flush buffer written between timed steps (untimed)", "reduced_system": f"{ld}x{ld} fp64 (10 keyframes per 64-row tile), nested-dissection tile order: {sky} of {(ld // 64) * (ld // 64 + 1) // 2} lower 64x64 tiles structurally nonzero in L (only those are stored), {tm['levels']} elimination levels",
-                      "parallelism": f"map points sharded x{world}, poses replicated, ONE NCCL all-reduce of the {sky} packed tiles + rhs ({(sky * 4096 + ld) * 8 / 1e6:.1f} MB) per LM trial + a 5-scalar all-reduce for the LM decision" if world > 1 else "1 GPU"},
+           "config": ba_config(K, P, world),
+           "solver": {"observations": int(E), "lm_iterations_per_step": iters / steps, "lm_trials_per_step": trials / steps,
+                      "reduced_system": f"{ld}x{ld} fp64 (10 keyframes per 64-row tile), nested-dissection tile order: {sky} of {(ld // 64) * (ld // 64 + 1) // 2} lower 64x64 tiles structurally nonzero in L (only those are stored), {tm['levels']} elimination levels",
+                      "exchange_bytes_per_trial": int((sky * 4096 + ld) * 8) if world > 1 else 0},
            "e2e": {"value": round(e2e, 2), "unit": "LM iterations/s", "h2d_bytes_per_step": int(graph_bytes), "d2h_bytes_per_step": int(K * 64 + P * 12 + E * 10)},
            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "wall_s": round(wall, 3)}
     out["lm_iterations"] = int(iters)
-    out["config"]["exchange"] = comm_mode
+    out["solver"]["exchange"] = comm_mode
     if sharded_parity is not None:
         out["sharded_parity"] = sharded_parity
         # what the multi-robot system actually runs: one LocalBA per robot (LocalMapping per System) = N independent solves, one per GPU, no collective
@@ -164,6 +164,14 @@ def bench_ba(args, rank, world):
     if rank == 0:
         out["cpu_baseline"] = cpu_baseline_ba(K, P, 1)
     return out
+
+
+def ba_config(K, P, world):
+    """The workload description both arms print verbatim; what the solver derives from the graph (observation count, tile structure, exchange mode) lives in `solver`."""
+    return {"workload": f"synthetic covisibility graph {K} KF / {P} points (3..9 observations per point, synth.ba_graph seed 42), LocalBA schedule 5 robust + 10 non-robust LM its",
+            "l2": "256 MiB flush buffer written between timed steps (untimed)",
+            "parallelism": (f"map points sharded x{world}, poses replicated, ONE exchange of the packed reduced system per LM trial + a 5-scalar exchange for the LM decision"
+                            if world > 1 else "1 GPU")}
 
 
 def cpu_baseline_ba(K, P, repeats):
@@ -215,6 +223,6 @@ def reference_line(args):
     return {"impl": "reference", "metric": "LocalBA LM iters/s @500KF/50k pts", "value": cb["value"], "unit": "LM iterations/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(15e3 / cb["value"], 2), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"synthetic covisibility graph {K} KF / {P} points, LocalBA schedule 5 robust + 10 non-robust LM its",
-                       "note": "value = the oracle port (fp64 restatement of the g2o path, 1 thread like the reference: g2o is built without OpenMP); cpu_baseline.reference_object_code = the reference's own Optimizer.cc + g2o over the Eigen stand-in (slower than a real-Eigen build)"},
+            "config": ba_config(K, P, args.gpus),
+            "note": "value = the oracle port (fp64 restatement of the g2o path, 1 thread like the reference: g2o is built without OpenMP); cpu_baseline.reference_object_code = the reference's own Optimizer.cc + g2o over the Eigen stand-in (slower than a real-Eigen build)",
             "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "LM iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}

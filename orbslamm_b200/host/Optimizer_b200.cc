@@ -354,7 +354,8 @@ S8 s8_inv(const S8 &a)                                            // Sim3::inver
 }
 void s8_map(const S8 &a, const double *x, double *o) { double r[3]; q_rot(a.v, x, r); for (int k = 0; k < 3; k++) o[k] = a.v[7] * r[k] + a.v[4 + k]; }   // s*(r*xyz) + t
 S8 s8_of(const g2o::Sim3 &s) { S8 r; r.v[0] = s.rotation().x(); r.v[1] = s.rotation().y(); r.v[2] = s.rotation().z(); r.v[3] = s.rotation().w();
-                        for (int k = 0; k < 3; k++) r.v[4 + k] = s.translation()[k]; r.v[7] = s.scale(); return r; }
+                        for (int k = 0; k < 3; k++) { r.v[4 + k] = s.translation()[k]; }
+                        r.v[7] = s.scale(); return r; }
 S8 s8_of_pose(KeyFrame *pKF)                                      // g2o::Sim3 Siw(Converter::toMatrix3d(Rcw), Converter::toVector3d(tcw), 1.0): Quaterniond(Matrix3d)
 {
     const cv::Mat Rm = pKF->GetRotation(), tm = pKF->GetTranslation();
