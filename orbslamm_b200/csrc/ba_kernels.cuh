@@ -649,7 +649,7 @@ __global__ void k_lm_decide(const BaDev B) { lm_decide(B); }
 // after the robust stage: edges with chi2 > 5.991 or non-positive depth leave the optimisation (setLevel(1), Optimizer.cc:691-705);
 // also reports chi2 / depth of every edge for the caller's outlier handling (Optimizer.cc:734-766)
 __global__ void __launch_bounds__(256)
-k_ba_edge_check(const BaDev B, double *__restrict__ chi2, uint8_t *__restrict__ depth_ok, int gate)
+k_ba_edge_check(const BaDev B, double *__restrict__ chi2, uint8_t *__restrict__ depth_ok, uint8_t *__restrict__ outlier, int gate)
 {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= B.E) return;
@@ -658,6 +658,7 @@ k_ba_edge_check(const BaDev B, double *__restrict__ chi2, uint8_t *__restrict__ 
     se3_map(B.pose[B.e_kf[e]], &B.pt[3 * B.e_point[e]], Xc);
     const bool dok = Xc[2] > 0.0;
     chi2[e] = c; depth_ok[e] = dok;
+    outlier[e] = (uint8_t)(c > 5.991 || !dok);
     if (gate && (c > 5.991 || !dok)) B.e_level[e] = 1;
 }
 
@@ -753,6 +754,23 @@ k_ba_seg_starts(const int *__restrict__ head, const int *__restrict__ scan, cons
     if (t >= n_cap) return;
     if (head[t]) seg_start[scan[t] - 1] = t;
     if (t == n_cap - 1) { const int ns = scan[t]; seg_start[ns] = *n_pairs; *n_seg = ns; }
+}
+
+// float32 inputs of the caller widened on the device (the host stages 4-byte values: its copy loop is bound by one core's memory bandwidth)
+__global__ void __launch_bounds__(256)
+k_ba_widen(size_t n_obs, const float *__restrict__ obs, double *__restrict__ obs_d, size_t n_w, const float *__restrict__ w, double *__restrict__ w_d,
+           size_t n_pt, const float *__restrict__ pt, double *__restrict__ pt_d)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_obs) obs_d[i] = (double)obs[i];
+    if (i < n_w) w_d[i] = (double)w[i];
+    if (i < n_pt) pt_d[i] = (double)pt[i];
+}
+
+__global__ void k_ba_iota(int n, int *__restrict__ v)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) v[i] = i;
 }
 
 __global__ void k_ba_import_poses(int K, const float *__restrict__ T, Se3 *__restrict__ pose)

@@ -452,8 +452,24 @@ int orbo_sim3_check_inliers(orbo_handle *h, int n_hyp, const float *T12, const f
 // The host never waits for a decision: it reads a pinned copy of the control block two slots later and stops enqueueing.
 namespace {
 
+// profiling aid (ORBS_BA_STAGES=1): wall-clock marks of the host-side stages of one orbo_bundle_adjust call, printed to stderr at the end of the call
+struct StageTrace {
+    bool on = false;
+    std::vector<std::pair<const char *, std::chrono::steady_clock::time_point>> v;
+    StageTrace() { on = getenv("ORBS_BA_STAGES") != nullptr; if (on) v.reserve(32); }
+    void mark(const char *name) { if (on) v.emplace_back(name, std::chrono::steady_clock::now()); }
+    void dump() const
+    {
+        if (!on || v.empty()) return;
+        fprintf(stderr, "[orbo_bundle_adjust stages, ms]");
+        for (size_t i = 1; i < v.size(); i++) fprintf(stderr, " %s %.3f", v[i].first, std::chrono::duration<double, std::milli>(v[i].second - v[i - 1].second).count());
+        fprintf(stderr, " | total %.3f\n", std::chrono::duration<double, std::milli>(v.back().second - v.front().second).count());
+    }
+};
+
 struct BaRun {
     orbo_handle *h = nullptr;
+    StageTrace *trace = nullptr;
     cudaStream_t st = nullptr;
     Stager *S = nullptr;
     BaDev B;
@@ -552,7 +568,9 @@ struct BaRun {
         std::vector<uint8_t> adj((size_t)ng * ng);
         ORBS_CUDA(cudaMemcpyAsync(adj.data(), d_adj, adj.size(), cudaMemcpyDeviceToHost, st));
         ORBS_CUDA(cudaStreamSynchronize(st));
+        if (trace) trace->mark("tile_adjacency");
         plan.build(adj, ng);
+        if (trace) trace->mark("tile_plan");
         B.ns = plan.ns;
         ORBS_REQUIRE(plan.ns < (1 << 24), ORBS_E_INVALID, "reduced pose system too large / too dense for the tiled Cholesky (more than 2^24 tiles)");
         std::vector<int> rowbase(std::max(nA, 1)), tile_pose((size_t)ng * kPosesPerTile, -1);
@@ -625,6 +643,7 @@ struct BaRun {
         ORBS_CUDA(cudaGetLastError());
         ORBS_CUDA(cudaMemcpyAsync(&n_seg, d_nseg, sizeof(int), cudaMemcpyDeviceToHost, st));
         ORBS_CUDA(cudaStreamSynchronize(st));
+        if (trace) trace->mark("pair_sort");
         B.pair_key = d_key[1]; B.pair_val = d_val[1]; B.seg_start = d_seg_start; B.n_seg = d_nseg;
         // work items of the Schur assembly: segments cut into pieces of kItemPairs pairs (d_head / d_scan are free again)
         n_items = 0;
@@ -636,6 +655,7 @@ struct BaRun {
             ORBS_CUDA(cudaStreamSynchronize(st));
             if (int rc = h->ba_items.reserve((size_t)std::max(n_items, 1) * kSchurVals * sizeof(double))) return rc;
         }
+        if (trace) trace->mark("schur_items");
         return ORBS_OK;
     }
 
@@ -782,28 +802,36 @@ extern "C" int orbo_bundle_adjust(orbo_handle *h, int K, float *poses, const uin
     ORBS_CUDA(cudaSetDevice(h->device));
     cudaStream_t st = h->stream;
     const auto t_begin = std::chrono::steady_clock::now();
+    StageTrace trace;
+    trace.mark("begin");
 
-    // ---- host-side graph layout: edges grouped by point (stable), second CSR by pose; every array that goes to the device is carved out of one pinned arena
+    // ---- host-side graph layout: edges grouped by point (stable); every array that goes to the device is carved out of one pinned arena.  The float32 inputs
+    // (observations, weights, points) are staged as they are and widened to fp64 on the device
     const bool want_edges = e_chi2 || e_depth_ok || e_outlier;
     auto up = [](size_t b) { return (b + 63) & ~(size_t)63; };
-    const size_t arena = up((P + 1) * sizeof(int)) + 3 * up((size_t)E * sizeof(int)) + up((K + 1) * sizeof(int)) + up(2 * (size_t)E * sizeof(double)) +
-                         up((size_t)E * sizeof(double)) + up(3 * (size_t)P * sizeof(double)) + (want_edges ? up((size_t)E * sizeof(double)) + up((size_t)E) : 0) + 64;
+    const size_t arena = up((P + 1) * sizeof(int)) + 2 * up((size_t)E * sizeof(int)) + up((K + 1) * sizeof(int)) + up(2 * (size_t)E * sizeof(float)) +
+                         up((size_t)E * sizeof(float)) + up(3 * (size_t)P * sizeof(float)) + (want_edges ? up((size_t)E * sizeof(double)) + 2 * up((size_t)E) : 0) + 64;
     if (int rc = h->ba_host.reserve(arena)) return rc;
     uint8_t *ap = h->ba_host.as<uint8_t>();
     auto carve = [&](size_t bytes) { uint8_t *p = ap; ap += up(bytes); return p; };
     int *pt_start = (int *)carve((P + 1) * sizeof(int)), *kf_s = (int *)carve((size_t)E * sizeof(int)), *pt_s = (int *)carve((size_t)E * sizeof(int));
-    int *pose_edges = (int *)carve((size_t)E * sizeof(int)), *pose_start = (int *)carve((K + 1) * sizeof(int));
-    double *obs_s = (double *)carve(2 * (size_t)E * sizeof(double)), *w_s = (double *)carve((size_t)E * sizeof(double)), *pts_d = (double *)carve(3 * (size_t)P * sizeof(double));
+    int *pose_start = (int *)carve((K + 1) * sizeof(int));
+    float *obs_s = (float *)carve(2 * (size_t)E * sizeof(float)), *w_s = (float *)carve((size_t)E * sizeof(float)), *pts_s = (float *)carve(3 * (size_t)P * sizeof(float));
     double *chi2_s = want_edges ? (double *)carve((size_t)E * sizeof(double)) : nullptr;
-    uint8_t *depth_s = want_edges ? carve((size_t)E) : nullptr;
-    std::vector<int> order(E);
+    uint8_t *depth_s = want_edges ? carve((size_t)E) : nullptr, *outl_s = want_edges ? carve((size_t)E) : nullptr;
     memset(pt_start, 0, (P + 1) * sizeof(int)); memset(pose_start, 0, (K + 1) * sizeof(int));
-    // pass A: validate + count per point and per keyframe;  pass B: stable scatter into point order;  pass C: second CSR by keyframe
+    trace.mark("arena");
+    // pass A: validate + count per point and per keyframe;  pass B: stable scatter into point order (a straight conversion copy when the caller's edges
+    // already come grouped by ascending point, as a graph built by walking the map points does);  the second CSR (edges of a keyframe, ascending) is
+    // a stable device sort of the uploaded keyframe column (below)
+    bool grouped = true;
     {
         bool ok = true;
+        int prev = 0;
         for (int e = 0; e < E; e++) {
             const int kf = e_kf[e], pt = e_pt[e];
             if ((unsigned)kf >= (unsigned)K || (unsigned)pt >= (unsigned)P) { ok = false; break; }
+            grouped &= pt >= prev; prev = pt;
             pt_start[pt + 1]++; pose_start[kf + 1]++;
         }
         ORBS_REQUIRE(ok, ORBS_E_INVALID, "edge references a vertex out of range");
@@ -813,7 +841,14 @@ extern "C" int orbo_bundle_adjust(orbo_handle *h, int K, float *poses, const uin
     ORBS_REQUIRE(pair_cap < (1ll << 31), ORBS_E_INVALID, "too many co-observations for one bundle adjustment (2^31 keyframe pairs)");
     pair_cap = std::max(pair_cap, 1ll);
     for (int k = 0; k < K; k++) pose_start[k + 1] += pose_start[k];
-    {
+    trace.mark("pass_A_count");
+    std::vector<int> order;                                                  // sorted position -> caller's edge index (empty: identity)
+    if (grouped) {
+        // (splitting these copies over helper threads was measured: the copy gets faster, the DMA out of lines owned by several cores slower by the same amount)
+        memcpy(kf_s, e_kf, (size_t)E * sizeof(int)); memcpy(pt_s, e_pt, (size_t)E * sizeof(int));
+        memcpy(obs_s, e_uv, 2 * (size_t)E * sizeof(float)); memcpy(w_s, e_inv_sigma2, (size_t)E * sizeof(float));
+    } else {
+        order.resize(E);
         std::vector<int> fill(pt_start, pt_start + P);
         for (int e = 0; e < E; e++) {
             const int pt = e_pt[e], j = fill[pt]++;
@@ -821,13 +856,13 @@ extern "C" int orbo_bundle_adjust(orbo_handle *h, int K, float *poses, const uin
             obs_s[2 * j] = e_uv[2 * e]; obs_s[2 * j + 1] = e_uv[2 * e + 1]; w_s[j] = e_inv_sigma2[e];
         }
     }
-    { std::vector<int> fill(pose_start, pose_start + K); for (int j = 0; j < E; j++) pose_edges[fill[kf_s[j]]++] = j; }
-    for (size_t i = 0; i < 3 * (size_t)P; i++) pts_d[i] = points[i];
+    memcpy(pts_s, points, 3 * (size_t)P * sizeof(float));
+    trace.mark("pass_B_scatter");
 
     // ---- device buffers
     Stager S(&h->ba_pool, st, ORBS_MEM_HOST);
     BaRun D;
-    D.h = h; D.st = st; D.S = &S; D.stop = stop_flag; D.fixed = fixed;
+    D.h = h; D.st = st; D.S = &S; D.stop = stop_flag; D.fixed = fixed; D.trace = &trace;
     D.h_ctl = h->h_scalars.as<LmCtl>(); D.h_stop = reinterpret_cast<int *>(D.h_ctl + orbo_handle::kCtlCopies);
     *D.h_stop = 0;
     BaDev &B = D.B;
@@ -837,14 +872,19 @@ extern "C" int orbo_bundle_adjust(orbo_handle *h, int K, float *poses, const uin
     const float *d_T = S.in(poses, (size_t)K * 16);
     const uint8_t *d_fixed = S.in(fixed, K);
     B.intr = S.in(intr, (size_t)K * 4);
-    B.pt = const_cast<double *>(S.in(pts_d, 3 * (size_t)P));
+    const float *d_pts_f = S.in(pts_s, 3 * (size_t)P);
+    B.pt = S.scratch<double>(3 * (size_t)P);
     B.pt_bak = S.scratch<double>(3 * (size_t)P);
     B.pose = S.scratch<Se3>(K); B.pose_bak = S.scratch<Se3>(K);
     B.pt_start = S.in(pt_start, (size_t)P + 1); B.e_kf = S.in(kf_s, E); B.e_point = S.in(pt_s, E);
-    B.e_obs = S.in(obs_s, 2 * (size_t)E); B.e_w = S.in(w_s, E);
+    const float *d_obs_f = S.in(obs_s, 2 * (size_t)E), *d_w_f = S.in(w_s, E);
+    double *d_obs = S.scratch<double>(2 * (size_t)E), *d_w = S.scratch<double>(E);
+    B.e_obs = d_obs; B.e_w = d_w;
     B.e_level = S.scratch<uint8_t>(E); B.e_err = S.scratch<double>(2 * (size_t)E);
     B.e_W = S.scratch<double>(18 * (size_t)E); B.e_Z = S.scratch<double>(18 * (size_t)E);
-    B.pose_start = S.in(pose_start, (size_t)K + 1); B.pose_edges = S.in(pose_edges, E);
+    B.pose_start = S.in(pose_start, (size_t)K + 1);
+    int *d_pose_edges = S.scratch<int>(E), *d_iota = S.scratch<int>(E), *d_kf_sorted = S.scratch<int>(E);
+    B.pose_edges = d_pose_edges;
     D.d_pose_idx = S.scratch<int>(K); B.pose_idx = D.d_pose_idx;
     B.pt_active = S.scratch<uint8_t>(P);
     B.Hpp = S.scratch<double>(36 * (size_t)K); B.bp = S.scratch<double>(6 * (size_t)K + 8);
@@ -869,9 +909,23 @@ extern "C" int orbo_bundle_adjust(orbo_handle *h, int K, float *poses, const uin
     D.d_key[0] = S.scratch<unsigned long long>(pair_cap); D.d_key[1] = S.scratch<unsigned long long>(pair_cap);
     D.d_val[0] = S.scratch<unsigned long long>(pair_cap); D.d_val[1] = S.scratch<unsigned long long>(pair_cap);
     D.d_head = S.scratch<int>(pair_cap); D.d_scan = S.scratch<int>(pair_cap); D.d_seg_start = S.scratch<int>(pair_cap + 2); D.d_nseg = S.scratch<int>(4);
-    double *d_chi2 = S.scratch<double>(E); uint8_t *d_depth = S.scratch<uint8_t>(E);
+    double *d_chi2 = S.scratch<double>(E); uint8_t *d_depth = S.scratch<uint8_t>(E), *d_outl = S.scratch<uint8_t>(E);
     float *d_Tout = S.scratch<float>((size_t)K * 16); float *d_pts_out = S.scratch<float>(3 * (size_t)P);
     if (S.rc) return S.rc;
+    {
+        const size_t nw = std::max(2 * (size_t)E, 3 * (size_t)P);
+        k_ba_widen<<<(unsigned)((nw + 255) / 256), 256, 0, st>>>(2 * (size_t)E, d_obs_f, d_obs, (size_t)E, d_w_f, d_w, 3 * (size_t)P, d_pts_f, B.pt);
+        h->launches++;
+    }
+    {   // edges of every keyframe in ascending (point-grouped) edge order: stable radix sort of the keyframe column, values = edge positions
+        const int kbits = std::max(1, 32 - __builtin_clz((unsigned)std::max(K - 1, 1)));
+        size_t need = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, need, B.e_kf, d_kf_sorted, d_iota, d_pose_edges, E, 0, kbits, st);
+        if (int rc = h->ba_cub.reserve(need + 256)) return rc;
+        k_ba_iota<<<(E + 255) / 256, 256, 0, st>>>(E, d_iota);
+        ORBS_CUDA(cub::DeviceRadixSort::SortPairs(h->ba_cub.p, need, B.e_kf, d_kf_sorted, d_iota, d_pose_edges, E, 0, kbits, st));
+        h->launches += 2;
+    }
     // LocalBundleAdjustment: const float thHuberMono = sqrt(5.991) (Optimizer.cc:592); BundleAdjustment: const float thHuber2D = sqrt(5.99) (:106)
     B.delta = two_stage ? (double)(float)sqrt(5.991) : (double)(float)sqrt(5.99);
     B.dsqr = (double)(float)(B.delta * B.delta);   // RobustKernelHuber keeps delta^2 in a FLOAT member (robust_kernel_impl.h:84): pinned against the reference's object code
@@ -894,8 +948,10 @@ extern "C" int orbo_bundle_adjust(orbo_handle *h, int K, float *poses, const uin
     // initializeOptimization(level 0) + buildIndexMapping, sparse_optimizer.cpp:166-267
     D.pose_idx.assign(K, -2);
     bool changed = false;
+    trace.mark("enqueue_uploads");
     int any = D.read_activity(&changed);
     if (any < 0) return ORBS_E_CUDA;
+    trace.mark("uploads_and_activity");
     int rc = D.build_structure();
     if (rc) return rc;
     const auto t_loop = std::chrono::steady_clock::now();
@@ -905,7 +961,7 @@ extern "C" int orbo_bundle_adjust(orbo_handle *h, int K, float *poses, const uin
     if ((rc = D.optimize(its0, any == 1, &fin))) return rc;
     if (two_stage && !*D.h_stop) {
         // chi2 / depth gating (Optimizer.cc:691-705) on the device; the structure is rebuilt only if a keyframe lost all its observations
-        k_ba_edge_check<<<(E + 255) / 256, 256, 0, st>>>(B, d_chi2, d_depth, 1);
+        k_ba_edge_check<<<(E + 255) / 256, 256, 0, st>>>(B, d_chi2, d_depth, d_outl, 1);
         h->launches++;
         B.robust = 0;
         any = D.read_activity(&changed);
@@ -932,24 +988,33 @@ extern "C" int orbo_bundle_adjust(orbo_handle *h, int K, float *poses, const uin
         }
     }
     const auto t_loop_end = std::chrono::steady_clock::now();          // optimize() returned after a stream synchronisation
-    k_ba_edge_check<<<(E + 255) / 256, 256, 0, st>>>(B, d_chi2, d_depth, 0);
+    trace.mark("lm_loops");
+    k_ba_edge_check<<<(E + 255) / 256, 256, 0, st>>>(B, d_chi2, d_depth, d_outl, 0);
     k_ba_export_poses<<<(K + 255) / 256, 256, 0, st>>>(K, B.pose, d_fixed, d_Tout);
     k_ba_export_points<<<(3 * P + 255) / 256, 256, 0, st>>>(P, B.pt, d_pts_out);
     h->launches += 3;
     if (want_edges) {
         ORBS_CUDA(cudaMemcpyAsync(chi2_s, d_chi2, E * sizeof(double), cudaMemcpyDeviceToHost, st));
         ORBS_CUDA(cudaMemcpyAsync(depth_s, d_depth, E, cudaMemcpyDeviceToHost, st));
+        ORBS_CUDA(cudaMemcpyAsync(outl_s, d_outl, E, cudaMemcpyDeviceToHost, st));
     }
     ORBS_CUDA(cudaMemcpyAsync(poses, d_Tout, (size_t)K * 16 * sizeof(float), cudaMemcpyDeviceToHost, st));
     ORBS_CUDA(cudaMemcpyAsync(points, d_pts_out, 3 * (size_t)P * sizeof(float), cudaMemcpyDeviceToHost, st));
     ORBS_CUDA(cudaStreamSynchronize(st));
-    if (want_edges)
-        for (int j = 0; j < E; j++) {                                                         // Optimizer.cc:734-766
-            const int e = order[j];
-            if (e_chi2) e_chi2[e] = chi2_s[j];
-            if (e_depth_ok) e_depth_ok[e] = depth_s[j];
-            if (e_outlier) e_outlier[e] = (uint8_t)(chi2_s[j] > 5.991 || !depth_s[j]);
-        }
+    trace.mark("download");
+    if (want_edges) {                                                                         // Optimizer.cc:734-766
+        if (order.empty()) {
+            if (e_chi2) memcpy(e_chi2, chi2_s, (size_t)E * sizeof(double));
+            if (e_depth_ok) memcpy(e_depth_ok, depth_s, (size_t)E);
+            if (e_outlier) memcpy(e_outlier, outl_s, (size_t)E);
+        } else
+            for (int j = 0; j < E; j++) {
+                const int e = order[j];
+                if (e_chi2) e_chi2[e] = chi2_s[j];
+                if (e_depth_ok) e_depth_ok[e] = depth_s[j];
+                if (e_outlier) e_outlier[e] = outl_s[j];
+            }
+    }
     {
         const auto t_end = std::chrono::steady_clock::now();
         auto sec = [](auto a, auto b) { return std::chrono::duration<double>(b - a).count(); };
@@ -957,6 +1022,8 @@ extern "C" int orbo_bundle_adjust(orbo_handle *h, int K, float *poses, const uin
         h->ba_timing[3] = (double)B.nt * TS;
         h->ba_skyline[0] = B.nt; h->ba_skyline[1] = B.ns; h->ba_skyline[2] = D.plan.nlevels;
     }
+    trace.mark("edge_flags");
+    trace.dump();
     if (stats) { stats[0] = fin.lm_iterations; stats[1] = fin.lm_trials; stats[2] = fin.chol_failures; stats[3] = 0; }
     if (D.multi() && h->peer_on) {
         int perr = 0;

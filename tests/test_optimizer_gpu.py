@@ -127,6 +127,28 @@ def test_local_ba_shuffled_keyframes_is_dense(lib):
     assert _rel(got["poses"][g["perm"]], got0["poses"]) < RTOL and _rel(got["points"], got0["points"]) < RTOL
 
 
+def test_local_ba_edge_order(lib):
+    """The caller's edge list in any order: edges already grouped by ascending point take the straight-copy layout path, anything else the stable scatter;
+    a round-robin order over the points (relative order inside a point kept) lays out the same device graph -> bit-identical poses / points, per-edge
+    outputs returned in the caller's order."""
+    import orbslamm_b200 as ob
+    g = synth.ba_graph(K=40, P=3000, seed=5)
+    pt = g["pt"]
+    assert np.all(np.diff(pt) >= 0)
+    first = np.r_[0, np.flatnonzero(np.diff(pt)) + 1]
+    rank_in_pt = np.arange(len(pt)) - np.repeat(first, np.diff(np.r_[first, len(pt)]))
+    perm = np.lexsort((pt, rank_in_pt))                       # all first observations, then all second ones, ...
+    assert not np.all(np.diff(pt[perm]) >= 0)
+    opt = ob.Optimizer()
+    a = opt.LocalBundleAdjustment(g["poses"], g["fixed"], g["intr"], g["points"], g["kf"], g["pt"], g["uv"], g["inv_sigma2"])
+    b = opt.LocalBundleAdjustment(g["poses"], g["fixed"], g["intr"], g["points"], g["kf"][perm], g["pt"][perm], g["uv"][perm], g["inv_sigma2"][perm])
+    assert a["lm_iterations"] == b["lm_iterations"] and a["lm_trials"] == b["lm_trials"]
+    assert np.array_equal(a["poses"], b["poses"]) and np.array_equal(a["points"], b["points"])
+    assert np.array_equal(a["chi2"][perm], b["chi2"]) and np.array_equal(a["outlier"][perm], b["outlier"])
+    ref = oracle.bundle_adjust(g["poses"], g["fixed"], g["intr"], g["points"], g["kf"], g["pt"], g["uv"], g["inv_sigma2"], True, 5, 10, True)
+    assert _rel(a["poses"], ref["poses"]) < RTOL and _rel(a["points"], ref["points"]) < RTOL
+
+
 def test_global_ba_and_abort(lib):
     import orbslamm_b200 as ob
     g = synth.ba_graph(K=30, P=1500, seed=7)
