@@ -394,7 +394,8 @@ int orbo_pose_optimization_matched(orbo_handle *h, int n_frames, float *Tcw, con
  * with `robust`) over flat arrays (HOST pointers):
  *   poses f32[K,16] in/out; fixed u8[K]: 0 free, 1 fixed but written back (mnId == 0), 2 fixed camera (never written);
  *   intr f64[K,4] fx fy cx cy per keyframe; points f32[P,3] in/out;
- *   edges: e_kf i32[E], e_pt i32[E], e_uv f32[E,2], e_inv_sigma2 f32[E];
+ *   edges: e_kf i32[E], e_pt i32[E], e_uv f32[E,2], e_inv_sigma2 f32[E], in ANY order (the per-edge outputs come back in the caller's order);
+ *          a list already grouped by ascending e_pt -- what walking the map points produces, Optimizer.cc:595-675 -- skips the stable scatter;
  *   stop_flag: optional host flag, ONE BYTE (a C++ `bool *` such as &mbAbortBA / &mbStopGBA is passed as is), watched by the
  *              calling thread while the LM slots run on the device and seen by the device before every trial decision
  *              (g2o: terminate() per iteration and per trial, sparse_optimizer.h:188, levenberg.cpp:149);
