@@ -80,7 +80,10 @@ int orbx_extract(orbx_handle *h, const uint8_t *images, int n_frames, int width,
                  int32_t *kp_octave, float *kp_size, uint8_t *desc, int cap, int32_t *counts);
 
 /* Same, but the images are already in DEVICE memory and the results stay on the device
- * inside the handle (see orbx_device_results).  Asynchronous on the handle's stream. */
+ * inside the handle (see orbx_device_results).  Asynchronous on the handle's stream.
+ * Any base pointer / stride works.  With a 4-byte (resp. 16-byte) aligned base, stride and frame_stride the rows are read with word loads
+ * (resp. by the TMA engine) up to the aligned end of the row: every row, the last one included, must then be backed by `stride` bytes
+ * (a buffer of n_frames * frame_stride bytes with frame_stride >= height * stride, as cudaMallocPitch / a padded tensor gives). */
 int orbx_extract_device(orbx_handle *h, const uint8_t *d_images, int n_frames, int width,
                         int height, int stride, size_t frame_stride);
 
